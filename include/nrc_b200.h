@@ -1,0 +1,233 @@
+/*
+ * nrc_b200.h -- C ABI of the B200-native radiance-cache query path.
+ *
+ * This is the drop-in boundary.  The reference
+ * (benattal/neural-radiance-caching) is pure JAX and has no FFI of its own;
+ * each entry point below names the reference Python function whose *body* it
+ * replaces (file:line relative to the reference root).  A JAX maintainer binds
+ * them through an XLA-FFI custom call + jax.custom_vjp; this
+ * repository binds them through ctypes on torch device memory
+ * (neural_radiance_caching_b200/_lib.py).
+ *
+ * Conventions
+ *   - Every pointer named d_* is a DEVICE pointer owned by the caller; nothing
+ *     is allocated, freed or retained by the library.  `stream` is a
+ *     cudaStream_t passed as void*; all work is enqueued asynchronously on it.
+ *   - All arrays are dense row-major fp32 unless stated (int32 where stated).
+ *   - Hash/grid tables stay in the reference's checkpoint layout:
+ *       dense level  [N,N,N,F] indexed grid[ix][iy][iz][f]  (internal/grid_utils.py:703-711)
+ *       hash  level  [T,F]                                    (internal/grid_utils.py:835-841)
+ *   - Gradient outputs are ACCUMULATED INTO (caller zero-fills).
+ *   - Return value: 0 on success, negative nrc_status_t otherwise.  No
+ *     exceptions cross the ABI; numerics never trap (safe_* guards reproduced).
+ *   - Entry points are re-entrant and thread-safe.
+ *   - Randomness is never generated here: kernels take uniforms / Gumbel
+ *     noise as input tensors (the JAX host keeps its threefry streams).
+ */
+#ifndef NRC_B200_H_
+#define NRC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRC_MAX_LEVELS 16
+#define NRC_ABI_VERSION 1
+
+typedef enum {
+  NRC_OK = 0,
+  NRC_E_INVALID_ARG = -1,   /* bad shape / null pointer / unsupported F, L, width  */
+  NRC_E_UNSUPPORTED = -2,   /* valid request outside the compiled configurations   */
+  NRC_E_CUDA = -3           /* launch failure; see nrc_last_cuda_error()           */
+} nrc_status_t;
+
+/* One resolution level of a HashEncoding (internal/grid_utils.py:830-852). */
+typedef struct {
+  const float* d_table;   /* [N,N,N,F] (dense) or [T,F] (hash), fp32            */
+  float* d_grad;          /* same shape, accumulated into by *_bwd; may be NULL  */
+  int32_t grid_size;      /* N                                                   */
+  int32_t is_hash;        /* 0: dense grid (N^3 <= T), 1: hash table             */
+  uint32_t table_size;    /* T for hash levels, N^3 for dense levels             */
+  uint32_t reserved;
+} nrc_level_t;
+
+/* A HashEncoding instance (internal/grid_utils.py:738-905). */
+typedef struct {
+  int32_t num_levels;           /* L, 1..NRC_MAX_LEVELS                           */
+  int32_t num_features;         /* F in {1,2,4,8}                                 */
+  float bbox_min[3];            /* bbox[0]                        (:800-805)      */
+  float bbox_max[3];            /* bbox[1]                                        */
+  float bbox_span[3];           /* float32(bbox[1]-bbox[0])       (:820)          */
+  float precondition_scaling;   /* 10.0                            (:903)         */
+  nrc_level_t levels[NRC_MAX_LEVELS];
+} nrc_encoding_t;
+
+/* Fused density MLP parameters (internal/geometry.py:123-168): Dense kernels are
+ * Flax layout [in,out] fp32, biases [out].  hidden = 64, depth = 2. */
+typedef struct {
+  const float* d_w0; const float* d_b0;   /* [in_dim,64], [64]                     */
+  const float* d_w1; const float* d_b1;   /* [64,64], [64]                         */
+  const float* d_wd; const float* d_bd;   /* output_density_layer [64,1], [1]      */
+  const float* d_wn; const float* d_bn;   /* pred_normals_layer [64,3], [3] or NULL*/
+  int32_t in_dim;                          /* L*F (6, 7 or 32 in the configs)      */
+  int32_t width;                           /* 64                                   */
+} nrc_density_mlp_t;
+
+typedef struct {
+  float* d_w0; float* d_b0; float* d_w1; float* d_b1;
+  float* d_wd; float* d_bd; float* d_wn; float* d_bn;
+} nrc_density_mlp_grad_t;
+
+/* ---------------------------------------------------------------- misc ---- */
+int32_t nrc_abi_version(void);
+const char* nrc_error_string(int32_t status);
+/* cudaError_t of the most recent failed launch on the calling thread. */
+int32_t nrc_last_cuda_error(void);
+
+/* ---------------------------------------------------- K1/K2: encoding ---- */
+/* Replaces HashEncoding.__call__ (internal/grid_utils.py:807-905) with
+ * x_scale=None, per_level_fn=mean over a size-1 multisample axis,
+ * feature_aggregator='concatenate': trilerp (:679-726) over
+ * jax_hash_resample_3d (:41-121) / jax_resample_3d (:352-445).
+ *   d_x   [P,3]   coordinates in the encoding's bbox frame (already warped)
+ *   d_out [P,L*F] concatenated features * precondition_scaling
+ */
+int32_t nrc_encode_fwd(void* stream, const nrc_encoding_t* enc, const float* d_x,
+                       int64_t num_points, float* d_out);
+
+/* Parity aid: the integer half of the same path for one level.  d_idx [P,8]
+ * int32 in the reference's corner order: hash levels -> table row index
+ * (grid_utils.py:101-111); dense levels -> flat index into the zero-padded
+ * (N+2)^3 volume, ((ix*(N+2))+iy)*(N+2)+iz  (grid_utils.py:384-438). */
+int32_t nrc_encode_indices(void* stream, const nrc_encoding_t* enc, int32_t level,
+                           const float* d_x, int64_t num_points, int32_t* d_idx);
+
+/* VJP of nrc_encode_fwd (XLA's transpose of the gathers).
+ *   d_g_out [P,L*F]  upstream gradient
+ *   levels[l].d_grad += scatter-add of g*w          (skipped when NULL)
+ *   d_g_x   [P,3]    written (not accumulated) when non-NULL: dL/dx
+ */
+int32_t nrc_encode_bwd(void* stream, const nrc_encoding_t* enc, const float* d_x,
+                       const float* d_g_out, int64_t num_points, float* d_g_x);
+
+/* -------------------------------------------------- contraction (row 7) ---- */
+/* coord.contract(x / c) (internal/coord.py:33-38,63-69); c <= 0 means identity. */
+int32_t nrc_contract_fwd(void* stream, const float* d_x, int64_t num_points, float c, float* d_z);
+/* d_g_x[P,3] = J^T d_g_z. */
+int32_t nrc_contract_bwd(void* stream, const float* d_x, const float* d_g_z, int64_t num_points,
+                         float c, float* d_g_x);
+
+/* ------------------------------------------------ K3: density MLP (row 8) -- */
+/* BaseDensityMLP.run_network (internal/geometry.py:155-168) for depth 2/width 64,
+ * plus pred_normals_layer (:467) when mlp->d_wn != NULL.
+ *   d_enc [P,in_dim] -> d_raw [P], d_feat [P,64] (may be NULL), d_grad_pred [P,3] (may be NULL)
+ * bf16 != 0 selects the tensor-core variant (bf16 operands, fp32 accumulate). */
+int32_t nrc_density_mlp_fwd(void* stream, const nrc_density_mlp_t* mlp, const float* d_enc,
+                            int64_t num_points, int32_t bf16, float* d_raw, float* d_feat,
+                            float* d_grad_pred);
+/* VJP.  Upstream grads d_g_raw [P], d_g_feat [P,64] or NULL, d_g_grad_pred [P,3] or NULL.
+ * Outputs: d_g_enc [P,in_dim] (written, may be NULL); weight grads accumulated into `grads`
+ * (may be NULL to skip). */
+int32_t nrc_density_mlp_bwd(void* stream, const nrc_density_mlp_t* mlp, const float* d_enc,
+                            const float* d_g_raw, const float* d_g_feat, const float* d_g_grad_pred,
+                            int64_t num_points, float* d_g_enc, const nrc_density_mlp_grad_t* grads);
+
+/* Fused point query: means -> contract(x/c) -> encode -> MLP ->
+ * density = safe_exp(raw + density_bias) masked to the bbox
+ * (internal/geometry.py:199-341), optionally the analytic normals' raw gradient
+ * d raw / d means (:442-460).
+ *   d_means [P,3]; outputs (each may be NULL): d_density [P], d_raw [P],
+ *   d_feat [P,64], d_grad_pred [P,3], d_raw_grad [P,3]. */
+int32_t nrc_density_query_fwd(void* stream, const nrc_encoding_t* enc, const nrc_density_mlp_t* mlp,
+                              const float* d_means, int64_t num_points, float warp_c,
+                              float density_bias, int32_t bf16, float* d_density, float* d_raw,
+                              float* d_feat, float* d_grad_pred, float* d_raw_grad);
+
+/* ------------------------------------------------------ K4: ray kernels ---- */
+/* render.compute_alpha_weights (internal/render.py:134-169), delta=None.
+ *   d_density [R,n], d_tdist [R,n+1], d_dirs [R,3] -> d_weights, d_alpha, d_trans [R,n]
+ *   (d_alpha / d_trans may be NULL). */
+int32_t nrc_ray_alpha_weights_fwd(void* stream, const float* d_density, const float* d_tdist,
+                                  const float* d_dirs, int64_t num_rays, int32_t n,
+                                  int32_t opaque_background, float* d_weights, float* d_alpha,
+                                  float* d_trans);
+/* VJP wrt density: d_g_density [R,n] written. Upstream d_g_weights (may be NULL),
+ * d_g_alpha (may be NULL), d_g_trans (may be NULL). */
+int32_t nrc_ray_alpha_weights_bwd(void* stream, const float* d_density, const float* d_tdist,
+                                  const float* d_dirs, const float* d_g_weights,
+                                  const float* d_g_alpha, const float* d_g_trans, int64_t num_rays,
+                                  int32_t n, float* d_g_density);
+
+/* stepfun.sample_intervals (internal/stepfun.py:207-250) with single_jitter=True,
+ * preceded by the sampler's annealed logits (internal/sampling.py:340):
+ *   logits = anneal * safe_log(weights + padding).
+ *   d_t [R,m+1] current fenceposts, d_w [R,m] current weights, d_u01 [R] uniforms in [0,1),
+ *   d_u_base [n] = linspace part of u (host computes it in fp32, see stepfun.sample_u_base)
+ *   -> d_t_new [R,n+1] sorted, clipped to [dom_lo,dom_hi]; d_bin_idx [R,n] int32 (idx0 of
+ *   math.sorted_lookup, internal/math.py:433-439; may be NULL). */
+int32_t nrc_ray_sample_intervals(void* stream, const float* d_t, const float* d_w,
+                                 const float* d_u01, const float* d_u_base, int64_t num_rays,
+                                 int32_t m, int32_t n, float anneal, float padding,
+                                 float max_jitter, float dom_lo, float dom_hi, float* d_t_new,
+                                 int32_t* d_bin_idx);
+
+/* s_to_t (internal/coord.py:223-260) + render.cast_rays means (internal/render.py:106-131,
+ * cone, stable mip-NeRF mean).  warp_kind 0: linear t = s*far + (1-s)*near; 1: power ladder
+ * (internal/math.py:295-341) with (p, premult).
+ *   d_sdist [R,n+1] -> d_tdist [R,n+1], d_means [R,n,3]. */
+int32_t nrc_ray_cast(void* stream, const float* d_sdist, const float* d_origins,
+                     const float* d_directions, const float* d_near, const float* d_far,
+                     int64_t num_rays, int32_t n, int32_t warp_kind, float p, float premult,
+                     float* d_tdist, float* d_means);
+
+/* render.volumetric_rendering (internal/render.py:172-247): acc, rgb (+bg), C channels
+ * composited with `weights`, distance mean and percentiles (5,50,95) from
+ * `weights_no_filter`.
+ *   d_values [R,k,C] (rgb first when has_rgb), d_weights [R,k],
+ *   d_weights_nf [R,n] (NULL: same as d_weights, k == n), d_tdist [R,n+1], d_bg [R,3] or NULL
+ *   -> d_out [R,C], d_acc [R] (may be NULL), d_dist [R,4] = (mean, p5, median, p95; may be NULL). */
+int32_t nrc_ray_composite_fwd(void* stream, const float* d_values, const float* d_weights, int32_t k,
+                              const float* d_weights_nf, const float* d_tdist, const float* d_bg,
+                              int64_t num_rays, int32_t n, int32_t channels, int32_t has_rgb,
+                              float* d_out, float* d_acc, float* d_dist);
+/* VJP wrt values, weights and weights_no_filter (rgb/extras/acc terms; the distance
+ * statistics carry no gradient here).  Outputs are written; d_g_weights_nf NULL with
+ * d_weights_nf NULL means weights == weights_no_filter and the acc term goes to d_g_weights. */
+int32_t nrc_ray_composite_bwd(void* stream, const float* d_values, const float* d_weights, int32_t k,
+                              const float* d_weights_nf, const float* d_bg, const float* d_g_out,
+                              const float* d_g_acc, int64_t num_rays, int32_t n, int32_t channels,
+                              int32_t has_rgb, float* d_g_values, float* d_g_weights,
+                              float* d_g_weights_nf);
+
+/* Model.maybe_resample (internal/models.py:193-292), resample_argmax=False:
+ *   logits = safe_log(w + bias) * mult; inds = argmax(logits + gumbel) per draw;
+ *   w_new = w[inds] / (num_resample * softmax(logits)[inds] + 1e-8).
+ *   d_weights [R,n], d_gumbel [R,n,k] -> d_inds [R,k] int32, d_w_new [R,k]. */
+int32_t nrc_ray_resample(void* stream, const float* d_weights, const float* d_gumbel,
+                         int64_t num_rays, int32_t n, int32_t k, float bias, float mult,
+                         int32_t* d_inds, float* d_w_new);
+/* take_along_axis of a per-sample field: d_field [R,n,C] -> d_out [R,k,C]. */
+int32_t nrc_ray_resample_gather(void* stream, const float* d_field, const int32_t* d_inds,
+                                int64_t num_rays, int32_t n, int32_t k, int32_t channels,
+                                float* d_out);
+
+/* ------------------------------------------------- K5: GGX integration ---- */
+/* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) for the
+ * microfacet material + integrate_reflect_rays (:1102-1193): Disney-GGX D*F*G and Lambert
+ * lobes, MIS-weighted Monte-Carlo mean of cache radiance.
+ *   d_wi [R,S,3] local-frame incoming dirs, d_wo [R,3] local outgoing, d_radiance [R,S,3],
+ *   d_weight [R,S] MIS weights, d_pdf [R,S], material: d_albedo [R,3], d_roughness [R],
+ *   d_metalness [R], d_f0 [R].  -> d_radiance_out [R,3], d_irradiance [R,3] (may be NULL). */
+int32_t nrc_ggx_integrate_fwd(void* stream, const float* d_wi, const float* d_wo,
+                              const float* d_radiance, const float* d_weight, const float* d_pdf,
+                              const float* d_albedo, const float* d_roughness,
+                              const float* d_metalness, const float* d_f0, int64_t num_points,
+                              int32_t num_samples, int32_t lobe_kind, float rgb_max,
+                              float* d_radiance_out, float* d_irradiance);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRC_B200_H_ */

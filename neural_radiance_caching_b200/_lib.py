@@ -1,0 +1,161 @@
+"""ctypes binding of include/nrc_b200.h (the C-ABI drop-in boundary).
+
+There is NO CPU fallback: importing the package works anywhere (so that the
+build check and host-logic tests run on a CPU box), but every compute call
+raises unless libnrc_b200.so is built in-tree and the tensors live on a CUDA
+device.
+"""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnrc_b200.so")
+NRC_MAX_LEVELS = 16
+
+
+class NrcError(RuntimeError):
+    pass
+
+
+class nrc_level_t(C.Structure):
+    _fields_ = [
+        ("d_table", C.c_void_p),
+        ("d_grad", C.c_void_p),
+        ("grid_size", C.c_int32),
+        ("is_hash", C.c_int32),
+        ("table_size", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class nrc_encoding_t(C.Structure):
+    _fields_ = [
+        ("num_levels", C.c_int32),
+        ("num_features", C.c_int32),
+        ("bbox_min", C.c_float * 3),
+        ("bbox_max", C.c_float * 3),
+        ("bbox_span", C.c_float * 3),
+        ("precondition_scaling", C.c_float),
+        ("levels", nrc_level_t * NRC_MAX_LEVELS),
+    ]
+
+
+class nrc_density_mlp_t(C.Structure):
+    _fields_ = [
+        ("d_w0", C.c_void_p), ("d_b0", C.c_void_p),
+        ("d_w1", C.c_void_p), ("d_b1", C.c_void_p),
+        ("d_wd", C.c_void_p), ("d_bd", C.c_void_p),
+        ("d_wn", C.c_void_p), ("d_bn", C.c_void_p),
+        ("in_dim", C.c_int32), ("width", C.c_int32),
+    ]
+
+
+class nrc_density_mlp_grad_t(C.Structure):
+    _fields_ = [
+        ("d_w0", C.c_void_p), ("d_b0", C.c_void_p),
+        ("d_w1", C.c_void_p), ("d_b1", C.c_void_p),
+        ("d_wd", C.c_void_p), ("d_bd", C.c_void_p),
+        ("d_wn", C.c_void_p), ("d_bn", C.c_void_p),
+    ]
+
+
+_P = C.c_void_p
+_I32 = C.c_int32
+_I64 = C.c_int64
+_F = C.c_float
+
+# name -> argtypes (restype is int32 unless listed in _RESTYPES).  Must list every
+# symbol include/nrc_b200.h declares (tests/test_abi.py checks this against the header).
+PROTOTYPES = {
+    "nrc_abi_version": [],
+    "nrc_error_string": [_I32],
+    "nrc_last_cuda_error": [],
+    "nrc_encode_fwd": [_P, C.POINTER(nrc_encoding_t), _P, _I64, _P],
+    "nrc_encode_indices": [_P, C.POINTER(nrc_encoding_t), _I32, _P, _I64, _P],
+    "nrc_encode_bwd": [_P, C.POINTER(nrc_encoding_t), _P, _P, _I64, _P],
+    "nrc_contract_fwd": [_P, _P, _I64, _F, _P],
+    "nrc_contract_bwd": [_P, _P, _P, _I64, _F, _P],
+    "nrc_density_mlp_fwd": [_P, C.POINTER(nrc_density_mlp_t), _P, _I64, _I32, _P, _P, _P],
+    "nrc_density_mlp_bwd": [_P, C.POINTER(nrc_density_mlp_t), _P, _P, _P, _P, _I64, _P,
+                            C.POINTER(nrc_density_mlp_grad_t)],
+    "nrc_density_query_fwd": [_P, C.POINTER(nrc_encoding_t), C.POINTER(nrc_density_mlp_t), _P, _I64, _F, _F,
+                              _I32, _P, _P, _P, _P, _P],
+    "nrc_ray_alpha_weights_fwd": [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P],
+    "nrc_ray_alpha_weights_bwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    "nrc_ray_sample_intervals": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _F, _F, _P, _P],
+    "nrc_ray_cast": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _P, _P],
+    "nrc_ray_composite_fwd": [_P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P],
+    "nrc_ray_composite_bwd": [_P, _P, _P, _I32, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P],
+    "nrc_ray_resample": [_P, _P, _P, _I64, _I32, _I32, _F, _F, _P, _P],
+    "nrc_ray_resample_gather": [_P, _P, _P, _I64, _I32, _I32, _I32, _P],
+    "nrc_ggx_integrate_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P],
+}
+_RESTYPES = {"nrc_error_string": C.c_char_p}
+
+_lib = None
+
+
+def load():
+    """Load libnrc_b200.so; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NrcError(
+            f"{LIB_PATH} is missing: build it with `python -m neural_radiance_caching_b200.build` "
+            "(there is no CPU fallback for the radiance-cache query path)."
+        )
+    lib = C.CDLL(LIB_PATH)
+    missing = []
+    for name, argtypes in PROTOTYPES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int32)
+    if missing:
+        raise NrcError(f"{LIB_PATH} does not export {missing}: stale build? run the build with --force")
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        lib = load()
+        msg = lib.nrc_error_string(status).decode()
+        extra = f" (cudaError {lib.nrc_last_cuda_error()})" if status == -3 else ""
+        raise NrcError(f"{what}: {msg}{extra}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32/int32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise NrcError(f"expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise NrcError("nrc_b200 kernels need CUDA tensors: there is no CPU fallback")
+    if not t.is_contiguous():
+        raise NrcError("nrc_b200 kernels need contiguous tensors")
+    if t.dtype not in (torch.float32, torch.int32):
+        raise NrcError(f"unsupported dtype {t.dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# Count of kernel-launching ABI calls (bench.py reports it as gpu_launches).
+launch_count = 0
+
+
+def call(name, *args):
+    global launch_count
+    lib = load()
+    launch_count += 1
+    check(getattr(lib, name)(*args), name)

@@ -1,0 +1,259 @@
+// K1 / K2: multiresolution hash-grid encoding, forward gather and backward
+// scatter-add.  Replaces HashEncoding.__call__ (internal/grid_utils.py:807-905)
+// and XLA's transpose of its gathers.
+//
+// Work decomposition: one thread per (point, level); blockIdx.y = level so that
+// the CTAs resident at any instant mostly touch ONE level's table (2-8 MB), which
+// stays L2/L1 resident; threadIdx.x runs over consecutive points (= consecutive
+// samples of one ray), so coarse-level corner fetches of a warp coalesce.
+#include "encode.cuh"
+
+namespace nrc {
+
+thread_local int g_last_cuda_error = 0;
+
+constexpr int kEncThreads = 256;
+
+template <int F>
+__global__ void __launch_bounds__(kEncThreads)
+encode_fwd_kernel(const __grid_constant__ EncDev enc, const float* __restrict__ x, int64_t P,
+                  float* __restrict__ out) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kEncThreads + threadIdx.x;
+  if (p >= P) return;
+  const int l = blockIdx.y;
+  const LevelDev& lv = enc.lv[l];
+  float xi[3] = {__ldg(x + 3 * p), __ldg(x + 3 * p + 1), __ldg(x + 3 * p + 2)};
+  float xn[3];
+  normalise_point(enc, xi, xn);
+  Corners c = level_setup(lv, xn);
+  FeatVec<F> acc = level_interp<F>(lv, c);
+  float* o = out + p * (enc.L * F) + l * F;
+  if constexpr (F == 4) {
+    float4 r = make_float4(__fmul_rn(acc.v[0], enc.scale), __fmul_rn(acc.v[1], enc.scale),
+                           __fmul_rn(acc.v[2], enc.scale), __fmul_rn(acc.v[3], enc.scale));
+    *reinterpret_cast<float4*>(o) = r;
+  } else {
+#pragma unroll
+    for (int f = 0; f < F; ++f) o[f] = __fmul_rn(acc.v[f], enc.scale);
+  }
+}
+
+__global__ void __launch_bounds__(kEncThreads)
+encode_indices_kernel(const __grid_constant__ EncDev enc, int level, const float* __restrict__ x,
+                      int64_t P, int32_t* __restrict__ idx) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kEncThreads + threadIdx.x;
+  if (p >= P) return;
+  const LevelDev& lv = enc.lv[level];
+  float xi[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
+  float xn[3];
+  normalise_point(enc, xi, xn);
+  Corners c = level_setup(lv, xn);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int bx, by, bz;
+    corner_bits(lv.is_hash, k, bx, by, bz);
+    idx[p * 8 + k] = lv.is_hash ? corner_row(lv, c, bx, by, bz) : corner_padded_index(lv, c, bx, by, bz);
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void atomic_add_row(float* grad, int32_t row, const float (&g)[F]) {
+  if constexpr (F == 4) {
+    atomicAdd(reinterpret_cast<float4*>(grad) + row, make_float4(g[0], g[1], g[2], g[3]));
+  } else if constexpr (F == 2) {
+    atomicAdd(reinterpret_cast<float2*>(grad) + row, make_float2(g[0], g[1]));
+  } else if constexpr (F == 8) {
+    atomicAdd(reinterpret_cast<float4*>(grad) + 2 * row, make_float4(g[0], g[1], g[2], g[3]));
+    atomicAdd(reinterpret_cast<float4*>(grad) + 2 * row + 1, make_float4(g[4], g[5], g[6], g[7]));
+  } else {
+    atomicAdd(grad + row, g[0]);
+  }
+}
+
+// Backward: scatter-add into the level's gradient table and (optionally) the VJP
+// with respect to x, accumulated over levels with atomics into a zeroed [P,3].
+template <int F, bool kTableGrad, bool kXGrad>
+__global__ void __launch_bounds__(kEncThreads)
+encode_bwd_kernel(const __grid_constant__ EncDev enc, const float* __restrict__ x,
+                  const float* __restrict__ g_out, int64_t P, float* __restrict__ g_x) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kEncThreads + threadIdx.x;
+  if (p >= P) return;
+  const int l = blockIdx.y;
+  const LevelDev& lv = enc.lv[l];
+  float xi[3] = {__ldg(x + 3 * p), __ldg(x + 3 * p + 1), __ldg(x + 3 * p + 2)};
+  float xn[3];
+  normalise_point(enc, xi, xn);
+  Corners c = level_setup(lv, xn);
+  float g[F];
+  const float* gp = g_out + p * (enc.L * F) + l * F;
+#pragma unroll
+  for (int f = 0; f < F; ++f) g[f] = __ldg(gp + f) * enc.scale;
+
+  float gx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int bx, by, bz;
+    corner_bits(lv.is_hash, k, bx, by, bz);
+    int32_t row = corner_row(lv, c, bx, by, bz);
+    if (row < 0) continue;
+    float wx = bx ? c.cw[0] : c.fw[0];
+    float wy = by ? c.cw[1] : c.fw[1];
+    float wz = bz ? c.cw[2] : c.fw[2];
+    if constexpr (kTableGrad) {
+      if (lv.grad) {
+        float w = wx * wy * wz;
+        float gw[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) gw[f] = g[f] * w;
+        atomic_add_row<F>(lv.grad, row, gw);
+      }
+    }
+    if constexpr (kXGrad) {
+      FeatVec<F> v = load_row<F>(lv.table, row);
+      float dot = 0.f;
+#pragma unroll
+      for (int f = 0; f < F; ++f) dot += g[f] * v.v[f];
+      gx[0] += (bx ? dot : -dot) * (wy * wz);
+      gx[1] += (by ? dot : -dot) * (wx * wz);
+      gx[2] += (bz ? dot : -dot) * (wx * wy);
+    }
+  }
+  if constexpr (kXGrad) {
+    const float fN = static_cast<float>(lv.N);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) atomicAdd(g_x + 3 * p + a, gx[a] * (fN / enc.span[a]));
+  }
+}
+
+template <int F>
+int32_t launch_fwd(cudaStream_t s, const EncDev& d, const float* x, int64_t P, float* out) {
+  dim3 grid(static_cast<unsigned>((P + kEncThreads - 1) / kEncThreads), d.L);
+  encode_fwd_kernel<F><<<grid, kEncThreads, 0, s>>>(d, x, P, out);
+  return check_launch();
+}
+
+template <int F>
+int32_t launch_bwd(cudaStream_t s, const EncDev& d, const float* x, const float* g, int64_t P,
+                   float* g_x, bool table_grad) {
+  dim3 grid(static_cast<unsigned>((P + kEncThreads - 1) / kEncThreads), d.L);
+  if (table_grad && g_x) encode_bwd_kernel<F, true, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x);
+  else if (table_grad) encode_bwd_kernel<F, true, false><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x);
+  else if (g_x) encode_bwd_kernel<F, false, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x);
+  return check_launch();
+}
+
+}  // namespace nrc
+
+using namespace nrc;
+
+extern "C" int32_t nrc_encode_fwd(void* stream, const nrc_encoding_t* enc, const float* d_x,
+                                  int64_t num_points, float* d_out) {
+  EncDev d;
+  int32_t st = make_enc_dev(enc, d);
+  if (st != NRC_OK) return st;
+  if (num_points < 0 || (num_points > 0 && (!d_x || !d_out))) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (d.F) {
+    case 1: return launch_fwd<1>(s, d, d_x, num_points, d_out);
+    case 2: return launch_fwd<2>(s, d, d_x, num_points, d_out);
+    case 4: return launch_fwd<4>(s, d, d_x, num_points, d_out);
+    case 8: return launch_fwd<8>(s, d, d_x, num_points, d_out);
+  }
+  return NRC_E_UNSUPPORTED;
+}
+
+extern "C" int32_t nrc_encode_indices(void* stream, const nrc_encoding_t* enc, int32_t level,
+                                      const float* d_x, int64_t num_points, int32_t* d_idx) {
+  EncDev d;
+  int32_t st = make_enc_dev(enc, d);
+  if (st != NRC_OK) return st;
+  if (level < 0 || level >= d.L || num_points < 0) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_x || !d_idx) return NRC_E_INVALID_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned grid = static_cast<unsigned>((num_points + kEncThreads - 1) / kEncThreads);
+  encode_indices_kernel<<<grid, kEncThreads, 0, s>>>(d, level, d_x, num_points, d_idx);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_encode_bwd(void* stream, const nrc_encoding_t* enc, const float* d_x,
+                                  const float* d_g_out, int64_t num_points, float* d_g_x) {
+  EncDev d;
+  int32_t st = make_enc_dev(enc, d);
+  if (st != NRC_OK) return st;
+  if (num_points < 0) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_x || !d_g_out) return NRC_E_INVALID_ARG;
+  bool table_grad = false;
+  for (int l = 0; l < d.L; ++l) table_grad |= (d.lv[l].grad != nullptr);
+  if (!table_grad && !d_g_x) return NRC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d_g_x) {
+    cudaError_t e = cudaMemsetAsync(d_g_x, 0, sizeof(float) * 3 * num_points, s);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return NRC_E_CUDA; }
+  }
+  switch (d.F) {
+    case 1: return launch_bwd<1>(s, d, d_x, d_g_out, num_points, d_g_x, table_grad);
+    case 2: return launch_bwd<2>(s, d, d_x, d_g_out, num_points, d_g_x, table_grad);
+    case 4: return launch_bwd<4>(s, d, d_x, d_g_out, num_points, d_g_x, table_grad);
+    case 8: return launch_bwd<8>(s, d, d_x, d_g_out, num_points, d_g_x, table_grad);
+  }
+  return NRC_E_UNSUPPORTED;
+}
+
+extern "C" int32_t nrc_abi_version(void) { return NRC_ABI_VERSION; }
+
+extern "C" const char* nrc_error_string(int32_t status) {
+  switch (status) {
+    case NRC_OK: return "ok";
+    case NRC_E_INVALID_ARG: return "invalid argument";
+    case NRC_E_UNSUPPORTED: return "unsupported configuration";
+    case NRC_E_CUDA: return "CUDA launch failure (see nrc_last_cuda_error)";
+  }
+  return "unknown status";
+}
+
+extern "C" int32_t nrc_last_cuda_error(void) { return g_last_cuda_error; }
+
+// ------------------------------------------------------------- contraction --
+namespace nrc {
+__global__ void contract_fwd_kernel(const float* __restrict__ x, int64_t P, float c,
+                                    float* __restrict__ z) {
+  int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float z0, z1, z2;
+  contract_point(c, x[3 * p], x[3 * p + 1], x[3 * p + 2], z0, z1, z2);
+  z[3 * p] = z0; z[3 * p + 1] = z1; z[3 * p + 2] = z2;
+}
+__global__ void contract_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gz,
+                                    int64_t P, float c, float* __restrict__ gx) {
+  int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float o0, o1, o2;
+  contract_vjp(c, x[3 * p], x[3 * p + 1], x[3 * p + 2], gz[3 * p], gz[3 * p + 1], gz[3 * p + 2], o0,
+               o1, o2);
+  gx[3 * p] = o0; gx[3 * p + 1] = o1; gx[3 * p + 2] = o2;
+}
+}  // namespace nrc
+
+extern "C" int32_t nrc_contract_fwd(void* stream, const float* d_x, int64_t num_points, float c,
+                                    float* d_z) {
+  if (num_points < 0) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_x || !d_z) return NRC_E_INVALID_ARG;
+  unsigned grid = static_cast<unsigned>((num_points + 255) / 256);
+  contract_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, num_points, c, d_z);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_contract_bwd(void* stream, const float* d_x, const float* d_g_z,
+                                    int64_t num_points, float c, float* d_g_x) {
+  if (num_points < 0) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_x || !d_g_z || !d_g_x) return NRC_E_INVALID_ARG;
+  unsigned grid = static_cast<unsigned>((num_points + 255) / 256);
+  contract_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_g_z, num_points, c,
+                                                                          d_g_x);
+  return check_launch();
+}

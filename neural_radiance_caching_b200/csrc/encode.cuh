@@ -1,0 +1,196 @@
+// Device-side corner enumeration of one HashEncoding level, shared by the
+// stand-alone encode kernels (encode.cu) and the fused query kernels (query.cu).
+//
+// Follows internal/grid_utils.py: hash levels :41-121, dense levels :352-445 via
+// trilerp :679-726.  Index arithmetic uses individually rounded fp32 ops in the
+// reference's order (no FMA contraction), so corner indices are bit-exact.
+#pragma once
+#include "nrc_common.cuh"
+
+namespace nrc {
+
+struct LevelDev {
+  const float* table;
+  float* grad;
+  int32_t N;
+  int32_t is_hash;
+  uint32_t T;
+  uint32_t pow2_mask;  // T-1 when T is a power of two, else 0
+};
+
+struct EncDev {
+  int32_t L;
+  int32_t F;
+  float b0[3];
+  float b1[3];
+  float span[3];
+  float scale;
+  LevelDev lv[NRC_MAX_LEVELS];
+};
+
+inline int32_t make_enc_dev(const nrc_encoding_t* enc, EncDev& d) {
+  if (!enc) return NRC_E_INVALID_ARG;
+  if (enc->num_levels < 1 || enc->num_levels > NRC_MAX_LEVELS) return NRC_E_INVALID_ARG;
+  int F = enc->num_features;
+  if (!(F == 1 || F == 2 || F == 4 || F == 8)) return NRC_E_UNSUPPORTED;
+  d.L = enc->num_levels;
+  d.F = F;
+  for (int a = 0; a < 3; ++a) {
+    d.b0[a] = enc->bbox_min[a];
+    d.b1[a] = enc->bbox_max[a];
+    d.span[a] = enc->bbox_span[a];
+    if (!(enc->bbox_span[a] > 0.f)) return NRC_E_INVALID_ARG;
+  }
+  d.scale = enc->precondition_scaling;
+  for (int l = 0; l < d.L; ++l) {
+    const nrc_level_t& s = enc->levels[l];
+    if (!s.d_table || s.grid_size < 1 || s.table_size == 0) return NRC_E_INVALID_ARG;
+    if (!s.is_hash && (uint64_t)s.grid_size * s.grid_size * s.grid_size != s.table_size)
+      return NRC_E_INVALID_ARG;
+    d.lv[l].table = s.d_table;
+    d.lv[l].grad = s.d_grad;
+    d.lv[l].N = s.grid_size;
+    d.lv[l].is_hash = s.is_hash;
+    d.lv[l].T = s.table_size;
+    d.lv[l].pow2_mask = ((s.table_size & (s.table_size - 1)) == 0) ? s.table_size - 1 : 0u;
+  }
+  return NRC_OK;
+}
+
+constexpr uint32_t kPi2 = 19349663u;  // internal/grid_utils.py:102
+constexpr uint32_t kPi3 = 83492791u;  // internal/grid_utils.py:103
+
+// Per-level interpolation set-up for one point.
+struct Corners {
+  int32_t fl[3];   // floor index per original axis (x,y,z); dense: padded-grid index
+  float cw[3];     // ceil weights  (loc - floor)
+  float fw[3];     // floor weights (1 - cw)
+};
+
+// xn: x mapped to [0,1]^3 (already (x-b0)/span).  HashEncoding.__call__ :863 multiplies
+// by N; trilerp / hash_resample subtract 0.5; the dense path then adds 1.0 (:390).
+__device__ __forceinline__ Corners level_setup(const LevelDev& lv, const float xn[3]) {
+  Corners c;
+  const float fN = static_cast<float>(lv.N);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float pos = __fmul_rn(xn[a], fN);
+    float loc = __fsub_rn(pos, 0.5f);
+    if (!lv.is_hash) loc = __fadd_rn(loc, 1.0f);
+    float f = floorf(loc);
+    c.cw[a] = __fsub_rn(loc, f);
+    c.fw[a] = __fsub_rn(1.0f, c.cw[a]);
+    c.fl[a] = __float2int_rz(f);  // saturating f32->s32, like XLA's convert
+  }
+  return c;
+}
+
+// Row index of corner (bx,by,bz) in {0,1}^3, or -1 for a zero-padding voxel.
+__device__ __forceinline__ int32_t corner_row(const LevelDev& lv, const Corners& c, int bx, int by,
+                                              int bz) {
+  if (lv.is_hash) {
+    // int32 -> uint32 wrap-around (:98-101), uint32 multiplies wrap (:105-108).
+    uint32_t ux = static_cast<uint32_t>(c.fl[0] + bx);
+    uint32_t uy = static_cast<uint32_t>(c.fl[1] + by);
+    uint32_t uz = static_cast<uint32_t>(c.fl[2] + bz);
+    uint32_t h = ux ^ ((uy * kPi2) ^ (uz * kPi3));
+    return static_cast<int32_t>(lv.pow2_mask ? (h & lv.pow2_mask) : (h % lv.T));
+  }
+  const int N = lv.N;
+  int ix = min(max(c.fl[0] + bx, 0), N + 1);  // clamp into the padded volume (:437-438)
+  int iy = min(max(c.fl[1] + by, 0), N + 1);
+  int iz = min(max(c.fl[2] + bz, 0), N + 1);
+  if (ix == 0 || iy == 0 || iz == 0 || ix == N + 1 || iy == N + 1 || iz == N + 1) return -1;
+  return ((ix - 1) * N + (iy - 1)) * N + (iz - 1);
+}
+
+// Flat index into the padded (N+2)^3 volume (parity aid for dense levels).
+__device__ __forceinline__ int32_t corner_padded_index(const LevelDev& lv, const Corners& c, int bx,
+                                                       int by, int bz) {
+  const int N = lv.N;
+  int ix = min(max(c.fl[0] + bx, 0), N + 1);
+  int iy = min(max(c.fl[1] + by, 0), N + 1);
+  int iz = min(max(c.fl[2] + bz, 0), N + 1);
+  return (ix * (N + 2) + iy) * (N + 2) + iz;
+}
+
+// Reference corner order k = 0..7 and weight product order.
+//   hash : x outermost, z innermost; w = (wx*wy)*wz          (:68-89)
+//   dense: operates on flipped coords -> z outermost, x innermost; w = (wz*wy)*wx
+__device__ __forceinline__ void corner_bits(int is_hash, int k, int& bx, int& by, int& bz) {
+  int hi = (k >> 2) & 1, mid = (k >> 1) & 1, lo = k & 1;
+  if (is_hash) { bx = hi; by = mid; bz = lo; }
+  else         { bz = hi; by = mid; bx = lo; }
+}
+
+__device__ __forceinline__ float corner_weight(int is_hash, const Corners& c, int bx, int by,
+                                               int bz) {
+  float wx = bx ? c.cw[0] : c.fw[0];
+  float wy = by ? c.cw[1] : c.fw[1];
+  float wz = bz ? c.cw[2] : c.fw[2];
+  return is_hash ? __fmul_rn(__fmul_rn(wx, wy), wz) : __fmul_rn(__fmul_rn(wz, wy), wx);
+}
+
+template <int F>
+struct FeatVec { float v[F]; };
+
+template <int F>
+__device__ __forceinline__ FeatVec<F> load_row(const float* __restrict__ table, int32_t row) {
+  FeatVec<F> r;
+  if constexpr (F == 1) {
+    r.v[0] = __ldg(table + row);
+  } else if constexpr (F == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(table) + row);
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else if constexpr (F == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(table) + row);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    static_assert(F == 8, "F in {1,2,4,8}");
+    float4 t0 = __ldg(reinterpret_cast<const float4*>(table) + 2 * row);
+    float4 t1 = __ldg(reinterpret_cast<const float4*>(table) + 2 * row + 1);
+    r.v[0] = t0.x; r.v[1] = t0.y; r.v[2] = t0.z; r.v[3] = t0.w;
+    r.v[4] = t1.x; r.v[5] = t1.y; r.v[6] = t1.z; r.v[7] = t1.w;
+  }
+  return r;
+}
+
+// Interpolated features of one level (before precondition scaling); products and
+// sums individually rounded in the reference's corner order so that the result
+// is bit-identical to the fp32 oracle.
+template <int F>
+__device__ __forceinline__ FeatVec<F> level_interp(const LevelDev& lv, const Corners& c) {
+  int32_t rows[8];
+  float w[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int bx, by, bz;
+    corner_bits(lv.is_hash, k, bx, by, bz);
+    rows[k] = corner_row(lv, c, bx, by, bz);
+    w[k] = corner_weight(lv.is_hash, c, bx, by, bz);
+  }
+  FeatVec<F> vals[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {  // issue all gathers before consuming any
+    if (rows[k] >= 0) vals[k] = load_row<F>(lv.table, rows[k]);
+    else {
+#pragma unroll
+      for (int f = 0; f < F; ++f) vals[k].v[f] = 0.f;
+    }
+  }
+  FeatVec<F> acc;
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc.v[f] = __fmul_rn(vals[0].v[f], w[0]);
+#pragma unroll
+  for (int k = 1; k < 8; ++k)
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc.v[f] = __fadd_rn(acc.v[f], __fmul_rn(vals[k].v[f], w[k]));
+  return acc;
+}
+
+__device__ __forceinline__ void normalise_point(const EncDev& enc, const float x[3], float xn[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) xn[a] = __fdiv_rn(__fsub_rn(x[a], enc.b0[a]), enc.span[a]);
+}
+
+}  // namespace nrc

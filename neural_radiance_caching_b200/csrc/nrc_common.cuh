@@ -1,0 +1,80 @@
+// Shared device/host helpers for the nrc_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nrc_b200.h"
+
+namespace nrc {
+
+extern thread_local int g_last_cuda_error;
+
+inline int32_t check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_last_cuda_error = static_cast<int>(e);
+    return NRC_E_CUDA;
+  }
+  return NRC_OK;
+}
+
+constexpr int kNumSMs = 148;  // B200
+
+// float32 limits used by the reference's safe_* guards (internal/math.py:24-26).
+__device__ __forceinline__ float f32_tiny() { return 1.17549435e-38f; }
+__device__ __forceinline__ float f32_max() { return 3.40282347e+38f; }
+__device__ __forceinline__ float f32_eps() { return 1.1920929e-07f; }
+
+// math.safe_exp (internal/math.py:186-192): exp(clip(x, min, 70)).
+__device__ __forceinline__ float safe_exp(float x) { return expf(fminf(x, 70.0f)); }
+// math.safe_log (internal/math.py:177-183): log(clip(x, tiny, max)).
+__device__ __forceinline__ float safe_log(float x) {
+  return logf(fminf(fmaxf(x, f32_tiny()), f32_max()));
+}
+
+// coord.contract(x / c) (internal/coord.py:33-38,63-69).  Each op individually
+// rounded (no FMA contraction) so that the coordinates fed to floor() follow the
+// oracle's op order.  c <= 0: identity.
+__device__ __forceinline__ void contract_point(float c, float x0, float x1, float x2, float& z0,
+                                               float& z1, float& z2, float* scale_out = nullptr,
+                                               float* mag_sq_out = nullptr) {
+  if (c <= 0.f) {
+    z0 = x0; z1 = x1; z2 = x2;
+    if (scale_out) *scale_out = 1.f;
+    if (mag_sq_out) *mag_sq_out = 0.f;
+    return;
+  }
+  float y0 = __fdiv_rn(x0, c), y1 = __fdiv_rn(x1, c), y2 = __fdiv_rn(x2, c);
+  float m = __fadd_rn(__fadd_rn(__fmul_rn(y0, y0), __fmul_rn(y1, y1)), __fmul_rn(y2, y2));
+  float ms = fmaxf(1.0f, m);
+  float scale = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, __fsqrt_rn(ms)), 1.0f), ms);
+  z0 = __fmul_rn(scale, y0); z1 = __fmul_rn(scale, y1); z2 = __fmul_rn(scale, y2);
+  if (scale_out) *scale_out = scale;
+  if (mag_sq_out) *mag_sq_out = m;
+}
+
+// J^T g for z = contract(x / c).
+__device__ __forceinline__ void contract_vjp(float c, float x0, float x1, float x2, float g0,
+                                             float g1, float g2, float& o0, float& o1, float& o2) {
+  if (c <= 0.f) { o0 = g0; o1 = g1; o2 = g2; return; }
+  float y0 = x0 / c, y1 = x1 / c, y2 = x2 / c;
+  float m = y0 * y0 + y1 * y1 + y2 * y2;
+  float a0, a1, a2;
+  if (m <= 1.0f) {
+    // maximum(1, m) passes no gradient to m when m < 1 (tie at m == 1: jnp.maximum
+    // splits 0.5/0.5; measure-zero, treated as the constant branch here).
+    a0 = g0; a1 = g1; a2 = g2;
+  } else {
+    float r = sqrtf(m);
+    float s = (2.0f * r - 1.0f) / m;
+    // ds/dm = 1/(r m) - (2r - 1)/m^2
+    float dsdm = 1.0f / (r * m) - (2.0f * r - 1.0f) / (m * m);
+    float gy = g0 * y0 + g1 * y1 + g2 * y2;
+    a0 = s * g0 + 2.0f * dsdm * gy * y0;
+    a1 = s * g1 + 2.0f * dsdm * gy * y1;
+    a2 = s * g2 + 2.0f * dsdm * gy * y2;
+  }
+  o0 = a0 / c; o1 = a1 / c; o2 = a2 / c;
+}
+
+}  // namespace nrc

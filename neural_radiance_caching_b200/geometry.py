@@ -1,0 +1,157 @@
+"""Host-side mirror of internal/geometry.py DensityMLP (CUDA bodies).
+
+Parameter names follow the Flax auto-names of the reference's setup() attributes
+(`density_layers_{i}`, `output_density_layer`, `pred_normals_layer`, `density_grid/...`;
+internal/geometry.py:123-151), kernels [in,out], biases [out], fp32.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, grid_utils
+
+
+def _mlp_desc(p, in_dim, use_pred_normals):
+    d = _lib.nrc_density_mlp_t()
+    d.d_w0 = _lib.ptr(p["density_layers_0"]["kernel"]).value
+    d.d_b0 = _lib.ptr(p["density_layers_0"]["bias"]).value
+    d.d_w1 = _lib.ptr(p["density_layers_1"]["kernel"]).value
+    d.d_b1 = _lib.ptr(p["density_layers_1"]["bias"]).value
+    d.d_wd = _lib.ptr(p["output_density_layer"]["kernel"]).value
+    d.d_bd = _lib.ptr(p["output_density_layer"]["bias"]).value
+    if use_pred_normals:
+        d.d_wn = _lib.ptr(p["pred_normals_layer"]["kernel"]).value
+        d.d_bn = _lib.ptr(p["pred_normals_layer"]["bias"]).value
+    d.in_dim = in_dim
+    d.width = 64
+    return d
+
+
+_MLP_KEYS = ("density_layers_0", "density_layers_1", "output_density_layer", "pred_normals_layer")
+
+
+class _RunNetworkFn(torch.autograd.Function):
+    """custom_vjp analogue over nrc_density_mlp_{fwd,bwd}."""
+
+    @staticmethod
+    def forward(ctx, mlp, x, bf16, *flat):
+        p = mlp._unflatten(flat)
+        x2 = x.reshape(-1, mlp.in_dim).contiguous()
+        P = x2.shape[0]
+        raw = torch.empty((P,), device=x.device, dtype=torch.float32)
+        feat = torch.empty((P, 64), device=x.device, dtype=torch.float32)
+        gp = torch.empty((P, 3), device=x.device, dtype=torch.float32) if mlp.enable_pred_normals else None
+        desc = _mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals)
+        _lib.call("nrc_density_mlp_fwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(x2), P, int(bf16),
+                  _lib.ptr(raw), _lib.ptr(feat), _lib.ptr(gp))
+        ctx.mlp = mlp
+        ctx.save_for_backward(x2, *flat)
+        ctx.lead = x.shape[:-1]
+        lead = x.shape[:-1]
+        outs = (raw.reshape(lead), feat.reshape(lead + (64,)))
+        if gp is not None:
+            outs = outs + (gp.reshape(lead + (3,)),)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_raw, g_feat, g_gp=None):
+        mlp = ctx.mlp
+        x2, *flat = ctx.saved_tensors
+        p = mlp._unflatten(flat)
+        P = x2.shape[0]
+        dev = x2.device
+        f = lambda g, shape: g.reshape(shape).contiguous() if g is not None else None
+        g_raw2 = f(g_raw, (P,)) if g_raw is not None else torch.zeros((P,), device=dev)
+        g_feat2 = f(g_feat, (P, 64))
+        g_gp2 = f(g_gp, (P, 3)) if mlp.enable_pred_normals else None
+        g_enc = torch.empty_like(x2) if ctx.needs_input_grad[1] else None
+        want_w = any(ctx.needs_input_grad[3:])
+        gflat = [torch.zeros_like(t) for t in flat] if want_w else None
+        gd = None
+        if want_w:
+            gp_ = mlp._unflatten(gflat)
+            gd = _lib.nrc_density_mlp_grad_t()
+            gd.d_w0 = _lib.ptr(gp_["density_layers_0"]["kernel"]).value
+            gd.d_b0 = _lib.ptr(gp_["density_layers_0"]["bias"]).value
+            gd.d_w1 = _lib.ptr(gp_["density_layers_1"]["kernel"]).value
+            gd.d_b1 = _lib.ptr(gp_["density_layers_1"]["bias"]).value
+            gd.d_wd = _lib.ptr(gp_["output_density_layer"]["kernel"]).value
+            gd.d_bd = _lib.ptr(gp_["output_density_layer"]["bias"]).value
+            if mlp.enable_pred_normals:
+                gd.d_wn = _lib.ptr(gp_["pred_normals_layer"]["kernel"]).value
+                gd.d_bn = _lib.ptr(gp_["pred_normals_layer"]["bias"]).value
+        desc = _mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals)
+        _lib.call("nrc_density_mlp_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(x2), _lib.ptr(g_raw2),
+                  _lib.ptr(g_feat2), _lib.ptr(g_gp2), P, _lib.ptr(g_enc), C.byref(gd) if gd is not None else None)
+        gx = g_enc.reshape(ctx.lead + (mlp.in_dim,)) if g_enc is not None else None
+        return (None, gx, None) + (tuple(gflat) if want_w else (None,) * len(flat))
+
+
+class DensityMLP:
+    """BaseDensityMLP/DensityMLP (internal/geometry.py:36-593) as configured by
+    configs/ngp_yobo.gin:137-140,206-230: depth 2, width 64, ReLU, safe_exp activation,
+    unscented basis 'mean', contraction warp, hash-grid input."""
+
+    def __init__(self, grid_params, net_depth=2, net_width=64, density_bias=-1.0, warp_c=2.0, bbox_scaling=1.0,
+                 enable_pred_normals=False, disable_density_normals=False, normals_for_filter_only=False,
+                 bf16=False):
+        if net_depth != 2 or net_width != 64:
+            raise NotImplementedError("the fused kernels are compiled for net_depth=2, net_width=64")
+        self.grid = grid_utils.HashEncoding(bbox_scaling=bbox_scaling, scale_supersample=1.0, **grid_params)
+        self.in_dim = self.grid.num_outputs
+        self.density_bias = density_bias
+        self.warp_c = warp_c if warp_c is not None else 0.0
+        self.enable_pred_normals = enable_pred_normals
+        self.disable_density_normals = disable_density_normals
+        self.normals_for_filter_only = normals_for_filter_only
+        self.bf16 = bf16
+
+    # -- parameters -------------------------------------------------------------
+    def from_oracle(self, p, device):
+        """Move a parameter tree (oracle/reference layout) to the device, tables in one arena."""
+        out = {}
+        names = [n for (n, _, _, _) in self.grid.level_layout]
+        arena = torch.cat([p["density_grid"][n].reshape(-1) for n in names]).to(device)
+        out["density_grid"] = self.grid.views(arena)
+        out["_arena"] = arena
+        for k in _MLP_KEYS:
+            if k in p:
+                out[k] = {kk: vv.to(device).contiguous() for kk, vv in p[k].items()}
+        return out
+
+    def _flatten(self, p):
+        keys = _MLP_KEYS if self.enable_pred_normals else _MLP_KEYS[:3]
+        return [p[k][kk] for k in keys for kk in ("kernel", "bias")]
+
+    def _unflatten(self, flat):
+        keys = _MLP_KEYS if self.enable_pred_normals else _MLP_KEYS[:3]
+        it = iter(flat)
+        return {k: {"kernel": next(it), "bias": next(it)} for k in keys}
+
+    # -- reference methods ------------------------------------------------------
+    def run_network(self, p, x, means=None):
+        """internal/geometry.py:155-168 -> (raw_density, x) [+ grad_pred when enabled]."""
+        outs = _RunNetworkFn.apply(self, x, self.bf16, *self._flatten(p))
+        return outs
+
+    def query(self, p, means, want_feat=True, want_normals=False):
+        """Fused predict_density + convert_raw_density (+ analytic raw gradient):
+        internal/geometry.py:199-341,442-460.  Inference path (no autograd)."""
+        m2 = means.reshape(-1, 3).contiguous()
+        P = m2.shape[0]
+        dev = m2.device
+        density = torch.empty((P,), device=dev, dtype=torch.float32)
+        raw = torch.empty((P,), device=dev, dtype=torch.float32)
+        feat = torch.empty((P, 64), device=dev, dtype=torch.float32) if want_feat else None
+        gp = torch.empty((P, 3), device=dev, dtype=torch.float32) if self.enable_pred_normals else None
+        rg = torch.empty((P, 3), device=dev, dtype=torch.float32) if want_normals else None
+        enc = self.grid._descriptor(self.grid.tables(p["density_grid"]), None)
+        mlp = _mlp_desc(p, self.in_dim, self.enable_pred_normals)
+        _lib.call("nrc_density_query_fwd", _lib.stream_ptr(), C.byref(enc), C.byref(mlp), _lib.ptr(m2), P,
+                  float(self.warp_c), float(self.density_bias), int(self.bf16), _lib.ptr(density), _lib.ptr(raw),
+                  _lib.ptr(feat), _lib.ptr(gp), _lib.ptr(rg))
+        lead = means.shape[:-1]
+        r = lambda t, *s: t.reshape(lead + s) if t is not None else None
+        return dict(density=r(density), raw_density=r(raw), feature=r(feat, 64), grad_pred=r(gp, 3),
+                    raw_grad_density=r(rg, 3))

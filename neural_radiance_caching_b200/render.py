@@ -1,0 +1,164 @@
+"""Host-side mirror of internal/render.py for the hot path (CUDA bodies, same signatures)."""
+import torch
+
+from . import _lib
+
+
+def _c(t):
+    return t.contiguous() if t is not None else None
+
+
+class _AlphaWeightsFn(torch.autograd.Function):
+    """custom_vjp analogue over nrc_ray_alpha_weights_{fwd,bwd}."""
+
+    @staticmethod
+    def forward(ctx, density, tdist, dirs, opaque_background):
+        n = density.shape[-1]
+        d2, t2, r2 = _c(density.reshape(-1, n)), _c(tdist.reshape(-1, n + 1)), _c(dirs.reshape(-1, 3))
+        R = d2.shape[0]
+        w, a, tr = torch.empty_like(d2), torch.empty_like(d2), torch.empty_like(d2)
+        _lib.call("nrc_ray_alpha_weights_fwd", _lib.stream_ptr(), _lib.ptr(d2), _lib.ptr(t2), _lib.ptr(r2), R, n,
+                  int(opaque_background), _lib.ptr(w), _lib.ptr(a), _lib.ptr(tr))
+        ctx.save_for_backward(d2, t2, r2)
+        ctx.shape = density.shape
+        ctx.opaque = opaque_background
+        return w.reshape(density.shape), a.reshape(density.shape), tr.reshape(density.shape)
+
+    @staticmethod
+    def backward(ctx, gw, ga, gt):
+        d2, t2, r2 = ctx.saved_tensors
+        if ctx.opaque:
+            raise NotImplementedError("gradient through opaque_background is outside the configs' scope")
+        R, n = d2.shape
+        gd = torch.empty_like(d2)
+        f = lambda g: _c(g.reshape(R, n)) if g is not None else None
+        _lib.call("nrc_ray_alpha_weights_bwd", _lib.stream_ptr(), _lib.ptr(d2), _lib.ptr(t2), _lib.ptr(r2),
+                  _lib.ptr(f(gw)), _lib.ptr(f(ga)), _lib.ptr(f(gt)), R, n, _lib.ptr(gd))
+        return gd.reshape(ctx.shape), None, None, None
+
+
+def compute_alpha_weights(density, tdist, dirs, opaque_background=False, delta=None):
+    """Helper function for computing alpha compositing weights (internal/render.py:134-169).
+
+    Returns (weights, alpha, trans).  `delta` overrides are not used on the hot path.
+    """
+    if delta is not None:
+        raise NotImplementedError("explicit `delta` is outside the CUDA path's scope")
+    return _AlphaWeightsFn.apply(density, tdist, dirs, bool(opaque_background))
+
+
+def cast_rays(tdist, origins, directions, radii, ray_shape, diag=True):
+    """Cast cone-shaped rays (internal/render.py:106-131): returns (means, covs).
+
+    Only the means feed the encoding under unscented basis 'mean' (SURVEY 8a row 13), so the
+    CUDA path returns covs=None; use ProposalVolumeSampler for the fused s->t + cast path.
+    """
+    if ray_shape != "cone":
+        raise ValueError("ray_shape must be 'cone' (cylinder rays are outside the hot path)")
+    n = tdist.shape[-1] - 1
+    t2 = _c(tdist.reshape(-1, n + 1))
+    R = t2.shape[0]
+    o2, d2 = _c(origins.reshape(-1, 3)), _c(directions.reshape(-1, 3))
+    zeros, ones = torch.zeros(R, device=t2.device), torch.ones(R, device=t2.device)
+    t_out = torch.empty_like(t2)
+    means = torch.empty((R, n, 3), device=t2.device, dtype=torch.float32)
+    # identity warp: near=0, far=1 => t = s*1 + (1-s)*0
+    _lib.call("nrc_ray_cast", _lib.stream_ptr(), _lib.ptr(t2), _lib.ptr(o2), _lib.ptr(d2), _lib.ptr(zeros),
+              _lib.ptr(ones), R, n, 0, 0.0, 1.0, _lib.ptr(t_out), _lib.ptr(means))
+    return means.reshape(tdist.shape[:-1] + (n, 3)), None
+
+
+class _CompositeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, values, weights, weights_nf, tdist, bg, has_rgb, want_dist):
+        k = weights.shape[-1]
+        C = values.shape[-1]
+        v2, w2 = _c(values.reshape(-1, k, C)), _c(weights.reshape(-1, k))
+        R = w2.shape[0]
+        same = weights_nf is None
+        wn2 = None if same else _c(weights_nf.reshape(R, -1))
+        n = k if same else wn2.shape[-1]
+        t2 = _c(tdist.reshape(R, n + 1)) if tdist is not None else None
+        b2 = _c(bg.expand(weights.shape[:-1] + (3,)).reshape(R, 3)) if bg is not None else None
+        out = torch.empty((R, C), device=w2.device, dtype=torch.float32)
+        acc = torch.empty((R,), device=w2.device, dtype=torch.float32)
+        dist = torch.empty((R, 4), device=w2.device, dtype=torch.float32) if want_dist else None
+        _lib.call("nrc_ray_composite_fwd", _lib.stream_ptr(), _lib.ptr(v2), _lib.ptr(w2), k, _lib.ptr(wn2),
+                  _lib.ptr(t2), _lib.ptr(b2), R, n, C, int(has_rgb), _lib.ptr(out), _lib.ptr(acc), _lib.ptr(dist))
+        ctx.save_for_backward(v2, w2, wn2, b2)
+        ctx.meta = (values.shape, weights.shape, None if same else weights_nf.shape, k, n, C, has_rgb)
+        lead = weights.shape[:-1]
+        return out.reshape(lead + (C,)), acc.reshape(lead), (dist.reshape(lead + (4,)) if want_dist else None)
+
+    @staticmethod
+    def backward(ctx, g_out, g_acc, _g_dist):
+        v2, w2, wn2, b2 = ctx.saved_tensors
+        vshape, wshape, wnshape, k, n, C, has_rgb = ctx.meta
+        R = w2.shape[0]
+        go = _c(g_out.reshape(R, C)) if g_out is not None else torch.zeros((R, C), device=w2.device)
+        ga = _c(g_acc.reshape(R)) if g_acc is not None else None
+        gv, gw = torch.empty_like(v2), torch.empty_like(w2)
+        gwn = torch.empty_like(wn2) if wn2 is not None else None
+        _lib.call("nrc_ray_composite_bwd", _lib.stream_ptr(), _lib.ptr(v2), _lib.ptr(w2), k, _lib.ptr(wn2),
+                  _lib.ptr(b2), _lib.ptr(go), _lib.ptr(ga), R, n, C, int(has_rgb), _lib.ptr(gv), _lib.ptr(gw),
+                  _lib.ptr(gwn))
+        return (gv.reshape(vshape), gw.reshape(wshape), gwn.reshape(wnshape) if gwn is not None else None, None,
+                None, None, None)
+
+
+def volumetric_rendering(
+    rgbs,
+    weights,
+    weights_no_filter,
+    tdist,
+    bg_rgbs,
+    compute_extras,
+    extras=None,
+    normalize_weights_for_extras=False,
+    percentiles=(5, 50, 95),
+    compute_distance=True,
+):
+    """Volumetric Rendering Function (internal/render.py:172-247).
+
+    rgb and every entry of `extras` are composited by ONE kernel launch over the
+    channel-concatenated values; distances come from the same launch.
+    """
+    if normalize_weights_for_extras:
+        raise NotImplementedError("normalize_weights_for_extras=True is outside the configs' scope")
+    if tuple(percentiles) != (5, 50, 95):
+        raise NotImplementedError("the CUDA path computes percentiles (5, 50, 95)")
+    names, chunks = [], []
+    if rgbs is not None:
+        chunks.append(rgbs)
+    if extras is not None:
+        for k_, v in extras.items():
+            if v is not None:
+                names.append((k_, v.shape[-1]))
+                chunks.append(v)
+    nf = None if weights_no_filter is weights else weights_no_filter
+    if chunks:
+        values = torch.cat(chunks, dim=-1) if len(chunks) > 1 else chunks[0]
+    else:
+        values = torch.zeros(weights.shape + (0,), device=weights.device)
+    bg = None
+    if rgbs is not None and bg_rgbs is not None:
+        bg = torch.as_tensor(bg_rgbs, device=weights.device, dtype=torch.float32)
+        bg = bg.expand(weights.shape[:-1] + (3,)) if bg.dim() > 0 else bg.reshape(1).expand(weights.shape[:-1] + (3,))
+    out, acc, dist = _CompositeFn.apply(values, weights, nf, tdist, bg, rgbs is not None, bool(compute_distance))
+    rendering = {}
+    off = 0
+    if rgbs is not None:
+        rendering["rgb"] = out[..., :3]
+        off = 3
+    else:
+        rendering["rgb"] = None
+    rendering["acc"] = acc
+    for k_, c in names:
+        rendering[k_] = out[..., off:off + c]
+        off += c
+    if compute_distance:
+        rendering["distance_mean"] = dist[..., 0]
+        for i, p in enumerate(percentiles):
+            s = "median" if p == 50 else "percentile_" + str(p)
+            rendering["distance_" + s] = dist[..., 1 + i]
+    return rendering

@@ -1,0 +1,154 @@
+"""Host-side mirror of internal/sampling.py ProposalVolumeSampler (CUDA bodies).
+
+Per level the path is four launches with nothing else touching HBM:
+  nrc_ray_sample_intervals  (anneal + safe_log + softmax + CDF + inverse + sort)
+  nrc_ray_cast              (s->t warp + Gaussian means)
+  nrc_density_query_fwd     (contract + hash-grid encode + fused MLP + activation [+ normals])
+  nrc_ray_alpha_weights_fwd (alpha compositing weights)
+The training path (`train=True`) runs the same kernels through their custom VJPs.
+"""
+import numpy as np
+import torch
+
+from . import _lib, coord, geometry, render, stepfun
+
+GRID_PARAMS = (
+    dict(hash_map_size=524288, max_grid_size=512, num_features=1),
+    dict(hash_map_size=524288, max_grid_size=1024, num_features=1),
+    dict(hash_map_size=524288, max_grid_size=2048, num_features=4),
+)
+MLP_PARAMS = (
+    dict(disable_density_normals=False, enable_pred_normals=False, normals_for_filter_only=True),
+    dict(disable_density_normals=False, enable_pred_normals=False, normals_for_filter_only=True),
+    dict(disable_density_normals=False, enable_pred_normals=True, normals_for_filter_only=False),
+)
+
+
+class _SafeExpFn(torch.autograd.Function):
+    """math.safe_exp (internal/math.py:186-192): exp(clip(x, ., 70)), grad = y * g."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = torch.exp(torch.clamp(x, max=70.0))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return g * y
+
+
+def _l2_normalize(x):
+    """ref_utils.l2_normalize forward value (internal/ref_utils.py:45-70)."""
+    tiny = float(np.finfo(np.float32).tiny)
+    denom_sq = torch.sum(x * x, dim=-1, keepdim=True)
+    n = x / torch.sqrt(torch.clamp(denom_sq, min=tiny))
+    return torch.where(denom_sq < tiny, torch.zeros_like(n), n)
+
+
+class ProposalVolumeSampler:
+    """internal/sampling.py:44-649 under configs/ngp_yobo.gin:178-242 and
+    configs/nerf_ngp_yobo.gin:521-562 (see oracle/sampling.py for the config trace)."""
+
+    def __init__(self, sampling_strategy=((0, 0, 64), (1, 1, 64), (2, 2, 32)), grid_params_per_level=GRID_PARAMS,
+                 mlp_params_per_level=MLP_PARAMS, anneal_slope=10.0, anneal_end=1.0, anneal_clip=0.4,
+                 resample_padding=1e-5, single_jitter=True, warp_c=2.0, bbox_scaling=1.0, raydist=(-1.5, 2.0),
+                 opaque_background=False, bf16=False):
+        if not single_jitter:
+            raise NotImplementedError("single_jitter=False is outside the configs' scope")
+        self.sampling_strategy = sampling_strategy
+        self.mlps = [
+            geometry.DensityMLP(grid_params=g, warp_c=warp_c, bbox_scaling=bbox_scaling, bf16=bf16, **m)
+            for g, m in zip(grid_params_per_level, mlp_params_per_level)
+        ]
+        self.anneal_slope, self.anneal_end, self.anneal_clip = anneal_slope, anneal_end, anneal_clip
+        self.resample_padding = resample_padding
+        self.raydist = raydist
+        self.opaque_background = opaque_background
+
+    def from_oracle(self, params, device):
+        return {f"MLP_{i}": m.from_oracle(params[f"MLP_{i}"], device) for i, m in enumerate(self.mlps)}
+
+    def anneal(self, train_frac):
+        """internal/sampling.py:326-336."""
+        if self.anneal_slope > 0:
+            bias = lambda x, s: (s * x) / ((s - 1) * x + 1)
+            return float(np.clip(bias(train_frac / self.anneal_end, self.anneal_slope), 0.0, self.anneal_clip))
+        return self.anneal_clip
+
+    def _cast(self, sdist, rays, use_raydist_fn):
+        R = sdist.shape[0]
+        n = sdist.shape[-1] - 1
+        tdist = torch.empty_like(sdist)
+        means = torch.empty((R, n, 3), device=sdist.device, dtype=torch.float32)
+        p, premult = self.raydist
+        _lib.call("nrc_ray_cast", _lib.stream_ptr(), _lib.ptr(sdist), _lib.ptr(rays["origins"]),
+                  _lib.ptr(rays["directions"]), _lib.ptr(rays["near"]), _lib.ptr(rays["far"]), R, n,
+                  1 if use_raydist_fn else 0, float(p), float(premult), _lib.ptr(tdist), _lib.ptr(means))
+        return tdist, means
+
+    def __call__(self, params, rays, u01_per_level, train_frac=1.0, train=False, use_raydist_fn=False,
+                 normals_all_levels=False):
+        """rays: dict of contiguous CUDA tensors origins/directions/viewdirs [R,3], near/far [R,1]."""
+        near = rays["near"]
+        R = near.shape[0]
+        dev = near.device
+        sdist = torch.cat([torch.zeros_like(near), torch.ones_like(near)], dim=-1)
+        weights = torch.ones_like(near)
+        anneal = self.anneal(train_frac)
+        history = []
+        for i_level, (i_mlp, _, num_samples) in enumerate(self.sampling_strategy):
+            mlp = self.mlps[i_mlp]
+            p = params[f"MLP_{i_mlp}"]
+            with torch.no_grad():  # stop_level_grad (sampling.py:353-354)
+                sdist = stepfun.sample_intervals_from_weights(
+                    u01_per_level[i_level], sdist, weights.detach(), num_samples, anneal=anneal,
+                    padding=self.resample_padding, domain=(0.0, 1.0))
+                tdist, means = self._cast(sdist, rays, use_raydist_fn)
+            want_normals = (normals_all_levels or not mlp.normals_for_filter_only) and not mlp.disable_density_normals
+            res = {}
+            if not train:
+                with torch.no_grad():
+                    q = mlp.query(p, means, want_feat=True, want_normals=want_normals)
+                density = q["density"]
+                res.update(feature=q["feature"], density=density, raw_density=q["raw_density"],
+                           raw_grad_density=q["raw_grad_density"], grad_pred=q["grad_pred"])
+            else:
+                z = coord._ContractFn.apply(means, mlp.warp_c)
+                enc = mlp.grid(p["density_grid"], z)
+                outs = mlp.run_network(p, enc)
+                raw, feat = outs[0], outs[1]
+                bbox = mlp.grid.bbox
+                b0 = torch.tensor(bbox[0].astype(np.float32), device=dev)
+                b1 = torch.tensor(bbox[1].astype(np.float32), device=dev)
+                valid = torch.all((z.detach() > b0) & (z.detach() < b1), dim=-1)
+                density = torch.where(valid, _SafeExpFn.apply(raw + mlp.density_bias), torch.zeros_like(raw))
+                res.update(feature=feat, density=density, raw_density=raw,
+                           grad_pred=outs[2] if mlp.enable_pred_normals else None, raw_grad_density=None)
+                if want_normals:
+                    with torch.no_grad():
+                        res["raw_grad_density"] = mlp.query(p, means, want_feat=False, want_normals=True)[
+                            "raw_grad_density"]
+            if res.get("raw_grad_density") is not None and want_normals:
+                res["normals"] = torch.nan_to_num(-_l2_normalize(res["raw_grad_density"]))
+            else:
+                res["normals"] = None
+            if mlp.enable_pred_normals:
+                res["normals_pred"] = torch.nan_to_num(-_l2_normalize(res["grad_pred"]))
+                res["normals_to_use"] = res["normals_pred"]
+            else:
+                res["normals_pred"] = None
+                res["normals_to_use"] = res["normals"]
+            if mlp.normals_for_filter_only and not normals_all_levels:
+                res["normals"] = res["normals_to_use"] = res["normals_pred"] = None
+            for k in list(res.keys()):
+                if k.startswith("normals") and res[k] is not None:
+                    pdot = torch.sum(res[k] * rays["viewdirs"][..., None, :], dim=-1, keepdim=True)
+                    res[k + "_rectified"] = res[k] * torch.where(pdot > 0, -1.0, 1.0)
+            weights, alphas, trans = render.compute_alpha_weights(
+                density, tdist, rays["directions"], opaque_background=self.opaque_background)
+            res.update(points=means, means=means, tdist=tdist, sdist=sdist, weights=weights, alphas=alphas,
+                       trans=trans)
+            history.append(res)
+        return history

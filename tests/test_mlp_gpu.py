@@ -1,0 +1,92 @@
+"""K3 parity: fused density MLP (fp32 variant) forward/backward and the fused point query vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as ogeo
+from neural_radiance_caching_b200 import geometry as ngeo
+from tests.util import f32, gen, rel_err
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = [
+    dict(hash_map_size=524288, max_grid_size=512, num_features=1),
+    dict(hash_map_size=524288, max_grid_size=1024, num_features=1),
+    dict(hash_map_size=524288, max_grid_size=2048, num_features=4),
+]
+
+
+def _pair(g, grid, pred_normals, device, table_range=0.1, warp_c=2.0, bbox=1.0):
+    kw = dict(grid_params=grid, enable_pred_normals=pred_normals, warp_c=warp_c, bbox_scaling=bbox)
+    o = ogeo.DensityMLP(**kw)
+    n = ngeo.DensityMLP(**kw)
+    po = o.init(g, table_init_range=table_range, bias_range=0.1)
+    pn = n.from_oracle(po, device)
+    return o, n, po, pn
+
+
+@pytest.mark.parametrize("gi,pred", [(0, False), (1, False), (2, True)])
+def test_run_network_forward_backward(cuda_device, gi, pred):
+    g = gen(10 + gi)
+    o, n, po, pn = _pair(g, GRIDS[gi], pred, cuda_device)
+    P = 1000  # not a multiple of the 128-point tile
+    x = f32(g.normal(size=(P, o.in_dim)))
+    g_raw, g_feat, g_gp = f32(g.normal(size=(P,))), f32(g.normal(size=(P, 64))), f32(g.normal(size=(P, 3)))
+    keys = [k for k in po if k != "density_grid"]
+    # oracle
+    xo = x.clone().requires_grad_(True)
+    for k in keys:
+        for kk in po[k]:
+            po[k][kk] = po[k][kk].clone().requires_grad_(True)
+    raw_o, feat_o = o.run_network(po, xo)
+    loss = (raw_o * g_raw).sum() + (feat_o * g_feat).sum()
+    if pred:
+        gp_o = ogeo.dense(po["pred_normals_layer"], feat_o)
+        loss = loss + (gp_o * g_gp).sum()
+    loss.backward()
+    # CUDA
+    xn = x.to(cuda_device).requires_grad_(True)
+    for k in keys:
+        for kk in pn[k]:
+            pn[k][kk] = pn[k][kk].clone().requires_grad_(True)
+    outs = n.run_network(pn, xn)
+    lossn = (outs[0] * g_raw.to(cuda_device)).sum() + (outs[1] * g_feat.to(cuda_device)).sum()
+    if pred:
+        lossn = lossn + (outs[2] * g_gp.to(cuda_device)).sum()
+    lossn.backward()
+    assert rel_err(outs[0], raw_o) <= 1e-5
+    assert rel_err(outs[1], feat_o) <= 1e-5
+    if pred:
+        assert rel_err(outs[2], gp_o) <= 1e-5
+    assert rel_err(xn.grad, xo.grad) <= 1e-5
+    for k in keys:
+        for kk in po[k]:
+            assert rel_err(pn[k][kk].grad, po[k][kk].grad) <= 2e-5, (k, kk)
+
+
+@pytest.mark.parametrize("gi,pred,warp_c,bbox", [(0, False, 2.0, 1.0), (1, False, 2.0, 1.0), (2, True, 2.0, 1.0),
+                                                  (2, True, 5.0, 2.0)])
+def test_fused_query_matches_oracle(cuda_device, gi, pred, warp_c, bbox):
+    g = gen(20 + gi)
+    o, n, po, pn = _pair(g, GRIDS[gi], pred, cuda_device, warp_c=warp_c, bbox=bbox)
+    P = 3000
+    means = f32(g.normal(size=(P, 3)) * 2.5)  # inside and outside the contraction radius / bbox
+    res_o = o(po, means)
+    res_n = n.query(pn, means.to(cuda_device), want_feat=True, want_normals=True)
+    assert rel_err(res_n["raw_density"], res_o["raw_density"]) <= 1e-5
+    assert rel_err(res_n["density"], res_o["density"]) <= 1e-5
+    # the bbox mask must agree exactly
+    assert torch.equal(res_n["density"].cpu() == 0, res_o["density"] == 0)
+    assert rel_err(res_n["feature"], res_o["feature"]) <= 1e-5
+    assert rel_err(res_n["raw_grad_density"], res_o["raw_grad_density"]) <= 2e-5
+    if pred:
+        assert rel_err(res_n["grad_pred"], res_o["grad_pred"]) <= 1e-5
+
+
+def test_query_empty_and_bad_args(cuda_device):
+    g = gen(30)
+    o, n, po, pn = _pair(g, GRIDS[0], False, cuda_device)
+    out = n.query(pn, torch.zeros((0, 3), device=cuda_device))
+    assert out["density"].shape == (0,)
+    with pytest.raises(NotImplementedError):
+        ngeo.DensityMLP(grid_params=GRIDS[0], net_width=256)

@@ -1,0 +1,89 @@
+"""End-to-end parity of the proposal sampling loop (BASELINE config 1, cache stage forward):
+3 levels x (sample_intervals -> ray cast -> contract+encode+MLP -> alpha weights)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampling as osamp
+from neural_radiance_caching_b200 import sampling as nsamp
+from tests.util import f32, gen, make_rays, rel_err, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("table_range,use_raydist", [(0.1, False), (None, False), (0.1, True)])
+def test_sampler_forward(cuda_device, table_range, use_raydist):
+    g = gen(100)
+    R = 256
+    o = osamp.ProposalVolumeSampler()
+    n = nsamp.ProposalVolumeSampler()
+    po = o.init(g, table_init_range=table_range, bias_range=0.05)
+    pn = n.from_oracle(po, cuda_device)
+    rays = make_rays(g, R, near=0.05, far=2.0, radius=0.7) if use_raydist else make_rays(g, R)
+    u = [f32(g.uniform(size=(R, 1))) for _ in range(3)]
+    ho = o(po, rays, u, use_raydist_fn=use_raydist)
+    hn = n(pn, to_dev(rays, cuda_device), to_dev(u, cuda_device), use_raydist_fn=use_raydist)
+    for lvl, (a, b) in enumerate(zip(hn, ho)):
+        for k in ("sdist", "tdist", "means", "density", "weights", "alphas", "trans", "feature"):
+            # positions feed floor(): a last-ulp difference in t can move a sample across a
+            # cell boundary, but trilinear interpolation is continuous, so values stay close.
+            tol = 1e-5 if k in ("sdist", "tdist", "means") else 2e-4
+            assert rel_err(a[k], b[k]) <= tol, (lvl, k, rel_err(a[k], b[k]))
+    # level 2: analytic + predicted normals
+    for k in ("normals_pred", "normals"):
+        d = (hn[2][k].cpu() - ho[2][k]).abs().max(dim=-1).values
+        assert float(d.median()) <= 1e-5, k
+        assert float((d > 1e-3).float().mean()) <= 5e-3, k
+    assert hn[0]["normals"] is None and hn[1]["normals"] is None
+
+
+def test_sampler_train_gradients(cuda_device):
+    """Backward of the cache-stage sampler: d(sum_l <weights_l, G_l>)/d(params) for all three
+    proposal levels (tables + MLP weights) vs oracle autograd."""
+    g = gen(101)
+    R = 128
+    o = osamp.ProposalVolumeSampler()
+    n = nsamp.ProposalVolumeSampler()
+    po = o.init(g, table_init_range=0.1, bias_range=0.05)
+    pn = n.from_oracle(po, cuda_device)
+    rays = make_rays(g, R)
+    u = [f32(g.uniform(size=(R, 1))) for _ in range(3)]
+    G = [f32(g.normal(size=(R, ns))) for (_, _, ns) in o.sampling_strategy]
+
+    def leaves(p):
+        out = []
+        for i in range(3):
+            m = p[f"MLP_{i}"]
+            for name in sorted(m["density_grid"].keys()):
+                out.append((f"MLP_{i}/density_grid/{name}", m["density_grid"], name))
+            for k in ("density_layers_0", "density_layers_1", "output_density_layer"):
+                for kk in ("kernel", "bias"):
+                    out.append((f"MLP_{i}/{k}/{kk}", m[k], kk))
+        return out
+
+    lo = leaves(po)
+    for _, d, k in lo:
+        d[k] = d[k].clone().requires_grad_(True)
+    ho = o(po, rays, u)
+    sum((h["weights"] * Gl).sum() for h, Gl in zip(ho, G)).backward()
+
+    # CUDA: make the arena the leaf so table grads land in one contiguous buffer
+    for i, m in enumerate(n.mlps):
+        p = pn[f"MLP_{i}"]
+        p["_arena"] = p["_arena"].clone().requires_grad_(True)
+        p["density_grid"] = m.grid.views(p["_arena"])
+    ln = leaves(pn)
+    for name, d, k in ln:
+        if "density_grid" not in name:
+            d[k] = d[k].clone().requires_grad_(True)
+    hn = n(pn, to_dev(rays, cuda_device), to_dev(u, cuda_device), train=True)
+    sum((h["weights"] * Gl.to(cuda_device)).sum() for h, Gl in zip(hn, G)).backward()
+    for i, m in enumerate(n.mlps):
+        gviews = m.grid.views(pn[f"MLP_{i}"]["_arena"].grad)
+        for name in gviews:
+            ref = po[f"MLP_{i}"]["density_grid"][name].grad
+            assert rel_err(gviews[name], ref) <= 2e-4, (i, name, rel_err(gviews[name], ref))
+    for (name, dn, kn), (_, do, ko) in zip(ln, lo):
+        if "density_grid" in name:
+            continue
+        assert rel_err(dn[kn].grad, do[ko].grad) <= 2e-4, (name, rel_err(dn[kn].grad, do[ko].grad))

@@ -1,0 +1,43 @@
+"""Shared helpers for the parity tests (synthetic workloads of BASELINE.md section 2)."""
+import numpy as np
+import torch
+
+SEED = 20200823  # the reference's Config.jax_rng_seed (internal/configs.py:180)
+
+
+def gen(seed_offset=0):
+    return np.random.Generator(np.random.PCG64(SEED + seed_offset))
+
+
+def f32(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+
+def make_rays(g, R, near=2.0, far=6.0, radius=4.0, radii=5e-4):
+    """BASELINE.md config 1 primary rays: origins on a sphere, non-unit directions."""
+    o = g.normal(size=(R, 3))
+    o = radius * o / np.linalg.norm(o, axis=-1, keepdims=True)
+    v = -o + 0.3 * g.normal(size=(R, 3))
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    d = v * g.uniform(1.0, 1.2, size=(R, 1))
+    return dict(
+        origins=f32(o), directions=f32(d), viewdirs=f32(v), radii=torch.full((R, 1), radii),
+        near=torch.full((R, 1), near), far=torch.full((R, 1), far),
+    )
+
+
+def to_dev(tree, device):
+    if isinstance(tree, dict):
+        return {k: to_dev(v, device) for k, v in tree.items()}
+    if isinstance(tree, (list, tuple)):
+        return type(tree)(to_dev(v, device) for v in tree)
+    if isinstance(tree, torch.Tensor):
+        return tree.to(device)
+    return tree
+
+
+def rel_err(a, b, floor=1e-30):
+    """max |a-b| / max(|b|) -- scale-relative error used with the 1e-5 fp32 tolerance."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / max(float(b.abs().max()), floor))
