@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the radiance-cache query path (contract: see the task statement / DESIGN.md 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--rays R]
+
+b200 arm   : one step = one pass of the cache-stage hot path (forward + backward) over one
+             batch of synthetic rays, captured in a CUDA graph.  `value` = cache samples/s
+             with inputs resident in HBM; `e2e` = the same through the public host API with a
+             pinned host->device copy of the ray batch and a device->host read of the loss
+             inside the timed region.
+reference  : the reference's own algorithm (restated CPU oracle, PyTorch-CPU fp32 -- JAX is
+             not installable in this image) on the host cores, same config and metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMPLES_PER_RAY = 160  # 64 + 64 + 32 (configs/nerf_ngp_yobo.gin:521-545)
+METRIC = "cache_samples_per_sec"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=int, default=1024, help="rays per GPU per step (config 2: 1024)")
+    ap.add_argument("--bf16", type=int, default=0, help="1: bf16 tensor-core MLP variant")
+    ap.add_argument("--cpu-rays", type=int, default=256, help="rays in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", help="print per-ABI-call device times")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_reference_throughput(rays, steps, warmup, threads=None):
+    """The reference's algorithm (oracle port) for the same step: cache sampler fwd+bwd."""
+    from oracle import sampling as osamp
+    from neural_radiance_caching_b200 import workload
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    g = np.random.Generator(np.random.PCG64(workload.SEED))
+    samp = osamp.ProposalVolumeSampler()
+    params = samp.init(g, table_init_range=0.1)
+    leaves = []
+    for i in range(3):
+        m = params[f"MLP_{i}"]
+        for k in m["density_grid"]:
+            m["density_grid"][k].requires_grad_(True)
+            leaves.append(m["density_grid"][k])
+        for k in ("density_layers_0", "density_layers_1", "output_density_layer"):
+            for kk in ("kernel", "bias"):
+                m[k][kk].requires_grad_(True)
+                leaves.append(m[k][kk])
+    rn = workload.make_rays_np(g, rays)
+    rt = {k: torch.from_numpy(v) for k, v in rn.items()}
+    u = [torch.from_numpy(g.uniform(size=(rays, 1)).astype(np.float32)) for _ in range(3)]
+    target = torch.from_numpy(g.uniform(size=(rays,)).astype(np.float32))
+
+    def step():
+        for t in leaves:
+            t.grad = None
+        # levels 0-1 discard their analytic normals (XLA dead-code-eliminates them); level 2's
+        # normals are forward-only here, matching the b200 step.
+        hist = samp(params, rt, u)
+        acc = [h["weights"].sum(-1) for h in hist]
+        loss = torch.sqrt((acc[2] - target) ** 2 + 1e-6).mean()
+        loss = loss + 0.01 * ((acc[0] - acc[2].detach()) ** 2).mean() + 0.01 * ((acc[1] - acc[2].detach()) ** 2).mean()
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return rays * SAMPLES_PER_RAY / dt, dt, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    val, dt, threads = cpu_reference_throughput(args.cpu_rays, steps, warm)
+    sample = f"{args.cpu_rays} rays x 160 samples per step, {steps} steps after {warm} warm-up"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step": args.cpu_rays,
+                   "note": "restated reference (oracle), PyTorch-CPU fp32 -- not JAX/XLA (not installable here)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rays_per_sec": val / SAMPLES_PER_RAY,
+    }
+    print(json.dumps(line))
+
+
+WORKLOAD = ("config2 cache training step, density path: nerf_ngp_yobo_lego proposal sampler (64,64,32) "
+            "hash-grid + MLP fwd+bwd with proposal resampling")
+
+
+# ----------------------------------------------------------------------------- b200 arm
+def run_b200(args):
+    import torch.distributed as dist
+
+    from neural_radiance_caching_b200 import _lib, workload
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    pk, pk_kind = peaks()
+
+    R = args.rays
+    step_obj = workload.CacheSamplerStep(dev, bf16=bool(args.bf16))
+    g = np.random.Generator(np.random.PCG64(workload.SEED + rank))
+    n_batches = 4
+    host = []
+    for _ in range(n_batches):
+        rn = workload.make_rays_np(g, R)
+        u = [g.uniform(size=(R, 1)).astype(np.float32) for _ in range(3)]
+        tgt = g.uniform(size=(R, 1)).astype(np.float32)
+        host.append(torch.from_numpy(workload.pack_rays(rn, u, tgt)).pin_memory())
+    dbuf = torch.empty_like(host[0], device=dev)
+    dbuf.copy_(host[0])
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    grads_flat = None
+
+    def allreduce_grads():
+        # gradient all-reduce (mean) over tables + MLP weights, the reference's lax.pmean
+        # (internal/train_utils.py:3132-3136); one NCCL call per contiguous arena.
+        if world == 1:
+            return
+        for t in step_obj.leaves:
+            dist.all_reduce(t.grad, op=dist.ReduceOp.AVG)
+
+    def one_step():
+        rays, u01, extra = workload.unpack_rays(dbuf)
+        loss = step_obj.step(rays, u01, extra[:, 0])
+        allreduce_grads()
+        return loss
+
+    # eager warm-up on a side stream (also counts kernel launches per step)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(3):
+            before = _lib.launch_count
+            loss = one_step()
+            launches = _lib.launch_count - before
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+
+    per_kernel = None
+    if args.profile_kernels or True:
+        per_kernel = profile_calls(one_step, _lib)
+
+    graph = torch.cuda.CUDAGraph()
+    use_graph = world == 1  # NCCL collectives are issued eagerly after the captured compute
+    if use_graph:
+        with torch.cuda.graph(graph):
+            static_loss = one_step()
+    else:
+        static_loss = None
+
+    def run_step():
+        if use_graph:
+            graph.replay()
+            return static_loss
+        return one_step()
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) -------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        run_step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    evs = []
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the timed events)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        run_step()
+        e.record()
+        evs.append((s, e))
+    barrier()
+    wall = time.perf_counter() - wall0
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs) / args.steps
+
+    # ---- end-to-end timing (e2e): pinned H2D of the ray batch + step + D2H of the loss ----
+    for i in range(2):
+        dbuf.copy_(host[i % n_batches], non_blocking=True)
+        loss_host.copy_(run_step(), non_blocking=True)
+    barrier()
+    evs2 = []
+    for i in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        dbuf.copy_(host[i % n_batches], non_blocking=True)
+        loss_host.copy_(run_step(), non_blocking=True)
+        e.record()
+        evs2.append((s, e))
+    barrier()
+    e2e_ms = sum(s.elapsed_time(e) for s, e in evs2) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_samples = world * R * SAMPLES_PER_RAY
+    value = total_samples / (dev_ms * 1e-3)
+    e2e_value = total_samples / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    roof = roofline(per_kernel, R, pk, pk_kind)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, threads = cpu_reference_throughput(args.cpu_rays, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_rays} rays x 160 samples per step, 3 steps after 1 warm-up "
+                         "(restated reference, PyTorch-CPU fp32; JAX not installable here)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16-mlp/f32" if args.bf16 else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": R, "samples_per_ray": [64, 64, 32],
+                   "tables": "MLP_0/1/2 density grids (7.5+9.6+46.7 MB fp32), U(+-0.1) trained-like init",
+                   "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
+                   "cuda_graph": bool(use_graph), "parallelism": f"dp{world} rays, params replicated"},
+        "rays_per_sec": value / SAMPLES_PER_RAY,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host[0].numel() * 4) * world,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms},
+        "gpu_launches": launches * args.steps,
+        "gpu_launches_per_step": launches,
+        "clocks": clk,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "kernel_ms": {k: round(v, 5) for k, v in (per_kernel or {}).items()},
+        "wall_s": wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_calls(one_step, _lib, iters=5):
+    """Average device time of every C-ABI call of one step, measured with CUDA events on
+    the launching stream (eager mode)."""
+    acc = {}
+    orig = _lib.call
+
+    def timed(name, *a):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig(name, *a)
+        e.record()
+        acc.setdefault(name, []).append((s, e))
+
+    _lib.call = timed
+    # the host mirrors resolve `_lib.call` at call time (module attribute), so this is seen
+    try:
+        for _ in range(iters):
+            one_step()
+        torch.cuda.synchronize()
+    finally:
+        _lib.call = orig
+    out = {}
+    for name, evs in acc.items():
+        out[name] = sum(s.elapsed_time(e) for s, e in evs) / iters
+    return out
+
+
+def roofline(per_kernel, R, pk, pk_kind):
+    """Roofline of the dominant kernel of the step.  Algorithmic bytes:
+    encode fwd per point = 12 (x) + 8*F*4*L (corner rows) + 4*L*F (features);
+    encode bwd per point = 12 + 4*L*F (upstream grad) + 2 * 8*F*4*L (atomic read-modify-write)."""
+    if not per_kernel:
+        return None
+    top = max(per_kernel, key=per_kernel.get)
+    pts = {0: 64 * R, 1: 64 * R, 2: 32 * R}
+    LF = {0: (6, 1), 1: (7, 1), 2: (8, 4)}
+    fwd = sum(pts[i] * (12 + 8 * F * 4 * L + 4 * L * F) for i, (L, F) in LF.items())
+    bwd = sum(pts[i] * (12 + 4 * L * F + 2 * 8 * F * 4 * L) for i, (L, F) in LF.items())
+    alg = {"nrc_encode_fwd": fwd, "nrc_encode_bwd": bwd, "nrc_density_query_fwd": fwd}
+    peak = pk["hbm_gbs"]
+    res = {"kernel": top, "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": pk_kind, "traffic": None}
+    if top in alg:
+        ach = alg[top] / (per_kernel[top] * 1e-3) / 1e9
+        res.update(achieved=ach, frac=ach / peak,
+                   note="sum over the 3 levels' launches of this entry point per step; per-call CUDA events")
+    else:
+        res.update(achieved=None, frac=None, note="dominant kernel is compute-bound (fp32 FFMA MLP); see DESIGN.md")
+    # always report the encode kernels too
+    for k in ("nrc_encode_fwd", "nrc_encode_bwd"):
+        if k in per_kernel:
+            a = alg[k] / (per_kernel[k] * 1e-3) / 1e9
+            res[k] = {"achieved": a, "frac": a / peak, "ms": per_kernel[k]}
+    return res
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

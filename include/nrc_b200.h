@@ -214,18 +214,28 @@ int32_t nrc_ray_resample_gather(void* stream, const float* d_field, const int32_
                                 float* d_out);
 
 /* ------------------------------------------------- K5: GGX integration ---- */
-/* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) for the
- * microfacet material + integrate_reflect_rays (:1102-1193): Disney-GGX D*F*G and Lambert
- * lobes, MIS-weighted Monte-Carlo mean of cache radiance.
- *   d_wi [R,S,3] local-frame incoming dirs, d_wo [R,3] local outgoing, d_radiance [R,S,3],
- *   d_weight [R,S] MIS weights, d_pdf [R,S], material: d_albedo [R,3], d_roughness [R],
- *   d_metalness [R], d_f0 [R].  -> d_radiance_out [R,3], d_irradiance [R,3] (may be NULL). */
+/* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) +
+ * integrate_reflect_rays (:1102-1193): Disney-GGX D*F*G and Lambert lobes evaluated in the
+ * local shading frame (normal = +z), MIS-weighted Monte-Carlo mean of cache radiance.
+ *   lobe_kind 0 'microfacet', 1 'microfacet_diffuse', 2 'microfacet_specular', 3 'lambertian'
+ *   d_wi [R,S,3] local incoming dirs, d_wo [R,S,3] local outgoing dirs, d_radiance [R,S,3],
+ *   d_weight [R,S] MIS weights, d_pdf [R,S], d_occ [R,S] or NULL; material: d_albedo [R,3],
+ *   d_roughness [R], d_metalness [R], d_f0 [R] (NULL allowed for 'lambertian').
+ *   -> d_radiance_out [R,3], d_irradiance [R,3] (may be NULL), d_occ_out [R] (may be NULL). */
 int32_t nrc_ggx_integrate_fwd(void* stream, const float* d_wi, const float* d_wo,
                               const float* d_radiance, const float* d_weight, const float* d_pdf,
-                              const float* d_albedo, const float* d_roughness,
+                              const float* d_occ, const float* d_albedo, const float* d_roughness,
                               const float* d_metalness, const float* d_f0, int64_t num_points,
                               int32_t num_samples, int32_t lobe_kind, float rgb_max,
-                              float* d_radiance_out, float* d_irradiance);
+                              float* d_radiance_out, float* d_irradiance, float* d_occ_out);
+/* VJP with respect to the incoming cache radiance: d_g_radiance [R,S,3] written from
+ * d_g_out [R,3] (may be NULL) and d_g_irradiance [R,3] (may be NULL). */
+int32_t nrc_ggx_integrate_bwd(void* stream, const float* d_wi, const float* d_wo,
+                              const float* d_radiance, const float* d_weight, const float* d_pdf,
+                              const float* d_albedo, const float* d_roughness,
+                              const float* d_metalness, const float* d_f0, const float* d_g_out,
+                              const float* d_g_irradiance, int64_t num_points, int32_t num_samples,
+                              int32_t lobe_kind, float rgb_max, float* d_g_radiance);
 
 #ifdef __cplusplus
 }

@@ -90,7 +90,8 @@ PROTOTYPES = {
     "nrc_ray_composite_bwd": [_P, _P, _P, _I32, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P],
     "nrc_ray_resample": [_P, _P, _P, _I64, _I32, _I32, _F, _F, _P, _P],
     "nrc_ray_resample_gather": [_P, _P, _P, _I64, _I32, _I32, _I32, _P],
-    "nrc_ggx_integrate_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P],
+    "nrc_ggx_integrate_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P],
+    "nrc_ggx_integrate_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],
 }
 _RESTYPES = {"nrc_error_string": C.c_char_p}
 

@@ -107,14 +107,23 @@ class DensityMLP:
         self.normals_for_filter_only = normals_for_filter_only
         self.bf16 = bf16
 
+    def bbox_tensors(self, device):
+        """Device copies of the grid bbox corners (cached: no H2D copy inside CUDA graphs)."""
+        key = str(device)
+        cache = self.__dict__.setdefault("_bbox_cache", {})
+        if key not in cache:
+            bbox = self.grid.bbox
+            cache[key] = (torch.tensor(bbox[0].astype(np.float32), device=device),
+                          torch.tensor(bbox[1].astype(np.float32), device=device))
+        return cache[key]
+
     # -- parameters -------------------------------------------------------------
     def from_oracle(self, p, device):
         """Move a parameter tree (oracle/reference layout) to the device, tables in one arena."""
         out = {}
         names = [n for (n, _, _, _) in self.grid.level_layout]
         arena = torch.cat([p["density_grid"][n].reshape(-1) for n in names]).to(device)
-        out["density_grid"] = self.grid.views(arena)
-        out["_arena"] = arena
+        out["density_grid"] = dict(self.grid.views(arena), _arena=arena)
         for k in _MLP_KEYS:
             if k in p:
                 out[k] = {kk: vv.to(device).contiguous() for kk, vv in p[k].items()}

@@ -36,15 +36,20 @@ def _require_cuda_mode(op_mode):
 
 
 class _EncodeFn(torch.autograd.Function):
-    """custom_vjp analogue: forward = nrc_encode_fwd, backward = nrc_encode_bwd."""
+    """custom_vjp analogue: forward = nrc_encode_fwd, backward = nrc_encode_bwd.
+
+    `tables` is either the per-level tensors or ONE flat arena holding all levels back to
+    back (then the table gradient is one arena-shaped buffer: no per-level zero-fill/add)."""
 
     @staticmethod
-    def forward(ctx, enc, x, *tables):
+    def forward(ctx, enc, x, use_arena, *tables):
         x2 = x.reshape(-1, 3).contiguous()
         out = torch.empty((x2.shape[0], enc.num_outputs), device=x.device, dtype=torch.float32)
-        desc = enc._descriptor(tables, None)
+        levels = enc.tables(enc.views(tables[0])) if use_arena else tables
+        desc = enc._descriptor(levels, None)
         _lib.call("nrc_encode_fwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(x2), x2.shape[0], _lib.ptr(out))
         ctx.enc = enc
+        ctx.use_arena = use_arena
         ctx.save_for_backward(x2, *tables)
         ctx.x_shape = x.shape
         return out.reshape(x.shape[:-1] + (enc.num_outputs,))
@@ -55,14 +60,19 @@ class _EncodeFn(torch.autograd.Function):
         x2, *tables = ctx.saved_tensors
         g2 = g.reshape(-1, enc.num_outputs).contiguous()
         need_x = ctx.needs_input_grad[1]
-        need_t = any(ctx.needs_input_grad[2:])
+        need_t = any(ctx.needs_input_grad[3:])
         grads = [torch.zeros_like(t) for t in tables] if need_t else None
+        if ctx.use_arena:
+            levels = enc.tables(enc.views(tables[0]))
+            glevels = enc.tables(enc.views(grads[0])) if need_t else None
+        else:
+            levels, glevels = tables, grads
         g_x = torch.empty_like(x2) if need_x else None
-        desc = enc._descriptor(tables, grads)
+        desc = enc._descriptor(levels, glevels)
         _lib.call("nrc_encode_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(x2), _lib.ptr(g2), x2.shape[0],
                   _lib.ptr(g_x))
         gx = g_x.reshape(ctx.x_shape) if need_x else None
-        return (None, gx) + (tuple(grads) if need_t else (None,) * len(tables))
+        return (None, gx, None) + (tuple(grads) if need_t else (None,) * len(tables))
 
 
 class HashEncoding:
@@ -203,6 +213,14 @@ class HashEncoding:
     def tables(self, params):
         return [params[name] for (name, _, _, _) in self.level_layout]
 
+    def apply(self, params, x):
+        """Encode through the custom VJP; `params["_arena"]` (flat buffer the level tensors are
+        views of) selects the single-gradient-buffer path."""
+        arena = params.get("_arena") if isinstance(params, dict) else None
+        if arena is not None:
+            return _EncodeFn.apply(self, x, True, arena)
+        return _EncodeFn.apply(self, x, False, *self.tables(params))
+
     # -- reference call signature --------------------------------------------
     def __call__(
         self,
@@ -234,7 +252,7 @@ class HashEncoding:
             if x.shape[-2] != 1:
                 raise NotImplementedError("per_level_fn with more than one multisample is outside the path's scope.")
             x = x[..., 0, :]
-        return _EncodeFn.apply(self, x, *self.tables(params))
+        return self.apply(params, x)
 
     def corner_indices(self, params, x, level):
         """Parity aid: integer corner indices of one level (nrc_encode_indices)."""
@@ -264,4 +282,4 @@ def trilerp(values, coordinates, datastructure, op_mode=ResampleOpMode.CUDA):
     enc = HashEncoding(hash_map_size=n**3, num_features=values.shape[-1], scale_supersample=1.0,
                        min_grid_size=n, max_grid_size=n, precondition_scaling=1.0,
                        bbox_scaling=((0.0, 0.0, 0.0), (float(n),) * 3))
-    return _EncodeFn.apply(enc, coordinates, values)
+    return _EncodeFn.apply(enc, coordinates, False, values)

@@ -119,9 +119,7 @@ class ProposalVolumeSampler:
                 enc = mlp.grid(p["density_grid"], z)
                 outs = mlp.run_network(p, enc)
                 raw, feat = outs[0], outs[1]
-                bbox = mlp.grid.bbox
-                b0 = torch.tensor(bbox[0].astype(np.float32), device=dev)
-                b1 = torch.tensor(bbox[1].astype(np.float32), device=dev)
+                b0, b1 = mlp.bbox_tensors(dev)
                 valid = torch.all((z.detach() > b0) & (z.detach() < b1), dim=-1)
                 density = torch.where(valid, _SafeExpFn.apply(raw + mlp.density_bias), torch.zeros_like(raw))
                 res.update(feature=feat, density=density, raw_density=raw,

@@ -8,7 +8,7 @@ from . import ref_math
 def contract(x):
     """internal/coord.py:63-69."""
     x_mag_sq = torch.clamp(torch.sum(x**2, dim=-1, keepdim=True), min=1.0)
-    scale = (2 * torch.sqrt(x_mag_sq) - 1) / x_mag_sq
+    scale = (2 * ref_math.sqrt(x_mag_sq) - 1) / x_mag_sq
     return scale * x
 
 

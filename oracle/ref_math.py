@@ -12,6 +12,13 @@ max_val = float(np.finfo(np.float32).max)  # internal/math.py:26
 EPS = float(np.finfo(np.float32).eps)
 
 
+def sqrt(x):
+    """Correctly rounded fp32 sqrt.  torch.sqrt on CPU dispatches large tensors to MKL VML,
+    which is NOT correctly rounded (0.4% of inputs are 1 ulp off); XLA:CPU and CUDA's
+    sqrtf are IEEE-exact, so the oracle goes through float64."""
+    return torch.sqrt(x.double()).to(x.dtype)
+
+
 class _SafeExp(torch.autograd.Function):
     """internal/math.py:186-192: exp(clip(x, min, 70)); grad = y * x_dot."""
 
@@ -126,14 +133,14 @@ def sorted_interp(x, xp, fp, eps=EPS**2):
 
 def approx_erf(x):
     """internal/math.py:365-367."""
-    return torch.sign(x) * torch.sqrt(1 - torch.exp(-(4 / np.pi) * x**2))
+    return torch.sign(x) * sqrt(1 - torch.exp(-(4 / np.pi) * x**2))
 
 
 def l2_normalize(x, grad_eps=EPS, tiny=tiny_val):
     """internal/ref_utils.py:45-70 (forward uses tiny, backward uses grad_eps)."""
     grad_eps = max(tiny, grad_eps)
     denom_sq = torch.sum(x**2, dim=-1, keepdim=True)
-    normal_val = x / torch.sqrt(torch.clamp(denom_sq, min=tiny))
-    normal_grad = x / torch.sqrt(torch.clamp(denom_sq, min=grad_eps))
+    normal_val = x / sqrt(torch.clamp(denom_sq, min=tiny))
+    normal_grad = x / sqrt(torch.clamp(denom_sq, min=grad_eps))
     normal = normal_val.detach() + (normal_grad - normal_grad.detach())
     return torch.where(denom_sq < tiny, torch.zeros_like(normal), normal)

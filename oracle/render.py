@@ -2,7 +2,7 @@
 import numpy as np
 import torch
 
-from . import stepfun
+from . import ref_math, stepfun
 
 EPS = float(np.finfo(np.float32).eps)
 
@@ -53,7 +53,7 @@ def compute_alpha_weights(density, tdist, dirs, opaque_background=False, delta=N
     """internal/render.py:134-169."""
     if delta is None:
         t_delta = tdist[..., 1:] - tdist[..., :-1]
-        delta = t_delta * torch.linalg.norm(dirs[..., None, :], dim=-1)
+        delta = t_delta * ref_math.sqrt(torch.sum(dirs[..., None, :] ** 2, dim=-1))
     density_delta = density * torch.abs(delta)
     if opaque_background:
         density_delta = torch.cat(

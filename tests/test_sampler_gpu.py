@@ -54,7 +54,7 @@ def test_sampler_train_gradients(cuda_device):
         out = []
         for i in range(3):
             m = p[f"MLP_{i}"]
-            for name in sorted(m["density_grid"].keys()):
+            for name in sorted(k for k in m["density_grid"].keys() if k != "_arena"):
                 out.append((f"MLP_{i}/density_grid/{name}", m["density_grid"], name))
             for k in ("density_layers_0", "density_layers_1", "output_density_layer"):
                 for kk in ("kernel", "bias"):
@@ -70,8 +70,8 @@ def test_sampler_train_gradients(cuda_device):
     # CUDA: make the arena the leaf so table grads land in one contiguous buffer
     for i, m in enumerate(n.mlps):
         p = pn[f"MLP_{i}"]
-        p["_arena"] = p["_arena"].clone().requires_grad_(True)
-        p["density_grid"] = m.grid.views(p["_arena"])
+        arena = p["density_grid"]["_arena"].clone().requires_grad_(True)
+        p["density_grid"] = dict(m.grid.views(arena), _arena=arena)
     ln = leaves(pn)
     for name, d, k in ln:
         if "density_grid" not in name:
@@ -79,7 +79,7 @@ def test_sampler_train_gradients(cuda_device):
     hn = n(pn, to_dev(rays, cuda_device), to_dev(u, cuda_device), train=True)
     sum((h["weights"] * Gl.to(cuda_device)).sum() for h, Gl in zip(hn, G)).backward()
     for i, m in enumerate(n.mlps):
-        gviews = m.grid.views(pn[f"MLP_{i}"]["_arena"].grad)
+        gviews = m.grid.views(pn[f"MLP_{i}"]["density_grid"]["_arena"].grad)
         for name in gviews:
             ref = po[f"MLP_{i}"]["density_grid"][name].grad
             assert rel_err(gviews[name], ref) <= 2e-4, (i, name, rel_err(gviews[name], ref))
