@@ -73,8 +73,9 @@ class _CompositeFn(torch.autograd.Function):
     def forward(ctx, values, weights, weights_nf, tdist, bg, has_rgb, want_dist):
         k = weights.shape[-1]
         C = values.shape[-1]
-        v2, w2 = _c(values.reshape(-1, k, C)), _c(weights.reshape(-1, k))
+        w2 = _c(weights.reshape(-1, k))
         R = w2.shape[0]
+        v2 = _c(values.reshape(R, k, C))
         same = weights_nf is None
         wn2 = None if same else _c(weights_nf.reshape(R, -1))
         n = k if same else wn2.shape[-1]

@@ -89,8 +89,13 @@ class ProposalVolumeSampler:
         return tdist, means
 
     def __call__(self, params, rays, u01_per_level, train_frac=1.0, train=False, use_raydist_fn=False,
-                 normals_all_levels=False):
-        """rays: dict of contiguous CUDA tensors origins/directions/viewdirs [R,3], near/far [R,1]."""
+                 normals_all_levels=False, sdist_override=None):
+        """rays: dict of contiguous CUDA tensors origins/directions/viewdirs [R,3], near/far [R,1].
+
+        `sdist_override` (list of per-level [R,n+1] tensors, test aid): use these fenceposts
+        instead of the resampled ones, so that each level can be checked against the oracle on
+        bit-identical sample positions; the resampled fenceposts are still computed and returned
+        as `sdist_sampled`."""
         near = rays["near"]
         R = near.shape[0]
         dev = near.device
@@ -105,6 +110,9 @@ class ProposalVolumeSampler:
                 sdist = stepfun.sample_intervals_from_weights(
                     u01_per_level[i_level], sdist, weights.detach(), num_samples, anneal=anneal,
                     padding=self.resample_padding, domain=(0.0, 1.0))
+                sdist_sampled = sdist
+                if sdist_override is not None:
+                    sdist = sdist_override[i_level].contiguous()
                 tdist, means = self._cast(sdist, rays, use_raydist_fn)
             want_normals = (normals_all_levels or not mlp.normals_for_filter_only) and not mlp.disable_density_normals
             res = {}
@@ -146,7 +154,7 @@ class ProposalVolumeSampler:
                     res[k + "_rectified"] = res[k] * torch.where(pdot > 0, -1.0, 1.0)
             weights, alphas, trans = render.compute_alpha_weights(
                 density, tdist, rays["directions"], opaque_background=self.opaque_background)
-            res.update(points=means, means=means, tdist=tdist, sdist=sdist, weights=weights, alphas=alphas,
-                       trans=trans)
+            res.update(points=means, means=means, tdist=tdist, sdist=sdist, sdist_sampled=sdist_sampled,
+                       weights=weights, alphas=alphas, trans=trans)
             history.append(res)
         return history
