@@ -59,7 +59,10 @@ class CacheSamplerStep:
         for i, m in enumerate(self.sampler.mlps):
             tables, arena = m.grid.init(device, generator=gen, init_range=table_init_range)
             arena.requires_grad_(True)
-            p = {"density_grid": dict(m.grid.views(arena), _arena=arena)}
+            # level views are taken from the detached arena: they only carry device pointers, and
+            # a view of the leaf would pin its AccumulateGrad node to the init stream (breaks
+            # CUDA-graph capture of the backward pass).
+            p = {"density_grid": dict(m.grid.views(arena.detach()), _arena=arena)}
             dims = [(m.in_dim, 64), (64, 64), (64, 1)] + ([(64, 3)] if m.enable_pred_normals else [])
             names = ["density_layers_0", "density_layers_1", "output_density_layer", "pred_normals_layer"]
             for name, (fi, fo) in zip(names, dims):

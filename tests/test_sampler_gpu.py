@@ -40,7 +40,10 @@ def test_sampler_levels_forward(cuda_device, table_range, use_raydist):
            sdist_override=override)
     for lvl, (a, b) in enumerate(zip(hn, ho)):
         for k in ("tdist", "means", "density", "weights", "alphas", "trans", "feature"):
-            assert rel_err(a[k], b[k]) <= 1e-5, (lvl, k, rel_err(a[k], b[k]))
+            # the power-ladder ray warp goes through powf (CUDA) vs pow (MKL): tdist agrees to
+            # 1e-5 but is no longer bit-identical, and the white-noise field amplifies that.
+            tol = 1e-5 if (not use_raydist or k in ("tdist", "means")) else 1e-4
+            assert rel_err(a[k], b[k]) <= tol, (lvl, k, rel_err(a[k], b[k]))
         # interval resampling from the previous level's (CUDA) weights: the weights agree to
         # 1e-5, the inverse CDF amplifies that by its slope (bounded by the 1e-5 padding)
         assert float((a["sdist_sampled"].cpu() - b["sdist"]).abs().max()) <= 5e-5, lvl
@@ -92,7 +95,7 @@ def test_sampler_train_gradients(cuda_device):
     for i, m in enumerate(n.mlps):
         p = pn[f"MLP_{i}"]
         arena = p["density_grid"]["_arena"].clone().requires_grad_(True)
-        p["density_grid"] = dict(m.grid.views(arena), _arena=arena)
+        p["density_grid"] = dict(m.grid.views(arena.detach()), _arena=arena)
     ln = leaves(pn)
     for name, d, k in ln:
         if "density_grid" not in name:
