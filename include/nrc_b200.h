@@ -128,22 +128,27 @@ int32_t nrc_density_mlp_fwd(void* stream, const nrc_density_mlp_t* mlp, const fl
                             int64_t num_points, int32_t bf16, float* d_raw, float* d_feat,
                             float* d_grad_pred);
 /* VJP.  Upstream grads d_g_raw [P], d_g_feat [P,64] or NULL, d_g_grad_pred [P,3] or NULL.
+ * d_density [P] (may be NULL): when given, d_g_raw is the gradient w.r.t. the *activated*
+ * density of nrc_density_query_fwd and is multiplied by d_density here -- the VJP of
+ * safe_exp (y * g, internal/math.py:186-192) and of the bbox mask (density == 0 outside).
  * Outputs: d_g_enc [P,in_dim] (written, may be NULL); weight grads accumulated into `grads`
  * (may be NULL to skip). */
 int32_t nrc_density_mlp_bwd(void* stream, const nrc_density_mlp_t* mlp, const float* d_enc,
-                            const float* d_g_raw, const float* d_g_feat, const float* d_g_grad_pred,
-                            int64_t num_points, float* d_g_enc, const nrc_density_mlp_grad_t* grads);
+                            const float* d_g_raw, const float* d_density, const float* d_g_feat,
+                            const float* d_g_grad_pred, int64_t num_points, int32_t bf16, float* d_g_enc,
+                            const nrc_density_mlp_grad_t* grads);
 
 /* Fused point query: means -> contract(x/c) -> encode -> MLP ->
  * density = safe_exp(raw + density_bias) masked to the bbox
  * (internal/geometry.py:199-341), optionally the analytic normals' raw gradient
  * d raw / d means (:442-460).
  *   d_means [P,3]; outputs (each may be NULL): d_density [P], d_raw [P],
- *   d_feat [P,64], d_grad_pred [P,3], d_raw_grad [P,3]. */
+ *   d_feat [P,64], d_grad_pred [P,3], d_raw_grad [P,3], d_enc_out [P,L*F] (the encoded
+ *   features, saved for nrc_density_mlp_bwd / nrc_encode_bwd in training). */
 int32_t nrc_density_query_fwd(void* stream, const nrc_encoding_t* enc, const nrc_density_mlp_t* mlp,
                               const float* d_means, int64_t num_points, float warp_c,
                               float density_bias, int32_t bf16, float* d_density, float* d_raw,
-                              float* d_feat, float* d_grad_pred, float* d_raw_grad);
+                              float* d_feat, float* d_grad_pred, float* d_raw_grad, float* d_enc_out);
 
 /* ------------------------------------------------------ K4: ray kernels ---- */
 /* render.compute_alpha_weights (internal/render.py:134-169), delta=None.

@@ -78,10 +78,10 @@ PROTOTYPES = {
     "nrc_contract_fwd": [_P, _P, _I64, _F, _P],
     "nrc_contract_bwd": [_P, _P, _P, _I64, _F, _P],
     "nrc_density_mlp_fwd": [_P, C.POINTER(nrc_density_mlp_t), _P, _I64, _I32, _P, _P, _P],
-    "nrc_density_mlp_bwd": [_P, C.POINTER(nrc_density_mlp_t), _P, _P, _P, _P, _I64, _P,
+    "nrc_density_mlp_bwd": [_P, C.POINTER(nrc_density_mlp_t), _P, _P, _P, _P, _P, _I64, _I32, _P,
                             C.POINTER(nrc_density_mlp_grad_t)],
     "nrc_density_query_fwd": [_P, C.POINTER(nrc_encoding_t), C.POINTER(nrc_density_mlp_t), _P, _I64, _F, _F,
-                              _I32, _P, _P, _P, _P, _P],
+                              _I32, _P, _P, _P, _P, _P, _P],
     "nrc_ray_alpha_weights_fwd": [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P],
     "nrc_ray_alpha_weights_bwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
     "nrc_ray_sample_intervals": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _F, _F, _P, _P],

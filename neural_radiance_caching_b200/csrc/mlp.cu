@@ -60,8 +60,9 @@ struct BwdSmem {
 // in registers, and issues one atomic pass at the end.
 __global__ void __launch_bounds__(kT)
 density_mlp_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc,
-                       const float* __restrict__ g_raw, const float* __restrict__ g_feat,
-                       const float* __restrict__ g_gp, int64_t P, float* __restrict__ g_enc,
+                       const float* __restrict__ g_raw, const float* __restrict__ density,
+                       const float* __restrict__ g_feat, const float* __restrict__ g_gp, int64_t P,
+                       float* __restrict__ g_enc,
                        const nrc_density_mlp_grad_t grads, int want_wgrad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& s = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -91,7 +92,7 @@ density_mlp_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc,
     mlp_forward_point(s.w, in_dim, s.x + tid, kPad, s.h1 + tid, kPad, acc);
     // upstream gradient of the 4 heads
     float go[4];
-    go[0] = valid ? g_raw[p] : 0.f;
+    go[0] = valid ? (density ? g_raw[p] * density[p] : g_raw[p]) : 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) go[1 + c] = (valid && g_gp) ? g_gp[3 * p + c] : 0.f;
 #pragma unroll
@@ -219,6 +220,9 @@ using namespace nrc;
 namespace nrc {
 int32_t density_mlp_fwd_bf16(cudaStream_t s, const nrc_density_mlp_t* mlp, const float* d_enc, int64_t P,
                              float* d_raw, float* d_feat, float* d_gp);
+int32_t density_mlp_bwd_bf16(cudaStream_t s, const nrc_density_mlp_t* mlp, const float* d_enc,
+                             const float* d_g_raw, const float* d_density, const float* d_g_feat,
+                             const float* d_g_gp, int64_t P, float* d_g_enc, const nrc_density_mlp_grad_t* grads);
 }
 
 extern "C" int32_t nrc_density_mlp_fwd(void* stream, const nrc_density_mlp_t* mlp, const float* d_enc,
@@ -236,9 +240,9 @@ extern "C" int32_t nrc_density_mlp_fwd(void* stream, const nrc_density_mlp_t* ml
 }
 
 extern "C" int32_t nrc_density_mlp_bwd(void* stream, const nrc_density_mlp_t* mlp, const float* d_enc,
-                                       const float* d_g_raw, const float* d_g_feat,
-                                       const float* d_g_grad_pred, int64_t num_points, float* d_g_enc,
-                                       const nrc_density_mlp_grad_t* grads) {
+                                       const float* d_g_raw, const float* d_density, const float* d_g_feat,
+                                       const float* d_g_grad_pred, int64_t num_points, int32_t bf16,
+                                       float* d_g_enc, const nrc_density_mlp_grad_t* grads) {
   int32_t st = validate_mlp(mlp);
   if (st != NRC_OK) return st;
   if (num_points < 0) return NRC_E_INVALID_ARG;
@@ -255,6 +259,9 @@ extern "C" int32_t nrc_density_mlp_bwd(void* stream, const nrc_density_mlp_t* ml
     want = 1;
   }
   if (!want && !d_g_enc) return NRC_OK;
+  if (bf16)
+    return density_mlp_bwd_bf16(static_cast<cudaStream_t>(stream), mlp, d_enc, d_g_raw, d_density, d_g_feat,
+                                d_g_grad_pred, num_points, d_g_enc, want ? &g : nullptr);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(density_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -264,6 +271,6 @@ extern "C" int32_t nrc_density_mlp_bwd(void* stream, const nrc_density_mlp_t* ml
   int64_t tiles = (num_points + kT - 1) / kT;
   unsigned grid = static_cast<unsigned>(tiles < kNumSMs ? tiles : kNumSMs);
   density_mlp_bwd_kernel<<<grid, kT, sizeof(BwdSmem), static_cast<cudaStream_t>(stream)>>>(
-      *mlp, d_enc, d_g_raw, d_g_feat, d_g_grad_pred, num_points, d_g_enc, g, want);
+      *mlp, d_enc, d_g_raw, d_density, d_g_feat, d_g_grad_pred, num_points, d_g_enc, g, want);
   return check_launch();
 }

@@ -1,8 +1,268 @@
-// K3 (tensor-core variant) -- placeholder until the bf16 kernel lands in this file.
-#include "mlp.cuh"
+// K3 (tensor-core variant): the fused density MLP with bf16 operands / fp32 accumulation on
+// mma.sync m16n8k16, layers chained in registers (see mma_bf16.cuh), optionally fused with the
+// contraction + hash-grid gather in front (features never reach HBM) and the analytic-normal
+// back-propagation behind.  One warp owns 32 points (two 16-row MMA tiles); a CTA is four
+// independent warps, so there is no block-level barrier on the forward path.
+//
+// Reference: internal/geometry.py:155-168,199-341,442-460 (same maths as mlp.cu / query.cu;
+// parity bar for this variant: rel 2e-2).
+#include "encode.cuh"
+#include "mma_bf16.cuh"
+
 namespace nrc {
-int32_t density_mlp_fwd_bf16(cudaStream_t, const nrc_density_mlp_t*, const float*, int64_t, float*, float*,
-                             float*) {
+
+constexpr int kBfWarps = 4;
+constexpr int kBfThreads = kBfWarps * 32;
+constexpr int kGStride = 33;  // fp32 row stride of the per-warp g_enc scratch
+
+struct WarpScratch {
+  __nv_bfloat16 x[32][kXStride];  // encoded features of the warp's 32 points (bf16, zero padded)
+  float g[32][kGStride];          // d raw / d enc (normals path)
+  int inside[32];                 // bbox mask per point
+};
+
+struct FwdSmemBf16 {
+  MlpWeightsBf16 w;
+  WarpScratch ws[kBfWarps];
+};
+
+struct QueryOut {
+  float* density; float* raw; float* feat; float* grad_pred; float* raw_grad; float* enc_out;
+};
+
+// kFused: `in` = means [P,3], features are gathered here; else `in` = enc [P,in_dim].
+template <int F, int KS0, bool kFused>
+__global__ void __launch_bounds__(kBfThreads)
+mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t m,
+                    const float* __restrict__ in, int64_t P, float warp_c, float density_bias,
+                    const QueryOut out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwdSmemBf16& s = *reinterpret_cast<FwdSmemBf16*>(smem_raw);
+  load_weights_bf16(s.w, m);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpScratch& ws = s.ws[warp];
+  const int in_dim = m.in_dim;
+  const int64_t num_tiles = (P + kBfThreads - 1) / kBfThreads;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kBfThreads + warp * 32;
+    if (base >= P) continue;  // warp-uniform
+    const int64_t p = base + lane;
+    const bool valid = p < P;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f, xn[3] = {0.f, 0.f, 0.f};
+    // ---------------- front end: one point per lane -> bf16 feature row -------------------
+    if constexpr (kFused) {
+      int inside = 0;
+      if (valid) {
+        x0 = __ldg(in + 3 * p); x1 = __ldg(in + 3 * p + 1); x2 = __ldg(in + 3 * p + 2);
+        float z[3];
+        contract_point(warp_c, x0, x1, x2, z[0], z[1], z[2]);
+        normalise_point(enc, z, xn);
+        inside = 1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) inside = inside && (z[a] > enc.b0[a]) && (z[a] < enc.b1[a]);
+        for (int l = 0; l < enc.L; ++l) {
+          Corners c = level_setup(enc.lv[l], xn);
+          FeatVec<F> v = level_interp<F>(enc.lv[l], c);
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            float e = __fmul_rn(v.v[f], enc.scale);
+            ws.x[lane][l * F + f] = __float2bfloat16(e);
+            if (out.enc_out) out.enc_out[p * in_dim + l * F + f] = e;
+          }
+        }
+      }
+      ws.inside[lane] = inside;
+      for (int k = valid ? in_dim : 0; k < KS0 * 16; ++k) ws.x[lane][k] = __float2bfloat16(0.f);
+    } else {
+      for (int k = 0; k < KS0 * 16; ++k)
+        ws.x[lane][k] = __float2bfloat16((valid && k < in_dim) ? __ldg(in + p * in_dim + k) : 0.f);
+      ws.inside[lane] = 1;
+    }
+    __syncwarp();
+    // ---------------- tensor-core MLP: two 16-point tiles per warp ------------------------
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      uint32_t a0[KS0][4];
+#pragma unroll
+      for (int ks = 0; ks < KS0; ++ks) load_a_frag(a0[ks], &ws.x[0][0], kXStride, mt * 16, ks * 16, lane);
+      float acc[8][4];
+      mma_layer64<KS0>(acc, a0, &s.w.w0t[0][0], kXStride, s.w.b0, lane);
+      uint32_t h1f[4][4];
+      acc_to_afrag<true>(acc, h1f);
+      mma_layer64<4>(acc, h1f, &s.w.w1t[0][0], kWStride, s.w.b1, lane);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = fmaxf(acc[nt][e], 0.f);
+      uint32_t h2f[4][4];
+      acc_to_afrag<false>(acc, h2f);
+      // heads (density + 3 pred-normal channels), N = 8 tile
+      float o[4];
+      {
+        const int c = (lane & 3) * 2;
+        o[0] = o[2] = c < 4 ? s.w.bo[c] : 0.f;
+        o[1] = o[3] = c + 1 < 4 ? s.w.bo[c + 1] : 0.f;
+        uint32_t b[4];
+        load_b_frag_k32(b, &s.w.wot[0][0], kWStride, 0, 0, lane);
+        mma_bf16(o, h2f[0], b[0], b[1]);
+        mma_bf16(o, h2f[1], b[2], b[3]);
+        load_b_frag_k32(b, &s.w.wot[0][0], kWStride, 0, 32, lane);
+        mma_bf16(o, h2f[2], b[0], b[1]);
+        mma_bf16(o, h2f[3], b[2], b[3]);
+      }
+      const int r = lane >> 2;
+      const int64_t pr[2] = {base + mt * 16 + r, base + mt * 16 + r + 8};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (pr[h] >= P) continue;
+        if ((lane & 3) == 0) {
+          float rawv = o[2 * h];
+          if (out.raw) out.raw[pr[h]] = rawv;
+          if (out.density) out.density[pr[h]] = ws.inside[mt * 16 + r + 8 * h] ? safe_exp(rawv + density_bias) : 0.f;
+          if (out.grad_pred) out.grad_pred[3 * pr[h]] = o[2 * h + 1];
+        } else if ((lane & 3) == 1 && out.grad_pred) {
+          out.grad_pred[3 * pr[h] + 1] = o[2 * h];
+          out.grad_pred[3 * pr[h] + 2] = o[2 * h + 1];
+        }
+        if (out.feat) {
+          float* f = out.feat + pr[h] * kHid + (lane & 3) * 2;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<float2*>(f + nt * 8) = make_float2(acc[nt][2 * h], acc[nt][2 * h + 1]);
+        }
+      }
+      if constexpr (kFused) {
+        if (out.raw_grad) {
+          // g_h2 = wd * [h2 > 0]
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + (lane & 3) * 2;
+            const float w0 = s.w.wo[c][0], w1 = s.w.wo[c + 1][0];
+            acc[nt][0] = acc[nt][0] > 0.f ? w0 : 0.f;
+            acc[nt][1] = acc[nt][1] > 0.f ? w1 : 0.f;
+            acc[nt][2] = acc[nt][2] > 0.f ? w0 : 0.f;
+            acc[nt][3] = acc[nt][3] > 0.f ? w1 : 0.f;
+          }
+          uint32_t gf[4][4];
+          acc_to_afrag<false>(acc, gf);
+          // g_h1 = (g_h2 W1^T) * [h1 > 0]
+          mma_layer64<4>(acc, gf, &s.w.w1[0][0], kWStride, nullptr, lane);
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            float2 lo = unpack_bf16(h1f[nt >> 1][2 * (nt & 1)]);
+            float2 hi = unpack_bf16(h1f[nt >> 1][2 * (nt & 1) + 1]);
+            acc[nt][0] = lo.x > 0.f ? acc[nt][0] : 0.f;
+            acc[nt][1] = lo.y > 0.f ? acc[nt][1] : 0.f;
+            acc[nt][2] = hi.x > 0.f ? acc[nt][2] : 0.f;
+            acc[nt][3] = hi.y > 0.f ? acc[nt][3] : 0.f;
+          }
+          acc_to_afrag<false>(acc, gf);
+          // g_enc = g_h1 W0^T  (N = 16 * KS0 columns, of which in_dim are real)
+          float ge[2 * KS0][4];
+#pragma unroll
+          for (int nt = 0; nt < 2 * KS0; ++nt) ge[nt][0] = ge[nt][1] = ge[nt][2] = ge[nt][3] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int np = 0; np < KS0; ++np) {
+              uint32_t b[4];
+              load_b_frag2(b, &s.w.w0[0][0], kWStride, np * 16, ks * 16, lane);
+              mma_bf16(ge[2 * np], gf[ks], b[0], b[1]);
+              mma_bf16(ge[2 * np + 1], gf[ks], b[2], b[3]);
+            }
+          }
+#pragma unroll
+          for (int nt = 0; nt < 2 * KS0; ++nt) {
+            const int c = nt * 8 + (lane & 3) * 2;
+            if (c < in_dim) { ws.g[mt * 16 + r][c] = ge[nt][0]; ws.g[mt * 16 + r + 8][c] = ge[nt][2]; }
+            if (c + 1 < in_dim) { ws.g[mt * 16 + r][c + 1] = ge[nt][1]; ws.g[mt * 16 + r + 8][c + 1] = ge[nt][3]; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if constexpr (kFused) {
+      if (out.raw_grad && valid) {
+        // VJP through the encoding (corner re-gather hits L1/L2) and the contraction.
+        float gz[3] = {0.f, 0.f, 0.f};
+        for (int l = 0; l < enc.L; ++l) {
+          const LevelDev& lv = enc.lv[l];
+          Corners c = level_setup(lv, xn);
+          float g[F];
+#pragma unroll
+          for (int f = 0; f < F; ++f) g[f] = ws.g[lane][l * F + f] * enc.scale;
+          float gl[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            int bx, by, bz;
+            corner_bits(lv.is_hash, k, bx, by, bz);
+            int32_t row = corner_row(lv, c, bx, by, bz);
+            if (row < 0) continue;
+            FeatVec<F> v = load_row<F>(lv.table, row);
+            float dot = 0.f;
+#pragma unroll
+            for (int f = 0; f < F; ++f) dot = fmaf(g[f], v.v[f], dot);
+            float wx = bx ? c.cw[0] : c.fw[0];
+            float wy = by ? c.cw[1] : c.fw[1];
+            float wz = bz ? c.cw[2] : c.fw[2];
+            gl[0] += (bx ? dot : -dot) * (wy * wz);
+            gl[1] += (by ? dot : -dot) * (wx * wz);
+            gl[2] += (bz ? dot : -dot) * (wx * wy);
+          }
+          const float fN = static_cast<float>(lv.N);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) gz[a] += gl[a] * (fN / enc.span[a]);
+        }
+        float o0, o1, o2;
+        contract_vjp(warp_c, x0, x1, x2, gz[0], gz[1], gz[2], o0, o1, o2);
+        out.raw_grad[3 * p] = o0; out.raw_grad[3 * p + 1] = o1; out.raw_grad[3 * p + 2] = o2;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int F, int KS0, bool kFused>
+int32_t launch_bf16_fwd(cudaStream_t st, const EncDev& d, const nrc_density_mlp_t* mlp, const float* in,
+                        int64_t P, float warp_c, float bias, const QueryOut& out) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mlp_bf16_fwd_kernel<F, KS0, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(sizeof(FwdSmemBf16)));
+    attr_set = true;
+  }
+  int64_t tiles = (P + kBfThreads - 1) / kBfThreads;
+  unsigned grid = static_cast<unsigned>(tiles < kNumSMs * 3 ? tiles : kNumSMs * 3);
+  mlp_bf16_fwd_kernel<F, KS0, kFused><<<grid, kBfThreads, sizeof(FwdSmemBf16), st>>>(d, *mlp, in, P, warp_c,
+                                                                                  bias, out);
+  return check_launch();
+}
+
+int32_t density_mlp_fwd_bf16(cudaStream_t s, const nrc_density_mlp_t* mlp, const float* d_enc, int64_t P,
+                             float* d_raw, float* d_feat, float* d_gp) {
+  EncDev d{};
+  QueryOut out{nullptr, d_raw, d_feat, d_gp, nullptr, nullptr};
+  if (mlp->in_dim <= 16) return launch_bf16_fwd<1, 1, false>(s, d, mlp, d_enc, P, 0.f, 0.f, out);
+  return launch_bf16_fwd<1, 2, false>(s, d, mlp, d_enc, P, 0.f, 0.f, out);
+}
+
+int32_t density_query_fwd_bf16(cudaStream_t s, const EncDev& d, const nrc_density_mlp_t* mlp,
+                               const float* d_means, int64_t P, float warp_c, float bias, float* density,
+                               float* raw, float* feat, float* gp, float* rg, float* enc_out) {
+  QueryOut out{density, raw, feat, gp, rg, enc_out};
+  const bool small = mlp->in_dim <= 16;
+  switch (d.F) {
+    case 1: return small ? launch_bf16_fwd<1, 1, true>(s, d, mlp, d_means, P, warp_c, bias, out)
+                         : launch_bf16_fwd<1, 2, true>(s, d, mlp, d_means, P, warp_c, bias, out);
+    case 2: return small ? launch_bf16_fwd<2, 1, true>(s, d, mlp, d_means, P, warp_c, bias, out)
+                         : launch_bf16_fwd<2, 2, true>(s, d, mlp, d_means, P, warp_c, bias, out);
+    case 4: return small ? launch_bf16_fwd<4, 1, true>(s, d, mlp, d_means, P, warp_c, bias, out)
+                         : launch_bf16_fwd<4, 2, true>(s, d, mlp, d_means, P, warp_c, bias, out);
+    case 8: return small ? launch_bf16_fwd<8, 1, true>(s, d, mlp, d_means, P, warp_c, bias, out)
+                         : launch_bf16_fwd<8, 2, true>(s, d, mlp, d_means, P, warp_c, bias, out);
+  }
   return NRC_E_UNSUPPORTED;
 }
+
 }  // namespace nrc

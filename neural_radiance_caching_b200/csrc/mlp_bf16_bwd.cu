@@ -1,0 +1,295 @@
+// K3 backward (tensor-core variant).  Persistent CTAs of four warps loop over 128-point tiles:
+//   phase 1 (per warp, 32 points): recompute the forward activations from the saved encoded
+//     features with register-chained MMAs, form g_h2 / g_h1 / g_enc (data gradients through the
+//     transposed weights), and leave bf16 copies of x, h1, h2, g2, g1, g_out in shared memory;
+//   phase 2 (per CTA): weight gradients dW = A^T G as MMAs over the 128-point tile with the
+//     transposed-ldmatrix trick, accumulated in fp32 registers across all tiles of the CTA.
+// One atomic pass per CTA at the end.  Reference: XLA autodiff of geometry.py:155-168,467.
+#include "mma_bf16.cuh"
+
+namespace nrc {
+
+constexpr int kBwWarps = 4;
+constexpr int kBwThreads = kBwWarps * 32;
+constexpr int kBwTile = kBwThreads;  // points per tile
+
+struct BwdSmemBf16 {
+  MlpWeightsBf16 w;
+  __nv_bfloat16 x[kBwTile][kXStride];
+  __nv_bfloat16 h1[kBwTile][kWStride];
+  __nv_bfloat16 h2[kBwTile][kWStride];
+  __nv_bfloat16 g2[kBwTile][kWStride];
+  __nv_bfloat16 g1[kBwTile][kWStride];
+  __nv_bfloat16 go[kBwTile][8];
+  float db1[kHid];
+  float db0[kHid];
+  float dbo[4];
+};
+
+// Store an A-fragment image (16 rows x 64 cols, bf16) back to a row-major tile.
+__device__ __forceinline__ void store_afrag(__nv_bfloat16* tile, int stride, int row0, const uint32_t (&a)[4][4],
+                                            int lane) {
+  const int r = lane >> 2, c = (lane & 3) * 2;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = (2 * kk + h) * 8 + c;
+      *reinterpret_cast<uint32_t*>(tile + (row0 + r) * stride + col) = a[kk][2 * h + 0];
+      *reinterpret_cast<uint32_t*>(tile + (row0 + r + 8) * stride + col) = a[kk][2 * h + 1];
+    }
+  }
+}
+
+// Column sums of a 16 x 64 accumulator fragment, added into a shared fp32 vector.
+__device__ __forceinline__ void colsum_to_smem(const float (&acc)[8][4], float* dst, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    float v0 = acc[nt][0] + acc[nt][2];
+    float v1 = acc[nt][1] + acc[nt][3];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+    }
+    if (lane < 4) {
+      atomicAdd(dst + nt * 8 + lane * 2, v0);
+      atomicAdd(dst + nt * 8 + lane * 2 + 1, v1);
+    }
+  }
+}
+
+template <int KS0>
+__global__ void __launch_bounds__(kBwThreads)
+mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, const float* __restrict__ g_raw,
+                    const float* __restrict__ density, const float* __restrict__ g_feat,
+                    const float* __restrict__ g_gp, int64_t P, float* __restrict__ g_enc,
+                    const nrc_density_mlp_grad_t grads, int want_wgrad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmemBf16& s = *reinterpret_cast<BwdSmemBf16*>(smem_raw);
+  load_weights_bf16(s.w, m);
+  for (int i = threadIdx.x; i < kHid; i += kBwThreads) { s.db1[i] = 0.f; s.db0[i] = 0.f; }
+  if (threadIdx.x < 4) s.dbo[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int in_dim = m.in_dim;
+  const int r = lane >> 2, cq = (lane & 3) * 2;
+
+  float accW1[8][4], accW0[KS0][2][4], accWo[4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) accW1[i][e] = 0.f;
+#pragma unroll
+  for (int i = 0; i < KS0; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) accW0[i][h][e] = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) accWo[e] = 0.f;
+
+  const int64_t num_tiles = (P + kBwTile - 1) / kBwTile;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kBwTile + warp * 32;
+    // ------------------------------ phase 1 ------------------------------------------------
+    {
+      const int64_t p = base + lane;
+      const bool valid = p < P;
+      const int row = warp * 32 + lane;
+      for (int k = 0; k < KS0 * 16; ++k)
+        s.x[row][k] = __float2bfloat16((valid && k < in_dim) ? __ldg(enc + p * in_dim + k) : 0.f);
+      float go[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        go[0] = density ? g_raw[p] * density[p] : g_raw[p];
+        if (g_gp) { go[1] = g_gp[3 * p]; go[2] = g_gp[3 * p + 1]; go[3] = g_gp[3 * p + 2]; }
+      }
+      *reinterpret_cast<uint2*>(&s.go[row][0]) = make_uint2(pack_bf16(go[0], go[1]), pack_bf16(go[2], go[3]));
+      *reinterpret_cast<uint2*>(&s.go[row][4]) = make_uint2(0u, 0u);
+      if (want_wgrad) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v = go[c];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) atomicAdd(&s.dbo[c], v);
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      const int row0 = warp * 32 + mt * 16;
+      uint32_t a0[KS0][4];
+#pragma unroll
+      for (int ks = 0; ks < KS0; ++ks) load_a_frag(a0[ks], &s.x[0][0], kXStride, row0, ks * 16, lane);
+      float acc[8][4];
+      mma_layer64<KS0>(acc, a0, &s.w.w0t[0][0], kXStride, s.w.b0, lane);
+      uint32_t h1f[4][4];
+      acc_to_afrag<true>(acc, h1f);
+      store_afrag(&s.h1[0][0], kWStride, row0, h1f, lane);
+      mma_layer64<4>(acc, h1f, &s.w.w1t[0][0], kWStride, s.w.b1, lane);
+      uint32_t f2[4][4];
+      acc_to_afrag<true>(acc, f2);
+      store_afrag(&s.h2[0][0], kWStride, row0, f2, lane);
+      // g_h2 = (Wo go + g_feat) * [h2 > 0], in accumulator layout
+      const int64_t pr[2] = {base + mt * 16 + r, base + mt * 16 + r + 8};
+      float gor[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool v = pr[h] < P;
+        gor[h][0] = v ? (density ? g_raw[pr[h]] * density[pr[h]] : g_raw[pr[h]]) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gor[h][1 + c] = (v && g_gp) ? g_gp[3 * pr[h] + c] : 0.f;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = nt * 8 + cq;
+        const float4 w0 = *reinterpret_cast<const float4*>(&s.w.wo[col][0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&s.w.wo[col + 1][0]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float ga = gor[h][0] * w0.x + gor[h][1] * w0.y + gor[h][2] * w0.z + gor[h][3] * w0.w;
+          float gb = gor[h][0] * w1.x + gor[h][1] * w1.y + gor[h][2] * w1.z + gor[h][3] * w1.w;
+          if (g_feat && pr[h] < P) {
+            float2 gf = *reinterpret_cast<const float2*>(g_feat + pr[h] * kHid + col);
+            ga += gf.x; gb += gf.y;
+          }
+          acc[nt][2 * h] = acc[nt][2 * h] > 0.f ? ga : 0.f;
+          acc[nt][2 * h + 1] = acc[nt][2 * h + 1] > 0.f ? gb : 0.f;
+        }
+      }
+      if (want_wgrad) colsum_to_smem(acc, s.db1, lane);
+      acc_to_afrag<false>(acc, f2);
+      store_afrag(&s.g2[0][0], kWStride, row0, f2, lane);
+      // g_h1 = (g_h2 W1^T) * [h1 > 0]
+      mma_layer64<4>(acc, f2, &s.w.w1[0][0], kWStride, nullptr, lane);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float2 lo = unpack_bf16(h1f[nt >> 1][2 * (nt & 1)]);
+        float2 hi = unpack_bf16(h1f[nt >> 1][2 * (nt & 1) + 1]);
+        acc[nt][0] = lo.x > 0.f ? acc[nt][0] : 0.f;
+        acc[nt][1] = lo.y > 0.f ? acc[nt][1] : 0.f;
+        acc[nt][2] = hi.x > 0.f ? acc[nt][2] : 0.f;
+        acc[nt][3] = hi.y > 0.f ? acc[nt][3] : 0.f;
+      }
+      if (want_wgrad) colsum_to_smem(acc, s.db0, lane);
+      acc_to_afrag<false>(acc, f2);
+      store_afrag(&s.g1[0][0], kWStride, row0, f2, lane);
+      if (g_enc) {
+        float ge[2 * KS0][4];
+#pragma unroll
+        for (int nt = 0; nt < 2 * KS0; ++nt) ge[nt][0] = ge[nt][1] = ge[nt][2] = ge[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+          for (int np = 0; np < KS0; ++np) {
+            uint32_t b[4];
+            load_b_frag2(b, &s.w.w0[0][0], kWStride, np * 16, ks * 16, lane);
+            mma_bf16(ge[2 * np], f2[ks], b[0], b[1]);
+            mma_bf16(ge[2 * np + 1], f2[ks], b[2], b[3]);
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2 * KS0; ++nt) {
+          const int c = nt * 8 + cq;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (pr[h] >= P) continue;
+            if (c < in_dim) g_enc[pr[h] * in_dim + c] = ge[nt][2 * h];
+            if (c + 1 < in_dim) g_enc[pr[h] * in_dim + c + 1] = ge[nt][2 * h + 1];
+          }
+        }
+      }
+    }
+    if (!want_wgrad) { __syncwarp(); continue; }
+    __syncthreads();
+    // ------------------------------ phase 2 ------------------------------------------------
+#pragma unroll 2
+    for (int ks = 0; ks < kBwTile / 16; ++ks) {
+      const int k0 = ks * 16;
+      uint32_t a[4], b[4];
+      // dW1[k][j]: rows k = 16*warp.., all 64 columns
+      load_a_frag_trans(a, &s.h1[0][0], kWStride, k0, warp * 16, lane);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        load_b_frag2_trans(b, &s.g2[0][0], kWStride, k0, np * 16, lane);
+        mma_bf16(accW1[2 * np], a, b[0], b[1]);
+        mma_bf16(accW1[2 * np + 1], a, b[2], b[3]);
+      }
+      // dW0[i][k]: all rows i, columns k = 16*warp..
+      load_b_frag2_trans(b, &s.g1[0][0], kWStride, k0, warp * 16, lane);
+#pragma unroll
+      for (int mi = 0; mi < KS0; ++mi) {
+        load_a_frag_trans(a, &s.x[0][0], kXStride, k0, mi * 16, lane);
+        mma_bf16(accW0[mi][0], a, b[0], b[1]);
+        mma_bf16(accW0[mi][1], a, b[2], b[3]);
+      }
+      // dWo[j][c]: rows j = 16*warp.., 8 head columns
+      load_a_frag_trans(a, &s.h2[0][0], kWStride, k0, warp * 16, lane);
+      uint32_t bo[2];
+      load_b_frag1_trans(bo, &s.go[0][0], 8, k0, 0, lane);
+      mma_bf16(accWo, a, bo[0], bo[1]);
+    }
+    __syncthreads();
+  }
+  if (!want_wgrad) return;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int row = warp * 16 + r + (e >= 2 ? 8 : 0), col = nt * 8 + cq + (e & 1);
+      atomicAdd(grads.d_w1 + row * kHid + col, accW1[nt][e]);
+    }
+#pragma unroll
+  for (int mi = 0; mi < KS0; ++mi)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = mi * 16 + r + (e >= 2 ? 8 : 0), col = warp * 16 + h * 8 + cq + (e & 1);
+        if (row < in_dim) atomicAdd(grads.d_w0 + row * kHid + col, accW0[mi][h][e]);
+      }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int j = warp * 16 + r + (e >= 2 ? 8 : 0), c = cq + (e & 1);
+    if (c == 0) atomicAdd(grads.d_wd + j, accWo[e]);
+    else if (c < 4 && grads.d_wn) atomicAdd(grads.d_wn + j * 3 + (c - 1), accWo[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kHid; i += kBwThreads) {
+    atomicAdd(grads.d_b1 + i, s.db1[i]);
+    atomicAdd(grads.d_b0 + i, s.db0[i]);
+  }
+  if (threadIdx.x == 0) atomicAdd(grads.d_bd, s.dbo[0]);
+  else if (threadIdx.x < 4 && grads.d_bn) atomicAdd(grads.d_bn + (threadIdx.x - 1), s.dbo[threadIdx.x]);
+}
+
+template <int KS0>
+int32_t launch_bf16_bwd(cudaStream_t st, const nrc_density_mlp_t* mlp, const float* enc, const float* g_raw,
+                        const float* density, const float* g_feat, const float* g_gp, int64_t P, float* g_enc,
+                        const nrc_density_mlp_grad_t* grads) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mlp_bf16_bwd_kernel<KS0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(sizeof(BwdSmemBf16)));
+    attr_set = true;
+  }
+  nrc_density_mlp_grad_t g{};
+  if (grads) g = *grads;
+  int64_t tiles = (P + kBwTile - 1) / kBwTile;
+  unsigned grid = static_cast<unsigned>(tiles < kNumSMs ? tiles : kNumSMs);
+  mlp_bf16_bwd_kernel<KS0><<<grid, kBwThreads, sizeof(BwdSmemBf16), st>>>(*mlp, enc, g_raw, density, g_feat, g_gp,
+                                                                          P, g_enc, g, grads ? 1 : 0);
+  return check_launch();
+}
+
+int32_t density_mlp_bwd_bf16(cudaStream_t s, const nrc_density_mlp_t* mlp, const float* d_enc,
+                             const float* d_g_raw, const float* d_density, const float* d_g_feat,
+                             const float* d_g_gp, int64_t P, float* d_g_enc, const nrc_density_mlp_grad_t* grads) {
+  if (mlp->in_dim <= 16)
+    return launch_bf16_bwd<1>(s, mlp, d_enc, d_g_raw, d_density, d_g_feat, d_g_gp, P, d_g_enc, grads);
+  return launch_bf16_bwd<2>(s, mlp, d_enc, d_g_raw, d_density, d_g_feat, d_g_gp, P, d_g_enc, grads);
+}
+
+}  // namespace nrc

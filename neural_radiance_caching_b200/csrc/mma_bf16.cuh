@@ -1,0 +1,184 @@
+// Warp-level bf16 tensor-core building blocks (mma.sync m16n8k16, fp32 accumulate) for the
+// fused density MLP.  The layers are 6/7/32 -> 64 -> 64 -> 4 wide: far below a tcgen05 tile
+// (M=128, TMEM accumulators, TMA-staged operands), and their A operand is produced in
+// registers by the hash-grid gather of the same warp, so the layers are chained in registers
+// with warp-synchronous MMAs: the accumulator fragment of layer l *is* the A fragment of
+// layer l+1 (no shared-memory or TMEM round trip between layers).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "nrc_common.cuh"
+
+namespace nrc {
+
+constexpr int kHid = 64;          // hidden width
+constexpr int kWStride = 72;      // bf16 row stride of 64-wide tiles (144 B: conflict-free ldmatrix)
+constexpr int kXStride = 40;      // bf16 row stride of the <=32-wide input tile (80 B)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
+               : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
+}
+
+// D += A(16x16, row) * B(16x8, col), bf16 in, fp32 accumulate.
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+// A fragment (16 rows x 16 k) from a row-major bf16 tile [row][k].
+__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], const __nv_bfloat16* tile, int stride,
+                                            int row0, int k0, int lane) {
+  const int r = row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int c = k0 + (lane >> 4) * 8;
+  ldmatrix_x4(a, tile + r * stride + c);
+}
+// B fragments of two adjacent n-tiles (16 n x 16 k) from a tile stored [n][k] (k contiguous):
+// b[0],b[1] -> n-tile n0/8, b[2],b[3] -> n-tile n0/8 + 1.
+__device__ __forceinline__ void load_b_frag2(uint32_t (&b)[4], const __nv_bfloat16* tile, int stride,
+                                             int n0, int k0, int lane) {
+  const int n = n0 + (lane & 7) + (lane >> 4) * 8;
+  const int c = k0 + ((lane >> 3) & 1) * 8;
+  ldmatrix_x4(b, tile + n * stride + c);
+}
+// B fragments of ONE n-tile (8 n) for two adjacent k-steps (32 k): b[0],b[1] -> k0, b[2],b[3] -> k0+16.
+__device__ __forceinline__ void load_b_frag_k32(uint32_t (&b)[4], const __nv_bfloat16* tile, int stride,
+                                                int n0, int k0, int lane) {
+  const int n = n0 + (lane & 7);
+  const int c = k0 + (lane >> 3) * 8;
+  ldmatrix_x4(b, tile + n * stride + c);
+}
+// A fragment of M^T where the tile is stored [k][m] (i.e. rows are the reduction index):
+// used for weight gradients dW = A^T G with the activations stored point-major.
+__device__ __forceinline__ void load_a_frag_trans(uint32_t (&a)[4], const __nv_bfloat16* tile, int stride,
+                                                  int k0, int m0, int lane) {
+  const int r = k0 + (lane & 7) + (lane >> 4) * 8;
+  const int c = m0 + ((lane >> 3) & 1) * 8;
+  ldmatrix_x4_trans(a, tile + r * stride + c);
+}
+// B fragments of two adjacent n-tiles from a tile stored [k][n] (n contiguous).
+__device__ __forceinline__ void load_b_frag2_trans(uint32_t (&b)[4], const __nv_bfloat16* tile, int stride,
+                                                   int k0, int n0, int lane) {
+  const int r = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int c = n0 + (lane >> 4) * 8;
+  ldmatrix_x4_trans(b, tile + r * stride + c);
+}
+// B fragment of one n-tile from a tile stored [k][n], one k-step.
+__device__ __forceinline__ void load_b_frag1_trans(uint32_t (&b)[2], const __nv_bfloat16* tile, int stride,
+                                                   int k0, int n0, int lane) {
+  const int r = k0 + (lane & 15);
+  ldmatrix_x2_trans(b, tile + r * stride + n0);
+}
+
+// Shared-memory image of the MLP parameters in bf16, both orientations.
+struct __align__(16) MlpWeightsBf16 {
+  __nv_bfloat16 w0t[kHid][kXStride];   // [out j][in i]   forward layer 0   (B of X W0)
+  __nv_bfloat16 w1t[kHid][kWStride];   // [out j][in k]   forward layer 1
+  __nv_bfloat16 wot[8][kWStride];      // [head c][in j]  heads: c=0 density, 1..3 pred normals
+  __nv_bfloat16 w1[kHid][kWStride];    // [in k][out j]   backward-data of layer 1
+  __nv_bfloat16 w0[32][kWStride];      // [in i][out k]   backward-data of layer 0
+  float b0[kHid];
+  float b1[kHid];
+  float bo[4];
+  float wo[kHid][4];                   // fp32 heads for the elementwise g_h2 term
+};
+
+__device__ __forceinline__ void load_weights_bf16(MlpWeightsBf16& s, const nrc_density_mlp_t& m) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int in_dim = m.in_dim;
+  for (int idx = tid; idx < kHid * kXStride; idx += nt) {
+    int j = idx / kXStride, i = idx % kXStride;
+    s.w0t[j][i] = __float2bfloat16((i < in_dim) ? m.d_w0[i * kHid + j] : 0.f);
+  }
+  for (int idx = tid; idx < kHid * kWStride; idx += nt) {
+    int r = idx / kWStride, c = idx % kWStride;
+    s.w1t[r][c] = __float2bfloat16((c < kHid) ? m.d_w1[c * kHid + r] : 0.f);
+    s.w1[r][c] = __float2bfloat16((c < kHid) ? m.d_w1[r * kHid + c] : 0.f);
+  }
+  for (int idx = tid; idx < 32 * kWStride; idx += nt) {
+    int i = idx / kWStride, c = idx % kWStride;
+    s.w0[i][c] = __float2bfloat16((i < in_dim && c < kHid) ? m.d_w0[i * kHid + c] : 0.f);
+  }
+  for (int idx = tid; idx < 8 * kWStride; idx += nt) {
+    int c = idx / kWStride, j = idx % kWStride;
+    float v = 0.f;
+    if (j < kHid) {
+      if (c == 0) v = m.d_wd[j];
+      else if (c < 4 && m.d_wn) v = m.d_wn[j * 3 + (c - 1)];
+    }
+    s.wot[c][j] = __float2bfloat16(v);
+  }
+  for (int j = tid; j < kHid; j += nt) {
+    s.b0[j] = m.d_b0[j];
+    s.b1[j] = m.d_b1[j];
+    s.wo[j][0] = m.d_wd[j];
+    for (int c = 0; c < 3; ++c) s.wo[j][1 + c] = m.d_wn ? m.d_wn[j * 3 + c] : 0.f;
+  }
+  if (tid < 4) s.bo[tid] = tid == 0 ? m.d_bd[0] : (m.d_bn ? m.d_bn[tid - 1] : 0.f);
+}
+
+// acc[nt][e] (16 rows x 64 cols, fp32) = bias + A(16 x 16*KS) * W^T, W^T stored [64][stride].
+template <int KS>
+__device__ __forceinline__ void mma_layer64(float (&acc)[8][4], const uint32_t (&a)[KS][4],
+                                            const __nv_bfloat16* wt, int stride, const float* bias,
+                                            int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    float bx = bias ? bias[nt * 8 + (lane & 3) * 2] : 0.f;
+    float by = bias ? bias[nt * 8 + (lane & 3) * 2 + 1] : 0.f;
+    acc[nt][0] = bx; acc[nt][1] = by; acc[nt][2] = bx; acc[nt][3] = by;
+  }
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      load_b_frag2(b, wt, stride, np * 16, ks * 16, lane);
+      mma_bf16(acc[2 * np], a[ks], b[0], b[1]);
+      mma_bf16(acc[2 * np + 1], a[ks], b[2], b[3]);
+    }
+  }
+}
+
+// Accumulator fragment (16 x 64 fp32) -> A fragments of the next layer (4 k-steps), with an
+// optional ReLU applied first.
+template <bool kRelu>
+__device__ __forceinline__ void acc_to_afrag(const float (&acc)[8][4], uint32_t (&a)[4][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float* c = acc[2 * kk + h];
+      float v0 = c[0], v1 = c[1], v2 = c[2], v3 = c[3];
+      if (kRelu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+      a[kk][2 * h + 0] = pack_bf16(v0, v1);
+      a[kk][2 * h + 1] = pack_bf16(v2, v3);
+    }
+  }
+}
+
+}  // namespace nrc

@@ -14,7 +14,8 @@ __global__ void __launch_bounds__(kT)
 density_query_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t m,
                          const float* __restrict__ means, int64_t P, float warp_c, float density_bias,
                          float* __restrict__ density, float* __restrict__ raw, float* __restrict__ feat,
-                         float* __restrict__ grad_pred, float* __restrict__ raw_grad) {
+                         float* __restrict__ grad_pred, float* __restrict__ raw_grad,
+                         float* __restrict__ enc_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmem& s = *reinterpret_cast<FwdSmem*>(smem_raw);
   load_weights(s.w, m);
@@ -34,7 +35,11 @@ density_query_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_m
       Corners c = level_setup(enc.lv[l], xn);
       FeatVec<F> v = level_interp<F>(enc.lv[l], c);
 #pragma unroll
-      for (int f = 0; f < F; ++f) s.x[(l * F + f) * kT + tid] = __fmul_rn(v.v[f], enc.scale);
+      for (int f = 0; f < F; ++f) {
+        const float e = __fmul_rn(v.v[f], enc.scale);
+        s.x[(l * F + f) * kT + tid] = e;
+        if (enc_out) enc_out[p * in_dim + l * F + f] = e;
+      }
     }
     float acc[kW];
     mlp_forward_point(s.w, in_dim, s.x + tid, kT, s.h1 + tid, kT, acc);
@@ -129,7 +134,7 @@ density_query_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_m
 template <int F>
 int32_t launch_query(cudaStream_t s, const EncDev& d, const nrc_density_mlp_t* mlp, const float* means,
                      int64_t P, float warp_c, float bias, float* density, float* raw, float* feat,
-                     float* gp, float* rg) {
+                     float* gp, float* rg, float* eo) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(density_query_fwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -139,9 +144,13 @@ int32_t launch_query(cudaStream_t s, const EncDev& d, const nrc_density_mlp_t* m
   int64_t tiles = (P + kT - 1) / kT;
   unsigned grid = static_cast<unsigned>(tiles < kNumSMs * 3 ? tiles : kNumSMs * 3);
   density_query_fwd_kernel<F><<<grid, kT, sizeof(FwdSmem), s>>>(d, *mlp, means, P, warp_c, bias, density,
-                                                               raw, feat, gp, rg);
+                                                               raw, feat, gp, rg, eo);
   return check_launch();
 }
+
+int32_t density_query_fwd_bf16(cudaStream_t s, const EncDev& d, const nrc_density_mlp_t* mlp,
+                               const float* d_means, int64_t P, float warp_c, float bias, float* density,
+                               float* raw, float* feat, float* gp, float* rg, float* enc_out);
 
 }  // namespace nrc
 
@@ -151,7 +160,7 @@ extern "C" int32_t nrc_density_query_fwd(void* stream, const nrc_encoding_t* enc
                                          const nrc_density_mlp_t* mlp, const float* d_means,
                                          int64_t num_points, float warp_c, float density_bias,
                                          int32_t bf16, float* d_density, float* d_raw, float* d_feat,
-                                         float* d_grad_pred, float* d_raw_grad) {
+                                         float* d_grad_pred, float* d_raw_grad, float* d_enc_out) {
   EncDev d;
   int32_t st = make_enc_dev(enc, d);
   if (st != NRC_OK) return st;
@@ -162,13 +171,15 @@ extern "C" int32_t nrc_density_query_fwd(void* stream, const nrc_encoding_t* enc
   if (num_points == 0) return NRC_OK;
   if (!d_means) return NRC_E_INVALID_ARG;
   if (d_grad_pred && !mlp->d_wn) return NRC_E_INVALID_ARG;
-  if (bf16) return NRC_E_UNSUPPORTED;  // tensor-core fused query: see mlp_bf16.cu (stand-alone MLP)
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bf16)
+    return density_query_fwd_bf16(s, d, mlp, d_means, num_points, warp_c, density_bias, d_density, d_raw,
+                                  d_feat, d_grad_pred, d_raw_grad, d_enc_out);
   switch (d.F) {
-    case 1: return launch_query<1>(s, d, mlp, d_means, num_points, warp_c, density_bias, d_density, d_raw, d_feat, d_grad_pred, d_raw_grad);
-    case 2: return launch_query<2>(s, d, mlp, d_means, num_points, warp_c, density_bias, d_density, d_raw, d_feat, d_grad_pred, d_raw_grad);
-    case 4: return launch_query<4>(s, d, mlp, d_means, num_points, warp_c, density_bias, d_density, d_raw, d_feat, d_grad_pred, d_raw_grad);
-    case 8: return launch_query<8>(s, d, mlp, d_means, num_points, warp_c, density_bias, d_density, d_raw, d_feat, d_grad_pred, d_raw_grad);
+    case 1: return launch_query<1>(s, d, mlp, d_means, num_points, warp_c, density_bias, d_density, d_raw, d_feat, d_grad_pred, d_raw_grad, d_enc_out);
+    case 2: return launch_query<2>(s, d, mlp, d_means, num_points, warp_c, density_bias, d_density, d_raw, d_feat, d_grad_pred, d_raw_grad, d_enc_out);
+    case 4: return launch_query<4>(s, d, mlp, d_means, num_points, warp_c, density_bias, d_density, d_raw, d_feat, d_grad_pred, d_raw_grad, d_enc_out);
+    case 8: return launch_query<8>(s, d, mlp, d_means, num_points, warp_c, density_bias, d_density, d_raw, d_feat, d_grad_pred, d_raw_grad, d_enc_out);
   }
   return NRC_E_UNSUPPORTED;
 }

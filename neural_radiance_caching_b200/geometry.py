@@ -46,6 +46,7 @@ class _RunNetworkFn(torch.autograd.Function):
         _lib.call("nrc_density_mlp_fwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(x2), P, int(bf16),
                   _lib.ptr(raw), _lib.ptr(feat), _lib.ptr(gp))
         ctx.mlp = mlp
+        ctx.bf16 = bool(bf16)
         ctx.save_for_backward(x2, *flat)
         ctx.lead = x.shape[:-1]
         lead = x.shape[:-1]
@@ -82,10 +83,90 @@ class _RunNetworkFn(torch.autograd.Function):
                 gd.d_wn = _lib.ptr(gp_["pred_normals_layer"]["kernel"]).value
                 gd.d_bn = _lib.ptr(gp_["pred_normals_layer"]["bias"]).value
         desc = _mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals)
-        _lib.call("nrc_density_mlp_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(x2), _lib.ptr(g_raw2),
-                  _lib.ptr(g_feat2), _lib.ptr(g_gp2), P, _lib.ptr(g_enc), C.byref(gd) if gd is not None else None)
+        _lib.call("nrc_density_mlp_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(x2), _lib.ptr(g_raw2), None,
+                  _lib.ptr(g_feat2), _lib.ptr(g_gp2), P, int(ctx.bf16), _lib.ptr(g_enc),
+                  C.byref(gd) if gd is not None else None)
         gx = g_enc.reshape(ctx.lead + (mlp.in_dim,)) if g_enc is not None else None
         return (None, gx, None) + (tuple(gflat) if want_w else (None,) * len(flat))
+
+
+def _grad_desc(mlp, gp_):
+    gd = _lib.nrc_density_mlp_grad_t()
+    gd.d_w0 = _lib.ptr(gp_["density_layers_0"]["kernel"]).value
+    gd.d_b0 = _lib.ptr(gp_["density_layers_0"]["bias"]).value
+    gd.d_w1 = _lib.ptr(gp_["density_layers_1"]["kernel"]).value
+    gd.d_b1 = _lib.ptr(gp_["density_layers_1"]["bias"]).value
+    gd.d_wd = _lib.ptr(gp_["output_density_layer"]["kernel"]).value
+    gd.d_bd = _lib.ptr(gp_["output_density_layer"]["bias"]).value
+    if mlp.enable_pred_normals:
+        gd.d_wn = _lib.ptr(gp_["pred_normals_layer"]["kernel"]).value
+        gd.d_bn = _lib.ptr(gp_["pred_normals_layer"]["bias"]).value
+    return gd
+
+
+class _DensityQueryFn(torch.autograd.Function):
+    """custom_vjp analogue of the fused training query.
+    forward : nrc_density_query_fwd (contract + encode + MLP + activation), saving the encoded
+              features [P, L*F];
+    backward: nrc_density_mlp_bwd (data + weight gradients; the safe_exp / bbox-mask VJP is the
+              multiplication by the saved density) then nrc_encode_bwd (scatter-add into one
+              arena-shaped table gradient).  No gradient flows to the sample positions
+              (stop_level_grad, internal/sampling.py:353-354)."""
+
+    @staticmethod
+    def forward(ctx, mlp, means, want_feat, arena, *flat):
+        p = mlp._unflatten(flat)
+        m2 = means.reshape(-1, 3).contiguous()
+        P = m2.shape[0]
+        dev = m2.device
+        density = torch.empty((P,), device=dev, dtype=torch.float32)
+        feat = torch.empty((P, 64), device=dev, dtype=torch.float32) if want_feat else None
+        gp = torch.empty((P, 3), device=dev, dtype=torch.float32) if mlp.enable_pred_normals else None
+        enc_out = torch.empty((P, mlp.in_dim), device=dev, dtype=torch.float32)
+        enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)), None)
+        desc = _mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals)
+        _lib.call("nrc_density_query_fwd", _lib.stream_ptr(), C.byref(enc), C.byref(desc), _lib.ptr(m2), P,
+                  float(mlp.warp_c), float(mlp.density_bias), int(mlp.bf16), _lib.ptr(density), None,
+                  _lib.ptr(feat), _lib.ptr(gp), None, _lib.ptr(enc_out))
+        ctx.mlp = mlp
+        ctx.save_for_backward(m2, enc_out, density, arena, *flat)
+        lead = means.shape[:-1]
+        ctx.lead = lead
+        ctx.has = (want_feat, gp is not None)
+        outs = [density.reshape(lead)]
+        outs.append(feat.reshape(lead + (64,)) if want_feat else None)
+        outs.append(gp.reshape(lead + (3,)) if gp is not None else None)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_density, g_feat, g_gp):
+        mlp = ctx.mlp
+        m2, enc_out, density, arena, *flat = ctx.saved_tensors
+        p = mlp._unflatten(flat)
+        P = m2.shape[0]
+        dev = m2.device
+        c = lambda g, shape: g.reshape(shape).contiguous() if g is not None else None
+        g_d = c(g_density, (P,)) if g_density is not None else torch.zeros((P,), device=dev)
+        g_f = c(g_feat, (P, 64)) if ctx.has[0] else None
+        g_g = c(g_gp, (P, 3)) if ctx.has[1] else None
+        want_w = any(ctx.needs_input_grad[4:])
+        want_t = ctx.needs_input_grad[3]
+        gflat = [torch.zeros_like(t) for t in flat] if want_w else None
+        gd = _grad_desc(mlp, mlp._unflatten(gflat)) if want_w else None
+        g_enc = torch.empty_like(enc_out) if want_t else None
+        desc = _mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals)
+        _lib.call("nrc_density_mlp_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(enc_out), _lib.ptr(g_d),
+                  _lib.ptr(density), _lib.ptr(g_f), _lib.ptr(g_g), P, int(mlp.bf16), _lib.ptr(g_enc),
+                  C.byref(gd) if gd is not None else None)
+        g_arena = None
+        if want_t:
+            z = torch.empty_like(m2)
+            _lib.call("nrc_contract_fwd", _lib.stream_ptr(), _lib.ptr(m2), P, float(mlp.warp_c), _lib.ptr(z))
+            g_arena = torch.zeros_like(arena)
+            enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)),
+                                       mlp.grid.tables(mlp.grid.views(g_arena)))
+            _lib.call("nrc_encode_bwd", _lib.stream_ptr(), C.byref(enc), _lib.ptr(z), _lib.ptr(g_enc), P, None)
+        return (None, None, None, g_arena) + (tuple(gflat) if want_w else (None,) * len(flat))
 
 
 class DensityMLP:
@@ -144,6 +225,14 @@ class DensityMLP:
         outs = _RunNetworkFn.apply(self, x, self.bf16, *self._flatten(p))
         return outs
 
+    def query_train(self, p, means, want_feat=True):
+        """Fused training query through the custom VJP: (density, feature|None, grad_pred|None).
+        Needs the tables in one arena (`p["density_grid"]["_arena"]`)."""
+        arena = p["density_grid"].get("_arena")
+        if arena is None:
+            raise ValueError("the fused training path needs the level tables in one arena")
+        return _DensityQueryFn.apply(self, means, bool(want_feat), arena, *self._flatten(p))
+
     def query(self, p, means, want_feat=True, want_normals=False):
         """Fused predict_density + convert_raw_density (+ analytic raw gradient):
         internal/geometry.py:199-341,442-460.  Inference path (no autograd)."""
@@ -159,7 +248,7 @@ class DensityMLP:
         mlp = _mlp_desc(p, self.in_dim, self.enable_pred_normals)
         _lib.call("nrc_density_query_fwd", _lib.stream_ptr(), C.byref(enc), C.byref(mlp), _lib.ptr(m2), P,
                   float(self.warp_c), float(self.density_bias), int(self.bf16), _lib.ptr(density), _lib.ptr(raw),
-                  _lib.ptr(feat), _lib.ptr(gp), _lib.ptr(rg))
+                  _lib.ptr(feat), _lib.ptr(gp), _lib.ptr(rg), None)
         lead = means.shape[:-1]
         r = lambda t, *s: t.reshape(lead + s) if t is not None else None
         return dict(density=r(density), raw_density=r(raw), feature=r(feat, 64), grad_pred=r(gp, 3),

@@ -123,15 +123,9 @@ class ProposalVolumeSampler:
                 res.update(feature=q["feature"], density=density, raw_density=q["raw_density"],
                            raw_grad_density=q["raw_grad_density"], grad_pred=q["grad_pred"])
             else:
-                z = coord._ContractFn.apply(means, mlp.warp_c)
-                enc = mlp.grid(p["density_grid"], z)
-                outs = mlp.run_network(p, enc)
-                raw, feat = outs[0], outs[1]
-                b0, b1 = mlp.bbox_tensors(dev)
-                valid = torch.all((z.detach() > b0) & (z.detach() < b1), dim=-1)
-                density = torch.where(valid, _SafeExpFn.apply(raw + mlp.density_bias), torch.zeros_like(raw))
-                res.update(feature=feat, density=density, raw_density=raw,
-                           grad_pred=outs[2] if mlp.enable_pred_normals else None, raw_grad_density=None)
+                last = i_level == len(self.sampling_strategy) - 1
+                density, feat, gp = mlp.query_train(p, means, want_feat=last or normals_all_levels)
+                res.update(feature=feat, density=density, raw_density=None, grad_pred=gp, raw_grad_density=None)
                 if want_normals:
                     with torch.no_grad():
                         res["raw_grad_density"] = mlp.query(p, means, want_feat=False, want_normals=True)[

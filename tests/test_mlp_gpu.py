@@ -90,3 +90,110 @@ def test_query_empty_and_bad_args(cuda_device):
     assert out["density"].shape == (0,)
     with pytest.raises(NotImplementedError):
         ngeo.DensityMLP(grid_params=GRIDS[0], net_width=256)
+
+
+# ------------------------------------------------------------------ bf16 tensor-core variant
+BF16_TOL = 2e-2  # bf16-MLP variant, rel 2e-2
+
+
+@pytest.mark.parametrize("gi,pred", [(0, False), (1, False), (2, True)])
+def test_bf16_run_network_forward_backward(cuda_device, gi, pred):
+    g = gen(40 + gi)
+    kw = dict(grid_params=GRIDS[gi], enable_pred_normals=pred)
+    o = ogeo.DensityMLP(**kw)
+    n = ngeo.DensityMLP(bf16=True, **kw)
+    po = o.init(g, table_init_range=0.1, bias_range=0.1)
+    pn = n.from_oracle(po, cuda_device)
+    P = 1000
+    x = f32(g.normal(size=(P, o.in_dim)))
+    g_raw, g_feat, g_gp = f32(g.normal(size=(P,))), f32(g.normal(size=(P, 64))), f32(g.normal(size=(P, 3)))
+    keys = [k for k in po if k != "density_grid"]
+    xo = x.clone().requires_grad_(True)
+    for k in keys:
+        for kk in po[k]:
+            po[k][kk] = po[k][kk].clone().requires_grad_(True)
+    raw_o, feat_o = o.run_network(po, xo)
+    loss = (raw_o * g_raw).sum() + (feat_o * g_feat).sum()
+    if pred:
+        gp_o = ogeo.dense(po["pred_normals_layer"], feat_o)
+        loss = loss + (gp_o * g_gp).sum()
+    loss.backward()
+    xn = x.to(cuda_device).requires_grad_(True)
+    for k in keys:
+        for kk in pn[k]:
+            pn[k][kk] = pn[k][kk].clone().requires_grad_(True)
+    outs = n.run_network(pn, xn)
+    lossn = (outs[0] * g_raw.to(cuda_device)).sum() + (outs[1] * g_feat.to(cuda_device)).sum()
+    if pred:
+        lossn = lossn + (outs[2] * g_gp.to(cuda_device)).sum()
+    lossn.backward()
+    assert rel_err(outs[0], raw_o) <= BF16_TOL
+    assert rel_err(outs[1], feat_o) <= BF16_TOL
+    if pred:
+        assert rel_err(outs[2], gp_o) <= BF16_TOL
+    assert rel_err(xn.grad, xo.grad) <= BF16_TOL
+    for k in keys:
+        for kk in po[k]:
+            assert rel_err(pn[k][kk].grad, po[k][kk].grad) <= BF16_TOL, (k, kk, rel_err(pn[k][kk].grad, po[k][kk].grad))
+
+
+@pytest.mark.parametrize("gi,pred", [(0, False), (1, False), (2, True)])
+def test_bf16_fused_query(cuda_device, gi, pred):
+    g = gen(50 + gi)
+    kw = dict(grid_params=GRIDS[gi], enable_pred_normals=pred)
+    o = ogeo.DensityMLP(**kw)
+    n = ngeo.DensityMLP(bf16=True, **kw)
+    po = o.init(g, table_init_range=0.1, bias_range=0.1)
+    pn = n.from_oracle(po, cuda_device)
+    P = 3001
+    means = f32(g.normal(size=(P, 3)) * 2.5)
+    res_o = o(po, means)
+    res_n = n.query(pn, means.to(cuda_device), want_feat=True, want_normals=True)
+    assert rel_err(res_n["raw_density"], res_o["raw_density"]) <= BF16_TOL
+    assert rel_err(res_n["density"], res_o["density"]) <= BF16_TOL
+    assert torch.equal(res_n["density"].cpu() == 0, res_o["density"] == 0)
+    assert rel_err(res_n["feature"], res_o["feature"]) <= BF16_TOL
+    assert rel_err(res_n["raw_grad_density"], res_o["raw_grad_density"]) <= 3e-2
+    if pred:
+        assert rel_err(res_n["grad_pred"], res_o["grad_pred"]) <= BF16_TOL
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_fused_training_query_gradients(cuda_device, bf16):
+    """_DensityQueryFn (fused fwd + MLP bwd + scatter) vs oracle autograd of the same maths."""
+    from oracle import ref_math
+
+    g = gen(60)
+    kw = dict(grid_params=GRIDS[2], enable_pred_normals=True)
+    o = ogeo.DensityMLP(**kw)
+    n = ngeo.DensityMLP(bf16=bf16, **kw)
+    po = o.init(g, table_init_range=0.1, bias_range=0.1)
+    pn = n.from_oracle(po, cuda_device)
+    P = 2000
+    means = f32(g.normal(size=(P, 3)) * 1.5)
+    Gd, Gf, Gg = f32(g.normal(size=(P,))), f32(g.normal(size=(P, 64))) * 0.1, f32(g.normal(size=(P, 3)))
+    for k in po["density_grid"]:
+        po["density_grid"][k].requires_grad_(True)
+    keys = [k for k in po if k != "density_grid"]
+    for k in keys:
+        for kk in po[k]:
+            po[k][kk].requires_grad_(True)
+    raw, feat = o.predict_density(po, means)
+    dens = o.convert_raw_density(raw, means)
+    gp = ogeo.dense(po["pred_normals_layer"], feat)
+    ((dens * Gd).sum() + (feat * Gf).sum() + (gp * Gg).sum()).backward()
+    arena = pn["density_grid"]["_arena"].clone().requires_grad_(True)
+    pn["density_grid"] = dict(n.grid.views(arena.detach()), _arena=arena)
+    for k in keys:
+        for kk in pn[k]:
+            pn[k][kk] = pn[k][kk].clone().requires_grad_(True)
+    d_n, f_n, g_n = n.query_train(pn, means.to(cuda_device), want_feat=True)
+    ((d_n * Gd.to(cuda_device)).sum() + (f_n * Gf.to(cuda_device)).sum() + (g_n * Gg.to(cuda_device)).sum()).backward()
+    tol = BF16_TOL if bf16 else 2e-5
+    assert rel_err(d_n, dens) <= tol
+    gviews = n.grid.views(arena.grad)
+    for name in gviews:
+        assert rel_err(gviews[name], po["density_grid"][name].grad) <= tol, name
+    for k in keys:
+        for kk in po[k]:
+            assert rel_err(pn[k][kk].grad, po[k][kk].grad) <= tol, (k, kk)
