@@ -22,6 +22,26 @@ def dense(p, x):
     return x @ p["kernel"] + p["bias"]
 
 
+class _RoundBf16(torch.autograd.Function):
+    """Round to bf16 (value) with a straight-through gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def dense_bf16(p, x):
+    """The bf16-MLP variant: operands rounded to bf16, fp32 accumulate,
+    fp32 bias.  Used as the reference for the tensor-core kernels' *gradients*: bf16 rounding
+    flips the ReLU mask of ~5% of the hidden units' near-zero pre-activations, so gradients are
+    only comparable against a reference that sees the same rounded activations."""
+    return _RoundBf16.apply(x) @ _RoundBf16.apply(p["kernel"]) + p["bias"]
+
+
 class DensityMLP:
     def __init__(
         self,
@@ -34,7 +54,9 @@ class DensityMLP:
         enable_pred_normals=False,
         disable_density_normals=False,
         normals_for_filter_only=False,
+        bf16=False,
     ):
+        self.dense = dense_bf16 if bf16 else dense
         self.grid = grid_utils.HashEncoding(bbox_scaling=bbox_scaling, scale_supersample=1.0, **grid_params)
         self.net_depth = net_depth
         self.net_width = net_width
@@ -69,8 +91,8 @@ class DensityMLP:
     def run_network(self, p, x):
         """internal/geometry.py:155-168."""
         for i in range(self.net_depth):
-            x = torch.relu(dense(p[f"density_layers_{i}"], x))
-        raw_density = dense(p["output_density_layer"], x)[..., 0]
+            x = torch.relu(self.dense(p[f"density_layers_{i}"], x))
+        raw_density = self.dense(p["output_density_layer"], x)[..., 0]
         return raw_density, x
 
     def encode(self, p, means):
@@ -111,7 +133,7 @@ class DensityMLP:
         density = self.convert_raw_density(raw_density, means)
         out = dict(feature=x, density=density, raw_density=raw_density, raw_grad_density=raw_grad, normals=normals)
         if self.enable_pred_normals:
-            grad_pred = dense(p["pred_normals_layer"], x)
+            grad_pred = self.dense(p["pred_normals_layer"], x)
             out["grad_pred"] = grad_pred
             out["normals_pred"] = torch.nan_to_num(-ref_math.l2_normalize(grad_pred))
             out["normals_to_use"] = out["normals_pred"]

@@ -94,29 +94,40 @@ def test_query_empty_and_bad_args(cuda_device):
 
 # ------------------------------------------------------------------ bf16 tensor-core variant
 BF16_TOL = 2e-2  # bf16-MLP variant, rel 2e-2
+# Forward values are checked against the fp32 oracle at 2e-2.  Gradients are checked against the
+# oracle's bf16 variant (operands rounded to bf16, fp32 accumulate): rounding flips the ReLU
+# mask of ~5% of near-zero hidden pre-activations per point, which changes single-point
+# gradients discontinuously, so only a reference that sees the same rounded activations is
+# comparable (measured: kernel vs bf16 emulation 1e-7, vs fp32 oracle up to 0.2).
+
+
+def _bf16_pair(g, gi, pred, device):
+    kw = dict(grid_params=GRIDS[gi], enable_pred_normals=pred)
+    o32 = ogeo.DensityMLP(**kw)
+    o16 = ogeo.DensityMLP(bf16=True, **kw)
+    n = ngeo.DensityMLP(bf16=True, **kw)
+    po = o32.init(g, table_init_range=0.1, bias_range=0.1)
+    return o32, o16, n, po, n.from_oracle(po, device)
 
 
 @pytest.mark.parametrize("gi,pred", [(0, False), (1, False), (2, True)])
 def test_bf16_run_network_forward_backward(cuda_device, gi, pred):
     g = gen(40 + gi)
-    kw = dict(grid_params=GRIDS[gi], enable_pred_normals=pred)
-    o = ogeo.DensityMLP(**kw)
-    n = ngeo.DensityMLP(bf16=True, **kw)
-    po = o.init(g, table_init_range=0.1, bias_range=0.1)
-    pn = n.from_oracle(po, cuda_device)
+    o32, o16, n, po, pn = _bf16_pair(g, gi, pred, cuda_device)
     P = 1000
-    x = f32(g.normal(size=(P, o.in_dim)))
+    x = f32(g.normal(size=(P, o32.in_dim)))
     g_raw, g_feat, g_gp = f32(g.normal(size=(P,))), f32(g.normal(size=(P, 64))), f32(g.normal(size=(P, 3)))
     keys = [k for k in po if k != "density_grid"]
+    raw32, feat32 = o32.run_network(po, x)
     xo = x.clone().requires_grad_(True)
     for k in keys:
         for kk in po[k]:
             po[k][kk] = po[k][kk].clone().requires_grad_(True)
-    raw_o, feat_o = o.run_network(po, xo)
+    raw_o, feat_o = o16.run_network(po, xo)
     loss = (raw_o * g_raw).sum() + (feat_o * g_feat).sum()
     if pred:
-        gp_o = ogeo.dense(po["pred_normals_layer"], feat_o)
-        loss = loss + (gp_o * g_gp).sum()
+        gp32 = ogeo.dense(po["pred_normals_layer"], feat32)
+        loss = loss + (ogeo.dense_bf16(po["pred_normals_layer"], feat_o) * g_gp).sum()
     loss.backward()
     xn = x.to(cuda_device).requires_grad_(True)
     for k in keys:
@@ -127,10 +138,10 @@ def test_bf16_run_network_forward_backward(cuda_device, gi, pred):
     if pred:
         lossn = lossn + (outs[2] * g_gp.to(cuda_device)).sum()
     lossn.backward()
-    assert rel_err(outs[0], raw_o) <= BF16_TOL
-    assert rel_err(outs[1], feat_o) <= BF16_TOL
+    assert rel_err(outs[0], raw32) <= BF16_TOL
+    assert rel_err(outs[1], feat32) <= BF16_TOL
     if pred:
-        assert rel_err(outs[2], gp_o) <= BF16_TOL
+        assert rel_err(outs[2], gp32) <= BF16_TOL
     assert rel_err(xn.grad, xo.grad) <= BF16_TOL
     for k in keys:
         for kk in po[k]:
@@ -140,20 +151,17 @@ def test_bf16_run_network_forward_backward(cuda_device, gi, pred):
 @pytest.mark.parametrize("gi,pred", [(0, False), (1, False), (2, True)])
 def test_bf16_fused_query(cuda_device, gi, pred):
     g = gen(50 + gi)
-    kw = dict(grid_params=GRIDS[gi], enable_pred_normals=pred)
-    o = ogeo.DensityMLP(**kw)
-    n = ngeo.DensityMLP(bf16=True, **kw)
-    po = o.init(g, table_init_range=0.1, bias_range=0.1)
-    pn = n.from_oracle(po, cuda_device)
+    o32, o16, n, po, pn = _bf16_pair(g, gi, pred, cuda_device)
     P = 3001
     means = f32(g.normal(size=(P, 3)) * 2.5)
-    res_o = o(po, means)
+    res_o = o32(po, means)
+    res_16 = o16(po, means)
     res_n = n.query(pn, means.to(cuda_device), want_feat=True, want_normals=True)
     assert rel_err(res_n["raw_density"], res_o["raw_density"]) <= BF16_TOL
     assert rel_err(res_n["density"], res_o["density"]) <= BF16_TOL
     assert torch.equal(res_n["density"].cpu() == 0, res_o["density"] == 0)
     assert rel_err(res_n["feature"], res_o["feature"]) <= BF16_TOL
-    assert rel_err(res_n["raw_grad_density"], res_o["raw_grad_density"]) <= 3e-2
+    assert rel_err(res_n["raw_grad_density"], res_16["raw_grad_density"]) <= BF16_TOL
     if pred:
         assert rel_err(res_n["grad_pred"], res_o["grad_pred"]) <= BF16_TOL
 
@@ -161,11 +169,9 @@ def test_bf16_fused_query(cuda_device, gi, pred):
 @pytest.mark.parametrize("bf16", [False, True])
 def test_fused_training_query_gradients(cuda_device, bf16):
     """_DensityQueryFn (fused fwd + MLP bwd + scatter) vs oracle autograd of the same maths."""
-    from oracle import ref_math
-
     g = gen(60)
     kw = dict(grid_params=GRIDS[2], enable_pred_normals=True)
-    o = ogeo.DensityMLP(**kw)
+    o = ogeo.DensityMLP(bf16=bf16, **kw)
     n = ngeo.DensityMLP(bf16=bf16, **kw)
     po = o.init(g, table_init_range=0.1, bias_range=0.1)
     pn = n.from_oracle(po, cuda_device)
@@ -180,7 +186,7 @@ def test_fused_training_query_gradients(cuda_device, bf16):
             po[k][kk].requires_grad_(True)
     raw, feat = o.predict_density(po, means)
     dens = o.convert_raw_density(raw, means)
-    gp = ogeo.dense(po["pred_normals_layer"], feat)
+    gp = o.dense(po["pred_normals_layer"], feat)
     ((dens * Gd).sum() + (feat * Gf).sum() + (gp * Gg).sum()).backward()
     arena = pn["density_grid"]["_arena"].clone().requires_grad_(True)
     pn["density_grid"] = dict(n.grid.views(arena.detach()), _arena=arena)
