@@ -218,6 +218,39 @@ int32_t nrc_ray_resample_gather(void* stream, const float* d_field, const int32_
                                 int64_t num_rays, int32_t n, int32_t k, int32_t channels,
                                 float* d_out);
 
+/* ------------------------------------------- cache shader building blocks ---- */
+/* flax.linen.Dense (internal/geometry.py:127-139, nerf.py:232-345,
+ * surface_light_field.py:352-403): y = act(x @ kernel + bias), kernel [in,out] fp32.
+ * Row strides ldx/ldy (in floats) let a layer read/write a column slice of a wider
+ * activation buffer, which is how the reference's concatenate skip connections
+ * (surface_light_field.py:480-500) are realised without copies.  relu != 0 applies ReLU;
+ * bf16 != 0 selects the tensor-core variant (bf16 operands, fp32 accumulate). */
+int32_t nrc_dense_fwd(void* stream, const float* d_x, int64_t ldx, const float* d_kernel,
+                      const float* d_bias, int64_t num_rows, int32_t in_dim, int32_t out_dim,
+                      int32_t relu, int32_t bf16, float* d_y, int64_t ldy);
+/* VJP of nrc_dense_fwd.  d_y (the forward output) supplies the ReLU mask when relu != 0.
+ *   d_g_x [rows,in] (stride ldgx) written, or accumulated into when accumulate_g_x != 0
+ *   (second consumer of a skip connection); may be NULL.
+ *   d_g_kernel [in,out] and d_g_bias [out] are ACCUMULATED INTO; may be NULL (both). */
+int32_t nrc_dense_bwd(void* stream, const float* d_x, int64_t ldx, const float* d_kernel,
+                      const float* d_y, int64_t ldy, const float* d_g_y, int64_t ldgy,
+                      int64_t num_rows, int32_t in_dim, int32_t out_dim, int32_t relu, int32_t bf16,
+                      float* d_g_x, int64_t ldgx, int32_t accumulate_g_x, float* d_g_kernel,
+                      float* d_g_bias);
+
+/* Integrated directional encoding, ref_utils.generate_ide_fn (internal/ref_utils.py:131-192).
+ * Host tables built like the reference: ml_m/ml_l [n_sh] from get_ml_array (:117-128),
+ * sigma[i] = 0.5*l*(l+1), d_mat [(l_max+1), n_sh] fp32 (device) from sph_harm_coeff (:107-114).
+ *   d_xyz [P,3], d_kappa_inv [P] -> d_out [P, 2*n_sh] (row stride ldo): real parts then imaginary. */
+int32_t nrc_ide_fwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32_t* ml_l,
+                    const float* sigma, const float* d_mat, const float* d_xyz,
+                    const float* d_kappa_inv, int64_t num_points, float* d_out, int64_t ldo);
+/* VJP: d_g_xyz [P,3] and d_g_kappa_inv [P] written (either may be NULL). */
+int32_t nrc_ide_bwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32_t* ml_l,
+                    const float* sigma, const float* d_mat, const float* d_xyz,
+                    const float* d_kappa_inv, const float* d_g_out, int64_t ldg, int64_t num_points,
+                    float* d_g_xyz, float* d_g_kappa_inv);
+
 /* ------------------------------------------------- K5: GGX integration ---- */
 /* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) +
  * integrate_reflect_rays (:1102-1193): Disney-GGX D*F*G and Lambert lobes evaluated in the

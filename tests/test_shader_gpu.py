@@ -1,0 +1,140 @@
+"""Row 16 parity: Dense layers, integrated directional encoding and the cache shader vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as ogeo, nerf as onerf
+from neural_radiance_caching_b200 import nerf as nnerf
+from tests.util import f32, gen, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,K,N,relu", [(1000, 96, 128, False), (777, 129, 64, True), (2048, 328, 128, True),
+                                         (513, 64, 1, False), (300, 38, 128, True), (256, 128, 3, False)])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_dense_forward_backward(cuda_device, M, K, N, relu, bf16):
+    g = gen(300 + M + K)
+    x = f32(g.normal(size=(M, K)))
+    p = {"kernel": ogeo.he_uniform(g, K, N), "bias": f32(g.normal(size=(N,)) * 0.1)}
+    gy = f32(g.normal(size=(M, N)))
+    ref = ogeo.dense_bf16 if bf16 else ogeo.dense
+    xo = x.clone().requires_grad_(True)
+    po = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    yo = ref(po, xo)
+    y32 = ogeo.dense(p, x)
+    if relu:
+        yo, y32 = torch.relu(yo), torch.relu(y32)
+    (yo * gy).sum().backward()
+    xn = x.to(cuda_device).requires_grad_(True)
+    pn = {k: v.to(cuda_device).requires_grad_(True) for k, v in p.items()}
+    yn = nnerf.dense(pn, xn, relu=relu, bf16=bf16)
+    (yn * gy.to(cuda_device)).sum().backward()
+    tol = 2e-2 if bf16 else 1e-5
+    assert rel_err(yn, y32) <= tol
+    # gradients of the bf16 variant vs the bf16-rounded reference (ReLU mask flips)
+    assert rel_err(xn.grad, xo.grad) <= tol
+    assert rel_err(pn["kernel"].grad, po["kernel"].grad) <= tol
+    assert rel_err(pn["bias"].grad, po["bias"].grad) <= tol
+
+
+@pytest.mark.parametrize("deg", [1, 4, 5])
+def test_ide_forward_backward(cuda_device, deg):
+    g = gen(320 + deg)
+    P = 2000
+    d = g.normal(size=(P, 3))
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    xyz = f32(d)
+    kinv = f32(g.gamma(1.0, 0.3, size=(P, 1)))
+    kinv[:10] = 0.0
+    go = f32(g.normal(size=(P, 2 * onerf.get_ml_array(deg).shape[1])))
+    xo, ko = xyz.clone().requires_grad_(True), kinv.clone().requires_grad_(True)
+    want = onerf.generate_ide_fn(deg)(xo, ko)
+    (want * go).sum().backward()
+    xn, kn = xyz.to(cuda_device).requires_grad_(True), kinv.to(cuda_device).requires_grad_(True)
+    got = nnerf.generate_ide_fn(deg)(xn, kn)
+    (got * go.to(cuda_device)).sum().backward()
+    assert got.shape == want.shape == (P, {1: 4, 4: 38, 5: 72}[deg])
+    # l = 16 terms are alternating sums with coefficients up to ~1e5 ("only deg_view <= 5 is
+    # numerically stable", ref_utils.py:143-144): fp32 evaluation order matters at 1e-5..1e-4
+    tol = 1e-5 if deg < 5 else 2e-4
+    assert rel_err(got, want) <= tol
+    assert rel_err(xn.grad, xo.grad) <= 10 * tol
+    assert rel_err(kn.grad, ko.grad) <= 10 * tol
+
+
+def _shader_inputs(g, R, n):
+    means = f32(g.normal(size=(R, n, 3)) * 1.2)
+    v = g.normal(size=(R, 3))
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    nrm = g.normal(size=(R, n, 3))
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    feat = f32(np.maximum(g.normal(size=(R, n, 64)), 0))
+    return f32(v), means, feat, f32(nrm)
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_cache_shader_forward(cuda_device, bf16):
+    g = gen(340)
+    o = onerf.NeRFMLP()
+    n = nnerf.NeRFMLP(bf16=bf16)
+    po = o.init(g, table_init_range=0.1)
+    pn = n.from_oracle(po, cuda_device)
+    v, means, feat, nrm = _shader_inputs(g, 64, 32)
+    want = o(po, v, means, feat, nrm)
+    with torch.no_grad():
+        got = n(pn, v.to(cuda_device), means.to(cuda_device), feat.to(cuda_device), nrm.to(cuda_device))
+    tol = 2e-2 if bf16 else 1e-5
+    for k in ("feature", "bottleneck", "roughness", "albedo_rgb", "integrated_brdf", "refdirs"):
+        assert rel_err(got[k], want[k]) <= tol, (k, rel_err(got[k], want[k]))
+    # downstream of the degree-5 IDE (see test_ide_forward_backward)
+    for k in ("env_rgb", "ref_rgb", "rgb", "diffuse_rgb", "specular_rgb"):
+        assert rel_err(got[k], want[k]) <= max(tol, 1e-4), (k, rel_err(got[k], want[k]))
+
+
+def test_cache_shader_gradients(cuda_device):
+    g = gen(341)
+    o = onerf.NeRFMLP()
+    n = nnerf.NeRFMLP()
+    po = o.init(g, table_init_range=0.1)
+    pn = n.from_oracle(po, cuda_device)
+    v, means, feat, nrm = _shader_inputs(g, 48, 32)
+    G = f32(g.normal(size=(48, 32, 3)))
+
+    def leaves(p, prefix=""):
+        out = []
+        for k in sorted(p.keys()):
+            if k == "_arena":
+                continue
+            if isinstance(p[k], dict):
+                out += leaves(p[k], prefix + k + "/")
+            else:
+                out.append((prefix + k, p, k))
+        return out
+
+    lo = leaves(po)
+    for _, d, k in lo:
+        d[k] = d[k].clone().requires_grad_(True)
+    fo, no = feat.clone().requires_grad_(True), nrm.clone().requires_grad_(True)
+    (o(po, v, means, fo, no)["rgb"] * G).sum().backward()
+
+    arena = pn["appearance_grid"]["_arena"].clone().requires_grad_(True)
+    pn["appearance_grid"] = dict(n.grid.views(arena.detach()), _arena=arena)
+    ln = leaves(pn)
+    for name, d, k in ln:
+        if "appearance_grid" not in name:
+            d[k] = d[k].clone().requires_grad_(True)
+    fn_, nn_ = feat.to(cuda_device).requires_grad_(True), nrm.to(cuda_device).requires_grad_(True)
+    (n(pn, v.to(cuda_device), means.to(cuda_device), fn_, nn_)["rgb"] * G.to(cuda_device)).sum().backward()
+    assert rel_err(fn_.grad, fo.grad) <= 2e-4
+    assert rel_err(nn_.grad, no.grad) <= 2e-3   # through d IDE / d direction (l = 16 terms)
+    gviews = n.grid.views(arena.grad)
+    for name in gviews:
+        assert rel_err(gviews[name], po["appearance_grid"][name].grad) <= 2e-4, name
+    for (name, dn, kn), (_, do, ko) in zip(ln, lo):
+        if "appearance_grid" in name:
+            continue
+        ref = do[ko].grad
+        if ref is None or float(ref.abs().max()) == 0.0:
+            continue  # EnvMap gets an exactly-zero gradient in this configuration (1 - ref_acc == 0)
+        assert rel_err(dn[kn].grad, ref) <= 2e-4, (name, rel_err(dn[kn].grad, ref))
