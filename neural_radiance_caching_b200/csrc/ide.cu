@@ -24,18 +24,24 @@ __global__ void ide_fwd_kernel(const __grid_constant__ IdeTable tab, const float
   if (p >= P) return;
   const float x = xyz[3 * p], y = xyz[3 * p + 1], z = xyz[3 * p + 2];
   const float kinv = kappa_inv[p];
-  float zp[kMaxL + 1], cr[kMaxL + 1], ci[kMaxL + 1];
-  zp[0] = 1.f; cr[0] = 1.f; ci[0] = 0.f;
+  // The l = 16 Legendre polynomials are alternating sums with coefficients up to ~1e5: in fp32
+  // (the reference) they carry ~1e-3 relative noise.  The z-polynomial is therefore accumulated
+  // in fp64 here (222 DFMA per point; B200 runs fp64 at full rate), which lands within fp32
+  // rounding of the exact value -- closer to the truth than any fp32 evaluation order.
+  double zp[kMaxL + 1];
+  float cr[kMaxL + 1], ci[kMaxL + 1];
+  zp[0] = 1.0; cr[0] = 1.f; ci[0] = 0.f;
   for (int k = 1; k <= tab.l_max; ++k) {
-    zp[k] = zp[k - 1] * z;
+    zp[k] = zp[k - 1] * static_cast<double>(z);
     cr[k] = cr[k - 1] * x - ci[k - 1] * y;
     ci[k] = cr[k - 1] * y + ci[k - 1] * x;
   }
   float* o = out + p * ldo;
   for (int i = 0; i < tab.n_sh; ++i) {
     const int m = tab.m[i], l = tab.l[i];
-    float poly = 0.f;
-    for (int k = 0; k <= l - m; ++k) poly = fmaf(zp[k], __ldg(mat + k * tab.n_sh + i), poly);
+    double polyd = 0.0;
+    for (int k = 0; k <= l - m; ++k) polyd = fma(zp[k], static_cast<double>(__ldg(mat + k * tab.n_sh + i)), polyd);
+    const float poly = static_cast<float>(polyd);
     const float att = expf(-tab.sigma[i] * kinv);
     o[i] = cr[m] * poly * att;
     o[tab.n_sh + i] = ci[m] * poly * att;
@@ -51,10 +57,11 @@ __global__ void ide_bwd_kernel(const __grid_constant__ IdeTable tab, const float
   if (p >= P) return;
   const float x = xyz[3 * p], y = xyz[3 * p + 1], z = xyz[3 * p + 2];
   const float kinv = kappa_inv[p];
-  float zp[kMaxL + 1], cr[kMaxL + 1], ci[kMaxL + 1];
-  zp[0] = 1.f; cr[0] = 1.f; ci[0] = 0.f;
+  double zp[kMaxL + 1];
+  float cr[kMaxL + 1], ci[kMaxL + 1];
+  zp[0] = 1.0; cr[0] = 1.f; ci[0] = 0.f;
   for (int k = 1; k <= tab.l_max; ++k) {
-    zp[k] = zp[k - 1] * z;
+    zp[k] = zp[k - 1] * static_cast<double>(z);
     cr[k] = cr[k - 1] * x - ci[k - 1] * y;
     ci[k] = cr[k - 1] * y + ci[k - 1] * x;
   }
@@ -62,12 +69,13 @@ __global__ void ide_bwd_kernel(const __grid_constant__ IdeTable tab, const float
   float gx = 0.f, gy = 0.f, gz = 0.f, gk = 0.f;
   for (int i = 0; i < tab.n_sh; ++i) {
     const int m = tab.m[i], l = tab.l[i];
-    float poly = 0.f, dpoly = 0.f;
+    double polyd = 0.0, dpolyd = 0.0;
     for (int k = 0; k <= l - m; ++k) {
-      const float c = __ldg(mat + k * tab.n_sh + i);
-      poly = fmaf(zp[k], c, poly);
-      if (k > 0) dpoly = fmaf(static_cast<float>(k) * zp[k - 1], c, dpoly);
+      const double c = static_cast<double>(__ldg(mat + k * tab.n_sh + i));
+      polyd = fma(zp[k], c, polyd);
+      if (k > 0) dpolyd = fma(static_cast<double>(k) * zp[k - 1], c, dpolyd);
     }
+    const float poly = static_cast<float>(polyd), dpoly = static_cast<float>(dpolyd);
     const float att = expf(-tab.sigma[i] * kinv);
     const float gr = g[i], gi = g[tab.n_sh + i];
     // out_r = cr[m] poly att, out_i = ci[m] poly att

@@ -63,11 +63,15 @@ def ide_tables(deg_view):
     return ml_array, mat, sigma
 
 
-def generate_ide_fn(deg_view):
-    """internal/ref_utils.py:131-192 (complex arithmetic written out in real/imaginary parts)."""
+def generate_ide_fn(deg_view, dtype=torch.float32):
+    """internal/ref_utils.py:131-192 (complex arithmetic written out in real/imaginary parts).
+
+    dtype=float64 gives the exact value of the same expression (with the reference's fp32-rounded
+    coefficient matrix): for deg_view = 5 the fp32 evaluation carries ~1e-3 relative noise from the
+    l = 16 alternating sums, so fp32 implementations can only be compared through this truth."""
     ml_array, mat, sigma = ide_tables(deg_view)
-    mat_t = torch.tensor(mat.astype(np.float32))
-    sigma_t = torch.tensor(sigma.astype(np.float32))
+    mat_t = torch.tensor(mat.astype(np.float32)).to(dtype)
+    sigma_t = torch.tensor(sigma.astype(np.float32)).to(dtype)
 
     def integrated_dir_enc_fn(xyz, kappa_inv):
         x, y, z = xyz[..., 0:1], xyz[..., 1:2], xyz[..., 2:3]

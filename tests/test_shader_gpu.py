@@ -55,12 +55,21 @@ def test_ide_forward_backward(cuda_device, deg):
     got = nnerf.generate_ide_fn(deg)(xn, kn)
     (got * go.to(cuda_device)).sum().backward()
     assert got.shape == want.shape == (P, {1: 4, 4: 38, 5: 72}[deg])
+    # float64 evaluation of the same expression on the same fp32 inputs = the exact value
+    x64, k64 = xyz.double().requires_grad_(True), kinv.double().requires_grad_(True)
+    truth = onerf.generate_ide_fn(deg, dtype=torch.float64)(x64, k64)
+    (truth * go.double()).sum().backward()
+    err_kernel = rel_err(got, truth)
+    err_oracle = rel_err(want, truth)
     # l = 16 terms are alternating sums with coefficients up to ~1e5 ("only deg_view <= 5 is
-    # numerically stable", ref_utils.py:143-144): fp32 evaluation order matters at 1e-5..1e-4
-    tol = 1e-5 if deg < 5 else 2e-4
-    assert rel_err(got, want) <= tol
-    assert rel_err(xn.grad, xo.grad) <= 10 * tol
-    assert rel_err(kn.grad, ko.grad) <= 10 * tol
+    # numerically stable", ref_utils.py:143-144): the fp32 oracle itself is ~1e-3 off at deg 5, so
+    # the kernel (fp64 polynomial accumulation) is held to the exact value instead.
+    assert err_kernel <= 1e-5, (err_kernel, err_oracle)
+    assert err_kernel <= max(err_oracle, 1e-6) * 2
+    if deg < 5:
+        assert rel_err(got, want) <= 1e-5
+    assert rel_err(xn.grad, x64.grad) <= 1e-5
+    assert rel_err(kn.grad, k64.grad) <= 1e-5
 
 
 def _shader_inputs(g, R, n):
