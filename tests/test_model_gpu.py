@@ -1,0 +1,107 @@
+"""Cache model parity (BASELINE configs 1-3): sampler -> [resample] -> shader -> integrator."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as omodels
+from neural_radiance_caching_b200 import models as nmodels
+from tests.util import f32, gen, make_rays, rel_err, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _gumbel(g, shape):
+    return f32(-np.log(-np.log(g.uniform(1e-12, 1.0, size=shape))))
+
+
+@pytest.mark.parametrize("secondary", [False, True])
+def test_cache_model_forward(cuda_device, secondary):
+    g = gen(400 + int(secondary))
+    R = 128
+    o, n = omodels.NeRFModel(), nmodels.NeRFModel()
+    po = o.init(g, table_init_range=0.1, bias_range=0.05)
+    pn = n.from_oracle(po, cuda_device)
+    rays = make_rays(g, R, near=0.05, far=2.0, radius=0.7) if secondary else make_rays(g, R)
+    u = [f32(g.uniform(size=(R, 1))) for _ in range(3)]
+    gum = _gumbel(g, (R, 32, 1)) if secondary else None
+    want = o(po, rays, u, gumbel=gum, is_secondary=secondary, resample=secondary, extras=True)
+    override = [h["sdist"].to(cuda_device) for h in want["sampler"]]
+    got = n(pn, to_dev(rays, cuda_device), to_dev(u, cuda_device),
+            gumbel=gum.to(cuda_device) if secondary else None, is_secondary=secondary, resample=secondary,
+            extras=True, sdist_override=override)
+    if secondary:
+        # categorical resample indices: bit-exact given the same Gumbel noise
+        assert torch.equal(got["inds"].cpu().long(), want["inds"])
+    tol = 1e-4 if not secondary else 5e-4   # power-ladder warp: positions agree to 1e-5, not bitwise
+    for k, v in want["render"].items():
+        if v is None:
+            continue
+        assert rel_err(got["render"][k], v) <= tol, (k, rel_err(got["render"][k], v))
+
+
+def test_cache_model_training_gradients(cuda_device):
+    """d loss / d params of the full cache step (tables of all 4 grids + every used MLP weight)."""
+    g = gen(410)
+    R = 96
+    o, n = omodels.NeRFModel(), nmodels.NeRFModel()
+    po = o.init(g, table_init_range=0.1, bias_range=0.05)
+    pn = n.from_oracle(po, cuda_device)
+    rays = make_rays(g, R)
+    u = [f32(g.uniform(size=(R, 1))) for _ in range(3)]
+    target = f32(g.uniform(size=(R, 3)))
+
+    def leaves(p, prefix=""):
+        out = []
+        for k in sorted(p.keys()):
+            if k == "_arena":
+                continue
+            if isinstance(p[k], dict):
+                out += leaves(p[k], prefix + k + "/")
+            else:
+                out.append((prefix + k, p, k))
+        return out
+
+    def loss_fn(res, tgt):
+        l = torch.sqrt((res["render"]["rgb"] - tgt) ** 2 + 1e-6).mean()
+        for h in res["sampler"][:-1]:
+            l = l + 0.01 * ((h["weights"].sum(-1) - res["sampler"][-1]["weights"].sum(-1).detach()) ** 2).mean()
+        return l
+
+    lo = leaves(po)
+    for _, d, k in lo:
+        d[k] = d[k].clone().requires_grad_(True)
+    ro = o(po, rays, u)
+    loss_fn(ro, target).backward()
+    override = [h["sdist"].to(cuda_device) for h in ro["sampler"]]
+
+    arenas = {}
+    for i, m in enumerate(n.sampler.mlps):
+        p = pn["Sampler"][f"MLP_{i}"]
+        a = p["density_grid"]["_arena"].clone().requires_grad_(True)
+        p["density_grid"] = dict(m.grid.views(a.detach()), _arena=a)
+        arenas[f"Sampler/MLP_{i}/density_grid/"] = (m.grid, a)
+    a = pn["Shader"]["appearance_grid"]["_arena"].clone().requires_grad_(True)
+    pn["Shader"]["appearance_grid"] = dict(n.shader.grid.views(a.detach()), _arena=a)
+    arenas["Shader/appearance_grid/"] = (n.shader.grid, a)
+    ln = leaves(pn)
+    for name, d, k in ln:
+        if not any(name.startswith(pre) for pre in arenas):
+            d[k] = d[k].clone().requires_grad_(True)
+    rn = n(pn, to_dev(rays, cuda_device), to_dev(u, cuda_device), train=True, sdist_override=override)
+    loss_fn(rn, target.to(cuda_device)).backward()
+    assert rel_err(rn["render"]["rgb"], ro["render"]["rgb"]) <= 1e-4
+    checked = 0
+    for (name, dn, kn), (_, do, ko) in zip(ln, lo):
+        ref = do[ko].grad
+        pre = [p for p in arenas if name.startswith(p)]
+        if pre:
+            grid, arena = arenas[pre[0]]
+            got = grid.views(arena.grad)[kn]
+        else:
+            got = dn[kn].grad
+        if ref is None or float(ref.abs().max()) == 0.0:
+            continue
+        assert got is not None, name
+        assert rel_err(got, ref) <= 5e-4, (name, rel_err(got, ref))
+        checked += 1
+    assert checked > 40
