@@ -105,39 +105,36 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_reference_throughput(rays, steps, warmup, threads=None):
-    """The reference's algorithm (oracle port) for the same step: cache sampler fwd+bwd."""
-    from oracle import sampling as osamp
+    """The reference's algorithm (oracle port) for the same step: full cache training step."""
+    from oracle import models as omodels
     from neural_radiance_caching_b200 import workload
 
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     g = np.random.Generator(np.random.PCG64(workload.SEED))
-    samp = osamp.ProposalVolumeSampler()
-    params = samp.init(g, table_init_range=0.1)
+    model = omodels.NeRFModel()
+    params = model.init(g, table_init_range=0.1)
     leaves = []
-    for i in range(3):
-        m = params[f"MLP_{i}"]
-        for k in m["density_grid"]:
-            m["density_grid"][k].requires_grad_(True)
-            leaves.append(m["density_grid"][k])
-        for k in ("density_layers_0", "density_layers_1", "output_density_layer"):
-            for kk in ("kernel", "bias"):
-                m[k][kk].requires_grad_(True)
-                leaves.append(m[k][kk])
+
+    def collect(p):
+        for k, v in p.items():
+            if isinstance(v, dict):
+                collect(v)
+            else:
+                v.requires_grad_(True)
+                leaves.append(v)
+
+    collect(params)
     rn = workload.make_rays_np(g, rays)
     rt = {k: torch.from_numpy(v) for k, v in rn.items()}
     u = [torch.from_numpy(g.uniform(size=(rays, 1)).astype(np.float32)) for _ in range(3)]
-    target = torch.from_numpy(g.uniform(size=(rays,)).astype(np.float32))
+    target = torch.from_numpy(g.uniform(size=(rays, 3)).astype(np.float32))
 
     def step():
         for t in leaves:
             t.grad = None
-        # levels 0-1 discard their analytic normals (XLA dead-code-eliminates them); level 2's
-        # normals are forward-only here, matching the b200 step.
-        hist = samp(params, rt, u)
-        acc = [h["weights"].sum(-1) for h in hist]
-        loss = torch.sqrt((acc[2] - target) ** 2 + 1e-6).mean()
-        loss = loss + 0.01 * ((acc[0] - acc[2].detach()) ** 2).mean() + 0.01 * ((acc[1] - acc[2].detach()) ** 2).mean()
+        res = model(params, rt, u)
+        loss = workload.cache_loss(res, target)
         loss.backward()
         return float(loss.detach())
 
@@ -170,8 +167,9 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-WORKLOAD = ("config2 cache training step, density path: nerf_ngp_yobo_lego proposal sampler (64,64,32) "
-            "hash-grid + MLP fwd+bwd with proposal resampling")
+WORKLOAD = ("config2 nerf_ngp_yobo_lego cache training step: proposal sampler (64,64,32) hash-grid + density MLP, "
+            "cache shader (appearance grid + bottleneck/heads/int-BRDF/IDE SurfaceLightField/EnvMap MLPs) on the "
+            "32 final samples, volumetric rendering, Charbonnier-sRGB loss, fwd+bwd (grads for 4 grids + all MLPs)")
 
 
 # ----------------------------------------------------------------------------- b200 arm
@@ -193,14 +191,14 @@ def run_b200(args):
     pk, pk_kind = peaks()
 
     R = args.rays
-    step_obj = workload.CacheSamplerStep(dev, bf16=bool(args.bf16))
+    step_obj = workload.CacheTrainStep(dev, bf16=bool(args.bf16))
     g = np.random.Generator(np.random.PCG64(workload.SEED + rank))
     n_batches = 4
     host = []
     for _ in range(n_batches):
         rn = workload.make_rays_np(g, R)
         u = [g.uniform(size=(R, 1)).astype(np.float32) for _ in range(3)]
-        tgt = g.uniform(size=(R, 1)).astype(np.float32)
+        tgt = g.uniform(size=(R, 3)).astype(np.float32)
         host.append(torch.from_numpy(workload.pack_rays(rn, u, tgt)).pin_memory())
     dbuf = torch.empty_like(host[0], device=dev)
     dbuf.copy_(host[0])
@@ -218,7 +216,7 @@ def run_b200(args):
 
     def one_step():
         rays, u01, extra = workload.unpack_rays(dbuf)
-        loss = step_obj.step(rays, u01, extra[:, 0])
+        loss = step_obj.step(rays, u01, extra)
         allreduce_grads()
         return loss
 
@@ -321,7 +319,9 @@ def run_b200(args):
         "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16-mlp/f32" if args.bf16 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": R, "samples_per_ray": [64, 64, 32],
-                   "tables": "MLP_0/1/2 density grids (7.5+9.6+46.7 MB fp32), U(+-0.1) trained-like init",
+                   "shaded_points_per_ray": 32,
+                   "tables": "MLP_0/1/2 density grids + appearance grid (7.5+9.6+46.7+46.7 MB fp32), "
+                             "U(+-0.1) trained-like init",
                    "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
                    "cuda_graph": bool(use_graph), "parallelism": f"dp{world} rays, params replicated"},
         "rays_per_sec": value / SAMPLES_PER_RAY,
@@ -378,7 +378,11 @@ def roofline(per_kernel, R, pk, pk_kind):
     LF = {0: (6, 1), 1: (7, 1), 2: (8, 4)}
     fwd = sum(pts[i] * (12 + 8 * F * 4 * L + 4 * L * F) for i, (L, F) in LF.items())
     bwd = sum(pts[i] * (12 + 4 * L * F + 2 * 8 * F * 4 * L) for i, (L, F) in LF.items())
-    alg = {"nrc_encode_fwd": fwd, "nrc_encode_bwd": bwd, "nrc_density_query_fwd": fwd}
+    app_fwd = 32 * R * (12 + 8 * 4 * 4 * 8 + 4 * 32)          # appearance grid, L=8 F=4
+    app_bwd = 32 * R * (12 + 4 * 32 + 2 * 8 * 4 * 4 * 8)
+    # nrc_encode_fwd is only the appearance grid (density grids are gathered inside the fused
+    # query); nrc_encode_bwd scatters into all four grids.
+    alg = {"nrc_encode_fwd": app_fwd, "nrc_encode_bwd": bwd + app_bwd, "nrc_density_query_fwd": fwd}
     peak = pk["hbm_gbs"]
     res = {"kernel": top, "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": pk_kind, "traffic": None}
     if top in alg:
@@ -386,9 +390,11 @@ def roofline(per_kernel, R, pk, pk_kind):
         res.update(achieved=ach, frac=ach / peak,
                    note="sum over the 3 levels' launches of this entry point per step; per-call CUDA events")
     else:
-        res.update(achieved=None, frac=None, note="dominant kernel is compute-bound (fp32 FFMA MLP); see DESIGN.md")
+        res.update(achieved=None, frac=None,
+                   note="dominant entry point is a dense/MLP kernel (FP32 or tensor pipe bound); the gather "
+                        "kernels' HBM fractions are listed beside it")
     # always report the encode kernels too
-    for k in ("nrc_encode_fwd", "nrc_encode_bwd"):
+    for k in ("nrc_encode_fwd", "nrc_encode_bwd", "nrc_density_query_fwd"):
         if k in per_kernel:
             a = alg[k] / (per_kernel[k] * 1e-3) / 1e9
             res[k] = {"achieved": a, "frac": a / peak, "ms": per_kernel[k]}

@@ -1,10 +1,10 @@
-"""Synthetic workloads of BASELINE.md section 2 and the cache-stage step built from the
+"""Synthetic workloads of BASELINE.md section 2 and the cache-stage training step built from the
 kernels.  Shared by bench.py, __graft_entry__.smoke() and the tests (no oracle imports here).
 """
 import numpy as np
 import torch
 
-from . import _lib, sampling
+from . import models
 
 SEED = 20200823  # the reference's Config.jax_rng_seed (internal/configs.py:180)
 SAMPLES_PER_RAY = (64, 64, 32)  # configs/nerf_ngp_yobo.gin:521-545
@@ -43,56 +43,103 @@ def unpack_rays(buf):
     return rays, u01, extra
 
 
-class CacheSamplerStep:
-    """Cache-stage proposal sampler, forward + backward (BASELINE config 2, density path):
-    3 levels x (interval resampling -> ray cast -> contract + hash-grid encode + fused MLP ->
-    alpha weights), loss on the level weights, gradients for the three density tables and
-    MLP weights into contiguous arenas."""
+def linear_to_srgb(linear):
+    """image.linear_to_srgb (internal/image.py:192-200)."""
+    eps = float(np.finfo(np.float32).eps)
+    srgb0 = 323 / 25 * linear
+    srgb1 = (211 * torch.clamp(linear, min=eps) ** (5 / 12) - 11) / 200
+    return torch.where(linear <= 0.0031308, srgb0, srgb1)
+
+
+def cache_loss(result, target_rgb, charb_padding=0.001):
+    """Cache-stage objective of the benchmark step (device-agnostic torch glue; also used on the
+    oracle's tensors by the CPU leg): Charbonnier data term on the sRGB-mapped render
+    (MaterialModel.cache_loss='charb', cache_linear_to_srgb=True, configs/ngp_yobo.gin:35-37;
+    internal/configs.py:330) plus a proposal-supervision stand-in that ties the accumulated
+    weights of the two proposal levels to the (stop-gradient) final level.  The reference's spline
+    interlevel, predicted-normal and mask losses are the SURVEY 8f 'next' rows."""
+    rgb = linear_to_srgb(result["render"]["rgb"])
+    loss = torch.sqrt((rgb - target_rgb) ** 2 + charb_padding**2).mean()
+    hist = result["sampler"]
+    acc_final = hist[-1]["weights"].sum(-1).detach()
+    for h in hist[:-1]:
+        loss = loss + 0.01 * ((h["weights"].sum(-1) - acc_final) ** 2).mean()
+    return loss
+
+
+def _he_uniform(gen, device, fan_in, fan_out):
+    lim = float(np.sqrt(6.0 / fan_in))  # jax he_uniform (geometry.py:127)
+    return torch.empty((fan_in, fan_out), device=device).uniform_(-lim, lim, generator=gen)
+
+
+class CacheTrainStep:
+    """BASELINE config 2: nerf_ngp_yobo_lego cache training step on a batch of rays --
+    proposal sampler (64,64,32) -> cache shader on the 32 final samples -> volumetric rendering ->
+    loss -> backward: gradients for the 4 hash-grid arenas (3 density grids + appearance grid) and
+    every MLP weight on the path."""
 
     def __init__(self, device, table_init_range=0.1, seed=SEED, bf16=False):
         self.device = device
-        self.sampler = sampling.ProposalVolumeSampler(bf16=bf16)
+        self.model = models.NeRFModel(bf16=bf16)
         gen = torch.Generator(device=device)
         gen.manual_seed(seed)
-        self.params = {}
         self.leaves = []
-        for i, m in enumerate(self.sampler.mlps):
-            tables, arena = m.grid.init(device, generator=gen, init_range=table_init_range)
-            arena.requires_grad_(True)
-            # level views are taken from the detached arena: they only carry device pointers, and
-            # a view of the leaf would pin its AccumulateGrad node to the init stream (breaks
-            # CUDA-graph capture of the backward pass).
-            p = {"density_grid": dict(m.grid.views(arena.detach()), _arena=arena)}
-            dims = [(m.in_dim, 64), (64, 64), (64, 1)] + ([(64, 3)] if m.enable_pred_normals else [])
-            names = ["density_layers_0", "density_layers_1", "output_density_layer", "pred_normals_layer"]
-            for name, (fi, fo) in zip(names, dims):
-                lim = float(np.sqrt(6.0 / fi))  # he_uniform (geometry.py:127)
-                k = torch.empty((fi, fo), device=device).uniform_(-lim, lim, generator=gen).requires_grad_(True)
-                b = torch.zeros((fo,), device=device).requires_grad_(True)
-                p[name] = {"kernel": k, "bias": b}
-                self.leaves += [k, b]
-            self.leaves.append(arena)
-            self.params[f"MLP_{i}"] = p
 
-    def num_table_params(self):
-        return sum(int(p["density_grid"]["_arena"].numel()) for p in self.params.values())
+        def layer(fi, fo):
+            k = _he_uniform(gen, device, fi, fo).requires_grad_(True)
+            b = torch.zeros((fo,), device=device).requires_grad_(True)
+            self.leaves += [k, b]
+            return {"kernel": k, "bias": b}
+
+        def grid(enc):
+            _, arena = enc.init(device, generator=gen, init_range=table_init_range)
+            arena.requires_grad_(True)
+            self.leaves.append(arena)
+            # views from the detached arena: pointers only; a view of the leaf would pin its
+            # AccumulateGrad node to the init stream and break CUDA-graph capture of backward.
+            return dict(enc.views(arena.detach()), _arena=arena)
+
+        sampler = {}
+        for i, m in enumerate(self.model.sampler.mlps):
+            p = {"density_grid": grid(m.grid), "density_layers_0": layer(m.in_dim, 64),
+                 "density_layers_1": layer(64, 64), "output_density_layer": layer(64, 1)}
+            if m.enable_pred_normals:
+                p["pred_normals_layer"] = layer(64, 3)
+            sampler[f"MLP_{i}"] = p
+        sh = self.model.shader
+
+        def slf(in_dim):
+            p, d = {}, in_dim
+            for j, name in enumerate(["layer_0", "layer_1", "layer_2", "layer_bottleneck"]):
+                p[name] = layer(d, 128)
+                d = 128 + (in_dim if (j % 2 == 0 and j > 0) else 0)
+            p["output_ambient_rgb_layer"] = layer(d, 3)
+            return p
+
+        shader = {
+            "appearance_grid": grid(sh.grid), "bottleneck_layer": layer(96, 128), "roughness_layer": layer(96, 1),
+            "ambient_irradiance_layer": layer(96, 3), "irradiance_layer": layer(96, 3), "tint_layer": layer(96, 3),
+            "integrated_brdf_layers_0": layer(129, 64), "integrated_brdf_layers_1": layer(64, 64),
+            "output_integrated_brdf_layer": layer(64, 1), "SurfaceLightField": slf(200), "EnvMap": slf(38),
+        }
+        self.params = {"Sampler": sampler, "Shader": shader}
+
+    def num_params(self):
+        return sum(int(t.numel()) for t in self.leaves)
 
     def zero_grad(self):
         for t in self.leaves:
             t.grad = None
 
-    def forward(self, rays, u01, train=True):
-        return self.sampler(self.params, rays, u01, train=train)
-
-    def step(self, rays, u01, target):
-        """One training step: forward, a scalar loss over the three levels' weights,
-        backward.  Returns the loss (device scalar)."""
+    def step(self, rays, u01, target_rgb):
+        """Forward + loss + backward of one ray batch; returns the loss (device scalar)."""
         self.zero_grad()
-        hist = self.forward(rays, u01, train=True)
-        # Charbonnier-style data term on the accumulated opacity of the final level plus an
-        # L2 tie between proposal and final accumulations: touches every level's weights.
-        acc = [h["weights"].sum(-1) for h in hist]
-        loss = torch.sqrt((acc[2] - target) ** 2 + 1e-6).mean()
-        loss = loss + 0.01 * ((acc[0] - acc[2].detach()) ** 2).mean() + 0.01 * ((acc[1] - acc[2].detach()) ** 2).mean()
+        res = self.model(self.params, rays, u01, train=True)
+        loss = cache_loss(res, target_rgb)
         loss.backward()
         return loss.detach()
+
+    def render(self, rays, u01):
+        """Forward-only evaluation (BASELINE config 1)."""
+        with torch.no_grad():
+            return self.model(self.params, rays, u01, train=False)["render"]
