@@ -143,8 +143,12 @@ def volumetric_rendering(
         values = torch.zeros(weights.shape + (0,), device=weights.device)
     bg = None
     if rgbs is not None and bg_rgbs is not None:
-        bg = torch.as_tensor(bg_rgbs, device=weights.device, dtype=torch.float32)
-        bg = bg.expand(weights.shape[:-1] + (3,)) if bg.dim() > 0 else bg.reshape(1).expand(weights.shape[:-1] + (3,))
+        if isinstance(bg_rgbs, (int, float)):
+            # fill on the device: no host->device copy (keeps the call CUDA-graph capturable)
+            bg = torch.full(weights.shape[:-1] + (3,), float(bg_rgbs), device=weights.device, dtype=torch.float32)
+        else:
+            bg = torch.as_tensor(bg_rgbs, device=weights.device, dtype=torch.float32)
+            bg = bg.expand(weights.shape[:-1] + (3,))
     out, acc, dist = _CompositeFn.apply(values, weights, nf, tdist, bg, rgbs is not None, bool(compute_distance))
     rendering = {}
     off = 0
