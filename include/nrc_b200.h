@@ -228,15 +228,18 @@ int32_t nrc_ray_resample_gather(void* stream, const float* d_field, const int32_
 int32_t nrc_dense_fwd(void* stream, const float* d_x, int64_t ldx, const float* d_kernel,
                       const float* d_bias, int64_t num_rows, int32_t in_dim, int32_t out_dim,
                       int32_t relu, int32_t bf16, float* d_y, int64_t ldy);
-/* VJP of nrc_dense_fwd.  d_y (the forward output) supplies the ReLU mask when relu != 0.
+/* ReLU VJP: d_g_pre[r,c] = d_y[r,c] > 0 ? d_g_y[r,c] : 0 (all with row strides). */
+int32_t nrc_relu_bwd(void* stream, const float* d_y, int64_t ldy, const float* d_g_y, int64_t ldgy,
+                     int64_t num_rows, int32_t num_cols, float* d_g_pre, int64_t ldgp);
+/* VJP of nrc_dense_fwd with respect to the PRE-activation output (apply nrc_relu_bwd first for
+ * ReLU layers).
  *   d_g_x [rows,in] (stride ldgx) written, or accumulated into when accumulate_g_x != 0
  *   (second consumer of a skip connection); may be NULL.
  *   d_g_kernel [in,out] and d_g_bias [out] are ACCUMULATED INTO; may be NULL (both). */
 int32_t nrc_dense_bwd(void* stream, const float* d_x, int64_t ldx, const float* d_kernel,
-                      const float* d_y, int64_t ldy, const float* d_g_y, int64_t ldgy,
-                      int64_t num_rows, int32_t in_dim, int32_t out_dim, int32_t relu, int32_t bf16,
-                      float* d_g_x, int64_t ldgx, int32_t accumulate_g_x, float* d_g_kernel,
-                      float* d_g_bias);
+                      const float* d_g_y, int64_t ldgy, int64_t num_rows, int32_t in_dim,
+                      int32_t out_dim, int32_t bf16, float* d_g_x, int64_t ldgx,
+                      int32_t accumulate_g_x, float* d_g_kernel, float* d_g_bias);
 
 /* Integrated directional encoding, ref_utils.generate_ide_fn (internal/ref_utils.py:131-192).
  * Host tables built like the reference: ml_m/ml_l [n_sh] from get_ml_array (:117-128),

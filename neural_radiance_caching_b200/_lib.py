@@ -91,7 +91,8 @@ PROTOTYPES = {
     "nrc_ray_resample": [_P, _P, _P, _I64, _I32, _I32, _F, _F, _P, _P],
     "nrc_ray_resample_gather": [_P, _P, _P, _I64, _I32, _I32, _I32, _P],
     "nrc_dense_fwd": [_P, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _I64],
-    "nrc_dense_bwd": [_P, _P, _I64, _P, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P, _I64, _I32, _P, _P],
+    "nrc_relu_bwd": [_P, _P, _I64, _P, _I64, _I64, _I32, _P, _I64],
+    "nrc_dense_bwd": [_P, _P, _I64, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, _I64, _I32, _P, _P],
     "nrc_ide_fwd": [_P, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), _P, _P, _P, _I64,
                     _P, _I64],
     "nrc_ide_bwd": [_P, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), _P, _P, _P, _P,

@@ -20,8 +20,6 @@ struct GemmArgs {
   const float* B; int64_t ldb;
   float* C; int64_t ldc;
   const float* bias;          // [N] or null (forward)
-  const float* maskA; int64_t ldma;  // relu mask source for A (same indexing as A) or null
-  const float* maskB; int64_t ldmb;  // relu mask source for B (same indexing as B) or null
   float* colsum;              // [N]: += column sums of opB(B) rows (bias gradient) or null
   int M, N, K;
   int relu;                   // epilogue activation
@@ -29,18 +27,76 @@ struct GemmArgs {
   int k_splits;               // >1: split the K loop over blockIdx.z, atomicAdd epilogue
 };
 
-// element (r, c) of op(X): X stored row-major with stride ld; trans => stored [c][r].
-template <bool TRANS>
-__device__ __forceinline__ float load_elem(const float* __restrict__ X, int64_t ld, const float* __restrict__ mask,
-                                           int64_t ldm, int r, int c, int R, int Cc) {
-  if (r >= R || c >= Cc) return 0.f;
-  const int64_t off = TRANS ? static_cast<int64_t>(c) * ld + r : static_cast<int64_t>(r) * ld + c;
-  float v = __ldg(X + off);
-  if (mask) {
-    const int64_t moff = TRANS ? static_cast<int64_t>(c) * ldm + r : static_cast<int64_t>(r) * ldm + c;
-    if (!(__ldg(mask + moff) > 0.f)) v = 0.f;
+// ---------------------------------------------------------------------------- tile loader
+// A tile is ROWS x COLS in the operand's *global* orientation (row-major, stride ld); each thread
+// moves NV = ROWS*COLS/4/threads float4 units.  The 16-byte path needs ld % 4 == 0 and a
+// 16-byte aligned base (the host pads odd widths); columns beyond the logical limit are zeroed.
+template <int ROWS, int COLS>
+struct TileLoader {
+  static constexpr int kUnits = ROWS * COLS / 4;
+  static constexpr int NV = kUnits / kGemmThreads;
+  static_assert(kUnits % kGemmThreads == 0, "tile must divide evenly");
+  float4 v[NV];
+
+  __device__ __forceinline__ void load(const float* __restrict__ X, int64_t ld, int row0, int col0, int row_lim,
+                                       int col_lim, bool vec_ok, int tid) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int u = tid + j * kGemmThreads;
+      const int r = u / (COLS / 4), c = (u % (COLS / 4)) * 4;
+      const int gr = row0 + r, gc = col0 + c;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < row_lim && gc < col_lim) {
+        const float* p = X + static_cast<int64_t>(gr) * ld + gc;
+        if (vec_ok && gc + 4 <= ld) {
+          t = __ldg(reinterpret_cast<const float4*>(p));
+          if (gc + 1 >= col_lim) t.y = 0.f;
+          if (gc + 2 >= col_lim) t.z = 0.f;
+          if (gc + 3 >= col_lim) t.w = 0.f;
+        } else {
+          t.x = __ldg(p);
+          if (gc + 1 < col_lim) t.y = __ldg(p + 1);
+          if (gc + 2 < col_lim) t.z = __ldg(p + 2);
+          if (gc + 3 < col_lim) t.w = __ldg(p + 3);
+        }
+      }
+      v[j] = t;
+    }
   }
-  return v;
+  // bf16 tile, same orientation, row stride `stride` halves
+  __device__ __forceinline__ void store_bf16(__nv_bfloat16* s, int stride, int tid) const {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int u = tid + j * kGemmThreads;
+      const int r = u / (COLS / 4), c = (u % (COLS / 4)) * 4;
+      *reinterpret_cast<uint2*>(s + r * stride + c) = make_uint2(pack_bf16(v[j].x, v[j].y), pack_bf16(v[j].z, v[j].w));
+    }
+  }
+  // fp32 tile; transposed => s[c][r]
+  template <bool TRANSPOSE>
+  __device__ __forceinline__ void store_f32(float* s, int stride, int tid) const {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int u = tid + j * kGemmThreads;
+      const int r = u / (COLS / 4), c = (u % (COLS / 4)) * 4;
+      if constexpr (!TRANSPOSE) {
+        *reinterpret_cast<float4*>(s + r * stride + c) = v[j];
+      } else {
+        s[(c + 0) * stride + r] = v[j].x; s[(c + 1) * stride + r] = v[j].y;
+        s[(c + 2) * stride + r] = v[j].z; s[(c + 3) * stride + r] = v[j].w;
+      }
+    }
+  }
+  __device__ __forceinline__ float sum() const {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) t += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    return t;
+  }
+};
+
+__device__ __forceinline__ bool vec_ok(const float* p, int64_t ld) {
+  return (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 }
 
 __device__ __forceinline__ void store_out(const GemmArgs& g, int row, int col, float v) {
@@ -53,16 +109,24 @@ __device__ __forceinline__ void store_out(const GemmArgs& g, int row, int col, f
   else *p = v;
 }
 
+// Column sums of the B operand (bias gradient), only for !TRANS_B tiles [BK][BN]: every float4
+// unit of a thread lies in columns (u % (BN/4))*4.. with u % 16 == tid % 16 fixed.
+template <typename Loader>
+__device__ __forceinline__ void add_colsum(const Loader& L, float (&cs)[4]) {
+#pragma unroll
+  for (int j = 0; j < Loader::NV; ++j) { cs[0] += L.v[j].x; cs[1] += L.v[j].y; cs[2] += L.v[j].z; cs[3] += L.v[j].w; }
+}
+
 // ------------------------------------------------------------------------------ bf16 tensor cores
 // smem tiles keep the global orientation: A [BM][BK] (or [BK][BM] when TRANS_A), B [BK][BN]
 // (or [BN][BK] when TRANS_B); ldmatrix(.trans) produces the fragments for every combination.
+// Global loads of chunk k+1 are issued into registers before the MMAs of chunk k.
 template <bool TRANS_A, bool TRANS_B>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_bf16_kernel(const GemmArgs g) {
-  constexpr int kAStride = TRANS_A ? BM + 8 : BK + 8;
-  constexpr int kARows = TRANS_A ? BK : BM;
-  constexpr int kBStride = TRANS_B ? BK + 8 : BN + 8;
-  constexpr int kBRows = TRANS_B ? BN : BK;
+  constexpr int kARows = TRANS_A ? BK : BM, kACols = TRANS_A ? BM : BK;
+  constexpr int kBRows = TRANS_B ? BN : BK, kBCols = TRANS_B ? BK : BN;
+  constexpr int kAStride = kACols + 8, kBStride = kBCols + 8;
   __shared__ __align__(16) __nv_bfloat16 sA[kARows * kAStride];
   __shared__ __align__(16) __nv_bfloat16 sB[kBRows * kBStride];
   __shared__ float s_colsum[BN];
@@ -71,6 +135,7 @@ gemm_bf16_kernel(const GemmArgs g) {
   const int k_chunks = (g.K + BK - 1) / BK;
   const int per = (k_chunks + g.k_splits - 1) / g.k_splits;
   const int kc_begin = blockIdx.z * per, kc_end = min(k_chunks, kc_begin + per);
+  const bool va = vec_ok(g.A, g.lda), vb = vec_ok(g.B, g.ldb);
   float acc[2][8][4];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -78,39 +143,25 @@ gemm_bf16_kernel(const GemmArgs g) {
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
-  float csum = 0.f;  // column sum of B for column (tid % BN), rows handled by tid / BN
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
   if (tid < BN) s_colsum[tid] = 0.f;
-
-  for (int kc = kc_begin; kc < kc_end; ++kc) {
+  TileLoader<kARows, kACols> la;
+  TileLoader<kBRows, kBCols> lb;
+  auto issue = [&](int kc) {
     const int k0 = kc * BK;
+    if constexpr (!TRANS_A) la.load(g.A, g.lda, m0, k0, g.M, g.K, va, tid);
+    else la.load(g.A, g.lda, k0, m0, g.K, g.M, va, tid);
+    if constexpr (!TRANS_B) lb.load(g.B, g.ldb, k0, n0, g.K, g.N, vb, tid);
+    else lb.load(g.B, g.ldb, n0, k0, g.N, g.K, vb, tid);
+  };
+  if (kc_begin < kc_end) issue(kc_begin);
+  for (int kc = kc_begin; kc < kc_end; ++kc) {
+    __syncthreads();                       // previous chunk's fragments are consumed
+    la.store_bf16(sA, kAStride, tid);
+    lb.store_bf16(sB, kBStride, tid);
+    if (g.colsum && !TRANS_B) add_colsum(lb, cs);
     __syncthreads();
-    // A tile
-    if constexpr (!TRANS_A) {
-      for (int idx = tid; idx < BM * BK; idx += kGemmThreads) {
-        int r = idx / BK, c = idx % BK;
-        sA[r * kAStride + c] = __float2bfloat16(load_elem<false>(g.A, g.lda, g.maskA, g.ldma, m0 + r, k0 + c, g.M, g.K));
-      }
-    } else {
-      for (int idx = tid; idx < BK * BM; idx += kGemmThreads) {
-        int kk = idx / BM, r = idx % BM;   // stored [k][m]
-        sA[kk * kAStride + r] = __float2bfloat16(load_elem<true>(g.A, g.lda, g.maskA, g.ldma, m0 + r, k0 + kk, g.M, g.K));
-      }
-    }
-    // B tile
-    if constexpr (!TRANS_B) {
-      for (int idx = tid; idx < BK * BN; idx += kGemmThreads) {
-        int kk = idx / BN, c = idx % BN;   // stored [k][n]
-        float v = load_elem<false>(g.B, g.ldb, g.maskB, g.ldmb, k0 + kk, n0 + c, g.K, g.N);
-        sB[kk * kBStride + c] = __float2bfloat16(v);
-        csum += v;                          // c == tid % BN for every idx of this thread
-      }
-    } else {
-      for (int idx = tid; idx < BN * BK; idx += kGemmThreads) {
-        int c = idx / BK, kk = idx % BK;   // stored [n][k]
-        sB[c * kBStride + kk] = __float2bfloat16(load_elem<true>(g.B, g.ldb, g.maskB, g.ldmb, k0 + kk, n0 + c, g.K, g.N));
-      }
-    }
-    __syncthreads();
+    if (kc + 1 < kc_end) issue(kc + 1);    // in flight during the MMAs below
 #pragma unroll
     for (int ks = 0; ks < BK / 16; ++ks) {
       uint32_t a[2][4];
@@ -141,9 +192,11 @@ gemm_bf16_kernel(const GemmArgs g) {
       for (int e = 0; e < 4; ++e)
         store_out(g, m0 + warp * 32 + mt * 16 + r + (e >= 2 ? 8 : 0), n0 + nt * 8 + cq + (e & 1), acc[mt][nt][e]);
   if (g.colsum && !TRANS_B && blockIdx.x == 0) {
-    // bias gradient: every CTA of the first M-tile row holds the sums of its K range
+    // bias gradient: the CTAs of the first M-tile row hold the column sums of their K range
     __syncthreads();
-    atomicAdd(&s_colsum[tid % BN], csum);
+    const int c = (tid % (BN / 4)) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(&s_colsum[c + i], cs[i]);
     __syncthreads();
     if (tid < BN && n0 + tid < g.N) atomicAdd(g.colsum + n0 + tid, s_colsum[tid]);
   }
@@ -153,6 +206,8 @@ gemm_bf16_kernel(const GemmArgs g) {
 template <bool TRANS_A, bool TRANS_B>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_f32_kernel(const GemmArgs g) {
+  constexpr int kARows = TRANS_A ? BK : BM, kACols = TRANS_A ? BM : BK;
+  constexpr int kBRows = TRANS_B ? BN : BK, kBCols = TRANS_B ? BK : BN;
   __shared__ __align__(16) float sA[BK][BM + 4];   // [k][m]
   __shared__ __align__(16) float sB[BK][BN + 4];   // [k][n]
   __shared__ float s_colsum[BN];
@@ -162,41 +217,31 @@ gemm_f32_kernel(const GemmArgs g) {
   const int k_chunks = (g.K + BK - 1) / BK;
   const int per = (k_chunks + g.k_splits - 1) / g.k_splits;
   const int kc_begin = blockIdx.z * per, kc_end = min(k_chunks, kc_begin + per);
+  const bool va = vec_ok(g.A, g.lda), vb = vec_ok(g.B, g.ldb);
   float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  float csum = 0.f;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
   if (tid < BN) s_colsum[tid] = 0.f;
-  for (int kc = kc_begin; kc < kc_end; ++kc) {
+  TileLoader<kARows, kACols> la;
+  TileLoader<kBRows, kBCols> lb;
+  auto issue = [&](int kc) {
     const int k0 = kc * BK;
+    if constexpr (!TRANS_A) la.load(g.A, g.lda, m0, k0, g.M, g.K, va, tid);
+    else la.load(g.A, g.lda, k0, m0, g.K, g.M, va, tid);
+    if constexpr (!TRANS_B) lb.load(g.B, g.ldb, k0, n0, g.K, g.N, vb, tid);
+    else lb.load(g.B, g.ldb, n0, k0, g.N, g.K, vb, tid);
+  };
+  if (kc_begin < kc_end) issue(kc_begin);
+  for (int kc = kc_begin; kc < kc_end; ++kc) {
     __syncthreads();
-    if constexpr (!TRANS_A) {
-      for (int idx = tid; idx < BM * BK; idx += kGemmThreads) {
-        int r = idx / BK, c = idx % BK;
-        sA[c][r] = load_elem<false>(g.A, g.lda, g.maskA, g.ldma, m0 + r, k0 + c, g.M, g.K);
-      }
-    } else {
-      for (int idx = tid; idx < BK * BM; idx += kGemmThreads) {
-        int kk = idx / BM, r = idx % BM;
-        sA[kk][r] = load_elem<true>(g.A, g.lda, g.maskA, g.ldma, m0 + r, k0 + kk, g.M, g.K);
-      }
-    }
-    if constexpr (!TRANS_B) {
-      for (int idx = tid; idx < BK * BN; idx += kGemmThreads) {
-        int kk = idx / BN, c = idx % BN;
-        float v = load_elem<false>(g.B, g.ldb, g.maskB, g.ldmb, k0 + kk, n0 + c, g.K, g.N);
-        sB[kk][c] = v;
-        csum += v;
-      }
-    } else {
-      for (int idx = tid; idx < BN * BK; idx += kGemmThreads) {
-        int c = idx / BK, kk = idx % BK;
-        sB[kk][c] = load_elem<true>(g.B, g.ldb, g.maskB, g.ldmb, k0 + kk, n0 + c, g.K, g.N);
-      }
-    }
+    la.template store_f32<!TRANS_A>(&sA[0][0], BM + 4, tid);   // smem is [k][m]: transpose when A is [m][k]
+    lb.template store_f32<TRANS_B>(&sB[0][0], BN + 4, tid);    // smem is [k][n]: transpose when B is [n][k]
+    if (g.colsum && !TRANS_B) add_colsum(lb, cs);
     __syncthreads();
+    if (kc + 1 < kc_end) issue(kc + 1);
 #pragma unroll 8
     for (int kk = 0; kk < BK; ++kk) {
       float a[8], b[8];
@@ -216,7 +261,9 @@ gemm_f32_kernel(const GemmArgs g) {
     for (int j = 0; j < 8; ++j) store_out(g, m0 + ty * 8 + i, n0 + tx * 8 + j, acc[i][j]);
   if (g.colsum && !TRANS_B && blockIdx.x == 0) {
     __syncthreads();
-    atomicAdd(&s_colsum[tid % BN], csum);
+    const int c = (tid % (BN / 4)) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(&s_colsum[c + i], cs[i]);
     __syncthreads();
     if (tid < BN && n0 + tid < g.N) atomicAdd(g.colsum + n0 + tid, s_colsum[tid]);
   }
@@ -247,21 +294,41 @@ extern "C" int32_t nrc_dense_fwd(void* stream, const float* d_x, int64_t ldx, co
   return launch_gemm<false, false>(static_cast<cudaStream_t>(stream), g, bf16);
 }
 
+namespace nrc {
+__global__ void relu_bwd_kernel(const float* __restrict__ y, int64_t ldy, const float* __restrict__ g, int64_t ldg,
+                                int64_t rows, int cols, float* __restrict__ out, int64_t ldo) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int64_t r = i / cols;
+  const int c = static_cast<int>(i - r * cols);
+  out[r * ldo + c] = y[r * ldy + c] > 0.f ? g[r * ldg + c] : 0.f;
+}
+}  // namespace nrc
+
+extern "C" int32_t nrc_relu_bwd(void* stream, const float* d_y, int64_t ldy, const float* d_g_y, int64_t ldgy,
+                                int64_t num_rows, int32_t num_cols, float* d_g_pre, int64_t ldgp) {
+  if (num_rows < 0 || num_cols < 1) return NRC_E_INVALID_ARG;
+  if (num_rows == 0) return NRC_OK;
+  if (!d_y || !d_g_y || !d_g_pre) return NRC_E_INVALID_ARG;
+  int64_t total = num_rows * num_cols;
+  relu_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_y, ldy, d_g_y, ldgy, num_rows, num_cols, d_g_pre, ldgp);
+  return check_launch();
+}
+
 extern "C" int32_t nrc_dense_bwd(void* stream, const float* d_x, int64_t ldx, const float* d_kernel,
-                                 const float* d_y, int64_t ldy, const float* d_g_y, int64_t ldgy,
-                                 int64_t num_rows, int32_t in_dim, int32_t out_dim, int32_t relu, int32_t bf16,
-                                 float* d_g_x, int64_t ldgx, int32_t accumulate_g_x, float* d_g_kernel,
-                                 float* d_g_bias) {
+                                 const float* d_g_y, int64_t ldgy, int64_t num_rows, int32_t in_dim,
+                                 int32_t out_dim, int32_t bf16, float* d_g_x, int64_t ldgx,
+                                 int32_t accumulate_g_x, float* d_g_kernel, float* d_g_bias) {
   if (num_rows < 0 || in_dim < 1 || out_dim < 1) return NRC_E_INVALID_ARG;
   if (num_rows == 0) return NRC_OK;
-  if (!d_g_y || !d_kernel || (relu && !d_y)) return NRC_E_INVALID_ARG;
+  if (!d_g_y || !d_kernel) return NRC_E_INVALID_ARG;
   if (num_rows > 0x7fffffff) return NRC_E_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const float* mask = relu ? d_y : nullptr;
   if (d_g_x) {
-    // g_x[M,K] = (g_y * [y > 0]) @ kernel^T
+    // g_x[M,K] = g_pre @ kernel^T
     GemmArgs g{};
-    g.A = d_g_y; g.lda = ldgy; g.maskA = mask; g.ldma = ldy;
+    g.A = d_g_y; g.lda = ldgy;
     g.B = d_kernel; g.ldb = out_dim;
     g.C = d_g_x; g.ldc = ldgx; g.accumulate = accumulate_g_x;
     g.M = static_cast<int>(num_rows); g.N = in_dim; g.K = out_dim; g.k_splits = 1;
@@ -270,11 +337,11 @@ extern "C" int32_t nrc_dense_bwd(void* stream, const float* d_x, int64_t ldx, co
   }
   if (d_g_kernel) {
     if (!d_x) return NRC_E_INVALID_ARG;
-    // g_kernel[K,N] += x^T @ (g_y * [y > 0]); g_bias[N] += column sums.  Reduction over rows is
-    // split across CTAs (atomic epilogue) so that the grid covers the 148 SMs.
+    // g_kernel[K,N] += x^T @ g_pre; g_bias[N] += column sums.  The reduction over rows is split
+    // across CTAs (atomic epilogue) so that the grid covers the 148 SMs.
     GemmArgs g{};
     g.A = d_x; g.lda = ldx;
-    g.B = d_g_y; g.ldb = ldgy; g.maskB = mask; g.ldmb = ldy;
+    g.B = d_g_y; g.ldb = ldgy;
     g.C = d_g_kernel; g.ldc = out_dim; g.colsum = d_g_bias;
     g.M = in_dim; g.N = out_dim; g.K = static_cast<int>(num_rows);
     int tiles = ((in_dim + BM - 1) / BM) * ((out_dim + BN - 1) / BN);

@@ -16,34 +16,48 @@ from . import _lib, coord, grid_utils
 
 
 # ----------------------------------------------------------------------------- Dense
+def _pad4(t):
+    """Row stride multiple of 4 floats (16-byte rows) so the GEMM tile loader can use LDG.128."""
+    k = t.shape[-1]
+    if k % 4 == 0:
+        return t.contiguous(), k
+    k4 = (k + 3) // 4 * 4
+    return torch.nn.functional.pad(t, (0, k4 - k)).contiguous(), k4
+
+
 class _DenseFn(torch.autograd.Function):
     """custom_vjp analogue of flax.linen.Dense (+ optional ReLU) over nrc_dense_{fwd,bwd}."""
 
     @staticmethod
     def forward(ctx, x, kernel, bias, relu, bf16):
         K, N = kernel.shape
-        x2 = x.reshape(-1, K).contiguous()
+        x2, ldx = _pad4(x.reshape(-1, K))
         M = x2.shape[0]
         y = torch.empty((M, N), device=x.device, dtype=torch.float32)
-        _lib.call("nrc_dense_fwd", _lib.stream_ptr(), _lib.ptr(x2), K, _lib.ptr(kernel), _lib.ptr(bias), M, K, N,
+        _lib.call("nrc_dense_fwd", _lib.stream_ptr(), _lib.ptr(x2), ldx, _lib.ptr(kernel), _lib.ptr(bias), M, K, N,
                   int(relu), int(bf16), _lib.ptr(y), N)
         ctx.save_for_backward(x2, kernel, y if relu else None)
-        ctx.meta = (x.shape, relu, bf16)
+        ctx.meta = (x.shape, relu, bf16, ldx)
         return y.reshape(x.shape[:-1] + (N,))
 
     @staticmethod
     def backward(ctx, g):
         x2, kernel, y = ctx.saved_tensors
-        xshape, relu, bf16 = ctx.meta
+        xshape, relu, bf16, ldx = ctx.meta
         K, N = kernel.shape
         M = x2.shape[0]
         g2 = g.reshape(M, N).contiguous()
-        gx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        if relu:
+            gpre = torch.empty_like(g2)
+            _lib.call("nrc_relu_bwd", _lib.stream_ptr(), _lib.ptr(y), N, _lib.ptr(g2), N, M, N, _lib.ptr(gpre), N)
+            g2 = gpre
+        g2, ldg = _pad4(g2)
+        gx = torch.empty((M, K), device=g.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         gk = torch.zeros_like(kernel) if want_w else None
         gb = torch.zeros((N,), device=g.device, dtype=torch.float32) if want_w else None
-        _lib.call("nrc_dense_bwd", _lib.stream_ptr(), _lib.ptr(x2), K, _lib.ptr(kernel), _lib.ptr(y), N,
-                  _lib.ptr(g2), N, M, K, N, int(relu), int(bf16), _lib.ptr(gx), K, 0, _lib.ptr(gk), _lib.ptr(gb))
+        _lib.call("nrc_dense_bwd", _lib.stream_ptr(), _lib.ptr(x2), ldx, _lib.ptr(kernel), _lib.ptr(g2), ldg, M, K, N,
+                  int(bf16), _lib.ptr(gx), K, 0, _lib.ptr(gk), _lib.ptr(gb))
         return (gx.reshape(xshape) if gx is not None else None), gk, gb, None, None
 
 
