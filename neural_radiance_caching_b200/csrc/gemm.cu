@@ -13,7 +13,7 @@
 namespace nrc {
 
 constexpr int BM = 128, BN = 64, BK = 32;
-constexpr int kGemmThreads = 128;
+constexpr int kGemmThreads = 256;   // 8 warps: 4 (M) x 2 (N), warp tile 32 x 32
 
 struct GemmArgs {
   const float* A; int64_t lda;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void add_colsum(const Loader& L, float (&cs)[4]) {
 // (or [BN][BK] when TRANS_B); ldmatrix(.trans) produces the fragments for every combination.
 // Global loads of chunk k+1 are issued into registers before the MMAs of chunk k.
 template <bool TRANS_A, bool TRANS_B>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_bf16_kernel(const GemmArgs g) {
   constexpr int kARows = TRANS_A ? BK : BM, kACols = TRANS_A ? BM : BK;
   constexpr int kBRows = TRANS_B ? BN : BK, kBCols = TRANS_B ? BK : BN;
@@ -131,16 +131,17 @@ gemm_bf16_kernel(const GemmArgs g) {
   __shared__ __align__(16) __nv_bfloat16 sB[kBRows * kBStride];
   __shared__ float s_colsum[BN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;   // warp tile origin inside the CTA tile
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int k_chunks = (g.K + BK - 1) / BK;
   const int per = (k_chunks + g.k_splits - 1) / g.k_splits;
   const int kc_begin = blockIdx.z * per, kc_end = min(k_chunks, kc_begin + per);
   const bool va = vec_ok(g.A, g.lda), vb = vec_ok(g.B, g.ldb);
-  float acc[2][8][4];
+  float acc[2][4][4];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
   float cs[4] = {0.f, 0.f, 0.f, 0.f};
@@ -167,14 +168,14 @@ gemm_bf16_kernel(const GemmArgs g) {
       uint32_t a[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        if constexpr (!TRANS_A) load_a_frag(a[mt], sA, kAStride, warp * 32 + mt * 16, ks * 16, lane);
-        else load_a_frag_trans(a[mt], sA, kAStride, ks * 16, warp * 32 + mt * 16, lane);
+        if constexpr (!TRANS_A) load_a_frag(a[mt], sA, kAStride, wm + mt * 16, ks * 16, lane);
+        else load_a_frag_trans(a[mt], sA, kAStride, ks * 16, wm + mt * 16, lane);
       }
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
+      for (int np = 0; np < 2; ++np) {
         uint32_t b[4];
-        if constexpr (!TRANS_B) load_b_frag2_trans(b, sB, kBStride, ks * 16, np * 16, lane);
-        else load_b_frag2(b, sB, kBStride, np * 16, ks * 16, lane);
+        if constexpr (!TRANS_B) load_b_frag2_trans(b, sB, kBStride, ks * 16, wn + np * 16, lane);
+        else load_b_frag2(b, sB, kBStride, wn + np * 16, ks * 16, lane);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           mma_bf16(acc[mt][2 * np], a[mt], b[0], b[1]);
@@ -187,10 +188,10 @@ gemm_bf16_kernel(const GemmArgs g) {
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        store_out(g, m0 + warp * 32 + mt * 16 + r + (e >= 2 ? 8 : 0), n0 + nt * 8 + cq + (e & 1), acc[mt][nt][e]);
+        store_out(g, m0 + wm + mt * 16 + r + (e >= 2 ? 8 : 0), n0 + wn + nt * 8 + cq + (e & 1), acc[mt][nt][e]);
   if (g.colsum && !TRANS_B && blockIdx.x == 0) {
     // bias gradient: the CTAs of the first M-tile row hold the column sums of their K range
     __syncthreads();
@@ -204,7 +205,7 @@ gemm_bf16_kernel(const GemmArgs g) {
 
 // ------------------------------------------------------------------------------ fp32 FFMA
 template <bool TRANS_A, bool TRANS_B>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_f32_kernel(const GemmArgs g) {
   constexpr int kARows = TRANS_A ? BK : BM, kACols = TRANS_A ? BM : BK;
   constexpr int kBRows = TRANS_B ? BN : BK, kBCols = TRANS_B ? BK : BN;
@@ -212,17 +213,17 @@ gemm_f32_kernel(const GemmArgs g) {
   __shared__ __align__(16) float sB[BK][BN + 4];   // [k][n]
   __shared__ float s_colsum[BN];
   const int tid = threadIdx.x;
-  const int ty = tid >> 3, tx = tid & 7;           // 16 x 8 threads, 8 x 8 outputs each
+  const int ty = tid >> 4, tx = tid & 15;          // 16 x 16 threads, 8 x 4 outputs each
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int k_chunks = (g.K + BK - 1) / BK;
   const int per = (k_chunks + g.k_splits - 1) / g.k_splits;
   const int kc_begin = blockIdx.z * per, kc_end = min(k_chunks, kc_begin + per);
   const bool va = vec_ok(g.A, g.lda), vb = vec_ok(g.B, g.ldb);
-  float acc[8][8];
+  float acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float cs[4] = {0.f, 0.f, 0.f, 0.f};
   if (tid < BN) s_colsum[tid] = 0.f;
   TileLoader<kARows, kACols> la;
@@ -244,21 +245,20 @@ gemm_f32_kernel(const GemmArgs g) {
     if (kc + 1 < kc_end) issue(kc + 1);
 #pragma unroll 8
     for (int kk = 0; kk < BK; ++kk) {
-      float a[8], b[8];
+      float a[8], b[4];
       *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sA[kk][ty * 8]);
       *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(&sA[kk][ty * 8 + 4]);
-      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&sB[kk][tx * 8]);
-      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&sB[kk][tx * 8 + 4]);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) store_out(g, m0 + ty * 8 + i, n0 + tx * 8 + j, acc[i][j]);
+    for (int j = 0; j < 4; ++j) store_out(g, m0 + ty * 8 + i, n0 + tx * 4 + j, acc[i][j]);
   if (g.colsum && !TRANS_B && blockIdx.x == 0) {
     __syncthreads();
     const int c = (tid % (BN / 4)) * 4;
