@@ -207,16 +207,18 @@ def run_b200(args):
     grads_flat = None
 
     def allreduce_grads():
-        # gradient all-reduce (mean) over tables + MLP weights, the reference's lax.pmean
-        # (internal/train_utils.py:3132-3136); one NCCL call per contiguous arena.
+        # gradient all-reduce (mean) over all tables + MLP weights, the reference's lax.pmean
+        # (internal/train_utils.py:3132-3136): ONE NCCL call over the flat gradient arena.
         if world == 1:
             return
-        for t in step_obj.leaves:
-            dist.all_reduce(t.grad, op=dist.ReduceOp.AVG)
+        dist.all_reduce(step_obj.flat_grad, op=dist.ReduceOp.AVG)
+
+    def compute_step():
+        rays, u01, extra = workload.unpack_rays(dbuf)
+        return step_obj.step(rays, u01, extra)
 
     def one_step():
-        rays, u01, extra = workload.unpack_rays(dbuf)
-        loss = step_obj.step(rays, u01, extra)
+        loss = compute_step()
         allreduce_grads()
         return loss
 
@@ -236,18 +238,14 @@ def run_b200(args):
         per_kernel = profile_calls(one_step, _lib)
 
     graph = torch.cuda.CUDAGraph()
-    use_graph = world == 1  # NCCL collectives are issued eagerly after the captured compute
-    if use_graph:
-        with torch.cuda.graph(graph):
-            static_loss = one_step()
-    else:
-        static_loss = None
+    use_graph = True  # compute is captured; the NCCL all-reduce is issued after each replay
+    with torch.cuda.graph(graph):
+        static_loss = compute_step()
 
     def run_step():
-        if use_graph:
-            graph.replay()
-            return static_loss
-        return one_step()
+        graph.replay()
+        allreduce_grads()
+        return static_loss
 
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
 

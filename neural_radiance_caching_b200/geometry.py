@@ -151,7 +151,11 @@ class _DensityQueryFn(torch.autograd.Function):
         g_g = c(g_gp, (P, 3)) if ctx.has[1] else None
         want_w = any(ctx.needs_input_grad[4:])
         want_t = ctx.needs_input_grad[3]
-        gflat = [torch.zeros_like(t) for t in flat] if want_w else None
+        gflat, w_sunk = None, False
+        if want_w:
+            sinks = [_lib.grad_sink(t) for t in flat]
+            w_sunk = all(s_ is not None for s_ in sinks)
+            gflat = sinks if w_sunk else [torch.zeros_like(t) for t in flat]
         gd = _grad_desc(mlp, mlp._unflatten(gflat)) if want_w else None
         g_enc = torch.empty_like(enc_out) if want_t else None
         desc = _mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals)
@@ -162,11 +166,16 @@ class _DensityQueryFn(torch.autograd.Function):
         if want_t:
             z = torch.empty_like(m2)
             _lib.call("nrc_contract_fwd", _lib.stream_ptr(), _lib.ptr(m2), P, float(mlp.warp_c), _lib.ptr(z))
-            g_arena = torch.zeros_like(arena)
+            t_sink = _lib.grad_sink(arena)
+            g_arena = t_sink if t_sink is not None else torch.zeros_like(arena)
             enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)),
                                        mlp.grid.tables(mlp.grid.views(g_arena)))
             _lib.call("nrc_encode_bwd", _lib.stream_ptr(), C.byref(enc), _lib.ptr(z), _lib.ptr(g_enc), P, None)
-        return (None, None, None, g_arena) + (tuple(gflat) if want_w else (None,) * len(flat))
+            if t_sink is not None:
+                g_arena = None
+        if w_sunk:
+            gflat = None
+        return (None, None, None, g_arena) + (tuple(gflat) if gflat is not None else (None,) * len(flat))
 
 
 class DensityMLP:

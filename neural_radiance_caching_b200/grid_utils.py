@@ -61,7 +61,11 @@ class _EncodeFn(torch.autograd.Function):
         g2 = g.reshape(-1, enc.num_outputs).contiguous()
         need_x = ctx.needs_input_grad[1]
         need_t = any(ctx.needs_input_grad[3:])
-        grads = [torch.zeros_like(t) for t in tables] if need_t else None
+        sunk = False
+        if need_t and ctx.use_arena and _lib.grad_sink(tables[0]) is not None:
+            grads, sunk = [_lib.grad_sink(tables[0])], True
+        else:
+            grads = [torch.zeros_like(t) for t in tables] if need_t else None
         if ctx.use_arena:
             levels = enc.tables(enc.views(tables[0]))
             glevels = enc.tables(enc.views(grads[0])) if need_t else None
@@ -72,7 +76,9 @@ class _EncodeFn(torch.autograd.Function):
         _lib.call("nrc_encode_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(x2), _lib.ptr(g2), x2.shape[0],
                   _lib.ptr(g_x))
         gx = g_x.reshape(ctx.x_shape) if need_x else None
-        return (None, gx, None) + (tuple(grads) if need_t else (None,) * len(tables))
+        if sunk:
+            grads = None   # accumulated into the registered sink
+        return (None, gx, None) + (tuple(grads) if grads is not None else (None,) * len(tables))
 
 
 class HashEncoding:

@@ -37,6 +37,7 @@ class _DenseFn(torch.autograd.Function):
         _lib.call("nrc_dense_fwd", _lib.stream_ptr(), _lib.ptr(x2), ldx, _lib.ptr(kernel), _lib.ptr(bias), M, K, N,
                   int(relu), int(bf16), _lib.ptr(y), N)
         ctx.save_for_backward(x2, kernel, y if relu else None)
+        ctx.bias_ref = bias
         ctx.meta = (x.shape, relu, bf16, ldx)
         return y.reshape(x.shape[:-1] + (N,))
 
@@ -54,10 +55,18 @@ class _DenseFn(torch.autograd.Function):
         g2, ldg = _pad4(g2)
         gx = torch.empty((M, K), device=g.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        gk = torch.zeros_like(kernel) if want_w else None
-        gb = torch.zeros((N,), device=g.device, dtype=torch.float32) if want_w else None
+        gk = gb = None
+        sunk = False
+        if want_w:
+            gk, gb = _lib.grad_sink(kernel), _lib.grad_sink(ctx.bias_ref)
+            sunk = gk is not None and gb is not None
+            if not sunk:
+                gk = torch.zeros_like(kernel)
+                gb = torch.zeros((N,), device=g.device, dtype=torch.float32)
         _lib.call("nrc_dense_bwd", _lib.stream_ptr(), _lib.ptr(x2), ldx, _lib.ptr(kernel), _lib.ptr(g2), ldg, M, K, N,
                   int(bf16), _lib.ptr(gx), K, 0, _lib.ptr(gk), _lib.ptr(gb))
+        if sunk:
+            gk = gb = None   # accumulated into the registered sinks
         return (gx.reshape(xshape) if gx is not None else None), gk, gb, None, None
 
 

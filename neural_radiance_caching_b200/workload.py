@@ -123,13 +123,27 @@ class CacheTrainStep:
             "output_integrated_brdf_layer": layer(64, 1), "SurfaceLightField": slf(200), "EnvMap": slf(38),
         }
         self.params = {"Sampler": sampler, "Shader": shader}
+        # One flat gradient arena for every parameter on the path: a single memset per step, a
+        # single NCCL all-reduce under data parallelism (the reference's lax.pmean over the grad
+        # pytree, internal/train_utils.py:3132-3136).  The kernels accumulate straight into it.
+        from . import _lib
+        align = 64  # floats: every sink starts 256-byte aligned (the kernels use 16-byte vector atomics)
+        pad = lambda n: (n + align - 1) // align * align
+        total = sum(pad(int(t.numel())) for t in self.leaves)
+        self.flat_grad = torch.zeros(total, device=device, dtype=torch.float32)
+        off = 0
+        for t in self.leaves:
+            n = int(t.numel())
+            sink = self.flat_grad[off:off + n].view(t.shape)
+            _lib.register_grad_sink(t, sink)
+            t.grad = sink
+            off += pad(n)
 
     def num_params(self):
         return sum(int(t.numel()) for t in self.leaves)
 
     def zero_grad(self):
-        for t in self.leaves:
-            t.grad = None
+        self.flat_grad.zero_()
 
     def step(self, rays, u01, target_rgb):
         """Forward + loss + backward of one ray batch; returns the loss (device scalar)."""
