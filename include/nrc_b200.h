@@ -254,6 +254,95 @@ int32_t nrc_ide_bwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32
                     const float* d_kappa_inv, const float* d_g_out, int64_t ldg, int64_t num_points,
                     float* d_g_xyz, float* d_g_kappa_inv);
 
+/* ------------------------------- fused MLP chains on tcgen05 tensor cores ---- */
+/* The Dense stacks of the cache shader / material / light-field MLPs
+ * (internal/nerf.py:232-345,561-689, internal/surface_light_field.py:352-403,480-500,
+ * internal/material.py:2073-2123) executed per 128-point tile as one PROGRAM, activations
+ * staying in shared memory (bf16, 128-byte-swizzled 128x64 "atoms") and accumulators in
+ * tensor memory.  Used for the forward pass and, with transposed weights and ReLU masks, for
+ * the data-gradient pass; nrc_chain_wgrad turns the saved tile images into weight gradients.
+ *
+ * Pointer table: every device pointer an op refers to is an index into `d_ptrs` (host array of
+ * device pointers, copied at launch).  A "tile image" is a bf16 buffer
+ * [ceil(rows/128)][img_atoms][16384 bytes] holding whole atoms in their shared-memory layout. */
+#define NRC_CHAIN_MAX_OPS 24
+#define NRC_CHAIN_MAX_PTRS 24
+#define NRC_CHAIN_MAX_ATOMS 8
+#define NRC_PACK_MAX_ENTRIES 64
+#define NRC_WGRAD_MAX_LAYERS 8
+#define NRC_WGRAD_MAX_X_ATOMS 6
+#define NRC_WGRAD_MAX_SEGS 5
+
+typedef enum { NRC_OP_LOAD = 0, NRC_OP_GEMM = 1, NRC_OP_EPI = 2, NRC_OP_SAVE = 3 } nrc_chain_op_kind_t;
+#define NRC_GEMM_ACCUMULATE 1     /* accumulate onto the accumulator's current contents (skip VJP) */
+#define NRC_EPI_RELU 1            /* max(0, .) after the bias                                      */
+#define NRC_EPI_OUT_ACCUMULATE 2  /* fp32 output: += instead of =                                  */
+
+typedef struct {
+  int32_t kind;       /* nrc_chain_op_kind_t                                                       */
+  int32_t slot;       /* LOAD/EPI/SAVE: first atom slot (EPI: -1 = no bf16 result)                 */
+  int32_t ptr;        /* LOAD: fp32 source (-1 = zeros); EPI: bias [ncols] or -1; SAVE: tile image  */
+  int32_t ld;         /* LOAD: source row stride; EPI: fp32 output row stride (floats)             */
+  int32_t col0;       /* LOAD: first destination column (x8); EPI: first output column;            */
+                      /* SAVE: first atom inside the image                                         */
+  int32_t ncols;      /* LOAD: source columns; EPI: valid result columns                           */
+  int32_t npad;       /* LOAD: columns written, zero padded (x8); EPI: columns processed (x16);    */
+                      /* SAVE: number of atoms                                                     */
+  int32_t tmem_col;   /* GEMM/EPI: first accumulator column (0..255, per context)                  */
+  int32_t n;          /* GEMM: N (x16, <= 128)                                                     */
+  int32_t flags;      /* NRC_GEMM_* / NRC_EPI_*                                                    */
+  int32_t out_ptr;    /* EPI: fp32 output matrix or -1                                             */
+  int32_t mask_ptr;   /* EPI: tile image of the forward activation; result zeroed where it is <= 0 */
+  int32_t mask_atom0; /* EPI: first atom of that activation inside the image                       */
+  int32_t img_atoms;  /* SAVE / EPI mask: atoms per tile of the image                              */
+  int32_t w_chunk;    /* GEMM: first 16 KB chunk of the packed weight image (one per K atom)       */
+  int32_t n_atoms;    /* GEMM: number of K atoms                                                   */
+  uint8_t a_slot[NRC_CHAIN_MAX_ATOMS];  /* GEMM: slot holding each K atom                          */
+  uint8_t a_klen[NRC_CHAIN_MAX_ATOMS];  /* GEMM: K extent used in each atom (x16, <= 64)           */
+} nrc_chain_op_t;
+
+typedef struct {
+  int32_t num_ops;
+  int32_t slots_per_ctx;   /* atom slots per tile context (2 contexts per CTA), 1..7 */
+  nrc_chain_op_t ops[NRC_CHAIN_MAX_OPS];
+} nrc_chain_program_t;
+
+/* One rectangular piece of a Flax kernel [in,out] (row stride ld) written into a 16 KB chunk:
+ *   transpose == 0: chunk[n0+n][k0+k] = W[row0+k][col0+n]  (forward: B = kernel^T, K = in)
+ *   transpose == 1: chunk[n0+n][k0+k] = W[row0+n][col0+k]  (data gradient: B = kernel, K = out)
+ * with n < (transpose ? nrows : ncols) and k < (transpose ? ncols : nrows). */
+typedef struct {
+  int32_t ptr, ld, row0, nrows, col0, ncols, chunk, n0, k0, transpose;
+} nrc_pack_entry_t;
+
+/* One Dense layer's weight gradient: kernel rows are gathered from up to 6 X atoms (skip
+ * connections concatenate atoms of two images), columns are split into up to 5 segments so
+ * that several reference layers sharing one input (shader heads) are one GEMM. */
+typedef struct {
+  int32_t n_x_atoms;
+  int32_t x_ptr[NRC_WGRAD_MAX_X_ATOMS];        /* tile image holding the atom                  */
+  int32_t x_img_atoms[NRC_WGRAD_MAX_X_ATOMS];  /* atoms per tile of that image                 */
+  int32_t x_atom[NRC_WGRAD_MAX_X_ATOMS];       /* atom index inside the image                  */
+  int32_t x_rows[NRC_WGRAD_MAX_X_ATOMS];       /* valid input features in the atom (<= 64)     */
+  int32_t w_row0[NRC_WGRAD_MAX_X_ATOMS];       /* kernel row of the atom's first feature       */
+  int32_t dy_ptr, dy_img_atoms, dy_atom0;      /* pre-activation gradient image                */
+  int32_t n;                                   /* columns of dY processed (x16, <= 128)        */
+  int32_t n_seg;
+  int32_t seg_col0[NRC_WGRAD_MAX_SEGS], seg_ncols[NRC_WGRAD_MAX_SEGS];
+  int32_t seg_w_ptr[NRC_WGRAD_MAX_SEGS];       /* fp32 [in, seg_ncols] gradient, accumulated   */
+  int32_t seg_b_ptr[NRC_WGRAD_MAX_SEGS];       /* fp32 [seg_ncols] bias gradient or -1         */
+} nrc_wgrad_layer_t;
+
+/* Run `prog` over ceil(num_rows/128) tiles.  d_weights_packed: chunks from nrc_chain_pack_weights. */
+int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
+                      const void* d_weights_packed, int64_t num_rows);
+/* (Re)build the packed bf16 weight image (num_chunks * 16 KB, zero filled first). */
+int32_t nrc_chain_pack_weights(void* stream, const nrc_pack_entry_t* entries, int32_t num_entries,
+                               void* const* d_ptrs, int32_t num_ptrs, void* d_packed, int32_t num_chunks);
+/* dW += X^T dY, db += 1^T dY for `num_layers` layers from saved tile images. */
+int32_t nrc_chain_wgrad(void* stream, const nrc_wgrad_layer_t* layers, int32_t num_layers,
+                        void* const* d_ptrs, int32_t num_ptrs, int64_t num_rows);
+
 /* ------------------------------------------------- K5: GGX integration ---- */
 /* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) +
  * integrate_reflect_rays (:1102-1193): Disney-GGX D*F*G and Lambert lobes evaluated in the

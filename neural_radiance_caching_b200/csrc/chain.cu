@@ -1,0 +1,625 @@
+// Fused MLP chains of the cache shader on the 5th-generation
+// tensor cores: tcgen05.mma with accumulators in tensor memory, operands in 128-byte-swizzled
+// shared-memory atoms (tc05.cuh), weights streamed by bulk async copies through an mbarrier ring.
+//
+// A chain is a small PROGRAM interpreted per 128-point tile (nrc_chain_program_t):
+//   LOAD  fp32 rows from global memory -> bf16 atom slots (concatenation = several LOADs)
+//   GEMM  D[tmem] (+)= A[slots] * W[packed chunks]            (consecutive GEMMs form a group)
+//   EPI   D -> (+bias, ReLU | ReLU-mask) -> bf16 atom slots and / or fp32 global output
+//   SAVE  atom slots -> global "tile image" (kept for the backward pass / weight gradients)
+// so that a whole MLP (all layers, skip connections as extra K atoms, forward or data-gradient)
+// runs without its activations leaving the SM.  Reference bodies replaced: flax.linen.Dense stacks of
+// internal/nerf.py:232-345,561-689, internal/surface_light_field.py:352-403,480-500,
+// internal/geometry.py:127-168, internal/material.py:2073-2123.
+//
+// Roles inside a CTA (320 threads, 1 CTA / SM, persistent over tile pairs):
+//   warp 0      weight producer  (cp.async.bulk global -> ring, one elected lane)
+//   warp 1      UMMA issuer      (one elected lane)
+//   warps 2-5   epilogue / loader warpgroup of context 0   (TMEM lane quadrant = warp % 4)
+//   warps 6-9   epilogue / loader warpgroup of context 1
+// Two contexts = two independent tiles in flight: while one context's warpgroup drains its
+// accumulator (TMEM -> registers -> bf16 -> shared memory), the tensor core runs the other
+// context's layer.
+#include <cuda_bf16.h>
+
+#include "nrc_common.cuh"
+#include "tc05.cuh"
+
+namespace nrc {
+using namespace tc;
+
+constexpr int kChainThreads = 320;
+constexpr int kCtxTmemCols = 256;
+
+struct ChainParams {
+  nrc_chain_program_t prog;
+  void* ptrs[NRC_CHAIN_MAX_PTRS];
+  const uint8_t* weights;
+  int64_t num_rows;
+  int32_t num_tiles;
+  int32_t ring_stages;
+};
+
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[16];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.prog.slots_per_ctx, R = p.ring_stages, nops = p.prog.num_ops;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring_base = base + 2u * S * kAtomBytes;
+  auto slot_addr = [&](int ctx, int s) { return base + static_cast<uint32_t>(ctx * S + s) * kAtomBytes; };
+  // barriers: [0,R) full, [4,4+R) empty, 8+c a_ready, 10+c acc_ready
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto a_ready = [&](int c) { return bar0 + 8u * (8 + c); };
+  auto acc_ready = [&](int c) { return bar0 + 8u * (10 + c); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int c = 0; c < 2; ++c) {
+      mbar_init(a_ready(c), 128);
+      mbar_init(acc_ready(c), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int num_pairs = (p.num_tiles + 1) >> 1;
+
+  if (warp == 0) {
+    // ===================================================================== weight producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int q = blockIdx.x; q < num_pairs; q += gridDim.x) {
+        for (int i = 0; i < nops;) {
+          if (p.prog.ops[i].kind != NRC_OP_GEMM) { ++i; continue; }
+          int j = i;
+          while (j < nops && p.prog.ops[j].kind == NRC_OP_GEMM) ++j;
+          for (int c = 0; c < 2; ++c) {
+            if (2 * q + c >= p.num_tiles) continue;
+            for (int o = i; o < j; ++o) {
+              const nrc_chain_op_t& op = p.prog.ops[o];
+              const uint32_t bytes = static_cast<uint32_t>(op.n) * 128u;
+              for (int a = 0; a < op.n_atoms; ++a) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_arrive_expect_tx(full_bar(stage), bytes);
+                bulk_g2s(ring_base + static_cast<uint32_t>(stage) * kAtomBytes,
+                         p.weights + static_cast<size_t>(op.w_chunk + a) * kAtomBytes, bytes, full_bar(stage));
+                if (++stage == R) { stage = 0; phase ^= 1u; }
+              }
+            }
+          }
+          i = j;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== UMMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t a_par[2] = {0u, 0u};
+      for (int q = blockIdx.x; q < num_pairs; q += gridDim.x) {
+        for (int i = 0; i < nops;) {
+          if (p.prog.ops[i].kind != NRC_OP_GEMM) { ++i; continue; }
+          int j = i;
+          while (j < nops && p.prog.ops[j].kind == NRC_OP_GEMM) ++j;
+          for (int c = 0; c < 2; ++c) {
+            if (2 * q + c >= p.num_tiles) continue;
+            mbar_wait(a_ready(c), a_par[c]);
+            a_par[c] ^= 1u;
+            tc_fence_after();
+            for (int o = i; o < j; ++o) {
+              const nrc_chain_op_t& op = p.prog.ops[o];
+              const uint32_t idesc = make_idesc(128, op.n, 0, 0);
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
+              for (int a = 0; a < op.n_atoms; ++a) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t a_addr = slot_addr(c, op.a_slot[a]);
+                const uint32_t b_addr = ring_base + static_cast<uint32_t>(stage) * kAtomBytes;
+                const int nk = op.a_klen[a] >> 4;
+                for (int k = 0; k < nk; ++k) {
+                  const uint32_t acc = ((op.flags & NRC_GEMM_ACCUMULATE) || a > 0 || k > 0) ? 1u : 0u;
+                  umma_bf16(d_tmem, kmajor_desc(a_addr, k), kmajor_desc(b_addr, k), idesc, acc);
+                }
+                umma_commit(empty_bar(stage));
+                if (++stage == R) { stage = 0; phase ^= 1u; }
+              }
+            }
+            umma_commit(acc_ready(c));
+          }
+          i = j;
+        }
+      }
+    }
+  } else {
+    // ===================================================================== loader / epilogue warpgroups
+    const int c = (warp - 2) >> 2;                 // context
+    const int wg_tid = threadIdx.x - 64 - 128 * c;
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;                // tile row owned in epilogues
+    const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
+    uint32_t acc_par = 0;
+    bool store_pending = false;
+
+    auto guard_slots = [&]() {  // before overwriting slots a bulk store may still be reading
+      if (store_pending) {
+        if (wg_tid == 0) bulk_wait_read0();
+        named_barrier_sync(1 + c, 128);
+        store_pending = false;
+      }
+    };
+
+    for (int q = blockIdx.x; q < num_pairs; q += gridDim.x) {
+      const int tile = 2 * q + c;
+      if (tile >= p.num_tiles) continue;
+      const int64_t row0 = static_cast<int64_t>(tile) * 128;
+      for (int i = 0; i < nops;) {
+        const nrc_chain_op_t& op = p.prog.ops[i];
+        if (op.kind == NRC_OP_GEMM) {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(a_ready(c));
+          while (i < nops && p.prog.ops[i].kind == NRC_OP_GEMM) ++i;
+          mbar_wait(acc_ready(c), acc_par);
+          acc_par ^= 1u;
+          tc_fence_after();
+          continue;
+        }
+        if (op.kind == NRC_OP_LOAD) {
+          guard_slots();
+          const float* src = op.ptr >= 0 ? static_cast<const float*>(p.ptrs[op.ptr]) : nullptr;
+          const int nch = op.npad >> 3;
+          const bool vec = src && (op.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+          for (int item = wg_tid; item < 128 * nch; item += 128) {
+            const int rr = item / nch, ch = item - rr * nch;
+            const int col = ch * 8;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            if (src && row0 + rr < p.num_rows && col < op.ncols) {
+              const float* s = src + (row0 + rr) * op.ld + col;
+              if (vec && col + 8 <= op.ncols) {
+                const float4 x0 = __ldg(reinterpret_cast<const float4*>(s));
+                const float4 x1 = __ldg(reinterpret_cast<const float4*>(s) + 1);
+                v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+                v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (col + e < op.ncols) v[e] = __ldg(s + e);
+              }
+            }
+            const int dcol = op.col0 + col;
+            const uint32_t dst = slot_addr(c, op.slot + (dcol >> 6)) + atom_chunk_offset(rr, (dcol & 63) >> 3);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack2_bf16(v[0], v[1])),
+                         "r"(pack2_bf16(v[2], v[3])), "r"(pack2_bf16(v[4], v[5])), "r"(pack2_bf16(v[6], v[7]))
+                         : "memory");
+          }
+        } else if (op.kind == NRC_OP_SAVE) {
+          fence_proxy_async_smem();
+          named_barrier_sync(1 + c, 128);
+          if (wg_tid == 0) {
+            uint8_t* img = static_cast<uint8_t*>(p.ptrs[op.ptr]);
+            for (int a = 0; a < op.npad; ++a)
+              bulk_s2g(img + (static_cast<size_t>(tile) * op.img_atoms + op.col0 + a) * kAtomBytes,
+                       slot_addr(c, op.slot + a), kAtomBytes);
+            bulk_commit();
+          }
+          store_pending = true;
+        } else {  // NRC_OP_EPI
+          if (op.slot >= 0) guard_slots();
+          const float* bias = op.ptr >= 0 ? static_cast<const float*>(p.ptrs[op.ptr]) : nullptr;
+          float* out = op.out_ptr >= 0 ? static_cast<float*>(p.ptrs[op.out_ptr]) : nullptr;
+          const uint8_t* mask = op.mask_ptr >= 0 ? static_cast<const uint8_t*>(p.ptrs[op.mask_ptr]) : nullptr;
+          const bool row_ok = row0 + r < p.num_rows;
+          const bool out_vec = out && (op.ld % 4 == 0) && (op.col0 % 4 == 0) &&
+                               ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+          const uint32_t taddr = tmem_base + t_lane + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
+          for (int j0 = 0; j0 < op.npad; j0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + j0, v);
+            uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+            if (mask) {
+              const int mc = op.mask_atom0 * 64 + j0;
+              const uint8_t* ma = mask + (static_cast<size_t>(tile) * op.img_atoms + (mc >> 6)) * kAtomBytes;
+              m0 = __ldg(reinterpret_cast<const uint4*>(ma + atom_chunk_offset(r, (mc & 63) >> 3)));
+              m1 = __ldg(reinterpret_cast<const uint4*>(ma + atom_chunk_offset(r, ((mc & 63) >> 3) + 1)));
+            }
+            tmem_ld_wait();
+            float x[16];
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float t = __uint_as_float(v[e]);
+              const int j = j0 + e;
+              if (bias && j < op.ncols) t += __ldg(bias + j);
+              if (op.flags & NRC_EPI_RELU) t = fmaxf(t, 0.f);
+              if (mask) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t h = (mw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+                if ((h & 0x8000u) || (h & 0x7FFFu) == 0u) t = 0.f;
+              }
+              if (j >= op.ncols) t = 0.f;
+              x[e] = t;
+            }
+            if (op.slot >= 0) {
+              const uint32_t d0 = slot_addr(c, op.slot + (j0 >> 6)) + atom_chunk_offset(r, (j0 & 63) >> 3);
+              const uint32_t d1 = slot_addr(c, op.slot + (j0 >> 6)) + atom_chunk_offset(r, ((j0 & 63) >> 3) + 1);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d0), "r"(pack2_bf16(x[0], x[1])),
+                           "r"(pack2_bf16(x[2], x[3])), "r"(pack2_bf16(x[4], x[5])), "r"(pack2_bf16(x[6], x[7]))
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d1), "r"(pack2_bf16(x[8], x[9])),
+                           "r"(pack2_bf16(x[10], x[11])), "r"(pack2_bf16(x[12], x[13])),
+                           "r"(pack2_bf16(x[14], x[15]))
+                           : "memory");
+            }
+            if (out && row_ok && j0 < op.ncols) {
+              float* o = out + (row0 + r) * op.ld + op.col0 + j0;
+              const bool accum = (op.flags & NRC_EPI_OUT_ACCUMULATE) != 0;
+              if (out_vec && j0 + 16 <= op.ncols) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                  float4 w = make_float4(x[e], x[e + 1], x[e + 2], x[e + 3]);
+                  if (accum) {
+                    const float4 old = *reinterpret_cast<const float4*>(o + e);
+                    w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(o + e) = w;
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if (j0 + e < op.ncols) o[e] = accum ? o[e] + x[e] : x[e];
+              }
+            }
+          }
+        }
+        ++i;
+      }
+    }
+    if (wg_tid == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: fp32 Flax kernels [in,out] -> bf16 16 KB chunks in the swizzled K-major atom
+// layout, chunk[n][k]:
+//   transpose == 0 : chunk[n0+n][k0+k] = W[row0+k][col0+n]   (forward, B = W^T)
+//   transpose == 1 : chunk[n0+n][k0+k] = W[row0+n][col0+k]   (data gradient, B = W)
+struct PackParams {
+  nrc_pack_entry_t e[NRC_PACK_MAX_ENTRIES];
+  void* ptrs[NRC_CHAIN_MAX_PTRS];
+  uint8_t* packed;
+};
+
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackParams p) {
+  const nrc_pack_entry_t& e = p.e[blockIdx.x];
+  const float* W = static_cast<const float*>(p.ptrs[e.ptr]);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.packed + static_cast<size_t>(e.chunk) * kAtomBytes);
+  const int nn = e.transpose ? e.nrows : e.ncols;   // destination rows
+  const int nk = e.transpose ? e.ncols : e.nrows;   // destination k extent
+  for (int idx = threadIdx.x; idx < nn * nk; idx += blockDim.x) {
+    int n, k;
+    float w;
+    if (e.transpose) {   // source row-major [n][k]: k fastest for coalesced reads
+      n = idx / nk; k = idx - n * nk;
+      w = W[static_cast<size_t>(e.row0 + n) * e.ld + e.col0 + k];
+    } else {             // source [k][n]: n fastest
+      k = idx / nn; n = idx - k * nn;
+      w = W[static_cast<size_t>(e.row0 + k) * e.ld + e.col0 + n];
+    }
+    const int dn = e.n0 + n, dk = e.k0 + k;
+    dst[(atom_chunk_offset(dn, dk >> 3) >> 1) + (dk & 7)] = __float2bfloat16_rn(w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradients dW[in,out] += X^T dY and db[out] += 1^T dY over all points, from the bf16 tile
+// images the forward (X) and data-gradient (dY) chains saved.  Both operands are read MN-major
+// straight from the [point][feature] atoms (no transpose anywhere).  One CTA = (layer, tile range);
+// accumulators for every 128-feature pair of X atoms (+ one for the bias, A = ones) live in TMEM over
+// the whole range and are flushed once with vector reductions into the fp32 gradient sinks.
+struct WgradParams {
+  nrc_wgrad_layer_t layers[NRC_WGRAD_MAX_LAYERS];
+  void* ptrs[NRC_CHAIN_MAX_PTRS];
+  int32_t num_tiles;
+  int32_t tiles_per_cta;
+};
+
+constexpr int kWgradThreads = 192;   // warp 0 producer, warp 1 UMMA issuer, warps 2-5 flush
+constexpr int kWgradRingAtoms = 12;
+
+__global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[16];
+  __shared__ uint32_t tmem_base_s;
+
+  const nrc_wgrad_layer_t& L = p.layers[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(p.num_tiles, t_begin + p.tiles_per_cta);
+  const int nB = (L.n + 63) >> 6;                       // dY atoms
+  const int nXp = (L.n_x_atoms + 1) & ~1;               // X atoms padded to whole pairs
+  const int G = ((nB + 1) & ~1) + nXp;                  // atoms per stage (pairs stay adjacent)
+  const int R = min(4, kWgradRingAtoms / G);            // stages
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ones_addr = base;                      // one atom of bf16 1.0
+  const uint32_t ring_base = base + kAtomBytes;
+  auto stage_addr = [&](int s) { return ring_base + static_cast<uint32_t>(s * G) * kAtomBytes; };
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (4 + s); };
+  const uint32_t done_bar = bar0 + 8u * 8;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < kAtomBytes / 4; i += blockDim.x)
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ones_addr + 4u * i), "r"(0x3F803F80u) : "memory");
+  fence_proxy_async_smem();
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int n_pairs = nXp >> 1;
+  const int Npad = L.n;                                  // multiple of 16
+
+  if (t_begin < t_end) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(nB + L.n_x_atoms) * kAtomBytes);
+          const uint32_t sa = stage_addr(stage);
+          const uint8_t* dy = static_cast<const uint8_t*>(p.ptrs[L.dy_ptr]);
+          for (int a = 0; a < nB; ++a)
+            bulk_g2s(sa + static_cast<uint32_t>(a) * kAtomBytes,
+                     dy + (static_cast<size_t>(t) * L.dy_img_atoms + L.dy_atom0 + a) * kAtomBytes, kAtomBytes,
+                     full_bar(stage));
+          for (int a = 0; a < L.n_x_atoms; ++a) {
+            const uint8_t* x = static_cast<const uint8_t*>(p.ptrs[L.x_ptr[a]]);
+            bulk_g2s(sa + static_cast<uint32_t>(((nB + 1) & ~1) + a) * kAtomBytes,
+                     x + (static_cast<size_t>(t) * L.x_img_atoms[a] + L.x_atom[a]) * kAtomBytes, kAtomBytes,
+                     full_bar(stage));
+          }
+          if (++stage == R) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t idesc = make_idesc(128, Npad, 1, 1);
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = stage_addr(stage);
+          const uint32_t b_addr = sa;
+          const uint32_t x_addr = sa + static_cast<uint32_t>((nB + 1) & ~1) * kAtomBytes;
+          const uint32_t first = (t == t_begin) ? 0u : 1u;
+          for (int pr = 0; pr < n_pairs; ++pr)
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem_base + static_cast<uint32_t>(pr * Npad),
+                        mnmajor_desc(x_addr + static_cast<uint32_t>(2 * pr) * kAtomBytes, k, kAtomBytes),
+                        mnmajor_desc(b_addr, k, kAtomBytes), idesc, (first | (k > 0)) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)   // bias gradient: ones^T dY
+            umma_bf16(tmem_base + static_cast<uint32_t>(n_pairs * Npad), mnmajor_desc(ones_addr, k, 0),
+                      mnmajor_desc(b_addr, k, kAtomBytes), idesc, (first | (k > 0)) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == R) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(done_bar);
+      }
+    } else {
+      // ------------------------------------------------------------------ flush
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;
+      const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      for (int pr = 0; pr <= n_pairs; ++pr) {
+        const bool is_bias = pr == n_pairs;
+        const int atom = 2 * pr + (r >> 6);
+        const int fr = r & 63;
+        const bool row_ok = is_bias ? (r == 0) : (atom < L.n_x_atoms && fr < L.x_rows[atom]);
+        const int krow = (!is_bias && atom < L.n_x_atoms) ? L.w_row0[atom] + fr : 0;
+        for (int j0 = 0; j0 < Npad; j0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + t_lane + static_cast<uint32_t>(pr * Npad + j0), v);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          for (int sgi = 0; sgi < L.n_seg; ++sgi) {
+            const int c0 = L.seg_col0[sgi], nc = L.seg_ncols[sgi];
+            const int pidx = is_bias ? L.seg_b_ptr[sgi] : L.seg_w_ptr[sgi];
+            if (pidx < 0) continue;
+            float* g = static_cast<float*>(p.ptrs[pidx]) + (is_bias ? 0 : static_cast<size_t>(krow) * nc);
+            const int lo = max(j0, c0), hi = min(j0 + 16, c0 + nc);
+            if (lo >= hi) continue;
+            if (hi - lo == 16 && ((nc & 3) == 0) && (((lo - c0) & 3) == 0) &&
+                ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+#pragma unroll
+              for (int e = 0; e < 16; e += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + (lo - c0) + e),
+                             "f"(__uint_as_float(v[e])), "f"(__uint_as_float(v[e + 1])),
+                             "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int j = j0 + e;
+                if (j >= lo && j < hi) atomicAdd(g + (j - c0), __uint_as_float(v[e]));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace nrc
+
+// ================================================================================================
+using namespace nrc;
+
+static int32_t validate_program(const nrc_chain_program_t* prog, int32_t num_ptrs) {
+  if (!prog || prog->num_ops < 1 || prog->num_ops > NRC_CHAIN_MAX_OPS) return NRC_E_INVALID_ARG;
+  const int S = prog->slots_per_ctx;
+  if (S < 1 || S > 7) return NRC_E_INVALID_ARG;
+  auto ptr_ok = [&](int32_t i, bool optional) { return (optional && i < 0) || (i >= 0 && i < num_ptrs); };
+  for (int i = 0; i < prog->num_ops; ++i) {
+    const nrc_chain_op_t& op = prog->ops[i];
+    switch (op.kind) {
+      case NRC_OP_LOAD:
+        if (!ptr_ok(op.ptr, true) || op.slot < 0 || (op.col0 & 7) || (op.npad & 7) || op.npad < op.ncols ||
+            op.npad <= 0 || op.slot + ((op.col0 + op.npad + 63) >> 6) > S)
+          return NRC_E_INVALID_ARG;
+        break;
+      case NRC_OP_GEMM:
+        if (op.n < 16 || op.n > 128 || (op.n & 15) || op.n_atoms < 1 || op.n_atoms > NRC_CHAIN_MAX_ATOMS ||
+            op.tmem_col < 0 || op.tmem_col + op.n > 256 || op.w_chunk < 0)
+          return NRC_E_INVALID_ARG;
+        for (int a = 0; a < op.n_atoms; ++a)
+          if (op.a_slot[a] >= S || op.a_klen[a] < 16 || op.a_klen[a] > 64 || (op.a_klen[a] & 15)) return NRC_E_INVALID_ARG;
+        break;
+      case NRC_OP_EPI:
+        if (op.npad <= 0 || (op.npad & 15) || op.ncols > op.npad || op.tmem_col < 0 || op.tmem_col + op.npad > 256 ||
+            !ptr_ok(op.ptr, true) || !ptr_ok(op.out_ptr, true) || !ptr_ok(op.mask_ptr, true) ||
+            (op.slot >= 0 && op.slot + ((op.npad + 63) >> 6) > S))
+          return NRC_E_INVALID_ARG;
+        break;
+      case NRC_OP_SAVE:
+        if (!ptr_ok(op.ptr, false) || op.slot < 0 || op.npad < 1 || op.slot + op.npad > S || op.col0 < 0 ||
+            op.col0 + op.npad > op.img_atoms)
+          return NRC_E_INVALID_ARG;
+        break;
+      default:
+        return NRC_E_INVALID_ARG;
+    }
+  }
+  return NRC_OK;
+}
+
+extern "C" int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
+                                 const void* d_weights_packed, int64_t num_rows) {
+  if (!d_ptrs || num_ptrs < 0 || num_ptrs > NRC_CHAIN_MAX_PTRS || num_rows < 0) return NRC_E_INVALID_ARG;
+  const int32_t st = validate_program(prog, num_ptrs);
+  if (st != NRC_OK) return st;
+  if (num_rows == 0) return NRC_OK;
+  static thread_local ChainParams hp;
+  hp.prog = *prog;
+  for (int i = 0; i < NRC_CHAIN_MAX_PTRS; ++i) hp.ptrs[i] = i < num_ptrs ? d_ptrs[i] : nullptr;
+  hp.weights = static_cast<const uint8_t*>(d_weights_packed);
+  hp.num_rows = num_rows;
+  hp.num_tiles = static_cast<int32_t>((num_rows + 127) / 128);
+  const int S = prog->slots_per_ctx;
+  const int max_atoms = (227 * 1024 - 2048) / kAtomBytes;   // 14
+  int R = max_atoms - 2 * S;
+  if (R < 1) return NRC_E_UNSUPPORTED;
+  if (R > 4) R = 4;
+  hp.ring_stages = R;
+  const size_t smem = static_cast<size_t>(2 * S + R) * kAtomBytes + 1024;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+      return check_launch();
+    attr_set = true;
+  }
+  const int pairs = (hp.num_tiles + 1) / 2;
+  const int grid = pairs < kNumSMs ? pairs : kNumSMs;
+  chain_kernel<<<grid, kChainThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_chain_pack_weights(void* stream, const nrc_pack_entry_t* entries, int32_t num_entries,
+                                          void* const* d_ptrs, int32_t num_ptrs, void* d_packed, int32_t num_chunks) {
+  if (!entries || num_entries < 1 || num_entries > NRC_PACK_MAX_ENTRIES || !d_ptrs || num_ptrs < 1 ||
+      num_ptrs > NRC_CHAIN_MAX_PTRS || !d_packed || num_chunks < 1)
+    return NRC_E_INVALID_ARG;
+  static thread_local PackParams hp;
+  for (int i = 0; i < num_entries; ++i) {
+    const nrc_pack_entry_t& e = entries[i];
+    const int nn = e.transpose ? e.nrows : e.ncols, nk = e.transpose ? e.ncols : e.nrows;
+    if (e.ptr < 0 || e.ptr >= num_ptrs || e.chunk < 0 || e.chunk >= num_chunks || e.n0 < 0 || e.k0 < 0 || nn < 1 ||
+        nk < 1 || e.n0 + nn > 128 || e.k0 + nk > 64)
+      return NRC_E_INVALID_ARG;
+    hp.e[i] = e;
+  }
+  for (int i = 0; i < NRC_CHAIN_MAX_PTRS; ++i) hp.ptrs[i] = i < num_ptrs ? d_ptrs[i] : nullptr;
+  hp.packed = static_cast<uint8_t*>(d_packed);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(d_packed, 0, static_cast<size_t>(num_chunks) * kAtomBytes, s) != cudaSuccess) return check_launch();
+  pack_kernel<<<num_entries, 256, 0, s>>>(hp);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_chain_wgrad(void* stream, const nrc_wgrad_layer_t* layers, int32_t num_layers,
+                                   void* const* d_ptrs, int32_t num_ptrs, int64_t num_rows) {
+  if (!layers || num_layers < 1 || num_layers > NRC_WGRAD_MAX_LAYERS || !d_ptrs || num_ptrs < 1 ||
+      num_ptrs > NRC_CHAIN_MAX_PTRS || num_rows < 0)
+    return NRC_E_INVALID_ARG;
+  if (num_rows == 0) return NRC_OK;
+  static thread_local WgradParams hp;
+  auto ok = [&](int32_t i) { return i >= 0 && i < num_ptrs; };
+  for (int l = 0; l < num_layers; ++l) {
+    const nrc_wgrad_layer_t& L = layers[l];
+    if (L.n < 16 || L.n > 128 || (L.n & 15) || L.n_x_atoms < 1 || L.n_x_atoms > NRC_WGRAD_MAX_X_ATOMS || !ok(L.dy_ptr) ||
+        L.n_seg < 1 || L.n_seg > NRC_WGRAD_MAX_SEGS)
+      return NRC_E_INVALID_ARG;
+    const int n_pairs = (L.n_x_atoms + 1) / 2;
+    if ((n_pairs + 1) * L.n > 512) return NRC_E_UNSUPPORTED;
+    for (int a = 0; a < L.n_x_atoms; ++a)
+      if (!ok(L.x_ptr[a]) || L.x_rows[a] < 1 || L.x_rows[a] > 64) return NRC_E_INVALID_ARG;
+    for (int s = 0; s < L.n_seg; ++s)
+      if (L.seg_w_ptr[s] >= num_ptrs || L.seg_b_ptr[s] >= num_ptrs || L.seg_ncols[s] < 1) return NRC_E_INVALID_ARG;
+    hp.layers[l] = L;
+  }
+  for (int i = 0; i < NRC_CHAIN_MAX_PTRS; ++i) hp.ptrs[i] = i < num_ptrs ? d_ptrs[i] : nullptr;
+  hp.num_tiles = static_cast<int32_t>((num_rows + 127) / 128);
+  int splits = (2 * kNumSMs + num_layers - 1) / num_layers;
+  if (splits > hp.num_tiles) splits = hp.num_tiles;
+  hp.tiles_per_cta = (hp.num_tiles + splits - 1) / splits;
+  splits = (hp.num_tiles + hp.tiles_per_cta - 1) / hp.tiles_per_cta;
+  static thread_local bool attr_set = false;
+  const size_t smem = static_cast<size_t>(1 + kWgradRingAtoms) * kAtomBytes + 1024;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return check_launch();
+    attr_set = true;
+  }
+  wgrad_kernel<<<dim3(splits, num_layers), kWgradThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
+  return check_launch();
+}

@@ -1,0 +1,524 @@
+"""Host side of the tcgen05 MLP chains (csrc/chain.cu): builds the per-tile PROGRAMS
+(nrc_chain_program_t) for the forward pass, the data-gradient pass and the weight-gradient
+GEMMs of a Dense stack, and wraps them in one torch.autograd.Function (the role jax.custom_vjp
+plays on the reference side).
+
+A stack is described the way the reference builds it (internal/surface_light_field.py:480-500,
+internal/nerf.py:461-482,561-689): concatenated inputs -> hidden Dense+ReLU layers (optionally
+re-concatenating the inputs after a layer: the skip connection) -> one or more linear output
+layers ("heads") reading the last activation.  Parameters stay Flax dicts {'kernel': [in,out],
+'bias': [out]}; bf16 operand images are (re)packed from them on the device.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+ATOM_BYTES = 16384
+MAX_OPS, MAX_PTRS, MAX_ATOMS = 24, 24, 8
+PACK_MAX, WGRAD_MAX_LAYERS, WGRAD_MAX_X, WGRAD_MAX_SEGS = 64, 8, 6, 5
+OP_LOAD, OP_GEMM, OP_EPI, OP_SAVE = 0, 1, 2, 3
+GEMM_ACCUMULATE, EPI_RELU, EPI_OUT_ACCUMULATE = 1, 1, 2
+
+
+class nrc_chain_op_t(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "kind", "slot", "ptr", "ld", "col0", "ncols", "npad", "tmem_col", "n", "flags", "out_ptr", "mask_ptr",
+        "mask_atom0", "img_atoms", "w_chunk", "n_atoms")] + [
+        ("a_slot", C.c_uint8 * MAX_ATOMS), ("a_klen", C.c_uint8 * MAX_ATOMS)]
+
+
+class nrc_chain_program_t(C.Structure):
+    _fields_ = [("num_ops", C.c_int32), ("slots_per_ctx", C.c_int32), ("ops", nrc_chain_op_t * MAX_OPS)]
+
+
+class nrc_pack_entry_t(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("ptr", "ld", "row0", "nrows", "col0", "ncols", "chunk", "n0", "k0",
+                                         "transpose")]
+
+
+class nrc_wgrad_layer_t(C.Structure):
+    _fields_ = [
+        ("n_x_atoms", C.c_int32),
+        ("x_ptr", C.c_int32 * WGRAD_MAX_X), ("x_img_atoms", C.c_int32 * WGRAD_MAX_X),
+        ("x_atom", C.c_int32 * WGRAD_MAX_X), ("x_rows", C.c_int32 * WGRAD_MAX_X), ("w_row0", C.c_int32 * WGRAD_MAX_X),
+        ("dy_ptr", C.c_int32), ("dy_img_atoms", C.c_int32), ("dy_atom0", C.c_int32), ("n", C.c_int32),
+        ("n_seg", C.c_int32),
+        ("seg_col0", C.c_int32 * WGRAD_MAX_SEGS), ("seg_ncols", C.c_int32 * WGRAD_MAX_SEGS),
+        ("seg_w_ptr", C.c_int32 * WGRAD_MAX_SEGS), ("seg_b_ptr", C.c_int32 * WGRAD_MAX_SEGS),
+    ]
+
+
+def _pad(n, m):
+    return (n + m - 1) // m * m
+
+
+def _atoms_of(width):
+    """[(first column, columns used)] of the 64-wide atoms covering `width` columns."""
+    return [(c, min(64, width - c)) for c in range(0, width, 64)]
+
+
+class _Ptrs:
+    """Pointer table of one launch: device tensors -> indices."""
+
+    def __init__(self):
+        self.tensors, self.index = [], {}
+
+    def add(self, t):
+        if t is None:
+            return -1
+        key = (t.data_ptr(), t.dtype)
+        if key not in self.index:
+            if len(self.tensors) >= MAX_PTRS:
+                raise _lib.NrcError("chain program refers to too many buffers")
+            self.index[key] = len(self.tensors)
+            self.tensors.append(t)
+        return self.index[key]
+
+    def array(self):
+        arr = (C.c_void_p * MAX_PTRS)()
+        for i, t in enumerate(self.tensors):
+            if not t.is_cuda:
+                raise _lib.NrcError("nrc_b200 kernels need CUDA tensors: there is no CPU fallback")
+            arr[i] = t.data_ptr()
+        return arr, len(self.tensors)
+
+
+class ChainSpec:
+    """Static description of a Dense stack.
+
+    in_widths : widths of the fp32 sources concatenated into the stack input (all but the last
+                must be multiples of 8).
+    hidden    : [(param_name, width, skip_after)] Dense+ReLU layers (width in {64, 128}); skip_after
+                re-concatenates the stack input behind the activation (reference: `x = cat([x, inputs])`).
+    heads     : [[(param_name, width), ...], ...] groups of linear output layers on the last activation;
+                each group is one GEMM (sum of widths <= 128).
+    """
+
+    def __init__(self, in_widths, hidden, heads):
+        self.in_widths = list(in_widths)
+        for w in self.in_widths[:-1]:
+            if w % 8:
+                raise ValueError("all but the last concatenated input must have a width that is a multiple of 8")
+        self.in_dim = sum(self.in_widths)
+        self.in_pad = _pad(self.in_dim, 16)
+        self.hidden = [tuple(h) for h in hidden]
+        self.heads = [[tuple(x) for x in grp] for grp in heads]
+        for _, w, _ in self.hidden:
+            if w % 16 or w > 128:
+                raise ValueError("hidden widths must be multiples of 16, at most 128")
+        self.in_atoms = _atoms_of(self.in_pad)
+        self.h_slot0 = len(self.in_atoms)
+        max_h = max([len(_atoms_of(w)) for _, w, _ in self.hidden] + [0])
+        self.fwd_slots = self.h_slot0 + max_h
+        # layer inputs: list of parts ('in' | 'h', width, padded width)
+        self.x_parts = []
+        parts = [("in", self.in_dim, self.in_pad)]
+        for _, w, skip in self.hidden:
+            self.x_parts.append(parts)
+            parts = [("h", w, w)] + ([("in", self.in_dim, self.in_pad)] if skip else [])
+        self.x_last = parts
+        self.head_widths = [sum(w for _, w in grp) for grp in self.heads]
+        for hw in self.head_widths:
+            if hw > 128:
+                raise ValueError("a head group is one GEMM: at most 128 output columns")
+        self.head_pads = [_pad(hw, 16) for hw in self.head_widths]
+        # image layouts (atoms per tile)
+        self.act_atoms = len(self.in_atoms) + sum(len(_atoms_of(w)) for _, w, _ in self.hidden)
+        self.dy_atoms = sum(len(_atoms_of(w)) for _, w, _ in self.hidden) + sum(
+            len(_atoms_of(p)) for p in self.head_pads)
+        if max(self.fwd_slots, self._bwd_slots()) > 7:
+            raise ValueError("stack does not fit the shared-memory slots of one tile context")
+
+    # ---- derived layouts -------------------------------------------------------------------
+    def act_atom0(self, layer):
+        """First atom of hidden activation `layer` inside the activation image (inputs first)."""
+        a = len(self.in_atoms)
+        for _, w, _ in self.hidden[:layer]:
+            a += len(_atoms_of(w))
+        return a
+
+    def dy_atom0_hidden(self, layer):
+        a = 0
+        for _, w, _ in self.hidden[:layer]:
+            a += len(_atoms_of(w))
+        return a
+
+    def dy_atom0_head(self, g):
+        a = sum(len(_atoms_of(w)) for _, w, _ in self.hidden)
+        for p in self.head_pads[:g]:
+            a += len(_atoms_of(p))
+        return a
+
+    def _bwd_slots(self):
+        head_atoms = sum(len(_atoms_of(p)) for p in self.head_pads)
+        max_h = max([len(_atoms_of(w)) for _, w, _ in self.hidden] + [0])
+        return max(head_atoms, max_h) + max_h   # head / current dY slots + next dY slots
+
+    def x_atoms(self, parts, fwd_slots=True):
+        """Atoms of a layer input: [(part kind, column inside the part, k extent padded to 16,
+        valid columns, kernel row of the first column, forward slot)]."""
+        out, row = [], 0
+        for kind, w, wp in parts:
+            for c, n in _atoms_of(wp):
+                valid = max(0, min(n, w - c))
+                slot = (self.h_slot0 if kind == "h" else 0) + c // 64
+                out.append((kind, c, _pad(n, 16), valid, row + c, slot))
+            row += w
+        return out
+
+
+class _Built:
+    pass
+
+
+def _build(spec):
+    """Programs and tables that depend only on the spec (cached per spec)."""
+    b = _Built()
+    # ------------------------------------------------------------------ weight chunks
+    # forward chunks: per layer, one chunk per K atom of the layer input; chunk[n][k] = W[row+k][n]
+    b.pack = []          # (param_name, ld, row0, nrows, col0, ncols, chunk, n0, k0, transpose)
+    chunk = 0
+    b.fwd_chunk = []     # per hidden layer
+    for li, (name, w, _) in enumerate(spec.hidden):
+        b.fwd_chunk.append(chunk)
+        for (_, _, _, valid, row, _) in spec.x_atoms(spec.x_parts[li]):
+            if valid > 0:
+                b.pack.append((name, w, row, valid, 0, w, chunk, 0, 0, 0))
+            chunk += 1
+    b.fwd_head_chunk = []
+    for g, grp in enumerate(spec.heads):
+        b.fwd_head_chunk.append(chunk)
+        for (_, _, _, valid, row, _) in spec.x_atoms(spec.x_last):
+            col = 0
+            for name, w in grp:
+                if valid > 0:
+                    b.pack.append((name, w, row, valid, 0, w, chunk, col, 0, 0))
+                col += w
+            chunk += 1
+    # data-gradient chunks: dX[part rows] = dY W^T -> B chunk[n][k] = W[row0+n][col0+k], K atoms over dY columns.
+    # One GEMM op per (part, <=128-row block); its chunks are contiguous, one per dY K atom.
+    def bwd_ops(parts, dy_cols_layout):
+        """dy_cols_layout: [(atom first col, k extent, [(param, ld, col0 in kernel, dest k0, ncols)])]"""
+        ops = []
+        nonlocal chunk
+        row = 0
+        for kind, w, wp in parts:
+            for n0 in range(0, wp, 128):
+                nrows_pad = min(128, wp - n0)
+                nvalid = max(0, min(nrows_pad, w - n0))
+                first = chunk
+                for (_, _, pieces) in dy_cols_layout:
+                    for (name, ld, kcol0, k0, ncols) in pieces:
+                        if nvalid > 0:
+                            b.pack.append((name, ld, row + n0, nvalid, kcol0, ncols, chunk, 0, k0, 1))
+                    chunk += 1
+                ops.append((kind, n0, nrows_pad, first))
+            row += w
+        return ops
+
+    b.bwd_hidden = []    # per hidden layer: list of (part kind, first column in part, N, first chunk)
+    for li, (name, w, _) in enumerate(spec.hidden):
+        layout = [(c, _pad(n, 16), [(name, w, c, 0, n)]) for c, n in _atoms_of(w)]
+        b.bwd_hidden.append(bwd_ops(spec.x_parts[li], layout))
+    # heads: dY = concatenation of all head groups' padded columns
+    head_layout = []
+    for g, grp in enumerate(spec.heads):
+        segs, col = [], 0
+        for name, w in grp:
+            segs.append((name, w, col))
+            col += w
+        for c, n in _atoms_of(spec.head_pads[g]):
+            pieces = []
+            for name, w, scol in segs:   # intersection of [scol, scol+w) with [c, c+n)
+                lo, hi = max(scol, c), min(scol + w, c + n)
+                if lo < hi:
+                    pieces.append((name, w, lo - scol, lo - c, hi - lo))
+            head_layout.append((c, _pad(n, 16), pieces))
+    b.bwd_heads = bwd_ops(spec.x_last, head_layout)
+    b.num_chunks = chunk
+    if len(b.pack) > PACK_MAX:
+        raise ValueError("too many weight pieces for one pack launch")
+    return b
+
+
+_BUILT = {}
+
+
+def _built(spec):
+    if id(spec) not in _BUILT:
+        _BUILT[id(spec)] = _build(spec)
+    return _BUILT[id(spec)]
+
+
+def _set_atoms(op, atoms):
+    op.n_atoms = len(atoms)
+    for i, (slot, klen) in enumerate(atoms):
+        op.a_slot[i], op.a_klen[i] = slot, klen
+
+
+def _op(prog, **kw):
+    if prog.num_ops >= MAX_OPS:
+        raise ValueError("chain program too long")
+    op = prog.ops[prog.num_ops]
+    prog.num_ops += 1
+    for f in ("slot", "ptr", "out_ptr", "mask_ptr"):
+        setattr(op, f, -1)
+    for k, v in kw.items():
+        if k == "atoms":
+            _set_atoms(op, v)
+        else:
+            setattr(op, k, v)
+    return op
+
+
+def pack_weights(spec, params, packed=None):
+    """bf16 operand images of every kernel of the stack (forward and data-gradient orientation)."""
+    b = _built(spec)
+    dev = params[spec.hidden[0][0] if spec.hidden else spec.heads[0][0][0]]["kernel"].device
+    if packed is None:
+        packed = torch.empty(b.num_chunks * ATOM_BYTES // 2, device=dev, dtype=torch.bfloat16)
+    ptrs = _Ptrs()
+    entries = (nrc_pack_entry_t * PACK_MAX)()
+    for i, (name, ld, row0, nrows, col0, ncols, chunk, n0, k0, tr) in enumerate(b.pack):
+        e = entries[i]
+        e.ptr = ptrs.add(params[name]["kernel"])
+        e.ld, e.row0, e.nrows, e.col0, e.ncols, e.chunk, e.n0, e.k0, e.transpose = ld, row0, nrows, col0, ncols, chunk, n0, k0, tr
+    arr, n = ptrs.array()
+    _lib.call("nrc_chain_pack_weights", _lib.stream_ptr(), entries, len(b.pack), arr, n,
+              C.c_void_p(packed.data_ptr()), b.num_chunks)
+    return packed
+
+
+def _num_tiles(rows):
+    return (rows + 127) // 128
+
+
+def run_forward(spec, params, sources, packed, save=True):
+    """sources: fp32 [P, w_i] tensors (row stride = shape[1], contiguous).  Returns (outputs per head
+    layer as fp32 [P, w], activation image or None)."""
+    b = _built(spec)
+    P = sources[0].shape[0]
+    dev = sources[0].device
+    ptrs = _Ptrs()
+    prog = nrc_chain_program_t()
+    prog.slots_per_ctx = spec.fwd_slots
+    act = torch.empty(_num_tiles(P) * spec.act_atoms * ATOM_BYTES // 2, device=dev, dtype=torch.bfloat16) if save else None
+    col = 0
+    for i, (src, w) in enumerate(zip(sources, spec.in_widths)):
+        last = i == len(sources) - 1
+        _op(prog, kind=OP_LOAD, slot=0, ptr=ptrs.add(src), ld=src.shape[1], col0=col, ncols=w,
+            npad=(spec.in_pad - col) if last else w)
+        col += w
+    # zero the unused tail of the last input atom's 16-column granule is covered by npad above
+    if save:
+        _op(prog, kind=OP_SAVE, slot=0, ptr=ptrs.add(act), col0=0, npad=len(spec.in_atoms), img_atoms=spec.act_atoms)
+    for li, (name, w, _) in enumerate(spec.hidden):
+        atoms = [(slot, klen) for (_, _, klen, _, _, slot) in spec.x_atoms(spec.x_parts[li])]
+        _op(prog, kind=OP_GEMM, n=w, tmem_col=0, w_chunk=b.fwd_chunk[li], atoms=atoms)
+        _op(prog, kind=OP_EPI, slot=spec.h_slot0, ptr=ptrs.add(params[name]["bias"]), ncols=w, npad=w, tmem_col=0,
+            flags=EPI_RELU)
+        if save:
+            _op(prog, kind=OP_SAVE, slot=spec.h_slot0, ptr=ptrs.add(act), col0=spec.act_atom0(li),
+                npad=len(_atoms_of(w)), img_atoms=spec.act_atoms)
+    outs = []
+    atoms = [(slot, klen) for (_, _, klen, _, _, slot) in spec.x_atoms(spec.x_last)]
+    tcol = 0
+    for g, grp in enumerate(spec.heads):
+        _op(prog, kind=OP_GEMM, n=spec.head_pads[g], tmem_col=tcol, w_chunk=b.fwd_head_chunk[g], atoms=atoms)
+        tcol += spec.head_pads[g]
+    if tcol > 256:
+        raise ValueError("head groups exceed the accumulator columns of one context")
+    tcol = 0
+    for g, grp in enumerate(spec.heads):
+        # one fp32 buffer per group [P, head_pad]; the per-layer outputs are column views of it
+        buf = torch.empty((P, spec.head_pads[g]), device=dev, dtype=torch.float32)
+        bias = torch.cat([params[name]["bias"] for name, _ in grp]) if len(grp) > 1 else params[grp[0][0]]["bias"]
+        _op(prog, kind=OP_EPI, slot=-1, ptr=ptrs.add(bias), ncols=spec.head_widths[g], npad=spec.head_pads[g],
+            tmem_col=tcol, out_ptr=ptrs.add(buf), ld=spec.head_pads[g], col0=0)
+        tcol += spec.head_pads[g]
+        c = 0
+        for name, w in grp:
+            outs.append(buf[:, c:c + w])
+            c += w
+    arr, n = ptrs.array()
+    _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
+    return outs, act
+
+
+def run_backward(spec, params, g_heads, act, packed, P, grad_sinks, need_input_grad=True):
+    """g_heads: per head GROUP an fp32 [P, head_pad] gradient buffer (columns beyond the group width
+    ignored).  Returns per-source input gradients; weight / bias gradients are accumulated into
+    grad_sinks[name] = (g_kernel, g_bias)."""
+    b = _built(spec)
+    dev = act.device
+    nt = _num_tiles(P)
+    dy = torch.empty(nt * spec.dy_atoms * ATOM_BYTES // 2, device=dev, dtype=torch.bfloat16)
+    ptrs = _Ptrs()
+    prog = nrc_chain_program_t()
+    S = spec._bwd_slots()
+    prog.slots_per_ctx = S
+    max_h = max([len(_atoms_of(w)) for _, w, _ in spec.hidden] + [0])
+    cur0 = 0                 # slots of the current dY
+    nxt0 = S - max_h         # slots of the next (earlier layer's) dY
+    # ---- heads' upstream gradients -> slots, saved for the weight gradients
+    slot = 0
+    head_atoms = []
+    for g, gbuf in enumerate(g_heads):
+        hp = spec.head_pads[g]
+        _op(prog, kind=OP_LOAD, slot=slot, ptr=ptrs.add(gbuf), ld=gbuf.shape[1], col0=0, ncols=spec.head_widths[g],
+            npad=_pad(hp, 8))
+        na = len(_atoms_of(hp))
+        _op(prog, kind=OP_SAVE, slot=slot, ptr=ptrs.add(dy), col0=spec.dy_atom0_head(g), npad=na, img_atoms=spec.dy_atoms)
+        for c, n in _atoms_of(hp):
+            head_atoms.append((slot + c // 64, _pad(n, 16)))
+        slot += na
+    d_in = torch.empty((P, spec.in_pad), device=dev, dtype=torch.float32) if need_input_grad else None
+    in_written = [False]
+
+    def emit(parts_ops, a_atoms, mask_layer, out_slot0):
+        """GEMMs + epilogues of one layer's data gradient.  parts_ops from _build; 'h' part ->
+        masked bf16 dY of the previous layer (+ SAVE), 'in' part -> fp32 d_in (store / accumulate)."""
+        for kind in ("in", "h"):   # input part first: it only writes global memory
+            ops = [o for o in parts_ops if o[0] == kind]
+            if not ops or (kind == "in" and d_in is None):
+                continue
+            for (_, n0, npad, first) in ops:
+                _op(prog, kind=OP_GEMM, n=npad, tmem_col=n0, w_chunk=first, atoms=a_atoms)
+            if kind == "in":
+                _op(prog, kind=OP_EPI, slot=-1, ncols=spec.in_pad, npad=spec.in_pad, tmem_col=0, out_ptr=ptrs.add(d_in),
+                    ld=spec.in_pad, col0=0, flags=EPI_OUT_ACCUMULATE if in_written[0] else 0)
+                in_written[0] = True
+            else:
+                w = spec.hidden[mask_layer][1]
+                _op(prog, kind=OP_EPI, slot=out_slot0, ncols=w, npad=w, tmem_col=0, mask_ptr=ptrs.add(act),
+                    mask_atom0=spec.act_atom0(mask_layer), img_atoms=spec.act_atoms)
+                _op(prog, kind=OP_SAVE, slot=out_slot0, ptr=ptrs.add(dy), col0=spec.dy_atom0_hidden(mask_layer),
+                    npad=len(_atoms_of(w)), img_atoms=spec.dy_atoms)
+
+    nh = len(spec.hidden)
+    emit(b.bwd_heads, head_atoms, nh - 1, nxt0)
+    cur0, nxt0 = nxt0, cur0
+    for li in range(nh - 1, -1, -1):
+        w = spec.hidden[li][1]
+        a_atoms = [(cur0 + c // 64, _pad(n, 16)) for c, n in _atoms_of(w)]
+        emit(b.bwd_hidden[li], a_atoms, li - 1, nxt0)
+        cur0, nxt0 = nxt0, cur0
+    arr, n = ptrs.array()
+    _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
+
+    # ---- weight gradients
+    layers = []
+    def x_desc(L, parts):
+        atoms = spec.x_atoms(parts)
+        atoms = [a for a in atoms if a[3] > 0]
+        if len(atoms) > WGRAD_MAX_X:
+            raise ValueError("layer input too wide for one weight-gradient pass")
+        L.n_x_atoms = len(atoms)
+        return atoms
+
+    wptrs = _Ptrs()
+    ia, idy = wptrs.add(act), wptrs.add(dy)
+
+    def fill_x(L, parts, layer_index):
+        for i, (kind, c, _, valid, row, _) in enumerate(x_desc(L, parts)):
+            L.x_ptr[i], L.x_img_atoms[i] = ia, spec.act_atoms
+            L.x_atom[i] = (spec.act_atom0(layer_index - 1) if kind == "h" else 0) + c // 64
+            L.x_rows[i], L.w_row0[i] = valid, row
+
+    for li, (name, w, _) in enumerate(spec.hidden):
+        L = nrc_wgrad_layer_t()
+        fill_x(L, spec.x_parts[li], li)
+        L.dy_ptr, L.dy_img_atoms, L.dy_atom0, L.n = idy, spec.dy_atoms, spec.dy_atom0_hidden(li), w
+        L.n_seg = 1
+        gk, gb = grad_sinks[name]
+        L.seg_col0[0], L.seg_ncols[0], L.seg_w_ptr[0], L.seg_b_ptr[0] = 0, w, wptrs.add(gk), wptrs.add(gb)
+        layers.append(L)
+    for g, grp in enumerate(spec.heads):
+        L = nrc_wgrad_layer_t()
+        fill_x(L, spec.x_last, nh)
+        L.dy_ptr, L.dy_img_atoms, L.dy_atom0, L.n = idy, spec.dy_atoms, spec.dy_atom0_head(g), spec.head_pads[g]
+        L.n_seg = len(grp)
+        col = 0
+        for s, (name, w) in enumerate(grp):
+            gk, gb = grad_sinks[name]
+            L.seg_col0[s], L.seg_ncols[s], L.seg_w_ptr[s], L.seg_b_ptr[s] = col, w, wptrs.add(gk), wptrs.add(gb)
+            col += w
+        layers.append(L)
+    warr, wn = wptrs.array()
+    for i in range(0, len(layers), WGRAD_MAX_LAYERS):
+        chunk_layers = layers[i:i + WGRAD_MAX_LAYERS]
+        carr = (nrc_wgrad_layer_t * len(chunk_layers))(*chunk_layers)
+        _lib.call("nrc_chain_wgrad", _lib.stream_ptr(), carr, len(chunk_layers), warr, wn, P)
+    if d_in is None:
+        return None
+    outs, c = [], 0
+    for w in spec.in_widths:
+        outs.append(d_in[:, c:c + w])
+        c += w
+    return outs
+
+
+class _ChainFn(torch.autograd.Function):
+    """custom_vjp of a whole Dense stack."""
+
+    @staticmethod
+    def forward(ctx, spec, names, n_src, *tensors):
+        sources = [t.contiguous() for t in tensors[:n_src]]
+        flat = tensors[n_src:]
+        params = {name: {"kernel": flat[2 * i], "bias": flat[2 * i + 1]} for i, name in enumerate(names)}
+        need_grad = any(t.requires_grad for t in tensors)
+        packed = pack_weights(spec, params)
+        outs, act = run_forward(spec, params, sources, packed, save=need_grad)
+        ctx.spec, ctx.names, ctx.n_src = spec, names, n_src
+        ctx.P = sources[0].shape[0]
+        ctx.save_for_backward(act, packed, *flat)
+        ctx.src_needs = [t.requires_grad for t in tensors[:n_src]]
+        return tuple(o.contiguous() for o in outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        spec, names, n_src = ctx.spec, ctx.names, ctx.n_src
+        act, packed, *flat = ctx.saved_tensors
+        params = {name: {"kernel": flat[2 * i], "bias": flat[2 * i + 1]} for i, name in enumerate(names)}
+        P = ctx.P
+        dev = act.device
+        # upstream gradients per head group, packed [P, head_pad]
+        g_heads, k = [], 0
+        for g, grp in enumerate(spec.heads):
+            buf = torch.zeros((P, spec.head_pads[g]), device=dev, dtype=torch.float32)
+            c = 0
+            for name, w in grp:
+                if g_outs[k] is not None:
+                    buf[:, c:c + w] = g_outs[k]
+                c += w
+                k += 1
+            g_heads.append(buf)
+        sinks, sunk, ret = {}, {}, {}
+        for i, name in enumerate(names):
+            kern, bias = flat[2 * i], flat[2 * i + 1]
+            sk, sb = _lib.grad_sink(kern), _lib.grad_sink(bias)
+            if sk is not None and sb is not None:
+                sinks[name], sunk[name] = (sk, sb), True
+            else:
+                sinks[name], sunk[name] = (torch.zeros_like(kern), torch.zeros_like(bias)), False
+        d_src = run_backward(spec, params, g_heads, act, packed, P, sinks, need_input_grad=any(ctx.src_needs))
+        grads = [None, None, None]
+        for i in range(n_src):
+            grads.append(d_src[i].contiguous() if (d_src is not None and ctx.src_needs[i]) else None)
+        for name in names:
+            if sunk[name]:
+                grads += [None, None]
+            else:
+                grads += list(sinks[name])
+        return tuple(grads)
+
+
+def apply(spec, params, sources):
+    """Run the stack; returns one fp32 [P, w] tensor per output layer (in spec.heads order)."""
+    names = [h[0] for h in spec.hidden] + [name for grp in spec.heads for name, _ in grp]
+    flat = []
+    for name in names:
+        flat += [params[name]["kernel"], params[name]["bias"]]
+    return _ChainFn.apply(spec, tuple(names), len(sources), *sources, *flat)
