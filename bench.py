@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="print per-ABI-call device times")
+    ap.add_argument("--ncu-mode", action="store_true",
+                    help="minimal run for an ncu launch list: 1 eager step, graph capture, 2 replays, no JSON")
     return ap.parse_args()
 
 
@@ -226,16 +228,25 @@ def run_b200(args):
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        for i in range(3):
+        for i in range(1 if args.ncu_mode else 3):
             before = _lib.launch_count
             loss = one_step()
             launches = _lib.launch_count - before
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
 
-    per_kernel = None
-    if args.profile_kernels or True:
-        per_kernel = profile_calls(one_step, _lib)
+    if args.ncu_mode:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            compute_step()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        print(json.dumps({"ncu_mode": True, "launches_per_step": launches}))
+        return
+
+    per_kernel = profile_calls(one_step, _lib)
 
     graph = torch.cuda.CUDAGraph()
     use_graph = True  # compute is captured; the NCCL all-reduce is issued after each replay

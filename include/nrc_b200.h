@@ -266,10 +266,10 @@ int32_t nrc_ide_bwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32
  * device pointers, copied at launch).  A "tile image" is a bf16 buffer
  * [ceil(rows/128)][img_atoms][16384 bytes] holding whole atoms in their shared-memory layout. */
 #define NRC_CHAIN_MAX_OPS 24
-#define NRC_CHAIN_MAX_PTRS 24
+#define NRC_CHAIN_MAX_PTRS 40
 #define NRC_CHAIN_MAX_ATOMS 8
-#define NRC_PACK_MAX_ENTRIES 64
-#define NRC_WGRAD_MAX_LAYERS 8
+#define NRC_PACK_MAX_ENTRIES 80
+#define NRC_WGRAD_MAX_LAYERS 12
 #define NRC_WGRAD_MAX_X_ATOMS 6
 #define NRC_WGRAD_MAX_SEGS 5
 
@@ -336,12 +336,50 @@ typedef struct {
 /* Run `prog` over ceil(num_rows/128) tiles.  d_weights_packed: chunks from nrc_chain_pack_weights. */
 int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
                       const void* d_weights_packed, int64_t num_rows);
-/* (Re)build the packed bf16 weight image (num_chunks * 16 KB, zero filled first). */
+/* (Re)build the packed bf16 weight image (num_chunks * 16 KB).  keep_existing == 0 zero-fills the
+ * whole image first; further calls with keep_existing != 0 add more pieces to the same image. */
 int32_t nrc_chain_pack_weights(void* stream, const nrc_pack_entry_t* entries, int32_t num_entries,
-                               void* const* d_ptrs, int32_t num_ptrs, void* d_packed, int32_t num_chunks);
+                               void* const* d_ptrs, int32_t num_ptrs, void* d_packed, int32_t num_chunks,
+                               int32_t keep_existing);
 /* dW += X^T dY, db += 1^T dY for `num_layers` layers from saved tile images. */
 int32_t nrc_chain_wgrad(void* stream, const nrc_wgrad_layer_t* layers, int32_t num_layers,
                         void* const* d_ptrs, int32_t num_ptrs, int64_t num_rows);
+
+/* --------------------------- cache shader: per-point stages between the stacks ---- */
+/* internal/nerf.py:940-1090 (_predict_appearance_passive), :461-482, :1344-1358,
+ * internal/ref_utils.py:25-42,131-192 with the activations of configs/nerf_ngp_yobo.gin:491-506.
+ * IDE tables as in nrc_ide_fwd (degree-5 list; the first n_sh_env harmonics are the EnvMap's
+ * degree-4 encoding).  d_heads [P,ldh]: column 0 roughness, 1-3 ambient irradiance, 4-6 irradiance,
+ * 7-9 tint (raw Dense outputs).  d_viewdirs [P/samples_per_ray, 3].
+ *   mid: roughness = softplus(raw + roughness_bias); dotprod = n.(-v); refdirs = reflect(-v, n);
+ *        d_ide_slf [P,2*n_sh] = IDE(refdirs, roughness); d_ide_env [P,2*n_sh_env] (may be NULL). */
+int32_t nrc_shader_mid_fwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32_t* ml_l,
+                           const float* sigma, const float* d_mat, int32_t n_sh_env, const float* d_heads,
+                           int64_t ldh, const float* d_normals, const float* d_viewdirs, int64_t num_points,
+                           int32_t samples_per_ray, float roughness_bias, float* d_roughness,
+                           float* d_dotprod, float* d_refdirs, float* d_ide_slf, float* d_ide_env);
+/* VJP: writes d_g_heads[:,0] (roughness raw) and d_g_normals [P,3] from the gradients of dotprod,
+ * the SLF encoding and (optionally) the EnvMap encoding; all with row strides. */
+int32_t nrc_shader_mid_bwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32_t* ml_l,
+                           const float* sigma, const float* d_mat, int32_t n_sh_env, const float* d_heads,
+                           int64_t ldh, const float* d_normals, const float* d_viewdirs, int64_t num_points,
+                           int32_t samples_per_ray, float roughness_bias, const float* d_g_dotprod,
+                           int64_t ldgd, const float* d_g_ide_slf, int64_t ldgs, const float* d_g_ide_env,
+                           int64_t ldge, float* d_g_heads, int64_t ldgh, float* d_g_normals);
+/*   out: rgb = ambient_diffuse + indirect_diffuse + tint*F*(env*(1-acc) + ref*acc), acc = 1 for the
+ *        IDE-form light field; d_extras [P,22] (may be NULL) = diffuse 3, specular 3, ambient 3,
+ *        indirect 3, albedo (tint) 3, integrated BRDF 1, env_rgb 3, ref_rgb 3. */
+int32_t nrc_shader_out_fwd(void* stream, const float* d_heads, int64_t ldh, const float* d_f_raw, int64_t ldf,
+                           const float* d_slf_raw, int64_t lds, const float* d_env_raw, int64_t lde,
+                           int64_t num_points, float rgb_max, float diffuse_bias, float light_bias,
+                           float brdf_bias, float* d_rgb, float* d_extras);
+/* VJP of rgb: writes d_g_heads[:,1:10], d_g_f_raw[:,0], d_g_slf_raw[:,0:3]; the EnvMap receives an
+ * exactly-zero gradient (1 - acc == 0). */
+int32_t nrc_shader_out_bwd(void* stream, const float* d_heads, int64_t ldh, const float* d_f_raw, int64_t ldf,
+                           const float* d_slf_raw, int64_t lds, int64_t num_points, float rgb_max,
+                           float diffuse_bias, float light_bias, float brdf_bias, const float* d_g_rgb,
+                           float* d_g_heads, int64_t ldgh, float* d_g_f_raw, int64_t ldgf,
+                           float* d_g_slf_raw, int64_t ldgs);
 
 /* ------------------------------------------------- K5: GGX integration ---- */
 /* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) +

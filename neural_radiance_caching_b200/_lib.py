@@ -98,8 +98,14 @@ PROTOTYPES = {
     "nrc_ide_bwd": [_P, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), _P, _P, _P, _P,
                     _I64, _I64, _P, _P],
     "nrc_chain_run": [_P, _P, _P, _I32, _P, _I64],
-    "nrc_chain_pack_weights": [_P, _P, _I32, _P, _I32, _P, _I32],
+    "nrc_chain_pack_weights": [_P, _P, _I32, _P, _I32, _P, _I32, _I32],
     "nrc_chain_wgrad": [_P, _P, _I32, _P, _I32, _I64],
+    "nrc_shader_mid_fwd": [_P, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), _P, _I32, _P, _I64,
+                           _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P],
+    "nrc_shader_mid_bwd": [_P, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), _P, _I32, _P, _I64,
+                           _P, _P, _I64, _I32, _F, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P],
+    "nrc_shader_out_fwd": [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _F, _F, _F, _F, _P, _P],
+    "nrc_shader_out_bwd": [_P, _P, _I64, _P, _I64, _P, _I64, _I64, _F, _F, _F, _F, _P, _P, _I64, _P, _I64, _P, _I64],
     "nrc_ggx_integrate_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P],
     "nrc_ggx_integrate_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],
 }

@@ -565,7 +565,8 @@ extern "C" int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, 
 }
 
 extern "C" int32_t nrc_chain_pack_weights(void* stream, const nrc_pack_entry_t* entries, int32_t num_entries,
-                                          void* const* d_ptrs, int32_t num_ptrs, void* d_packed, int32_t num_chunks) {
+                                          void* const* d_ptrs, int32_t num_ptrs, void* d_packed, int32_t num_chunks,
+                                          int32_t keep_existing) {
   if (!entries || num_entries < 1 || num_entries > NRC_PACK_MAX_ENTRIES || !d_ptrs || num_ptrs < 1 ||
       num_ptrs > NRC_CHAIN_MAX_PTRS || !d_packed || num_chunks < 1)
     return NRC_E_INVALID_ARG;
@@ -581,7 +582,9 @@ extern "C" int32_t nrc_chain_pack_weights(void* stream, const nrc_pack_entry_t* 
   for (int i = 0; i < NRC_CHAIN_MAX_PTRS; ++i) hp.ptrs[i] = i < num_ptrs ? d_ptrs[i] : nullptr;
   hp.packed = static_cast<uint8_t*>(d_packed);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cudaMemsetAsync(d_packed, 0, static_cast<size_t>(num_chunks) * kAtomBytes, s) != cudaSuccess) return check_launch();
+  if (!keep_existing &&
+      cudaMemsetAsync(d_packed, 0, static_cast<size_t>(num_chunks) * kAtomBytes, s) != cudaSuccess)
+    return check_launch();
   pack_kernel<<<num_entries, 256, 0, s>>>(hp);
   return check_launch();
 }

@@ -1,0 +1,228 @@
+// Per-point stages of the cache shader between its Dense stacks:
+// internal/nerf.py:940-1090 (_predict_appearance_passive), :461-482 (integrated BRDF input),
+// :1344-1358 (_get_refdirs), internal/ref_utils.py:25-42 (reflect), :131-192 (IDE) and the
+// activations of configs/nerf_ngp_yobo.gin:491-506.  One thread per shaded point; everything a point
+// needs between two MLP stacks happens in one kernel, so the only tensors that touch HBM are the
+// stacks' inputs and outputs.
+//   mid : head outputs + normal + view direction -> roughness, n.v, reflection direction, IDE_5 (SLF
+//         input) and IDE_4 (EnvMap input; the degree-4 harmonics are a prefix of the degree-5 list)
+//   out : raw outputs of the heads / integrated-BRDF / SLF / EnvMap stacks -> rgb and the extras
+#include "ide.cuh"
+
+namespace nrc {
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+struct ShaderGeom {
+  float nx, ny, nz, wx, wy, wz, dot, rx, ry, rz;
+  __device__ __forceinline__ void load(const float* __restrict__ normals, const float* __restrict__ viewdirs,
+                                       int64_t p, int32_t spr) {
+    nx = normals[3 * p]; ny = normals[3 * p + 1]; nz = normals[3 * p + 2];
+    const int64_t ray = p / spr;
+    wx = -viewdirs[3 * ray]; wy = -viewdirs[3 * ray + 1]; wz = -viewdirs[3 * ray + 2];
+    dot = nx * wx + ny * wy + nz * wz;
+    // reflect(w, n) = 2 (n.w) n - w
+    rx = 2.f * dot * nx - wx; ry = 2.f * dot * ny - wy; rz = 2.f * dot * nz - wz;
+  }
+};
+
+__global__ void shader_mid_fwd_kernel(const __grid_constant__ IdeTable tab, int n_sh_env, const float* __restrict__ mat,
+                                      const float* __restrict__ heads, int64_t ldh, const float* __restrict__ normals,
+                                      const float* __restrict__ viewdirs, int64_t P, int32_t spr, float rough_bias,
+                                      float* __restrict__ roughness, float* __restrict__ dotprod,
+                                      float* __restrict__ refdirs, float* __restrict__ ide_slf,
+                                      float* __restrict__ ide_env) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  ShaderGeom g;
+  g.load(normals, viewdirs, p, spr);
+  const float rough = softplus_f(heads[p * ldh] + rough_bias);
+  if (roughness) roughness[p] = rough;
+  dotprod[p] = g.dot;
+  if (refdirs) { refdirs[3 * p] = g.rx; refdirs[3 * p + 1] = g.ry; refdirs[3 * p + 2] = g.rz; }
+  IdePowers pw;
+  pw.init(tab.l_max, g.rx, g.ry, g.rz);
+  float* o5 = ide_slf + p * (2 * tab.n_sh);
+  float* o4 = ide_env ? ide_env + p * (2 * n_sh_env) : nullptr;
+  for (int i = 0; i < tab.n_sh; ++i) {
+    float re, im;
+    ide_term(tab, mat, pw, rough, i, re, im);
+    o5[i] = re;
+    o5[tab.n_sh + i] = im;
+    if (o4 && i < n_sh_env) { o4[i] = re; o4[n_sh_env + i] = im; }
+  }
+}
+
+__global__ void shader_mid_bwd_kernel(const __grid_constant__ IdeTable tab, int n_sh_env, const float* __restrict__ mat,
+                                      const float* __restrict__ heads, int64_t ldh, const float* __restrict__ normals,
+                                      const float* __restrict__ viewdirs, int64_t P, int32_t spr, float rough_bias,
+                                      const float* __restrict__ g_dot, int64_t ldgd, const float* __restrict__ g_ide_slf,
+                                      int64_t ldgs, const float* __restrict__ g_ide_env, int64_t ldge,
+                                      float* __restrict__ g_heads, int64_t ldgh, float* __restrict__ g_normals) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  ShaderGeom g;
+  g.load(normals, viewdirs, p, spr);
+  const float r_raw = heads[p * ldh] + rough_bias;
+  const float rough = softplus_f(r_raw);
+  IdePowers pw;
+  pw.init(tab.l_max, g.rx, g.ry, g.rz);
+  const float* g5 = g_ide_slf + p * ldgs;
+  const float* g4 = g_ide_env ? g_ide_env + p * ldge : nullptr;
+  float grx = 0.f, gry = 0.f, grz = 0.f, gk = 0.f;
+  for (int i = 0; i < tab.n_sh; ++i) {
+    float gr = g5[i], gi = g5[tab.n_sh + i];
+    if (g4 && i < n_sh_env) { gr += g4[i]; gi += g4[n_sh_env + i]; }
+    ide_term_vjp(tab, mat, pw, rough, i, gr, gi, grx, gry, grz, gk);
+  }
+  // softplus'(x) = sigmoid(x)
+  g_heads[p * ldgh] = gk * sigmoid_f(r_raw);
+  // dot = n.w ; r = 2 dot n - w  =>  dL/dn = g_dot w + 2 dot g_r + 2 (g_r.n) w
+  const float gd = g_dot[p * ldgd];
+  const float grn = grx * g.nx + gry * g.ny + grz * g.nz;
+  const float s = gd + 2.f * grn;
+  g_normals[3 * p] = s * g.wx + 2.f * g.dot * grx;
+  g_normals[3 * p + 1] = s * g.wy + 2.f * g.dot * gry;
+  g_normals[3 * p + 2] = s * g.wz + 2.f * g.dot * grz;
+}
+
+// heads columns: 0 roughness, 1-3 ambient irradiance, 4-6 irradiance, 7-9 tint
+__global__ void shader_out_fwd_kernel(const float* __restrict__ heads, int64_t ldh, const float* __restrict__ f_raw,
+                                      int64_t ldf, const float* __restrict__ slf_raw, int64_t lds,
+                                      const float* __restrict__ env_raw, int64_t lde, int64_t P, float rgb_max,
+                                      float diffuse_bias, float light_bias, float brdf_bias, float* __restrict__ rgb,
+                                      float* __restrict__ extras) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float* h = heads + p * ldh;
+  const float F = sigmoid_f(f_raw[p * ldf] + brdf_bias);
+  float* e = extras ? extras + p * 22 : nullptr;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float amb_d = fminf(fmaxf(softplus_f(h[1 + c] + diffuse_bias), 0.f), rgb_max);
+    const float ind_d = fminf(fmaxf(softplus_f(h[4 + c] + diffuse_bias), 0.f), rgb_max);
+    const float tint = sigmoid_f(h[7 + c]);
+    const float env = fmaxf(softplus_f(env_raw[p * lde + c] + light_bias), 0.f);
+    const float ref = fmaxf(softplus_f(slf_raw[p * lds + c] + light_bias), 0.f);
+    const float acc = 1.0f;   // incoming_acc of the IDE-form light field (surface_light_field.py:1046-1069)
+    const float amb_s = fminf(fmaxf(tint * F * (env * (1.0f - acc)), 0.f), rgb_max);
+    const float ind_s = fminf(fmaxf(tint * F * (ref * acc), 0.f), rgb_max);
+    const float ambient = amb_d + amb_s, indirect = ind_d + ind_s;
+    rgb[3 * p + c] = ambient + indirect;
+    if (e) {
+      e[c] = amb_d + ind_d;       // diffuse_rgb
+      e[3 + c] = amb_s + ind_s;   // specular_rgb
+      e[6 + c] = ambient;         // ambient_rgb
+      e[9 + c] = indirect;        // indirect_rgb
+      e[12 + c] = tint;           // albedo_rgb
+      e[16 + c] = env;            // env_rgb
+      e[19 + c] = ref;            // ref_rgb
+    }
+  }
+  if (e) e[15] = F;
+}
+
+// VJP of rgb only (the extras are diagnostics; the cache loss reads rgb).
+__global__ void shader_out_bwd_kernel(const float* __restrict__ heads, int64_t ldh, const float* __restrict__ f_raw,
+                                      int64_t ldf, const float* __restrict__ slf_raw, int64_t lds, int64_t P,
+                                      float rgb_max, float diffuse_bias, float light_bias, float brdf_bias,
+                                      const float* __restrict__ g_rgb, float* __restrict__ g_heads, int64_t ldgh,
+                                      float* __restrict__ g_f, int64_t ldgf, float* __restrict__ g_slf, int64_t ldgs) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float* h = heads + p * ldh;
+  const float F = sigmoid_f(f_raw[p * ldf] + brdf_bias);
+  float gF = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float g = g_rgb[3 * p + c];
+    const float xa = h[1 + c] + diffuse_bias, xi = h[4 + c] + diffuse_bias;
+    // clip passes the gradient on the closed interval [0, rgb_max] (jnp.clip / torch.clamp)
+    g_heads[p * ldgh + 1 + c] = softplus_f(xa) <= rgb_max ? g * sigmoid_f(xa) : 0.f;
+    g_heads[p * ldgh + 4 + c] = softplus_f(xi) <= rgb_max ? g * sigmoid_f(xi) : 0.f;
+    const float tint = sigmoid_f(h[7 + c]);
+    const float xs = slf_raw[p * lds + c] + light_bias;
+    const float ref = fmaxf(softplus_f(xs), 0.f);
+    const float spec = tint * F * ref;
+    const float gs = (spec >= 0.f && spec <= rgb_max) ? g : 0.f;
+    g_heads[p * ldgh + 7 + c] = gs * F * ref * tint * (1.f - tint);
+    gF += gs * tint * ref;
+    g_slf[p * ldgs + c] = gs * tint * F * sigmoid_f(xs);
+  }
+  g_f[p * ldgf] = gF * F * (1.f - F);
+}
+
+}  // namespace nrc
+
+using namespace nrc;
+
+extern "C" int32_t nrc_shader_mid_fwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32_t* ml_l,
+                                      const float* sigma, const float* d_mat, int32_t n_sh_env, const float* d_heads,
+                                      int64_t ldh, const float* d_normals, const float* d_viewdirs, int64_t num_points,
+                                      int32_t samples_per_ray, float roughness_bias, float* d_roughness,
+                                      float* d_dotprod, float* d_refdirs, float* d_ide_slf, float* d_ide_env) {
+  IdeTable t;
+  int32_t st = make_ide_table(n_sh, ml_m, ml_l, sigma, t);
+  if (st != NRC_OK) return st;
+  if (num_points < 0 || samples_per_ray < 1 || ldh < 1 || n_sh_env < 0 || n_sh_env > n_sh) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_mat || !d_heads || !d_normals || !d_viewdirs || !d_dotprod || !d_ide_slf) return NRC_E_INVALID_ARG;
+  const unsigned grid = static_cast<unsigned>((num_points + 127) / 128);
+  shader_mid_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, n_sh_env, d_mat, d_heads, ldh, d_normals, d_viewdirs, num_points, samples_per_ray, roughness_bias, d_roughness,
+      d_dotprod, d_refdirs, d_ide_slf, d_ide_env);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_shader_mid_bwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32_t* ml_l,
+                                      const float* sigma, const float* d_mat, int32_t n_sh_env, const float* d_heads,
+                                      int64_t ldh, const float* d_normals, const float* d_viewdirs, int64_t num_points,
+                                      int32_t samples_per_ray, float roughness_bias, const float* d_g_dotprod,
+                                      int64_t ldgd, const float* d_g_ide_slf, int64_t ldgs, const float* d_g_ide_env,
+                                      int64_t ldge, float* d_g_heads, int64_t ldgh, float* d_g_normals) {
+  IdeTable t;
+  int32_t st = make_ide_table(n_sh, ml_m, ml_l, sigma, t);
+  if (st != NRC_OK) return st;
+  if (num_points < 0 || samples_per_ray < 1 || ldh < 1 || ldgh < 1 || ldgd < 1 || ldgs < 2 * n_sh || n_sh_env < 0 ||
+      n_sh_env > n_sh || (d_g_ide_env && ldge < 2 * n_sh_env))
+    return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_mat || !d_heads || !d_normals || !d_viewdirs || !d_g_dotprod || !d_g_ide_slf || !d_g_heads || !d_g_normals)
+    return NRC_E_INVALID_ARG;
+  const unsigned grid = static_cast<unsigned>((num_points + 127) / 128);
+  shader_mid_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, n_sh_env, d_mat, d_heads, ldh, d_normals, d_viewdirs, num_points, samples_per_ray, roughness_bias, d_g_dotprod,
+      ldgd, d_g_ide_slf, ldgs, d_g_ide_env, ldge, d_g_heads, ldgh, d_g_normals);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_shader_out_fwd(void* stream, const float* d_heads, int64_t ldh, const float* d_f_raw, int64_t ldf,
+                                      const float* d_slf_raw, int64_t lds, const float* d_env_raw, int64_t lde,
+                                      int64_t num_points, float rgb_max, float diffuse_bias, float light_bias,
+                                      float brdf_bias, float* d_rgb, float* d_extras) {
+  if (num_points < 0 || ldh < 10 || ldf < 1 || lds < 3 || lde < 3) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_heads || !d_f_raw || !d_slf_raw || !d_env_raw || !d_rgb) return NRC_E_INVALID_ARG;
+  const unsigned grid = static_cast<unsigned>((num_points + 127) / 128);
+  shader_out_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_heads, ldh, d_f_raw, ldf, d_slf_raw, lds, d_env_raw, lde, num_points, rgb_max, diffuse_bias, light_bias,
+      brdf_bias, d_rgb, d_extras);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_shader_out_bwd(void* stream, const float* d_heads, int64_t ldh, const float* d_f_raw, int64_t ldf,
+                                      const float* d_slf_raw, int64_t lds, int64_t num_points, float rgb_max,
+                                      float diffuse_bias, float light_bias, float brdf_bias, const float* d_g_rgb,
+                                      float* d_g_heads, int64_t ldgh, float* d_g_f_raw, int64_t ldgf,
+                                      float* d_g_slf_raw, int64_t ldgs) {
+  if (num_points < 0 || ldh < 10 || ldf < 1 || lds < 3 || ldgh < 10 || ldgf < 1 || ldgs < 3) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_heads || !d_f_raw || !d_slf_raw || !d_g_rgb || !d_g_heads || !d_g_f_raw || !d_g_slf_raw)
+    return NRC_E_INVALID_ARG;
+  const unsigned grid = static_cast<unsigned>((num_points + 127) / 128);
+  shader_out_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_heads, ldh, d_f_raw, ldf, d_slf_raw, lds, num_points, rgb_max, diffuse_bias, light_bias, brdf_bias, d_g_rgb,
+      d_g_heads, ldgh, d_g_f_raw, ldgf, d_g_slf_raw, ldgs);
+  return check_launch();
+}

@@ -16,8 +16,8 @@ import torch
 from . import _lib
 
 ATOM_BYTES = 16384
-MAX_OPS, MAX_PTRS, MAX_ATOMS = 24, 24, 8
-PACK_MAX, WGRAD_MAX_LAYERS, WGRAD_MAX_X, WGRAD_MAX_SEGS = 64, 8, 6, 5
+MAX_OPS, MAX_PTRS, MAX_ATOMS = 24, 40, 8
+PACK_MAX, WGRAD_MAX_LAYERS, WGRAD_MAX_X, WGRAD_MAX_SEGS = 80, 12, 6, 5
 OP_LOAD, OP_GEMM, OP_EPI, OP_SAVE = 0, 1, 2, 3
 GEMM_ACCUMULATE, EPI_RELU, EPI_OUT_ACCUMULATE = 1, 1, 2
 
@@ -243,13 +243,10 @@ def _build(spec):
     return b
 
 
-_BUILT = {}
-
-
 def _built(spec):
-    if id(spec) not in _BUILT:
-        _BUILT[id(spec)] = _build(spec)
-    return _BUILT[id(spec)]
+    if getattr(spec, "_built_tables", None) is None:
+        spec._built_tables = _build(spec)
+    return spec._built_tables
 
 
 def _set_atoms(op, atoms):
@@ -273,22 +270,52 @@ def _op(prog, **kw):
     return op
 
 
-def pack_weights(spec, params, packed=None):
-    """bf16 operand images of every kernel of the stack (forward and data-gradient orientation)."""
-    b = _built(spec)
-    dev = params[spec.hidden[0][0] if spec.hidden else spec.heads[0][0][0]]["kernel"].device
+def _ld(t):
+    """Row stride of a 2-D fp32 view whose rows are contiguous (column slices of wider buffers are fine)."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1) or t.dtype != torch.float32:
+        raise _lib.NrcError("chain sources must be 2-D fp32 tensors with contiguous rows")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def pack_weights_many(items, packed=None):
+    """bf16 operand images (forward and data-gradient orientation) of several stacks in ONE launch.
+    items: [(spec, params)].  Returns (packed buffer, [per-stack view of it])."""
+    bases, total = [], 0
+    for spec, _ in items:
+        bases.append(total)
+        total += _built(spec).num_chunks
+    dev = next(iter(items[0][1].values()))["kernel"].device
     if packed is None:
-        packed = torch.empty(b.num_chunks * ATOM_BYTES // 2, device=dev, dtype=torch.bfloat16)
+        packed = torch.empty(total * ATOM_BYTES // 2, device=dev, dtype=torch.bfloat16)
     ptrs = _Ptrs()
     entries = (nrc_pack_entry_t * PACK_MAX)()
-    for i, (name, ld, row0, nrows, col0, ncols, chunk, n0, k0, tr) in enumerate(b.pack):
-        e = entries[i]
-        e.ptr = ptrs.add(params[name]["kernel"])
-        e.ld, e.row0, e.nrows, e.col0, e.ncols, e.chunk, e.n0, e.k0, e.transpose = ld, row0, nrows, col0, ncols, chunk, n0, k0, tr
-    arr, n = ptrs.array()
-    _lib.call("nrc_chain_pack_weights", _lib.stream_ptr(), entries, len(b.pack), arr, n,
-              C.c_void_p(packed.data_ptr()), b.num_chunks)
-    return packed
+    n = 0
+
+    def flush():
+        nonlocal n, ptrs
+        if n:
+            arr, k = ptrs.array()
+            _lib.call("nrc_chain_pack_weights", _lib.stream_ptr(), entries, n, arr, k, C.c_void_p(packed.data_ptr()),
+                      total, 0 if flush.first else 1)
+            flush.first = False
+        n, ptrs = 0, _Ptrs()
+
+    flush.first = True
+    for (spec, params), base in zip(items, bases):
+        for (name, ld, row0, nrows, col0, ncols, chunk, n0, k0, tr) in _built(spec).pack:
+            if n == PACK_MAX or len(ptrs.tensors) >= MAX_PTRS - 1:
+                flush()
+            e = entries[n]
+            e.ptr = ptrs.add(params[name]["kernel"])
+            e.ld, e.row0, e.nrows, e.col0, e.ncols, e.chunk, e.n0, e.k0, e.transpose = (
+                ld, row0, nrows, col0, ncols, base + chunk, n0, k0, tr)
+            n += 1
+    flush()
+    return packed, [packed[b * (ATOM_BYTES // 2):] for b in bases]
+
+
+def pack_weights(spec, params):
+    return pack_weights_many([(spec, params)])[1][0]
 
 
 def _num_tiles(rows):
@@ -296,8 +323,8 @@ def _num_tiles(rows):
 
 
 def run_forward(spec, params, sources, packed, save=True):
-    """sources: fp32 [P, w_i] tensors (row stride = shape[1], contiguous).  Returns (outputs per head
-    layer as fp32 [P, w], activation image or None)."""
+    """sources: fp32 [P, w_i] views with contiguous rows.  Returns (per head GROUP fp32 buffers
+    [P, head_pad], per head layer column views of them, activation image or None)."""
     b = _built(spec)
     P = sources[0].shape[0]
     dev = sources[0].device
@@ -308,10 +335,11 @@ def run_forward(spec, params, sources, packed, save=True):
     col = 0
     for i, (src, w) in enumerate(zip(sources, spec.in_widths)):
         last = i == len(sources) - 1
-        _op(prog, kind=OP_LOAD, slot=0, ptr=ptrs.add(src), ld=src.shape[1], col0=col, ncols=w,
+        if src.shape[1] != w:
+            raise _lib.NrcError(f"chain source {i} has width {src.shape[1]}, expected {w}")
+        _op(prog, kind=OP_LOAD, slot=0, ptr=ptrs.add(src), ld=_ld(src), col0=col, ncols=w,
             npad=(spec.in_pad - col) if last else w)
         col += w
-    # zero the unused tail of the last input atom's 16-column granule is covered by npad above
     if save:
         _op(prog, kind=OP_SAVE, slot=0, ptr=ptrs.add(act), col0=0, npad=len(spec.in_atoms), img_atoms=spec.act_atoms)
     for li, (name, w, _) in enumerate(spec.hidden):
@@ -322,7 +350,6 @@ def run_forward(spec, params, sources, packed, save=True):
         if save:
             _op(prog, kind=OP_SAVE, slot=spec.h_slot0, ptr=ptrs.add(act), col0=spec.act_atom0(li),
                 npad=len(_atoms_of(w)), img_atoms=spec.act_atoms)
-    outs = []
     atoms = [(slot, klen) for (_, _, klen, _, _, slot) in spec.x_atoms(spec.x_last)]
     tcol = 0
     for g, grp in enumerate(spec.heads):
@@ -331,26 +358,27 @@ def run_forward(spec, params, sources, packed, save=True):
     if tcol > 256:
         raise ValueError("head groups exceed the accumulator columns of one context")
     tcol = 0
+    bufs, outs = [], []
     for g, grp in enumerate(spec.heads):
-        # one fp32 buffer per group [P, head_pad]; the per-layer outputs are column views of it
         buf = torch.empty((P, spec.head_pads[g]), device=dev, dtype=torch.float32)
         bias = torch.cat([params[name]["bias"] for name, _ in grp]) if len(grp) > 1 else params[grp[0][0]]["bias"]
         _op(prog, kind=OP_EPI, slot=-1, ptr=ptrs.add(bias), ncols=spec.head_widths[g], npad=spec.head_pads[g],
             tmem_col=tcol, out_ptr=ptrs.add(buf), ld=spec.head_pads[g], col0=0)
         tcol += spec.head_pads[g]
+        bufs.append(buf)
         c = 0
         for name, w in grp:
             outs.append(buf[:, c:c + w])
             c += w
     arr, n = ptrs.array()
     _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
-    return outs, act
+    return bufs, outs, act
 
 
-def run_backward(spec, params, g_heads, act, packed, P, grad_sinks, need_input_grad=True):
-    """g_heads: per head GROUP an fp32 [P, head_pad] gradient buffer (columns beyond the group width
-    ignored).  Returns per-source input gradients; weight / bias gradients are accumulated into
-    grad_sinks[name] = (g_kernel, g_bias)."""
+def run_backward_data(spec, params, g_heads, act, packed, P, d_src=None):
+    """Data-gradient pass.  g_heads: per head GROUP an fp32 [P, >= group width] view (rows contiguous).
+    d_src: None (no input gradient) or per source (fp32 [P, w_i] view, accumulate flag): written
+    (or accumulated into).  Returns the dY tile image for the weight gradients."""
     b = _built(spec)
     dev = act.device
     nt = _num_tiles(P)
@@ -360,36 +388,41 @@ def run_backward(spec, params, g_heads, act, packed, P, grad_sinks, need_input_g
     S = spec._bwd_slots()
     prog.slots_per_ctx = S
     max_h = max([len(_atoms_of(w)) for _, w, _ in spec.hidden] + [0])
-    cur0 = 0                 # slots of the current dY
-    nxt0 = S - max_h         # slots of the next (earlier layer's) dY
-    # ---- heads' upstream gradients -> slots, saved for the weight gradients
+    cur0, nxt0 = 0, S - max_h
     slot = 0
     head_atoms = []
     for g, gbuf in enumerate(g_heads):
         hp = spec.head_pads[g]
-        _op(prog, kind=OP_LOAD, slot=slot, ptr=ptrs.add(gbuf), ld=gbuf.shape[1], col0=0, ncols=spec.head_widths[g],
-            npad=_pad(hp, 8))
+        _op(prog, kind=OP_LOAD, slot=slot, ptr=ptrs.add(gbuf), ld=_ld(gbuf), col0=0, ncols=spec.head_widths[g], npad=hp)
         na = len(_atoms_of(hp))
         _op(prog, kind=OP_SAVE, slot=slot, ptr=ptrs.add(dy), col0=spec.dy_atom0_head(g), npad=na, img_atoms=spec.dy_atoms)
         for c, n in _atoms_of(hp):
             head_atoms.append((slot + c // 64, _pad(n, 16)))
         slot += na
-    d_in = torch.empty((P, spec.in_pad), device=dev, dtype=torch.float32) if need_input_grad else None
-    in_written = [False]
+    written = [False] * len(spec.in_widths)
+    if d_src is not None:
+        c = 0
+        for w in spec.in_widths:
+            if c % 16:
+                raise ValueError("input gradients need 16-aligned source offsets")
+            c += w
 
     def emit(parts_ops, a_atoms, mask_layer, out_slot0):
-        """GEMMs + epilogues of one layer's data gradient.  parts_ops from _build; 'h' part ->
-        masked bf16 dY of the previous layer (+ SAVE), 'in' part -> fp32 d_in (store / accumulate)."""
         for kind in ("in", "h"):   # input part first: it only writes global memory
             ops = [o for o in parts_ops if o[0] == kind]
-            if not ops or (kind == "in" and d_in is None):
+            if not ops or (kind == "in" and d_src is None):
                 continue
             for (_, n0, npad, first) in ops:
                 _op(prog, kind=OP_GEMM, n=npad, tmem_col=n0, w_chunk=first, atoms=a_atoms)
             if kind == "in":
-                _op(prog, kind=OP_EPI, slot=-1, ncols=spec.in_pad, npad=spec.in_pad, tmem_col=0, out_ptr=ptrs.add(d_in),
-                    ld=spec.in_pad, col0=0, flags=EPI_OUT_ACCUMULATE if in_written[0] else 0)
-                in_written[0] = True
+                c = 0
+                for i, w in enumerate(spec.in_widths):
+                    t, accumulate = d_src[i]
+                    if t is not None:
+                        _op(prog, kind=OP_EPI, slot=-1, ncols=w, npad=_pad(w, 16), tmem_col=c, out_ptr=ptrs.add(t),
+                            ld=_ld(t), col0=0, flags=EPI_OUT_ACCUMULATE if (accumulate or written[i]) else 0)
+                        written[i] = True
+                    c += w
             else:
                 w = spec.hidden[mask_layer][1]
                 _op(prog, kind=OP_EPI, slot=out_slot0, ncols=w, npad=w, tmem_col=0, mask_ptr=ptrs.add(act),
@@ -407,22 +440,21 @@ def run_backward(spec, params, g_heads, act, packed, P, grad_sinks, need_input_g
         cur0, nxt0 = nxt0, cur0
     arr, n = ptrs.array()
     _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
+    return dy
 
-    # ---- weight gradients
+
+def wgrad_layers(spec, act, dy, grad_sinks, wptrs):
+    """Weight-gradient descriptors of one stack; grad_sinks[name] = (g_kernel, g_bias) accumulated into."""
+    ia, idy = wptrs.add(act), wptrs.add(dy)
+    nh = len(spec.hidden)
     layers = []
-    def x_desc(L, parts):
-        atoms = spec.x_atoms(parts)
-        atoms = [a for a in atoms if a[3] > 0]
+
+    def fill_x(L, parts, layer_index):
+        atoms = [a for a in spec.x_atoms(parts) if a[3] > 0]
         if len(atoms) > WGRAD_MAX_X:
             raise ValueError("layer input too wide for one weight-gradient pass")
         L.n_x_atoms = len(atoms)
-        return atoms
-
-    wptrs = _Ptrs()
-    ia, idy = wptrs.add(act), wptrs.add(dy)
-
-    def fill_x(L, parts, layer_index):
-        for i, (kind, c, _, valid, row, _) in enumerate(x_desc(L, parts)):
+        for i, (kind, c, _, valid, row, _) in enumerate(atoms):
             L.x_ptr[i], L.x_img_atoms[i] = ia, spec.act_atoms
             L.x_atom[i] = (spec.act_atom0(layer_index - 1) if kind == "h" else 0) + c // 64
             L.x_rows[i], L.w_row0[i] = valid, row
@@ -446,18 +478,28 @@ def run_backward(spec, params, g_heads, act, packed, P, grad_sinks, need_input_g
             L.seg_col0[s], L.seg_ncols[s], L.seg_w_ptr[s], L.seg_b_ptr[s] = col, w, wptrs.add(gk), wptrs.add(gb)
             col += w
         layers.append(L)
+    return layers
+
+
+def wgrad_launch(layers, wptrs, P):
     warr, wn = wptrs.array()
     for i in range(0, len(layers), WGRAD_MAX_LAYERS):
-        chunk_layers = layers[i:i + WGRAD_MAX_LAYERS]
-        carr = (nrc_wgrad_layer_t * len(chunk_layers))(*chunk_layers)
-        _lib.call("nrc_chain_wgrad", _lib.stream_ptr(), carr, len(chunk_layers), warr, wn, P)
-    if d_in is None:
-        return None
-    outs, c = [], 0
-    for w in spec.in_widths:
-        outs.append(d_in[:, c:c + w])
-        c += w
-    return outs
+        part = layers[i:i + WGRAD_MAX_LAYERS]
+        carr = (nrc_wgrad_layer_t * len(part))(*part)
+        _lib.call("nrc_chain_wgrad", _lib.stream_ptr(), carr, len(part), warr, wn, P)
+
+
+def resolve_sinks(named_params):
+    """named_params: {name: (kernel, bias)} -> ({name: (g_kernel, g_bias)}, {name: sunk?}).  Registered
+    gradient sinks (_lib.register_grad_sink) are accumulated into directly; otherwise fresh zeros."""
+    sinks, sunk = {}, {}
+    for name, (kern, bias) in named_params.items():
+        sk, sb = _lib.grad_sink(kern), _lib.grad_sink(bias)
+        if sk is not None and sb is not None:
+            sinks[name], sunk[name] = (sk, sb), True
+        else:
+            sinks[name], sunk[name] = (torch.zeros_like(kern), torch.zeros_like(bias)), False
+    return sinks, sunk
 
 
 class _ChainFn(torch.autograd.Function):
@@ -465,12 +507,12 @@ class _ChainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, names, n_src, *tensors):
-        sources = [t.contiguous() for t in tensors[:n_src]]
+        sources = [t if (t.dim() == 2 and t.stride(-1) == 1) else t.contiguous() for t in tensors[:n_src]]
         flat = tensors[n_src:]
         params = {name: {"kernel": flat[2 * i], "bias": flat[2 * i + 1]} for i, name in enumerate(names)}
         need_grad = any(t.requires_grad for t in tensors)
         packed = pack_weights(spec, params)
-        outs, act = run_forward(spec, params, sources, packed, save=need_grad)
+        _, outs, act = run_forward(spec, params, sources, packed, save=need_grad)
         ctx.spec, ctx.names, ctx.n_src = spec, names, n_src
         ctx.P = sources[0].shape[0]
         ctx.save_for_backward(act, packed, *flat)
@@ -484,7 +526,6 @@ class _ChainFn(torch.autograd.Function):
         params = {name: {"kernel": flat[2 * i], "bias": flat[2 * i + 1]} for i, name in enumerate(names)}
         P = ctx.P
         dev = act.device
-        # upstream gradients per head group, packed [P, head_pad]
         g_heads, k = [], 0
         for g, grp in enumerate(spec.heads):
             buf = torch.zeros((P, spec.head_pads[g]), device=dev, dtype=torch.float32)
@@ -495,23 +536,18 @@ class _ChainFn(torch.autograd.Function):
                 c += w
                 k += 1
             g_heads.append(buf)
-        sinks, sunk, ret = {}, {}, {}
-        for i, name in enumerate(names):
-            kern, bias = flat[2 * i], flat[2 * i + 1]
-            sk, sb = _lib.grad_sink(kern), _lib.grad_sink(bias)
-            if sk is not None and sb is not None:
-                sinks[name], sunk[name] = (sk, sb), True
-            else:
-                sinks[name], sunk[name] = (torch.zeros_like(kern), torch.zeros_like(bias)), False
-        d_src = run_backward(spec, params, g_heads, act, packed, P, sinks, need_input_grad=any(ctx.src_needs))
+        sinks, sunk = resolve_sinks({name: (flat[2 * i], flat[2 * i + 1]) for i, name in enumerate(names)})
+        d_src = None
+        if any(ctx.src_needs):
+            d_src = [(torch.empty((P, w), device=dev, dtype=torch.float32), False) for w in spec.in_widths]
+        dy = run_backward_data(spec, params, g_heads, act, packed, P, d_src)
+        wptrs = _Ptrs()
+        wgrad_launch(wgrad_layers(spec, act, dy, sinks, wptrs), wptrs, P)
         grads = [None, None, None]
         for i in range(n_src):
-            grads.append(d_src[i].contiguous() if (d_src is not None and ctx.src_needs[i]) else None)
+            grads.append(d_src[i][0] if (d_src is not None and ctx.src_needs[i]) else None)
         for name in names:
-            if sunk[name]:
-                grads += [None, None]
-            else:
-                grads += list(sinks[name])
+            grads += [None, None] if sunk[name] else list(sinks[name])
         return tuple(grads)
 
 

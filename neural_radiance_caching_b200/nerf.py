@@ -12,7 +12,7 @@ import math as pymath
 import numpy as np
 import torch
 
-from . import _lib, coord, grid_utils
+from . import _lib, coord, grid_utils, mlp_chain
 
 
 # ----------------------------------------------------------------------------- Dense
@@ -181,6 +181,13 @@ class SurfaceLightFieldMLP:
         self.ambient_rgb_bias, self.ambient_rgb_max = ambient_rgb_bias, ambient_rgb_max
         self.dir_enc_fn = generate_ide_fn(deg_view)
         self.bf16 = bf16
+        # tcgen05 chain (bf16 variant): the whole Dense stack is one fused program per 128-point tile
+        ide_dim = 2 * _IdeTables.get(deg_view).n_sh
+        names = self.layer_names()
+        self.chain = mlp_chain.ChainSpec(
+            in_widths=([bottleneck_width] if use_shader_bottleneck else []) + [ide_dim],
+            hidden=[(n, net_width_viewdirs, (i % skip_layer_dir == 0 and i > 0)) for i, n in enumerate(names)],
+            heads=[[("output_ambient_rgb_layer", 3)]]) if net_width_viewdirs <= 128 else None
 
     def layer_names(self):
         return [f"layer_{i}" for i in range(self.depth - 1)] + ["layer_bottleneck"]
@@ -190,6 +197,12 @@ class SurfaceLightFieldMLP:
         if self.use_shader_bottleneck:
             x.append(shader_bottleneck)
         x.append(self.dir_enc_fn(refdirs, roughness))
+        if self.bf16 and self.chain is not None:
+            lead = x[0].shape[:-1]
+            (raw,) = mlp_chain.apply(self.chain, p, [t.reshape(-1, t.shape[-1]) for t in x])
+            ambient = torch.nn.functional.softplus(raw.reshape(lead + (3,)) + self.ambient_rgb_bias)
+            return dict(incoming_ambient_rgb=torch.clamp(ambient, 0.0, self.ambient_rgb_max),
+                        incoming_acc=torch.ones(lead, device=raw.device, dtype=torch.float32))
         x = torch.cat(x, dim=-1) if len(x) > 1 else x[0]
         inputs = x
         for i, name in enumerate(self.layer_names()):  # run_surface_lightfield_network :480-500
@@ -206,6 +219,131 @@ class SurfaceLightFieldMLP:
 APPEARANCE_GRID = dict(hash_map_size=524288, max_grid_size=2048, num_features=4)
 
 
+class _ShaderBf16Fn(torch.autograd.Function):
+    """The whole cache shader (bf16 tensor-core variant) as ONE custom VJP: appearance-grid encode ->
+    trunk stack (bottleneck + heads) -> per-point `mid` stage (roughness, n.v, reflection, IDE) ->
+    integrated-BRDF / EnvMap / SurfaceLightField stacks -> per-point `out` stage.  Forward: 1 weight
+    pack, 4 chain launches, 2 encode/contract launches, 2 per-point launches.  Backward: 3 data-gradient
+    chain launches (the EnvMap's gradient is exactly zero: 1 - incoming_acc == 0), 1 weight-gradient
+    launch, 2 per-point launches, 1 encode scatter."""
+
+    @staticmethod
+    def forward(ctx, shader, names, viewdirs, means, density_feature, normals, arena, *flat):
+        lead = means.shape[:-1]
+        P = means.numel() // 3
+        spr = int(lead[-1]) if len(lead) > 1 else 1
+        dev = means.device
+        params = _unflatten_shader(names, flat)
+        specs = [(shader.trunk_chain, params[""]), (shader.brdf_chain, params[""]),
+                 (shader.surface_lf.chain, params["SurfaceLightField"]), (shader.env_map.chain, params["EnvMap"])]
+        packed, views = mlp_chain.pack_weights_many(specs)
+        train = any(t.requires_grad for t in flat) or density_feature.requires_grad or normals.requires_grad
+        m2 = means.reshape(P, 3).contiguous()
+        z = torch.empty_like(m2)
+        _lib.call("nrc_contract_fwd", _lib.stream_ptr(), _lib.ptr(m2), P, float(shader.warp_c), _lib.ptr(z))
+        enc = torch.empty((P, shader.grid.num_outputs), device=dev, dtype=torch.float32)
+        desc = shader.grid._descriptor(shader.grid.tables(shader.grid.views(arena)), None)
+        _lib.call("nrc_encode_fwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(z), P, _lib.ptr(enc))
+        feat = density_feature.reshape(P, 64).contiguous()
+        nrm = normals.reshape(P, 3).contiguous()
+        vd = viewdirs.reshape(-1, 3).contiguous()
+        (bott, heads), _, act_t = mlp_chain.run_forward(shader.trunk_chain, params[""], [feat, enc], views[0], save=train)
+        t5, t4 = _IdeTables.get(5), _IdeTables.get(4)
+        rough = torch.empty((P,), device=dev, dtype=torch.float32)
+        dot = torch.empty((P, 1), device=dev, dtype=torch.float32)
+        refdirs = torch.empty((P, 3), device=dev, dtype=torch.float32)
+        ide5 = torch.empty((P, 2 * t5.n_sh), device=dev, dtype=torch.float32)
+        ide4 = torch.empty((P, 2 * t4.n_sh), device=dev, dtype=torch.float32)
+        _lib.call("nrc_shader_mid_fwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
+                  _lib.ptr(heads), heads.shape[1], _lib.ptr(nrm), _lib.ptr(vd), P, spr, -1.0, _lib.ptr(rough),
+                  _lib.ptr(dot), _lib.ptr(refdirs), _lib.ptr(ide5), _lib.ptr(ide4))
+        (fbuf,), _, act_b = mlp_chain.run_forward(shader.brdf_chain, params[""], [bott, dot], views[1], save=train)
+        (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], [ide4], views[3], save=False)
+        (sbuf,), _, act_s = mlp_chain.run_forward(shader.surface_lf.chain, params["SurfaceLightField"], [bott, ide5],
+                                                  views[2], save=train)
+        rgb = torch.empty((P, 3), device=dev, dtype=torch.float32)
+        extras = torch.empty((P, 22), device=dev, dtype=torch.float32)
+        lb = float(shader.surface_lf.ambient_rgb_bias)
+        _lib.call("nrc_shader_out_fwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
+                  _lib.ptr(sbuf), sbuf.shape[1], _lib.ptr(ebuf), ebuf.shape[1], P, float(shader.rgb_max), -2.0, lb,
+                  float(np.log(3.0)), _lib.ptr(rgb), _lib.ptr(extras))
+        ctx.shader, ctx.names, ctx.meta = shader, names, (lead, P, spr)
+        ctx.save_for_backward(z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed, arena, *flat)
+        outs = (rgb.reshape(lead + (3,)), extras.reshape(lead + (22,)), rough.reshape(lead + (1,)),
+                bott.reshape(lead + (128,)), refdirs.reshape(lead + (3,)), enc.reshape(lead + (-1,)))
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_rgb, *_unused):
+        shader, names = ctx.shader, ctx.names
+        lead, P, spr = ctx.meta
+        z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed, arena, *flat = ctx.saved_tensors
+        dev = z.device
+        params = _unflatten_shader(names, flat)
+        b0 = 0
+        views = []
+        for spec in (shader.trunk_chain, shader.brdf_chain, shader.surface_lf.chain, shader.env_map.chain):
+            views.append(packed[b0 * (mlp_chain.ATOM_BYTES // 2):])
+            b0 += mlp_chain._built(spec).num_chunks
+        g2 = g_rgb.reshape(P, 3).contiguous()
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        g_heads, g_f, g_s = new(P, 16), new(P, 16), new(P, 16)
+        lb = float(shader.surface_lf.ambient_rgb_bias)
+        _lib.call("nrc_shader_out_bwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
+                  _lib.ptr(sbuf), sbuf.shape[1], P, float(shader.rgb_max), -2.0, lb, float(np.log(3.0)), _lib.ptr(g2),
+                  _lib.ptr(g_heads), 16, _lib.ptr(g_f), 16, _lib.ptr(g_s), 16)
+        d_bott, g_ide5, g_dot = new(P, 128), new(P, 72), new(P, 1)
+        dy_s = mlp_chain.run_backward_data(shader.surface_lf.chain, params["SurfaceLightField"], [g_s], act_s, views[2], P,
+                                           [(d_bott, False), (g_ide5, False)])
+        dy_b = mlp_chain.run_backward_data(shader.brdf_chain, params[""], [g_f], act_b, views[1], P,
+                                           [(d_bott, True), (g_dot, False)])
+        g_nrm = new(P, 3)
+        t5, t4 = _IdeTables.get(5), _IdeTables.get(4)
+        _lib.call("nrc_shader_mid_bwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
+                  _lib.ptr(heads), heads.shape[1], _lib.ptr(nrm), _lib.ptr(vd), P, spr, -1.0, _lib.ptr(g_dot), 1,
+                  _lib.ptr(g_ide5), 72, None, 0, _lib.ptr(g_heads), 16, _lib.ptr(g_nrm))
+        d_feat, d_enc = new(P, 64), new(P, 32)
+        dy_t = mlp_chain.run_backward_data(shader.trunk_chain, params[""], [d_bott, g_heads], act_t, views[0], P,
+                                           [(d_feat, False), (d_enc, False)])
+        # weight gradients of the three stacks in one launch
+        named = {}
+        for i, (scope, name) in enumerate(names):
+            named[(scope, name)] = (flat[2 * i], flat[2 * i + 1])
+        sinks, sunk = mlp_chain.resolve_sinks(named)
+        wptrs = mlp_chain._Ptrs()
+        layers = []
+        for spec, scope, act, dy in ((shader.surface_lf.chain, "SurfaceLightField", act_s, dy_s),
+                                     (shader.brdf_chain, "", act_b, dy_b), (shader.trunk_chain, "", act_t, dy_t)):
+            local = {n: sinks[(sc, n)] for (sc, n) in sinks if sc == scope}
+            layers += mlp_chain.wgrad_layers(spec, act, dy, local, wptrs)
+        mlp_chain.wgrad_launch(layers, wptrs, P)
+        # appearance grid scatter
+        g_arena = None
+        if ctx.needs_input_grad[6]:
+            sink = _lib.grad_sink(arena)
+            g_arena = sink if sink is not None else torch.zeros_like(arena)
+            desc = shader.grid._descriptor(shader.grid.tables(shader.grid.views(arena)),
+                                           shader.grid.tables(shader.grid.views(g_arena)))
+            _lib.call("nrc_encode_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(z), _lib.ptr(d_enc), P, None)
+            if sink is not None:
+                g_arena = None
+        grads = [None, None, None, None, d_feat.reshape(lead + (64,)), g_nrm.reshape(lead + (3,)), g_arena]
+        for (scope, name) in names:
+            if sunk[(scope, name)] or scope == "EnvMap":
+                grads += [None, None]     # sunk, or exactly zero (EnvMap: 1 - incoming_acc == 0)
+            else:
+                grads += list(sinks[(scope, name)])
+        return tuple(grads)
+
+
+def _unflatten_shader(names, flat):
+    params = {"": {}, "SurfaceLightField": {}, "EnvMap": {}}
+    for i, (scope, name) in enumerate(names):
+        params[scope][name] = {"kernel": flat[2 * i], "bias": flat[2 * i + 1]}
+    return params
+
+
 class NeRFMLP:
     """Cache shader (internal/nerf.py:561-689,940-1090) under configs/ngp_yobo.gin:143-176 and
     configs/nerf_ngp_yobo.gin:491-506."""
@@ -215,8 +353,33 @@ class NeRFMLP:
         self.warp_c = warp_c if warp_c is not None else 0.0
         self.rgb_max = rgb_max
         self.bf16 = bf16
+        self.fused = True   # bf16 variant: whole shader as one custom VJP (_ShaderBf16Fn)
         self.surface_lf = SurfaceLightFieldMLP(5, True, bf16=bf16)
         self.env_map = SurfaceLightFieldMLP(4, False, bf16=bf16)
+        # bf16 variant: bottleneck + the four heads are ONE GEMM over the shared 96-wide feature
+        self.trunk_chain = mlp_chain.ChainSpec(
+            in_widths=[64, 32], hidden=[],
+            heads=[[("bottleneck_layer", 128)],
+                   [("roughness_layer", 1), ("ambient_irradiance_layer", 3), ("irradiance_layer", 3), ("tint_layer", 3)]])
+        self.brdf_chain = mlp_chain.ChainSpec(
+            in_widths=[128, 1], hidden=[("integrated_brdf_layers_0", 64, False), ("integrated_brdf_layers_1", 64, False)],
+            heads=[[("output_integrated_brdf_layer", 1)]])
+
+    def _call_fused(self, p, viewdirs, means, density_feature, normals, return_feature):
+        names, flat = [], []
+        for scope, spec in (("", self.trunk_chain), ("", self.brdf_chain), ("SurfaceLightField", self.surface_lf.chain),
+                            ("EnvMap", self.env_map.chain)):
+            src = p[scope] if scope else p
+            for name in [h[0] for h in spec.hidden] + [n for grp in spec.heads for n, _ in grp]:
+                names.append((scope, name))
+                flat += [src[name]["kernel"], src[name]["bias"]]
+        rgb, ex, rough, bott, refdirs, enc = _ShaderBf16Fn.apply(
+            self, tuple(names), viewdirs, means, density_feature, normals, p["appearance_grid"]["_arena"], *flat)
+        out = dict(rgb=rgb, diffuse_rgb=ex[..., 0:3], specular_rgb=ex[..., 3:6], ambient_rgb=ex[..., 6:9],
+                   indirect_rgb=ex[..., 9:12], albedo_rgb=ex[..., 12:15], integrated_brdf=ex[..., 15:16],
+                   env_rgb=ex[..., 16:19], ref_rgb=ex[..., 19:22], roughness=rough, bottleneck=bott, refdirs=refdirs,
+                   feature=torch.cat([density_feature, enc], dim=-1) if return_feature else None)
+        return out
 
     def from_oracle(self, p, device):
         def mv(t):
@@ -236,22 +399,44 @@ class NeRFMLP:
         enc = self.grid(p["appearance_grid"], z)
         return torch.cat([density_feature, enc], dim=-1)
 
-    def __call__(self, p, viewdirs, means, density_feature, normals):
+    def __call__(self, p, viewdirs, means, density_feature, normals, return_feature=False):
         sp = torch.nn.functional.softplus
         b = self.bf16
-        feature = self.predict_appearance_feature(p, density_feature, means)
-        bottleneck = dense(p["bottleneck_layer"], feature, bf16=b)
-        roughness = sp(dense(p["roughness_layer"], feature, bf16=b) - 1.0)
-        ambient_diffuse = torch.clamp(sp(dense(p["ambient_irradiance_layer"], feature, bf16=b) - 2.0), 0.0, self.rgb_max)
-        tint = torch.sigmoid(dense(p["tint_layer"], feature, bf16=b))
+        if b and self.fused:
+            return self._call_fused(p, viewdirs, means, density_feature, normals, return_feature)
+        if b:
+            z = coord._ContractFn.apply(means, self.warp_c)
+            enc = self.grid(p["appearance_grid"], z)
+            lead = enc.shape[:-1]
+            bott, r_raw, ai_raw, irr_raw, tint_raw = mlp_chain.apply(
+                self.trunk_chain, p, [density_feature.reshape(-1, 64), enc.reshape(-1, 32)])
+            # the concatenated feature only exists inside the chain's shared-memory tile
+            feature = torch.cat([density_feature, enc], dim=-1) if return_feature else None
+            bottleneck = bott.reshape(lead + (128,))
+            r_raw, ai_raw, irr_raw, tint_raw = (t.reshape(lead + (t.shape[-1],)) for t in (r_raw, ai_raw, irr_raw, tint_raw))
+        else:
+            feature = self.predict_appearance_feature(p, density_feature, means)
+            bottleneck = dense(p["bottleneck_layer"], feature)
+            r_raw = dense(p["roughness_layer"], feature)
+            ai_raw = dense(p["ambient_irradiance_layer"], feature)
+            irr_raw = dense(p["irradiance_layer"], feature)
+            tint_raw = dense(p["tint_layer"], feature)
+        roughness = sp(r_raw - 1.0)
+        ambient_diffuse = torch.clamp(sp(ai_raw - 2.0), 0.0, self.rgb_max)
+        tint = torch.sigmoid(tint_raw)
         dotprod = torch.sum(normals * (-viewdirs[..., None, :]), dim=-1, keepdim=True)
-        x = torch.cat([bottleneck, dotprod], dim=-1)
-        x = dense(p["integrated_brdf_layers_0"], x, relu=True, bf16=b)
-        x = dense(p["integrated_brdf_layers_1"], x, relu=True, bf16=b)
-        F = torch.sigmoid(dense(p["output_integrated_brdf_layer"], x, bf16=b) + float(np.log(3.0)))
+        if b:
+            (f_raw,) = mlp_chain.apply(self.brdf_chain, p, [bottleneck.reshape(-1, 128), dotprod.reshape(-1, 1)])
+            f_raw = f_raw.reshape(dotprod.shape)
+        else:
+            x = torch.cat([bottleneck, dotprod], dim=-1)
+            x = dense(p["integrated_brdf_layers_0"], x, relu=True)
+            x = dense(p["integrated_brdf_layers_1"], x, relu=True)
+            f_raw = dense(p["output_integrated_brdf_layer"], x)
+        F = torch.sigmoid(f_raw + float(np.log(3.0)))
         refdirs = reflect(-viewdirs[..., None, :], normals)
         env_rgb = self.env_map(p["EnvMap"], refdirs, roughness, None)["incoming_ambient_rgb"]
-        indirect_diffuse = torch.clamp(sp(dense(p["irradiance_layer"], feature, bf16=b) - 2.0), 0.0, self.rgb_max)
+        indirect_diffuse = torch.clamp(sp(irr_raw - 2.0), 0.0, self.rgb_max)
         inc = self.surface_lf(p["SurfaceLightField"], refdirs, roughness, bottleneck)
         ref_rgb = inc["incoming_ambient_rgb"]
         ref_acc = inc["incoming_acc"][..., None]

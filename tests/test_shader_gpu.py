@@ -5,7 +5,7 @@ import torch
 
 from oracle import geometry as ogeo, nerf as onerf
 from neural_radiance_caching_b200 import nerf as nnerf
-from tests.util import f32, gen, rel_err
+from tests.util import f32, gen, rel_err, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -92,7 +92,8 @@ def test_cache_shader_forward(cuda_device, bf16):
     v, means, feat, nrm = _shader_inputs(g, 64, 32)
     want = o(po, v, means, feat, nrm)
     with torch.no_grad():
-        got = n(pn, v.to(cuda_device), means.to(cuda_device), feat.to(cuda_device), nrm.to(cuda_device))
+        got = n(pn, v.to(cuda_device), means.to(cuda_device), feat.to(cuda_device), nrm.to(cuda_device),
+                return_feature=True)
     tol = 2e-2 if bf16 else 1e-5
     for k in ("feature", "bottleneck", "roughness", "albedo_rgb", "integrated_brdf", "refdirs"):
         assert rel_err(got[k], want[k]) <= tol, (k, rel_err(got[k], want[k]))
@@ -101,10 +102,17 @@ def test_cache_shader_forward(cuda_device, bf16):
         assert rel_err(got[k], want[k]) <= max(tol, 1e-4), (k, rel_err(got[k], want[k]))
 
 
-def test_cache_shader_gradients(cuda_device):
+@pytest.mark.parametrize("bf16", [False, True])
+def test_cache_shader_gradients(cuda_device, bf16):
+    """fp32 path: 2e-4.  bf16 tcgen05 chains: operands are bf16-rounded at every layer and a few
+    ReLU masks flip (tests/test_chain_gpu.py pins the kernels against a rounding-exact reference),
+    so the end-to-end gradient is checked in the L2 norm at 5e-2 (the north-star's 2e-2 is a bound on the
+    forward radiance / weights, asserted in test_cache_shader_forward)."""
     g = gen(341)
     o = onerf.NeRFMLP()
-    n = nnerf.NeRFMLP()
+    n = nnerf.NeRFMLP(bf16=bf16)
+    t1, t2 = (5e-2, 5e-2) if bf16 else (2e-4, 2e-3)
+    rel_err = rel_l2 if bf16 else globals()["rel_err"]
     po = o.init(g, table_init_range=0.1)
     pn = n.from_oracle(po, cuda_device)
     v, means, feat, nrm = _shader_inputs(g, 48, 32)
@@ -135,15 +143,15 @@ def test_cache_shader_gradients(cuda_device):
             d[k] = d[k].clone().requires_grad_(True)
     fn_, nn_ = feat.to(cuda_device).requires_grad_(True), nrm.to(cuda_device).requires_grad_(True)
     (n(pn, v.to(cuda_device), means.to(cuda_device), fn_, nn_)["rgb"] * G.to(cuda_device)).sum().backward()
-    assert rel_err(fn_.grad, fo.grad) <= 2e-4
-    assert rel_err(nn_.grad, no.grad) <= 2e-3   # through d IDE / d direction (l = 16 terms)
+    assert rel_err(fn_.grad, fo.grad) <= t1
+    assert rel_err(nn_.grad, no.grad) <= t2   # through d IDE / d direction (l = 16 terms)
     gviews = n.grid.views(arena.grad)
     for name in gviews:
-        assert rel_err(gviews[name], po["appearance_grid"][name].grad) <= 2e-4, name
+        assert rel_err(gviews[name], po["appearance_grid"][name].grad) <= t1, name
     for (name, dn, kn), (_, do, ko) in zip(ln, lo):
         if "appearance_grid" in name:
             continue
         ref = do[ko].grad
         if ref is None or float(ref.abs().max()) == 0.0:
             continue  # EnvMap gets an exactly-zero gradient in this configuration (1 - ref_acc == 0)
-        assert rel_err(dn[kn].grad, ref) <= 2e-4, (name, rel_err(dn[kn].grad, ref))
+        assert rel_err(dn[kn].grad, ref) <= t1, (name, rel_err(dn[kn].grad, ref))

@@ -41,3 +41,10 @@ def rel_err(a, b, floor=1e-30):
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     return float((a - b).abs().max() / max(float(b.abs().max()), floor))
+
+
+def rel_l2(a, b, floor=1e-30):
+    """||a-b||_2 / ||b||_2 -- used for bf16 gradients, where a flipped ReLU mask moves single entries."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), floor))
