@@ -381,6 +381,22 @@ int32_t nrc_shader_out_bwd(void* stream, const float* d_heads, int64_t ldh, cons
                            float* d_g_heads, int64_t ldgh, float* d_g_f_raw, int64_t ldgf,
                            float* d_g_slf_raw, int64_t ldgs);
 
+/* ------------------------------------------- training-step glue (fused) ---- */
+/* normals = nan_to_num(-l2_normalize(grad)) (internal/ref_utils.py:45-70, internal/geometry.py:442-479):
+ * d_grad [P,3] -> d_normals [P,3]. */
+int32_t nrc_normals_fwd(void* stream, const float* d_grad, int64_t num_points, float* d_normals);
+/* VJP with the reference's gradient override (denominator clamped at float32 eps in the backward pass). */
+int32_t nrc_normals_bwd(void* stream, const float* d_grad, const float* d_g_normals, int64_t num_points,
+                        float* d_g_grad);
+/* Cache-stage objective of the benchmark step and its gradients in one pass (the loss is the root of
+ * the backward pass): mean Charbonnier(linear_to_srgb(rgb) - target) (internal/image.py:192-200,
+ * configs/ngp_yobo.gin:35-37) + prop_weight * sum_l mean((sum w_l - stop_grad(sum w_2))^2), l = 0,1.
+ *   d_rgb, d_target [R,3]; d_w{0,1,2} [R,n{0,1,2}] -> d_loss [1], d_g_rgb [R,3], d_g_w0, d_g_w1. */
+int32_t nrc_cache_loss(void* stream, const float* d_rgb, const float* d_target, const float* d_w0, int32_t n0,
+                       const float* d_w1, int32_t n1, const float* d_w2, int32_t n2, int64_t num_rays,
+                       float charb_padding, float prop_weight, float* d_loss, float* d_g_rgb, float* d_g_w0,
+                       float* d_g_w1);
+
 /* ------------------------------------------------- K5: GGX integration ---- */
 /* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) +
  * integrate_reflect_rays (:1102-1193): Disney-GGX D*F*G and Lambert lobes evaluated in the

@@ -106,6 +106,9 @@ PROTOTYPES = {
                            _P, _P, _I64, _I32, _F, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P],
     "nrc_shader_out_fwd": [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _F, _F, _F, _F, _P, _P],
     "nrc_shader_out_bwd": [_P, _P, _I64, _P, _I64, _P, _I64, _I64, _F, _F, _F, _F, _P, _P, _I64, _P, _I64, _P, _I64],
+    "nrc_normals_fwd": [_P, _P, _I64, _P],
+    "nrc_normals_bwd": [_P, _P, _P, _I64, _P],
+    "nrc_cache_loss": [_P, _P, _P, _P, _I32, _P, _I32, _P, _I32, _I64, _F, _F, _P, _P, _P, _P],
     "nrc_ggx_integrate_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P],
     "nrc_ggx_integrate_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],
 }
@@ -190,7 +193,8 @@ _grad_sinks = {}
 def register_grad_sink(param, sink):
     if sink.shape != param.shape or not sink.is_contiguous():
         raise NrcError("gradient sink must be a contiguous tensor of the parameter's shape")
-    _grad_sinks[param.data_ptr()] = sink
+    import weakref
+    _grad_sinks[param.data_ptr()] = (weakref.ref(param), sink)
 
 
 def clear_grad_sinks():
@@ -198,4 +202,15 @@ def clear_grad_sinks():
 
 
 def grad_sink(param):
-    return _grad_sinks.get(param.data_ptr())
+    """Sink registered for the parameter whose storage `param` views, or None.  Entries die with the
+    registered parameter (the allocator may hand its address to an unrelated tensor afterwards)."""
+    ent = _grad_sinks.get(param.data_ptr())
+    if ent is None:
+        return None
+    ref, sink = ent
+    owner = ref()
+    if owner is None or owner.data_ptr() != param.data_ptr() or owner.shape != param.shape:
+        if owner is None:
+            del _grad_sinks[param.data_ptr()]
+        return None
+    return sink

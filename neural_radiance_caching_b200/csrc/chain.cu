@@ -45,6 +45,93 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Epilogue of one accumulator region for the tile row this thread owns: 16 columns at a time
+// TMEM -> registers -> (+bias, ReLU | ReLU mask) -> bf16 atom slots and / or fp32 global row.
+// Specialised at compile time so the per-element work is 2-3 instructions.
+struct EpiArgs {
+  uint32_t taddr;            // TMEM address (lane quadrant + first column)
+  const float* bias;         // [ncols] or nullptr
+  float* out_row;            // fp32 output row (already offset to col0) or nullptr
+  const uint8_t* mask_tile;  // forward-activation image of this tile or nullptr
+  uint32_t slot0_addr;       // shared-memory address of the first destination slot
+  int ncols, npad, mask_atom0, r;
+  bool out_vec, accum, has_slot;
+};
+
+template <bool BIAS, bool RELU, bool MASK, bool FULL>
+__device__ __forceinline__ void epi_run(const EpiArgs& a) {
+  for (int j0 = 0; j0 < a.npad; j0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(a.taddr + j0, v);
+    uint32_t mw[8];
+    if (MASK) {
+      const int mc = a.mask_atom0 * 64 + j0;
+      const uint8_t* ma = a.mask_tile + static_cast<size_t>(mc >> 6) * kAtomBytes;
+      const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(ma + atom_chunk_offset(a.r, (mc & 63) >> 3)));
+      const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(ma + atom_chunk_offset(a.r, ((mc & 63) >> 3) + 1)));
+      mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
+      mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+    }
+    float b[16];
+    if (BIAS) {
+      if (FULL) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(a.bias + j0) + q);
+          b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) b[e] = (j0 + e < a.ncols) ? __ldg(a.bias + j0 + e) : 0.f;
+      }
+    }
+    tmem_ld_wait();
+    float x[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float t = __uint_as_float(v[e]);
+      if (BIAS) t += b[e];
+      if (RELU) t = fmaxf(t, 0.f);
+      if (MASK) {   // bf16 activation > 0  <=>  its 16 bits, read as a signed short, are > 0
+        const short h = static_cast<short>((mw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
+        t = h > 0 ? t : 0.f;
+      }
+      if (!FULL && j0 + e >= a.ncols) t = 0.f;
+      x[e] = t;
+    }
+    if (a.has_slot) {
+      const uint32_t sa = a.slot0_addr + static_cast<uint32_t>(j0 >> 6) * kAtomBytes;
+      const uint32_t d0 = sa + atom_chunk_offset(a.r, (j0 & 63) >> 3);
+      const uint32_t d1 = sa + atom_chunk_offset(a.r, ((j0 & 63) >> 3) + 1);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d0), "r"(pack2_bf16(x[0], x[1])),
+                   "r"(pack2_bf16(x[2], x[3])), "r"(pack2_bf16(x[4], x[5])), "r"(pack2_bf16(x[6], x[7]))
+                   : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d1), "r"(pack2_bf16(x[8], x[9])),
+                   "r"(pack2_bf16(x[10], x[11])), "r"(pack2_bf16(x[12], x[13])), "r"(pack2_bf16(x[14], x[15]))
+                   : "memory");
+    }
+    if (a.out_row && (FULL || j0 < a.ncols)) {
+      float* o = a.out_row + j0;
+      if (a.out_vec && (FULL || j0 + 16 <= a.ncols)) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          float4 w = make_float4(x[e], x[e + 1], x[e + 2], x[e + 3]);
+          if (a.accum) {
+            const float4 old = *reinterpret_cast<const float4*>(o + e);
+            w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+          }
+          *reinterpret_cast<float4*>(o + e) = w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (j0 + e < a.ncols) o[e] = a.accum ? o[e] + x[e] : x[e];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[16];
@@ -226,70 +313,30 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           store_pending = true;
         } else {  // NRC_OP_EPI
           if (op.slot >= 0) guard_slots();
-          const float* bias = op.ptr >= 0 ? static_cast<const float*>(p.ptrs[op.ptr]) : nullptr;
+          EpiArgs a;
+          a.bias = op.ptr >= 0 ? static_cast<const float*>(p.ptrs[op.ptr]) : nullptr;
           float* out = op.out_ptr >= 0 ? static_cast<float*>(p.ptrs[op.out_ptr]) : nullptr;
-          const uint8_t* mask = op.mask_ptr >= 0 ? static_cast<const uint8_t*>(p.ptrs[op.mask_ptr]) : nullptr;
-          const bool row_ok = row0 + r < p.num_rows;
-          const bool out_vec = out && (op.ld % 4 == 0) && (op.col0 % 4 == 0) &&
-                               ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-          const uint32_t taddr = tmem_base + t_lane + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
-          for (int j0 = 0; j0 < op.npad; j0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + j0, v);
-            uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
-            if (mask) {
-              const int mc = op.mask_atom0 * 64 + j0;
-              const uint8_t* ma = mask + (static_cast<size_t>(tile) * op.img_atoms + (mc >> 6)) * kAtomBytes;
-              m0 = __ldg(reinterpret_cast<const uint4*>(ma + atom_chunk_offset(r, (mc & 63) >> 3)));
-              m1 = __ldg(reinterpret_cast<const uint4*>(ma + atom_chunk_offset(r, ((mc & 63) >> 3) + 1)));
-            }
-            tmem_ld_wait();
-            float x[16];
-            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              float t = __uint_as_float(v[e]);
-              const int j = j0 + e;
-              if (bias && j < op.ncols) t += __ldg(bias + j);
-              if (op.flags & NRC_EPI_RELU) t = fmaxf(t, 0.f);
-              if (mask) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                const uint32_t h = (mw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
-                if ((h & 0x8000u) || (h & 0x7FFFu) == 0u) t = 0.f;
-              }
-              if (j >= op.ncols) t = 0.f;
-              x[e] = t;
-            }
-            if (op.slot >= 0) {
-              const uint32_t d0 = slot_addr(c, op.slot + (j0 >> 6)) + atom_chunk_offset(r, (j0 & 63) >> 3);
-              const uint32_t d1 = slot_addr(c, op.slot + (j0 >> 6)) + atom_chunk_offset(r, ((j0 & 63) >> 3) + 1);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d0), "r"(pack2_bf16(x[0], x[1])),
-                           "r"(pack2_bf16(x[2], x[3])), "r"(pack2_bf16(x[4], x[5])), "r"(pack2_bf16(x[6], x[7]))
-                           : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d1), "r"(pack2_bf16(x[8], x[9])),
-                           "r"(pack2_bf16(x[10], x[11])), "r"(pack2_bf16(x[12], x[13])),
-                           "r"(pack2_bf16(x[14], x[15]))
-                           : "memory");
-            }
-            if (out && row_ok && j0 < op.ncols) {
-              float* o = out + (row0 + r) * op.ld + op.col0 + j0;
-              const bool accum = (op.flags & NRC_EPI_OUT_ACCUMULATE) != 0;
-              if (out_vec && j0 + 16 <= op.ncols) {
-#pragma unroll
-                for (int e = 0; e < 16; e += 4) {
-                  float4 w = make_float4(x[e], x[e + 1], x[e + 2], x[e + 3]);
-                  if (accum) {
-                    const float4 old = *reinterpret_cast<const float4*>(o + e);
-                    w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
-                  }
-                  *reinterpret_cast<float4*>(o + e) = w;
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                  if (j0 + e < op.ncols) o[e] = accum ? o[e] + x[e] : x[e];
-              }
-            }
+          a.out_row = (out && row0 + r < p.num_rows) ? out + (row0 + r) * op.ld + op.col0 : nullptr;
+          a.out_vec = out && (op.ld % 4 == 0) && (op.col0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+          a.accum = (op.flags & NRC_EPI_OUT_ACCUMULATE) != 0;
+          a.mask_tile = op.mask_ptr >= 0 ? static_cast<const uint8_t*>(p.ptrs[op.mask_ptr]) +
+                                               static_cast<size_t>(tile) * op.img_atoms * kAtomBytes
+                                         : nullptr;
+          a.mask_atom0 = op.mask_atom0;
+          a.taddr = tmem_base + t_lane + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
+          a.has_slot = op.slot >= 0;
+          a.slot0_addr = a.has_slot ? slot_addr(c, op.slot) : 0u;
+          a.ncols = op.ncols; a.npad = op.npad; a.r = r;
+          const bool full = (op.ncols == op.npad) && (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
+          const bool relu = (op.flags & NRC_EPI_RELU) != 0;
+          if (a.mask_tile) {
+            if (full) epi_run<false, false, true, true>(a); else epi_run<false, false, true, false>(a);
+          } else if (a.bias) {
+            if (relu) { if (full) epi_run<true, true, false, true>(a); else epi_run<true, true, false, false>(a); }
+            else      { if (full) epi_run<true, false, false, true>(a); else epi_run<true, false, false, false>(a); }
+          } else {
+            if (relu) { if (full) epi_run<false, true, false, true>(a); else epi_run<false, true, false, false>(a); }
+            else      { if (full) epi_run<false, false, false, true>(a); else epi_run<false, false, false, false>(a); }
           }
         }
         ++i;

@@ -1,0 +1,145 @@
+"""Static schedule of the cache-stage training step (BASELINE config 2) over the C ABI.
+
+The autograd mirrors (sampling.py / nerf.py / render.py / models.py) keep the reference's call
+structure; this module runs the SAME kernels as one hand-ordered launch sequence -- forward, fused
+loss (+ its gradients), backward -- with every gradient accumulated straight into the flat gradient
+arena.  No elementwise glue runs between the launches, so a step is ~50 kernels and is captured in one
+CUDA graph by bench.py.  tests/test_engine_gpu.py pins it against the autograd path.
+
+Schedule (reference call sites in brackets):
+  per level l = 0,1,2   nrc_ray_sample_intervals  [sampling.py:326-354, stepfun.py:207-250]
+                        nrc_ray_cast              [coord.py:223-260, render.py:106-131]
+                        nrc_density_query_fwd     [geometry.py:199-341,442-479]
+                        nrc_ray_alpha_weights_fwd [render.py:134-169]
+  nrc_normals_fwd x2 (predicted + analytic)       [geometry.py:442-479]
+  shader_fused_forward                            [nerf.py:561-689,940-1090, surface_light_field.py:782-1069]
+  nrc_ray_composite_fwd                           [render.py:172-247]
+  nrc_cache_loss                                  [loss + d loss / d rgb, d loss / d proposal weights]
+  nrc_ray_composite_bwd, shader_fused_backward, nrc_normals_bwd
+  per level l = 2,1,0   nrc_ray_alpha_weights_bwd, nrc_density_mlp_bwd, nrc_contract_fwd, nrc_encode_bwd
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, geometry, nerf, stepfun
+
+
+class FusedCacheStep:
+    def __init__(self, model, params, charb_padding=0.001, prop_weight=0.01):
+        self.model, self.params = model, params
+        self.charb_padding, self.prop_weight = charb_padding, prop_weight
+        self._bg = {}
+
+    def _bg_ones(self, R, dev):
+        key = (R, str(dev))
+        if key not in self._bg:
+            self._bg[key] = torch.ones((R, 3), device=dev, dtype=torch.float32)
+        return self._bg[key]
+
+    def _initial_step_function(self, R, dev):
+        """sdist = [0, 1], weights = [1] per ray (sampling.py:300-309), built once per batch size."""
+        key = ("s0", R, str(dev))
+        if key not in self._bg:
+            sd = torch.zeros((R, 2), device=dev, dtype=torch.float32)
+            sd[:, 1] = 1.0
+            self._bg[key] = (sd, torch.ones((R, 1), device=dev, dtype=torch.float32))
+        return self._bg[key]
+
+    def step(self, rays, u01, target_rgb, train_frac=1.0):
+        """One forward + loss + backward; gradients land in the registered sinks.  Returns the loss
+        (device scalar) and leaves the per-level sampler state in self.last (for tests)."""
+        sampler, shader = self.model.sampler, self.model.shader
+        sp = self.params["Sampler"]
+        near = rays["near"]
+        R, dev = near.shape[0], near.device
+        st = _lib.stream_ptr
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        anneal = sampler.anneal(train_frac)
+        # ------------------------------------------------------------------ forward: proposal sampler
+        sdist, weights = self._initial_step_function(R, dev)
+        levels = []
+        nl = len(sampler.sampling_strategy)
+        for i_level, (i_mlp, _, n) in enumerate(sampler.sampling_strategy):
+            mlp, p = sampler.mlps[i_mlp], sp[f"MLP_{i_mlp}"]
+            last = i_level == nl - 1
+            sdist = stepfun.sample_intervals_from_weights(u01[i_level], sdist, weights, n, anneal=anneal,
+                                                          padding=sampler.resample_padding, domain=(0.0, 1.0))
+            tdist, means = sampler._cast(sdist, rays, False)
+            P = R * n
+            density, enc_out = new(P), new(P, mlp.in_dim)
+            feat = new(P, 64) if last else None
+            gp = new(P, 3) if mlp.enable_pred_normals else None
+            want_normals = (not mlp.normals_for_filter_only) and not mlp.disable_density_normals
+            rg = new(P, 3) if want_normals else None
+            arena = p["density_grid"]["_arena"]
+            enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)), None)
+            flat = mlp._flatten(p)
+            desc = geometry._mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals)
+            _lib.call("nrc_density_query_fwd", st(), C.byref(enc), C.byref(desc), _lib.ptr(means), P, float(mlp.warp_c),
+                      float(mlp.density_bias), int(mlp.bf16), _lib.ptr(density), None, _lib.ptr(feat), _lib.ptr(gp),
+                      _lib.ptr(rg), _lib.ptr(enc_out))
+            weights = new(R, n)
+            _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(density), _lib.ptr(tdist), _lib.ptr(rays["directions"]),
+                      R, n, int(sampler.opaque_background), _lib.ptr(weights), None, None)
+            levels.append(dict(mlp=mlp, p=p, n=n, sdist=sdist, tdist=tdist, means=means, density=density, enc_out=enc_out,
+                               feat=feat, gp=gp, rg=rg, weights=weights, arena=arena, flat=flat, desc=desc))
+        L2 = levels[-1]
+        P2 = R * L2["n"]
+        normals_pred = new(P2, 3)
+        _lib.call("nrc_normals_fwd", st(), _lib.ptr(L2["gp"]), P2, _lib.ptr(normals_pred))
+        if L2["rg"] is not None:   # analytic normals: computed like the reference, consumed by the 8f losses
+            L2["normals"] = new(P2, 3)
+            _lib.call("nrc_normals_fwd", st(), _lib.ptr(L2["rg"]), P2, _lib.ptr(L2["normals"]))
+        # ------------------------------------------------------------------ forward: shader + integrator + loss
+        shp = self.params["Shader"]
+        names, sflat = shader.fused_params(shp)
+        app_arena = shp["appearance_grid"]["_arena"]
+        outs, saved, meta = nerf.shader_fused_forward(
+            shader, names, sflat, rays["viewdirs"], L2["means"], L2["feat"].reshape(R, L2["n"], 64),
+            normals_pred.reshape(R, L2["n"], 3), app_arena, True)
+        rgb_s = outs[0].reshape(R, L2["n"], 3)
+        k = L2["n"]
+        bg = self._bg_ones(R, dev)
+        out_rgb, acc, dist = new(R, 3), new(R), new(R, 4)
+        _lib.call("nrc_ray_composite_fwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(L2["tdist"]),
+                  _lib.ptr(bg), R, k, 3, 1, _lib.ptr(out_rgb), _lib.ptr(acc), _lib.ptr(dist))
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        g_rgb = new(R, 3)
+        g_w = [new(R, lv["n"]) for lv in levels]
+        _lib.call("nrc_cache_loss", st(), _lib.ptr(out_rgb), _lib.ptr(target_rgb), _lib.ptr(levels[0]["weights"]),
+                  levels[0]["n"], _lib.ptr(levels[1]["weights"]), levels[1]["n"], _lib.ptr(L2["weights"]), k, R,
+                  float(self.charb_padding), float(self.prop_weight), _lib.ptr(loss), _lib.ptr(g_rgb), _lib.ptr(g_w[0]),
+                  _lib.ptr(g_w[1]))
+        # ------------------------------------------------------------------ backward
+        gv = new(R, k, 3)
+        _lib.call("nrc_ray_composite_bwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(bg),
+                  _lib.ptr(g_rgb), None, R, k, 3, 1, _lib.ptr(gv), _lib.ptr(g_w[2]), None)
+        d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
+        g_gp = new(P2, 3)
+        _lib.call("nrc_normals_bwd", st(), _lib.ptr(L2["gp"]), _lib.ptr(g_nrm), P2, _lib.ptr(g_gp))
+        for i_level in range(nl - 1, -1, -1):
+            lv = levels[i_level]
+            mlp, n = lv["mlp"], lv["n"]
+            P = R * n
+            last = i_level == nl - 1
+            g_density = new(P)
+            _lib.call("nrc_ray_alpha_weights_bwd", st(), _lib.ptr(lv["density"]), _lib.ptr(lv["tdist"]),
+                      _lib.ptr(rays["directions"]), _lib.ptr(g_w[i_level]), None, None, R, n, _lib.ptr(g_density))
+            sinks = [_lib.grad_sink(t) for t in lv["flat"]]
+            t_sink = _lib.grad_sink(lv["arena"])
+            if t_sink is None or any(s is None for s in sinks):
+                raise _lib.NrcError("FusedCacheStep needs registered gradient sinks for every parameter")
+            gd = geometry._grad_desc(mlp, mlp._unflatten(sinks))
+            g_enc = new(P, mlp.in_dim)
+            _lib.call("nrc_density_mlp_bwd", st(), C.byref(lv["desc"]), _lib.ptr(lv["enc_out"]), _lib.ptr(g_density),
+                      _lib.ptr(lv["density"]), _lib.ptr(d_feat) if last else None,
+                      _lib.ptr(g_gp) if (last and lv["gp"] is not None) else None, P, int(mlp.bf16), _lib.ptr(g_enc),
+                      C.byref(gd))
+            z = new(P, 3)
+            _lib.call("nrc_contract_fwd", st(), _lib.ptr(lv["means"].reshape(P, 3)), P, float(mlp.warp_c), _lib.ptr(z))
+            enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(lv["arena"])),
+                                       mlp.grid.tables(mlp.grid.views(t_sink)))
+            _lib.call("nrc_encode_bwd", st(), C.byref(enc), _lib.ptr(z), _lib.ptr(g_enc), P, None)
+        self.last = dict(levels=levels, rgb=out_rgb, acc=acc, dist=dist, shader_rgb=rgb_s)
+        return loss

@@ -219,121 +219,134 @@ class SurfaceLightFieldMLP:
 APPEARANCE_GRID = dict(hash_map_size=524288, max_grid_size=2048, num_features=4)
 
 
+def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, normals, arena, train):
+    """Forward schedule of the bf16 cache shader (no autograd): 1 weight pack, contract + appearance-grid
+    encode, trunk stack, per-point `mid` stage, integrated-BRDF / EnvMap / SurfaceLightField stacks,
+    per-point `out` stage.  Returns (outputs, saved-for-backward, meta)."""
+    lead = means.shape[:-1]
+    P = means.numel() // 3
+    spr = int(lead[-1]) if len(lead) > 1 else 1
+    dev = means.device
+    params = _unflatten_shader(names, flat)
+    specs = [(shader.trunk_chain, params[""]), (shader.brdf_chain, params[""]),
+             (shader.surface_lf.chain, params["SurfaceLightField"]), (shader.env_map.chain, params["EnvMap"])]
+    packed, views = mlp_chain.pack_weights_many(specs)
+    m2 = means.reshape(P, 3).contiguous()
+    z = torch.empty_like(m2)
+    _lib.call("nrc_contract_fwd", _lib.stream_ptr(), _lib.ptr(m2), P, float(shader.warp_c), _lib.ptr(z))
+    enc = torch.empty((P, shader.grid.num_outputs), device=dev, dtype=torch.float32)
+    desc = shader.grid._descriptor(shader.grid.tables(shader.grid.views(arena)), None)
+    _lib.call("nrc_encode_fwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(z), P, _lib.ptr(enc))
+    feat = density_feature.reshape(P, 64).contiguous()
+    nrm = normals.reshape(P, 3).contiguous()
+    vd = viewdirs.reshape(-1, 3).contiguous()
+    (bott, heads), _, act_t = mlp_chain.run_forward(shader.trunk_chain, params[""], [feat, enc], views[0], save=train)
+    t5, t4 = _IdeTables.get(5), _IdeTables.get(4)
+    rough = torch.empty((P,), device=dev, dtype=torch.float32)
+    dot = torch.empty((P, 1), device=dev, dtype=torch.float32)
+    refdirs = torch.empty((P, 3), device=dev, dtype=torch.float32)
+    ide5 = torch.empty((P, 2 * t5.n_sh), device=dev, dtype=torch.float32)
+    ide4 = torch.empty((P, 2 * t4.n_sh), device=dev, dtype=torch.float32)
+    _lib.call("nrc_shader_mid_fwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
+              _lib.ptr(heads), heads.shape[1], _lib.ptr(nrm), _lib.ptr(vd), P, spr, -1.0, _lib.ptr(rough),
+              _lib.ptr(dot), _lib.ptr(refdirs), _lib.ptr(ide5), _lib.ptr(ide4))
+    (fbuf,), _, act_b = mlp_chain.run_forward(shader.brdf_chain, params[""], [bott, dot], views[1], save=train)
+    (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], [ide4], views[3], save=False)
+    (sbuf,), _, act_s = mlp_chain.run_forward(shader.surface_lf.chain, params["SurfaceLightField"], [bott, ide5],
+                                              views[2], save=train)
+    rgb = torch.empty((P, 3), device=dev, dtype=torch.float32)
+    extras = torch.empty((P, 22), device=dev, dtype=torch.float32)
+    lb = float(shader.surface_lf.ambient_rgb_bias)
+    _lib.call("nrc_shader_out_fwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
+              _lib.ptr(sbuf), sbuf.shape[1], _lib.ptr(ebuf), ebuf.shape[1], P, float(shader.rgb_max), -2.0, lb,
+              float(np.log(3.0)), _lib.ptr(rgb), _lib.ptr(extras))
+    outs = (rgb.reshape(lead + (3,)), extras.reshape(lead + (22,)), rough.reshape(lead + (1,)),
+            bott.reshape(lead + (128,)), refdirs.reshape(lead + (3,)), enc.reshape(lead + (-1,)))
+    saved = (z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed)
+    return outs, saved, (lead, P, spr)
+
+
+def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_arena_grad=True):
+    """Backward schedule: per-point `out` VJP, SurfaceLightField and integrated-BRDF data-gradient chains
+    (the EnvMap's gradient is exactly zero: 1 - incoming_acc == 0), per-point `mid` VJP (IDE), trunk
+    data-gradient chain, ONE weight-gradient launch for the three stacks, appearance-grid scatter.
+    Returns (d_density_feature [P,64], d_normals [P,3], g_arena | None, sinks, sunk)."""
+    lead, P, spr = meta
+    z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed = saved
+    dev = z.device
+    params = _unflatten_shader(names, flat)
+    b0, views = 0, []
+    for spec in (shader.trunk_chain, shader.brdf_chain, shader.surface_lf.chain, shader.env_map.chain):
+        views.append(packed[b0 * (mlp_chain.ATOM_BYTES // 2):])
+        b0 += mlp_chain._built(spec).num_chunks
+    g2 = g_rgb.reshape(P, 3).contiguous()
+    new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+    g_heads, g_f, g_s = new(P, 16), new(P, 16), new(P, 16)
+    lb = float(shader.surface_lf.ambient_rgb_bias)
+    _lib.call("nrc_shader_out_bwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
+              _lib.ptr(sbuf), sbuf.shape[1], P, float(shader.rgb_max), -2.0, lb, float(np.log(3.0)), _lib.ptr(g2),
+              _lib.ptr(g_heads), 16, _lib.ptr(g_f), 16, _lib.ptr(g_s), 16)
+    d_bott, g_ide5, g_dot = new(P, 128), new(P, 72), new(P, 1)
+    dy_s = mlp_chain.run_backward_data(shader.surface_lf.chain, params["SurfaceLightField"], [g_s], act_s, views[2], P,
+                                       [(d_bott, False), (g_ide5, False)])
+    dy_b = mlp_chain.run_backward_data(shader.brdf_chain, params[""], [g_f], act_b, views[1], P,
+                                       [(d_bott, True), (g_dot, False)])
+    g_nrm = new(P, 3)
+    t5, t4 = _IdeTables.get(5), _IdeTables.get(4)
+    _lib.call("nrc_shader_mid_bwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
+              _lib.ptr(heads), heads.shape[1], _lib.ptr(nrm), _lib.ptr(vd), P, spr, -1.0, _lib.ptr(g_dot), 1,
+              _lib.ptr(g_ide5), 72, None, 0, _lib.ptr(g_heads), 16, _lib.ptr(g_nrm))
+    d_feat, d_enc = new(P, 64), new(P, 32)
+    dy_t = mlp_chain.run_backward_data(shader.trunk_chain, params[""], [d_bott, g_heads], act_t, views[0], P,
+                                       [(d_feat, False), (d_enc, False)])
+    named = {(scope, name): (flat[2 * i], flat[2 * i + 1]) for i, (scope, name) in enumerate(names)}
+    sinks, sunk = mlp_chain.resolve_sinks({k: v for k, v in named.items() if k[0] != "EnvMap"})
+    wptrs = mlp_chain._Ptrs()
+    layers = []
+    for spec, scope, act, dy in ((shader.surface_lf.chain, "SurfaceLightField", act_s, dy_s),
+                                 (shader.brdf_chain, "", act_b, dy_b), (shader.trunk_chain, "", act_t, dy_t)):
+        local = {n: sinks[(sc, n)] for (sc, n) in sinks if sc == scope}
+        layers += mlp_chain.wgrad_layers(spec, act, dy, local, wptrs)
+    mlp_chain.wgrad_launch(layers, wptrs, P)
+    g_arena = None
+    if need_arena_grad:
+        sink = _lib.grad_sink(arena)
+        g_arena = sink if sink is not None else torch.zeros_like(arena)
+        desc = shader.grid._descriptor(shader.grid.tables(shader.grid.views(arena)),
+                                       shader.grid.tables(shader.grid.views(g_arena)))
+        _lib.call("nrc_encode_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(z), _lib.ptr(d_enc), P, None)
+        if sink is not None:
+            g_arena = None
+    return d_feat, g_nrm, g_arena, sinks, sunk
+
+
 class _ShaderBf16Fn(torch.autograd.Function):
-    """The whole cache shader (bf16 tensor-core variant) as ONE custom VJP: appearance-grid encode ->
-    trunk stack (bottleneck + heads) -> per-point `mid` stage (roughness, n.v, reflection, IDE) ->
-    integrated-BRDF / EnvMap / SurfaceLightField stacks -> per-point `out` stage.  Forward: 1 weight
-    pack, 4 chain launches, 2 encode/contract launches, 2 per-point launches.  Backward: 3 data-gradient
-    chain launches (the EnvMap's gradient is exactly zero: 1 - incoming_acc == 0), 1 weight-gradient
-    launch, 2 per-point launches, 1 encode scatter."""
+    """The whole cache shader (bf16 tensor-core variant) as ONE custom VJP over
+    shader_fused_forward / shader_fused_backward."""
 
     @staticmethod
     def forward(ctx, shader, names, viewdirs, means, density_feature, normals, arena, *flat):
-        lead = means.shape[:-1]
-        P = means.numel() // 3
-        spr = int(lead[-1]) if len(lead) > 1 else 1
-        dev = means.device
-        params = _unflatten_shader(names, flat)
-        specs = [(shader.trunk_chain, params[""]), (shader.brdf_chain, params[""]),
-                 (shader.surface_lf.chain, params["SurfaceLightField"]), (shader.env_map.chain, params["EnvMap"])]
-        packed, views = mlp_chain.pack_weights_many(specs)
         train = any(t.requires_grad for t in flat) or density_feature.requires_grad or normals.requires_grad
-        m2 = means.reshape(P, 3).contiguous()
-        z = torch.empty_like(m2)
-        _lib.call("nrc_contract_fwd", _lib.stream_ptr(), _lib.ptr(m2), P, float(shader.warp_c), _lib.ptr(z))
-        enc = torch.empty((P, shader.grid.num_outputs), device=dev, dtype=torch.float32)
-        desc = shader.grid._descriptor(shader.grid.tables(shader.grid.views(arena)), None)
-        _lib.call("nrc_encode_fwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(z), P, _lib.ptr(enc))
-        feat = density_feature.reshape(P, 64).contiguous()
-        nrm = normals.reshape(P, 3).contiguous()
-        vd = viewdirs.reshape(-1, 3).contiguous()
-        (bott, heads), _, act_t = mlp_chain.run_forward(shader.trunk_chain, params[""], [feat, enc], views[0], save=train)
-        t5, t4 = _IdeTables.get(5), _IdeTables.get(4)
-        rough = torch.empty((P,), device=dev, dtype=torch.float32)
-        dot = torch.empty((P, 1), device=dev, dtype=torch.float32)
-        refdirs = torch.empty((P, 3), device=dev, dtype=torch.float32)
-        ide5 = torch.empty((P, 2 * t5.n_sh), device=dev, dtype=torch.float32)
-        ide4 = torch.empty((P, 2 * t4.n_sh), device=dev, dtype=torch.float32)
-        _lib.call("nrc_shader_mid_fwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
-                  _lib.ptr(heads), heads.shape[1], _lib.ptr(nrm), _lib.ptr(vd), P, spr, -1.0, _lib.ptr(rough),
-                  _lib.ptr(dot), _lib.ptr(refdirs), _lib.ptr(ide5), _lib.ptr(ide4))
-        (fbuf,), _, act_b = mlp_chain.run_forward(shader.brdf_chain, params[""], [bott, dot], views[1], save=train)
-        (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], [ide4], views[3], save=False)
-        (sbuf,), _, act_s = mlp_chain.run_forward(shader.surface_lf.chain, params["SurfaceLightField"], [bott, ide5],
-                                                  views[2], save=train)
-        rgb = torch.empty((P, 3), device=dev, dtype=torch.float32)
-        extras = torch.empty((P, 22), device=dev, dtype=torch.float32)
-        lb = float(shader.surface_lf.ambient_rgb_bias)
-        _lib.call("nrc_shader_out_fwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
-                  _lib.ptr(sbuf), sbuf.shape[1], _lib.ptr(ebuf), ebuf.shape[1], P, float(shader.rgb_max), -2.0, lb,
-                  float(np.log(3.0)), _lib.ptr(rgb), _lib.ptr(extras))
-        ctx.shader, ctx.names, ctx.meta = shader, names, (lead, P, spr)
-        ctx.save_for_backward(z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed, arena, *flat)
-        outs = (rgb.reshape(lead + (3,)), extras.reshape(lead + (22,)), rough.reshape(lead + (1,)),
-                bott.reshape(lead + (128,)), refdirs.reshape(lead + (3,)), enc.reshape(lead + (-1,)))
+        outs, saved, meta = shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, normals, arena,
+                                                 train)
+        ctx.shader, ctx.names, ctx.meta = shader, names, meta
+        ctx.save_for_backward(*saved, arena, *flat)
         ctx.mark_non_differentiable(*outs[1:])
         return outs
 
     @staticmethod
     def backward(ctx, g_rgb, *_unused):
         shader, names = ctx.shader, ctx.names
-        lead, P, spr = ctx.meta
-        z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed, arena, *flat = ctx.saved_tensors
-        dev = z.device
-        params = _unflatten_shader(names, flat)
-        b0 = 0
-        views = []
-        for spec in (shader.trunk_chain, shader.brdf_chain, shader.surface_lf.chain, shader.env_map.chain):
-            views.append(packed[b0 * (mlp_chain.ATOM_BYTES // 2):])
-            b0 += mlp_chain._built(spec).num_chunks
-        g2 = g_rgb.reshape(P, 3).contiguous()
-        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
-        g_heads, g_f, g_s = new(P, 16), new(P, 16), new(P, 16)
-        lb = float(shader.surface_lf.ambient_rgb_bias)
-        _lib.call("nrc_shader_out_bwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
-                  _lib.ptr(sbuf), sbuf.shape[1], P, float(shader.rgb_max), -2.0, lb, float(np.log(3.0)), _lib.ptr(g2),
-                  _lib.ptr(g_heads), 16, _lib.ptr(g_f), 16, _lib.ptr(g_s), 16)
-        d_bott, g_ide5, g_dot = new(P, 128), new(P, 72), new(P, 1)
-        dy_s = mlp_chain.run_backward_data(shader.surface_lf.chain, params["SurfaceLightField"], [g_s], act_s, views[2], P,
-                                           [(d_bott, False), (g_ide5, False)])
-        dy_b = mlp_chain.run_backward_data(shader.brdf_chain, params[""], [g_f], act_b, views[1], P,
-                                           [(d_bott, True), (g_dot, False)])
-        g_nrm = new(P, 3)
-        t5, t4 = _IdeTables.get(5), _IdeTables.get(4)
-        _lib.call("nrc_shader_mid_bwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
-                  _lib.ptr(heads), heads.shape[1], _lib.ptr(nrm), _lib.ptr(vd), P, spr, -1.0, _lib.ptr(g_dot), 1,
-                  _lib.ptr(g_ide5), 72, None, 0, _lib.ptr(g_heads), 16, _lib.ptr(g_nrm))
-        d_feat, d_enc = new(P, 64), new(P, 32)
-        dy_t = mlp_chain.run_backward_data(shader.trunk_chain, params[""], [d_bott, g_heads], act_t, views[0], P,
-                                           [(d_feat, False), (d_enc, False)])
-        # weight gradients of the three stacks in one launch
-        named = {}
-        for i, (scope, name) in enumerate(names):
-            named[(scope, name)] = (flat[2 * i], flat[2 * i + 1])
-        sinks, sunk = mlp_chain.resolve_sinks(named)
-        wptrs = mlp_chain._Ptrs()
-        layers = []
-        for spec, scope, act, dy in ((shader.surface_lf.chain, "SurfaceLightField", act_s, dy_s),
-                                     (shader.brdf_chain, "", act_b, dy_b), (shader.trunk_chain, "", act_t, dy_t)):
-            local = {n: sinks[(sc, n)] for (sc, n) in sinks if sc == scope}
-            layers += mlp_chain.wgrad_layers(spec, act, dy, local, wptrs)
-        mlp_chain.wgrad_launch(layers, wptrs, P)
-        # appearance grid scatter
-        g_arena = None
-        if ctx.needs_input_grad[6]:
-            sink = _lib.grad_sink(arena)
-            g_arena = sink if sink is not None else torch.zeros_like(arena)
-            desc = shader.grid._descriptor(shader.grid.tables(shader.grid.views(arena)),
-                                           shader.grid.tables(shader.grid.views(g_arena)))
-            _lib.call("nrc_encode_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(z), _lib.ptr(d_enc), P, None)
-            if sink is not None:
-                g_arena = None
+        lead = ctx.meta[0]
+        saved, arena, flat = ctx.saved_tensors[:10], ctx.saved_tensors[10], ctx.saved_tensors[11:]
+        d_feat, g_nrm, g_arena, sinks, sunk = shader_fused_backward(
+            shader, names, flat, saved, ctx.meta, arena, g_rgb, need_arena_grad=ctx.needs_input_grad[6])
         grads = [None, None, None, None, d_feat.reshape(lead + (64,)), g_nrm.reshape(lead + (3,)), g_arena]
-        for (scope, name) in names:
-            if sunk[(scope, name)] or scope == "EnvMap":
-                grads += [None, None]     # sunk, or exactly zero (EnvMap: 1 - incoming_acc == 0)
+        for key in names:
+            if key[0] == "EnvMap" or sunk[key]:
+                grads += [None, None]     # exactly zero (EnvMap: 1 - incoming_acc == 0), or sunk
             else:
-                grads += list(sinks[(scope, name)])
+                grads += list(sinks[key])
         return tuple(grads)
 
 
@@ -365,7 +378,8 @@ class NeRFMLP:
             in_widths=[128, 1], hidden=[("integrated_brdf_layers_0", 64, False), ("integrated_brdf_layers_1", 64, False)],
             heads=[[("output_integrated_brdf_layer", 1)]])
 
-    def _call_fused(self, p, viewdirs, means, density_feature, normals, return_feature):
+    def fused_params(self, p):
+        """((scope, name) list, [kernel, bias, ...]) of every Dense layer, in stack order."""
         names, flat = [], []
         for scope, spec in (("", self.trunk_chain), ("", self.brdf_chain), ("SurfaceLightField", self.surface_lf.chain),
                             ("EnvMap", self.env_map.chain)):
@@ -373,8 +387,12 @@ class NeRFMLP:
             for name in [h[0] for h in spec.hidden] + [n for grp in spec.heads for n, _ in grp]:
                 names.append((scope, name))
                 flat += [src[name]["kernel"], src[name]["bias"]]
+        return tuple(names), flat
+
+    def _call_fused(self, p, viewdirs, means, density_feature, normals, return_feature):
+        names, flat = self.fused_params(p)
         rgb, ex, rough, bott, refdirs, enc = _ShaderBf16Fn.apply(
-            self, tuple(names), viewdirs, means, density_feature, normals, p["appearance_grid"]["_arena"], *flat)
+            self, names, viewdirs, means, density_feature, normals, p["appearance_grid"]["_arena"], *flat)
         out = dict(rgb=rgb, diffuse_rgb=ex[..., 0:3], specular_rgb=ex[..., 3:6], ambient_rgb=ex[..., 6:9],
                    indirect_rgb=ex[..., 9:12], albedo_rgb=ex[..., 12:15], integrated_brdf=ex[..., 15:16],
                    env_rgb=ex[..., 16:19], ref_rgb=ex[..., 19:22], roughness=rough, bottleneck=bott, refdirs=refdirs,

@@ -39,12 +39,25 @@ class _SafeExpFn(torch.autograd.Function):
         return g * y
 
 
-def _l2_normalize(x):
-    """ref_utils.l2_normalize forward value (internal/ref_utils.py:45-70)."""
-    tiny = float(np.finfo(np.float32).tiny)
-    denom_sq = torch.sum(x * x, dim=-1, keepdim=True)
-    n = x / torch.sqrt(torch.clamp(denom_sq, min=tiny))
-    return torch.where(denom_sq < tiny, torch.zeros_like(n), n)
+class _NormalsFn(torch.autograd.Function):
+    """nan_to_num(-ref_utils.l2_normalize(x)) (internal/ref_utils.py:45-70, geometry.py:442-479) with the
+    reference's gradient override (forward clamps |x|^2 at tiny, backward at eps): nrc_normals_{fwd,bwd}."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x2 = x.reshape(-1, 3).contiguous()
+        n = torch.empty_like(x2)
+        _lib.call("nrc_normals_fwd", _lib.stream_ptr(), _lib.ptr(x2), x2.shape[0], _lib.ptr(n))
+        ctx.save_for_backward(x2)
+        return n.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x2,) = ctx.saved_tensors
+        g2 = g.reshape(-1, 3).contiguous()
+        out = torch.empty_like(x2)
+        _lib.call("nrc_normals_bwd", _lib.stream_ptr(), _lib.ptr(x2), _lib.ptr(g2), x2.shape[0], _lib.ptr(out))
+        return out.reshape(g.shape)
 
 
 class ProposalVolumeSampler:
@@ -131,11 +144,11 @@ class ProposalVolumeSampler:
                         res["raw_grad_density"] = mlp.query(p, means, want_feat=False, want_normals=True)[
                             "raw_grad_density"]
             if res.get("raw_grad_density") is not None and want_normals:
-                res["normals"] = torch.nan_to_num(-_l2_normalize(res["raw_grad_density"]))
+                res["normals"] = _NormalsFn.apply(res["raw_grad_density"])
             else:
                 res["normals"] = None
             if mlp.enable_pred_normals:
-                res["normals_pred"] = torch.nan_to_num(-_l2_normalize(res["grad_pred"]))
+                res["normals_pred"] = _NormalsFn.apply(res["grad_pred"])
                 res["normals_to_use"] = res["normals_pred"]
             else:
                 res["normals_pred"] = None

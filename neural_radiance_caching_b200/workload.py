@@ -23,23 +23,32 @@ def make_rays_np(g, R, near=2.0, far=6.0, radius=4.0, radii=5e-4):
                 near=np.full((R, 1), near, np.float32), far=np.full((R, 1), far, np.float32))
 
 
+_RAY_FIELDS = (("origins", 3), ("directions", 3), ("viewdirs", 3), ("radii", 1), ("near", 1), ("far", 1))
+
+
 def pack_rays(rays_np, u01_np, extra=None):
-    """One [R, C] fp32 host buffer per step (a single pinned H2D copy): origins 3, directions 3,
-    viewdirs 3, radii 1, near 1, far 1, u01 x3, then `extra` columns (e.g. target rgb)."""
-    cols = [rays_np["origins"], rays_np["directions"], rays_np["viewdirs"], rays_np["radii"], rays_np["near"],
-            rays_np["far"]] + list(u01_np)
+    """One flat fp32 host buffer per step (a single pinned H2D copy), structure-of-arrays: the blocks
+    origins [R,3] | directions [R,3] | viewdirs [R,3] | radii [R,1] | near [R,1] | far [R,1] | u01 x3 [R,1]
+    | `extra` [R,E] (e.g. target rgb) lie back to back, so the device-side views are contiguous."""
+    blocks = [rays_np[k] for k, _ in _RAY_FIELDS] + list(u01_np)
     if extra is not None:
-        cols.append(extra)
-    return np.ascontiguousarray(np.concatenate(cols, axis=-1), dtype=np.float32)
+        blocks.append(extra)
+    return np.ascontiguousarray(np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1) for b in blocks]))
 
 
-def unpack_rays(buf):
-    """Views (made contiguous) into the packed device buffer."""
-    c = lambda a: a.contiguous()
-    rays = dict(origins=c(buf[:, 0:3]), directions=c(buf[:, 3:6]), viewdirs=c(buf[:, 6:9]), radii=c(buf[:, 9:10]),
-                near=c(buf[:, 10:11]), far=c(buf[:, 11:12]))
-    u01 = [c(buf[:, 12 + i:13 + i]) for i in range(3)]
-    extra = c(buf[:, 15:]) if buf.shape[1] > 15 else None
+def unpack_rays(buf, extra_cols=3):
+    """Zero-copy views into the packed device buffer (see pack_rays)."""
+    cols = sum(c for _, c in _RAY_FIELDS) + 3 + extra_cols
+    R = buf.numel() // cols
+    off, rays = 0, {}
+    for k, c in _RAY_FIELDS:
+        rays[k] = buf[off:off + R * c].view(R, c)
+        off += R * c
+    u01 = []
+    for _ in range(3):
+        u01.append(buf[off:off + R].view(R, 1))
+        off += R
+    extra = buf[off:off + R * extra_cols].view(R, extra_cols) if extra_cols else None
     return rays, u01, extra
 
 
@@ -78,7 +87,7 @@ class CacheTrainStep:
     loss -> backward: gradients for the 4 hash-grid arenas (3 density grids + appearance grid) and
     every MLP weight on the path."""
 
-    def __init__(self, device, table_init_range=0.1, seed=SEED, bf16=False):
+    def __init__(self, device, table_init_range=0.1, seed=SEED, bf16=False, fused=True):
         self.device = device
         self.model = models.NeRFModel(bf16=bf16)
         gen = torch.Generator(device=device)
@@ -138,6 +147,8 @@ class CacheTrainStep:
             _lib.register_grad_sink(t, sink)
             t.grad = sink
             off += pad(n)
+        from . import engine as _engine
+        self.engine = _engine.FusedCacheStep(self.model, self.params) if (bf16 and fused) else None
 
     def num_params(self):
         return sum(int(t.numel()) for t in self.leaves)
@@ -146,7 +157,15 @@ class CacheTrainStep:
         self.flat_grad.zero_()
 
     def step(self, rays, u01, target_rgb):
-        """Forward + loss + backward of one ray batch; returns the loss (device scalar)."""
+        """Forward + loss + backward of one ray batch; returns the loss (device scalar).  The bf16
+        variant runs the hand-ordered launch schedule of engine.FusedCacheStep (same kernels, no
+        elementwise glue); the fp32 parity variant goes through the autograd mirrors."""
+        if self.engine is not None:
+            self.zero_grad()
+            return self.engine.step(rays, u01, target_rgb)
+        return self.step_autograd(rays, u01, target_rgb)
+
+    def step_autograd(self, rays, u01, target_rgb):
         self.zero_grad()
         res = self.model(self.params, rays, u01, train=True)
         loss = cache_loss(res, target_rgb)

@@ -1,0 +1,47 @@
+"""engine.FusedCacheStep (hand-ordered launch schedule of the config-2 training step) against the
+autograd mirrors running the same kernels: loss and every gradient must agree up to the summation
+order of the atomic reductions."""
+import numpy as np
+import pytest
+import torch
+
+from neural_radiance_caching_b200 import workload
+from tests.util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(dev, R, seed_offset=0):
+    g = np.random.Generator(np.random.PCG64(workload.SEED + 7 + seed_offset))
+    rn = workload.make_rays_np(g, R)
+    u = [g.uniform(size=(R, 1)).astype(np.float32) for _ in range(3)]
+    tgt = g.uniform(size=(R, 3)).astype(np.float32)
+    buf = torch.from_numpy(workload.pack_rays(rn, u, tgt)).to(dev)
+    return workload.unpack_rays(buf)
+
+
+@pytest.mark.parametrize("R", [256, 1000])
+def test_fused_step_matches_autograd(cuda_device, R):
+    step = workload.CacheTrainStep(cuda_device, bf16=True)
+    assert step.engine is not None
+    rays, u01, tgt = _batch(cuda_device, R)
+    loss_a = float(step.step_autograd(rays, u01, tgt))
+    grad_a = step.flat_grad.clone()
+    loss_f = float(step.step(rays, u01, tgt))
+    grad_f = step.flat_grad.clone()
+    assert abs(loss_f - loss_a) <= 1e-5 * max(1.0, abs(loss_a))
+    assert float(grad_a.abs().max()) > 0
+    off = 0
+    for t in step.leaves:   # per parameter, so that small tensors are not hidden by large ones
+        n = t.numel()
+        pad = (n + 63) // 64 * 64
+        a, f = grad_a[off:off + n], grad_f[off:off + n]
+        if float(a.abs().max()) > 0:
+            assert rel_l2(f, a) <= 1e-3, (tuple(t.shape), rel_l2(f, a))
+        else:
+            assert float(f.abs().max()) == 0.0
+        off += pad
+    # the forward state the engine exposes matches the autograd model's rendering
+    with torch.no_grad():
+        res = step.model(step.params, rays, u01, train=False)
+    assert rel_err(step.engine.last["rgb"], res["render"]["rgb"]) <= 1e-5
