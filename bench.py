@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=1024, help="rays per GPU per step (config 2: 1024)")
-    ap.add_argument("--bf16", type=int, default=0, help="1: bf16 tensor-core MLP variant")
+    ap.add_argument("--bf16", type=int, default=1,
+                    help="1 (default): bf16 tensor-core MLPs (tcgen05), north-star tolerance 2e-2; 0: fp32 parity variant")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="print per-ABI-call device times")
@@ -316,7 +317,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    roof = roofline(per_kernel, R, pk, pk_kind)
+    roof = roofline(per_kernel, R, pk, pk_kind, bool(args.bf16))
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, dt, threads = cpu_reference_throughput(args.cpu_rays, 3, 1)
@@ -326,9 +327,12 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16-mlp/f32" if args.bf16 else "f32", "data": "synthetic",
+        "dtype": "bf16" if args.bf16 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": R, "samples_per_ray": [64, 64, 32],
                    "shaded_points_per_ray": 32,
+                   "precision": ("MLP operands bf16 on tcgen05 tensor cores with fp32 accumulation (north-star bf16-MLP "
+                                 "variant, tolerance 2e-2); hash grids, gathers, scatters and ray kernels fp32")
+                   if args.bf16 else "fp32 parity variant (1e-5)",
                    "tables": "MLP_0/1/2 density grids + appearance grid (7.5+9.6+46.7+46.7 MB fp32), "
                              "U(+-0.1) trained-like init",
                    "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
@@ -376,10 +380,28 @@ def profile_calls(one_step, _lib, iters=5):
     return out
 
 
-def roofline(per_kernel, R, pk, pk_kind):
-    """Roofline of the dominant kernel of the step.  Algorithmic bytes:
-    encode fwd per point = 12 (x) + 8*F*4*L (corner rows) + 4*L*F (features);
-    encode bwd per point = 12 + 4*L*F (upstream grad) + 2 * 8*F*4*L (atomic read-modify-write)."""
+def _traffic(kernel):
+    """Measured DRAM bytes per launch of `kernel` from the committed ncu --set full summary, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get(kernel)
+    except Exception:
+        return None
+
+
+# Dense MACs per shaded point of the cache shader's stacks (SURVEY 8d / DESIGN.md 5)
+SHADER_MAC_FWD = 96 * 138 + (129 * 64 + 64 * 64 + 64) + (200 * 128 + 128 * 128 + 128 * 128 + 328 * 128 + 128 * 3) + (
+    38 * 128 + 128 * 128 + 128 * 128 + 166 * 128 + 128 * 3)
+SHADER_MAC_ENV = 38 * 128 + 128 * 128 + 128 * 128 + 166 * 128 + 128 * 3
+
+
+def roofline(per_kernel, R, pk, pk_kind, bf16):
+    """Roofline of the dominant entry point of the step (per-call CUDA events on the launching stream).
+    Algorithmic work:
+      encode fwd per point = 12 (x) + 8*F*4*L (corner rows) + 4*L*F (features) bytes;
+      encode bwd per point = 12 + 4*L*F (upstream grad) + 2 * 8*F*4*L (atomic read-modify-write) bytes;
+      shader stacks per shaded point = SHADER_MAC_FWD MACs forward, the same minus the EnvMap (whose
+      gradient is exactly zero) for the data-gradient pass, and again for the weight gradients."""
     if not per_kernel:
         return None
     top = max(per_kernel, key=per_kernel.get)
@@ -391,22 +413,35 @@ def roofline(per_kernel, R, pk, pk_kind):
     app_bwd = 32 * R * (12 + 4 * 32 + 2 * 8 * 4 * 4 * 8)
     # nrc_encode_fwd is only the appearance grid (density grids are gathered inside the fused
     # query); nrc_encode_bwd scatters into all four grids.
-    alg = {"nrc_encode_fwd": app_fwd, "nrc_encode_bwd": bwd + app_bwd, "nrc_density_query_fwd": fwd}
-    peak = pk["hbm_gbs"]
-    res = {"kernel": top, "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": pk_kind, "traffic": None}
-    if top in alg:
-        ach = alg[top] / (per_kernel[top] * 1e-3) / 1e9
-        res.update(achieved=ach, frac=ach / peak,
-                   note="sum over the 3 levels' launches of this entry point per step; per-call CUDA events")
+    alg_bytes = {"nrc_encode_fwd": app_fwd, "nrc_encode_bwd": bwd + app_bwd, "nrc_density_query_fwd": fwd}
+    shaded = 32 * R
+    alg_flops = {"nrc_chain_run": 2.0 * shaded * (2 * SHADER_MAC_FWD - SHADER_MAC_ENV),
+                 "nrc_chain_wgrad": 2.0 * shaded * (SHADER_MAC_FWD - SHADER_MAC_ENV)}
+    if not bf16:
+        alg_flops = {"nrc_dense_fwd": 2.0 * shaded * SHADER_MAC_FWD, "nrc_dense_bwd": 4.0 * shaded * SHADER_MAC_FWD}
+    res = {"kernel": top, "peak_source": pk_kind, "traffic": _traffic(top)}
+    if top in alg_bytes:
+        ach = alg_bytes[top] / (per_kernel[top] * 1e-3) / 1e9
+        res.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], achieved=ach, frac=ach / pk["hbm_gbs"],
+                   note="all launches of this entry point in one step; algorithmic bytes / summed CUDA-event time")
+    elif top in alg_flops:
+        peak = pk["bf16_tflops"] if bf16 else None
+        ach = alg_flops[top] / (per_kernel[top] * 1e-3) / 1e12
+        res.update(bound="tensor", unit="TFLOP/s", peak=peak, achieved=ach, frac=(ach / peak) if peak else None,
+                   note="all launches of this entry point in one step (shader stacks fwd + data-gradient); "
+                        "algorithmic FLOPs / summed CUDA-event time; peak = measured cuBLAS bf16 burst")
     else:
-        res.update(achieved=None, frac=None,
-                   note="dominant entry point is a dense/MLP kernel (FP32 or tensor pipe bound); the gather "
-                        "kernels' HBM fractions are listed beside it")
-    # always report the encode kernels too
-    for k in ("nrc_encode_fwd", "nrc_encode_bwd", "nrc_density_query_fwd"):
+        res.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], achieved=None, frac=None,
+                   note="dominant entry point has no closed-form work model; see the per-kernel list")
+    for k in alg_bytes:
         if k in per_kernel:
-            a = alg[k] / (per_kernel[k] * 1e-3) / 1e9
-            res[k] = {"achieved": a, "frac": a / peak, "ms": per_kernel[k]}
+            a = alg_bytes[k] / (per_kernel[k] * 1e-3) / 1e9
+            res[k] = {"bound": "hbm", "achieved": a, "frac": a / pk["hbm_gbs"], "ms": per_kernel[k], "unit": "GB/s"}
+    for k in alg_flops:
+        if k in per_kernel and bf16:
+            a = alg_flops[k] / (per_kernel[k] * 1e-3) / 1e12
+            res[k] = {"bound": "tensor", "achieved": a, "frac": a / pk["bf16_tflops"], "ms": per_kernel[k],
+                      "unit": "TFLOP/s"}
     return res
 
 

@@ -30,6 +30,13 @@ class FusedCacheStep:
         self.model, self.params = model, params
         self.charb_padding, self.prop_weight = charb_padding, prop_weight
         self._bg = {}
+        self._side = None
+        self.concurrent = True   # independent branches of the schedule on side streams (fork/join events)
+
+    def _streams(self, n):
+        if self._side is None or len(self._side) < n:
+            self._side = [torch.cuda.Stream() for _ in range(n)]
+        return self._side
 
     def _bg_ones(self, R, dev):
         key = (R, str(dev))
@@ -56,6 +63,18 @@ class FusedCacheStep:
         st = _lib.stream_ptr
         new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
         anneal = sampler.anneal(train_frac)
+        main = torch.cuda.current_stream()
+        s_pack, s_enc, s_env, s_prop = self._streams(4) if self.concurrent else (None,) * 4
+        shp = self.params["Shader"]
+        names, sflat = shader.fused_params(shp)
+        app_arena = shp["appearance_grid"]["_arena"]
+        # weight packing does not depend on the rays: runs beside the sampler
+        if s_pack is not None:
+            s_pack.wait_stream(main)
+            with torch.cuda.stream(s_pack):
+                packed = nerf.shader_pack(shader, names, sflat)
+        else:
+            packed = nerf.shader_pack(shader, names, sflat)
         # ------------------------------------------------------------------ forward: proposal sampler
         sdist, weights = self._initial_step_function(R, dev)
         levels = []
@@ -67,6 +86,13 @@ class FusedCacheStep:
                                                           padding=sampler.resample_padding, domain=(0.0, 1.0))
             tdist, means = sampler._cast(sdist, rays, False)
             P = R * n
+            if last:   # the appearance-grid gather only needs the final sample positions
+                if s_enc is not None:
+                    s_enc.wait_stream(main)
+                    with torch.cuda.stream(s_enc):
+                        encoded = nerf.shader_encode(shader, means, app_arena)
+                else:
+                    encoded = nerf.shader_encode(shader, means, app_arena)
             density, enc_out = new(P), new(P, mlp.in_dim)
             feat = new(P, 64) if last else None
             gp = new(P, 3) if mlp.enable_pred_normals else None
@@ -92,12 +118,12 @@ class FusedCacheStep:
             L2["normals"] = new(P2, 3)
             _lib.call("nrc_normals_fwd", st(), _lib.ptr(L2["rg"]), P2, _lib.ptr(L2["normals"]))
         # ------------------------------------------------------------------ forward: shader + integrator + loss
-        shp = self.params["Shader"]
-        names, sflat = shader.fused_params(shp)
-        app_arena = shp["appearance_grid"]["_arena"]
+        if self.concurrent:
+            main.wait_stream(s_pack)
+            main.wait_stream(s_enc)
         outs, saved, meta = nerf.shader_fused_forward(
             shader, names, sflat, rays["viewdirs"], L2["means"], L2["feat"].reshape(R, L2["n"], 64),
-            normals_pred.reshape(R, L2["n"], 3), app_arena, True)
+            normals_pred.reshape(R, L2["n"], 3), app_arena, True, packed=packed, encoded=encoded, env_stream=s_env)
         rgb_s = outs[0].reshape(R, L2["n"], 3)
         k = L2["n"]
         bg = self._bg_ones(R, dev)
@@ -112,34 +138,46 @@ class FusedCacheStep:
                   float(self.charb_padding), float(self.prop_weight), _lib.ptr(loss), _lib.ptr(g_rgb), _lib.ptr(g_w[0]),
                   _lib.ptr(g_w[1]))
         # ------------------------------------------------------------------ backward
+        # The proposal levels' gradients only depend on the loss kernel: they run beside the shader's.
+        if s_prop is not None:
+            s_prop.wait_stream(main)
+            with torch.cuda.stream(s_prop):
+                for i_level in range(nl - 2, -1, -1):
+                    self._level_backward(levels[i_level], rays, g_w[i_level], None, None, R)
         gv = new(R, k, 3)
         _lib.call("nrc_ray_composite_bwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(bg),
                   _lib.ptr(g_rgb), None, R, k, 3, 1, _lib.ptr(gv), _lib.ptr(g_w[2]), None)
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
         g_gp = new(P2, 3)
         _lib.call("nrc_normals_bwd", st(), _lib.ptr(L2["gp"]), _lib.ptr(g_nrm), P2, _lib.ptr(g_gp))
-        for i_level in range(nl - 1, -1, -1):
-            lv = levels[i_level]
-            mlp, n = lv["mlp"], lv["n"]
-            P = R * n
-            last = i_level == nl - 1
-            g_density = new(P)
-            _lib.call("nrc_ray_alpha_weights_bwd", st(), _lib.ptr(lv["density"]), _lib.ptr(lv["tdist"]),
-                      _lib.ptr(rays["directions"]), _lib.ptr(g_w[i_level]), None, None, R, n, _lib.ptr(g_density))
-            sinks = [_lib.grad_sink(t) for t in lv["flat"]]
-            t_sink = _lib.grad_sink(lv["arena"])
-            if t_sink is None or any(s is None for s in sinks):
-                raise _lib.NrcError("FusedCacheStep needs registered gradient sinks for every parameter")
-            gd = geometry._grad_desc(mlp, mlp._unflatten(sinks))
-            g_enc = new(P, mlp.in_dim)
-            _lib.call("nrc_density_mlp_bwd", st(), C.byref(lv["desc"]), _lib.ptr(lv["enc_out"]), _lib.ptr(g_density),
-                      _lib.ptr(lv["density"]), _lib.ptr(d_feat) if last else None,
-                      _lib.ptr(g_gp) if (last and lv["gp"] is not None) else None, P, int(mlp.bf16), _lib.ptr(g_enc),
-                      C.byref(gd))
-            z = new(P, 3)
-            _lib.call("nrc_contract_fwd", st(), _lib.ptr(lv["means"].reshape(P, 3)), P, float(mlp.warp_c), _lib.ptr(z))
-            enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(lv["arena"])),
-                                       mlp.grid.tables(mlp.grid.views(t_sink)))
-            _lib.call("nrc_encode_bwd", st(), C.byref(enc), _lib.ptr(z), _lib.ptr(g_enc), P, None)
+        self._level_backward(L2, rays, g_w[nl - 1], d_feat, g_gp if L2["gp"] is not None else None, R)
+        if s_prop is not None:
+            main.wait_stream(s_prop)
+        else:
+            for i_level in range(nl - 2, -1, -1):
+                self._level_backward(levels[i_level], rays, g_w[i_level], None, None, R)
         self.last = dict(levels=levels, rgb=out_rgb, acc=acc, dist=dist, shader_rgb=rgb_s)
         return loss
+
+    def _level_backward(self, lv, rays, g_weights, g_feat, g_gp, R):
+        """alpha-weights VJP -> fused density-MLP VJP -> hash-grid scatter of one sampler level."""
+        mlp, n = lv["mlp"], lv["n"]
+        P = R * n
+        dev = lv["density"].device
+        st = _lib.stream_ptr
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        g_density = new(P)
+        _lib.call("nrc_ray_alpha_weights_bwd", st(), _lib.ptr(lv["density"]), _lib.ptr(lv["tdist"]),
+                  _lib.ptr(rays["directions"]), _lib.ptr(g_weights), None, None, R, n, _lib.ptr(g_density))
+        sinks = [_lib.grad_sink(t) for t in lv["flat"]]
+        t_sink = _lib.grad_sink(lv["arena"])
+        if t_sink is None or any(s is None for s in sinks):
+            raise _lib.NrcError("FusedCacheStep needs registered gradient sinks for every parameter")
+        gd = geometry._grad_desc(mlp, mlp._unflatten(sinks))
+        g_enc = new(P, mlp.in_dim)
+        _lib.call("nrc_density_mlp_bwd", st(), C.byref(lv["desc"]), _lib.ptr(lv["enc_out"]), _lib.ptr(g_density),
+                  _lib.ptr(lv["density"]), _lib.ptr(g_feat), _lib.ptr(g_gp), P, int(mlp.bf16), _lib.ptr(g_enc), C.byref(gd))
+        z = new(P, 3)
+        _lib.call("nrc_contract_fwd", st(), _lib.ptr(lv["means"].reshape(P, 3)), P, float(mlp.warp_c), _lib.ptr(z))
+        enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(lv["arena"])), mlp.grid.tables(mlp.grid.views(t_sink)))
+        _lib.call("nrc_encode_bwd", st(), C.byref(enc), _lib.ptr(z), _lib.ptr(g_enc), P, None)

@@ -219,24 +219,40 @@ class SurfaceLightFieldMLP:
 APPEARANCE_GRID = dict(hash_map_size=524288, max_grid_size=2048, num_features=4)
 
 
-def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, normals, arena, train):
+def shader_pack(shader, names, flat):
+    """bf16 operand images of the four stacks (one launch): (packed buffer, per-stack views)."""
+    params = _unflatten_shader(names, flat)
+    specs = [(shader.trunk_chain, params[""]), (shader.brdf_chain, params[""]),
+             (shader.surface_lf.chain, params["SurfaceLightField"]), (shader.env_map.chain, params["EnvMap"])]
+    return mlp_chain.pack_weights_many(specs)
+
+
+def shader_encode(shader, means, arena):
+    """contract + appearance-grid encode of the shaded points (shading.py:133-220): (z [P,3], enc [P,32])."""
+    P = means.numel() // 3
+    m2 = means.reshape(P, 3).contiguous()
+    z = torch.empty_like(m2)
+    _lib.call("nrc_contract_fwd", _lib.stream_ptr(), _lib.ptr(m2), P, float(shader.warp_c), _lib.ptr(z))
+    enc = torch.empty((P, shader.grid.num_outputs), device=means.device, dtype=torch.float32)
+    desc = shader.grid._descriptor(shader.grid.tables(shader.grid.views(arena)), None)
+    _lib.call("nrc_encode_fwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(z), P, _lib.ptr(enc))
+    return z, enc
+
+
+def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, normals, arena, train, packed=None,
+                         encoded=None, env_stream=None):
     """Forward schedule of the bf16 cache shader (no autograd): 1 weight pack, contract + appearance-grid
     encode, trunk stack, per-point `mid` stage, integrated-BRDF / EnvMap / SurfaceLightField stacks,
-    per-point `out` stage.  Returns (outputs, saved-for-backward, meta)."""
+    per-point `out` stage.  `packed` / `encoded` may be supplied by a caller that produced them earlier on
+    another stream; `env_stream` runs the (independent) EnvMap stack concurrently.  Returns (outputs,
+    saved-for-backward, meta)."""
     lead = means.shape[:-1]
     P = means.numel() // 3
     spr = int(lead[-1]) if len(lead) > 1 else 1
     dev = means.device
     params = _unflatten_shader(names, flat)
-    specs = [(shader.trunk_chain, params[""]), (shader.brdf_chain, params[""]),
-             (shader.surface_lf.chain, params["SurfaceLightField"]), (shader.env_map.chain, params["EnvMap"])]
-    packed, views = mlp_chain.pack_weights_many(specs)
-    m2 = means.reshape(P, 3).contiguous()
-    z = torch.empty_like(m2)
-    _lib.call("nrc_contract_fwd", _lib.stream_ptr(), _lib.ptr(m2), P, float(shader.warp_c), _lib.ptr(z))
-    enc = torch.empty((P, shader.grid.num_outputs), device=dev, dtype=torch.float32)
-    desc = shader.grid._descriptor(shader.grid.tables(shader.grid.views(arena)), None)
-    _lib.call("nrc_encode_fwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(z), P, _lib.ptr(enc))
+    packed, views = packed if packed is not None else shader_pack(shader, names, flat)
+    z, enc = encoded if encoded is not None else shader_encode(shader, means, arena)
     feat = density_feature.reshape(P, 64).contiguous()
     nrm = normals.reshape(P, 3).contiguous()
     vd = viewdirs.reshape(-1, 3).contiguous()
@@ -250,10 +266,17 @@ def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, 
     _lib.call("nrc_shader_mid_fwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
               _lib.ptr(heads), heads.shape[1], _lib.ptr(nrm), _lib.ptr(vd), P, spr, -1.0, _lib.ptr(rough),
               _lib.ptr(dot), _lib.ptr(refdirs), _lib.ptr(ide5), _lib.ptr(ide4))
+    if env_stream is not None:
+        env_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(env_stream):
+            (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], [ide4], views[3], save=False)
+    else:
+        (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], [ide4], views[3], save=False)
     (fbuf,), _, act_b = mlp_chain.run_forward(shader.brdf_chain, params[""], [bott, dot], views[1], save=train)
-    (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], [ide4], views[3], save=False)
     (sbuf,), _, act_s = mlp_chain.run_forward(shader.surface_lf.chain, params["SurfaceLightField"], [bott, ide5],
                                               views[2], save=train)
+    if env_stream is not None:
+        torch.cuda.current_stream().wait_stream(env_stream)
     rgb = torch.empty((P, 3), device=dev, dtype=torch.float32)
     extras = torch.empty((P, 22), device=dev, dtype=torch.float32)
     lb = float(shader.surface_lf.ambient_rgb_bias)
