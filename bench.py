@@ -179,7 +179,7 @@ WORKLOAD = ("config2 nerf_ngp_yobo_lego cache training step: proposal sampler (6
 def run_b200(args):
     import torch.distributed as dist
 
-    from neural_radiance_caching_b200 import _lib, workload
+    from neural_radiance_caching_b200 import _lib, dist as ndist, workload
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -212,9 +212,7 @@ def run_b200(args):
     def allreduce_grads():
         # gradient all-reduce (mean) over all tables + MLP weights, the reference's lax.pmean
         # (internal/train_utils.py:3132-3136): ONE NCCL call over the flat gradient arena.
-        if world == 1:
-            return
-        dist.all_reduce(step_obj.flat_grad, op=dist.ReduceOp.AVG)
+        ndist.allreduce_mean_(step_obj.flat_grad)
 
     def compute_step():
         rays, u01, extra = workload.unpack_rays(dbuf)
