@@ -397,6 +397,30 @@ int32_t nrc_cache_loss(void* stream, const float* d_rgb, const float* d_target, 
                        float charb_padding, float prop_weight, float* d_loss, float* d_g_rgb, float* d_g_w0,
                        float* d_g_w1);
 
+/* ------------------------------------------- material stage (rows 18-19) ---- */
+/* importance_sample_rays + get_secondary_rays (internal/inverse_render/render_utils.py:722-1056) for ONE
+ * sampler set: n_microfacet MicrofacetSampler (:485-546) + n_cosine CosineSampler (:417-444) + n_light
+ * LightSampler (vMF mixture, :1335-1490) samples per shaded point, in this order, with the MIS power
+ * heuristic (:817-853) over the samplers present.  Local frame from get_rotation_matrix (:145-168).
+ *   d_means, d_viewdirs (camera view directions), d_normals [R,3]; d_roughness [R];
+ *   d_u [R,S,2] uniforms in [0,1) (a light sample's own uniform travels in its first slot);
+ *   light sampler (NULL when n_light == 0): d_vmf_means [R,K,3], d_vmf_kappas, d_vmf_logits [R,K],
+ *   d_latent [R] int32 (mixture component drawn per point), d_normal2 [R,n_light,2] Gaussian pairs.
+ *   -> d_origins = means + normal * normal_eps, d_directions (global) [R,S,3], d_local_lightdirs [R,S,3],
+ *      d_local_viewdirs [R,3], d_pdf, d_weight [R,S]. */
+int32_t nrc_secondary_sample(void* stream, const float* d_means, const float* d_viewdirs, const float* d_normals,
+                             const float* d_roughness, int64_t num_points, int32_t n_microfacet, int32_t n_cosine,
+                             int32_t n_light, const float* d_u, const float* d_vmf_means, const float* d_vmf_kappas,
+                             const float* d_vmf_logits, int32_t num_lobes, const int32_t* d_latent,
+                             const float* d_normal2, float normal_eps, float* d_origins, float* d_directions,
+                             float* d_local_lightdirs, float* d_local_viewdirs, float* d_pdf, float* d_weight);
+/* _get_microfacet_material (internal/material.py:1290-1322, table :957-1023, configs/ngp_yobo.gin:256-303):
+ * d_brdf_params [P,ld] (10 raw channels of pred_brdf_layer) -> albedo [P,3], roughness, metalness, F_0 [P]
+ * (constant Fresnel), specular_albedo [P] (may be NULL). */
+int32_t nrc_material_head(void* stream, const float* d_brdf_params, int64_t ld, int64_t num_points,
+                          float min_roughness, float default_f0, float* d_albedo, float* d_roughness,
+                          float* d_metalness, float* d_f0, float* d_specular_albedo);
+
 /* ------------------------------------------------- K5: GGX integration ---- */
 /* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) +
  * integrate_reflect_rays (:1102-1193): Disney-GGX D*F*G and Lambert lobes evaluated in the

@@ -109,6 +109,9 @@ PROTOTYPES = {
     "nrc_normals_fwd": [_P, _P, _I64, _P],
     "nrc_normals_bwd": [_P, _P, _P, _I64, _P],
     "nrc_cache_loss": [_P, _P, _P, _P, _I32, _P, _I32, _P, _I32, _I64, _F, _F, _P, _P, _P, _P],
+    "nrc_secondary_sample": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _F, _P, _P, _P, _P,
+                             _P, _P],
+    "nrc_material_head": [_P, _P, _I64, _I64, _F, _F, _P, _P, _P, _P, _P],
     "nrc_ggx_integrate_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P],
     "nrc_ggx_integrate_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],
 }
@@ -161,7 +164,7 @@ def ptr(t):
         raise NrcError("nrc_b200 kernels need CUDA tensors: there is no CPU fallback")
     if not t.is_contiguous():
         raise NrcError("nrc_b200 kernels need contiguous tensors")
-    if t.dtype not in (torch.float32, torch.int32):
+    if t.dtype not in (torch.float32, torch.int32, torch.bfloat16):
         raise NrcError(f"unsupported dtype {t.dtype}")
     return C.c_void_p(t.data_ptr())
 

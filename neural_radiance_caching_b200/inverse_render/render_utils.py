@@ -74,3 +74,111 @@ def integrate_reflect_rays(
         res["integrated_multiplier"] = samples["brdf_correction"][:, 0]
         res["integrated_multiplier_irradiance"] = samples["brdf_correction"][:, 0, :1]
     return res
+
+
+# ----------------------------------------------------------------------------- secondary rays
+class CosineSampler:
+    """internal/inverse_render/render_utils.py:417-444 (body: nrc_secondary_sample)."""
+    global_dirs = False
+
+
+class MicrofacetSampler:
+    """internal/inverse_render/render_utils.py:485-546 (body: nrc_secondary_sample)."""
+    global_dirs = False
+
+
+class LightSampler:
+    """vMF-mixture sampler, internal/inverse_render/render_utils.py:1419-1490 (body: nrc_secondary_sample)."""
+    global_dirs = True
+
+
+_SAMPLER_ORDER = (MicrofacetSampler, CosineSampler, LightSampler)
+
+
+def get_secondary_rays(
+    rng,
+    rays,
+    means,
+    viewdirs,
+    normals,
+    material,
+    normal_eps=1e-2,
+    refdir_eps=1e-2,
+    random_generator_2d=None,
+    stratified_sampling=False,
+    use_mis=True,
+    samplers=None,
+    num_secondary_samples=None,
+    light_sampler_results=None,
+    offset_origins=False,
+    light_rotation=None,
+    far=None,
+):
+    """Secondary rays for one sampler set (internal/inverse_render/render_utils.py:927-1056 over
+    importance_sample_rays :722-924), one shaded point per ray.
+
+    `rng` carries the random draws instead of a JAX key (the kernels never generate randomness):
+    dict(u=[R,S,2] uniforms; latent=[R] int32 and normal2=[R,n_light,2] when a LightSampler is present).
+    `samplers` = [(sampler, count)] with sampler classes in the order Microfacet, Cosine, Light and counts
+    summing to num_secondary_samples.  means / viewdirs / normals [R,3]; material['roughness'] [R,1];
+    light_sampler_results = dict(vmf_means [R,K,3], vmf_kappas [R,K,1], vmf_logits [R,K,1]).
+    Returns (ref_rays, ref_samples) like the reference (rays as a dict of [R,S,...] tensors)."""
+    if not use_mis or offset_origins or light_rotation is not None or stratified_sampling:
+        raise NotImplementedError("the CUDA path covers use_mis=True without origin offsets / light rotation")
+    counts = {MicrofacetSampler: 0, CosineSampler: 0, LightSampler: 0}
+    order = []
+    for s_, c_ in samplers:
+        cls = s_ if isinstance(s_, type) else type(s_)
+        if cls not in counts:
+            raise ValueError(f"unsupported sampler {cls}")
+        counts[cls] += int(c_)
+        order.append(cls)
+    if order != [c for c in _SAMPLER_ORDER if c in order]:
+        raise ValueError("samplers must be ordered Microfacet, Cosine, Light")
+    S = sum(counts.values())
+    if num_secondary_samples is not None and S != num_secondary_samples:
+        raise NotImplementedError("resampling of secondary samples (sum of counts != num_secondary_samples)")
+    R = means.shape[0]
+    dev = means.device
+    c = lambda t: t.contiguous() if t is not None else None
+    new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+    origins, dirs, lld, lvd, pdf, weight = new(R, S, 3), new(R, S, 3), new(R, S, 3), new(R, 3), new(R, S), new(R, S)
+    nl = counts[LightSampler]
+    lsr = light_sampler_results if nl > 0 else None
+    vm = c(lsr["vmf_means"]) if lsr else None
+    vk = c(lsr["vmf_kappas"].reshape(R, -1)) if lsr else None
+    vl = c(lsr["vmf_logits"].reshape(R, -1)) if lsr else None
+    lat = c(rng["latent"].to(torch.int32)) if nl > 0 else None
+    n2 = c(rng["normal2"]) if nl > 0 else None
+    u = c(rng["u"])
+    rough = c(material["roughness"].reshape(R))
+    m2, v2, nn = c(means), c(viewdirs), c(normals)
+    _lib.call("nrc_secondary_sample", _lib.stream_ptr(), _lib.ptr(m2), _lib.ptr(v2), _lib.ptr(nn), _lib.ptr(rough), R,
+              counts[MicrofacetSampler], counts[CosineSampler], nl, _lib.ptr(u), _lib.ptr(vm), _lib.ptr(vk), _lib.ptr(vl),
+              int(vk.shape[1]) if vk is not None else 0, _lib.ptr(lat), _lib.ptr(n2), float(normal_eps), _lib.ptr(origins),
+              _lib.ptr(dirs), _lib.ptr(lld), _lib.ptr(lvd), _lib.ptr(pdf), _lib.ptr(weight))
+    far_v = float(far) if far is not None else None
+    ref_rays = dict(origins=origins, directions=dirs, viewdirs=dirs, radii=torch.ones((R, S, 1), device=dev),
+                    near=torch.full((R, S, 1), float(refdir_eps), device=dev),
+                    far=torch.full((R, S, 1), far_v, device=dev) if far_v is not None
+                    else rays["far"].reshape(R, 1, 1).expand(R, S, 1).contiguous())
+    ref_samples = dict(local_lightdirs=lld, local_viewdirs=lvd[:, None, :].expand(R, S, 3),
+                       global_lightdirs=dirs, global_viewdirs=(-v2)[:, None, :].expand(R, S, 3),
+                       pdf=pdf[..., None], weight=weight[..., None])
+    return ref_rays, ref_samples
+
+
+def microfacet_material(brdf_params, min_roughness=0.01, default_F_0=0.04):
+    """MaterialMLP._get_microfacet_material (internal/material.py:1290-1322) for pred_brdf_layer's raw
+    output [..., 10]: dict albedo [...,3], roughness / metalness / F_0 / specular_albedo [...,1]."""
+    lead = brdf_params.shape[:-1]
+    raw = brdf_params.reshape(-1, brdf_params.shape[-1]).contiguous()
+    P = raw.shape[0]
+    dev = raw.device
+    new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+    albedo, rough, metal, f0, spec = new(P, 3), new(P), new(P), new(P), new(P)
+    _lib.call("nrc_material_head", _lib.stream_ptr(), _lib.ptr(raw), raw.shape[1], P, float(min_roughness),
+              float(default_F_0), _lib.ptr(albedo), _lib.ptr(rough), _lib.ptr(metal), _lib.ptr(f0), _lib.ptr(spec))
+    r = lambda t, *s: t.reshape(lead + s)
+    return dict(albedo=r(albedo, 3), roughness=r(rough, 1), metalness=r(metal, 1), F_0=r(f0, 1),
+                specular_albedo=r(spec, 1))
