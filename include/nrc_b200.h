@@ -397,6 +397,11 @@ int32_t nrc_cache_loss(void* stream, const float* d_rgb, const float* d_target, 
                        float charb_padding, float prop_weight, float* d_loss, float* d_g_rgb, float* d_g_w0,
                        float* d_g_w1);
 
+/* coord.pos_enc (internal/coord.py:298-312): d_x [P,dim] -> d_out [P, (append_identity ? dim : 0) +
+ * 2*dim*(max_deg-min_deg)] (row stride ldo): [x | sin(2^j x) | sin(2^j x + pi/2)]. */
+int32_t nrc_pos_enc(void* stream, const float* d_x, int64_t num_points, int32_t dim, int32_t min_deg,
+                    int32_t max_deg, int32_t append_identity, float* d_out, int64_t ldo);
+
 /* ------------------------------------------- material stage (rows 18-19) ---- */
 /* importance_sample_rays + get_secondary_rays (internal/inverse_render/render_utils.py:722-1056) for ONE
  * sampler set: n_microfacet MicrofacetSampler (:485-546) + n_cosine CosineSampler (:417-444) + n_light

@@ -153,9 +153,42 @@ __global__ void shader_out_bwd_kernel(const float* __restrict__ heads, int64_t l
   g_f[p * ldgf] = gF * F * (1.f - F);
 }
 
+// coord.pos_enc (internal/coord.py:298-312): [x, sin(2^j x), sin(2^j x + pi/2)], j = min_deg..max_deg-1
+__global__ void pos_enc_kernel(const float* __restrict__ x, int64_t P, int dim, int min_deg, int max_deg,
+                               int append_identity, float* __restrict__ out, int64_t ldo) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float* o = out + p * ldo;
+  const int nd = max_deg - min_deg;
+  int base = 0;
+  if (append_identity) {
+    for (int c = 0; c < dim; ++c) o[c] = x[p * dim + c];
+    base = dim;
+  }
+  for (int j = 0; j < nd; ++j) {
+    const float scale = exp2f(static_cast<float>(min_deg + j));
+    for (int c = 0; c < dim; ++c) {
+      const float v = __fmul_rn(x[p * dim + c], scale);
+      o[base + j * dim + c] = sinf(v);
+      o[base + nd * dim + j * dim + c] = sinf(__fadd_rn(v, 0.5f * 3.14159265358979323846f));
+    }
+  }
+}
+
 }  // namespace nrc
 
 using namespace nrc;
+
+extern "C" int32_t nrc_pos_enc(void* stream, const float* d_x, int64_t num_points, int32_t dim, int32_t min_deg,
+                               int32_t max_deg, int32_t append_identity, float* d_out, int64_t ldo) {
+  if (num_points < 0 || dim < 1 || max_deg < min_deg || ldo < (append_identity ? dim : 0) + 2 * dim * (max_deg - min_deg))
+    return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_x || !d_out) return NRC_E_INVALID_ARG;
+  pos_enc_kernel<<<static_cast<unsigned>((num_points + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_x, num_points, dim, min_deg, max_deg, append_identity, d_out, ldo);
+  return check_launch();
+}
 
 extern "C" int32_t nrc_shader_mid_fwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32_t* ml_l,
                                       const float* sigma, const float* d_mat, int32_t n_sh_env, const float* d_heads,

@@ -90,8 +90,9 @@ class ChainSpec:
 
     in_widths : widths of the fp32 sources concatenated into the stack input (all but the last
                 must be multiples of 8).
-    hidden    : [(param_name, width, skip_after)] Dense+ReLU layers (width in {64, 128}); skip_after
-                re-concatenates the stack input behind the activation (reference: `x = cat([x, inputs])`).
+    hidden    : [(param_name, width, skip_after[, 'relu' | 'linear'])] Dense layers (ReLU unless 'linear';
+                width a multiple of 16 up to 256, forward-only above 128); skip_after re-concatenates the
+                stack input behind the activation (reference: `x = cat([x, inputs])`).
     heads     : [[(param_name, width), ...], ...] groups of linear output layers on the last activation;
                 each group is one GEMM (sum of widths <= 128).
     """
@@ -103,11 +104,15 @@ class ChainSpec:
                 raise ValueError("all but the last concatenated input must have a width that is a multiple of 8")
         self.in_dim = sum(self.in_widths)
         self.in_pad = _pad(self.in_dim, 16)
-        self.hidden = [tuple(h) for h in hidden]
+        self.hidden_act = [(h[3] if len(h) > 3 else "relu") for h in hidden]
+        for a in self.hidden_act:
+            if a not in ("relu", "linear"):
+                raise ValueError("hidden activations are 'relu' or 'linear'")
+        self.hidden = [tuple(h[:3]) for h in hidden]
         self.heads = [[tuple(x) for x in grp] for grp in heads]
         for _, w, _ in self.hidden:
-            if w % 16 or w > 128:
-                raise ValueError("hidden widths must be multiples of 16, at most 128")
+            if w % 16 or w > 256:
+                raise ValueError("hidden widths must be multiples of 16, at most 256")
         self.in_atoms = _atoms_of(self.in_pad)
         self.h_slot0 = len(self.in_atoms)
         max_h = max([len(_atoms_of(w)) for _, w, _ in self.hidden] + [0])
@@ -128,8 +133,11 @@ class ChainSpec:
         self.act_atoms = len(self.in_atoms) + sum(len(_atoms_of(w)) for _, w, _ in self.hidden)
         self.dy_atoms = sum(len(_atoms_of(w)) for _, w, _ in self.hidden) + sum(
             len(_atoms_of(p)) for p in self.head_pads)
-        if max(self.fwd_slots, self._bwd_slots()) > 7:
+        if self.fwd_slots > 7:
             raise ValueError("stack does not fit the shared-memory slots of one tile context")
+        # the data-gradient program keeps two activation-gradient tiles per context and the weight-gradient
+        # kernel handles <= 128 output columns per layer: 256-wide stacks are forward-only for now
+        self.supports_backward = self._bwd_slots() <= 7 and all(w <= 128 for _, w, _ in self.hidden)
 
     # ---- derived layouts -------------------------------------------------------------------
     def act_atom0(self, layer):
@@ -180,13 +188,17 @@ def _build(spec):
     # forward chunks: per layer, one chunk per K atom of the layer input; chunk[n][k] = W[row+k][n]
     b.pack = []          # (param_name, ld, row0, nrows, col0, ncols, chunk, n0, k0, transpose)
     chunk = 0
-    b.fwd_chunk = []     # per hidden layer
+    b.fwd_chunk = []     # per hidden layer: [(first column, columns, first chunk)] per <=128-column block
     for li, (name, w, _) in enumerate(spec.hidden):
-        b.fwd_chunk.append(chunk)
-        for (_, _, _, valid, row, _) in spec.x_atoms(spec.x_parts[li]):
-            if valid > 0:
-                b.pack.append((name, w, row, valid, 0, w, chunk, 0, 0, 0))
-            chunk += 1
+        blocks = []
+        for nb in range(0, w, 128):
+            nc = min(128, w - nb)
+            blocks.append((nb, nc, chunk))
+            for (_, _, _, valid, row, _) in spec.x_atoms(spec.x_parts[li]):
+                if valid > 0:
+                    b.pack.append((name, w, row, valid, nb, nc, chunk, 0, 0, 0))
+                chunk += 1
+        b.fwd_chunk.append(blocks)
     b.fwd_head_chunk = []
     for g, grp in enumerate(spec.heads):
         b.fwd_head_chunk.append(chunk)
@@ -218,25 +230,26 @@ def _build(spec):
             row += w
         return ops
 
-    b.bwd_hidden = []    # per hidden layer: list of (part kind, first column in part, N, first chunk)
-    for li, (name, w, _) in enumerate(spec.hidden):
-        layout = [(c, _pad(n, 16), [(name, w, c, 0, n)]) for c, n in _atoms_of(w)]
-        b.bwd_hidden.append(bwd_ops(spec.x_parts[li], layout))
-    # heads: dY = concatenation of all head groups' padded columns
-    head_layout = []
-    for g, grp in enumerate(spec.heads):
-        segs, col = [], 0
-        for name, w in grp:
-            segs.append((name, w, col))
-            col += w
-        for c, n in _atoms_of(spec.head_pads[g]):
-            pieces = []
-            for name, w, scol in segs:   # intersection of [scol, scol+w) with [c, c+n)
-                lo, hi = max(scol, c), min(scol + w, c + n)
-                if lo < hi:
-                    pieces.append((name, w, lo - scol, lo - c, hi - lo))
-            head_layout.append((c, _pad(n, 16), pieces))
-    b.bwd_heads = bwd_ops(spec.x_last, head_layout)
+    b.bwd_hidden, b.bwd_heads = [], []
+    if spec.supports_backward:
+        for li, (name, w, _) in enumerate(spec.hidden):
+            layout = [(c, _pad(n, 16), [(name, w, c, 0, n)]) for c, n in _atoms_of(w)]
+            b.bwd_hidden.append(bwd_ops(spec.x_parts[li], layout))
+        # heads: dY = concatenation of all head groups' padded columns
+        head_layout = []
+        for g, grp in enumerate(spec.heads):
+            segs, col = [], 0
+            for name, w in grp:
+                segs.append((name, w, col))
+                col += w
+            for c, n in _atoms_of(spec.head_pads[g]):
+                pieces = []
+                for name, w, scol in segs:   # intersection of [scol, scol+w) with [c, c+n)
+                    lo, hi = max(scol, c), min(scol + w, c + n)
+                    if lo < hi:
+                        pieces.append((name, w, lo - scol, lo - c, hi - lo))
+                head_layout.append((c, _pad(n, 16), pieces))
+        b.bwd_heads = bwd_ops(spec.x_last, head_layout)
     b.num_chunks = chunk
     if len(b.pack) > PACK_MAX:
         raise ValueError("too many weight pieces for one pack launch")
@@ -344,9 +357,10 @@ def run_forward(spec, params, sources, packed, save=True):
         _op(prog, kind=OP_SAVE, slot=0, ptr=ptrs.add(act), col0=0, npad=len(spec.in_atoms), img_atoms=spec.act_atoms)
     for li, (name, w, _) in enumerate(spec.hidden):
         atoms = [(slot, klen) for (_, _, klen, _, _, slot) in spec.x_atoms(spec.x_parts[li])]
-        _op(prog, kind=OP_GEMM, n=w, tmem_col=0, w_chunk=b.fwd_chunk[li], atoms=atoms)
+        for (nb, nc, first) in b.fwd_chunk[li]:
+            _op(prog, kind=OP_GEMM, n=nc, tmem_col=nb, w_chunk=first, atoms=atoms)
         _op(prog, kind=OP_EPI, slot=spec.h_slot0, ptr=ptrs.add(params[name]["bias"]), ncols=w, npad=w, tmem_col=0,
-            flags=EPI_RELU)
+            flags=EPI_RELU if spec.hidden_act[li] == "relu" else 0)
         if save:
             _op(prog, kind=OP_SAVE, slot=spec.h_slot0, ptr=ptrs.add(act), col0=spec.act_atom0(li),
                 npad=len(_atoms_of(w)), img_atoms=spec.act_atoms)
@@ -379,6 +393,8 @@ def run_backward_data(spec, params, g_heads, act, packed, P, d_src=None):
     """Data-gradient pass.  g_heads: per head GROUP an fp32 [P, >= group width] view (rows contiguous).
     d_src: None (no input gradient) or per source (fp32 [P, w_i] view, accumulate flag): written
     (or accumulated into).  Returns the dY tile image for the weight gradients."""
+    if not spec.supports_backward:
+        raise NotImplementedError("this stack is forward-only (hidden width > 128)")
     b = _built(spec)
     dev = act.device
     nt = _num_tiles(P)
@@ -425,8 +441,11 @@ def run_backward_data(spec, params, g_heads, act, packed, P, d_src=None):
                     c += w
             else:
                 w = spec.hidden[mask_layer][1]
-                _op(prog, kind=OP_EPI, slot=out_slot0, ncols=w, npad=w, tmem_col=0, mask_ptr=ptrs.add(act),
-                    mask_atom0=spec.act_atom0(mask_layer), img_atoms=spec.act_atoms)
+                if spec.hidden_act[mask_layer] == "relu":
+                    _op(prog, kind=OP_EPI, slot=out_slot0, ncols=w, npad=w, tmem_col=0, mask_ptr=ptrs.add(act),
+                        mask_atom0=spec.act_atom0(mask_layer), img_atoms=spec.act_atoms)
+                else:
+                    _op(prog, kind=OP_EPI, slot=out_slot0, ncols=w, npad=w, tmem_col=0)
                 _op(prog, kind=OP_SAVE, slot=out_slot0, ptr=ptrs.add(dy), col0=spec.dy_atom0_hidden(mask_layer),
                     npad=len(_atoms_of(w)), img_atoms=spec.dy_atoms)
 
@@ -511,6 +530,8 @@ class _ChainFn(torch.autograd.Function):
         flat = tensors[n_src:]
         params = {name: {"kernel": flat[2 * i], "bias": flat[2 * i + 1]} for i, name in enumerate(names)}
         need_grad = any(t.requires_grad for t in tensors)
+        if need_grad and not spec.supports_backward:
+            raise NotImplementedError("this stack is forward-only (hidden width > 128): call it under torch.no_grad()")
         packed = pack_weights(spec, params)
         _, outs, act = run_forward(spec, params, sources, packed, save=need_grad)
         ctx.spec, ctx.names, ctx.n_src = spec, names, n_src

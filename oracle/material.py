@@ -197,3 +197,106 @@ def microfacet_material(brdf_params, min_roughness=0.01, default_F_0=0.04):
         albedo=sig(brdf_params[..., 0:3] - 1.0), specular_albedo=sig(brdf_params[..., 5:6] - 1.0), roughness=rough,
         F_0=torch.full_like(brdf_params[..., 9:10], default_F_0), metalness=sig(brdf_params[..., 8:9]),
         diffuseness=torch.zeros_like(brdf_params[..., 3:4]), mirrorness=torch.zeros_like(brdf_params[..., 4:5]))
+
+
+# ------------------------------------------------------------------------------------ material stage
+class MaterialMLP:
+    """internal/material.py:1901-1926,2073-2123 under configs/ngp_yobo.gin:315-333: material grid -> bottleneck
+    Dense (linear) -> pred_brdf_layer -> microfacet material."""
+
+    def __init__(self, warp_c=2.0, bbox_scaling=1.0):
+        from . import grid_utils as og
+        self.grid = og.HashEncoding(hash_map_size=524288, num_features=4, scale_supersample=1.0, max_grid_size=2048,
+                                    bbox_scaling=bbox_scaling)
+        self.warp_c = warp_c
+
+    def init(self, gen, table_init_range=0.1):
+        from . import geometry as ogeo
+        d = 32
+        return {"material_grid": self.grid.init(gen, init_range=table_init_range),
+                "bottleneck_layer": {"kernel": ogeo.he_uniform(gen, d, 128), "bias": torch.zeros(128)},
+                "pred_brdf_layer": {"kernel": ogeo.he_uniform(gen, 128, 10), "bias": torch.zeros(10)}}
+
+    def predict_material(self, p, means, dense=None):
+        from . import coord as ocoord, geometry as ogeo
+        dense = dense or ogeo.dense
+        enc = self.grid(p["material_grid"], ocoord.contract_radius(means, self.warp_c))
+        raw = dense(p["pred_brdf_layer"], dense(p["bottleneck_layer"], enc))
+        return microfacet_material(raw)
+
+
+class EnvMapMLP:
+    """models.py:801-812 / configs/nerf_ngp_yobo.gin:253-297 (directional encoding, no IDE)."""
+
+    def __init__(self, deg_view=4, width=256, depth=4, skip=2, rgb_bias=-1.0):
+        self.deg_view, self.width, self.depth, self.skip, self.rgb_bias = deg_view, width, depth, skip, rgb_bias
+        self.in_dim = 3 + 6 * deg_view
+        self.names = [f"layer_{i}" for i in range(depth - 1)] + ["layer_bottleneck"]
+
+    def init(self, gen):
+        from . import geometry as ogeo
+        p, d = {}, self.in_dim
+        for i, n in enumerate(self.names):
+            p[n] = {"kernel": ogeo.he_uniform(gen, d, self.width), "bias": torch.zeros(self.width)}
+            d = self.width + (self.in_dim if (i % self.skip == 0 and i > 0) else 0)
+        p["output_rgba_layer"] = {"kernel": ogeo.he_uniform(gen, d, 4), "bias": torch.zeros(4)}
+        p["output_ambient_rgb_layer"] = {"kernel": ogeo.he_uniform(gen, d, 3), "bias": torch.zeros(3)}
+        return p
+
+    def __call__(self, p, viewdirs, dense=None):
+        from . import coord as ocoord, geometry as ogeo
+        dense = dense or ogeo.dense
+        enc = ocoord.pos_enc(viewdirs, 0, self.deg_view, True)
+        x = enc
+        for i, n in enumerate(self.names):
+            x = torch.relu(dense(p[n], x))
+            if i % self.skip == 0 and i > 0:
+                x = torch.cat([x, enc], dim=-1)
+        rgba = dense(p["output_rgba_layer"], x)
+        return dict(incoming_rgb=torch.nn.functional.softplus(rgba[..., :3] + self.rgb_bias))
+
+
+class MaterialModel:
+    """One chunk of the material stage's render path (see neural_radiance_caching_b200/material.py)."""
+
+    def __init__(self, cache_model, n_specular=16, n_cosine=8, n_light=8, near_min=0.05, far=2.0, normal_eps=1e-2,
+                 rgb_max=10000.0):
+        self.cache, self.material_mlp, self.env_map = cache_model, MaterialMLP(), EnvMapMLP()
+        self.n_specular, self.n_cosine, self.n_light = n_specular, n_cosine, n_light
+        self.near_min, self.far, self.normal_eps, self.rgb_max = near_min, far, normal_eps, rgb_max
+
+    def render_chunk(self, params, means, viewdirs, normals, draws, material=None, light_aux=None, sdist_hook=None):
+        from . import render_utils as oru
+        R = means.shape[0]
+        ns, nc, nl = self.n_specular, self.n_cosine, self.n_light
+        S = ns + nc + nl
+        if material is None:
+            material = self.material_mlp.predict_material(params["Material"], means)
+        u = draws["u"]
+        rays_s, smp_s = get_secondary_rays(means, viewdirs, normals, material["roughness"], [(MicrofacetSampler(), ns)],
+                                           [(u[:, :ns, 0], u[:, :ns, 1])], None, self.normal_eps, self.near_min, self.far)
+        dsamplers, dunif = [(CosineSampler(), nc)], [(u[:, ns:ns + nc, 0], u[:, ns:ns + nc, 1])]
+        aux = None
+        if nl:
+            aux = dict(light_aux, latent=draws["latent"], normal2=draws["normal2"], u=u[:, ns + nc:, 0])
+            dsamplers.append((LightSampler(), nl))
+            dunif.append((u[:, ns + nc:, 0], u[:, ns + nc:, 1]))
+        rays_d, smp_d = get_secondary_rays(means, viewdirs, normals, material["roughness"], dsamplers, dunif, aux,
+                                           self.normal_eps, self.near_min, self.far)
+        rays = {k: torch.cat([rays_s[k], rays_d[k]], dim=1).reshape(R * S, -1) for k in
+                ("origins", "directions", "near", "far", "radii")}
+        rays["viewdirs"] = rays["directions"]
+        out = self.cache(params["Cache"], rays, draws["u01"], gumbel=draws["gumbel"], is_secondary=True, resample=True)
+        rgb = torch.clamp(torch.nan_to_num(out["render"]["rgb"]), min=0.0)
+        acc = out["render"]["acc"]
+        env = self.env_map(params["EnvMap"], rays["directions"])["incoming_rgb"]
+        radiance_in = (rgb + env * (1.0 - acc)[:, None]).reshape(R, S, 3)
+        occ = acc.reshape(R, S, 1)
+        ones2 = torch.ones(R, ns, 2)
+        spec = oru.integrate_reflect_rays("microfacet_specular", material, dict(
+            smp_s, radiance_in=radiance_in[:, :ns], indirect_occ=occ[:, :ns], brdf_correction=ones2), self.rgb_max)
+        diff = oru.integrate_reflect_rays("microfacet_diffuse", material, dict(
+            smp_d, radiance_in=radiance_in[:, ns:], indirect_occ=occ[:, ns:], brdf_correction=torch.ones(R, S - ns, 2)),
+            self.rgb_max)
+        return dict(rgb=spec["radiance_out"] + diff["radiance_out"], specular=spec, diffuse=diff, material=material,
+                    radiance_in=radiance_in, acc=acc.reshape(R, S), rays=rays, cache_out=out)

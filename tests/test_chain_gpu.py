@@ -50,8 +50,9 @@ def ref_stack(spec, p, sources, rounded):
     cat = torch.cat(sources, dim=-1)
     inputs = (bf(cat.detach()) + (cat - cat.detach())) if rounded else cat   # d_in stays fp32 in the kernel
     x = inputs
-    for name, w, skip in spec.hidden:
-        x = rnd(torch.relu(x @ wq(p[name]["kernel"]) + p[name]["bias"]))
+    for (name, w, skip), act in zip(spec.hidden, spec.hidden_act):
+        z = x @ wq(p[name]["kernel"]) + p[name]["bias"]
+        x = rnd(torch.relu(z) if act == "relu" else z)
         if skip:
             x = torch.cat([x, inputs], dim=-1)
     outs = []
@@ -67,6 +68,7 @@ SPECS = {
     "int_brdf": dict(in_widths=[128, 1], hidden=[("l0", 64, False), ("l1", 64, False)], heads=[[("out", 1)]]),
     "slf": dict(in_widths=[128, 72], hidden=[("l0", 128, False), ("l1", 128, False), ("l2", 128, True), ("lb", 128, False)],
                 heads=[[("rgb", 3)]]),
+    "material": dict(in_widths=[32], hidden=[("bottleneck", 128, False, "linear")], heads=[[("pred_brdf", 10)]]),
     "env": dict(in_widths=[38], hidden=[("l0", 128, False), ("l1", 128, False), ("l2", 128, True), ("lb", 128, False)],
                 heads=[[("rgb", 3)]]),
 }
@@ -118,6 +120,26 @@ def test_chain_rejects_bad_specs():
     with pytest.raises(ValueError):
         mc.ChainSpec(in_widths=[3, 5], hidden=[], heads=[[("a", 3)]])
     with pytest.raises(ValueError):
-        mc.ChainSpec(in_widths=[8], hidden=[("l0", 256, False)], heads=[[("a", 3)]])
+        mc.ChainSpec(in_widths=[8], hidden=[("l0", 512, False)], heads=[[("a", 3)]])
     with pytest.raises(ValueError):
         mc.ChainSpec(in_widths=[8], hidden=[], heads=[[("a", 100), ("b", 100)]])
+
+
+def test_chain_256_wide_forward(cuda_device):
+    """Model-level EnvMap shape (configs/nerf_ngp_yobo.gin:253-297): pos_enc(dir, 4) = 27 -> 4 x 256 with the
+    input re-concatenated after layer 2 -> rgba (4) + ambient (3).  Forward-only on the chain kernel."""
+    g = gen(560)
+    spec = mc.ChainSpec(in_widths=[27], hidden=[("l0", 256, False), ("l1", 256, False), ("l2", 256, True), ("lb", 256, False)],
+                        heads=[[("rgba", 4), ("amb", 3)]])
+    assert not spec.supports_backward
+    p = make_params(g, spec)
+    P = 3000
+    srcs = [f32(g.normal(size=(P, 27)))]
+    want = ref_stack(spec, p, srcs, True)
+    want32 = ref_stack(spec, p, srcs, False)
+    pn = {k: {a: b.to(cuda_device) for a, b in v.items()} for k, v in p.items()}
+    with torch.no_grad():
+        got = mc.apply(spec, pn, [s.to(cuda_device) for s in srcs])
+    for a, b, c in zip(got, want, want32):
+        assert rel_err(a, b) <= 5e-3
+        assert rel_err(a, c) <= 2e-2
