@@ -93,4 +93,5 @@ class NeRFModel:
             ex["normals_to_use"] = nrm
         wnf = last["weights"] if resample else w
         rendering = render.volumetric_rendering(shade["rgb"], w, wnf, last["tdist"], bg, True, extras=ex)
-        return dict(sampler=hist, shader=shade, render=rendering, inds=inds)
+        return dict(sampler=hist, shader=shade, render=rendering, inds=inds,
+                    shaded=dict(means=means, normals=nrm, weights=w))

@@ -176,3 +176,115 @@ class CacheTrainStep:
         """Forward-only evaluation (BASELINE config 1)."""
         with torch.no_grad():
             return self.model(self.params, rays, u01, train=False)["render"]
+
+
+# ----------------------------------------------------------------------------- configs 3 and 5 (render path)
+def _cache_params(model, device, gen, table_init_range):
+    """Random-init parameters of the cache model in the reference's layout (no gradients: render path)."""
+    step = CacheTrainStep.__new__(CacheTrainStep)
+    step.device, step.model, step.leaves = device, model, []
+
+    def layer(fi, fo):
+        return {"kernel": _he_uniform(gen, device, fi, fo), "bias": torch.zeros((fo,), device=device)}
+
+    def grid(enc):
+        _, arena = enc.init(device, generator=gen, init_range=table_init_range)
+        return dict(enc.views(arena), _arena=arena)
+
+    sampler = {}
+    for i, m in enumerate(model.sampler.mlps):
+        p = {"density_grid": grid(m.grid), "density_layers_0": layer(m.in_dim, 64), "density_layers_1": layer(64, 64),
+             "output_density_layer": layer(64, 1)}
+        if m.enable_pred_normals:
+            p["pred_normals_layer"] = layer(64, 3)
+        sampler[f"MLP_{i}"] = p
+
+    def slf(in_dim):
+        p, d = {}, in_dim
+        for j, name in enumerate(["layer_0", "layer_1", "layer_2", "layer_bottleneck"]):
+            p[name] = layer(d, 128)
+            d = 128 + (in_dim if (j % 2 == 0 and j > 0) else 0)
+        p["output_ambient_rgb_layer"] = layer(d, 3)
+        return p
+
+    shader = {"appearance_grid": grid(model.shader.grid), "bottleneck_layer": layer(96, 128), "roughness_layer": layer(96, 1),
+              "ambient_irradiance_layer": layer(96, 3), "irradiance_layer": layer(96, 3), "tint_layer": layer(96, 3),
+              "integrated_brdf_layers_0": layer(129, 64), "integrated_brdf_layers_1": layer(64, 64),
+              "output_integrated_brdf_layer": layer(64, 1), "SurfaceLightField": slf(200), "EnvMap": slf(38)}
+    return {"Sampler": sampler, "Shader": shader}
+
+
+def make_surface_np(g, R):
+    """Config 3 inputs: surface points p ~ U(ball r=1), unit normals, camera view directions facing them."""
+    p = g.normal(size=(R, 3))
+    p = p / np.linalg.norm(p, axis=-1, keepdims=True) * g.uniform(size=(R, 1)) ** (1 / 3)
+    n = g.normal(size=(R, 3))
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    v = -n + 0.5 * g.normal(size=(R, 3))
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return f(p), f(v), f(n)
+
+
+class MaterialRenderStep:
+    """BASELINE config 3 (material_light_from_scratch_resample, chunk of 1024 shaded points): 32 secondary
+    rays per point (16 microfacet + 8 cosine + 8 vMF mixture with 128 lobes), radiance-cache query along every
+    secondary ray (proposal sampler (64,64,32), power-ladder warp, categorical resample to one shaded sample,
+    cache shader), environment map behind it, GGX / Lambert Monte-Carlo integration."""
+
+    NUM_LOBES = 128
+
+    def __init__(self, device, table_init_range=0.1, seed=SEED, bf16=True):
+        from . import material
+        self.device = device
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        self.gen = gen
+        self.cache = models.NeRFModel(bf16=bf16)
+        self.model = material.MaterialModel(self.cache, bf16=bf16)
+        self.params = {"Cache": _cache_params(self.cache, device, gen, table_init_range),
+                       "Material": self.model.material_mlp.init(device, gen, table_init_range),
+                       "EnvMap": self.model.env_map.init(device, gen)}
+
+    def draws(self, R):
+        """All random inputs of one chunk, generated on the device (the kernels take them as tensors)."""
+        S, dev, gen = self.model.num_secondary, self.device, self.gen
+        u = lambda *shape: torch.rand(shape, device=dev, generator=gen)
+        gum = -torch.log(-torch.log(torch.clamp(u(R * S, 32, 1), min=1e-12)))
+        return dict(u=u(R, S, 2), latent=torch.randint(0, self.NUM_LOBES, (R,), device=dev, generator=gen, dtype=torch.int32),
+                    normal2=torch.randn((R, self.model.n_light, 2), device=dev, generator=gen),
+                    u01=[u(R * S, 1) for _ in range(3)], gumbel=gum)
+
+    def light_lobes(self, R):
+        dev, gen = self.device, self.gen
+        return dict(vmf_means=torch.randn((R, self.NUM_LOBES, 3), device=dev, generator=gen),
+                    vmf_kappas=torch.rand((R, self.NUM_LOBES, 1), device=dev, generator=gen) * 50.0,
+                    vmf_logits=torch.randn((R, self.NUM_LOBES, 1), device=dev, generator=gen))
+
+    def render(self, means, viewdirs, normals, draws, lobes, material=None):
+        return self.model.render_chunk(self.params, means, viewdirs, normals, draws, material=material,
+                                       light_sampler_results=lobes)
+
+
+class FrameRenderer:
+    """BASELINE config 5: one 1024-ray chunk of a full-view render = cache stage on the primary rays
+    (config 1, resampled to one shaded point per ray) + material stage at that point (config 3) +
+    compositing with the resampled weight over a white background."""
+
+    def __init__(self, device, bf16=True, seed=SEED):
+        self.stage = MaterialRenderStep(device, seed=seed, bf16=bf16)
+        self.device = device
+
+    def render_chunk(self, rays, repeat=0):
+        st, dev, gen = self.stage, self.device, self.stage.gen
+        R = rays["origins"].shape[0]
+        with torch.no_grad():
+            u01 = [torch.rand((R, 1), device=dev, generator=gen) for _ in range(3)]
+            gum = -torch.log(-torch.log(torch.clamp(torch.rand((R, 32, 1), device=dev, generator=gen), min=1e-12)))
+            prim = st.cache(st.params["Cache"], rays, u01, gumbel=gum, train=False, is_secondary=False, resample=True)
+            sh = prim["shaded"]
+            means, normals, w = sh["means"].reshape(R, 3), sh["normals"].reshape(R, 3), sh["weights"].reshape(R, 1)
+            out = st.render(means.contiguous(), rays["viewdirs"], normals.contiguous(), st.draws(R), st.light_lobes(R))
+            acc = prim["render"]["acc"].reshape(R, 1)
+            rgb = out["rgb"] * w + (1.0 - acc)
+        return dict(rgb=rgb, cache_rgb=prim["render"]["rgb"], acc=acc, albedo=out["material"]["albedo"])

@@ -62,3 +62,36 @@ def test_row_bands_cover_image():
             assert all(b0[1] == b1[0] for b0, b1 in zip(bands, bands[1:]))
             sizes = [b - a for a, b in bands]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_welford_matches_batch_statistics():
+    from neural_radiance_caching_b200.render_image import Welford
+    g = np.random.Generator(np.random.PCG64(3))
+    xs = [torch.from_numpy(g.normal(size=(50, 3)).astype(np.float32)) for _ in range(7)]
+    w = Welford()
+    for x in xs:
+        w.update(x)
+    st = torch.stack(xs)
+    assert torch.allclose(w.mean, st.mean(0), atol=1e-6)
+    assert torch.allclose(w.variance(), st.var(0, unbiased=True), atol=1e-5)
+
+
+def test_render_image_chunking_and_bands_cpu():
+    """Host logic of render_image on CPU tensors with a fake per-chunk renderer: edge padding, chunk
+    scatter, and equality with a single-pass evaluation."""
+    from neural_radiance_caching_b200 import render_image as ri
+    H, W, focal = 13, 9, 20.0
+    c2w = ri.orbit_camera()
+    calls = []
+
+    def fake(rays, rep):
+        calls.append(rays["origins"].shape[0])
+        return dict(rgb=rays["viewdirs"] * 0.5 + 0.5, depth=rays["directions"][:, :1])
+
+    img = ri.render_image(fake, H, W, focal, c2w, torch.device("cpu"), chunk=32)
+    assert all(c == 32 for c in calls) and len(calls) == -(-H * W // 32)
+    full = ri.pinhole_rays(H, W, focal, c2w, torch.device("cpu"))
+    assert torch.allclose(img["rgb"].reshape(-1, 3), full["viewdirs"] * 0.5 + 0.5)
+    assert img["rgb"].shape == (H, W, 3) and img["depth"].shape == (H, W, 1)
+    # unit view directions, non-unit ray directions whose z-component in camera space is -1
+    assert torch.allclose(torch.linalg.norm(full["viewdirs"], dim=-1), torch.ones(H * W), atol=1e-6)
