@@ -181,3 +181,89 @@ class FusedCacheStep:
         _lib.call("nrc_contract_fwd", st(), _lib.ptr(lv["means"].reshape(P, 3)), P, float(mlp.warp_c), _lib.ptr(z))
         enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(lv["arena"])), mlp.grid.tables(mlp.grid.views(t_sink)))
         _lib.call("nrc_encode_bwd", st(), C.byref(enc), _lib.ptr(z), _lib.ptr(g_enc), P, None)
+
+
+class FusedCacheQuery:
+    """Forward-only static schedule of one radiance-cache query (render path; BASELINE configs 1, 3, 5):
+    proposal sampler -> [categorical resample] -> cache shader -> volumetric rendering, as ~25 launches with
+    no elementwise glue.  It is the body of the material stage's `radiance_cache_fn`
+    (internal/material.py:2174-2231 -> models.py:656-774 with is_secondary=True, resample=True) and of the
+    primary-ray cache render.  Same kernels as models.NeRFModel.__call__, pinned against it by
+    tests/test_engine_gpu.py.  Quantities nobody downstream reads on this path (analytic normals, rectified
+    normals, per-level alpha / transmittance) are not computed -- the reference's XLA program dead-code
+    eliminates them too."""
+
+    def __init__(self, model):
+        self.model = model
+        self._const = {}
+
+    def _initial(self, R, dev):
+        key = (R, str(dev))
+        if key not in self._const:
+            sd = torch.zeros((R, 2), device=dev, dtype=torch.float32)
+            sd[:, 1] = 1.0
+            self._const[key] = (sd, torch.ones((R, 1), device=dev, dtype=torch.float32),
+                                torch.ones((R, 3), device=dev, dtype=torch.float32),
+                                torch.zeros((R, 3), device=dev, dtype=torch.float32))
+        return self._const[key]
+
+    def __call__(self, params, rays, u01, gumbel=None, is_secondary=False, resample=False, train_frac=1.0):
+        """rays: dict of contiguous [R,·] tensors; u01: 3 x [R,1]; gumbel [R,n_last,k] when resample.
+        Returns dict(rgb [R,3], acc [R], distance [R,4], extras [R,k|n,22], weights, means, normals, inds)."""
+        sampler, shader = self.model.sampler, self.model.shader
+        sp, shp = params["Sampler"], params["Shader"]
+        R, dev = rays["near"].shape[0], rays["near"].device
+        st = _lib.stream_ptr
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        anneal = sampler.anneal(train_frac)
+        sdist, weights, bg_one, bg_zero = self._initial(R, dev)
+        nl = len(sampler.sampling_strategy)
+        for i_level, (i_mlp, _, n) in enumerate(sampler.sampling_strategy):
+            mlp, p = sampler.mlps[i_mlp], sp[f"MLP_{i_mlp}"]
+            last = i_level == nl - 1
+            sdist = stepfun.sample_intervals_from_weights(u01[i_level], sdist, weights, n, anneal=anneal,
+                                                          padding=sampler.resample_padding, domain=(0.0, 1.0))
+            tdist, means = sampler._cast(sdist, rays, is_secondary)
+            P = R * n
+            density = new(P)
+            feat = new(P, 64) if last else None
+            gp = new(P, 3) if (last and mlp.enable_pred_normals) else None
+            enc = mlp.grid._descriptor(mlp.grid.tables(p["density_grid"]), None)
+            desc = geometry._mlp_desc(p, mlp.in_dim, gp is not None)
+            _lib.call("nrc_density_query_fwd", st(), C.byref(enc), C.byref(desc), _lib.ptr(means), P, float(mlp.warp_c),
+                      float(mlp.density_bias), int(mlp.bf16), _lib.ptr(density), None, _lib.ptr(feat), _lib.ptr(gp), None,
+                      None)
+            weights = new(R, n)
+            _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(density), _lib.ptr(tdist), _lib.ptr(rays["directions"]),
+                      R, n, int(sampler.opaque_background), _lib.ptr(weights), None, None)
+        n_last = n
+        inds = None
+        if resample:
+            k = gumbel.shape[-1]
+            inds = torch.empty((R, k), device=dev, dtype=torch.int32)
+            w_sh = new(R, k)
+            _lib.call("nrc_ray_resample", st(), _lib.ptr(weights), _lib.ptr(gumbel), R, n_last, k,
+                      float(self.model.weights_bias), 1.0, _lib.ptr(inds), _lib.ptr(w_sh))
+
+            def take(field, c):
+                out = new(R, k, c)
+                _lib.call("nrc_ray_resample_gather", st(), _lib.ptr(field), _lib.ptr(inds), R, n_last, k, c, _lib.ptr(out))
+                return out
+
+            means_sh, feat_sh, gp_sh = take(means, 3), take(feat, 64), take(gp, 3)
+        else:
+            k, w_sh, means_sh, feat_sh, gp_sh = n_last, weights, means, feat.reshape(R, n_last, 64), gp
+        Psh = R * k
+        normals = new(Psh, 3)
+        _lib.call("nrc_normals_fwd", st(), _lib.ptr(gp_sh), Psh, _lib.ptr(normals))
+        names, sflat = shader.fused_params(shp)
+        outs, _, _ = nerf.shader_fused_forward(shader, names, sflat, rays["viewdirs"], means_sh.reshape(R, k, 3),
+                                               feat_sh.reshape(R, k, 64), normals.reshape(R, k, 3),
+                                               shp["appearance_grid"]["_arena"], False)
+        rgb_s = outs[0].reshape(R, k, 3)
+        out_rgb, acc, dist = new(R, 3), new(R), new(R, 4)
+        _lib.call("nrc_ray_composite_fwd", st(), _lib.ptr(rgb_s), _lib.ptr(w_sh), k, _lib.ptr(weights) if resample else None,
+                  _lib.ptr(tdist), _lib.ptr(bg_zero if is_secondary else bg_one), R, n_last, 3, 1, _lib.ptr(out_rgb),
+                  _lib.ptr(acc), _lib.ptr(dist))
+        return dict(rgb=out_rgb, acc=acc, distance=dist, extras=outs[1], weights=w_sh, weights_all=weights,
+                    means=means_sh.reshape(R, k, 3), normals=normals.reshape(R, k, 3), inds=inds, tdist=tdist)

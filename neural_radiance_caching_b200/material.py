@@ -123,6 +123,9 @@ class MaterialModel:
     def __init__(self, cache_model, bf16=True, n_specular=16, n_cosine=8, n_light=8, near_min=0.05, far=2.0,
                  normal_eps=1e-2, rgb_max=10000.0):
         self.cache = cache_model
+        # bf16 variant: the cache recursion runs as a hand-ordered launch schedule (engine.FusedCacheQuery)
+        from . import engine
+        self.fused_query = engine.FusedCacheQuery(cache_model) if bf16 else None
         self.material_mlp = MaterialMLP(bf16=bf16)
         self.env_map = EnvMapMLP(bf16=bf16)
         self.n_specular, self.n_cosine, self.n_light = n_specular, n_cosine, n_light
@@ -163,10 +166,15 @@ class MaterialModel:
             if material is None:
                 material = self.material_mlp.predict_material(params["Material"], means)
             rays, smp_s, smp_d = self.secondary_rays(means, viewdirs, normals, material, draws, light_sampler_results)
-            out = self.cache(params["Cache"], rays, draws["u01"], gumbel=draws["gumbel"], train=False, is_secondary=True,
-                             resample=True)
-            rgb = torch.clamp(torch.nan_to_num(out["render"]["rgb"]), min=0.0)
-            acc = out["render"]["acc"]
+            if self.fused_query is not None:
+                q = self.fused_query(params["Cache"], rays, draws["u01"], gumbel=draws["gumbel"], is_secondary=True,
+                                     resample=True)
+                rgb_raw, acc = q["rgb"], q["acc"]
+            else:
+                out = self.cache(params["Cache"], rays, draws["u01"], gumbel=draws["gumbel"], train=False,
+                                 is_secondary=True, resample=True)
+                rgb_raw, acc = out["render"]["rgb"], out["render"]["acc"]
+            rgb = torch.clamp(torch.nan_to_num(rgb_raw), min=0.0)
             env = self.env_map(params["EnvMap"], rays["directions"])["incoming_rgb"]
             radiance_in = (rgb + env * (1.0 - acc)[:, None]).reshape(R, S, 3)     # models.py:423-460
             ns = self.n_specular

@@ -281,10 +281,15 @@ class FrameRenderer:
         with torch.no_grad():
             u01 = [torch.rand((R, 1), device=dev, generator=gen) for _ in range(3)]
             gum = -torch.log(-torch.log(torch.clamp(torch.rand((R, 32, 1), device=dev, generator=gen), min=1e-12)))
-            prim = st.cache(st.params["Cache"], rays, u01, gumbel=gum, train=False, is_secondary=False, resample=True)
-            sh = prim["shaded"]
-            means, normals, w = sh["means"].reshape(R, 3), sh["normals"].reshape(R, 3), sh["weights"].reshape(R, 1)
+            if st.model.fused_query is not None:
+                q = st.model.fused_query(st.params["Cache"], rays, u01, gumbel=gum, is_secondary=False, resample=True)
+                means, normals, w = q["means"].reshape(R, 3), q["normals"].reshape(R, 3), q["weights"].reshape(R, 1)
+                cache_rgb, acc = q["rgb"], q["acc"].reshape(R, 1)
+            else:
+                prim = st.cache(st.params["Cache"], rays, u01, gumbel=gum, train=False, is_secondary=False, resample=True)
+                sh = prim["shaded"]
+                means, normals, w = sh["means"].reshape(R, 3), sh["normals"].reshape(R, 3), sh["weights"].reshape(R, 1)
+                cache_rgb, acc = prim["render"]["rgb"], prim["render"]["acc"].reshape(R, 1)
             out = st.render(means.contiguous(), rays["viewdirs"], normals.contiguous(), st.draws(R), st.light_lobes(R))
-            acc = prim["render"]["acc"].reshape(R, 1)
             rgb = out["rgb"] * w + (1.0 - acc)
-        return dict(rgb=rgb, cache_rgb=prim["render"]["rgb"], acc=acc, albedo=out["material"]["albedo"])
+        return dict(rgb=rgb, cache_rgb=cache_rgb, acc=acc, albedo=out["material"]["albedo"])

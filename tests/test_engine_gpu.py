@@ -45,3 +45,29 @@ def test_fused_step_matches_autograd(cuda_device, R):
     with torch.no_grad():
         res = step.model(step.params, rays, u01, train=False)
     assert rel_err(step.engine.last["rgb"], res["render"]["rgb"]) <= 1e-5
+
+
+@pytest.mark.parametrize("secondary", [False, True])
+def test_fused_query_matches_model(cuda_device, secondary):
+    """engine.FusedCacheQuery (render path schedule) == models.NeRFModel.__call__ on the same kernels."""
+    from neural_radiance_caching_b200 import engine
+    step = workload.CacheTrainStep(cuda_device, bf16=True)
+    R = 500
+    g = np.random.Generator(np.random.PCG64(workload.SEED + 11 + int(secondary)))
+    rn = workload.make_rays_np(g, R, near=0.05, far=2.0, radius=0.7) if secondary else workload.make_rays_np(g, R)
+    rays = {k: torch.from_numpy(v).to(cuda_device) for k, v in rn.items()}
+    u01 = [torch.from_numpy(g.uniform(size=(R, 1)).astype(np.float32)).to(cuda_device) for _ in range(3)]
+    gum = torch.from_numpy(g.gumbel(size=(R, 32, 1)).astype(np.float32)).to(cuda_device)
+    for resample in (False, True):
+        with torch.no_grad():
+            want = step.model(step.params, rays, u01, gumbel=gum if resample else None, train=False,
+                              is_secondary=secondary, resample=resample)
+            got = engine.FusedCacheQuery(step.model)(step.params, rays, u01, gumbel=gum if resample else None,
+                                                     is_secondary=secondary, resample=resample)
+        assert rel_err(got["rgb"], want["render"]["rgb"]) <= 1e-5
+        assert rel_err(got["acc"], want["render"]["acc"]) <= 1e-5
+        assert rel_err(got["distance"][:, 0], want["render"]["distance_mean"]) <= 1e-5
+        if resample:
+            assert torch.equal(got["inds"], want["inds"])
+            assert rel_err(got["means"], want["shaded"]["means"]) <= 1e-6
+            assert rel_err(got["normals"], want["shaded"]["normals"]) <= 1e-6
