@@ -553,7 +553,7 @@ def run_render(args):
         focal = 1111.0 * H / 800.0
 
         def step():
-            return ri.render_image(fr.render_chunk, H, W, focal, c2w, dev, chunk=args.rays)["rgb"]
+            return ri.render_image(fr.render_chunk_graphed, H, W, focal, c2w, dev, chunk=args.rays)["rgb"]
 
         before = _lib.launch_count
         img = step()
@@ -571,6 +571,7 @@ def run_render(args):
               "material stage (config 3); image row bands over the ranks, one all_gather of the bands" % (H, W))
         h2d, d2h = 0, H * W * 3 * 4
         scaling = "strong"
+        use_graph = True
         roof = None
     t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:

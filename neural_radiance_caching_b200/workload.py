@@ -271,9 +271,38 @@ class FrameRenderer:
     (config 1, resampled to one shaded point per ray) + material stage at that point (config 3) +
     compositing with the resampled weight over a white background."""
 
-    def __init__(self, device, bf16=True, seed=SEED):
+    def __init__(self, device, bf16=True, seed=SEED, use_graph=True):
         self.stage = MaterialRenderStep(device, seed=seed, bf16=bf16)
+        # random draws inside the captured chunk come from the default CUDA generator (graph-safe Philox offsets)
+        self.stage.gen = None
         self.device = device
+        self.use_graph = use_graph
+        self._graphs = {}
+
+    def render_chunk_graphed(self, rays, repeat=0):
+        """render_chunk behind one CUDA graph per chunk size: ray buffers are static, the ~70 launches of a
+        chunk replay without host work (the per-chunk host sync of models.render_image disappears)."""
+        if not self.use_graph:
+            return self.render_chunk(rays, repeat)
+        R = rays["origins"].shape[0]
+        if R not in self._graphs:
+            static = {k: v.clone() for k, v in rays.items()}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.render_chunk(static, repeat)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.render_chunk(static, repeat)
+            self._graphs[R] = (graph, static, out)
+        graph, static, out = self._graphs[R]
+        for k, v in rays.items():
+            static[k].copy_(v)
+        graph.replay()
+        return out
 
     def render_chunk(self, rays, repeat=0):
         st, dev, gen = self.stage, self.device, self.stage.gen
