@@ -506,6 +506,11 @@ def run_render(args):
         before = _lib.launch_count
         step()
         launches = _lib.launch_count - before
+        if args.ncu_mode:
+            step()
+            torch.cuda.synchronize()
+            print(json.dumps({"ncu_mode": True, "launches_per_step": launches}))
+            return
         per_kernel = profile_calls(step, _lib, iters=3)
         # the chunk is a static launch sequence (inputs and random draws resident): capture it once
         side = torch.cuda.Stream()

@@ -426,6 +426,24 @@ int32_t nrc_material_head(void* stream, const float* d_brdf_params, int64_t ld, 
                           float min_roughness, float default_f0, float* d_albedo, float* d_roughness,
                           float* d_metalness, float* d_f0, float* d_specular_albedo);
 
+/* ------------------------------------ transient (time-resolved) rendering, row 22 ---- */
+/* render.volumetric_transient_rendering (internal/render.py:250-449: shift_direct :452-490,
+ * shift_map_coordinates :493-507) fused with the transient heads' post-processing
+ * (internal/nerf.py:1660-1777: softplus(raw + bias) * indirect_scale, specular = tint*F * ref * indirect_scale,
+ * clip to [0, rgb_max]) and render_utils.zero_invalid_bins (internal/inverse_render/render_utils.py:1699-1767).
+ *   d_direct_rgbs [R,n,C]; d_diffuse_raw [R,n,B,C] raw irradiance-head output or NULL; d_specular [R,n,B,C]
+ *   activated light-field output or NULL with d_spec_scale [R,n,C] (tint * integrated BRDF);
+ *   d_weights, d_ray_dists, d_light_dists, d_cam_dists [R,n] (cam_dists = |o - x| + |o - cam_origin|)
+ *   -> d_transient_direct, d_transient_indirect, d_rgb [R,B,C]  (rgb = direct + indirect + dark_level).
+ * The [R,n,B,C] inputs are read once; nothing of that size is written. */
+int32_t nrc_transient_render_fwd(void* stream, const float* d_direct_rgbs, const float* d_diffuse_raw,
+                                 const float* d_specular, const float* d_spec_scale, const float* d_weights,
+                                 const float* d_ray_dists, const float* d_light_dists, const float* d_cam_dists,
+                                 int64_t num_rays, int32_t n, int32_t n_bins, int32_t channels, float exposure_time,
+                                 float shift, float diffuse_bias, float indirect_scale, float bin_zero_threshold_light,
+                                 int32_t light_zero, float light_near, float rgb_max, float dark_level,
+                                 float* d_transient_direct, float* d_transient_indirect, float* d_rgb);
+
 /* ------------------------------------------------- K5: GGX integration ---- */
 /* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) +
  * integrate_reflect_rays (:1102-1193): Disney-GGX D*F*G and Lambert lobes evaluated in the

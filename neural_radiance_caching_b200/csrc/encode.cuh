@@ -188,6 +188,58 @@ __device__ __forceinline__ FeatVec<F> level_interp(const LevelDev& lv, const Cor
   return acc;
 }
 
+// G consecutive HASH levels at once, branch-free: every gather of the group (8*G rows) is issued before the
+// first one is consumed, so a lane keeps 16-32 independent L2 requests in flight instead of 8 (the fused
+// query kernels are latency bound on these gathers).  Arithmetic and its order are those of level_interp.
+// Levels beyond enc.L repeat the last level (results discarded by the caller).
+template <int F, int G>
+__device__ __forceinline__ void hash_interp_group(const EncDev& enc, int l0, const float xn[3], FeatVec<F> (&out)[G]) {
+  uint32_t rows[G][8];
+  float w[G][8];
+  const float* tables[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const LevelDev& lv = enc.lv[min(l0 + g, enc.L - 1)];
+    tables[g] = lv.table;
+    const float fN = static_cast<float>(lv.N);
+    uint32_t u[3][2];
+    float wt[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float loc = __fsub_rn(__fmul_rn(xn[a], fN), 0.5f);
+      const float f = floorf(loc);
+      wt[a][1] = __fsub_rn(loc, f);
+      wt[a][0] = __fsub_rn(1.0f, wt[a][1]);
+      const int32_t fi = __float2int_rz(f);
+      u[a][0] = static_cast<uint32_t>(fi);
+      u[a][1] = static_cast<uint32_t>(fi + 1);
+    }
+    const uint32_t hy[2] = {u[1][0] * kPi2, u[1][1] * kPi2};
+    const uint32_t hz[2] = {u[2][0] * kPi3, u[2][1] * kPi3};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {   // hash corner order: x outermost, z innermost; w = (wx*wy)*wz
+      const int bx = (k >> 2) & 1, by = (k >> 1) & 1, bz = k & 1;
+      const uint32_t h = u[0][bx] ^ (hy[by] ^ hz[bz]);
+      rows[g][k] = lv.pow2_mask ? (h & lv.pow2_mask) : (h % lv.T);
+      w[g][k] = __fmul_rn(__fmul_rn(wt[0][bx], wt[1][by]), wt[2][bz]);
+    }
+  }
+  FeatVec<F> vals[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) vals[g][k] = load_row<F>(tables[g], static_cast<int32_t>(rows[g][k]));
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int f = 0; f < F; ++f) out[g].v[f] = __fmul_rn(vals[g][0].v[f], w[g][0]);
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+#pragma unroll
+      for (int f = 0; f < F; ++f) out[g].v[f] = __fadd_rn(out[g].v[f], __fmul_rn(vals[g][k].v[f], w[g][k]));
+  }
+}
+
 __device__ __forceinline__ void normalise_point(const EncDev& enc, const float x[3], float xn[3]) {
 #pragma unroll
   for (int a = 0; a < 3; ++a) xn[a] = __fdiv_rn(__fsub_rn(x[a], enc.b0[a]), enc.span[a]);

@@ -6,6 +6,8 @@
 //
 // Reference: internal/geometry.py:155-168,199-341,442-460 (same maths as mlp.cu / query.cu;
 // parity bar for this variant: rel 2e-2).
+#include <cstdlib>
+
 #include "encode.cuh"
 #include "mma_bf16.cuh"
 
@@ -35,7 +37,7 @@ template <int F, int KS0, bool kFused>
 __global__ void __launch_bounds__(kBfThreads)
 mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t m,
                     const float* __restrict__ in, int64_t P, float warp_c, float density_bias,
-                    const QueryOut out) {
+                    const QueryOut out, const int g_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmemBf16& s = *reinterpret_cast<FwdSmemBf16*>(smem_raw);
   load_weights_bf16(s.w, m);
@@ -61,14 +63,35 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
         inside = 1;
 #pragma unroll
         for (int a = 0; a < 3; ++a) inside = inside && (z[a] > enc.b0[a]) && (z[a] < enc.b1[a]);
-        for (int l = 0; l < enc.L; ++l) {
-          Corners c = level_setup(enc.lv[l], xn);
-          FeatVec<F> v = level_interp<F>(enc.lv[l], c);
+        auto emit = [&](int l, const FeatVec<F>& v) {
 #pragma unroll
           for (int f = 0; f < F; ++f) {
             float e = __fmul_rn(v.v[f], enc.scale);
             ws.x[lane][l * F + f] = __float2bfloat16(e);
             if (out.enc_out) out.enc_out[p * in_dim + l * F + f] = e;
+          }
+        };
+        // dense levels come first in the level schedule (N^3 <= T), hash levels after them
+        int l = 0;
+        for (; l < enc.L && !enc.lv[l].is_hash; ++l) {
+          Corners c = level_setup(enc.lv[l], xn);
+          emit(l, level_interp<F>(enc.lv[l], c));
+        }
+        constexpr int G = 2;   // hash levels gathered two at a time (16 rows in flight per lane)
+        for (; l < enc.L; l += G) {
+          bool all_hash = true;
+          for (int g = 0; g < G && l + g < enc.L; ++g) all_hash = all_hash && enc.lv[l + g].is_hash;
+          if (all_hash && g_group) {
+            FeatVec<F> v[G];
+            hash_interp_group<F, G>(enc, l, xn, v);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              if (l + g < enc.L) emit(l + g, v[g]);
+          } else {
+            for (int g = 0; g < G && l + g < enc.L; ++g) {
+              Corners c = level_setup(enc.lv[l + g], xn);
+              emit(l + g, level_interp<F>(enc.lv[l + g], c));
+            }
           }
         }
       }
@@ -233,9 +256,11 @@ int32_t launch_bf16_fwd(cudaStream_t st, const EncDev& d, const nrc_density_mlp_
     attr_set = true;
   }
   int64_t tiles = (P + kBfThreads - 1) / kBfThreads;
-  unsigned grid = static_cast<unsigned>(tiles < kNumSMs * 3 ? tiles : kNumSMs * 3);
+  static const int mult = getenv("NRC_QUERY_GRID_MULT") ? atoi(getenv("NRC_QUERY_GRID_MULT")) : 3;
+  static const int group = getenv("NRC_QUERY_GROUP") ? atoi(getenv("NRC_QUERY_GROUP")) : 0;
+  unsigned grid = static_cast<unsigned>(tiles < kNumSMs * mult ? tiles : kNumSMs * mult);
   mlp_bf16_fwd_kernel<F, KS0, kFused><<<grid, kBfThreads, sizeof(FwdSmemBf16), st>>>(d, *mlp, in, P, warp_c,
-                                                                                  bias, out);
+                                                                                  bias, out, group);
   return check_launch();
 }
 

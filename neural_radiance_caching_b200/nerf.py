@@ -491,3 +491,35 @@ class NeRFMLP:
             albedo_rgb=tint, roughness=roughness, integrated_brdf=F, env_rgb=env_rgb, ref_rgb=ref_rgb,
             bottleneck=bottleneck, feature=feature, refdirs=refdirs,
         )
+
+
+# ----------------------------------------------------------------------------- transient heads (row 22)
+class TransientIndirectHead:
+    """TransientNeRFMLP.get_indirect (internal/nerf.py:1757-1777): [shader feature 96 || pos_enc(light position,
+    0..2) 15] = 111 -> Dense 64 + ReLU -> Dense 64 + ReLU -> transient_indirect_layer 64 -> n_bins * C (raw;
+    softplus(. + irradiance_bias), indirect_scale, validity masks and the time shift are fused into
+    render.volumetric_transient_rendering).  The 2100-wide output layer runs on the generic GEMM
+    (nrc_dense_fwd); the [P, n_bins*C] result is the only large tensor of the transient path."""
+
+    def __init__(self, n_bins=700, channels=3, deg_lights=2, width=64, bf16=False):
+        self.n_bins, self.channels, self.deg, self.width, self.bf16 = n_bins, channels, deg_lights, width, bf16
+        self.in_dim = 96 + 3 + 6 * deg_lights
+
+    def init(self, device, generator=None):
+        def layer(fi, fo):
+            lim = float(np.sqrt(6.0 / fi))
+            return {"kernel": torch.empty((fi, fo), device=device).uniform_(-lim, lim, generator=generator),
+                    "bias": torch.zeros((fo,), device=device)}
+        return {"irradiance_layers_0": layer(self.in_dim, self.width), "irradiance_layers_1": layer(self.width, self.width),
+                "transient_indirect_layer": layer(self.width, self.n_bins * self.channels)}
+
+    def __call__(self, p, feature, lights):
+        """feature [P,96], lights [P,3] -> raw transient indirect [P, n_bins, C]."""
+        P = feature.shape[0]
+        l2 = lights.reshape(P, 3).contiguous()
+        enc = torch.empty((P, 3 + 6 * self.deg), device=feature.device, dtype=torch.float32)
+        _lib.call("nrc_pos_enc", _lib.stream_ptr(), _lib.ptr(l2), P, 3, 0, self.deg, 1, _lib.ptr(enc), enc.shape[1])
+        x = torch.cat([feature.reshape(P, -1), enc], dim=-1)
+        x = dense(p["irradiance_layers_0"], x, relu=True, bf16=self.bf16)
+        x = dense(p["irradiance_layers_1"], x, relu=True, bf16=self.bf16)
+        return dense(p["transient_indirect_layer"], x, bf16=self.bf16).reshape(P, self.n_bins, self.channels)

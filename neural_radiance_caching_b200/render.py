@@ -167,3 +167,25 @@ def volumetric_rendering(
             s = "median" if p == 50 else "percentile_" + str(p)
             rendering["distance_" + s] = dist[..., 1 + i]
     return rendering
+
+
+def volumetric_transient_rendering(direct_rgbs, diffuse_raw, specular, spec_scale, weights, ray_dists, light_dists,
+                                   cam_dists, n_bins=700, exposure_time=0.01, shift=0.0, diffuse_bias=-1.0,
+                                   indirect_scale=1.0, bin_zero_threshold_light=0.0, light_zero=False, light_near=0.0,
+                                   rgb_max=10000.0, dark_level=0.0):
+    """Time-resolved rendering (internal/render.py:250-449) fused with the transient heads' post-processing
+    (internal/nerf.py:1660-1777) and zero_invalid_bins (render_utils.py:1699-1767): see nrc_transient_render_fwd.
+    direct_rgbs [R,n,C]; diffuse_raw / specular [R,n,B,C] (either may be None); spec_scale [R,n,C];
+    weights / ray_dists / light_dists / cam_dists [R,n].  Returns dict(transient_direct, transient_indirect,
+    rgb [R,B,C], integrated_rgb [R,C]).  Forward path (the temporal filter convolution is not applied)."""
+    R, n, C = direct_rgbs.shape
+    dev = direct_rgbs.device
+    c = lambda t: t.contiguous() if t is not None else None
+    new = lambda: torch.empty((R, n_bins, C), device=dev, dtype=torch.float32)
+    t_direct, t_indirect, rgb = new(), new(), new()
+    args = [c(direct_rgbs), c(diffuse_raw), c(specular), c(spec_scale), c(weights), c(ray_dists), c(light_dists), c(cam_dists)]
+    _lib.call("nrc_transient_render_fwd", _lib.stream_ptr(), *[_lib.ptr(a) for a in args], R, n, n_bins, C,
+              float(exposure_time), float(shift), float(diffuse_bias), float(indirect_scale), float(bin_zero_threshold_light),
+              int(bool(light_zero)), float(light_near), float(rgb_max), float(dark_level), _lib.ptr(t_direct),
+              _lib.ptr(t_indirect), _lib.ptr(rgb))
+    return dict(transient_direct=t_direct, transient_indirect=t_indirect, rgb=rgb, integrated_rgb=rgb.sum(-2))

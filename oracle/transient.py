@@ -1,0 +1,67 @@
+"""CPU restatement (test infrastructure) of the time-resolved rendering path, BASELINE config 4:
+internal/render.py volumetric_transient_rendering (:250-449, the rgb / transient outputs), shift_direct
+(:452-490), shift_map_coordinates (:493-507; jax.scipy.ndimage.map_coordinates order 1, mode='constant'),
+internal/inverse_render/render_utils.py zero_invalid_bins (:1699-1767) and the head post-processing of
+internal/nerf.py:1660-1777 (softplus(raw + bias) * indirect_scale; tint * F * ref_rgb * indirect_scale; clip).
+Parity unpinned (no reference vectors; JAX not installable here)."""
+import numpy as np
+import torch
+
+
+def shift_direct(dists, direct_rgbs, weights, n_bins, C):
+    R, n = dists.shape
+    rgb = torch.zeros((R * n_bins, C), dtype=direct_rgbs.dtype)
+    lo = torch.clamp(torch.floor(dists), min=0)
+    hi = torch.ceil(dists)
+    w_hi = dists - lo
+    w_lo = 1.0 - w_hi
+    base = torch.arange(R).repeat_interleave(n) * n_bins
+    vals = (weights[..., None] * direct_rgbs).reshape(-1, C)
+    for idx, w in ((base + lo.reshape(-1).to(torch.int32), w_lo), (base + hi.reshape(-1).to(torch.int32), w_hi)):
+        ok = (idx >= 0) & (idx < R * n_bins)              # out-of-bounds scatter updates are dropped
+        rgb.index_add_(0, idx[ok].long(), (vals * w.reshape(-1, 1))[ok])
+    return rgb.reshape(R, n_bins, C)
+
+
+def shift_map_coordinates(x, bins_move, exposure_time, n_bins):
+    """x [N, n_bins, C]: out[i, b] = linear interpolation of x[i] at b - bins_move[i]/exposure, zero outside."""
+    y = torch.arange(n_bins, dtype=x.dtype)[None, :] - (bins_move / exposure_time)[:, None]
+    y0 = torch.floor(y)
+    t = (y - y0)[..., None]
+    i0 = y0.long()
+
+    def tap(i):
+        ok = ((i >= 0) & (i < n_bins))[..., None]
+        g = torch.gather(x, 1, i.clamp(0, n_bins - 1)[..., None].expand(-1, -1, x.shape[-1]))
+        return torch.where(ok, g, torch.zeros_like(g))
+
+    return (1.0 - t) * tap(i0) + t * tap(i0 + 1)
+
+
+def zero_invalid_bins(diffuse, specular, light_dists, cam_dists, n_bins, exposure_time, bin_zero_threshold_light,
+                      light_zero, light_near):
+    """diffuse / specular [..., n_bins, C]; light_dists / cam_dists [..., 1]."""
+    bins = torch.arange(n_bins, dtype=diffuse.dtype).reshape((1,) * (diffuse.dim() - 2) + (n_bins, 1))
+    too_close = (bins + bin_zero_threshold_light) * exposure_time < light_dists[..., None, :]
+    too_far = (bins * exposure_time + cam_dists[..., None, :]) > (n_bins - 1) * exposure_time
+    bad = too_close | too_far
+    if light_zero:
+        bad = bad | (light_dists[..., None, :] < light_near)
+    z = lambda v: torch.where(bad, torch.zeros_like(v), v)
+    return z(diffuse), z(specular)
+
+
+def transient_render(direct_rgbs, diffuse_raw, specular, spec_scale, weights, ray_dists, light_dists, cam_dists, n_bins,
+                     exposure_time=0.01, shift=0.0, diffuse_bias=-1.0, indirect_scale=1.0, bin_zero_threshold_light=0.0,
+                     light_zero=False, light_near=0.0, rgb_max=10000.0, dark_level=0.0):
+    R, n, C = direct_rgbs.shape
+    diffuse = torch.nn.functional.softplus(diffuse_raw + diffuse_bias) * indirect_scale
+    spec = spec_scale[..., None, :] * specular * indirect_scale
+    diffuse, spec = zero_invalid_bins(diffuse, spec, light_dists[..., None], cam_dists[..., None], n_bins, exposure_time,
+                                      bin_zero_threshold_light, light_zero, light_near)
+    indirect = torch.clamp(diffuse, 0.0, rgb_max) + torch.clamp(spec, 0.0, rgb_max)
+    d = (light_dists + ray_dists) / exposure_time
+    t_direct = shift_direct(d + shift / exposure_time, direct_rgbs, weights, n_bins, C)
+    shifted = shift_map_coordinates(indirect.reshape(R * n, n_bins, C), ray_dists.reshape(-1) + shift, exposure_time, n_bins)
+    t_indirect = (shifted.reshape(R, n, n_bins, C) * weights[..., None, None]).sum(1)
+    return dict(transient_direct=t_direct, transient_indirect=t_indirect, rgb=t_direct + t_indirect + dark_level)
