@@ -252,14 +252,39 @@ def run_b200(args):
     per_kernel = profile_calls(one_step, _lib)
 
     graph = torch.cuda.CUDAGraph()
-    use_graph = True  # compute is captured; the NCCL all-reduce is issued after each replay
-    with torch.cuda.graph(graph):
-        static_loss = compute_step()
+    use_graph = True
+    overlap = world > 1 and step_obj.engine is not None
+    if not overlap:
+        with torch.cuda.graph(graph):
+            static_loss = compute_step()
 
-    def run_step():
-        graph.replay()
-        allreduce_grads()
-        return static_loss
+        def run_step():
+            graph.replay()
+            allreduce_grads()
+            return static_loss
+    else:
+        # Data parallel: the step is captured as TWO graphs.  When the first one (forward, loss, shader backward)
+        # has run, the Shader half of the gradient arena is final: its all-reduce starts on a communication
+        # stream and overlaps the second graph (the sampler's backward); the Sampler half follows.
+        graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            rays_, u01_, extra_ = workload.unpack_rays(dbuf)
+            state = step_obj.step_front(rays_, u01_, extra_)
+        with torch.cuda.graph(graph_b, pool=graph.pool()):
+            static_loss = step_obj.step_back(state)
+        comm = torch.cuda.Stream()
+        so = step_obj.shader_offset
+
+        def run_step():
+            cur = torch.cuda.current_stream()
+            graph.replay()
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                ndist.allreduce_mean_(step_obj.flat_grad[so:])
+            graph_b.replay()
+            ndist.allreduce_mean_(step_obj.flat_grad[:so])
+            cur.wait_stream(comm)
+            return static_loss
 
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
 
@@ -338,7 +363,10 @@ def run_b200(args):
                    "tables": "MLP_0/1/2 density grids + appearance grid (7.5+9.6+46.7+46.7 MB fp32), "
                              "U(+-0.1) trained-like init",
                    "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
-                   "cuda_graph": bool(use_graph), "parallelism": f"dp{world} rays, params replicated"},
+                   "cuda_graph": bool(use_graph),
+                   "parallelism": f"dp{world} rays, params replicated" + (
+                       "; gradient all-reduce in 2 buckets, the shader bucket overlapping the sampler's backward"
+                       if overlap else "")},
         "rays_per_sec": value / SAMPLES_PER_RAY,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host[0].numel() * 4) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms},

@@ -56,6 +56,14 @@ class FusedCacheStep:
     def step(self, rays, u01, target_rgb, train_frac=1.0):
         """One forward + loss + backward; gradients land in the registered sinks.  Returns the loss
         (device scalar) and leaves the per-level sampler state in self.last (for tests)."""
+        state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True)
+        self.step_back(state)
+        return state["loss"]
+
+    def step_front(self, rays, u01, target_rgb, train_frac=1.0, fork_proposals=False):
+        """Forward, loss and the SHADER's backward: when this returns (in stream order) every gradient of the
+        `Shader` parameters (appearance grid + all stacks) is final, so a data-parallel harness can start
+        all-reducing that half of the gradient arena while step_back() produces the sampler's half."""
         sampler, shader = self.model.sampler, self.model.shader
         sp = self.params["Sampler"]
         near = rays["near"]
@@ -139,6 +147,8 @@ class FusedCacheStep:
                   _lib.ptr(g_w[1]))
         # ------------------------------------------------------------------ backward
         # The proposal levels' gradients only depend on the loss kernel: they run beside the shader's.
+        if not fork_proposals:
+            s_prop = None
         if s_prop is not None:
             s_prop.wait_stream(main)
             with torch.cuda.stream(s_prop):
@@ -148,16 +158,36 @@ class FusedCacheStep:
         _lib.call("nrc_ray_composite_bwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(bg),
                   _lib.ptr(g_rgb), None, R, k, 3, 1, _lib.ptr(gv), _lib.ptr(g_w[2]), None)
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
-        g_gp = new(P2, 3)
-        _lib.call("nrc_normals_bwd", st(), _lib.ptr(L2["gp"]), _lib.ptr(g_nrm), P2, _lib.ptr(g_gp))
-        self._level_backward(L2, rays, g_w[nl - 1], d_feat, g_gp if L2["gp"] is not None else None, R)
+        self.last = dict(levels=levels, rgb=out_rgb, acc=acc, dist=dist, shader_rgb=rgb_s)
+        return dict(loss=loss, levels=levels, rays=rays, g_w=g_w, d_feat=d_feat, g_nrm=g_nrm, R=R,
+                    forked=s_prop, keep=(saved, gv, g_rgb))
+
+    def step_back(self, state):
+        """Backward of the proposal sampler (three levels) from the state of step_front()."""
+        levels, rays, g_w, R = state["levels"], state["rays"], state["g_w"], state["R"]
+        nl = len(levels)
+        L2 = levels[-1]
+        P2 = R * L2["n"]
+        dev = L2["density"].device
+        main = torch.cuda.current_stream()
+        s_prop = state["forked"]
+        own_fork = None
+        if s_prop is None and self.concurrent:      # split mode: fork the proposal levels here
+            own_fork = self._streams(4)[3]
+            own_fork.wait_stream(main)
+            with torch.cuda.stream(own_fork):
+                for i_level in range(nl - 2, -1, -1):
+                    self._level_backward(levels[i_level], rays, g_w[i_level], None, None, R)
+        g_gp = torch.empty((P2, 3), device=dev, dtype=torch.float32)
+        _lib.call("nrc_normals_bwd", _lib.stream_ptr(), _lib.ptr(L2["gp"]), _lib.ptr(state["g_nrm"]), P2, _lib.ptr(g_gp))
+        self._level_backward(L2, rays, g_w[nl - 1], state["d_feat"], g_gp if L2["gp"] is not None else None, R)
         if s_prop is not None:
             main.wait_stream(s_prop)
+        elif own_fork is not None:
+            main.wait_stream(own_fork)
         else:
             for i_level in range(nl - 2, -1, -1):
                 self._level_backward(levels[i_level], rays, g_w[i_level], None, None, R)
-        self.last = dict(levels=levels, rgb=out_rgb, acc=acc, dist=dist, shader_rgb=rgb_s)
-        return loss
 
     def _level_backward(self, lv, rays, g_weights, g_feat, g_gp, R):
         """alpha-weights VJP -> fused density-MLP VJP -> hash-grid scatter of one sampler level."""

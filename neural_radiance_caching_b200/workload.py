@@ -115,6 +115,7 @@ class CacheTrainStep:
             if m.enable_pred_normals:
                 p["pred_normals_layer"] = layer(64, 3)
             sampler[f"MLP_{i}"] = p
+        self.num_sampler_leaves = len(self.leaves)   # leaves (and the gradient arena) are ordered Sampler | Shader
         sh = self.model.shader
 
         def slf(in_dim):
@@ -141,7 +142,10 @@ class CacheTrainStep:
         total = sum(pad(int(t.numel())) for t in self.leaves)
         self.flat_grad = torch.zeros(total, device=device, dtype=torch.float32)
         off = 0
-        for t in self.leaves:
+        self.shader_offset = 0
+        for i, t in enumerate(self.leaves):
+            if i == self.num_sampler_leaves:
+                self.shader_offset = off       # flat_grad[:shader_offset] = sampler grads, [shader_offset:] = shader grads
             n = int(t.numel())
             sink = self.flat_grad[off:off + n].view(t.shape)
             _lib.register_grad_sink(t, sink)
@@ -164,6 +168,15 @@ class CacheTrainStep:
             self.zero_grad()
             return self.engine.step(rays, u01, target_rgb)
         return self.step_autograd(rays, u01, target_rgb)
+
+    def step_front(self, rays, u01, target_rgb):
+        """First half of step() (forward, loss, shader backward); see engine.FusedCacheStep.step_front."""
+        self.zero_grad()
+        return self.engine.step_front(rays, u01, target_rgb)
+
+    def step_back(self, state):
+        self.engine.step_back(state)
+        return state["loss"]
 
     def step_autograd(self, rays, u01, target_rgb):
         self.zero_grad()
