@@ -59,75 +59,86 @@ struct EpiArgs {
 };
 
 template <bool BIAS, bool RELU, bool MASK, bool FULL>
+__device__ __forceinline__ void epi_chunk(const EpiArgs& a, int j0, const uint32_t (&v)[16], const uint32_t (&mw)[8],
+                                          const float (&b)[16]) {
+  float x[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    float t = __uint_as_float(v[e]);
+    if (BIAS) t += b[e];
+    if (RELU) t = fmaxf(t, 0.f);
+    if (MASK) {   // bf16 activation > 0  <=>  its 16 bits, read as a signed short, are > 0
+      const short h = static_cast<short>((mw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
+      t = h > 0 ? t : 0.f;
+    }
+    if (!FULL && j0 + e >= a.ncols) t = 0.f;
+    x[e] = t;
+  }
+  if (a.has_slot) {
+    const uint32_t sa = a.slot0_addr + static_cast<uint32_t>(j0 >> 6) * kAtomBytes;
+    const uint32_t d0 = sa + atom_chunk_offset(a.r, (j0 & 63) >> 3);
+    const uint32_t d1 = sa + atom_chunk_offset(a.r, ((j0 & 63) >> 3) + 1);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d0), "r"(pack2_bf16(x[0], x[1])),
+                 "r"(pack2_bf16(x[2], x[3])), "r"(pack2_bf16(x[4], x[5])), "r"(pack2_bf16(x[6], x[7]))
+                 : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d1), "r"(pack2_bf16(x[8], x[9])),
+                 "r"(pack2_bf16(x[10], x[11])), "r"(pack2_bf16(x[12], x[13])), "r"(pack2_bf16(x[14], x[15]))
+                 : "memory");
+  }
+  if (a.out_row && (FULL || j0 < a.ncols)) {
+    float* o = a.out_row + j0;
+    if (a.out_vec && (FULL || j0 + 16 <= a.ncols)) {
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        float4 w = make_float4(x[e], x[e + 1], x[e + 2], x[e + 3]);
+        if (a.accum) {
+          const float4 old = *reinterpret_cast<const float4*>(o + e);
+          w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+        }
+        *reinterpret_cast<float4*>(o + e) = w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (j0 + e < a.ncols) o[e] = a.accum ? o[e] + x[e] : x[e];
+    }
+  }
+}
+
+template <bool BIAS, bool RELU, bool MASK, bool FULL>
+__device__ __forceinline__ void epi_loads(const EpiArgs& a, int j0, uint32_t (&mw)[8], float (&b)[16]) {
+  if (MASK) {
+    const int mc = a.mask_atom0 * 64 + j0;
+    const uint8_t* ma = a.mask_tile + static_cast<size_t>(mc >> 6) * kAtomBytes;
+    const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(ma + atom_chunk_offset(a.r, (mc & 63) >> 3)));
+    const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(ma + atom_chunk_offset(a.r, ((mc & 63) >> 3) + 1)));
+    mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
+    mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+  }
+  if (BIAS) {
+    if (FULL) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.bias + j0) + q);
+        b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) b[e] = (j0 + e < a.ncols) ? __ldg(a.bias + j0 + e) : 0.f;
+    }
+  }
+}
+
+// 16 columns per iteration; the mask / bias loads are issued between the TMEM load and its wait.
+template <bool BIAS, bool RELU, bool MASK, bool FULL>
 __device__ __forceinline__ void epi_run(const EpiArgs& a) {
   for (int j0 = 0; j0 < a.npad; j0 += 16) {
-    uint32_t v[16];
-    tmem_ld16(a.taddr + j0, v);
-    uint32_t mw[8];
-    if (MASK) {
-      const int mc = a.mask_atom0 * 64 + j0;
-      const uint8_t* ma = a.mask_tile + static_cast<size_t>(mc >> 6) * kAtomBytes;
-      const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(ma + atom_chunk_offset(a.r, (mc & 63) >> 3)));
-      const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(ma + atom_chunk_offset(a.r, ((mc & 63) >> 3) + 1)));
-      mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
-      mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
-    }
+    uint32_t v[16], mw[8];
     float b[16];
-    if (BIAS) {
-      if (FULL) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(a.bias + j0) + q);
-          b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) b[e] = (j0 + e < a.ncols) ? __ldg(a.bias + j0 + e) : 0.f;
-      }
-    }
+    tmem_ld16(a.taddr + j0, v);
+    epi_loads<BIAS, RELU, MASK, FULL>(a, j0, mw, b);
     tmem_ld_wait();
-    float x[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      float t = __uint_as_float(v[e]);
-      if (BIAS) t += b[e];
-      if (RELU) t = fmaxf(t, 0.f);
-      if (MASK) {   // bf16 activation > 0  <=>  its 16 bits, read as a signed short, are > 0
-        const short h = static_cast<short>((mw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
-        t = h > 0 ? t : 0.f;
-      }
-      if (!FULL && j0 + e >= a.ncols) t = 0.f;
-      x[e] = t;
-    }
-    if (a.has_slot) {
-      const uint32_t sa = a.slot0_addr + static_cast<uint32_t>(j0 >> 6) * kAtomBytes;
-      const uint32_t d0 = sa + atom_chunk_offset(a.r, (j0 & 63) >> 3);
-      const uint32_t d1 = sa + atom_chunk_offset(a.r, ((j0 & 63) >> 3) + 1);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d0), "r"(pack2_bf16(x[0], x[1])),
-                   "r"(pack2_bf16(x[2], x[3])), "r"(pack2_bf16(x[4], x[5])), "r"(pack2_bf16(x[6], x[7]))
-                   : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d1), "r"(pack2_bf16(x[8], x[9])),
-                   "r"(pack2_bf16(x[10], x[11])), "r"(pack2_bf16(x[12], x[13])), "r"(pack2_bf16(x[14], x[15]))
-                   : "memory");
-    }
-    if (a.out_row && (FULL || j0 < a.ncols)) {
-      float* o = a.out_row + j0;
-      if (a.out_vec && (FULL || j0 + 16 <= a.ncols)) {
-#pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          float4 w = make_float4(x[e], x[e + 1], x[e + 2], x[e + 3]);
-          if (a.accum) {
-            const float4 old = *reinterpret_cast<const float4*>(o + e);
-            w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
-          }
-          *reinterpret_cast<float4*>(o + e) = w;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (j0 + e < a.ncols) o[e] = a.accum ? o[e] + x[e] : x[e];
-      }
-    }
+    epi_chunk<BIAS, RELU, MASK, FULL>(a, j0, v, mw, b);
   }
 }
 
@@ -275,30 +286,44 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           const float* src = op.ptr >= 0 ? static_cast<const float*>(p.ptrs[op.ptr]) : nullptr;
           const int nch = op.npad >> 3;
           const bool vec = src && (op.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-          for (int item = wg_tid; item < 128 * nch; item += 128) {
-            const int rr = item / nch, ch = item - rr * nch;
-            const int col = ch * 8;
-            float v[8];
+          // four independent 32-byte loads in flight per thread before the first conversion
+          constexpr int kU = 4;
+          const int total = 128 * nch;
+          for (int item0 = wg_tid; item0 < total; item0 += 128 * kU) {
+            float v[kU][8];
+            int rrs[kU], cols[kU];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-            if (src && row0 + rr < p.num_rows && col < op.ncols) {
-              const float* s = src + (row0 + rr) * op.ld + col;
-              if (vec && col + 8 <= op.ncols) {
-                const float4 x0 = __ldg(reinterpret_cast<const float4*>(s));
-                const float4 x1 = __ldg(reinterpret_cast<const float4*>(s) + 1);
-                v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
-                v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-              } else {
+            for (int q = 0; q < kU; ++q) {
+              const int item = item0 + q * 128;
+              const int rr = item / nch;
+              rrs[q] = rr;
+              cols[q] = (item - rr * nch) * 8;
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  if (col + e < op.ncols) v[e] = __ldg(s + e);
+              for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
+              if (item < total && src && row0 + rr < p.num_rows && cols[q] < op.ncols) {
+                const float* s = src + (row0 + rr) * op.ld + cols[q];
+                if (vec && cols[q] + 8 <= op.ncols) {
+                  const float4 x0 = __ldg(reinterpret_cast<const float4*>(s));
+                  const float4 x1 = __ldg(reinterpret_cast<const float4*>(s) + 1);
+                  v[q][0] = x0.x; v[q][1] = x0.y; v[q][2] = x0.z; v[q][3] = x0.w;
+                  v[q][4] = x1.x; v[q][5] = x1.y; v[q][6] = x1.z; v[q][7] = x1.w;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (cols[q] + e < op.ncols) v[q][e] = __ldg(s + e);
+                }
               }
             }
-            const int dcol = op.col0 + col;
-            const uint32_t dst = slot_addr(c, op.slot + (dcol >> 6)) + atom_chunk_offset(rr, (dcol & 63) >> 3);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack2_bf16(v[0], v[1])),
-                         "r"(pack2_bf16(v[2], v[3])), "r"(pack2_bf16(v[4], v[5])), "r"(pack2_bf16(v[6], v[7]))
-                         : "memory");
+#pragma unroll
+            for (int q = 0; q < kU; ++q) {
+              if (item0 + q * 128 >= total) continue;
+              const int dcol = op.col0 + cols[q];
+              const uint32_t dst = slot_addr(c, op.slot + (dcol >> 6)) + atom_chunk_offset(rrs[q], (dcol & 63) >> 3);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack2_bf16(v[q][0], v[q][1])),
+                           "r"(pack2_bf16(v[q][2], v[q][3])), "r"(pack2_bf16(v[q][4], v[q][5])),
+                           "r"(pack2_bf16(v[q][6], v[q][7]))
+                           : "memory");
+            }
           }
         } else if (op.kind == NRC_OP_SAVE) {
           fence_proxy_async_smem();

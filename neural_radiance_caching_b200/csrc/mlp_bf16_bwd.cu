@@ -5,6 +5,8 @@
 //   phase 2 (per CTA): weight gradients dW = A^T G as MMAs over the 128-point tile with the
 //     transposed-ldmatrix trick, accumulated in fp32 registers across all tiles of the CTA.
 // One atomic pass per CTA at the end.  Reference: XLA autodiff of geometry.py:155-168,467.
+#include <cstdlib>
+
 #include "mma_bf16.cuh"
 
 namespace nrc {
@@ -278,7 +280,10 @@ int32_t launch_bf16_bwd(cudaStream_t st, const nrc_density_mlp_t* mlp, const flo
   nrc_density_mlp_grad_t g{};
   if (grads) g = *grads;
   int64_t tiles = (P + kBwTile - 1) / kBwTile;
-  unsigned grid = static_cast<unsigned>(tiles < kNumSMs ? tiles : kNumSMs);
+  // persistent CTAs, one per SM: measured on B200 at 65 536 points, 2-4 CTAs per SM are SLOWER (0.911 / 0.923 /
+  // 0.937 ms per step vs 0.891) -- the per-CTA weight staging and gradient flush outweigh the extra warps
+  static const int mult = getenv("NRC_MLP_BWD_GRID_MULT") ? atoi(getenv("NRC_MLP_BWD_GRID_MULT")) : 1;
+  unsigned grid = static_cast<unsigned>(tiles < kNumSMs * mult ? tiles : kNumSMs * mult);
   mlp_bf16_bwd_kernel<KS0><<<grid, kBwThreads, sizeof(BwdSmemBf16), st>>>(*mlp, enc, g_raw, density, g_feat, g_gp,
                                                                           P, g_enc, g, grads ? 1 : 0);
   return check_launch();
