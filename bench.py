@@ -113,7 +113,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_reference_throughput(rays, steps, warmup, threads=None):
     """The reference's algorithm (oracle port) for the same step: full cache training step."""
-    from oracle import models as omodels
+    from oracle import loss_utils as oloss, models as omodels
     from neural_radiance_caching_b200 import workload
 
     threads = threads or os.cpu_count()
@@ -141,7 +141,7 @@ def cpu_reference_throughput(rays, steps, warmup, threads=None):
         for t in leaves:
             t.grad = None
         res = model(params, rt, u)
-        loss = workload.cache_loss(res, target)
+        loss = workload.cache_loss(res, target, interlevel_fn=oloss.spline_interlevel_loss)
         loss.backward()
         return float(loss.detach())
 
@@ -176,7 +176,8 @@ def run_reference(args):
 
 WORKLOAD = ("config2 nerf_ngp_yobo_lego cache training step: proposal sampler (64,64,32) hash-grid + density MLP, "
             "cache shader (appearance grid + bottleneck/heads/int-BRDF/IDE SurfaceLightField/EnvMap MLPs) on the "
-            "32 final samples, volumetric rendering, Charbonnier-sRGB loss, fwd+bwd (grads for 4 grids + all MLPs)")
+            "32 final samples, volumetric rendering, Charbonnier-sRGB data loss + spline interlevel loss on both proposal "
+            "levels, fwd+bwd (grads for 4 grids + all MLPs)")
 
 
 # ----------------------------------------------------------------------------- b200 arm

@@ -444,6 +444,19 @@ int32_t nrc_transient_render_fwd(void* stream, const float* d_direct_rgbs, const
                                  int32_t light_zero, float light_near, float rgb_max, float dark_level,
                                  float* d_transient_direct, float* d_transient_indirect, float* d_rgb);
 
+/* Proposal supervision: one level of loss_utils.spline_interlevel_loss
+ * (internal/loss_utils.py:74-108; blur_and_resample_weights, internal/stepfun.py:463-483, over
+ * internal/linspline.py:95-141,187-221):  w_blur = stop_gradient(blur(t, w, blur_halfwidth) resampled into tq),
+ * loss += mult * mean(max(0, w_blur - wp)^2 / (wp + eps)) (ACCUMULATED into d_loss[0]), d_g_wp [R,nq] = d loss / d wp.
+ *   d_t [R,m+1], d_w [R,m] final-level step function (m <= 64); d_tq [R,nq+1], d_wp [R,nq] proposal level (nq <= 128);
+ *   d_w_blur [R,nq] optional output. */
+int32_t nrc_interlevel_loss(void* stream, const float* d_t, const float* d_w, int32_t m, const float* d_tq,
+                            const float* d_wp, int32_t nq, int64_t num_rays, float blur_halfwidth, float mult,
+                            float eps, float* d_loss, float* d_g_wp, float* d_w_blur);
+/* Data term: loss += mean Charbonnier(linear_to_srgb(rgb) - target) (accumulated), d_g_rgb [R,3] written. */
+int32_t nrc_charb_srgb_loss(void* stream, const float* d_rgb, const float* d_target, int64_t num_rays,
+                            float charb_padding, float* d_loss, float* d_g_rgb);
+
 /* ------------------------------------------------- K5: GGX integration ---- */
 /* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) +
  * integrate_reflect_rays (:1102-1193): Disney-GGX D*F*G and Lambert lobes evaluated in the

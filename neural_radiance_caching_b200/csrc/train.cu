@@ -103,6 +103,157 @@ __global__ void cache_loss_kernel(const float* __restrict__ rgb, const float* __
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Proposal supervision: loss_utils.spline_interlevel_loss (internal/loss_utils.py:74-108) =
+// stepfun.blur_and_resample_weights (internal/stepfun.py:463-483) over linspline.blur_stepfun /
+// compute_integral / interpolate_integral (internal/linspline.py:187-221, 95-109, 124-141), then the truncated
+// chi-squared loss max(0, w_blur - wp)^2 / (wp + eps).  w_blur is a stop_gradient in the reference, so the
+// only gradient is d loss / d wp, produced here together with the loss.  One warp per ray: lane 0 performs the
+// 2(m+1)-knot merge and the three running sums in the reference's left-to-right order (bitwise reproducible),
+// all lanes evaluate the piecewise quadratic at the proposal fenceposts.
+constexpr int kMaxKnots = 2 * (64 + 1);
+
+__device__ __forceinline__ float plus_eps_f(float x) {
+  return fabsf(x) < f32_tiny() ? f32_tiny() : nextafterf(x, INFINITY);
+}
+__device__ __forceinline__ float minus_eps_f(float x) {
+  return fabsf(x) < f32_tiny() ? -f32_tiny() : nextafterf(x, -INFINITY);
+}
+
+struct InterlevelSmem {
+  float tp[kMaxKnots], dyp[kMaxKnots], yp[kMaxKnots], a[kMaxKnots], c[kMaxKnots], acc[130];
+  float lo[66], hi[66], dy[66], pdf[66];
+};
+
+__global__ void interlevel_loss_kernel(const float* __restrict__ t, const float* __restrict__ w, int m,
+                                       const float* __restrict__ tq, const float* __restrict__ wp, int nq, int64_t R,
+                                       float halfwidth, float mult, float eps_loss, float* __restrict__ loss,
+                                       float* __restrict__ g_wp, float* __restrict__ w_blur_out) {
+  __shared__ InterlevelSmem sm[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+  float contrib = 0.f;
+  if (ray < R) {
+    InterlevelSmem& s = sm[warp];
+    const float* ts = t + ray * (m + 1);
+    const float* ws = w + ray * m;
+    const int K = 2 * (m + 1);
+    // weight_to_pdf (stepfun.py:75-79, math.safe_div) and the dilated knots of blur_stepfun, all lanes
+    for (int i = lane; i <= m; i += 32) {
+      const float ti = ts[i];
+      s.lo[i] = fminf(minus_eps_f(ti), __fsub_rn(ti, halfwidth));
+      s.hi[i] = fmaxf(plus_eps_f(ti), __fadd_rn(ti, halfwidth));
+      float p = 0.f;
+      if (i < m) {
+        const float td = __fsub_rn(ts[i + 1], ti);
+        if (!(td < f32_tiny())) p = fminf(fmaxf(__fdiv_rn(ws[i], td), -f32_max()), f32_max());
+      }
+      s.pdf[i] = p;   // pdf[m] = 0 (zero padding)
+    }
+    __syncwarp();
+    for (int i = lane; i <= m; i += 32)
+      s.dy[i] = __fdiv_rn(__fsub_rn(s.pdf[i], i > 0 ? s.pdf[i - 1] : 0.f), __fsub_rn(s.hi[i], s.lo[i]));
+    __syncwarp();
+    if (lane == 0) {
+      // merge of the (individually sorted) knots ts_lo, ts_hi; stable: on ties the ts_lo element (lower original
+      // index) comes first, like jnp.argsort.  Running sums in the reference's left-to-right order, every
+      // product / sum individually rounded (no FMA contraction) so they reproduce the fp32 oracle.
+      int il = 0, ih = 0;
+      for (int k = 0; k < K; ++k) {
+        const bool take_lo = il <= m && (ih > m || s.lo[il] <= s.hi[ih]);
+        if (take_lo) { s.tp[k] = s.lo[il]; s.dyp[k] = s.dy[il]; ++il; }
+        else         { s.tp[k] = s.hi[ih]; s.dyp[k] = -s.dy[ih]; ++ih; }
+      }
+      // yp = [0, cumsum(diff(tp)[:-1] * cumsum(dyp[:K-2])), 0].  The double running sums are ill conditioned
+      // (O(p / halfwidth) terms that cancel back to zero at the last knot): they are carried in fp64 and rounded
+      // to fp32 per element -- what the oracle's torch.cumsum does on the host, and tighter than any fp32 order.
+      double cs = 0.0, ys = 0.0;
+      s.yp[0] = 0.f;
+      for (int k = 0; k < K - 2; ++k) {
+        cs += static_cast<double>(s.dyp[k]);
+        ys += static_cast<double>(__fmul_rn(__fsub_rn(s.tp[k + 1], s.tp[k]), static_cast<float>(cs)));
+        s.yp[k + 1] = static_cast<float>(ys);
+      }
+      s.yp[K - 1] = 0.f;
+      // compute_integral: a, b = yp[:-1], c
+      const float e2 = f32_eps() * f32_eps();
+      double cc = 0.0;
+      for (int k = 0; k < K - 1; ++k) {
+        const float dt = __fsub_rn(s.tp[k + 1], s.tp[k]);
+        s.a[k] = __fdiv_rn(__fsub_rn(s.yp[k + 1], s.yp[k]), fmaxf(e2, __fmul_rn(2.f, dt)));
+        s.c[k] = __fmul_rn(0.5f, static_cast<float>(cc));
+        if (k < K - 2) cc += static_cast<double>(__fmul_rn(dt, __fadd_rn(s.yp[k], s.yp[k + 1])));
+      }
+    }
+    __syncwarp();
+    // interpolate_integral at the nq + 1 proposal fenceposts
+    const float t_first = s.tp[0], t_last = minus_eps_f(s.tp[K - 1]);
+    for (int q = lane; q <= nq; q += 32) {
+      float x = tq[ray * (nq + 1) + q];
+      x = fmaxf(fminf(x, t_last), t_first);
+      int lo_i = 0, hi_i = K;            // searchsorted(side='right'): first index with tp > x
+      while (lo_i < hi_i) {
+        const int mid = (lo_i + hi_i) >> 1;
+        if (s.tp[mid] <= x) lo_i = mid + 1; else hi_i = mid;
+      }
+      const int i0 = max(lo_i - 1, 0);
+      const float td = __fsub_rn(x, s.tp[i0]);
+      s.acc[q] = __fadd_rn(__fadd_rn(__fmul_rn(s.a[i0], __fmul_rn(td, td)), __fmul_rn(s.yp[i0], td)), s.c[i0]);
+    }
+    __syncwarp();
+    const float scale = mult / (static_cast<float>(R) * static_cast<float>(nq));
+    for (int j = lane; j < nq; j += 32) {
+      const float wb = fmaxf(0.f, __fsub_rn(s.acc[j + 1], s.acc[j]));
+      const float p = wp[ray * nq + j];
+      const float d = fmaxf(0.f, wb - p);
+      const float den = p + eps_loss;
+      contrib += d * d / den;
+      // d/dp [ d^2 / (p + eps) ] = -2 d / (p + eps) - d^2 / (p + eps)^2   (d > 0)
+      g_wp[ray * nq + j] = scale * (-2.f * d / den - d * d / (den * den));
+      if (w_blur_out) w_blur_out[ray * nq + j] = wb;
+    }
+    contrib *= scale;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+  }
+  __shared__ float part[4];
+  if (lane == 0) part[warp] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(loss, part[0] + part[1] + part[2] + part[3]);
+}
+
+// data term only: mean Charbonnier(linear_to_srgb(rgb) - target); thread per (ray, channel)
+__global__ void charb_srgb_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ target, int64_t R,
+                                       float charb_padding, float* __restrict__ loss, float* __restrict__ g_rgb) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float contrib = 0.f;
+  if (i < R * 3) {
+    const float x = rgb[i];
+    const float eps = f32_eps();
+    const float xc = fmaxf(x, eps);
+    const float p512 = powf(xc, 5.0f / 12.0f);
+    const bool lin = x <= 0.0031308f;
+    const float srgb = lin ? (323.0f / 25.0f) * x : (211.0f * p512 - 11.0f) / 200.0f;
+    const float dsrgb = lin ? (323.0f / 25.0f) : (x > eps ? (211.0f / 200.0f) * (5.0f / 12.0f) * p512 / xc : 0.f);
+    const float diff = srgb - target[i];
+    const float ch = sqrtf(diff * diff + charb_padding * charb_padding);
+    const float inv = 1.0f / (3.0f * static_cast<float>(R));
+    g_rgb[i] = (diff / ch) * dsrgb * inv;
+    contrib = ch * inv;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) sum += part[k];
+    atomicAdd(loss, sum);
+  }
+}
+
 }  // namespace nrc
 
 using namespace nrc;
@@ -138,5 +289,25 @@ extern "C" int32_t nrc_cache_loss(void* stream, const float* d_rgb, const float*
   const unsigned grid = static_cast<unsigned>((num_rays * 32 + 255) / 256);
   cache_loss_kernel<<<grid, 256, 0, s>>>(d_rgb, d_target, d_w0, n0, d_w1, n1, d_w2, n2, num_rays, charb_padding,
                                          prop_weight, d_loss, d_g_rgb, d_g_w0, d_g_w1);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_interlevel_loss(void* stream, const float* d_t, const float* d_w, int32_t m, const float* d_tq,
+                                       const float* d_wp, int32_t nq, int64_t num_rays, float blur_halfwidth, float mult,
+                                       float eps, float* d_loss, float* d_g_wp, float* d_w_blur) {
+  if (num_rays < 1 || m < 1 || m > 64 || nq < 1 || nq > 128) return NRC_E_INVALID_ARG;
+  if (!d_t || !d_w || !d_tq || !d_wp || !d_loss || !d_g_wp) return NRC_E_INVALID_ARG;
+  interlevel_loss_kernel<<<static_cast<unsigned>((num_rays + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_t, d_w, m, d_tq, d_wp, nq, num_rays, blur_halfwidth, mult, eps, d_loss, d_g_wp, d_w_blur);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_charb_srgb_loss(void* stream, const float* d_rgb, const float* d_target, int64_t num_rays,
+                                       float charb_padding, float* d_loss, float* d_g_rgb) {
+  if (num_rays < 1) return NRC_E_INVALID_ARG;
+  if (!d_rgb || !d_target || !d_loss || !d_g_rgb) return NRC_E_INVALID_ARG;
+  const int64_t n = num_rays * 3;
+  charb_srgb_loss_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_rgb, d_target, num_rays, charb_padding, d_loss, d_g_rgb);
   return check_launch();
 }

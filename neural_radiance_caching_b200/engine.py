@@ -14,7 +14,8 @@ Schedule (reference call sites in brackets):
   nrc_normals_fwd x2 (predicted + analytic)       [geometry.py:442-479]
   shader_fused_forward                            [nerf.py:561-689,940-1090, surface_light_field.py:782-1069]
   nrc_ray_composite_fwd                           [render.py:172-247]
-  nrc_cache_loss                                  [loss + d loss / d rgb, d loss / d proposal weights]
+  nrc_charb_srgb_loss, nrc_interlevel_loss x2     [loss + d loss / d rgb, d loss / d proposal weights;
+                                                   image.py:192-200, loss_utils.py:74-108]
   nrc_ray_composite_bwd, shader_fused_backward, nrc_normals_bwd
   per level l = 2,1,0   nrc_ray_alpha_weights_bwd, nrc_density_mlp_bwd, nrc_contract_fwd, nrc_encode_bwd
 """
@@ -26,9 +27,10 @@ from . import _lib, geometry, nerf, stepfun
 
 
 class FusedCacheStep:
-    def __init__(self, model, params, charb_padding=0.001, prop_weight=0.01):
+    def __init__(self, model, params, charb_padding=0.001, interlevel_mults=(0.01, 0.01), interlevel_blurs=(0.03, 0.003)):
         self.model, self.params = model, params
-        self.charb_padding, self.prop_weight = charb_padding, prop_weight
+        self.charb_padding = charb_padding
+        self.interlevel_mults, self.interlevel_blurs = interlevel_mults, interlevel_blurs
         self._bg = {}
         self._side = None
         self.concurrent = True   # independent branches of the schedule on side streams (fork/join events)
@@ -141,10 +143,14 @@ class FusedCacheStep:
         loss = torch.empty((), device=dev, dtype=torch.float32)
         g_rgb = new(R, 3)
         g_w = [new(R, lv["n"]) for lv in levels]
-        _lib.call("nrc_cache_loss", st(), _lib.ptr(out_rgb), _lib.ptr(target_rgb), _lib.ptr(levels[0]["weights"]),
-                  levels[0]["n"], _lib.ptr(levels[1]["weights"]), levels[1]["n"], _lib.ptr(L2["weights"]), k, R,
-                  float(self.charb_padding), float(self.prop_weight), _lib.ptr(loss), _lib.ptr(g_rgb), _lib.ptr(g_w[0]),
-                  _lib.ptr(g_w[1]))
+        loss.zero_()
+        _lib.call("nrc_charb_srgb_loss", st(), _lib.ptr(out_rgb), _lib.ptr(target_rgb), R, float(self.charb_padding),
+                  _lib.ptr(loss), _lib.ptr(g_rgb))
+        for i_level in range(nl - 1):   # spline interlevel loss of every proposal level (loss_utils.py:74-108)
+            lv = levels[i_level]
+            _lib.call("nrc_interlevel_loss", st(), _lib.ptr(L2["sdist"]), _lib.ptr(L2["weights"]), k, _lib.ptr(lv["sdist"]),
+                      _lib.ptr(lv["weights"]), lv["n"], R, float(self.interlevel_blurs[i_level]),
+                      float(self.interlevel_mults[i_level]), 1e-5, _lib.ptr(loss), _lib.ptr(g_w[i_level]), None)
         # ------------------------------------------------------------------ backward
         # The proposal levels' gradients only depend on the loss kernel: they run beside the shader's.
         if not fork_proposals:

@@ -60,19 +60,25 @@ def linear_to_srgb(linear):
     return torch.where(linear <= 0.0031308, srgb0, srgb1)
 
 
-def cache_loss(result, target_rgb, charb_padding=0.001):
-    """Cache-stage objective of the benchmark step (device-agnostic torch glue; also used on the
-    oracle's tensors by the CPU leg): Charbonnier data term on the sRGB-mapped render
+INTERLEVEL_MULTS = (0.01, 0.01)     # configs/ngp_yobo.gin:246
+INTERLEVEL_BLURS = (0.03, 0.003)    # configs/ngp_yobo.gin:247
+
+
+def cache_loss(result, target_rgb, charb_padding=0.001, interlevel_fn=None):
+    """Cache-stage objective of the benchmark step: Charbonnier data term on the sRGB-mapped render
     (MaterialModel.cache_loss='charb', cache_linear_to_srgb=True, configs/ngp_yobo.gin:35-37;
-    internal/configs.py:330) plus a proposal-supervision stand-in that ties the accumulated
-    weights of the two proposal levels to the (stop-gradient) final level.  The reference's spline
-    interlevel, predicted-normal and mask losses are the SURVEY 8f 'next' rows."""
+    internal/configs.py:330) + the spline interlevel loss supervising the two proposal levels
+    (Config.use_spline_interlevel_loss, mults (0.01, 0.01), blurs (0.03, 0.003), configs/ngp_yobo.gin:245-247;
+    internal/loss_utils.py:74-108).  `interlevel_fn(ray_history, mults=, blurs=)` is the CUDA mirror
+    (loss_utils.spline_interlevel_loss) on the device and the oracle's restatement in the CPU leg.  The
+    geometry losses (orientation / predicted normals) are SURVEY 8f rank 1."""
     rgb = linear_to_srgb(result["render"]["rgb"])
     loss = torch.sqrt((rgb - target_rgb) ** 2 + charb_padding**2).mean()
-    hist = result["sampler"]
-    acc_final = hist[-1]["weights"].sum(-1).detach()
-    for h in hist[:-1]:
-        loss = loss + 0.01 * ((h["weights"].sum(-1) - acc_final) ** 2).mean()
+    if interlevel_fn is None:
+        from . import loss_utils
+        interlevel_fn = loss_utils.spline_interlevel_loss
+    for l in interlevel_fn(result["sampler"], mults=INTERLEVEL_MULTS, blurs=INTERLEVEL_BLURS):
+        loss = loss + l
     return loss
 
 

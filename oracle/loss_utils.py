@@ -1,0 +1,77 @@
+"""CPU restatement (test infrastructure) of the proposal supervision of the cache stage:
+internal/loss_utils.py spline_interlevel_loss (:74-108), internal/stepfun.py weight_to_pdf (:75-79),
+blur_and_resample_weights (:463-483), internal/linspline.py blur_stepfun (:187-221), compute_integral (:95-109),
+interpolate_integral (:124-141), internal/math.py plus_eps / minus_eps (:56-66); configs/ngp_yobo.gin:245-247
+(mults (0.01, 0.01), blurs (0.03, 0.003)).  Parity unpinned (no reference vectors; JAX not installable here).  Note: torch.cumsum on the host carries its
+running sum in float64 and rounds per element, so this restatement is MORE accurate than XLA's fp32 cumsum in the
+ill-conditioned double running sum of blur_stepfun; the CUDA body does the same."""
+import numpy as np
+import torch
+
+from . import ref_math
+
+TINY = float(np.finfo(np.float32).tiny)
+EPS = float(np.finfo(np.float32).eps)
+
+
+def plus_eps(x):
+    return torch.where(torch.abs(x) < TINY, torch.full_like(x, TINY), torch.nextafter(x, torch.full_like(x, float("inf"))))
+
+
+def minus_eps(x):
+    return torch.where(torch.abs(x) < TINY, torch.full_like(x, -TINY), torch.nextafter(x, torch.full_like(x, -float("inf"))))
+
+
+def weight_to_pdf(t, w):
+    td = torch.diff(t, dim=-1)
+    return torch.where(td < TINY, torch.zeros_like(w), ref_math.safe_div(w, td))
+
+
+def blur_stepfun(ts, ys, halfwidth):
+    ts_lo = torch.minimum(minus_eps(ts), ts - halfwidth)
+    ts_hi = torch.maximum(plus_eps(ts), ts + halfwidth)
+    z = torch.zeros_like(ys[..., :1])
+    ys0 = torch.cat([z, ys, z], dim=-1)
+    dy = torch.diff(ys0, dim=-1) / (ts_hi - ts_lo)
+    tp = torch.cat([ts_lo, ts_hi], dim=-1)
+    dyp = torch.cat([dy, -dy], dim=-1)
+    idx = torch.argsort(tp, dim=-1, stable=True)
+    tp = torch.gather(tp, -1, idx)
+    dyp = torch.gather(dyp, -1, idx[..., :-2])
+    yp = torch.cumsum(torch.diff(tp, dim=-1)[..., :-1] * torch.cumsum(dyp, dim=-1), dim=-1)
+    return tp, torch.cat([torch.zeros_like(yp[..., :1]), yp, torch.zeros_like(yp[..., -1:])], dim=-1)
+
+
+def compute_integral(t, y):
+    dt = torch.diff(t, dim=-1)
+    a = torch.diff(y, dim=-1) / torch.clamp(2 * dt, min=EPS**2)
+    b = y[..., :-1]
+    c1 = 0.5 * torch.cumsum(dt[..., :-1] * (y[..., :-2] + y[..., 1:-1]), dim=-1)
+    return a, b, torch.cat([torch.zeros_like(y[..., :1]), c1], dim=-1)
+
+
+def interpolate_integral(tq, t, a, b, c):
+    tq = torch.maximum(torch.minimum(tq, minus_eps(t[..., -1:])), t[..., :1])
+    idx = torch.searchsorted(t.contiguous(), tq.contiguous(), right=True)
+    idx0 = torch.clamp(idx - 1, min=0)
+    t0, a0, b0, c0 = (torch.gather(v, -1, idx0) for v in (t, a, b, c))
+    td = tq - t0
+    return a0 * td**2 + b0 * td + c0
+
+
+def blur_and_resample_weights(tq, t, w, blur_halfwidth):
+    p = weight_to_pdf(t, w)
+    tl, pl = blur_stepfun(t, p, blur_halfwidth)
+    acc = interpolate_integral(tq, tl, *compute_integral(tl, pl))
+    return torch.clamp(torch.diff(acc, dim=-1), min=0)
+
+
+def spline_interlevel_loss(ray_history, mults=(0.01, 0.01), blurs=(0.03, 0.003), eps=1e-5):
+    """-> list of per-level losses (gradient flows to the proposal weights only: w_blur is stop_gradient)."""
+    c, w = ray_history[-1]["sdist"], ray_history[-1]["weights"]
+    out = []
+    for mult, blur, h in zip(mults, blurs, ray_history[:-1]):
+        w_blur = blur_and_resample_weights(h["sdist"], c, w, blur).detach()
+        wp = h["weights"]
+        out.append(mult * torch.mean(torch.clamp(w_blur - wp, min=0) ** 2 / (wp + eps)))
+    return out
