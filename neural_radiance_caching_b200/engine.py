@@ -127,6 +127,29 @@ class FusedCacheStep:
         if L2["rg"] is not None:   # analytic normals: computed like the reference, consumed by the 8f losses
             L2["normals"] = new(P2, 3)
             _lib.call("nrc_normals_fwd", st(), _lib.ptr(L2["rg"]), P2, _lib.ptr(L2["normals"]))
+        # ------------------------------------------------------------------ proposal supervision (side stream)
+        # The spline interlevel loss and the proposal levels' backward depend only on the final level's step
+        # function (sdist, weights): they start here and run beside the shader's forward / backward.
+        k = L2["n"]
+        loss = torch.zeros((), device=dev, dtype=torch.float32)
+        g_w = [new(R, lv["n"]) for lv in levels]
+
+        def interlevel():   # loss_utils.spline_interlevel_loss, one launch per proposal level
+            for i_level in range(nl - 1):
+                lv = levels[i_level]
+                _lib.call("nrc_interlevel_loss", _lib.stream_ptr(), _lib.ptr(L2["sdist"]), _lib.ptr(L2["weights"]), k,
+                          _lib.ptr(lv["sdist"]), _lib.ptr(lv["weights"]), lv["n"], R, float(self.interlevel_blurs[i_level]),
+                          float(self.interlevel_mults[i_level]), 1e-5, _lib.ptr(loss), _lib.ptr(g_w[i_level]), None)
+
+        if s_prop is not None:
+            s_prop.wait_stream(main)
+            with torch.cuda.stream(s_prop):
+                interlevel()
+                if fork_proposals:
+                    for i_level in range(nl - 2, -1, -1):
+                        self._level_backward(levels[i_level], rays, g_w[i_level], None, None, R)
+        else:
+            interlevel()
         # ------------------------------------------------------------------ forward: shader + integrator + loss
         if self.concurrent:
             main.wait_stream(s_pack)
@@ -135,38 +158,22 @@ class FusedCacheStep:
             shader, names, sflat, rays["viewdirs"], L2["means"], L2["feat"].reshape(R, L2["n"], 64),
             normals_pred.reshape(R, L2["n"], 3), app_arena, True, packed=packed, encoded=encoded, env_stream=s_env)
         rgb_s = outs[0].reshape(R, L2["n"], 3)
-        k = L2["n"]
         bg = self._bg_ones(R, dev)
         out_rgb, acc, dist = new(R, 3), new(R), new(R, 4)
         _lib.call("nrc_ray_composite_fwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(L2["tdist"]),
                   _lib.ptr(bg), R, k, 3, 1, _lib.ptr(out_rgb), _lib.ptr(acc), _lib.ptr(dist))
-        loss = torch.empty((), device=dev, dtype=torch.float32)
         g_rgb = new(R, 3)
-        g_w = [new(R, lv["n"]) for lv in levels]
-        loss.zero_()
         _lib.call("nrc_charb_srgb_loss", st(), _lib.ptr(out_rgb), _lib.ptr(target_rgb), R, float(self.charb_padding),
                   _lib.ptr(loss), _lib.ptr(g_rgb))
-        for i_level in range(nl - 1):   # spline interlevel loss of every proposal level (loss_utils.py:74-108)
-            lv = levels[i_level]
-            _lib.call("nrc_interlevel_loss", st(), _lib.ptr(L2["sdist"]), _lib.ptr(L2["weights"]), k, _lib.ptr(lv["sdist"]),
-                      _lib.ptr(lv["weights"]), lv["n"], R, float(self.interlevel_blurs[i_level]),
-                      float(self.interlevel_mults[i_level]), 1e-5, _lib.ptr(loss), _lib.ptr(g_w[i_level]), None)
-        # ------------------------------------------------------------------ backward
-        # The proposal levels' gradients only depend on the loss kernel: they run beside the shader's.
-        if not fork_proposals:
-            s_prop = None
-        if s_prop is not None:
-            s_prop.wait_stream(main)
-            with torch.cuda.stream(s_prop):
-                for i_level in range(nl - 2, -1, -1):
-                    self._level_backward(levels[i_level], rays, g_w[i_level], None, None, R)
         gv = new(R, k, 3)
         _lib.call("nrc_ray_composite_bwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(bg),
                   _lib.ptr(g_rgb), None, R, k, 3, 1, _lib.ptr(gv), _lib.ptr(g_w[2]), None)
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
+        if s_prop is not None and not fork_proposals:
+            main.wait_stream(s_prop)     # split mode: the side stream only ran the interlevel losses
         self.last = dict(levels=levels, rgb=out_rgb, acc=acc, dist=dist, shader_rgb=rgb_s)
         return dict(loss=loss, levels=levels, rays=rays, g_w=g_w, d_feat=d_feat, g_nrm=g_nrm, R=R,
-                    forked=s_prop, keep=(saved, gv, g_rgb))
+                    forked=s_prop if fork_proposals else None, keep=(saved, gv, g_rgb))
 
     def step_back(self, state):
         """Backward of the proposal sampler (three levels) from the state of step_front()."""
