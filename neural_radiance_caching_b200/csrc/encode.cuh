@@ -160,14 +160,51 @@ __device__ __forceinline__ FeatVec<F> load_row(const float* __restrict__ table, 
 // is bit-identical to the fp32 oracle.
 template <int F>
 __device__ __forceinline__ FeatVec<F> level_interp(const LevelDev& lv, const Corners& c) {
+  // Per-axis factorisation of the eight corners: two indices / hash terms / validity flags / weights per axis,
+  // combined per corner with two integer ops and one multiply.  The weight products keep the reference's
+  // association ((wx*wy)*wz for hash levels, (wz*wy)*wx for dense levels) and the corner order, so the result
+  // is bit-identical to the per-corner evaluation (corner_row / corner_weight above).
   int32_t rows[8];
   float w[8];
+  const float wx[2] = {c.fw[0], c.cw[0]}, wy[2] = {c.fw[1], c.cw[1]}, wz[2] = {c.fw[2], c.cw[2]};
+  if (lv.is_hash) {
+    const uint32_t hx[2] = {static_cast<uint32_t>(c.fl[0]), static_cast<uint32_t>(c.fl[0] + 1)};
+    const uint32_t hy[2] = {static_cast<uint32_t>(c.fl[1]) * kPi2, static_cast<uint32_t>(c.fl[1] + 1) * kPi2};
+    const uint32_t hz[2] = {static_cast<uint32_t>(c.fl[2]) * kPi3, static_cast<uint32_t>(c.fl[2] + 1) * kPi3};
+    float wxy[2][2];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    int bx, by, bz;
-    corner_bits(lv.is_hash, k, bx, by, bz);
-    rows[k] = corner_row(lv, c, bx, by, bz);
-    w[k] = corner_weight(lv.is_hash, c, bx, by, bz);
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) wxy[i][j] = __fmul_rn(wx[i], wy[j]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int bx = (k >> 2) & 1, by = (k >> 1) & 1, bz = k & 1;
+      const uint32_t h = hx[bx] ^ (hy[by] ^ hz[bz]);
+      rows[k] = static_cast<int32_t>(lv.pow2_mask ? (h & lv.pow2_mask) : (h % lv.T));
+      w[k] = __fmul_rn(wxy[bx][by], wz[bz]);
+    }
+  } else {
+    const int N = lv.N;
+    int ox[2], oy[2], oz[2];
+    bool vx[2], vy[2], vz[2];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int ix = min(max(c.fl[0] + b, 0), N + 1), iy = min(max(c.fl[1] + b, 0), N + 1),
+                iz = min(max(c.fl[2] + b, 0), N + 1);
+      vx[b] = ix >= 1 && ix <= N; vy[b] = iy >= 1 && iy <= N; vz[b] = iz >= 1 && iz <= N;
+      ox[b] = (ix - 1) * N * N; oy[b] = (iy - 1) * N; oz[b] = iz - 1;
+    }
+    float wzy[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) wzy[i][j] = __fmul_rn(wz[i], wy[j]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int bz = (k >> 2) & 1, by = (k >> 1) & 1, bx = k & 1;
+      rows[k] = (vx[bx] && vy[by] && vz[bz]) ? ox[bx] + oy[by] + oz[bz] : -1;
+      w[k] = __fmul_rn(wzy[bz][by], wx[bx]);
+    }
   }
   FeatVec<F> vals[8];
 #pragma unroll
