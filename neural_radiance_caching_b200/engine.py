@@ -23,7 +23,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib, geometry, nerf, stepfun
+from . import _lib, geometry, mlp_chain, nerf, stepfun
 
 
 class FusedCacheStep:
@@ -239,6 +239,7 @@ class FusedCacheQuery:
     def __init__(self, model):
         self.model = model
         self._const = {}
+        self._pack_cache = mlp_chain.PackCache()
 
     def _initial(self, R, dev):
         key = (R, str(dev))
@@ -300,9 +301,10 @@ class FusedCacheQuery:
         normals = new(Psh, 3)
         _lib.call("nrc_normals_fwd", st(), _lib.ptr(gp_sh), Psh, _lib.ptr(normals))
         names, sflat = shader.fused_params(shp)
+        packed = self._pack_cache.get(sflat[0::2], lambda: nerf.shader_pack(shader, names, sflat))
         outs, _, _ = nerf.shader_fused_forward(shader, names, sflat, rays["viewdirs"], means_sh.reshape(R, k, 3),
                                                feat_sh.reshape(R, k, 64), normals.reshape(R, k, 3),
-                                               shp["appearance_grid"]["_arena"], False)
+                                               shp["appearance_grid"]["_arena"], False, packed=packed)
         rgb_s = outs[0].reshape(R, k, 3)
         out_rgb, acc, dist = new(R, 3), new(R), new(R, 4)
         _lib.call("nrc_ray_composite_fwd", st(), _lib.ptr(rgb_s), _lib.ptr(w_sh), k, _lib.ptr(weights) if resample else None,

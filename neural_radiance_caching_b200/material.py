@@ -37,6 +37,7 @@ class MaterialMLP:
         self.chain = mlp_chain.ChainSpec(in_widths=[self.grid.num_outputs],
                                          hidden=[("bottleneck_layer", 128, False, "linear")],
                                          heads=[[("pred_brdf_layer", 10)]])
+        self._pack_cache = mlp_chain.PackCache()
 
     def init(self, device, generator=None, table_init_range=0.1):
         _, arena = self.grid.init(device, generator=generator, init_range=table_init_range)
@@ -57,7 +58,9 @@ class MaterialMLP:
         lead = means.shape[:-1]
         z = coord._ContractFn.apply(means, self.warp_c)
         enc = self.grid(p["material_grid"], z).reshape(-1, self.grid.num_outputs)
-        if self.bf16:
+        if self.bf16 and not torch.is_grad_enabled():
+            (raw,) = mlp_chain.forward_cached(self.chain, p, [enc], self._pack_cache)
+        elif self.bf16:
             (raw,) = mlp_chain.apply(self.chain, p, [enc])
         else:
             raw = nerf.dense(p["pred_brdf_layer"], nerf.dense(p["bottleneck_layer"], enc))
@@ -80,6 +83,7 @@ class EnvMapMLP:
             in_widths=[self.in_dim],
             hidden=[(n, width, (i % skip == 0 and i > 0)) for i, n in enumerate(self.names)],
             heads=[[("output_rgba_layer", 4), ("output_ambient_rgb_layer", 3)]])
+        self._pack_cache = mlp_chain.PackCache()
 
     def init(self, device, generator=None):
         p, d = {}, self.in_dim
@@ -100,8 +104,7 @@ class EnvMapMLP:
         enc = torch.empty((P, self.in_dim), device=v2.device, dtype=torch.float32)
         _lib.call("nrc_pos_enc", _lib.stream_ptr(), _lib.ptr(v2), P, 3, 0, self.deg_view, 1, _lib.ptr(enc), self.in_dim)
         if self.bf16:
-            with torch.no_grad():
-                rgba, amb = mlp_chain.apply(self.chain, p, [enc])
+            rgba, amb = mlp_chain.forward_cached(self.chain, p, [enc], self._pack_cache)
         else:
             x = enc
             for i, n in enumerate(self.names):

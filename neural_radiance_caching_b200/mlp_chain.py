@@ -297,7 +297,9 @@ def pack_weights_many(items, packed=None):
     for spec, _ in items:
         bases.append(total)
         total += _built(spec).num_chunks
-    dev = next(iter(items[0][1].values()))["kernel"].device
+    spec0, params0 = items[0]
+    first = spec0.hidden[0][0] if spec0.hidden else spec0.heads[0][0][0]
+    dev = params0[first]["kernel"].device
     if packed is None:
         packed = torch.empty(total * ATOM_BYTES // 2, device=dev, dtype=torch.bfloat16)
     ptrs = _Ptrs()
@@ -570,6 +572,31 @@ class _ChainFn(torch.autograd.Function):
         for name in names:
             grads += [None, None] if sunk[name] else list(sinks[name])
         return tuple(grads)
+
+
+class PackCache:
+    """Packed bf16 operand images keyed by the parameters' identity and version counters: a render loop
+    packs once per parameter update instead of once per chunk."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key_tensors, build):
+        key = tuple((t.data_ptr(), t._version) for t in key_tensors)
+        hit = self._store.get("k")
+        if hit is None or hit[0] != key:
+            self._store["k"] = (key, build())
+        return self._store["k"][1]
+
+
+def forward_cached(spec, params, sources, cache):
+    """Forward-only evaluation (no autograd) with the packed weights taken from `cache` (PackCache)."""
+    names = [h[0] for h in spec.hidden] + [name for grp in spec.heads for name, _ in grp]
+    keys = [params[n]["kernel"] for n in names]
+    packed = cache.get(keys, lambda: pack_weights(spec, params))
+    srcs = [t if (t.dim() == 2 and t.stride(-1) == 1) else t.contiguous() for t in sources]
+    _, outs, _ = run_forward(spec, params, srcs, packed, save=False)
+    return outs
 
 
 def apply(spec, params, sources):
