@@ -273,10 +273,11 @@ int32_t nrc_ide_bwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32
 #define NRC_WGRAD_MAX_X_ATOMS 6
 #define NRC_WGRAD_MAX_SEGS 5
 
-typedef enum { NRC_OP_LOAD = 0, NRC_OP_GEMM = 1, NRC_OP_EPI = 2, NRC_OP_SAVE = 3 } nrc_chain_op_kind_t;
+typedef enum { NRC_OP_LOAD = 0, NRC_OP_GEMM = 1, NRC_OP_EPI = 2, NRC_OP_SAVE = 3, NRC_OP_GATHER = 4 } nrc_chain_op_kind_t;
 #define NRC_GEMM_ACCUMULATE 1     /* accumulate onto the accumulator's current contents (skip VJP) */
 #define NRC_EPI_RELU 1            /* max(0, .) after the bias                                      */
 #define NRC_EPI_OUT_ACCUMULATE 2  /* fp32 output: += instead of =                                  */
+#define NRC_EPI_DENSITY 4         /* density head (nrc_chain_query): see below                     */
 
 typedef struct {
   int32_t kind;       /* nrc_chain_op_kind_t                                                       */
@@ -299,6 +300,7 @@ typedef struct {
   int32_t n_atoms;    /* GEMM: number of K atoms                                                   */
   uint8_t a_slot[NRC_CHAIN_MAX_ATOMS];  /* GEMM: slot holding each K atom                          */
   uint8_t a_klen[NRC_CHAIN_MAX_ATOMS];  /* GEMM: K extent used in each atom (x16, <= 64)           */
+  float fparam;       /* EPI with NRC_EPI_DENSITY: density_bias                                   */
 } nrc_chain_op_t;
 
 typedef struct {
@@ -336,6 +338,17 @@ typedef struct {
 /* Run `prog` over ceil(num_rows/128) tiles.  d_weights_packed: chunks from nrc_chain_pack_weights. */
 int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
                       const void* d_weights_packed, int64_t num_rows);
+/* nrc_chain_run with a hash-grid front end: the fused point query (predict_density + convert_raw_density,
+ * internal/geometry.py:199-341) on the tensor-core chain kernel.  Two extra op behaviours:
+ *   GATHER  slot = destination atom, ptr = means [P,3], out_ptr = encoded features fp32 [P, L*F] or -1,
+ *           ncols = L*F (<= 32), npad = ncols rounded up to 16: every tile row contracts its point
+ *           (coord.contract(x / warp_c)), gathers `enc` (same arithmetic as nrc_encode_fwd) and writes the bf16
+ *           feature row; the bbox mask of the point stays in a register of the row's thread.
+ *   EPI with NRC_EPI_DENSITY: column 0 -> density = inside ? safe_exp(raw + fparam) : 0 to out_ptr [P];
+ *           columns 1..3 -> predicted-normal gradient to mask_ptr [P,3] (-1: none); bias = ptr [4]. */
+int32_t nrc_chain_query(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
+                        const void* d_weights_packed, int64_t num_rows, const nrc_encoding_t* enc, float warp_c);
+
 /* (Re)build the packed bf16 weight image (num_chunks * 16 KB).  keep_existing == 0 zero-fills the
  * whole image first; further calls with keep_existing != 0 add more pieces to the same image. */
 int32_t nrc_chain_pack_weights(void* stream, const nrc_pack_entry_t* entries, int32_t num_entries,

@@ -98,6 +98,7 @@ PROTOTYPES = {
     "nrc_ide_bwd": [_P, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), _P, _P, _P, _P,
                     _I64, _I64, _P, _P],
     "nrc_chain_run": [_P, _P, _P, _I32, _P, _I64],
+    "nrc_chain_query": [_P, _P, _P, _I32, _P, _I64, _P, _F],
     "nrc_chain_pack_weights": [_P, _P, _I32, _P, _I32, _P, _I32, _I32],
     "nrc_chain_wgrad": [_P, _P, _I32, _P, _I32, _I64],
     "nrc_shader_mid_fwd": [_P, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), _P, _I32, _P, _I64,

@@ -22,6 +22,7 @@
 // context's layer.
 #include <cuda_bf16.h>
 
+#include "encode.cuh"
 #include "nrc_common.cuh"
 #include "tc05.cuh"
 
@@ -29,7 +30,7 @@ namespace nrc {
 using namespace tc;
 
 constexpr int kChainThreads = 320;
-constexpr int kCtxTmemCols = 256;
+constexpr int kCtxTmemCols = 256;   // TMEM columns per tile context of ordinary programs (queries allocate fewer)
 
 struct ChainParams {
   nrc_chain_program_t prog;
@@ -38,7 +39,58 @@ struct ChainParams {
   int64_t num_rows;
   int32_t num_tiles;
   int32_t ring_stages;
+  int32_t ctx_tmem_cols;   // TMEM columns per tile context (power of two; the CTA allocates twice this)
+  EncDev enc;       // hash-grid front end of GATHER ops (nrc_chain_query); unused otherwise
+  float warp_c;
 };
+
+// GATHER op: the thread owning tile row r contracts point row0 + r, gathers the multiresolution features
+// (level_interp: bit-identical to nrc_encode_fwd) and writes them as one bf16 row of the destination atom.
+template <int F>
+__device__ __forceinline__ bool gather_row(const ChainParams& p, const nrc_chain_op_t& op, int64_t pt, bool valid,
+                                           uint32_t slot_base, int r) {
+  constexpr int kMaxL = 32 / F > 8 ? 8 : 32 / F;
+  float feat[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) feat[i] = 0.f;
+  bool inside = false;
+  if (valid) {
+    const float* m = static_cast<const float*>(p.ptrs[op.ptr]) + 3 * pt;
+    const float x0 = __ldg(m), x1 = __ldg(m + 1), x2 = __ldg(m + 2);
+    float z[3], xn[3];
+    contract_point(p.warp_c, x0, x1, x2, z[0], z[1], z[2]);
+    normalise_point(p.enc, z, xn);
+    inside = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) inside = inside && (z[a] > p.enc.b0[a]) && (z[a] < p.enc.b1[a]);
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l) {
+      if (l < p.enc.L) {
+        const Corners c = level_setup(p.enc.lv[l], xn);
+        const FeatVec<F> v = level_interp<F>(p.enc.lv[l], c);
+#pragma unroll
+        for (int f = 0; f < F; ++f) feat[l * F + f] = __fmul_rn(v.v[f], p.enc.scale);
+      }
+    }
+    if (op.out_ptr >= 0) {
+      float* eo = static_cast<float*>(p.ptrs[op.out_ptr]) + pt * op.ncols;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < op.ncols) eo[i] = feat[i];
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    if (ch * 8 < op.npad) {
+      const uint32_t dst = slot_base + atom_chunk_offset(r, ch);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack2_bf16(feat[8 * ch], feat[8 * ch + 1])),
+                   "r"(pack2_bf16(feat[8 * ch + 2], feat[8 * ch + 3])), "r"(pack2_bf16(feat[8 * ch + 4], feat[8 * ch + 5])),
+                   "r"(pack2_bf16(feat[8 * ch + 6], feat[8 * ch + 7]))
+                   : "memory");
+    }
+  }
+  return inside;
+}
 
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -143,7 +195,8 @@ __device__ __forceinline__ void epi_run(const EpiArgs& a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
+template <int kMinCtas>
+__global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[16];
   __shared__ uint32_t tmem_base_s;
@@ -171,7 +224,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 2u * p.ctx_tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -226,7 +279,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             for (int o = i; o < j; ++o) {
               const nrc_chain_op_t& op = p.prog.ops[o];
               const uint32_t idesc = make_idesc(128, op.n, 0, 0);
-              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(c * p.ctx_tmem_cols + op.tmem_col);
               for (int a = 0; a < op.n_atoms; ++a) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
@@ -256,6 +309,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t acc_par = 0;
     bool store_pending = false;
+    bool inside_reg = false;   // bbox mask of the point this thread gathered (GATHER -> NRC_EPI_DENSITY)
 
     auto guard_slots = [&]() {  // before overwriting slots a bulk store may still be reading
       if (store_pending) {
@@ -281,7 +335,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           tc_fence_after();
           continue;
         }
-        if (op.kind == NRC_OP_LOAD) {
+        if (op.kind == NRC_OP_GATHER) {
+          guard_slots();
+          const int64_t pt = row0 + r;
+          const bool valid = pt < p.num_rows;
+          const uint32_t sb = slot_addr(c, op.slot);
+          switch (p.enc.F) {
+            case 1: inside_reg = gather_row<1>(p, op, pt, valid, sb, r); break;
+            case 2: inside_reg = gather_row<2>(p, op, pt, valid, sb, r); break;
+            default: inside_reg = gather_row<4>(p, op, pt, valid, sb, r); break;
+          }
+        } else if (op.kind == NRC_OP_LOAD) {
           guard_slots();
           const float* src = op.ptr >= 0 ? static_cast<const float*>(p.ptrs[op.ptr]) : nullptr;
           const int nch = op.npad >> 3;
@@ -336,6 +400,22 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
             bulk_commit();
           }
           store_pending = true;
+        } else if (op.kind == NRC_OP_EPI && (op.flags & NRC_EPI_DENSITY)) {
+          // density head: column 0 -> safe_exp(raw + density_bias) masked to the bbox; columns 1..3 -> grad_pred
+          uint32_t v[16];
+          tmem_ld16(tmem_base + t_lane + static_cast<uint32_t>(c * p.ctx_tmem_cols + op.tmem_col), v);
+          tmem_ld_wait();
+          const int64_t pt = row0 + r;
+          if (pt < p.num_rows) {
+            const float* bias = op.ptr >= 0 ? static_cast<const float*>(p.ptrs[op.ptr]) : nullptr;
+            const float raw = __uint_as_float(v[0]) + (bias ? __ldg(bias) : 0.f);
+            static_cast<float*>(p.ptrs[op.out_ptr])[pt] = inside_reg ? safe_exp(raw + op.fparam) : 0.f;
+            if (op.mask_ptr >= 0) {
+              float* gp = static_cast<float*>(p.ptrs[op.mask_ptr]) + 3 * pt;
+#pragma unroll
+              for (int j = 0; j < 3; ++j) gp[j] = __uint_as_float(v[1 + j]) + (bias ? __ldg(bias + 1 + j) : 0.f);
+            }
+          }
         } else {  // NRC_OP_EPI
           if (op.slot >= 0) guard_slots();
           EpiArgs a;
@@ -348,7 +428,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
                                                static_cast<size_t>(tile) * op.img_atoms * kAtomBytes
                                          : nullptr;
           a.mask_atom0 = op.mask_atom0;
-          a.taddr = tmem_base + t_lane + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
+          a.taddr = tmem_base + t_lane + static_cast<uint32_t>(c * p.ctx_tmem_cols + op.tmem_col);
           a.has_slot = op.slot >= 0;
           a.slot0_addr = a.has_slot ? slot_addr(c, op.slot) : 0u;
           a.ncols = op.ncols; a.npad = op.npad; a.r = r;
@@ -372,7 +452,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, 2u * p.ctx_tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -588,9 +668,15 @@ static int32_t validate_program(const nrc_chain_program_t* prog, int32_t num_ptr
           if (op.a_slot[a] >= S || op.a_klen[a] < 16 || op.a_klen[a] > 64 || (op.a_klen[a] & 15)) return NRC_E_INVALID_ARG;
         break;
       case NRC_OP_EPI:
+        if ((op.flags & NRC_EPI_DENSITY) && (!ptr_ok(op.out_ptr, false) || op.npad != 16)) return NRC_E_INVALID_ARG;
         if (op.npad <= 0 || (op.npad & 15) || op.ncols > op.npad || op.tmem_col < 0 || op.tmem_col + op.npad > 256 ||
             !ptr_ok(op.ptr, true) || !ptr_ok(op.out_ptr, true) || !ptr_ok(op.mask_ptr, true) ||
             (op.slot >= 0 && op.slot + ((op.npad + 63) >> 6) > S))
+          return NRC_E_INVALID_ARG;
+        break;
+      case NRC_OP_GATHER:
+        if (!ptr_ok(op.ptr, false) || !ptr_ok(op.out_ptr, true) || op.slot < 0 || op.slot >= S || op.ncols < 1 ||
+            op.ncols > 32 || op.npad < op.ncols || (op.npad & 15) || op.npad > 32)
           return NRC_E_INVALID_ARG;
         break;
       case NRC_OP_SAVE:
@@ -605,8 +691,8 @@ static int32_t validate_program(const nrc_chain_program_t* prog, int32_t num_ptr
   return NRC_OK;
 }
 
-extern "C" int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
-                                 const void* d_weights_packed, int64_t num_rows) {
+static int32_t chain_launch(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
+                            const void* d_weights_packed, int64_t num_rows, const EncDev* enc, float warp_c) {
   if (!d_ptrs || num_ptrs < 0 || num_ptrs > NRC_CHAIN_MAX_PTRS || num_rows < 0) return NRC_E_INVALID_ARG;
   const int32_t st = validate_program(prog, num_ptrs);
   if (st != NRC_OK) return st;
@@ -617,23 +703,57 @@ extern "C" int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, 
   hp.weights = static_cast<const uint8_t*>(d_weights_packed);
   hp.num_rows = num_rows;
   hp.num_tiles = static_cast<int32_t>((num_rows + 127) / 128);
+  bool has_gather = false;
+  for (int i = 0; i < prog->num_ops; ++i) has_gather = has_gather || prog->ops[i].kind == NRC_OP_GATHER;
+  if (has_gather && !enc) return NRC_E_INVALID_ARG;
+  if (enc) hp.enc = *enc;
+  hp.warp_c = warp_c;
   const int S = prog->slots_per_ctx;
   const int max_atoms = (227 * 1024 - 2048) / kAtomBytes;   // 14
   int R = max_atoms - 2 * S;
   if (R < 1) return NRC_E_UNSUPPORTED;
   if (R > 4) R = 4;
+  if (has_gather && R > 2) R = 2;   // queries: small weights, two CTAs per SM so gathers of one hide behind the other
   hp.ring_stages = R;
   const size_t smem = static_cast<size_t>(2 * S + R) * kAtomBytes + 1024;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024) != cudaSuccess)
       return check_launch();
     attr_set = true;
   }
   const int pairs = (hp.num_tiles + 1) / 2;
-  const int grid = pairs < kNumSMs ? pairs : kNumSMs;
-  chain_kernel<<<grid, kChainThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
+  hp.ctx_tmem_cols = kCtxTmemCols;
+  if (has_gather && smem <= 113 * 1024) {
+    int need = 32;
+    for (int i = 0; i < prog->num_ops; ++i)
+      if (prog->ops[i].kind == NRC_OP_GEMM)
+        while (need < prog->ops[i].tmem_col + prog->ops[i].n) need *= 2;
+    if (need > 128) return NRC_E_UNSUPPORTED;
+    hp.ctx_tmem_cols = need;
+    const int grid = pairs < 2 * kNumSMs ? pairs : 2 * kNumSMs;
+    chain_kernel<2><<<grid, kChainThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
+  } else {
+    const int grid = pairs < kNumSMs ? pairs : kNumSMs;
+    chain_kernel<1><<<grid, kChainThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
+  }
   return check_launch();
+}
+
+extern "C" int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
+                                 const void* d_weights_packed, int64_t num_rows) {
+  return chain_launch(stream, prog, d_ptrs, num_ptrs, d_weights_packed, num_rows, nullptr, 0.f);
+}
+
+extern "C" int32_t nrc_chain_query(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
+                                   const void* d_weights_packed, int64_t num_rows, const nrc_encoding_t* enc,
+                                   float warp_c) {
+  EncDev d;
+  const int32_t st = make_enc_dev(enc, d);
+  if (st != NRC_OK) return st;
+  if (d.L * d.F > 32 || d.F == 8) return NRC_E_UNSUPPORTED;
+  return chain_launch(stream, prog, d_ptrs, num_ptrs, d_weights_packed, num_rows, &d, warp_c);
 }
 
 extern "C" int32_t nrc_chain_pack_weights(void* stream, const nrc_pack_entry_t* entries, int32_t num_entries,

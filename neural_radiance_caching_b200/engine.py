@@ -20,6 +20,7 @@ Schedule (reference call sites in brackets):
   per level l = 2,1,0   nrc_ray_alpha_weights_bwd, nrc_density_mlp_bwd, nrc_contract_fwd, nrc_encode_bwd
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -240,6 +241,10 @@ class FusedCacheQuery:
         self.model = model
         self._const = {}
         self._pack_cache = mlp_chain.PackCache()
+        self._density_packs = {}
+        # density queries as tcgen05 chains with the hash-grid gather as their front end (NRC_QUERY_TC=0: the
+        # mma.sync query kernel the training step uses)
+        self.tensor_core_query = os.environ.get("NRC_QUERY_TC", "1") != "0"
 
     def _initial(self, R, dev):
         key = (R, str(dev))
@@ -272,11 +277,14 @@ class FusedCacheQuery:
             density = new(P)
             feat = new(P, 64) if last else None
             gp = new(P, 3) if (last and mlp.enable_pred_normals) else None
-            enc = mlp.grid._descriptor(mlp.grid.tables(p["density_grid"]), None)
-            desc = geometry._mlp_desc(p, mlp.in_dim, gp is not None)
-            _lib.call("nrc_density_query_fwd", st(), C.byref(enc), C.byref(desc), _lib.ptr(means), P, float(mlp.warp_c),
-                      float(mlp.density_bias), int(mlp.bf16), _lib.ptr(density), None, _lib.ptr(feat), _lib.ptr(gp), None,
-                      None)
+            if self.tensor_core_query and mlp.bf16 and mlp.supports_query_tc():
+                mlp.query_tc(p, means, density, feat, gp, cache=self._density_packs.setdefault(i_mlp, mlp_chain.PackCache()))
+            else:
+                enc = mlp.grid._descriptor(mlp.grid.tables(p["density_grid"]), None)
+                desc = geometry._mlp_desc(p, mlp.in_dim, gp is not None)
+                _lib.call("nrc_density_query_fwd", st(), C.byref(enc), C.byref(desc), _lib.ptr(means), P,
+                          float(mlp.warp_c), float(mlp.density_bias), int(mlp.bf16), _lib.ptr(density), None,
+                          _lib.ptr(feat), _lib.ptr(gp), None, None)
             weights = new(R, n)
             _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(density), _lib.ptr(tdist), _lib.ptr(rays["directions"]),
                       R, n, int(sampler.opaque_background), _lib.ptr(weights), None, None)

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib, grid_utils
+from . import _lib, grid_utils, mlp_chain
 
 
 def _mlp_desc(p, in_dim, use_pred_normals):
@@ -241,6 +241,34 @@ class DensityMLP:
         if arena is None:
             raise ValueError("the fused training path needs the level tables in one arena")
         return _DensityQueryFn.apply(self, means, bool(want_feat), arena, *self._flatten(p))
+
+    def chain_spec(self):
+        """The density stack as a tensor-core chain: two 64-wide ReLU layers, density (+ predicted-normal) head."""
+        if getattr(self, "_chain_spec", None) is None:
+            head = [("output_density_layer", 1)] + ([("pred_normals_layer", 3)] if self.enable_pred_normals else [])
+            self._chain_spec = mlp_chain.ChainSpec(
+                [self.in_dim], [("density_layers_0", 64, False), ("density_layers_1", 64, False)], [head])
+        return self._chain_spec
+
+    def supports_query_tc(self):
+        return self.in_dim <= 32 and self.grid.num_features in (1, 2, 4)
+
+    def query_tc(self, p, means, density, feat=None, grad_pred=None, enc_out=None, cache=None):
+        """predict_density + convert_raw_density (internal/geometry.py:199-341,442-460) through nrc_chain_query:
+        the hash-grid gather feeds tcgen05 GEMMs tile by tile.  Inference path; outputs are written in place.
+        `cache` (mlp_chain.PackCache) keeps the packed bf16 weights across calls."""
+        spec = self.chain_spec()
+        names = [n for grp in spec.heads for n, _ in grp]
+
+        def build():
+            hb = torch.cat([p[n]["bias"] for n in names]) if len(names) > 1 else p[names[0]]["bias"]
+            return mlp_chain.pack_weights(spec, p), hb
+
+        keys = [p[n][k] for n in ("density_layers_0", "density_layers_1", *names) for k in ("kernel", "bias")]
+        packed, hb = cache.get(keys, build) if cache is not None else build()
+        enc = self.grid._descriptor(self.grid.tables(p["density_grid"]), None)
+        mlp_chain.run_density_query(spec, p, enc, means.reshape(-1, 3), packed, hb, self.warp_c, self.density_bias,
+                                    density, feat, grad_pred if self.enable_pred_normals else None, enc_out)
 
     def query(self, p, means, want_feat=True, want_normals=False):
         """Fused predict_density + convert_raw_density (+ analytic raw gradient):

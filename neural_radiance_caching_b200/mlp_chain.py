@@ -18,15 +18,15 @@ from . import _lib
 ATOM_BYTES = 16384
 MAX_OPS, MAX_PTRS, MAX_ATOMS = 24, 40, 8
 PACK_MAX, WGRAD_MAX_LAYERS, WGRAD_MAX_X, WGRAD_MAX_SEGS = 80, 12, 6, 5
-OP_LOAD, OP_GEMM, OP_EPI, OP_SAVE = 0, 1, 2, 3
-GEMM_ACCUMULATE, EPI_RELU, EPI_OUT_ACCUMULATE = 1, 1, 2
+OP_LOAD, OP_GEMM, OP_EPI, OP_SAVE, OP_GATHER = 0, 1, 2, 3, 4
+GEMM_ACCUMULATE, EPI_RELU, EPI_OUT_ACCUMULATE, EPI_DENSITY = 1, 1, 2, 4
 
 
 class nrc_chain_op_t(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "kind", "slot", "ptr", "ld", "col0", "ncols", "npad", "tmem_col", "n", "flags", "out_ptr", "mask_ptr",
         "mask_atom0", "img_atoms", "w_chunk", "n_atoms")] + [
-        ("a_slot", C.c_uint8 * MAX_ATOMS), ("a_klen", C.c_uint8 * MAX_ATOMS)]
+        ("a_slot", C.c_uint8 * MAX_ATOMS), ("a_klen", C.c_uint8 * MAX_ATOMS), ("fparam", C.c_float)]
 
 
 class nrc_chain_program_t(C.Structure):
@@ -389,6 +389,34 @@ def run_forward(spec, params, sources, packed, save=True):
     arr, n = ptrs.array()
     _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
     return bufs, outs, act
+
+
+def run_density_query(spec, params, enc_desc, means, packed, head_bias, warp_c, density_bias, density, feat=None,
+                      grad_pred=None, enc_out=None):
+    """Fused point query on the tensor-core chain kernel (nrc_chain_query): contract + hash-grid gather as the
+    tile's front end, the two hidden layers and the density / predicted-normal heads as three accumulator passes.
+    spec: ChainSpec([L*F], two 64-wide hidden layers, one head group [density(1) (, pred normals(3))]);
+    means [P,3]; outputs are written in place (feat [P,64], grad_pred [P,3], enc_out [P,L*F] optional)."""
+    b = _built(spec)
+    P = means.shape[0]
+    ptrs = _Ptrs()
+    prog = nrc_chain_program_t()
+    prog.slots_per_ctx = 2
+    _op(prog, kind=OP_GATHER, slot=0, ptr=ptrs.add(means), out_ptr=ptrs.add(enc_out), ncols=spec.in_dim,
+        npad=spec.in_pad)
+    for li, (name, w, _) in enumerate(spec.hidden):
+        last = li == len(spec.hidden) - 1
+        (nb, nc, first), = b.fwd_chunk[li]
+        _op(prog, kind=OP_GEMM, n=nc, tmem_col=0, w_chunk=first, atoms=[(0, spec.in_pad)] if li == 0 else [(1, 64)])
+        _op(prog, kind=OP_EPI, slot=1, ptr=ptrs.add(params[name]["bias"]), ncols=w, npad=w, tmem_col=0, flags=EPI_RELU,
+            out_ptr=ptrs.add(feat) if last else -1, ld=w, col0=0)
+    _op(prog, kind=OP_GEMM, n=16, tmem_col=0, w_chunk=b.fwd_head_chunk[0], atoms=[(1, 64)])
+    op = _op(prog, kind=OP_EPI, slot=-1, ptr=ptrs.add(head_bias), ncols=spec.head_widths[0], npad=16, tmem_col=0,
+             flags=EPI_DENSITY, out_ptr=ptrs.add(density), mask_ptr=ptrs.add(grad_pred))
+    op.fparam = float(density_bias)
+    arr, n = ptrs.array()
+    _lib.call("nrc_chain_query", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P,
+              C.byref(enc_desc), float(warp_c))
 
 
 def run_backward_data(spec, params, g_heads, act, packed, P, d_src=None):
