@@ -150,6 +150,17 @@ int32_t nrc_density_query_fwd(void* stream, const nrc_encoding_t* enc, const nrc
                               float density_bias, int32_t bf16, float* d_density, float* d_raw,
                               float* d_feat, float* d_grad_pred, float* d_raw_grad, float* d_enc_out);
 
+/* Second-order path of the analytic normals.  The reference back-propagates losses through
+ * normals = -l2_normalize(d raw / d means) (internal/geometry.py:442-460; predicted_normal_loss with
+ * pred='normals', internal/loss_utils.py:169-199, internal/train_utils.py:1049-1070).  Given
+ * d_g_raw_grad [P,3] = dL / d(d raw / d means), accumulates the parameter gradient of < g, d raw / d means >
+ * (= of the forward-mode tangent of raw along g) into grads->d_w0 / d_w1 / d_wd (biases and the predicted-normal
+ * head do not enter) and into the level gradient tables enc->levels[l].d_grad.  Sample positions are constants
+ * (stop_level_grad, internal/sampling.py:353-354).  fp32 arithmetic. */
+int32_t nrc_density_normals_bwd(void* stream, const nrc_encoding_t* enc, const nrc_density_mlp_t* mlp,
+                                const float* d_means, const float* d_g_raw_grad, int64_t num_points, float warp_c,
+                                const nrc_density_mlp_grad_t* grads);
+
 /* ------------------------------------------------------ K4: ray kernels ---- */
 /* render.compute_alpha_weights (internal/render.py:134-169), delta=None.
  *   d_density [R,n], d_tdist [R,n+1], d_dirs [R,3] -> d_weights, d_alpha, d_trans [R,n]
@@ -469,6 +480,25 @@ int32_t nrc_interlevel_loss(void* stream, const float* d_t, const float* d_w, in
 /* Data term: loss += mean Charbonnier(linear_to_srgb(rgb) - target) (accumulated), d_g_rgb [R,3] written. */
 int32_t nrc_charb_srgb_loss(void* stream, const float* d_rgb, const float* d_target, int64_t num_rays,
                             float charb_padding, float* d_loss, float* d_g_rgb);
+/* compute_mask_loss (internal/train_utils.py:785-836) with lossmult == 1: loss += mean(Charbonnier(acc - mask) *
+ * (mask > 0.5 ? opaque_weight : empty_weight)); d_mask NULL = all ones; d_g_acc [R] written.  n > 0: d_acc is the
+ * ray's weights [R,n] (acc = their sum, the weights_only pass) and d_g_acc [R,n] their gradient.  The backward-mask
+ * pass (train_utils.py:2929-2945,3348-3401) calls it with a zero mask, opaque_weight 0 and
+ * empty_weight = backward_mask_loss_weight on the accumulation of the extra rays. */
+int32_t nrc_mask_loss(void* stream, const float* d_acc, int32_t n, const float* d_mask, int64_t num_rays,
+                      float charb_padding, float opaque_weight, float empty_weight, float* d_loss, float* d_g_acc);
+/* Geometry losses on the final sampler level (internal/train_utils.py:3255-3311, internal/loss_utils.py:127-199):
+ * orientation loss on the predicted normals (orientation_loss_target='normals_pred'), predicted-normal loss
+ * (gt = stop_gradient(normals_pred), pred = the analytic normals; weights through stopgrad_with_weight) and its
+ * reverse (gt = stop_gradient(normals), pred = normals_pred, weights stop-gradiented); the ease / decay schedule
+ * factors are folded into the mults by the caller.
+ *   d_weights [R,n], d_normals [R,n,3] (analytic; NULL disables both predicted-normal terms), d_normals_pred
+ *   [R,n,3], d_viewdirs [R,3].  loss += ...; d_g_weights [R,n] and d_g_normals_pred [R,n,3] are ACCUMULATED,
+ *   d_g_normals [R,n,3] is written (feed it to nrc_normals_bwd, then nrc_density_normals_bwd). */
+int32_t nrc_geometry_losses(void* stream, const float* d_weights, const float* d_normals, const float* d_normals_pred,
+                            const float* d_viewdirs, int64_t num_rays, int32_t n, float orientation_mult,
+                            float predicted_normal_mult, float predicted_normal_reverse_mult, float stopgrad_weight,
+                            float* d_loss, float* d_g_weights, float* d_g_normals_pred, float* d_g_normals);
 
 /* ------------------------------------------------- K5: GGX integration ---- */
 /* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) +

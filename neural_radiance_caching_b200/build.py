@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     # IEEE division / sqrt and no flush-to-zero: parity with the fp32 oracle.
     "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-]
+] + os.environ.get("NRC_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DNRC_CHAIN_TRACE for tools/trace_chain.py
 
 
 def sources():

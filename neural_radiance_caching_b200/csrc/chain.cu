@@ -15,11 +15,12 @@
 // Roles inside a CTA (320 threads, 1 CTA / SM, persistent over tile pairs):
 //   warp 0      weight producer  (cp.async.bulk global -> ring, one elected lane)
 //   warp 1      UMMA issuer      (one elected lane)
-//   warps 2-5   epilogue / loader warpgroup of context 0   (TMEM lane quadrant = warp % 4)
-//   warps 6-9   epilogue / loader warpgroup of context 1
-// Two contexts = two independent tiles in flight: while one context's warpgroup drains its
-// accumulator (TMEM -> registers -> bf16 -> shared memory), the tensor core runs the other
-// context's layer.
+//   warps 2-9   epilogue / loader warps of context 0   (TMEM lane quadrant = warp % 4; the two warps of a
+//   warps 10-17 epilogue / loader warps of context 1    quadrant take alternate 16-column chunks)
+// Two contexts = two independent tiles in flight: while one context's warps drain their accumulator
+// (TMEM -> registers -> bf16 -> shared memory), the tensor core runs the other context's layer.  (Staging each
+// weight atom once for both tiles was measured: running the contexts in phase costs more than the halved ring
+// traffic saves.)
 #include <cuda_bf16.h>
 
 #include "encode.cuh"
@@ -29,8 +30,28 @@
 namespace nrc {
 using namespace tc;
 
-constexpr int kChainThreads = 320;
-constexpr int kCtxTmemCols = 256;   // TMEM columns per tile context of ordinary programs (queries allocate fewer)
+constexpr int kCtxThreads = 256;                   // loader / epilogue threads per tile context
+constexpr int kChainThreads = 64 + 2 * kCtxThreads;
+constexpr int kCtxTmemCols = 256;                  // TMEM columns per tile context
+constexpr int kTailBytes = 3072;   // shared-memory tail: mbarriers (128 B), TMEM base (16 B), the program, staged biases
+
+// The program as the kernel reads it: built once per CTA in shared memory from the launch parameters (pointers
+// resolved, fields narrowed), because the per-tile interpreter touches it constantly and indexed constant-bank
+// loads cost hundreds of cycles each.
+struct __align__(8) DevOp {
+  int8_t kind, slot;
+  uint8_t flags, n_atoms;
+  int16_t ncols, npad, tmem_col, n;
+  int32_t ld;
+  int16_t col0, mask_atom0, img_atoms, bias_off;   // bias_off: float index of the staged bias, -1 = read global
+  int32_t w_chunk;
+  float fparam;
+  void* ptr;
+  void* out;
+  void* mask;
+  uint8_t a_src[NRC_CHAIN_MAX_ATOMS];   // low nibble: slot, high nibble: K extent / 16
+};
+static_assert(sizeof(DevOp) == 64, "DevOp layout");
 
 struct ChainParams {
   nrc_chain_program_t prog;
@@ -39,54 +60,76 @@ struct ChainParams {
   int64_t num_rows;
   int32_t num_tiles;
   int32_t ring_stages;
-  int32_t ctx_tmem_cols;   // TMEM columns per tile context (power of two; the CTA allocates twice this)
   EncDev enc;       // hash-grid front end of GATHER ops (nrc_chain_query); unused otherwise
   float warp_c;
 };
 
-// GATHER op: the thread owning tile row r contracts point row0 + r, gathers the multiresolution features
-// (level_interp: bit-identical to nrc_encode_fwd) and writes them as one bf16 row of the destination atom.
+#ifdef NRC_CHAIN_TRACE
+// Debug builds only (NRC_EXTRA_NVCC_FLAGS=-DNRC_CHAIN_TRACE): CTA 0 stamps clock64() at the end of every op of
+// every tile it processes; tools/trace_chain.py prints the per-op timeline.
+constexpr int kTraceTiles = 48, kTraceOps = 32;
+__device__ long long g_chain_trace[2][kTraceTiles][kTraceOps];
+__device__ long long g_chain_marks[16];
+#define TRACE_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 64) g_chain_marks[i] = clock64(); } while (0)
+#else
+#define TRACE_MARK(i) do {} while (0)
+#endif
+
+// GATHER op: the two threads owning tile row r (one per half) contract point row0 + r and gather alternate levels
+// of the multiresolution features (level_interp: bit-identical to nrc_encode_fwd); each writes its levels' bf16
+// values into the row of the destination atom, half 0 also the zero padding up to npad.
 template <int F>
-__device__ __forceinline__ bool gather_row(const ChainParams& p, const nrc_chain_op_t& op, int64_t pt, bool valid,
-                                           uint32_t slot_base, int r) {
+__device__ __forceinline__ bool gather_row(const ChainParams& p, const DevOp& op, int64_t pt, bool valid,
+                                           uint32_t slot_base, int r, int half) {
   constexpr int kMaxL = 32 / F > 8 ? 8 : 32 / F;
-  float feat[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) feat[i] = 0.f;
   bool inside = false;
+  float xn[3] = {0.f, 0.f, 0.f};
   if (valid) {
-    const float* m = static_cast<const float*>(p.ptrs[op.ptr]) + 3 * pt;
+    const float* m = static_cast<const float*>(op.ptr) + 3 * pt;
     const float x0 = __ldg(m), x1 = __ldg(m + 1), x2 = __ldg(m + 2);
-    float z[3], xn[3];
+    float z[3];
     contract_point(p.warp_c, x0, x1, x2, z[0], z[1], z[2]);
     normalise_point(p.enc, z, xn);
     inside = true;
 #pragma unroll
     for (int a = 0; a < 3; ++a) inside = inside && (z[a] > p.enc.b0[a]) && (z[a] < p.enc.b1[a]);
+  }
+  float* eo = (valid && op.out) ? static_cast<float*>(op.out) + pt * op.ncols : nullptr;
 #pragma unroll
-    for (int l = 0; l < kMaxL; ++l) {
-      if (l < p.enc.L) {
+  for (int k = 0; k < kMaxL / 2; ++k) {
+    const int l = 2 * k + half;
+    if (l < p.enc.L) {
+      float e[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) e[f] = 0.f;
+      if (valid) {
         const Corners c = level_setup(p.enc.lv[l], xn);
         const FeatVec<F> v = level_interp<F>(p.enc.lv[l], c);
 #pragma unroll
-        for (int f = 0; f < F; ++f) feat[l * F + f] = __fmul_rn(v.v[f], p.enc.scale);
+        for (int f = 0; f < F; ++f) e[f] = __fmul_rn(v.v[f], p.enc.scale);
+        if (eo) {
+#pragma unroll
+          for (int f = 0; f < F; ++f) eo[l * F + f] = e[f];
+        }
+      }
+      const int col = l * F;
+      const uint32_t dst = slot_base + atom_chunk_offset(r, col >> 3) + static_cast<uint32_t>(col & 7) * 2u;
+      if (F == 4) {
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(pack2_bf16(e[0], e[1])),
+                     "r"(pack2_bf16(e[F > 2 ? 2 : 0], e[F > 2 ? 3 : 0])) : "memory");
+      } else if (F == 2) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(pack2_bf16(e[0], e[F > 1 ? 1 : 0])) : "memory");
+      } else {
+        const unsigned short hbits = __bfloat16_as_ushort(__float2bfloat16_rn(e[0]));
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"(hbits) : "memory");
       }
     }
-    if (op.out_ptr >= 0) {
-      float* eo = static_cast<float*>(p.ptrs[op.out_ptr]) + pt * op.ncols;
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < op.ncols) eo[i] = feat[i];
-    }
   }
-#pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    if (ch * 8 < op.npad) {
-      const uint32_t dst = slot_base + atom_chunk_offset(r, ch);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack2_bf16(feat[8 * ch], feat[8 * ch + 1])),
-                   "r"(pack2_bf16(feat[8 * ch + 2], feat[8 * ch + 3])), "r"(pack2_bf16(feat[8 * ch + 4], feat[8 * ch + 5])),
-                   "r"(pack2_bf16(feat[8 * ch + 6], feat[8 * ch + 7]))
-                   : "memory");
+  if (half == 0) {
+    for (int col = op.ncols; col < op.npad; ++col) {
+      const uint32_t dst = slot_base + atom_chunk_offset(r, col >> 3) + static_cast<uint32_t>(col & 7) * 2u;
+      const unsigned short zero = 0;
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"(zero) : "memory");
     }
   }
   return inside;
@@ -103,10 +146,11 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
 struct EpiArgs {
   uint32_t taddr;            // TMEM address (lane quadrant + first column)
   const float* bias;         // [ncols] or nullptr
+  const float* bias_s;       // the same bias staged in shared memory, zero padded to npad (or nullptr)
   float* out_row;            // fp32 output row (already offset to col0) or nullptr
   const uint8_t* mask_tile;  // forward-activation image of this tile or nullptr
   uint32_t slot0_addr;       // shared-memory address of the first destination slot
-  int ncols, npad, mask_atom0, r;
+  int ncols, npad, mask_atom0, r, half;
   bool out_vec, accum, has_slot;
 };
 
@@ -157,8 +201,8 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& a, int j0, const uint32
   }
 }
 
-template <bool BIAS, bool RELU, bool MASK, bool FULL>
-__device__ __forceinline__ void epi_loads(const EpiArgs& a, int j0, uint32_t (&mw)[8], float (&b)[16]) {
+template <bool MASK>
+__device__ __forceinline__ void epi_mask_load(const EpiArgs& a, int j0, uint32_t (&mw)[8]) {
   if (MASK) {
     const int mc = a.mask_atom0 * 64 + j0;
     const uint8_t* ma = a.mask_tile + static_cast<size_t>(mc >> 6) * kAtomBytes;
@@ -167,8 +211,18 @@ __device__ __forceinline__ void epi_loads(const EpiArgs& a, int j0, uint32_t (&m
     mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
     mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
   }
+}
+
+template <bool BIAS, bool FULL>
+__device__ __forceinline__ void epi_bias_load(const EpiArgs& a, int j0, float (&b)[16]) {
   if (BIAS) {
-    if (FULL) {
+    if (a.bias_s) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = *(reinterpret_cast<const float4*>(a.bias_s + j0) + q);
+        b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+      }
+    } else if (FULL) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(a.bias + j0) + q);
@@ -181,30 +235,49 @@ __device__ __forceinline__ void epi_loads(const EpiArgs& a, int j0, uint32_t (&m
   }
 }
 
-// 16 columns per iteration; the mask / bias loads are issued between the TMEM load and its wait.
+// This thread's 16-column chunks (every other one: the quadrant's second warp takes the rest), kEpiBatch chunks
+// per TMEM round trip: all their tcgen05.ld (and the mask loads) are issued before the one wait.
+constexpr int kEpiBatch = 1;
 template <bool BIAS, bool RELU, bool MASK, bool FULL>
 __device__ __forceinline__ void epi_run(const EpiArgs& a) {
-  for (int j0 = 0; j0 < a.npad; j0 += 16) {
-    uint32_t v[16], mw[8];
-    float b[16];
-    tmem_ld16(a.taddr + j0, v);
-    epi_loads<BIAS, RELU, MASK, FULL>(a, j0, mw, b);
+  for (int j0 = 16 * a.half; j0 < a.npad; j0 += 32 * kEpiBatch) {
+    uint32_t v[kEpiBatch][16], mw[kEpiBatch][8];
+#pragma unroll
+    for (int k = 0; k < kEpiBatch; ++k)
+      if (j0 + 32 * k < a.npad) tmem_ld16(a.taddr + j0 + 32 * k, v[k]);
+    TRACE_MARK(2);
+#pragma unroll
+    for (int k = 0; k < kEpiBatch; ++k)
+      if (j0 + 32 * k < a.npad) epi_mask_load<MASK>(a, j0 + 32 * k, mw[k]);
     tmem_ld_wait();
-    epi_chunk<BIAS, RELU, MASK, FULL>(a, j0, v, mw, b);
+    TRACE_MARK(3);
+#pragma unroll
+    for (int k = 0; k < kEpiBatch; ++k) {
+      if (j0 + 32 * k < a.npad) {
+        float b[16];
+        epi_bias_load<BIAS, FULL>(a, j0 + 32 * k, b);
+        epi_chunk<BIAS, RELU, MASK, FULL>(a, j0 + 32 * k, v[k], mw[k], b);
+      }
+    }
+    TRACE_MARK(4);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int kMinCtas>
-__global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __grid_constant__ ChainParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[16];
-  __shared__ uint32_t tmem_base_s;
-
+__global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
+  // dynamic shared memory only: [2S slot atoms][R ring atoms][tail: mbarriers, TMEM base, staged biases]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.prog.slots_per_ctx, R = p.ring_stages, nops = p.prog.num_ops;
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();   // swizzled atoms need 1024-byte alignment
   const uint32_t ring_base = base + 2u * S * kAtomBytes;
+  uint8_t* tail = smem_raw + static_cast<size_t>(2 * S + R) * kAtomBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(tail + 128);
+  DevOp* sops = reinterpret_cast<DevOp*>(tail + 144);
+  float* sbias = reinterpret_cast<float*>(tail + 144 + sizeof(DevOp) * nops);
+  const int bias_cap = (kTailBytes - 144 - static_cast<int>(sizeof(DevOp)) * nops) / 4;
   auto slot_addr = [&](int ctx, int s) { return base + static_cast<uint32_t>(ctx * S + s) * kAtomBytes; };
   // barriers: [0,R) full, [4,4+R) empty, 8+c a_ready, 10+c acc_ready
   const uint32_t bar0 = smem_u32(bars);
@@ -219,12 +292,47 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
       mbar_init(empty_bar(s), 1);
     }
     for (int c = 0; c < 2; ++c) {
-      mbar_init(a_ready(c), 128);
+      mbar_init(a_ready(c), kCtxThreads);
       mbar_init(acc_ready(c), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 2u * p.ctx_tmem_cols);
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  if (threadIdx.x < nops) {
+    const nrc_chain_op_t& o = p.prog.ops[threadIdx.x];
+    DevOp d;
+    d.kind = static_cast<int8_t>(o.kind); d.slot = static_cast<int8_t>(o.slot);
+    d.flags = static_cast<uint8_t>(o.flags); d.n_atoms = static_cast<uint8_t>(o.n_atoms);
+    d.ncols = static_cast<int16_t>(o.ncols); d.npad = static_cast<int16_t>(o.npad);
+    d.tmem_col = static_cast<int16_t>(o.tmem_col); d.n = static_cast<int16_t>(o.n);
+    d.ld = o.ld;
+    d.col0 = static_cast<int16_t>(o.col0); d.mask_atom0 = static_cast<int16_t>(o.mask_atom0);
+    d.img_atoms = static_cast<int16_t>(o.img_atoms);
+    d.w_chunk = o.w_chunk; d.fparam = o.fparam;
+    d.ptr = o.ptr >= 0 ? p.ptrs[o.ptr] : nullptr;
+    d.out = o.out_ptr >= 0 ? p.ptrs[o.out_ptr] : nullptr;
+    d.mask = o.mask_ptr >= 0 ? p.ptrs[o.mask_ptr] : nullptr;
+#pragma unroll
+    for (int a = 0; a < NRC_CHAIN_MAX_ATOMS; ++a) d.a_src[a] = static_cast<uint8_t>((o.a_slot[a] & 15) | ((o.a_klen[a] >> 4) << 4));
+    // biases of the epilogues are staged behind the program, in op order, while they fit
+    int cur = 0, off = -1;
+    for (int k = 0; k <= static_cast<int>(threadIdx.x); ++k) {
+      const nrc_chain_op_t& e = p.prog.ops[k];
+      if (e.kind != NRC_OP_EPI || e.ptr < 0 || e.mask_ptr >= 0 || (e.flags & NRC_EPI_DENSITY)) continue;
+      if (cur + e.npad > bias_cap) break;
+      if (k == static_cast<int>(threadIdx.x)) off = cur;
+      cur += e.npad;
+    }
+    d.bias_off = static_cast<int16_t>(off);
+    sops[threadIdx.x] = d;
+  }
+  __syncthreads();
+  for (int i = 0; i < nops; ++i) {
+    const DevOp& op = sops[i];
+    if (op.bias_off < 0) continue;
+    const float* b = static_cast<const float*>(op.ptr);
+    for (int k = threadIdx.x; k < op.npad; k += kChainThreads) sbias[op.bias_off + k] = k < op.ncols ? __ldg(b + k) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -239,13 +347,13 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
       uint32_t phase = 0;
       for (int q = blockIdx.x; q < num_pairs; q += gridDim.x) {
         for (int i = 0; i < nops;) {
-          if (p.prog.ops[i].kind != NRC_OP_GEMM) { ++i; continue; }
+          if (sops[i].kind != NRC_OP_GEMM) { ++i; continue; }
           int j = i;
-          while (j < nops && p.prog.ops[j].kind == NRC_OP_GEMM) ++j;
+          while (j < nops && sops[j].kind == NRC_OP_GEMM) ++j;
           for (int c = 0; c < 2; ++c) {
             if (2 * q + c >= p.num_tiles) continue;
             for (int o = i; o < j; ++o) {
-              const nrc_chain_op_t& op = p.prog.ops[o];
+              const DevOp& op = sops[o];
               const uint32_t bytes = static_cast<uint32_t>(op.n) * 128u;
               for (int a = 0; a < op.n_atoms; ++a) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -268,24 +376,24 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
       uint32_t a_par[2] = {0u, 0u};
       for (int q = blockIdx.x; q < num_pairs; q += gridDim.x) {
         for (int i = 0; i < nops;) {
-          if (p.prog.ops[i].kind != NRC_OP_GEMM) { ++i; continue; }
+          if (sops[i].kind != NRC_OP_GEMM) { ++i; continue; }
           int j = i;
-          while (j < nops && p.prog.ops[j].kind == NRC_OP_GEMM) ++j;
+          while (j < nops && sops[j].kind == NRC_OP_GEMM) ++j;
           for (int c = 0; c < 2; ++c) {
             if (2 * q + c >= p.num_tiles) continue;
             mbar_wait(a_ready(c), a_par[c]);
             a_par[c] ^= 1u;
             tc_fence_after();
             for (int o = i; o < j; ++o) {
-              const nrc_chain_op_t& op = p.prog.ops[o];
+              const DevOp& op = sops[o];
               const uint32_t idesc = make_idesc(128, op.n, 0, 0);
-              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(c * p.ctx_tmem_cols + op.tmem_col);
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
               for (int a = 0; a < op.n_atoms; ++a) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t a_addr = slot_addr(c, op.a_slot[a]);
+                const uint32_t a_addr = slot_addr(c, op.a_src[a] & 15);
                 const uint32_t b_addr = ring_base + static_cast<uint32_t>(stage) * kAtomBytes;
-                const int nk = op.a_klen[a] >> 4;
+                const int nk = op.a_src[a] >> 4;
                 for (int k = 0; k < nk; ++k) {
                   const uint32_t acc = ((op.flags & NRC_GEMM_ACCUMULATE) || a > 0 || k > 0) ? 1u : 0u;
                   umma_bf16(d_tmem, kmajor_desc(a_addr, k), kmajor_desc(b_addr, k), idesc, acc);
@@ -302,9 +410,10 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
     }
   } else {
     // ===================================================================== loader / epilogue warpgroups
-    const int c = (warp - 2) >> 2;                 // context
-    const int wg_tid = threadIdx.x - 64 - 128 * c;
+    const int c = (warp - 2) >> 3;                 // context
+    const int wg_tid = threadIdx.x - 64 - kCtxThreads * c;
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int half = ((warp - 2) >> 2) & 1;        // which of the quadrant's two warps: alternate 16-column chunks
     const int r = quad * 32 + lane;                // tile row owned in epilogues
     const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t acc_par = 0;
@@ -314,7 +423,7 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
     auto guard_slots = [&]() {  // before overwriting slots a bulk store may still be reading
       if (store_pending) {
         if (wg_tid == 0) bulk_wait_read0();
-        named_barrier_sync(1 + c, 128);
+        named_barrier_sync(1 + c, kCtxThreads);
         store_pending = false;
       }
     };
@@ -323,16 +432,24 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
       const int tile = 2 * q + c;
       if (tile >= p.num_tiles) continue;
       const int64_t row0 = static_cast<int64_t>(tile) * 128;
+#ifdef NRC_CHAIN_TRACE
+      const int trace_it = (q - blockIdx.x) / gridDim.x;
+      const bool tracing = blockIdx.x == 0 && wg_tid == 0 && trace_it < kTraceTiles;
+      if (tracing) g_chain_trace[c][trace_it][kTraceOps - 1] = clock64();
+#endif
       for (int i = 0; i < nops;) {
-        const nrc_chain_op_t& op = p.prog.ops[i];
+        const DevOp& op = sops[i];
         if (op.kind == NRC_OP_GEMM) {
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(a_ready(c));
-          while (i < nops && p.prog.ops[i].kind == NRC_OP_GEMM) ++i;
+          while (i < nops && sops[i].kind == NRC_OP_GEMM) ++i;
           mbar_wait(acc_ready(c), acc_par);
           acc_par ^= 1u;
           tc_fence_after();
+#ifdef NRC_CHAIN_TRACE
+          if (tracing) g_chain_trace[c][trace_it][i - 1] = clock64();
+#endif
           continue;
         }
         if (op.kind == NRC_OP_GATHER) {
@@ -341,32 +458,30 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
           const bool valid = pt < p.num_rows;
           const uint32_t sb = slot_addr(c, op.slot);
           switch (p.enc.F) {
-            case 1: inside_reg = gather_row<1>(p, op, pt, valid, sb, r); break;
-            case 2: inside_reg = gather_row<2>(p, op, pt, valid, sb, r); break;
-            default: inside_reg = gather_row<4>(p, op, pt, valid, sb, r); break;
+            case 1: inside_reg = gather_row<1>(p, op, pt, valid, sb, r, half); break;
+            case 2: inside_reg = gather_row<2>(p, op, pt, valid, sb, r, half); break;
+            default: inside_reg = gather_row<4>(p, op, pt, valid, sb, r, half); break;
           }
         } else if (op.kind == NRC_OP_LOAD) {
           guard_slots();
-          const float* src = op.ptr >= 0 ? static_cast<const float*>(p.ptrs[op.ptr]) : nullptr;
+          const float* src = static_cast<const float*>(op.ptr);
           const int nch = op.npad >> 3;
           const bool vec = src && (op.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-          // four independent 32-byte loads in flight per thread before the first conversion
+          // six independent 32-byte loads in flight per thread before the first conversion
           constexpr int kU = 4;
           const int total = 128 * nch;
-          for (int item0 = wg_tid; item0 < total; item0 += 128 * kU) {
+          for (int item0 = wg_tid; item0 < total; item0 += kCtxThreads * kU) {
             float v[kU][8];
-            int rrs[kU], cols[kU];
 #pragma unroll
             for (int q = 0; q < kU; ++q) {
-              const int item = item0 + q * 128;
+              const int item = item0 + q * kCtxThreads;
               const int rr = item / nch;
-              rrs[q] = rr;
-              cols[q] = (item - rr * nch) * 8;
+              const int col = (item - rr * nch) * 8;
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
-              if (item < total && src && row0 + rr < p.num_rows && cols[q] < op.ncols) {
-                const float* s = src + (row0 + rr) * op.ld + cols[q];
-                if (vec && cols[q] + 8 <= op.ncols) {
+              if (item < total && src && row0 + rr < p.num_rows && col < op.ncols) {
+                const float* s = src + (row0 + rr) * op.ld + col;
+                if (vec && col + 8 <= op.ncols) {
                   const float4 x0 = __ldg(reinterpret_cast<const float4*>(s));
                   const float4 x1 = __ldg(reinterpret_cast<const float4*>(s) + 1);
                   v[q][0] = x0.x; v[q][1] = x0.y; v[q][2] = x0.z; v[q][3] = x0.w;
@@ -374,15 +489,17 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
                 } else {
 #pragma unroll
                   for (int e = 0; e < 8; ++e)
-                    if (cols[q] + e < op.ncols) v[q][e] = __ldg(s + e);
+                    if (col + e < op.ncols) v[q][e] = __ldg(s + e);
                 }
               }
             }
 #pragma unroll
             for (int q = 0; q < kU; ++q) {
-              if (item0 + q * 128 >= total) continue;
-              const int dcol = op.col0 + cols[q];
-              const uint32_t dst = slot_addr(c, op.slot + (dcol >> 6)) + atom_chunk_offset(rrs[q], (dcol & 63) >> 3);
+              const int item = item0 + q * kCtxThreads;
+              if (item >= total) continue;
+              const int rr = item / nch;
+              const int dcol = op.col0 + (item - rr * nch) * 8;
+              const uint32_t dst = slot_addr(c, op.slot + (dcol >> 6)) + atom_chunk_offset(rr, (dcol & 63) >> 3);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack2_bf16(v[q][0], v[q][1])),
                            "r"(pack2_bf16(v[q][2], v[q][3])), "r"(pack2_bf16(v[q][4], v[q][5])),
                            "r"(pack2_bf16(v[q][6], v[q][7]))
@@ -391,9 +508,9 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
           }
         } else if (op.kind == NRC_OP_SAVE) {
           fence_proxy_async_smem();
-          named_barrier_sync(1 + c, 128);
+          named_barrier_sync(1 + c, kCtxThreads);
           if (wg_tid == 0) {
-            uint8_t* img = static_cast<uint8_t*>(p.ptrs[op.ptr]);
+            uint8_t* img = static_cast<uint8_t*>(op.ptr);
             for (int a = 0; a < op.npad; ++a)
               bulk_s2g(img + (static_cast<size_t>(tile) * op.img_atoms + op.col0 + a) * kAtomBytes,
                        slot_addr(c, op.slot + a), kAtomBytes);
@@ -402,38 +519,42 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
           store_pending = true;
         } else if (op.kind == NRC_OP_EPI && (op.flags & NRC_EPI_DENSITY)) {
           // density head: column 0 -> safe_exp(raw + density_bias) masked to the bbox; columns 1..3 -> grad_pred
+          if (half == 0) {
           uint32_t v[16];
-          tmem_ld16(tmem_base + t_lane + static_cast<uint32_t>(c * p.ctx_tmem_cols + op.tmem_col), v);
+          tmem_ld16(tmem_base + t_lane + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col), v);
           tmem_ld_wait();
           const int64_t pt = row0 + r;
           if (pt < p.num_rows) {
-            const float* bias = op.ptr >= 0 ? static_cast<const float*>(p.ptrs[op.ptr]) : nullptr;
+            const float* bias = static_cast<const float*>(op.ptr);
             const float raw = __uint_as_float(v[0]) + (bias ? __ldg(bias) : 0.f);
-            static_cast<float*>(p.ptrs[op.out_ptr])[pt] = inside_reg ? safe_exp(raw + op.fparam) : 0.f;
-            if (op.mask_ptr >= 0) {
-              float* gp = static_cast<float*>(p.ptrs[op.mask_ptr]) + 3 * pt;
+            static_cast<float*>(op.out)[pt] = inside_reg ? safe_exp(raw + op.fparam) : 0.f;
+            if (op.mask) {
+              float* gp = static_cast<float*>(op.mask) + 3 * pt;
 #pragma unroll
               for (int j = 0; j < 3; ++j) gp[j] = __uint_as_float(v[1 + j]) + (bias ? __ldg(bias + 1 + j) : 0.f);
             }
           }
+          }
         } else {  // NRC_OP_EPI
+          TRACE_MARK(0);
           if (op.slot >= 0) guard_slots();
           EpiArgs a;
-          a.bias = op.ptr >= 0 ? static_cast<const float*>(p.ptrs[op.ptr]) : nullptr;
-          float* out = op.out_ptr >= 0 ? static_cast<float*>(p.ptrs[op.out_ptr]) : nullptr;
+          a.bias = static_cast<const float*>(op.ptr);
+          a.bias_s = op.bias_off >= 0 ? sbias + op.bias_off : nullptr;
+          float* out = static_cast<float*>(op.out);
           a.out_row = (out && row0 + r < p.num_rows) ? out + (row0 + r) * op.ld + op.col0 : nullptr;
           a.out_vec = out && (op.ld % 4 == 0) && (op.col0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
           a.accum = (op.flags & NRC_EPI_OUT_ACCUMULATE) != 0;
-          a.mask_tile = op.mask_ptr >= 0 ? static_cast<const uint8_t*>(p.ptrs[op.mask_ptr]) +
-                                               static_cast<size_t>(tile) * op.img_atoms * kAtomBytes
-                                         : nullptr;
+          a.mask_tile = op.mask ? static_cast<const uint8_t*>(op.mask) + static_cast<size_t>(tile) * op.img_atoms * kAtomBytes
+                                : nullptr;
           a.mask_atom0 = op.mask_atom0;
-          a.taddr = tmem_base + t_lane + static_cast<uint32_t>(c * p.ctx_tmem_cols + op.tmem_col);
+          a.taddr = tmem_base + t_lane + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
           a.has_slot = op.slot >= 0;
           a.slot0_addr = a.has_slot ? slot_addr(c, op.slot) : 0u;
-          a.ncols = op.ncols; a.npad = op.npad; a.r = r;
+          a.ncols = op.ncols; a.npad = op.npad; a.r = r; a.half = half;
           const bool full = (op.ncols == op.npad) && (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
           const bool relu = (op.flags & NRC_EPI_RELU) != 0;
+          TRACE_MARK(1);
           if (a.mask_tile) {
             if (full) epi_run<false, false, true, true>(a); else epi_run<false, false, true, false>(a);
           } else if (a.bias) {
@@ -443,7 +564,11 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
             if (relu) { if (full) epi_run<false, true, false, true>(a); else epi_run<false, true, false, false>(a); }
             else      { if (full) epi_run<false, false, false, true>(a); else epi_run<false, false, false, false>(a); }
           }
+          TRACE_MARK(5);
         }
+#ifdef NRC_CHAIN_TRACE
+        if (tracing) g_chain_trace[c][trace_it][i] = clock64();
+#endif
         ++i;
       }
     }
@@ -452,7 +577,7 @@ __global__ void __launch_bounds__(kChainThreads, kMinCtas) chain_kernel(const __
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 2u * p.ctx_tmem_cols);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -713,33 +838,31 @@ static int32_t chain_launch(void* stream, const nrc_chain_program_t* prog, void*
   int R = max_atoms - 2 * S;
   if (R < 1) return NRC_E_UNSUPPORTED;
   if (R > 4) R = 4;
-  if (has_gather && R > 2) R = 2;   // queries: small weights, two CTAs per SM so gathers of one hide behind the other
   hp.ring_stages = R;
-  const size_t smem = static_cast<size_t>(2 * S + R) * kAtomBytes + 1024;
+  const size_t smem = static_cast<size_t>(2 * S + R) * kAtomBytes + kTailBytes;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * kAtomBytes + kTailBytes) != cudaSuccess)
       return check_launch();
     attr_set = true;
   }
   const int pairs = (hp.num_tiles + 1) / 2;
-  hp.ctx_tmem_cols = kCtxTmemCols;
-  if (has_gather && smem <= 113 * 1024) {
-    int need = 32;
-    for (int i = 0; i < prog->num_ops; ++i)
-      if (prog->ops[i].kind == NRC_OP_GEMM)
-        while (need < prog->ops[i].tmem_col + prog->ops[i].n) need *= 2;
-    if (need > 128) return NRC_E_UNSUPPORTED;
-    hp.ctx_tmem_cols = need;
-    const int grid = pairs < 2 * kNumSMs ? pairs : 2 * kNumSMs;
-    chain_kernel<2><<<grid, kChainThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
-  } else {
-    const int grid = pairs < kNumSMs ? pairs : kNumSMs;
-    chain_kernel<1><<<grid, kChainThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
-  }
+  const int grid = pairs < kNumSMs ? pairs : kNumSMs;
+  chain_kernel<<<grid, kChainThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
   return check_launch();
 }
+
+#ifdef NRC_CHAIN_TRACE
+extern "C" int32_t nrc_chain_trace_dump(long long* host_out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, g_chain_trace, sizeof(long long) * 2 * kTraceTiles * kTraceOps) == cudaSuccess
+             ? NRC_OK : NRC_E_CUDA;
+}
+extern "C" int32_t nrc_chain_marks_dump(long long* host_out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, g_chain_marks, sizeof(long long) * 16) == cudaSuccess ? NRC_OK : NRC_E_CUDA;
+}
+#endif
 
 extern "C" int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
                                  const void* d_weights_packed, int64_t num_rows) {

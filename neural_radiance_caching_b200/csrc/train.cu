@@ -254,9 +254,135 @@ __global__ void charb_srgb_loss_kernel(const float* __restrict__ rgb, const floa
   }
 }
 
+// compute_mask_loss (internal/train_utils.py:785-836): mean(lossmult * Charbonnier(acc - mask) * weight),
+// weight = opaque_w where mask > 0.5 else empty_w; lossmult == 1.  mask == nullptr: all ones.
+__global__ void mask_loss_kernel(const float* __restrict__ acc, int n, const float* __restrict__ mask, int64_t R,
+                                 float charb_padding, float opaque_w, float empty_w, float* __restrict__ loss,
+                                 float* __restrict__ g_acc) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float contrib = 0.f;
+  if (i < R) {
+    float a;
+    if (n > 0) {   // acc = sum of the ray's weights (render.py: acc = weights.sum(-1))
+      a = 0.f;
+      for (int j = 0; j < n; ++j) a += acc[i * n + j];
+    } else {
+      a = acc[i];
+    }
+    const float mk = mask ? mask[i] : 1.0f;
+    const float wt = (mk > 0.5f ? opaque_w : empty_w) / static_cast<float>(R);
+    const float diff = a - mk;
+    const float ch = sqrtf(diff * diff + charb_padding * charb_padding);
+    const float g = wt * diff / ch;
+    if (n > 0) {
+      for (int j = 0; j < n; ++j) g_acc[i * n + j] = g;
+    } else {
+      g_acc[i] = g;
+    }
+    contrib = wt * ch;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) sum += part[k];
+    atomicAdd(loss, sum);
+  }
+}
+
+// Geometry losses of the final sampler level, one warp per ray (internal/train_utils.py:3255-3311):
+//   orientation (internal/loss_utils.py:127-166, target 'normals_pred'):
+//       mult_o * mean_r | sum_i |w_i min(0, n_i . v)^2| + 1e-5 |,  v = -viewdirs
+//   predicted normals (loss_utils.py:169-199 called with gt='normals_pred' (stop-gradient), pred='normals'
+//       (the ANALYTIC normals: second-order path), w = stopgrad_with_weight(w, sg_w)):
+//       mult_p * mean_r | sum_i |w_i (1 - n_pred_i . n_i)| + 1e-5 |
+//   reverse (gt='normals' stop-gradient, pred='normals_pred', w stop-gradient): same value, mult_r.
+// Gradients: g_w and g_npred are ACCUMULATED (they already hold the compositing / shader terms), g_n is written.
+__device__ __forceinline__ float nan0(float x) { return x == x ? x : 0.f; }
+__device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+__global__ void geometry_losses_kernel(const float* __restrict__ w, const float* __restrict__ nrm,
+                                       const float* __restrict__ npred, const float* __restrict__ viewdirs, int64_t R,
+                                       int n, float mult_o, float mult_p, float mult_r, float sg_w,
+                                       float* __restrict__ loss, float* __restrict__ g_w, float* __restrict__ g_npred,
+                                       float* __restrict__ g_n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= R) return;
+  const float invR = 1.0f / static_cast<float>(R);
+  const float v0 = -viewdirs[3 * r], v1 = -viewdirs[3 * r + 1], v2 = -viewdirs[3 * r + 2];
+  float so = 0.f, sp = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const int64_t q = r * n + i;
+    const float wi = w[q];
+    const float p0 = nan0(npred[3 * q]), p1 = nan0(npred[3 * q + 1]), p2 = nan0(npred[3 * q + 2]);
+    float gw = 0.f, gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
+    // orientation on the predicted normals
+    const float ndv = p0 * v0 + p1 * v1 + p2 * v2;
+    const float mn = fminf(0.f, ndv);
+    const float to = wi * mn * mn;
+    so += fabsf(to);
+    const float so_sign = sgn(to) * mult_o * invR;
+    gw += so_sign * mn * mn;
+    const float co = so_sign * wi * 2.f * mn;   // mn == 0 when n.v >= 0: no gradient
+    gp0 += co * v0; gp1 += co * v1; gp2 += co * v2;
+    if (nrm) {
+      const float a0 = nan0(nrm[3 * q]), a1 = nan0(nrm[3 * q + 1]), a2 = nan0(nrm[3 * q + 2]);
+      const float one_m = 1.0f - (p0 * a0 + p1 * a1 + p2 * a2);
+      const float tp = wi * one_m;
+      sp += fabsf(tp);
+      const float s = sgn(tp) * invR;
+      gw += s * mult_p * sg_w * one_m;                       // stopgrad_with_weight(w, sg_w)
+      const float ca = -s * mult_p * wi;                     // predicted-normal loss -> analytic normals
+      g_n[3 * q] = ca * p0; g_n[3 * q + 1] = ca * p1; g_n[3 * q + 2] = ca * p2;
+      const float cp = -s * mult_r * wi;                     // reverse loss -> predicted normals
+      gp0 += cp * a0; gp1 += cp * a1; gp2 += cp * a2;
+    }
+    g_w[q] += gw;
+    g_npred[3 * q] += gp0; g_npred[3 * q + 1] += gp1; g_npred[3 * q + 2] += gp2;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    so += __shfl_xor_sync(0xffffffffu, so, o);
+    sp += __shfl_xor_sync(0xffffffffu, sp, o);
+  }
+  if (lane == 0) {
+    float l = mult_o * fabsf(so + 1e-5f);
+    if (nrm) l += (mult_p + mult_r) * fabsf(sp + 1e-5f);
+    atomicAdd(loss, l * invR);
+  }
+}
+
 }  // namespace nrc
 
 using namespace nrc;
+
+extern "C" int32_t nrc_mask_loss(void* stream, const float* d_acc, int32_t n, const float* d_mask, int64_t num_rays,
+                                 float charb_padding, float opaque_weight, float empty_weight, float* d_loss,
+                                 float* d_g_acc) {
+  if (num_rays < 1 || n < 0 || !d_acc || !d_loss || !d_g_acc) return NRC_E_INVALID_ARG;
+  mask_loss_kernel<<<static_cast<unsigned>((num_rays + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_acc, n, d_mask, num_rays, charb_padding, opaque_weight, empty_weight, d_loss, d_g_acc);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_geometry_losses(void* stream, const float* d_weights, const float* d_normals,
+                                       const float* d_normals_pred, const float* d_viewdirs, int64_t num_rays,
+                                       int32_t n, float orientation_mult, float predicted_normal_mult,
+                                       float predicted_normal_reverse_mult, float stopgrad_weight, float* d_loss,
+                                       float* d_g_weights, float* d_g_normals_pred, float* d_g_normals) {
+  if (num_rays < 1 || n < 1) return NRC_E_INVALID_ARG;
+  if (!d_weights || !d_normals_pred || !d_viewdirs || !d_loss || !d_g_weights || !d_g_normals_pred) return NRC_E_INVALID_ARG;
+  if (d_normals && !d_g_normals) return NRC_E_INVALID_ARG;
+  const int64_t threads = num_rays * 32;
+  geometry_losses_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_weights, d_normals, d_normals_pred, d_viewdirs, num_rays, n, orientation_mult, predicted_normal_mult,
+      predicted_normal_reverse_mult, stopgrad_weight, d_loss, d_g_weights, d_g_normals_pred, d_g_normals);
+  return check_launch();
+}
 
 extern "C" int32_t nrc_normals_fwd(void* stream, const float* d_grad, int64_t num_points, float* d_normals) {
   if (num_points < 0) return NRC_E_INVALID_ARG;

@@ -28,10 +28,17 @@ from . import _lib, geometry, mlp_chain, nerf, stepfun
 
 
 class FusedCacheStep:
-    def __init__(self, model, params, charb_padding=0.001, interlevel_mults=(0.01, 0.01), interlevel_blurs=(0.03, 0.003)):
+    def __init__(self, model, params, charb_padding=0.001, interlevel_mults=(0.01, 0.01), interlevel_blurs=(0.03, 0.003),
+                 geometry_mults=(0.01, 0.001, 0.01), predicted_normal_stopgrad_weight=0.1, mask_weights=(1.0, 1.0),
+                 backward_mask_weight=0.1):
         self.model, self.params = model, params
         self.charb_padding = charb_padding
         self.interlevel_mults, self.interlevel_blurs = interlevel_mults, interlevel_blurs
+        # geometry / mask losses (configs/nerf_ngp_yobo_lego.gin:7-11, nerf_ngp_yobo.gin:59-72,367-376)
+        self.geometry_mults = geometry_mults            # orientation, predicted normals, reverse; None: off
+        self.sg_w = predicted_normal_stopgrad_weight
+        self.mask_weights = mask_weights                # opaque, empty; None: off
+        self.backward_mask_weight = backward_mask_weight
         self._bg = {}
         self._side = None
         self.concurrent = True   # independent branches of the schedule on side streams (fork/join events)
@@ -56,14 +63,60 @@ class FusedCacheStep:
             self._bg[key] = (sd, torch.ones((R, 1), device=dev, dtype=torch.float32))
         return self._bg[key]
 
-    def step(self, rays, u01, target_rgb, train_frac=1.0):
+    def step(self, rays, u01, target_rgb, train_frac=1.0, extra=None):
         """One forward + loss + backward; gradients land in the registered sinks.  Returns the loss
-        (device scalar) and leaves the per-level sampler state in self.last (for tests)."""
-        state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True)
+        (device scalar) and leaves the per-level sampler state in self.last (for tests).
+        `extra` = (rays, u01) of the backward-mask pass (train_utils.py:3348-3401) or None."""
+        state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra)
         self.step_back(state)
         return state["loss"]
 
-    def step_front(self, rays, u01, target_rgb, train_frac=1.0, fork_proposals=False):
+    def _weights_only_pass(self, rays, u01, train_frac, loss):
+        """Backward-mask term: sampler-only forward on the extra rays (weights_only=True), mask loss against a zero
+        mask on acc = sum(weights), and the final level's backward (the proposal levels receive nothing from this
+        pass: they are supervised by the main rays' interlevel loss only and positions are stop-gradiented)."""
+        sampler = self.model.sampler
+        sp = self.params["Sampler"]
+        R, dev = rays["near"].shape[0], rays["near"].device
+        st = _lib.stream_ptr
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        anneal = sampler.anneal(train_frac)
+        sdist, weights = self._initial_step_function(R, dev)
+        nl = len(sampler.sampling_strategy)
+        lv = None
+        for i_level, (i_mlp, _, n) in enumerate(sampler.sampling_strategy):
+            mlp, p = sampler.mlps[i_mlp], sp[f"MLP_{i_mlp}"]
+            last = i_level == nl - 1
+            sdist = stepfun.sample_intervals_from_weights(u01[i_level], sdist, weights, n, anneal=anneal,
+                                                          padding=sampler.resample_padding, domain=(0.0, 1.0))
+            tdist, means = sampler._cast(sdist, rays, False)
+            P = R * n
+            density = new(P)
+            enc_out = new(P, mlp.in_dim) if last else None
+            arena = p["density_grid"]["_arena"]
+            enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)), None)
+            desc = geometry._mlp_desc(p, mlp.in_dim, False)
+            _lib.call("nrc_density_query_fwd", st(), C.byref(enc), C.byref(desc), _lib.ptr(means), P, float(mlp.warp_c),
+                      float(mlp.density_bias), int(mlp.bf16), _lib.ptr(density), None, None, None, None, _lib.ptr(enc_out))
+            weights = new(R, n)
+            _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(density), _lib.ptr(tdist), _lib.ptr(rays["directions"]),
+                      R, n, int(sampler.opaque_background), _lib.ptr(weights), None, None)
+            if last:
+                lv = dict(mlp=mlp, p=p, n=n, tdist=tdist, means=means, density=density, enc_out=enc_out, weights=weights,
+                          arena=arena, flat=mlp._flatten(p), desc=geometry._mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals))
+        g_w = new(R, lv["n"])
+        _lib.call("nrc_mask_loss", st(), _lib.ptr(lv["weights"]), lv["n"], self._zero_mask(R, dev), R,
+                  float(self.charb_padding), 0.0, float(self.backward_mask_weight), _lib.ptr(loss), _lib.ptr(g_w))
+        self._level_backward(lv, rays, g_w, None, None, R)
+        self.last_extra = lv
+
+    def _zero_mask(self, R, dev):
+        key = ("m0", R, str(dev))
+        if key not in self._bg:
+            self._bg[key] = torch.zeros((R,), device=dev, dtype=torch.float32)
+        return _lib.ptr(self._bg[key])
+
+    def step_front(self, rays, u01, target_rgb, train_frac=1.0, fork_proposals=False, extra=None):
         """Forward, loss and the SHADER's backward: when this returns (in stream order) every gradient of the
         `Shader` parameters (appearance grid + all stacks) is final, so a data-parallel harness can start
         all-reducing that half of the gradient arena while step_back() produces the sampler's half."""
@@ -75,10 +128,23 @@ class FusedCacheStep:
         new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
         anneal = sampler.anneal(train_frac)
         main = torch.cuda.current_stream()
-        s_pack, s_enc, s_env, s_prop = self._streams(4) if self.concurrent else (None,) * 4
+        s_pack, s_enc, s_env, s_prop = self._streams(5)[:4] if self.concurrent else (None,) * 4
         shp = self.params["Shader"]
         names, sflat = shader.fused_params(shp)
         app_arena = shp["appearance_grid"]["_arena"]
+        loss = torch.zeros((), device=dev, dtype=torch.float32)
+        # backward-mask pass: independent rays, its own stream (joined in step_back); in split mode
+        # (fork_proposals False: two graphs) it is issued by step_back instead
+        s_x = None
+        if extra is not None and fork_proposals:
+            if self.concurrent:
+                s_x = self._streams(5)[4]
+                s_x.wait_stream(main)
+                with torch.cuda.stream(s_x):
+                    self._weights_only_pass(extra[0], extra[1], train_frac, loss)
+            else:
+                self._weights_only_pass(extra[0], extra[1], train_frac, loss)
+            extra = None
         # weight packing does not depend on the rays: runs beside the sampler
         if s_pack is not None:
             s_pack.wait_stream(main)
@@ -132,7 +198,6 @@ class FusedCacheStep:
         # The spline interlevel loss and the proposal levels' backward depend only on the final level's step
         # function (sdist, weights): they start here and run beside the shader's forward / backward.
         k = L2["n"]
-        loss = torch.zeros((), device=dev, dtype=torch.float32)
         g_w = [new(R, lv["n"]) for lv in levels]
 
         def interlevel():   # loss_utils.spline_interlevel_loss, one launch per proposal level
@@ -166,15 +231,34 @@ class FusedCacheStep:
         g_rgb = new(R, 3)
         _lib.call("nrc_charb_srgb_loss", st(), _lib.ptr(out_rgb), _lib.ptr(target_rgb), R, float(self.charb_padding),
                   _lib.ptr(loss), _lib.ptr(g_rgb))
+        g_acc = None
+        if self.mask_weights is not None:   # compute_mask_loss on the accumulation, masks == 1
+            g_acc = new(R)
+            _lib.call("nrc_mask_loss", st(), _lib.ptr(acc), 0, None, R, float(self.charb_padding),
+                      float(self.mask_weights[0]), float(self.mask_weights[1]), _lib.ptr(loss), _lib.ptr(g_acc))
         gv = new(R, k, 3)
         _lib.call("nrc_ray_composite_bwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(bg),
-                  _lib.ptr(g_rgb), None, R, k, 3, 1, _lib.ptr(gv), _lib.ptr(g_w[2]), None)
+                  _lib.ptr(g_rgb), _lib.ptr(g_acc), R, k, 3, 1, _lib.ptr(gv), _lib.ptr(g_w[2]), None)
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
+        g_rg = None
+        if self.geometry_mults is not None:
+            # orientation / predicted-normal / reverse losses: += into the compositing's g_w and the shader's g_nrm;
+            # the gradient w.r.t. the analytic normals goes through the l2_normalize VJP to d raw / d means
+            has_n = L2.get("normals") is not None
+            g_na = new(P2, 3) if has_n else None
+            mo, mp, mr = self.geometry_mults
+            _lib.call("nrc_geometry_losses", st(), _lib.ptr(L2["weights"]), _lib.ptr(L2["normals"]) if has_n else None,
+                      _lib.ptr(normals_pred), _lib.ptr(rays["viewdirs"]), R, k, float(mo), float(mp), float(mr),
+                      float(self.sg_w), _lib.ptr(loss), _lib.ptr(g_w[2]), _lib.ptr(g_nrm), _lib.ptr(g_na))
+            if has_n:
+                g_rg = new(P2, 3)
+                _lib.call("nrc_normals_bwd", st(), _lib.ptr(L2["rg"]), _lib.ptr(g_na), P2, _lib.ptr(g_rg))
         if s_prop is not None and not fork_proposals:
             main.wait_stream(s_prop)     # split mode: the side stream only ran the interlevel losses
         self.last = dict(levels=levels, rgb=out_rgb, acc=acc, dist=dist, shader_rgb=rgb_s)
-        return dict(loss=loss, levels=levels, rays=rays, g_w=g_w, d_feat=d_feat, g_nrm=g_nrm, R=R,
-                    forked=s_prop if fork_proposals else None, keep=(saved, gv, g_rgb))
+        return dict(loss=loss, levels=levels, rays=rays, g_w=g_w, d_feat=d_feat, g_nrm=g_nrm, R=R, g_rg=g_rg,
+                    forked=s_prop if fork_proposals else None, keep=(saved, gv, g_rgb, g_acc), extra=extra,
+                    extra_stream=s_x, train_frac=train_frac)
 
     def step_back(self, state):
         """Backward of the proposal sampler (three levels) from the state of step_front()."""
@@ -192,9 +276,29 @@ class FusedCacheStep:
             with torch.cuda.stream(own_fork):
                 for i_level in range(nl - 2, -1, -1):
                     self._level_backward(levels[i_level], rays, g_w[i_level], None, None, R)
+        x_fork = None
+        if state.get("extra") is not None:      # split mode: the backward-mask pass starts here
+            if self.concurrent:
+                x_fork = self._streams(5)[4]
+                x_fork.wait_stream(main)
+                with torch.cuda.stream(x_fork):
+                    self._weights_only_pass(state["extra"][0], state["extra"][1], state["train_frac"], state["loss"])
+            else:
+                self._weights_only_pass(state["extra"][0], state["extra"][1], state["train_frac"], state["loss"])
+        elif state.get("extra_stream") is not None:
+            x_fork = state["extra_stream"]
         g_gp = torch.empty((P2, 3), device=dev, dtype=torch.float32)
         _lib.call("nrc_normals_bwd", _lib.stream_ptr(), _lib.ptr(L2["gp"]), _lib.ptr(state["g_nrm"]), P2, _lib.ptr(g_gp))
+        if state.get("g_rg") is not None:
+            # second-order path of the predicted-normal loss: d/d theta <g_rg, d raw / d means> (nrc_density_normals_bwd)
+            mlp = L2["mlp"]
+            sinks = [_lib.grad_sink(t) for t in L2["flat"]]
+            t_sink = _lib.grad_sink(L2["arena"])
+            geometry.density_normals_bwd(mlp, L2["p"], L2["arena"], L2["means"].reshape(P2, 3), state["g_rg"],
+                                         mlp._unflatten(sinks), t_sink)
         self._level_backward(L2, rays, g_w[nl - 1], state["d_feat"], g_gp if L2["gp"] is not None else None, R)
+        if x_fork is not None:
+            main.wait_stream(x_fork)
         if s_prop is not None:
             main.wait_stream(s_prop)
         elif own_fork is not None:

@@ -178,6 +178,53 @@ class _DensityQueryFn(torch.autograd.Function):
         return (None, None, None, g_arena) + (tuple(gflat) if gflat is not None else (None,) * len(flat))
 
 
+class _RawGradFn(torch.autograd.Function):
+    """Analytic raw-density gradient d raw / d means (internal/geometry.py:442-460: jax.vjp of predict_density
+    w.r.t. the means) WITH its parameter VJP, i.e. the second-order path the predicted-normal loss takes
+    (SURVEY 8f-1).  forward: nrc_density_query_fwd (raw-gradient output only); backward:
+    nrc_density_normals_bwd.  No gradient to the sample positions (stop_level_grad)."""
+
+    @staticmethod
+    def forward(ctx, mlp, means, arena, *flat):
+        p = mlp._unflatten(flat)
+        m2 = means.reshape(-1, 3).contiguous()
+        P = m2.shape[0]
+        rg = torch.empty((P, 3), device=m2.device, dtype=torch.float32)
+        enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)), None)
+        desc = _mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals)
+        _lib.call("nrc_density_query_fwd", _lib.stream_ptr(), C.byref(enc), C.byref(desc), _lib.ptr(m2), P,
+                  float(mlp.warp_c), float(mlp.density_bias), int(mlp.bf16), None, None, None, None, _lib.ptr(rg), None)
+        ctx.mlp = mlp
+        ctx.save_for_backward(m2, arena, *flat)
+        ctx.lead = means.shape[:-1]
+        return rg.reshape(ctx.lead + (3,))
+
+    @staticmethod
+    def backward(ctx, g_rg):
+        mlp = ctx.mlp
+        m2, arena, *flat = ctx.saved_tensors
+        g = g_rg.reshape(-1, 3).contiguous()
+        sinks = [_lib.grad_sink(t) for t in flat]
+        w_sunk = all(s_ is not None for s_ in sinks)
+        gflat = sinks if w_sunk else [torch.zeros_like(t) for t in flat]
+        t_sink = _lib.grad_sink(arena)
+        g_arena = t_sink if t_sink is not None else torch.zeros_like(arena)
+        density_normals_bwd(mlp, mlp._unflatten(flat), arena, m2, g, mlp._unflatten(gflat), g_arena)
+        return (None, None, None if t_sink is not None else g_arena) + (
+            (None,) * len(flat) if w_sunk else tuple(gflat))
+
+
+def density_normals_bwd(mlp, p, arena, means, g_raw_grad, grad_p, grad_arena):
+    """nrc_density_normals_bwd: accumulate d/d theta <g_raw_grad, d raw / d means> into `grad_p` (a parameter-
+    shaped tree of gradient buffers; only the three kernels receive anything) and `grad_arena`."""
+    enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)), mlp.grid.tables(mlp.grid.views(grad_arena)))
+    desc = _mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals)
+    gd = _grad_desc(mlp, grad_p)
+    P = means.shape[0]
+    _lib.call("nrc_density_normals_bwd", _lib.stream_ptr(), C.byref(enc), C.byref(desc), _lib.ptr(means),
+              _lib.ptr(g_raw_grad), P, float(mlp.warp_c), C.byref(gd))
+
+
 class DensityMLP:
     """BaseDensityMLP/DensityMLP (internal/geometry.py:36-593) as configured by
     configs/ngp_yobo.gin:137-140,206-230: depth 2, width 64, ReLU, safe_exp activation,
@@ -241,6 +288,13 @@ class DensityMLP:
         if arena is None:
             raise ValueError("the fused training path needs the level tables in one arena")
         return _DensityQueryFn.apply(self, means, bool(want_feat), arena, *self._flatten(p))
+
+    def raw_grad_density(self, p, means):
+        """d raw / d means with the second-order parameter VJP attached (internal/geometry.py:442-460)."""
+        arena = p["density_grid"].get("_arena")
+        if arena is None:
+            raise ValueError("the fused training path needs the level tables in one arena")
+        return _RawGradFn.apply(self, means, arena, *self._flatten(p))
 
     def chain_spec(self):
         """The density stack as a tensor-core chain: two 64-wide ReLU layers, density (+ predicted-normal) head."""

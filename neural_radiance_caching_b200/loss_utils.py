@@ -54,3 +54,66 @@ def spline_interlevel_loss(ray_history, *, mults=(0.01, 0.01), blurs=(0.03, 0.00
     w = ray_history[-1]["weights"].detach()
     return [_InterlevelLossFn.apply(c, w, h["sdist"].detach(), h["weights"], blur, mult, eps)
             for mult, blur, h in zip(mults, blurs, ray_history[:-1])]
+
+
+# ------------------------------------------------------------------ geometry / mask losses
+class _GeometryLossFn(torch.autograd.Function):
+    """orientation + predicted-normal (+ reverse) losses of the final sampler level in one pass
+    (internal/train_utils.py:3255-3311, internal/loss_utils.py:127-199): nrc_geometry_losses."""
+
+    @staticmethod
+    def forward(ctx, weights, normals, normals_pred, viewdirs, mult_o, mult_p, mult_r, sg_w):
+        R, n = weights.shape
+        dev = weights.device
+        loss = torch.zeros((), device=dev, dtype=torch.float32)
+        g_w = torch.zeros((R, n), device=dev, dtype=torch.float32)
+        g_np = torch.zeros((R, n, 3), device=dev, dtype=torch.float32)
+        g_n = torch.empty((R, n, 3), device=dev, dtype=torch.float32)
+        _lib.call("nrc_geometry_losses", _lib.stream_ptr(), _lib.ptr(weights.contiguous()), _lib.ptr(normals.contiguous()),
+                  _lib.ptr(normals_pred.contiguous()), _lib.ptr(viewdirs.contiguous()), R, n, float(mult_o), float(mult_p),
+                  float(mult_r), float(sg_w), _lib.ptr(loss), _lib.ptr(g_w), _lib.ptr(g_np), _lib.ptr(g_n))
+        ctx.save_for_backward(g_w, g_n, g_np)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        g_w, g_n, g_np = ctx.saved_tensors
+        return g_w * g, g_n * g, g_np * g, None, None, None, None, None
+
+
+def geometry_losses(rays, geometry, orientation_mult=0.01, predicted_normal_mult=0.001,
+                    predicted_normal_reverse_mult=0.01, stopgrad_weight=0.1):
+    """_compute_geometry_losses as configured by configs/nerf_ngp_yobo_lego.gin:7-11 at train_frac = 1: the sum of
+    the orientation loss (target 'normals_pred'), the predicted-normal loss (pred = the analytic normals: second-
+    order path) and its reverse."""
+    return [_GeometryLossFn.apply(geometry["weights"], geometry["normals"], geometry["normals_pred"], rays["viewdirs"],
+                                  orientation_mult, predicted_normal_mult, predicted_normal_reverse_mult, stopgrad_weight)]
+
+
+class _MaskLossFn(torch.autograd.Function):
+    """compute_mask_loss (internal/train_utils.py:785-836): nrc_mask_loss."""
+
+    @staticmethod
+    def forward(ctx, acc, masks, charb_padding, opaque_w, empty_w):
+        R = acc.shape[0]
+        loss = torch.zeros((), device=acc.device, dtype=torch.float32)
+        g_acc = torch.empty((R,), device=acc.device, dtype=torch.float32)
+        _lib.call("nrc_mask_loss", _lib.stream_ptr(), _lib.ptr(acc.contiguous()), 0,
+                  _lib.ptr(masks.reshape(R).contiguous()) if masks is not None else None, R, float(charb_padding),
+                  float(opaque_w), float(empty_w), _lib.ptr(loss), _lib.ptr(g_acc))
+        ctx.save_for_backward(g_acc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (g_acc,) = ctx.saved_tensors
+        return g_acc * g, None, None, None, None
+
+
+def compute_mask_loss(acc, masks=None, charb_padding=0.001, opaque_loss_weight=1.0, empty_loss_weight=1.0,
+                      backward=False):
+    """`backward=True`: the backward-mask call (train_utils.py:2929-2945): zero masks, opaque part off."""
+    if backward:
+        masks = torch.zeros_like(acc) if masks is None else masks
+        return _MaskLossFn.apply(acc, masks, charb_padding, 0.0, empty_loss_weight)
+    return _MaskLossFn.apply(acc, masks, charb_padding, opaque_loss_weight, empty_loss_weight)

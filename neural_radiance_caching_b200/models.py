@@ -72,6 +72,12 @@ class NeRFModel:
         return {"Sampler": self.sampler.from_oracle(params["Sampler"], device),
                 "Shader": self.shader.from_oracle(params["Shader"], device)}
 
+    def weights_only(self, params, rays, u01, train=True):
+        """The weights_only pass (models.py:1265ff, passes=('cache',), weights_only=True): sampler only, returns
+        the accumulation acc = sum of the final level's weights [R]."""
+        hist = self.sampler(params["Sampler"], rays, u01, train=train, use_raydist_fn=False, weights_only=True)
+        return hist[-1]["weights"].sum(dim=-1)
+
     def __call__(self, params, rays, u01, gumbel=None, train=False, is_secondary=False, resample=False,
                  extras=False, sdist_override=None):
         hist = self.sampler(params["Sampler"], rays, u01, train=train, use_raydist_fn=is_secondary,

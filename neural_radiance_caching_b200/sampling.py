@@ -102,7 +102,7 @@ class ProposalVolumeSampler:
         return tdist, means
 
     def __call__(self, params, rays, u01_per_level, train_frac=1.0, train=False, use_raydist_fn=False,
-                 normals_all_levels=False, sdist_override=None):
+                 normals_all_levels=False, sdist_override=None, weights_only=False):
         """rays: dict of contiguous CUDA tensors origins/directions/viewdirs [R,3], near/far [R,1].
 
         `sdist_override` (list of per-level [R,n+1] tensors, test aid): use these fenceposts
@@ -128,6 +128,7 @@ class ProposalVolumeSampler:
                     sdist = sdist_override[i_level].contiguous()
                 tdist, means = self._cast(sdist, rays, use_raydist_fn)
             want_normals = (normals_all_levels or not mlp.normals_for_filter_only) and not mlp.disable_density_normals
+            want_normals = want_normals and not weights_only   # weights_only pass (models.py:1265ff): densities only
             res = {}
             if not train:
                 with torch.no_grad():
@@ -137,17 +138,15 @@ class ProposalVolumeSampler:
                            raw_grad_density=q["raw_grad_density"], grad_pred=q["grad_pred"])
             else:
                 last = i_level == len(self.sampling_strategy) - 1
-                density, feat, gp = mlp.query_train(p, means, want_feat=last or normals_all_levels)
+                density, feat, gp = mlp.query_train(p, means, want_feat=(last or normals_all_levels) and not weights_only)
                 res.update(feature=feat, density=density, raw_density=None, grad_pred=gp, raw_grad_density=None)
-                if want_normals:
-                    with torch.no_grad():
-                        res["raw_grad_density"] = mlp.query(p, means, want_feat=False, want_normals=True)[
-                            "raw_grad_density"]
+                if want_normals:   # analytic raw gradient with its parameter VJP (second-order path, 8f-1)
+                    res["raw_grad_density"] = mlp.raw_grad_density(p, means)
             if res.get("raw_grad_density") is not None and want_normals:
                 res["normals"] = _NormalsFn.apply(res["raw_grad_density"])
             else:
                 res["normals"] = None
-            if mlp.enable_pred_normals:
+            if mlp.enable_pred_normals and not weights_only:
                 res["normals_pred"] = _NormalsFn.apply(res["grad_pred"])
                 res["normals_to_use"] = res["normals_pred"]
             else:

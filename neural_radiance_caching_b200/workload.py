@@ -23,6 +23,39 @@ def make_rays_np(g, R, near=2.0, far=6.0, radius=4.0, radii=5e-4):
                 near=np.full((R, 1), near, np.float32), far=np.full((R, 1), far, np.float32))
 
 
+SHADOW_NEAR_MAX = 0.2        # Config.shadow_near_max (internal/configs.py:635)
+SECONDARY_NORMAL_EPS = 1e-2  # Config.secondary_normal_eps (internal/configs.py:643)
+SECONDARY_FAR = 2.0          # Config.secondary_far (configs/nerf_ngp_yobo.gin:19)
+
+
+def backward_mask_rays_np(g, rays_np):
+    """Extra rays of the backward-mask loss (_compute_backward_mask_loss, internal/train_utils.py:3348-3401): one
+    uniform-hemisphere direction (UniformHemisphereSampler, render_utils.py:387-414) around the normal `-look` at
+    `origins + look * shadow_near_max`, origin lifted by normal_eps along the normal, near = shadow_near_max,
+    far = secondary_far, radii = 1.  The synthetic batches have no camera, so the per-ray view direction stands
+    in for `rays.look`.  They depend on the batch and on random draws only (no parameters): like `u01`, they are
+    generated with the batch and travel in the same packed host buffer."""
+    R = rays_np["origins"].shape[0]
+    look = rays_np["viewdirs"].astype(np.float64)
+    normal = -look
+    means = rays_np["origins"].astype(np.float64) + look * SHADOW_NEAR_MAX
+    u1, u2 = g.uniform(size=(R, 1)), g.uniform(size=(R, 1))
+    phi = u2 * 2.0 * np.pi - np.pi
+    sin_t = np.sqrt((2.0 - u1) * u1)
+    local = np.concatenate([sin_t * np.cos(phi), sin_t * np.sin(phi), 1.0 - u1], axis=-1)
+    # frame with new_z = normal (render_utils.py:145-168)
+    up = np.where(np.abs(normal[:, 2:3]) < 0.9, np.array([[0.0, 0.0, 1.0]]), np.array([[0.0, 1.0, 0.0]]))
+    new_x = np.cross(up, normal)
+    new_x /= np.linalg.norm(new_x, axis=-1, keepdims=True) + 1e-10
+    new_y = np.cross(normal, new_x)
+    new_y /= np.linalg.norm(new_y, axis=-1, keepdims=True) + 1e-10
+    d = local[:, 0:1] * new_x + local[:, 1:2] * new_y + local[:, 2:3] * normal
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return dict(origins=f(means + normal * SECONDARY_NORMAL_EPS), directions=f(d), viewdirs=f(d),
+                radii=np.ones((R, 1), np.float32), near=np.full((R, 1), SHADOW_NEAR_MAX, np.float32),
+                far=np.full((R, 1), SECONDARY_FAR, np.float32))
+
+
 _RAY_FIELDS = (("origins", 3), ("directions", 3), ("viewdirs", 3), ("radii", 1), ("near", 1), ("far", 1))
 
 
@@ -52,6 +85,22 @@ def unpack_rays(buf, extra_cols=3):
     return rays, u01, extra
 
 
+def pack_batch(rays_np, u01_np, target, extra_rays_np, u01x_np):
+    """Packed host buffer of one config-2 batch: pack_rays(main rays, u01, target) followed by
+    pack_rays(backward-mask rays, their u01)."""
+    return np.concatenate([pack_rays(rays_np, u01_np, target), pack_rays(extra_rays_np, u01x_np)])
+
+
+def unpack_batch(buf, target_cols=3):
+    """Views into a pack_batch buffer: (rays, u01, target, (extra_rays, u01x))."""
+    per_ray = sum(c for _, c in _RAY_FIELDS)
+    cols_main, cols_extra = per_ray + 3 + target_cols, per_ray + 3
+    R = buf.numel() // (cols_main + cols_extra)
+    rays, u01, target = unpack_rays(buf[:R * cols_main], target_cols)
+    xrays, u01x, _ = unpack_rays(buf[R * cols_main:], 0)
+    return rays, u01, target, (xrays, u01x)
+
+
 def linear_to_srgb(linear):
     """image.linear_to_srgb (internal/image.py:192-200)."""
     eps = float(np.finfo(np.float32).eps)
@@ -64,21 +113,39 @@ INTERLEVEL_MULTS = (0.01, 0.01)     # configs/ngp_yobo.gin:246
 INTERLEVEL_BLURS = (0.03, 0.003)    # configs/ngp_yobo.gin:247
 
 
-def cache_loss(result, target_rgb, charb_padding=0.001, interlevel_fn=None):
-    """Cache-stage objective of the benchmark step: Charbonnier data term on the sRGB-mapped render
-    (MaterialModel.cache_loss='charb', cache_linear_to_srgb=True, configs/ngp_yobo.gin:35-37;
-    internal/configs.py:330) + the spline interlevel loss supervising the two proposal levels
-    (Config.use_spline_interlevel_loss, mults (0.01, 0.01), blurs (0.03, 0.003), configs/ngp_yobo.gin:245-247;
-    internal/loss_utils.py:74-108).  `interlevel_fn(ray_history, mults=, blurs=)` is the CUDA mirror
-    (loss_utils.spline_interlevel_loss) on the device and the oracle's restatement in the CPU leg.  The
-    geometry losses (orientation / predicted normals) are SURVEY 8f rank 1."""
+GEOMETRY_MULTS = (0.01, 0.001, 0.01)   # orientation, predicted normals, reverse (configs/nerf_ngp_yobo_lego.gin:7-11)
+PREDICTED_NORMAL_STOPGRAD_WEIGHT = 0.1  # configs/nerf_ngp_yobo.gin:60
+MASK_WEIGHTS = (1.0, 1.0)              # opaque_loss_weight, empty_loss_weight (configs/nerf_ngp_yobo.gin:367-368)
+BACKWARD_MASK_WEIGHT = 0.1             # configs/nerf_ngp_yobo.gin:375
+
+
+def cache_loss(result, target_rgb, charb_padding=0.001, interlevel_fn=None, rays=None, extra_acc=None, lib=None):
+    """Cache-stage objective of the config-2 step (internal/train_utils.py:2880-2950):
+      data   Charbonnier on the sRGB-mapped render (cache_loss='charb', cache_linear_to_srgb=True,
+             configs/ngp_yobo.gin:35-37; internal/configs.py:330)
+      sampler  spline interlevel loss on the two proposal levels (mults (0.01, 0.01), blurs (0.03, 0.003),
+             configs/ngp_yobo.gin:245-247; internal/loss_utils.py:74-108)
+      geometry (when `rays` is given) orientation + predicted-normal + reverse losses on the final level
+             (train_utils.py:3255-3311), the middle one through the analytic normals' second-order path
+      mask   compute_mask_loss on the accumulation (masks == 1 for the synthetic batches), and, when `extra_acc`
+             (accumulation of the backward-mask rays' weights_only pass) is given, the backward-mask term.
+    `lib` supplies spline_interlevel_loss / geometry_losses / compute_mask_loss: this package's CUDA mirrors by
+    default, the oracle's restatement in the CPU legs."""
+    if lib is None:
+        from . import loss_utils as lib
     rgb = linear_to_srgb(result["render"]["rgb"])
     loss = torch.sqrt((rgb - target_rgb) ** 2 + charb_padding**2).mean()
     if interlevel_fn is None:
-        from . import loss_utils
-        interlevel_fn = loss_utils.spline_interlevel_loss
+        interlevel_fn = lib.spline_interlevel_loss
     for l in interlevel_fn(result["sampler"], mults=INTERLEVEL_MULTS, blurs=INTERLEVEL_BLURS):
         loss = loss + l
+    if rays is not None:
+        for l in lib.geometry_losses(rays, result["sampler"][-1], *GEOMETRY_MULTS, PREDICTED_NORMAL_STOPGRAD_WEIGHT):
+            loss = loss + l
+        loss = loss + lib.compute_mask_loss(result["render"]["acc"], None, charb_padding, *MASK_WEIGHTS)
+    if extra_acc is not None:
+        loss = loss + lib.compute_mask_loss(extra_acc, None, charb_padding, empty_loss_weight=BACKWARD_MASK_WEIGHT,
+                                            backward=True)
     return loss
 
 
@@ -166,28 +233,30 @@ class CacheTrainStep:
     def zero_grad(self):
         self.flat_grad.zero_()
 
-    def step(self, rays, u01, target_rgb):
+    def step(self, rays, u01, target_rgb, extra=None):
         """Forward + loss + backward of one ray batch; returns the loss (device scalar).  The bf16
         variant runs the hand-ordered launch schedule of engine.FusedCacheStep (same kernels, no
-        elementwise glue); the fp32 parity variant goes through the autograd mirrors."""
+        elementwise glue); the fp32 parity variant goes through the autograd mirrors.
+        `extra` = (backward-mask rays, their u01): see backward_mask_rays_np."""
         if self.engine is not None:
             self.zero_grad()
-            return self.engine.step(rays, u01, target_rgb)
-        return self.step_autograd(rays, u01, target_rgb)
+            return self.engine.step(rays, u01, target_rgb, extra=extra)
+        return self.step_autograd(rays, u01, target_rgb, extra)
 
-    def step_front(self, rays, u01, target_rgb):
+    def step_front(self, rays, u01, target_rgb, extra=None):
         """First half of step() (forward, loss, shader backward); see engine.FusedCacheStep.step_front."""
         self.zero_grad()
-        return self.engine.step_front(rays, u01, target_rgb)
+        return self.engine.step_front(rays, u01, target_rgb, extra=extra)
 
     def step_back(self, state):
         self.engine.step_back(state)
         return state["loss"]
 
-    def step_autograd(self, rays, u01, target_rgb):
+    def step_autograd(self, rays, u01, target_rgb, extra=None):
         self.zero_grad()
         res = self.model(self.params, rays, u01, train=True)
-        loss = cache_loss(res, target_rgb)
+        extra_acc = self.model.weights_only(self.params, extra[0], extra[1]) if extra is not None else None
+        loss = cache_loss(res, target_rgb, rays=rays, extra_acc=extra_acc)
         loss.backward()
         return loss.detach()
 

@@ -75,3 +75,71 @@ def spline_interlevel_loss(ray_history, mults=(0.01, 0.01), blurs=(0.03, 0.003),
         wp = h["weights"]
         out.append(mult * torch.mean(torch.clamp(w_blur - wp, min=0) ** 2 / (wp + eps)))
     return out
+
+
+# ------------------------------------------------------------------ geometry / mask losses
+def stopgrad_with_weight(x, weight):
+    """internal/utils.py:87-95."""
+    if weight is None or weight == 1.0:
+        return x
+    if weight == 0.0:
+        return x.detach()
+    return (x - x.detach()) * weight + x.detach()
+
+
+def orientation_loss(rays, ray_results, target="normals", mult=1.0, normalize=False, stopgrad=False):
+    """internal/loss_utils.py:127-166 (lossmult == 1)."""
+    w = ray_results["weights"]
+    if normalize:
+        w = w / torch.sum(w, dim=-1, keepdim=True)
+    if stopgrad:
+        w = w.detach()
+    n = torch.nan_to_num(ray_results[target])
+    v = -rays["viewdirs"]
+    n_dot_v = (n * v[..., None, :]).sum(dim=-1)
+    loss = torch.mean(torch.abs(torch.abs(w * torch.clamp(n_dot_v, max=0.0) ** 2).sum(dim=-1) + 1e-5))
+    return loss * mult
+
+
+def predicted_normal_loss(ray_results, beta, mult=1.0, gt="normals", pred="normals_pred", normalize=False,
+                          stopgrad=False, stopgrad_weight=1.0):
+    """internal/loss_utils.py:169-199 (lossmult == 1)."""
+    w = ray_results["weights"]
+    if normalize:
+        w = w / (torch.sum(w, dim=-1, keepdim=True) + 1e-8)
+    w = w.detach() if stopgrad else stopgrad_with_weight(w, stopgrad_weight)
+    n = torch.nan_to_num(ray_results[gt]).detach()
+    n_pred = torch.nan_to_num(ray_results[pred])
+    loss = torch.mean(torch.abs(
+        (torch.abs(w * (1.0 - torch.sum(n * n_pred, dim=-1))) * beta[..., 0]).sum(dim=-1, keepdim=True) + 1e-5))
+    return loss * mult
+
+
+def geometry_losses(rays, geometry, orientation_mult=0.01, predicted_normal_mult=0.001,
+                    predicted_normal_reverse_mult=0.01, stopgrad_weight=0.1):
+    """_compute_geometry_losses (internal/train_utils.py:3255-3311) as configured by
+    configs/nerf_ngp_yobo_lego.gin:7-11 + configs/nerf_ngp_yobo.gin:59-72 at train_frac = 1 (ease / decay
+    factors 1): orientation on 'normals_pred'; predicted normals with gt='normals_pred', pred='normals'
+    (train_utils.py:1049-1070); reverse with gt='normals', pred='normals_pred', stopgrad (:1073-1093)."""
+    beta = torch.ones_like(geometry["normals"][..., :1])
+    return [
+        orientation_loss(rays, geometry, target="normals_pred", mult=orientation_mult),
+        predicted_normal_loss(geometry, beta, mult=predicted_normal_mult, gt="normals_pred", pred="normals",
+                              stopgrad=False, stopgrad_weight=stopgrad_weight),
+        predicted_normal_loss(geometry, beta, mult=predicted_normal_reverse_mult, gt="normals", pred="normals_pred",
+                              stopgrad=True),
+    ]
+
+
+def compute_mask_loss(acc, masks=None, charb_padding=0.001, opaque_loss_weight=1.0, empty_loss_weight=1.0,
+                      backward=False):
+    """compute_mask_loss (internal/train_utils.py:785-836), lossmult == 1, schedule factors 1.  `backward=True` is
+    the backward-mask call (:2929-2945): zero masks, opaque part off, empty part weighted by `empty_loss_weight`."""
+    if masks is None:
+        masks = torch.ones_like(acc)[..., None]
+    data_loss = torch.sqrt((acc[..., None] - masks) ** 2 + charb_padding**2)
+    if backward:
+        data_loss = torch.where(masks > 0.5, data_loss * 0.0, data_loss * empty_loss_weight)
+    else:
+        data_loss = torch.where(masks > 0.5, data_loss * opaque_loss_weight, data_loss * empty_loss_weight)
+    return torch.mean(data_loss)

@@ -33,8 +33,14 @@ class NeRFModel:
         return {"Sampler": self.sampler.init(gen, table_init_range, bias_range),
                 "Shader": self.shader.init(gen, table_init_range)}
 
-    def __call__(self, params, rays, u01, gumbel=None, is_secondary=False, resample=False, extras=False):
-        hist = self.sampler(params["Sampler"], rays, u01, use_raydist_fn=is_secondary)
+    def weights_only(self, params, rays, u01):
+        """weights_only pass (internal/models.py:1265ff): sampler only -> acc [R]."""
+        hist = self.sampler(params["Sampler"], rays, u01, use_raydist_fn=False, weights_only=True)
+        return hist[-1]["weights"].sum(dim=-1)
+
+    def __call__(self, params, rays, u01, gumbel=None, is_secondary=False, resample=False, extras=False,
+                 create_graph=False):
+        hist = self.sampler(params["Sampler"], rays, u01, use_raydist_fn=is_secondary, create_graph=create_graph)
         last = hist[-1]
         take = lambda x, inds: torch.gather(x, 1, inds[..., None].expand(inds.shape + (x.shape[-1],)))
         if resample:

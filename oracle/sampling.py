@@ -64,7 +64,7 @@ class ProposalVolumeSampler:
         return self.anneal_clip
 
     def __call__(self, params, rays, u01_per_level, train_frac=1.0, use_raydist_fn=False, normals_all_levels=False,
-                 create_graph=False):
+                 create_graph=False, weights_only=False):
         """internal/sampling.py:142-649.
 
         rays: dict(origins[R,3], directions[R,3], viewdirs[R,3], radii[R,1], near[R,1], far[R,1]).
@@ -91,7 +91,7 @@ class ProposalVolumeSampler:
             means, covs = render.cast_rays(
                 tdist, rays["origins"], rays["directions"], rays["radii"], "cone", diag=False
             )  # :361-368
-            want_normals = normals_all_levels or not mlp.normals_for_filter_only
+            want_normals = (normals_all_levels or not mlp.normals_for_filter_only) and not weights_only
             saved = mlp.disable_density_normals
             if not want_normals:
                 # levels 0-1 compute and immediately discard the analytic normals

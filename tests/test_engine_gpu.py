@@ -20,14 +20,30 @@ def _batch(dev, R, seed_offset=0):
     return workload.unpack_rays(buf)
 
 
-@pytest.mark.parametrize("R", [256, 1000])
-def test_fused_step_matches_autograd(cuda_device, R):
+def _full_batch(dev, R, seed_offset=0):
+    """Main rays + the backward-mask rays, through the packed batch buffer the bench uses."""
+    g = np.random.Generator(np.random.PCG64(workload.SEED + 7 + seed_offset))
+    rn = workload.make_rays_np(g, R)
+    u = [g.uniform(size=(R, 1)).astype(np.float32) for _ in range(3)]
+    tgt = g.uniform(size=(R, 3)).astype(np.float32)
+    xr = workload.backward_mask_rays_np(g, rn)
+    ux = [g.uniform(size=(R, 1)).astype(np.float32) for _ in range(3)]
+    buf = torch.from_numpy(workload.pack_batch(rn, u, tgt, xr, ux)).to(dev)
+    return workload.unpack_batch(buf)
+
+
+@pytest.mark.parametrize("R,with_extra", [(256, True), (1000, True), (512, False)])
+def test_fused_step_matches_autograd(cuda_device, R, with_extra):
+    """The whole config-2 objective: data + interlevel + geometry (incl. the second-order path) + mask
+    (+ backward-mask pass on the extra rays)."""
     step = workload.CacheTrainStep(cuda_device, bf16=True)
     assert step.engine is not None
-    rays, u01, tgt = _batch(cuda_device, R)
-    loss_a = float(step.step_autograd(rays, u01, tgt))
+    rays, u01, tgt, extra = _full_batch(cuda_device, R)
+    if not with_extra:
+        extra = None
+    loss_a = float(step.step_autograd(rays, u01, tgt, extra))
     grad_a = step.flat_grad.clone()
-    loss_f = float(step.step(rays, u01, tgt))
+    loss_f = float(step.step(rays, u01, tgt, extra))
     grad_f = step.flat_grad.clone()
     assert abs(loss_f - loss_a) <= 1e-5 * max(1.0, abs(loss_a))
     assert float(grad_a.abs().max()) > 0
