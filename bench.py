@@ -136,12 +136,17 @@ def cpu_reference_throughput(rays, steps, warmup, threads=None):
     rt = {k: torch.from_numpy(v) for k, v in rn.items()}
     u = [torch.from_numpy(g.uniform(size=(rays, 1)).astype(np.float32)) for _ in range(3)]
     target = torch.from_numpy(g.uniform(size=(rays, 3)).astype(np.float32))
+    xt = {k: torch.from_numpy(v) for k, v in workload.backward_mask_rays_np(g, rn).items()}
+    ux = [torch.from_numpy(g.uniform(size=(rays, 1)).astype(np.float32)) for _ in range(3)]
 
     def step():
+        # the same objective as the CUDA arm: data + interlevel + geometry losses (analytic normals with
+        # create_graph: second-order path) + mask + the backward-mask weights_only pass on the extra rays
         for t in leaves:
             t.grad = None
-        res = model(params, rt, u)
-        loss = workload.cache_loss(res, target, interlevel_fn=oloss.spline_interlevel_loss)
+        res = model(params, rt, u, create_graph=True)
+        extra_acc = model.weights_only(params, xt, ux)
+        loss = workload.cache_loss(res, target, rays=rt, extra_acc=extra_acc, lib=oloss)
         loss.backward()
         return float(loss.detach())
 
@@ -176,8 +181,9 @@ def run_reference(args):
 
 WORKLOAD = ("config2 nerf_ngp_yobo_lego cache training step: proposal sampler (64,64,32) hash-grid + density MLP, "
             "cache shader (appearance grid + bottleneck/heads/int-BRDF/IDE SurfaceLightField/EnvMap MLPs) on the "
-            "32 final samples, volumetric rendering, Charbonnier-sRGB data loss + spline interlevel loss on both proposal "
-            "levels, fwd+bwd (grads for 4 grids + all MLPs)")
+            "32 final samples, volumetric rendering; losses: Charbonnier-sRGB data, spline interlevel on both proposal "
+            "levels, orientation + predicted-normal + reverse (analytic normals, second-order path), mask, and the "
+            "backward-mask weights_only pass on one extra ray per training ray; fwd+bwd (grads for 4 grids + all MLPs)")
 
 
 # ----------------------------------------------------------------------------- b200 arm
@@ -207,7 +213,9 @@ def run_b200(args):
         rn = workload.make_rays_np(g, R)
         u = [g.uniform(size=(R, 1)).astype(np.float32) for _ in range(3)]
         tgt = g.uniform(size=(R, 3)).astype(np.float32)
-        host.append(torch.from_numpy(workload.pack_rays(rn, u, tgt)).pin_memory())
+        xr = workload.backward_mask_rays_np(g, rn)     # extra rays of the backward-mask loss + their jitter draws
+        ux = [g.uniform(size=(R, 1)).astype(np.float32) for _ in range(3)]
+        host.append(torch.from_numpy(workload.pack_batch(rn, u, tgt, xr, ux)).pin_memory())
     dbuf = torch.empty_like(host[0], device=dev)
     dbuf.copy_(host[0])
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
@@ -220,8 +228,8 @@ def run_b200(args):
         ndist.allreduce_mean_(step_obj.flat_grad)
 
     def compute_step():
-        rays, u01, extra = workload.unpack_rays(dbuf)
-        return step_obj.step(rays, u01, extra)
+        rays, u01, target, extra = workload.unpack_batch(dbuf)
+        return step_obj.step(rays, u01, target, extra)
 
     def one_step():
         loss = compute_step()
@@ -269,8 +277,8 @@ def run_b200(args):
         # stream and overlaps the second graph (the sampler's backward); the Sampler half follows.
         graph_b = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            rays_, u01_, extra_ = workload.unpack_rays(dbuf)
-            state = step_obj.step_front(rays_, u01_, extra_)
+            rays_, u01_, target_, extra_ = workload.unpack_batch(dbuf)
+            state = step_obj.step_front(rays_, u01_, target_, extra_)
         with torch.cuda.graph(graph_b, pool=graph.pool()):
             static_loss = step_obj.step_back(state)
         comm = torch.cuda.Stream()
@@ -358,6 +366,7 @@ def run_b200(args):
         "dtype": "bf16" if args.bf16 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": R, "samples_per_ray": [64, 64, 32],
                    "shaded_points_per_ray": 32,
+                   "backward_mask_rays_per_step": R,   # 160 more density samples each; NOT counted in `value`
                    "precision": ("MLP operands bf16 on tcgen05 tensor cores with fp32 accumulation (north-star bf16-MLP "
                                  "variant, tolerance 2e-2); hash grids, gathers, scatters and ray kernels fp32")
                    if args.bf16 else "fp32 parity variant (1e-5)",

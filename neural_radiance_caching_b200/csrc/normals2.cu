@@ -22,17 +22,17 @@
 
 namespace nrc {
 
-struct Normals2Smem {
+struct Normals2Smem {      // 109 KB: two CTAs per SM
   MlpWeights w;
   float x[kMaxIn * kPad];    // e, then ge, then edot
   float b1[kW * kPad];       // h1, then a1
   float h1d[kW * kPad];      // h1dot
-  float a2[kW * kPad];       // a2
-  float h2d[kW * kPad];      // h2dot
+  uint32_t m2[2 * kT];       // M2 of every point of the tile as two bit words (a2 = M2 wd is rebuilt from it)
+  float dwd[kW];             // per-CTA partial of d wd
 };
 
 template <int F>
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 2)
 density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t m,
                            const float* __restrict__ means, const float* __restrict__ g_raw_grad, int64_t P,
                            float warp_c, const nrc_density_mlp_grad_t grads) {
@@ -43,7 +43,11 @@ density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density
   const int tid = threadIdx.x;
   const int in_dim = enc.L * F;
   const int rk = tid >> 3, cj = tid & 7;
-  float aW1[4][8], aW0[2][8], aWd = 0.f;
+  float aW1[4][8], aW0[2][8];
+  float wdc[8];              // wd[j * 8 + cj]: this thread's columns of a2 in the dW1 update
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wdc[j] = s.w.wo[4 * (j * 8 + cj)];
+  if (tid < kW) s.dwd[tid] = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -74,13 +78,16 @@ density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density
     for (int k = in_dim; k < kMaxIn; ++k) s.x[k * kPad + tid] = 0.f;
     float acc[kW];
     mlp_forward_point(s.w, in_dim, s.x + tid, kPad, s.b1 + tid, kPad, acc);
-    // a2 = M2 wd ; keep M2 in acc (as 0/1) for the tangent pass
+    // a2 = M2 wd (in acc); M2 itself goes to two bit words for the tangent pass and the dW1 update
+    uint32_t m2lo = 0u, m2hi = 0u;
 #pragma unroll
     for (int j = 0; j < kW; ++j) {
-      const float on = acc[j] > 0.f ? 1.f : 0.f;
-      acc[j] = on;
-      s.a2[j * kPad + tid] = on * s.w.wo[4 * j];
+      const bool on = acc[j] > 0.f;
+      if (on) { if (j < 32) m2lo |= 1u << j; else m2hi |= 1u << (j - 32); }
+      acc[j] = on ? s.w.wo[4 * j] : 0.f;
     }
+    s.m2[tid] = m2lo;
+    s.m2[kT + tid] = m2hi;
     // a1[k] = M1[k] sum_j W1[k][j] a2[j]   (overwrites the h1 column; M1 kept as the sign of what is stored: the
     // tangent pass needs it too, so keep it in a bit mask)
     uint32_t m1lo = 0u, m1hi = 0u;
@@ -90,8 +97,8 @@ density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density
 #pragma unroll
       for (int q = 0; q < kW / 4; ++q) {
         const float4 w = w4[q];
-        g = fmaf(w.x, s.a2[(4 * q + 0) * kPad + tid], g); g = fmaf(w.y, s.a2[(4 * q + 1) * kPad + tid], g);
-        g = fmaf(w.z, s.a2[(4 * q + 2) * kPad + tid], g); g = fmaf(w.w, s.a2[(4 * q + 3) * kPad + tid], g);
+        g = fmaf(w.x, acc[4 * q + 0], g); g = fmaf(w.y, acc[4 * q + 1], g);
+        g = fmaf(w.z, acc[4 * q + 2], g); g = fmaf(w.w, acc[4 * q + 3], g);
       }
       const bool on = s.b1[k * kPad + tid] > 0.f;
       if (on) { if (k < 32) m1lo |= 1u << k; else m1hi |= 1u << (k - 32); }
@@ -156,8 +163,15 @@ density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density
       for (int j = 0; j < kW; ++j) t[j] = 0.f;
 #pragma unroll 4
       for (int k = 0; k < kW; ++k) axpy64(t, s.h1d[k * kPad + tid], s.w.w1 + k * kW);
+      // d wd += h2dot = M2 t: reduced over the warp's 32 points, then one shared-memory atomic per warp and column
 #pragma unroll
-      for (int j = 0; j < kW; ++j) s.h2d[j * kPad + tid] = valid ? acc[j] * t[j] : 0.f;
+      for (int j = 0; j < kW; ++j) {
+        const bool on = j < 32 ? ((m2lo >> j) & 1u) : ((m2hi >> (j - 32)) & 1u);
+        float v = (valid && on) ? t[j] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) atomicAdd(&s.dwd[j], v);
+      }
     }
     __syncthreads();
     // weight gradients of this tile, reduced over its points in registers
@@ -165,8 +179,13 @@ density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density
       float a[4], b[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = s.h1d[(i * 16 + rk) * kPad + pp];
+      const uint32_t lo = s.m2[pp], hi = s.m2[kT + pp];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = s.a2[(j * 8 + cj) * kPad + pp];
+      for (int j = 0; j < 8; ++j) {
+        const int col = j * 8 + cj;
+        const bool on = col < 32 ? ((lo >> col) & 1u) : ((hi >> (col - 32)) & 1u);
+        b[j] = on ? wdc[j] : 0.f;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -180,7 +199,6 @@ density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) aW0[i][j] = fmaf(xa[i], gb[j], aW0[i][j]);
-      if (tid < kW) aWd += s.h2d[tid * kPad + pp];
     }
     __syncthreads();
   }
@@ -196,7 +214,7 @@ density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density
       for (int j = 0; j < 8; ++j) atomicAdd(grads.d_w0 + row * kW + j * 8 + cj, aW0[i][j]);
     }
   }
-  if (tid < kW) atomicAdd(grads.d_wd + tid, aWd);
+  if (tid < kW) atomicAdd(grads.d_wd + tid, s.dwd[tid]);
 }
 
 template <int F>
@@ -209,7 +227,7 @@ int32_t launch_normals2(cudaStream_t s, const EncDev& d, const nrc_density_mlp_t
     attr_set = true;
   }
   const int64_t tiles = (P + kT - 1) / kT;
-  const unsigned grid = static_cast<unsigned>(tiles < kNumSMs ? tiles : kNumSMs);
+  const unsigned grid = static_cast<unsigned>(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
   density_normals_bwd_kernel<F><<<grid, kT, sizeof(Normals2Smem), s>>>(d, *mlp, means, g, P, warp_c, grads);
   return check_launch();
 }

@@ -128,7 +128,7 @@ class FusedCacheStep:
         new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
         anneal = sampler.anneal(train_frac)
         main = torch.cuda.current_stream()
-        s_pack, s_enc, s_env, s_prop = self._streams(5)[:4] if self.concurrent else (None,) * 4
+        s_pack, s_enc, s_env, s_prop = self._streams(6)[:4] if self.concurrent else (None,) * 4
         shp = self.params["Shader"]
         names, sflat = shader.fused_params(shp)
         app_arena = shp["appearance_grid"]["_arena"]
@@ -138,7 +138,7 @@ class FusedCacheStep:
         s_x = None
         if extra is not None and fork_proposals:
             if self.concurrent:
-                s_x = self._streams(5)[4]
+                s_x = self._streams(6)[4]
                 s_x.wait_stream(main)
                 with torch.cuda.stream(s_x):
                     self._weights_only_pass(extra[0], extra[1], train_frac, loss)
@@ -279,7 +279,7 @@ class FusedCacheStep:
         x_fork = None
         if state.get("extra") is not None:      # split mode: the backward-mask pass starts here
             if self.concurrent:
-                x_fork = self._streams(5)[4]
+                x_fork = self._streams(6)[4]
                 x_fork.wait_stream(main)
                 with torch.cuda.stream(x_fork):
                     self._weights_only_pass(state["extra"][0], state["extra"][1], state["train_frac"], state["loss"])
@@ -289,16 +289,28 @@ class FusedCacheStep:
             x_fork = state["extra_stream"]
         g_gp = torch.empty((P2, 3), device=dev, dtype=torch.float32)
         _lib.call("nrc_normals_bwd", _lib.stream_ptr(), _lib.ptr(L2["gp"]), _lib.ptr(state["g_nrm"]), P2, _lib.ptr(g_gp))
+        n2_fork = None
         if state.get("g_rg") is not None:
-            # second-order path of the predicted-normal loss: d/d theta <g_rg, d raw / d means> (nrc_density_normals_bwd)
-            mlp = L2["mlp"]
-            sinks = [_lib.grad_sink(t) for t in L2["flat"]]
-            t_sink = _lib.grad_sink(L2["arena"])
-            geometry.density_normals_bwd(mlp, L2["p"], L2["arena"], L2["means"].reshape(P2, 3), state["g_rg"],
-                                         mlp._unflatten(sinks), t_sink)
+            # second-order path of the predicted-normal loss: d/d theta <g_rg, d raw / d means>
+            # (nrc_density_normals_bwd); independent of the level's first-order backward: its own stream
+            def second_order():
+                mlp = L2["mlp"]
+                sinks = [_lib.grad_sink(t) for t in L2["flat"]]
+                t_sink = _lib.grad_sink(L2["arena"])
+                geometry.density_normals_bwd(mlp, L2["p"], L2["arena"], L2["means"].reshape(P2, 3), state["g_rg"],
+                                             mlp._unflatten(sinks), t_sink)
+            if self.concurrent:
+                n2_fork = self._streams(6)[5]
+                n2_fork.wait_stream(main)
+                with torch.cuda.stream(n2_fork):
+                    second_order()
+            else:
+                second_order()
         self._level_backward(L2, rays, g_w[nl - 1], state["d_feat"], g_gp if L2["gp"] is not None else None, R)
         if x_fork is not None:
             main.wait_stream(x_fork)
+        if n2_fork is not None:
+            main.wait_stream(n2_fork)
         if s_prop is not None:
             main.wait_stream(s_prop)
         elif own_fork is not None:
