@@ -39,8 +39,13 @@ def test_cache_model_forward(cuda_device, secondary):
         assert rel_err(got["render"][k], v) <= tol, (k, rel_err(got["render"][k], v))
 
 
-def test_cache_model_training_gradients(cuda_device):
-    """d loss / d params of the full cache step (tables of all 4 grids + every used MLP weight)."""
+@pytest.mark.parametrize("objective", ["simple", "config2"])
+def test_cache_model_training_gradients(cuda_device, objective):
+    """d loss / d params of the full cache step (tables of all 4 grids + every used MLP weight).  'config2' is the
+    benchmark's objective (workload.cache_loss: data + spline interlevel + geometry losses through the analytic
+    normals' second-order path + mask) against the same objective on the oracle with create_graph=True."""
+    from oracle import loss_utils as oloss
+    from neural_radiance_caching_b200 import workload
     g = gen(410)
     R = 96
     o, n = omodels.NeRFModel(), nmodels.NeRFModel()
@@ -61,7 +66,9 @@ def test_cache_model_training_gradients(cuda_device):
                 out.append((prefix + k, p, k))
         return out
 
-    def loss_fn(res, tgt):
+    def loss_fn(res, tgt, rays_, lib=None):
+        if objective == "config2":
+            return workload.cache_loss(res, tgt, rays=rays_, lib=lib)
         l = torch.sqrt((res["render"]["rgb"] - tgt) ** 2 + 1e-6).mean()
         for h in res["sampler"][:-1]:
             l = l + 0.01 * ((h["weights"].sum(-1) - res["sampler"][-1]["weights"].sum(-1).detach()) ** 2).mean()
@@ -70,8 +77,9 @@ def test_cache_model_training_gradients(cuda_device):
     lo = leaves(po)
     for _, d, k in lo:
         d[k] = d[k].clone().requires_grad_(True)
-    ro = o(po, rays, u)
-    loss_fn(ro, target).backward()
+    ro = o(po, rays, u, create_graph=objective == "config2")
+    loss_o = loss_fn(ro, target, rays, oloss)
+    loss_o.backward()
     override = [h["sdist"].to(cuda_device) for h in ro["sampler"]]
 
     arenas = {}
@@ -87,8 +95,11 @@ def test_cache_model_training_gradients(cuda_device):
     for name, d, k in ln:
         if not any(name.startswith(pre) for pre in arenas):
             d[k] = d[k].clone().requires_grad_(True)
-    rn = n(pn, to_dev(rays, cuda_device), to_dev(u, cuda_device), train=True, sdist_override=override)
-    loss_fn(rn, target.to(cuda_device)).backward()
+    rays_d = to_dev(rays, cuda_device)
+    rn = n(pn, rays_d, to_dev(u, cuda_device), train=True, sdist_override=override)
+    loss_n = loss_fn(rn, target.to(cuda_device), rays_d)
+    loss_n.backward()
+    assert abs(float(loss_n) - float(loss_o)) <= 1e-4 * abs(float(loss_o))
     assert rel_err(rn["render"]["rgb"], ro["render"]["rgb"]) <= 1e-4
     checked = 0
     for (name, dn, kn), (_, do, ko) in zip(ln, lo):
@@ -105,3 +116,26 @@ def test_cache_model_training_gradients(cuda_device):
         assert rel_err(got, ref) <= 5e-4, (name, rel_err(got, ref))
         checked += 1
     assert checked > 40
+
+
+def test_weights_only_pass_matches_oracle(cuda_device):
+    """The backward-mask rays' weights_only pass (sampler only -> acc) against the oracle; positions are resampled
+    independently on both sides (no override), hence the looser tolerance."""
+    import numpy as np
+    from neural_radiance_caching_b200 import workload
+    g = gen(420)
+    R = 128
+    o, n = omodels.NeRFModel(), nmodels.NeRFModel()
+    po = o.init(g, table_init_range=0.1, bias_range=0.05)
+    pn = n.from_oracle(po, cuda_device)
+    rays = make_rays(g, R)
+    xr = {k: torch.from_numpy(v) for k, v in workload.backward_mask_rays_np(
+        np.random.Generator(np.random.PCG64(3)), {k: v.numpy() for k, v in rays.items()}).items()}
+    # the extra rays are unit-length, start 0.2 along the view direction and point into the hemisphere behind the camera
+    assert torch.allclose(xr["directions"].norm(dim=-1), torch.ones(R), atol=1e-5)
+    assert float((xr["directions"] * rays["viewdirs"]).sum(-1).max()) <= 1e-6
+    u = [f32(g.uniform(size=(R, 1))) for _ in range(3)]
+    with torch.no_grad():
+        want = o.weights_only(po, xr, u)
+        got = n.weights_only(pn, to_dev(xr, cuda_device), to_dev(u, cuda_device), train=False)
+    assert rel_err(got, want) <= 2e-3
