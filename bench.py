@@ -453,7 +453,9 @@ def roofline(per_kernel, R, pk, pk_kind, bf16):
     app_bwd = 32 * R * (12 + 4 * 32 + 2 * 8 * 4 * 4 * 8)
     # nrc_encode_fwd is only the appearance grid (density grids are gathered inside the fused
     # query); nrc_encode_bwd scatters into all four grids.
-    alg_bytes = {"nrc_encode_fwd": app_fwd, "nrc_encode_bwd": bwd + app_bwd, "nrc_density_query_fwd": fwd}
+    # the backward-mask pass repeats the three query levels on the extra rays and back-propagates its final level
+    bwd_extra = pts[2] * (12 + 4 * 32 + 2 * 8 * 4 * 4 * 8)
+    alg_bytes = {"nrc_encode_fwd": app_fwd, "nrc_encode_bwd": bwd + app_bwd + bwd_extra, "nrc_density_query_fwd": 2 * fwd}
     shaded = 32 * R
     alg_flops = {"nrc_chain_run": 2.0 * shaded * (2 * SHADER_MAC_FWD - SHADER_MAC_ENV),
                  "nrc_chain_wgrad": 2.0 * shaded * (SHADER_MAC_FWD - SHADER_MAC_ENV)}
