@@ -60,3 +60,37 @@ def test_alpha_weights_properties():
     assert torch.allclose(w, a * t)
     assert torch.allclose(w.sum(-1), 1 - torch.prod(1 - a.double(), -1).float(), atol=2e-6)
     assert float(t[:, 0].min()) == 1.0 and bool((t[:, 1:] <= t[:, :-1] + 1e-7).all())
+
+
+# ------------------------------------------------------------------ SURVEY 8f-1 pieces (oracle_v2.npz)
+def test_oracle_reproduces_golden_vectors_v2():
+    from tests.golden import make_golden_v2
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_v2.npz"))
+    now = make_golden_v2.build()
+    assert set(now.keys()) == set(gold.files)
+    for k in gold.files:
+        np.testing.assert_allclose(now[k], gold[k], rtol=2e-6, atol=1e-7, err_msg=k)
+
+
+def test_geometry_and_mask_loss_known_answers():
+    """Worked by hand from internal/loss_utils.py:127-199 and internal/train_utils.py:785-836."""
+    from oracle import loss_utils as oloss
+    rays = {"viewdirs": torch.tensor([[0.0, 0.0, 1.0]])}             # v = -viewdirs = (0, 0, -1)
+    n_pred = torch.tensor([[[0.0, 0.8, 0.6], [0.0, 0.0, -1.0]]])     # n.v = -0.6 (back-facing), +1 (front-facing)
+    n = torch.tensor([[[0.0, 0.6, 0.8], [0.0, 0.0, -1.0]]])
+    res = {"weights": torch.tensor([[0.5, 0.25]]), "normals": n, "normals_pred": n_pred}
+    lo = oloss.orientation_loss(rays, res, target="normals_pred", mult=0.01)
+    assert abs(float(lo) - 0.01 * (0.5 * 0.36 + 1e-5)) < 1e-9        # only the back-facing sample counts
+    beta = torch.ones(1, 2, 1)
+    lp = oloss.predicted_normal_loss(res, beta, mult=0.001, gt="normals_pred", pred="normals", stopgrad_weight=0.1)
+    assert abs(float(lp) - 0.001 * (0.5 * (1 - 0.96) + 0.0 + 1e-5)) < 1e-9   # n.n_pred = 0.48 + 0.48, and 1
+    acc = torch.tensor([1.0, 0.25])
+    lm = oloss.compute_mask_loss(acc, None, 0.001, 1.0, 1.0)
+    assert abs(float(lm) - 0.5 * (0.001 + np.sqrt(0.75**2 + 1e-6))) < 1e-7
+    lb = oloss.compute_mask_loss(acc, torch.zeros(2, 1), 0.001, empty_loss_weight=0.1, backward=True)
+    assert abs(float(lb) - 0.5 * 0.1 * (np.sqrt(1 + 1e-6) + np.sqrt(0.0625 + 1e-6))) < 1e-7
+    # stopgrad_with_weight: value unchanged, gradient scaled
+    x = torch.tensor([2.0], requires_grad=True)
+    y = oloss.stopgrad_with_weight(x, 0.1)
+    y.backward()
+    assert float(y) == 2.0 and abs(float(x.grad) - 0.1) < 1e-7

@@ -59,3 +59,50 @@ def test_ide_and_ggx(cuda_device):
     res = nru.integrate_reflect_rays("microfacet", False, material, samples, max_radiance=10000.0)
     for k in ("radiance_out", "irradiance", "indirect_occ"):
         assert rel_err(res[k], f32(GOLD["ggx_" + k])) <= 1e-5, k
+
+
+# ------------------------------------------------------------------ SURVEY 8f-1 pieces (oracle_v2.npz)
+def test_geometry_mask_losses_and_second_order_against_golden(cuda_device):
+    from oracle import geometry as ogeo
+    from neural_radiance_caching_b200 import geometry as ngeo, loss_utils as nloss
+    from tests.golden import make_golden_v2 as mg2
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_v2.npz"))
+    d = lambda k: f32(gold[k]).to(cuda_device)
+    # geometry losses
+    W, N, NP = (d(k).requires_grad_(True) for k in ("gl_w", "gl_n", "gl_np"))
+    total = sum(nloss.geometry_losses({"viewdirs": d("gl_vd")}, {"weights": W, "normals": N, "normals_pred": NP},
+                                      *mg2.MULTS, 0.1))
+    total.backward()
+    assert abs(float(total.detach()) - float(gold["gl_terms"].sum())) <= 1e-5 * float(gold["gl_terms"].sum())
+    assert rel_err(W.grad, f32(gold["gl_gw"])) <= 1e-5
+    assert rel_err(N.grad, f32(gold["gl_gn"])) <= 1e-5
+    assert rel_err(NP.grad, f32(gold["gl_gnp"])) <= 1e-5
+    # mask losses
+    A = d("ml_acc").requires_grad_(True)
+    l = nloss.compute_mask_loss(A, None, 0.001, 1.0, 1.0)
+    l.backward()
+    assert abs(float(l.detach()) - float(gold["ml_loss"])) <= 1e-5 * float(gold["ml_loss"])
+    assert rel_err(A.grad, f32(gold["ml_g"])) <= 1e-5
+    A.grad = None
+    l = nloss.compute_mask_loss(A, None, 0.001, empty_loss_weight=0.1, backward=True)
+    l.backward()
+    assert abs(float(l.detach()) - float(gold["mlb_loss"])) <= 1e-5 * float(gold["mlb_loss"])
+    assert rel_err(A.grad, f32(gold["mlb_g"])) <= 1e-5
+    # second-order path
+    o = ogeo.DensityMLP(grid_params=mg2.GRID, enable_pred_normals=True)
+    po = o.init(np.random.Generator(np.random.PCG64(mg2.SEED + 1)), table_init_range=0.5, bias_range=0.1)
+    n = ngeo.DensityMLP(grid_params=mg2.GRID, enable_pred_normals=True)
+    pn = n.from_oracle(po, cuda_device)
+    arena = pn["density_grid"]["_arena"].requires_grad_(True)
+    for k in ("density_layers_0", "density_layers_1", "output_density_layer", "pred_normals_layer"):
+        for kk in pn[k]:
+            pn[k][kk].requires_grad_(True)
+    rg = n.raw_grad_density(pn, d("so_means"))
+    assert rel_err(rg, f32(gold["so_raw_grad"])) <= 1e-5
+    (rg * d("so_G")).sum().backward()
+    for k in ("density_layers_0", "density_layers_1", "output_density_layer"):
+        assert rel_err(pn[k]["kernel"].grad, f32(gold[f"so_d_{k}"])) <= 2e-5, k
+    names = sorted(po["density_grid"].keys())
+    views = n.grid.views(arena.grad)
+    got = torch.cat([views[k].reshape(-1) for k in names])
+    assert rel_err(got, f32(gold["so_d_tables"])) <= 2e-5
