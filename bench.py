@@ -146,7 +146,8 @@ def cpu_reference_throughput(rays, steps, warmup, threads=None):
             t.grad = None
         res = model(params, rt, u, create_graph=True)
         extra_acc = model.weights_only(params, xt, ux)
-        loss = workload.cache_loss(res, target, rays=rt, extra_acc=extra_acc, lib=oloss)
+        loss = workload.cache_loss(res, target, rays=rt, extra_acc=extra_acc, lib=oloss,
+                                   reg_tables=workload.density_grid_tables(params))
         loss.backward()
         return float(loss.detach())
 
@@ -182,7 +183,8 @@ def run_reference(args):
 WORKLOAD = ("config2 nerf_ngp_yobo_lego cache training step: proposal sampler (64,64,32) hash-grid + density MLP, "
             "cache shader (appearance grid + bottleneck/heads/int-BRDF/IDE SurfaceLightField/EnvMap MLPs) on the "
             "32 final samples, volumetric rendering; losses: Charbonnier-sRGB data, spline interlevel on both proposal "
-            "levels, orientation + predicted-normal + reverse (analytic normals, second-order path), mask, and the "
+            "levels, distortion, orientation + predicted-normal + reverse (analytic normals, second-order path), mask, "
+            "density-grid parameter regularizer, and the "
             "backward-mask weights_only pass on one extra ray per training ray; fwd+bwd (grads for 4 grids + all MLPs)")
 
 

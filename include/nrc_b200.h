@@ -487,6 +487,17 @@ int32_t nrc_charb_srgb_loss(void* stream, const float* d_rgb, const float* d_tar
  * empty_weight = backward_mask_loss_weight on the accumulation of the extra rays. */
 int32_t nrc_mask_loss(void* stream, const float* d_acc, int32_t n, const float* d_mask, int64_t num_rays,
                       float charb_padding, float opaque_weight, float empty_weight, float* d_loss, float* d_g_acc);
+/* param_regularizer_loss (internal/train_utils.py:1169-1216) for one grid module with the common setting
+ * (mult, jnp.mean, alpha=2, scale=1; Config.param_regularizers, configs/nerf_ngp_yobo.gin:47-51): for every level
+ * table T of `enc`: loss += mult * 0.5 * mean(T^2), levels[l].d_grad += mult * T / numel(T) (atomic reductions: may run
+ * concurrently with nrc_encode_bwd on the same tables). */
+int32_t nrc_grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss);
+/* Distortion loss of mip-NeRF 360 on the final level (internal/loss_utils.py:108-123, internal/stepfun.py:253-269;
+ * Config.distortion_loss_target='tdist', curve_fn = math.power_ladder(p, premult), configs/ngp_yobo.gin:250-253,
+ * mult configs/nerf_ngp_yobo_lego.gin:10): d_t [R,n+1] metric fenceposts, d_weights [R,n], n <= 128.
+ * loss += mult * mean_r(...); d_g_weights [R,n] is ACCUMULATED. */
+int32_t nrc_distortion_loss(void* stream, const float* d_t, const float* d_weights, int32_t n, int64_t num_rays, float p,
+                            float premult, float mult, float* d_loss, float* d_g_weights);
 /* Geometry losses on the final sampler level (internal/train_utils.py:3255-3311, internal/loss_utils.py:127-199):
  * orientation loss on the predicted normals (orientation_loss_target='normals_pred'), predicted-normal loss
  * (gt = stop_gradient(normals_pred), pred = the analytic normals; weights through stopgrad_with_weight) and its

@@ -142,9 +142,62 @@ int32_t launch_bwd(cudaStream_t s, const EncDev& d, const float* x, const float*
   return check_launch();
 }
 
+// param_regularizer_loss (internal/train_utils.py:1169-1216) for one grid module with the common setting
+// (mult, jnp.mean, alpha = 2, scale = 1): per level table  loss += mult * 0.5 * mean(T^2),  dT += mult * T / numel.
+// blockIdx.y = level; grid-stride over the table; one atomic per block for the loss.
+__global__ void __launch_bounds__(256) grid_regularizer_kernel(const __grid_constant__ EncDev d, float mult,
+                                                                 float* __restrict__ loss) {
+  const LevelDev& lv = d.lv[blockIdx.y];
+  const size_t n = static_cast<size_t>(lv.T) * d.F;
+  const float inv_n = 1.0f / static_cast<float>(n);
+  const float* __restrict__ t = lv.table;
+  float* __restrict__ g = lv.grad;
+  float acc = 0.f;
+  const size_t n4 = n >> 2;   // tables are 16-byte aligned slices of the arena with numel % 4 == 0 in every config
+  const bool vec = ((reinterpret_cast<uintptr_t>(t) | reinterpret_cast<uintptr_t>(g)) & 15) == 0 && (n & 3) == 0;
+  if (vec) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(t) + i);
+      const float k = mult * inv_n;
+      // 16-byte reduction: commutes with the scatter kernels' atomics on the same tables, so no stream ordering
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + 4 * i), "f"(k * v.x), "f"(k * v.y),
+                   "f"(k * v.z), "f"(k * v.w)
+                   : "memory");
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const float v = __ldg(t + i);
+      atomicAdd(g + i, mult * inv_n * v);
+      acc += v * v;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int k = 0; k < 8; ++k) sum += part[k];
+    atomicAdd(loss, 0.5f * mult * inv_n * sum);
+  }
+}
+
 }  // namespace nrc
 
 using namespace nrc;
+
+extern "C" int32_t nrc_grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss) {
+  EncDev d;
+  const int32_t st = make_enc_dev(enc, d);
+  if (st != NRC_OK) return st;
+  if (!d_loss) return NRC_E_INVALID_ARG;
+  for (int l = 0; l < d.L; ++l)
+    if (!d.lv[l].grad) return NRC_E_INVALID_ARG;
+  grid_regularizer_kernel<<<dim3(2 * kNumSMs, d.L), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, mult, d_loss);
+  return check_launch();
+}
 
 extern "C" int32_t nrc_encode_fwd(void* stream, const nrc_encoding_t* enc, const float* d_x,
                                   int64_t num_points, float* d_out) {

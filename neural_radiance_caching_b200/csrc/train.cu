@@ -293,6 +293,58 @@ __global__ void mask_loss_kernel(const float* __restrict__ acc, int n, const flo
   }
 }
 
+// distortion loss (internal/loss_utils.py:108-123 over stepfun.lossfun_distortion, internal/stepfun.py:253-269) on the
+// final level, target 'tdist' through curve_fn = power_ladder(p, premult) (configs/ngp_yobo.gin:250-253):
+//   c = curve(t);  u = midpoints(c);  loss_ray = sum_i w_i sum_j w_j |u_i - u_j| + sum_i w_i^2 (c_{i+1} - c_i) / 3
+//   loss += mult * mean_r loss_ray;  g_w (ACCUMULATED) += mult / R * (2 sum_j w_j |u_i - u_j| + 2 w_i dc_i / 3).
+// One warp per ray, n <= 128; positions carry no gradient (stop_level_grad).
+__device__ __forceinline__ float power_ladder_pos(float x, float p, float premult) {
+  // internal/math.py:295-316, general branch, x >= 0:  |p-1|/p * ((x/|p-1| + 1)^p - 1)
+  x *= premult;
+  const float a = fabsf(p - 1.0f);
+  return (a / p) * (powf(fabsf(x) / a + 1.0f, p) - 1.0f) * (x < 0.f ? -1.f : 1.f);
+}
+
+__global__ void distortion_loss_kernel(const float* __restrict__ t, const float* __restrict__ w, int n, int64_t R,
+                                       float p, float premult, float mult, float* __restrict__ loss,
+                                       float* __restrict__ g_w) {
+  __shared__ float su[8][128], sw[8][128];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= R) return;
+  float dc[4], wi[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = lane + 32 * q;
+    dc[q] = wi[q] = 0.f;
+    if (i < n) {
+      const float c0 = power_ladder_pos(t[r * (n + 1) + i], p, premult);
+      const float c1 = power_ladder_pos(t[r * (n + 1) + i + 1], p, premult);
+      su[wib][i] = 0.5f * (c0 + c1);
+      dc[q] = c1 - c0;
+      wi[q] = w[r * n + i];
+      sw[wib][i] = wi[q];
+    }
+  }
+  __syncwarp();
+  float total = 0.f;
+  const float k = mult / static_cast<float>(R);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = lane + 32 * q;
+    if (i < n) {
+      const float ui = su[wib][i];
+      float s = 0.f;
+      for (int j = 0; j < n; ++j) s = fmaf(sw[wib][j], fabsf(ui - su[wib][j]), s);
+      total += wi[q] * s + wi[q] * wi[q] * dc[q] * (1.0f / 3.0f);
+      g_w[r * n + i] += k * (2.f * s + 2.f * wi[q] * dc[q] * (1.0f / 3.0f));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  if (lane == 0) atomicAdd(loss, k * total);
+}
+
 // Geometry losses of the final sampler level, one warp per ray (internal/train_utils.py:3255-3311):
 //   orientation (internal/loss_utils.py:127-166, target 'normals_pred'):
 //       mult_o * mean_r | sum_i |w_i min(0, n_i . v)^2| + 1e-5 |,  v = -viewdirs
@@ -366,6 +418,17 @@ extern "C" int32_t nrc_mask_loss(void* stream, const float* d_acc, int32_t n, co
   if (num_rays < 1 || n < 0 || !d_acc || !d_loss || !d_g_acc) return NRC_E_INVALID_ARG;
   mask_loss_kernel<<<static_cast<unsigned>((num_rays + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       d_acc, n, d_mask, num_rays, charb_padding, opaque_weight, empty_weight, d_loss, d_g_acc);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_distortion_loss(void* stream, const float* d_t, const float* d_weights, int32_t n, int64_t num_rays,
+                                       float p, float premult, float mult, float* d_loss, float* d_g_weights) {
+  if (num_rays < 1 || n < 1 || n > 128) return NRC_E_INVALID_ARG;
+  if (!d_t || !d_weights || !d_loss || !d_g_weights) return NRC_E_INVALID_ARG;
+  if (p == 0.f || p == 1.f) return NRC_E_UNSUPPORTED;   // the special branches of power_ladder are not configured
+  const int64_t threads = num_rays * 32;
+  distortion_loss_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_t, d_weights, n, num_rays, p, premult, mult, d_loss, d_g_weights);
   return check_launch();
 }
 

@@ -30,7 +30,7 @@ from . import _lib, geometry, mlp_chain, nerf, stepfun
 class FusedCacheStep:
     def __init__(self, model, params, charb_padding=0.001, interlevel_mults=(0.01, 0.01), interlevel_blurs=(0.03, 0.003),
                  geometry_mults=(0.01, 0.001, 0.01), predicted_normal_stopgrad_weight=0.1, mask_weights=(1.0, 1.0),
-                 backward_mask_weight=0.1):
+                 backward_mask_weight=0.1, distortion=(0.01, -0.25, 10000.0), density_grid_regularizer=1.0):
         self.model, self.params = model, params
         self.charb_padding = charb_padding
         self.interlevel_mults, self.interlevel_blurs = interlevel_mults, interlevel_blurs
@@ -39,6 +39,8 @@ class FusedCacheStep:
         self.sg_w = predicted_normal_stopgrad_weight
         self.mask_weights = mask_weights                # opaque, empty; None: off
         self.backward_mask_weight = backward_mask_weight
+        self.distortion = distortion                    # mult, power_ladder p, premult; None: off
+        self.density_grid_regularizer = density_grid_regularizer   # Config.param_regularizers['density_grid']; None: off
         self._bg = {}
         self._side = None
         self.concurrent = True   # independent branches of the schedule on side streams (fork/join events)
@@ -145,13 +147,25 @@ class FusedCacheStep:
             else:
                 self._weights_only_pass(extra[0], extra[1], train_frac, loss)
             extra = None
-        # weight packing does not depend on the rays: runs beside the sampler
+        def regularize():   # param_regularizer_loss on the three density grids: atomic, order-free
+            if self.density_grid_regularizer is None or self.geometry_mults is None:
+                return
+            for i_mlp, mlp in enumerate(sampler.mlps):
+                arena = sp[f"MLP_{i_mlp}"]["density_grid"]["_arena"]
+                t_sink = _lib.grad_sink(arena)
+                enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)), mlp.grid.tables(mlp.grid.views(t_sink)))
+                _lib.call("nrc_grid_regularizer", _lib.stream_ptr(), C.byref(enc), float(self.density_grid_regularizer),
+                          _lib.ptr(loss))
+
+        # weight packing and the parameter regularizer do not depend on the rays: they run beside the sampler
         if s_pack is not None:
             s_pack.wait_stream(main)
             with torch.cuda.stream(s_pack):
                 packed = nerf.shader_pack(shader, names, sflat)
+                regularize()
         else:
             packed = nerf.shader_pack(shader, names, sflat)
+            regularize()
         # ------------------------------------------------------------------ forward: proposal sampler
         sdist, weights = self._initial_step_function(R, dev)
         levels = []
@@ -240,6 +254,10 @@ class FusedCacheStep:
         _lib.call("nrc_ray_composite_bwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(bg),
                   _lib.ptr(g_rgb), _lib.ptr(g_acc), R, k, 3, 1, _lib.ptr(gv), _lib.ptr(g_w[2]), None)
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
+        if self.distortion is not None and self.geometry_mults is not None:
+            dm, dp, dpre = self.distortion     # distortion loss on the final level: += into g_w
+            _lib.call("nrc_distortion_loss", st(), _lib.ptr(L2["tdist"]), _lib.ptr(L2["weights"]), k, R, float(dp),
+                      float(dpre), float(dm), _lib.ptr(loss), _lib.ptr(g_w[2]))
         g_rg = None
         if self.geometry_mults is not None:
             # orientation / predicted-normal / reverse losses: += into the compositing's g_w and the shader's g_nrm;

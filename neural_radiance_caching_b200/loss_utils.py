@@ -117,3 +117,37 @@ def compute_mask_loss(acc, masks=None, charb_padding=0.001, opaque_loss_weight=1
         masks = torch.zeros_like(acc) if masks is None else masks
         return _MaskLossFn.apply(acc, masks, charb_padding, 0.0, empty_loss_weight)
     return _MaskLossFn.apply(acc, masks, charb_padding, opaque_loss_weight, empty_loss_weight)
+
+
+class _DistortionLossFn(torch.autograd.Function):
+    """loss_utils.distortion_loss over stepfun.lossfun_distortion: nrc_distortion_loss (VJP w.r.t. the weights)."""
+
+    @staticmethod
+    def forward(ctx, t, w, p, premult, mult):
+        R, n = w.shape
+        loss = torch.zeros((), device=w.device, dtype=torch.float32)
+        g_w = torch.zeros((R, n), device=w.device, dtype=torch.float32)
+        _lib.call("nrc_distortion_loss", _lib.stream_ptr(), _lib.ptr(t.contiguous()), _lib.ptr(w.contiguous()), n, R,
+                  float(p), float(premult), float(mult), _lib.ptr(loss), _lib.ptr(g_w))
+        ctx.save_for_backward(g_w)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (g_w,) = ctx.saved_tensors
+        return None, g_w * g, None, None, None
+
+
+def distortion_loss(ray_history, mult=0.01, p=-0.25, premult=10000.0, target="tdist"):
+    """internal/loss_utils.py:108-123 with configs/ngp_yobo.gin:250-253 and nerf_ngp_yobo_lego.gin:10."""
+    last = ray_history[-1]
+    return _DistortionLossFn.apply(last[target].detach(), last["weights"], p, premult, mult)
+
+
+def param_regularizer_loss(tables, mult=1.0):
+    """param_regularizer_loss (internal/train_utils.py:1169-1216), (mult, jnp.mean, 2, 1) setting: autograd mirror in
+    torch ops over the level tables (the fused step uses nrc_grid_regularizer)."""
+    loss = 0.0
+    for t in tables:
+        loss = loss + mult * 0.5 * torch.mean(t**2)
+    return loss

@@ -117,18 +117,42 @@ GEOMETRY_MULTS = (0.01, 0.001, 0.01)   # orientation, predicted normals, reverse
 PREDICTED_NORMAL_STOPGRAD_WEIGHT = 0.1  # configs/nerf_ngp_yobo.gin:60
 MASK_WEIGHTS = (1.0, 1.0)              # opaque_loss_weight, empty_loss_weight (configs/nerf_ngp_yobo.gin:367-368)
 BACKWARD_MASK_WEIGHT = 0.1             # configs/nerf_ngp_yobo.gin:375
+DENSITY_GRID_REGULARIZER = 1.0         # Config.param_regularizers['density_grid'] (configs/nerf_ngp_yobo.gin:47-51)
+DISTORTION = (0.01, -0.25, 10000.0)    # mult (nerf_ngp_yobo_lego.gin:10), power_ladder p, premult (ngp_yobo.gin:250-253)
 
 
-def cache_loss(result, target_rgb, charb_padding=0.001, interlevel_fn=None, rays=None, extra_acc=None, lib=None):
+def density_grid_tables(params):
+    """Level tables of every `density_grid` module of the cache model (the parameters the 'density_grid' regularizer
+    prefix matches, internal/train_utils.py:1192-1201).  When the tables live in one arena leaf, differentiable
+    views of that leaf are returned (the stored per-level views are pointer-only, see CacheTrainStep)."""
+    out = []
+    for name in sorted(params["Sampler"].keys()):
+        grid = params["Sampler"][name]["density_grid"]
+        arena = grid.get("_arena")
+        for k in sorted(k for k in grid.keys() if k != "_arena"):
+            t = grid[k]
+            if arena is not None and arena.requires_grad and not t.requires_grad:
+                off = (t.data_ptr() - arena.data_ptr()) // 4
+                t = arena[off:off + t.numel()].view(t.shape)
+            out.append(t)
+    return out
+
+
+def cache_loss(result, target_rgb, charb_padding=0.001, interlevel_fn=None, rays=None, extra_acc=None, lib=None,
+               reg_tables=None):
     """Cache-stage objective of the config-2 step (internal/train_utils.py:2880-2950):
       data   Charbonnier on the sRGB-mapped render (cache_loss='charb', cache_linear_to_srgb=True,
              configs/ngp_yobo.gin:35-37; internal/configs.py:330)
       sampler  spline interlevel loss on the two proposal levels (mults (0.01, 0.01), blurs (0.03, 0.003),
              configs/ngp_yobo.gin:245-247; internal/loss_utils.py:74-108)
+      distortion (when `rays` is given) mip-NeRF-360 distortion loss on the final level's metric distances through
+             power_ladder(-0.25, 1e4) (loss_utils.py:108-123; mult 0.01 in the lego config)
       geometry (when `rays` is given) orientation + predicted-normal + reverse losses on the final level
              (train_utils.py:3255-3311), the middle one through the analytic normals' second-order path
       mask   compute_mask_loss on the accumulation (masks == 1 for the synthetic batches), and, when `extra_acc`
              (accumulation of the backward-mask rays' weights_only pass) is given, the backward-mask term.
+      regularizer (when `reg_tables` is given) 0.5 * mean(T^2) over every density-grid level table
+             (param_regularizer_loss, train_utils.py:1169-1216; nerf_ngp_yobo.gin:47-51)
     `lib` supplies spline_interlevel_loss / geometry_losses / compute_mask_loss: this package's CUDA mirrors by
     default, the oracle's restatement in the CPU legs."""
     if lib is None:
@@ -140,9 +164,12 @@ def cache_loss(result, target_rgb, charb_padding=0.001, interlevel_fn=None, rays
     for l in interlevel_fn(result["sampler"], mults=INTERLEVEL_MULTS, blurs=INTERLEVEL_BLURS):
         loss = loss + l
     if rays is not None:
+        loss = loss + lib.distortion_loss(result["sampler"], *DISTORTION)
         for l in lib.geometry_losses(rays, result["sampler"][-1], *GEOMETRY_MULTS, PREDICTED_NORMAL_STOPGRAD_WEIGHT):
             loss = loss + l
         loss = loss + lib.compute_mask_loss(result["render"]["acc"], None, charb_padding, *MASK_WEIGHTS)
+    if reg_tables is not None:
+        loss = loss + lib.param_regularizer_loss(reg_tables, DENSITY_GRID_REGULARIZER)
     if extra_acc is not None:
         loss = loss + lib.compute_mask_loss(extra_acc, None, charb_padding, empty_loss_weight=BACKWARD_MASK_WEIGHT,
                                             backward=True)
@@ -256,7 +283,7 @@ class CacheTrainStep:
         self.zero_grad()
         res = self.model(self.params, rays, u01, train=True)
         extra_acc = self.model.weights_only(self.params, extra[0], extra[1]) if extra is not None else None
-        loss = cache_loss(res, target_rgb, rays=rays, extra_acc=extra_acc)
+        loss = cache_loss(res, target_rgb, rays=rays, extra_acc=extra_acc, reg_tables=density_grid_tables(self.params))
         loss.backward()
         return loss.detach()
 

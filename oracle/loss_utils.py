@@ -143,3 +143,31 @@ def compute_mask_loss(acc, masks=None, charb_padding=0.001, opaque_loss_weight=1
     else:
         data_loss = torch.where(masks > 0.5, data_loss * opaque_loss_weight, data_loss * empty_loss_weight)
     return torch.mean(data_loss)
+
+
+def lossfun_distortion(t, w):
+    """stepfun.lossfun_distortion (internal/stepfun.py:253-269), normalize=False."""
+    ut = (t[..., 1:] + t[..., :-1]) / 2
+    dut = torch.abs(ut[..., :, None] - ut[..., None, :])
+    loss_inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
+    loss_intra = torch.sum(w**2 * torch.diff(t, dim=-1), dim=-1) / 3
+    return loss_inter + loss_intra
+
+
+def distortion_loss(ray_history, mult=0.01, p=-0.25, premult=10000.0, target="tdist"):
+    """loss_utils.distortion_loss (internal/loss_utils.py:108-123) as configured by configs/ngp_yobo.gin:250-253
+    (target 'tdist', curve_fn power_ladder(p=-0.25, premult=10000)) and nerf_ngp_yobo_lego.gin:10 (mult 0.01)."""
+    from . import ref_math
+    last = ray_history[-1]
+    c = ref_math.power_ladder(last[target], p, premult=premult)
+    return mult * torch.mean(lossfun_distortion(c, last["weights"]))
+
+
+def param_regularizer_loss(tables, mult=1.0):
+    """param_regularizer_loss (internal/train_utils.py:1169-1216) for the (mult, jnp.mean, alpha=2, scale=1) setting of
+    Config.param_regularizers (configs/nerf_ngp_yobo.gin:47-51): sum over the given parameter tensors of
+    mult * 0.5 * mean(param^2).  `tables`: the level tables of every module whose name matches the prefix."""
+    loss = 0.0
+    for t in tables:
+        loss = loss + mult * 0.5 * torch.mean(t**2)
+    return loss

@@ -52,6 +52,15 @@ def build():
     l = oloss.compute_mask_loss(A, torch.zeros(16, 1), 0.001, empty_loss_weight=0.1, backward=True)
     l.backward()
     out["mlb_loss"], out["mlb_g"] = np.float32(float(l)), A.grad.numpy().copy()
+    # ---- distortion loss on metric distances through power_ladder(-0.25, 1e4)
+    Rd, nd = 5, 32
+    t = np.sort(g.uniform(2.0, 6.0, size=(Rd, nd + 1)).astype(np.float32), axis=-1)
+    wd = (g.uniform(0, 1, size=(Rd, nd)).astype(np.float32) ** 3) * 0.2
+    out["dl_t"], out["dl_w"] = t, wd
+    Wd = f32(wd).requires_grad_(True)
+    l = oloss.distortion_loss([{"tdist": f32(t), "weights": Wd}], 0.01, -0.25, 10000.0)
+    l.backward()
+    out["dl_loss"], out["dl_g"] = np.float32(float(l.detach())), Wd.grad.numpy().copy()
     # ---- second-order path: d/d theta <G, d raw / d means>
     mlp = ogeo.DensityMLP(grid_params=GRID, enable_pred_normals=True)
     gp = np.random.Generator(np.random.PCG64(SEED + 1))

@@ -89,6 +89,9 @@ def test_geometry_and_mask_loss_known_answers():
     assert abs(float(lm) - 0.5 * (0.001 + np.sqrt(0.75**2 + 1e-6))) < 1e-7
     lb = oloss.compute_mask_loss(acc, torch.zeros(2, 1), 0.001, empty_loss_weight=0.1, backward=True)
     assert abs(float(lb) - 0.5 * 0.1 * (np.sqrt(1 + 1e-6) + np.sqrt(0.0625 + 1e-6))) < 1e-7
+    # lossfun_distortion (stepfun.py:253-269): t = [0,1,3], w = [.5,.25]: u = [.5, 2] -> inter .375, intra .125
+    ld = oloss.lossfun_distortion(torch.tensor([[0.0, 1.0, 3.0]]), torch.tensor([[0.5, 0.25]]))
+    assert abs(float(ld) - 0.5) < 1e-7
     # stopgrad_with_weight: value unchanged, gradient scaled
     x = torch.tensor([2.0], requires_grad=True)
     y = oloss.stopgrad_with_weight(x, 0.1)

@@ -88,6 +88,12 @@ def test_geometry_mask_losses_and_second_order_against_golden(cuda_device):
     l.backward()
     assert abs(float(l.detach()) - float(gold["mlb_loss"])) <= 1e-5 * float(gold["mlb_loss"])
     assert rel_err(A.grad, f32(gold["mlb_g"])) <= 1e-5
+    # distortion loss
+    Wd = d("dl_w").requires_grad_(True)
+    l = nloss.distortion_loss([{"tdist": d("dl_t"), "weights": Wd}], 0.01, -0.25, 10000.0)
+    l.backward()
+    assert abs(float(l.detach()) - float(gold["dl_loss"])) <= 2e-5 * float(gold["dl_loss"])
+    assert rel_err(Wd.grad, f32(gold["dl_g"])) <= 2e-5
     # second-order path
     o = ogeo.DensityMLP(grid_params=mg2.GRID, enable_pred_normals=True)
     po = o.init(np.random.Generator(np.random.PCG64(mg2.SEED + 1)), table_init_range=0.5, bias_range=0.1)

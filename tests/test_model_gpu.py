@@ -66,9 +66,9 @@ def test_cache_model_training_gradients(cuda_device, objective):
                 out.append((prefix + k, p, k))
         return out
 
-    def loss_fn(res, tgt, rays_, lib=None):
+    def loss_fn(res, tgt, rays_, lib=None, reg=None):
         if objective == "config2":
-            return workload.cache_loss(res, tgt, rays=rays_, lib=lib)
+            return workload.cache_loss(res, tgt, rays=rays_, lib=lib, reg_tables=reg)
         l = torch.sqrt((res["render"]["rgb"] - tgt) ** 2 + 1e-6).mean()
         for h in res["sampler"][:-1]:
             l = l + 0.01 * ((h["weights"].sum(-1) - res["sampler"][-1]["weights"].sum(-1).detach()) ** 2).mean()
@@ -78,7 +78,7 @@ def test_cache_model_training_gradients(cuda_device, objective):
     for _, d, k in lo:
         d[k] = d[k].clone().requires_grad_(True)
     ro = o(po, rays, u, create_graph=objective == "config2")
-    loss_o = loss_fn(ro, target, rays, oloss)
+    loss_o = loss_fn(ro, target, rays, oloss, workload.density_grid_tables(po))
     loss_o.backward()
     override = [h["sdist"].to(cuda_device) for h in ro["sampler"]]
 
@@ -97,7 +97,11 @@ def test_cache_model_training_gradients(cuda_device, objective):
             d[k] = d[k].clone().requires_grad_(True)
     rays_d = to_dev(rays, cuda_device)
     rn = n(pn, rays_d, to_dev(u, cuda_device), train=True, sdist_override=override)
-    loss_n = loss_fn(rn, target.to(cuda_device), rays_d)
+    reg_n = []   # level tables as differentiable views of the arenas (same order as density_grid_tables)
+    for i, m in enumerate(n.sampler.mlps):
+        v = m.grid.views(arenas[f"Sampler/MLP_{i}/density_grid/"][1])
+        reg_n += [v[k] for k in sorted(v.keys())]
+    loss_n = loss_fn(rn, target.to(cuda_device), rays_d, None, reg_n)
     loss_n.backward()
     assert abs(float(loss_n) - float(loss_o)) <= 1e-4 * abs(float(loss_o))
     assert rel_err(rn["render"]["rgb"], ro["render"]["rgb"]) <= 1e-4
