@@ -511,6 +511,27 @@ int32_t nrc_geometry_losses(void* stream, const float* d_weights, const float* d
                             float predicted_normal_mult, float predicted_normal_reverse_mult, float stopgrad_weight,
                             float* d_loss, float* d_g_weights, float* d_g_normals_pred, float* d_g_normals);
 
+/* --------------------------------------------- light sampler ---- */
+/* vMF head of LightMLP: get_vmfs + the recentring of predict_lighting (internal/light_sampler.py:135-160,203-204).
+ *   d_raw [P, K*5] (output layer), d_means_random [P,K,3] (means_random_per_point = 1) or [K,3] (0), d_positions [P,3]
+ *   -> d_means [P,K,3] = raw[0:3]*vmf_scale + means_random - position, d_kappas [P,K] = min(softplus(raw[3]+1), 50),
+ *      d_logits [P,K] = max(raw[4]+1, -50).  The reference draws means_random from a fixed JAX key: an input here. */
+int32_t nrc_vmf_head_fwd(void* stream, const float* d_raw, const float* d_means_random, int32_t means_random_per_point,
+                         const float* d_positions, int64_t num_points, int32_t num_lobes, float vmf_scale,
+                         float* d_means, float* d_kappas, float* d_logits);
+int32_t nrc_vmf_head_bwd(void* stream, const float* d_raw, const float* d_g_means, const float* d_g_kappas,
+                         const float* d_g_logits, int64_t num_points, int32_t num_lobes, float vmf_scale, float* d_g_raw);
+/* render_utils.vmf_loss_fn (internal/inverse_render/render_utils.py:1493-1550) as called by
+ * train_utils.light_sampling_loss (internal/train_utils.py:1985-2071), function_vals_nocorr == function_vals:
+ *   d_means [P,K,3], d_kappas [P,K], d_logits [P,K] (K <= 128), d_normals [P,3], d_dirs [P,S,3], d_pdf / d_weight /
+ *   d_function_vals [P,S], lossmult (1/S), linear_to_srgb flag.  loss += mean over (P,S); gradients w.r.t. means
+ *   (through l2_normalize, grad_eps 1e-5), kappas and logits are written. */
+int32_t nrc_vmf_loss(void* stream, const float* d_means, const float* d_kappas, const float* d_logits,
+                     const float* d_normals, const float* d_dirs, const float* d_pdf, const float* d_weight,
+                     const float* d_function_vals, int64_t num_points, int32_t num_lobes, int32_t num_samples,
+                     float lossmult, int32_t linear_to_srgb, float* d_loss, float* d_g_means, float* d_g_kappas,
+                     float* d_g_logits);
+
 /* ------------------------------------------------- K5: GGX integration ---- */
 /* render_utils.get_lobe (internal/inverse_render/render_utils.py:566-695) +
  * integrate_reflect_rays (:1102-1193): Disney-GGX D*F*G and Lambert lobes evaluated in the

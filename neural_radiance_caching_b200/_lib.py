@@ -98,6 +98,9 @@ PROTOTYPES = {
     "nrc_ide_bwd": [_P, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), _P, _P, _P, _P,
                     _I64, _I64, _P, _P],
     "nrc_mask_loss": [_P, _P, _I32, _P, _I64, _F, _F, _F, _P, _P],
+    "nrc_vmf_head_fwd": [_P, _P, _P, _I32, _P, _I64, _I32, _F, _P, _P, _P],
+    "nrc_vmf_head_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _F, _P],
+    "nrc_vmf_loss": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _I32, _P, _P, _P, _P],
     "nrc_grid_regularizer": [_P, _P, _F, _P],
     "nrc_distortion_loss": [_P, _P, _P, _I32, _I64, _F, _F, _F, _P, _P],
     "nrc_geometry_losses": [_P, _P, _P, _P, _P, _I64, _I32, _F, _F, _F, _F, _P, _P, _P, _P],

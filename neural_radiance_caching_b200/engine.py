@@ -208,10 +208,46 @@ class FusedCacheStep:
         if L2["rg"] is not None:   # analytic normals: computed like the reference, consumed by the 8f losses
             L2["normals"] = new(P2, 3)
             _lib.call("nrc_normals_fwd", st(), _lib.ptr(L2["rg"]), P2, _lib.ptr(L2["normals"]))
+        # ------------------------------------------------------------------ geometry branch (side stream)
+        # distortion / orientation / predicted-normal losses need only the final level's step function and normals:
+        # they, the l2_normalize VJP and the second-order kernel (nrc_density_normals_bwd, the longest kernel of the
+        # step) start here and run beside the shader; their g_w / g_normals_pred terms are added after the shader's.
+        k = L2["n"]
+        geo, s_geo = None, None
+        if self.geometry_mults is not None:
+            def geometry_branch():
+                gw_geo = torch.zeros((R, k), device=dev, dtype=torch.float32)
+                gnp_geo = torch.zeros((P2, 3), device=dev, dtype=torch.float32)
+                if self.distortion is not None:
+                    dm, dp, dpre = self.distortion
+                    _lib.call("nrc_distortion_loss", _lib.stream_ptr(), _lib.ptr(L2["tdist"]), _lib.ptr(L2["weights"]), k,
+                              R, float(dp), float(dpre), float(dm), _lib.ptr(loss), _lib.ptr(gw_geo))
+                has_n = L2.get("normals") is not None
+                g_na = new(P2, 3) if has_n else None
+                mo, mp, mr = self.geometry_mults
+                _lib.call("nrc_geometry_losses", _lib.stream_ptr(), _lib.ptr(L2["weights"]),
+                          _lib.ptr(L2["normals"]) if has_n else None, _lib.ptr(normals_pred), _lib.ptr(rays["viewdirs"]),
+                          R, k, float(mo), float(mp), float(mr), float(self.sg_w), _lib.ptr(loss), _lib.ptr(gw_geo),
+                          _lib.ptr(gnp_geo), _lib.ptr(g_na))
+                if has_n:   # second-order path of the predicted-normal loss: d/d theta <g_rg, d raw / d means>
+                    g_rg = new(P2, 3)
+                    _lib.call("nrc_normals_bwd", _lib.stream_ptr(), _lib.ptr(L2["rg"]), _lib.ptr(g_na), P2, _lib.ptr(g_rg))
+                    mlp2 = L2["mlp"]
+                    sinks = [_lib.grad_sink(t) for t in L2["flat"]]
+                    geometry.density_normals_bwd(mlp2, L2["p"], L2["arena"], L2["means"].reshape(P2, 3), g_rg,
+                                                 mlp2._unflatten(sinks), _lib.grad_sink(L2["arena"]))
+                    return gw_geo, gnp_geo, g_na, g_rg
+                return gw_geo, gnp_geo, g_na, None
+            if self.concurrent:
+                s_geo = self._streams(6)[5]
+                s_geo.wait_stream(main)
+                with torch.cuda.stream(s_geo):
+                    geo = geometry_branch()
+            else:
+                geo = geometry_branch()
         # ------------------------------------------------------------------ proposal supervision (side stream)
         # The spline interlevel loss and the proposal levels' backward depend only on the final level's step
         # function (sdist, weights): they start here and run beside the shader's forward / backward.
-        k = L2["n"]
         g_w = [new(R, lv["n"]) for lv in levels]
 
         def interlevel():   # loss_utils.spline_interlevel_loss, one launch per proposal level
@@ -254,28 +290,16 @@ class FusedCacheStep:
         _lib.call("nrc_ray_composite_bwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(bg),
                   _lib.ptr(g_rgb), _lib.ptr(g_acc), R, k, 3, 1, _lib.ptr(gv), _lib.ptr(g_w[2]), None)
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
-        if self.distortion is not None and self.geometry_mults is not None:
-            dm, dp, dpre = self.distortion     # distortion loss on the final level: += into g_w
-            _lib.call("nrc_distortion_loss", st(), _lib.ptr(L2["tdist"]), _lib.ptr(L2["weights"]), k, R, float(dp),
-                      float(dpre), float(dm), _lib.ptr(loss), _lib.ptr(g_w[2]))
-        g_rg = None
-        if self.geometry_mults is not None:
-            # orientation / predicted-normal / reverse losses: += into the compositing's g_w and the shader's g_nrm;
-            # the gradient w.r.t. the analytic normals goes through the l2_normalize VJP to d raw / d means
-            has_n = L2.get("normals") is not None
-            g_na = new(P2, 3) if has_n else None
-            mo, mp, mr = self.geometry_mults
-            _lib.call("nrc_geometry_losses", st(), _lib.ptr(L2["weights"]), _lib.ptr(L2["normals"]) if has_n else None,
-                      _lib.ptr(normals_pred), _lib.ptr(rays["viewdirs"]), R, k, float(mo), float(mp), float(mr),
-                      float(self.sg_w), _lib.ptr(loss), _lib.ptr(g_w[2]), _lib.ptr(g_nrm), _lib.ptr(g_na))
-            if has_n:
-                g_rg = new(P2, 3)
-                _lib.call("nrc_normals_bwd", st(), _lib.ptr(L2["rg"]), _lib.ptr(g_na), P2, _lib.ptr(g_rg))
+        if geo is not None:
+            if s_geo is not None:
+                main.wait_stream(s_geo)
+            g_w[2].add_(geo[0])
+            g_nrm.add_(geo[1].view_as(g_nrm))
         if s_prop is not None and not fork_proposals:
             main.wait_stream(s_prop)     # split mode: the side stream only ran the interlevel losses
         self.last = dict(levels=levels, rgb=out_rgb, acc=acc, dist=dist, shader_rgb=rgb_s)
-        return dict(loss=loss, levels=levels, rays=rays, g_w=g_w, d_feat=d_feat, g_nrm=g_nrm, R=R, g_rg=g_rg,
-                    forked=s_prop if fork_proposals else None, keep=(saved, gv, g_rgb, g_acc), extra=extra,
+        return dict(loss=loss, levels=levels, rays=rays, g_w=g_w, d_feat=d_feat, g_nrm=g_nrm, R=R,
+                    forked=s_prop if fork_proposals else None, keep=(saved, gv, g_rgb, g_acc, geo), extra=extra,
                     extra_stream=s_x, train_frac=train_frac)
 
     def step_back(self, state):
@@ -307,28 +331,9 @@ class FusedCacheStep:
             x_fork = state["extra_stream"]
         g_gp = torch.empty((P2, 3), device=dev, dtype=torch.float32)
         _lib.call("nrc_normals_bwd", _lib.stream_ptr(), _lib.ptr(L2["gp"]), _lib.ptr(state["g_nrm"]), P2, _lib.ptr(g_gp))
-        n2_fork = None
-        if state.get("g_rg") is not None:
-            # second-order path of the predicted-normal loss: d/d theta <g_rg, d raw / d means>
-            # (nrc_density_normals_bwd); independent of the level's first-order backward: its own stream
-            def second_order():
-                mlp = L2["mlp"]
-                sinks = [_lib.grad_sink(t) for t in L2["flat"]]
-                t_sink = _lib.grad_sink(L2["arena"])
-                geometry.density_normals_bwd(mlp, L2["p"], L2["arena"], L2["means"].reshape(P2, 3), state["g_rg"],
-                                             mlp._unflatten(sinks), t_sink)
-            if self.concurrent:
-                n2_fork = self._streams(6)[5]
-                n2_fork.wait_stream(main)
-                with torch.cuda.stream(n2_fork):
-                    second_order()
-            else:
-                second_order()
         self._level_backward(L2, rays, g_w[nl - 1], state["d_feat"], g_gp if L2["gp"] is not None else None, R)
         if x_fork is not None:
             main.wait_stream(x_fork)
-        if n2_fork is not None:
-            main.wait_stream(n2_fork)
         if s_prop is not None:
             main.wait_stream(s_prop)
         elif own_fork is not None:

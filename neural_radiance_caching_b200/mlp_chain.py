@@ -367,25 +367,32 @@ def run_forward(spec, params, sources, packed, save=True):
             _op(prog, kind=OP_SAVE, slot=spec.h_slot0, ptr=ptrs.add(act), col0=spec.act_atom0(li),
                 npad=len(_atoms_of(w)), img_atoms=spec.act_atoms)
     atoms = [(slot, klen) for (_, _, klen, _, _, slot) in spec.x_atoms(spec.x_last)]
-    tcol = 0
-    for g, grp in enumerate(spec.heads):
-        _op(prog, kind=OP_GEMM, n=spec.head_pads[g], tmem_col=tcol, w_chunk=b.fwd_head_chunk[g], atoms=atoms)
-        tcol += spec.head_pads[g]
-    if tcol > 256:
-        raise ValueError("head groups exceed the accumulator columns of one context")
-    tcol = 0
+    # head groups in batches that fit the 256 accumulator columns of a context: GEMMs of a batch, then its epilogues
     bufs, outs = [], []
-    for g, grp in enumerate(spec.heads):
-        buf = torch.empty((P, spec.head_pads[g]), device=dev, dtype=torch.float32)
-        bias = torch.cat([params[name]["bias"] for name, _ in grp]) if len(grp) > 1 else params[grp[0][0]]["bias"]
-        _op(prog, kind=OP_EPI, slot=-1, ptr=ptrs.add(bias), ncols=spec.head_widths[g], npad=spec.head_pads[g],
-            tmem_col=tcol, out_ptr=ptrs.add(buf), ld=spec.head_pads[g], col0=0)
-        tcol += spec.head_pads[g]
-        bufs.append(buf)
-        c = 0
-        for name, w in grp:
-            outs.append(buf[:, c:c + w])
-            c += w
+    g0 = 0
+    while g0 < len(spec.heads):
+        g1, cols = g0, 0
+        while g1 < len(spec.heads) and cols + spec.head_pads[g1] <= 256:
+            cols += spec.head_pads[g1]
+            g1 += 1
+        tcol = 0
+        for g in range(g0, g1):
+            _op(prog, kind=OP_GEMM, n=spec.head_pads[g], tmem_col=tcol, w_chunk=b.fwd_head_chunk[g], atoms=atoms)
+            tcol += spec.head_pads[g]
+        tcol = 0
+        for g in range(g0, g1):
+            grp = spec.heads[g]
+            buf = torch.empty((P, spec.head_pads[g]), device=dev, dtype=torch.float32)
+            bias = torch.cat([params[name]["bias"] for name, _ in grp]) if len(grp) > 1 else params[grp[0][0]]["bias"]
+            _op(prog, kind=OP_EPI, slot=-1, ptr=ptrs.add(bias), ncols=spec.head_widths[g], npad=spec.head_pads[g],
+                tmem_col=tcol, out_ptr=ptrs.add(buf), ld=spec.head_pads[g], col0=0)
+            tcol += spec.head_pads[g]
+            bufs.append(buf)
+            c = 0
+            for name, w in grp:
+                outs.append(buf[:, c:c + w])
+                c += w
+        g0 = g1
     arr, n = ptrs.array()
     _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
     return bufs, outs, act
