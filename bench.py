@@ -538,11 +538,12 @@ def run_render(args):
         g = np.random.Generator(np.random.PCG64(workload.SEED + rank))
         host = torch.from_numpy(np.concatenate([a.reshape(-1) for a in workload.make_surface_np(g, R)])).pin_memory()
         dbuf = host.to(dev)
-        draws, lobes = stage.draws(R), stage.light_lobes(R)
+        draws = stage.draws(R)
         out_host = torch.zeros((R, 3), dtype=torch.float32).pin_memory()
 
         def step():
             m, v, n = (dbuf[i * R * 3:(i + 1) * R * 3].view(R, 3) for i in range(3))
+            lobes = stage.light_lobes(R, m, n)      # LightMLP at the shaded points: part of the chunk
             return stage.render(m, v, n, draws, lobes)["rgb"]
 
         before = _lib.launch_count

@@ -95,6 +95,16 @@ class LightMLP:
                                          heads=[[(f"output_layer_{i}", w)] for i, (_, w) in enumerate(self.splits)])
         self._pack_cache = mlp_chain.PackCache()
 
+    def init(self, device, generator=None, table_init_range=0.1):
+        """Random-init parameters in the reference's layout (he_uniform kernels, zero biases)."""
+        def layer(fi, fo):
+            lim = float((6.0 / fi) ** 0.5)
+            return {"kernel": torch.empty((fi, fo), device=device).uniform_(-lim, lim, generator=generator),
+                    "bias": torch.zeros((fo,), device=device)}
+        _, arena = self.grid.init(device, generator=generator, init_range=table_init_range)
+        return {"light_grid": dict(self.grid.views(arena), _arena=arena), "layers_0": layer(self.grid.num_outputs, 64),
+                "layers_1": layer(64, 64), "output_layer": layer(64, self.out_dim)}
+
     def from_oracle(self, p, device):
         names = [n for (n, _, _, _) in self.grid.level_layout]
         arena = torch.cat([p["light_grid"][n].detach().reshape(-1) for n in names]).to(device)

@@ -357,9 +357,14 @@ class MaterialRenderStep:
         self.gen = gen
         self.cache = models.NeRFModel(bf16=bf16)
         self.model = material.MaterialModel(self.cache, bf16=bf16)
+        from . import light_sampler
+        self.light = light_sampler.LightMLP(bf16=bf16)      # the vMF lobes of the light sampler
         self.params = {"Cache": _cache_params(self.cache, device, gen, table_init_range),
                        "Material": self.model.material_mlp.init(device, gen, table_init_range),
-                       "EnvMap": self.model.env_map.init(device, gen)}
+                       "EnvMap": self.model.env_map.init(device, gen),
+                       "Light": self.light.init(device, gen, table_init_range)}
+        # LightMLP.get_vmfs adds a fixed-key normal draw * vmf_scale / 2 to the lobe means (light_sampler.py:141-143)
+        self.means_random = torch.randn((self.NUM_LOBES, 3), device=device, generator=gen) * (self.light.vmf_scale / 2.0)
 
     def draws(self, R):
         """All random inputs of one chunk, generated on the device (the kernels take them as tensors)."""
@@ -370,7 +375,12 @@ class MaterialRenderStep:
                     normal2=torch.randn((R, self.model.n_light, 2), device=dev, generator=gen),
                     u01=[u(R * S, 1) for _ in range(3)], gumbel=gum)
 
-    def light_lobes(self, R):
+    def light_lobes(self, R, means=None, normals=None):
+        """vMF lobes of the light sampler at the shaded points: LightMLP.predict_lighting (light grid -> tcgen05
+        stack -> vMF head) when `means` is given; synthetic lobes otherwise."""
+        if means is not None:
+            with torch.no_grad():
+                return self.light.predict_lighting(self.params["Light"], means, self.means_random, normals=normals)
         dev, gen = self.device, self.gen
         return dict(vmf_means=torch.randn((R, self.NUM_LOBES, 3), device=dev, generator=gen),
                     vmf_kappas=torch.rand((R, self.NUM_LOBES, 1), device=dev, generator=gen) * 50.0,
@@ -434,6 +444,7 @@ class FrameRenderer:
                 sh = prim["shaded"]
                 means, normals, w = sh["means"].reshape(R, 3), sh["normals"].reshape(R, 3), sh["weights"].reshape(R, 1)
                 cache_rgb, acc = prim["render"]["rgb"], prim["render"]["acc"].reshape(R, 1)
-            out = st.render(means.contiguous(), rays["viewdirs"], normals.contiguous(), st.draws(R), st.light_lobes(R))
+            means, normals = means.contiguous(), normals.contiguous()
+            out = st.render(means, rays["viewdirs"], normals, st.draws(R), st.light_lobes(R, means, normals))
             rgb = out["rgb"] * w + (1.0 - acc)
         return dict(rgb=rgb, cache_rgb=cache_rgb, acc=acc, albedo=out["material"]["albedo"])
