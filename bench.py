@@ -355,7 +355,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    roof = roofline(per_kernel, R, pk, pk_kind, bool(args.bf16))
+    roof = roofline(per_kernel, R, pk, pk_kind, bool(args.bf16), l2_gather_probe(dev) if per_kernel else None)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, dt, threads = cpu_reference_throughput(args.cpu_rays, 3, 1)
@@ -422,6 +422,33 @@ def profile_calls(one_step, _lib, iters=5):
     return out
 
 
+def l2_gather_probe(dev):
+    """SURVEY 8d L2 roofline denominator: uniformly random row gathers (4-byte and 16-byte rows, 8 in flight per
+    thread) over a 32 MiB table that stays L2-resident (126 MB L2), timed with CUDA events.  Rates in G rows/s."""
+    import ctypes as C
+    from neural_radiance_caching_b200 import _lib
+    table = torch.rand(8 << 20, device=dev)          # 32 MiB
+    sink = torch.zeros(1, device=dev)
+    out = {"table_mib": 32, "in_flight_per_thread": 8}
+    n_thr, per = 148 * 2048 * 4, 64
+    for row_bytes in (4, 16):
+        rows = table.numel() * 4 // row_bytes
+        call = lambda: _lib.call("nrc_probe_gather", _lib.stream_ptr(), _lib.ptr(table), rows, row_bytes, n_thr, per,
+                                 _lib.ptr(sink))
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); call(); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        rate = n_thr * per / (best * 1e-3) / 1e9
+        out[f"row{row_bytes}_grows_s"] = rate
+        out[f"row{row_bytes}_sector_gbs"] = rate * 32.0     # every random row costs one 32-byte sector
+    return out
+
+
 def _traffic(kernel):
     """Measured DRAM bytes per launch of `kernel` from the committed ncu --set full summary, or None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
@@ -437,7 +464,7 @@ SHADER_MAC_FWD = 96 * 138 + (129 * 64 + 64 * 64 + 64) + (200 * 128 + 128 * 128 +
 SHADER_MAC_ENV = 38 * 128 + 128 * 128 + 128 * 128 + 166 * 128 + 128 * 3
 
 
-def roofline(per_kernel, R, pk, pk_kind, bf16):
+def roofline(per_kernel, R, pk, pk_kind, bf16, l2=None):
     """Roofline of the dominant entry point of the step (per-call CUDA events on the launching stream).
     Algorithmic work:
       encode fwd per point = 12 (x) + 8*F*4*L (corner rows) + 4*L*F (features) bytes;
@@ -481,6 +508,18 @@ def roofline(per_kernel, R, pk, pk_kind, bf16):
         if k in per_kernel:
             a = alg_bytes[k] / (per_kernel[k] * 1e-3) / 1e9
             res[k] = {"bound": "hbm", "achieved": a, "frac": a / pk["hbm_gbs"], "ms": per_kernel[k], "unit": "GB/s"}
+    if l2:
+        # corner rows gathered per step (8 per point and level), by row size; time the measured L2 random-gather
+        # rate would need for them = the bound the gather-side of these entry points is held against
+        g4 = 8 * (pts[0] * 6 + pts[1] * 7)
+        g16 = 8 * pts[2] * 8
+        rows = {"nrc_density_query_fwd": (2 * g4, 2 * g16), "nrc_encode_fwd": (0, 8 * 32 * R * 8)}
+        res["l2_gather"] = dict(l2)
+        for k, (a4, a16) in rows.items():
+            if k in per_kernel and k in res:
+                t_bound = a4 / (l2["row4_grows_s"] * 1e9) + a16 / (l2["row16_grows_s"] * 1e9)
+                res[k]["l2_gather_frac"] = t_bound / (per_kernel[k] * 1e-3)
+                res[k]["grows_s"] = (a4 + a16) / (per_kernel[k] * 1e-3) / 1e9
     for k in alg_flops:
         if k in per_kernel and bf16:
             a = alg_flops[k] / (per_kernel[k] * 1e-3) / 1e12
@@ -592,6 +631,12 @@ def run_render(args):
             roof.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], achieved=ach, frac=ach / pk["hbm_gbs"],
                         note="3 launches (proposal levels) on 32768 secondary rays; algorithmic gather bytes / summed "
                              "CUDA-event time; tables are L2-resident, so values above the HBM peak are possible")
+            l2 = l2_gather_probe(dev)
+            rays = R * S
+            t_bound = (rays * 8 * 64 * (6 + 7)) / (l2["row4_grows_s"] * 1e9) + (rays * 8 * 32 * 8) / (l2["row16_grows_s"] * 1e9)
+            roof["l2_gather"] = l2
+            roof["l2_gather_frac"] = t_bound / (per_kernel[top] * 1e-3)
+            roof["grows_s"] = rays * 8 * (64 * 13 + 32 * 8) / (per_kernel[top] * 1e-3) / 1e9
         else:
             roof.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], achieved=None, frac=None)
     else:

@@ -492,6 +492,12 @@ int32_t nrc_mask_loss(void* stream, const float* d_acc, int32_t n, const float* 
  * table T of `enc`: loss += mult * 0.5 * mean(T^2), levels[l].d_grad += mult * T / numel(T) (atomic reductions: may run
  * concurrently with nrc_encode_bwd on the same tables). */
 int32_t nrc_grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss);
+/* Measurement aid ("L2 roofline denominator"): every thread issues `per_thread` independent, uniformly random
+ * row reads (row_bytes = 4 or 16, 8 in flight) from a table of `table_rows` rows and adds them up; d_sink [1] keeps the
+ * loads alive.  bench.py times it on an L2-resident table to get the B200's random-gather rate, the bound the
+ * hash-level gathers of HashEncoding (internal/grid_utils.py:41-121) are reported against beside the HBM peak. */
+int32_t nrc_probe_gather(void* stream, const float* d_table, int64_t table_rows, int32_t row_bytes, int64_t num_threads,
+                         int32_t per_thread, float* d_sink);
 /* Distortion loss of mip-NeRF 360 on the final level (internal/loss_utils.py:108-123, internal/stepfun.py:253-269;
  * Config.distortion_loss_target='tdist', curve_fn = math.power_ladder(p, premult), configs/ngp_yobo.gin:250-253,
  * mult configs/nerf_ngp_yobo_lego.gin:10): d_t [R,n+1] metric fenceposts, d_weights [R,n], n <= 128.

@@ -184,9 +184,50 @@ __global__ void __launch_bounds__(256) grid_regularizer_kernel(const __grid_cons
   }
 }
 
+// Random-gather probe (measurement aid, see nrc_probe_gather in the header): the per-thread row sequence is a
+// counter-based integer hash, so consecutive lanes and consecutive iterations hit unrelated rows.
+template <int F>
+__global__ void __launch_bounds__(256) probe_gather_kernel(const float* __restrict__ table, uint32_t rows,
+                                                            int64_t n, int per_thread, float* __restrict__ sink) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= n) return;
+  uint32_t state = static_cast<uint32_t>(tid) * 2654435761u + 12345u;
+  float acc = 0.f;
+  for (int it = 0; it < per_thread; it += 8) {
+    uint32_t r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      state ^= state << 13; state ^= state >> 17; state ^= state << 5;   // xorshift32
+      r[k] = state % rows;
+    }
+    FeatVec<F> v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = load_row<F>(table, static_cast<int32_t>(r[k]));
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc += v[k].v[f];
+  }
+  if (acc == 123456.789f) atomicAdd(sink, acc);   // never true for the bench tables; keeps the loads alive
+}
+
 }  // namespace nrc
 
 using namespace nrc;
+
+extern "C" int32_t nrc_probe_gather(void* stream, const float* d_table, int64_t table_rows, int32_t row_bytes,
+                                    int64_t num_threads, int32_t per_thread, float* d_sink) {
+  if (!d_table || !d_sink || table_rows < 1 || table_rows > 0x7fffffff || num_threads < 0 || per_thread < 8 ||
+      (per_thread & 7))
+    return NRC_E_INVALID_ARG;
+  if (num_threads == 0) return NRC_OK;
+  const unsigned grid = static_cast<unsigned>((num_threads + 255) / 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (row_bytes == 4) probe_gather_kernel<1><<<grid, 256, 0, s>>>(d_table, (uint32_t)table_rows, num_threads, per_thread, d_sink);
+  else if (row_bytes == 16) probe_gather_kernel<4><<<grid, 256, 0, s>>>(d_table, (uint32_t)table_rows, num_threads, per_thread, d_sink);
+  else return NRC_E_UNSUPPORTED;
+  return check_launch();
+}
 
 extern "C" int32_t nrc_grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss) {
   EncDev d;

@@ -277,6 +277,93 @@ __device__ __forceinline__ void hash_interp_group(const EncDev& enc, int l0, con
   }
 }
 
+// Lane-pair gather.  Two adjacent lanes (side = lane & 1) share ONE point and split its eight corners along
+// the axis that is outermost in the reference's summation order: x for hash levels, z for dense levels.
+// That axis is also the one whose two corners sit next to each other in memory - x and x+1 differ in their
+// trailing bits only, so the two hash rows h ^ x, h ^ (x+1) fall into the same aligned 2^(k+1)-row block
+// (k = trailing ones of x; same 128-byte line 97 % of the time at F = 1, 87.5 % at F = 4); z is the
+// contiguous axis of the dense [N,N,N,F] layout.  One warp-wide load instruction then touches ~16 lines
+// instead of ~32: the fused query is bound by L1TEX wavefronts (one per distinct line per instruction,
+// ~2 cycles each), not by bytes.  H points per lane are processed together so that 4*H gathers are in
+// flight per lane.  The even lane sums its four products in the reference's order and hands the partial
+// sum to the odd lane, which continues the same left-to-right sum: bit-identical to level_interp.
+// All 32 lanes must call this (full-mask shuffle); the result is valid on ODD lanes.
+template <int F, int H>
+__device__ __forceinline__ void level_interp_pair(const LevelDev& lv, const float (&xn)[H][3], const int side,
+                                                  FeatVec<F> (&out)[H]) {
+  int32_t rows[H][4];
+  float w[H][4];
+  const float fN = static_cast<float>(lv.N);
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    int32_t fl[3];
+    float wt[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float loc = __fsub_rn(__fmul_rn(xn[h][a], fN), 0.5f);
+      if (!lv.is_hash) loc = __fadd_rn(loc, 1.0f);
+      const float f = floorf(loc);
+      wt[a][1] = __fsub_rn(loc, f);
+      wt[a][0] = __fsub_rn(1.0f, wt[a][1]);
+      fl[a] = __float2int_rz(f);
+    }
+    if (lv.is_hash) {
+      const uint32_t hx = static_cast<uint32_t>(fl[0] + side);
+      const uint32_t hy[2] = {static_cast<uint32_t>(fl[1]) * kPi2, static_cast<uint32_t>(fl[1] + 1) * kPi2};
+      const uint32_t hz[2] = {static_cast<uint32_t>(fl[2]) * kPi3, static_cast<uint32_t>(fl[2] + 1) * kPi3};
+      const float wo = side ? wt[0][1] : wt[0][0];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int by = j >> 1, bz = j & 1;
+        const uint32_t hh = hx ^ (hy[by] ^ hz[bz]);
+        rows[h][j] = static_cast<int32_t>(lv.pow2_mask ? (hh & lv.pow2_mask) : (hh % lv.T));
+        w[h][j] = __fmul_rn(__fmul_rn(wo, wt[1][by]), wt[2][bz]);
+      }
+    } else {
+      const int N = lv.N;
+      const int iz = min(max(fl[2] + side, 0), N + 1);
+      const bool vz = iz >= 1 && iz <= N;
+      int ox[2], oy[2];
+      bool vx[2], vy[2];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ix = min(max(fl[0] + b, 0), N + 1), iy = min(max(fl[1] + b, 0), N + 1);
+        vx[b] = ix >= 1 && ix <= N; vy[b] = iy >= 1 && iy <= N;
+        ox[b] = (ix - 1) * N * N; oy[b] = (iy - 1) * N;
+      }
+      const float wo = side ? wt[2][1] : wt[2][0];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int by = j >> 1, bx = j & 1;
+        rows[h][j] = (vz && vy[by] && vx[bx]) ? ox[bx] + oy[by] + (iz - 1) : -1;
+        w[h][j] = __fmul_rn(__fmul_rn(wo, wt[1][by]), wt[0][bx]);
+      }
+    }
+  }
+  FeatVec<F> vals[H][4];
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (rows[h][j] >= 0) vals[h][j] = load_row<F>(lv.table, rows[h][j]);
+      else {
+#pragma unroll
+        for (int f = 0; f < F; ++f) vals[h][j].v[f] = 0.f;
+      }
+    }
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      float p[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p[j] = __fmul_rn(vals[h][j].v[f], w[h][j]);
+      const float s = __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[2]), p[3]);
+      const float lo = __shfl_xor_sync(0xffffffffu, s, 1);
+      out[h].v[f] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(lo, p[0]), p[1]), p[2]), p[3]);
+    }
+}
+
 __device__ __forceinline__ void normalise_point(const EncDev& enc, const float x[3], float xn[3]) {
 #pragma unroll
   for (int a = 0; a < 3; ++a) xn[a] = __fdiv_rn(__fsub_rn(x[a], enc.b0[a]), enc.span[a]);

@@ -6,6 +6,7 @@
 //
 // Reference: internal/geometry.py:155-168,199-341,442-460 (same maths as mlp.cu / query.cu;
 // parity bar for this variant: rel 2e-2).
+#include <cstddef>
 #include <cstdlib>
 
 #include "encode.cuh"
@@ -19,33 +20,101 @@ constexpr int kGStride = 33;  // fp32 row stride of the per-warp g_enc scratch
 
 struct WarpScratch {
   __nv_bfloat16 x[32][kXStride];  // encoded features of the warp's 32 points (bf16, zero padded)
-  float g[32][kGStride];          // d raw / d enc (normals path)
   int inside[32];                 // bbox mask per point
 };
+struct WarpGradScratch {
+  float g[32][kGStride];          // d raw / d enc (normals path)
+};
 
+// Dynamic shared memory of the forward kernel.  Everything from `wg` on is only needed when the analytic
+// normals (raw_grad) are requested; a launch without them allocates offsetof(FwdSmemBf16, wg) bytes
+// (27 KB instead of 45 KB: more of the 256 KB L1/shared array left to L1; four CTAs per SM either way,
+// bounded by registers).
 struct FwdSmemBf16 {
-  MlpWeightsBf16 w;
+  MlpWeightsFwdBf16 w;
   WarpScratch ws[kBfWarps];
+  MlpWeightsGradBf16 wg;
+  WarpGradScratch gs[kBfWarps];
 };
 
 struct QueryOut {
   float* density; float* raw; float* feat; float* grad_pred; float* raw_grad; float* enc_out;
 };
 
+// Two 16-row tiles through one 64-wide layer with every B fragment loaded ONCE (half the ldmatrix wavefronts
+// of two mma_layer64 calls: shared-memory wavefronts were half of the kernel's L1TEX traffic).
+template <int KS>
+__device__ __forceinline__ void mma_layer64_x2(float (&acc)[2][8][4], const uint32_t (&a)[2][KS][4],
+                                               const __nv_bfloat16* wt, int stride, const float* bias, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const float2 bv = *reinterpret_cast<const float2*>(bias + nt * 8 + (lane & 3) * 2);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) { acc[t][nt][0] = bv.x; acc[t][nt][1] = bv.y; acc[t][nt][2] = bv.x; acc[t][nt][3] = bv.y; }
+  }
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      load_b_frag2(b, wt, stride, np * 16, ks * 16, lane);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        mma_bf16(acc[t][2 * np], a[t][ks], b[0], b[1]);
+        mma_bf16(acc[t][2 * np + 1], a[t][ks], b[2], b[3]);
+      }
+    }
+  }
+}
+
+// Head outputs of one 16-point tile (accumulator layout) -> global memory.
+__device__ __forceinline__ void store_tile_outputs(const QueryOut& out, const float (&o)[4], const float (&acc)[8][4],
+                                                   const int* inside, int64_t base, int mt, int64_t P,
+                                                   float density_bias, int lane) {
+  const int r = lane >> 2;
+  const int64_t pr[2] = {base + mt * 16 + r, base + mt * 16 + r + 8};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (pr[h] >= P) continue;
+    if ((lane & 3) == 0) {
+      float rawv = o[2 * h];
+      if (out.raw) out.raw[pr[h]] = rawv;
+      if (out.density) out.density[pr[h]] = inside[mt * 16 + r + 8 * h] ? safe_exp(rawv + density_bias) : 0.f;
+      if (out.grad_pred) out.grad_pred[3 * pr[h]] = o[2 * h + 1];
+    } else if ((lane & 3) == 1 && out.grad_pred) {
+      out.grad_pred[3 * pr[h] + 1] = o[2 * h];
+      out.grad_pred[3 * pr[h] + 2] = o[2 * h + 1];
+    }
+    if (out.feat) {
+      float* f = out.feat + pr[h] * kHid + (lane & 3) * 2;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+        *reinterpret_cast<float2*>(f + nt * 8) = make_float2(acc[nt][2 * h], acc[nt][2 * h + 1]);
+    }
+  }
+}
+
 // kFused: `in` = means [P,3], features are gathered here; else `in` = enc [P,in_dim].
-template <int F, int KS0, bool kFused>
-__global__ void __launch_bounds__(kBfThreads)
+template <int F, int KS0, bool kFused, int kMinCtas>
+__global__ void __launch_bounds__(kBfThreads, kMinCtas)
 mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t m,
                     const float* __restrict__ in, int64_t P, float warp_c, float density_bias,
                     const QueryOut out, const int g_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmemBf16& s = *reinterpret_cast<FwdSmemBf16*>(smem_raw);
-  load_weights_bf16(s.w, m);
+  const bool want_grad = kFused && out.raw_grad != nullptr;   // the launcher sizes the allocation accordingly
+  load_weights_bf16(s.w, want_grad ? &s.wg : nullptr, m);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpScratch& ws = s.ws[warp];
+  WarpGradScratch& gs = s.gs[warp];
   const int in_dim = m.in_dim;
   const int64_t num_tiles = (P + kBfThreads - 1) / kBfThreads;
+  if constexpr (kFused) {
+    uint32_t* xz = reinterpret_cast<uint32_t*>(&ws.x[0][0]);
+    for (int i = lane; i < 32 * kXStride / 2; i += 32) xz[i] = 0u;
+    __syncwarp();
+  }
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int64_t base = tile * kBfThreads + warp * 32;
     if (base >= P) continue;  // warp-uniform
@@ -63,6 +132,34 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
         inside = 1;
 #pragma unroll
         for (int a = 0; a < 3; ++a) inside = inside && (z[a] > enc.b0[a]) && (z[a] < enc.b1[a]);
+      }
+      ws.inside[lane] = inside;
+      if (g_group & 2) {
+        // Lane-pair gather (encode.cuh: level_interp_pair): lanes 2i, 2i+1 share point i of each 16-point half.
+        const int side = lane & 1;
+        float xq[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int a = 0; a < 3; ++a) xq[h][a] = __shfl_sync(0xffffffffu, xn[a], h * 16 + (lane >> 1));
+        for (int l = 0; l < enc.L; ++l) {
+          FeatVec<F> v[2];
+          level_interp_pair<F, 2>(enc.lv[l], xq, side, v);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int q = h * 16 + (lane >> 1);
+            if (side && base + q < P) {
+#pragma unroll
+              for (int f = 0; f < F; ++f) {
+                float e = __fmul_rn(v[h].v[f], enc.scale);
+                ws.x[q][l * F + f] = __float2bfloat16(e);
+                if (out.enc_out) out.enc_out[(base + q) * in_dim + l * F + f] = e;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      } else if (valid) {
         auto emit = [&](int l, const FeatVec<F>& v) {
 #pragma unroll
           for (int f = 0; f < F; ++f) {
@@ -81,7 +178,7 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
         for (; l < enc.L; l += G) {
           bool all_hash = true;
           for (int g = 0; g < G && l + g < enc.L; ++g) all_hash = all_hash && enc.lv[l + g].is_hash;
-          if (all_hash && g_group) {
+          if (all_hash && (g_group & 1)) {
             FeatVec<F> v[G];
             hash_interp_group<F, G>(enc, l, xn, v);
 #pragma unroll
@@ -95,8 +192,9 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
           }
         }
       }
-      ws.inside[lane] = inside;
-      for (int k = valid ? in_dim : 0; k < KS0 * 16; ++k) ws.x[lane][k] = __float2bfloat16(0.f);
+      // padding columns [in_dim, 16*KS0) were zeroed once before the tile loop and are never written again
+      if (!valid)
+        for (int k = 0; k < in_dim; ++k) ws.x[lane][k] = __float2bfloat16(0.f);
     } else {
       for (int k = 0; k < KS0 * 16; ++k)
         ws.x[lane][k] = __float2bfloat16((valid && k < in_dim) ? __ldg(in + p * in_dim + k) : 0.f);
@@ -104,6 +202,48 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
     }
     __syncwarp();
     // ---------------- tensor-core MLP: two 16-point tiles per warp ------------------------
+    if (!want_grad && (g_group & 4)) {
+      // forward only: both tiles together, B fragments shared
+      uint32_t af[2][KS0][4];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int ks = 0; ks < KS0; ++ks) load_a_frag(af[t][ks], &ws.x[0][0], kXStride, t * 16, ks * 16, lane);
+      float acc[2][8][4];
+      mma_layer64_x2<KS0>(acc, af, &s.w.w0t[0][0], kXStride, s.w.b0, lane);
+      uint32_t hf[2][4][4];
+      acc_to_afrag<true>(acc[0], hf[0]);
+      acc_to_afrag<true>(acc[1], hf[1]);
+      mma_layer64_x2<4>(acc, hf, &s.w.w1t[0][0], kWStride, s.w.b1, lane);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[t][nt][e] = fmaxf(acc[t][nt][e], 0.f);
+        acc_to_afrag<false>(acc[t], hf[t]);
+      }
+      float o[2][4];
+      {
+        const int c = (lane & 3) * 2;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          o[t][0] = o[t][2] = c < 4 ? s.w.bo[c] : 0.f;
+          o[t][1] = o[t][3] = c + 1 < 4 ? s.w.bo[c + 1] : 0.f;
+        }
+        uint32_t b[4];
+        load_b_frag_k32(b, &s.w.wot[0][0], kWStride, 0, 0, lane);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { mma_bf16(o[t], hf[t][0], b[0], b[1]); mma_bf16(o[t], hf[t][1], b[2], b[3]); }
+        load_b_frag_k32(b, &s.w.wot[0][0], kWStride, 0, 32, lane);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { mma_bf16(o[t], hf[t][2], b[0], b[1]); mma_bf16(o[t], hf[t][3], b[2], b[3]); }
+      }
+      store_tile_outputs(out, o[0], acc[0], ws.inside, base, 0, P, density_bias, lane);
+      store_tile_outputs(out, o[1], acc[1], ws.inside, base, 1, P, density_bias, lane);
+      __syncwarp();
+      continue;
+    }
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
       uint32_t a0[KS0][4];
@@ -134,34 +274,15 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
         mma_bf16(o, h2f[2], b[0], b[1]);
         mma_bf16(o, h2f[3], b[2], b[3]);
       }
+      store_tile_outputs(out, o, acc, ws.inside, base, mt, P, density_bias, lane);
       const int r = lane >> 2;
-      const int64_t pr[2] = {base + mt * 16 + r, base + mt * 16 + r + 8};
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (pr[h] >= P) continue;
-        if ((lane & 3) == 0) {
-          float rawv = o[2 * h];
-          if (out.raw) out.raw[pr[h]] = rawv;
-          if (out.density) out.density[pr[h]] = ws.inside[mt * 16 + r + 8 * h] ? safe_exp(rawv + density_bias) : 0.f;
-          if (out.grad_pred) out.grad_pred[3 * pr[h]] = o[2 * h + 1];
-        } else if ((lane & 3) == 1 && out.grad_pred) {
-          out.grad_pred[3 * pr[h] + 1] = o[2 * h];
-          out.grad_pred[3 * pr[h] + 2] = o[2 * h + 1];
-        }
-        if (out.feat) {
-          float* f = out.feat + pr[h] * kHid + (lane & 3) * 2;
-#pragma unroll
-          for (int nt = 0; nt < 8; ++nt)
-            *reinterpret_cast<float2*>(f + nt * 8) = make_float2(acc[nt][2 * h], acc[nt][2 * h + 1]);
-        }
-      }
       if constexpr (kFused) {
         if (out.raw_grad) {
           // g_h2 = wd * [h2 > 0]
 #pragma unroll
           for (int nt = 0; nt < 8; ++nt) {
             const int c = nt * 8 + (lane & 3) * 2;
-            const float w0 = s.w.wo[c][0], w1 = s.w.wo[c + 1][0];
+            const float w0 = s.wg.wo[c][0], w1 = s.wg.wo[c + 1][0];
             acc[nt][0] = acc[nt][0] > 0.f ? w0 : 0.f;
             acc[nt][1] = acc[nt][1] > 0.f ? w1 : 0.f;
             acc[nt][2] = acc[nt][2] > 0.f ? w0 : 0.f;
@@ -170,7 +291,7 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
           uint32_t gf[4][4];
           acc_to_afrag<false>(acc, gf);
           // g_h1 = (g_h2 W1^T) * [h1 > 0]
-          mma_layer64<4>(acc, gf, &s.w.w1[0][0], kWStride, nullptr, lane);
+          mma_layer64_t<4>(acc, gf, &s.w.w1t[0][0], kWStride, lane);
 #pragma unroll
           for (int nt = 0; nt < 8; ++nt) {
             float2 lo = unpack_bf16(h1f[nt >> 1][2 * (nt & 1)]);
@@ -190,7 +311,7 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
 #pragma unroll
             for (int np = 0; np < KS0; ++np) {
               uint32_t b[4];
-              load_b_frag2(b, &s.w.w0[0][0], kWStride, np * 16, ks * 16, lane);
+              load_b_frag2_trans(b, &s.w.w0t[0][0], kXStride, ks * 16, np * 16, lane);
               mma_bf16(ge[2 * np], gf[ks], b[0], b[1]);
               mma_bf16(ge[2 * np + 1], gf[ks], b[2], b[3]);
             }
@@ -198,8 +319,8 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
 #pragma unroll
           for (int nt = 0; nt < 2 * KS0; ++nt) {
             const int c = nt * 8 + (lane & 3) * 2;
-            if (c < in_dim) { ws.g[mt * 16 + r][c] = ge[nt][0]; ws.g[mt * 16 + r + 8][c] = ge[nt][2]; }
-            if (c + 1 < in_dim) { ws.g[mt * 16 + r][c + 1] = ge[nt][1]; ws.g[mt * 16 + r + 8][c + 1] = ge[nt][3]; }
+            if (c < in_dim) { gs.g[mt * 16 + r][c] = ge[nt][0]; gs.g[mt * 16 + r + 8][c] = ge[nt][2]; }
+            if (c + 1 < in_dim) { gs.g[mt * 16 + r][c + 1] = ge[nt][1]; gs.g[mt * 16 + r + 8][c + 1] = ge[nt][3]; }
           }
         }
       }
@@ -214,7 +335,7 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
           Corners c = level_setup(lv, xn);
           float g[F];
 #pragma unroll
-          for (int f = 0; f < F; ++f) g[f] = ws.g[lane][l * F + f] * enc.scale;
+          for (int f = 0; f < F; ++f) g[f] = gs.g[lane][l * F + f] * enc.scale;
           float gl[3] = {0.f, 0.f, 0.f};
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -246,22 +367,40 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
   }
 }
 
-template <int F, int KS0, bool kFused>
-int32_t launch_bf16_fwd(cudaStream_t st, const EncDev& d, const nrc_density_mlp_t* mlp, const float* in,
-                        int64_t P, float warp_c, float bias, const QueryOut& out) {
+template <int F, int KS0, bool kFused, int kMinCtas>
+int32_t launch_bf16_fwd_occ(cudaStream_t st, const EncDev& d, const nrc_density_mlp_t* mlp, const float* in,
+                            int64_t P, float warp_c, float bias, const QueryOut& out) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(mlp_bf16_fwd_kernel<F, KS0, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(mlp_bf16_fwd_kernel<F, KS0, kFused, kMinCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          static_cast<int>(sizeof(FwdSmemBf16)));
     attr_set = true;
   }
   int64_t tiles = (P + kBfThreads - 1) / kBfThreads;
-  static const int mult = getenv("NRC_QUERY_GRID_MULT") ? atoi(getenv("NRC_QUERY_GRID_MULT")) : 3;
-  static const int group = getenv("NRC_QUERY_GROUP") ? atoi(getenv("NRC_QUERY_GROUP")) : 0;
-  unsigned grid = static_cast<unsigned>(tiles < kNumSMs * mult ? tiles : kNumSMs * mult);
-  mlp_bf16_fwd_kernel<F, KS0, kFused><<<grid, kBfThreads, sizeof(FwdSmemBf16), st>>>(d, *mlp, in, P, warp_c,
-                                                                                  bias, out, group);
+  static const int mult_env = getenv("NRC_QUERY_GRID_MULT") ? atoi(getenv("NRC_QUERY_GRID_MULT")) : 0;
+  // bit 0: hash levels gathered two at a time; bit 1: lane-pair gather (default); bit 2: forward-only launches
+  // run both 16-point tiles together (default)
+  static const int group = (getenv("NRC_QUERY_GROUP") ? atoi(getenv("NRC_QUERY_GROUP")) : 0) |
+                           ((getenv("NRC_QUERY_PAIR") ? atoi(getenv("NRC_QUERY_PAIR")) : 1) ? 2 : 0) |
+                           ((getenv("NRC_QUERY_DUAL") ? atoi(getenv("NRC_QUERY_DUAL")) : 1) ? 4 : 0);
+  const bool grad = kFused && out.raw_grad != nullptr;
+  const size_t smem = grad ? sizeof(FwdSmemBf16) : offsetof(FwdSmemBf16, wg);
+  // resident CTAs per SM: kMinCtas by registers; the gradient scratch (45 KB per CTA) caps it at 4
+  const int resident = (grad && kMinCtas > 4) ? 4 : kMinCtas;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * (mult_env > 0 ? mult_env : resident);
+  const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+  mlp_bf16_fwd_kernel<F, KS0, kFused, kMinCtas><<<grid, kBfThreads, smem, st>>>(d, *mlp, in, P, warp_c, bias, out,
+                                                                               group);
   return check_launch();
+}
+
+// Resident CTAs per SM: 4 (128 registers).  Measured on B200 (gpurun_out/j2_*): capping registers for 5 or 6 CTAs
+// per SM (96 / 80 registers, a few spills) is 3-8 % SLOWER on every workload - the kernel is bound by L1TEX
+// wavefronts (gathers + ldmatrix), and more resident shared memory leaves less L1.
+template <int F, int KS0, bool kFused>
+int32_t launch_bf16_fwd(cudaStream_t st, const EncDev& d, const nrc_density_mlp_t* mlp, const float* in,
+                        int64_t P, float warp_c, float bias, const QueryOut& out) {
+  return launch_bf16_fwd_occ<F, KS0, kFused, 4>(st, d, mlp, in, P, warp_c, bias, out);
 }
 
 int32_t density_mlp_fwd_bf16(cudaStream_t s, const nrc_density_mlp_t* mlp, const float* d_enc, int64_t P,

@@ -165,7 +165,7 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
       acc_to_afrag<false>(acc, f2);
       store_afrag(&s.g2[0][0], kWStride, row0, f2, lane);
       // g_h1 = (g_h2 W1^T) * [h1 > 0]
-      mma_layer64<4>(acc, f2, &s.w.w1[0][0], kWStride, nullptr, lane);
+      mma_layer64_t<4>(acc, f2, &s.w.w1t[0][0], kWStride, lane);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         float2 lo = unpack_bf16(h1f[nt >> 1][2 * (nt & 1)]);
@@ -187,7 +187,7 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
 #pragma unroll
           for (int np = 0; np < KS0; ++np) {
             uint32_t b[4];
-            load_b_frag2(b, &s.w.w0[0][0], kWStride, np * 16, ks * 16, lane);
+            load_b_frag2_trans(b, &s.w.w0t[0][0], kXStride, ks * 16, np * 16, lane);
             mma_bf16(ge[2 * np], f2[ks], b[0], b[1]);
             mma_bf16(ge[2 * np + 1], f2[ks], b[2], b[3]);
           }
@@ -280,9 +280,10 @@ int32_t launch_bf16_bwd(cudaStream_t st, const nrc_density_mlp_t* mlp, const flo
   nrc_density_mlp_grad_t g{};
   if (grads) g = *grads;
   int64_t tiles = (P + kBwTile - 1) / kBwTile;
-  // persistent CTAs, one per SM: measured on B200 at 65 536 points, 2-4 CTAs per SM are SLOWER (0.911 / 0.923 /
-  // 0.937 ms per step vs 0.891) -- the per-CTA weight staging and gradient flush outweigh the extra warps
-  static const int mult = getenv("NRC_MLP_BWD_GRID_MULT") ? atoi(getenv("NRC_MLP_BWD_GRID_MULT")) : 1;
+  // persistent CTAs, two per SM (103 KB of shared memory each, since the data-gradient GEMMs read the forward weight
+  // tiles through transposing loads instead of a second copy).  An earlier "2-4 CTAs per SM are slower" measurement
+  // was taken when only ONE 117 KB CTA fitted per SM, i.e. it measured extra staging passes, not extra warps.
+  static const int mult = getenv("NRC_MLP_BWD_GRID_MULT") ? atoi(getenv("NRC_MLP_BWD_GRID_MULT")) : 2;
   unsigned grid = static_cast<unsigned>(tiles < kNumSMs * mult ? tiles : kNumSMs * mult);
   mlp_bf16_bwd_kernel<KS0><<<grid, kBwThreads, sizeof(BwdSmemBf16), st>>>(*mlp, enc, g_raw, density, g_feat, g_gp,
                                                                           P, g_enc, g, grads ? 1 : 0);

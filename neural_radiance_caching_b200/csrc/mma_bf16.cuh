@@ -94,34 +94,42 @@ __device__ __forceinline__ void load_b_frag1_trans(uint32_t (&b)[2], const __nv_
   ldmatrix_x2_trans(b, tile + r * stride + n0);
 }
 
-// Shared-memory image of the MLP parameters in bf16, both orientations.
-struct __align__(16) MlpWeightsBf16 {
+// Shared-memory image of the MLP parameters in bf16, both orientations.  The forward-only part and the
+// part needed for data gradients are separate structs so that a forward-only launch can leave the second
+// one (and its per-warp scratch) out of its dynamic shared memory.
+struct __align__(16) MlpWeightsFwdBf16 {
   __nv_bfloat16 w0t[kHid][kXStride];   // [out j][in i]   forward layer 0   (B of X W0)
   __nv_bfloat16 w1t[kHid][kWStride];   // [out j][in k]   forward layer 1
   __nv_bfloat16 wot[8][kWStride];      // [head c][in j]  heads: c=0 density, 1..3 pred normals
-  __nv_bfloat16 w1[kHid][kWStride];    // [in k][out j]   backward-data of layer 1
-  __nv_bfloat16 w0[32][kWStride];      // [in i][out k]   backward-data of layer 0
   float b0[kHid];
   float b1[kHid];
   float bo[4];
+};
+// The data-gradient GEMMs (g W1^T, g W0^T) read the SAME tiles through transposing ldmatrix loads
+// (mma_layer64_t / load_b_frag2_trans): no second copy of the weights.
+struct __align__(16) MlpWeightsGradBf16 {
   float wo[kHid][4];                   // fp32 heads for the elementwise g_h2 term
 };
+struct __align__(16) MlpWeightsBf16 : MlpWeightsFwdBf16, MlpWeightsGradBf16 {};
 
-__device__ __forceinline__ void load_weights_bf16(MlpWeightsBf16& s, const nrc_density_mlp_t& m) {
+// Global reads run in the parameters' own (Flax [in][out]) order, i.e. coalesced; the transposed copies are
+// scattered into shared memory instead (a strided global read costs one L1TEX wavefront per lane, and this
+// prologue runs once per CTA: with one tile per CTA at 1024 rays it was a visible share of the launch).
+__device__ __forceinline__ void load_weights_bf16(MlpWeightsFwdBf16& s, MlpWeightsGradBf16* g,
+                                                  const nrc_density_mlp_t& m) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int in_dim = m.in_dim;
-  for (int idx = tid; idx < kHid * kXStride; idx += nt) {
-    int j = idx / kXStride, i = idx % kXStride;
-    s.w0t[j][i] = __float2bfloat16((i < in_dim) ? m.d_w0[i * kHid + j] : 0.f);
+  for (int idx = tid; idx < kXStride * kHid; idx += nt) {          // idx = i * 64 + j
+    const int i = idx / kHid, j = idx % kHid;
+    s.w0t[j][i] = __float2bfloat16((i < in_dim) ? m.d_w0[idx] : 0.f);
   }
-  for (int idx = tid; idx < kHid * kWStride; idx += nt) {
-    int r = idx / kWStride, c = idx % kWStride;
-    s.w1t[r][c] = __float2bfloat16((c < kHid) ? m.d_w1[c * kHid + r] : 0.f);
-    s.w1[r][c] = __float2bfloat16((c < kHid) ? m.d_w1[r * kHid + c] : 0.f);
+  for (int idx = tid; idx < kHid * kHid; idx += nt) {              // idx = k * 64 + j
+    const int k = idx / kHid, j = idx % kHid;
+    s.w1t[j][k] = __float2bfloat16(m.d_w1[idx]);
   }
-  for (int idx = tid; idx < 32 * kWStride; idx += nt) {
-    int i = idx / kWStride, c = idx % kWStride;
-    s.w0[i][c] = __float2bfloat16((i < in_dim && c < kHid) ? m.d_w0[i * kHid + c] : 0.f);
+  for (int idx = tid; idx < kHid * (kWStride - kHid); idx += nt) { // zero the padding columns
+    const int r = idx / (kWStride - kHid), c = kHid + idx % (kWStride - kHid);
+    s.w1t[r][c] = __float2bfloat16(0.f);
   }
   for (int idx = tid; idx < 8 * kWStride; idx += nt) {
     int c = idx / kWStride, j = idx % kWStride;
@@ -135,10 +143,15 @@ __device__ __forceinline__ void load_weights_bf16(MlpWeightsBf16& s, const nrc_d
   for (int j = tid; j < kHid; j += nt) {
     s.b0[j] = m.d_b0[j];
     s.b1[j] = m.d_b1[j];
-    s.wo[j][0] = m.d_wd[j];
-    for (int c = 0; c < 3; ++c) s.wo[j][1 + c] = m.d_wn ? m.d_wn[j * 3 + c] : 0.f;
+    if (g) {
+      g->wo[j][0] = m.d_wd[j];
+      for (int c = 0; c < 3; ++c) g->wo[j][1 + c] = m.d_wn ? m.d_wn[j * 3 + c] : 0.f;
+    }
   }
   if (tid < 4) s.bo[tid] = tid == 0 ? m.d_bd[0] : (m.d_bn ? m.d_bn[tid - 1] : 0.f);
+}
+__device__ __forceinline__ void load_weights_bf16(MlpWeightsBf16& s, const nrc_density_mlp_t& m) {
+  load_weights_bf16(s, &s, m);
 }
 
 // acc[nt][e] (16 rows x 64 cols, fp32) = bias + A(16 x 16*KS) * W^T, W^T stored [64][stride].
@@ -148,9 +161,8 @@ __device__ __forceinline__ void mma_layer64(float (&acc)[8][4], const uint32_t (
                                             int lane) {
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    float bx = bias ? bias[nt * 8 + (lane & 3) * 2] : 0.f;
-    float by = bias ? bias[nt * 8 + (lane & 3) * 2 + 1] : 0.f;
-    acc[nt][0] = bx; acc[nt][1] = by; acc[nt][2] = bx; acc[nt][3] = by;
+    const float2 bv = bias ? *reinterpret_cast<const float2*>(bias + nt * 8 + (lane & 3) * 2) : make_float2(0.f, 0.f);
+    acc[nt][0] = bv.x; acc[nt][1] = bv.y; acc[nt][2] = bv.x; acc[nt][3] = bv.y;
   }
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) {
@@ -158,6 +170,25 @@ __device__ __forceinline__ void mma_layer64(float (&acc)[8][4], const uint32_t (
     for (int np = 0; np < 4; ++np) {
       uint32_t b[4];
       load_b_frag2(b, wt, stride, np * 16, ks * 16, lane);
+      mma_bf16(acc[2 * np], a[ks], b[0], b[1]);
+      mma_bf16(acc[2 * np + 1], a[ks], b[2], b[3]);
+    }
+  }
+}
+
+// acc (16 x 64) = A(16 x 64) * W with W^T stored [j][k] (the forward tile): the reduction runs over the
+// tile's ROW index j, i.e. the data-gradient GEMM g W^T of a layer whose forward GEMM is mma_layer64.
+template <int KS>
+__device__ __forceinline__ void mma_layer64_t(float (&acc)[8][4], const uint32_t (&a)[KS][4],
+                                              const __nv_bfloat16* wt, int stride, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      load_b_frag2_trans(b, wt, stride, ks * 16, np * 16, lane);
       mma_bf16(acc[2 * np], a[ks], b[0], b[1]);
       mma_bf16(acc[2 * np + 1], a[ks], b[2], b[3]);
     }
