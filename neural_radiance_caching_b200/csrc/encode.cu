@@ -6,6 +6,8 @@
 // the CTAs resident at any instant mostly touch ONE level's table (2-8 MB), which
 // stays L2/L1 resident; threadIdx.x runs over consecutive points (= consecutive
 // samples of one ray), so coarse-level corner fetches of a warp coalesce.
+#include <cstdlib>
+
 #include "encode.cuh"
 
 namespace nrc {
@@ -56,30 +58,43 @@ encode_indices_kernel(const __grid_constant__ EncDev enc, int level, const float
   }
 }
 
-template <int F>
-__device__ __forceinline__ void atomic_add_row(float* grad, int32_t row, const float (&g)[F]) {
-  if constexpr (F == 4) {
-    atomicAdd(reinterpret_cast<float4*>(grad) + row, make_float4(g[0], g[1], g[2], g[3]));
-  } else if constexpr (F == 2) {
-    atomicAdd(reinterpret_cast<float2*>(grad) + row, make_float2(g[0], g[1]));
-  } else if constexpr (F == 8) {
-    atomicAdd(reinterpret_cast<float4*>(grad) + 2 * row, make_float4(g[0], g[1], g[2], g[3]));
-    atomicAdd(reinterpret_cast<float4*>(grad) + 2 * row + 1, make_float4(g[4], g[5], g[6], g[7]));
-  } else {
-    atomicAdd(grad + row, g[0]);
-  }
-}
-
 // Backward: scatter-add into the level's gradient table and (optionally) the VJP
 // with respect to x, accumulated over levels with atomics into a zeroed [P,3].
 template <int F, bool kTableGrad, bool kXGrad>
 __global__ void __launch_bounds__(kEncThreads)
 encode_bwd_kernel(const __grid_constant__ EncDev enc, const float* __restrict__ x,
-                  const float* __restrict__ g_out, int64_t P, float* __restrict__ g_x) {
+                  const float* __restrict__ g_out, int64_t P, float* __restrict__ g_x, const int aggregate) {
   const int64_t p = static_cast<int64_t>(blockIdx.x) * kEncThreads + threadIdx.x;
-  if (p >= P) return;
   const int l = blockIdx.y;
   const LevelDev& lv = enc.lv[l];
+  if constexpr (kTableGrad && !kXGrad) {
+    if (aggregate && !lv.is_hash && lv.grad) {   // block-uniform: every lane stays for the shuffles
+      const bool valid = p < P;
+      const int64_t pc = valid ? p : P - 1;
+      float xi[3] = {__ldg(x + 3 * pc), __ldg(x + 3 * pc + 1), __ldg(x + 3 * pc + 2)};
+      float xn[3];
+      normalise_point(enc, xi, xn);
+      const Corners c = level_setup(lv, xn);
+      float g[F];
+      const float* gp = g_out + pc * (enc.L * F) + l * F;
+#pragma unroll
+      for (int f = 0; f < F; ++f) g[f] = valid ? __ldg(gp + f) * enc.scale : 0.f;
+      const int lane = threadIdx.x & 31;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int bx, by, bz;
+        corner_bits(0, k, bx, by, bz);
+        const int32_t row = valid ? corner_row(lv, c, bx, by, bz) : -1;
+        const float w = (bx ? c.cw[0] : c.fw[0]) * (by ? c.cw[1] : c.fw[1]) * (bz ? c.cw[2] : c.fw[2]);
+        float gw[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) gw[f] = g[f] * w;
+        warp_run_atomic_add<F>(lv.grad, row, gw, lane);
+      }
+      return;
+    }
+  }
+  if (p >= P) return;
   float xi[3] = {__ldg(x + 3 * p), __ldg(x + 3 * p + 1), __ldg(x + 3 * p + 2)};
   float xn[3];
   normalise_point(enc, xi, xn);
@@ -136,9 +151,10 @@ template <int F>
 int32_t launch_bwd(cudaStream_t s, const EncDev& d, const float* x, const float* g, int64_t P,
                    float* g_x, bool table_grad) {
   dim3 grid(static_cast<unsigned>((P + kEncThreads - 1) / kEncThreads), d.L);
-  if (table_grad && g_x) encode_bwd_kernel<F, true, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x);
-  else if (table_grad) encode_bwd_kernel<F, true, false><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x);
-  else if (g_x) encode_bwd_kernel<F, false, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x);
+  static const int agg = getenv("NRC_ENC_BWD_AGG") ? atoi(getenv("NRC_ENC_BWD_AGG")) : 1;
+  if (table_grad && g_x) encode_bwd_kernel<F, true, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, 0);
+  else if (table_grad) encode_bwd_kernel<F, true, false><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, agg);
+  else if (g_x) encode_bwd_kernel<F, false, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, 0);
   return check_launch();
 }
 

@@ -288,7 +288,10 @@ __device__ __forceinline__ void hash_interp_group(const EncDev& enc, int l0, con
 // flight per lane.  The even lane sums its four products in the reference's order and hands the partial
 // sum to the odd lane, which continues the same left-to-right sum: bit-identical to level_interp.
 // All 32 lanes must call this (full-mask shuffle); the result is valid on ODD lanes.
-template <int F, int H>
+// kExact = false (bf16-MLP variant, whose features are rounded to 8 mantissa bits right after): the weighted
+// sum is contracted into FMAs (5 instead of 11 FP instructions per feature); corner INDICES and weights are
+// computed exactly as above in both modes.
+template <int F, int H, bool kExact>
 __device__ __forceinline__ void level_interp_pair(const LevelDev& lv, const float (&xn)[H][3], const int side,
                                                   FeatVec<F> (&out)[H]) {
   int32_t rows[H][4];
@@ -355,13 +358,61 @@ __device__ __forceinline__ void level_interp_pair(const LevelDev& lv, const floa
   for (int h = 0; h < H; ++h)
 #pragma unroll
     for (int f = 0; f < F; ++f) {
-      float p[4];
+      if constexpr (kExact) {
+        float p[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) p[j] = __fmul_rn(vals[h][j].v[f], w[h][j]);
-      const float s = __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[2]), p[3]);
-      const float lo = __shfl_xor_sync(0xffffffffu, s, 1);
-      out[h].v[f] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(lo, p[0]), p[1]), p[2]), p[3]);
+        for (int j = 0; j < 4; ++j) p[j] = __fmul_rn(vals[h][j].v[f], w[h][j]);
+        const float s = __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[2]), p[3]);
+        const float lo = __shfl_xor_sync(0xffffffffu, s, 1);
+        out[h].v[f] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(lo, p[0]), p[1]), p[2]), p[3]);
+      } else {
+        float s = vals[h][0].v[f] * w[h][0];
+#pragma unroll
+        for (int j = 1; j < 4; ++j) s = fmaf(vals[h][j].v[f], w[h][j], s);
+        out[h].v[f] = s + __shfl_xor_sync(0xffffffffu, s, 1);
+      }
     }
+}
+
+// ---- table-gradient scatter helpers (encode.cu, normals2.cu) ----
+template <int F>
+__device__ __forceinline__ void atomic_add_row(float* grad, int32_t row, const float (&g)[F]) {
+  if constexpr (F == 4) {
+    atomicAdd(reinterpret_cast<float4*>(grad) + row, make_float4(g[0], g[1], g[2], g[3]));
+  } else if constexpr (F == 2) {
+    atomicAdd(reinterpret_cast<float2*>(grad) + row, make_float2(g[0], g[1]));
+  } else if constexpr (F == 8) {
+    atomicAdd(reinterpret_cast<float4*>(grad) + 2 * row, make_float4(g[0], g[1], g[2], g[3]));
+    atomicAdd(reinterpret_cast<float4*>(grad) + 2 * row + 1, make_float4(g[4], g[5], g[6], g[7]));
+  } else {
+    atomicAdd(grad + row, g[0]);
+  }
+}
+
+// Contiguous runs of lanes that hit the SAME row are summed into the run's first lane, which issues one
+// atomic for the run.  Consecutive lanes are consecutive samples of a ray, and on the coarse dense levels
+// (16^3, 32^3, 64^3) whole stretches of a ray fall into one cell: without this the cells around the scene
+// centre receive thousands of same-address atomics per step, which the L2 serialises.  Segmented reduction
+// by shuffles: after the step with distance d lane i holds the sum of lanes [i, i+2d) of its run.
+template <int F>
+__device__ __forceinline__ void warp_run_atomic_add(float* grad, int32_t row, float (&gw)[F], int lane) {
+  // a run starts wherever the row differs from the previous lane's; lanes i and i+d belong to the same run
+  // iff no run starts in (i, i+d]  (equal rows in DIFFERENT runs stay separate: each run issues its own atomic)
+  const int32_t rp = __shfl_up_sync(0xffffffffu, row, 1);
+  const bool head = lane == 0 || rp != row;
+  const uint32_t heads = __ballot_sync(0xffffffffu, head);
+  const uint32_t after = lane == 31 ? 0xffffffffu : (heads >> (lane + 1));   // bit j: a run starts at lane+1+j
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float o[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) o[f] = __shfl_down_sync(0xffffffffu, gw[f], d);
+    if (lane + d < 32 && (after & ((1u << d) - 1u)) == 0u) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) gw[f] += o[f];
+    }
+  }
+  if (head && row >= 0) atomic_add_row<F>(grad, row, gw);
 }
 
 __device__ __forceinline__ void normalise_point(const EncDev& enc, const float x[3], float xn[3]) {

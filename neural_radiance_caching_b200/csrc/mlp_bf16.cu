@@ -144,7 +144,7 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
           for (int a = 0; a < 3; ++a) xq[h][a] = __shfl_sync(0xffffffffu, xn[a], h * 16 + (lane >> 1));
         for (int l = 0; l < enc.L; ++l) {
           FeatVec<F> v[2];
-          level_interp_pair<F, 2>(enc.lv[l], xq, side, v);
+          level_interp_pair<F, 2, false>(enc.lv[l], xq, side, v);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int q = h * 16 + (lane >> 1);

@@ -5,6 +5,7 @@
 //   phase 2 (per CTA): weight gradients dW = A^T G as MMAs over the 128-point tile with the
 //     transposed-ldmatrix trick, accumulated in fp32 registers across all tiles of the CTA.
 // One atomic pass per CTA at the end.  Reference: XLA autodiff of geometry.py:155-168,467.
+#include <cstdint>
 #include <cstdlib>
 
 #include "mma_bf16.cuh"
@@ -236,21 +237,39 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
     __syncthreads();
   }
   if (!want_wgrad) return;
+  // Each lane holds column pairs (cq, cq+1); the odd lane of a pair hands its two values to the even one, which issues
+  // ONE 16-byte reduction for columns cq..cq+3 (cq = 0 or 4 there).  Scalar fallback for unaligned gradient buffers.
+  const bool vec = ((reinterpret_cast<uintptr_t>(grads.d_w1) | reinterpret_cast<uintptr_t>(grads.d_w0)) & 15) == 0;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int row = warp * 16 + r + (e >= 2 ? 8 : 0), col = nt * 8 + cq + (e & 1);
-      atomicAdd(grads.d_w1 + row * kHid + col, accW1[nt][e]);
+    for (int h = 0; h < 2; ++h) {
+      const int row = warp * 16 + r + 8 * h, col = nt * 8 + cq;
+      const float v0 = accW1[nt][2 * h], v1 = accW1[nt][2 * h + 1];
+      const float o0 = __shfl_xor_sync(0xffffffffu, v0, 1), o1 = __shfl_xor_sync(0xffffffffu, v1, 1);
+      if (vec) {
+        if ((lane & 1) == 0) red_add_v4(grads.d_w1 + row * kHid + col, v0, v1, o0, o1);
+      } else {
+        atomicAdd(grads.d_w1 + row * kHid + col, v0);
+        atomicAdd(grads.d_w1 + row * kHid + col + 1, v1);
+      }
     }
 #pragma unroll
   for (int mi = 0; mi < KS0; ++mi)
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int row = mi * 16 + r + (e >= 2 ? 8 : 0), col = warp * 16 + h * 8 + cq + (e & 1);
-        if (row < in_dim) atomicAdd(grads.d_w0 + row * kHid + col, accW0[mi][h][e]);
+      for (int h = 0; h < 2; ++h) {
+        const int row = mi * 16 + r + 8 * h, col = warp * 16 + hh * 8 + cq;
+        const float v0 = accW0[mi][hh][2 * h], v1 = accW0[mi][hh][2 * h + 1];
+        const float o0 = __shfl_xor_sync(0xffffffffu, v0, 1), o1 = __shfl_xor_sync(0xffffffffu, v1, 1);
+        if (row >= in_dim) continue;   // uniform within a lane pair (same row)
+        if (vec) {
+          if ((lane & 1) == 0) red_add_v4(grads.d_w0 + row * kHid + col, v0, v1, o0, o1);
+        } else {
+          atomicAdd(grads.d_w0 + row * kHid + col, v0);
+          atomicAdd(grads.d_w0 + row * kHid + col + 1, v1);
+        }
       }
 #pragma unroll
   for (int e = 0; e < 4; ++e) {

@@ -17,6 +17,8 @@
 // Biases get nothing (the tangent map has no bias term); sample positions are constants
 // (stop_level_grad, internal/sampling.py:353-354).  fp32 FFMA, one point per thread: this runs on the 32 final
 // samples per ray only (32 768 points per 1024-ray batch), 19 k MAC per point.
+#include <cstdint>
+
 #include "encode.cuh"
 #include "mlp.cuh"
 
@@ -131,17 +133,28 @@ density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density
       for (int k = 0; k < 8; ++k) {
         int bx, by, bz;
         corner_bits(lv.is_hash, k, bx, by, bz);
-        const int32_t row = corner_row(lv, c, bx, by, bz);
-        if (row < 0 || !valid) continue;
+        // no early-out: every lane stays for the shuffles of the run-aggregated scatter
+        const int32_t row = valid ? corner_row(lv, c, bx, by, bz) : -1;
         const float wx = bx ? c.cw[0] : c.fw[0];
         const float wy = by ? c.cw[1] : c.fw[1];
         const float wz = bz ? c.cw[2] : c.fw[2];
         const float dw = (bx ? t0 : -t0) * (wy * wz) + (by ? t1 : -t1) * (wx * wz) + (bz ? t2 : -t2) * (wx * wy);
-        const FeatVec<F> v = load_row<F>(lv.table, row);
+        FeatVec<F> v;
+        if (row >= 0) v = load_row<F>(lv.table, row);
+        else {
+#pragma unroll
+          for (int f = 0; f < F; ++f) v.v[f] = 0.f;
+        }
+        float gw[F];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
           ed[f] = fmaf(dw, v.v[f], ed[f]);
-          if (lv.grad) atomicAdd(lv.grad + static_cast<size_t>(row) * F + f, dw * g[f]);
+          gw[f] = dw * g[f];
+        }
+        // one vector reduction per corner row; on dense levels runs of lanes in the same cell are summed first
+        if (lv.grad) {
+          if (!lv.is_hash) warp_run_atomic_add<F>(lv.grad, row, gw, tid & 31);
+          else if (row >= 0) atomic_add_row<F>(lv.grad, row, gw);
         }
       }
 #pragma unroll
@@ -202,16 +215,32 @@ density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density
     }
     __syncthreads();
   }
+  // Adjacent lanes hold adjacent columns (cj = tid & 7): the lanes with cj % 4 == 0 collect their three neighbours'
+  // values and issue ONE 16-byte reduction per four columns.  Scalar fallback for unaligned gradient buffers.
+  const bool vec = ((reinterpret_cast<uintptr_t>(grads.d_w1) | reinterpret_cast<uintptr_t>(grads.d_w0)) & 15) == 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(grads.d_w1 + (i * 16 + rk) * kW + j * 8 + cj, aW1[i][j]);
+    for (int j = 0; j < 8; ++j) {
+      const float v = aW1[i][j];
+      const float v1 = __shfl_down_sync(0xffffffffu, v, 1), v2 = __shfl_down_sync(0xffffffffu, v, 2),
+                  v3 = __shfl_down_sync(0xffffffffu, v, 3);
+      float* dst = grads.d_w1 + (i * 16 + rk) * kW + j * 8 + cj;
+      if (vec) { if ((cj & 3) == 0) red_add_v4(dst, v, v1, v2, v3); }
+      else atomicAdd(dst, v);
+    }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int row = i * 16 + rk;
-    if (row < in_dim) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(grads.d_w0 + row * kW + j * 8 + cj, aW0[i][j]);
+    for (int j = 0; j < 8; ++j) {
+      const float v = aW0[i][j];
+      const float v1 = __shfl_down_sync(0xffffffffu, v, 1), v2 = __shfl_down_sync(0xffffffffu, v, 2),
+                  v3 = __shfl_down_sync(0xffffffffu, v, 3);
+      if (row >= in_dim) continue;
+      float* dst = grads.d_w0 + row * kW + j * 8 + cj;
+      if (vec) { if ((cj & 3) == 0) red_add_v4(dst, v, v1, v2, v3); }
+      else atomicAdd(dst, v);
     }
   }
   if (tid < kW) atomicAdd(grads.d_wd + tid, s.dwd[tid]);

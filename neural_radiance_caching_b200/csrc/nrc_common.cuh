@@ -77,4 +77,12 @@ __device__ __forceinline__ void contract_vjp(float c, float x0, float x1, float 
   o0 = a0 / c; o1 = a1 / c; o2 = a2 / c;
 }
 
+// 16-byte vector reduction (sm_90+): one L2 atomic transaction for four adjacent floats.  The per-CTA weight-gradient
+// flushes put a few hundred CTAs' worth of partial sums onto the SAME few thousand addresses at the same moment, and the
+// L2 serialises same-address atomics: four floats per transaction is four times fewer of them.  addr must be 16-byte
+// aligned.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 }  // namespace nrc
