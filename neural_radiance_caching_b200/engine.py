@@ -65,15 +65,17 @@ class FusedCacheStep:
             self._bg[key] = (sd, torch.ones((R, 1), device=dev, dtype=torch.float32))
         return self._bg[key]
 
-    def step(self, rays, u01, target_rgb, train_frac=1.0, extra=None):
+    def step(self, rays, u01, target_rgb, train_frac=1.0, extra=None, zero_grad=None):
         """One forward + loss + backward; gradients land in the registered sinks.  Returns the loss
         (device scalar) and leaves the per-level sampler state in self.last (for tests).
-        `extra` = (rays, u01) of the backward-mask pass (train_utils.py:3348-3401) or None."""
-        state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra)
+        `extra` = (rays, u01) of the backward-mask pass (train_utils.py:3348-3401) or None.
+        `zero_grad` = callable that clears the gradient sinks (the 110 MB arena memset): issued here on a side
+        stream beside the sampler's forward instead of in front of the step."""
+        state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra, zero_grad=zero_grad)
         self.step_back(state)
         return state["loss"]
 
-    def _weights_only_pass(self, rays, u01, train_frac, loss):
+    def _weights_only_pass(self, rays, u01, train_frac, loss, grads_ready=None):
         """Backward-mask term: sampler-only forward on the extra rays (weights_only=True), mask loss against a zero
         mask on acc = sum(weights), and the final level's backward (the proposal levels receive nothing from this
         pass: they are supervised by the main rays' interlevel loss only and positions are stop-gradiented)."""
@@ -109,6 +111,8 @@ class FusedCacheStep:
         g_w = new(R, lv["n"])
         _lib.call("nrc_mask_loss", st(), _lib.ptr(lv["weights"]), lv["n"], self._zero_mask(R, dev), R,
                   float(self.charb_padding), 0.0, float(self.backward_mask_weight), _lib.ptr(loss), _lib.ptr(g_w))
+        if grads_ready is not None:     # the gradient arena's memset (side stream) must be done before the first scatter
+            torch.cuda.current_stream().wait_event(grads_ready)
         self._level_backward(lv, rays, g_w, None, None, R)
         self.last_extra = lv
 
@@ -118,7 +122,7 @@ class FusedCacheStep:
             self._bg[key] = torch.zeros((R,), device=dev, dtype=torch.float32)
         return _lib.ptr(self._bg[key])
 
-    def step_front(self, rays, u01, target_rgb, train_frac=1.0, fork_proposals=False, extra=None):
+    def step_front(self, rays, u01, target_rgb, train_frac=1.0, fork_proposals=False, extra=None, zero_grad=None):
         """Forward, loss and the SHADER's backward: when this returns (in stream order) every gradient of the
         `Shader` parameters (appearance grid + all stacks) is final, so a data-parallel harness can start
         all-reducing that half of the gradient arena while step_back() produces the sampler's half."""
@@ -135,6 +139,18 @@ class FusedCacheStep:
         names, sflat = shader.fused_params(shp)
         app_arena = shp["appearance_grid"]["_arena"]
         loss = torch.zeros((), device=dev, dtype=torch.float32)
+        # gradient-arena memset: nothing reads or writes gradients before the first backward / regularizer launch, so it
+        # runs on the packing stream beside the sampler's forward; every gradient-writing stream waits on `grads_ready`
+        grads_ready = None
+        if zero_grad is not None:
+            if s_pack is not None:
+                s_pack.wait_stream(main)
+                with torch.cuda.stream(s_pack):
+                    zero_grad()
+                    grads_ready = torch.cuda.Event()
+                    grads_ready.record()
+            else:
+                zero_grad()
         # backward-mask pass: independent rays, its own stream (joined in step_back); in split mode
         # (fork_proposals False: two graphs) it is issued by step_back instead
         s_x = None
@@ -143,7 +159,7 @@ class FusedCacheStep:
                 s_x = self._streams(6)[4]
                 s_x.wait_stream(main)
                 with torch.cuda.stream(s_x):
-                    self._weights_only_pass(extra[0], extra[1], train_frac, loss)
+                    self._weights_only_pass(extra[0], extra[1], train_frac, loss, grads_ready)
             else:
                 self._weights_only_pass(extra[0], extra[1], train_frac, loss)
             extra = None
@@ -213,6 +229,8 @@ class FusedCacheStep:
         # they, the l2_normalize VJP and the second-order kernel (nrc_density_normals_bwd, the longest kernel of the
         # step) start here and run beside the shader; their g_w / g_normals_pred terms are added after the shader's.
         k = L2["n"]
+        if grads_ready is not None:     # long done by now (memset ~20 us vs the sampler's forward); orders every later fork
+            main.wait_event(grads_ready)
         geo, s_geo = None, None
         if self.geometry_mults is not None:
             def geometry_branch():

@@ -266,14 +266,12 @@ class CacheTrainStep:
         elementwise glue); the fp32 parity variant goes through the autograd mirrors.
         `extra` = (backward-mask rays, their u01): see backward_mask_rays_np."""
         if self.engine is not None:
-            self.zero_grad()
-            return self.engine.step(rays, u01, target_rgb, extra=extra)
+            return self.engine.step(rays, u01, target_rgb, extra=extra, zero_grad=self.zero_grad)
         return self.step_autograd(rays, u01, target_rgb, extra)
 
     def step_front(self, rays, u01, target_rgb, extra=None):
         """First half of step() (forward, loss, shader backward); see engine.FusedCacheStep.step_front."""
-        self.zero_grad()
-        return self.engine.step_front(rays, u01, target_rgb, extra=extra)
+        return self.engine.step_front(rays, u01, target_rgb, extra=extra, zero_grad=self.zero_grad)
 
     def step_back(self, state):
         self.engine.step_back(state)
