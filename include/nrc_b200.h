@@ -197,6 +197,15 @@ int32_t nrc_ray_cast(void* stream, const float* d_sdist, const float* d_origins,
                      const float* d_directions, const float* d_near, const float* d_far,
                      int64_t num_rays, int32_t n, int32_t warp_kind, float p, float premult,
                      float* d_tdist, float* d_means);
+/* nrc_ray_sample_intervals followed by nrc_ray_cast in ONE launch (the sampler's per-level pair sampling.py:340-349 ->
+ * render.cast_rays, internal/render.py:26-131): same arguments and bit-identical outputs; d_sdist_new [R,n+1] are the
+ * resampled normalised fenceposts, d_tdist [R,n+1] their metric distances, d_means [R,n,3] (may be NULL) the
+ * Gaussian means. */
+int32_t nrc_ray_sample_cast(void* stream, const float* d_t, const float* d_w, const float* d_u01, const float* d_u_base,
+                            int64_t num_rays, int32_t m, int32_t n, float anneal, float padding, float max_jitter,
+                            float dom_lo, float dom_hi, const float* d_origins, const float* d_directions,
+                            const float* d_near, const float* d_far, int32_t warp_kind, float p, float premult,
+                            float* d_sdist_new, float* d_tdist, float* d_means);
 
 /* render.volumetric_rendering (internal/render.py:172-247): acc, rgb (+bg), C channels
  * composited with `weights`, distance mean and percentiles (5,50,95) from

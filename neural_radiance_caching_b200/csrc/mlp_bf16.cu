@@ -99,7 +99,7 @@ template <int F, int KS0, bool kFused, int kMinCtas>
 __global__ void __launch_bounds__(kBfThreads, kMinCtas)
 mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t m,
                     const float* __restrict__ in, int64_t P, float warp_c, float density_bias,
-                    const QueryOut out, const int g_group) {
+                    const QueryOut out, const int g_group, const int ppw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmemBf16& s = *reinterpret_cast<FwdSmemBf16*>(smem_raw);
   const bool want_grad = kFused && out.raw_grad != nullptr;   // the launcher sizes the allocation accordingly
@@ -109,17 +109,20 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
   WarpScratch& ws = s.ws[warp];
   WarpGradScratch& gs = s.gs[warp];
   const int in_dim = m.in_dim;
-  const int64_t num_tiles = (P + kBfThreads - 1) / kBfThreads;
+  // ppw = points per warp: 32 (two 16-row MMA tiles), or 16 for launches too small to fill the machine with
+  // 128-point CTAs (32 768 points = 256 CTAs on 148 SMs): twice the CTAs, half the serial work per warp
+  const int64_t pts_per_cta = static_cast<int64_t>(kBfWarps) * ppw;
+  const int64_t num_tiles = (P + pts_per_cta - 1) / pts_per_cta;
   if constexpr (kFused) {
     uint32_t* xz = reinterpret_cast<uint32_t*>(&ws.x[0][0]);
     for (int i = lane; i < 32 * kXStride / 2; i += 32) xz[i] = 0u;
     __syncwarp();
   }
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t base = tile * kBfThreads + warp * 32;
+    const int64_t base = tile * pts_per_cta + warp * ppw;
     if (base >= P) continue;  // warp-uniform
     const int64_t p = base + lane;
-    const bool valid = p < P;
+    const bool valid = lane < ppw && p < P;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f, xn[3] = {0.f, 0.f, 0.f};
     // ---------------- front end: one point per lane -> bf16 feature row -------------------
     if constexpr (kFused) {
@@ -134,7 +137,26 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
         for (int a = 0; a < 3; ++a) inside = inside && (z[a] > enc.b0[a]) && (z[a] < enc.b1[a]);
       }
       ws.inside[lane] = inside;
-      if (g_group & 2) {
+      if ((g_group & 2) && ppw == 16) {
+        // Lane-pair gather, one 16-point tile per warp
+        const int side = lane & 1, q = lane >> 1;
+        float xq[1][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) xq[0][a] = __shfl_sync(0xffffffffu, xn[a], q);
+        for (int l = 0; l < enc.L; ++l) {
+          FeatVec<F> v[1];
+          level_interp_pair<F, 1, false>(enc.lv[l], xq, side, v);
+          if (side && base + q < P) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+              float e = __fmul_rn(v[0].v[f], enc.scale);
+              ws.x[q][l * F + f] = __float2bfloat16(e);
+              if (out.enc_out) out.enc_out[(base + q) * in_dim + l * F + f] = e;
+            }
+          }
+        }
+        __syncwarp();
+      } else if (g_group & 2) {
         // Lane-pair gather (encode.cuh: level_interp_pair): lanes 2i, 2i+1 share point i of each 16-point half.
         const int side = lane & 1;
         float xq[2][3];
@@ -193,7 +215,7 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
         }
       }
       // padding columns [in_dim, 16*KS0) were zeroed once before the tile loop and are never written again
-      if (!valid)
+      if (!valid && lane < ppw)
         for (int k = 0; k < in_dim; ++k) ws.x[lane][k] = __float2bfloat16(0.f);
     } else {
       for (int k = 0; k < KS0 * 16; ++k)
@@ -202,7 +224,7 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
     }
     __syncwarp();
     // ---------------- tensor-core MLP: two 16-point tiles per warp ------------------------
-    if (!want_grad && (g_group & 4)) {
+    if (!want_grad && (g_group & 4) && ppw == 32) {
       // forward only: both tiles together, B fragments shared
       uint32_t af[2][KS0][4];
 #pragma unroll
@@ -245,7 +267,7 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
       continue;
     }
 #pragma unroll 1
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < (ppw >> 4); ++mt) {
       uint32_t a0[KS0][4];
 #pragma unroll
       for (int ks = 0; ks < KS0; ++ks) load_a_frag(a0[ks], &ws.x[0][0], kXStride, mt * 16, ks * 16, lane);
@@ -376,7 +398,7 @@ int32_t launch_bf16_fwd_occ(cudaStream_t st, const EncDev& d, const nrc_density_
                          static_cast<int>(sizeof(FwdSmemBf16)));
     attr_set = true;
   }
-  int64_t tiles = (P + kBfThreads - 1) / kBfThreads;
+  static const int ppw_env = getenv("NRC_QUERY_PPW") ? atoi(getenv("NRC_QUERY_PPW")) : 0;
   static const int mult_env = getenv("NRC_QUERY_GRID_MULT") ? atoi(getenv("NRC_QUERY_GRID_MULT")) : 0;
   // bit 0: hash levels gathered two at a time; bit 1: lane-pair gather (default); bit 2: forward-only launches
   // run both 16-point tiles together (default)
@@ -388,9 +410,15 @@ int32_t launch_bf16_fwd_occ(cudaStream_t st, const EncDev& d, const nrc_density_
   // resident CTAs per SM: kMinCtas by registers; the gradient scratch (45 KB per CTA) caps it at 4
   const int resident = (grad && kMinCtas > 4) ? 4 : kMinCtas;
   const int64_t cap = static_cast<int64_t>(kNumSMs) * (mult_env > 0 ? mult_env : resident);
+  // 32 points per warp.  The 16-point mode (NRC_QUERY_PPW=16: twice the CTAs for launches that leave SMs idle, e.g.
+  // 32 768 points = 256 CTAs) measured SLOWER on the config-2 step (0.979 vs 0.951 ms, gpurun_out/j7_*): the weight
+  // staging per CTA is paid twice as often and the side streams already fill the idle SMs.
+  int ppw = 32;
+  if (ppw_env == 16 && kFused) ppw = 16;
+  const int64_t tiles = (P + kBfWarps * ppw - 1) / (kBfWarps * ppw);
   const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
   mlp_bf16_fwd_kernel<F, KS0, kFused, kMinCtas><<<grid, kBfThreads, smem, st>>>(d, *mlp, in, P, warp_c, bias, out,
-                                                                               group);
+                                                                               group, ppw);
   return check_launch();
 }
 

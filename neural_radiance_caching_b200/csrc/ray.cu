@@ -111,6 +111,29 @@ alpha_weights_bwd_kernel(const float* __restrict__ density, const float* __restr
   }
 }
 
+// power-ladder ray warp (used by the cast below and by the fused sample + cast)
+__device__ __forceinline__ float power_ladder_fwd(float x, float p, float premult) {
+  // math.power_ladder general branch (internal/math.py:295-316)
+  x = __fmul_rn(x, premult);
+  float xp = fabsf(x);
+  float xs = __fdiv_rn(xp, fmaxf(f32_tiny(), fabsf(p - 1.0f)));
+  float y = __fmul_rn(__fdiv_rn(fabsf(p - 1.0f), p), __fsub_rn(powf(__fadd_rn(xs, 1.0f), p), 1.0f));
+  return x < 0.f ? -y : y;
+}
+__device__ __forceinline__ float power_ladder_inv(float y, float p, float premult) {
+  // math.inv_power_ladder general branch (internal/math.py:319-341)
+  float yp = fabsf(y);
+  float ymax = nextafterf((p - 1.0f) / p, -INFINITY);  // minus_eps(power_ladder_max_output(p)), p < 0
+  if (p >= 0.f) ymax = f32_max();
+  yp = fminf(fmaxf(yp, -ymax), ymax);
+  float ratio = __fdiv_rn(p, fabsf(p - 1.0f));
+  float base = __fadd_rn(__fmul_rn(ratio, yp), 1.0f);
+  float x = __fmul_rn(fabsf(p - 1.0f), __fsub_rn(powf(base, __fdiv_rn(1.0f, p)), 1.0f));
+  x = y < 0.f ? -x : x;
+  return __fdiv_rn(x, premult);
+}
+
+
 // --------------------------------------------------------- sample_intervals --
 // sampling.py:340 (annealed logits) + stepfun.sample_intervals :207-250
 // (sample :158-204 -> invert_cdf :147-155 -> integrate_weights :125-144 ->
@@ -119,7 +142,11 @@ __global__ void __launch_bounds__(kRayThreads)
 sample_intervals_kernel(const float* __restrict__ t_in, const float* __restrict__ w_in,
                         const float* __restrict__ u01, const float* __restrict__ u_base, int64_t R,
                         int m, int n, float anneal, float padding, float max_jitter, float dom_lo,
-                        float dom_hi, float* __restrict__ t_new, int32_t* __restrict__ bin_idx) {
+                        float dom_hi, float* __restrict__ t_new, int32_t* __restrict__ bin_idx,
+                        // optional fused cast_rays (nrc_ray_sample_cast): tdist == nullptr -> sampling only
+                        const float* __restrict__ origins, const float* __restrict__ directions,
+                        const float* __restrict__ near, const float* __restrict__ far, int warp_kind, float p,
+                        float premult, float* __restrict__ tdist, float* __restrict__ means) {
   __shared__ float s_t[kRayWarps][kMaxN + 1];
   __shared__ float s_w[kRayWarps][kMaxN];       // softmax weights
   __shared__ float s_cw[kRayWarps][kMaxN + 1];  // integrated weights
@@ -188,40 +215,58 @@ sample_intervals_kernel(const float* __restrict__ t_in, const float* __restrict_
     s_s[warp][j] = fminf(fmaxf(v, dom_lo), dom_hi);
   }
   __syncwarp();
-  // jnp.sort: stable rank sort (the input is sorted up to last-ulp inversions)
-  for (int j = lane; j <= n; j += 32) {
-    float v = s_s[warp][j];
-    int rank = 0;
-    for (int k = 0; k <= n; ++k) {
-      float o = s_s[warp][k];
-      rank += (o < v) || (o == v && k < j);
+  // jnp.sort.  The fenceposts are sorted up to last-ulp inversions: a warp vote finds the (usual) already-sorted
+  // case, where the stable sort is the identity; otherwise a stable rank sort (O(n^2), same result as before).
+  bool ok = true;
+  for (int j = lane; j < n; j += 32) ok = ok && (s_s[warp][j] <= s_s[warp][j + 1]);
+  const float* sorted = s_s[warp];
+  if (!__all_sync(0xffffffffu, ok)) {
+    for (int j = lane; j <= n; j += 32) {
+      float v = s_s[warp][j];
+      int rank = 0;
+      for (int k = 0; k <= n; ++k) {
+        float o = s_s[warp][k];
+        rank += (o < v) || (o == v && k < j);
+      }
+      s_cw[warp][rank] = v;   // the integrated weights are no longer needed
     }
-    t_new[r * (n + 1) + rank] = v;
+    __syncwarp();
+    sorted = s_cw[warp];
+  }
+  for (int j = lane; j <= n; j += 32) t_new[r * (n + 1) + j] = sorted[j];
+  if (tdist == nullptr) return;
+  // ---- fused cast_rays (same expressions as ray_cast_kernel; every metric distance is computed once) ----
+  float s_near = near[r], s_far = far[r];
+  if (warp_kind == 1) {
+    s_near = power_ladder_fwd(s_near, p, premult);
+    s_far = power_ladder_fwd(s_far, p, premult);
+  }
+  for (int j = lane; j <= n; j += 32) {
+    const float sv = sorted[j];
+    float v = __fadd_rn(__fmul_rn(sv, s_far), __fmul_rn(__fsub_rn(1.0f, sv), s_near));
+    if (warp_kind == 1) v = power_ladder_inv(v, p, premult);
+    tdist[r * (n + 1) + j] = v;
+    s_t[warp][j] = v;           // the input fenceposts are no longer needed
+  }
+  if (means == nullptr) return;
+  __syncwarp();
+  const float o0 = origins[3 * r], o1 = origins[3 * r + 1], o2 = origins[3 * r + 2];
+  const float d0 = directions[3 * r], d1 = directions[3 * r + 1], d2 = directions[3 * r + 2];
+  const float eps2c = f32_eps() * f32_eps();
+  for (int i = lane; i < n; i += 32) {
+    const float t0 = s_t[warp][i], t1 = s_t[warp][i + 1];
+    const float sm = __fadd_rn(t0, t1), d = __fsub_rn(t1, t0);
+    const float dsq = __fmul_rn(d, d);
+    const float ratio = __fdiv_rn(dsq, fmaxf(eps2c, __fadd_rn(__fmul_rn(3.0f, __fmul_rn(sm, sm)), dsq)));
+    const float t_mean = __fmul_rn(sm, __fadd_rn(0.5f, ratio));
+    float* mo = means + (r * n + i) * 3;
+    mo[0] = __fadd_rn(__fmul_rn(d0, t_mean), o0);
+    mo[1] = __fadd_rn(__fmul_rn(d1, t_mean), o1);
+    mo[2] = __fadd_rn(__fmul_rn(d2, t_mean), o2);
   }
 }
 
 // ------------------------------------------------------------------ ray cast --
-__device__ __forceinline__ float power_ladder_fwd(float x, float p, float premult) {
-  // math.power_ladder general branch (internal/math.py:295-316)
-  x = __fmul_rn(x, premult);
-  float xp = fabsf(x);
-  float xs = __fdiv_rn(xp, fmaxf(f32_tiny(), fabsf(p - 1.0f)));
-  float y = __fmul_rn(__fdiv_rn(fabsf(p - 1.0f), p), __fsub_rn(powf(__fadd_rn(xs, 1.0f), p), 1.0f));
-  return x < 0.f ? -y : y;
-}
-__device__ __forceinline__ float power_ladder_inv(float y, float p, float premult) {
-  // math.inv_power_ladder general branch (internal/math.py:319-341)
-  float yp = fabsf(y);
-  float ymax = nextafterf((p - 1.0f) / p, -INFINITY);  // minus_eps(power_ladder_max_output(p)), p < 0
-  if (p >= 0.f) ymax = f32_max();
-  yp = fminf(fmaxf(yp, -ymax), ymax);
-  float ratio = __fdiv_rn(p, fabsf(p - 1.0f));
-  float base = __fadd_rn(__fmul_rn(ratio, yp), 1.0f);
-  float x = __fmul_rn(fabsf(p - 1.0f), __fsub_rn(powf(base, __fdiv_rn(1.0f, p)), 1.0f));
-  x = y < 0.f ? -x : x;
-  return __fdiv_rn(x, premult);
-}
-
 __global__ void ray_cast_kernel(const float* __restrict__ sdist, const float* __restrict__ origins,
                                 const float* __restrict__ directions, const float* __restrict__ near,
                                 const float* __restrict__ far, int64_t R, int n, int warp_kind, float p,
@@ -452,7 +497,25 @@ extern "C" int32_t nrc_ray_sample_intervals(void* stream, const float* d_t, cons
   if (!d_t || !d_w || !d_u01 || !d_u_base || !d_t_new) return NRC_E_INVALID_ARG;
   sample_intervals_kernel<<<ray_grid(num_rays), kRayThreads, 0, NRC_STREAM>>>(
       d_t, d_w, d_u01, d_u_base, num_rays, m, n, anneal, padding, max_jitter, dom_lo, dom_hi, d_t_new,
-      d_bin_idx);
+      d_bin_idx, nullptr, nullptr, nullptr, nullptr, 0, 0.f, 0.f, nullptr, nullptr);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_ray_sample_cast(void* stream, const float* d_t, const float* d_w, const float* d_u01,
+                                       const float* d_u_base, int64_t num_rays, int32_t m, int32_t n, float anneal,
+                                       float padding, float max_jitter, float dom_lo, float dom_hi,
+                                       const float* d_origins, const float* d_directions, const float* d_near,
+                                       const float* d_far, int32_t warp_kind, float p, float premult, float* d_sdist_new,
+                                       float* d_tdist, float* d_means) {
+  if (num_rays < 0 || m < 1 || m > kMaxN || n <= 1 || n > kMaxN || (warp_kind != 0 && warp_kind != 1))
+    return NRC_E_INVALID_ARG;
+  if (warp_kind == 1 && (p == 1.0f || p == 0.0f || isinf(p))) return NRC_E_UNSUPPORTED;
+  if (num_rays == 0) return NRC_OK;
+  if (!d_t || !d_w || !d_u01 || !d_u_base || !d_sdist_new || !d_origins || !d_directions || !d_near || !d_far || !d_tdist)
+    return NRC_E_INVALID_ARG;
+  sample_intervals_kernel<<<ray_grid(num_rays), kRayThreads, 0, NRC_STREAM>>>(
+      d_t, d_w, d_u01, d_u_base, num_rays, m, n, anneal, padding, max_jitter, dom_lo, dom_hi, d_sdist_new, nullptr,
+      d_origins, d_directions, d_near, d_far, warp_kind, p, premult, d_tdist, d_means);
   return check_launch();
 }
 

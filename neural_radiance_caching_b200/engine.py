@@ -91,9 +91,7 @@ class FusedCacheStep:
         for i_level, (i_mlp, _, n) in enumerate(sampler.sampling_strategy):
             mlp, p = sampler.mlps[i_mlp], sp[f"MLP_{i_mlp}"]
             last = i_level == nl - 1
-            sdist = stepfun.sample_intervals_from_weights(u01[i_level], sdist, weights, n, anneal=anneal,
-                                                          padding=sampler.resample_padding, domain=(0.0, 1.0))
-            tdist, means = sampler._cast(sdist, rays, False)
+            sdist, tdist, means = sampler.sample_and_cast(u01[i_level], sdist, weights, n, anneal, rays, False)
             P = R * n
             density = new(P)
             enc_out = new(P, mlp.in_dim) if last else None
@@ -189,9 +187,7 @@ class FusedCacheStep:
         for i_level, (i_mlp, _, n) in enumerate(sampler.sampling_strategy):
             mlp, p = sampler.mlps[i_mlp], sp[f"MLP_{i_mlp}"]
             last = i_level == nl - 1
-            sdist = stepfun.sample_intervals_from_weights(u01[i_level], sdist, weights, n, anneal=anneal,
-                                                          padding=sampler.resample_padding, domain=(0.0, 1.0))
-            tdist, means = sampler._cast(sdist, rays, False)
+            sdist, tdist, means = sampler.sample_and_cast(u01[i_level], sdist, weights, n, anneal, rays, False)
             P = R * n
             if last:   # the appearance-grid gather only needs the final sample positions
                 if s_enc is not None:
@@ -428,9 +424,7 @@ class FusedCacheQuery:
         for i_level, (i_mlp, _, n) in enumerate(sampler.sampling_strategy):
             mlp, p = sampler.mlps[i_mlp], sp[f"MLP_{i_mlp}"]
             last = i_level == nl - 1
-            sdist = stepfun.sample_intervals_from_weights(u01[i_level], sdist, weights, n, anneal=anneal,
-                                                          padding=sampler.resample_padding, domain=(0.0, 1.0))
-            tdist, means = sampler._cast(sdist, rays, is_secondary)
+            sdist, tdist, means = sampler.sample_and_cast(u01[i_level], sdist, weights, n, anneal, rays, is_secondary)
             P = R * n
             density = new(P)
             feat = new(P, 64) if last else None

@@ -101,6 +101,32 @@ class ProposalVolumeSampler:
                   1 if use_raydist_fn else 0, float(p), float(premult), _lib.ptr(tdist), _lib.ptr(means))
         return tdist, means
 
+    def sample_and_cast(self, u01, sdist, weights, num_samples, anneal, rays, use_raydist_fn):
+        """One level of the sampler's resampling (sampling.py:340-349: annealed logits -> stepfun.sample_intervals)
+        followed by render.cast_rays in ONE launch (nrc_ray_sample_cast): bit-identical to
+        stepfun.sample_intervals_from_weights(...) + self._cast(...).  Returns (sdist_new, tdist, means)."""
+        if num_samples <= 1:
+            raise ValueError(f"num_samples must be > 1, is {num_samples}.")
+        m = weights.shape[-1]
+        if sdist.shape[-1] != m + 1:
+            raise ValueError(f"Invalid shapes ({sdist.shape}, {weights.shape}) for a step function.")
+        R = sdist.shape[0]
+        u2 = u01.reshape(-1)
+        if u2.shape[0] != R:
+            raise ValueError("single_jitter=True needs one uniform per ray")
+        base, max_jitter = stepfun.u_base(num_samples, sdist.device)
+        dev = sdist.device
+        sd = torch.empty((R, num_samples + 1), device=dev, dtype=torch.float32)
+        tdist = torch.empty_like(sd)
+        means = torch.empty((R, num_samples, 3), device=dev, dtype=torch.float32)
+        p, premult = self.raydist
+        _lib.call("nrc_ray_sample_cast", _lib.stream_ptr(), _lib.ptr(sdist.contiguous()), _lib.ptr(weights.contiguous()),
+                  _lib.ptr(u2.contiguous()), _lib.ptr(base), R, m, num_samples, float(anneal),
+                  float(self.resample_padding), max_jitter, 0.0, 1.0, _lib.ptr(rays["origins"]), _lib.ptr(rays["directions"]),
+                  _lib.ptr(rays["near"]), _lib.ptr(rays["far"]), 1 if use_raydist_fn else 0, float(p), float(premult),
+                  _lib.ptr(sd), _lib.ptr(tdist), _lib.ptr(means))
+        return sd, tdist, means
+
     def __call__(self, params, rays, u01_per_level, train_frac=1.0, train=False, use_raydist_fn=False,
                  normals_all_levels=False, sdist_override=None, weights_only=False):
         """rays: dict of contiguous CUDA tensors origins/directions/viewdirs [R,3], near/far [R,1].

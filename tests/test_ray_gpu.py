@@ -119,6 +119,41 @@ def test_ray_cast(cuda_device, use_raydist):
     assert torch.allclose(t_n[:, -1].cpu(), rays["far"][:, 0], rtol=1e-5)
 
 
+@pytest.mark.parametrize("use_raydist", [False, True])
+@pytest.mark.parametrize("m,n", [(1, 64), (64, 64), (64, 32), (100, 128)])
+def test_sample_cast_fused_is_bit_identical(cuda_device, use_raydist, m, n):
+    """nrc_ray_sample_cast (one launch per sampler level) against nrc_ray_sample_intervals + nrc_ray_cast, which the
+    tests above hold to the oracle: resampled fenceposts, metric distances and means must agree bit for bit - also on
+    rays whose fenceposts need the rank sort (near-duplicate CDF knots) and on the already-sorted fast path."""
+    from neural_radiance_caching_b200.sampling import ProposalVolumeSampler
+
+    g = gen(90 + m + n)
+    R = 257
+    rays = make_rays(g, R, near=0.05 if use_raydist else 2.0, far=2.0 if use_raydist else 6.0)
+    t = f32(np.sort(g.uniform(0, 1, size=(R, m + 1)), axis=-1))
+    t[:, 0], t[:, -1] = 0.0, 1.0
+    w = f32(g.gamma(0.3, 1.0, size=(R, m)))
+    w[0] = 0.0
+    if m > 1:
+        w[1, 1:] = 0.0                         # one spike: many samples land in one bin
+        t[2, 1:-1] = t[2, 1:2]                 # degenerate bins: equal fenceposts -> ties in the sort
+    u01 = f32(g.uniform(size=(R, 1)))
+    sampler = ProposalVolumeSampler()
+    rd = to_dev(rays, cuda_device)
+    td, wd, ud = t.to(cuda_device), w.to(cuda_device), u01.to(cuda_device)
+    anneal = 0.4
+    s_ref = nstep.sample_intervals_from_weights(ud, td, wd, n, anneal=anneal, padding=sampler.resample_padding,
+                                                domain=(0.0, 1.0))
+    t_ref, means_ref = sampler._cast(s_ref, rd, use_raydist)
+    s_new, t_new, means_new = sampler.sample_and_cast(ud, td, wd, n, anneal, rd, use_raydist)
+    assert torch.all(s_new[:, 1:] >= s_new[:, :-1])
+    assert torch.equal(s_new, s_ref)
+    assert torch.equal(t_new, t_ref)
+    assert torch.equal(means_new, means_ref)
+    with pytest.raises(ValueError):
+        sampler.sample_and_cast(ud, td, wd, 1, anneal, rd, use_raydist)
+
+
 @pytest.mark.parametrize("n,C", [(32, 3), (64, 10), (32, 0)])
 def test_volumetric_rendering(cuda_device, n, C):
     g = gen(80 + n + C)
