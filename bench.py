@@ -224,14 +224,20 @@ def run_b200(args):
 
     grads_flat = None
 
+    # NRC_DP_INGRAPH=1 (default with the peer-memory arena): both buckets' all-reduces are part of the step and of its
+    # CUDA graph, the Shader bucket beside the sampler's backward (workload.CacheTrainStep.step).
+    ingraph = (world > 1 and getattr(step_obj, "peer", None) is not None and step_obj.engine is not None
+               and os.environ.get("NRC_DP_INGRAPH", "1") == "1" and os.environ.get("NRC_DP_OVERLAP", "0") != "1")
+
     def allreduce_grads():
         # gradient all-reduce (mean) over all tables + MLP weights, the reference's lax.pmean
-        # (internal/train_utils.py:3132-3136): ONE NCCL call over the flat gradient arena.
-        ndist.allreduce_mean_(step_obj.flat_grad)
+        # (internal/train_utils.py:3132-3136): one collective over the flat gradient arena.
+        if not ingraph:
+            step_obj.allreduce_grads()
 
     def compute_step():
         rays, u01, target, extra = workload.unpack_batch(dbuf)
-        return step_obj.step(rays, u01, target, extra)
+        return step_obj.step(rays, u01, target, extra, fused_allreduce=ingraph)
 
     def one_step():
         loss = compute_step()
@@ -264,7 +270,11 @@ def run_b200(args):
 
     graph = torch.cuda.CUDAGraph()
     use_graph = True
-    overlap = world > 1 and step_obj.engine is not None
+    # Data parallel: ONE graph + ONE peer-memory all-reduce of the whole arena after it (default), or
+    # NRC_DP_OVERLAP=1: two graphs with the shader bucket's all-reduce overlapping the sampler's backward.  Measured at
+    # N = 2 (gpurun_out/j8_*): the split loses more inside the step (proposal supervision no longer beside the shader,
+    # the collective's CTAs competing with the backward kernels) than the overlap hides.
+    overlap = world > 1 and step_obj.engine is not None and os.environ.get("NRC_DP_OVERLAP", "0") == "1"
     if not overlap:
         with torch.cuda.graph(graph):
             static_loss = compute_step()
@@ -291,9 +301,9 @@ def run_b200(args):
             graph.replay()
             comm.wait_stream(cur)
             with torch.cuda.stream(comm):
-                ndist.allreduce_mean_(step_obj.flat_grad[so:])
+                step_obj.allreduce_grads(so, None, channel=1)
             graph_b.replay()
-            ndist.allreduce_mean_(step_obj.flat_grad[:so])
+            step_obj.allreduce_grads(0, so, channel=0)
             cur.wait_stream(comm)
             return static_loss
 
@@ -378,7 +388,9 @@ def run_b200(args):
                    "cuda_graph": bool(use_graph),
                    "parallelism": f"dp{world} rays, params replicated" + (
                        "; gradient all-reduce in 2 buckets, the shader bucket overlapping the sampler's backward"
-                       if overlap else "")},
+                       if overlap else ""),
+                   "allreduce": (step_obj.allreduce_kind + ("; both buckets inside the step's CUDA graph, the shader bucket "
+                                 "beside the sampler's backward" if ingraph else "")) if world > 1 else None},
         "rays_per_sec": value / SAMPLES_PER_RAY,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host[0].numel() * 4) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms},

@@ -501,6 +501,17 @@ int32_t nrc_mask_loss(void* stream, const float* d_acc, int32_t n, const float* 
  * table T of `enc`: loss += mult * 0.5 * mean(T^2), levels[l].d_grad += mult * T / numel(T) (atomic reductions: may run
  * concurrently with nrc_encode_bwd on the same tables). */
 int32_t nrc_grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss);
+/* Gradient all-reduce (MEAN over ranks) of the flat gradient arena over NVLink / NVSwitch peer memory: the reference's
+ * lax.pmean over the gradient pytree (internal/train_utils.py:3132-3136).  The arena is symmetric memory (same size on
+ * every rank); rank r reduces the r-th slice of floats [offset, offset+count) and writes the mean into EVERY rank's copy.
+ * `mc_base` = multicast (NVLS) address of the arena: in-switch reduction (multimem.ld_reduce / multimem.st);
+ * `peer_bases` = HOST array of the `world` peer mappings of the arena: plain peer loads / stores (no multicast object).
+ * offset and count are multiples of 4 floats.  The caller brackets the launch with a cross-rank barrier on `stream`
+ * (all producers done before, all slices written after); num_ctas <= 0 picks the default. */
+int32_t nrc_allreduce_mean_multicast(void* stream, float* mc_base, int64_t offset, int64_t count, int32_t rank,
+                                     int32_t world, int32_t num_ctas);
+int32_t nrc_allreduce_mean_peer(void* stream, float* const* peer_bases, int64_t offset, int64_t count, int32_t rank,
+                                int32_t world, int32_t num_ctas);
 /* Measurement aid ("L2 roofline denominator"): every thread issues `per_thread` independent, uniformly random
  * row reads (row_bytes = 4 or 16, 8 in flight) from a table of `table_rows` rows and adds them up; d_sink [1] keeps the
  * loads alive.  bench.py times it on an L2-resident table to get the B200's random-gather rate, the bound the

@@ -104,6 +104,8 @@ PROTOTYPES = {
     "nrc_vmf_loss": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _I32, _P, _P, _P, _P],
     "nrc_grid_regularizer": [_P, _P, _F, _P],
     "nrc_probe_gather": [_P, _P, _I64, _I32, _I64, _I32, _P],
+    "nrc_allreduce_mean_multicast": [_P, _P, _I64, _I64, _I32, _I32, _I32],
+    "nrc_allreduce_mean_peer": [_P, _P, _I64, _I64, _I32, _I32, _I32],
     "nrc_distortion_loss": [_P, _P, _P, _I32, _I64, _F, _F, _F, _P, _P],
     "nrc_geometry_losses": [_P, _P, _P, _P, _P, _I64, _I32, _F, _F, _F, _F, _P, _P, _P, _P],
     "nrc_density_normals_bwd": [_P, _P, _P, _P, _P, _I64, _F, _P],

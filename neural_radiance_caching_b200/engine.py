@@ -65,13 +65,16 @@ class FusedCacheStep:
             self._bg[key] = (sd, torch.ones((R, 1), device=dev, dtype=torch.float32))
         return self._bg[key]
 
-    def step(self, rays, u01, target_rgb, train_frac=1.0, extra=None, zero_grad=None):
+    def step(self, rays, u01, target_rgb, train_frac=1.0, extra=None, zero_grad=None, on_shader_grads=None):
         """One forward + loss + backward; gradients land in the registered sinks.  Returns the loss
         (device scalar) and leaves the per-level sampler state in self.last (for tests).
         `extra` = (rays, u01) of the backward-mask pass (train_utils.py:3348-3401) or None.
         `zero_grad` = callable that clears the gradient sinks (the 110 MB arena memset): issued here on a side
-        stream beside the sampler's forward instead of in front of the step."""
-        state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra, zero_grad=zero_grad)
+        stream beside the sampler's forward instead of in front of the step.
+        `on_shader_grads` = callable invoked (in stream order on the main stream) as soon as every gradient of the
+        `Shader` parameters is final: a data-parallel harness forks that bucket's all-reduce there."""
+        state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra, zero_grad=zero_grad,
+                                on_shader_grads=on_shader_grads)
         self.step_back(state)
         return state["loss"]
 
@@ -120,7 +123,8 @@ class FusedCacheStep:
             self._bg[key] = torch.zeros((R,), device=dev, dtype=torch.float32)
         return _lib.ptr(self._bg[key])
 
-    def step_front(self, rays, u01, target_rgb, train_frac=1.0, fork_proposals=False, extra=None, zero_grad=None):
+    def step_front(self, rays, u01, target_rgb, train_frac=1.0, fork_proposals=False, extra=None, zero_grad=None,
+                   on_shader_grads=None):
         """Forward, loss and the SHADER's backward: when this returns (in stream order) every gradient of the
         `Shader` parameters (appearance grid + all stacks) is final, so a data-parallel harness can start
         all-reducing that half of the gradient arena while step_back() produces the sampler's half."""
@@ -304,6 +308,8 @@ class FusedCacheStep:
         _lib.call("nrc_ray_composite_bwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(bg),
                   _lib.ptr(g_rgb), _lib.ptr(g_acc), R, k, 3, 1, _lib.ptr(gv), _lib.ptr(g_w[2]), None)
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
+        if on_shader_grads is not None:
+            on_shader_grads()
         if geo is not None:
             if s_geo is not None:
                 main.wait_stream(s_geo)

@@ -1,6 +1,8 @@
 """Synthetic workloads of BASELINE.md section 2 and the cache-stage training step built from the
 kernels.  Shared by bench.py, __graft_entry__.smoke() and the tests (no oracle imports here).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -240,7 +242,13 @@ class CacheTrainStep:
         align = 64  # floats: every sink starts 256-byte aligned (the kernels use 16-byte vector atomics)
         pad = lambda n: (n + align - 1) // align * align
         total = sum(pad(int(t.numel())) for t in self.leaves)
-        self.flat_grad = torch.zeros(total, device=device, dtype=torch.float32)
+        # Under data parallelism the arena lives in symmetric memory so that the all-reduce can be the library's own
+        # peer-memory kernel (dist.PeerArena); None -> plain tensor + NCCL.
+        from . import dist as _ndist
+        self._comm = None
+        self.peer = _ndist.PeerArena.create(total, device)
+        self.flat_grad = self.peer.buf[:total] if self.peer is not None else torch.zeros(total, device=device,
+                                                                                         dtype=torch.float32)
         off = 0
         self.shader_offset = 0
         for i, t in enumerate(self.leaves):
@@ -260,12 +268,44 @@ class CacheTrainStep:
     def zero_grad(self):
         self.flat_grad.zero_()
 
-    def step(self, rays, u01, target_rgb, extra=None):
+    def allreduce_grads(self, lo=0, hi=None, channel=0, num_ctas=0):
+        """Mean over ranks of flat_grad[lo:hi] in place on the current stream (the reference's lax.pmean,
+        internal/train_utils.py:3132-3136).  Concurrent buckets (different streams) need different channels."""
+        from . import dist as _ndist
+        hi = self.flat_grad.numel() if hi is None else hi
+        if self.peer is not None:
+            self.peer.allreduce_mean_(lo, hi - lo, channel, num_ctas)
+        else:
+            _ndist.allreduce_mean_(self.flat_grad[lo:hi])
+
+    @property
+    def allreduce_kind(self):
+        return f"peer-memory kernel ({self.peer.mode})" if self.peer is not None else "nccl"
+
+    def step(self, rays, u01, target_rgb, extra=None, fused_allreduce=False):
         """Forward + loss + backward of one ray batch; returns the loss (device scalar).  The bf16
         variant runs the hand-ordered launch schedule of engine.FusedCacheStep (same kernels, no
         elementwise glue); the fp32 parity variant goes through the autograd mirrors.
         `extra` = (backward-mask rays, their u01): see backward_mask_rays_np."""
         if self.engine is not None:
+            if fused_allreduce and self.peer is not None:
+                # Data parallel, all-reduce INSIDE the step (and inside its CUDA graph): the Shader bucket's peer-memory
+                # all-reduce is forked onto a communication stream the moment the shader's backward is done and runs
+                # beside the sampler's backward; the Sampler bucket follows at the end of the step.
+                if self._comm is None:
+                    self._comm = torch.cuda.Stream()
+                comm, so = self._comm, self.shader_offset
+
+                def shader_bucket():
+                    comm.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(comm):   # fewer CTAs: it shares the SMs with the sampler's backward
+                        self.allreduce_grads(so, None, channel=1, num_ctas=int(os.environ.get("NRC_AR_CTAS_OVERLAP", "74")))
+
+                loss = self.engine.step(rays, u01, target_rgb, extra=extra, zero_grad=self.zero_grad,
+                                        on_shader_grads=shader_bucket)
+                self.allreduce_grads(0, so, channel=0)
+                torch.cuda.current_stream().wait_stream(comm)
+                return loss
             return self.engine.step(rays, u01, target_rgb, extra=extra, zero_grad=self.zero_grad)
         return self.step_autograd(rays, u01, target_rgb, extra)
 
