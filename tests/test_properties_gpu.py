@@ -88,3 +88,25 @@ def test_empty_and_ragged_inputs(cuda_device):
     # invalid arguments are reported as status codes, not crashes
     st = _lib.load().nrc_encode_fwd(None, None, None, 5, None)
     assert st == -1
+
+
+def test_peer_allreduce_kernel_single_rank(cuda_device):
+    """nrc_allreduce_mean_peer with world = 1 (the arena is its own only peer): the mean over one rank is the identity on
+    the bucket and nothing outside the bucket may change; bad arguments come back as status codes.  The N >= 2 check
+    against NCCL (bit-identical at N = 2) is tools/test_allreduce.py (needs several GPUs)."""
+    import ctypes as C
+    from neural_radiance_caching_b200 import _lib
+
+    n = 1 << 20
+    g = torch.Generator(device=cuda_device).manual_seed(5)
+    buf = torch.randn(n, device=cuda_device, generator=g)
+    ref = buf.clone()
+    peers = (C.c_void_p * 1)(buf.data_ptr())
+    lo, cnt = 4096, n - 8192
+    _lib.call("nrc_allreduce_mean_peer", _lib.stream_ptr(), C.cast(peers, C.c_void_p), lo, cnt, 0, 1, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(buf, ref)
+    lib = _lib.load()
+    assert lib.nrc_allreduce_mean_peer(None, C.cast(peers, C.c_void_p), 2, cnt, 0, 1, 0) == -1      # offset % 4
+    assert lib.nrc_allreduce_mean_peer(None, C.cast(peers, C.c_void_p), 0, cnt, 1, 1, 0) == -1      # rank >= world
+    assert lib.nrc_allreduce_mean_multicast(None, None, 0, cnt, 0, 1, 0) == -1
