@@ -486,6 +486,16 @@ int32_t nrc_transient_render_fwd(void* stream, const float* d_direct_rgbs, const
 int32_t nrc_interlevel_loss(void* stream, const float* d_t, const float* d_w, int32_t m, const float* d_tq,
                             const float* d_wp, int32_t nq, int64_t num_rays, float blur_halfwidth, float mult,
                             float eps, float* d_loss, float* d_g_wp, float* d_w_blur);
+/* Tail of the cache training step in one launch: volumetric_rendering's rgb [R,3] and acc [R] from the shaded samples
+ * d_values [R,n,3] and d_weights [R,n] over the background d_bg [R,3] (may be NULL) (internal/render.py:172-224), the
+ * Charbonnier-sRGB data term against d_target [R,3], compute_mask_loss on acc (use_mask != 0; d_mask NULL = all ones;
+ * internal/train_utils.py:785-836) and the VJP of the compositing: loss += both terms (accumulated), d_g_values [R,n,3]
+ * and d_g_weights [R,n] written.  Equivalent to nrc_ray_composite_fwd + nrc_charb_srgb_loss + nrc_mask_loss +
+ * nrc_ray_composite_bwd (without the distance statistics, which the objective does not consume). */
+int32_t nrc_render_loss(void* stream, const float* d_values, const float* d_weights, const float* d_bg,
+                        const float* d_target, const float* d_mask, int64_t num_rays, int32_t n, float charb_padding,
+                        int32_t use_mask, float opaque_weight, float empty_weight, float* d_loss, float* d_out_rgb,
+                        float* d_acc, float* d_g_values, float* d_g_weights);
 /* Data term: loss += mean Charbonnier(linear_to_srgb(rgb) - target) (accumulated), d_g_rgb [R,3] written. */
 int32_t nrc_charb_srgb_loss(void* stream, const float* d_rgb, const float* d_target, int64_t num_rays,
                             float charb_padding, float* d_loss, float* d_g_rgb);

@@ -402,6 +402,92 @@ composite_bwd_kernel(const float* __restrict__ values, const float* __restrict__
     for (int i = lane; i < n; i += 32) g_weights_nf[r * n + i] = gacc;
 }
 
+// ---------------------------------------------------- render + data/mask loss --
+// The tail of the cache training step in ONE launch (one warp per ray): volumetric_rendering's rgb and acc
+// (internal/render.py:172-224; the distance statistics are not consumed by the objective - XLA eliminates them from
+// the reference's training step too), the Charbonnier-sRGB data term (internal/image.py:192-200,
+// configs/ngp_yobo.gin:35-37), compute_mask_loss on acc (internal/train_utils.py:785-836, lossmult == 1) and the VJP
+// of the compositing.  Same expressions and summation order as composite_fwd_kernel / charb_srgb_loss_kernel /
+// mask_loss_kernel / composite_bwd_kernel, which remain the reference points of the parity tests.
+__global__ void __launch_bounds__(kRayThreads)
+render_loss_kernel(const float* __restrict__ values, const float* __restrict__ weights, const float* __restrict__ bg,
+                   const float* __restrict__ target, const float* __restrict__ mask, int64_t R, int n,
+                   float charb_padding, int use_mask, float opaque_w, float empty_w, float* __restrict__ loss,
+                   float* __restrict__ out_rgb, float* __restrict__ acc_out, float* __restrict__ g_values,
+                   float* __restrict__ g_weights) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * kRayWarps + warp;
+  float contrib = 0.f;
+  if (r < R) {
+    float a = 0.f;
+    for (int i = lane; i < n; i += 32) a += weights[r * n + i];
+    const float acc = warp_sum(a);
+    const float bg_w = fmaxf(0.f, 1.0f - acc);
+    float out[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float sc = 0.f;
+      for (int i = lane; i < n; i += 32) sc += weights[r * n + i] * values[(r * n + i) * 3 + c];
+      sc = warp_sum(sc);
+      if (bg) sc += bg_w * bg[3 * r + c];
+      out[c] = sc;
+    }
+    if (lane < 3) out_rgb[3 * r + lane] = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
+    if (lane == 0 && acc_out) acc_out[r] = acc;
+    // lanes 0..2: data term of one channel; lane 3: mask term
+    float g = 0.f;
+    const float invR = 1.0f / static_cast<float>(R);
+    if (lane < 3) {
+      const float x = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
+      const float eps = f32_eps();
+      const float xc = fmaxf(x, eps);
+      const float p512 = powf(xc, 5.0f / 12.0f);
+      const bool lin = x <= 0.0031308f;
+      const float srgb = lin ? (323.0f / 25.0f) * x : (211.0f * p512 - 11.0f) / 200.0f;
+      const float dsrgb = lin ? (323.0f / 25.0f) : (x > eps ? (211.0f / 200.0f) * (5.0f / 12.0f) * p512 / xc : 0.f);
+      const float diff = srgb - target[3 * r + lane];
+      const float ch = sqrtf(diff * diff + charb_padding * charb_padding);
+      const float inv = 1.0f / (3.0f * static_cast<float>(R));
+      g = (diff / ch) * dsrgb * inv;
+      contrib = ch * inv;
+    } else if (lane == 3 && use_mask) {
+      const float mk = mask ? mask[r] : 1.0f;
+      const float wt = (mk > 0.5f ? opaque_w : empty_w) * invR;
+      const float diff = acc - mk;
+      const float ch = sqrtf(diff * diff + charb_padding * charb_padding);
+      g = wt * diff / ch;
+      contrib = wt * ch;
+    }
+    const float go0 = __shfl_sync(0xffffffffu, g, 0), go1 = __shfl_sync(0xffffffffu, g, 1),
+                go2 = __shfl_sync(0xffffffffu, g, 2);
+    float gacc = __shfl_sync(0xffffffffu, g, 3);
+    if (bg && (1.0f - acc) > 0.f) {
+      gacc -= go0 * bg[3 * r];
+      gacc -= go1 * bg[3 * r + 1];
+      gacc -= go2 * bg[3 * r + 2];
+    }
+    for (int i = lane; i < n; i += 32) {
+      const float w = weights[r * n + i];
+      const float* v = values + (r * n + i) * 3;
+      float gw = gacc;
+      gw += go0 * v[0]; gw += go1 * v[1]; gw += go2 * v[2];
+      float* gv = g_values + (r * n + i) * 3;
+      gv[0] = go0 * w; gv[1] = go1 * w; gv[2] = go2 * w;
+      g_weights[r * n + i] = gw;
+    }
+    contrib = warp_sum(contrib);
+  }
+  __shared__ float part[kRayWarps];
+  if (lane == 0) part[warp] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRayWarps; ++k) sum += part[k];
+    atomicAdd(loss, sum);
+  }
+}
+
 // ----------------------------------------------------------------- resample --
 __global__ void __launch_bounds__(kRayThreads)
 resample_kernel(const float* __restrict__ weights, const float* __restrict__ gumbel, int64_t R, int n,
@@ -588,5 +674,17 @@ extern "C" int32_t nrc_ray_resample_gather(void* stream, const float* d_field, c
   int64_t total = num_rays * k * channels;
   resample_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, NRC_STREAM>>>(
       d_field, d_inds, num_rays, n, k, channels, d_out);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_render_loss(void* stream, const float* d_values, const float* d_weights, const float* d_bg,
+                                   const float* d_target, const float* d_mask, int64_t num_rays, int32_t n,
+                                   float charb_padding, int32_t use_mask, float opaque_weight, float empty_weight,
+                                   float* d_loss, float* d_out_rgb, float* d_acc, float* d_g_values, float* d_g_weights) {
+  if (num_rays < 1 || n < 1) return NRC_E_INVALID_ARG;
+  if (!d_values || !d_weights || !d_target || !d_loss || !d_out_rgb || !d_g_values || !d_g_weights) return NRC_E_INVALID_ARG;
+  render_loss_kernel<<<ray_grid(num_rays), kRayThreads, 0, NRC_STREAM>>>(
+      d_values, d_weights, d_bg, d_target, d_mask, num_rays, n, charb_padding, use_mask, opaque_weight, empty_weight,
+      d_loss, d_out_rgb, d_acc, d_g_values, d_g_weights);
   return check_launch();
 }

@@ -293,20 +293,15 @@ class FusedCacheStep:
             normals_pred.reshape(R, L2["n"], 3), app_arena, True, packed=packed, encoded=encoded, env_stream=s_env)
         rgb_s = outs[0].reshape(R, L2["n"], 3)
         bg = self._bg_ones(R, dev)
-        out_rgb, acc, dist = new(R, 3), new(R), new(R, 4)
-        _lib.call("nrc_ray_composite_fwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(L2["tdist"]),
-                  _lib.ptr(bg), R, k, 3, 1, _lib.ptr(out_rgb), _lib.ptr(acc), _lib.ptr(dist))
-        g_rgb = new(R, 3)
-        _lib.call("nrc_charb_srgb_loss", st(), _lib.ptr(out_rgb), _lib.ptr(target_rgb), R, float(self.charb_padding),
-                  _lib.ptr(loss), _lib.ptr(g_rgb))
-        g_acc = None
-        if self.mask_weights is not None:   # compute_mask_loss on the accumulation, masks == 1
-            g_acc = new(R)
-            _lib.call("nrc_mask_loss", st(), _lib.ptr(acc), 0, None, R, float(self.charb_padding),
-                      float(self.mask_weights[0]), float(self.mask_weights[1]), _lib.ptr(loss), _lib.ptr(g_acc))
+        # volumetric rendering (rgb, acc), data term, mask loss and the compositing VJP: one launch
+        out_rgb, acc, dist = new(R, 3), new(R), None
         gv = new(R, k, 3)
-        _lib.call("nrc_ray_composite_bwd", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), k, None, _lib.ptr(bg),
-                  _lib.ptr(g_rgb), _lib.ptr(g_acc), R, k, 3, 1, _lib.ptr(gv), _lib.ptr(g_w[2]), None)
+        g_rgb = g_acc = None
+        mw = self.mask_weights
+        _lib.call("nrc_render_loss", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), _lib.ptr(bg), _lib.ptr(target_rgb), None,
+                  R, k, float(self.charb_padding), 0 if mw is None else 1, 0.0 if mw is None else float(mw[0]),
+                  0.0 if mw is None else float(mw[1]), _lib.ptr(loss), _lib.ptr(out_rgb), _lib.ptr(acc), _lib.ptr(gv),
+                  _lib.ptr(g_w[2]))
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
         if on_shader_grads is not None:
             on_shader_grads()

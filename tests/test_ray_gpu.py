@@ -184,3 +184,48 @@ def test_volumetric_rendering(cuda_device, n, C):
         ((got["rgb"] * g_rgb.to(cuda_device)).sum() + (got["acc"] * g_acc.to(cuda_device)).sum()).backward()
         assert rel_err(wn.grad, wo.grad) <= 1e-5
         assert rel_err(rn.grad, ro.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_render_loss_fused(cuda_device, use_mask):
+    """nrc_render_loss (rendering + data term + mask loss + compositing VJP in one launch) against the four entry
+    points it replaces in the training step, each of which is held to the oracle elsewhere: rgb and acc bit-identical,
+    loss and gradients to rounding."""
+    g = gen(333)
+    R, n = 257, 32
+    w = f32(g.dirichlet(np.ones(n) * 0.2, size=R) * g.uniform(0, 1.2, size=(R, 1)))   # some rays with acc > 1
+    w[0] = 0.0
+    vals = f32(g.uniform(size=(R, n, 3)))
+    vals[1] = 0.0                                                                      # linear branch of the sRGB curve
+    bg, target = f32(g.uniform(size=(R, 3))), f32(g.uniform(size=(R, 3)))
+    t = _tdist(g, R, n)
+    d = lambda a: a.to(cuda_device).contiguous()
+    wd, vd, bd, td, tt = d(w), d(vals), d(bg), d(target), d(t)
+    new = lambda *shape: torch.empty(shape, device=cuda_device, dtype=torch.float32)
+    pad, ow, ew = 1e-3, 0.7, 0.3
+    # reference sequence
+    out_r, acc_r, dist_r = new(R, 3), new(R), new(R, 4)
+    loss_r = torch.zeros((), device=cuda_device)
+    _lib.call("nrc_ray_composite_fwd", _lib.stream_ptr(), _lib.ptr(vd), _lib.ptr(wd), n, None, _lib.ptr(tt), _lib.ptr(bd), R, n,
+              3, 1, _lib.ptr(out_r), _lib.ptr(acc_r), _lib.ptr(dist_r))
+    g_rgb = new(R, 3)
+    _lib.call("nrc_charb_srgb_loss", _lib.stream_ptr(), _lib.ptr(out_r), _lib.ptr(td), R, pad, _lib.ptr(loss_r), _lib.ptr(g_rgb))
+    g_acc = None
+    if use_mask:
+        g_acc = new(R)
+        _lib.call("nrc_mask_loss", _lib.stream_ptr(), _lib.ptr(acc_r), 0, None, R, pad, ow, ew, _lib.ptr(loss_r), _lib.ptr(g_acc))
+    gv_r, gw_r = new(R, n, 3), new(R, n)
+    _lib.call("nrc_ray_composite_bwd", _lib.stream_ptr(), _lib.ptr(vd), _lib.ptr(wd), n, None, _lib.ptr(bd), _lib.ptr(g_rgb),
+              _lib.ptr(g_acc), R, n, 3, 1, _lib.ptr(gv_r), _lib.ptr(gw_r), None)
+    # fused
+    out_f, acc_f, gv_f, gw_f = new(R, 3), new(R), new(R, n, 3), new(R, n)
+    loss_f = torch.zeros((), device=cuda_device)
+    _lib.call("nrc_render_loss", _lib.stream_ptr(), _lib.ptr(vd), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(td), None, R, n, pad,
+              1 if use_mask else 0, ow, ew, _lib.ptr(loss_f), _lib.ptr(out_f), _lib.ptr(acc_f), _lib.ptr(gv_f), _lib.ptr(gw_f))
+    torch.cuda.synchronize()
+    assert torch.equal(out_f, out_r) and torch.equal(acc_f, acc_r)
+    assert abs(float(loss_f) - float(loss_r)) <= 1e-6 * abs(float(loss_r))
+    assert rel_err(gv_f, gv_r) <= 1e-6
+    assert rel_err(gw_f, gw_r) <= 1e-6
+    lib = _lib.load()
+    assert lib.nrc_render_loss(None, None, None, None, None, None, 4, 8, pad, 0, 0.0, 0.0, None, None, None, None, None) == -1
