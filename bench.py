@@ -272,7 +272,7 @@ def run_b200(args):
     use_graph = True
     # Data parallel: ONE graph + ONE peer-memory all-reduce of the whole arena after it (default), or
     # NRC_DP_OVERLAP=1: two graphs with the shader bucket's all-reduce overlapping the sampler's backward.  Measured at
-    # N = 2 (gpurun_out/j8_*): the split loses more inside the step (proposal supervision no longer beside the shader,
+    # N = 2 (profiles/r01j_ab_runs.txt): the split loses more inside the step (proposal supervision no longer beside the shader,
     # the collective's CTAs competing with the backward kernels) than the overlap hides.
     overlap = world > 1 and step_obj.engine is not None and os.environ.get("NRC_DP_OVERLAP", "0") == "1"
     if not overlap:

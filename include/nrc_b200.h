@@ -511,6 +511,9 @@ int32_t nrc_mask_loss(void* stream, const float* d_acc, int32_t n, const float* 
  * table T of `enc`: loss += mult * 0.5 * mean(T^2), levels[l].d_grad += mult * T / numel(T) (atomic reductions: may run
  * concurrently with nrc_encode_bwd on the same tables). */
 int32_t nrc_grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss);
+/* Same loss, but levels[l].d_grad is OVERWRITTEN with mult * T / numel(T) (plain stores): the launch doubles as the
+ * per-step zero-fill of these gradient tables.  Must be ordered BEFORE every scatter into them. */
+int32_t nrc_grid_regularizer_init(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss);
 /* Gradient all-reduce (MEAN over ranks) of the flat gradient arena over NVLink / NVSwitch peer memory: the reference's
  * lax.pmean over the gradient pytree (internal/train_utils.py:3132-3136).  The arena is symmetric memory (same size on
  * every rank); rank r reduces the r-th slice of floats [offset, offset+count) and writes the mean into EVERY rank's copy.

@@ -161,8 +161,10 @@ int32_t launch_bwd(cudaStream_t s, const EncDev& d, const float* x, const float*
 // param_regularizer_loss (internal/train_utils.py:1169-1216) for one grid module with the common setting
 // (mult, jnp.mean, alpha = 2, scale = 1): per level table  loss += mult * 0.5 * mean(T^2),  dT += mult * T / numel.
 // blockIdx.y = level; grid-stride over the table; one atomic per block for the loss.
+// overwrite != 0: the gradient tables are INITIALISED with the regularizer's gradient (plain 16-byte stores) instead of
+// being zero-filled first and then atomically added to: the launch doubles as the memset of these tables.
 __global__ void __launch_bounds__(256) grid_regularizer_kernel(const __grid_constant__ EncDev d, float mult,
-                                                                 float* __restrict__ loss) {
+                                                                 float* __restrict__ loss, const int overwrite) {
   const LevelDev& lv = d.lv[blockIdx.y];
   const size_t n = static_cast<size_t>(lv.T) * d.F;
   const float inv_n = 1.0f / static_cast<float>(n);
@@ -175,16 +177,21 @@ __global__ void __launch_bounds__(256) grid_regularizer_kernel(const __grid_cons
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(t) + i);
       const float k = mult * inv_n;
-      // 16-byte reduction: commutes with the scatter kernels' atomics on the same tables, so no stream ordering
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + 4 * i), "f"(k * v.x), "f"(k * v.y),
-                   "f"(k * v.z), "f"(k * v.w)
-                   : "memory");
+      if (overwrite) {
+        *reinterpret_cast<float4*>(g + 4 * i) = make_float4(k * v.x, k * v.y, k * v.z, k * v.w);
+      } else {
+        // 16-byte reduction: commutes with the scatter kernels' atomics on the same tables, so no stream ordering
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + 4 * i), "f"(k * v.x), "f"(k * v.y),
+                     "f"(k * v.z), "f"(k * v.w)
+                     : "memory");
+      }
       acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
   } else {
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
       const float v = __ldg(t + i);
-      atomicAdd(g + i, mult * inv_n * v);
+      if (overwrite) g[i] = mult * inv_n * v;
+      else atomicAdd(g + i, mult * inv_n * v);
       acc += v * v;
     }
   }
@@ -245,14 +252,23 @@ extern "C" int32_t nrc_probe_gather(void* stream, const float* d_table, int64_t 
   return check_launch();
 }
 
+static int32_t grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss, int overwrite);
+
 extern "C" int32_t nrc_grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss) {
+  return grid_regularizer(stream, enc, mult, d_loss, 0);
+}
+extern "C" int32_t nrc_grid_regularizer_init(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss) {
+  return grid_regularizer(stream, enc, mult, d_loss, 1);
+}
+
+static int32_t grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss, int overwrite) {
   EncDev d;
   const int32_t st = make_enc_dev(enc, d);
   if (st != NRC_OK) return st;
   if (!d_loss) return NRC_E_INVALID_ARG;
   for (int l = 0; l < d.L; ++l)
     if (!d.lv[l].grad) return NRC_E_INVALID_ARG;
-  grid_regularizer_kernel<<<dim3(2 * kNumSMs, d.L), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, mult, d_loss);
+  grid_regularizer_kernel<<<dim3(2 * kNumSMs, d.L), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, mult, d_loss, overwrite);
   return check_launch();
 }
 

@@ -411,7 +411,7 @@ int32_t launch_bf16_fwd_occ(cudaStream_t st, const EncDev& d, const nrc_density_
   const int resident = (grad && kMinCtas > 4) ? 4 : kMinCtas;
   const int64_t cap = static_cast<int64_t>(kNumSMs) * (mult_env > 0 ? mult_env : resident);
   // 32 points per warp.  The 16-point mode (NRC_QUERY_PPW=16: twice the CTAs for launches that leave SMs idle, e.g.
-  // 32 768 points = 256 CTAs) measured SLOWER on the config-2 step (0.979 vs 0.951 ms, gpurun_out/j7_*): the weight
+  // 32 768 points = 256 CTAs) measured SLOWER on the config-2 step (0.979 vs 0.951 ms, profiles/r01j_ab_runs.txt, block j7): the weight
   // staging per CTA is paid twice as often and the side streams already fill the idle SMs.
   int ppw = 32;
   if (ppw_env == 16 && kFused) ppw = 16;
@@ -422,7 +422,7 @@ int32_t launch_bf16_fwd_occ(cudaStream_t st, const EncDev& d, const nrc_density_
   return check_launch();
 }
 
-// Resident CTAs per SM: 4 (128 registers).  Measured on B200 (gpurun_out/j2_*): capping registers for 5 or 6 CTAs
+// Resident CTAs per SM: 4 (128 registers).  Measured on B200 (profiles/r01j_ab_runs.txt, block j2): capping registers for 5 or 6 CTAs
 // per SM (96 / 80 registers, a few spills) is 3-8 % SLOWER on every workload - the kernel is bound by L1TEX
 // wavefronts (gathers + ldmatrix), and more resident shared memory leaves less L1.
 template <int F, int KS0, bool kFused>

@@ -81,7 +81,7 @@ class PeerArena:
             hdl = symm.rendezvous(buf, dist.group.WORLD)
             mc = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
             # default: plain peer loads / stores (measured at N = 2 on the 110.6 MB arena: 0.186 ms vs 0.238 ms NCCL vs
-            # 0.314 ms for the multimem variant, gpurun_out/j8_allreduce_n2.json); NRC_ALLREDUCE=multicast opts in
+            # 0.314 ms for the multimem variant, profiles/r01j_allreduce_n2.json); NRC_ALLREDUCE=multicast opts in
             mode = "multicast" if (mc and want == "multicast") else "peer"
             return PeerArena(buf, hdl, mode)
         except Exception as e:   # no NVLink peer access / symmetric memory unavailable: NCCL path

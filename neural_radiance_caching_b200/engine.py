@@ -141,18 +141,34 @@ class FusedCacheStep:
         names, sflat = shader.fused_params(shp)
         app_arena = shp["appearance_grid"]["_arena"]
         loss = torch.zeros((), device=dev, dtype=torch.float32)
-        # gradient-arena memset: nothing reads or writes gradients before the first backward / regularizer launch, so it
-        # runs on the packing stream beside the sampler's forward; every gradient-writing stream waits on `grads_ready`
+        reg_on = self.density_grid_regularizer is not None and self.geometry_mults is not None
+
+        def regularize(init=False):   # param_regularizer_loss on the three density grids: atomic, order-free;
+            if not reg_on:            # init=True: plain stores that double as the zero-fill of these gradient tables
+                return
+            for i_mlp, mlp in enumerate(sampler.mlps):
+                arena = sp[f"MLP_{i_mlp}"]["density_grid"]["_arena"]
+                t_sink = _lib.grad_sink(arena)
+                enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)), mlp.grid.tables(mlp.grid.views(t_sink)))
+                _lib.call("nrc_grid_regularizer_init" if init else "nrc_grid_regularizer", _lib.stream_ptr(), C.byref(enc),
+                          float(self.density_grid_regularizer), _lib.ptr(loss))
+
+        # Gradient-arena memset and the parameter regularizer: nothing reads or writes gradients before the first backward
+        # launch, so they run on the packing stream beside the sampler's forward; every gradient-writing stream waits on
+        # `grads_ready`.  When the caller hands over the memset (zero_grad), the regularizer INITIALISES the density grids'
+        # gradient tables (its gradient is dense over them) and zero_grad(skip_density_grids=True) clears only the rest.
         grads_ready = None
         if zero_grad is not None:
             if s_pack is not None:
                 s_pack.wait_stream(main)
                 with torch.cuda.stream(s_pack):
-                    zero_grad()
+                    zero_grad(skip_density_grids=reg_on)
+                    regularize(init=True)
                     grads_ready = torch.cuda.Event()
                     grads_ready.record()
             else:
-                zero_grad()
+                zero_grad(skip_density_grids=reg_on)
+                regularize(init=True)
         # backward-mask pass: independent rays, its own stream (joined in step_back); in split mode
         # (fork_proposals False: two graphs) it is issued by step_back instead
         s_x = None
@@ -165,25 +181,18 @@ class FusedCacheStep:
             else:
                 self._weights_only_pass(extra[0], extra[1], train_frac, loss)
             extra = None
-        def regularize():   # param_regularizer_loss on the three density grids: atomic, order-free
-            if self.density_grid_regularizer is None or self.geometry_mults is None:
-                return
-            for i_mlp, mlp in enumerate(sampler.mlps):
-                arena = sp[f"MLP_{i_mlp}"]["density_grid"]["_arena"]
-                t_sink = _lib.grad_sink(arena)
-                enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)), mlp.grid.tables(mlp.grid.views(t_sink)))
-                _lib.call("nrc_grid_regularizer", _lib.stream_ptr(), C.byref(enc), float(self.density_grid_regularizer),
-                          _lib.ptr(loss))
-
-        # weight packing and the parameter regularizer do not depend on the rays: they run beside the sampler
+        # weight packing does not depend on the rays: it runs beside the sampler (with the regularizer, when the caller
+        # cleared the gradients itself)
         if s_pack is not None:
             s_pack.wait_stream(main)
             with torch.cuda.stream(s_pack):
                 packed = nerf.shader_pack(shader, names, sflat)
-                regularize()
+                if zero_grad is None:
+                    regularize()
         else:
             packed = nerf.shader_pack(shader, names, sflat)
-            regularize()
+            if zero_grad is None:
+                regularize()
         # ------------------------------------------------------------------ forward: proposal sampler
         sdist, weights = self._initial_step_function(R, dev)
         levels = []

@@ -250,6 +250,7 @@ class CacheTrainStep:
         self.flat_grad = self.peer.buf[:total] if self.peer is not None else torch.zeros(total, device=device,
                                                                                          dtype=torch.float32)
         off = 0
+        ranges = {}
         self.shader_offset = 0
         for i, t in enumerate(self.leaves):
             if i == self.num_sampler_leaves:
@@ -258,15 +259,31 @@ class CacheTrainStep:
             sink = self.flat_grad[off:off + n].view(t.shape)
             _lib.register_grad_sink(t, sink)
             t.grad = sink
+            ranges[id(t)] = (off, off + n)
             off += pad(n)
+        # complement of the density grids' tables (see zero_grad): what a step still has to zero-fill itself
+        skip = sorted(ranges[id(sampler[f"MLP_{i}"]["density_grid"]["_arena"])] for i in range(len(self.model.sampler.mlps)))
+        self._zero_ranges, lo = [], 0
+        for a, b in skip:
+            if a > lo:
+                self._zero_ranges.append((lo, a))
+            lo = b
+        if lo < total:
+            self._zero_ranges.append((lo, total))
         from . import engine as _engine
         self.engine = _engine.FusedCacheStep(self.model, self.params) if (bf16 and fused) else None
 
     def num_params(self):
         return sum(int(t.numel()) for t in self.leaves)
 
-    def zero_grad(self):
-        self.flat_grad.zero_()
+    def zero_grad(self, skip_density_grids=False):
+        """Clear the gradient arena.  skip_density_grids=True leaves out the three density grids' tables, which the
+        fused step initialises with the parameter regularizer's (dense) gradient instead (nrc_grid_regularizer_init)."""
+        if not skip_density_grids:
+            self.flat_grad.zero_()
+            return
+        for lo, hi in self._zero_ranges:
+            self.flat_grad[lo:hi].zero_()
 
     def allreduce_grads(self, lo=0, hi=None, channel=0, num_ctas=0):
         """Mean over ranks of flat_grad[lo:hi] in place on the current stream (the reference's lax.pmean,

@@ -104,3 +104,10 @@ def test_grid_regularizer_matches_oracle(cuda_device):
     torch.cuda.synchronize()
     for a, b in zip(enc.tables(enc.views(grad)), tables_o):
         assert rel_err(a, 2 * b.grad) <= 1e-5
+    # init mode: the gradient tables are OVERWRITTEN (stale contents, here 2x the gradient, are replaced), loss accumulated
+    loss.zero_()
+    _lib.call("nrc_grid_regularizer_init", _lib.stream_ptr(), C.byref(d), 1.0, _lib.ptr(loss))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(lo.detach())) <= 1e-5 * float(lo.detach())
+    for a, b in zip(enc.tables(enc.views(grad)), tables_o):
+        assert rel_err(a, b.grad) <= 1e-5
