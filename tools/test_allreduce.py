@@ -52,9 +52,13 @@ def main():
         err2 = float((arena.buf[lo:n] - ref[lo:]).abs().max())
         untouched = bool(torch.equal(arena.buf[:lo], src[:lo]))
         ms = timeit(lambda: arena.allreduce_mean_(0, n))
+        sweep = {}
+        if os.environ.get("NRC_AR_SWEEP"):
+            for ctas in (16, 32, 64, 148, 296, 592):
+                sweep[ctas] = round(timeit(lambda: arena.allreduce_mean_(0, n, num_ctas=ctas), iters=10, warm=3), 4)
         res[mode if arena.mode == mode else mode + "->" + arena.mode] = {"max_abs_err_vs_nccl": err, "bucket_err": err2,
                                                          "outside_bucket_untouched": untouched, "ms_110MB": ms,
-                                                         "algbw_GBs": n * 4 / ms / 1e6}
+                                                         "algbw_GBs": n * 4 / ms / 1e6, "ms_by_ctas": sweep}
         del arena
     x = torch.randn(n, device=dev)
     ms = timeit(lambda: dist.all_reduce(x, op=dist.ReduceOp.AVG))
