@@ -1,10 +1,10 @@
 """A/B of the two density-query kernels (mma.sync fused query vs nrc_chain_query) on ray-coherent points.
-python tools/bench_query.py [--points 2097152] [--reps 10] [--only tc|mma]"""
+python tests/tools/bench_query.py [--points 2097152] [--reps 10] [--only tc|mma]"""
 import argparse, os, sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from neural_radiance_caching_b200 import geometry, mlp_chain, sampling  # noqa: E402
 
 

@@ -3,7 +3,7 @@ O=gpurun_out
 for occ in 4 5 6; do
   NRC_QUERY_OCC=$occ python bench.py --no-cpu-baseline > $O/j2_c2_occ$occ.json 2>/dev/null
   NRC_QUERY_OCC=$occ python bench.py --workload config3 --no-cpu-baseline > $O/j2_c3_occ$occ.json 2>/dev/null
-  NRC_QUERY_OCC=$occ python tools/bench_query.py --only mma > $O/j2_query_occ$occ.log 2>&1
+  NRC_QUERY_OCC=$occ python tests/tools/bench_query.py --only mma > $O/j2_query_occ$occ.log 2>&1
 done
 for f in $O/j2_c*.json; do echo $f; python - "$f" <<'PY'
 import json,sys
