@@ -161,6 +161,22 @@ int32_t nrc_density_normals_bwd(void* stream, const nrc_encoding_t* enc, const n
                                 const float* d_means, const float* d_g_raw_grad, int64_t num_points, float warp_c,
                                 const nrc_density_mlp_grad_t* grads);
 
+/* The same second-order term on tensor cores (bf16-MLP variant), as three launches that reuse the first-order kernels'
+ * structure.  With zdot = J_contract d_g and dw_c the derivative of corner c's trilinear weight along zdot:
+ *   nrc_encode_tangent_fwd       d_edot [P, L*F]   = scale * sum_c dw_c T[c]                     (fp32)
+ *   nrc_density_mlp_bwd_tangent  the MLP's backward pass on the TANGENT network (same ReLU masks as the primal, recomputed
+ *                                from d_enc = the primal features saved by nrc_density_query_fwd; no biases; upstream 1):
+ *                                grads->d_w0 += edot (x) a1, d_w1 += h1dot (x) a2, d_wd += h2dot (accumulated; biases and
+ *                                the normal head untouched), d_g_enc [P, L*F] = W0 a1                (bf16 mma.sync)
+ *   nrc_encode_tangent_bwd       levels[l].d_grad[c] += dw_c * scale * d_ge                         (fp32 atomics)
+ * d_means, d_g [P,3] as for nrc_density_normals_bwd. */
+int32_t nrc_encode_tangent_fwd(void* stream, const nrc_encoding_t* enc, const float* d_means, const float* d_g,
+                               int64_t num_points, float warp_c, float* d_edot);
+int32_t nrc_density_mlp_bwd_tangent(void* stream, const nrc_density_mlp_t* mlp, const float* d_enc, const float* d_enc_dot,
+                                    int64_t num_points, float* d_g_enc, const nrc_density_mlp_grad_t* grads);
+int32_t nrc_encode_tangent_bwd(void* stream, const nrc_encoding_t* enc, const float* d_means, const float* d_g,
+                               const float* d_ge, int64_t num_points, float warp_c);
+
 /* ------------------------------------------------------ K4: ray kernels ---- */
 /* render.compute_alpha_weights (internal/render.py:134-169), delta=None.
  *   d_density [R,n], d_tdist [R,n+1], d_dirs [R,3] -> d_weights, d_alpha, d_trans [R,n]

@@ -110,6 +110,9 @@ PROTOTYPES = {
     "nrc_distortion_loss": [_P, _P, _P, _I32, _I64, _F, _F, _F, _P, _P],
     "nrc_geometry_losses": [_P, _P, _P, _P, _P, _I64, _I32, _F, _F, _F, _F, _P, _P, _P, _P],
     "nrc_density_normals_bwd": [_P, _P, _P, _P, _P, _I64, _F, _P],
+    "nrc_encode_tangent_fwd": [_P, _P, _P, _P, _I64, _F, _P],
+    "nrc_density_mlp_bwd_tangent": [_P, _P, _P, _P, _I64, _P, _P],
+    "nrc_encode_tangent_bwd": [_P, _P, _P, _P, _P, _I64, _F],
     "nrc_chain_run": [_P, _P, _P, _I32, _P, _I64],
     "nrc_chain_query": [_P, _P, _P, _I32, _P, _I64, _P, _F],
     "nrc_chain_pack_weights": [_P, _P, _I32, _P, _I32, _P, _I32, _I32],

@@ -140,6 +140,81 @@ encode_bwd_kernel(const __grid_constant__ EncDev enc, const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Tangent of the encoding along a per-point direction (second-order path of the analytic normals, SURVEY 8f-1,
+// internal/geometry.py:442-460 differentiated again by the predicted-normal loss).  With x the sample mean,
+// z = contract(x / c), zdot = J_contract g (J is symmetric: the VJP routine gives the JVP) and, per level and corner,
+//     dw_c = sum_a (+-) zdot_a * N / span_a * prod_{b != a} w_b          (the derivative of the trilinear weight),
+// kTangentFwd:  edot[l*F+f]  = scale * sum_c dw_c T[c][f]                 (tangent features, [P, L*F])
+// else       :  dT[c][f]    += dw_c * scale * ge[l*F+f]                   (table gradient of <ge, edot>)
+// Same thread mapping as encode_fwd/bwd (thread per point, blockIdx.y = level); the scatter uses the dense-level
+// run aggregation.  fp32 throughout; the MLP between the two is nrc_density_mlp_bwd_tangent (bf16 tensor cores).
+template <int F, bool kTangentFwd>
+__global__ void __launch_bounds__(kEncThreads)
+encode_tangent_kernel(const __grid_constant__ EncDev enc, const float* __restrict__ means, const float* __restrict__ g,
+                      const float* __restrict__ ge, int64_t P, float warp_c, float* __restrict__ edot) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kEncThreads + threadIdx.x;
+  const int l = blockIdx.y;
+  const LevelDev& lv = enc.lv[l];
+  const bool valid = p < P;
+  const int64_t pc = valid ? p : P - 1;
+  const float x0 = __ldg(means + 3 * pc), x1 = __ldg(means + 3 * pc + 1), x2 = __ldg(means + 3 * pc + 2);
+  float z[3], xn[3], zd[3];
+  contract_point(warp_c, x0, x1, x2, z[0], z[1], z[2]);
+  normalise_point(enc, z, xn);
+  contract_vjp(warp_c, x0, x1, x2, __ldg(g + 3 * pc), __ldg(g + 3 * pc + 1), __ldg(g + 3 * pc + 2), zd[0], zd[1], zd[2]);
+  const Corners c = level_setup(lv, xn);
+  const float fN = static_cast<float>(lv.N);
+  const float t0 = zd[0] * (fN / enc.span[0]), t1 = zd[1] * (fN / enc.span[1]), t2 = zd[2] * (fN / enc.span[2]);
+  const int LF = enc.L * F;
+  float gl[F], ed[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    ed[f] = 0.f;
+    gl[f] = 0.f;
+    if constexpr (!kTangentFwd) gl[f] = valid ? __ldg(ge + pc * LF + l * F + f) * enc.scale : 0.f;
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int bx, by, bz;
+    corner_bits(lv.is_hash, k, bx, by, bz);
+    const int32_t row = valid ? corner_row(lv, c, bx, by, bz) : -1;
+    const float wx = bx ? c.cw[0] : c.fw[0];
+    const float wy = by ? c.cw[1] : c.fw[1];
+    const float wz = bz ? c.cw[2] : c.fw[2];
+    const float dw = (bx ? t0 : -t0) * (wy * wz) + (by ? t1 : -t1) * (wx * wz) + (bz ? t2 : -t2) * (wx * wy);
+    if constexpr (kTangentFwd) {
+      if (row >= 0) {
+        const FeatVec<F> v = load_row<F>(lv.table, row);
+#pragma unroll
+        for (int f = 0; f < F; ++f) ed[f] = fmaf(dw, v.v[f], ed[f]);
+      }
+    } else {
+      float gw[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) gw[f] = dw * gl[f];
+      if (!lv.is_hash) warp_run_atomic_add<F>(lv.grad, row, gw, lane);     // block-uniform branch
+      else if (row >= 0) atomic_add_row<F>(lv.grad, row, gw);
+    }
+  }
+  if constexpr (kTangentFwd) {
+    if (valid) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) edot[p * LF + l * F + f] = ed[f] * enc.scale;
+    }
+  }
+}
+
+template <int F>
+int32_t launch_tangent(cudaStream_t s, const EncDev& d, const float* means, const float* g, const float* ge, int64_t P,
+                       float warp_c, float* edot) {
+  dim3 grid(static_cast<unsigned>((P + kEncThreads - 1) / kEncThreads), d.L);
+  if (edot) encode_tangent_kernel<F, true><<<grid, kEncThreads, 0, s>>>(d, means, g, nullptr, P, warp_c, edot);
+  else encode_tangent_kernel<F, false><<<grid, kEncThreads, 0, s>>>(d, means, g, ge, P, warp_c, nullptr);
+  return check_launch();
+}
+
 template <int F>
 int32_t launch_fwd(cudaStream_t s, const EncDev& d, const float* x, int64_t P, float* out) {
   dim3 grid(static_cast<unsigned>((P + kEncThreads - 1) / kEncThreads), d.L);
@@ -382,4 +457,37 @@ extern "C" int32_t nrc_contract_bwd(void* stream, const float* d_x, const float*
   contract_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_g_z, num_points, c,
                                                                           d_g_x);
   return check_launch();
+}
+
+static int32_t encode_tangent(void* stream, const nrc_encoding_t* enc, const float* d_means, const float* d_g,
+                              const float* d_ge, int64_t num_points, float warp_c, float* d_edot) {
+  EncDev d;
+  const int32_t st = make_enc_dev(enc, d);
+  if (st != NRC_OK) return st;
+  if (num_points < 0) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_means || !d_g || (!d_ge && !d_edot)) return NRC_E_INVALID_ARG;
+  if (!d_edot)
+    for (int l = 0; l < d.L; ++l)
+      if (!d.lv[l].grad) return NRC_E_INVALID_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (d.F) {
+    case 1: return launch_tangent<1>(s, d, d_means, d_g, d_ge, num_points, warp_c, d_edot);
+    case 2: return launch_tangent<2>(s, d, d_means, d_g, d_ge, num_points, warp_c, d_edot);
+    case 4: return launch_tangent<4>(s, d, d_means, d_g, d_ge, num_points, warp_c, d_edot);
+    case 8: return launch_tangent<8>(s, d, d_means, d_g, d_ge, num_points, warp_c, d_edot);
+  }
+  return NRC_E_UNSUPPORTED;
+}
+
+extern "C" int32_t nrc_encode_tangent_fwd(void* stream, const nrc_encoding_t* enc, const float* d_means, const float* d_g,
+                                          int64_t num_points, float warp_c, float* d_edot) {
+  if (!d_edot) return NRC_E_INVALID_ARG;
+  return encode_tangent(stream, enc, d_means, d_g, nullptr, num_points, warp_c, d_edot);
+}
+
+extern "C" int32_t nrc_encode_tangent_bwd(void* stream, const nrc_encoding_t* enc, const float* d_means, const float* d_g,
+                                          const float* d_ge, int64_t num_points, float warp_c) {
+  if (!d_ge) return NRC_E_INVALID_ARG;
+  return encode_tangent(stream, enc, d_means, d_g, d_ge, num_points, warp_c, nullptr);
 }

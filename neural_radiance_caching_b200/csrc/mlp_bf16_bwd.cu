@@ -19,6 +19,7 @@ constexpr int kBwTile = kBwThreads;  // points per tile
 struct BwdSmemBf16 {
   MlpWeightsBf16 w;
   __nv_bfloat16 x[kBwTile][kXStride];
+  __nv_bfloat16 xd[kBwTile][kXStride];   // tangent mode: edot (the A operand of dW0 there); 113.8 KB total, 2 CTAs/SM
   __nv_bfloat16 h1[kBwTile][kWStride];
   __nv_bfloat16 h2[kBwTile][kWStride];
   __nv_bfloat16 g2[kBwTile][kWStride];
@@ -67,7 +68,13 @@ __global__ void __launch_bounds__(kBwThreads)
 mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, const float* __restrict__ g_raw,
                     const float* __restrict__ density, const float* __restrict__ g_feat,
                     const float* __restrict__ g_gp, int64_t P, float* __restrict__ g_enc,
-                    const nrc_density_mlp_grad_t grads, int want_wgrad) {
+                    const nrc_density_mlp_grad_t grads, int want_wgrad, const float* __restrict__ enc_dot) {
+  // enc_dot != nullptr: TANGENT mode (second-order path of the analytic normals).  The MLP is piecewise linear, so
+  // d/d theta <g, d raw / d x> is the ordinary backward pass of the TANGENT network - same ReLU masks as the primal,
+  // activations replaced by the tangents h1dot = M1 (W0^T edot), h2dot = M2 (W1^T h1dot), no biases - with upstream
+  // d rawdot = 1:  dW0 += edot (x) a1, dW1 += h1dot (x) a2, dwd += h2dot, g_enc = W0 a1 (= d raw / d e, for the table
+  // scatter).  The primal forward is recomputed from `enc` for the masks only.
+  const bool tangent = enc_dot != nullptr;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmemBf16& s = *reinterpret_cast<BwdSmemBf16*>(smem_raw);
   load_weights_bf16(s.w, m);
@@ -103,13 +110,15 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
       for (int k = 0; k < KS0 * 16; ++k)
         s.x[row][k] = __float2bfloat16((valid && k < in_dim) ? __ldg(enc + p * in_dim + k) : 0.f);
       float go[4] = {0.f, 0.f, 0.f, 0.f};
-      if (valid) {
+      if (valid && tangent) {
+        go[0] = 1.0f;                                   // upstream of the tangent network: d rawdot = 1
+      } else if (valid) {
         go[0] = density ? g_raw[p] * density[p] : g_raw[p];
         if (g_gp) { go[1] = g_gp[3 * p]; go[2] = g_gp[3 * p + 1]; go[3] = g_gp[3 * p + 2]; }
       }
       *reinterpret_cast<uint2*>(&s.go[row][0]) = make_uint2(pack_bf16(go[0], go[1]), pack_bf16(go[2], go[3]));
       *reinterpret_cast<uint2*>(&s.go[row][4]) = make_uint2(0u, 0u);
-      if (want_wgrad) {
+      if (want_wgrad && !tangent) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float v = go[c];
@@ -130,20 +139,58 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
       mma_layer64<KS0>(acc, a0, &s.w.w0t[0][0], kXStride, s.w.b0, lane);
       uint32_t h1f[4][4];
       acc_to_afrag<true>(acc, h1f);
-      store_afrag(&s.h1[0][0], kWStride, row0, h1f, lane);
-      mma_layer64<4>(acc, h1f, &s.w.w1t[0][0], kWStride, s.w.b1, lane);
       uint32_t f2[4][4];
-      acc_to_afrag<true>(acc, f2);
-      store_afrag(&s.h2[0][0], kWStride, row0, f2, lane);
+      uint32_t m1 = 0u, m2 = 0u;     // ReLU masks of the primal in accumulator layout (bit nt*4+e), tangent mode
+      if (!tangent) {
+        store_afrag(&s.h1[0][0], kWStride, row0, h1f, lane);
+        mma_layer64<4>(acc, h1f, &s.w.w1t[0][0], kWStride, s.w.b1, lane);
+        acc_to_afrag<true>(acc, f2);
+        store_afrag(&s.h2[0][0], kWStride, row0, f2, lane);
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) m1 |= (acc[nt][e] > 0.f ? 1u : 0u) << (nt * 4 + e);
+        mma_layer64<4>(acc, h1f, &s.w.w1t[0][0], kWStride, s.w.b1, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) m2 |= (acc[nt][e] > 0.f ? 1u : 0u) << (nt * 4 + e);
+        // tangent forward: the warp's rows of the x tile now take edot (they are private to the warp until phase 2)
+        __syncwarp();
+        if (mt == 0) {
+          const int64_t pl = base + lane;
+          const int rowl = warp * 32 + lane;
+          for (int k = 0; k < KS0 * 16; ++k)
+            s.xd[rowl][k] = __float2bfloat16((pl < P && k < in_dim) ? __ldg(enc_dot + pl * in_dim + k) : 0.f);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < KS0; ++ks) load_a_frag(a0[ks], &s.xd[0][0], kXStride, row0, ks * 16, lane);
+        mma_layer64<KS0>(acc, a0, &s.w.w0t[0][0], kXStride, nullptr, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[nt][e] = ((m1 >> (nt * 4 + e)) & 1u) ? acc[nt][e] : 0.f;
+        acc_to_afrag<false>(acc, f2);
+        store_afrag(&s.h1[0][0], kWStride, row0, f2, lane);                 // h1 tile <- h1dot
+        mma_layer64<4>(acc, f2, &s.w.w1t[0][0], kWStride, nullptr, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[nt][e] = ((m2 >> (nt * 4 + e)) & 1u) ? acc[nt][e] : 0.f;
+        acc_to_afrag<false>(acc, f2);
+        store_afrag(&s.h2[0][0], kWStride, row0, f2, lane);                 // h2 tile <- h2dot
+      }
       // g_h2 = (Wo go + g_feat) * [h2 > 0], in accumulator layout
       const int64_t pr[2] = {base + mt * 16 + r, base + mt * 16 + r + 8};
       float gor[2][4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const bool v = pr[h] < P;
-        gor[h][0] = v ? (density ? g_raw[pr[h]] * density[pr[h]] : g_raw[pr[h]]) : 0.f;
+        gor[h][0] = v ? (tangent ? 1.0f : (density ? g_raw[pr[h]] * density[pr[h]] : g_raw[pr[h]])) : 0.f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) gor[h][1 + c] = (v && g_gp) ? g_gp[3 * pr[h] + c] : 0.f;
+        for (int c = 0; c < 3; ++c) gor[h][1 + c] = (v && g_gp && !tangent) ? g_gp[3 * pr[h] + c] : 0.f;
       }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -154,15 +201,17 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
         for (int h = 0; h < 2; ++h) {
           float ga = gor[h][0] * w0.x + gor[h][1] * w0.y + gor[h][2] * w0.z + gor[h][3] * w0.w;
           float gb = gor[h][0] * w1.x + gor[h][1] * w1.y + gor[h][2] * w1.z + gor[h][3] * w1.w;
-          if (g_feat && pr[h] < P) {
+          if (g_feat && !tangent && pr[h] < P) {
             float2 gf = *reinterpret_cast<const float2*>(g_feat + pr[h] * kHid + col);
             ga += gf.x; gb += gf.y;
           }
-          acc[nt][2 * h] = acc[nt][2 * h] > 0.f ? ga : 0.f;
-          acc[nt][2 * h + 1] = acc[nt][2 * h + 1] > 0.f ? gb : 0.f;
+          const bool on0 = tangent ? ((m2 >> (nt * 4 + 2 * h)) & 1u) : (acc[nt][2 * h] > 0.f);
+          const bool on1 = tangent ? ((m2 >> (nt * 4 + 2 * h + 1)) & 1u) : (acc[nt][2 * h + 1] > 0.f);
+          acc[nt][2 * h] = on0 ? ga : 0.f;
+          acc[nt][2 * h + 1] = on1 ? gb : 0.f;
         }
       }
-      if (want_wgrad) colsum_to_smem(acc, s.db1, lane);
+      if (want_wgrad && !tangent) colsum_to_smem(acc, s.db1, lane);      // the tangent network has no biases
       acc_to_afrag<false>(acc, f2);
       store_afrag(&s.g2[0][0], kWStride, row0, f2, lane);
       // g_h1 = (g_h2 W1^T) * [h1 > 0]
@@ -171,12 +220,13 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
       for (int nt = 0; nt < 8; ++nt) {
         float2 lo = unpack_bf16(h1f[nt >> 1][2 * (nt & 1)]);
         float2 hi = unpack_bf16(h1f[nt >> 1][2 * (nt & 1) + 1]);
+        // h1f holds relu(h1) of the primal in A-fragment layout, i.e. the same (row, column) pairs as acc[nt][0..3]
         acc[nt][0] = lo.x > 0.f ? acc[nt][0] : 0.f;
         acc[nt][1] = lo.y > 0.f ? acc[nt][1] : 0.f;
         acc[nt][2] = hi.x > 0.f ? acc[nt][2] : 0.f;
         acc[nt][3] = hi.y > 0.f ? acc[nt][3] : 0.f;
       }
-      if (want_wgrad) colsum_to_smem(acc, s.db0, lane);
+      if (want_wgrad && !tangent) colsum_to_smem(acc, s.db0, lane);
       acc_to_afrag<false>(acc, f2);
       store_afrag(&s.g1[0][0], kWStride, row0, f2, lane);
       if (g_enc) {
@@ -224,7 +274,7 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
       load_b_frag2_trans(b, &s.g1[0][0], kWStride, k0, warp * 16, lane);
 #pragma unroll
       for (int mi = 0; mi < KS0; ++mi) {
-        load_a_frag_trans(a, &s.x[0][0], kXStride, k0, mi * 16, lane);
+        load_a_frag_trans(a, tangent ? &s.xd[0][0] : &s.x[0][0], kXStride, k0, mi * 16, lane);
         mma_bf16(accW0[mi][0], a, b[0], b[1]);
         mma_bf16(accW0[mi][1], a, b[2], b[3]);
       }
@@ -277,6 +327,7 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
     if (c == 0) atomicAdd(grads.d_wd + j, accWo[e]);
     else if (c < 4 && grads.d_wn) atomicAdd(grads.d_wn + j * 3 + (c - 1), accWo[e]);
   }
+  if (tangent) return;          // no bias terms in the tangent network (and the caller may not pass bias buffers)
   __syncthreads();
   for (int i = threadIdx.x; i < kHid; i += kBwThreads) {
     atomicAdd(grads.d_b1 + i, s.db1[i]);
@@ -289,7 +340,7 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
 template <int KS0>
 int32_t launch_bf16_bwd(cudaStream_t st, const nrc_density_mlp_t* mlp, const float* enc, const float* g_raw,
                         const float* density, const float* g_feat, const float* g_gp, int64_t P, float* g_enc,
-                        const nrc_density_mlp_grad_t* grads) {
+                        const nrc_density_mlp_grad_t* grads, const float* enc_dot = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(mlp_bf16_bwd_kernel<KS0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -305,7 +356,7 @@ int32_t launch_bf16_bwd(cudaStream_t st, const nrc_density_mlp_t* mlp, const flo
   static const int mult = getenv("NRC_MLP_BWD_GRID_MULT") ? atoi(getenv("NRC_MLP_BWD_GRID_MULT")) : 2;
   unsigned grid = static_cast<unsigned>(tiles < kNumSMs * mult ? tiles : kNumSMs * mult);
   mlp_bf16_bwd_kernel<KS0><<<grid, kBwThreads, sizeof(BwdSmemBf16), st>>>(*mlp, enc, g_raw, density, g_feat, g_gp,
-                                                                          P, g_enc, g, grads ? 1 : 0);
+                                                                          P, g_enc, g, grads ? 1 : 0, enc_dot);
   return check_launch();
 }
 
@@ -317,4 +368,29 @@ int32_t density_mlp_bwd_bf16(cudaStream_t s, const nrc_density_mlp_t* mlp, const
   return launch_bf16_bwd<2>(s, mlp, d_enc, d_g_raw, d_density, d_g_feat, d_g_gp, P, d_g_enc, grads);
 }
 
+// Tangent mode (see the kernel): d_enc = primal features (masks), d_enc_dot = tangent features, both [P, in_dim];
+// d_g_enc [P, in_dim] <- W0 a1; grads: d_w0, d_w1, d_wd accumulated (biases and the normal head receive nothing).
+int32_t density_mlp_bwd_tangent_bf16(cudaStream_t s, const nrc_density_mlp_t* mlp, const float* d_enc,
+                                     const float* d_enc_dot, int64_t P, float* d_g_enc,
+                                     const nrc_density_mlp_grad_t* grads) {
+  if (mlp->in_dim <= 16)
+    return launch_bf16_bwd<1>(s, mlp, d_enc, nullptr, nullptr, nullptr, nullptr, P, d_g_enc, grads, d_enc_dot);
+  return launch_bf16_bwd<2>(s, mlp, d_enc, nullptr, nullptr, nullptr, nullptr, P, d_g_enc, grads, d_enc_dot);
+}
+
 }  // namespace nrc
+
+// Second-order path of the analytic normals on tensor cores: the MLP part (see the kernel's tangent mode).  Reference:
+// internal/geometry.py:442-460 (jax.vjp of predict_density w.r.t. the means) differentiated by the predicted-normal loss
+// (internal/loss_utils.py:169-199); fp32 counterpart: nrc_density_normals_bwd.
+extern "C" int32_t nrc_density_mlp_bwd_tangent(void* stream, const nrc_density_mlp_t* mlp, const float* d_enc,
+                                               const float* d_enc_dot, int64_t num_points, float* d_g_enc,
+                                               const nrc_density_mlp_grad_t* grads) {
+  if (!mlp || !mlp->d_w0 || !mlp->d_b0 || !mlp->d_w1 || !mlp->d_b1 || !mlp->d_wd || !mlp->d_bd) return NRC_E_INVALID_ARG;
+  if (mlp->width != nrc::kHid || mlp->in_dim < 1 || mlp->in_dim > 32) return NRC_E_UNSUPPORTED;
+  if (num_points < 0) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_enc || !d_enc_dot || !grads || !grads->d_w0 || !grads->d_w1 || !grads->d_wd) return NRC_E_INVALID_ARG;
+  return nrc::density_mlp_bwd_tangent_bf16(static_cast<cudaStream_t>(stream), mlp, d_enc, d_enc_dot, num_points, d_g_enc,
+                                           grads);
+}

@@ -262,7 +262,8 @@ class FusedCacheStep:
                     mlp2 = L2["mlp"]
                     sinks = [_lib.grad_sink(t) for t in L2["flat"]]
                     geometry.density_normals_bwd(mlp2, L2["p"], L2["arena"], L2["means"].reshape(P2, 3), g_rg,
-                                                 mlp2._unflatten(sinks), _lib.grad_sink(L2["arena"]))
+                                                 mlp2._unflatten(sinks), _lib.grad_sink(L2["arena"]),
+                                                 enc_out=L2["enc_out"])
                     return gw_geo, gnp_geo, g_na, g_rg
                 return gw_geo, gnp_geo, g_na, None
             if self.concurrent:

@@ -5,6 +5,7 @@ Parameter names follow the Flax auto-names of the reference's setup() attributes
 internal/geometry.py:123-151), kernels [in,out], biases [out], fp32.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -214,13 +215,25 @@ class _RawGradFn(torch.autograd.Function):
             (None,) * len(flat) if w_sunk else tuple(gflat))
 
 
-def density_normals_bwd(mlp, p, arena, means, g_raw_grad, grad_p, grad_arena):
+def density_normals_bwd(mlp, p, arena, means, g_raw_grad, grad_p, grad_arena, enc_out=None):
     """nrc_density_normals_bwd: accumulate d/d theta <g_raw_grad, d raw / d means> into `grad_p` (a parameter-
-    shaped tree of gradient buffers; only the three kernels receive anything) and `grad_arena`."""
+    shaped tree of gradient buffers; only the three kernels receive anything) and `grad_arena`.
+    With the bf16 variant and `enc_out` (the primal features [P, L*F] saved by the query) the term runs on tensor cores:
+    tangent gather -> the MLP's backward pass on the tangent network -> weighted table scatter (three launches)."""
     enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)), mlp.grid.tables(mlp.grid.views(grad_arena)))
     desc = _mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals)
     gd = _grad_desc(mlp, grad_p)
     P = means.shape[0]
+    if mlp.bf16 and enc_out is not None and os.environ.get("NRC_NORMALS2_TC", "1") == "1":
+        edot = torch.empty((P, mlp.in_dim), device=means.device, dtype=torch.float32)
+        ge = torch.empty_like(edot)
+        _lib.call("nrc_encode_tangent_fwd", _lib.stream_ptr(), C.byref(enc), _lib.ptr(means), _lib.ptr(g_raw_grad), P,
+                  float(mlp.warp_c), _lib.ptr(edot))
+        _lib.call("nrc_density_mlp_bwd_tangent", _lib.stream_ptr(), C.byref(desc), _lib.ptr(enc_out), _lib.ptr(edot), P,
+                  _lib.ptr(ge), C.byref(gd))
+        _lib.call("nrc_encode_tangent_bwd", _lib.stream_ptr(), C.byref(enc), _lib.ptr(means), _lib.ptr(g_raw_grad),
+                  _lib.ptr(ge), P, float(mlp.warp_c))
+        return
     _lib.call("nrc_density_normals_bwd", _lib.stream_ptr(), C.byref(enc), C.byref(desc), _lib.ptr(means),
               _lib.ptr(g_raw_grad), P, float(mlp.warp_c), C.byref(gd))
 
