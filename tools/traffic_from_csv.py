@@ -5,7 +5,8 @@ import collections, csv, json, re, sys
 MAP = {"mlp_bf16_fwd_kernel": "nrc_density_query_fwd", "chain_kernel": "nrc_chain_run", "wgrad_kernel": "nrc_chain_wgrad",
        "encode_bwd_kernel": "nrc_encode_bwd", "mlp_bf16_bwd_kernel": "nrc_density_mlp_bwd",
        "interlevel_loss_kernel": "nrc_interlevel_loss", "density_normals_bwd_kernel": "nrc_density_normals_bwd",
-       "encode_fwd_kernel": "nrc_encode_fwd", "grid_regularizer_kernel": "nrc_grid_regularizer"}
+       "encode_fwd_kernel": "nrc_encode_fwd", "grid_regularizer_kernel": "nrc_grid_regularizer_init",
+       "encode_tangent_kernel": "nrc_encode_tangent_fwd+bwd"}
 
 
 def main(path, tag):
