@@ -13,14 +13,24 @@ Rules (see DESIGN.md "Oracle"):
 
 Pinning status: the reference ships no tests, golden vectors or fixtures for
 this path and JAX/XLA is not installable here, so the restatement cannot be
-checked against XLA itself ("parity unpinned" w.r.t. XLA).  It IS pinned to
-the reference's own *source*: tests/golden/make_golden.py imports the
-reference's modules unmodified from /root/reference under a small NumPy
-stand-in for `jax.numpy` and freezes their outputs into tests/golden/*.npz;
-tests/test_oracle_golden.py checks this oracle against those vectors.
-Assumed XLA semantics (IEEE-754 fp32 round-to-nearest per op, no FMA
-contraction, saturating f32->s32 convert, uint32 wrap-around multiply) are
-listed in DESIGN.md.
+checked against XLA itself ("parity unpinned" w.r.t. XLA's own rounding).  It IS
+pinned to the reference's own *source*: tests/golden/make_reference_vectors.py
+imports the reference's modules unmodified from /root/reference under a small
+NumPy stand-in for jax (tests/golden/jax_numpy_shim.py), runs their functions
+(internal/math.py, coord.py, stepfun.py, render.py, grid_utils.py, ref_utils.py)
+on seeded float32 inputs and freezes inputs and outputs into
+tests/golden/reference_np.npz; tests/test_reference_vectors.py checks this
+oracle against those vectors (corner indices / interpolation / contraction /
+cast_rays / l2_normalize bit-exact, the rest to fp32 rounding) and
+tests/test_reference_vectors_gpu.py checks the CUDA kernels against them
+directly.  Modules whose reference counterpart needs flax Modules (the model
+classes in geometry.py, nerf.py, material.py, light_sampler.py, transient.py)
+are pinned only through these building blocks: they say "parity unpinned" in
+their own headers.  The oracle's own outputs are additionally frozen in
+tests/golden/oracle_v*.npz (make_golden*.py) so that any later edit of the
+restatement is caught.  Assumed XLA semantics (IEEE-754 fp32 round-to-nearest
+per op, no FMA contraction, saturating f32->s32 convert, uint32 wrap-around
+multiply) are listed in DESIGN.md.
 """
 import torch
 

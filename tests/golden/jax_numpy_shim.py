@@ -1,0 +1,221 @@
+"""A minimal stand-in for `jax` / `jax.numpy` / `flax` / `gin` built on NumPy, used ONLY by
+tests/golden/make_reference_vectors.py to EXECUTE the reference's own function bodies (internal/math.py, stepfun.py,
+coord.py, render.py, linspline.py, grid_utils.py, ref_utils.py under /root/reference) in this container, where JAX is
+not installable.  It makes the golden vectors "the reference's source run with NumPy float32 semantics" - not XLA: op
+order inside a NumPy primitive (cumsum, sum) is NumPy's, transcendental functions are libm's.
+
+Semantics reproduced on purpose:
+  * default float dtype float32 (linspace / arange / zeros / array of Python floats);
+  * jax.random.uniform(key, shape, minval, maxval): `key` IS a pre-drawn U[0,1) array -> minval + key * (maxval - minval)
+    (how the kernels and the oracle take their randomness);
+  * custom_jvp / custom_vjp: the primal function; stop_gradient: identity; vmap over the leading axis by a Python loop;
+  * uint32 arithmetic wraps (NumPy does for arrays).
+Not reproduced: JAX's weak-type promotion of int32 * float32 (NumPy widens to float64; the generator rounds such
+results back to float32 when saving, which is exact for the +-1 sign factors where it occurs)."""
+import functools
+import sys
+import types
+
+import numpy as np
+
+f32 = np.float32
+
+
+def _as(x):
+    a = np.asarray(x)
+    if a.dtype == np.float64:
+        a = a.astype(np.float32)
+    if a.dtype == np.int64:
+        a = a.astype(np.int32)
+    return a
+
+
+class _JnpModule(types.ModuleType):
+    """numpy with float32 / int32 defaults; anything not overridden falls through to numpy."""
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+jnp = _JnpModule("jax.numpy")
+jnp.ndarray = np.ndarray
+jnp.float32, jnp.int32, jnp.uint32, jnp.bool_ = np.float32, np.int32, np.uint32, np.bool_
+jnp.inf, jnp.pi, jnp.newaxis, jnp.nan = np.inf, np.pi, None, np.nan
+
+
+def _wrap_f32(fn):
+    @functools.wraps(fn)
+    def w(*a, **k):
+        out = fn(*a, **k)
+        if isinstance(out, np.ndarray) and out.dtype == np.float64:
+            return out.astype(np.float32)
+        if isinstance(out, np.ndarray) and out.dtype == np.int64:
+            return out.astype(np.int32)
+        if isinstance(out, np.float64):
+            return np.float32(out)
+        return out
+    return w
+
+
+for _n in ("linspace", "arange", "zeros", "ones", "eye", "array", "asarray", "full", "geomspace", "logspace", "mean", "sum",
+           "cumsum", "sqrt", "exp", "log", "sin", "cos", "arccos", "power", "where", "interp", "diff", "floor", "ceil",
+           "maximum", "minimum", "clip", "abs", "square", "reciprocal", "cbrt", "log1p", "expm1", "tanh", "arctan2",
+           "concatenate", "stack", "matmul", "cross", "prod", "max", "min", "sign", "nan_to_num", "select", "round",
+           "meshgrid", "zeros_like", "ones_like", "full_like", "searchsorted", "argsort", "sort", "take_along_axis"):
+    if hasattr(np, _n):
+        setattr(jnp, _n, _wrap_f32(getattr(np, _n)))
+
+
+def _matmul(a, b, precision=None, **k):
+    out = np.matmul(a, b)
+    return out.astype(np.float32) if out.dtype == np.float64 else out
+
+
+jnp.matmul = _matmul
+
+
+def _nan_to_num(x, copy=True, nan=0.0, posinf=None, neginf=None):
+    # jnp.nan_to_num(x, jnp.inf): the second positional argument is `copy` (as in NumPy), so NaN -> 0
+    return np.nan_to_num(x, nan=nan, posinf=posinf, neginf=neginf).astype(np.asarray(x).dtype)
+
+
+jnp.nan_to_num = _nan_to_num
+
+
+def _vectorize(fn=None, *, signature=None, excluded=None):
+    def deco(f):
+        v = np.vectorize(f, signature=signature, excluded=excluded or set())
+
+        @functools.wraps(f)
+        def w(*a, **k):
+            out = v(*a, **k)
+            return tuple(_as(o) for o in out) if isinstance(out, tuple) else _as(out)
+        return w
+    return deco(fn) if fn is not None else deco
+
+
+jnp.vectorize = _vectorize
+
+
+def _finfo(dt):
+    return np.finfo(np.float32 if dt in (jnp.float32, np.float32, float) else dt)
+
+
+jnp.finfo = _finfo
+linalg = types.ModuleType("jax.numpy.linalg")
+for _n in ("norm", "det", "slogdet", "inv", "eigh", "cholesky"):
+    setattr(linalg, _n, _wrap_f32(getattr(np.linalg, _n)))
+jnp.linalg = linalg
+
+
+class _Custom:
+    """jax.custom_jvp / jax.custom_vjp: only the primal is executed."""
+
+    def __init__(self, fn, *a, **k):
+        self.fn = fn
+        functools.update_wrapper(self, fn)
+
+    def __call__(self, *a, **k):
+        return self.fn(*a, **k)
+
+    def defjvp(self, f, *a, **k):
+        return f
+
+    def defjvps(self, *f):
+        return None
+
+    def defvjp(self, fwd, bwd, *a, **k):
+        return None
+
+
+def _custom(fn=None, **kw):
+    if fn is None:
+        return lambda f: _Custom(f)
+    return _Custom(fn)
+
+
+def _vmap(fn, in_axes=0, out_axes=0):
+    def w(*args):
+        axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+        n = next(np.asarray(a).shape[ax] for a, ax in zip(args, axes) if ax is not None)
+        outs = [fn(*[np.take(a, i, axis=ax) if ax is not None else a for a, ax in zip(args, axes)]) for i in range(n)]
+        if isinstance(outs[0], tuple):
+            return tuple(np.stack([o[j] for o in outs], axis=out_axes) for j in range(len(outs[0])))
+        return np.stack(outs, axis=out_axes)
+    return w
+
+
+random = types.ModuleType("jax.random")
+random.uniform = lambda key, shape=(), dtype=np.float32, minval=0.0, maxval=1.0: (
+    np.float32(minval) + np.asarray(key, np.float32).reshape(shape) * np.float32(maxval - minval)).astype(np.float32)
+random.split = lambda key, num=2: [key] * num
+random.PRNGKey = lambda seed: seed
+
+lax = types.ModuleType("jax.lax")
+lax.stop_gradient = lambda x: x
+lax.Precision = types.SimpleNamespace(HIGHEST=None, DEFAULT=None, HIGH=None)
+
+nn_mod = types.ModuleType("jax.nn")
+nn_mod.softmax = lambda x, axis=-1: (lambda e: e / e.sum(axis=axis, keepdims=True))(np.exp(x - x.max(axis=axis, keepdims=True)))
+nn_mod.softplus = lambda x: np.logaddexp(x, np.float32(0)).astype(np.float32)
+nn_mod.sigmoid = lambda x: (1 / (1 + np.exp(-x))).astype(np.float32)
+nn_mod.relu = lambda x: np.maximum(x, 0)
+nn_mod.tanh = np.tanh
+
+jax = types.ModuleType("jax")
+jax.numpy, jax.random, jax.lax, jax.nn = jnp, random, lax, nn_mod
+jax.custom_jvp, jax.custom_vjp = _custom, _custom
+jax.vmap = _vmap
+jax.jit = lambda f=None, **k: (f if f is not None else (lambda g: g))
+jax.named_scope = lambda name: (lambda f: f)
+jax.Array = np.ndarray
+tree_util = types.ModuleType("jax.tree_util")
+tree_util.tree_map = lambda f, t: {k: f(v) for k, v in t.items()} if isinstance(t, dict) else f(t)
+jax.tree_util = tree_util
+experimental = types.ModuleType("jax.experimental")
+checkify = types.ModuleType("jax.experimental.checkify")
+checkify.check = lambda cond, msg, **k: None
+checkify.checkify = lambda f, **k: f
+experimental.checkify = checkify
+jax.experimental = experimental
+jscipy = types.ModuleType("jax.scipy")
+jax.scipy = jscipy
+
+
+class _Passthrough(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+
+        def deco(*a, **k):
+            if len(a) == 1 and callable(a[0]) and not k:
+                return a[0]
+            return lambda f: f
+        return deco
+
+
+def install():
+    """Put the stand-ins into sys.modules (idempotent).  Heavy optional imports of the reference that the numeric
+    functions never touch (tensorflow, cv2, flax, gin, absl, PIL, ...) become empty pass-through modules."""
+    if not hasattr(np, "math"):
+        import math as _math
+        np.math = _math          # the reference calls np.math.factorial (removed in NumPy 2)
+    mods = {"jax": jax, "jax.numpy": jnp, "jax.random": random, "jax.lax": lax, "jax.nn": nn_mod,
+            "jax.tree_util": tree_util, "jax.experimental": experimental, "jax.experimental.checkify": checkify,
+            "jax.scipy": jscipy, "jax.numpy.linalg": linalg}
+    for k, v in mods.items():
+        sys.modules[k] = v
+    gin = _Passthrough("gin")
+    gin.configurable = lambda *a, **k: (a[0] if (len(a) == 1 and callable(a[0]) and not k) else (lambda f: f))
+    gin.config = _Passthrough("gin.config")
+    sys.modules["gin"] = gin
+    sys.modules["gin.config"] = gin.config
+    flax = types.ModuleType("flax")
+    linen = types.ModuleType("flax.linen")
+    linen.Module = type("Module", (), {})
+    linen.compact = lambda f: f
+    linen.initializers = _Passthrough("flax.linen.initializers")
+    flax.linen = linen
+    sys.modules["flax"] = flax
+    sys.modules["flax.linen"] = linen
+    return jax

@@ -1,0 +1,149 @@
+"""Golden vectors from the REFERENCE'S OWN SOURCE (/root/reference/internal/*.py), executed in this container under the
+NumPy stand-in for jax (tests/golden/jax_numpy_shim.py - JAX itself is not installable here).  Run from the repo root:
+
+    python tests/golden/make_reference_vectors.py          # writes tests/golden/reference_np.npz
+
+The file pins the oracle (tests/test_reference_vectors.py, CPU) and, through the oracle-independent GPU test, the
+kernels to what the reference's code computes on the same float32 inputs.  /root/reference exists only in the build
+container; the .npz travels."""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import jax_numpy_shim as shim  # noqa: E402
+
+REF = os.environ.get("NRC_REFERENCE", "/root/reference")
+
+
+def load_reference():
+    shim.install()
+    sys.path.insert(0, REF)
+    importlib.import_module("internal")
+    # internal/utils.py imports tensorflow / cv2 / flax / PIL.  The numeric modules use three helpers of it, none of them
+    # numerics: two shape assertions and a platform query.  Stand-ins with the same contract:
+    u = types.ModuleType("internal.utils")
+
+    def _check(t, y, delta, what):
+        if t.shape[-1] != y.shape[-1] + delta:
+            raise ValueError(f"Invalid shapes ({t.shape}, {y.shape}) for a {what}.")
+
+    u.assert_valid_stepfun = lambda t, y: _check(t, y, 1, "step function")
+    u.assert_valid_linspline = lambda t, y: _check(t, y, 0, "linear spline")
+    u.device_is_tpu = lambda: False
+    sys.modules["internal.utils"] = u
+    names = ["math", "linspline", "stepfun", "coord", "render", "ref_utils", "grid_utils"]
+    return {n: importlib.import_module("internal." + n) for n in names}
+
+
+def main():
+    R = load_reference()
+    rmath, rstep, rcoord, rrender, rgrid, rref, rlin = (R[k] for k in ("math", "stepfun", "coord", "render", "grid_utils",
+                                                                        "ref_utils", "linspline"))
+    g = np.random.Generator(np.random.PCG64(20200823))
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    out = {}
+
+    # ---- internal/math.py ------------------------------------------------------------------------------------------
+    x = f(np.concatenate([g.normal(size=200) * 3, [0.0, -0.0, 1e-30, -1e-30, 50.0, 100.0, -100.0, 1e6]]))
+    out["math_x"] = x
+    out["math_safe_exp"] = rmath.safe_exp(x)
+    out["math_safe_log"] = rmath.safe_log(np.abs(x))
+    out["math_safe_sign"] = rmath.safe_sign(x)
+    for p, pre in ((-1.5, 2.0), (-0.25, 1e4)):
+        xs = f(np.abs(g.normal(size=256)) * 3)
+        p32, pre32 = np.float32(p), np.float32(pre)        # JAX weak typing keeps everything float32
+        y = rmath.power_ladder(xs, p32, premult=pre32)
+        out[f"math_pl_x_{p}"] = xs
+        out[f"math_pl_y_{p}"] = y
+        out[f"math_ipl_{p}"] = rmath.inv_power_ladder(y, p32, premult=pre32)
+
+    # ---- internal/coord.py -----------------------------------------------------------------------------------------
+    pts = f(g.normal(size=(512, 3)) * 2.5)
+    pts[:4] = [[0, 0, 0], [1, 0, 0], [0.3, 0.4, 0.5], [10, -20, 30]]
+    out["coord_x"] = pts
+    out["coord_contract"] = rcoord.contract(pts)
+    out["coord_contract_radius_2"] = rcoord.contract_radius_2(pts)
+    out["coord_contract_radius_5"] = rcoord.contract_radius_5(pts)
+
+    # ---- internal/stepfun.py ---------------------------------------------------------------------------------------
+    nr, m, n = 64, 64, 32
+    t = f(np.sort(g.uniform(0, 1, size=(nr, m + 1)), axis=-1)); t[:, 0], t[:, -1] = 0.0, 1.0
+    w = f(g.gamma(0.3, 1.0, size=(nr, m))); w[0] = 0.0; w[1, 1:] = 0.0
+    logits = f(0.4 * np.asarray(rmath.safe_log(w + np.float32(1e-5))))
+    u01 = f(g.uniform(size=(nr, 1)))
+    out.update(step_t=t, step_w=w, step_logits=logits, step_u01=u01)
+    wsm = np.asarray(shim.nn_mod.softmax(logits, axis=-1), np.float32)
+    out["step_integrate_weights"] = rstep.integrate_weights(wsm)
+    out["step_sample_intervals"] = rstep.sample_intervals(u01, t, logits, n, single_jitter=True, domain=(0.0, 1.0))
+    out["step_sample_centres"] = rstep.sample(u01, t, logits, n, single_jitter=True)
+    tm = f(np.sort(g.uniform(2, 6, size=(nr, n + 1)), axis=-1))
+    wn = f(g.dirichlet(np.ones(n) * 0.3, size=nr) * g.uniform(0.2, 1, size=(nr, 1)))
+    out.update(dist_t=tm, dist_w=wn)
+    out["step_lossfun_distortion"] = rstep.lossfun_distortion(tm, wn)
+    out["step_weighted_percentile"] = rstep.weighted_percentile(tm, wn, [5, 50, 95])
+    tq = f(np.sort(g.uniform(0, 1, size=(nr, 48 + 1)), axis=-1)); tq[:, 0], tq[:, -1] = 0.0, 1.0
+    tb = f(np.sort(g.uniform(0, 1, size=(nr, n + 1)), axis=-1)); tb[:, 0], tb[:, -1] = 0.0, 1.0
+    out.update(blur_tq=tq, blur_t=tb)
+    for hw in (0.03, 0.003):
+        out[f"step_blur_and_resample_{hw}"] = rstep.blur_and_resample_weights(tq, tb, wn, np.float32(hw))
+
+    # ---- internal/render.py ----------------------------------------------------------------------------------------
+    dens = f(np.exp(g.normal(size=(nr, n)) * 2))
+    dirs = f(g.normal(size=(nr, 3)))
+    out.update(render_density=dens, render_dirs=dirs)
+    for opaque in (False, True):
+        wts, alpha, trans = rrender.compute_alpha_weights(dens, tm, dirs, opaque_background=opaque)[:3]
+        out[f"render_weights_{int(opaque)}"] = wts
+        out[f"render_alpha_{int(opaque)}"] = alpha
+        out[f"render_trans_{int(opaque)}"] = trans
+    origins = f(g.normal(size=(nr, 3)) * 4)
+    radii = f(np.full((nr, 1), 5e-4))
+    means, covs = rrender.cast_rays(tm, origins, dirs, radii, "cone", diag=False)
+    out.update(render_origins=origins, render_means=means)
+    rgbs = f(g.uniform(size=(nr, n, 3)))
+    bg = f(g.uniform(size=(nr, 3)))
+    vr = rrender.volumetric_rendering(rgbs, wn, wn, tm, bg, True)
+    out.update(render_rgbs=rgbs, render_bg=bg)
+    for k in ("rgb", "acc", "distance_mean", "distance_median", "distance_percentile_5", "distance_percentile_95"):
+        if k in vr:
+            out["render_vr_" + k] = vr[k]
+
+    # ---- internal/grid_utils.py: trilerp on a hash level and on a dense level --------------------------------------
+    T, F, N = 4096, 4, 16
+    table = f(g.normal(size=(T, F)))
+    grid = f(g.normal(size=(N, N, N, F)))
+    loc = f(g.uniform(-0.2, 1.2, size=(777, 3)))          # in units of the unit cube; includes out-of-range points
+    out.update(grid_table=table, grid_dense=grid, grid_loc=loc)
+    for res in (64, 256):
+        out[f"grid_hash_{res}"] = rgrid.trilerp(table, loc * np.float32(res), "hash", rgrid.ResampleOpMode.DEFAULT_JAX)
+    out["grid_dense_16"] = rgrid.trilerp(grid, loc * np.float32(N), "grid", rgrid.ResampleOpMode.DEFAULT_JAX)
+
+    # ---- internal/ref_utils.py -------------------------------------------------------------------------------------
+    v = f(g.normal(size=(300, 3))); v[0] = 0.0; v[1] = [1e-20, 0, 0]
+    out["ref_l2n_x"] = v
+    out["ref_l2n"] = rref.l2_normalize(v)
+    d = v[2:] / np.linalg.norm(v[2:], axis=-1, keepdims=True)
+    kappa_inv = f(g.uniform(0.01, 1.0, size=(d.shape[0], 1)))
+    out.update(ide_dirs=f(d), ide_kappa_inv=kappa_inv)
+    for deg in (4, 5):
+        try:
+            out[f"ref_ide_{deg}"] = rref.generate_ide_fn(deg)(f(d), kappa_inv)
+        except Exception as e:   # recorded, not hidden
+            print(f"generate_ide_fn({deg}) not runnable under the shim: {type(e).__name__}: {e}")
+
+    out = {k: np.asarray(v_) for k, v_ in out.items()}
+    out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
+    path = os.path.join(HERE, "reference_np.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KB")
+    for k, v_ in sorted(out.items()):
+        print(f"  {k:34s} {str(v_.dtype):8s} {v_.shape}")
+
+
+if __name__ == "__main__":
+    main()

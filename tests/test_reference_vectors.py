@@ -1,0 +1,96 @@
+"""The oracle against the REFERENCE'S OWN SOURCE.  tests/golden/reference_np.npz holds outputs of the functions of
+/root/reference/internal/{math,coord,stepfun,render,grid_utils,ref_utils}.py, executed in the build container under a
+NumPy stand-in for jax (tests/golden/make_reference_vectors.py + jax_numpy_shim.py; JAX itself is not installable
+there), on seeded float32 inputs stored in the same file.  This pins the restatement in oracle/ to the reference's code:
+corner indices / trilinear interpolation / contraction / cast_rays / l2_normalize BIT-EXACT, everything else to float32
+rounding (different primitive implementations: NumPy vs PyTorch reductions and libm).  What it cannot pin is XLA's own
+rounding inside a primitive - DESIGN.md section 3 lists those assumptions."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import coord as ocoord, grid_utils as ogrid, loss_utils as oloss, nerf as onerf, ref_math, render as orender
+from oracle import stepfun as ostep
+
+V = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_np.npz"))
+T = lambda k: torch.from_numpy(V[k])
+
+
+def _np(x):
+    return x.detach().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def exact(got, key):
+    assert np.array_equal(_np(got), V[key], equal_nan=True), key
+
+
+def close(got, key, tol, per_element=False):
+    got, want = _np(got).astype(np.float64), V[key].astype(np.float64)
+    assert got.shape == want.shape, key
+    assert np.array_equal(np.isfinite(got), np.isfinite(want)), key
+    m = np.isfinite(want)
+    err = np.abs(got[m] - want[m])
+    scale = np.maximum(np.abs(want[m]), 1e-30) if per_element else max(np.abs(want[m]).max(), 1e-30)
+    assert float((err / scale).max()) <= tol, (key, float((err / scale).max()))
+
+
+def test_math():
+    x = T("math_x")
+    close(ref_math.safe_exp(x), "math_safe_exp", 1e-6, per_element=True)     # internal/math.py:186-192
+    close(ref_math.safe_log(x.abs()), "math_safe_log", 1e-6)                 # :177-183
+    exact(ref_math.safe_sign(x), "math_safe_sign")                           # :122-124
+    for p, pre in ((-1.5, 2.0), (-0.25, 1e4)):                               # :295-341 (both configured ladders)
+        close(ref_math.power_ladder(T(f"math_pl_x_{p}"), p, premult=pre), f"math_pl_y_{p}", 1e-6)
+        close(ref_math.inv_power_ladder(T(f"math_pl_y_{p}"), p, premult=pre), f"math_ipl_{p}", 1e-6)
+
+
+def test_coord_contract_bit_exact():
+    pts = T("coord_x")
+    exact(ocoord.contract(pts), "coord_contract")                            # internal/coord.py:63-69
+    exact(ocoord.contract_radius(pts, 2.0), "coord_contract_radius_2")       # :37-38
+    exact(ocoord.contract_radius(pts, 5.0), "coord_contract_radius_5")       # :33-34
+
+
+def test_stepfun():
+    t, lg, u01 = T("step_t"), T("step_logits"), T("step_u01")
+    close(ostep.integrate_weights(torch.softmax(lg, -1)), "step_integrate_weights", 1e-5)           # stepfun.py:125-144
+    # the CDF inversion amplifies last-ulp differences of softmax / cumsum (NumPy vs PyTorch) into ~1e-6 shifts
+    close(ostep.sample_intervals(u01, t, lg, 32, single_jitter=True, domain=(0.0, 1.0)), "step_sample_intervals", 1e-5)
+    close(ostep.sample(u01, t, lg, 32, single_jitter=True), "step_sample_centres", 1e-5)             # :158-204
+    tm, wn = T("dist_t"), T("dist_w")
+    close(oloss.lossfun_distortion(tm, wn), "step_lossfun_distortion", 1e-6)                         # :253-269
+    close(ostep.weighted_percentile(tm, wn, [5, 50, 95]), "step_weighted_percentile", 1e-5)          # :306-314
+    for hw in (0.03, 0.003):   # :463-483 over linspline.py: piecewise-quadratic evaluation with fp32 cancellation
+        close(oloss.blur_and_resample_weights(T("blur_tq"), T("blur_t"), wn, hw), f"step_blur_and_resample_{hw}", 2e-4)
+
+
+def test_render():
+    tm, wn, dens, dirs = T("dist_t"), T("dist_w"), T("render_density"), T("render_dirs")
+    for op in (0, 1):                                                                                # render.py:134-169
+        w, a, tr = orender.compute_alpha_weights(dens, tm, dirs, opaque_background=bool(op))[:3]
+        close(w, f"render_weights_{op}", 1e-6)
+        close(a, f"render_alpha_{op}", 1e-6)
+        close(tr, f"render_trans_{op}", 1e-6)
+    means, _ = orender.cast_rays(tm, T("render_origins"), dirs, torch.full((64, 1), 5e-4), "cone", diag=False)
+    exact(means, "render_means")                                                                     # :26-131
+    vr = orender.volumetric_rendering(T("render_rgbs"), wn, wn, tm, T("render_bg"), True)            # :172-247
+    for k in ("rgb", "acc", "distance_mean", "distance_median", "distance_percentile_5", "distance_percentile_95"):
+        close(vr[k], "render_vr_" + k, 1e-6)
+
+
+def test_trilerp_bit_exact():
+    """Hash indices (spatial hash, uint32 wrap-around) and dense padded-volume indices + interpolation order."""
+    loc = T("grid_loc")
+    for res in (64, 256):
+        exact(ogrid.trilerp(T("grid_table"), loc * res, "hash"), f"grid_hash_{res}")   # grid_utils.py:41-121, 679-726
+    exact(ogrid.trilerp(T("grid_dense"), loc * 16, "grid"), "grid_dense_16")           # :352-445
+
+
+def test_ref_utils():
+    exact(ref_math.l2_normalize(T("ref_l2n_x")), "ref_l2n")                            # ref_utils.py:45-70
+    # integrated directional encoding (ref_utils.py:131-192); the degree-5 basis has l = 16 harmonics whose fp32
+    # evaluation carries ~1e-4 noise in the reference itself
+    close(onerf.generate_ide_fn(4)(T("ide_dirs"), T("ide_kappa_inv")), "ref_ide_4", 1e-5)
+    close(onerf.generate_ide_fn(5)(T("ide_dirs"), T("ide_kappa_inv")), "ref_ide_5", 2e-4)

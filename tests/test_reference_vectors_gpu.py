@@ -1,0 +1,74 @@
+"""The CUDA kernels against the REFERENCE'S OWN SOURCE: tests/golden/reference_np.npz (outputs of the reference's
+functions under the NumPy stand-in for jax, see tests/test_reference_vectors.py) compared with the C-ABI entry points
+directly - no oracle in between.  Corner indices / interpolation / contraction bit-exact, the rest fp32 rel 1e-5
+(BASELINE north star), per-level conditioning notes as in tests/test_ray_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from neural_radiance_caching_b200 import coord as ncoord, grid_utils as ng, render as nrender, stepfun as nstep
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+V = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_np.npz"))
+
+
+def D(key, dev):
+    return torch.from_numpy(V[key]).to(dev).contiguous()
+
+
+def test_contract_bit_exact(cuda_device):
+    x = D("coord_x", cuda_device)
+    assert np.array_equal(ncoord.contract(x).cpu().numpy(), V["coord_contract"])
+    assert np.array_equal(ncoord.contract_radius_2(x).cpu().numpy(), V["coord_contract_radius_2"])
+    assert np.array_equal(ncoord.contract_radius_5(x).cpu().numpy(), V["coord_contract_radius_5"])
+
+
+def test_trilerp_dense_bit_exact(cuda_device):
+    got = ng.trilerp(D("grid_dense", cuda_device), D("grid_loc", cuda_device) * 16.0, "grid")
+    assert np.array_equal(got.cpu().numpy(), V["grid_dense_16"])
+
+
+@pytest.mark.parametrize("res", [64, 256])
+def test_trilerp_hash_bit_exact(cuda_device, res):
+    """One hash level (N^3 > T) of HashEncoding whose bbox maps voxel units back to [0,1] (exact for power-of-two N):
+    the spatial hash, the uint32 wrap-around and the interpolation order of jax_hash_resample_3d."""
+    table = D("grid_table", cuda_device)
+    enc = ng.HashEncoding(hash_map_size=table.shape[0], num_features=table.shape[1], scale_supersample=1.0,
+                          min_grid_size=res, max_grid_size=res, precondition_scaling=1.0,
+                          bbox_scaling=((0.0, 0.0, 0.0), (float(res),) * 3))
+    got = ng._EncodeFn.apply(enc, D("grid_loc", cuda_device) * float(res), False, table)
+    assert np.array_equal(got.cpu().numpy(), V[f"grid_hash_{res}"])
+
+
+def test_sample_intervals(cuda_device):
+    # logits = 0.4 * safe_log(w + 1e-5) in the generator = the sampler's annealed logits (sampling.py:340)
+    got = nstep.sample_intervals_from_weights(D("step_u01", cuda_device), D("step_t", cuda_device), D("step_w", cuda_device),
+                                              32, anneal=0.4, padding=1e-5, domain=(0.0, 1.0))
+    assert float((got.cpu() - torch.from_numpy(V["step_sample_intervals"])).abs().max()) <= 1e-5
+
+
+def test_alpha_weights_and_rendering(cuda_device):
+    tm, dens, dirs = D("dist_t", cuda_device), D("render_density", cuda_device), D("render_dirs", cuda_device)
+    for op in (0, 1):
+        w = nrender.compute_alpha_weights(dens, tm, dirs, opaque_background=bool(op))[0]
+        assert rel_err(w, torch.from_numpy(V[f"render_weights_{op}"])) <= 1e-5
+    wn = D("dist_w", cuda_device)
+    vr = nrender.volumetric_rendering(D("render_rgbs", cuda_device), wn, wn, tm, D("render_bg", cuda_device), True)
+    for k in ("rgb", "acc", "distance_mean", "distance_median", "distance_percentile_5", "distance_percentile_95"):
+        assert rel_err(vr[k], torch.from_numpy(V["render_vr_" + k])) <= 2e-5, k
+
+
+def test_cast_rays_means(cuda_device):
+    from neural_radiance_caching_b200.sampling import ProposalVolumeSampler
+
+    # the kernel takes normalised fenceposts and the ray warp; with near = 0, far = 1 and the linear warp s == t
+    tm = D("dist_t", cuda_device)
+    R = tm.shape[0]
+    rays = dict(origins=D("render_origins", cuda_device), directions=D("render_dirs", cuda_device),
+                near=torch.zeros((R, 1), device=cuda_device), far=torch.ones((R, 1), device=cuda_device))
+    t_n, means = ProposalVolumeSampler()._cast(tm, rays, False)
+    assert np.array_equal(t_n.cpu().numpy(), V["dist_t"])
+    assert rel_err(means, torch.from_numpy(V["render_means"])) <= 1e-6
