@@ -194,6 +194,31 @@ class _Passthrough(types.ModuleType):
         return deco
 
 
+STUBBED = ("dm_pix", "chex", "ml_collections", "optax", "tensorflow", "cv2", "absl", "PIL", "mediapy", "rawpy", "scipy_stub",
+           "orbax", "jaxcam", "trimesh", "matplotlib", "tqdm", "skimage", "sklearn", "torchvision", "pdb_stub", "jaxopt",
+           "tensorflow_graphics", "pycolmap", "camp_zipnerf", "open3d", "plotly", "imageio")
+
+
+class _StubFinder:
+    """Empty pass-through modules for the reference's non-numeric dependencies (decorators return their argument,
+    attribute access never fails): nothing numeric is ever taken from them."""
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery
+        top = name.split(".")[0]
+        if top in STUBBED and name not in sys.modules:
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _Passthrough(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
 def install():
     """Put the stand-ins into sys.modules (idempotent).  Heavy optional imports of the reference that the numeric
     functions never touch (tensorflow, cv2, flax, gin, absl, PIL, ...) become empty pass-through modules."""
@@ -210,12 +235,18 @@ def install():
     gin.config = _Passthrough("gin.config")
     sys.modules["gin"] = gin
     sys.modules["gin.config"] = gin.config
-    flax = types.ModuleType("flax")
-    linen = types.ModuleType("flax.linen")
+    flax = _Passthrough("flax")
+    flax.__path__ = []
+    linen = _Passthrough("flax.linen")
+    linen.__path__ = []
     linen.Module = type("Module", (), {})
     linen.compact = lambda f: f
-    linen.initializers = _Passthrough("flax.linen.initializers")
+    linen.relu, linen.softplus, linen.sigmoid, linen.tanh = nn_mod.relu, nn_mod.softplus, nn_mod.sigmoid, np.tanh
     flax.linen = linen
+    flax.struct = _Passthrough("flax.struct")
     sys.modules["flax"] = flax
     sys.modules["flax.linen"] = linen
+    sys.modules["flax.struct"] = flax.struct
+    if not any(isinstance(f, _StubFinder) for f in sys.meta_path):
+        sys.meta_path.append(_StubFinder())
     return jax

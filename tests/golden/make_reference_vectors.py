@@ -36,8 +36,10 @@ def load_reference():
     u.assert_valid_linspline = lambda t, y: _check(t, y, 0, "linear spline")
     u.device_is_tpu = lambda: False
     sys.modules["internal.utils"] = u
-    names = ["math", "linspline", "stepfun", "coord", "render", "ref_utils", "grid_utils"]
-    return {n: importlib.import_module("internal." + n) for n in names}
+    names = ["math", "linspline", "stepfun", "coord", "render", "ref_utils", "grid_utils", "loss_utils", "image"]
+    mods = {n: importlib.import_module("internal." + n) for n in names}
+    mods["render_utils"] = importlib.import_module("internal.inverse_render.render_utils")
+    return mods
 
 
 def main():
@@ -135,6 +137,52 @@ def main():
             out[f"ref_ide_{deg}"] = rref.generate_ide_fn(deg)(f(d), kappa_inv)
         except Exception as e:   # recorded, not hidden
             print(f"generate_ide_fn({deg}) not runnable under the shim: {type(e).__name__}: {e}")
+
+    # ---- internal/image.py, internal/loss_utils.py ----------------------------------------------------------------
+    rimage, rloss, rru = R["image"], R["loss_utils"], R["render_utils"]
+    lin = f(np.concatenate([g.uniform(0, 1, size=500), [0.0, 0.0031308, 0.0031309, 1e-9, 1.0, 2.5]]))
+    out["image_linear"] = lin
+    out["image_linear_to_srgb"] = rimage.linear_to_srgb(lin)
+    one = np.float32(1.0)
+    w0 = f(g.dirichlet(np.ones(m) * 0.3, size=nr) * g.uniform(0.2, 1, size=(nr, 1)))
+    w1 = f(g.dirichlet(np.ones(48) * 0.3, size=nr) * g.uniform(0.2, 1, size=(nr, 1)))
+    hist = [dict(sdist=t, weights=w0, lossmult=one), dict(sdist=tq, weights=w1, lossmult=one),
+            dict(sdist=tb, weights=wn, lossmult=one, tdist=tm)]
+    out.update(loss_w0=w0, loss_w1=w1)
+    out["loss_spline_interlevel"] = np.stack(rloss.spline_interlevel_loss(hist, mults=(0.01, 0.01), blurs=(0.03, 0.003)))
+    out["loss_distortion"] = np.asarray(rloss.distortion_loss(
+        hist, target="tdist", mult=np.float32(0.01),
+        curve_fn=lambda x: rmath.power_ladder(x, np.float32(-0.25), premult=np.float32(1e4))))
+
+    # ---- internal/inverse_render/render_utils.py: GGX lobe, Monte Carlo integration, frames, vMF ---------------------
+    P_, S_ = 96, 16
+    unit = lambda a: a / np.linalg.norm(a, axis=-1, keepdims=True)
+    wi = f(unit(g.normal(size=(P_, S_, 3)))); wi[:, :, 2] = np.abs(wi[:, :, 2]) * np.where(g.uniform(size=(P_, S_)) < 0.9, 1, -1)
+    wo = f(unit(g.normal(size=(P_, 1, 3)))); wo[..., 2] = np.abs(wo[..., 2])
+    material = dict(albedo=f(g.uniform(size=(P_, 3))), roughness=f(g.uniform(0.01, 1.0, size=(P_, 1))),
+                    F_0=f(np.full((P_, 1), 0.04)), metalness=f(g.uniform(size=(P_, 1))))
+    samples = dict(local_lightdirs=wi, local_viewdirs=np.broadcast_to(wo, wi.shape).copy(),
+                   brdf_correction=f(np.ones((P_, S_, 2))), pdf=f(g.uniform(0.0, 3.0, size=(P_, S_, 1))),
+                   weight=f(g.uniform(-0.1, 1.0, size=(P_, S_, 1))), radiance_in=f(g.uniform(0, 4, size=(P_, S_, 3))),
+                   indirect_occ=f(g.uniform(size=(P_, S_, 1))))
+    for k_, v_ in material.items():
+        out["ggx_mat_" + k_] = v_
+    for k_, v_ in samples.items():
+        out["ggx_smp_" + k_] = v_
+    cth, rough = f(g.uniform(0, 1, size=512)), f(g.uniform(0.01, 1, size=512))
+    out.update(ggx_costheta=cth, ggx_a=rough)
+    out["ggx_D"] = rru.GGX_D(cth, rough)
+    res = rru.integrate_reflect_rays("microfacet", False, dict(material), dict(samples))
+    for k_ in ("radiance_out", "indirect_occ", "irradiance"):
+        out["ggx_int_" + k_] = res[k_]
+    nrm = f(unit(g.normal(size=(256, 3)))); nrm[0] = [0, 0, 1]; nrm[1] = [0, 1, 0]; nrm[2] = [0.1, 0.2, 0.97]
+    nrm = f(unit(nrm))
+    out["rot_normal"] = nrm
+    out["rot_matrix"] = rru.get_rotation_matrix(nrm)
+    vx = f(unit(g.normal(size=(200, 8, 3)))); vmu = f(unit(g.normal(size=(200, 8, 3))))
+    vk = f(g.uniform(0, 50, size=(200, 8))); vk[0] = 0.0
+    out.update(vmf_x=vx, vmf_means=vmu, vmf_kappa=vk)
+    out["vmf_eval"] = rru.eval_vmf(vx, vmu, vk)
 
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header

@@ -94,3 +94,30 @@ def test_ref_utils():
     # evaluation carries ~1e-4 noise in the reference itself
     close(onerf.generate_ide_fn(4)(T("ide_dirs"), T("ide_kappa_inv")), "ref_ide_4", 1e-5)
     close(onerf.generate_ide_fn(5)(T("ide_dirs"), T("ide_kappa_inv")), "ref_ide_5", 2e-4)
+
+
+def test_image_and_losses():
+    from oracle import light_sampler as olight
+
+    close(olight.linear_to_srgb(T("image_linear")), "image_linear_to_srgb", 1e-6)                    # image.py:192-200
+    hist = [dict(sdist=T("step_t"), weights=T("loss_w0")), dict(sdist=T("blur_tq"), weights=T("loss_w1")),
+            dict(sdist=T("blur_t"), weights=T("dist_w"), tdist=T("dist_t"))]
+    got = torch.stack(oloss.spline_interlevel_loss(hist, mults=(0.01, 0.01), blurs=(0.03, 0.003)))   # loss_utils.py:74-108
+    close(got, "loss_spline_interlevel", 1e-4)
+    # loss_utils.py:108-123 with curve_fn = power_ladder(-0.25, 1e4): the curve compresses [2, 6] into a 0.03-wide
+    # interval, so the fp32 loss carries cancellation noise in either implementation
+    close(oloss.distortion_loss(hist, mult=0.01, p=-0.25, premult=1e4, target="tdist"), "loss_distortion", 2e-4)
+
+
+def test_ggx_and_frames():
+    from oracle import material as omat, render_utils as oru
+
+    close(oru.GGX_D(T("ggx_costheta"), T("ggx_a")), "ggx_D", 1e-5, per_element=True)   # render_utils.py:480-482
+    material = {k: T("ggx_mat_" + k) for k in ("albedo", "roughness", "F_0", "metalness")}
+    samples = {k: T("ggx_smp_" + k) for k in ("local_lightdirs", "local_viewdirs", "brdf_correction", "pdf", "weight",
+                                               "radiance_in", "indirect_occ")}
+    res = oru.integrate_reflect_rays("microfacet", material, samples)                  # :566-695, :1102-1193
+    for k in ("radiance_out", "indirect_occ", "irradiance"):
+        close(res[k], "ggx_int_" + k, 1e-5)
+    close(omat.get_rotation_matrix(T("rot_normal")), "rot_matrix", 1e-6)               # :145-168
+    close(omat.eval_vmf(T("vmf_x"), T("vmf_means"), T("vmf_kappa")), "vmf_eval", 1e-5, per_element=True)   # :1335-1346
