@@ -184,6 +184,35 @@ def main():
     out.update(vmf_x=vx, vmf_means=vmu, vmf_kappa=vk)
     out["vmf_eval"] = rru.eval_vmf(vx, vmu, vk)
 
+    # ---- importance samplers (render_utils.py:417-546, 1431-1490) and the light-sampling loss (:1493-1550) -------------
+    Ps, Ss = 200, 16
+    su1, su2 = f(g.uniform(size=(Ps, Ss))), f(g.uniform(size=(Ps, Ss)))
+    su1[0, :4] = [0.0, 1.0 - 2.0 ** -24, 0.5, 1e-7]
+    swo = f(unit(g.normal(size=(Ps, 1, 3)))); swo[..., 2] = np.abs(swo[..., 2]) + 0.02
+    swo = f(np.broadcast_to(unit(swo), (Ps, Ss, 3)).copy())
+    salpha = f(np.broadcast_to(g.uniform(0.01, 1.0, size=(Ps, 1, 1)) ** 2, (Ps, Ss, 1)).copy())
+    swi = f(unit(g.normal(size=(Ps, Ss, 3))))
+    out.update(smp_u1=su1, smp_u2=su2, smp_wo=swo, smp_alpha=salpha, smp_wi=swi)
+    for name, cls in (("cosine", rru.CosineSampler), ("microfacet", rru.MicrofacetSampler)):
+        smp = cls()
+        dirs, pdf = smp.sample_directions(None, su1, su2, swo, salpha, None, {})
+        out[f"smp_{name}_dirs"], out[f"smp_{name}_pdf"] = dirs, pdf
+        out[f"smp_{name}_pdf_of_wi"] = smp.pdf(swo, swi, salpha, {})
+    K_ = 8
+    lmeans = f(g.normal(size=(Ps, K_, 3)) * g.uniform(0.2, 3.0, size=(Ps, K_, 1)))
+    lkappas = f(g.uniform(0.0, 40.0, size=(Ps, K_, 1))); lkappas[0, 0] = 0.0
+    llogits = f(g.normal(size=(Ps, K_, 1)))
+    out.update(light_means=lmeans, light_kappas=lkappas, light_logits=llogits)
+    out["smp_light_pdf_of_wi"] = rru.LightSampler().pdf(swo, swi, salpha, dict(vmf_means=lmeans, vmf_kappas=lkappas,
+                                                                                  vmf_logits=llogits))
+    lnormals = f(unit(g.normal(size=(Ps, 3))))
+    lpdf = f(g.uniform(0.0, 2.0, size=(Ps, Ss, 1))); lwt = f(g.uniform(-0.5, 12.0, size=(Ps, Ss, 1)))
+    lfv = f(g.gamma(1.0, 1.0, size=(Ps, Ss))); lmult = f(np.full((Ps, Ss), 1.0 / Ss))
+    out.update(light_normals=lnormals, light_pdf=lpdf, light_weight=lwt, light_fv=lfv, light_lossmult=lmult)
+    for srgb in (True, False):
+        out[f"light_vmf_loss_{int(srgb)}"] = np.asarray(rru.vmf_loss_fn(
+            (lmeans, lkappas, llogits), lnormals, swi, dict(pdf=lpdf, weight=lwt), lfv, lfv, lmult, linear_to_srgb=srgb))
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

@@ -121,3 +121,21 @@ def test_ggx_and_frames():
         close(res[k], "ggx_int_" + k, 1e-5)
     close(omat.get_rotation_matrix(T("rot_normal")), "rot_matrix", 1e-6)               # :145-168
     close(omat.eval_vmf(T("vmf_x"), T("vmf_means"), T("vmf_kappa")), "vmf_eval", 1e-5, per_element=True)   # :1335-1346
+
+
+def test_importance_samplers_and_light_loss():
+    from oracle import light_sampler as olight, material as omat
+
+    u1, u2, wo, alpha, wi = T("smp_u1"), T("smp_u2"), T("smp_wo"), T("smp_alpha"), T("smp_wi")
+    for name, smp in (("cosine", omat.CosineSampler()), ("microfacet", omat.MicrofacetSampler())):   # render_utils.py:417-546
+        dirs, pdf = smp.sample_directions(u1, u2, wo, alpha, None)
+        close(dirs, f"smp_{name}_dirs", 1e-5)
+        close(pdf, f"smp_{name}_pdf", 1e-5)
+        close(smp.pdf(wo, wi, alpha, None), f"smp_{name}_pdf_of_wi", 1e-5)
+    aux = dict(vmf_means=T("light_means"), vmf_kappas=T("light_kappas"), vmf_logits=T("light_logits"))
+    close(omat.LightSampler().pdf(wo, wi, alpha, aux), "smp_light_pdf_of_wi", 1e-5)                # :1470-1490
+    v = (aux["vmf_means"], aux["vmf_kappas"], aux["vmf_logits"])
+    for srgb in (True, False):                                                                       # :1493-1550
+        got = olight.vmf_loss_fn(v, T("light_normals"), wi, T("light_pdf")[..., 0], T("light_weight")[..., 0], T("light_fv"),
+                                 T("light_lossmult"), srgb=srgb)
+        close(got, f"light_vmf_loss_{int(srgb)}", 1e-5)

@@ -72,3 +72,34 @@ def test_cast_rays_means(cuda_device):
     t_n, means = ProposalVolumeSampler()._cast(tm, rays, False)
     assert np.array_equal(t_n.cpu().numpy(), V["dist_t"])
     assert rel_err(means, torch.from_numpy(V["render_means"])) <= 1e-6
+
+
+def _history(dev):
+    return [dict(sdist=D("step_t", dev), weights=D("loss_w0", dev)), dict(sdist=D("blur_tq", dev), weights=D("loss_w1", dev)),
+            dict(sdist=D("blur_t", dev), weights=D("dist_w", dev), tdist=D("dist_t", dev))]
+
+
+def test_proposal_losses(cuda_device):
+    """nrc_interlevel_loss / nrc_distortion_loss against loss_utils.spline_interlevel_loss (internal/loss_utils.py:74-108)
+    and distortion_loss through power_ladder(-0.25, 1e4) (:108-123) as run from the reference's source."""
+    from neural_radiance_caching_b200 import loss_utils as nloss
+
+    hist = _history(cuda_device)
+    got = torch.stack(nloss.spline_interlevel_loss(hist, mults=(0.01, 0.01), blurs=(0.03, 0.003))).cpu()
+    assert rel_err(got, torch.from_numpy(V["loss_spline_interlevel"])) <= 2e-5
+    # the curve compresses [2, 6] into a 0.03-wide interval: fp32 cancellation in either implementation
+    d = nloss.distortion_loss(hist, mult=0.01, p=-0.25, premult=1e4, target="tdist").cpu()
+    assert abs(float(d) - float(V["loss_distortion"])) <= 3e-4 * float(V["loss_distortion"])
+
+
+def test_ggx_integration(cuda_device):
+    """nrc_ggx_integrate_fwd against integrate_reflect_rays('microfacet') of the reference's render_utils.py:1102-1193
+    (GGX_D :480-482, get_lobe :566-695), incl. below-horizon samples, negative weights and near-zero pdfs."""
+    from neural_radiance_caching_b200.inverse_render import render_utils as nru
+
+    material = {k: D("ggx_mat_" + k, cuda_device) for k in ("albedo", "roughness", "F_0", "metalness")}
+    samples = {k: D("ggx_smp_" + k, cuda_device) for k in ("local_lightdirs", "local_viewdirs", "pdf", "weight",
+                                                           "radiance_in", "indirect_occ")}
+    res = nru.integrate_reflect_rays("microfacet", False, material, samples)
+    for k in ("radiance_out", "indirect_occ", "irradiance"):
+        assert rel_err(res[k], torch.from_numpy(V["ggx_int_" + k])) <= 2e-5, k
