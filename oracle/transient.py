@@ -3,7 +3,9 @@ internal/render.py volumetric_transient_rendering (:250-449, the rgb / transient
 (:452-490), shift_map_coordinates (:493-507; jax.scipy.ndimage.map_coordinates order 1, mode='constant'),
 internal/inverse_render/render_utils.py zero_invalid_bins (:1699-1767) and the head post-processing of
 internal/nerf.py:1660-1777 (softplus(raw + bias) * indirect_scale; tint * F * ref_rgb * indirect_scale; clip).
-Parity unpinned (no reference vectors; JAX not installable here)."""
+Pinned to the reference's source for shift_direct, shift_map_coordinates, zero_invalid_bins and the whole of
+volumetric_transient_rendering (tests/test_reference_vectors.py::test_transient; map_coordinates there is SciPy's with
+JAX's boundary rule); the head post-processing lives in a flax Module and is restated only."""
 import numpy as np
 import torch
 
@@ -51,6 +53,19 @@ def zero_invalid_bins(diffuse, specular, light_dists, cam_dists, n_bins, exposur
     return z(diffuse), z(specular)
 
 
+def volumetric_transient_rendering(direct_rgbs, indirect, weights, ray_dists, light_dists, n_bins, exposure_time=0.01,
+                                   shift=0.0, dark_level=0.0):
+    """The transient outputs of render.volumetric_transient_rendering (:322-449) without temporal filter / median filter /
+    vis offsets (all off in the configs): direct splat at (light + ray distance) / exposure, indirect histograms shifted
+    by the ray distance and reduced with the weights."""
+    R, n, C = direct_rgbs.shape
+    d = (light_dists + ray_dists) / exposure_time
+    t_direct = shift_direct(d + shift / exposure_time, direct_rgbs, weights, n_bins, C)
+    shifted = shift_map_coordinates(indirect.reshape(R * n, n_bins, C), ray_dists.reshape(-1) + shift, exposure_time, n_bins)
+    t_indirect = (shifted.reshape(R, n, n_bins, C) * weights[..., None, None]).sum(1)
+    return dict(transient_direct=t_direct, transient_indirect=t_indirect, rgb=t_direct + t_indirect + dark_level)
+
+
 def transient_render(direct_rgbs, diffuse_raw, specular, spec_scale, weights, ray_dists, light_dists, cam_dists, n_bins,
                      exposure_time=0.01, shift=0.0, diffuse_bias=-1.0, indirect_scale=1.0, bin_zero_threshold_light=0.0,
                      light_zero=False, light_near=0.0, rgb_max=10000.0, dark_level=0.0):
@@ -60,8 +75,5 @@ def transient_render(direct_rgbs, diffuse_raw, specular, spec_scale, weights, ra
     diffuse, spec = zero_invalid_bins(diffuse, spec, light_dists[..., None], cam_dists[..., None], n_bins, exposure_time,
                                       bin_zero_threshold_light, light_zero, light_near)
     indirect = torch.clamp(diffuse, 0.0, rgb_max) + torch.clamp(spec, 0.0, rgb_max)
-    d = (light_dists + ray_dists) / exposure_time
-    t_direct = shift_direct(d + shift / exposure_time, direct_rgbs, weights, n_bins, C)
-    shifted = shift_map_coordinates(indirect.reshape(R * n, n_bins, C), ray_dists.reshape(-1) + shift, exposure_time, n_bins)
-    t_indirect = (shifted.reshape(R, n, n_bins, C) * weights[..., None, None]).sum(1)
-    return dict(transient_direct=t_direct, transient_indirect=t_indirect, rgb=t_direct + t_indirect + dark_level)
+    return volumetric_transient_rendering(direct_rgbs, indirect, weights, ray_dists, light_dists, n_bins, exposure_time, shift,
+                                          dark_level)

@@ -182,6 +182,55 @@ jscipy = types.ModuleType("jax.scipy")
 jax.scipy = jscipy
 
 
+class _AtArray(np.ndarray):
+    """`x.at[idx].add(v)` / `.set(v)` of jax arrays: functional update, duplicate indices accumulate, negative indices
+    wrap, out-of-bounds updates are dropped (jax's default scatter mode)."""
+
+    @property
+    def at(self):
+        arr = self
+
+        class _Idx:
+            def __getitem__(self, idx):
+                class _Op:
+                    def _apply(self, v, add):
+                        out = np.array(arr, copy=True).view(_AtArray)
+                        i = np.asarray(idx).astype(np.int64)
+                        i = np.where(i < 0, i + out.shape[0], i)
+                        ok = (i >= 0) & (i < out.shape[0])
+                        vb = np.broadcast_to(np.asarray(v, out.dtype), i.shape + out.shape[1:])
+                        if add:
+                            np.add.at(out, i[ok], vb[ok])
+                        else:
+                            out[i[ok]] = vb[ok]
+                        return out
+
+                    def add(self, v):
+                        return self._apply(v, True)
+
+                    def set(self, v):
+                        return self._apply(v, False)
+                return _Op()
+        return _Idx()
+
+
+_zeros = jnp.zeros
+jnp.zeros = lambda *a, **k: _zeros(*a, **k).view(_AtArray)
+
+
+def _map_coordinates(input, coordinates, order, mode="constant", cval=0.0):
+    """jax.scipy.ndimage.map_coordinates: coordinates in float32; an out-of-range TAP contributes cval (jax interpolates
+    across the edge - SciPy calls that rule 'grid-constant'; SciPy's own 'constant' cuts at the edge instead)."""
+    import scipy.ndimage
+    coords = np.stack([np.asarray(c, np.float32) for c in coordinates]).astype(np.float64)
+    m = {"constant": "grid-constant"}.get(mode, mode)
+    return scipy.ndimage.map_coordinates(np.asarray(input, np.float32), coords, order=order, mode=m, cval=cval).astype(np.float32)
+
+
+jscipy.ndimage = types.ModuleType("jax.scipy.ndimage")
+jscipy.ndimage.map_coordinates = _map_coordinates
+
+
 class _Passthrough(types.ModuleType):
     def __getattr__(self, name):
         if name.startswith("__"):
@@ -227,7 +276,7 @@ def install():
         np.math = _math          # the reference calls np.math.factorial (removed in NumPy 2)
     mods = {"jax": jax, "jax.numpy": jnp, "jax.random": random, "jax.lax": lax, "jax.nn": nn_mod,
             "jax.tree_util": tree_util, "jax.experimental": experimental, "jax.experimental.checkify": checkify,
-            "jax.scipy": jscipy, "jax.numpy.linalg": linalg}
+            "jax.scipy": jscipy, "jax.scipy.ndimage": jscipy.ndimage, "jax.numpy.linalg": linalg}
     for k, v in mods.items():
         sys.modules[k] = v
     gin = _Passthrough("gin")

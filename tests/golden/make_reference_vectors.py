@@ -213,6 +213,39 @@ def main():
         out[f"light_vmf_loss_{int(srgb)}"] = np.asarray(rru.vmf_loss_fn(
             (lmeans, lkappas, llogits), lnormals, swi, dict(pdf=lpdf, weight=lwt), lfv, lfv, lmult, linear_to_srgb=srgb))
 
+    # ---- time-resolved rendering: render.py:250-507, render_utils.zero_invalid_bins (:1699-1767) ----------------------
+    import types as _types
+    Rt, nt, Bt, Ct, expo = 24, 8, 96, 3, np.float32(0.01)
+    tw = f(g.dirichlet(np.ones(nt) * 0.4, size=Rt) * g.uniform(0.3, 1.0, size=(Rt, 1)))
+    ttd = f(np.sort(g.uniform(0.05, 1.0, size=(Rt, nt + 1)), axis=-1))
+    tdirect = f(g.uniform(0, 2, size=(Rt, nt, Ct)))
+    tind = f(g.gamma(1.0, 1.0, size=(Rt, nt, Bt, Ct)))
+    tray = f(g.uniform(0.0, 0.55, size=(Rt, nt, 1))); tlight = f(g.uniform(0.0, 0.55, size=(Rt, nt, 1)))
+    tray[0, 0], tlight[0, 0] = 0.25, 0.13              # integer bin: floor == ceil
+    tray[-1, -1], tlight[-1, -1] = 0.55, 0.47          # past the last bin of the last ray: dropped, not wrapped
+    tray[1, 1], tlight[1, 1] = 0.5, 0.49               # past the last bin of an inner ray: lands in the NEXT ray's bins
+    out.update(tr_weights=tw, tr_tdist=ttd, tr_direct=tdirect, tr_indirect=tind, tr_ray_dists=tray, tr_light_dists=tlight)
+    cfg = _types.SimpleNamespace(no_shift_direct=False, vis_only=False)
+    for shift_ in (0.0, 0.0137):
+        res = rrender.volumetric_transient_rendering(
+            tdirect, tind, tw, tw, ttd, None, False, extras=dict(light_dists=tlight, ray_dists=tray, transient_indirect=None),
+            n_bins=Bt, shift=np.float32(shift_), dark_level=np.float32(0.001), exposure_time=expo, config=cfg)
+        tag = "tr_s%d_" % int(shift_ > 0)
+        for k_ in ("transient_direct", "transient_indirect", "rgb"):
+            out[tag + k_] = res[k_]
+    out["tr_shift_direct"] = rrender.shift_direct((tray + tlight)[..., 0] / expo, tdirect, tw, Bt, Ct, None)
+    out["tr_shift_map"] = rrender.shift_map_coordinates(tind.reshape(-1, Bt, Ct), tray.reshape(-1), expo, Bt, Ct)
+    tmeans = f(g.uniform(-0.4, 0.4, size=(Rt, nt, 3)))
+    trays = _types.SimpleNamespace(lights=f(g.uniform(-0.4, 0.4, size=(Rt, 3))), origins=f(g.uniform(-0.4, 0.4, size=(Rt, 3))),
+                                   cam_origins=f(g.uniform(-0.4, 0.4, size=(Rt, 3))))
+    tspec = f(g.gamma(1.0, 1.0, size=(Rt, nt, Bt, Ct)))
+    out.update(tr_means=tmeans, tr_lights=trays.lights, tr_origins=trays.origins, tr_cam_origins=trays.cam_origins, tr_spec=tspec)
+    for lz in (False, True):
+        zc = _types.SimpleNamespace(n_bins=Bt, bin_zero_threshold_light=np.float32(2.0), exposure_time=expo, light_zero=lz,
+                                    light_near=np.float32(0.3))
+        zd, zs = rru.zero_invalid_bins(tind, tspec, trays, tmeans, zc)
+        out[f"tr_zero_diffuse_{int(lz)}"], out[f"tr_zero_specular_{int(lz)}"] = zd, zs
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

@@ -139,3 +139,28 @@ def test_importance_samplers_and_light_loss():
         got = olight.vmf_loss_fn(v, T("light_normals"), wi, T("light_pdf")[..., 0], T("light_weight")[..., 0], T("light_fv"),
                                  T("light_lossmult"), srgb=srgb)
         close(got, f"light_vmf_loss_{int(srgb)}", 1e-5)
+
+
+def test_transient():
+    """render.volumetric_transient_rendering (:250-449), shift_direct (:452-490: flat-index splat - a bin past the end of
+    an inner ray lands in the next ray, past the end of the array it is dropped), shift_map_coordinates (:493-507),
+    render_utils.zero_invalid_bins (:1699-1767)."""
+    from oracle import transient as otr
+
+    w, direct, ind = T("tr_weights"), T("tr_direct"), T("tr_indirect")
+    ray, light = T("tr_ray_dists")[..., 0], T("tr_light_dists")[..., 0]
+    R, n, B, C = ind.shape
+    close(otr.shift_direct((ray + light) / 0.01, direct, w, B, C), "tr_shift_direct", 1e-6)
+    close(otr.shift_map_coordinates(ind.reshape(-1, B, C), ray.reshape(-1), 0.01, B), "tr_shift_map", 1e-6)
+    for tag, shift in (("tr_s0_", 0.0), ("tr_s1_", 0.0137)):
+        res = otr.volumetric_transient_rendering(direct, ind, w, ray, light, B, exposure_time=0.01, shift=shift, dark_level=0.001)
+        for k in ("transient_direct", "transient_indirect", "rgb"):
+            close(res[k], tag + k, 2e-6)
+    means = T("tr_means")
+    light_d = torch.linalg.norm(T("tr_lights")[:, None, :] - means, dim=-1, keepdim=True)
+    cam_d = (torch.linalg.norm(T("tr_origins")[:, None, :] - means, dim=-1, keepdim=True)
+             + torch.linalg.norm(T("tr_origins") - T("tr_cam_origins"), dim=-1, keepdim=True)[:, None, :])
+    for lz in (False, True):
+        zd, zs = otr.zero_invalid_bins(ind, T("tr_spec"), light_d, cam_d, B, 0.01, 2.0, lz, 0.3)
+        exact(zd, f"tr_zero_diffuse_{int(lz)}")
+        exact(zs, f"tr_zero_specular_{int(lz)}")
