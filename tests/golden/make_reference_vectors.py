@@ -235,14 +235,14 @@ def main():
             out[tag + k_] = res[k_]
     out["tr_shift_direct"] = rrender.shift_direct((tray + tlight)[..., 0] / expo, tdirect, tw, Bt, Ct, None)
     out["tr_shift_map"] = rrender.shift_map_coordinates(tind.reshape(-1, Bt, Ct), tray.reshape(-1), expo, Bt, Ct)
-    tmeans = f(g.uniform(-0.4, 0.4, size=(Rt, nt, 3)))
-    trays = _types.SimpleNamespace(lights=f(g.uniform(-0.4, 0.4, size=(Rt, 3))), origins=f(g.uniform(-0.4, 0.4, size=(Rt, 3))),
-                                   cam_origins=f(g.uniform(-0.4, 0.4, size=(Rt, 3))))
+    tmeans = f(g.uniform(-0.12, 0.12, size=(Rt, nt, 3)))
+    trays = _types.SimpleNamespace(lights=f(g.uniform(-0.12, 0.12, size=(Rt, 3))), origins=f(g.uniform(-0.12, 0.12, size=(Rt, 3))),
+                                   cam_origins=f(g.uniform(-0.12, 0.12, size=(Rt, 3))))
     tspec = f(g.gamma(1.0, 1.0, size=(Rt, nt, Bt, Ct)))
     out.update(tr_means=tmeans, tr_lights=trays.lights, tr_origins=trays.origins, tr_cam_origins=trays.cam_origins, tr_spec=tspec)
     for lz in (False, True):
         zc = _types.SimpleNamespace(n_bins=Bt, bin_zero_threshold_light=np.float32(2.0), exposure_time=expo, light_zero=lz,
-                                    light_near=np.float32(0.3))
+                                    light_near=np.float32(0.12))
         zd, zs = rru.zero_invalid_bins(tind, tspec, trays, tmeans, zc)
         out[f"tr_zero_diffuse_{int(lz)}"], out[f"tr_zero_specular_{int(lz)}"] = zd, zs
 
