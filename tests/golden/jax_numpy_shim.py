@@ -161,6 +161,7 @@ nn_mod.softplus = lambda x: np.logaddexp(x, np.float32(0)).astype(np.float32)
 nn_mod.sigmoid = lambda x: (1 / (1 + np.exp(-x))).astype(np.float32)
 nn_mod.relu = lambda x: np.maximum(x, 0)
 nn_mod.tanh = np.tanh
+nn_mod.silu = lambda x: (x / (1 + np.exp(-x))).astype(np.float32)
 
 jax = types.ModuleType("jax")
 jax.numpy, jax.random, jax.lax, jax.nn = jnp, random, lax, nn_mod
@@ -231,19 +232,35 @@ jscipy.ndimage = types.ModuleType("jax.scipy.ndimage")
 jscipy.ndimage.map_coordinates = _map_coordinates
 
 
+class _Anything:
+    """Attribute access never fails (tf.io.gfile.GFile ...); called with one callable it returns it (a decorator),
+    called with anything else it returns another _Anything (a decorator factory / an opaque object)."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Anything()
+
+    def __getitem__(self, item):
+        return _Anything()
+
+    def __iter__(self):
+        return iter(())
+
+    def __call__(self, *a, **k):
+        if len(a) == 1 and callable(a[0]) and not k and not isinstance(a[0], _Anything):
+            return a[0]
+        return _Anything()
+
+
 class _Passthrough(types.ModuleType):
     def __getattr__(self, name):
         if name.startswith("__"):
             raise AttributeError(name)
-
-        def deco(*a, **k):
-            if len(a) == 1 and callable(a[0]) and not k:
-                return a[0]
-            return lambda f: f
-        return deco
+        return _Anything()
 
 
-STUBBED = ("dm_pix", "chex", "ml_collections", "optax", "tensorflow", "cv2", "absl", "PIL", "mediapy", "rawpy", "scipy_stub",
+STUBBED = ("flax", "etils", "third_party", "jmp", "plyfile", "h5py", "scipy_io_stub", "pyexr", "OpenEXR", "Imath", "gdown", "lpips", "jaxlib", "clu", "tensorboardX", "torch_stub", "dm_pix", "chex", "ml_collections", "optax", "tensorflow", "cv2", "absl", "PIL", "mediapy", "rawpy", "scipy_stub",
            "orbax", "jaxcam", "trimesh", "matplotlib", "tqdm", "skimage", "sklearn", "torchvision", "pdb_stub", "jaxopt",
            "tensorflow_graphics", "pycolmap", "camp_zipnerf", "open3d", "plotly", "imageio")
 
@@ -268,12 +285,20 @@ class _StubFinder:
         pass
 
 
+def _fallback(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
+    return _Anything()
+
+
 def install():
     """Put the stand-ins into sys.modules (idempotent).  Heavy optional imports of the reference that the numeric
     functions never touch (tensorflow, cv2, flax, gin, absl, PIL, ...) become empty pass-through modules."""
     if not hasattr(np, "math"):
         import math as _math
         np.math = _math          # the reference calls np.math.factorial (removed in NumPy 2)
+    for m_ in (jax, nn_mod, lax, random, jscipy, experimental):   # non-numeric names only (initializers, tree utilities ...);
+        m_.__getattr__ = _fallback                                 # a numeric call through one fails loudly at np.asarray
     mods = {"jax": jax, "jax.numpy": jnp, "jax.random": random, "jax.lax": lax, "jax.nn": nn_mod,
             "jax.tree_util": tree_util, "jax.experimental": experimental, "jax.experimental.checkify": checkify,
             "jax.scipy": jscipy, "jax.scipy.ndimage": jscipy.ndimage, "jax.numpy.linalg": linalg}
@@ -293,6 +318,8 @@ def install():
     linen.relu, linen.softplus, linen.sigmoid, linen.tanh = nn_mod.relu, nn_mod.softplus, nn_mod.sigmoid, np.tanh
     flax.linen = linen
     flax.struct = _Passthrough("flax.struct")
+    import dataclasses
+    flax.struct.dataclass = dataclasses.dataclass
     sys.modules["flax"] = flax
     sys.modules["flax.linen"] = linen
     sys.modules["flax.struct"] = flax.struct

@@ -24,19 +24,10 @@ def load_reference():
     shim.install()
     sys.path.insert(0, REF)
     importlib.import_module("internal")
-    # internal/utils.py imports tensorflow / cv2 / flax / PIL.  The numeric modules use three helpers of it, none of them
-    # numerics: two shape assertions and a platform query.  Stand-ins with the same contract:
-    u = types.ModuleType("internal.utils")
-
-    def _check(t, y, delta, what):
-        if t.shape[-1] != y.shape[-1] + delta:
-            raise ValueError(f"Invalid shapes ({t.shape}, {y.shape}) for a {what}.")
-
-    u.assert_valid_stepfun = lambda t, y: _check(t, y, 1, "step function")
-    u.assert_valid_linspline = lambda t, y: _check(t, y, 0, "linear spline")
-    u.device_is_tpu = lambda: False
-    sys.modules["internal.utils"] = u
-    names = ["math", "linspline", "stepfun", "coord", "render", "ref_utils", "grid_utils", "loss_utils", "image"]
+    # internal/utils.py itself is the reference's (its tensorflow / cv2 / flax / PIL imports are pass-through stubs);
+    # utils.device_is_tpu() evaluates to False under the shim (no device is a "tpu").
+    names = ["utils", "math", "linspline", "stepfun", "coord", "render", "ref_utils", "grid_utils", "loss_utils", "image",
+             "geometry", "shading", "nerf", "sampling", "models", "material", "light_sampler", "train_utils"]
     mods = {n: importlib.import_module("internal." + n) for n in names}
     mods["render_utils"] = importlib.import_module("internal.inverse_render.render_utils")
     return mods
