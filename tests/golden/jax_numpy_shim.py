@@ -149,6 +149,9 @@ random = types.ModuleType("jax.random")
 random.uniform = lambda key, shape=(), dtype=np.float32, minval=0.0, maxval=1.0: (
     np.float32(minval) + np.asarray(key, np.float32).reshape(shape) * np.float32(maxval - minval)).astype(np.float32)
 random.split = lambda key, num=2: [key] * num
+# jax.random.categorical(key, logits, axis, shape) = argmax(gumbel(key, <shape with the category axis re-inserted>) + logits,
+# axis): `key` IS that pre-drawn Gumbel array (how the kernels and the oracle take the noise)
+random.categorical = lambda key, logits, axis=-1, shape=None: np.argmax(np.asarray(key, np.float32) + logits, axis=axis).astype(np.int32)
 random.PRNGKey = lambda seed: seed
 
 lax = types.ModuleType("jax.lax")
@@ -172,6 +175,16 @@ jax.named_scope = lambda name: (lambda f: f)
 jax.Array = np.ndarray
 tree_util = types.ModuleType("jax.tree_util")
 tree_util.tree_map = lambda f, t: {k: f(v) for k, v in t.items()} if isinstance(t, dict) else f(t)
+
+
+class _DictKey:
+    """jax.tree_util.DictKey: a path element (NOT a str - `"name" in path` is False, as in jax)."""
+
+    def __init__(self, key):
+        self.key = key
+
+
+tree_util.tree_map_with_path = lambda f, t: {k: f((_DictKey(k),), v) for k, v in t.items()}
 jax.tree_util = tree_util
 experimental = types.ModuleType("jax.experimental")
 checkify = types.ModuleType("jax.experimental.checkify")

@@ -237,6 +237,20 @@ def main():
         zd, zs = rru.zero_invalid_bins(tind, tspec, trays, tmeans, zc)
         out[f"tr_zero_diffuse_{int(lz)}"], out[f"tr_zero_specular_{int(lz)}"] = zd, zs
 
+    # ---- Model.maybe_resample (models.py:193-292), resample_argmax off, as configured (ngp_yobo.gin:369) ----------------
+    Rr, nr_, kr = 128, 32, 4
+    rw = f(g.dirichlet(np.ones(nr_) * 0.2, size=Rr) * g.uniform(0.0, 1.0, size=(Rr, 1))); rw[0] = 0.0
+    gum = f(g.gumbel(size=(Rr, nr_, kr)))
+    sres = dict(points=f(g.normal(size=(Rr, nr_, 3))), weights=rw, tdist=f(np.sort(g.uniform(size=(Rr, nr_ + 1)), -1)),
+                sdist=f(np.sort(g.uniform(size=(Rr, nr_ + 1)), -1)), feature=f(g.normal(size=(Rr, nr_, 5))))
+    out.update(rs_weights=rw, rs_gumbel=gum, rs_points=sres["points"], rs_feature=sres["feature"])
+    for kk, bias in ((1, 0.0), (kr, 1e-3)):
+        self_ = _types.SimpleNamespace(weights_bias=np.float32(bias), resample_argmax=False)
+        fres, inds = R["models"].Model.maybe_resample(self_, gum[..., :kk], True, dict(sres), kk)
+        out[f"rs_inds_{kk}"], out[f"rs_new_weights_{kk}"] = inds, fres["weights"]
+        out[f"rs_new_points_{kk}"], out[f"rs_new_feature_{kk}"] = fres["points"], fres["feature"]
+        assert fres["weights_no_filter"] is rw and fres["tdist"] is sres["tdist"]
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

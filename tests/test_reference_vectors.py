@@ -165,3 +165,18 @@ def test_transient():
         zd, zs = otr.zero_invalid_bins(ind, T("tr_spec"), light_d, cam_d, B, 0.01, 2.0, lz, 0.12)
         exact(zd, f"tr_zero_diffuse_{int(lz)}")
         exact(zs, f"tr_zero_specular_{int(lz)}")
+
+
+def test_maybe_resample():
+    """Model.maybe_resample (internal/models.py:193-292), resample_argmax off: categorical draw = argmax(logits + Gumbel),
+    indices BIT-EXACT, importance-corrected weights, gathered points / features."""
+    from oracle import models as omodels
+
+    w, gum = T("rs_weights"), T("rs_gumbel")
+    for k, bias in ((1, 0.0), (4, 1e-3)):
+        inds, nw = omodels.maybe_resample(w, gum[..., :k], k, weights_bias=bias)
+        exact(inds.to(torch.int32), f"rs_inds_{k}")
+        close(nw, f"rs_new_weights_{k}", 1e-6)
+        take = lambda x: torch.gather(x, 1, inds[..., None].expand(inds.shape + (x.shape[-1],)))
+        exact(take(T("rs_points")), f"rs_new_points_{k}")
+        exact(take(T("rs_feature")), f"rs_new_feature_{k}")
