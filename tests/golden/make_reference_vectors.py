@@ -251,6 +251,33 @@ def main():
         out[f"rs_new_points_{kk}"], out[f"rs_new_feature_{kk}"] = fres["points"], fres["feature"]
         assert fres["weights_no_filter"] is rw and fres["tdist"] is sres["tdist"]
 
+    # ---- geometry losses (loss_utils.py:127-199) and the mask loss (train_utils.py:785-836) ----------------------------
+    Rg, ng = 96, 32
+    gw = f(g.dirichlet(np.ones(ng) * 0.3, size=Rg) * g.uniform(0.2, 1, size=(Rg, 1)))
+    gn = f(unit(g.normal(size=(Rg, ng, 3)))); gnp = f(unit(gn + 0.4 * g.normal(size=(Rg, ng, 3))))
+    gn[0, 0] = np.nan                                      # nan_to_num'd by both losses
+    gview = f(unit(g.normal(size=(Rg, 3))))
+    out.update(gl_weights=gw, gl_normals=gn, gl_normals_pred=gnp, gl_viewdirs=gview)
+    rr = dict(weights=gw, lossmult=one, normals=gn, normals_pred=gnp)
+    grays = _types.SimpleNamespace(viewdirs=gview, lossmult=f(np.ones((Rg, 1))))
+    beta = f(np.ones((Rg, ng, 1)))
+    out["gl_orientation"] = rloss.orientation_loss(grays, rr, target="normals_pred", mult=np.float32(0.01))
+    out["gl_predicted_normal"] = rloss.predicted_normal_loss(rr, beta, mult=np.float32(0.001), gt="normals_pred", pred="normals",
+                                                             stopgrad=False, stopgrad_weight=0.1)
+    out["gl_predicted_normal_reverse"] = rloss.predicted_normal_loss(rr, beta, mult=np.float32(0.01), gt="normals",
+                                                                     pred="normals_pred", stopgrad=True)
+    gacc = f(g.uniform(0, 1, size=(Rg,))); gmask = f((g.uniform(size=(Rg, 1)) > 0.4))
+    out.update(gl_acc=gacc, gl_masks=gmask)
+    mcfg = _types.SimpleNamespace(charb_padding=np.float32(0.001), opaque_loss_weight=np.float32(1.0), empty_loss_weight=np.float32(10.0),
+                                  use_mask_weight_decay=False, mask_weight_decay_start=0.0, mask_weight_decay_frac=0.1,
+                                  mask_weight_decay_min=0.0, use_mask_weight_ease=False, mask_weight_ease_start=0.0,
+                                  mask_weight_ease_frac=0.1, mask_weight_ease_min=0.0)
+    rtrain = R["train_utils"]
+    out["gl_mask_loss"] = rtrain.compute_mask_loss(_types.SimpleNamespace(masks=gmask), dict(acc=gacc), grays, mcfg)
+    out["gl_mask_loss_none"] = rtrain.compute_mask_loss(_types.SimpleNamespace(masks=None), dict(acc=gacc), grays, mcfg)
+    out["gl_mask_loss_backward"] = rtrain.compute_mask_loss(_types.SimpleNamespace(masks=f(np.zeros((Rg, 1)))), dict(acc=gacc),
+                                                            grays, mcfg, empty_loss_weight=np.float32(0.5))
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

@@ -180,3 +180,19 @@ def test_maybe_resample():
         take = lambda x: torch.gather(x, 1, inds[..., None].expand(inds.shape + (x.shape[-1],)))
         exact(take(T("rs_points")), f"rs_new_points_{k}")
         exact(take(T("rs_feature")), f"rs_new_feature_{k}")
+
+
+def test_geometry_and_mask_losses():
+    """orientation_loss / predicted_normal_loss (internal/loss_utils.py:127-199) in the three configured uses
+    (train_utils.py:1027-1093) and compute_mask_loss (train_utils.py:785-836) incl. the backward-mask call (:2929-2945)."""
+    geo = dict(weights=T("gl_weights"), normals=T("gl_normals"), normals_pred=T("gl_normals_pred"))
+    rays = dict(viewdirs=T("gl_viewdirs"))
+    lo, lp, lr = oloss.geometry_losses(rays, geo, orientation_mult=0.01, predicted_normal_mult=0.001,
+                                       predicted_normal_reverse_mult=0.01, stopgrad_weight=0.1)
+    close(lo, "gl_orientation", 1e-6)
+    close(lp, "gl_predicted_normal", 1e-6)
+    close(lr, "gl_predicted_normal_reverse", 1e-6)
+    acc, masks = T("gl_acc"), T("gl_masks")
+    close(oloss.compute_mask_loss(acc, masks, 0.001, 1.0, 10.0), "gl_mask_loss", 1e-6)
+    close(oloss.compute_mask_loss(acc, None, 0.001, 1.0, 10.0), "gl_mask_loss_none", 1e-6)
+    close(oloss.compute_mask_loss(acc, torch.zeros_like(masks), 0.001, 1.0, 0.5, backward=True), "gl_mask_loss_backward", 1e-6)
