@@ -228,6 +228,26 @@ class _AtArray(np.ndarray):
         return _Idx()
 
 
+class F32Array(np.ndarray):
+    """jax's type promotion with x64 disabled, for the two cases NumPy gets differently: a float64 operand (a NumPy
+    constant such as HashEncoding.bbox) is demoted to float32, and an int32 operand meeting a float32 one (x * grid_size)
+    is promoted to float32, not float64.  Inputs wrapped in it keep every intermediate float32, as under jax."""
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kw):
+        arrs = [np.asarray(i) if isinstance(i, (np.ndarray, np.generic)) else i for i in inputs]
+        has_f = any(isinstance(a, np.ndarray) and a.dtype.kind == "f" for a in arrs)
+        conv = []
+        for a in arrs:
+            if isinstance(a, np.ndarray) and (a.dtype == np.float64 or (has_f and a.dtype.kind in "iu")):
+                a = a.astype(np.float32)
+            conv.append(a)
+        if out is not None:
+            kw["out"] = tuple(np.asarray(o) for o in out)
+        res = getattr(ufunc, method)(*conv, **kw)
+        wrap = lambda r: r.view(F32Array) if isinstance(r, np.ndarray) else r
+        return tuple(wrap(r) for r in res) if isinstance(res, tuple) else wrap(res)
+
+
 _zeros = jnp.zeros
 jnp.zeros = lambda *a, **k: _zeros(*a, **k).view(_AtArray)
 

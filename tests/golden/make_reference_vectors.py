@@ -278,6 +278,35 @@ def main():
     out["gl_mask_loss_backward"] = rtrain.compute_mask_loss(_types.SimpleNamespace(masks=f(np.zeros((Rg, 1)))), dict(acc=gacc),
                                                             grays, mcfg, empty_loss_weight=np.float32(0.5))
 
+    # ---- HashEncoding.__call__ (grid_utils.py:738-905): level schedule, dense / hash choice, parameter names, bbox map,
+    #      per-level multisample mean, precondition scaling.  Tables are a closed form of the entry index (level_table
+    #      below, repeated in the test) so that only inputs and outputs are stored. ------------------------------------
+    def level_table(shape, salt):
+        idx = np.arange(int(np.prod(shape)), dtype=np.uint64)
+        h = (idx * np.uint64(2654435761) + np.uint64(salt) * np.uint64(40503)) % np.uint64(1 << 32)
+        return ((h.astype(np.float64) / float(1 << 32) - 0.5) * 2e-2).astype(np.float32).reshape(shape)
+
+    class _Enc(rgrid.HashEncoding):
+        def param(self, name, init_fn):
+            self.seen.append(name)
+            shape = init_fn.keywords["shape"]
+            return level_table(shape, len(self.seen))
+
+    hx = f(g.normal(size=(600, 1, 3)) * 1.2); hx[0, 0] = [-2.0, 2.0, 0.0]; hx[1, 0] = [2.5, -2.5, 0.3]   # corners, outside
+    out["enc_x"] = hx
+    for tag, kw in (("a", dict(hash_map_size=2 ** 15, num_features=2, scale_supersample=1.0, max_grid_size=256)),
+                    ("b", dict(hash_map_size=2 ** 12, num_features=4, scale_supersample=1.0, max_grid_size=128,
+                               precondition_scaling=1.0, bbox_scaling=((-1.0, -2.0, -3.0), (1.5, 2.0, 2.5))))):
+        enc = _Enc()
+        for k_, v_ in kw.items():
+            setattr(enc, k_, v_)
+        enc.seen = []
+        feats = enc(hx.view(shim.F32Array), per_level_fn=rmath.average_across_multisamples)
+        assert feats.dtype == np.float32
+        out[f"enc_{tag}_features"] = np.asarray(feats)
+        out[f"enc_{tag}_names"] = np.array(enc.seen)
+        out[f"enc_{tag}_grid_sizes"] = np.asarray(enc.grid_sizes)
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

@@ -196,3 +196,30 @@ def test_geometry_and_mask_losses():
     close(oloss.compute_mask_loss(acc, masks, 0.001, 1.0, 10.0), "gl_mask_loss", 1e-6)
     close(oloss.compute_mask_loss(acc, None, 0.001, 1.0, 10.0), "gl_mask_loss_none", 1e-6)
     close(oloss.compute_mask_loss(acc, torch.zeros_like(masks), 0.001, 1.0, 0.5, backward=True), "gl_mask_loss_backward", 1e-6)
+
+
+def _level_table(shape, salt):
+    """The closed-form table of tests/golden/make_reference_vectors.py (kept in step with it)."""
+    idx = np.arange(int(np.prod(shape)), dtype=np.uint64)
+    h = (idx * np.uint64(2654435761) + np.uint64(salt) * np.uint64(40503)) % np.uint64(1 << 32)
+    return ((h.astype(np.float64) / float(1 << 32) - 0.5) * 2e-2).astype(np.float32).reshape(shape)
+
+
+ENC_CONFIGS = {
+    "a": dict(hash_map_size=2 ** 15, num_features=2, scale_supersample=1.0, max_grid_size=256),
+    "b": dict(hash_map_size=2 ** 12, num_features=4, scale_supersample=1.0, max_grid_size=128, precondition_scaling=1.0,
+              bbox_scaling=((-1.0, -2.0, -3.0), (1.5, 2.0, 2.5))),
+}
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_hash_encoding_call(tag):
+    """HashEncoding.__call__ (internal/grid_utils.py:738-905) executed from the reference's class: level schedule, dense /
+    hash choice per level, parameter names, bbox map (cubic and non-cubic), per-level multisample mean, precondition
+    scaling - features BIT-EXACT."""
+    enc = ogrid.HashEncoding(**ENC_CONFIGS[tag])
+    assert list(enc.grid_sizes) == list(V[f"enc_{tag}_grid_sizes"])
+    assert enc.param_names() == list(V[f"enc_{tag}_names"])
+    params = {name: torch.from_numpy(_level_table(shape, i + 1))
+              for i, (name, (_, _, shape)) in enumerate(zip(enc.param_names(), enc.layout))}
+    exact(enc(params, T("enc_x"), per_level_mean=True), f"enc_{tag}_features")
