@@ -14,6 +14,7 @@ import torch
 
 from oracle import coord as ocoord, grid_utils as ogrid, loss_utils as oloss, nerf as onerf, ref_math, render as orender
 from oracle import stepfun as ostep
+from tests.util import ENC_CONFIGS, level_table as _level_table
 
 V = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_np.npz"))
 T = lambda k: torch.from_numpy(V[k])
@@ -196,20 +197,6 @@ def test_geometry_and_mask_losses():
     close(oloss.compute_mask_loss(acc, masks, 0.001, 1.0, 10.0), "gl_mask_loss", 1e-6)
     close(oloss.compute_mask_loss(acc, None, 0.001, 1.0, 10.0), "gl_mask_loss_none", 1e-6)
     close(oloss.compute_mask_loss(acc, torch.zeros_like(masks), 0.001, 1.0, 0.5, backward=True), "gl_mask_loss_backward", 1e-6)
-
-
-def _level_table(shape, salt):
-    """The closed-form table of tests/golden/make_reference_vectors.py (kept in step with it)."""
-    idx = np.arange(int(np.prod(shape)), dtype=np.uint64)
-    h = (idx * np.uint64(2654435761) + np.uint64(salt) * np.uint64(40503)) % np.uint64(1 << 32)
-    return ((h.astype(np.float64) / float(1 << 32) - 0.5) * 2e-2).astype(np.float32).reshape(shape)
-
-
-ENC_CONFIGS = {
-    "a": dict(hash_map_size=2 ** 15, num_features=2, scale_supersample=1.0, max_grid_size=256),
-    "b": dict(hash_map_size=2 ** 12, num_features=4, scale_supersample=1.0, max_grid_size=128, precondition_scaling=1.0,
-              bbox_scaling=((-1.0, -2.0, -3.0), (1.5, 2.0, 2.5))),
-}
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])

@@ -103,3 +103,19 @@ def test_ggx_integration(cuda_device):
     res = nru.integrate_reflect_rays("microfacet", False, material, samples)
     for k in ("radiance_out", "indirect_occ", "irradiance"):
         assert rel_err(res[k], torch.from_numpy(V["ggx_int_" + k])) <= 2e-5, k
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_hash_encoding_call_bit_exact(cuda_device, tag):
+    """nrc_encode_fwd through HashEncoding.__call__ against the reference's own class (internal/grid_utils.py:738-905):
+    dense and hash levels, cubic and non-cubic bbox, multisample mean, precondition scaling, points outside the box."""
+    from tests.util import ENC_CONFIGS, level_table
+
+    enc = ng.HashEncoding(**ENC_CONFIGS[tag])
+    layout = enc.level_layout
+    assert [int(n) for n in enc.grid_sizes] == [int(n) for n in V[f"enc_{tag}_grid_sizes"]]
+    assert [name for (name, _, _, _) in layout] == list(V[f"enc_{tag}_names"])
+    params = {name: torch.from_numpy(level_table(shape, i + 1)).to(cuda_device)
+              for i, (name, _, _, shape) in enumerate(layout)}
+    got = enc(params, D("enc_x", cuda_device), per_level_fn=lambda f: f.mean(dim=-2))
+    assert np.array_equal(got.cpu().numpy(), V[f"enc_{tag}_features"])

@@ -48,3 +48,17 @@ def rel_l2(a, b, floor=1e-30):
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     return float((a - b).norm() / max(float(b.norm()), floor))
+
+
+def level_table(shape, salt):
+    """The closed-form table of tests/golden/make_reference_vectors.py (kept in step with it)."""
+    idx = np.arange(int(np.prod(shape)), dtype=np.uint64)
+    h = (idx * np.uint64(2654435761) + np.uint64(salt) * np.uint64(40503)) % np.uint64(1 << 32)
+    return ((h.astype(np.float64) / float(1 << 32) - 0.5) * 2e-2).astype(np.float32).reshape(shape)
+
+
+ENC_CONFIGS = {
+    "a": dict(hash_map_size=2 ** 15, num_features=2, scale_supersample=1.0, max_grid_size=256),
+    "b": dict(hash_map_size=2 ** 12, num_features=4, scale_supersample=1.0, max_grid_size=128, precondition_scaling=1.0,
+              bbox_scaling=((-1.0, -2.0, -3.0), (1.5, 2.0, 2.5))),
+}
