@@ -40,7 +40,7 @@ def local_to_global(d, R):
 
 def normalize(v):
     """internal/inverse_render/math.py:85-86."""
-    return v / torch.sqrt(1e-10 + torch.sum(v**2, dim=-1, keepdim=True))
+    return v / ref_math.sqrt(1e-10 + torch.sum(v**2, dim=-1, keepdim=True))
 
 
 def reflect(w, v):
@@ -56,10 +56,10 @@ class CosineSampler:
     global_dirs = False
 
     def sample_directions(self, u1, u2, wo, alpha, aux):
-        r = torch.sqrt(u1)
+        r = ref_math.sqrt(u1)
         phi = u2 * 2.0 * np.pi - np.pi
         x, y = r * torch.cos(phi), r * torch.sin(phi)
-        z = torch.sqrt(torch.clamp(1.0 - x**2 - y**2, min=DENOMINATOR_EPS))
+        z = ref_math.sqrt(torch.clamp(1.0 - x**2 - y**2, min=DENOMINATOR_EPS))
         return torch.stack([x, y, z], dim=-1), torch.clamp(z / np.pi, min=0.0)
 
     def pdf(self, wo, wi, alpha, aux):
@@ -73,8 +73,8 @@ class MicrofacetSampler:
     def sample_directions(self, u1, u2, wo, alpha, aux):
         a = alpha[..., 0]
         tan2 = a**2 * u1 / torch.clamp(1.0 - u1, min=EPS)
-        cost = 1.0 / torch.sqrt(torch.clamp(1.0 + tan2, min=EPS))
-        sint = torch.sqrt(torch.clamp(1.0 - cost**2, min=DENOMINATOR_EPS))
+        cost = 1.0 / ref_math.sqrt(torch.clamp(1.0 + tan2, min=EPS))
+        sint = ref_math.sqrt(torch.clamp(1.0 - cost**2, min=DENOMINATOR_EPS))
         phi = u2 * 2.0 * np.pi - np.pi
         normals = torch.stack([sint * torch.cos(phi), sint * torch.sin(phi), cost], dim=-1)
         npdf = torch.clamp(GGX_D(cost, a) * torch.abs(cost), min=0.0)
@@ -124,7 +124,7 @@ class LightSampler:
         tmp = aux["u"]
         w = 1.0 + (1.0 / torch.clamp(kappa[..., None], min=EPS)) * ref_math.safe_log(
             tmp + (1.0 - tmp) * torch.exp(-2.0 * kappa[..., None]))
-        s = torch.sqrt(torch.clamp(1.0 - w**2, min=0.0))
+        s = ref_math.sqrt(torch.clamp(1.0 - w**2, min=0.0))
         dirs = (t_vec[:, None, :] * (s * v[..., 0])[..., None] + b_vec[:, None, :] * (s * v[..., 1])[..., None]
                 + mean[:, None, :] * w[..., None])
         return dirs, self.mixture_pdf(dirs, aux)

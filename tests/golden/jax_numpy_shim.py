@@ -146,12 +146,16 @@ def _vmap(fn, in_axes=0, out_axes=0):
 
 
 random = types.ModuleType("jax.random")
+# a key is the pre-drawn array itself, or a dict of pre-drawn arrays by distribution when one key (split = identity)
+# reaches several draws: {"uniform": ..., "normal": ..., "gumbel": ...}
+_draw = lambda key, name: np.asarray(key[name] if isinstance(key, dict) else key, np.float32)
 random.uniform = lambda key, shape=(), dtype=np.float32, minval=0.0, maxval=1.0: (
-    np.float32(minval) + np.asarray(key, np.float32).reshape(shape) * np.float32(maxval - minval)).astype(np.float32)
+    np.float32(minval) + _draw(key, "uniform").reshape(shape) * np.float32(maxval - minval)).astype(np.float32)
+random.normal = lambda key, shape=(), dtype=np.float32: _draw(key, "normal").reshape(shape)
 random.split = lambda key, num=2: [key] * num
 # jax.random.categorical(key, logits, axis, shape) = argmax(gumbel(key, <shape with the category axis re-inserted>) + logits,
 # axis): `key` IS that pre-drawn Gumbel array (how the kernels and the oracle take the noise)
-random.categorical = lambda key, logits, axis=-1, shape=None: np.argmax(np.asarray(key, np.float32) + logits, axis=axis).astype(np.int32)
+random.categorical = lambda key, logits, axis=-1, shape=None: np.argmax(_draw(key, "gumbel") + logits, axis=axis).astype(np.int32)
 random.PRNGKey = lambda seed: seed
 
 lax = types.ModuleType("jax.lax")

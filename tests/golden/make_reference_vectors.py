@@ -307,6 +307,36 @@ def main():
         out[f"enc_{tag}_names"] = np.array(enc.seen)
         out[f"enc_{tag}_grid_sizes"] = np.asarray(enc.grid_sizes)
 
+    # ---- importance_sample_rays (render_utils.py:722-924): shading frame, per-sampler draws, MIS power heuristic with
+    #      energy correction, for the two-sampler and the three-sampler (vMF light sampler) set-ups -----------------------
+    class _Pre2D:                                          # random_generator_2d: hands out the pre-drawn (uh, uw)
+        def __init__(self, draws):
+            self.draws = list(draws)
+
+        def sample(self, rng, n_, stratified):
+            uh, uw = self.draws.pop(0)
+            assert uh.size == n_
+            return uh.reshape(-1), uw.reshape(-1)
+
+    Pi, counts = 160, (16, 8, 8)
+    iv = f(unit(g.normal(size=(Pi, 3)))); inrm = f(unit(iv + 0.8 * g.normal(size=(Pi, 3))))   # mostly front facing
+    irough = f(g.uniform(0.05, 1.0, size=(Pi, 1)) ** 2)
+    iu = [(f(g.uniform(size=(Pi, c_))), f(g.uniform(size=(Pi, c_)))) for c_ in counts]
+    ikey = dict(gumbel=f(g.gumbel(size=(Pi, K_))), normal=f(g.normal(size=(Pi, counts[2], 2))),
+                uniform=f(g.uniform(size=(Pi, counts[2]))))
+    laux = dict(vmf_means=lmeans[:Pi], vmf_kappas=lkappas[:Pi], vmf_logits=llogits[:Pi])
+    out.update(is_viewdirs=iv, is_normals=inrm, is_roughness=irough, is_light_normal2=ikey["normal"], is_light_u=ikey["uniform"],
+               is_light_latent=np.argmax(ikey["gumbel"] + llogits[:Pi, :, 0], axis=-1).astype(np.int32))
+    for j_, (uh_, uw_) in enumerate(iu):
+        out[f"is_uh_{j_}"], out[f"is_uw_{j_}"] = uh_, uw_
+    smps = [(rru.MicrofacetSampler(), counts[0]), (rru.CosineSampler(), counts[1]), (rru.LightSampler(), counts[2])]
+    for ns_ in (2, 3):
+        res = rru.importance_sample_rays(ikey, iv, inrm, dict(roughness=irough), random_generator_2d=_Pre2D(iu[:ns_]),
+                                         use_mis=True, samplers=smps[:ns_], num_secondary_samples=sum(counts[:ns_]),
+                                         light_sampler_results=laux if ns_ == 3 else None)
+        for k_ in ("local_lightdirs", "local_viewdirs", "global_lightdirs", "pdf", "weight"):
+            out[f"is{ns_}_{k_}"] = res[k_]
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

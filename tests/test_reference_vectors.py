@@ -210,3 +210,26 @@ def test_hash_encoding_call(tag):
     params = {name: torch.from_numpy(_level_table(shape, i + 1))
               for i, (name, (_, _, shape)) in enumerate(zip(enc.param_names(), enc.layout))}
     exact(enc(params, T("enc_x"), per_level_mean=True), f"enc_{tag}_features")
+
+
+@pytest.mark.parametrize("ns", [2, 3])
+def test_importance_sample_rays(ns):
+    """importance_sample_rays (render_utils.py:722-924) run from the reference with pre-drawn randoms: Microfacet (16) +
+    Cosine (8) [+ vMF-mixture Light (8)] samplers, shading frame, MIS power heuristic and the energy correction."""
+    from oracle import material as omat
+
+    counts = (16, 8, 8)[:ns]
+    samplers = [(omat.MicrofacetSampler(), 16), (omat.CosineSampler(), 8), (omat.LightSampler(), 8)][:ns]
+    uniforms = [(T(f"is_uh_{j}"), T(f"is_uw_{j}")) for j in range(ns)]
+    P = V["is_viewdirs"].shape[0]
+    aux = None
+    if ns == 3:
+        aux = dict(vmf_means=T("light_means")[:P], vmf_kappas=T("light_kappas")[:P], vmf_logits=T("light_logits")[:P],
+                   latent=T("is_light_latent").long(), normal2=T("is_light_normal2"), u=T("is_light_u"))
+    res = omat.importance_sample_rays(T("is_viewdirs"), T("is_normals"), T("is_roughness"), samplers, uniforms, aux=aux)
+    assert res["pdf"].shape[1] == sum(counts)
+    for k in ("local_lightdirs", "local_viewdirs", "global_lightdirs"):
+        close(res[k], f"is{ns}_{k}", 2e-6)
+    # GGX pdfs at low roughness are ill conditioned in fp32 (DESIGN section 3): relative to the largest pdf / weight
+    close(res["pdf"], f"is{ns}_pdf", 1e-5)
+    close(res["weight"], f"is{ns}_weight", 1e-5)
