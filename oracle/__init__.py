@@ -17,16 +17,20 @@ checked against XLA itself ("parity unpinned" w.r.t. XLA's own rounding).  It IS
 pinned to the reference's own *source*: tests/golden/make_reference_vectors.py
 imports the reference's modules unmodified from /root/reference under a small
 NumPy stand-in for jax (tests/golden/jax_numpy_shim.py), runs their functions
-(internal/math.py, coord.py, stepfun.py, render.py, grid_utils.py, ref_utils.py)
+(internal/math.py, coord.py, stepfun.py, render.py incl. the transient renderer,
+grid_utils.py incl. the HashEncoding class, ref_utils.py, image.py,
+loss_utils.py, train_utils.compute_mask_loss, Model.maybe_resample,
+inverse_render/render_utils.py: GGX lobe + integration, samplers,
+importance_sample_rays, vMF pdf / loss, zero_invalid_bins)
 on seeded float32 inputs and freezes inputs and outputs into
 tests/golden/reference_np.npz; tests/test_reference_vectors.py checks this
 oracle against those vectors (corner indices / interpolation / contraction /
 cast_rays / l2_normalize bit-exact, the rest to fp32 rounding) and
 tests/test_reference_vectors_gpu.py checks the CUDA kernels against them
-directly.  Modules whose reference counterpart needs flax Modules (the model
-classes in geometry.py, nerf.py, material.py, light_sampler.py, transient.py)
-are pinned only through these building blocks: they say "parity unpinned" in
-their own headers.  The oracle's own outputs are additionally frozen in
+directly.  Classes whose reference counterpart needs flax parameter scoping (the
+MLP classes in geometry.py, nerf.py, material.py, light_sampler.py and the
+sampler loop in sampling.py) are pinned only through these building blocks and
+say so in their own headers.  The oracle's own outputs are additionally frozen in
 tests/golden/oracle_v*.npz (make_golden*.py) so that any later edit of the
 restatement is caught.  Assumed XLA semantics (IEEE-754 fp32 round-to-nearest
 per op, no FMA contraction, saturating f32->s32 convert, uint32 wrap-around

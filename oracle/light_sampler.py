@@ -7,7 +7,8 @@ train_utils.light_sampling_loss (internal/train_utils.py:1985-2071).
 `means_random` (jax.random.normal(PRNGKey(random_seed)) * vmf_scale / 2, light_sampler.py:141-143) is an INPUT, like
 every other random draw at the C ABI: JAX's threefry stream cannot be reproduced without JAX.
 
-Parity unpinned: the reference ships no vectors for this path and JAX is not installable here."""
+vmf_loss_fn and linear_to_srgb are pinned to the reference's source (tests/test_reference_vectors.py, 1e-5); the LightMLP
+class (flax parameter scoping) is restated only.  Unpinned against XLA's own rounding (JAX is not installable here)."""
 import numpy as np
 import torch
 

@@ -2,7 +2,9 @@
 internal/loss_utils.py spline_interlevel_loss (:74-108), internal/stepfun.py weight_to_pdf (:75-79),
 blur_and_resample_weights (:463-483), internal/linspline.py blur_stepfun (:187-221), compute_integral (:95-109),
 interpolate_integral (:124-141), internal/math.py plus_eps / minus_eps (:56-66); configs/ngp_yobo.gin:245-247
-(mults (0.01, 0.01), blurs (0.03, 0.003)).  Parity unpinned (no reference vectors; JAX not installable here).  Note: torch.cumsum on the host carries its
+(mults (0.01, 0.01), blurs (0.03, 0.003)).  Pinned to the reference's source (tests/test_reference_vectors.py:
+blur_and_resample_weights, spline_interlevel_loss, distortion_loss, orientation / predicted-normal losses, compute_mask_loss);
+unpinned against XLA's own rounding (JAX not installable here).  Note: torch.cumsum on the host carries its
 running sum in float64 and rounds per element, so this restatement is MORE accurate than XLA's fp32 cumsum in the
 ill-conditioned double running sum of blur_stepfun; the CUDA body does the same."""
 import numpy as np

@@ -7,7 +7,10 @@ num_real_samples == num_secondary_samples branch with MIS power heuristic), get_
 (:957-1023) under configs/ngp_yobo.gin:256-303.  Random draws are INPUTS (uniforms, the vMF latent index,
 the 2-D normal pairs), as at the C ABI: the JAX host keeps its threefry streams.
 
-Parity unpinned: the reference ships no vectors for this path and JAX is not installable here."""
+Pinned to the reference's source (tests/test_reference_vectors.py: the shading frame, both analytic samplers, the vMF
+mixture pdf, eval_vmf and the whole of importance_sample_rays with 2 and 3 samplers, executed from
+/root/reference under the NumPy stand-in for jax); unpinned against XLA's own rounding (JAX is not installable here).
+The material / environment MLP classes are restated only."""
 import numpy as np
 import torch
 
