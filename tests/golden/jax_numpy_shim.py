@@ -350,7 +350,28 @@ def install():
     flax.__path__ = []
     linen = _Passthrough("flax.linen")
     linen.__path__ = []
-    linen.Module = type("Module", (), {})
+
+    class Module:
+        """flax.linen.Module as a plain class: dataclass-style keyword construction, no parameter scoping - a test drives
+        `setup()` itself and assigns parameters to the Dense stand-ins below."""
+
+        def __init__(self, **kw):
+            for k_, v_ in kw.items():
+                setattr(self, k_, v_)
+
+    class Dense(Module):
+        """flax.linen.Dense: x @ kernel + bias in float32; `kernel` [in, features] / `bias` [features] assigned by the caller."""
+
+        def __init__(self, features, use_bias=True, **kw):
+            super().__init__(features=features, use_bias=use_bias, **kw)
+            self.kernel = self.bias = None
+
+        def __call__(self, x):
+            assert self.kernel is not None and self.kernel.shape == (x.shape[-1], self.features), (self.kernel, x.shape)
+            y = np.matmul(np.asarray(x, np.float32), self.kernel)
+            return (y + self.bias).astype(np.float32) if self.use_bias else y.astype(np.float32)
+
+    linen.Module, linen.Dense = Module, Dense
     linen.compact = lambda f: f
     linen.relu, linen.softplus, linen.sigmoid, linen.tanh = nn_mod.relu, nn_mod.softplus, nn_mod.sigmoid, np.tanh
     flax.linen = linen

@@ -294,7 +294,8 @@ def main():
 
     hx = f(g.normal(size=(600, 1, 3)) * 1.2); hx[0, 0] = [-2.0, 2.0, 0.0]; hx[1, 0] = [2.5, -2.5, 0.3]   # corners, outside
     out["enc_x"] = hx
-    for tag, kw in (("a", dict(hash_map_size=2 ** 15, num_features=2, scale_supersample=1.0, max_grid_size=256)),
+    ENC_A = dict(hash_map_size=2 ** 15, num_features=2, scale_supersample=1.0, max_grid_size=256)
+    for tag, kw in (("a", ENC_A),
                     ("b", dict(hash_map_size=2 ** 12, num_features=4, scale_supersample=1.0, max_grid_size=128,
                                precondition_scaling=1.0, bbox_scaling=((-1.0, -2.0, -3.0), (1.5, 2.0, 2.5))))):
         enc = _Enc()
@@ -336,6 +337,29 @@ def main():
                                          light_sampler_results=laux if ns_ == 3 else None)
         for k_ in ("local_lightdirs", "local_viewdirs", "global_lightdirs", "pdf", "weight"):
             out[f"is{ns_}_{k_}"] = res[k_]
+
+    # ---- DensityMLP.predict_density / run_network / convert_raw_density (geometry.py:155-341) as configured
+    #      (ngp_yobo.gin:137-140,206-230: depth 2, width 64, ReLU, safe_exp, bias -1, 'mean' basis, contract_radius_2) ------
+    def dense_params(n_in, n_out, salt):
+        k = level_table((n_in, n_out), salt) * np.float32(100.0 * np.sqrt(6.0 / n_in))
+        return k.astype(np.float32), (level_table((n_out,), salt + 50) * np.float32(10.0)).astype(np.float32)
+
+    mlp = R["geometry"].DensityMLP(config=_types.SimpleNamespace(num_rgb_channels=3, n_bins=1), net_depth=2, net_width=64,
+                                    net_activation=shim.nn_mod.relu,   # the class default (an instance field in flax)
+                                    density_activation=rmath.safe_exp, density_bias=-1.0, warp_fn=rcoord.contract_radius_2,
+                                    grid_params=dict(ENC_A, bbox_scaling=2.0))
+    mlp.setup()
+    mlp.grid.seen = []
+    mlp.grid.param = lambda name, init_fn: (mlp.grid.seen.append(name), level_table(init_fn.keywords["shape"], len(mlp.grid.seen)))[1]
+    d_in = 10
+    for i_, layer in enumerate(mlp.density_layers + [mlp.output_density_layer]):
+        layer.kernel, layer.bias = dense_params(d_in, layer.features, 100 + i_)
+        d_in = layer.features
+    dmeans = f(g.normal(size=(700, 3)) * 1.5); dmeans[0] = 0.0; dmeans[1] = [30.0, -2.0, 5.0]
+    raw, feat = mlp.predict_density(dmeans.view(shim.F32Array), None, control_offsets=f(np.zeros((1, 3))), perp_mag=None)
+    dens = mlp.convert_raw_density(raw, dmeans.view(shim.F32Array))
+    assert raw.dtype == np.float32 and dens.dtype == np.float32
+    out.update(dmlp_means=dmeans, dmlp_raw_density=np.asarray(raw), dmlp_feature=np.asarray(feat), dmlp_density=np.asarray(dens))
 
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header

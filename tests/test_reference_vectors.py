@@ -233,3 +233,27 @@ def test_importance_sample_rays(ns):
     # GGX pdfs at low roughness are ill conditioned in fp32: relative to the largest pdf / weight
     close(res["pdf"], f"is{ns}_pdf", 1e-5)
     close(res["weight"], f"is{ns}_weight", 1e-5)
+
+
+def test_density_mlp():
+    """DensityMLP.predict_density / run_network / convert_raw_density (internal/geometry.py:155-341) executed from the
+    reference's class (flax Dense = x @ kernel + bias) in the configured shape: contract_radius_2 -> HashEncoding with the
+    multisample mean -> 2 x 64 ReLU -> 1, safe_exp(raw - 1).  Encoding bit-exact (test_hash_encoding_call); the matmuls
+    differ by summation order (OpenBLAS vs MKL sgemm)."""
+    from oracle import geometry as ogeo
+    from tests.util import dense_params
+
+    mlp = ogeo.DensityMLP({k: v for k, v in ENC_CONFIGS["a"].items() if k != "scale_supersample"}, net_depth=2, net_width=64,
+                          density_bias=-1.0, warp_c=2.0, bbox_scaling=2.0)
+    p = {"density_grid": {name: torch.from_numpy(_level_table(shape, i + 1))
+                          for i, (name, (_, _, shape)) in enumerate(zip(mlp.grid.param_names(), mlp.grid.layout))}}
+    d_in = mlp.in_dim
+    for i, (name, d_out) in enumerate([("density_layers_0", 64), ("density_layers_1", 64), ("output_density_layer", 1)]):
+        k, b = dense_params(d_in, d_out, 100 + i)
+        p[name] = {"kernel": torch.from_numpy(k), "bias": torch.from_numpy(b)}
+        d_in = d_out
+    means = T("dmlp_means")
+    raw, feat = mlp.predict_density(p, means)
+    close(feat, "dmlp_feature", 2e-6)
+    close(raw, "dmlp_raw_density", 2e-6)
+    close(mlp.convert_raw_density(raw, means), "dmlp_density", 2e-6)

@@ -62,3 +62,9 @@ ENC_CONFIGS = {
     "b": dict(hash_map_size=2 ** 12, num_features=4, scale_supersample=1.0, max_grid_size=128, precondition_scaling=1.0,
               bbox_scaling=((-1.0, -2.0, -3.0), (1.5, 2.0, 2.5))),
 }
+
+
+def dense_params(n_in, n_out, salt):
+    """Closed-form Dense kernel [in,out] / bias [out] of tests/golden/make_reference_vectors.py (kept in step with it)."""
+    k = level_table((n_in, n_out), salt) * np.float32(100.0 * np.sqrt(6.0 / n_in))
+    return k.astype(np.float32), (level_table((n_out,), salt + 50) * np.float32(10.0)).astype(np.float32)
