@@ -377,7 +377,13 @@ def install():
     flax.linen = linen
     flax.struct = _Passthrough("flax.struct")
     import dataclasses
-    flax.struct.dataclass = dataclasses.dataclass
+
+    def _struct_dataclass(cls):
+        cls = dataclasses.dataclass(cls)
+        cls.replace = lambda self, **kw: dataclasses.replace(self, **kw)
+        return cls
+
+    flax.struct.dataclass = _struct_dataclass
     sys.modules["flax"] = flax
     sys.modules["flax.linen"] = linen
     sys.modules["flax.struct"] = flax.struct

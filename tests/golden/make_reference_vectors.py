@@ -361,6 +361,41 @@ def main():
     assert raw.dtype == np.float32 and dens.dtype == np.float32
     out.update(dmlp_means=dmeans, dmlp_raw_density=np.asarray(raw), dmlp_feature=np.asarray(feat), dmlp_density=np.asarray(dens))
 
+    # ---- ProposalVolumeSampler.__call__ (sampling.py:142-649), the whole level loop as configured (ngp_yobo.gin:178-242):
+    #      ray warps (identity, and the power ladder of the secondary pass), annealed resampling logits, sample_intervals,
+    #      s_to_t, cast_rays, compute_alpha_weights.  The three density MLPs are replaced by closed-form rational fields
+    #      (IEEE +, *, / only - the same values in NumPy and PyTorch) so that the LOOP is what is pinned. ------------------
+    def field(scale, k, c):
+        scale, k, c = np.float32(scale), np.float32(k), [np.float32(v_) for v_ in c]
+
+        def mlp(rng=None, rays=None, gaussians=None, tdist=None, **kw):
+            m_ = np.asarray(gaussians[0])
+            dx, dy, dz = m_[..., 0] - c[0], m_[..., 1] - c[1], m_[..., 2] - c[2]
+            return dict(density=scale / (np.float32(1.0) + k * (dx * dx + dy * dy + dz * dz)))
+        return mlp
+
+    FIELDS = ((4.0, 3.0, (0.1, -0.2, 0.3)), (9.0, 6.0, (0.0, -0.1, 0.2)), (40.0, 14.0, (0.05, -0.15, 0.25)))
+    Rp = 48
+    po = f(g.normal(size=(Rp, 3)) * 0.3 + [0.0, 0.0, -2.5]); pd = f(g.normal(size=(Rp, 3)) * 0.25 + [0.0, 0.0, 1.3])
+    pv = f(pd / np.linalg.norm(pd, axis=-1, keepdims=True))
+    prays = R["utils"].Rays(origins=po, lights=None, directions=pd, viewdirs=pv, radii=f(g.uniform(2e-4, 2e-3, size=(Rp, 1))),
+                            imageplane=None, look=None, up=None, cam_origins=None, vcam_look=None, vcam_up=None, vcam_origins=None,
+                            lossmult=f(np.ones((Rp, 1))), near=f(g.uniform(0.1, 0.4, size=(Rp, 1))),
+                            far=f(g.uniform(4.0, 7.0, size=(Rp, 1))), cam_idx=None, light_idx=None)
+    pu = f(g.uniform(size=(Rp, 1)))
+    out.update(pvs_origins=po, pvs_directions=pd, pvs_viewdirs=pv, pvs_radii=prays.radii, pvs_near=prays.near, pvs_far=prays.far,
+               pvs_u01=pu)
+    pvs = R["sampling"].ProposalVolumeSampler(
+        config=None, sampling_strategy=((0, 0, 64), (1, 1, 64), (2, 2, 32)), anneal_slope=10.0, anneal_end=1.0, anneal_clip=0.4,
+        resample_padding=1e-5, dilation_bias=0.0, dilation_multiplier=0.0,
+        raydist_fn=(rmath.power_ladder, rmath.inv_power_ladder, dict(p=np.float32(-1.5), premult=np.float32(2.0))))
+    pvs.mlps = [field(*a_) for a_ in FIELDS]
+    for tag, use_rd in (("id", False), ("pl", True)):
+        hist = pvs(pu, prays, train_frac=1.0, train=True, use_raydist_fn=use_rd)
+        for lvl, h_ in enumerate(hist):
+            for k_ in ("sdist", "tdist", "means", "weights"):
+                out[f"pvs_{tag}_{lvl}_{k_}"] = h_[k_]
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

@@ -257,3 +257,35 @@ def test_density_mlp():
     close(feat, "dmlp_feature", 2e-6)
     close(raw, "dmlp_raw_density", 2e-6)
     close(mlp.convert_raw_density(raw, means), "dmlp_density", 2e-6)
+
+
+class _Field:
+    """Closed-form rational density field of the generator (IEEE +, *, / only) standing in for a DensityMLP."""
+    normals_for_filter_only = True
+    disable_density_normals = True
+
+    def __init__(self, scale, k, c):
+        self.scale, self.k, self.c = scale, k, c
+
+    def __call__(self, p, means, **kw):
+        dx, dy, dz = means[..., 0] - self.c[0], means[..., 1] - self.c[1], means[..., 2] - self.c[2]
+        return dict(density=self.scale / (1.0 + self.k * (dx * dx + dy * dy + dz * dz)))
+
+
+@pytest.mark.parametrize("tag,use_raydist", [("id", False), ("pl", True)])
+def test_proposal_sampler_loop(tag, use_raydist):
+    """ProposalVolumeSampler.__call__ (internal/sampling.py:142-649) executed from the reference's class with the configured
+    strategy (64, 64, 32), annealing, padding and ray warps (identity / power_ladder(-1.5, 2)); the density MLPs replaced by
+    the same closed-form fields on both sides, so the level loop itself is what is compared."""
+    from oracle import sampling as osamp
+
+    s = osamp.ProposalVolumeSampler()
+    s.mlps = [_Field(4.0, 3.0, (0.1, -0.2, 0.3)), _Field(9.0, 6.0, (0.0, -0.1, 0.2)), _Field(40.0, 14.0, (0.05, -0.15, 0.25))]
+    rays = {k: T("pvs_" + k) for k in ("origins", "directions", "viewdirs", "radii", "near", "far")}
+    hist = s({f"MLP_{i}": None for i in range(3)}, rays, [T("pvs_u01")] * 3, use_raydist_fn=use_raydist)
+    # the CDF inversion amplifies last-ulp differences (NumPy vs PyTorch softmax / cumsum, libm pow in the ladder) level by
+    # level: tolerances are relative to the ray length / largest weight
+    for lvl, h in enumerate(hist):
+        for k in ("sdist", "tdist", "means", "weights"):
+            tol = 1e-4 if k == "weights" else (2e-6 if lvl == 0 else 2e-5)     # measured: 1e-6 / 8e-6 / 3e-5 (weights)
+            close(h[k], f"pvs_{tag}_{lvl}_{k}", tol)
