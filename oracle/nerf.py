@@ -179,6 +179,14 @@ class NeRFMLP:
         enc = self.grid(p["appearance_grid"], control, per_level_mean=True)
         return torch.cat([density_feature, enc], dim=-1)
 
+    def get_integrated_brdf(self, p, normals, viewdirs, bottleneck):
+        """nerf.py:423-434,461-482: [bottleneck | n . (-v)] -> 2 x 64 ReLU -> sigmoid(. + log 3)."""
+        dotprod = torch.sum(normals * (-viewdirs[..., None, :]), dim=-1, keepdim=True)
+        x = torch.cat([bottleneck, dotprod], dim=-1)
+        x = torch.relu(self.dense(p["integrated_brdf_layers_0"], x))
+        x = torch.relu(self.dense(p["integrated_brdf_layers_1"], x))
+        return torch.sigmoid(self.dense(p["output_integrated_brdf_layer"], x) + float(np.log(3.0)))
+
     def __call__(self, p, viewdirs, means, density_feature, normals):
         """viewdirs [R,3]; means [R,n,3]; density_feature [R,n,64]; normals [R,n,3] (normals_to_use)."""
         sp = torch.nn.functional.softplus
@@ -187,12 +195,7 @@ class NeRFMLP:
         roughness = sp(self.dense(p["roughness_layer"], feature) - 1.0)  # :633-634
         ambient_diffuse = torch.clamp(sp(self.dense(p["ambient_irradiance_layer"], feature) - 2.0), 0.0, self.rgb_max)
         tint = torch.sigmoid(self.dense(p["tint_layer"], feature))  # :975
-        # get_integrated_brdf :461-482
-        dotprod = torch.sum(normals * (-viewdirs[..., None, :]), dim=-1, keepdim=True)
-        x = torch.cat([bottleneck, dotprod], dim=-1)
-        x = torch.relu(self.dense(p["integrated_brdf_layers_0"], x))
-        x = torch.relu(self.dense(p["integrated_brdf_layers_1"], x))
-        F = torch.sigmoid(self.dense(p["output_integrated_brdf_layer"], x) + float(np.log(3.0)))
+        F = self.get_integrated_brdf(p, normals, viewdirs, bottleneck)
         refdirs = reflect(-viewdirs[..., None, :], normals)  # :1344-1358
         env = self.env_map(p["EnvMap"], refdirs, roughness, None)  # :984-996
         env_rgb = env["incoming_ambient_rgb"]

@@ -372,6 +372,8 @@ def install():
             return (y + self.bias).astype(np.float32) if self.use_bias else y.astype(np.float32)
 
     linen.Module, linen.Dense = Module, Dense
+    global nn_mod_linen
+    nn_mod_linen = linen
     linen.compact = lambda f: f
     linen.relu, linen.softplus, linen.sigmoid, linen.tanh = nn_mod.relu, nn_mod.softplus, nn_mod.sigmoid, np.tanh
     flax.linen = linen

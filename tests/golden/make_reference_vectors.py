@@ -396,6 +396,31 @@ def main():
             for k_ in ("sdist", "tdist", "means", "weights"):
                 out[f"pvs_{tag}_{lvl}_{k_}"] = h_[k_]
 
+    # ---- cache shader pieces: BaseShader.predict_appearance_feature with net_depth 0 (shading.py:133-220),
+    #      NeRFMLP.get_integrated_brdf (nerf.py:423-434,461-482) and _get_refdirs (:1344-1358, ref_utils.reflect) ------------
+    ENC_S = dict(hash_map_size=2 ** 15, num_features=4, scale_supersample=1.0, max_grid_size=256, bbox_scaling=2.0)
+    sh = R["shading"].BaseShader(net_depth=0, use_density_feature=True, warp_fn=rcoord.contract_radius_2)
+    sh.grid = rgrid.HashEncoding(**ENC_S)
+    sh.grid.seen = []
+    sh.grid.param = lambda name, init_fn: (sh.grid.seen.append(name), level_table(init_fn.keywords["shape"], len(sh.grid.seen)))[1]
+    Rs, ns = 40, 6
+    smeans = f(g.normal(size=(Rs, ns, 3)) * 1.5); sfeat = f(g.normal(size=(Rs, ns, 64)))
+    afeat = sh.predict_appearance_feature(dict(means=smeans.view(shim.F32Array), covs=None, feature=sfeat),
+                                          control_offsets=f(np.zeros((1, 3))), perp_mag=None)
+    out.update(shd_means=smeans, shd_density_feature=sfeat, shd_appearance_feature=np.asarray(afeat))
+    nm = R["nerf"].NeRFMLP(net_activation=shim.nn_mod.relu, net_depth_integrated_brdf=2, skip_layer_integrated_brdf=4,
+                           use_reflections=True)
+    nm.integrated_brdf_layers = [shim.nn_mod_linen.Dense(64), shim.nn_mod_linen.Dense(64)]
+    nm.output_integrated_brdf_layer = shim.nn_mod_linen.Dense(1)
+    d_in = 129
+    for i_, layer in enumerate(nm.integrated_brdf_layers + [nm.output_integrated_brdf_layer]):
+        layer.kernel, layer.bias = dense_params(d_in, layer.features, 200 + i_)
+        d_in = layer.features
+    snrm = f(unit(g.normal(size=(Rs, ns, 3)))); sview = f(unit(g.normal(size=(Rs, 3)))); sbott = f(g.normal(size=(Rs, ns, 128)))
+    out.update(shd_normals=snrm, shd_viewdirs=sview, shd_bottleneck=sbott)
+    out["shd_integrated_brdf"] = nm.get_integrated_brdf(snrm, sview, sbott)
+    out["shd_refdirs"] = nm._get_refdirs(sview, snrm, {})
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

@@ -289,3 +289,25 @@ def test_proposal_sampler_loop(tag, use_raydist):
         for k in ("sdist", "tdist", "means", "weights"):
             tol = 1e-4 if k == "weights" else (2e-6 if lvl == 0 else 2e-5)     # measured: 1e-6 / 8e-6 / 3e-5 (weights)
             close(h[k], f"pvs_{tag}_{lvl}_{k}", tol)
+
+
+def test_cache_shader_pieces():
+    """BaseShader.predict_appearance_feature with net_depth 0 (internal/shading.py:133-220: [density feature | appearance grid
+    of the contracted mean]) BIT-EXACT; NeRFMLP.get_integrated_brdf (internal/nerf.py:423-434,461-482) and _get_refdirs
+    (:1344-1358) executed from the reference's classes."""
+    from oracle import nerf as onerf2
+    from tests.util import dense_params
+
+    sh = onerf2.NeRFMLP(warp_c=2.0)
+    sh.grid = ogrid.HashEncoding(hash_map_size=2 ** 15, num_features=4, scale_supersample=1.0, max_grid_size=256, bbox_scaling=2.0)
+    p = {"appearance_grid": {name: torch.from_numpy(_level_table(shape, i + 1))
+                             for i, (name, (_, _, shape)) in enumerate(zip(sh.grid.param_names(), sh.grid.layout))}}
+    exact(sh.predict_appearance_feature(p, T("shd_density_feature"), T("shd_means")), "shd_appearance_feature")
+    d_in = 129
+    for i, (name, d_out) in enumerate([("integrated_brdf_layers_0", 64), ("integrated_brdf_layers_1", 64),
+                                       ("output_integrated_brdf_layer", 1)]):
+        k, b = dense_params(d_in, d_out, 200 + i)
+        p[name] = {"kernel": torch.from_numpy(k), "bias": torch.from_numpy(b)}
+        d_in = d_out
+    close(sh.get_integrated_brdf(p, T("shd_normals"), T("shd_viewdirs"), T("shd_bottleneck")), "shd_integrated_brdf", 2e-6)
+    close(onerf2.reflect(-T("shd_viewdirs")[..., None, :], T("shd_normals")), "shd_refdirs", 1e-6)
