@@ -389,6 +389,10 @@ def install():
     sys.modules["flax"] = flax
     sys.modules["flax.linen"] = linen
     sys.modules["flax.struct"] = flax.struct
+    mlc = _Passthrough("ml_collections")          # class-level defaults such as LightMLP.vmf_activation must survive
+    mlc.__path__ = []
+    mlc.FrozenConfigDict = mlc.ConfigDict = dict
+    sys.modules["ml_collections"] = mlc
     if not any(isinstance(f, _StubFinder) for f in sys.meta_path):
         sys.meta_path.append(_StubFinder())
     return jax

@@ -421,6 +421,15 @@ def main():
     out["shd_integrated_brdf"] = nm.get_integrated_brdf(snrm, sview, sbott)
     out["shd_refdirs"] = nm._get_refdirs(sview, snrm, {})
 
+    # ---- LightMLP.get_vmfs (light_sampler.py:135-160) with the class's own bias / activation tables ---------------------
+    vraw = f(g.normal(size=(64, 16, 5)) * 3.0); vraw[0, 0, 3:] = [60.0, -80.0]     # both clamps
+    vnorm = f(g.normal(size=(64, 16, 3)))
+    lm = R["light_sampler"].LightMLP(num_components=16, random_seed={"normal": vnorm})   # PRNGKey(seed) = the pre-drawn normals
+    vm = lm.get_vmfs(vraw)
+    out.update(vmfs_raw=vraw, vmfs_normal=vnorm)
+    for k_ in ("vmf_means", "vmf_kappas", "vmf_logits"):
+        out["vmfs_" + k_] = vm[k_]
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

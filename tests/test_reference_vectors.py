@@ -311,3 +311,15 @@ def test_cache_shader_pieces():
         d_in = d_out
     close(sh.get_integrated_brdf(p, T("shd_normals"), T("shd_viewdirs"), T("shd_bottleneck")), "shd_integrated_brdf", 2e-6)
     close(onerf2.reflect(-T("shd_viewdirs")[..., None, :], T("shd_normals")), "shd_refdirs", 1e-6)
+
+
+def test_light_mlp_get_vmfs():
+    """LightMLP.get_vmfs (internal/light_sampler.py:135-160) executed from the reference's class with its own bias and
+    activation tables (:73-84): means scale + pre-drawn offsets, softplus kappas clamped at 50, logits clamped at -50."""
+    from oracle import light_sampler as olight
+
+    means_random = T("vmfs_normal") * 20.0 / 2.0
+    got = olight.get_vmfs(T("vmfs_raw"), means_random)
+    close(got["vmf_means"], "vmfs_vmf_means", 1e-6)
+    close(got["vmf_kappas"], "vmfs_vmf_kappas", 1e-6)
+    exact(got["vmf_logits"], "vmfs_vmf_logits")
