@@ -430,6 +430,23 @@ def main():
     for k_ in ("vmf_means", "vmf_kappas", "vmf_logits"):
         out["vmfs_" + k_] = vm[k_]
 
+    # ---- MaterialMLP._get_microfacet_material (material.py:1276-1322) over its own property table (:957-1023), fields
+    #      set as configs/ngp_yobo.gin:256-303 sets them ------------------------------------------------------------------
+    sig = shim.nn_mod.sigmoid
+    props = ("albedo", "specular_albedo", "roughness", "F_0", "metalness", "diffuseness", "mirrorness")
+    mm = R["material"].MaterialMLP(
+        num_rgb_channels=3, brdf_activation={k_: sig for k_ in props},
+        brdf_bias=dict(albedo=-1.0, specular_albedo=-1.0, roughness=-1.0, F_0=-3.078, metalness=0.0, diffuseness=0.0, mirrorness=2.0),
+        brdf_stopgrad=dict(albedo=1.0, specular_albedo=1.0, roughness=0.25, F_0=1.0, metalness=1.0, diffuseness=1.0, mirrorness=1.0),
+        use_diffuseness=False, use_mirrorness=False, use_constant_metalness=False, use_constant_fresnel=True,
+        min_roughness=0.01, default_F_0=0.04, max_F_0=1.0, reparam_roughness=False)
+    mm._initialize_microfacet_properties()
+    braw = f(g.normal(size=(300, 10)) * 3.0)
+    mat = mm._get_microfacet_material(braw)
+    out["mat_brdf_params"] = braw
+    for k_ in props:
+        out["mat_" + k_] = mat[k_]
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

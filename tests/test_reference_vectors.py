@@ -323,3 +323,14 @@ def test_light_mlp_get_vmfs():
     close(got["vmf_means"], "vmfs_vmf_means", 1e-6)
     close(got["vmf_kappas"], "vmfs_vmf_kappas", 1e-6)
     exact(got["vmf_logits"], "vmfs_vmf_logits")
+
+
+def test_microfacet_material_head():
+    """MaterialMLP._get_microfacet_material (internal/material.py:1276-1322) over the class's own property table
+    (:957-1023) with the fields of configs/ngp_yobo.gin:256-303: slices, biases, sigmoid, the roughness floor, constant
+    Fresnel, diffuseness / mirrorness off."""
+    from oracle import material as omat
+
+    got = omat.microfacet_material(T("mat_brdf_params"), min_roughness=0.01, default_F_0=0.04)
+    for k in ("albedo", "specular_albedo", "roughness", "F_0", "metalness", "diffuseness", "mirrorness"):
+        close(got[k], "mat_" + k, 1e-6)
