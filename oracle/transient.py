@@ -5,7 +5,8 @@ internal/inverse_render/render_utils.py zero_invalid_bins (:1699-1767) and the h
 internal/nerf.py:1660-1777 (softplus(raw + bias) * indirect_scale; tint * F * ref_rgb * indirect_scale; clip).
 Pinned to the reference's source for shift_direct, shift_map_coordinates, zero_invalid_bins and the whole of
 volumetric_transient_rendering (tests/test_reference_vectors.py::test_transient; map_coordinates there is SciPy's with
-JAX's boundary rule); the head post-processing lives in a flax Module and is restated only."""
+JAX's boundary rule); the head (get_indirect Dense stack + post-processing) is pinned through
+TransientNeRFMLP._compute_indirect_lighting executed from the reference's class (test_transient_head)."""
 import numpy as np
 import torch
 
@@ -66,14 +67,23 @@ def volumetric_transient_rendering(direct_rgbs, indirect, weights, ray_dists, li
     return dict(transient_direct=t_direct, transient_indirect=t_indirect, rgb=t_direct + t_indirect + dark_level)
 
 
-def transient_render(direct_rgbs, diffuse_raw, specular, spec_scale, weights, ray_dists, light_dists, cam_dists, n_bins,
-                     exposure_time=0.01, shift=0.0, diffuse_bias=-1.0, indirect_scale=1.0, bin_zero_threshold_light=0.0,
-                     light_zero=False, light_near=0.0, rgb_max=10000.0, dark_level=0.0):
-    R, n, C = direct_rgbs.shape
+def transient_head(diffuse_raw, specular, spec_scale, light_dists, cam_dists, n_bins, exposure_time=0.01, diffuse_bias=-1.0,
+                   indirect_scale=1.0, bin_zero_threshold_light=0.0, light_zero=False, light_near=0.0, rgb_max=10000.0):
+    """Post-processing of TransientNeRFMLP._compute_indirect_lighting (nerf.py:1689-1745): diffuse = softplus(raw + bias) *
+    scale; specular = (tint * F) * ref_rgb * scale; zero_invalid_bins; clip to [0, rgb_max].  diffuse_raw / specular
+    [..., n_bins, C]; spec_scale [..., C]; light_dists / cam_dists [...]."""
     diffuse = torch.nn.functional.softplus(diffuse_raw + diffuse_bias) * indirect_scale
     spec = spec_scale[..., None, :] * specular * indirect_scale
     diffuse, spec = zero_invalid_bins(diffuse, spec, light_dists[..., None], cam_dists[..., None], n_bins, exposure_time,
                                       bin_zero_threshold_light, light_zero, light_near)
-    indirect = torch.clamp(diffuse, 0.0, rgb_max) + torch.clamp(spec, 0.0, rgb_max)
+    return torch.clamp(diffuse, 0.0, rgb_max), torch.clamp(spec, 0.0, rgb_max)
+
+
+def transient_render(direct_rgbs, diffuse_raw, specular, spec_scale, weights, ray_dists, light_dists, cam_dists, n_bins,
+                     exposure_time=0.01, shift=0.0, diffuse_bias=-1.0, indirect_scale=1.0, bin_zero_threshold_light=0.0,
+                     light_zero=False, light_near=0.0, rgb_max=10000.0, dark_level=0.0):
+    diffuse, spec = transient_head(diffuse_raw, specular, spec_scale, light_dists, cam_dists, n_bins, exposure_time,
+                                   diffuse_bias, indirect_scale, bin_zero_threshold_light, light_zero, light_near, rgb_max)
+    indirect = diffuse + spec
     return volumetric_transient_rendering(direct_rgbs, indirect, weights, ray_dists, light_dists, n_bins, exposure_time, shift,
                                           dark_level)

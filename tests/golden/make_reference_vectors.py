@@ -447,6 +447,39 @@ def main():
     for k_ in props:
         out["mat_" + k_] = mat[k_]
 
+    # ---- TransientNeRFMLP._compute_indirect_lighting / get_indirect (nerf.py:1660-1777) as configured
+    #      (transient_ngp_yobo.gin:176-179: irradiance stack 2 x 64, skip 2; deg_lights 2) --------------------------------
+    Dn = shim.nn_mod_linen.Dense
+    Rh, nh, Bh = 12, 4, 48
+    hcfg = _types.SimpleNamespace(n_bins=Bh, num_rgb_channels=3, light_intensity_conditioning=False,
+                                  bin_zero_threshold_light=np.float32(2.0), exposure_time=expo, light_zero=False,
+                                  light_near=np.float32(0.0))
+    tn = R["nerf"].TransientNeRFMLP(config=hcfg, use_indirect=True, net_activation=shim.nn_mod.relu, deg_lights=2,
+                                    net_depth_irradiance=2, net_width_irradiance=64, bottleneck_irradiance=64,
+                                    skip_layer_irradiance=2, irradiance_activation=shim.nn_mod.softplus, irradiance_bias=-2.0,
+                                    indirect_scale=np.float32(0.7), rgb_max=np.float32(1.5), net_depth_integrated_brdf=2,
+                                    skip_layer_integrated_brdf=4, dense_layer=Dn)
+    tn._initialize_irradiance_layers()
+    tn.integrated_brdf_layers, tn.output_integrated_brdf_layer = [Dn(64), Dn(64)], Dn(1)
+    tn.tint_layer, tn.transient_indirect_layer = Dn(3), Dn(Bh * 3)
+    for layers, d_in, salt in ((tn.irradiance_layers + [tn.transient_indirect_layer], 96 + 15, 300),
+                               (tn.integrated_brdf_layers + [tn.output_integrated_brdf_layer], 129, 200),
+                               ([tn.tint_layer], 96, 320)):
+        for i_, layer in enumerate(layers):
+            layer.kernel, layer.bias = dense_params(d_in, layer.features, salt + i_)
+            d_in = layer.features
+    hfeat = f(g.normal(size=(Rh, nh, 96))); hmeans = f(g.uniform(-0.05, 0.05, size=(Rh, nh, 3)))
+    hnrm = f(unit(g.normal(size=(Rh, nh, 3)))); href = f(g.gamma(1.0, 1.0, size=(Rh, nh, Bh * 3)))
+    hbott = f(g.normal(size=(Rh, nh, 128))); hview = f(unit(g.normal(size=(Rh, 3))))
+    hrays = _types.SimpleNamespace(lights=f(g.uniform(-0.05, 0.05, size=(Rh, 3))), origins=f(g.uniform(-0.05, 0.05, size=(Rh, 3))),
+                                   cam_origins=f(g.uniform(-0.05, 0.05, size=(Rh, 3))))
+    out.update(th_feature=hfeat, th_means=hmeans, th_normals=hnrm, th_ref_rgb=href, th_bottleneck=hbott, th_viewdirs=hview,
+               th_lights=hrays.lights, th_origins=hrays.origins, th_cam_origins=hrays.cam_origins)
+    res = tn._compute_indirect_lighting(hfeat, hmeans, hnrm, hnrm, href, hbott, hview, None, hrays, None, None)
+    for k_, v_ in zip(("indirect_diffuse", "indirect_specular", "transient_indirect", "transient_indirect_diffuse",
+                       "transient_indirect_specular"), res):
+        out["th_" + k_] = v_
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

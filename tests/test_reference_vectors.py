@@ -334,3 +334,38 @@ def test_microfacet_material_head():
     got = omat.microfacet_material(T("mat_brdf_params"), min_roughness=0.01, default_F_0=0.04)
     for k in ("albedo", "specular_albedo", "roughness", "F_0", "metalness", "diffuseness", "mirrorness"):
         close(got[k], "mat_" + k, 1e-6)
+
+
+def test_transient_head():
+    """TransientNeRFMLP._compute_indirect_lighting + get_indirect (internal/nerf.py:1660-1777) executed from the reference's
+    class: pos_enc(lights) -> irradiance stack -> n_bins*3 bins, softplus(. - 2) * scale; tint * F * ref_rgb * scale;
+    zero_invalid_bins; clip; per-bin and summed outputs."""
+    from oracle import coord as ocoord, geometry as ogeo, nerf as onerf2, transient as otr
+    from tests.util import dense_params
+
+    feat, means, nrm, ref = T("th_feature"), T("th_means"), T("th_normals"), T("th_ref_rgb")
+    R, n, B = ref.shape[0], ref.shape[1], ref.shape[2] // 3
+    p, names = {}, (("irradiance_layers_0", 64), ("irradiance_layers_1", 64), ("transient_indirect_layer", B * 3))
+    for group, d_in, salt in ((names, 96 + 15, 300), ((("integrated_brdf_layers_0", 64), ("integrated_brdf_layers_1", 64),
+                                                        ("output_integrated_brdf_layer", 1)), 129, 200), ((("tint_layer", 3),), 96, 320)):
+        for i, (name, d_out) in enumerate(group):
+            k, b = dense_params(d_in, d_out, salt + i)
+            p[name] = {"kernel": torch.from_numpy(k), "bias": torch.from_numpy(b)}
+            d_in = d_out
+    lights = T("th_lights")[:, None, :] * torch.ones_like(nrm)
+    x = torch.cat([feat, ocoord.pos_enc(lights, 0, 2, True)], dim=-1)                       # get_indirect :1757-1777
+    x = torch.relu(ogeo.dense(p["irradiance_layers_0"], x))
+    x = torch.relu(ogeo.dense(p["irradiance_layers_1"], x))
+    diffuse_raw = ogeo.dense(p["transient_indirect_layer"], x).reshape(R, n, B, 3)
+    F = onerf2.NeRFMLP().get_integrated_brdf(p, nrm, T("th_viewdirs"), T("th_bottleneck"))
+    tint = torch.sigmoid(ogeo.dense(p["tint_layer"], feat))
+    light_d = torch.linalg.norm(T("th_lights")[:, None, :] - means, dim=-1)
+    cam_d = (torch.linalg.norm(T("th_origins")[:, None, :] - means, dim=-1)
+             + torch.linalg.norm(T("th_origins") - T("th_cam_origins"), dim=-1)[:, None])
+    diffuse, spec = otr.transient_head(diffuse_raw, ref.reshape(R, n, B, 3), tint * F, light_d, cam_d, B, exposure_time=0.01,
+                                       diffuse_bias=-2.0, indirect_scale=0.7, bin_zero_threshold_light=2.0, rgb_max=1.5)
+    close(diffuse, "th_transient_indirect_diffuse", 2e-6)
+    close(spec, "th_transient_indirect_specular", 2e-6)
+    close(diffuse + spec, "th_transient_indirect", 2e-6)
+    close(diffuse.sum(-2), "th_indirect_diffuse", 2e-6)
+    close(spec.sum(-2), "th_indirect_specular", 2e-6)
