@@ -480,6 +480,20 @@ def main():
                        "transient_indirect_specular"), res):
         out["th_" + k_] = v_
 
+    # ---- train_utils.light_sampling_loss (:1985-2071): the call site of vmf_loss_fn (function values = |radiance_in|,
+    #      lossmult / S, one suffix present -> multiplier 2 and the / 2 inside the loop) ---------------------------------
+    lrad = f(g.gamma(1.0, 1.0, size=(Ps, Ss, 3)))
+    out["light_radiance_in"] = lrad
+    mres = dict(light_sampler=dict(vmf_means=lmeans[:, None], vmf_kappas=lkappas[:, None], vmf_logits=llogits[:, None],
+                                   vmf_normals=lnormals[:, None, None, :]),
+                shader=dict(ref_rays_indirect_diffuse=None, ref_samples_indirect_diffuse=None,
+                            ref_rays_indirect_specular=_types.SimpleNamespace(viewdirs=swi.reshape(-1, 3)),
+                            ref_samples_indirect_specular=dict(radiance_in=lrad, pdf=lpdf, weight=lwt)))
+    for srgb in (True, False):
+        out[f"light_sampling_loss_{int(srgb)}"] = np.asarray(rtrain.light_sampling_loss(
+            None, None, None, _types.SimpleNamespace(lossmult=f(np.ones((Ps, 1)))),
+            _types.SimpleNamespace(light_sampling_linear_to_srgb=srgb), None, mres))
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

@@ -369,3 +369,16 @@ def test_transient_head():
     close(diffuse + spec, "th_transient_indirect", 2e-6)
     close(diffuse.sum(-2), "th_indirect_diffuse", 2e-6)
     close(spec.sum(-2), "th_indirect_specular", 2e-6)
+
+
+def test_light_sampling_loss_call_site():
+    """train_utils.light_sampling_loss (internal/train_utils.py:1985-2071) executed from the reference: function values =
+    |radiance_in|, lossmult / S, only the specular suffix present (multiplier 2, / 2 inside the loop)."""
+    from oracle import light_sampler as olight
+
+    vmfs = dict(vmf_means=T("light_means"), vmf_kappas=T("light_kappas"), vmf_logits=T("light_logits"),
+                vmf_normals=T("light_normals")[:, None, :])
+    for srgb in (True, False):
+        got = olight.light_sampling_loss(vmfs, T("smp_wi"), T("light_pdf")[..., 0], T("light_weight")[..., 0],
+                                         T("light_radiance_in"), srgb=srgb)
+        close(got, f"light_sampling_loss_{int(srgb)}", 1e-5)
