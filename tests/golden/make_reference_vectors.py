@@ -360,6 +360,21 @@ def main():
     dens = mlp.convert_raw_density(raw, dmeans.view(shim.F32Array))
     assert raw.dtype == np.float32 and dens.dtype == np.float32
     out.update(dmlp_means=dmeans, dmlp_raw_density=np.asarray(raw), dmlp_feature=np.asarray(feat), dmlp_density=np.asarray(dens))
+    # the module call itself (geometry.py:381-584) without the jax.value_and_grad branch: control points of the 'mean' basis
+    # (coord.compute_control_points), predicted normals head, ray distances
+    mlp.disable_density_normals, mlp.enable_pred_normals = True, True
+    mlp.grid.seen = []                                     # the table salts count parameter requests from 1 again
+    mlp.pred_normals_layer.kernel, mlp.pred_normals_layer.bias = dense_params(64, 3, 110)
+    cm = dmeans[:696].reshape(58, 12, 3)
+    g2 = np.random.Generator(np.random.PCG64(58))          # own stream: blocks added later leave earlier vectors unchanged
+    crays = _types.SimpleNamespace(origins=f(g2.normal(size=(58, 3))), directions=f(g2.normal(size=(58, 3))),
+                                   viewdirs=f(unit(g2.normal(size=(58, 3)))), radii=f(np.full((58, 1), 1e-3)),
+                                   lights=f(g2.normal(size=(58, 3))))
+    cres = mlp(None, crays, (cm.view(shim.F32Array), f(np.zeros((58, 12, 3, 3)))), tdist=None)
+    out.update(dmlp_call_origins=crays.origins, dmlp_call_viewdirs=crays.viewdirs)
+    for k_ in ("feature", "density", "grad_pred", "normals_pred", "normals_to_use", "ray_dists"):
+        out["dmlp_call_" + k_] = np.asarray(cres[k_])
+    assert cres["normals"] is None and cres["raw_grad_density"] is None
 
     # ---- ProposalVolumeSampler.__call__ (sampling.py:142-649), the whole level loop as configured (ngp_yobo.gin:178-242):
     #      ray warps (identity, and the power ladder of the secondary pass), annealed resampling logits, sample_intervals,

@@ -382,3 +382,26 @@ def test_light_sampling_loss_call_site():
         got = olight.light_sampling_loss(vmfs, T("smp_wi"), T("light_pdf")[..., 0], T("light_weight")[..., 0],
                                          T("light_radiance_in"), srgb=srgb)
         close(got, f"light_sampling_loss_{int(srgb)}", 1e-5)
+
+
+def test_density_mlp_module_call():
+    """DensityMLP.__call__ -> predict_density_normals -> get_predict_density_kwargs -> coord.compute_control_points
+    (internal/geometry.py:343-584, coord.py:568-611) executed from the reference's class on the branch without
+    jax.value_and_grad: the 'mean' basis yields exactly one control point (= the mean), predicted-normals head,
+    normals_to_use = normals_pred, ray distances."""
+    from oracle import geometry as ogeo
+    from tests.util import dense_params
+
+    mlp = ogeo.DensityMLP({k: v for k, v in ENC_CONFIGS["a"].items() if k != "scale_supersample"}, net_depth=2, net_width=64,
+                          density_bias=-1.0, warp_c=2.0, bbox_scaling=2.0, enable_pred_normals=True, disable_density_normals=True)
+    p = {"density_grid": {name: torch.from_numpy(_level_table(shape, i + 1))
+                          for i, (name, (_, _, shape)) in enumerate(zip(mlp.grid.param_names(), mlp.grid.layout))}}
+    for name, d_in, d_out, salt in (("density_layers_0", mlp.in_dim, 64, 100), ("density_layers_1", 64, 64, 101),
+                                    ("output_density_layer", 64, 1, 102), ("pred_normals_layer", 64, 3, 110)):
+        k, b = dense_params(d_in, d_out, salt)
+        p[name] = {"kernel": torch.from_numpy(k), "bias": torch.from_numpy(b)}
+    means = T("dmlp_means")[:696].reshape(58, 12, 3)
+    res = mlp(p, means, viewdirs=T("dmlp_call_viewdirs"), origins=T("dmlp_call_origins"))
+    assert res["normals"] is None and res["raw_grad_density"] is None
+    for k in ("feature", "density", "grad_pred", "normals_pred", "normals_to_use", "ray_dists"):
+        close(res[k], "dmlp_call_" + k, 2e-6 if k != "normals_pred" and k != "normals_to_use" else 1e-5)
