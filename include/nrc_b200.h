@@ -82,6 +82,9 @@ typedef struct {
 
 /* ---------------------------------------------------------------- misc ---- */
 int32_t nrc_abi_version(void);
+/* SHA-256 of the sources this library was compiled from (neural_radiance_caching_b200/build.py): the loader refuses a
+ * library whose digest differs from the sources beside it. */
+const char* nrc_build_digest(void);
 const char* nrc_error_string(int32_t status);
 /* cudaError_t of the most recent failed launch on the calling thread. */
 int32_t nrc_last_cuda_error(void);
@@ -309,7 +312,7 @@ int32_t nrc_ide_bwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32
 #define NRC_WGRAD_MAX_X_ATOMS 6
 #define NRC_WGRAD_MAX_SEGS 5
 
-typedef enum { NRC_OP_LOAD = 0, NRC_OP_GEMM = 1, NRC_OP_EPI = 2, NRC_OP_SAVE = 3, NRC_OP_GATHER = 4 } nrc_chain_op_kind_t;
+typedef enum { NRC_OP_LOAD = 0, NRC_OP_GEMM = 1, NRC_OP_EPI = 2, NRC_OP_SAVE = 3, NRC_OP_GATHER = 4, NRC_OP_LOADIMG = 5 } nrc_chain_op_kind_t;
 #define NRC_GEMM_ACCUMULATE 1     /* accumulate onto the accumulator's current contents (skip VJP) */
 #define NRC_EPI_RELU 1            /* max(0, .) after the bias                                      */
 #define NRC_EPI_OUT_ACCUMULATE 2  /* fp32 output: += instead of =                                  */
@@ -317,15 +320,20 @@ typedef enum { NRC_OP_LOAD = 0, NRC_OP_GEMM = 1, NRC_OP_EPI = 2, NRC_OP_SAVE = 3
 
 typedef struct {
   int32_t kind;       /* nrc_chain_op_kind_t                                                       */
-  int32_t slot;       /* LOAD/EPI/SAVE: first atom slot (EPI: -1 = no bf16 result)                 */
-  int32_t ptr;        /* LOAD: fp32 source (-1 = zeros); EPI: bias [ncols] or -1; SAVE: tile image  */
+  int32_t slot;       /* LOAD/LOADIMG/EPI/SAVE: first atom slot (EPI: -1 = no bf16 result)         */
+  int32_t ptr;        /* LOAD: fp32 source (-1 = zeros); EPI: bias [ncols] or -1; SAVE / LOADIMG:   */
+                      /* tile image (LOADIMG = the inverse of SAVE: npad atoms starting at atom     */
+                      /* col0 of the tile's image are bulk-copied into the slots; the producer of   */
+                      /* the image - another chain's SAVE or a per-point kernel - wrote bf16 atoms, */
+                      /* so no fp32 row is read or converted; CTA-pair kernel only)                 */
   int32_t ld;         /* LOAD: source row stride; EPI: fp32 output row stride (floats)             */
   int32_t col0;       /* LOAD: first destination column (x8); EPI: first output column;            */
                       /* SAVE: first atom inside the image                                         */
   int32_t ncols;      /* LOAD: source columns; EPI: valid result columns                           */
   int32_t npad;       /* LOAD: columns written, zero padded (x8); EPI: columns processed (x16);    */
                       /* SAVE: number of atoms                                                     */
-  int32_t tmem_col;   /* GEMM/EPI: first accumulator column (0..255, per context)                  */
+  int32_t tmem_col;   /* GEMM/EPI: first accumulator column (0..255 per context; up to 511 when the */
+                      /* program runs with one tile context per CTA: CTA-pair kernel only)          */
   int32_t n;          /* GEMM: N (x16, <= 128)                                                     */
   int32_t flags;      /* NRC_GEMM_* / NRC_EPI_*                                                    */
   int32_t out_ptr;    /* EPI: fp32 output matrix or -1                                             */

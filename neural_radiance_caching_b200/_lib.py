@@ -70,6 +70,7 @@ _F = C.c_float
 # symbol include/nrc_b200.h declares (tests/test_abi.py checks this against the header).
 PROTOTYPES = {
     "nrc_abi_version": [],
+    "nrc_build_digest": [],
     "nrc_error_string": [_I32],
     "nrc_last_cuda_error": [],
     "nrc_encode_fwd": [_P, C.POINTER(nrc_encoding_t), _P, _I64, _P],
@@ -138,7 +139,7 @@ PROTOTYPES = {
     "nrc_ggx_integrate_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P],
     "nrc_ggx_integrate_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],
 }
-_RESTYPES = {"nrc_error_string": C.c_char_p}
+_RESTYPES = {"nrc_error_string": C.c_char_p, "nrc_build_digest": C.c_char_p}
 
 _lib = None
 
@@ -165,6 +166,13 @@ def load():
         fn.restype = _RESTYPES.get(name, C.c_int32)
     if missing:
         raise NrcError(f"{LIB_PATH} does not export {missing}: stale build? run the build with --force")
+    # the library must have been compiled from the sources beside it (the .so is git-ignored and survives a pull)
+    if os.path.isdir(os.path.join(HERE, "csrc")) and os.environ.get("NRC_SKIP_DIGEST_CHECK") != "1":
+        from . import build as _build
+        have, want = lib.nrc_build_digest().decode(), _build._digest()
+        if have != want:
+            raise NrcError(f"{LIB_PATH} was built from other sources (digest {have[:12]} != {want[:12]}): "
+                           "run `python -m neural_radiance_caching_b200.build`")
     _lib = lib
     return lib
 

@@ -15,7 +15,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnrc_b200.so")
-STAMP = os.path.join(HERE, ".libnrc_b200.stamp")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -36,7 +35,7 @@ def _digest():
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     files.append(os.path.join(ROOT, "include", "nrc_b200.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, ROOT).encode())   # repo-relative: the digest does not depend on the checkout path
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -50,17 +49,34 @@ def nvcc_path():
     return "nvcc"
 
 
+def built_digest():
+    """Digest compiled into the existing library (nrc_build_digest), or None."""
+    if not os.path.exists(LIB):
+        return None
+    import ctypes
+    try:
+        lib = ctypes.CDLL(LIB)
+        fn = lib.nrc_build_digest
+    except (OSError, AttributeError):
+        return None
+    fn.restype = ctypes.c_char_p
+    return fn().decode()
+
+
 def build(force=False, verbose=False):
+    """Compile when the digest EMBEDDED in the existing .so differs from the sources' (the .so is git-ignored: a
+    stamp file beside it could describe another checkout's binary)."""
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
-        if open(STAMP).read().strip() == digest:
-            return LIB
+    if not force and built_digest() == digest:
+        return LIB
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc_path(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", src, "-o", obj]
+        if os.path.basename(src) == "encode.cu":   # exports nrc_build_digest()
+            cmd.insert(1, f'-DNRC_BUILD_DIGEST="{digest}"')
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -77,8 +93,6 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc compilation failed")
     cmd = [nvcc_path(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
-    with open(STAMP, "w") as fh:
-        fh.write(digest)
     return LIB
 
 

@@ -23,6 +23,8 @@
 // traffic saves.)
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "encode.cuh"
 #include "nrc_common.cuh"
 #include "tc05.cuh"
@@ -70,6 +72,7 @@ struct ChainParams {
 constexpr int kTraceTiles = 48, kTraceOps = 32;
 __device__ long long g_chain_trace[2][kTraceTiles][kTraceOps];
 __device__ long long g_chain_marks[16];
+__device__ long long g_chain_mma[kTraceTiles][8][2];   // v2: UMMA issuer of CTA 0, per tile and GEMM group: operands ready, issued
 #define TRACE_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 64) g_chain_marks[i] = clock64(); } while (0)
 #else
 #define TRACE_MARK(i) do {} while (0)
@@ -151,6 +154,7 @@ struct EpiArgs {
   const uint8_t* mask_tile;  // forward-activation image of this tile or nullptr
   uint32_t slot0_addr;       // shared-memory address of the first destination slot
   int ncols, npad, mask_atom0, r, half;
+  int nparts = 2;           // warps sharing this thread's TMEM lane quadrant: warp `half` takes every nparts-th chunk
   bool out_vec, accum, has_slot;
 };
 
@@ -237,26 +241,26 @@ __device__ __forceinline__ void epi_bias_load(const EpiArgs& a, int j0, float (&
 
 // This thread's 16-column chunks (every other one: the quadrant's second warp takes the rest), kEpiBatch chunks
 // per TMEM round trip: all their tcgen05.ld (and the mask loads) are issued before the one wait.
-constexpr int kEpiBatch = 1;
-template <bool BIAS, bool RELU, bool MASK, bool FULL>
+template <bool BIAS, bool RELU, bool MASK, bool FULL, int kEpiBatch = 1>
 __device__ __forceinline__ void epi_run(const EpiArgs& a) {
-  for (int j0 = 16 * a.half; j0 < a.npad; j0 += 32 * kEpiBatch) {
+  const int step = 16 * a.nparts;
+  for (int j0 = 16 * a.half; j0 < a.npad; j0 += step * kEpiBatch) {
     uint32_t v[kEpiBatch][16], mw[kEpiBatch][8];
 #pragma unroll
     for (int k = 0; k < kEpiBatch; ++k)
-      if (j0 + 32 * k < a.npad) tmem_ld16(a.taddr + j0 + 32 * k, v[k]);
+      if (j0 + step * k < a.npad) tmem_ld16(a.taddr + j0 + step * k, v[k]);
     TRACE_MARK(2);
 #pragma unroll
     for (int k = 0; k < kEpiBatch; ++k)
-      if (j0 + 32 * k < a.npad) epi_mask_load<MASK>(a, j0 + 32 * k, mw[k]);
+      if (j0 + step * k < a.npad) epi_mask_load<MASK>(a, j0 + step * k, mw[k]);
     tmem_ld_wait();
     TRACE_MARK(3);
 #pragma unroll
     for (int k = 0; k < kEpiBatch; ++k) {
-      if (j0 + 32 * k < a.npad) {
+      if (j0 + step * k < a.npad) {
         float b[16];
-        epi_bias_load<BIAS, FULL>(a, j0 + 32 * k, b);
-        epi_chunk<BIAS, RELU, MASK, FULL>(a, j0 + 32 * k, v[k], mw[k], b);
+        epi_bias_load<BIAS, FULL>(a, j0 + step * k, b);
+        epi_chunk<BIAS, RELU, MASK, FULL>(a, j0 + step * k, v[k], mw[k], b);
       }
     }
     TRACE_MARK(4);
@@ -580,6 +584,423 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// Fast epilogue of the common case - the accumulator becomes the next layer's bf16 operand and nothing else: TMEM ->
+// (+ staged bias) -> bf16 pairs -> ReLU / ReLU mask applied on the PACKED pairs (max(.,0) commutes with the rounding;
+// the mask is an AND) -> two 16-byte shared-memory stores per 16 columns.  ~45 instructions per chunk instead of ~80.
+template <bool BIAS, bool RELU, bool MASK>
+__device__ __forceinline__ void epi_slot_fast(uint32_t taddr, const float* bias_s, uint32_t slot0_addr, int r, int npad,
+                                              int part, int nparts, const uint8_t* mask_tile, int mask_atom0) {
+  const uint32_t row_off = static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128);
+  const uint32_t rx = static_cast<uint32_t>(r & 7);
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+  for (int j0 = 16 * part; j0 < npad; j0 += 16 * nparts) {
+    uint32_t v[16], mw[8];
+    tmem_ld16(taddr + j0, v);
+    if (MASK) {
+      const int mc = mask_atom0 * 64 + j0;
+      const uint8_t* ma = mask_tile + static_cast<size_t>(mc >> 6) * kAtomBytes + row_off;
+      const uint32_t c8 = static_cast<uint32_t>((mc & 63) >> 3);
+      const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(ma + ((c8 ^ rx) << 4)));
+      const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(ma + (((c8 + 1) ^ rx) << 4)));
+      mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
+      mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+    }
+    float b[16];
+    if (BIAS) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = *(reinterpret_cast<const float4*>(bias_s + j0) + q);
+        b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+      }
+    }
+    const uint32_t c8 = static_cast<uint32_t>((j0 & 63) >> 3);
+    const uint32_t d = slot0_addr + static_cast<uint32_t>(j0 >> 6) * kAtomBytes + row_off;
+    tmem_ld_wait();
+    uint32_t o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float x0 = __uint_as_float(v[2 * e]), x1 = __uint_as_float(v[2 * e + 1]);
+      if (BIAS) { x0 += b[2 * e]; x1 += b[2 * e + 1]; }
+      __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+      if (RELU) h = __hmax2(h, zero2);
+      uint32_t w = *reinterpret_cast<uint32_t*>(&h);
+      if (MASK) {
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&mw[e]);
+        w &= __hgt2_mask(a, zero2);
+      }
+      o[e] = w;
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + ((c8 ^ rx) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                 "r"(o[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + (((c8 + 1) ^ rx) << 4)), "r"(o[4]), "r"(o[5]),
+                 "r"(o[6]), "r"(o[7]) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Version 2 of the chain kernel: CTA PAIRS with the stack's weights RESIDENT in shared memory.
+//   * a cluster of two CTAs executes one 256-row tile (128 rows per CTA) with tcgen05.mma.cta_group::2: the B operand
+//     (weights) is split by N between the two CTAs, so each SM holds HALF of every layer's weights - the whole
+//     SurfaceLightField stack (228 KB of bf16 operands) fits beside the activations and is loaded ONCE per CTA
+//     instead of being streamed through a ring for every tile (the v1 kernel moves 256 KB of weights per 128-row
+//     tile through a 2-4 stage ring: its GEMMs wait on L2, not on the tensor core);
+//   * the ring, its barriers and the producer loop are gone: the UMMA issuer never waits for operands after the
+//     first tile; a tile's layer costs one cluster-scope barrier round trip + the MMAs + the epilogue;
+//   * epilogue warps issue all their TMEM loads of a layer before the single wait.
+// Programs, weight images, tile images and the op semantics are those of the v1 kernel (a 256-row pair tile is
+// the two consecutive 128-row tiles 2t and 2t+1 of every tile image).
+constexpr int kTail2Bytes = 6144;
+constexpr int kMaxMma = 96;   // UMMA instructions of one program (precomputed descriptor list in shared memory)
+struct Chain2Params {
+  nrc_chain_program_t prog;
+  void* ptrs[NRC_CHAIN_MAX_PTRS];
+  const uint8_t* weights;
+  int64_t num_rows;
+  int32_t num_tiles;     // 128-row tiles
+  int32_t num_ptiles;    // 256-row pair tiles
+  int32_t w_bytes;       // resident weight bytes per CTA (multiple of 1024)
+  int32_t w_off[NRC_CHAIN_MAX_OPS];   // GEMM ops: byte offset of the op's first K atom inside the resident region
+};
+
+template <int NCTX>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1)
+chain2_kernel(const __grid_constant__ Chain2Params p) {
+  // dynamic shared memory: [resident weights][NCTX * S slot atoms][tail: mbarriers, TMEM base, program, staged biases]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kThreads = kChainThreads;
+  constexpr int kCtxT = 2 * kCtxThreads / NCTX;   // loader / epilogue threads per tile context: 16 warps (one context) or 8
+  constexpr int kParts = kCtxT / 128;             // warps per TMEM lane quadrant
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.prog.slots_per_ctx, nops = p.prog.num_ops;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();
+  const uint32_t w_base = base;
+  const uint32_t slot_base = base + static_cast<uint32_t>(p.w_bytes);
+  uint8_t* tail = smem_raw + p.w_bytes + static_cast<size_t>(NCTX * S) * kAtomBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(tail + 128);
+  DevOp* sops = reinterpret_cast<DevOp*>(tail + 144);
+  uint4* smma = reinterpret_cast<uint4*>(tail + 144 + sizeof(DevOp) * NRC_CHAIN_MAX_OPS);
+  float* sbias = reinterpret_cast<float*>(tail + 144 + sizeof(DevOp) * NRC_CHAIN_MAX_OPS + sizeof(uint4) * kMaxMma);
+  const int bias_cap = (kTail2Bytes - 144 - static_cast<int>(sizeof(DevOp)) * NRC_CHAIN_MAX_OPS - static_cast<int>(sizeof(uint4)) * kMaxMma) / 4;
+  auto slot_addr = [&](int ctx, int s) { return slot_base + static_cast<uint32_t>(ctx * S + s) * kAtomBytes; };
+  // barriers: 0 weights resident, 2+c operands of context c ready (count 2: one arrival per CTA, used in the
+  // issuing CTA only), 4+c accumulator of context c ready (multicast commit)
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t w_ready = bar0;
+  auto a_ready = [&](int c) { return bar0 + 8u * (2 + c); };
+  auto acc_ready = [&](int c) { return bar0 + 8u * (4 + c); };
+  auto img_ready = [&](int c) { return bar0 + 8u * (6 + c); };   // LOADIMG bulk copies of context c landed
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_ready, 1);
+    for (int c = 0; c < 2; ++c) {
+      mbar_init(a_ready(c), 2);
+      mbar_init(acc_ready(c), 1);
+      mbar_init(img_ready(c), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc2(smem_u32(&tmem_base_s), 512);
+  if (threadIdx.x < nops) {
+    const nrc_chain_op_t& o = p.prog.ops[threadIdx.x];
+    DevOp d;
+    d.kind = static_cast<int8_t>(o.kind); d.slot = static_cast<int8_t>(o.slot);
+    d.flags = static_cast<uint8_t>(o.flags); d.n_atoms = static_cast<uint8_t>(o.n_atoms);
+    d.ncols = static_cast<int16_t>(o.ncols); d.npad = static_cast<int16_t>(o.npad);
+    d.tmem_col = static_cast<int16_t>(o.tmem_col); d.n = static_cast<int16_t>(o.n);
+    d.ld = o.ld;
+    d.col0 = static_cast<int16_t>(o.col0); d.mask_atom0 = static_cast<int16_t>(o.mask_atom0);
+    d.img_atoms = static_cast<int16_t>(o.img_atoms);
+    d.w_chunk = o.kind == NRC_OP_GEMM ? p.w_off[threadIdx.x] : o.w_chunk;   // GEMM: resident byte offset
+    d.fparam = o.fparam;
+    d.ptr = o.ptr >= 0 ? p.ptrs[o.ptr] : nullptr;
+    d.out = o.out_ptr >= 0 ? p.ptrs[o.out_ptr] : nullptr;
+    d.mask = o.mask_ptr >= 0 ? p.ptrs[o.mask_ptr] : nullptr;
+#pragma unroll
+    for (int a = 0; a < NRC_CHAIN_MAX_ATOMS; ++a) d.a_src[a] = static_cast<uint8_t>((o.a_slot[a] & 15) | ((o.a_klen[a] >> 4) << 4));
+    int cur = 0, off = -1;
+    for (int k = 0; k <= static_cast<int>(threadIdx.x); ++k) {
+      const nrc_chain_op_t& e = p.prog.ops[k];
+      if (e.kind != NRC_OP_EPI || e.ptr < 0 || e.mask_ptr >= 0) continue;
+      if (cur + e.npad > bias_cap) break;
+      if (k == static_cast<int>(threadIdx.x)) off = cur;
+      cur += e.npad;
+    }
+    d.bias_off = static_cast<int16_t>(off);
+    if (o.kind == NRC_OP_GEMM) {
+      // this op's UMMA instructions as ready-made descriptor words (context 0; the issuer adds the context's slot
+      // offset): the issuing thread then spends a handful of instructions per UMMA instead of re-deriving
+      // everything from the program (measured: ~150 cycles per UMMA, more than twice its execution time)
+      int first = 0;
+      for (int k = 0; k < static_cast<int>(threadIdx.x); ++k) {
+        const nrc_chain_op_t& e = p.prog.ops[k];
+        if (e.kind != NRC_OP_GEMM) continue;
+        for (int a = 0; a < e.n_atoms; ++a) first += e.a_klen[a] >> 4;
+      }
+      int cnt = 0;
+      const uint32_t idesc = make_idesc(256, o.n, 0, 0);
+      const uint32_t half_bytes = static_cast<uint32_t>(o.n) * 64u;
+      for (int a = 0; a < o.n_atoms; ++a) {
+        const uint32_t a_addr = slot_base + static_cast<uint32_t>(o.a_slot[a]) * kAtomBytes;
+        const uint32_t b_addr = w_base + static_cast<uint32_t>(p.w_off[threadIdx.x]) + static_cast<uint32_t>(a) * half_bytes;
+        for (int k = 0; k < (o.a_klen[a] >> 4); ++k) {
+          const uint32_t acc = ((o.flags & NRC_GEMM_ACCUMULATE) || a > 0 || k > 0) ? 0x80000000u : 0u;
+          if (first + cnt < kMaxMma)
+            smma[first + cnt] = make_uint4(((a_addr + 32u * k) >> 4) | (1u << 16), ((b_addr + 32u * k) >> 4) | (1u << 16),
+                                           static_cast<uint32_t>(o.tmem_col) | acc, idesc);
+          ++cnt;
+        }
+      }
+      d.ld = first;
+      d.col0 = static_cast<int16_t>(cnt);
+    }
+    sops[threadIdx.x] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // this CTA's half of every weight atom, once: rows [rank n/2, (rank+1) n/2) of the K-major chunk are the
+    // contiguous bytes [rank n/2 * 128, ...) of the swizzled atom (8-row groups of 1024 bytes)
+    mbar_arrive_expect_tx(w_ready, static_cast<uint32_t>(p.w_bytes));
+    for (int i = 0; i < nops; ++i) {
+      const nrc_chain_op_t& o = p.prog.ops[i];
+      if (o.kind != NRC_OP_GEMM) continue;
+      const uint32_t half_bytes = static_cast<uint32_t>(o.n) * 64u;
+      for (int a = 0; a < o.n_atoms; ++a)
+        bulk_g2s(w_base + static_cast<uint32_t>(p.w_off[i]) + static_cast<uint32_t>(a) * half_bytes,
+                 p.weights + static_cast<size_t>(o.w_chunk + a) * kAtomBytes + rank * half_bytes, half_bytes, w_ready);
+    }
+  }
+  for (int i = 0; i < nops; ++i) {
+    const DevOp& op = sops[i];
+    if (op.kind != NRC_OP_EPI || op.bias_off < 0) continue;
+    const float* b = static_cast<const float*>(op.ptr);
+    for (int k = threadIdx.x; k < op.npad; k += kThreads) sbias[op.bias_off + k] = k < op.ncols ? __ldg(b + k) : 0.f;
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated, program staged
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int num_super = (p.num_ptiles + NCTX - 1) / NCTX;
+
+  if (warp == 1) {
+    // ===================================================================== UMMA issuer (even CTA of the pair)
+    if (rank == 0 && lane == 0) {
+      uint32_t a_par[2] = {0u, 0u};
+      for (int q = pair; q < num_super; q += npairs) {
+#ifdef NRC_CHAIN_TRACE
+        const int trace_it = (q - pair) / npairs;
+        int trace_g = 0;
+#endif
+        for (int i = 0; i < nops;) {
+          if (sops[i].kind != NRC_OP_GEMM) { ++i; continue; }
+          int j = i;
+          while (j < nops && sops[j].kind == NRC_OP_GEMM) ++j;
+          for (int c = 0; c < NCTX; ++c) {
+            if (NCTX * q + c >= p.num_ptiles) continue;
+            mbar_wait_cluster(a_ready(c), a_par[c]);
+            a_par[c] ^= 1u;
+            tc_fence_after();
+#ifdef NRC_CHAIN_TRACE
+            if (blockIdx.x == 0 && c == 0 && trace_it < kTraceTiles && trace_g < 8) g_chain_mma[trace_it][trace_g][0] = clock64();
+#endif
+            {
+              const int e0 = sops[i].ld, e1 = sops[j - 1].ld + sops[j - 1].col0;
+              const uint32_t d0 = tmem_base + static_cast<uint32_t>(c * kCtxTmemCols);
+              const uint32_t a_off = static_cast<uint32_t>(c * S) * (kAtomBytes >> 4);
+              constexpr uint64_t kDescHi = static_cast<uint64_t>(64u | (1u << 14) | (2u << 29)) << 32;   // SBO 1024, v1, SW128
+              uint4 m = smma[e0];
+              for (int e = e0; e < e1; ++e) {
+                const uint4 cur = m;
+                if (e + 1 < e1) m = smma[e + 1];
+                umma2_bf16(d0 + (cur.z & 0x7FFFFFFFu), kDescHi | (cur.x + a_off), kDescHi | cur.y, cur.w, cur.z >> 31);
+              }
+            }
+            umma2_commit_mc(acc_ready(c), 3);
+#ifdef NRC_CHAIN_TRACE
+            if (blockIdx.x == 0 && c == 0 && trace_it < kTraceTiles && trace_g < 8) g_chain_mma[trace_it][trace_g][1] = clock64();
+            if (c == 0) ++trace_g;
+#endif
+          }
+          i = j;
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    // ===================================================================== loader / epilogue warpgroups
+    const int c = (warp - 2) / (kCtxT / 32);
+    const int wg_tid = threadIdx.x - 64 - kCtxT * c;
+    const int quad = warp & 3;
+    const int half = ((warp - 2) >> 2) % kParts;
+    const int r = quad * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t a_ready_remote = mapa_shared(a_ready(c), 0);
+    uint32_t acc_par = 0, img_par = 0;
+    bool store_pending = false, w_waited = false, img_pending = false;
+
+    auto guard_slots = [&]() {
+      if (store_pending) {
+        if (wg_tid == 0) bulk_wait_read0();
+        named_barrier_sync(1 + c, kCtxT);
+        store_pending = false;
+      }
+    };
+
+    for (int q = pair; q < num_super; q += npairs) {
+      const int ptile = NCTX * q + c;
+      if (ptile >= p.num_ptiles) continue;
+      const int tile = 2 * ptile + static_cast<int>(rank);     // 128-row tile of every tile image
+      const bool tile_ok = tile < p.num_tiles;
+      const int64_t row0 = static_cast<int64_t>(tile) * 128;
+#ifdef NRC_CHAIN_TRACE
+      const int trace_it = (q - pair) / npairs;
+      const bool tracing = blockIdx.x == 0 && wg_tid == 0 && trace_it < kTraceTiles;
+      if (tracing) g_chain_trace[c][trace_it][kTraceOps - 1] = clock64();
+#endif
+      for (int i = 0; i < nops;) {
+        const DevOp& op = sops[i];
+        if (op.kind == NRC_OP_GEMM) {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          named_barrier_sync(1 + c, kCtxT);
+          if (wg_tid == 0) {
+            if (!w_waited) { mbar_wait(w_ready, 0); w_waited = true; }
+            if (img_pending) { mbar_wait(img_ready(c), img_par); img_par ^= 1u; img_pending = false; }
+            mbar_arrive_cluster(a_ready_remote);
+          }
+          while (i < nops && sops[i].kind == NRC_OP_GEMM) ++i;
+          mbar_wait(acc_ready(c), acc_par);
+          acc_par ^= 1u;
+          tc_fence_after();
+#ifdef NRC_CHAIN_TRACE
+          if (tracing) g_chain_trace[c][trace_it][i - 1] = clock64();
+#endif
+          continue;
+        }
+        if (op.kind == NRC_OP_LOADIMG) {
+          // bf16 atoms written by the producer (another chain's SAVE, a per-point kernel) straight into the slots;
+          // consecutive LOADIMG ops before a GEMM share one barrier phase
+          guard_slots();
+          if (wg_tid == 0 && tile_ok) {
+            int tot = 0;
+            int k = i;
+            while (k < nops && sops[k].kind == NRC_OP_LOADIMG) tot += sops[k++].npad;
+            if (!img_pending) {
+              mbar_arrive_expect_tx(img_ready(c), static_cast<uint32_t>(tot) * kAtomBytes);
+              img_pending = true;
+            }
+            const uint8_t* img = static_cast<const uint8_t*>(op.ptr);
+            for (int a = 0; a < op.npad; ++a)
+              bulk_g2s(slot_addr(c, op.slot + a), img + (static_cast<size_t>(tile) * op.img_atoms + op.col0 + a) * kAtomBytes,
+                       kAtomBytes, img_ready(c));
+          }
+        } else if (op.kind == NRC_OP_LOAD) {
+          guard_slots();
+          const float* src = static_cast<const float*>(op.ptr);
+          const int nch = op.npad >> 3;
+          const bool vec = src && (op.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+          constexpr int kU = 4;
+          const int total = 128 * nch;
+          for (int item0 = wg_tid; item0 < total; item0 += kCtxT * kU) {
+            float v[kU][8];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+              const int item = item0 + u * kCtxT;
+              const int rr = item / nch;
+              const int col = (item - rr * nch) * 8;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+              if (item < total && src && row0 + rr < p.num_rows && col < op.ncols) {
+                const float* s = src + (row0 + rr) * op.ld + col;
+                if (vec && col + 8 <= op.ncols) {
+                  const float4 x0 = __ldg(reinterpret_cast<const float4*>(s));
+                  const float4 x1 = __ldg(reinterpret_cast<const float4*>(s) + 1);
+                  v[u][0] = x0.x; v[u][1] = x0.y; v[u][2] = x0.z; v[u][3] = x0.w;
+                  v[u][4] = x1.x; v[u][5] = x1.y; v[u][6] = x1.z; v[u][7] = x1.w;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (col + e < op.ncols) v[u][e] = __ldg(s + e);
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+              const int item = item0 + u * kCtxT;
+              if (item >= total) continue;
+              const int rr = item / nch;
+              const int dcol = op.col0 + (item - rr * nch) * 8;
+              const uint32_t dst = slot_addr(c, op.slot + (dcol >> 6)) + atom_chunk_offset(rr, (dcol & 63) >> 3);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack2_bf16(v[u][0], v[u][1])),
+                           "r"(pack2_bf16(v[u][2], v[u][3])), "r"(pack2_bf16(v[u][4], v[u][5])),
+                           "r"(pack2_bf16(v[u][6], v[u][7]))
+                           : "memory");
+            }
+          }
+        } else if (op.kind == NRC_OP_SAVE) {
+          fence_proxy_async_smem();
+          named_barrier_sync(1 + c, kCtxT);
+          if (wg_tid == 0 && tile_ok) {
+            uint8_t* img = static_cast<uint8_t*>(op.ptr);
+            for (int a = 0; a < op.npad; ++a)
+              bulk_s2g(img + (static_cast<size_t>(tile) * op.img_atoms + op.col0 + a) * kAtomBytes,
+                       slot_addr(c, op.slot + a), kAtomBytes);
+            bulk_commit();
+          }
+          store_pending = true;
+        } else {  // NRC_OP_EPI
+          if (op.slot >= 0) guard_slots();
+          EpiArgs a;
+          a.bias = static_cast<const float*>(op.ptr);
+          a.bias_s = op.bias_off >= 0 ? sbias + op.bias_off : nullptr;
+          float* out = static_cast<float*>(op.out);
+          a.out_row = (out && row0 + r < p.num_rows) ? out + (row0 + r) * op.ld + op.col0 : nullptr;
+          a.out_vec = out && (op.ld % 4 == 0) && (op.col0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+          a.accum = (op.flags & NRC_EPI_OUT_ACCUMULATE) != 0;
+          a.mask_tile = (op.mask && tile_ok)
+                            ? static_cast<const uint8_t*>(op.mask) + static_cast<size_t>(tile) * op.img_atoms * kAtomBytes
+                            : nullptr;
+          a.mask_atom0 = op.mask_atom0;
+          a.taddr = tmem_base + t_lane + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
+          a.has_slot = op.slot >= 0;
+          a.slot0_addr = a.has_slot ? slot_addr(c, op.slot) : 0u;
+          a.ncols = op.ncols; a.npad = op.npad; a.r = r; a.half = half; a.nparts = kParts;
+          const bool full = (op.ncols == op.npad) && (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
+          const bool relu = (op.flags & NRC_EPI_RELU) != 0;
+          if (a.has_slot && !out && op.ncols == op.npad && (!a.bias || a.bias_s) && (tile_ok || !op.mask)) {
+            // the accumulator only becomes the next operand: tight path
+            if (a.mask_tile)  epi_slot_fast<false, false, true>(a.taddr, nullptr, a.slot0_addr, r, op.npad, half, kParts, a.mask_tile, a.mask_atom0);
+            else if (a.bias)  { if (relu) epi_slot_fast<true, true, false>(a.taddr, a.bias_s, a.slot0_addr, r, op.npad, half, kParts, nullptr, 0);
+                                else      epi_slot_fast<true, false, false>(a.taddr, a.bias_s, a.slot0_addr, r, op.npad, half, kParts, nullptr, 0); }
+            else              { if (relu) epi_slot_fast<false, true, false>(a.taddr, nullptr, a.slot0_addr, r, op.npad, half, kParts, nullptr, 0);
+                                else      epi_slot_fast<false, false, false>(a.taddr, nullptr, a.slot0_addr, r, op.npad, half, kParts, nullptr, 0); }
+          } else if (a.mask_tile) {
+            if (full) epi_run<false, false, true, true>(a); else epi_run<false, false, true, false>(a);
+          } else if (a.bias) {
+            if (relu) { if (full) epi_run<true, true, false, true>(a); else epi_run<true, true, false, false>(a); }
+            else      { if (full) epi_run<true, false, false, true>(a); else epi_run<true, false, false, false>(a); }
+          } else {
+            if (relu) { if (full) epi_run<false, true, false, true>(a); else epi_run<false, true, false, false>(a); }
+            else      { if (full) epi_run<false, false, false, true>(a); else epi_run<false, false, false, false>(a); }
+          }
+        }
+#ifdef NRC_CHAIN_TRACE
+        if (tracing) g_chain_trace[c][trace_it][i] = clock64();
+#endif
+        ++i;
+      }
+    }
+    if (wg_tid == 0) bulk_wait0();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();   // no CTA leaves (or frees tensor memory) while its partner may still use its memories
+  if (warp == 0) tmem_dealloc2(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight packing: fp32 Flax kernels [in,out] -> bf16 16 KB chunks in the swizzled K-major atom
 // layout, chunk[n][k]:
@@ -787,14 +1208,14 @@ static int32_t validate_program(const nrc_chain_program_t* prog, int32_t num_ptr
         break;
       case NRC_OP_GEMM:
         if (op.n < 16 || op.n > 128 || (op.n & 15) || op.n_atoms < 1 || op.n_atoms > NRC_CHAIN_MAX_ATOMS ||
-            op.tmem_col < 0 || op.tmem_col + op.n > 256 || op.w_chunk < 0)
+            op.tmem_col < 0 || op.tmem_col + op.n > 512 || op.w_chunk < 0)
           return NRC_E_INVALID_ARG;
         for (int a = 0; a < op.n_atoms; ++a)
           if (op.a_slot[a] >= S || op.a_klen[a] < 16 || op.a_klen[a] > 64 || (op.a_klen[a] & 15)) return NRC_E_INVALID_ARG;
         break;
       case NRC_OP_EPI:
         if ((op.flags & NRC_EPI_DENSITY) && (!ptr_ok(op.out_ptr, false) || op.npad != 16)) return NRC_E_INVALID_ARG;
-        if (op.npad <= 0 || (op.npad & 15) || op.ncols > op.npad || op.tmem_col < 0 || op.tmem_col + op.npad > 256 ||
+        if (op.npad <= 0 || (op.npad & 15) || op.ncols > op.npad || op.tmem_col < 0 || op.tmem_col + op.npad > 512 ||
             !ptr_ok(op.ptr, true) || !ptr_ok(op.out_ptr, true) || !ptr_ok(op.mask_ptr, true) ||
             (op.slot >= 0 && op.slot + ((op.npad + 63) >> 6) > S))
           return NRC_E_INVALID_ARG;
@@ -805,6 +1226,7 @@ static int32_t validate_program(const nrc_chain_program_t* prog, int32_t num_ptr
           return NRC_E_INVALID_ARG;
         break;
       case NRC_OP_SAVE:
+      case NRC_OP_LOADIMG:
         if (!ptr_ok(op.ptr, false) || op.slot < 0 || op.npad < 1 || op.slot + op.npad > S || op.col0 < 0 ||
             op.col0 + op.npad > op.img_atoms)
           return NRC_E_INVALID_ARG;
@@ -816,12 +1238,89 @@ static int32_t validate_program(const nrc_chain_program_t* prog, int32_t num_ptr
   return NRC_OK;
 }
 
+// v2 launch (CTA pairs, resident weights): returns NRC_E_UNSUPPORTED when the program does not fit, so the caller
+// can fall back to the streaming kernel.
+static int sm_count() {
+  static thread_local int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 2)
+      n = kNumSMs;
+  }
+  return n;
+}
+
+static int32_t chain2_launch(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
+                             const void* d_weights_packed, int64_t num_rows) {
+  static thread_local Chain2Params hp;
+  hp.prog = *prog;
+  int w_bytes = 0;
+  for (int i = 0; i < prog->num_ops; ++i) {
+    const nrc_chain_op_t& op = prog->ops[i];
+    hp.w_off[i] = 0;
+    if (op.kind == NRC_OP_GATHER || (op.kind == NRC_OP_EPI && (op.flags & NRC_EPI_DENSITY))) return NRC_E_UNSUPPORTED;
+    if (op.kind != NRC_OP_GEMM) continue;
+    hp.w_off[i] = w_bytes;
+    w_bytes += op.n_atoms * op.n * 64;   // n/2 rows of 128 bytes per K atom
+  }
+  int n_mma = 0;
+  for (int i = 0; i < prog->num_ops; ++i)
+    if (prog->ops[i].kind == NRC_OP_GEMM)
+      for (int a = 0; a < prog->ops[i].n_atoms; ++a) n_mma += prog->ops[i].a_klen[a] >> 4;
+  if (n_mma > kMaxMma) return NRC_E_UNSUPPORTED;
+  const int S = prog->slots_per_ctx;
+  const int budget = 227 * 1024 - kTail2Bytes - 1024;
+  int nctx = 2;
+  if (w_bytes + 2 * S * kAtomBytes > budget) nctx = 1;
+  for (int i = 0; i < prog->num_ops; ++i) {   // accumulators beyond a context's 256 columns: one context owns all 512
+    const nrc_chain_op_t& op = prog->ops[i];
+    if ((op.kind == NRC_OP_GEMM && op.tmem_col + op.n > 256) || (op.kind == NRC_OP_EPI && op.tmem_col + op.npad > 256)) nctx = 1;
+  }
+  if (w_bytes + nctx * S * kAtomBytes > budget) return NRC_E_UNSUPPORTED;
+  const char* force = getenv("NRC_CHAIN_NCTX");
+  if (force && force[0] == '1') nctx = 1;
+  for (int i = 0; i < NRC_CHAIN_MAX_PTRS; ++i) hp.ptrs[i] = i < num_ptrs ? d_ptrs[i] : nullptr;
+  hp.weights = static_cast<const uint8_t*>(d_weights_packed);
+  hp.num_rows = num_rows;
+  hp.num_tiles = static_cast<int32_t>((num_rows + 127) / 128);
+  hp.num_ptiles = (hp.num_tiles + 1) / 2;
+  hp.w_bytes = w_bytes;
+  const size_t smem = static_cast<size_t>(w_bytes) + static_cast<size_t>(nctx * S) * kAtomBytes + kTail2Bytes;
+  const int num_super = (hp.num_ptiles + nctx - 1) / nctx;
+  const int max_pairs = sm_count() / 2;
+  const int pairs = num_super < max_pairs ? num_super : max_pairs;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (nctx == 1) {
+    if (cudaFuncSetAttribute(chain2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+      return check_launch();
+    chain2_kernel<1><<<2 * pairs, kChainThreads, smem, s>>>(hp);
+  } else {
+    if (cudaFuncSetAttribute(chain2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+      return check_launch();
+    chain2_kernel<2><<<2 * pairs, kChainThreads, smem, s>>>(hp);
+  }
+  return check_launch();
+}
+
 static int32_t chain_launch(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
                             const void* d_weights_packed, int64_t num_rows, const EncDev* enc, float warp_c) {
   if (!d_ptrs || num_ptrs < 0 || num_ptrs > NRC_CHAIN_MAX_PTRS || num_rows < 0) return NRC_E_INVALID_ARG;
   const int32_t st = validate_program(prog, num_ptrs);
   if (st != NRC_OK) return st;
   if (num_rows == 0) return NRC_OK;
+  if (!enc) {   // CTA-pair kernel with resident weights whenever the program fits (NRC_CHAIN_V1=1: streaming kernel)
+    const char* v1 = getenv("NRC_CHAIN_V1");
+    if (!(v1 && v1[0] == '1')) {
+      const int32_t s2 = chain2_launch(stream, prog, d_ptrs, num_ptrs, d_weights_packed, num_rows);
+      if (s2 != NRC_E_UNSUPPORTED) return s2;
+    }
+  }
+  for (int i = 0; i < prog->num_ops; ++i) {   // features of the CTA-pair kernel only
+    const nrc_chain_op_t& op = prog->ops[i];
+    if (op.kind == NRC_OP_LOADIMG) return NRC_E_UNSUPPORTED;
+    if (op.kind == NRC_OP_GEMM && op.tmem_col + op.n > 256) return NRC_E_UNSUPPORTED;
+    if (op.kind == NRC_OP_EPI && op.tmem_col + op.npad > 256) return NRC_E_UNSUPPORTED;
+  }
   static thread_local ChainParams hp;
   hp.prog = *prog;
   for (int i = 0; i < NRC_CHAIN_MAX_PTRS; ++i) hp.ptrs[i] = i < num_ptrs ? d_ptrs[i] : nullptr;
@@ -857,6 +1356,10 @@ extern "C" int32_t nrc_chain_trace_dump(long long* host_out) {
   cudaDeviceSynchronize();
   return cudaMemcpyFromSymbol(host_out, g_chain_trace, sizeof(long long) * 2 * kTraceTiles * kTraceOps) == cudaSuccess
              ? NRC_OK : NRC_E_CUDA;
+}
+extern "C" int32_t nrc_chain_mma_dump(long long* host_out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, g_chain_mma, sizeof(long long) * kTraceTiles * 8 * 2) == cudaSuccess ? NRC_OK : NRC_E_CUDA;
 }
 extern "C" int32_t nrc_chain_marks_dump(long long* host_out) {
   cudaDeviceSynchronize();

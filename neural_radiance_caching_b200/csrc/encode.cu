@@ -404,6 +404,10 @@ extern "C" int32_t nrc_encode_bwd(void* stream, const nrc_encoding_t* enc, const
 }
 
 extern "C" int32_t nrc_abi_version(void) { return NRC_ABI_VERSION; }
+#ifndef NRC_BUILD_DIGEST
+#define NRC_BUILD_DIGEST "unknown"
+#endif
+extern "C" const char* nrc_build_digest(void) { return NRC_BUILD_DIGEST; }
 
 extern "C" const char* nrc_error_string(int32_t status) {
   switch (status) {

@@ -63,3 +63,15 @@ marks = np.zeros(16, dtype=np.int64)
 lib.nrc_chain_marks_dump.argtypes = [C.POINTER(C.c_longlong)]
 lib.nrc_chain_marks_dump(marks.ctypes.data_as(C.POINTER(C.c_longlong)))
 print("last EPI of ctx0 thread 0 (begin, args, ld issued, ld waited, chunk done, end):", [int(m - marks[0]) for m in marks[:6]])
+
+try:
+    mma = np.zeros((48, 8, 2), dtype=np.int64)
+    lib.nrc_chain_mma_dump.argtypes = [C.POINTER(C.c_longlong)]
+    lib.nrc_chain_mma_dump(mma.ctypes.data_as(C.POINTER(C.c_longlong)))
+    for it in range(0, 4):
+        if mma[it, 0, 0] == 0:
+            continue
+        print(f"it{it} UMMA issuer (v2, ctx0): " + " ".join(
+            f"g{g}: ready@{mma[it, g, 0] - buf[0, it, 31]} issue {mma[it, g, 1] - mma[it, g, 0]}" for g in range(8) if mma[it, g, 0]))
+except AttributeError:
+    pass
