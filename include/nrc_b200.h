@@ -410,11 +410,20 @@ int32_t nrc_chain_wgrad(void* stream, const nrc_wgrad_layer_t* layers, int32_t n
  * 7-9 tint (raw Dense outputs).  d_viewdirs [P/samples_per_ray, 3].
  *   mid: roughness = softplus(raw + roughness_bias); dotprod = n.(-v); refdirs = reflect(-v, n);
  *        d_ide_slf [P,2*n_sh] = IDE(refdirs, roughness); d_ide_env [P,2*n_sh_env] (may be NULL). */
+/* Optional bf16 outputs of the mid stage in the chains' operand layout (tile images, see above): IDE_5 -> the
+ * SurfaceLightField stack's input atoms, IDE_4 -> the EnvMap stack's, n.v -> the integrated-BRDF stack's last atom
+ * (column 0; 16 columns written).  With an image given the matching fp32 output may be NULL. */
+typedef struct {
+  void* slf_img; int32_t slf_img_atoms, slf_atom0;
+  void* env_img; int32_t env_img_atoms, env_atom0;
+  void* dot_img; int32_t dot_img_atoms, dot_atom0;
+} nrc_shader_images_t;
 int32_t nrc_shader_mid_fwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32_t* ml_l,
                            const float* sigma, const float* d_mat, int32_t n_sh_env, const float* d_heads,
                            int64_t ldh, const float* d_normals, const float* d_viewdirs, int64_t num_points,
                            int32_t samples_per_ray, float roughness_bias, float* d_roughness,
-                           float* d_dotprod, float* d_refdirs, float* d_ide_slf, float* d_ide_env);
+                           float* d_dotprod, float* d_refdirs, float* d_ide_slf, float* d_ide_env,
+                           const nrc_shader_images_t* images);
 /* VJP: writes d_g_heads[:,0] (roughness raw) and d_g_normals [P,3] from the gradients of dotprod,
  * the SLF encoding and (optionally) the EnvMap encoding; all with row strides. */
 int32_t nrc_shader_mid_bwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32_t* ml_l,

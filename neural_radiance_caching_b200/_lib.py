@@ -42,6 +42,12 @@ class nrc_encoding_t(C.Structure):
     ]
 
 
+class nrc_shader_images_t(C.Structure):
+    _fields_ = [("slf_img", C.c_void_p), ("slf_img_atoms", C.c_int32), ("slf_atom0", C.c_int32),
+                ("env_img", C.c_void_p), ("env_img_atoms", C.c_int32), ("env_atom0", C.c_int32),
+                ("dot_img", C.c_void_p), ("dot_img_atoms", C.c_int32), ("dot_atom0", C.c_int32)]
+
+
 class nrc_density_mlp_t(C.Structure):
     _fields_ = [
         ("d_w0", C.c_void_p), ("d_b0", C.c_void_p),
@@ -119,7 +125,7 @@ PROTOTYPES = {
     "nrc_chain_pack_weights": [_P, _P, _I32, _P, _I32, _P, _I32, _I32],
     "nrc_chain_wgrad": [_P, _P, _I32, _P, _I32, _I64],
     "nrc_shader_mid_fwd": [_P, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), _P, _I32, _P, _I64,
-                           _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P],
+                           _P, _P, _I64, _I32, _F, _P, _P, _P, _P, _P, _P],
     "nrc_shader_mid_bwd": [_P, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), _P, _I32, _P, _I64,
                            _P, _P, _I64, _I32, _F, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P],
     "nrc_shader_out_fwd": [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _F, _F, _F, _F, _P, _P],

@@ -714,7 +714,7 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
     d.ld = o.ld;
     d.col0 = static_cast<int16_t>(o.col0); d.mask_atom0 = static_cast<int16_t>(o.mask_atom0);
     d.img_atoms = static_cast<int16_t>(o.img_atoms);
-    d.w_chunk = o.kind == NRC_OP_GEMM ? p.w_off[threadIdx.x] : o.w_chunk;   // GEMM: resident byte offset
+    d.w_chunk = o.w_chunk;
     d.fparam = o.fparam;
     d.ptr = o.ptr >= 0 ? p.ptrs[o.ptr] : nullptr;
     d.out = o.out_ptr >= 0 ? p.ptrs[o.out_ptr] : nullptr;
@@ -745,7 +745,8 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
       const uint32_t half_bytes = static_cast<uint32_t>(o.n) * 64u;
       for (int a = 0; a < o.n_atoms; ++a) {
         const uint32_t a_addr = slot_base + static_cast<uint32_t>(o.a_slot[a]) * kAtomBytes;
-        const uint32_t b_addr = w_base + static_cast<uint32_t>(p.w_off[threadIdx.x]) + static_cast<uint32_t>(a) * half_bytes;
+        const int32_t woff = p.w_off[threadIdx.x] >= 0 ? p.w_off[threadIdx.x] : -(p.w_off[threadIdx.x] + 1);
+        const uint32_t b_addr = w_base + static_cast<uint32_t>(woff) + static_cast<uint32_t>(a) * half_bytes;
         for (int k = 0; k < (o.a_klen[a] >> 4); ++k) {
           const uint32_t acc = ((o.flags & NRC_GEMM_ACCUMULATE) || a > 0 || k > 0) ? 0x80000000u : 0u;
           if (first + cnt < kMaxMma)
@@ -766,7 +767,7 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
     mbar_arrive_expect_tx(w_ready, static_cast<uint32_t>(p.w_bytes));
     for (int i = 0; i < nops; ++i) {
       const nrc_chain_op_t& o = p.prog.ops[i];
-      if (o.kind != NRC_OP_GEMM) continue;
+      if (o.kind != NRC_OP_GEMM || p.w_off[i] < 0) continue;   // < 0: shares an earlier op's resident weights
       const uint32_t half_bytes = static_cast<uint32_t>(o.n) * 64u;
       for (int a = 0; a < o.n_atoms; ++a)
         bulk_g2s(w_base + static_cast<uint32_t>(p.w_off[i]) + static_cast<uint32_t>(a) * half_bytes,
@@ -867,7 +868,7 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
           named_barrier_sync(1 + c, kCtxT);
           if (wg_tid == 0) {
             if (!w_waited) { mbar_wait(w_ready, 0); w_waited = true; }
-            if (img_pending) { mbar_wait(img_ready(c), img_par); img_par ^= 1u; img_pending = false; }
+            if (img_pending) { mbar_arrive(img_ready(c)); mbar_wait(img_ready(c), img_par); img_par ^= 1u; img_pending = false; }
             mbar_arrive_cluster(a_ready_remote);
           }
           while (i < nops && sops[i].kind == NRC_OP_GEMM) ++i;
@@ -884,13 +885,9 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
           // consecutive LOADIMG ops before a GEMM share one barrier phase
           guard_slots();
           if (wg_tid == 0 && tile_ok) {
-            int tot = 0;
-            int k = i;
-            while (k < nops && sops[k].kind == NRC_OP_LOADIMG) tot += sops[k++].npad;
-            if (!img_pending) {
-              mbar_arrive_expect_tx(img_ready(c), static_cast<uint32_t>(tot) * kAtomBytes);
-              img_pending = true;
-            }
+            // every LOADIMG adds its bytes to the phase; the one arrival follows at the GEMM that consumes them
+            mbar_expect_tx(img_ready(c), static_cast<uint32_t>(op.npad) * kAtomBytes);
+            img_pending = true;
             const uint8_t* img = static_cast<const uint8_t*>(op.ptr);
             for (int a = 0; a < op.npad; ++a)
               bulk_g2s(slot_addr(c, op.slot + a), img + (static_cast<size_t>(tile) * op.img_atoms + op.col0 + a) * kAtomBytes,
@@ -1260,6 +1257,19 @@ static int32_t chain2_launch(void* stream, const nrc_chain_program_t* prog, void
     hp.w_off[i] = 0;
     if (op.kind == NRC_OP_GATHER || (op.kind == NRC_OP_EPI && (op.flags & NRC_EPI_DENSITY))) return NRC_E_UNSUPPORTED;
     if (op.kind != NRC_OP_GEMM) continue;
+    // a GEMM that multiplies further operand atoms with weights an earlier op already holds (summed upstream
+    // gradients) reuses the resident copy: its chunks are a sub-range of the earlier op's
+    int shared = -1;
+    for (int k = 0; k < i && shared < 0; ++k) {
+      const nrc_chain_op_t& e = prog->ops[k];
+      if (e.kind == NRC_OP_GEMM && e.n == op.n && op.w_chunk >= e.w_chunk && op.w_chunk + op.n_atoms <= e.w_chunk + e.n_atoms &&
+          hp.w_off[k] >= 0)
+        shared = k;
+    }
+    if (shared >= 0) {
+      hp.w_off[i] = -(hp.w_off[shared] + (op.w_chunk - prog->ops[shared].w_chunk) * op.n * 64) - 1;   // < 0: no load of its own
+      continue;
+    }
     hp.w_off[i] = w_bytes;
     w_bytes += op.n_atoms * op.n * 64;   // n/2 rows of 128 bytes per K atom
   }

@@ -7,9 +7,33 @@
 //   mid : head outputs + normal + view direction -> roughness, n.v, reflection direction, IDE_5 (SLF
 //         input) and IDE_4 (EnvMap input; the degree-4 harmonics are a prefix of the degree-5 list)
 //   out : raw outputs of the heads / integrated-BRDF / SLF / EnvMap stacks -> rgb and the extras
+#include <cuda_bf16.h>
+
 #include "ide.cuh"
+#include "tc05.cuh"
 
 namespace nrc {
+
+// Row `p` of a bf16 tile image [tiles][img_atoms][16 KB] (the operand layout of the tensor-core chains, tc05.cuh):
+// columns [0, npad) of the atoms starting at `atom0`, taken from vals[0, ncols) and zero padded; npad % 8 == 0.
+// The per-point kernels hand their results to the chains in this form, so the chains bulk-copy operands instead of
+// reading and converting fp32 rows.
+__device__ __forceinline__ void store_row_atoms(uint8_t* __restrict__ img, int img_atoms, int atom0, int64_t p,
+                                                const float* vals, int ncols, int npad) {
+  const int64_t tile = p >> 7;
+  const int r = static_cast<int>(p & 127);
+  uint8_t* base = img + (tile * img_atoms + atom0) * static_cast<int64_t>(tc::kAtomBytes);
+  for (int c0 = 0; c0 < npad; c0 += 8) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c0 + 2 * e;
+      w[e] = tc::pack2_bf16(c < ncols ? vals[c] : 0.f, c + 1 < ncols ? vals[c + 1] : 0.f);
+    }
+    *reinterpret_cast<uint4*>(base + static_cast<size_t>(c0 >> 6) * tc::kAtomBytes + tc::atom_chunk_offset(r, (c0 & 63) >> 3)) =
+        make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
@@ -32,26 +56,37 @@ __global__ void shader_mid_fwd_kernel(const __grid_constant__ IdeTable tab, int 
                                       const float* __restrict__ viewdirs, int64_t P, int32_t spr, float rough_bias,
                                       float* __restrict__ roughness, float* __restrict__ dotprod,
                                       float* __restrict__ refdirs, float* __restrict__ ide_slf,
-                                      float* __restrict__ ide_env) {
+                                      float* __restrict__ ide_env, const nrc_shader_images_t im) {
   const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= P) return;
   ShaderGeom g;
   g.load(normals, viewdirs, p, spr);
   const float rough = softplus_f(heads[p * ldh] + rough_bias);
   if (roughness) roughness[p] = rough;
-  dotprod[p] = g.dot;
+  if (dotprod) dotprod[p] = g.dot;
   if (refdirs) { refdirs[3 * p] = g.rx; refdirs[3 * p + 1] = g.ry; refdirs[3 * p + 2] = g.rz; }
   IdePowers pw;
   pw.init(tab.l_max, g.rx, g.ry, g.rz);
-  float* o5 = ide_slf + p * (2 * tab.n_sh);
+  float* o5 = ide_slf ? ide_slf + p * (2 * tab.n_sh) : nullptr;
   float* o4 = ide_env ? ide_env + p * (2 * n_sh_env) : nullptr;
+  float v5[2 * kMaxSh];   // [re | im] of the degree-5 list, kept for the image rows
   for (int i = 0; i < tab.n_sh; ++i) {
-    float re, im;
-    ide_term(tab, mat, pw, rough, i, re, im);
-    o5[i] = re;
-    o5[tab.n_sh + i] = im;
-    if (o4 && i < n_sh_env) { o4[i] = re; o4[n_sh_env + i] = im; }
+    float re, imv;
+    ide_term(tab, mat, pw, rough, i, re, imv);
+    v5[i] = re;
+    v5[tab.n_sh + i] = imv;
+    if (o5) { o5[i] = re; o5[tab.n_sh + i] = imv; }
+    if (o4 && i < n_sh_env) { o4[i] = re; o4[n_sh_env + i] = imv; }
   }
+  if (im.slf_img) store_row_atoms(static_cast<uint8_t*>(im.slf_img), im.slf_img_atoms, im.slf_atom0, p, v5, 2 * tab.n_sh,
+                                  (2 * tab.n_sh + 15) & ~15);
+  if (im.env_img) {
+    float v4[2 * kMaxSh];
+    for (int i = 0; i < n_sh_env; ++i) { v4[i] = v5[i]; v4[n_sh_env + i] = v5[tab.n_sh + i]; }
+    store_row_atoms(static_cast<uint8_t*>(im.env_img), im.env_img_atoms, im.env_atom0, p, v4, 2 * n_sh_env,
+                    (2 * n_sh_env + 15) & ~15);
+  }
+  if (im.dot_img) store_row_atoms(static_cast<uint8_t*>(im.dot_img), im.dot_img_atoms, im.dot_atom0, p, &g.dot, 1, 16);
 }
 
 __global__ void shader_mid_bwd_kernel(const __grid_constant__ IdeTable tab, int n_sh_env, const float* __restrict__ mat,
@@ -194,17 +229,21 @@ extern "C" int32_t nrc_shader_mid_fwd(void* stream, int32_t n_sh, const int32_t*
                                       const float* sigma, const float* d_mat, int32_t n_sh_env, const float* d_heads,
                                       int64_t ldh, const float* d_normals, const float* d_viewdirs, int64_t num_points,
                                       int32_t samples_per_ray, float roughness_bias, float* d_roughness,
-                                      float* d_dotprod, float* d_refdirs, float* d_ide_slf, float* d_ide_env) {
+                                      float* d_dotprod, float* d_refdirs, float* d_ide_slf, float* d_ide_env,
+                                      const nrc_shader_images_t* images) {
   IdeTable t;
   int32_t st = make_ide_table(n_sh, ml_m, ml_l, sigma, t);
   if (st != NRC_OK) return st;
   if (num_points < 0 || samples_per_ray < 1 || ldh < 1 || n_sh_env < 0 || n_sh_env > n_sh) return NRC_E_INVALID_ARG;
   if (num_points == 0) return NRC_OK;
-  if (!d_mat || !d_heads || !d_normals || !d_viewdirs || !d_dotprod || !d_ide_slf) return NRC_E_INVALID_ARG;
+  nrc_shader_images_t im = {};
+  if (images) im = *images;
+  if (!d_mat || !d_heads || !d_normals || !d_viewdirs || (!d_dotprod && !im.dot_img) || (!d_ide_slf && !im.slf_img))
+    return NRC_E_INVALID_ARG;
   const unsigned grid = static_cast<unsigned>((num_points + 127) / 128);
   shader_mid_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       t, n_sh_env, d_mat, d_heads, ldh, d_normals, d_viewdirs, num_points, samples_per_ray, roughness_bias, d_roughness,
-      d_dotprod, d_refdirs, d_ide_slf, d_ide_env);
+      d_dotprod, d_refdirs, d_ide_slf, d_ide_env, im);
   return check_launch();
 }
 

@@ -300,7 +300,8 @@ class FusedCacheStep:
             main.wait_stream(s_enc)
         outs, saved, meta = nerf.shader_fused_forward(
             shader, names, sflat, rays["viewdirs"], L2["means"], L2["feat"].reshape(R, L2["n"], 64),
-            normals_pred.reshape(R, L2["n"], 3), app_arena, True, packed=packed, encoded=encoded, env_stream=s_env)
+            normals_pred.reshape(R, L2["n"], 3), app_arena, True, packed=packed, encoded=encoded, env_stream=s_env,
+            want_bottleneck=False)
         rgb_s = outs[0].reshape(R, L2["n"], 3)
         bg = self._bg_ones(R, dev)
         # volumetric rendering (rgb, acc), data term, mask loss and the compositing VJP: one launch
@@ -475,7 +476,7 @@ class FusedCacheQuery:
         packed = self._pack_cache.get(sflat[0::2], lambda: nerf.shader_pack(shader, names, sflat))
         outs, _, _ = nerf.shader_fused_forward(shader, names, sflat, rays["viewdirs"], means_sh.reshape(R, k, 3),
                                                feat_sh.reshape(R, k, 64), normals.reshape(R, k, 3),
-                                               shp["appearance_grid"]["_arena"], False, packed=packed)
+                                               shp["appearance_grid"]["_arena"], False, packed=packed, want_bottleneck=False)
         rgb_s = outs[0].reshape(R, k, 3)
         out_rgb, acc, dist = new(R, 3), new(R), new(R, 4)
         _lib.call("nrc_ray_composite_fwd", st(), _lib.ptr(rgb_s), _lib.ptr(w_sh), k, _lib.ptr(weights) if resample else None,

@@ -18,7 +18,7 @@ from . import _lib
 ATOM_BYTES = 16384
 MAX_OPS, MAX_PTRS, MAX_ATOMS = 24, 40, 8
 PACK_MAX, WGRAD_MAX_LAYERS, WGRAD_MAX_X, WGRAD_MAX_SEGS = 80, 12, 6, 5
-OP_LOAD, OP_GEMM, OP_EPI, OP_SAVE, OP_GATHER = 0, 1, 2, 3, 4
+OP_LOAD, OP_GEMM, OP_EPI, OP_SAVE, OP_GATHER, OP_LOADIMG = 0, 1, 2, 3, 4, 5
 GEMM_ACCUMULATE, EPI_RELU, EPI_OUT_ACCUMULATE, EPI_DENSITY = 1, 1, 2, 4
 
 
@@ -57,6 +57,39 @@ def _pad(n, m):
 def _atoms_of(width):
     """[(first column, columns used)] of the 64-wide atoms covering `width` columns."""
     return [(c, min(64, width - c)) for c in range(0, width, 64)]
+
+
+class ImgRef:
+    """`natoms` consecutive atoms, starting at atom `atom0`, of every 128-row tile of a bf16 tile image
+    [tiles][img_atoms][16 KB] (the layout SAVE writes).  Passing one where a chain takes an fp32 source / head
+    gradient makes the kernel bulk-copy the atoms (NRC_OP_LOADIMG) instead of reading and converting fp32 rows;
+    passing one as a destination makes the epilogue write bf16 atoms (EPI -> slot -> SAVE) instead of fp32 rows."""
+
+    def __init__(self, img, atom0, natoms, img_atoms):
+        self.img, self.atom0, self.natoms, self.img_atoms = img, atom0, natoms, img_atoms
+
+
+def new_image(P, atoms, device):
+    return torch.empty(_num_tiles(P) * atoms * ATOM_BYTES // 2, device=device, dtype=torch.bfloat16)
+
+
+class ActImage:
+    """Activations a forward chain kept for the backward pass: the tile image it saved plus, per INPUT atom, where
+    that atom lives (None = in `img` at its own index; (tensor, img_atoms, atom) = in the producer's image)."""
+
+    def __init__(self, img, in_refs):
+        self.img, self.in_refs = img, in_refs
+
+    @property
+    def device(self):
+        return self.img.device
+
+
+class DyImage:
+    """Pre-activation gradients a data-gradient chain saved, with per-head-atom overrides like ActImage."""
+
+    def __init__(self, img, head_refs):
+        self.img, self.head_refs = img, head_refs
 
 
 class _Ptrs:
@@ -337,30 +370,57 @@ def _num_tiles(rows):
     return (rows + 127) // 128
 
 
-def run_forward(spec, params, sources, packed, save=True):
-    """sources: fp32 [P, w_i] views with contiguous rows.  Returns (per head GROUP fp32 buffers
-    [P, head_pad], per head layer column views of them, activation image or None)."""
+def run_forward(spec, params, sources, packed, save=True, head_images=None, head_fp32=None, P=None):
+    """sources: per stack input an fp32 [P, w_i] view with contiguous rows, or an ImgRef (whole atoms: the source
+    must start on a 64-column boundary).  head_images: {head group: ImgRef} - the group's result is ALSO written as
+    bf16 atoms; head_fp32: {head group: False} drops the fp32 copy of such a group.  Returns (per head GROUP fp32
+    buffers [P, head_pad] (None if dropped), per head layer column views of them, ActImage or None)."""
     b = _built(spec)
-    P = sources[0].shape[0]
-    dev = sources[0].device
+    first = next(t for t in sources if not isinstance(t, ImgRef)) if any(not isinstance(t, ImgRef) for t in sources) else None
+    dev = first.device if first is not None else sources[0].img.device
+    P = first.shape[0] if first is not None else P
+    head_images = head_images or {}
+    head_fp32 = head_fp32 or {}
     ptrs = _Ptrs()
     prog = nrc_chain_program_t()
-    prog.slots_per_ctx = spec.fwd_slots
-    act = torch.empty(_num_tiles(P) * spec.act_atoms * ATOM_BYTES // 2, device=dev, dtype=torch.bfloat16) if save else None
+    extra = max([ref.natoms for ref in head_images.values()] + [0])
+    prog.slots_per_ctx = spec.fwd_slots + extra
+    in_refs = [None] * len(spec.in_atoms)
     col = 0
     for i, (src, w) in enumerate(zip(sources, spec.in_widths)):
         last = i == len(sources) - 1
-        if src.shape[1] != w:
-            raise _lib.NrcError(f"chain source {i} has width {src.shape[1]}, expected {w}")
-        _op(prog, kind=OP_LOAD, slot=0, ptr=ptrs.add(src), ld=_ld(src), col0=col, ncols=w,
-            npad=(spec.in_pad - col) if last else w)
+        if isinstance(src, ImgRef):
+            wpad = (spec.in_pad - col) if last else w
+            if col % 64 or src.natoms != len(_atoms_of(wpad)) or (not last and (col + w) % 64):
+                raise _lib.NrcError("image sources must cover whole atoms of the stack input")
+            _op(prog, kind=OP_LOADIMG, slot=col // 64, ptr=ptrs.add(src.img), col0=src.atom0, npad=src.natoms,
+                img_atoms=src.img_atoms)
+            for a in range(src.natoms):
+                in_refs[col // 64 + a] = (src.img, src.img_atoms, src.atom0 + a)
+        else:
+            if src.shape[1] != w:
+                raise _lib.NrcError(f"chain source {i} has width {src.shape[1]}, expected {w}")
+            _op(prog, kind=OP_LOAD, slot=0, ptr=ptrs.add(src), ld=_ld(src), col0=col, ncols=w,
+                npad=(spec.in_pad - col) if last else w)
         col += w
+    if P is None:
+        raise _lib.NrcError("run_forward needs the point count P when every source is an image")
+    act = new_image(P, spec.act_atoms, dev) if save else None
     if save:
-        _op(prog, kind=OP_SAVE, slot=0, ptr=ptrs.add(act), col0=0, npad=len(spec.in_atoms), img_atoms=spec.act_atoms)
+        a = 0
+        while a < len(in_refs):   # input atoms that came as fp32 rows are kept for the weight gradients
+            if in_refs[a] is not None:
+                a += 1
+                continue
+            a1 = a
+            while a1 < len(in_refs) and in_refs[a1] is None:
+                a1 += 1
+            _op(prog, kind=OP_SAVE, slot=a, ptr=ptrs.add(act), col0=a, npad=a1 - a, img_atoms=spec.act_atoms)
+            a = a1
     for li, (name, w, _) in enumerate(spec.hidden):
         atoms = [(slot, klen) for (_, _, klen, _, _, slot) in spec.x_atoms(spec.x_parts[li])]
-        for (nb, nc, first) in b.fwd_chunk[li]:
-            _op(prog, kind=OP_GEMM, n=nc, tmem_col=nb, w_chunk=first, atoms=atoms)
+        for (nb, nc, first_chunk) in b.fwd_chunk[li]:
+            _op(prog, kind=OP_GEMM, n=nc, tmem_col=nb, w_chunk=first_chunk, atoms=atoms)
         _op(prog, kind=OP_EPI, slot=spec.h_slot0, ptr=ptrs.add(params[name]["bias"]), ncols=w, npad=w, tmem_col=0,
             flags=EPI_RELU if spec.hidden_act[li] == "relu" else 0)
         if save:
@@ -382,20 +442,28 @@ def run_forward(spec, params, sources, packed, save=True):
         tcol = 0
         for g in range(g0, g1):
             grp = spec.heads[g]
-            buf = torch.empty((P, spec.head_pads[g]), device=dev, dtype=torch.float32)
+            want32 = head_fp32.get(g, True) or g not in head_images
+            buf = torch.empty((P, spec.head_pads[g]), device=dev, dtype=torch.float32) if want32 else None
             bias = torch.cat([params[name]["bias"] for name, _ in grp]) if len(grp) > 1 else params[grp[0][0]]["bias"]
-            _op(prog, kind=OP_EPI, slot=-1, ptr=ptrs.add(bias), ncols=spec.head_widths[g], npad=spec.head_pads[g],
-                tmem_col=tcol, out_ptr=ptrs.add(buf), ld=spec.head_pads[g], col0=0)
+            ref = head_images.get(g)
+            if ref is not None and ref.natoms != len(_atoms_of(spec.head_pads[g])):
+                raise _lib.NrcError("head image must hold the whole padded head group")
+            _op(prog, kind=OP_EPI, slot=spec.fwd_slots if ref is not None else -1, ptr=ptrs.add(bias),
+                ncols=spec.head_widths[g], npad=spec.head_pads[g], tmem_col=tcol, out_ptr=ptrs.add(buf),
+                ld=spec.head_pads[g], col0=0)
+            if ref is not None:
+                _op(prog, kind=OP_SAVE, slot=spec.fwd_slots, ptr=ptrs.add(ref.img), col0=ref.atom0, npad=ref.natoms,
+                    img_atoms=ref.img_atoms)
             tcol += spec.head_pads[g]
             bufs.append(buf)
             c = 0
             for name, w in grp:
-                outs.append(buf[:, c:c + w])
+                outs.append(buf[:, c:c + w] if buf is not None else None)
                 c += w
         g0 = g1
     arr, n = ptrs.array()
     _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
-    return bufs, outs, act
+    return bufs, outs, (ActImage(act, in_refs) if save else None)
 
 
 def run_density_query(spec, params, enc_desc, means, packed, head_bias, warp_c, density_bias, density, feat=None,
@@ -427,81 +495,151 @@ def run_density_query(spec, params, enc_desc, means, packed, head_bias, warp_c, 
 
 
 def run_backward_data(spec, params, g_heads, act, packed, P, d_src=None):
-    """Data-gradient pass.  g_heads: per head GROUP an fp32 [P, >= group width] view (rows contiguous).
-    d_src: None (no input gradient) or per source (fp32 [P, w_i] view, accumulate flag): written
-    (or accumulated into).  Returns the dY tile image for the weight gradients."""
+    """Data-gradient pass.  g_heads: per head GROUP an fp32 [P, >= group width] view (rows contiguous) or an ImgRef
+    holding the group's padded columns as bf16 atoms.  d_src: None (no input gradient) or per source one of
+    None / (fp32 [P, w_i] view, accumulate flag) / ImgRef (bf16 atoms; the source must start on a 64-column
+    boundary).  The gradient of the stack input is accumulated over the skip connections in tensor memory
+    (accumulator columns beside the working ones) and leaves the SM once.  Returns the DyImage for the weight
+    gradients."""
     if not spec.supports_backward:
         raise NotImplementedError("this stack is forward-only (hidden width > 128)")
     b = _built(spec)
-    dev = act.device
-    nt = _num_tiles(P)
-    dy = torch.empty(nt * spec.dy_atoms * ATOM_BYTES // 2, device=dev, dtype=torch.bfloat16)
+    act_img = act.img if isinstance(act, ActImage) else act
+    dev = act_img.device
+    dy = new_image(P, spec.dy_atoms, dev)
     ptrs = _Ptrs()
     prog = nrc_chain_program_t()
-    S = spec._bwd_slots()
-    prog.slots_per_ctx = S
     max_h = max([len(_atoms_of(w)) for _, w, _ in spec.hidden] + [0])
-    cur0, nxt0 = 0, S - max_h
+    head_atoms_n = sum(len(_atoms_of(p)) for p in spec.head_pads)
+    out_atoms = 0
+    if d_src is not None:
+        c = 0
+        for i, w in enumerate(spec.in_widths):
+            if isinstance(d_src[i], ImgRef):
+                last = i == len(spec.in_widths) - 1
+                wpad = (spec.in_pad - c) if last else w
+                if c % 64 or d_src[i].natoms != len(_atoms_of(wpad)):
+                    raise _lib.NrcError("image destinations must cover whole atoms of the stack input")
+                out_atoms = max(out_atoms, d_src[i].natoms)
+            c += w
+    n_extra = sum(len(_atoms_of(spec.head_pads[g])) for g, gb in enumerate(g_heads)
+                  if isinstance(gb, (list, tuple)) for _ in gb[1:])
+    head_atoms_n += n_extra
+    S = max(spec._bwd_slots() + n_extra, max(head_atoms_n, max_h) + out_atoms)
+    if S > 7:
+        raise ValueError("data-gradient program does not fit the shared-memory slots of one tile context")
+    prog.slots_per_ctx = S
+    cur0, nxt0 = 0, S - max(max_h, out_atoms)
     slot = 0
-    head_atoms = []
+    head_atoms, head_refs = [], []
+    extra_sets = []   # (head group, first slot): further images summed into the group's gradient (dX is linear in dY)
     for g, gbuf in enumerate(g_heads):
         hp = spec.head_pads[g]
-        _op(prog, kind=OP_LOAD, slot=slot, ptr=ptrs.add(gbuf), ld=_ld(gbuf), col0=0, ncols=spec.head_widths[g], npad=hp)
         na = len(_atoms_of(hp))
-        _op(prog, kind=OP_SAVE, slot=slot, ptr=ptrs.add(dy), col0=spec.dy_atom0_head(g), npad=na, img_atoms=spec.dy_atoms)
+        if isinstance(gbuf, (list, tuple)):
+            gbuf, more = gbuf[0], list(gbuf[1:])
+        else:
+            more = []
+        if isinstance(gbuf, ImgRef):
+            if gbuf.natoms != na:
+                raise _lib.NrcError("head-gradient image must hold the whole padded head group")
+            _op(prog, kind=OP_LOADIMG, slot=slot, ptr=ptrs.add(gbuf.img), col0=gbuf.atom0, npad=na, img_atoms=gbuf.img_atoms)
+            head_refs += [(gbuf.img, gbuf.img_atoms, gbuf.atom0 + a) for a in range(na)]
+            for ref in more:
+                extra_sets.append((g, ref))
+        else:
+            _op(prog, kind=OP_LOAD, slot=slot, ptr=ptrs.add(gbuf), ld=_ld(gbuf), col0=0, ncols=spec.head_widths[g], npad=hp)
+            _op(prog, kind=OP_SAVE, slot=slot, ptr=ptrs.add(dy), col0=spec.dy_atom0_head(g), npad=na, img_atoms=spec.dy_atoms)
+            head_refs += [None] * na
         for c, n in _atoms_of(hp):
             head_atoms.append((slot + c // 64, _pad(n, 16)))
         slot += na
-    written = [False] * len(spec.in_widths)
+    extra_gemms = []   # (first K atom inside the head layout, [(slot, klen)])
+    for g, ref in extra_sets:
+        hp = spec.head_pads[g]
+        na = len(_atoms_of(hp))
+        if ref.natoms != na:
+            raise _lib.NrcError("head-gradient image must hold the whole padded head group")
+        _op(prog, kind=OP_LOADIMG, slot=slot, ptr=ptrs.add(ref.img), col0=ref.atom0, npad=na, img_atoms=ref.img_atoms)
+        k0 = sum(len(_atoms_of(p)) for p in spec.head_pads[:g])
+        extra_gemms.append((k0, [(slot + c // 64, _pad(n, 16)) for c, n in _atoms_of(hp)]))
+        slot += na
     if d_src is not None:
         c = 0
         for w in spec.in_widths:
             if c % 16:
                 raise ValueError("input gradients need 16-aligned source offsets")
             c += w
+    # accumulator columns of the input gradient: beside the working columns [0, 128)
+    acc_in0 = 128 if spec.in_pad <= 128 else 256
+    in_started = [False]
 
-    def emit(parts_ops, a_atoms, mask_layer, out_slot0):
-        for kind in ("in", "h"):   # input part first: it only writes global memory
-            ops = [o for o in parts_ops if o[0] == kind]
-            if not ops or (kind == "in" and d_src is None):
-                continue
-            for (_, n0, npad, first) in ops:
-                _op(prog, kind=OP_GEMM, n=npad, tmem_col=n0, w_chunk=first, atoms=a_atoms)
-            if kind == "in":
-                c = 0
-                for i, w in enumerate(spec.in_widths):
-                    t, accumulate = d_src[i]
-                    if t is not None:
-                        _op(prog, kind=OP_EPI, slot=-1, ncols=w, npad=_pad(w, 16), tmem_col=c, out_ptr=ptrs.add(t),
-                            ld=_ld(t), col0=0, flags=EPI_OUT_ACCUMULATE if (accumulate or written[i]) else 0)
-                        written[i] = True
-                    c += w
-            else:
-                w = spec.hidden[mask_layer][1]
-                if spec.hidden_act[mask_layer] == "relu":
-                    _op(prog, kind=OP_EPI, slot=out_slot0, ncols=w, npad=w, tmem_col=0, mask_ptr=ptrs.add(act),
-                        mask_atom0=spec.act_atom0(mask_layer), img_atoms=spec.act_atoms)
-                else:
-                    _op(prog, kind=OP_EPI, slot=out_slot0, ncols=w, npad=w, tmem_col=0)
-                _op(prog, kind=OP_SAVE, slot=out_slot0, ptr=ptrs.add(dy), col0=spec.dy_atom0_hidden(mask_layer),
-                    npad=len(_atoms_of(w)), img_atoms=spec.dy_atoms)
+    def emit(parts_ops, a_atoms, mask_layer, out_slot0, extra=()):
+        """GEMMs of one layer's data gradient: the input part accumulates in its own tensor-memory columns, the
+        hidden part becomes the next dY (ReLU mask of the layer below applied by the epilogue).  extra: further
+        operand sets (first K atom, atoms) multiplied with the same weights and accumulated."""
+        if d_src is not None:
+            for (_, n0, npad, first) in [o for o in parts_ops if o[0] == "in"]:
+                _op(prog, kind=OP_GEMM, n=npad, tmem_col=acc_in0 + n0, w_chunk=first, atoms=a_atoms,
+                    flags=GEMM_ACCUMULATE if in_started[0] else 0)
+                for (k0, atoms) in extra:
+                    _op(prog, kind=OP_GEMM, n=npad, tmem_col=acc_in0 + n0, w_chunk=first + k0, atoms=atoms, flags=GEMM_ACCUMULATE)
+            if any(o[0] == "in" for o in parts_ops):
+                in_started[0] = True
+        ops = [o for o in parts_ops if o[0] == "h"]
+        if not ops:
+            return
+        for (_, n0, npad, first) in ops:
+            _op(prog, kind=OP_GEMM, n=npad, tmem_col=n0, w_chunk=first, atoms=a_atoms)
+            for (k0, atoms) in extra:
+                _op(prog, kind=OP_GEMM, n=npad, tmem_col=n0, w_chunk=first + k0, atoms=atoms, flags=GEMM_ACCUMULATE)
+        w = spec.hidden[mask_layer][1]
+        if spec.hidden_act[mask_layer] == "relu":
+            _op(prog, kind=OP_EPI, slot=out_slot0, ncols=w, npad=w, tmem_col=0, mask_ptr=ptrs.add(act_img),
+                mask_atom0=spec.act_atom0(mask_layer), img_atoms=spec.act_atoms)
+        else:
+            _op(prog, kind=OP_EPI, slot=out_slot0, ncols=w, npad=w, tmem_col=0)
+        _op(prog, kind=OP_SAVE, slot=out_slot0, ptr=ptrs.add(dy), col0=spec.dy_atom0_hidden(mask_layer),
+            npad=len(_atoms_of(w)), img_atoms=spec.dy_atoms)
 
     nh = len(spec.hidden)
-    emit(b.bwd_heads, head_atoms, nh - 1, nxt0)
+    emit(b.bwd_heads, head_atoms, nh - 1, nxt0, extra_gemms)
     cur0, nxt0 = nxt0, cur0
     for li in range(nh - 1, -1, -1):
         w = spec.hidden[li][1]
         a_atoms = [(cur0 + c // 64, _pad(n, 16)) for c, n in _atoms_of(w)]
         emit(b.bwd_hidden[li], a_atoms, li - 1, nxt0)
         cur0, nxt0 = nxt0, cur0
+    if d_src is not None and in_started[0]:
+        out0 = S - out_atoms
+        c = 0
+        for i, w in enumerate(spec.in_widths):
+            dst = d_src[i]
+            last = i == len(spec.in_widths) - 1
+            if isinstance(dst, ImgRef):
+                wpad = (spec.in_pad - c) if last else w
+                _op(prog, kind=OP_EPI, slot=out0, ncols=_pad(wpad, 16), npad=_pad(wpad, 16), tmem_col=acc_in0 + c)
+                _op(prog, kind=OP_SAVE, slot=out0, ptr=ptrs.add(dst.img), col0=dst.atom0, npad=dst.natoms,
+                    img_atoms=dst.img_atoms)
+            elif dst is not None and dst[0] is not None:
+                t, accumulate = dst
+                _op(prog, kind=OP_EPI, slot=-1, ncols=w, npad=_pad(w, 16), tmem_col=acc_in0 + c, out_ptr=ptrs.add(t),
+                    ld=_ld(t), col0=0, flags=EPI_OUT_ACCUMULATE if accumulate else 0)
+            c += w
     arr, n = ptrs.array()
     _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
-    return dy
+    return DyImage(dy, head_refs)
 
 
-def wgrad_layers(spec, act, dy, grad_sinks, wptrs):
-    """Weight-gradient descriptors of one stack; grad_sinks[name] = (g_kernel, g_bias) accumulated into."""
-    ia, idy = wptrs.add(act), wptrs.add(dy)
+def wgrad_layers(spec, act, dy, grad_sinks, wptrs, extra_head_dy=None):
+    """Weight-gradient descriptors of one stack; grad_sinks[name] = (g_kernel, g_bias) accumulated into.
+    act: ActImage, dy: DyImage.  extra_head_dy: {head group: [ImgRef, ...]} further dY images of a head group whose
+    upstream gradient arrives as a SUM of several images (each adds one more descriptor: dW is linear in dY)."""
+    act_img = act.img if isinstance(act, ActImage) else act
+    in_refs = act.in_refs if isinstance(act, ActImage) else [None] * len(spec.in_atoms)
+    dy_img = dy.img if isinstance(dy, DyImage) else dy
+    head_refs = dy.head_refs if isinstance(dy, DyImage) else None
+    ia, idy = wptrs.add(act_img), wptrs.add(dy_img)
     nh = len(spec.hidden)
     layers = []
 
@@ -511,8 +649,12 @@ def wgrad_layers(spec, act, dy, grad_sinks, wptrs):
             raise ValueError("layer input too wide for one weight-gradient pass")
         L.n_x_atoms = len(atoms)
         for i, (kind, c, _, valid, row, _) in enumerate(atoms):
-            L.x_ptr[i], L.x_img_atoms[i] = ia, spec.act_atoms
-            L.x_atom[i] = (spec.act_atom0(layer_index - 1) if kind == "h" else 0) + c // 64
+            ref = in_refs[c // 64] if kind == "in" else None
+            if ref is not None:
+                L.x_ptr[i], L.x_img_atoms[i], L.x_atom[i] = wptrs.add(ref[0]), ref[1], ref[2]
+            else:
+                L.x_ptr[i], L.x_img_atoms[i] = ia, spec.act_atoms
+                L.x_atom[i] = (spec.act_atom0(layer_index - 1) if kind == "h" else 0) + c // 64
             L.x_rows[i], L.w_row0[i] = valid, row
 
     for li, (name, w, _) in enumerate(spec.hidden):
@@ -523,17 +665,25 @@ def wgrad_layers(spec, act, dy, grad_sinks, wptrs):
         gk, gb = grad_sinks[name]
         L.seg_col0[0], L.seg_ncols[0], L.seg_w_ptr[0], L.seg_b_ptr[0] = 0, w, wptrs.add(gk), wptrs.add(gb)
         layers.append(L)
+    ha = 0
     for g, grp in enumerate(spec.heads):
-        L = nrc_wgrad_layer_t()
-        fill_x(L, spec.x_last, nh)
-        L.dy_ptr, L.dy_img_atoms, L.dy_atom0, L.n = idy, spec.dy_atoms, spec.dy_atom0_head(g), spec.head_pads[g]
-        L.n_seg = len(grp)
-        col = 0
-        for s, (name, w) in enumerate(grp):
-            gk, gb = grad_sinks[name]
-            L.seg_col0[s], L.seg_ncols[s], L.seg_w_ptr[s], L.seg_b_ptr[s] = col, w, wptrs.add(gk), wptrs.add(gb)
-            col += w
-        layers.append(L)
+        na = len(_atoms_of(spec.head_pads[g]))
+        ref = head_refs[ha] if head_refs is not None else None
+        srcs = [(idy, spec.dy_atoms, spec.dy_atom0_head(g))] if ref is None else [(wptrs.add(ref[0]), ref[1], ref[2])]
+        for extra in (extra_head_dy or {}).get(g, []):
+            srcs.append((wptrs.add(extra.img), extra.img_atoms, extra.atom0))
+        ha += na
+        for (p_dy, dy_atoms, dy_atom0) in srcs:
+            L = nrc_wgrad_layer_t()
+            fill_x(L, spec.x_last, nh)
+            L.dy_ptr, L.dy_img_atoms, L.dy_atom0, L.n = p_dy, dy_atoms, dy_atom0, spec.head_pads[g]
+            L.n_seg = len(grp)
+            col = 0
+            for s, (name, w) in enumerate(grp):
+                gk, gb = grad_sinks[name]
+                L.seg_col0[s], L.seg_ncols[s], L.seg_w_ptr[s], L.seg_b_ptr[s] = col, w, wptrs.add(gk), wptrs.add(gb)
+                col += w
+            layers.append(L)
     return layers
 
 
@@ -573,7 +723,7 @@ class _ChainFn(torch.autograd.Function):
         _, outs, act = run_forward(spec, params, sources, packed, save=need_grad)
         ctx.spec, ctx.names, ctx.n_src = spec, names, n_src
         ctx.P = sources[0].shape[0]
-        ctx.save_for_backward(act, packed, *flat)
+        ctx.save_for_backward(act.img if act is not None else None, packed, *flat)
         ctx.src_needs = [t.requires_grad for t in tensors[:n_src]]
         return tuple(o.contiguous() for o in outs)
 
@@ -581,6 +731,7 @@ class _ChainFn(torch.autograd.Function):
     def backward(ctx, *g_outs):
         spec, names, n_src = ctx.spec, ctx.names, ctx.n_src
         act, packed, *flat = ctx.saved_tensors
+        act = ActImage(act, [None] * len(spec.in_atoms))
         params = {name: {"kernel": flat[2 * i], "bias": flat[2 * i + 1]} for i, name in enumerate(names)}
         P = ctx.P
         dev = act.device

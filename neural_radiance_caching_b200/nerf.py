@@ -240,7 +240,7 @@ def shader_encode(shader, means, arena):
 
 
 def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, normals, arena, train, packed=None,
-                         encoded=None, env_stream=None):
+                         encoded=None, env_stream=None, want_bottleneck=True):
     """Forward schedule of the bf16 cache shader (no autograd): 1 weight pack, contract + appearance-grid
     encode, trunk stack, per-point `mid` stage, integrated-BRDF / EnvMap / SurfaceLightField stacks,
     per-point `out` stage.  `packed` / `encoded` may be supplied by a caller that produced them earlier on
@@ -256,25 +256,32 @@ def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, 
     feat = density_feature.reshape(P, 64).contiguous()
     nrm = normals.reshape(P, 3).contiguous()
     vd = viewdirs.reshape(-1, 3).contiguous()
-    (bott, heads), _, act_t = mlp_chain.run_forward(shader.trunk_chain, params[""], [feat, enc], views[0], save=train)
+    # Stack inputs travel as bf16 tile images in the chains' operand layout: the trunk's epilogue writes the bottleneck
+    # atoms, the mid stage the IDE / n.v atoms; the downstream chains bulk-copy them (no fp32 rows are re-read and
+    # converted, the 128-wide fp32 bottleneck is only written when the caller wants it).
+    Img = mlp_chain.ImgRef
+    img_in = mlp_chain.new_image(P, 4, dev)     # atoms 0-1 bottleneck, 2-3 IDE_5 (72 -> 80 columns)
+    img_aux = mlp_chain.new_image(P, 2, dev)    # atom 0: n.v (16 columns), atom 1: IDE_4 (38 -> 48 columns)
+    (bott, heads), _, act_t = mlp_chain.run_forward(shader.trunk_chain, params[""], [feat, enc], views[0], save=train,
+                                                    head_images={0: Img(img_in, 0, 2, 4)}, head_fp32={0: want_bottleneck})
     t5, t4 = _IdeTables.get(5), _IdeTables.get(4)
     rough = torch.empty((P,), device=dev, dtype=torch.float32)
-    dot = torch.empty((P, 1), device=dev, dtype=torch.float32)
     refdirs = torch.empty((P, 3), device=dev, dtype=torch.float32)
-    ide5 = torch.empty((P, 2 * t5.n_sh), device=dev, dtype=torch.float32)
-    ide4 = torch.empty((P, 2 * t4.n_sh), device=dev, dtype=torch.float32)
+    images = _lib.nrc_shader_images_t(img_in.data_ptr(), 4, 2, img_aux.data_ptr(), 2, 1, img_aux.data_ptr(), 2, 0)
     _lib.call("nrc_shader_mid_fwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
               _lib.ptr(heads), heads.shape[1], _lib.ptr(nrm), _lib.ptr(vd), P, spr, -1.0, _lib.ptr(rough),
-              _lib.ptr(dot), _lib.ptr(refdirs), _lib.ptr(ide5), _lib.ptr(ide4))
+              None, _lib.ptr(refdirs), None, None, C.byref(images))
+    env_src = [Img(img_aux, 1, 1, 2)]
     if env_stream is not None:
         env_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(env_stream):
-            (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], [ide4], views[3], save=False)
+            (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], env_src, views[3], save=False, P=P)
     else:
-        (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], [ide4], views[3], save=False)
-    (fbuf,), _, act_b = mlp_chain.run_forward(shader.brdf_chain, params[""], [bott, dot], views[1], save=train)
-    (sbuf,), _, act_s = mlp_chain.run_forward(shader.surface_lf.chain, params["SurfaceLightField"], [bott, ide5],
-                                              views[2], save=train)
+        (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], env_src, views[3], save=False, P=P)
+    (fbuf,), _, act_b = mlp_chain.run_forward(shader.brdf_chain, params[""], [Img(img_in, 0, 2, 4), Img(img_aux, 0, 1, 2)],
+                                              views[1], save=train, P=P)
+    (sbuf,), _, act_s = mlp_chain.run_forward(shader.surface_lf.chain, params["SurfaceLightField"],
+                                              [Img(img_in, 0, 2, 4), Img(img_in, 2, 2, 4)], views[2], save=train, P=P)
     if env_stream is not None:
         torch.cuda.current_stream().wait_stream(env_stream)
     rgb = torch.empty((P, 3), device=dev, dtype=torch.float32)
@@ -284,7 +291,8 @@ def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, 
               _lib.ptr(sbuf), sbuf.shape[1], _lib.ptr(ebuf), ebuf.shape[1], P, float(shader.rgb_max), -2.0, lb,
               float(np.log(3.0)), _lib.ptr(rgb), _lib.ptr(extras))
     outs = (rgb.reshape(lead + (3,)), extras.reshape(lead + (22,)), rough.reshape(lead + (1,)),
-            bott.reshape(lead + (128,)), refdirs.reshape(lead + (3,)), enc.reshape(lead + (-1,)))
+            bott.reshape(lead + (128,)) if bott is not None else None, refdirs.reshape(lead + (3,)),
+            enc.reshape(lead + (-1,)))
     saved = (z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed)
     return outs, saved, (lead, P, spr)
 
@@ -309,19 +317,23 @@ def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_a
     _lib.call("nrc_shader_out_bwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
               _lib.ptr(sbuf), sbuf.shape[1], P, float(shader.rgb_max), -2.0, lb, float(np.log(3.0)), _lib.ptr(g2),
               _lib.ptr(g_heads), 16, _lib.ptr(g_f), 16, _lib.ptr(g_s), 16)
-    d_bott, g_ide5, g_dot = new(P, 128), new(P, 72), new(P, 1)
+    # d(bottleneck) leaves the SurfaceLightField and integrated-BRDF gradient chains as bf16 atoms (two images; the
+    # trunk's gradient chain takes their SUM as its upstream gradient: dX and dW are linear in dY)
+    Img = mlp_chain.ImgRef
+    img_db = mlp_chain.new_image(P, 4, dev)
+    g_ide5, g_dot = new(P, 72), new(P, 1)
     dy_s = mlp_chain.run_backward_data(shader.surface_lf.chain, params["SurfaceLightField"], [g_s], act_s, views[2], P,
-                                       [(d_bott, False), (g_ide5, False)])
+                                       [Img(img_db, 0, 2, 4), (g_ide5, False)])
     dy_b = mlp_chain.run_backward_data(shader.brdf_chain, params[""], [g_f], act_b, views[1], P,
-                                       [(d_bott, True), (g_dot, False)])
+                                       [Img(img_db, 2, 2, 4), (g_dot, False)])
     g_nrm = new(P, 3)
     t5, t4 = _IdeTables.get(5), _IdeTables.get(4)
     _lib.call("nrc_shader_mid_bwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
               _lib.ptr(heads), heads.shape[1], _lib.ptr(nrm), _lib.ptr(vd), P, spr, -1.0, _lib.ptr(g_dot), 1,
               _lib.ptr(g_ide5), 72, None, 0, _lib.ptr(g_heads), 16, _lib.ptr(g_nrm))
     d_feat, d_enc = new(P, 64), new(P, 32)
-    dy_t = mlp_chain.run_backward_data(shader.trunk_chain, params[""], [d_bott, g_heads], act_t, views[0], P,
-                                       [(d_feat, False), (d_enc, False)])
+    dy_t = mlp_chain.run_backward_data(shader.trunk_chain, params[""], [[Img(img_db, 0, 2, 4), Img(img_db, 2, 2, 4)], g_heads],
+                                       act_t, views[0], P, [(d_feat, False), (d_enc, False)])
     named = {(scope, name): (flat[2 * i], flat[2 * i + 1]) for i, (scope, name) in enumerate(names)}
     sinks, sunk = mlp_chain.resolve_sinks({k: v for k, v in named.items() if k[0] != "EnvMap"})
     wptrs = mlp_chain._Ptrs()
@@ -329,7 +341,8 @@ def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_a
     for spec, scope, act, dy in ((shader.surface_lf.chain, "SurfaceLightField", act_s, dy_s),
                                  (shader.brdf_chain, "", act_b, dy_b), (shader.trunk_chain, "", act_t, dy_t)):
         local = {n: sinks[(sc, n)] for (sc, n) in sinks if sc == scope}
-        layers += mlp_chain.wgrad_layers(spec, act, dy, local, wptrs)
+        extra = {0: [mlp_chain.ImgRef(img_db, 2, 2, 4)]} if spec is shader.trunk_chain else None
+        layers += mlp_chain.wgrad_layers(spec, act, dy, local, wptrs, extra_head_dy=extra)
     mlp_chain.wgrad_launch(layers, wptrs, P)
     g_arena = None
     if need_arena_grad:
@@ -353,15 +366,22 @@ class _ShaderBf16Fn(torch.autograd.Function):
         outs, saved, meta = shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, normals, arena,
                                                  train)
         ctx.shader, ctx.names, ctx.meta = shader, names, meta
-        ctx.save_for_backward(*saved, arena, *flat)
-        ctx.mark_non_differentiable(*outs[1:])
+        # the saved tuple mixes tensors with ActImage records (tile images + where each input atom lives): tensors go
+        # through save_for_backward (version checks), the records stay on ctx
+        ctx.saved_layout = [isinstance(t, torch.Tensor) or t is None for t in saved]
+        ctx.saved_objs = [None if is_t else t for t, is_t in zip(saved, ctx.saved_layout)]
+        ctx.save_for_backward(*[t for t, is_t in zip(saved, ctx.saved_layout) if is_t], arena, *flat)
+        ctx.mark_non_differentiable(*[o for o in outs[1:] if o is not None])
         return outs
 
     @staticmethod
     def backward(ctx, g_rgb, *_unused):
         shader, names = ctx.shader, ctx.names
         lead = ctx.meta[0]
-        saved, arena, flat = ctx.saved_tensors[:10], ctx.saved_tensors[10], ctx.saved_tensors[11:]
+        n_t = sum(ctx.saved_layout)
+        tensors = list(ctx.saved_tensors[:n_t])
+        saved = tuple(tensors.pop(0) if is_t else obj for is_t, obj in zip(ctx.saved_layout, ctx.saved_objs))
+        arena, flat = ctx.saved_tensors[n_t], ctx.saved_tensors[n_t + 1:]
         d_feat, g_nrm, g_arena, sinks, sunk = shader_fused_backward(
             shader, names, flat, saved, ctx.meta, arena, g_rgb, need_arena_grad=ctx.needs_input_grad[6])
         grads = [None, None, None, None, d_feat.reshape(lead + (64,)), g_nrm.reshape(lead + (3,)), g_arena]

@@ -198,9 +198,26 @@ def test_shader_point_stages(cuda_device):
     o_rough, o_dot, o_ref, o_i5, o_i4 = new(P), new(P, 1), new(P, 3), new(P, 72), new(P, 38)
     _lib.call("nrc_shader_mid_fwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
               _lib.ptr(hd), 16, _lib.ptr(nd), _lib.ptr(vd), P, n, -1.0, _lib.ptr(o_rough), _lib.ptr(o_dot),
-              _lib.ptr(o_ref), _lib.ptr(o_i5), _lib.ptr(o_i4))
+              _lib.ptr(o_ref), _lib.ptr(o_i5), _lib.ptr(o_i4), None)
     assert rel_err(o_rough, rough[:, 0]) <= 1e-5 and rel_err(o_dot, dot) <= 1e-5 and rel_err(o_ref, ref) <= 1e-5
     assert rel_err(o_i5, i5) <= 1e-5 and rel_err(o_i4, i4) <= 1e-5
+    # the same stage writing bf16 operand images for the chains (fp32 outputs omitted): rows must be the bf16
+    # rounding of the fp32 outputs, zero padded to the K extent
+    from neural_radiance_caching_b200 import mlp_chain as mc
+    from tests.util import decode_image
+    img_a, img_b = mc.new_image(P, 4, dev), mc.new_image(P, 2, dev)
+    img_a.zero_(); img_b.fill_(7.0)
+    images = _lib.nrc_shader_images_t(img_a.data_ptr(), 4, 2, img_b.data_ptr(), 2, 1, img_b.data_ptr(), 2, 0)
+    import ctypes
+    _lib.call("nrc_shader_mid_fwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
+              _lib.ptr(hd), 16, _lib.ptr(nd), _lib.ptr(vd), P, n, -1.0, None, None, None, None, None, ctypes.byref(images))
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    got5 = decode_image(img_a, 4, 2, 80, P)
+    assert torch.equal(got5[:, :72], bf(o_i5).cpu()) and float(got5[:, 72:].abs().max()) == 0.0
+    got4 = decode_image(img_b, 2, 1, 48, P)
+    assert torch.equal(got4[:, :38], bf(o_i4).cpu()) and float(got4[:, 38:].abs().max()) == 0.0
+    gotd = decode_image(img_b, 2, 0, 16, P)
+    assert torch.equal(gotd[:, :1], bf(o_dot).cpu()) and float(gotd[:, 1:].abs().max()) == 0.0
     gh, gn = torch.zeros((P, 16), device=dev), new(P, 3)
     gd_d, g5_d, g4_d = d(g_dot), d(g_i5), d(g_i4)   # keep the device copies alive across the launch
     _lib.call("nrc_shader_mid_bwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,

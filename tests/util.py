@@ -68,3 +68,19 @@ def dense_params(n_in, n_out, salt):
     """Closed-form Dense kernel [in,out] / bias [out] of tests/golden/make_reference_vectors.py (kept in step with it)."""
     k = level_table((n_in, n_out), salt) * np.float32(100.0 * np.sqrt(6.0 / n_in))
     return k.astype(np.float32), (level_table((n_out,), salt + 50) * np.float32(10.0)).astype(np.float32)
+
+
+def decode_image(img, img_atoms, atom0, ncols, P):
+    """Columns [0, ncols) of the atoms starting at `atom0` of a bf16 tile image [tiles][img_atoms][16 KB]
+    (neural_radiance_caching_b200/csrc/tc05.cuh: 128 rows x 64 bf16 per atom, row r at (r/8)*1024 + (r%8)*128 bytes,
+    16-byte chunks XOR-swizzled with r%8) as an fp32 [P, ncols] CPU tensor."""
+    import torch
+    flat = img.detach().cpu().view(torch.int16).reshape(-1)
+    p = torch.arange(P).reshape(-1, 1)
+    c = torch.arange(ncols).reshape(1, -1)
+    tile, r = p // 128, p % 128
+    atom = atom0 + c // 64
+    chunk = (c % 64) // 8
+    byte = (tile * img_atoms + atom) * 16384 + (r // 8) * 1024 + (r % 8) * 128 + ((chunk ^ (r % 8)) << 4) + (c % 8) * 2
+    vals = flat[(byte // 2).reshape(-1)].reshape(P, ncols)
+    return vals.view(torch.bfloat16).to(torch.float32)

@@ -14,6 +14,7 @@ from tests.util import gen, f32
 name = sys.argv[1] if len(sys.argv) > 1 else "slf"
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 524288
 mode = sys.argv[3] if len(sys.argv) > 3 else "fwd"
+use_img = len(sys.argv) > 4 and sys.argv[4] == "img"   # sources / destinations as bf16 tile images
 dev = torch.device("cuda:0")
 g = gen(1)
 spec = mc.ChainSpec(**T.SPECS[name])
@@ -28,10 +29,27 @@ def spy(fn, *a):
     return orig(fn, *a)
 mc._lib.call = spy
 _lib.call = spy
-bufs, outs, act = mc.run_forward(spec, p, srcs, packed, save=(mode != "fwd"))
+if use_img:
+    n_in = len(spec.in_atoms)
+    img = mc.new_image(P, n_in, dev)
+    img.copy_(torch.randn(img.shape, device=dev).to(torch.bfloat16))
+    fsrcs, a0 = [], 0
+    col = 0
+    for i, w in enumerate(spec.in_widths):
+        wpad = (spec.in_pad - col) if i == len(spec.in_widths) - 1 else w
+        na = len(mc._atoms_of(wpad))
+        fsrcs.append(mc.ImgRef(img, a0, na, n_in))
+        a0 += na
+        col += w
+else:
+    fsrcs = srcs
+bufs, outs, act = mc.run_forward(spec, p, fsrcs, packed, save=(mode != "fwd"), P=P)
 if mode != "fwd":
     gh = [torch.randn_like(b) for b in bufs]
     d_src = [(torch.empty((P, w), device=dev), False) for w in spec.in_widths]
+    if use_img:
+        dimg = mc.new_image(P, n_in, dev)
+        d_src[0] = mc.ImgRef(dimg, 0, fsrcs[0].natoms, n_in)
     progs.clear()
     mc.run_backward_data(spec, p, gh, act, packed, P, d_src)
 torch.cuda.synchronize()
@@ -41,7 +59,7 @@ lib.nrc_chain_trace_dump.argtypes = [C.POINTER(C.c_longlong)]
 buf = np.zeros((2, 48, 32), dtype=np.int64)
 rc = lib.nrc_chain_trace_dump(buf.ctypes.data_as(C.POINTER(C.c_longlong)))
 assert rc == 0
-kinds = {0: "LOAD", 1: "GEMM", 2: "EPI", 3: "SAVE", 4: "GATH"}
+kinds = {0: "LOAD", 1: "GEMM", 2: "EPI", 3: "SAVE", 4: "GATH", 5: "LIMG"}
 ops = [(kinds[prog.ops[i].kind], prog.ops[i].n if prog.ops[i].kind == 1 else prog.ops[i].npad) for i in range(prog.num_ops)]
 print("ops:", ops)
 t00 = buf[0, 0, 31]
