@@ -334,7 +334,8 @@ typedef struct {
                       /* SAVE: number of atoms                                                     */
   int32_t tmem_col;   /* GEMM/EPI: first accumulator column (0..255 per context; up to 511 when the */
                       /* program runs with one tile context per CTA: CTA-pair kernel only)          */
-  int32_t n;          /* GEMM: N (x16, <= 128)                                                     */
+  int32_t n;          /* GEMM: N (x16, <= 128).  EPI with out_ptr: staging slot + 1 (0 = direct stores): the
+                       * fp32 rows leave through that free slot as coalesced 16-byte stores              */
   int32_t flags;      /* NRC_GEMM_* / NRC_EPI_*                                                    */
   int32_t out_ptr;    /* EPI: fp32 output matrix or -1                                             */
   int32_t mask_ptr;   /* EPI: tile image of the forward activation; result zeroed where it is <= 0 */

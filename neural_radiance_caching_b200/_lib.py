@@ -11,7 +11,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnrc_b200.so")
+LIB_PATH = os.environ.get("NRC_LIB_PATH") or os.path.join(HERE, "libnrc_b200.so")
 NRC_MAX_LEVELS = 16
 
 

@@ -14,7 +14,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libnrc_b200.so")
+# NRC_LIB_PATH: an alternative library file (debug / trace builds beside the product build)
+LIB = os.environ.get("NRC_LIB_PATH") or os.path.join(HERE, "libnrc_b200.so")
+OBJ_DIR = os.path.join(HERE, "build" if not os.environ.get("NRC_LIB_PATH") else "build_alt")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -71,9 +73,9 @@ def build(force=False, verbose=False):
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc_path(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", src, "-o", obj]
         if os.path.basename(src) == "encode.cu":   # exports nrc_build_digest()
             cmd.insert(1, f'-DNRC_BUILD_DIGEST="{digest}"')

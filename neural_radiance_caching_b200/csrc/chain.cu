@@ -74,7 +74,10 @@ __device__ long long g_chain_trace[2][kTraceTiles][kTraceOps];
 __device__ long long g_chain_marks[16];
 __device__ long long g_chain_mma[kTraceTiles][8][2];   // v2: UMMA issuer of CTA 0, per tile and GEMM group: operands ready, issued
 #define TRACE_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 64) g_chain_marks[i] = clock64(); } while (0)
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TRACE_NS(i) do { if (blockIdx.x == 0 && threadIdx.x == 64) g_chain_marks[i] = global_ns(); } while (0)
 #else
+#define TRACE_NS(i) do {} while (0)
 #define TRACE_MARK(i) do {} while (0)
 #endif
 
@@ -587,9 +590,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 // Fast epilogue of the common case - the accumulator becomes the next layer's bf16 operand and nothing else: TMEM ->
 // (+ staged bias) -> bf16 pairs -> ReLU / ReLU mask applied on the PACKED pairs (max(.,0) commutes with the rounding;
 // the mask is an AND) -> two 16-byte shared-memory stores per 16 columns.  ~45 instructions per chunk instead of ~80.
-template <bool BIAS, bool RELU, bool MASK>
-__device__ __forceinline__ void epi_slot_fast(uint32_t taddr, const float* bias_s, uint32_t slot0_addr, int r, int npad,
+template <bool MASK>
+__device__ __forceinline__ void epi_slot_fast(uint32_t taddr, const float* bias_s, bool relu, uint32_t slot0_addr, int r, int npad,
                                               int part, int nparts, const uint8_t* mask_tile, int mask_atom0) {
+  // (two chunks per tensor-memory round trip were measured: the second 16-register buffer spills at the 96-register
+  // cap of 18 warps and the SurfaceLightField forward went from 34.6 to 49 us)
+  const bool has_bias = bias_s != nullptr;
   const uint32_t row_off = static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128);
   const uint32_t rx = static_cast<uint32_t>(r & 7);
   const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
@@ -605,14 +611,6 @@ __device__ __forceinline__ void epi_slot_fast(uint32_t taddr, const float* bias_
       mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
       mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
     }
-    float b[16];
-    if (BIAS) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 t = *(reinterpret_cast<const float4*>(bias_s + j0) + q);
-        b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
-      }
-    }
     const uint32_t c8 = static_cast<uint32_t>((j0 & 63) >> 3);
     const uint32_t d = slot0_addr + static_cast<uint32_t>(j0 >> 6) * kAtomBytes + row_off;
     tmem_ld_wait();
@@ -620,9 +618,12 @@ __device__ __forceinline__ void epi_slot_fast(uint32_t taddr, const float* bias_
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float x0 = __uint_as_float(v[2 * e]), x1 = __uint_as_float(v[2 * e + 1]);
-      if (BIAS) { x0 += b[2 * e]; x1 += b[2 * e + 1]; }
+      if (has_bias) {
+        const float2 bb = *reinterpret_cast<const float2*>(bias_s + j0 + 2 * e);
+        x0 += bb.x; x1 += bb.y;
+      }
       __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-      if (RELU) h = __hmax2(h, zero2);
+      if (relu) h = __hmax2(h, zero2);
       uint32_t w = *reinterpret_cast<uint32_t*>(&h);
       if (MASK) {
         const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&mw[e]);
@@ -634,6 +635,75 @@ __device__ __forceinline__ void epi_slot_fast(uint32_t taddr, const float* bias_
                  "r"(o[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + (((c8 + 1) ^ rx) << 4)), "r"(o[4]), "r"(o[5]),
                  "r"(o[6]), "r"(o[7]) : "memory");
+  }
+}
+
+// Epilogue with an fp32 ROW output (head results, input gradients) staged through a free shared-memory slot: a thread
+// owns one tile row in tensor memory, so direct stores put 32 different 128-byte lines behind every store instruction
+// (measured ~4 cycles per 16 bytes per SM: 5-9.5 k cycles for a 72-column gradient).  Here 32 columns at a time go
+// TMEM -> registers -> (+bias, ReLU) -> an XOR-swizzled [128 rows][32 floats] staging tile -> coalesced 16-byte
+// stores (eight consecutive lanes write 128 contiguous bytes of one output row).  Optionally the same values are also
+// written as bf16 into the destination atom slots.
+__device__ __forceinline__ void epi_staged(uint32_t taddr, const float* bias_s, bool relu, uint32_t stage_addr, int r, int part,
+                                           int ncols, int npad, float* out, int64_t row0, int64_t num_rows, int ld,
+                                           bool accum, bool has_slot, uint32_t slot0_addr, int bar_id, int nthreads,
+                                           int tid) {
+  const uint32_t rx = static_cast<uint32_t>(r & 7);
+  const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (int g0 = 0; g0 < npad; g0 += 32) {
+    const int j0 = g0 + 16 * part;
+    if (part < 2 && j0 < npad) {
+      uint32_t v[16];
+      tmem_ld16(taddr + j0, v);
+      tmem_ld_wait();
+      float x[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float t = __uint_as_float(v[e]);
+        if (bias_s) t += bias_s[j0 + e];
+        if (relu) t = fmaxf(t, 0.f);
+        x[e] = t;
+      }
+      const uint32_t srow = stage_addr + static_cast<uint32_t>(r) * 128u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t c = static_cast<uint32_t>(4 * part + q);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((c ^ rx) << 4)), "f"(x[4 * q]), "f"(x[4 * q + 1]),
+                     "f"(x[4 * q + 2]), "f"(x[4 * q + 3]) : "memory");
+      }
+      if (has_slot) {
+        const uint32_t row_off = static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128);
+        const uint32_t c8 = static_cast<uint32_t>((j0 & 63) >> 3);
+        const uint32_t d = slot0_addr + static_cast<uint32_t>(j0 >> 6) * kAtomBytes + row_off;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + ((c8 ^ rx) << 4)), "r"(pack2_bf16(x[0], x[1])),
+                     "r"(pack2_bf16(x[2], x[3])), "r"(pack2_bf16(x[4], x[5])), "r"(pack2_bf16(x[6], x[7])) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + (((c8 + 1) ^ rx) << 4)), "r"(pack2_bf16(x[8], x[9])),
+                     "r"(pack2_bf16(x[10], x[11])), "r"(pack2_bf16(x[12], x[13])), "r"(pack2_bf16(x[14], x[15])) : "memory");
+      }
+    }
+    named_barrier_sync(bar_id, nthreads);
+    for (int piece = tid; piece < 1024; piece += nthreads) {
+      const int row = piece >> 3, c = piece & 7;
+      const int col = g0 + 4 * c;
+      if (col >= ncols || row0 + row >= num_rows) continue;
+      float4 w;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
+                   : "r"(stage_addr + static_cast<uint32_t>(row) * 128u + ((static_cast<uint32_t>(c) ^ static_cast<uint32_t>(row & 7)) << 4)));
+      float* o = out + (row0 + row) * ld + col;
+      if (vec && col + 4 <= ncols) {
+        if (accum) {
+          const float4 old = *reinterpret_cast<const float4*>(o);
+          w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+        }
+        *reinterpret_cast<float4*>(o) = w;
+      } else {
+        const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col + e < ncols) o[e] = accum ? o[e] + ww[e] : ww[e];
+      }
+    }
+    if (g0 + 32 < npad) named_barrier_sync(bar_id, nthreads);   // the staging tile is rewritten by the next round
   }
 }
 
@@ -650,28 +720,46 @@ __device__ __forceinline__ void epi_slot_fast(uint32_t taddr, const float* bias_
 // Programs, weight images, tile images and the op semantics are those of the v1 kernel (a 256-row pair tile is
 // the two consecutive 128-row tiles 2t and 2t+1 of every tile image).
 constexpr int kTail2Bytes = 6144;
-constexpr int kMaxMma = 96;   // UMMA instructions of one program (precomputed descriptor list in shared memory)
+constexpr int kMaxMma = 96;     // UMMA instructions of one program (precomputed descriptor list in shared memory)
+constexpr int kMaxWcopy = 48;   // bulk copies that make a program's weights resident (one per K atom of every GEMM)
+constexpr int kMaxBias = 12;    // epilogue biases staged in shared memory
+
+// Everything the kernel needs about the program, RESOLVED ON THE HOST (pointers, bias offsets, the UMMA descriptor list,
+// the list of weight copies) and copied from the parameter space to shared memory with one coalesced pass.  Decoding the
+// program in the kernel cost 4-10 us per launch (thread-indexed reads of the parameter space serialise; measured with
+// the trace build: `decode` + `prologue` marks of tools/trace_chain.py), more than the tile work of the small stacks.
+struct __align__(16) Chain2Plan {
+  DevOp ops[NRC_CHAIN_MAX_OPS];
+  uint4 mma[kMaxMma];        // x: A descriptor low word, address relative to the CTA's dynamic shared memory (context 0);
+                             // y: B descriptor low word (same); z: accumulator column | accumulate << 31; w: idesc
+  uint4 wcopy[kMaxWcopy];    // x: destination byte offset in the resident region, y: source byte offset inside the packed
+                             // weights of CTA rank 0, z: bytes, w: extra source offset of CTA rank 1
+  uint4 bias[kMaxBias];      // x, y: source pointer (lo, hi), z: valid floats | padded floats << 16, w: destination float offset
+  int32_t n_ops, n_mma, n_wcopy, n_bias;
+};
 struct Chain2Params {
-  nrc_chain_program_t prog;
-  void* ptrs[NRC_CHAIN_MAX_PTRS];
+  Chain2Plan plan;
   const uint8_t* weights;
   int64_t num_rows;
   int32_t num_tiles;     // 128-row tiles
   int32_t num_ptiles;    // 256-row pair tiles
   int32_t w_bytes;       // resident weight bytes per CTA (multiple of 1024)
-  int32_t w_off[NRC_CHAIN_MAX_OPS];   // GEMM ops: byte offset of the op's first K atom inside the resident region
+  int32_t slots_per_ctx;
 };
+static_assert(sizeof(Chain2Plan) % 16 == 0, "plan is copied as 16-byte words");
 
 template <int NCTX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1)
 chain2_kernel(const __grid_constant__ Chain2Params p) {
   // dynamic shared memory: [resident weights][NCTX * S slot atoms][tail: mbarriers, TMEM base, program, staged biases]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TRACE_NS(14);
+  TRACE_MARK(8);
   constexpr int kThreads = kChainThreads;
   constexpr int kCtxT = 2 * kCtxThreads / NCTX;   // loader / epilogue threads per tile context: 16 warps (one context) or 8
   constexpr int kParts = kCtxT / 128;             // warps per TMEM lane quadrant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = p.prog.slots_per_ctx, nops = p.prog.num_ops;
+  const int S = p.slots_per_ctx, nops = p.plan.n_ops;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const uint32_t base = smem_u32(smem_raw);
@@ -684,7 +772,6 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
   DevOp* sops = reinterpret_cast<DevOp*>(tail + 144);
   uint4* smma = reinterpret_cast<uint4*>(tail + 144 + sizeof(DevOp) * NRC_CHAIN_MAX_OPS);
   float* sbias = reinterpret_cast<float*>(tail + 144 + sizeof(DevOp) * NRC_CHAIN_MAX_OPS + sizeof(uint4) * kMaxMma);
-  const int bias_cap = (kTail2Bytes - 144 - static_cast<int>(sizeof(DevOp)) * NRC_CHAIN_MAX_OPS - static_cast<int>(sizeof(uint4)) * kMaxMma) / 4;
   auto slot_addr = [&](int ctx, int s) { return slot_base + static_cast<uint32_t>(ctx * S + s) * kAtomBytes; };
   // barriers: 0 weights resident, 2+c operands of context c ready (count 2: one arrival per CTA, used in the
   // issuing CTA only), 4+c accumulator of context c ready (multicast commit)
@@ -694,95 +781,85 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
   auto acc_ready = [&](int c) { return bar0 + 8u * (4 + c); };
   auto img_ready = [&](int c) { return bar0 + 8u * (6 + c); };   // LOADIMG bulk copies of context c landed
 
-  if (threadIdx.x == 0) {
-    mbar_init(w_ready, 1);
-    for (int c = 0; c < 2; ++c) {
-      mbar_init(a_ready(c), 2);
-      mbar_init(acc_ready(c), 1);
-      mbar_init(img_ready(c), 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc2(smem_u32(&tmem_base_s), 512);
-  if (threadIdx.x < nops) {
-    const nrc_chain_op_t& o = p.prog.ops[threadIdx.x];
-    DevOp d;
-    d.kind = static_cast<int8_t>(o.kind); d.slot = static_cast<int8_t>(o.slot);
-    d.flags = static_cast<uint8_t>(o.flags); d.n_atoms = static_cast<uint8_t>(o.n_atoms);
-    d.ncols = static_cast<int16_t>(o.ncols); d.npad = static_cast<int16_t>(o.npad);
-    d.tmem_col = static_cast<int16_t>(o.tmem_col); d.n = static_cast<int16_t>(o.n);
-    d.ld = o.ld;
-    d.col0 = static_cast<int16_t>(o.col0); d.mask_atom0 = static_cast<int16_t>(o.mask_atom0);
-    d.img_atoms = static_cast<int16_t>(o.img_atoms);
-    d.w_chunk = o.w_chunk;
-    d.fparam = o.fparam;
-    d.ptr = o.ptr >= 0 ? p.ptrs[o.ptr] : nullptr;
-    d.out = o.out_ptr >= 0 ? p.ptrs[o.out_ptr] : nullptr;
-    d.mask = o.mask_ptr >= 0 ? p.ptrs[o.mask_ptr] : nullptr;
-#pragma unroll
-    for (int a = 0; a < NRC_CHAIN_MAX_ATOMS; ++a) d.a_src[a] = static_cast<uint8_t>((o.a_slot[a] & 15) | ((o.a_klen[a] >> 4) << 4));
-    int cur = 0, off = -1;
-    for (int k = 0; k <= static_cast<int>(threadIdx.x); ++k) {
-      const nrc_chain_op_t& e = p.prog.ops[k];
-      if (e.kind != NRC_OP_EPI || e.ptr < 0 || e.mask_ptr >= 0) continue;
-      if (cur + e.npad > bias_cap) break;
-      if (k == static_cast<int>(threadIdx.x)) off = cur;
-      cur += e.npad;
-    }
-    d.bias_off = static_cast<int16_t>(off);
-    if (o.kind == NRC_OP_GEMM) {
-      // this op's UMMA instructions as ready-made descriptor words (context 0; the issuer adds the context's slot
-      // offset): the issuing thread then spends a handful of instructions per UMMA instead of re-deriving
-      // everything from the program (measured: ~150 cycles per UMMA, more than twice its execution time)
-      int first = 0;
-      for (int k = 0; k < static_cast<int>(threadIdx.x); ++k) {
-        const nrc_chain_op_t& e = p.prog.ops[k];
-        if (e.kind != NRC_OP_GEMM) continue;
-        for (int a = 0; a < e.n_atoms; ++a) first += e.a_klen[a] >> 4;
+  // Prologue, every role in parallel: warp 0 allocates tensor memory, warp 1 initialises the tile barriers, warp 2 arms
+  // the weight barrier and issues the bulk copies that make this CTA's half of every weight atom resident (rows
+  // [rank n/2, (rank+1) n/2) of a K-major chunk are the contiguous bytes [rank n/2 * 128, ...) of the swizzled atom),
+  // warps 3-6 stage the epilogue biases, the rest copy the program + UMMA list out of the parameter space with
+  // warp-uniform (replay-free) constant loads.
+  if (warp == 0) {
+    tmem_alloc2(smem_u32(&tmem_base_s), 512);
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int c = 0; c < 2; ++c) {
+        mbar_init(a_ready(c), 2);
+        mbar_init(acc_ready(c), 1);
+        mbar_init(img_ready(c), 1);
       }
-      int cnt = 0;
-      const uint32_t idesc = make_idesc(256, o.n, 0, 0);
-      const uint32_t half_bytes = static_cast<uint32_t>(o.n) * 64u;
-      for (int a = 0; a < o.n_atoms; ++a) {
-        const uint32_t a_addr = slot_base + static_cast<uint32_t>(o.a_slot[a]) * kAtomBytes;
-        const int32_t woff = p.w_off[threadIdx.x] >= 0 ? p.w_off[threadIdx.x] : -(p.w_off[threadIdx.x] + 1);
-        const uint32_t b_addr = w_base + static_cast<uint32_t>(woff) + static_cast<uint32_t>(a) * half_bytes;
-        for (int k = 0; k < (o.a_klen[a] >> 4); ++k) {
-          const uint32_t acc = ((o.flags & NRC_GEMM_ACCUMULATE) || a > 0 || k > 0) ? 0x80000000u : 0u;
-          if (first + cnt < kMaxMma)
-            smma[first + cnt] = make_uint4(((a_addr + 32u * k) >> 4) | (1u << 16), ((b_addr + 32u * k) >> 4) | (1u << 16),
-                                           static_cast<uint32_t>(o.tmem_col) | acc, idesc);
-          ++cnt;
+      fence_barrier_init();
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      mbar_init(w_ready, 1);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(w_ready, static_cast<uint32_t>(p.w_bytes));
+    }
+    __syncwarp();
+    for (int i = lane; i < p.plan.n_wcopy; i += 32) {
+      // every CTA pair starts at another entry: 74 CTAs otherwise ask the same L2 lines at the same moment
+      const uint4 e = p.plan.wcopy[(i + pair * 5) % p.plan.n_wcopy];
+      bulk_g2s(w_base + e.x, p.weights + e.y + rank * e.w, e.z, w_ready);
+    }
+  } else if (warp < 7) {
+    // biases of the epilogues (<= 256 floats each): thread k of these 128 takes elements k and k + 128 of every bias,
+    // eight loads in flight
+    const int k = threadIdx.x - 96;
+    for (int b0 = 0; b0 < p.plan.n_bias; b0 += 4) {
+      float v[4][2];
+      uint32_t dst[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          dst[u][h] = 0xFFFFFFFFu;
+          v[u][h] = 0.f;
+          if (b0 + u < p.plan.n_bias) {
+            const uint4 e = p.plan.bias[b0 + u];
+            const float* bsrc = reinterpret_cast<const float*>(static_cast<uintptr_t>(e.x) | (static_cast<uintptr_t>(e.y) << 32));
+            const int nvalid = static_cast<int>(e.z & 0xFFFFu), npad = static_cast<int>(e.z >> 16);
+            const int kk = k + 128 * h;
+            if (kk < npad) dst[u][h] = e.w + static_cast<uint32_t>(kk);
+            if (kk < nvalid) v[u][h] = __ldg(bsrc + kk);
+          }
         }
       }
-      d.ld = first;
-      d.col0 = static_cast<int16_t>(cnt);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (dst[u][h] != 0xFFFFFFFFu) sbias[dst[u][h]] = v[u][h];
     }
-    sops[threadIdx.x] = d;
+  } else {
+    constexpr int kWords = static_cast<int>((sizeof(DevOp) * NRC_CHAIN_MAX_OPS + sizeof(uint4) * kMaxMma) / 16);
+    constexpr int kCopyWarps = kThreads / 32 - 7;
+    constexpr int kPerWarp = (kWords + kCopyWarps - 1) / kCopyWarps;
+    const uint4* src = reinterpret_cast<const uint4*>(&p.plan);
+    uint4* dst = reinterpret_cast<uint4*>(sops);
+    const int w0 = (warp - 7) * kPerWarp;
+#pragma unroll
+    for (int j = 0; j < kPerWarp; ++j) {
+      const int i = w0 + j;                 // warp-uniform index: one constant load serves the warp
+      if (i < kWords) {
+        const uint4 v = src[i];
+        if (lane == (j & 31)) dst[i] = v;
+      }
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    // this CTA's half of every weight atom, once: rows [rank n/2, (rank+1) n/2) of the K-major chunk are the
-    // contiguous bytes [rank n/2 * 128, ...) of the swizzled atom (8-row groups of 1024 bytes)
-    mbar_arrive_expect_tx(w_ready, static_cast<uint32_t>(p.w_bytes));
-    for (int i = 0; i < nops; ++i) {
-      const nrc_chain_op_t& o = p.prog.ops[i];
-      if (o.kind != NRC_OP_GEMM || p.w_off[i] < 0) continue;   // < 0: shares an earlier op's resident weights
-      const uint32_t half_bytes = static_cast<uint32_t>(o.n) * 64u;
-      for (int a = 0; a < o.n_atoms; ++a)
-        bulk_g2s(w_base + static_cast<uint32_t>(p.w_off[i]) + static_cast<uint32_t>(a) * half_bytes,
-                 p.weights + static_cast<size_t>(o.w_chunk + a) * kAtomBytes + rank * half_bytes, half_bytes, w_ready);
-    }
-  }
-  for (int i = 0; i < nops; ++i) {
-    const DevOp& op = sops[i];
-    if (op.kind != NRC_OP_EPI || op.bias_off < 0) continue;
-    const float* b = static_cast<const float*>(op.ptr);
-    for (int k = threadIdx.x; k < op.npad; k += kThreads) sbias[op.bias_off + k] = k < op.ncols ? __ldg(b + k) : 0.f;
-  }
+  TRACE_MARK(9);
   tc_fence_before();
   cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated, program staged
   tc_fence_after();
+  TRACE_MARK(10);
   const uint32_t tmem_base = tmem_base_s;
   const int num_super = (p.num_ptiles + NCTX - 1) / NCTX;
 
@@ -810,13 +887,14 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
             {
               const int e0 = sops[i].ld, e1 = sops[j - 1].ld + sops[j - 1].col0;
               const uint32_t d0 = tmem_base + static_cast<uint32_t>(c * kCtxTmemCols);
-              const uint32_t a_off = static_cast<uint32_t>(c * S) * (kAtomBytes >> 4);
+              const uint32_t a_off = static_cast<uint32_t>(c * S) * (kAtomBytes >> 4) + (base >> 4);
+              const uint32_t b_off = base >> 4;
               constexpr uint64_t kDescHi = static_cast<uint64_t>(64u | (1u << 14) | (2u << 29)) << 32;   // SBO 1024, v1, SW128
               uint4 m = smma[e0];
               for (int e = e0; e < e1; ++e) {
                 const uint4 cur = m;
                 if (e + 1 < e1) m = smma[e + 1];
-                umma2_bf16(d0 + (cur.z & 0x7FFFFFFFu), kDescHi | (cur.x + a_off), kDescHi | cur.y, cur.w, cur.z >> 31);
+                umma2_bf16(d0 + (cur.z & 0x7FFFFFFFu), kDescHi | (cur.x + a_off), kDescHi | (cur.y + b_off), cur.w, cur.z >> 31);
               }
             }
             umma2_commit_mc(acc_ready(c), 3);
@@ -867,7 +945,7 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
           tc_fence_before();
           named_barrier_sync(1 + c, kCtxT);
           if (wg_tid == 0) {
-            if (!w_waited) { mbar_wait(w_ready, 0); w_waited = true; }
+            if (!w_waited) { mbar_wait(w_ready, 0); w_waited = true; TRACE_MARK(11); }
             if (img_pending) { mbar_arrive(img_ready(c)); mbar_wait(img_ready(c), img_par); img_par ^= 1u; img_pending = false; }
             mbar_arrive_cluster(a_ready_remote);
           }
@@ -966,13 +1044,17 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
           a.ncols = op.ncols; a.npad = op.npad; a.r = r; a.half = half; a.nparts = kParts;
           const bool full = (op.ncols == op.npad) && (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
           const bool relu = (op.flags & NRC_EPI_RELU) != 0;
-          if (a.has_slot && !out && op.ncols == op.npad && (!a.bias || a.bias_s) && (tile_ok || !op.mask)) {
+          if (out && op.n > 0 && !op.mask && (!a.bias || a.bias_s)) {
+            // fp32 row output through the staging slot the program names (op.n - 1)
+            guard_slots();
+            float* obase = out + op.col0;
+            const uint32_t st = slot_addr(c, op.n - 1);
+            epi_staged(a.taddr, a.bias ? a.bias_s : nullptr, relu, st, r, half, op.ncols, op.npad, obase, row0, p.num_rows, op.ld,
+                       a.accum, a.has_slot, a.slot0_addr, 1 + c, kCtxT, wg_tid);
+          } else if (a.has_slot && !out && op.ncols == op.npad && (!a.bias || a.bias_s) && (tile_ok || !op.mask)) {
             // the accumulator only becomes the next operand: tight path
-            if (a.mask_tile)  epi_slot_fast<false, false, true>(a.taddr, nullptr, a.slot0_addr, r, op.npad, half, kParts, a.mask_tile, a.mask_atom0);
-            else if (a.bias)  { if (relu) epi_slot_fast<true, true, false>(a.taddr, a.bias_s, a.slot0_addr, r, op.npad, half, kParts, nullptr, 0);
-                                else      epi_slot_fast<true, false, false>(a.taddr, a.bias_s, a.slot0_addr, r, op.npad, half, kParts, nullptr, 0); }
-            else              { if (relu) epi_slot_fast<false, true, false>(a.taddr, nullptr, a.slot0_addr, r, op.npad, half, kParts, nullptr, 0);
-                                else      epi_slot_fast<false, false, false>(a.taddr, nullptr, a.slot0_addr, r, op.npad, half, kParts, nullptr, 0); }
+            if (a.mask_tile) epi_slot_fast<true>(a.taddr, nullptr, false, a.slot0_addr, r, op.npad, half, kParts, a.mask_tile, a.mask_atom0);
+            else             epi_slot_fast<false>(a.taddr, a.bias ? a.bias_s : nullptr, relu, a.slot0_addr, r, op.npad, half, kParts, nullptr, 0);
           } else if (a.mask_tile) {
             if (full) epi_run<false, false, true, true>(a); else epi_run<false, false, true, false>(a);
           } else if (a.bias) {
@@ -989,13 +1071,16 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
         ++i;
       }
     }
+    TRACE_MARK(12);
     if (wg_tid == 0) bulk_wait0();
   }
 
   __syncwarp();
   tc_fence_before();
+  TRACE_MARK(13);
   cluster_sync_all();   // no CTA leaves (or frees tensor memory) while its partner may still use its memories
   if (warp == 0) tmem_dealloc2(tmem_base, 512);
+  TRACE_NS(15);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1216,6 +1301,9 @@ static int32_t validate_program(const nrc_chain_program_t* prog, int32_t num_ptr
             !ptr_ok(op.ptr, true) || !ptr_ok(op.out_ptr, true) || !ptr_ok(op.mask_ptr, true) ||
             (op.slot >= 0 && op.slot + ((op.npad + 63) >> 6) > S))
           return NRC_E_INVALID_ARG;
+        // fp32 output staged through slot n - 1: inside the context and not one of the destination slots
+        if (op.n < 0 || op.n > S || (op.n > 0 && op.slot >= 0 && op.n - 1 >= op.slot && op.n - 1 < op.slot + ((op.npad + 63) >> 6)))
+          return NRC_E_INVALID_ARG;
         break;
       case NRC_OP_GATHER:
         if (!ptr_ok(op.ptr, false) || !ptr_ok(op.out_ptr, true) || op.slot < 0 || op.slot >= S || op.ncols < 1 ||
@@ -1250,11 +1338,16 @@ static int sm_count() {
 static int32_t chain2_launch(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
                              const void* d_weights_packed, int64_t num_rows) {
   static thread_local Chain2Params hp;
-  hp.prog = *prog;
+  Chain2Plan& pl = hp.plan;
+  const int nops = prog->num_ops;
+  const int S = prog->slots_per_ctx;
+  // resident weight layout: byte offset of every GEMM's first K atom inside the CTA's weight region
+  int w_off[NRC_CHAIN_MAX_OPS];
   int w_bytes = 0;
-  for (int i = 0; i < prog->num_ops; ++i) {
+  pl.n_wcopy = 0;
+  for (int i = 0; i < nops; ++i) {
     const nrc_chain_op_t& op = prog->ops[i];
-    hp.w_off[i] = 0;
+    w_off[i] = 0;
     if (op.kind == NRC_OP_GATHER || (op.kind == NRC_OP_EPI && (op.flags & NRC_EPI_DENSITY))) return NRC_E_UNSUPPORTED;
     if (op.kind != NRC_OP_GEMM) continue;
     // a GEMM that multiplies further operand atoms with weights an earlier op already holds (summed upstream
@@ -1262,39 +1355,88 @@ static int32_t chain2_launch(void* stream, const nrc_chain_program_t* prog, void
     int shared = -1;
     for (int k = 0; k < i && shared < 0; ++k) {
       const nrc_chain_op_t& e = prog->ops[k];
-      if (e.kind == NRC_OP_GEMM && e.n == op.n && op.w_chunk >= e.w_chunk && op.w_chunk + op.n_atoms <= e.w_chunk + e.n_atoms &&
-          hp.w_off[k] >= 0)
+      if (e.kind == NRC_OP_GEMM && e.n == op.n && op.w_chunk >= e.w_chunk && op.w_chunk + op.n_atoms <= e.w_chunk + e.n_atoms)
         shared = k;
     }
     if (shared >= 0) {
-      hp.w_off[i] = -(hp.w_off[shared] + (op.w_chunk - prog->ops[shared].w_chunk) * op.n * 64) - 1;   // < 0: no load of its own
+      w_off[i] = w_off[shared] + (op.w_chunk - prog->ops[shared].w_chunk) * op.n * 64;
       continue;
     }
-    hp.w_off[i] = w_bytes;
-    w_bytes += op.n_atoms * op.n * 64;   // n/2 rows of 128 bytes per K atom
+    w_off[i] = w_bytes;
+    const uint32_t half_bytes = static_cast<uint32_t>(op.n) * 64u;   // n/2 rows of 128 bytes per K atom
+    for (int a = 0; a < op.n_atoms; ++a) {
+      if (pl.n_wcopy >= kMaxWcopy) return NRC_E_UNSUPPORTED;
+      pl.wcopy[pl.n_wcopy++] = make_uint4(static_cast<uint32_t>(w_bytes) + a * half_bytes,
+                                          static_cast<uint32_t>(op.w_chunk + a) * kAtomBytes, half_bytes, half_bytes);
+    }
+    w_bytes += op.n_atoms * static_cast<int>(half_bytes);
   }
-  int n_mma = 0;
-  for (int i = 0; i < prog->num_ops; ++i)
-    if (prog->ops[i].kind == NRC_OP_GEMM)
-      for (int a = 0; a < prog->ops[i].n_atoms; ++a) n_mma += prog->ops[i].a_klen[a] >> 4;
-  if (n_mma > kMaxMma) return NRC_E_UNSUPPORTED;
-  const int S = prog->slots_per_ctx;
   const int budget = 227 * 1024 - kTail2Bytes - 1024;
   int nctx = 2;
   if (w_bytes + 2 * S * kAtomBytes > budget) nctx = 1;
-  for (int i = 0; i < prog->num_ops; ++i) {   // accumulators beyond a context's 256 columns: one context owns all 512
+  for (int i = 0; i < nops; ++i) {   // accumulators beyond a context's 256 columns: one context owns all 512
     const nrc_chain_op_t& op = prog->ops[i];
     if ((op.kind == NRC_OP_GEMM && op.tmem_col + op.n > 256) || (op.kind == NRC_OP_EPI && op.tmem_col + op.npad > 256)) nctx = 1;
   }
   if (w_bytes + nctx * S * kAtomBytes > budget) return NRC_E_UNSUPPORTED;
   const char* force = getenv("NRC_CHAIN_NCTX");
   if (force && force[0] == '1') nctx = 1;
-  for (int i = 0; i < NRC_CHAIN_MAX_PTRS; ++i) hp.ptrs[i] = i < num_ptrs ? d_ptrs[i] : nullptr;
+
+  // the program with resolved pointers, staged biases and the UMMA descriptor list
+  const int bias_cap = (kTail2Bytes - 144 - static_cast<int>(sizeof(DevOp)) * NRC_CHAIN_MAX_OPS - static_cast<int>(sizeof(uint4)) * kMaxMma) / 4;
+  int bias_cur = 0;
+  pl.n_ops = nops; pl.n_mma = 0; pl.n_bias = 0;
+  auto ptr_of = [&](int32_t i) -> void* { return i >= 0 ? d_ptrs[i] : nullptr; };
+  for (int i = 0; i < nops; ++i) {
+    const nrc_chain_op_t& o = prog->ops[i];
+    DevOp& d = pl.ops[i];
+    d.kind = static_cast<int8_t>(o.kind); d.slot = static_cast<int8_t>(o.slot);
+    d.flags = static_cast<uint8_t>(o.flags); d.n_atoms = static_cast<uint8_t>(o.n_atoms);
+    d.ncols = static_cast<int16_t>(o.ncols); d.npad = static_cast<int16_t>(o.npad);
+    d.tmem_col = static_cast<int16_t>(o.tmem_col); d.n = static_cast<int16_t>(o.n);
+    d.ld = o.ld;
+    d.col0 = static_cast<int16_t>(o.col0); d.mask_atom0 = static_cast<int16_t>(o.mask_atom0);
+    d.img_atoms = static_cast<int16_t>(o.img_atoms);
+    d.w_chunk = o.w_chunk;
+    d.fparam = o.fparam;
+    d.ptr = ptr_of(o.ptr); d.out = ptr_of(o.out_ptr); d.mask = ptr_of(o.mask_ptr);
+    for (int a = 0; a < NRC_CHAIN_MAX_ATOMS; ++a) d.a_src[a] = static_cast<uint8_t>((o.a_slot[a] & 15) | ((o.a_klen[a] >> 4) << 4));
+    d.bias_off = -1;
+    if (o.kind == NRC_OP_EPI && o.ptr >= 0 && o.mask_ptr < 0 && pl.n_bias < kMaxBias && bias_cur + o.npad <= bias_cap) {
+      const uintptr_t bp = reinterpret_cast<uintptr_t>(d.ptr);
+      pl.bias[pl.n_bias++] = make_uint4(static_cast<uint32_t>(bp), static_cast<uint32_t>(static_cast<uint64_t>(bp) >> 32),
+                                        static_cast<uint32_t>(o.ncols) | (static_cast<uint32_t>(o.npad) << 16),
+                                        static_cast<uint32_t>(bias_cur));
+      d.bias_off = static_cast<int16_t>(bias_cur);
+      bias_cur += o.npad;
+    }
+    if (o.kind == NRC_OP_GEMM) {
+      // this op's UMMA instructions as ready-made descriptor words (context 0, addresses relative to the CTA's dynamic
+      // shared memory; the issuer adds the base and the context's slot offset): the issuing thread spends a handful of
+      // instructions per UMMA instead of re-deriving everything from the program
+      const int first = pl.n_mma;
+      const uint32_t idesc = make_idesc(256, o.n, 0, 0);
+      const uint32_t half_bytes = static_cast<uint32_t>(o.n) * 64u;
+      for (int a = 0; a < o.n_atoms; ++a) {
+        const uint32_t a_addr = static_cast<uint32_t>(w_bytes) + static_cast<uint32_t>(o.a_slot[a]) * kAtomBytes;
+        const uint32_t b_addr = static_cast<uint32_t>(w_off[i]) + static_cast<uint32_t>(a) * half_bytes;
+        for (int k = 0; k < (o.a_klen[a] >> 4); ++k) {
+          if (pl.n_mma >= kMaxMma) return NRC_E_UNSUPPORTED;
+          const uint32_t acc = ((o.flags & NRC_GEMM_ACCUMULATE) || a > 0 || k > 0) ? 0x80000000u : 0u;
+          pl.mma[pl.n_mma++] = make_uint4(((a_addr + 32u * k) >> 4) | (1u << 16), ((b_addr + 32u * k) >> 4) | (1u << 16),
+                                          static_cast<uint32_t>(o.tmem_col) | acc, idesc);
+        }
+      }
+      d.ld = first;
+      d.col0 = static_cast<int16_t>(pl.n_mma - first);
+    }
+  }
   hp.weights = static_cast<const uint8_t*>(d_weights_packed);
   hp.num_rows = num_rows;
   hp.num_tiles = static_cast<int32_t>((num_rows + 127) / 128);
   hp.num_ptiles = (hp.num_tiles + 1) / 2;
   hp.w_bytes = w_bytes;
+  hp.slots_per_ctx = S;
   const size_t smem = static_cast<size_t>(w_bytes) + static_cast<size_t>(nctx * S) * kAtomBytes + kTail2Bytes;
   const int num_super = (hp.num_ptiles + nctx - 1) / nctx;
   const int max_pairs = sm_count() / 2;

@@ -448,9 +448,17 @@ def run_forward(spec, params, sources, packed, save=True, head_images=None, head
             ref = head_images.get(g)
             if ref is not None and ref.natoms != len(_atoms_of(spec.head_pads[g])):
                 raise _lib.NrcError("head image must hold the whole padded head group")
+            # fp32 rows leave through a staging slot (coalesced stores): after the LAST batch's GEMMs every input slot is
+            # dead; an earlier batch may only use a slot its successors do not read
+            if g1 == len(spec.heads):
+                stage = 0
+            else:
+                busy = {sl for (sl, _) in atoms} | set(range(spec.fwd_slots, spec.fwd_slots + extra))
+                stage = next((sl for sl in range(prog.slots_per_ctx) if sl not in busy), -1)
             _op(prog, kind=OP_EPI, slot=spec.fwd_slots if ref is not None else -1, ptr=ptrs.add(bias),
                 ncols=spec.head_widths[g], npad=spec.head_pads[g], tmem_col=tcol, out_ptr=ptrs.add(buf),
-                ld=spec.head_pads[g], col0=0)
+                ld=spec.head_pads[g], col0=0,
+                n=(stage + 1) if (buf is not None and spec.head_widths[g] >= 32) else 0)   # narrow heads: direct stores are faster
             if ref is not None:
                 _op(prog, kind=OP_SAVE, slot=spec.fwd_slots, ptr=ptrs.add(ref.img), col0=ref.atom0, npad=ref.natoms,
                     img_atoms=ref.img_atoms)
@@ -624,7 +632,8 @@ def run_backward_data(spec, params, g_heads, act, packed, P, d_src=None):
             elif dst is not None and dst[0] is not None:
                 t, accumulate = dst
                 _op(prog, kind=OP_EPI, slot=-1, ncols=w, npad=_pad(w, 16), tmem_col=acc_in0 + c, out_ptr=ptrs.add(t),
-                    ld=_ld(t), col0=0, flags=EPI_OUT_ACCUMULATE if accumulate else 0)
+                    ld=_ld(t), col0=0, flags=EPI_OUT_ACCUMULATE if accumulate else 0,
+                    n=1 if ((out_atoms == 0 or out0 > 0) and w >= 32) else 0)   # staged through slot 0 (every GEMM is done)
             c += w
     arr, n = ptrs.array()
     _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)

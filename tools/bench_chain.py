@@ -34,7 +34,10 @@ def timeit(fn, iters=20):
     torch.cuda.synchronize()
     return s.elapsed_time(e) / iters * 1e3  # us
 
+only = sys.argv[2].split(',') if len(sys.argv) > 2 else None
 for name in T.SPECS:
+    if only and name not in only:
+        continue
     g = gen(1)
     spec = mc.ChainSpec(**T.SPECS[name])
     p = {k: {a: b.to(dev) for a, b in v.items()} for k, v in T.make_params(g, spec).items()}

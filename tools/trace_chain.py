@@ -80,6 +80,8 @@ for it in range(0, 8):
 marks = np.zeros(16, dtype=np.int64)
 lib.nrc_chain_marks_dump.argtypes = [C.POINTER(C.c_longlong)]
 lib.nrc_chain_marks_dump(marks.ctypes.data_as(C.POINTER(C.c_longlong)))
+print("v2 phases (cycles from kernel entry): decode %d, prologue done %d, weights resident %d, tiles done %d, before exit sync %d; "
+      "entry->exit %.2f us" % tuple([int(marks[i] - marks[8]) for i in (9, 10, 11, 12, 13)] + [(marks[15] - marks[14]) * 1e-3]))
 print("last EPI of ctx0 thread 0 (begin, args, ld issued, ld waited, chunk done, end):", [int(m - marks[0]) for m in marks[:6]])
 
 try:
