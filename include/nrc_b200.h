@@ -307,6 +307,7 @@ int32_t nrc_ide_bwd(void* stream, int32_t n_sh, const int32_t* ml_m, const int32
 #define NRC_CHAIN_MAX_OPS 24
 #define NRC_CHAIN_MAX_PTRS 40
 #define NRC_CHAIN_MAX_ATOMS 8
+#define NRC_CHAIN_MAX_PROGRAMS 3
 #define NRC_PACK_MAX_ENTRIES 80
 #define NRC_WGRAD_MAX_LAYERS 12
 #define NRC_WGRAD_MAX_X_ATOMS 6
@@ -383,6 +384,14 @@ typedef struct {
 /* Run `prog` over ceil(num_rows/128) tiles.  d_weights_packed: chunks from nrc_chain_pack_weights. */
 int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
                       const void* d_weights_packed, int64_t num_rows);
+/* Several INDEPENDENT programs over the same rows in one launch (e.g. the integrated-BRDF, SurfaceLightField and EnvMap
+ * stacks of internal/nerf.py:940-1090, which all read the bottleneck / reflection encoding of one shaded point and do
+ * not read each other): their (program, tile) work items are dealt to the CTA pairs in cost-balanced contiguous
+ * ranges.  progs / d_ptrs / num_ptrs / d_weights_packed are arrays of num_programs (<= NRC_CHAIN_MAX_PROGRAMS) entries
+ * with the meaning of nrc_chain_run's arguments.  Equivalent to num_programs calls of nrc_chain_run. */
+int32_t nrc_chain_run_multi(void* stream, int32_t num_programs, const nrc_chain_program_t* const* progs,
+                            void* const* const* d_ptrs, const int32_t* num_ptrs, const void* const* d_weights_packed,
+                            int64_t num_rows);
 /* nrc_chain_run with a hash-grid front end: the fused point query (predict_density + convert_raw_density,
  * internal/geometry.py:199-341) on the tensor-core chain kernel.  Two extra op behaviours:
  *   GATHER  slot = destination atom, ptr = means [P,3], out_ptr = encoded features fp32 [P, L*F] or -1,

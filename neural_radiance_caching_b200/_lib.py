@@ -121,6 +121,7 @@ PROTOTYPES = {
     "nrc_density_mlp_bwd_tangent": [_P, _P, _P, _P, _I64, _P, _P],
     "nrc_encode_tangent_bwd": [_P, _P, _P, _P, _P, _I64, _F],
     "nrc_chain_run": [_P, _P, _P, _I32, _P, _I64],
+    "nrc_chain_run_multi": [_P, _I32, _P, _P, _P, _P, _I64],
     "nrc_chain_query": [_P, _P, _P, _I32, _P, _I64, _P, _F],
     "nrc_chain_pack_weights": [_P, _P, _I32, _P, _I32, _P, _I32, _I32],
     "nrc_chain_wgrad": [_P, _P, _I32, _P, _I32, _I64],

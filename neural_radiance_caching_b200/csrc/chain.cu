@@ -708,26 +708,34 @@ __device__ __forceinline__ void epi_staged(uint32_t taddr, const float* bias_s, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Version 2 of the chain kernel: CTA PAIRS with the stack's weights RESIDENT in shared memory.
+// The CTA-PAIR kernel: stack weights RESIDENT in shared memory, up to three PROGRAMS per launch.
 //   * a cluster of two CTAs executes one 256-row tile (128 rows per CTA) with tcgen05.mma.cta_group::2: the B operand
 //     (weights) is split by N between the two CTAs, so each SM holds HALF of every layer's weights - the whole
 //     SurfaceLightField stack (228 KB of bf16 operands) fits beside the activations and is loaded ONCE per CTA
-//     instead of being streamed through a ring for every tile (the v1 kernel moves 256 KB of weights per 128-row
-//     tile through a 2-4 stage ring: its GEMMs wait on L2, not on the tensor core);
-//   * the ring, its barriers and the producer loop are gone: the UMMA issuer never waits for operands after the
-//     first tile; a tile's layer costs one cluster-scope barrier round trip + the MMAs + the epilogue;
-//   * epilogue warps issue all their TMEM loads of a layer before the single wait.
-// Programs, weight images, tile images and the op semantics are those of the v1 kernel (a 256-row pair tile is
+//     instead of being streamed through a ring for every tile (the streaming kernel above moves 256 KB of weights per
+//     128-row tile through a 2-4 stage ring: its GEMMs wait on L2, not on the tensor core);
+//   * no ring, no producer: the UMMA issuer never waits for operands after the first tile; a tile's layer costs one
+//     cluster-scope barrier round trip + the MMAs + the epilogue;
+//   * one launch runs several independent programs (the integrated-BRDF, SurfaceLightField and EnvMap stacks of the
+//     forward pass; the SurfaceLightField and integrated-BRDF data gradients of the backward pass): the (program, tile)
+//     work items of all of them are dealt to the CTA pairs in contiguous, cost-balanced ranges, so that at 32 768
+//     points (128 pair tiles per program on 74 pairs) the launch is ONE balanced wave instead of three launches of
+//     one-and-three-quarter waves each with its own prologue; a pair that crosses a program boundary reloads its
+//     weights (2-3 us) behind a cluster barrier.
+// Programs, weight images, tile images and the op semantics are those of the streaming kernel (a 256-row pair tile is
 // the two consecutive 128-row tiles 2t and 2t+1 of every tile image).
-constexpr int kTail2Bytes = 6144;
+constexpr int kTail2Bytes = 6144;   // shared-memory head: mbarriers (128 B), TMEM base (16 B), program, UMMA list, staged biases
 constexpr int kMaxMma = 96;     // UMMA instructions of one program (precomputed descriptor list in shared memory)
 constexpr int kMaxWcopy = 48;   // bulk copies that make a program's weights resident (one per K atom of every GEMM)
 constexpr int kMaxBias = 12;    // epilogue biases staged in shared memory
+constexpr int kMaxProgs = NRC_CHAIN_MAX_PROGRAMS;    // programs per launch
+constexpr int kMaxPairs = 96;   // CTA pairs per launch (SM count / 2)
 
-// Everything the kernel needs about the program, RESOLVED ON THE HOST (pointers, bias offsets, the UMMA descriptor list,
-// the list of weight copies) and copied from the parameter space to shared memory with one coalesced pass.  Decoding the
-// program in the kernel cost 4-10 us per launch (thread-indexed reads of the parameter space serialise; measured with
-// the trace build: `decode` + `prologue` marks of tools/trace_chain.py), more than the tile work of the small stacks.
+// Everything the kernel needs about a program, RESOLVED ON THE HOST (pointers, bias offsets, the UMMA descriptor list,
+// the list of weight copies) and copied from the parameter space to shared memory with warp-uniform constant loads.
+// Decoding the program in the kernel cost 4-10 us per launch (thread-indexed reads of the parameter space serialise;
+// measured with the trace build: `decode` + `prologue` marks of tools/trace_chain.py), more than the tile work of the
+// small stacks.
 struct __align__(16) Chain2Plan {
   DevOp ops[NRC_CHAIN_MAX_OPS];
   uint4 mma[kMaxMma];        // x: A descriptor low word, address relative to the CTA's dynamic shared memory (context 0);
@@ -737,349 +745,372 @@ struct __align__(16) Chain2Plan {
   uint4 bias[kMaxBias];      // x, y: source pointer (lo, hi), z: valid floats | padded floats << 16, w: destination float offset
   int32_t n_ops, n_mma, n_wcopy, n_bias;
 };
-struct Chain2Params {
+static_assert(sizeof(Chain2Plan) % 16 == 0, "plan is copied as 16-byte words");
+struct Chain2Prog {
   Chain2Plan plan;
   const uint8_t* weights;
+  int32_t w_bytes;         // resident weight bytes per CTA (multiple of 1024)
+  int32_t slots_per_ctx;
+  int32_t nctx;            // tile contexts: 2 (8 + 8 epilogue warps) when two fit, else 1 (16 epilogue warps)
+  int32_t pad;
+};
+struct Chain2Params {
+  Chain2Prog prog[kMaxProgs];
   int64_t num_rows;
   int32_t num_tiles;     // 128-row tiles
   int32_t num_ptiles;    // 256-row pair tiles
-  int32_t w_bytes;       // resident weight bytes per CTA (multiple of 1024)
-  int32_t slots_per_ctx;
+  int32_t n_progs;
+  int32_t pad;
+  uint16_t seg_t0[kMaxProgs][kMaxPairs];   // per program and CTA pair: first super tile (nctx pair tiles) ...
+  uint16_t seg_n[kMaxProgs][kMaxPairs];    // ... and how many
 };
-static_assert(sizeof(Chain2Plan) % 16 == 0, "plan is copied as 16-byte words");
 
-template <int NCTX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1)
 chain2_kernel(const __grid_constant__ Chain2Params p) {
-  // dynamic shared memory: [resident weights][NCTX * S slot atoms][tail: mbarriers, TMEM base, program, staged biases]
+  // dynamic shared memory: [head: mbarriers, TMEM base, program, UMMA list, staged biases][resident weights][nctx * S slot atoms]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TRACE_NS(14);
   TRACE_MARK(8);
   constexpr int kThreads = kChainThreads;
-  constexpr int kCtxT = 2 * kCtxThreads / NCTX;   // loader / epilogue threads per tile context: 16 warps (one context) or 8
-  constexpr int kParts = kCtxT / 128;             // warps per TMEM lane quadrant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = p.slots_per_ctx, nops = p.plan.n_ops;
   const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pair = blockIdx.x >> 1;
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
-  const uint32_t w_base = base;
-  const uint32_t slot_base = base + static_cast<uint32_t>(p.w_bytes);
-  uint8_t* tail = smem_raw + p.w_bytes + static_cast<size_t>(NCTX * S) * kAtomBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
-  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(tail + 128);
-  DevOp* sops = reinterpret_cast<DevOp*>(tail + 144);
-  uint4* smma = reinterpret_cast<uint4*>(tail + 144 + sizeof(DevOp) * NRC_CHAIN_MAX_OPS);
-  float* sbias = reinterpret_cast<float*>(tail + 144 + sizeof(DevOp) * NRC_CHAIN_MAX_OPS + sizeof(uint4) * kMaxMma);
-  auto slot_addr = [&](int ctx, int s) { return slot_base + static_cast<uint32_t>(ctx * S + s) * kAtomBytes; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(smem_raw + 128);
+  DevOp* sops = reinterpret_cast<DevOp*>(smem_raw + 144);
+  uint4* smma = reinterpret_cast<uint4*>(smem_raw + 144 + sizeof(DevOp) * NRC_CHAIN_MAX_OPS);
+  float* sbias = reinterpret_cast<float*>(smem_raw + 144 + sizeof(DevOp) * NRC_CHAIN_MAX_OPS + sizeof(uint4) * kMaxMma);
+  const uint32_t w_base = base + kTail2Bytes;
   // barriers: 0 weights resident, 2+c operands of context c ready (count 2: one arrival per CTA, used in the
-  // issuing CTA only), 4+c accumulator of context c ready (multicast commit)
+  // issuing CTA only), 4+c accumulator of context c ready (multicast commit), 6+c LOADIMG bulk copies of context c landed
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t w_ready = bar0;
   auto a_ready = [&](int c) { return bar0 + 8u * (2 + c); };
   auto acc_ready = [&](int c) { return bar0 + 8u * (4 + c); };
-  auto img_ready = [&](int c) { return bar0 + 8u * (6 + c); };   // LOADIMG bulk copies of context c landed
+  auto img_ready = [&](int c) { return bar0 + 8u * (6 + c); };
 
-  // Prologue, every role in parallel: warp 0 allocates tensor memory, warp 1 initialises the tile barriers, warp 2 arms
-  // the weight barrier and issues the bulk copies that make this CTA's half of every weight atom resident (rows
-  // [rank n/2, (rank+1) n/2) of a K-major chunk are the contiguous bytes [rank n/2 * 128, ...) of the swizzled atom),
-  // warps 3-6 stage the epilogue biases, the rest copy the program + UMMA list out of the parameter space with
-  // warp-uniform (replay-free) constant loads.
-  if (warp == 0) {
-    tmem_alloc2(smem_u32(&tmem_base_s), 512);
-  } else if (warp == 1) {
-    if (lane == 0) {
-      for (int c = 0; c < 2; ++c) {
-        mbar_init(a_ready(c), 2);
-        mbar_init(acc_ready(c), 1);
-        mbar_init(img_ready(c), 1);
-      }
-      fence_barrier_init();
+  bool first = true;
+  uint32_t tmem_base = 0;
+  for (int k = 0; k < p.n_progs; ++k) {
+    const int n_super = p.seg_n[k][pair];
+    if (n_super == 0) continue;            // the same for both CTAs of the pair
+    const int q0 = p.seg_t0[k][pair];
+    const Chain2Prog& pg = p.prog[k];
+    const int S = pg.slots_per_ctx, nops = pg.plan.n_ops, nctx = pg.nctx;
+    const int ctxT = 2 * kCtxThreads / nctx;   // loader / epilogue threads per tile context: 16 warps (one context) or 8
+    const int parts = ctxT / 128;              // warps per TMEM lane quadrant
+    const uint32_t slot_base = w_base + static_cast<uint32_t>(pg.w_bytes);
+    auto slot_addr = [&](int ctx, int s) { return slot_base + static_cast<uint32_t>(ctx * S + s) * kAtomBytes; };
+
+    // ------------------------------------------------------------------ program set-up, every role in parallel:
+    // warp 0 allocates tensor memory (first program), warp 1 (re)initialises the tile barriers, warp 2 arms the weight
+    // barrier and issues the bulk copies that make this CTA's half of every weight atom resident (rows [rank n/2,
+    // (rank+1) n/2) of a K-major chunk are the contiguous bytes [rank n/2 * 128, ...) of the swizzled atom), warps 3-6
+    // stage the epilogue biases, the rest copy the program + UMMA list out of the parameter space.
+    if (!first) {
+      tc_fence_before();
+      cluster_sync_all();   // both CTAs drained the previous program: its weights, slots and barriers can be reused
+      tc_fence_after();
     }
-  } else if (warp == 2) {
-    if (lane == 0) {
-      mbar_init(w_ready, 1);
-      fence_barrier_init();
-      mbar_arrive_expect_tx(w_ready, static_cast<uint32_t>(p.w_bytes));
-    }
-    __syncwarp();
-    for (int i = lane; i < p.plan.n_wcopy; i += 32) {
-      // every CTA pair starts at another entry: 74 CTAs otherwise ask the same L2 lines at the same moment
-      const uint4 e = p.plan.wcopy[(i + pair * 5) % p.plan.n_wcopy];
-      bulk_g2s(w_base + e.x, p.weights + e.y + rank * e.w, e.z, w_ready);
-    }
-  } else if (warp < 7) {
-    // biases of the epilogues (<= 256 floats each): thread k of these 128 takes elements k and k + 128 of every bias,
-    // eight loads in flight
-    const int k = threadIdx.x - 96;
-    for (int b0 = 0; b0 < p.plan.n_bias; b0 += 4) {
-      float v[4][2];
-      uint32_t dst[4][2];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          dst[u][h] = 0xFFFFFFFFu;
-          v[u][h] = 0.f;
-          if (b0 + u < p.plan.n_bias) {
-            const uint4 e = p.plan.bias[b0 + u];
-            const float* bsrc = reinterpret_cast<const float*>(static_cast<uintptr_t>(e.x) | (static_cast<uintptr_t>(e.y) << 32));
-            const int nvalid = static_cast<int>(e.z & 0xFFFFu), npad = static_cast<int>(e.z >> 16);
-            const int kk = k + 128 * h;
-            if (kk < npad) dst[u][h] = e.w + static_cast<uint32_t>(kk);
-            if (kk < nvalid) v[u][h] = __ldg(bsrc + kk);
-          }
+    if (warp == 0) {
+      if (first) tmem_alloc2(smem_u32(&tmem_base_s), 512);
+    } else if (warp == 1) {
+      if (lane == 0) {
+        for (int c = 0; c < 2; ++c) {
+          if (!first) { mbar_inval(a_ready(c)); mbar_inval(acc_ready(c)); mbar_inval(img_ready(c)); }
+          mbar_init(a_ready(c), 2);
+          mbar_init(acc_ready(c), 1);
+          mbar_init(img_ready(c), 1);
         }
+        fence_barrier_init();
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          if (dst[u][h] != 0xFFFFFFFFu) sbias[dst[u][h]] = v[u][h];
-    }
-  } else {
-    constexpr int kWords = static_cast<int>((sizeof(DevOp) * NRC_CHAIN_MAX_OPS + sizeof(uint4) * kMaxMma) / 16);
-    constexpr int kCopyWarps = kThreads / 32 - 7;
-    constexpr int kPerWarp = (kWords + kCopyWarps - 1) / kCopyWarps;
-    const uint4* src = reinterpret_cast<const uint4*>(&p.plan);
-    uint4* dst = reinterpret_cast<uint4*>(sops);
-    const int w0 = (warp - 7) * kPerWarp;
-#pragma unroll
-    for (int j = 0; j < kPerWarp; ++j) {
-      const int i = w0 + j;                 // warp-uniform index: one constant load serves the warp
-      if (i < kWords) {
-        const uint4 v = src[i];
-        if (lane == (j & 31)) dst[i] = v;
+    } else if (warp == 2) {
+      if (lane == 0) {
+        if (!first) mbar_inval(w_ready);
+        mbar_init(w_ready, 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(w_ready, static_cast<uint32_t>(pg.w_bytes));
       }
-    }
-  }
-  __syncthreads();
-  TRACE_MARK(9);
-  tc_fence_before();
-  cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated, program staged
-  tc_fence_after();
-  TRACE_MARK(10);
-  const uint32_t tmem_base = tmem_base_s;
-  const int num_super = (p.num_ptiles + NCTX - 1) / NCTX;
-
-  if (warp == 1) {
-    // ===================================================================== UMMA issuer (even CTA of the pair)
-    if (rank == 0 && lane == 0) {
-      uint32_t a_par[2] = {0u, 0u};
-      for (int q = pair; q < num_super; q += npairs) {
-#ifdef NRC_CHAIN_TRACE
-        const int trace_it = (q - pair) / npairs;
-        int trace_g = 0;
-#endif
-        for (int i = 0; i < nops;) {
-          if (sops[i].kind != NRC_OP_GEMM) { ++i; continue; }
-          int j = i;
-          while (j < nops && sops[j].kind == NRC_OP_GEMM) ++j;
-          for (int c = 0; c < NCTX; ++c) {
-            if (NCTX * q + c >= p.num_ptiles) continue;
-            mbar_wait_cluster(a_ready(c), a_par[c]);
-            a_par[c] ^= 1u;
-            tc_fence_after();
-#ifdef NRC_CHAIN_TRACE
-            if (blockIdx.x == 0 && c == 0 && trace_it < kTraceTiles && trace_g < 8) g_chain_mma[trace_it][trace_g][0] = clock64();
-#endif
-            {
-              const int e0 = sops[i].ld, e1 = sops[j - 1].ld + sops[j - 1].col0;
-              const uint32_t d0 = tmem_base + static_cast<uint32_t>(c * kCtxTmemCols);
-              const uint32_t a_off = static_cast<uint32_t>(c * S) * (kAtomBytes >> 4) + (base >> 4);
-              const uint32_t b_off = base >> 4;
-              constexpr uint64_t kDescHi = static_cast<uint64_t>(64u | (1u << 14) | (2u << 29)) << 32;   // SBO 1024, v1, SW128
-              uint4 m = smma[e0];
-              for (int e = e0; e < e1; ++e) {
-                const uint4 cur = m;
-                if (e + 1 < e1) m = smma[e + 1];
-                umma2_bf16(d0 + (cur.z & 0x7FFFFFFFu), kDescHi | (cur.x + a_off), kDescHi | (cur.y + b_off), cur.w, cur.z >> 31);
-              }
+      __syncwarp();
+      for (int i = lane; i < pg.plan.n_wcopy; i += 32) {
+        // every CTA pair starts at another entry: 74 CTAs otherwise ask the same L2 lines at the same moment
+        const uint4 e = pg.plan.wcopy[(i + pair * 5) % pg.plan.n_wcopy];
+        bulk_g2s(w_base + e.x, pg.weights + e.y + rank * e.w, e.z, w_ready);
+      }
+    } else if (warp < 7) {
+      // biases of the epilogues (<= 256 floats each): thread t of these 128 takes elements t and t + 128 of every bias,
+      // eight loads in flight
+      const int t = threadIdx.x - 96;
+      for (int b0 = 0; b0 < pg.plan.n_bias; b0 += 4) {
+        float v[4][2];
+        uint32_t dst[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            dst[u][h] = 0xFFFFFFFFu;
+            v[u][h] = 0.f;
+            if (b0 + u < pg.plan.n_bias) {
+              const uint4 e = pg.plan.bias[b0 + u];
+              const float* bsrc = reinterpret_cast<const float*>(static_cast<uintptr_t>(e.x) | (static_cast<uintptr_t>(e.y) << 32));
+              const int nvalid = static_cast<int>(e.z & 0xFFFFu), npad = static_cast<int>(e.z >> 16);
+              const int kk = t + 128 * h;
+              if (kk < npad) dst[u][h] = e.w + static_cast<uint32_t>(kk);
+              if (kk < nvalid) v[u][h] = __ldg(bsrc + kk);
             }
-            umma2_commit_mc(acc_ready(c), 3);
-#ifdef NRC_CHAIN_TRACE
-            if (blockIdx.x == 0 && c == 0 && trace_it < kTraceTiles && trace_g < 8) g_chain_mma[trace_it][trace_g][1] = clock64();
-            if (c == 0) ++trace_g;
-#endif
           }
-          i = j;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (dst[u][h] != 0xFFFFFFFFu) sbias[dst[u][h]] = v[u][h];
+      }
+    } else {
+      constexpr int kWords = static_cast<int>((sizeof(DevOp) * NRC_CHAIN_MAX_OPS + sizeof(uint4) * kMaxMma) / 16);
+      constexpr int kCopyWarps = kThreads / 32 - 7;
+      constexpr int kPerWarp = (kWords + kCopyWarps - 1) / kCopyWarps;
+      const uint4* src = reinterpret_cast<const uint4*>(&pg.plan);
+      uint4* dst = reinterpret_cast<uint4*>(sops);
+      const int w0 = (warp - 7) * kPerWarp;
+#pragma unroll
+      for (int j = 0; j < kPerWarp; ++j) {
+        const int i = w0 + j;                 // warp-uniform index: one constant load serves the warp
+        if (i < kWords) {
+          const uint4 v = src[i];
+          if (lane == (j & 31)) dst[i] = v;
         }
       }
     }
-  } else if (warp >= 2) {
-    // ===================================================================== loader / epilogue warpgroups
-    const int c = (warp - 2) / (kCtxT / 32);
-    const int wg_tid = threadIdx.x - 64 - kCtxT * c;
-    const int quad = warp & 3;
-    const int half = ((warp - 2) >> 2) % kParts;
-    const int r = quad * 32 + lane;
-    const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t a_ready_remote = mapa_shared(a_ready(c), 0);
-    uint32_t acc_par = 0, img_par = 0;
-    bool store_pending = false, w_waited = false, img_pending = false;
+    __syncthreads();
+    if (first) TRACE_MARK(9);
+    tc_fence_before();
+    cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated, program staged
+    tc_fence_after();
+    if (first) TRACE_MARK(10);
+    tmem_base = tmem_base_s;
 
-    auto guard_slots = [&]() {
-      if (store_pending) {
-        if (wg_tid == 0) bulk_wait_read0();
-        named_barrier_sync(1 + c, kCtxT);
-        store_pending = false;
-      }
-    };
-
-    for (int q = pair; q < num_super; q += npairs) {
-      const int ptile = NCTX * q + c;
-      if (ptile >= p.num_ptiles) continue;
-      const int tile = 2 * ptile + static_cast<int>(rank);     // 128-row tile of every tile image
-      const bool tile_ok = tile < p.num_tiles;
-      const int64_t row0 = static_cast<int64_t>(tile) * 128;
+    if (warp == 1) {
+      // ===================================================================== UMMA issuer (even CTA of the pair)
+      if (rank == 0 && lane == 0) {
+        uint32_t a_par[2] = {0u, 0u};
+        for (int q = q0; q < q0 + n_super; ++q) {
 #ifdef NRC_CHAIN_TRACE
-      const int trace_it = (q - pair) / npairs;
-      const bool tracing = blockIdx.x == 0 && wg_tid == 0 && trace_it < kTraceTiles;
-      if (tracing) g_chain_trace[c][trace_it][kTraceOps - 1] = clock64();
+          const int trace_it = q - q0;
+          int trace_g = 0;
 #endif
-      for (int i = 0; i < nops;) {
-        const DevOp& op = sops[i];
-        if (op.kind == NRC_OP_GEMM) {
-          fence_proxy_async_smem();
-          tc_fence_before();
-          named_barrier_sync(1 + c, kCtxT);
-          if (wg_tid == 0) {
-            if (!w_waited) { mbar_wait(w_ready, 0); w_waited = true; TRACE_MARK(11); }
-            if (img_pending) { mbar_arrive(img_ready(c)); mbar_wait(img_ready(c), img_par); img_par ^= 1u; img_pending = false; }
-            mbar_arrive_cluster(a_ready_remote);
-          }
-          while (i < nops && sops[i].kind == NRC_OP_GEMM) ++i;
-          mbar_wait(acc_ready(c), acc_par);
-          acc_par ^= 1u;
-          tc_fence_after();
+          for (int i = 0; i < nops;) {
+            if (sops[i].kind != NRC_OP_GEMM) { ++i; continue; }
+            int j = i;
+            while (j < nops && sops[j].kind == NRC_OP_GEMM) ++j;
+            for (int c = 0; c < nctx; ++c) {
+              if (nctx * q + c >= p.num_ptiles) continue;
+              mbar_wait_cluster(a_ready(c), a_par[c]);
+              a_par[c] ^= 1u;
+              tc_fence_after();
 #ifdef NRC_CHAIN_TRACE
-          if (tracing) g_chain_trace[c][trace_it][i - 1] = clock64();
+              if (blockIdx.x == 0 && first && c == 0 && trace_it < kTraceTiles && trace_g < 8) g_chain_mma[trace_it][trace_g][0] = clock64();
 #endif
-          continue;
-        }
-        if (op.kind == NRC_OP_LOADIMG) {
-          // bf16 atoms written by the producer (another chain's SAVE, a per-point kernel) straight into the slots;
-          // consecutive LOADIMG ops before a GEMM share one barrier phase
-          guard_slots();
-          if (wg_tid == 0 && tile_ok) {
-            // every LOADIMG adds its bytes to the phase; the one arrival follows at the GEMM that consumes them
-            mbar_expect_tx(img_ready(c), static_cast<uint32_t>(op.npad) * kAtomBytes);
-            img_pending = true;
-            const uint8_t* img = static_cast<const uint8_t*>(op.ptr);
-            for (int a = 0; a < op.npad; ++a)
-              bulk_g2s(slot_addr(c, op.slot + a), img + (static_cast<size_t>(tile) * op.img_atoms + op.col0 + a) * kAtomBytes,
-                       kAtomBytes, img_ready(c));
-          }
-        } else if (op.kind == NRC_OP_LOAD) {
-          guard_slots();
-          const float* src = static_cast<const float*>(op.ptr);
-          const int nch = op.npad >> 3;
-          const bool vec = src && (op.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-          constexpr int kU = 4;
-          const int total = 128 * nch;
-          for (int item0 = wg_tid; item0 < total; item0 += kCtxT * kU) {
-            float v[kU][8];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-              const int item = item0 + u * kCtxT;
-              const int rr = item / nch;
-              const int col = (item - rr * nch) * 8;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
-              if (item < total && src && row0 + rr < p.num_rows && col < op.ncols) {
-                const float* s = src + (row0 + rr) * op.ld + col;
-                if (vec && col + 8 <= op.ncols) {
-                  const float4 x0 = __ldg(reinterpret_cast<const float4*>(s));
-                  const float4 x1 = __ldg(reinterpret_cast<const float4*>(s) + 1);
-                  v[u][0] = x0.x; v[u][1] = x0.y; v[u][2] = x0.z; v[u][3] = x0.w;
-                  v[u][4] = x1.x; v[u][5] = x1.y; v[u][6] = x1.z; v[u][7] = x1.w;
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (col + e < op.ncols) v[u][e] = __ldg(s + e);
+              {
+                const int e0 = sops[i].ld, e1 = sops[j - 1].ld + sops[j - 1].col0;
+                const uint32_t d0 = tmem_base + static_cast<uint32_t>(c * kCtxTmemCols);
+                const uint32_t a_off = static_cast<uint32_t>(c * S) * (kAtomBytes >> 4) + (base >> 4);
+                const uint32_t b_off = base >> 4;
+                constexpr uint64_t kDescHi = static_cast<uint64_t>(64u | (1u << 14) | (2u << 29)) << 32;   // SBO 1024, v1, SW128
+                uint4 m = smma[e0];
+                for (int e = e0; e < e1; ++e) {
+                  const uint4 cur = m;
+                  if (e + 1 < e1) m = smma[e + 1];
+                  umma2_bf16(d0 + (cur.z & 0x7FFFFFFFu), kDescHi | (cur.x + a_off), kDescHi | (cur.y + b_off), cur.w, cur.z >> 31);
                 }
               }
+              umma2_commit_mc(acc_ready(c), 3);
+#ifdef NRC_CHAIN_TRACE
+              if (blockIdx.x == 0 && first && c == 0 && trace_it < kTraceTiles && trace_g < 8) g_chain_mma[trace_it][trace_g][1] = clock64();
+              if (c == 0) ++trace_g;
+#endif
             }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-              const int item = item0 + u * kCtxT;
-              if (item >= total) continue;
-              const int rr = item / nch;
-              const int dcol = op.col0 + (item - rr * nch) * 8;
-              const uint32_t dst = slot_addr(c, op.slot + (dcol >> 6)) + atom_chunk_offset(rr, (dcol & 63) >> 3);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack2_bf16(v[u][0], v[u][1])),
-                           "r"(pack2_bf16(v[u][2], v[u][3])), "r"(pack2_bf16(v[u][4], v[u][5])),
-                           "r"(pack2_bf16(v[u][6], v[u][7]))
-                           : "memory");
-            }
-          }
-        } else if (op.kind == NRC_OP_SAVE) {
-          fence_proxy_async_smem();
-          named_barrier_sync(1 + c, kCtxT);
-          if (wg_tid == 0 && tile_ok) {
-            uint8_t* img = static_cast<uint8_t*>(op.ptr);
-            for (int a = 0; a < op.npad; ++a)
-              bulk_s2g(img + (static_cast<size_t>(tile) * op.img_atoms + op.col0 + a) * kAtomBytes,
-                       slot_addr(c, op.slot + a), kAtomBytes);
-            bulk_commit();
-          }
-          store_pending = true;
-        } else {  // NRC_OP_EPI
-          if (op.slot >= 0) guard_slots();
-          EpiArgs a;
-          a.bias = static_cast<const float*>(op.ptr);
-          a.bias_s = op.bias_off >= 0 ? sbias + op.bias_off : nullptr;
-          float* out = static_cast<float*>(op.out);
-          a.out_row = (out && row0 + r < p.num_rows) ? out + (row0 + r) * op.ld + op.col0 : nullptr;
-          a.out_vec = out && (op.ld % 4 == 0) && (op.col0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-          a.accum = (op.flags & NRC_EPI_OUT_ACCUMULATE) != 0;
-          a.mask_tile = (op.mask && tile_ok)
-                            ? static_cast<const uint8_t*>(op.mask) + static_cast<size_t>(tile) * op.img_atoms * kAtomBytes
-                            : nullptr;
-          a.mask_atom0 = op.mask_atom0;
-          a.taddr = tmem_base + t_lane + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
-          a.has_slot = op.slot >= 0;
-          a.slot0_addr = a.has_slot ? slot_addr(c, op.slot) : 0u;
-          a.ncols = op.ncols; a.npad = op.npad; a.r = r; a.half = half; a.nparts = kParts;
-          const bool full = (op.ncols == op.npad) && (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
-          const bool relu = (op.flags & NRC_EPI_RELU) != 0;
-          if (out && op.n > 0 && !op.mask && (!a.bias || a.bias_s)) {
-            // fp32 row output through the staging slot the program names (op.n - 1)
-            guard_slots();
-            float* obase = out + op.col0;
-            const uint32_t st = slot_addr(c, op.n - 1);
-            epi_staged(a.taddr, a.bias ? a.bias_s : nullptr, relu, st, r, half, op.ncols, op.npad, obase, row0, p.num_rows, op.ld,
-                       a.accum, a.has_slot, a.slot0_addr, 1 + c, kCtxT, wg_tid);
-          } else if (a.has_slot && !out && op.ncols == op.npad && (!a.bias || a.bias_s) && (tile_ok || !op.mask)) {
-            // the accumulator only becomes the next operand: tight path
-            if (a.mask_tile) epi_slot_fast<true>(a.taddr, nullptr, false, a.slot0_addr, r, op.npad, half, kParts, a.mask_tile, a.mask_atom0);
-            else             epi_slot_fast<false>(a.taddr, a.bias ? a.bias_s : nullptr, relu, a.slot0_addr, r, op.npad, half, kParts, nullptr, 0);
-          } else if (a.mask_tile) {
-            if (full) epi_run<false, false, true, true>(a); else epi_run<false, false, true, false>(a);
-          } else if (a.bias) {
-            if (relu) { if (full) epi_run<true, true, false, true>(a); else epi_run<true, true, false, false>(a); }
-            else      { if (full) epi_run<true, false, false, true>(a); else epi_run<true, false, false, false>(a); }
-          } else {
-            if (relu) { if (full) epi_run<false, true, false, true>(a); else epi_run<false, true, false, false>(a); }
-            else      { if (full) epi_run<false, false, false, true>(a); else epi_run<false, false, false, false>(a); }
+            i = j;
           }
         }
-#ifdef NRC_CHAIN_TRACE
-        if (tracing) g_chain_trace[c][trace_it][i] = clock64();
-#endif
-        ++i;
       }
+    } else if (warp >= 2) {
+      // ===================================================================== loader / epilogue warpgroups
+      const int c = (warp - 2) / (ctxT / 32);
+      const int wg_tid = threadIdx.x - 64 - ctxT * c;
+      const int quad = warp & 3;
+      const int half = ((warp - 2) >> 2) % parts;
+      const int r = quad * 32 + lane;
+      const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
+      const uint32_t a_ready_remote = mapa_shared(a_ready(c), 0);
+      uint32_t acc_par = 0, img_par = 0;
+      bool store_pending = false, w_waited = false, img_pending = false;
+
+      auto guard_slots = [&]() {
+        if (store_pending) {
+          if (wg_tid == 0) bulk_wait_read0();
+          named_barrier_sync(1 + c, ctxT);
+          store_pending = false;
+        }
+      };
+
+      for (int q = q0; q < q0 + n_super; ++q) {
+        const int ptile = nctx * q + c;
+        if (ptile >= p.num_ptiles) continue;
+        const int tile = 2 * ptile + static_cast<int>(rank);     // 128-row tile of every tile image
+        const bool tile_ok = tile < p.num_tiles;
+        const int64_t row0 = static_cast<int64_t>(tile) * 128;
+#ifdef NRC_CHAIN_TRACE
+        const int trace_it = q - q0;
+        const bool tracing = blockIdx.x == 0 && first && wg_tid == 0 && trace_it < kTraceTiles;
+        if (tracing) g_chain_trace[c][trace_it][kTraceOps - 1] = clock64();
+#endif
+        for (int i = 0; i < nops;) {
+          const DevOp& op = sops[i];
+          if (op.kind == NRC_OP_GEMM) {
+            fence_proxy_async_smem();
+            tc_fence_before();
+            named_barrier_sync(1 + c, ctxT);
+            if (wg_tid == 0) {
+              if (!w_waited) { mbar_wait(w_ready, 0); w_waited = true; if (first) TRACE_MARK(11); }
+              if (img_pending) { mbar_arrive(img_ready(c)); mbar_wait(img_ready(c), img_par); img_par ^= 1u; img_pending = false; }
+              mbar_arrive_cluster(a_ready_remote);
+            }
+            while (i < nops && sops[i].kind == NRC_OP_GEMM) ++i;
+            mbar_wait(acc_ready(c), acc_par);
+            acc_par ^= 1u;
+            tc_fence_after();
+#ifdef NRC_CHAIN_TRACE
+            if (tracing) g_chain_trace[c][trace_it][i - 1] = clock64();
+#endif
+            continue;
+          }
+          if (op.kind == NRC_OP_LOADIMG) {
+            // bf16 atoms written by the producer (another chain's SAVE, a per-point kernel) straight into the slots;
+            // consecutive LOADIMG ops before a GEMM share one barrier phase
+            guard_slots();
+            if (wg_tid == 0 && tile_ok) {
+              // every LOADIMG adds its bytes to the phase; the one arrival follows at the GEMM that consumes them
+              mbar_expect_tx(img_ready(c), static_cast<uint32_t>(op.npad) * kAtomBytes);
+              img_pending = true;
+              const uint8_t* img = static_cast<const uint8_t*>(op.ptr);
+              for (int a = 0; a < op.npad; ++a)
+                bulk_g2s(slot_addr(c, op.slot + a), img + (static_cast<size_t>(tile) * op.img_atoms + op.col0 + a) * kAtomBytes,
+                         kAtomBytes, img_ready(c));
+            }
+          } else if (op.kind == NRC_OP_LOAD) {
+            guard_slots();
+            const float* src = static_cast<const float*>(op.ptr);
+            const int nch = op.npad >> 3;
+            const bool vec = src && (op.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+            constexpr int kU = 4;
+            const int total = 128 * nch;
+            for (int item0 = wg_tid; item0 < total; item0 += ctxT * kU) {
+              float v[kU][8];
+#pragma unroll
+              for (int u = 0; u < kU; ++u) {
+                const int item = item0 + u * ctxT;
+                const int rr = item / nch;
+                const int col = (item - rr * nch) * 8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+                if (item < total && src && row0 + rr < p.num_rows && col < op.ncols) {
+                  const float* sp = src + (row0 + rr) * op.ld + col;
+                  if (vec && col + 8 <= op.ncols) {
+                    const float4 x0 = __ldg(reinterpret_cast<const float4*>(sp));
+                    const float4 x1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+                    v[u][0] = x0.x; v[u][1] = x0.y; v[u][2] = x0.z; v[u][3] = x0.w;
+                    v[u][4] = x1.x; v[u][5] = x1.y; v[u][6] = x1.z; v[u][7] = x1.w;
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                      if (col + e < op.ncols) v[u][e] = __ldg(sp + e);
+                  }
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < kU; ++u) {
+                const int item = item0 + u * ctxT;
+                if (item >= total) continue;
+                const int rr = item / nch;
+                const int dcol = op.col0 + (item - rr * nch) * 8;
+                const uint32_t dst = slot_addr(c, op.slot + (dcol >> 6)) + atom_chunk_offset(rr, (dcol & 63) >> 3);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack2_bf16(v[u][0], v[u][1])),
+                             "r"(pack2_bf16(v[u][2], v[u][3])), "r"(pack2_bf16(v[u][4], v[u][5])),
+                             "r"(pack2_bf16(v[u][6], v[u][7]))
+                             : "memory");
+              }
+            }
+          } else if (op.kind == NRC_OP_SAVE) {
+            fence_proxy_async_smem();
+            named_barrier_sync(1 + c, ctxT);
+            if (wg_tid == 0 && tile_ok) {
+              uint8_t* img = static_cast<uint8_t*>(op.ptr);
+              for (int a = 0; a < op.npad; ++a)
+                bulk_s2g(img + (static_cast<size_t>(tile) * op.img_atoms + op.col0 + a) * kAtomBytes,
+                         slot_addr(c, op.slot + a), kAtomBytes);
+              bulk_commit();
+            }
+            store_pending = true;
+          } else {  // NRC_OP_EPI
+            if (op.slot >= 0) guard_slots();
+            EpiArgs a;
+            a.bias = static_cast<const float*>(op.ptr);
+            a.bias_s = op.bias_off >= 0 ? sbias + op.bias_off : nullptr;
+            float* out = static_cast<float*>(op.out);
+            a.out_row = (out && row0 + r < p.num_rows) ? out + (row0 + r) * op.ld + op.col0 : nullptr;
+            a.out_vec = out && (op.ld % 4 == 0) && (op.col0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+            a.accum = (op.flags & NRC_EPI_OUT_ACCUMULATE) != 0;
+            a.mask_tile = (op.mask && tile_ok)
+                              ? static_cast<const uint8_t*>(op.mask) + static_cast<size_t>(tile) * op.img_atoms * kAtomBytes
+                              : nullptr;
+            a.mask_atom0 = op.mask_atom0;
+            a.taddr = tmem_base + t_lane + static_cast<uint32_t>(c * kCtxTmemCols + op.tmem_col);
+            a.has_slot = op.slot >= 0;
+            a.slot0_addr = a.has_slot ? slot_addr(c, op.slot) : 0u;
+            a.ncols = op.ncols; a.npad = op.npad; a.r = r; a.half = half; a.nparts = parts;
+            const bool full = (op.ncols == op.npad) && (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
+            const bool relu = (op.flags & NRC_EPI_RELU) != 0;
+            if (out && op.n > 0 && !op.mask && (!a.bias || a.bias_s)) {
+              // fp32 row output through the staging slot the program names (op.n - 1)
+              guard_slots();
+              float* obase = out + op.col0;
+              const uint32_t st = slot_addr(c, op.n - 1);
+              epi_staged(a.taddr, a.bias ? a.bias_s : nullptr, relu, st, r, half, op.ncols, op.npad, obase, row0, p.num_rows, op.ld,
+                         a.accum, a.has_slot, a.slot0_addr, 1 + c, ctxT, wg_tid);
+            } else if (a.has_slot && !out && op.ncols == op.npad && (!a.bias || a.bias_s) && (tile_ok || !op.mask)) {
+              // the accumulator only becomes the next operand: tight path
+              if (a.mask_tile) epi_slot_fast<true>(a.taddr, nullptr, false, a.slot0_addr, r, op.npad, half, parts, a.mask_tile, a.mask_atom0);
+              else             epi_slot_fast<false>(a.taddr, a.bias ? a.bias_s : nullptr, relu, a.slot0_addr, r, op.npad, half, parts, nullptr, 0);
+            } else if (a.mask_tile) {
+              if (full) epi_run<false, false, true, true>(a); else epi_run<false, false, true, false>(a);
+            } else if (a.bias) {
+              if (relu) { if (full) epi_run<true, true, false, true>(a); else epi_run<true, true, false, false>(a); }
+              else      { if (full) epi_run<true, false, false, true>(a); else epi_run<true, false, false, false>(a); }
+            } else {
+              if (relu) { if (full) epi_run<false, true, false, true>(a); else epi_run<false, true, false, false>(a); }
+              else      { if (full) epi_run<false, false, false, true>(a); else epi_run<false, false, false, false>(a); }
+            }
+          }
+#ifdef NRC_CHAIN_TRACE
+          if (tracing) g_chain_trace[c][trace_it][i] = clock64();
+#endif
+          ++i;
+        }
+      }
+      if (first) TRACE_MARK(12);
+      if (wg_tid == 0) bulk_wait0();
     }
-    TRACE_MARK(12);
-    if (wg_tid == 0) bulk_wait0();
+    __syncwarp();
+    first = false;
   }
 
-  __syncwarp();
   tc_fence_before();
   TRACE_MARK(13);
   cluster_sync_all();   // no CTA leaves (or frees tensor memory) while its partner may still use its memories
-  if (warp == 0) tmem_dealloc2(tmem_base, 512);
+  if (warp == 0 && !first) tmem_dealloc2(tmem_base, 512);
   TRACE_NS(15);
 }
 
@@ -1335,10 +1366,11 @@ static int sm_count() {
   return n;
 }
 
-static int32_t chain2_launch(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
-                             const void* d_weights_packed, int64_t num_rows) {
-  static thread_local Chain2Params hp;
-  Chain2Plan& pl = hp.plan;
+// Resolve one program into the plan the pair kernel executes.  NRC_E_UNSUPPORTED when it does not fit (the caller
+// then falls back to the streaming kernel).
+static int32_t chain2_build(const nrc_chain_program_t* prog, void* const* d_ptrs, const void* d_weights_packed,
+                            Chain2Prog& out, int& cost) {
+  Chain2Plan& pl = out.plan;
   const int nops = prog->num_ops;
   const int S = prog->slots_per_ctx;
   // resident weight layout: byte offset of every GEMM's first K atom inside the CTA's weight region
@@ -1387,6 +1419,8 @@ static int32_t chain2_launch(void* stream, const nrc_chain_program_t* prog, void
   int bias_cur = 0;
   pl.n_ops = nops; pl.n_mma = 0; pl.n_bias = 0;
   auto ptr_of = [&](int32_t i) -> void* { return i >= 0 ? d_ptrs[i] : nullptr; };
+  const uint32_t slot0 = static_cast<uint32_t>(kTail2Bytes + w_bytes);   // context 0's first slot, relative to the CTA's shared memory
+  int n_groups = 0, epi_cols = 0;
   for (int i = 0; i < nops; ++i) {
     const nrc_chain_op_t& o = prog->ops[i];
     DevOp& d = pl.ops[i];
@@ -1402,6 +1436,7 @@ static int32_t chain2_launch(void* stream, const nrc_chain_program_t* prog, void
     d.ptr = ptr_of(o.ptr); d.out = ptr_of(o.out_ptr); d.mask = ptr_of(o.mask_ptr);
     for (int a = 0; a < NRC_CHAIN_MAX_ATOMS; ++a) d.a_src[a] = static_cast<uint8_t>((o.a_slot[a] & 15) | ((o.a_klen[a] >> 4) << 4));
     d.bias_off = -1;
+    if (o.kind == NRC_OP_EPI) epi_cols += o.npad;
     if (o.kind == NRC_OP_EPI && o.ptr >= 0 && o.mask_ptr < 0 && pl.n_bias < kMaxBias && bias_cur + o.npad <= bias_cap) {
       const uintptr_t bp = reinterpret_cast<uintptr_t>(d.ptr);
       pl.bias[pl.n_bias++] = make_uint4(static_cast<uint32_t>(bp), static_cast<uint32_t>(static_cast<uint64_t>(bp) >> 32),
@@ -1414,12 +1449,13 @@ static int32_t chain2_launch(void* stream, const nrc_chain_program_t* prog, void
       // this op's UMMA instructions as ready-made descriptor words (context 0, addresses relative to the CTA's dynamic
       // shared memory; the issuer adds the base and the context's slot offset): the issuing thread spends a handful of
       // instructions per UMMA instead of re-deriving everything from the program
+      if (i == 0 || prog->ops[i - 1].kind != NRC_OP_GEMM) ++n_groups;
       const int first = pl.n_mma;
       const uint32_t idesc = make_idesc(256, o.n, 0, 0);
       const uint32_t half_bytes = static_cast<uint32_t>(o.n) * 64u;
       for (int a = 0; a < o.n_atoms; ++a) {
-        const uint32_t a_addr = static_cast<uint32_t>(w_bytes) + static_cast<uint32_t>(o.a_slot[a]) * kAtomBytes;
-        const uint32_t b_addr = static_cast<uint32_t>(w_off[i]) + static_cast<uint32_t>(a) * half_bytes;
+        const uint32_t a_addr = slot0 + static_cast<uint32_t>(o.a_slot[a]) * kAtomBytes;
+        const uint32_t b_addr = static_cast<uint32_t>(kTail2Bytes + w_off[i]) + static_cast<uint32_t>(a) * half_bytes;
         for (int k = 0; k < (o.a_klen[a] >> 4); ++k) {
           if (pl.n_mma >= kMaxMma) return NRC_E_UNSUPPORTED;
           const uint32_t acc = ((o.flags & NRC_GEMM_ACCUMULATE) || a > 0 || k > 0) ? 0x80000000u : 0u;
@@ -1431,26 +1467,73 @@ static int32_t chain2_launch(void* stream, const nrc_chain_program_t* prog, void
       d.col0 = static_cast<int16_t>(pl.n_mma - first);
     }
   }
-  hp.weights = static_cast<const uint8_t*>(d_weights_packed);
+  out.weights = static_cast<const uint8_t*>(d_weights_packed);
+  out.w_bytes = w_bytes;
+  out.slots_per_ctx = S;
+  out.nctx = nctx;
+  // cycles one super tile (nctx pair tiles in flight together) takes, from the per-op timelines of the trace build:
+  // ~100 per UMMA, ~11 per accumulator column drained, ~900 per GEMM group (barrier round trip), ~100 per op
+  cost = pl.n_mma * 100 + epi_cols * 11 + n_groups * 900 + nops * 100 + 1500;
+  if (nctx == 2) cost += cost / 4;
+  return NRC_OK;
+}
+
+// Launch of up to kMaxProgs programs over the same rows on the CTA-pair kernel.
+static int32_t chain2_launch(void* stream, int32_t n_progs, const nrc_chain_program_t* const* progs, void* const* const* d_ptrs,
+                             const void* const* d_weights, int64_t num_rows) {
+  static thread_local Chain2Params hp;
+  if (n_progs < 1 || n_progs > kMaxProgs) return NRC_E_INVALID_ARG;
+  int cost[kMaxProgs], n_super[kMaxProgs];
   hp.num_rows = num_rows;
   hp.num_tiles = static_cast<int32_t>((num_rows + 127) / 128);
   hp.num_ptiles = (hp.num_tiles + 1) / 2;
-  hp.w_bytes = w_bytes;
-  hp.slots_per_ctx = S;
-  const size_t smem = static_cast<size_t>(w_bytes) + static_cast<size_t>(nctx * S) * kAtomBytes + kTail2Bytes;
-  const int num_super = (hp.num_ptiles + nctx - 1) / nctx;
-  const int max_pairs = sm_count() / 2;
-  const int pairs = num_super < max_pairs ? num_super : max_pairs;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (nctx == 1) {
-    if (cudaFuncSetAttribute(chain2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
-      return check_launch();
-    chain2_kernel<1><<<2 * pairs, kChainThreads, smem, s>>>(hp);
-  } else {
-    if (cudaFuncSetAttribute(chain2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
-      return check_launch();
-    chain2_kernel<2><<<2 * pairs, kChainThreads, smem, s>>>(hp);
+  hp.n_progs = n_progs;
+  size_t smem = 0;
+  long long total = 0;
+  int total_units = 0;
+  for (int k = 0; k < n_progs; ++k) {
+    const int32_t st = chain2_build(progs[k], d_ptrs[k], d_weights[k], hp.prog[k], cost[k]);
+    if (st != NRC_OK) return st;
+    const Chain2Prog& pg = hp.prog[k];
+    const size_t need = static_cast<size_t>(kTail2Bytes) + pg.w_bytes + static_cast<size_t>(pg.nctx * pg.slots_per_ctx) * kAtomBytes;
+    if (need > smem) smem = need;
+    n_super[k] = (hp.num_ptiles + pg.nctx - 1) / pg.nctx;
+    if (n_super[k] > 65535) return NRC_E_UNSUPPORTED;
+    total += static_cast<long long>(n_super[k]) * cost[k];
+    total_units += n_super[k];
   }
+  int pairs = sm_count() / 2;
+  if (pairs > kMaxPairs) pairs = kMaxPairs;
+  if (pairs > total_units) pairs = total_units;
+  // deal the (program, super tile) items to the pairs in contiguous ranges of equal estimated time; a pair that
+  // starts a further program pays its set-up (weights + barriers) on top
+  for (int k = 0; k < n_progs; ++k)
+    for (int i = 0; i < kMaxPairs; ++i) hp.seg_t0[k][i] = hp.seg_n[k][i] = 0;
+  {
+    int k = 0, t = 0;
+    long long done = 0;
+    for (int i = 0; i < pairs; ++i) {
+      const long long goal = total * (i + 1) / pairs;
+      bool any = false;
+      while (k < n_progs) {
+        if (t >= n_super[k]) { ++k; t = 0; continue; }
+        // take the item if the pair has none yet or taking it stays closer to the goal than leaving it
+        if (any && done + cost[k] / 2 > goal && i + 1 < pairs) break;
+        if (hp.seg_n[k][i] == 0) hp.seg_t0[k][i] = static_cast<uint16_t>(t);
+        ++hp.seg_n[k][i];
+        ++t;
+        done += cost[k];
+        any = true;
+      }
+    }
+  }
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+      return check_launch();
+    attr_set = true;
+  }
+  chain2_kernel<<<2 * pairs, kChainThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
   return check_launch();
 }
 
@@ -1463,7 +1546,7 @@ static int32_t chain_launch(void* stream, const nrc_chain_program_t* prog, void*
   if (!enc) {   // CTA-pair kernel with resident weights whenever the program fits (NRC_CHAIN_V1=1: streaming kernel)
     const char* v1 = getenv("NRC_CHAIN_V1");
     if (!(v1 && v1[0] == '1')) {
-      const int32_t s2 = chain2_launch(stream, prog, d_ptrs, num_ptrs, d_weights_packed, num_rows);
+      const int32_t s2 = chain2_launch(stream, 1, &prog, &d_ptrs, &d_weights_packed, num_rows);
       if (s2 != NRC_E_UNSUPPORTED) return s2;
     }
   }
@@ -1522,6 +1605,29 @@ extern "C" int32_t nrc_chain_marks_dump(long long* host_out) {
 extern "C" int32_t nrc_chain_run(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,
                                  const void* d_weights_packed, int64_t num_rows) {
   return chain_launch(stream, prog, d_ptrs, num_ptrs, d_weights_packed, num_rows, nullptr, 0.f);
+}
+
+extern "C" int32_t nrc_chain_run_multi(void* stream, int32_t num_programs, const nrc_chain_program_t* const* progs,
+                                       void* const* const* d_ptrs, const int32_t* num_ptrs, const void* const* d_weights_packed,
+                                       int64_t num_rows) {
+  if (num_programs < 1 || num_programs > NRC_CHAIN_MAX_PROGRAMS || !progs || !d_ptrs || !num_ptrs || !d_weights_packed || num_rows < 0)
+    return NRC_E_INVALID_ARG;
+  for (int k = 0; k < num_programs; ++k) {
+    if (!d_ptrs[k] || num_ptrs[k] < 0 || num_ptrs[k] > NRC_CHAIN_MAX_PTRS) return NRC_E_INVALID_ARG;
+    const int32_t st = validate_program(progs[k], num_ptrs[k]);
+    if (st != NRC_OK) return st;
+  }
+  if (num_rows == 0) return NRC_OK;
+  const char* v1 = getenv("NRC_CHAIN_V1");
+  if (!(v1 && v1[0] == '1')) {
+    const int32_t s2 = chain2_launch(stream, num_programs, progs, d_ptrs, d_weights_packed, num_rows);
+    if (s2 != NRC_E_UNSUPPORTED) return s2;
+  }
+  for (int k = 0; k < num_programs; ++k) {   // a program the pair kernel cannot hold: one launch per program
+    const int32_t st = chain_launch(stream, progs[k], d_ptrs[k], num_ptrs[k], d_weights_packed[k], num_rows, nullptr, 0.f);
+    if (st != NRC_OK) return st;
+  }
+  return NRC_OK;
 }
 
 extern "C" int32_t nrc_chain_query(void* stream, const nrc_chain_program_t* prog, void* const* d_ptrs, int32_t num_ptrs,

@@ -9,12 +9,18 @@ namespace nrc {
 constexpr int kMaxL = 16;      // deg_view <= 5
 constexpr int kMaxSh = 36;     // 2+3+5+9+17
 
+constexpr int kIdeLanes = 8;   // threads that share one point in the fused shader stages (shader.cu)
+constexpr int kIdePerLane = 8;
+
 struct IdeTable {
   int n_sh;
   int l_max;
   int m[kMaxSh];
   int l[kMaxSh];
   float sigma[kMaxSh];
+  // harmonics each of the kIdeLanes threads of a point evaluates, most expensive first (0xFF = none): the lanes of a
+  // warp walk their lists in lockstep, step j costs about the same in every lane
+  unsigned char lane_list[kIdeLanes][kIdePerLane];
 };
 
 // Powers shared by the forward and the VJP.  The l = 16 Legendre polynomials are alternating sums
@@ -33,6 +39,20 @@ struct IdePowers {
     }
   }
 };
+
+// The z-polynomial of harmonic i and its derivative by Horner's rule in fp64 (no power table: l - m fused multiply-adds
+// in a thread that owns only a few harmonics).
+__device__ __forceinline__ void ide_poly_horner(const IdeTable& tab, const float* __restrict__ mat, int i, double z,
+                                                float& poly, float& dpoly) {
+  const int n = tab.l[i] - tab.m[i];
+  double pv = static_cast<double>(__ldg(mat + n * tab.n_sh + i)), dv = 0.0;
+  for (int k = n - 1; k >= 0; --k) {
+    dv = fma(dv, z, pv);
+    pv = fma(pv, z, static_cast<double>(__ldg(mat + k * tab.n_sh + i)));
+  }
+  poly = static_cast<float>(pv);
+  dpoly = static_cast<float>(dv);
+}
 
 // i-th harmonic: (real, imaginary) parts.
 __device__ __forceinline__ void ide_term(const IdeTable& tab, const float* __restrict__ mat, const IdePowers& pw,
@@ -81,6 +101,23 @@ inline int32_t make_ide_table(int32_t n_sh, const int32_t* ml_m, const int32_t* 
     if (ml_l[i] < 0 || ml_l[i] > kMaxL || ml_m[i] < 0 || ml_m[i] > ml_l[i]) return NRC_E_INVALID_ARG;
     t.m[i] = ml_m[i]; t.l[i] = ml_l[i]; t.sigma[i] = sigma[i];
     if (ml_l[i] > t.l_max) t.l_max = ml_l[i];
+  }
+  // longest-processing-time assignment of the harmonics to the lanes of a point
+  int load[kIdeLanes] = {0}, cnt[kIdeLanes] = {0};
+  bool done[kMaxSh] = {false};
+  for (int q = 0; q < kIdeLanes; ++q)
+    for (int j = 0; j < kIdePerLane; ++j) t.lane_list[q][j] = 0xFF;
+  for (int it = 0; it < n_sh; ++it) {
+    int best = -1;
+    for (int i = 0; i < n_sh; ++i)
+      if (!done[i] && (best < 0 || ml_l[i] - ml_m[i] > ml_l[best] - ml_m[best])) best = i;
+    int lane = -1;
+    for (int q = 0; q < kIdeLanes; ++q)
+      if (cnt[q] < kIdePerLane && (lane < 0 || load[q] < load[lane])) lane = q;
+    if (lane < 0) return NRC_E_UNSUPPORTED;
+    t.lane_list[lane][cnt[lane]++] = static_cast<unsigned char>(best);
+    load[lane] += ml_l[best] - ml_m[best] + 6;
+    done[best] = true;
   }
   return NRC_OK;
 }

@@ -51,66 +51,173 @@ struct ShaderGeom {
   }
 };
 
-__global__ void shader_mid_fwd_kernel(const __grid_constant__ IdeTable tab, int n_sh_env, const float* __restrict__ mat,
-                                      const float* __restrict__ heads, int64_t ldh, const float* __restrict__ normals,
-                                      const float* __restrict__ viewdirs, int64_t P, int32_t spr, float rough_bias,
-                                      float* __restrict__ roughness, float* __restrict__ dotprod,
-                                      float* __restrict__ refdirs, float* __restrict__ ide_slf,
-                                      float* __restrict__ ide_env, const nrc_shader_images_t im) {
-  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= P) return;
+// mid stages: kIdeLanes threads per point (a 128-thread-per-CTA, thread-per-point version was latency bound: 222
+// dependent fp64 multiply-adds per thread at ~7 resident warps per SM took 30 us (forward) / 40 us (VJP) for 32 768
+// points).  Each lane evaluates the harmonics the table assigns to it (Horner in fp64), the point's values meet in
+// shared memory, and the bf16 operand rows of the downstream stacks leave as whole 16-byte chunks.
+constexpr int kMidPts = 32;                      // points per CTA
+constexpr int kMidThreads = kMidPts * kIdeLanes;
+constexpr int kMidRow = 2 * kMaxSh + 4;          // staged floats per point: [re | im] of the degree-5 list, n.v
+
+__global__ void __launch_bounds__(kMidThreads)
+shader_mid_fwd_kernel(const __grid_constant__ IdeTable tab, int n_sh_env, const float* __restrict__ mat,
+                      const float* __restrict__ heads, int64_t ldh, const float* __restrict__ normals,
+                      const float* __restrict__ viewdirs, int64_t P, int32_t spr, float rough_bias,
+                      float* __restrict__ roughness, float* __restrict__ dotprod, float* __restrict__ refdirs,
+                      float* __restrict__ ide_slf, float* __restrict__ ide_env, const nrc_shader_images_t im) {
+  __shared__ float sv[kMidPts][kMidRow];
+  __shared__ float2 spw[kMidPts][kMaxL + 1];
+  const int pl = threadIdx.x / kIdeLanes, ln = threadIdx.x % kIdeLanes;
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kMidPts + pl;
+  const bool valid = p < P;
+  const int64_t pc = valid ? p : P - 1;   // out-of-range lanes follow the last point and store nothing
+  const int n_sh = tab.n_sh;
   ShaderGeom g;
-  g.load(normals, viewdirs, p, spr);
-  const float rough = softplus_f(heads[p * ldh] + rough_bias);
-  if (roughness) roughness[p] = rough;
-  if (dotprod) dotprod[p] = g.dot;
-  if (refdirs) { refdirs[3 * p] = g.rx; refdirs[3 * p + 1] = g.ry; refdirs[3 * p + 2] = g.rz; }
-  IdePowers pw;
-  pw.init(tab.l_max, g.rx, g.ry, g.rz);
-  float* o5 = ide_slf ? ide_slf + p * (2 * tab.n_sh) : nullptr;
-  float* o4 = ide_env ? ide_env + p * (2 * n_sh_env) : nullptr;
-  float v5[2 * kMaxSh];   // [re | im] of the degree-5 list, kept for the image rows
-  for (int i = 0; i < tab.n_sh; ++i) {
-    float re, imv;
-    ide_term(tab, mat, pw, rough, i, re, imv);
-    v5[i] = re;
-    v5[tab.n_sh + i] = imv;
-    if (o5) { o5[i] = re; o5[tab.n_sh + i] = imv; }
-    if (o4 && i < n_sh_env) { o4[i] = re; o4[n_sh_env + i] = imv; }
+  g.load(normals, viewdirs, pc, spr);
+  const float rough = softplus_f(heads[pc * ldh] + rough_bias);
+  if (ln == 0) {
+    if (valid) {
+      if (roughness) roughness[p] = rough;
+      if (dotprod) dotprod[p] = g.dot;
+      if (refdirs) { refdirs[3 * p] = g.rx; refdirs[3 * p + 1] = g.ry; refdirs[3 * p + 2] = g.rz; }
+    }
+    sv[pl][2 * kMaxSh] = g.dot;
+    // (x + iy)^k of the reflection direction, shared by the point's lanes
+    float cr = 1.f, ci = 0.f;
+    spw[pl][0] = make_float2(1.f, 0.f);
+    for (int k = 1; k <= tab.l_max; ++k) {
+      const float nr = cr * g.rx - ci * g.ry;
+      ci = cr * g.ry + ci * g.rx;
+      cr = nr;
+      spw[pl][k] = make_float2(cr, ci);
+    }
   }
-  if (im.slf_img) store_row_atoms(static_cast<uint8_t*>(im.slf_img), im.slf_img_atoms, im.slf_atom0, p, v5, 2 * tab.n_sh,
-                                  (2 * tab.n_sh + 15) & ~15);
-  if (im.env_img) {
-    float v4[2 * kMaxSh];
-    for (int i = 0; i < n_sh_env; ++i) { v4[i] = v5[i]; v4[n_sh_env + i] = v5[tab.n_sh + i]; }
-    store_row_atoms(static_cast<uint8_t*>(im.env_img), im.env_img_atoms, im.env_atom0, p, v4, 2 * n_sh_env,
-                    (2 * n_sh_env + 15) & ~15);
+  __syncwarp();
+  const double z = static_cast<double>(g.rz);
+  for (int j = 0; j < kIdePerLane; ++j) {
+    const int i = tab.lane_list[ln][j];
+    if (i == 0xFF) break;
+    float poly, dpoly;
+    ide_poly_horner(tab, mat, i, z, poly, dpoly);
+    const float att = expf(-tab.sigma[i] * rough);
+    const float2 c = spw[pl][tab.m[i]];
+    sv[pl][i] = c.x * poly * att;
+    sv[pl][n_sh + i] = c.y * poly * att;
   }
-  if (im.dot_img) store_row_atoms(static_cast<uint8_t*>(im.dot_img), im.dot_img_atoms, im.dot_atom0, p, &g.dot, 1, 16);
+  __syncwarp();   // the kIdeLanes threads of a point sit in one warp
+  if (valid) {    // optional fp32 copies (exact-mode stacks read these)
+    if (ide_slf)
+      for (int j = ln; j < 2 * n_sh; j += kIdeLanes) ide_slf[p * (2 * n_sh) + j] = sv[pl][j];
+    if (ide_env)
+      for (int j = ln; j < 2 * n_sh_env; j += kIdeLanes)
+        ide_env[p * (2 * n_sh_env) + j] = sv[pl][j < n_sh_env ? j : n_sh + (j - n_sh_env)];
+  }
+  // bf16 operand rows: 16-byte chunks dealt to the lanes of the warp (its 32 / kIdeLanes points)
+  const int wl = threadIdx.x & 31;
+  const int pts_per_warp = 32 / kIdeLanes;
+  const int n_slf = im.slf_img ? (((2 * n_sh + 15) & ~15) >> 3) : 0;
+  const int n_env = im.env_img ? (((2 * n_sh_env + 15) & ~15) >> 3) : 0;
+  const int n_dot = im.dot_img ? 2 : 0;
+  const int per_pt = n_slf + n_env + n_dot;
+  const int pl0 = (threadIdx.x >> 5) * pts_per_warp;
+  for (int id = wl; id < per_pt * pts_per_warp; id += 32) {
+    const int q = id / per_pt;
+    int ch = id - q * per_pt;
+    const int64_t pp = static_cast<int64_t>(blockIdx.x) * kMidPts + pl0 + q;
+    if (pp >= P) continue;
+    const float* row = sv[pl0 + q];
+    float v[8];
+    uint8_t* img;
+    int img_atoms, atom0;
+    if (ch < n_slf) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (8 * ch + e < 2 * n_sh) ? row[8 * ch + e] : 0.f;
+      img = static_cast<uint8_t*>(im.slf_img); img_atoms = im.slf_img_atoms; atom0 = im.slf_atom0;
+    } else if (ch < n_slf + n_env) {
+      ch -= n_slf;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = 8 * ch + e;
+        v[e] = j < n_sh_env ? row[j] : (j < 2 * n_sh_env ? row[n_sh + (j - n_sh_env)] : 0.f);
+      }
+      img = static_cast<uint8_t*>(im.env_img); img_atoms = im.env_img_atoms; atom0 = im.env_atom0;
+    } else {
+      ch -= n_slf + n_env;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (ch == 0) v[0] = row[2 * kMaxSh];
+      img = static_cast<uint8_t*>(im.dot_img); img_atoms = im.dot_img_atoms; atom0 = im.dot_atom0;
+    }
+    const int64_t tile = pp >> 7;
+    const int r = static_cast<int>(pp & 127);
+    uint8_t* dst = img + (tile * img_atoms + atom0 + (ch >> 3)) * static_cast<int64_t>(tc::kAtomBytes) + tc::atom_chunk_offset(r, ch & 7);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(tc::pack2_bf16(v[0], v[1]), tc::pack2_bf16(v[2], v[3]), tc::pack2_bf16(v[4], v[5]),
+                                                tc::pack2_bf16(v[6], v[7]));
+  }
 }
 
-__global__ void shader_mid_bwd_kernel(const __grid_constant__ IdeTable tab, int n_sh_env, const float* __restrict__ mat,
-                                      const float* __restrict__ heads, int64_t ldh, const float* __restrict__ normals,
-                                      const float* __restrict__ viewdirs, int64_t P, int32_t spr, float rough_bias,
-                                      const float* __restrict__ g_dot, int64_t ldgd, const float* __restrict__ g_ide_slf,
-                                      int64_t ldgs, const float* __restrict__ g_ide_env, int64_t ldge,
-                                      float* __restrict__ g_heads, int64_t ldgh, float* __restrict__ g_normals) {
-  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= P) return;
+__global__ void __launch_bounds__(kMidThreads)
+shader_mid_bwd_kernel(const __grid_constant__ IdeTable tab, int n_sh_env, const float* __restrict__ mat,
+                      const float* __restrict__ heads, int64_t ldh, const float* __restrict__ normals,
+                      const float* __restrict__ viewdirs, int64_t P, int32_t spr, float rough_bias,
+                      const float* __restrict__ g_dot, int64_t ldgd, const float* __restrict__ g_ide_slf, int64_t ldgs,
+                      const float* __restrict__ g_ide_env, int64_t ldge, float* __restrict__ g_heads, int64_t ldgh,
+                      float* __restrict__ g_normals) {
+  const int pl = threadIdx.x / kIdeLanes, ln = threadIdx.x % kIdeLanes;
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kMidPts + pl;
+  const bool valid = p < P;
+  const int64_t pc = valid ? p : P - 1;   // out-of-range lanes follow the last point (the shuffles below are warp wide)
   ShaderGeom g;
-  g.load(normals, viewdirs, p, spr);
-  const float r_raw = heads[p * ldh] + rough_bias;
+  g.load(normals, viewdirs, pc, spr);
+  const float r_raw = heads[pc * ldh] + rough_bias;
   const float rough = softplus_f(r_raw);
-  IdePowers pw;
-  pw.init(tab.l_max, g.rx, g.ry, g.rz);
-  const float* g5 = g_ide_slf + p * ldgs;
-  const float* g4 = g_ide_env ? g_ide_env + p * ldge : nullptr;
-  float grx = 0.f, gry = 0.f, grz = 0.f, gk = 0.f;
-  for (int i = 0; i < tab.n_sh; ++i) {
-    float gr = g5[i], gi = g5[tab.n_sh + i];
-    if (g4 && i < n_sh_env) { gr += g4[i]; gi += g4[n_sh_env + i]; }
-    ide_term_vjp(tab, mat, pw, rough, i, gr, gi, grx, gry, grz, gk);
+  __shared__ float2 spw[kMidPts][kMaxL + 1];
+  if (ln == 0) {
+    float cr = 1.f, ci = 0.f;
+    spw[pl][0] = make_float2(1.f, 0.f);
+    for (int k = 1; k <= tab.l_max; ++k) {
+      const float nr = cr * g.rx - ci * g.ry;
+      ci = cr * g.ry + ci * g.rx;
+      cr = nr;
+      spw[pl][k] = make_float2(cr, ci);
+    }
   }
+  __syncwarp();
+  const double z = static_cast<double>(g.rz);
+  const float* g5 = g_ide_slf + pc * ldgs;
+  const float* g4 = g_ide_env ? g_ide_env + pc * ldge : nullptr;
+  const int n_sh = tab.n_sh;
+  float grx = 0.f, gry = 0.f, grz = 0.f, gk = 0.f;
+  for (int j = 0; j < kIdePerLane; ++j) {
+    const int i = tab.lane_list[ln][j];
+    if (i == 0xFF) break;
+    float gr = g5[i], gi = g5[n_sh + i];
+    if (g4 && i < n_sh_env) { gr += g4[i]; gi += g4[n_sh_env + i]; }
+    float poly, dpoly;
+    ide_poly_horner(tab, mat, i, z, poly, dpoly);
+    const float sig = tab.sigma[i];
+    const float att = expf(-sig * rough);
+    const int m = tab.m[i];
+    const float2 c = spw[pl][m];
+    // out_r = c.x poly att, out_i = c.y poly att
+    const float s = gr * c.x + gi * c.y;
+    grz += s * dpoly * att;
+    gk += -sig * s * poly * att;
+    if (m > 0) {
+      const float2 pm = spw[pl][m - 1];   // d (x+iy)^m / dx = m (x+iy)^(m-1);  d/dy = i m (x+iy)^(m-1)
+      const float fm = static_cast<float>(m) * poly * att;
+      grx += fm * (gr * pm.x + gi * pm.y);
+      gry += fm * (-gr * pm.y + gi * pm.x);
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < kIdeLanes; o <<= 1) {
+    grx += __shfl_xor_sync(0xffffffffu, grx, o);
+    gry += __shfl_xor_sync(0xffffffffu, gry, o);
+    grz += __shfl_xor_sync(0xffffffffu, grz, o);
+    gk += __shfl_xor_sync(0xffffffffu, gk, o);
+  }
+  if (!valid || ln != 0) return;
   // softplus'(x) = sigmoid(x)
   g_heads[p * ldgh] = gk * sigmoid_f(r_raw);
   // dot = n.w ; r = 2 dot n - w  =>  dL/dn = g_dot w + 2 dot g_r + 2 (g_r.n) w
@@ -240,8 +347,8 @@ extern "C" int32_t nrc_shader_mid_fwd(void* stream, int32_t n_sh, const int32_t*
   if (images) im = *images;
   if (!d_mat || !d_heads || !d_normals || !d_viewdirs || (!d_dotprod && !im.dot_img) || (!d_ide_slf && !im.slf_img))
     return NRC_E_INVALID_ARG;
-  const unsigned grid = static_cast<unsigned>((num_points + 127) / 128);
-  shader_mid_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  const unsigned grid = static_cast<unsigned>((num_points + kMidPts - 1) / kMidPts);
+  shader_mid_fwd_kernel<<<grid, kMidThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       t, n_sh_env, d_mat, d_heads, ldh, d_normals, d_viewdirs, num_points, samples_per_ray, roughness_bias, d_roughness,
       d_dotprod, d_refdirs, d_ide_slf, d_ide_env, im);
   return check_launch();
@@ -262,8 +369,8 @@ extern "C" int32_t nrc_shader_mid_bwd(void* stream, int32_t n_sh, const int32_t*
   if (num_points == 0) return NRC_OK;
   if (!d_mat || !d_heads || !d_normals || !d_viewdirs || !d_g_dotprod || !d_g_ide_slf || !d_g_heads || !d_g_normals)
     return NRC_E_INVALID_ARG;
-  const unsigned grid = static_cast<unsigned>((num_points + 127) / 128);
-  shader_mid_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  const unsigned grid = static_cast<unsigned>((num_points + kMidPts - 1) / kMidPts);
+  shader_mid_bwd_kernel<<<grid, kMidThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       t, n_sh_env, d_mat, d_heads, ldh, d_normals, d_viewdirs, num_points, samples_per_ray, roughness_bias, d_g_dotprod,
       ldgd, d_g_ide_slf, ldgs, d_g_ide_env, ldge, d_g_heads, ldgh, d_g_normals);
   return check_launch();

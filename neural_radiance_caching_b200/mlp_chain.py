@@ -370,7 +370,44 @@ def _num_tiles(rows):
     return (rows + 127) // 128
 
 
-def run_forward(spec, params, sources, packed, save=True, head_images=None, head_fp32=None, P=None):
+class Batch:
+    """Collects chain launches over the same rows and issues them as ONE nrc_chain_run_multi call (independent stacks:
+    their tiles are dealt to the CTA pairs together).  Pass `batch=` to run_forward / run_backward_data, then flush()."""
+
+    MAX = 3
+
+    def __init__(self):
+        self.items = []   # (program, pointer array, count, packed weights, P, keep-alive)
+
+    def add(self, prog, ptrs, packed, P):
+        arr, n = ptrs.array()
+        if self.items and self.items[0][4] != P:
+            raise _lib.NrcError("batched chain launches must cover the same rows")
+        self.items.append((prog, arr, n, packed, P, ptrs.tensors))
+        if len(self.items) == self.MAX:
+            self.flush()
+
+    def flush(self):
+        if not self.items:
+            return
+        n = len(self.items)
+        progs = (C.POINTER(nrc_chain_program_t) * n)(*[C.pointer(it[0]) for it in self.items])
+        parr = (C.c_void_p * n)(*[C.cast(it[1], C.c_void_p) for it in self.items])
+        narr = (C.c_int32 * n)(*[it[2] for it in self.items])
+        warr = (C.c_void_p * n)(*[it[3].data_ptr() for it in self.items])
+        _lib.call("nrc_chain_run_multi", _lib.stream_ptr(), n, progs, parr, narr, warr, self.items[0][4])
+        self.items = []
+
+
+def _launch(prog, ptrs, packed, P, batch):
+    if batch is not None:
+        batch.add(prog, ptrs, packed, P)
+        return
+    arr, n = ptrs.array()
+    _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
+
+
+def run_forward(spec, params, sources, packed, save=True, head_images=None, head_fp32=None, P=None, batch=None):
     """sources: per stack input an fp32 [P, w_i] view with contiguous rows, or an ImgRef (whole atoms: the source
     must start on a 64-column boundary).  head_images: {head group: ImgRef} - the group's result is ALSO written as
     bf16 atoms; head_fp32: {head group: False} drops the fp32 copy of such a group.  Returns (per head GROUP fp32
@@ -469,8 +506,7 @@ def run_forward(spec, params, sources, packed, save=True, head_images=None, head
                 outs.append(buf[:, c:c + w] if buf is not None else None)
                 c += w
         g0 = g1
-    arr, n = ptrs.array()
-    _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
+    _launch(prog, ptrs, packed, P, batch)
     return bufs, outs, (ActImage(act, in_refs) if save else None)
 
 
@@ -502,7 +538,7 @@ def run_density_query(spec, params, enc_desc, means, packed, head_bias, warp_c, 
               C.byref(enc_desc), float(warp_c))
 
 
-def run_backward_data(spec, params, g_heads, act, packed, P, d_src=None):
+def run_backward_data(spec, params, g_heads, act, packed, P, d_src=None, batch=None):
     """Data-gradient pass.  g_heads: per head GROUP an fp32 [P, >= group width] view (rows contiguous) or an ImgRef
     holding the group's padded columns as bf16 atoms.  d_src: None (no input gradient) or per source one of
     None / (fp32 [P, w_i] view, accumulate flag) / ImgRef (bf16 atoms; the source must start on a 64-column
@@ -635,8 +671,7 @@ def run_backward_data(spec, params, g_heads, act, packed, P, d_src=None):
                     ld=_ld(t), col0=0, flags=EPI_OUT_ACCUMULATE if accumulate else 0,
                     n=1 if ((out_atoms == 0 or out0 > 0) and w >= 32) else 0)   # staged through slot 0 (every GEMM is done)
             c += w
-    arr, n = ptrs.array()
-    _lib.call("nrc_chain_run", _lib.stream_ptr(), C.byref(prog), arr, n, C.c_void_p(packed.data_ptr()), P)
+    _launch(prog, ptrs, packed, P, batch)
     return DyImage(dy, head_refs)
 
 

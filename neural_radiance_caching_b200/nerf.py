@@ -244,7 +244,7 @@ def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, 
     """Forward schedule of the bf16 cache shader (no autograd): 1 weight pack, contract + appearance-grid
     encode, trunk stack, per-point `mid` stage, integrated-BRDF / EnvMap / SurfaceLightField stacks,
     per-point `out` stage.  `packed` / `encoded` may be supplied by a caller that produced them earlier on
-    another stream; `env_stream` runs the (independent) EnvMap stack concurrently.  Returns (outputs,
+    another stream; `env_stream` is accepted for compatibility (the EnvMap stack now shares one launch with the integrated-BRDF and SurfaceLightField stacks).  Returns (outputs,
     saved-for-backward, meta)."""
     lead = means.shape[:-1]
     P = means.numel() // 3
@@ -271,19 +271,15 @@ def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, 
     _lib.call("nrc_shader_mid_fwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,
               _lib.ptr(heads), heads.shape[1], _lib.ptr(nrm), _lib.ptr(vd), P, spr, -1.0, _lib.ptr(rough),
               None, _lib.ptr(refdirs), None, None, C.byref(images))
-    env_src = [Img(img_aux, 1, 1, 2)]
-    if env_stream is not None:
-        env_stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(env_stream):
-            (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], env_src, views[3], save=False, P=P)
-    else:
-        (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], env_src, views[3], save=False, P=P)
+    # the three stacks behind the mid stage are independent: ONE launch, their tiles dealt to the CTA pairs together
+    batch = mlp_chain.Batch()
     (fbuf,), _, act_b = mlp_chain.run_forward(shader.brdf_chain, params[""], [Img(img_in, 0, 2, 4), Img(img_aux, 0, 1, 2)],
-                                              views[1], save=train, P=P)
+                                              views[1], save=train, P=P, batch=batch)
+    (ebuf,), _, _ = mlp_chain.run_forward(shader.env_map.chain, params["EnvMap"], [Img(img_aux, 1, 1, 2)], views[3], save=False,
+                                          P=P, batch=batch)
     (sbuf,), _, act_s = mlp_chain.run_forward(shader.surface_lf.chain, params["SurfaceLightField"],
-                                              [Img(img_in, 0, 2, 4), Img(img_in, 2, 2, 4)], views[2], save=train, P=P)
-    if env_stream is not None:
-        torch.cuda.current_stream().wait_stream(env_stream)
+                                              [Img(img_in, 0, 2, 4), Img(img_in, 2, 2, 4)], views[2], save=train, P=P, batch=batch)
+    batch.flush()
     rgb = torch.empty((P, 3), device=dev, dtype=torch.float32)
     extras = torch.empty((P, 22), device=dev, dtype=torch.float32)
     lb = float(shader.surface_lf.ambient_rgb_bias)
@@ -322,10 +318,12 @@ def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_a
     Img = mlp_chain.ImgRef
     img_db = mlp_chain.new_image(P, 4, dev)
     g_ide5, g_dot = new(P, 72), new(P, 1)
-    dy_s = mlp_chain.run_backward_data(shader.surface_lf.chain, params["SurfaceLightField"], [g_s], act_s, views[2], P,
-                                       [Img(img_db, 0, 2, 4), (g_ide5, False)])
+    batch = mlp_chain.Batch()
     dy_b = mlp_chain.run_backward_data(shader.brdf_chain, params[""], [g_f], act_b, views[1], P,
-                                       [Img(img_db, 2, 2, 4), (g_dot, False)])
+                                       [Img(img_db, 2, 2, 4), (g_dot, False)], batch=batch)
+    dy_s = mlp_chain.run_backward_data(shader.surface_lf.chain, params["SurfaceLightField"], [g_s], act_s, views[2], P,
+                                       [Img(img_db, 0, 2, 4), (g_ide5, False)], batch=batch)
+    batch.flush()
     g_nrm = new(P, 3)
     t5, t4 = _IdeTables.get(5), _IdeTables.get(4)
     _lib.call("nrc_shader_mid_bwd", _lib.stream_ptr(), t5.n_sh, t5.m, t5.l, t5.sigma, _lib.ptr(t5.mat(dev)), t4.n_sh,

@@ -64,3 +64,32 @@ for name in T.SPECS:
     print(f"{name:9s} P={P} MAC/pt={macs:7d} | fwd(save) {t_f:7.1f} us {fl/t_f/1e6:7.1f} TF/s ({100*fl/t_f/1e6/peak:4.1f}%) | "
           f"fwd(nosave) {t_f0:7.1f} us {fl/t_f0/1e6:7.1f} TF/s | bwd-data {t_b:7.1f} us {fl/t_b/1e6:7.1f} TF/s | "
           f"wgrad {t_w:7.1f} us {fl/t_w/1e6:7.1f} TF/s | pack {t_p:5.1f} us", flush=True)
+
+# the three stacks behind the shader's mid stage: separate launches vs. one multi-program launch
+if only is None or "multi" in only:
+    names = ["int_brdf", "env", "slf"]
+    st = {}
+    for name in names:
+        g = gen(1)
+        spec = mc.ChainSpec(**T.SPECS[name])
+        p = {k: {a: b.to(dev) for a, b in v.items()} for k, v in T.make_params(g, spec).items()}
+        srcs = [f32(g.normal(size=(P, w))).to(dev) for w in spec.in_widths]
+        packed = mc.pack_weights(spec, p)
+        bufs, outs, act = mc.run_forward(spec, p, srcs, packed, save=True)
+        gh = [torch.randn_like(b) for b in bufs]
+        d_src = [(torch.empty((P, w), device=dev), False) for w in spec.in_widths]
+        st[name] = (spec, p, srcs, packed, act, gh, d_src)
+    def fwd(batched):
+        b = mc.Batch() if batched else None
+        for name in names:
+            spec, p, srcs, packed, act, gh, d_src = st[name]
+            mc.run_forward(spec, p, srcs, packed, save=(name != "env"), batch=b)
+        if b: b.flush()
+    def bwd(batched):
+        b = mc.Batch() if batched else None
+        for name in ("int_brdf", "slf"):
+            spec, p, srcs, packed, act, gh, d_src = st[name]
+            mc.run_backward_data(spec, p, gh, act, packed, P, d_src, batch=b)
+        if b: b.flush()
+    print(f"shader stacks P={P}: fwd separate {timeit(lambda: fwd(False)):.1f} us, one launch {timeit(lambda: fwd(True)):.1f} us | "
+          f"bwd separate {timeit(lambda: bwd(False)):.1f} us, one launch {timeit(lambda: bwd(True)):.1f} us", flush=True)
