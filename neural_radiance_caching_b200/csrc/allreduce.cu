@@ -88,7 +88,7 @@ extern "C" int32_t nrc_allreduce_mean_multicast(void* stream, float* mc_base, in
   int64_t v0, v1;
   slice(offset, count, rank, world, v0, v1);
   if (v1 <= v0) return NRC_OK;
-  const int ctas = num_ctas > 0 ? num_ctas : 2 * kNumSMs;
+  const int ctas = num_ctas > 0 ? num_ctas : 2 * num_sms();
   allreduce_mc_kernel<<<ctas, kArThreads, 0, static_cast<cudaStream_t>(stream)>>>(mc_base, v0, v1, 1.0f / world);
   return check_launch();
 }
@@ -107,7 +107,7 @@ extern "C" int32_t nrc_allreduce_mean_peer(void* stream, float* const* peer_base
   int64_t v0, v1;
   slice(offset, count, rank, world, v0, v1);
   if (v1 <= v0) return NRC_OK;
-  const int ctas = num_ctas > 0 ? num_ctas : 2 * kNumSMs;
+  const int ctas = num_ctas > 0 ? num_ctas : 2 * num_sms();
   allreduce_peer_kernel<<<ctas, kArThreads, 0, static_cast<cudaStream_t>(stream)>>>(pp, world, rank, v0, v1, 1.0f / world);
   return check_launch();
 }

@@ -1356,16 +1356,6 @@ static int32_t validate_program(const nrc_chain_program_t* prog, int32_t num_ptr
 
 // v2 launch (CTA pairs, resident weights): returns NRC_E_UNSUPPORTED when the program does not fit, so the caller
 // can fall back to the streaming kernel.
-static int sm_count() {
-  static thread_local int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 2)
-      n = kNumSMs;
-  }
-  return n;
-}
-
 // Resolve one program into the plan the pair kernel executes.  NRC_E_UNSUPPORTED when it does not fit (the caller
 // then falls back to the streaming kernel).
 static int32_t chain2_build(const nrc_chain_program_t* prog, void* const* d_ptrs, const void* d_weights_packed,
@@ -1502,7 +1492,7 @@ static int32_t chain2_launch(void* stream, int32_t n_progs, const nrc_chain_prog
     total += static_cast<long long>(n_super[k]) * cost[k];
     total_units += n_super[k];
   }
-  int pairs = sm_count() / 2;
+  int pairs = num_sms() / 2;
   if (pairs > kMaxPairs) pairs = kMaxPairs;
   if (pairs > total_units) pairs = total_units;
   // deal the (program, super tile) items to the pairs in contiguous ranges of equal estimated time; a pair that
@@ -1527,12 +1517,7 @@ static int32_t chain2_launch(void* stream, int32_t n_progs, const nrc_chain_prog
       }
     }
   }
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
-      return check_launch();
-    attr_set = true;
-  }
+  if (const int32_t st_attr = ensure_dynamic_smem<chain2_kernel>(227 * 1024 - 1024); st_attr != NRC_OK) return st_attr;
   chain2_kernel<<<2 * pairs, kChainThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
   return check_launch();
 }
@@ -1574,14 +1559,9 @@ static int32_t chain_launch(void* stream, const nrc_chain_program_t* prog, void*
   if (R > 4) R = 4;
   hp.ring_stages = R;
   const size_t smem = static_cast<size_t>(2 * S + R) * kAtomBytes + kTailBytes;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * kAtomBytes + kTailBytes) != cudaSuccess)
-      return check_launch();
-    attr_set = true;
-  }
+  if (const int32_t st_attr = ensure_dynamic_smem<chain_kernel>(14 * kAtomBytes + kTailBytes); st_attr != NRC_OK) return st_attr;
   const int pairs = (hp.num_tiles + 1) / 2;
-  const int grid = pairs < kNumSMs ? pairs : kNumSMs;
+  const int grid = pairs < num_sms() ? pairs : num_sms();
   chain_kernel<<<grid, kChainThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
   return check_launch();
 }
@@ -1688,17 +1668,12 @@ extern "C" int32_t nrc_chain_wgrad(void* stream, const nrc_wgrad_layer_t* layers
   }
   for (int i = 0; i < NRC_CHAIN_MAX_PTRS; ++i) hp.ptrs[i] = i < num_ptrs ? d_ptrs[i] : nullptr;
   hp.num_tiles = static_cast<int32_t>((num_rows + 127) / 128);
-  int splits = (2 * kNumSMs + num_layers - 1) / num_layers;
+  int splits = (2 * num_sms() + num_layers - 1) / num_layers;
   if (splits > hp.num_tiles) splits = hp.num_tiles;
   hp.tiles_per_cta = (hp.num_tiles + splits - 1) / splits;
   splits = (hp.num_tiles + hp.tiles_per_cta - 1) / hp.tiles_per_cta;
-  static thread_local bool attr_set = false;
   const size_t smem = static_cast<size_t>(1 + kWgradRingAtoms) * kAtomBytes + 1024;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
-      return check_launch();
-    attr_set = true;
-  }
+  if (const int32_t st_attr = ensure_dynamic_smem<wgrad_kernel>(static_cast<int>(smem)); st_attr != NRC_OK) return st_attr;
   wgrad_kernel<<<dim3(splits, num_layers), kWgradThreads, smem, static_cast<cudaStream_t>(stream)>>>(hp);
   return check_launch();
 }

@@ -343,7 +343,7 @@ static int32_t grid_regularizer(void* stream, const nrc_encoding_t* enc, float m
   if (!d_loss) return NRC_E_INVALID_ARG;
   for (int l = 0; l < d.L; ++l)
     if (!d.lv[l].grad) return NRC_E_INVALID_ARG;
-  grid_regularizer_kernel<<<dim3(2 * kNumSMs, d.L), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, mult, d_loss, overwrite);
+  grid_regularizer_kernel<<<dim3(2 * num_sms(), d.L), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, mult, d_loss, overwrite);
   return check_launch();
 }
 

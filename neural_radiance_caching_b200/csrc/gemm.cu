@@ -346,7 +346,7 @@ extern "C" int32_t nrc_dense_bwd(void* stream, const float* d_x, int64_t ldx, co
     g.M = in_dim; g.N = out_dim; g.K = static_cast<int>(num_rows);
     int tiles = ((in_dim + BM - 1) / BM) * ((out_dim + BN - 1) / BN);
     int chunks = (g.K + BK - 1) / BK;
-    int splits = (2 * kNumSMs + tiles - 1) / tiles;
+    int splits = (2 * num_sms() + tiles - 1) / tiles;
     g.k_splits = splits < 1 ? 1 : (splits > chunks ? chunks : splits);
     if (g.k_splits == 1) g.accumulate = 1;
     int32_t s = launch_gemm<true, false>(st, g, bf16);

@@ -201,14 +201,9 @@ density_mlp_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc,
 
 int32_t density_mlp_fwd_f32(cudaStream_t s, const nrc_density_mlp_t* mlp, const float* d_enc, int64_t P,
                             float* d_raw, float* d_feat, float* d_gp) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(density_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(sizeof(FwdSmem)));
-    attr_set = true;
-  }
+  if (const int32_t st_attr = ensure_dynamic_smem<density_mlp_fwd_kernel>(static_cast<int>(sizeof(FwdSmem))); st_attr != NRC_OK) return st_attr;
   int64_t tiles = (P + kT - 1) / kT;
-  unsigned grid = static_cast<unsigned>(tiles < kNumSMs * 3 ? tiles : kNumSMs * 3);
+  unsigned grid = static_cast<unsigned>(tiles < num_sms() * 3 ? tiles : num_sms() * 3);
   density_mlp_fwd_kernel<<<grid, kT, sizeof(FwdSmem), s>>>(*mlp, d_enc, P, d_raw, d_feat, d_gp);
   return check_launch();
 }
@@ -262,14 +257,9 @@ extern "C" int32_t nrc_density_mlp_bwd(void* stream, const nrc_density_mlp_t* ml
   if (bf16)
     return density_mlp_bwd_bf16(static_cast<cudaStream_t>(stream), mlp, d_enc, d_g_raw, d_density, d_g_feat,
                                 d_g_grad_pred, num_points, d_g_enc, want ? &g : nullptr);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(density_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(sizeof(BwdSmem)));
-    attr_set = true;
-  }
+  if (const int32_t st_attr = ensure_dynamic_smem<density_mlp_bwd_kernel>(static_cast<int>(sizeof(BwdSmem))); st_attr != NRC_OK) return st_attr;
   int64_t tiles = (num_points + kT - 1) / kT;
-  unsigned grid = static_cast<unsigned>(tiles < kNumSMs ? tiles : kNumSMs);
+  unsigned grid = static_cast<unsigned>(tiles < num_sms() ? tiles : num_sms());
   density_mlp_bwd_kernel<<<grid, kT, sizeof(BwdSmem), static_cast<cudaStream_t>(stream)>>>(
       *mlp, d_enc, d_g_raw, d_density, d_g_feat, d_g_grad_pred, num_points, d_g_enc, g, want);
   return check_launch();

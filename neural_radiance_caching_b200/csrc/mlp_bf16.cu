@@ -392,12 +392,7 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
 template <int F, int KS0, bool kFused, int kMinCtas>
 int32_t launch_bf16_fwd_occ(cudaStream_t st, const EncDev& d, const nrc_density_mlp_t* mlp, const float* in,
                             int64_t P, float warp_c, float bias, const QueryOut& out) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(mlp_bf16_fwd_kernel<F, KS0, kFused, kMinCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(sizeof(FwdSmemBf16)));
-    attr_set = true;
-  }
+  if (const int32_t st_attr = ensure_dynamic_smem<mlp_bf16_fwd_kernel<F, KS0, kFused, kMinCtas>>(static_cast<int>(sizeof(FwdSmemBf16))); st_attr != NRC_OK) return st_attr;
   static const int ppw_env = getenv("NRC_QUERY_PPW") ? atoi(getenv("NRC_QUERY_PPW")) : 0;
   static const int mult_env = getenv("NRC_QUERY_GRID_MULT") ? atoi(getenv("NRC_QUERY_GRID_MULT")) : 0;
   // bit 0: hash levels gathered two at a time; bit 1: lane-pair gather (default); bit 2: forward-only launches
@@ -409,7 +404,7 @@ int32_t launch_bf16_fwd_occ(cudaStream_t st, const EncDev& d, const nrc_density_
   const size_t smem = grad ? sizeof(FwdSmemBf16) : offsetof(FwdSmemBf16, wg);
   // resident CTAs per SM: kMinCtas by registers; the gradient scratch (45 KB per CTA) caps it at 4
   const int resident = (grad && kMinCtas > 4) ? 4 : kMinCtas;
-  const int64_t cap = static_cast<int64_t>(kNumSMs) * (mult_env > 0 ? mult_env : resident);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * (mult_env > 0 ? mult_env : resident);
   // 32 points per warp.  The 16-point mode (NRC_QUERY_PPW=16: twice the CTAs for launches that leave SMs idle, e.g.
   // 32 768 points = 256 CTAs) measured SLOWER on the config-2 step (0.979 vs 0.951 ms, profiles/r01j_ab_runs.txt, block j7): the weight
   // staging per CTA is paid twice as often and the side streams already fill the idle SMs.

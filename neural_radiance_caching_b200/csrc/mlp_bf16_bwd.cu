@@ -341,12 +341,7 @@ template <int KS0>
 int32_t launch_bf16_bwd(cudaStream_t st, const nrc_density_mlp_t* mlp, const float* enc, const float* g_raw,
                         const float* density, const float* g_feat, const float* g_gp, int64_t P, float* g_enc,
                         const nrc_density_mlp_grad_t* grads, const float* enc_dot = nullptr) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(mlp_bf16_bwd_kernel<KS0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(sizeof(BwdSmemBf16)));
-    attr_set = true;
-  }
+  if (const int32_t st_attr = ensure_dynamic_smem<mlp_bf16_bwd_kernel<KS0>>(static_cast<int>(sizeof(BwdSmemBf16))); st_attr != NRC_OK) return st_attr;
   nrc_density_mlp_grad_t g{};
   if (grads) g = *grads;
   int64_t tiles = (P + kBwTile - 1) / kBwTile;
@@ -354,7 +349,7 @@ int32_t launch_bf16_bwd(cudaStream_t st, const nrc_density_mlp_t* mlp, const flo
   // tiles through transposing loads instead of a second copy).  An earlier "2-4 CTAs per SM are slower" measurement
   // was taken when only ONE 117 KB CTA fitted per SM, i.e. it measured extra staging passes, not extra warps.
   static const int mult = getenv("NRC_MLP_BWD_GRID_MULT") ? atoi(getenv("NRC_MLP_BWD_GRID_MULT")) : 2;
-  unsigned grid = static_cast<unsigned>(tiles < kNumSMs * mult ? tiles : kNumSMs * mult);
+  unsigned grid = static_cast<unsigned>(tiles < num_sms() * mult ? tiles : num_sms() * mult);
   mlp_bf16_bwd_kernel<KS0><<<grid, kBwThreads, sizeof(BwdSmemBf16), st>>>(*mlp, enc, g_raw, density, g_feat, g_gp,
                                                                           P, g_enc, g, grads ? 1 : 0, enc_dot);
   return check_launch();

@@ -249,14 +249,9 @@ density_normals_bwd_kernel(const __grid_constant__ EncDev enc, const nrc_density
 template <int F>
 int32_t launch_normals2(cudaStream_t s, const EncDev& d, const nrc_density_mlp_t* mlp, const float* means,
                         const float* g, int64_t P, float warp_c, const nrc_density_mlp_grad_t& grads) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(density_normals_bwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(sizeof(Normals2Smem)));
-    attr_set = true;
-  }
+  if (const int32_t st_attr = ensure_dynamic_smem<density_normals_bwd_kernel<F>>(static_cast<int>(sizeof(Normals2Smem))); st_attr != NRC_OK) return st_attr;
   const int64_t tiles = (P + kT - 1) / kT;
-  const unsigned grid = static_cast<unsigned>(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+  const unsigned grid = static_cast<unsigned>(tiles < 2 * num_sms() ? tiles : 2 * num_sms());
   density_normals_bwd_kernel<F><<<grid, kT, sizeof(Normals2Smem), s>>>(d, *mlp, means, g, P, warp_c, grads);
   return check_launch();
 }

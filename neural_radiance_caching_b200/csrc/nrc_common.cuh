@@ -18,7 +18,31 @@ inline int32_t check_launch() {
   return NRC_OK;
 }
 
-constexpr int kNumSMs = 148;  // B200
+// Multiprocessors of the CURRENT device (148 on a B200), asked once per device: grids are sized from it.
+inline int num_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cache[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cache[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (kernel, device) and report
+// a failure (the launch that follows would otherwise fail with an unrelated message).
+template <auto Kernel>
+inline int32_t ensure_dynamic_smem(int bytes) {
+  static unsigned long long done = 0;   // one bit per device ordinal; a racing second call only repeats the (idempotent) set
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return check_launch();
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done & bit) return NRC_OK;
+  if (cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return check_launch();
+  done |= bit;
+  return NRC_OK;
+}
 
 // float32 limits used by the reference's safe_* guards (internal/math.py:24-26).
 __device__ __forceinline__ float f32_tiny() { return 1.17549435e-38f; }

@@ -135,14 +135,9 @@ template <int F>
 int32_t launch_query(cudaStream_t s, const EncDev& d, const nrc_density_mlp_t* mlp, const float* means,
                      int64_t P, float warp_c, float bias, float* density, float* raw, float* feat,
                      float* gp, float* rg, float* eo) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(density_query_fwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(sizeof(FwdSmem)));
-    attr_set = true;
-  }
+  if (const int32_t st_attr = ensure_dynamic_smem<density_query_fwd_kernel<F>>(static_cast<int>(sizeof(FwdSmem))); st_attr != NRC_OK) return st_attr;
   int64_t tiles = (P + kT - 1) / kT;
-  unsigned grid = static_cast<unsigned>(tiles < kNumSMs * 3 ? tiles : kNumSMs * 3);
+  unsigned grid = static_cast<unsigned>(tiles < num_sms() * 3 ? tiles : num_sms() * 3);
   density_query_fwd_kernel<F><<<grid, kT, sizeof(FwdSmem), s>>>(d, *mlp, means, P, warp_c, bias, density,
                                                                raw, feat, gp, rg, eo);
   return check_launch();

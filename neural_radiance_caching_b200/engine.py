@@ -44,6 +44,17 @@ class FusedCacheStep:
         self._bg = {}
         self._side = None
         self.concurrent = True   # independent branches of the schedule on side streams (fork/join events)
+        if model.sampler.opaque_background:
+            # nrc_ray_alpha_weights_bwd recomputes a finite density * delta for the last sample: with an opaque background
+            # its gradients would be wrong (render.compute_alpha_weights raises for the same combination)
+            raise NotImplementedError("FusedCacheStep: opaque_background=True has no backward pass")
+
+    def _constants(self, R, dev):
+        """Per-batch-size constants, created and filled on the CALLER's stream before any side stream is forked: a side
+        stream that first-used them would leave the main stream reading memory it never ordered itself behind."""
+        self._bg_ones(R, dev)
+        self._initial_step_function(R, dev)
+        self._zero_mask(R, dev)
 
     def _streams(self, n):
         if self._side is None or len(self._side) < n:
@@ -136,6 +147,7 @@ class FusedCacheStep:
         new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
         anneal = sampler.anneal(train_frac)
         main = torch.cuda.current_stream()
+        self._constants(R, dev)
         s_pack, s_enc, s_env, s_prop = self._streams(6)[:4] if self.concurrent else (None,) * 4
         shp = self.params["Shader"]
         names, sflat = shader.fused_params(shp)
@@ -312,14 +324,14 @@ class FusedCacheStep:
         _lib.call("nrc_render_loss", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), _lib.ptr(bg), _lib.ptr(target_rgb), None,
                   R, k, float(self.charb_padding), 0 if mw is None else 1, 0.0 if mw is None else float(mw[0]),
                   0.0 if mw is None else float(mw[1]), _lib.ptr(loss), _lib.ptr(out_rgb), _lib.ptr(acc), _lib.ptr(gv),
-                  _lib.ptr(g_w[2]))
+                  _lib.ptr(g_w[-1]))
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
         if on_shader_grads is not None:
             on_shader_grads()
         if geo is not None:
             if s_geo is not None:
                 main.wait_stream(s_geo)
-            g_w[2].add_(geo[0])
+            g_w[-1].add_(geo[0])
             g_nrm.add_(geo[1].view_as(g_nrm))
         if s_prop is not None and not fork_proposals:
             main.wait_stream(s_prop)     # split mode: the side stream only ran the interlevel losses

@@ -804,18 +804,33 @@ class _ChainFn(torch.autograd.Function):
         return tuple(grads)
 
 
+_param_generation = [0]
+
+
+def bump_param_generation():
+    """Tell every PackCache that parameters may have changed WITHOUT torch noticing: updates through raw device pointers
+    (an external optimizer, C-ABI kernels, in-place updates replayed inside a CUDA graph) do not bump `_version`.  A
+    training harness calls this once per optimizer step (workload.CacheTrainStep does)."""
+    _param_generation[0] += 1
+
+
 class PackCache:
-    """Packed bf16 operand images keyed by the parameters' identity and version counters: a render loop
-    packs once per parameter update instead of once per chunk."""
+    """Packed bf16 operand images keyed by the parameters' identity, torch version counters and the parameter
+    generation (bump_param_generation): a render loop packs once per parameter update instead of once per chunk.  The
+    keyed tensors are held, so a freed parameter's address cannot be recycled by a different tensor that would then hit
+    the stale entry.  invalidate() drops the entry explicitly (e.g. after loading a checkpoint into the same storage)."""
 
     def __init__(self):
         self._store = {}
 
+    def invalidate(self):
+        self._store.clear()
+
     def get(self, key_tensors, build):
-        key = tuple((t.data_ptr(), t._version) for t in key_tensors)
+        key = (_param_generation[0],) + tuple((id(t), t.data_ptr(), t._version) for t in key_tensors)
         hit = self._store.get("k")
         if hit is None or hit[0] != key:
-            self._store["k"] = (key, build())
+            self._store["k"] = (key, build(), list(key_tensors))
         return self._store["k"][1]
 
 
