@@ -187,12 +187,14 @@ class NeRFMLP:
         x = torch.relu(self.dense(p["integrated_brdf_layers_1"], x))
         return torch.sigmoid(self.dense(p["output_integrated_brdf_layer"], x) + float(np.log(3.0)))
 
-    def __call__(self, p, viewdirs, means, density_feature, normals):
-        """viewdirs [R,3]; means [R,n,3]; density_feature [R,n,64]; normals [R,n,3] (normals_to_use)."""
+    def heads(self, p, feature):
+        """Bottleneck (nerf.py:385-408, no noise / exposure) and roughness (:633-634) of the appearance feature."""
         sp = torch.nn.functional.softplus
-        feature = self.predict_appearance_feature(p, density_feature, means)
-        bottleneck = self.dense(p["bottleneck_layer"], feature)  # nerf.py:391-414
-        roughness = sp(self.dense(p["roughness_layer"], feature) - 1.0)  # :633-634
+        return self.dense(p["bottleneck_layer"], feature), sp(self.dense(p["roughness_layer"], feature) - 1.0)
+
+    def predict_appearance_passive(self, p, feature, bottleneck, roughness, normals, viewdirs):
+        """NeRFMLP._predict_appearance_passive (nerf.py:940-1090) with use_env_map and the IDE-form sub-networks."""
+        sp = torch.nn.functional.softplus
         ambient_diffuse = torch.clamp(sp(self.dense(p["ambient_irradiance_layer"], feature) - 2.0), 0.0, self.rgb_max)
         tint = torch.sigmoid(self.dense(p["tint_layer"], feature))  # :975
         F = self.get_integrated_brdf(p, normals, viewdirs, bottleneck)
@@ -210,6 +212,13 @@ class NeRFMLP:
         return dict(
             rgb=ambient + indirect, diffuse_rgb=ambient_diffuse + indirect_diffuse,
             specular_rgb=ambient_specular + indirect_specular, ambient_rgb=ambient, indirect_rgb=indirect,
-            albedo_rgb=tint, roughness=roughness, integrated_brdf=F, env_rgb=env_rgb, ref_rgb=ref_rgb,
-            bottleneck=bottleneck, feature=feature, refdirs=refdirs,
+            albedo_rgb=tint, integrated_brdf=F, env_rgb=env_rgb, ref_rgb=ref_rgb, refdirs=refdirs,
         )
+
+    def __call__(self, p, viewdirs, means, density_feature, normals):
+        """viewdirs [R,3]; means [R,n,3]; density_feature [R,n,64]; normals [R,n,3] (normals_to_use)."""
+        feature = self.predict_appearance_feature(p, density_feature, means)
+        bottleneck, roughness = self.heads(p, feature)
+        out = self.predict_appearance_passive(p, feature, bottleneck, roughness, normals, viewdirs)
+        out.update(roughness=roughness, bottleneck=bottleneck, feature=feature)
+        return out

@@ -509,6 +509,106 @@ def main():
             None, None, None, _types.SimpleNamespace(lossmult=f(np.ones((Ps, 1)))),
             _types.SimpleNamespace(light_sampling_linear_to_srgb=srgb), None, mres))
 
+    # ---- SurfaceLightFieldMLP.__call__ (surface_light_field.py:782-1069) in the two configured shapes
+    #      (nerf_ngp_yobo.gin:232-251 `SurfaceLightField`: IDE_5 + shader bottleneck; :253-297 shader `EnvMap`: IDE_4), and
+    #      the cache shader's composition around them: NeRFMLP.get_bottleneck_feature (nerf.py:385-408), the roughness head
+    #      (:633-634), _predict_appearance_passive (:940-1090) with both sub-networks attached.  setup() is the class's own:
+    #      it builds the encodings and every Dense (the flax stand-in's Dense = x @ kernel + bias); parameters are the closed
+    #      form dense_params.  Callable CLASS defaults (activations) are passed as constructor fields: a plain class attribute
+    #      would bind as a method here, flax stores them per instance. ------------------------------------------------------
+    rslf = importlib.import_module("internal.surface_light_field")
+    sp_, sg_, relu_ = shim.nn_mod.softplus, shim.nn_mod.sigmoid, shim.nn_mod.relu
+    scfg = _types.SimpleNamespace(num_rgb_channels=3, n_bins=1, multi_illumination=False, rotate_illumination=False,
+                                  num_illuminations=1, multiple_illumination_outputs=False, env_map_distance=float("inf"))
+
+    def make_slf(deg_view, use_shader_bottleneck, salt):
+        m_ = rslf.SurfaceLightFieldMLP(
+            config=scfg, net_depth=2, net_width=64, skip_layer=2, bottleneck_width=128, use_directional_enc=True, use_ide=True,
+            deg_view=deg_view, net_depth_viewdirs=4, net_width_viewdirs=128, bottleneck_viewdirs=128, skip_layer_dir=2,
+            use_grid=False, use_bottleneck=False, use_density_feature=False, use_shader_bottleneck=use_shader_bottleneck,
+            use_lights=False, net_activation=relu_, rgb_activation=sp_, rgb_bias=-2.0, ambient_rgb_activation=sp_,
+            ambient_rgb_bias=-1.0, alpha_activation=sg_)
+        m_.setup()
+        n_in = (128 if use_shader_bottleneck else 0) + {4: 38, 5: 72}[deg_view]
+        d_in_ = n_in
+        for i_, layer in enumerate(m_.view_dependent_layers):
+            layer.kernel, layer.bias = dense_params(d_in_, layer.features, salt + i_)
+            d_in_ = layer.features + (n_in if (i_ % 2 == 0 and i_ > 0) else 0)
+        for j_, layer in enumerate((m_.output_ambient_rgb_layer, m_.output_rgba_layer)):
+            layer.kernel, layer.bias = dense_params(d_in_, layer.features, salt + 10 + j_)
+        return m_
+
+    Rq, nq = 24, 8
+    qdirs = f(unit(g.normal(size=(Rq, nq, 3)))); qrough = f(g.uniform(0.02, 1.5, size=(Rq, nq, 1)))
+    qbott = f(g.normal(size=(Rq, nq, 128))); qmeans = f(g.normal(size=(Rq, nq, 3)) * 1.2)
+    qrays = _types.SimpleNamespace(viewdirs=f(unit(g.normal(size=(Rq, 3)))), origins=f(g.normal(size=(Rq, 3)) * 3.0),
+                                   light_idx=None, lights=None)
+    out.update(slf_refdirs=qdirs, slf_roughness=qrough, slf_bottleneck=qbott)
+    slf5, slf4 = make_slf(5, True, 400), make_slf(4, False, 420)
+    for tag, net, bott_ in (("slf5", slf5, qbott), ("slf4", slf4, None)):
+        res = net(None, qrays, dict(means=qmeans), qmeans, qdirs, roughness=qrough, shader_bottleneck=bott_, train=False)
+        out[tag + "_incoming_ambient_rgb"] = res["incoming_ambient_rgb"]
+        out[tag + "_incoming_acc"] = res["incoming_acc"]
+
+    ENC_P = dict(hash_map_size=2 ** 15, num_features=4, scale_supersample=1.0, max_grid_size=2048, bbox_scaling=2.0)
+    shp = R["shading"].BaseShader(net_depth=0, use_density_feature=True, warp_fn=rcoord.contract_radius_2)
+    class _Enc64(rgrid.HashEncoding):
+        # `grid_size**3 <= hash_map_size` (grid_utils.py:837) is evaluated on NumPy int32 scalars: NumPy 1.x (the reference's
+        # pin) promotes int32 ** python-int to int64, NumPy 2 keeps int32 and 2048**3 wraps to 0.  Same values, wider type.
+        grid_sizes = property(lambda self: rgrid.HashEncoding.grid_sizes.fget(self).astype(np.int64))
+
+    shp.grid = _Enc64(**ENC_P)
+    shp.grid.seen = []
+    shp.grid.param = lambda name, init_fn: (shp.grid.seen.append(name), level_table(init_fn.keywords["shape"], len(shp.grid.seen)))[1]
+    qdf = f(g.normal(size=(Rq, nq, 64))); qnrm = f(unit(g.normal(size=(Rq, nq, 3))))
+    qfeat = np.asarray(shp.predict_appearance_feature(dict(means=qmeans.view(shim.F32Array), covs=None, feature=qdf),
+                                                      control_offsets=f(np.zeros((1, 3))), perp_mag=None)).astype(np.float32)
+    assert qfeat.shape == (Rq, nq, 96)
+    Dn_ = shim.nn_mod_linen.Dense
+    pm = R["nerf"].NeRFMLP(config=scfg, net_activation=relu_, net_depth_integrated_brdf=2, skip_layer_integrated_brdf=2,
+                           use_reflections=True, bottleneck_width=128, bottleneck_noise=0.0, use_exposure_at_bottleneck=False,
+                           roughness_activation=sp_, roughness_bias=-1.0, irradiance_activation=sp_, irradiance_bias=-2.0,
+                           ambient_irradiance_activation=sp_, ambient_irradiance_bias=-2.0, rgb_max=np.float32(10000.0),
+                           use_env_map=True, stopgrad_ambient_weight=1.0, stopgrad_indirect_weight=1.0)
+    pm.bottleneck_layer, pm.roughness_layer = Dn_(128), Dn_(1)
+    pm.ambient_irradiance_layer, pm.irradiance_layer, pm.tint_layer = Dn_(3), Dn_(3), Dn_(3)
+    pm.integrated_brdf_layers, pm.output_integrated_brdf_layer = [Dn_(64), Dn_(64)], Dn_(1)
+    for layers, d_in, salt in (([pm.bottleneck_layer], 96, 440), ([pm.roughness_layer], 96, 441),
+                               ([pm.ambient_irradiance_layer], 96, 442), ([pm.irradiance_layer], 96, 443),
+                               ([pm.tint_layer], 96, 444),
+                               (pm.integrated_brdf_layers + [pm.output_integrated_brdf_layer], 129, 445)):
+        for i_, layer in enumerate(layers):
+            layer.kernel, layer.bias = dense_params(d_in, layer.features, salt + 10 * i_ if len(layers) > 1 else salt)
+            d_in = layer.features
+    pm.surface_lf, pm.env_map = slf5, slf4
+    qb = pm.get_bottleneck_feature(None, qfeat, None)                                            # nerf.py:385-408
+    qr = pm.roughness_activation(pm.roughness_layer(qfeat) + pm.roughness_bias)                  # nerf.py:633-634
+    res = pm._predict_appearance_passive(None, qrays, dict(means=qmeans), qfeat, qb, qr, qnrm, qnrm, train=False)
+    out.update(shp_means=qmeans, shp_density_feature=qdf, shp_normals=qnrm, shp_viewdirs=qrays.viewdirs, shp_origins=qrays.origins,
+               shp_feature=qfeat, shp_bottleneck=qb, shp_roughness=qr)
+    for k_ in ("rgb", "diffuse_rgb", "specular_rgb", "ambient_rgb", "indirect_rgb", "albedo_rgb", "indirect_occ", "ray_dists"):
+        out["shp_" + k_] = res[k_]
+
+    # ---- analytic normals (geometry.py:442-460): jax.value_and_grad(predict_density) cannot be executed without JAX; the
+    #      VALUE it returns - d raw_density / d mean - is pinned by CENTRAL DIFFERENCES of the reference's own predict_density
+    #      (h = 2^-11 per axis, the realised step taken from the rounded fp32 arguments).  The field is piecewise trilinear
+    #      through a ReLU MLP: a difference that straddles a cell face or a ReLU kink averages two one-sided slopes, so the
+    #      consumers compare quantiles, not the maximum. ------------------------------------------------------------------
+    hfd = np.float32(2.0 ** -11)
+
+    def raw_at(x_):
+        mlp.grid.seen = []                                 # the table salts count parameter requests from 1 again
+        r_, _ = mlp.predict_density(x_.view(shim.F32Array), None, control_offsets=f(np.zeros((1, 3))), perp_mag=None)
+        return np.asarray(r_).astype(np.float64)
+
+    npts = np.ascontiguousarray(dmeans[2:402])
+    fd = np.zeros((npts.shape[0], 3), np.float64)
+    for a_ in range(3):
+        e_ = np.zeros(3, np.float32); e_[a_] = hfd
+        xp, xm = (npts + e_).astype(np.float32), (npts - e_).astype(np.float32)
+        fd[:, a_] = (raw_at(xp) - raw_at(xm)) / (xp[:, a_].astype(np.float64) - xm[:, a_].astype(np.float64))
+    out.update(dnrm_means=npts, dnrm_fd_raw_grad=fd.astype(np.float32))
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

@@ -405,3 +405,101 @@ def test_density_mlp_module_call():
     assert res["normals"] is None and res["raw_grad_density"] is None
     for k in ("feature", "density", "grad_pred", "normals_pred", "normals_to_use", "ray_dists"):
         close(res[k], "dmlp_call_" + k, 2e-6 if k != "normals_pred" and k != "normals_to_use" else 1e-5)
+
+
+def _slf_params(deg_view, use_bottleneck, salt):
+    """Parameters of tests/golden/make_reference_vectors.py:make_slf (closed-form dense_params)."""
+    from tests.util import dense_params
+    n_in = (128 if use_bottleneck else 0) + {4: 38, 5: 72}[deg_view]
+    p, d_in = {}, n_in
+    for i, name in enumerate(("layer_0", "layer_1", "layer_2", "layer_bottleneck")):
+        k, b = dense_params(d_in, 128, salt + i)
+        p[name] = {"kernel": torch.from_numpy(k), "bias": torch.from_numpy(b)}
+        d_in = 128 + (n_in if (i % 2 == 0 and i > 0) else 0)
+    k, b = dense_params(d_in, 3, salt + 10)
+    p["output_ambient_rgb_layer"] = {"kernel": torch.from_numpy(k), "bias": torch.from_numpy(b)}
+    return p
+
+
+def _shader_params():
+    from tests.util import dense_params
+    p = {}
+    for name, d_in, d_out, salt in (("bottleneck_layer", 96, 128, 440), ("roughness_layer", 96, 1, 441),
+                                    ("ambient_irradiance_layer", 96, 3, 442), ("irradiance_layer", 96, 3, 443),
+                                    ("tint_layer", 96, 3, 444), ("integrated_brdf_layers_0", 129, 64, 445),
+                                    ("integrated_brdf_layers_1", 64, 64, 455), ("output_integrated_brdf_layer", 64, 1, 465)):
+        k, b = dense_params(d_in, d_out, salt)
+        p[name] = {"kernel": torch.from_numpy(k), "bias": torch.from_numpy(b)}
+    p["SurfaceLightField"], p["EnvMap"] = _slf_params(5, True, 400), _slf_params(4, False, 420)
+    return p
+
+
+def test_surface_light_field_call():
+    """SurfaceLightFieldMLP.__call__ (internal/surface_light_field.py:782-1069) EXECUTED FROM THE REFERENCE'S CLASS (its own
+    setup(): encodings + every Dense) in the two configured shapes - `SurfaceLightField` (IDE_5 + shader bottleneck, skip
+    after layer 2) and the shader-level `EnvMap` (IDE_4): incoming_ambient_rgb and incoming_acc == 1.  The degree-5 IDE
+    is evaluated in float32 by both (the oracle follows the reference's op order), so the outputs agree to summation order."""
+    from oracle import nerf as onerf2
+
+    for tag, deg, use_b, salt, tol in (("slf5", 5, True, 400, 5e-6), ("slf4", 4, False, 420, 5e-6)):
+        net = onerf2.SurfaceLightFieldMLP(deg, use_b)
+        got = net(_slf_params(deg, use_b, salt), T("slf_refdirs"), T("slf_roughness"), T("slf_bottleneck") if use_b else None)
+        close(got["incoming_ambient_rgb"], tag + "_incoming_ambient_rgb", tol)   # measured 3e-7 / 2e-7
+        exact(got["incoming_acc"], tag + "_incoming_acc")
+
+
+def test_predict_appearance_passive():
+    """NeRFMLP.get_bottleneck_feature (internal/nerf.py:385-408), the roughness head (:633-634) and
+    _predict_appearance_passive (:940-1090) EXECUTED FROM THE REFERENCE'S CLASS with both SurfaceLightFieldMLP instances
+    attached, on the feature BaseShader.predict_appearance_feature (internal/shading.py:133-220) produced for an 8-level
+    appearance grid: every output of the cache shader."""
+    from oracle import nerf as onerf2
+
+    sh = onerf2.NeRFMLP(warp_c=2.0)
+    sh.grid = ogrid.HashEncoding(hash_map_size=2 ** 15, num_features=4, scale_supersample=1.0, max_grid_size=2048, bbox_scaling=2.0)
+    p = _shader_params()
+    p["appearance_grid"] = {name: torch.from_numpy(_level_table(shape, i + 1))
+                            for i, (name, (_, _, shape)) in enumerate(zip(sh.grid.param_names(), sh.grid.layout))}
+    feature = sh.predict_appearance_feature(p, T("shp_density_feature"), T("shp_means"))
+    exact(feature, "shp_feature")
+    bott, rough = sh.heads(p, feature)
+    close(bott, "shp_bottleneck", 2e-6)
+    close(rough, "shp_roughness", 2e-6)
+    got = sh.predict_appearance_passive(p, feature, bott, rough, T("shp_normals"), T("shp_viewdirs"))
+    for k in ("rgb", "diffuse_rgb", "specular_rgb", "ambient_rgb", "indirect_rgb", "albedo_rgb"):
+        close(got[k], "shp_" + k, 2e-4 if k not in ("albedo_rgb", "diffuse_rgb") else 2e-6)
+    whole = sh(p, T("shp_viewdirs"), T("shp_means"), T("shp_density_feature"), T("shp_normals"))
+    close(whole["rgb"], "shp_rgb", 2e-4)
+
+
+def fd_quantiles(got, key):
+    """|got - central differences of the reference| relative to the largest gradient: (median, 65 % quantile)."""
+    ref = torch.from_numpy(V[key]).double()
+    d = (got.detach().double().cpu() - ref).abs().flatten() / float(ref.abs().max())
+    return float(torch.quantile(d, 0.5)), float(torch.quantile(d, 0.65))
+
+
+def test_analytic_normals_against_reference_differences():
+    """Analytic normals (internal/geometry.py:442-460): the reference takes jax.value_and_grad of predict_density, which
+    cannot run without JAX; its value d raw / d mean is pinned by central differences of the REFERENCE'S OWN predict_density
+    (tests/golden/make_reference_vectors.py, h = 2^-11).  A difference that straddles a grid-cell face or a ReLU kink
+    averages two slopes, hence quantiles: a wrong Jacobian (contraction, bbox map, level scale) would move the median by
+    O(1)."""
+    from oracle import geometry as ogeo
+    from tests.util import dense_params
+
+    mlp = ogeo.DensityMLP({k: v for k, v in ENC_CONFIGS["a"].items() if k != "scale_supersample"}, net_depth=2, net_width=64,
+                          density_bias=-1.0, warp_c=2.0, bbox_scaling=2.0)
+    p = {"density_grid": {name: torch.from_numpy(_level_table(shape, i + 1))
+                          for i, (name, (_, _, shape)) in enumerate(zip(mlp.grid.param_names(), mlp.grid.layout))}}
+    d_in = mlp.in_dim
+    for i, (name, d_out) in enumerate([("density_layers_0", 64), ("density_layers_1", 64), ("output_density_layer", 1)]):
+        k, b = dense_params(d_in, d_out, 100 + i)
+        p[name] = {"kernel": torch.from_numpy(k), "bias": torch.from_numpy(b)}
+        d_in = d_out
+    means = T("dnrm_means").clone().requires_grad_(True)
+    raw, _ = mlp.predict_density(p, means)
+    (grad,) = torch.autograd.grad(raw.sum(), means)
+    med, q80 = fd_quantiles(grad, "dnrm_fd_raw_grad")
+    assert med <= 3e-4 and q80 <= 3e-3, (med, q80)    # measured 7e-5 / ...; ~30 % of the differences straddle a face of
+    # the finest level (cell 1/64 of the contracted box against 2h = 1e-3, three axes, five levels)

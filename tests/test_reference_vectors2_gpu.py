@@ -300,3 +300,85 @@ def test_density_mlp_module_call(cuda_device):
         assert rel_err(q[k], torch.from_numpy(V["dmlp_call_" + k])) <= 1e-5, (k, rel_err(q[k], torch.from_numpy(V["dmlp_call_" + k])))
     npred = _NormalsFn.apply(q["grad_pred"])
     assert rel_err(npred, torch.from_numpy(V["dmlp_call_normals_pred"])) <= 2e-5
+
+
+# ----------------------------------------------------------------------------- row 16
+def _slf_params(deg_view, use_bottleneck, salt, dev):
+    n_in = (128 if use_bottleneck else 0) + {4: 38, 5: 72}[deg_view]
+    p, d_in = {}, n_in
+    for i, name in enumerate(("layer_0", "layer_1", "layer_2", "layer_bottleneck")):
+        k, b = dense_params(d_in, 128, salt + i)
+        p[name] = {"kernel": torch.from_numpy(k).to(dev), "bias": torch.from_numpy(b).to(dev)}
+        d_in = 128 + (n_in if (i % 2 == 0 and i > 0) else 0)
+    k, b = dense_params(d_in, 3, salt + 10)
+    p["output_ambient_rgb_layer"] = {"kernel": torch.from_numpy(k).to(dev), "bias": torch.from_numpy(b).to(dev)}
+    return p
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_surface_light_field_call(cuda_device, bf16):
+    """The SurfaceLightField / EnvMap stacks (fp32 GEMM path; tcgen05 chain kernel) against SurfaceLightFieldMLP.__call__
+    (internal/surface_light_field.py:782-1069) executed from the reference's own class in both configured shapes."""
+    from neural_radiance_caching_b200 import nerf as nnerf
+
+    dev = cuda_device
+    for tag, deg, use_b, salt in (("slf5", 5, True, 400), ("slf4", 4, False, 420)):
+        net = nnerf.SurfaceLightFieldMLP(deg, use_b, bf16=bf16)
+        with torch.no_grad():
+            got = net(_slf_params(deg, use_b, salt, dev), D("slf_refdirs", dev), D("slf_roughness", dev),
+                      D("slf_bottleneck", dev) if use_b else None)
+        # the fp32 kernels evaluate the l = 16 Legendre sums in float64, the reference in float32 (~1e-3 noise, DESIGN section 3)
+        tol = 2e-2 if bf16 else 2e-4
+        e = rel_err(got["incoming_ambient_rgb"], torch.from_numpy(V[tag + "_incoming_ambient_rgb"]))
+        assert e <= tol, (tag, bf16, e)
+        assert np.array_equal(got["incoming_acc"].cpu().numpy(), V[tag + "_incoming_acc"])
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_predict_appearance_passive(cuda_device, bf16):
+    """The WHOLE cache shader (appearance grid -> bottleneck / heads -> integrated BRDF, EnvMap, SurfaceLightField ->
+    composition) against the reference's own classes: BaseShader.predict_appearance_feature, NeRFMLP.get_bottleneck_feature,
+    the roughness head and NeRFMLP._predict_appearance_passive (internal/nerf.py:385-408,633-634,940-1090) with both
+    SurfaceLightFieldMLP instances attached.  fp32 kernels at the conditioning of the degree-5 IDE, the bf16 tensor-core
+    path (trunk -> mid -> one launch of three stacks -> out) at the north star's 2e-2."""
+    from neural_radiance_caching_b200 import grid_utils as ng, nerf as nnerf
+
+    dev = cuda_device
+    sh = nnerf.NeRFMLP(warp_c=2.0, bf16=bf16)
+    sh.grid = ng.HashEncoding(hash_map_size=2 ** 15, num_features=4, scale_supersample=1.0, max_grid_size=2048, bbox_scaling=2.0)
+    p = {}
+    for name, d_in, d_out, salt in (("bottleneck_layer", 96, 128, 440), ("roughness_layer", 96, 1, 441),
+                                    ("ambient_irradiance_layer", 96, 3, 442), ("irradiance_layer", 96, 3, 443),
+                                    ("tint_layer", 96, 3, 444), ("integrated_brdf_layers_0", 129, 64, 445),
+                                    ("integrated_brdf_layers_1", 64, 64, 455), ("output_integrated_brdf_layer", 64, 1, 465)):
+        k, b = dense_params(d_in, d_out, salt)
+        p[name] = {"kernel": torch.from_numpy(k).to(dev), "bias": torch.from_numpy(b).to(dev)}
+    p["SurfaceLightField"], p["EnvMap"] = _slf_params(5, True, 400, dev), _slf_params(4, False, 420, dev)
+    arena = torch.cat([torch.from_numpy(level_table(shape, i + 1)).reshape(-1)
+                       for i, (name, _, _, shape) in enumerate(sh.grid.level_layout)]).to(dev)
+    p["appearance_grid"] = dict(sh.grid.views(arena), _arena=arena)
+    with torch.no_grad():
+        got = sh(p, D("shp_viewdirs", dev), D("shp_means", dev), D("shp_density_feature", dev), D("shp_normals", dev),
+                 return_feature=True)
+    assert np.array_equal(got["feature"].cpu().numpy(), V["shp_feature"])       # appearance feature: bit-exact
+    tol = 2e-2 if bf16 else 2e-4
+    for k in ("rgb", "diffuse_rgb", "specular_rgb", "ambient_rgb", "indirect_rgb", "albedo_rgb"):
+        e = rel_err(got[k], torch.from_numpy(V["shp_" + k]))
+        assert e <= tol, (k, bf16, e)
+    if got["bottleneck"] is not None:
+        assert rel_err(got["bottleneck"], torch.from_numpy(V["shp_bottleneck"])) <= (2e-2 if bf16 else 1e-5)
+    assert rel_err(got["roughness"], torch.from_numpy(V["shp_roughness"])) <= (2e-2 if bf16 else 1e-5)
+
+
+# ----------------------------------------------------------------------------- row 9
+def test_analytic_normals_against_reference_differences(cuda_device):
+    """The in-kernel back-propagation of nrc_density_query_fwd (d raw / d mean, internal/geometry.py:442-460) against
+    central differences of the REFERENCE'S OWN predict_density (h = 2^-11, tests/golden/make_reference_vectors.py).
+    Differences that straddle a grid-cell face or a ReLU kink average two slopes: quantiles, as in the CPU test of the
+    oracle's autograd."""
+    mlp, p = _dmlp(cuda_device, False)
+    q = mlp.query(p, D("dnrm_means", cuda_device), want_feat=False, want_normals=True)
+    ref = torch.from_numpy(V["dnrm_fd_raw_grad"]).double()
+    d = (q["raw_grad_density"].double().cpu() - ref).abs().flatten() / float(ref.abs().max())
+    med, q65 = float(torch.quantile(d, 0.5)), float(torch.quantile(d, 0.65))
+    assert med <= 3e-4 and q65 <= 3e-3, (med, q65)
