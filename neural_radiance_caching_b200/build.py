@@ -36,6 +36,7 @@ def _digest():
     h = hashlib.sha256()
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     files.append(os.path.join(ROOT, "include", "nrc_b200.h"))
+    files.append(os.path.join(ROOT, "include", "nrc_xla.h"))
     for f in files:
         h.update(os.path.relpath(f, ROOT).encode())   # repo-relative: the digest does not depend on the checkout path
         with open(f, "rb") as fh:

@@ -102,3 +102,49 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_xla_custom_call_targets(lib, tmp_path):
+    """include/nrc_xla.h: every declared custom-call target is exported and listed by nrc_xla_targets(); the descriptor
+    structs the JAX side packs into `opaque` (neural_radiance_caching_b200/jax_binding/nrc_jax.py) have the layout gcc
+    gives the header's; a descriptor of the wrong size is refused with a status, not a crash."""
+    import subprocess
+
+    from neural_radiance_caching_b200.jax_binding import nrc_jax
+
+    src = open(os.path.join(ROOT, "include", "nrc_xla.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\bvoid\s+(nrc_xla_[a-z0-9_]+)\s*\(", src)))
+    assert declared == sorted(nrc_jax.TARGETS) and len(declared) == 15
+    for name in declared:
+        assert hasattr(lib, name), name
+
+    class Target(ctypes.Structure):
+        _fields_ = [("name", ctypes.c_char_p), ("fn", ctypes.c_void_p)]
+
+    lib.nrc_xla_targets.restype = ctypes.POINTER(Target)
+    table, listed = lib.nrc_xla_targets(), []
+    while table[len(listed)].name:
+        listed.append(table[len(listed)].name.decode())
+    assert sorted(listed) == declared
+
+    c = tmp_path / "x.c"
+    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nrc_xla.h"\n'
+                 'int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(nrc_xla_encode_desc_t),'
+                 ' offsetof(nrc_xla_encode_desc_t, enc), sizeof(nrc_xla_contract_desc_t), sizeof(nrc_xla_density_query_desc_t),'
+                 ' offsetof(nrc_xla_density_query_desc_t, warp_c), sizeof(nrc_xla_ray_desc_t), offsetof(nrc_xla_ray_desc_t, bias),'
+                 ' sizeof(nrc_xla_ggx_desc_t), offsetof(nrc_xla_ggx_desc_t, rgb_max)); return 0; }\n')
+    exe = tmp_path / "x"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    J = nrc_jax
+    want = [ctypes.sizeof(J.nrc_xla_encode_desc_t), J.nrc_xla_encode_desc_t.enc.offset, ctypes.sizeof(J.nrc_xla_contract_desc_t),
+            ctypes.sizeof(J.nrc_xla_density_query_desc_t), J.nrc_xla_density_query_desc_t.warp_c.offset,
+            ctypes.sizeof(J.nrc_xla_ray_desc_t), J.nrc_xla_ray_desc_t.bias.offset, ctypes.sizeof(J.nrc_xla_ggx_desc_t),
+            J.nrc_xla_ggx_desc_t.rgb_max.offset]
+    assert got == want
+
+    lib.nrc_xla_last_status.restype = ctypes.c_int32
+    lib.nrc_xla_encode_fwd.restype = None
+    lib.nrc_xla_encode_fwd(None, None, b"short", ctypes.c_size_t(5))
+    assert lib.nrc_xla_last_status() == -1 and lib.nrc_xla_last_status() == 0
