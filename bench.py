@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--rays", type=int, default=1024, help="rays per GPU per step (config 2: 1024)")
     ap.add_argument("--bf16", type=int, default=1,
                     help="1 (default): bf16 tensor-core MLPs (tcgen05), north-star tolerance 2e-2; 0: fp32 parity variant")
-    ap.add_argument("--cpu-rays", type=int, default=256, help="rays in the bounded CPU sample")
+    ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per step of the CPU arm (config 2: 1024, the same batch)")
+    ap.add_argument("--no-others", action="store_true", help="skip the `others` table (configs 1, 3, 5, fp32, 16384 rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="print per-ABI-call device times")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config5"],
@@ -189,7 +190,7 @@ WORKLOAD = ("config2 nerf_ngp_yobo_lego cache training step: proposal sampler (6
 
 
 # ----------------------------------------------------------------------------- b200 arm
-def run_b200(args):
+def run_b200_main(args):
     import torch.distributed as dist
 
     from neural_radiance_caching_b200 import _lib, dist as ndist, workload
@@ -264,7 +265,7 @@ def run_b200(args):
             graph.replay()
         torch.cuda.synchronize()
         print(json.dumps({"ncu_mode": True, "launches_per_step": launches}))
-        return
+        return False, None
 
     per_kernel = profile_calls(one_step, _lib)
 
@@ -361,9 +362,7 @@ def run_b200(args):
     e2e_value = total_samples / (e2e_ms * 1e-3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None, (step_obj, graph)
 
     roof = roofline(per_kernel, R, pk, pk_kind, bool(args.bf16), l2_gather_probe(dev) if per_kernel else None)
     cpu = None
@@ -400,23 +399,138 @@ def run_b200(args):
         "roofline": roof,
         "cpu_baseline": cpu,
         "kernel_ms": {k: round(v, 5) for k, v in (per_kernel or {}).items()},
+        "kernel_ms_note": "per-launch device time from back-to-back replays of each call (warm caches, no host gap), summed per "
+                          "entry point over one step; agrees with the ncu launch list (profiles/), not with eager per-call events",
         "wall_s": wall,
     }
-    print(json.dumps(line))
+    return line, (step_obj, graph)
+
+
+def measure_train_variant(dev, R, bf16, steps, warmup, pk, pk_kind, forward_only=False):
+    """One single-GPU line of the config-2 step at another batch size / precision, or (forward_only) of config 1:
+    the cache stage's forward evaluation of 1024 rays x (64, 64, 32) samples with the shader on the final 32."""
+    from neural_radiance_caching_b200 import _lib, workload
+
+    step_obj = workload.CacheTrainStep(dev, bf16=bool(bf16))
+    g = np.random.Generator(np.random.PCG64(workload.SEED + 7))
+    rn = workload.make_rays_np(g, R)
+    u = [g.uniform(size=(R, 1)).astype(np.float32) for _ in range(3)]
+    tgt = g.uniform(size=(R, 3)).astype(np.float32)
+    xr = workload.backward_mask_rays_np(g, rn)
+    ux = [g.uniform(size=(R, 1)).astype(np.float32) for _ in range(3)]
+    dbuf = torch.from_numpy(workload.pack_batch(rn, u, tgt, xr, ux)).to(dev)
+
+    def compute():
+        rays, u01, target, extra = workload.unpack_batch(dbuf)
+        if forward_only:
+            with torch.no_grad():
+                return step_obj.render(rays, u01)["rgb"]
+        return step_obj.step(rays, u01, target, extra)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            before = _lib.launch_count
+            compute()
+            launches = _lib.launch_count - before
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    per_kernel = profile_calls(compute, _lib, iters=2)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        compute()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+    ms = _timed(graph.replay, steps, warmup, flush, torch.cuda.synchronize)
+    roof = roofline(per_kernel, R, pk, pk_kind, bool(bf16)) if not forward_only else None
+    if forward_only and "nrc_density_query_fwd" in per_kernel:
+        pts = {0: 64 * R, 1: 64 * R, 2: 32 * R}
+        fwd = sum(pts[i] * (12 + 8 * F * 4 * L + 4 * L * F) for i, (L, F) in {0: (6, 1), 1: (7, 1), 2: (8, 4)}.items())
+        ach = fwd / (per_kernel["nrc_density_query_fwd"] * 1e-3) / 1e9
+        roof = {"kernel": "nrc_density_query_fwd", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm_gbs"], "achieved": ach,
+                "frac": ach / pk["hbm_gbs"], "peak_source": pk_kind, "traffic": None,
+                "note": "3 launches; algorithmic gather bytes / summed per-launch device time; tables are L2-resident"}
+    del graph, step_obj
+    torch.cuda.empty_cache()
+    return {"metric": METRIC, "value": R * SAMPLES_PER_RAY / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": 1,
+            "steps": steps, "dtype": "bf16" if bf16 else "f32", "rays_per_step": R, "gpu_launches_per_step": launches,
+            "roofline": roof, "kernel_ms": {k: round(v, 5) for k, v in per_kernel.items()}}
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    line, keep = run_b200_main(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.ncu_mode or line is False:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    del keep
+    torch.cuda.empty_cache()
+    others = None
+    if not (args.no_others or args.profile_kernels):
+        # The rest of BASELINE's configs beside the headline (config 2, bf16, 1024 rays).  config 5 runs on every rank
+        # (strong scaling: row bands + one all_gather of the tiles); the single-GPU variants only at N = 1.
+        others = {}
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        pk, pk_kind = peaks()
+
+        def guarded(name, fn):
+            try:
+                res = fn()
+                if rank == 0:
+                    others[name] = res
+            except Exception as ex:        # a failing side measurement must not lose the headline
+                if rank == 0:
+                    others[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
+        guarded("config5_800x800_frame", lambda: _slim(render_line(args, "config5", world, rank, dev, 2, 1, rays=1024, image=800),
+                                                        frame=True))
+        if world == 1:
+            guarded("config3_chunk", lambda: _slim(render_line(args, "config3", 1, 0, dev, 5, 3, rays=1024)))
+            guarded("config1_forward", lambda: measure_train_variant(dev, 1024, 1, 10, 3, pk, pk_kind, forward_only=True))
+            guarded("config2_fp32", lambda: measure_train_variant(dev, 1024, 0, 10, 3, pk, pk_kind))
+            guarded("config2_bf16_16384rays", lambda: measure_train_variant(dev, 16384, 1, 5, 3, pk, pk_kind))
+            others["config4"] = {"unmeasured": "time-resolved path: forward kernels only (nrc_transient_render_fwd + heads), "
+                                               "no end-to-end workload yet (DESIGN section 9)"}
+    if rank == 0:
+        line["others"] = others
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def profile_calls(one_step, _lib, iters=5):
-    """Average device time of every C-ABI call of one step, measured with CUDA events on
-    the launching stream (eager mode)."""
+def _slim(line, frame=False):
+    if line is None:
+        return None
+    out = {k: line[k] for k in ("metric", "value", "unit", "ms_per_step", "n_gpus", "steps", "dtype", "scaling",
+                                "gpu_launches_per_step", "roofline", "kernel_ms", "e2e")}
+    out["workload"] = line["config"]["workload"]
+    if frame:
+        out["seconds_per_frame"] = line["ms_per_step"] * 1e-3
+    return out
+
+
+def profile_calls(one_step, _lib, iters=3, repeats=6):
+    """Device time of every C-ABI call of one step.  Each call is issued once for real and then `repeats` more times
+    back to back inside one CUDA-event pair on the launching stream (same arguments, the tensors still alive): the
+    average is the kernel's duration with warm caches and no host launch gap in front of it - what the kernel costs inside
+    the step's CUDA graph, and what the ncu launch list shows (profiles/*_launch_shares*).  A single eager call timed by
+    its own event pair (the previous method) included the host's launch latency: +20-40 % on 15-60 us kernels.
+    Repeats are harmless: outputs are rewritten, gradient sinks only accumulate more.  Collectives are not repeated."""
     acc = {}
     orig = _lib.call
 
     def timed(name, *a):
+        orig(name, *a)
+        if "allreduce" in name:
+            return
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        orig(name, *a)
+        for _ in range(repeats):
+            orig(name, *a)
         e.record()
         acc.setdefault(name, []).append((s, e))
 
@@ -430,7 +544,7 @@ def profile_calls(one_step, _lib, iters=5):
         _lib.call = orig
     out = {}
     for name, evs in acc.items():
-        out[name] = sum(s.elapsed_time(e) for s, e in evs) / iters
+        out[name] = sum(s.elapsed_time(e) for s, e in evs) / iters / repeats
     return out
 
 
@@ -485,6 +599,9 @@ def roofline(per_kernel, R, pk, pk_kind, bf16, l2=None):
       gradient is exactly zero) for the data-gradient pass, and again for the weight gradients."""
     if not per_kernel:
         return None
+    per_kernel = dict(per_kernel)
+    if "nrc_chain_run_multi" in per_kernel:   # the shader stacks run through both entry points: one roofline entry
+        per_kernel["nrc_chain_run"] = per_kernel.get("nrc_chain_run", 0.0) + per_kernel.pop("nrc_chain_run_multi")
     top = max(per_kernel, key=per_kernel.get)
     pts = {0: 64 * R, 1: 64 * R, 2: 32 * R}
     LF = {0: (6, 1), 1: (7, 1), 2: (8, 4)}
@@ -506,13 +623,15 @@ def roofline(per_kernel, R, pk, pk_kind, bf16, l2=None):
     if top in alg_bytes:
         ach = alg_bytes[top] / (per_kernel[top] * 1e-3) / 1e9
         res.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], achieved=ach, frac=ach / pk["hbm_gbs"],
-                   note="all launches of this entry point in one step; algorithmic bytes / summed CUDA-event time")
+                   note="all launches of this entry point in one step; algorithmic bytes / summed per-launch device time "
+                        "(back-to-back replays)")
     elif top in alg_flops:
         peak = pk["bf16_tflops"] if bf16 else None
         ach = alg_flops[top] / (per_kernel[top] * 1e-3) / 1e12
         res.update(bound="tensor", unit="TFLOP/s", peak=peak, achieved=ach, frac=(ach / peak) if peak else None,
-                   note="all launches of this entry point in one step (shader stacks fwd + data-gradient); "
-                        "algorithmic FLOPs / summed CUDA-event time; peak = measured cuBLAS bf16 burst")
+                   note="all launches of nrc_chain_run + nrc_chain_run_multi in one step (shader stacks fwd + data-gradient); "
+                        "algorithmic FLOPs / summed per-launch device time (back-to-back replays); peak = measured cuBLAS "
+                        "bf16 burst")
     else:
         res.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], achieved=None, frac=None,
                    note="dominant entry point has no closed-form work model; see the per-kernel list")
@@ -557,11 +676,8 @@ def _timed(fn, steps, warmup, flush, barrier):
     return sum(s.elapsed_time(e) for s, e in evs) / steps
 
 
-def run_render(args):
-    """Render-path workloads (not the BASELINE headline metric; reported for the 8d table)."""
+def _dist_ctx():
     import torch.distributed as dist
-
-    from neural_radiance_caching_b200 import _lib, dist as ndist, render_image as ri, workload
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -570,8 +686,29 @@ def run_render(args):
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local, dev
+
+
+def run_render(args):
+    """Render-path workloads (not the BASELINE headline metric; reported for the 8d table)."""
+    import torch.distributed as dist
+
+    world, rank, local, dev = _dist_ctx()
+    line = render_line(args, args.workload, world, rank, dev, args.steps, args.warmup)
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def render_line(args, workload_name, world, rank, dev, steps, warmup, rays=None, image=None):
+    """One bench line (dict, on rank 0; None elsewhere) of a render-path workload: config3 or config5."""
+    import torch.distributed as dist
+
+    from neural_radiance_caching_b200 import _lib, dist as ndist, render_image as ri, workload
+
     _lib.load()
     pk, pk_kind = peaks()
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
@@ -583,8 +720,8 @@ def run_render(args):
 
     S = 32
     use_graph = False
-    if args.workload == "config3":
-        R = args.rays
+    if workload_name == "config3":
+        R = rays or args.rays
         stage = workload.MaterialRenderStep(dev, bf16=bool(args.bf16))
         g = np.random.Generator(np.random.PCG64(workload.SEED + rank))
         host = torch.from_numpy(np.concatenate([a.reshape(-1) for a in workload.make_surface_np(g, R)])).pin_memory()
@@ -604,7 +741,7 @@ def run_render(args):
             step()
             torch.cuda.synchronize()
             print(json.dumps({"ncu_mode": True, "launches_per_step": launches}))
-            return
+            return None
         per_kernel = profile_calls(step, _lib, iters=3)
         # the chunk is a static launch sequence (inputs and random draws resident): capture it once
         side = torch.cuda.Stream()
@@ -622,13 +759,13 @@ def run_render(args):
             graph.replay()
             return static_rgb
 
-        dev_ms = _timed(gstep, args.steps, args.warmup, flush, barrier)
+        dev_ms = _timed(gstep, steps, warmup, flush, barrier)
 
         def e2e_step():
             dbuf.copy_(host, non_blocking=True)
             out_host.copy_(gstep(), non_blocking=True)
 
-        e2e_ms = _timed(e2e_step, args.steps, args.warmup, flush, barrier)
+        e2e_ms = _timed(e2e_step, steps, warmup, flush, barrier)
         units = world * R * S * SAMPLES_PER_RAY
         wl = ("config3 material_light_from_scratch_resample chunk: %d shaded points x 32 secondary rays (16 microfacet + 8 "
               "cosine + 8 vMF-mixture/128 lobes, MIS), cache query per ray (64,64,32, power-ladder warp, categorical "
@@ -652,49 +789,61 @@ def run_render(args):
         else:
             roof.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], achieved=None, frac=None)
     else:
-        H = W = args.image
+        H = W = image or args.image
         fr = workload.FrameRenderer(dev, bf16=bool(args.bf16))
         c2w = ri.orbit_camera()
         focal = 1111.0 * H / 800.0
 
         def step():
-            return ri.render_image(fr.render_chunk_graphed, H, W, focal, c2w, dev, chunk=args.rays)["rgb"]
+            return ri.render_image(fr.render_chunk_graphed, H, W, focal, c2w, dev, chunk=rays or args.rays)["rgb"]
 
         before = _lib.launch_count
         img = step()
         launches = _lib.launch_count - before
-        per_kernel = {}
-        dev_ms = _timed(step, args.steps, args.warmup, flush, barrier)
+        # the kernels of ONE chunk (the frame is ceil(H*W / chunk / N) replays of the same graph per rank)
+        chunk_rays = {k: v[:(rays or args.rays)].contiguous() for k, v in ri.pinhole_rays(H, W, focal, c2w, dev, rows=(0, 8)).items()}
+        per_kernel = profile_calls(lambda: fr.render_chunk(chunk_rays), _lib, iters=2)
+        dev_ms = _timed(step, steps, warmup, flush, barrier)
         out_host = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory()
 
         def e2e_step():
             out_host.copy_(step(), non_blocking=True)
 
-        e2e_ms = _timed(e2e_step, args.steps, args.warmup, flush, barrier)
+        e2e_ms = _timed(e2e_step, steps, warmup, flush, barrier)
         units = H * W * (SAMPLES_PER_RAY + S * SAMPLES_PER_RAY)
         wl = ("config5 full %dx%d view: per 1024-ray chunk cache stage on the primary rays (config 1, resampled) + "
               "material stage (config 3); image row bands over the ranks, one all_gather of the bands" % (H, W))
         h2d, d2h = 0, H * W * 3 * 4
         scaling = "strong"
         use_graph = True
-        roof = None
+        top = max(per_kernel, key=per_kernel.get)
+        roof = {"kernel": top, "peak_source": pk_kind, "traffic": _traffic(top), "bound": "hbm", "unit": "GB/s",
+                "peak": pk["hbm_gbs"], "achieved": None, "frac": None, "per": "one 1024-ray chunk"}
+        if top == "nrc_density_query_fwd":
+            Rc = rays or args.rays
+            nray = Rc * (1 + S)          # primary rays + 32 secondary rays per shaded point
+            per_ray = 64 * (12 + 192 + 24) + 64 * (12 + 224 + 28) + 32 * (12 + 1024 + 128)
+            ach = nray * per_ray / (per_kernel[top] * 1e-3) / 1e9
+            l2 = l2_gather_probe(dev)
+            t_bound = (nray * 8 * 64 * (6 + 7)) / (l2["row4_grows_s"] * 1e9) + (nray * 8 * 32 * 8) / (l2["row16_grows_s"] * 1e9)
+            roof.update(achieved=ach, frac=ach / pk["hbm_gbs"], l2_gather=l2, l2_gather_frac=t_bound / (per_kernel[top] * 1e-3),
+                        note="density queries of one chunk (primary + secondary rays); algorithmic gather bytes / summed "
+                             "per-launch device time; tables are L2-resident: the L2 random-gather rate is the bound")
     t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
-    if rank == 0:
-        line = {"metric": METRIC, "value": units / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": scaling,
-                "vs_baseline": None, "dtype": "bf16" if args.bf16 else "f32", "data": "synthetic",
-                "config": {"workload": wl, "l2": "flushed between timed steps", "cuda_graph": use_graph,
-                           "parallelism": f"dp{world}"},
-                "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms},
-                "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "roofline": roof,
-                "kernel_ms": {k: round(v, 5) for k, v in per_kernel.items()}}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    return {"metric": METRIC, "value": units / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(3, warmup), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "bf16" if args.bf16 else "f32", "data": "synthetic",
+            "config": {"workload": wl, "l2": "flushed between timed steps", "cuda_graph": use_graph,
+                       "parallelism": f"dp{world}"},
+            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": launches * steps, "gpu_launches_per_step": launches, "roofline": roof,
+            "kernel_ms": {k: round(v, 5) for k, v in per_kernel.items()}}
 
 
 if __name__ == "__main__":
