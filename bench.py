@@ -794,8 +794,10 @@ def render_line(args, workload_name, world, rank, dev, steps, warmup, rays=None,
         c2w = ri.orbit_camera()
         focal = 1111.0 * H / 800.0
 
+        graphs = {}    # the captured chunk (camera rays -> cache + material stage -> band stores -> counter) per band
+
         def step():
-            return ri.render_image(fr.render_chunk_graphed, H, W, focal, c2w, dev, chunk=rays or args.rays)["rgb"]
+            return ri.render_image(fr.render_chunk, H, W, focal, c2w, dev, chunk=rays or args.rays, _graphs=graphs)["rgb"]
 
         before = _lib.launch_count
         img = step()
@@ -812,7 +814,8 @@ def render_line(args, workload_name, world, rank, dev, steps, warmup, rays=None,
         e2e_ms = _timed(e2e_step, steps, warmup, flush, barrier)
         units = H * W * (SAMPLES_PER_RAY + S * SAMPLES_PER_RAY)
         wl = ("config5 full %dx%d view: per 1024-ray chunk cache stage on the primary rays (config 1, resampled) + "
-              "material stage (config 3); image row bands over the ranks, one all_gather of the bands" % (H, W))
+              "material stage (config 3); image row bands over the ranks, one all_gather of the bands; the chunk loop is one CUDA "
+              "graph replayed per chunk with the chunk counter and the camera-ray generation on the device" % (H, W))
         h2d, d2h = 0, H * W * 3 * 4
         scaling = "strong"
         use_graph = True

@@ -593,6 +593,26 @@ int32_t nrc_geometry_losses(void* stream, const float* d_weights, const float* d
                             float predicted_normal_mult, float predicted_normal_reverse_mult, float stopgrad_weight,
                             float* d_loss, float* d_g_weights, float* d_g_normals_pred, float* d_g_normals);
 
+/* ------------------------------- camera rays and the whole-image chunk loop (rows 23, 8f-3) ---- */
+/* camera_utils.pixels_to_rays (internal/camera_utils.py:896-1073) for the perspective camera without distortion, NDC or
+ * jitter + the near / far broadcast of cast_ray_batch (:1225-1330), for `num_rays` consecutive pixels of a row-major
+ * image starting at flat index first_pixel (y * width + x); d_first_pixel != NULL reads that index from device memory
+ * (the chunk counter of a graph-replayed render).  Indices beyond last_pixel repeat last_pixel (edge padding of
+ * internal/models.py:2434-2445).  pixtocam [9] / camtoworld [12] are HOST arrays (row major).
+ *   -> d_origins, d_directions (not normalised), d_viewdirs [N,3], d_radii [N], d_imageplane [N,2] (may be NULL),
+ *      d_near, d_far [N] (may be NULL). */
+int32_t nrc_camera_rays(void* stream, const float* pixtocam, const float* camtoworld, int32_t width, int32_t height,
+                        int64_t first_pixel, const int64_t* d_first_pixel, int64_t last_pixel, int64_t num_rays,
+                        float near, float far, float* d_origins, float* d_directions, float* d_viewdirs,
+                        float* d_radii, float* d_imageplane, float* d_near, float* d_far);
+/* The chunk loop of models.render_image (internal/models.py:2361-2525) without host work per chunk: *d_counter += step
+ * (last node of a chunk's CUDA graph) ... */
+int32_t nrc_chunk_advance(void* stream, int64_t* d_counter, int64_t step);
+/* ... and the chunk's results [chunk, channels] stored at the band position of its first pixel (*d_first_pixel -
+ * band_first_pixel); rows outside [0, band_pixels) - the padding rays of the last chunk - are dropped. */
+int32_t nrc_band_store(void* stream, const float* d_src, int32_t channels, const int64_t* d_first_pixel,
+                       int64_t band_first_pixel, int64_t band_pixels, int64_t chunk, float* d_band);
+
 /* --------------------------------------------- light sampler ---- */
 /* vMF head of LightMLP: get_vmfs + the recentring of predict_lighting (internal/light_sampler.py:135-160,203-204).
  *   d_raw [P, K*5] (output layer), d_means_random [P,K,3] (means_random_per_point = 1) or [K,3] (0), d_positions [P,3]

@@ -609,6 +609,24 @@ def main():
         fd[:, a_] = (raw_at(xp) - raw_at(xm)) / (xp[:, a_].astype(np.float64) - xm[:, a_].astype(np.float64))
     out.update(dnrm_means=npts, dnrm_fd_raw_grad=fd.astype(np.float32))
 
+    # ---- camera_utils.pixels_to_rays (camera_utils.py:896-1073), perspective camera without distortion / NDC / jitter, and
+    #      get_pixtocam (:749-763): a 20 x 12 image seen from an orbit pose.  Pixel coordinates are passed as float32 (jnp
+    #      promotes int32 + 0.5 to float32; NumPy would make it float64). -------------------------------------------------
+    rcam = importlib.import_module("internal.camera_utils")
+    Wc, Hc, fc = 20, 12, 17.3
+    az, el = np.deg2rad(30.0), np.deg2rad(25.0)
+    cpos = 4.0 * np.array([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)])
+    cfwd = -cpos / np.linalg.norm(cpos)
+    cright = np.cross(cfwd, [0.0, 0.0, 1.0]); cright /= np.linalg.norm(cright)
+    cup = np.cross(cright, cfwd)
+    c2w_ = f(np.concatenate([np.stack([cright, cup, -cfwd], axis=1), cpos[:, None]], axis=1))
+    k_ = f(rcam.get_pixtocam(fc, Wc, Hc))
+    cys, cxs = np.meshgrid(np.arange(Hc, dtype=np.float32), np.arange(Wc, dtype=np.float32), indexing="ij")
+    cres = rcam.pixels_to_rays(cxs, cys, k_, c2w_, xnp=shim.jnp)
+    out.update(cam_pixtocam=k_, cam_camtoworld=c2w_, cam_size=np.array([Wc, Hc], np.int32))
+    for k_name, v_ in zip(("origins", "directions", "viewdirs", "radii", "imageplane"), cres[:5]):
+        out["cam_" + k_name] = np.asarray(v_)
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

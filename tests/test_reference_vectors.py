@@ -503,3 +503,16 @@ def test_analytic_normals_against_reference_differences():
     med, q80 = fd_quantiles(grad, "dnrm_fd_raw_grad")
     assert med <= 3e-4 and q80 <= 3e-3, (med, q80)    # measured 7e-5 / ...; ~30 % of the differences straddle a face of
     # the finest level (cell 1/64 of the contracted box against 2h = 1e-3, three axes, five levels)
+
+
+def test_pixels_to_rays():
+    """camera_utils.pixels_to_rays (internal/camera_utils.py:896-1073) and get_pixtocam (:749-763) executed from the
+    reference: perspective camera, pixel centres, OpenCV -> OpenGL flip, rotation, unit view directions, cone radii."""
+    from oracle import camera_utils as ocam
+
+    Wc, Hc = (int(v) for v in V["cam_size"])
+    ys, xs = np.meshgrid(np.arange(Hc, dtype=np.float32), np.arange(Wc, dtype=np.float32), indexing="ij")
+    got = ocam.pixels_to_rays(xs, ys, V["cam_pixtocam"], V["cam_camtoworld"])
+    assert np.allclose(ocam.get_pixtocam(17.3, Wc, Hc).astype(np.float32), V["cam_pixtocam"], rtol=0, atol=0)
+    for name, g_ in zip(("origins", "directions", "viewdirs", "radii", "imageplane"), got):
+        close(torch.from_numpy(np.ascontiguousarray(g_)), "cam_" + name, 1e-6)
