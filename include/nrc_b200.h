@@ -593,6 +593,40 @@ int32_t nrc_geometry_losses(void* stream, const float* d_weights, const float* d
                             float predicted_normal_mult, float predicted_normal_reverse_mult, float stopgrad_weight,
                             float* d_loss, float* d_g_weights, float* d_g_normals_pred, float* d_g_normals);
 
+/* ------------------------------------------- time-resolved path, fused (row 22, config 4) ---- */
+/* nrc_transient_render_fwd with the LAST LAYER of both transient heads inside: the per-sample histograms
+ * [R, n, n_bins, C] the reference materialises (internal/nerf.py:1660-1777 get_indirect / transient SurfaceLightField
+ * output, internal/surface_light_field.py:1033-1041) never reach HBM.
+ *   d_h_diffuse  [R*n, 64]  hidden activation of the irradiance stack (after its last ReLU), d_w_diffuse Flax kernel
+ *                [64, >= n_bins*C] (row stride ld_w_diffuse), d_b_diffuse [n_bins*C]:
+ *                diffuse = clip(softplus(h W + b + diffuse_bias) * indirect_scale, 0, rgb_max)
+ *   d_h_specular [R*n, 128] hidden activation of the transient SurfaceLightField stack, d_w_specular [128, >= n_bins*C]
+ *                (the 2101-wide output layer: row stride ld_w_specular, the alpha column is not read), d_b_specular:
+ *                specular = clip(spec_scale * clip(softplus(spec_premult * (h W + b) + spec_bias), 0, spec_max)
+ *                                * indirect_scale, 0, rgb_max),   d_spec_scale [R,n,C] = tint * integrated BRDF
+ *   either head may be NULL.  Validity masks, sub-bin shift, weighted reduction and outputs as nrc_transient_render_fwd.
+ *   The head GEMMs run on the tensor cores with bf16 operands (north-star bf16-MLP variant). */
+int32_t nrc_transient_head_render_fwd(
+    void* stream, const float* d_direct_rgbs, const float* d_h_diffuse, int32_t k_diffuse, const float* d_w_diffuse,
+    int64_t ld_w_diffuse, const float* d_b_diffuse, const float* d_h_specular, int32_t k_specular, const float* d_w_specular,
+    int64_t ld_w_specular, const float* d_b_specular, const float* d_spec_scale, const float* d_weights, const float* d_ray_dists,
+    const float* d_light_dists, const float* d_cam_dists, int64_t num_rays, int32_t n, int32_t n_bins, int32_t channels,
+    float exposure_time, float shift, float diffuse_bias, float spec_premult, float spec_bias, float spec_max,
+    float indirect_scale, float bin_zero_threshold_light, int32_t light_zero, float light_near, float rgb_max, float dark_level,
+    float* d_transient_direct, float* d_transient_indirect, float* d_rgb);
+/* The temporal filter of volumetric_transient_rendering (internal/render.py:397-415): convolution along the bin axis with
+ * the impulse response / normalised Gaussian d_filter [taps], mode 'same'.  d_x, d_y [R, n_bins, C] (not in place). */
+int32_t nrc_transient_filter(void* stream, const float* d_x, const float* d_filter, int32_t taps, int64_t num_rays,
+                             int32_t n_bins, int32_t channels, float* d_y);
+/* transient_integrate_reflect_rays, direct=False (internal/inverse_render/render_utils.py:1195-1302): like
+ * nrc_ggx_integrate_fwd with a histogram of incoming radiance per secondary ray, d_radiance [R,S,n_bins,3]
+ *   -> d_radiance_out, d_irradiance [R,n_bins,3] (the second may be NULL), d_occ_out [R] (with d_occ [R,S]). */
+int32_t nrc_ggx_integrate_transient_fwd(void* stream, const float* d_wi, const float* d_wo, const float* d_radiance,
+                                        const float* d_weight, const float* d_pdf, const float* d_occ, const float* d_albedo,
+                                        const float* d_roughness, const float* d_metalness, const float* d_f0,
+                                        int64_t num_points, int32_t num_samples, int32_t n_bins, int32_t lobe_kind,
+                                        float rgb_max, float* d_radiance_out, float* d_irradiance, float* d_occ_out);
+
 /* ------------------------------- camera rays and the whole-image chunk loop (rows 23, 8f-3) ---- */
 /* camera_utils.pixels_to_rays (internal/camera_utils.py:896-1073) for the perspective camera without distortion, NDC or
  * jitter + the near / far broadcast of cast_ray_batch (:1225-1330), for `num_rays` consecutive pixels of a row-major

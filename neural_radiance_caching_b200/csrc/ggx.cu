@@ -158,6 +158,62 @@ ggx_integrate_bwd_radiance_kernel(const float* __restrict__ wi, const float* __r
   }
 }
 
+
+// transient_integrate_reflect_rays with direct=False (internal/inverse_render/render_utils.py:1195-1302): the incoming
+// radiance of every secondary ray is a HISTOGRAM [n_bins, 3]; lobe, weight and pdf are per sample.  One CTA per shaded
+// point: the per-sample factors are computed once (warp 0 style: threads over samples) into shared memory, then threads
+// over (bin, channel) reduce over the samples.
+__global__ void __launch_bounds__(256)
+ggx_integrate_transient_fwd_kernel(const float* __restrict__ wi, const float* __restrict__ wo, const float* __restrict__ radiance,
+                                   const float* __restrict__ weight, const float* __restrict__ pdf, const float* __restrict__ occ,
+                                   const float* __restrict__ albedo, const float* __restrict__ roughness,
+                                   const float* __restrict__ metalness, const float* __restrict__ f0, int64_t R, int S, int n_bins,
+                                   int kind, float rgb_max, float* __restrict__ radiance_out, float* __restrict__ irradiance,
+                                   float* __restrict__ occ_out) {
+  extern __shared__ float sm[];       // per sample: lobe[3], diffuse lobe, weight / denominator
+  const int64_t r = blockIdx.x;
+  float* s_lobe = sm;
+  float* s_dl = sm + 3 * S;
+  float* s_wd = s_dl + S;
+  Material m;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) m.albedo[ch] = albedo[3 * r + ch];
+  m.rough = roughness ? roughness[r] : 1.f;
+  m.metal = metalness ? metalness[r] : 0.f;
+  m.f0 = f0 ? f0[r] : 0.04f;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const int64_t q = r * S + s;
+    float li[3] = {wi[3 * q], wi[3 * q + 1], wi[3 * q + 2]};
+    float lo[3] = {wo[3 * q], wo[3 * q + 1], wo[3 * q + 2]};
+    float lobe[3];
+    eval_lobe(kind, li, lo, m, lobe);
+    float w = fmaxf(weight[q], 0.f);
+    if (!(li[2] > 0.f)) w = 0.f;
+    s_lobe[3 * s] = lobe[0]; s_lobe[3 * s + 1] = lobe[1]; s_lobe[3 * s + 2] = lobe[2];
+    s_dl[s] = fmaxf(0.f, li[2]) / kPi;
+    s_wd[s] = w / fmaxf(pdf[q], kDenEps);
+  }
+  __syncthreads();
+  const float inv = 1.f / static_cast<float>(S);
+  for (int e = threadIdx.x; e < n_bins * 3; e += blockDim.x) {
+    const int ch = e % 3;
+    float ro = 0.f, ir = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float L = radiance[((r * S + s) * n_bins) * 3 + e];
+      // (clip(L * lobe) * weight) / denominator in the reference: weight / denominator folded, as in the static kernel
+      ro += fminf(fmaxf(L * s_lobe[3 * s + ch], 0.f), rgb_max) * s_wd[s];
+      ir += fminf(fmaxf(L * s_dl[s], 0.f), rgb_max) * s_wd[s];
+    }
+    radiance_out[r * n_bins * 3 + e] = ro * inv;
+    if (irradiance) irradiance[r * n_bins * 3 + e] = ir * inv;
+  }
+  if (occ && occ_out && threadIdx.x == 0) {
+    float oc = 0.f;
+    for (int s = 0; s < S; ++s) oc += occ[r * S + s];
+    occ_out[r] = oc * inv;
+  }
+}
+
 }  // namespace nrc
 
 using namespace nrc;
@@ -195,5 +251,22 @@ extern "C" int32_t nrc_ggx_integrate_bwd(void* stream, const float* d_wi, const 
   ggx_integrate_bwd_radiance_kernel<<<grid, kGgxWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       d_wi, d_wo, d_radiance, d_weight, d_pdf, d_albedo, d_roughness, d_metalness, d_f0, d_g_out,
       d_g_irradiance, num_points, num_samples, lobe_kind, rgb_max, d_g_radiance);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_ggx_integrate_transient_fwd(void* stream, const float* d_wi, const float* d_wo, const float* d_radiance,
+                                                   const float* d_weight, const float* d_pdf, const float* d_occ,
+                                                   const float* d_albedo, const float* d_roughness, const float* d_metalness,
+                                                   const float* d_f0, int64_t num_points, int32_t num_samples, int32_t n_bins,
+                                                   int32_t lobe_kind, float rgb_max, float* d_radiance_out, float* d_irradiance,
+                                                   float* d_occ_out) {
+  if (num_points < 0 || num_samples < 1 || num_samples > 4096 || n_bins < 1 || lobe_kind < 0 || lobe_kind > 3)
+    return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_wi || !d_wo || !d_radiance || !d_weight || !d_pdf || !d_albedo || !d_radiance_out) return NRC_E_INVALID_ARG;
+  ggx_integrate_transient_fwd_kernel<<<static_cast<unsigned>(num_points), 256, static_cast<size_t>(num_samples) * 5 * sizeof(float),
+                                       static_cast<cudaStream_t>(stream)>>>(
+      d_wi, d_wo, d_radiance, d_weight, d_pdf, d_occ, d_albedo, d_roughness, d_metalness, d_f0, num_points, num_samples, n_bins,
+      lobe_kind, rgb_max, d_radiance_out, d_irradiance, d_occ_out);
   return check_launch();
 }

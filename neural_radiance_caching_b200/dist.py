@@ -62,10 +62,8 @@ class PeerArena:
     def __init__(self, buf, hdl, mode):
         self.buf, self.hdl, self.mode = buf, hdl, mode
         self.rank, self.world = hdl.rank, hdl.world_size
-        self._peers = None
-        if mode == "peer":
-            arr = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
-            self._peers = arr
+        self._peers = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+        self.multicast_ptr = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
         self._next_channel = 0
 
     @staticmethod
@@ -80,9 +78,20 @@ class PeerArena:
             buf.zero_()
             hdl = symm.rendezvous(buf, dist.group.WORLD)
             mc = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
-            # default: plain peer loads / stores (measured at N = 2 on the 110.6 MB arena: 0.186 ms vs 0.238 ms NCCL vs
-            # 0.314 ms for the multimem variant, profiles/r01j_allreduce_n2.json); NRC_ALLREDUCE=multicast opts in
-            mode = "multicast" if (mc and want == "multicast") else "peer"
+            # Which kernel by default (NRC_ALLREDUCE=peer|multicast forces one):
+            #   N = 2: plain peer loads / stores (110.6 MB arena: 0.186 ms vs 0.238 ms NCCL vs 0.314 ms multimem,
+            #          profiles/r01j_allreduce_n2.json);
+            #   N >= 4: multimem (in-switch reduction).  The two-shot peer scheme moves 2 (N-1)/N of the arena through every
+            #          GPU's links and needs >= 148 CTAs to keep them busy; the multimem kernel moves the arena once, is as
+            #          fast at N = 8 (0.304 vs 0.320 ms, profiles/r01j_allreduce_n8.json) and is flat from 16 CTAs up
+            #          (profiles/r01k_allreduce_cta_sweep_n2.json) - so a bucket that overlaps the backward pass leaves
+            #          the SMs to it.
+            if want == "multicast":
+                mode = "multicast" if mc else "peer"
+            elif want == "peer-only":
+                mode = "peer"
+            else:
+                mode = "multicast" if (mc and dist.get_world_size() >= 4) else "peer"
             return PeerArena(buf, hdl, mode)
         except Exception as e:   # no NVLink peer access / symmetric memory unavailable: NCCL path
             if dist.get_rank() == 0:
@@ -90,16 +99,20 @@ class PeerArena:
                       file=sys.stderr)
             return None
 
-    def allreduce_mean_(self, offset=0, count=None, channel=0, num_ctas=0):
+    def allreduce_mean_(self, offset=0, count=None, channel=0, num_ctas=0, mode=None):
         """Mean over ranks of buf[offset:offset+count] in place, on the current stream.  Concurrent calls (different
-        streams) must use different `channel`s (each call uses barrier channels 2*channel and 2*channel+1)."""
+        streams) must use different `channel`s (each call uses barrier channels 2*channel and 2*channel+1).
+        `mode` overrides the arena's default kernel for this bucket ('peer' | 'multicast')."""
         from . import _lib
         count = self.buf.numel() - offset if count is None else count
         if offset % 4 or count % 4:
             raise ValueError("offset and count must be multiples of 4 floats")
+        mode = mode or self.mode
+        if mode == "multicast" and not self.multicast_ptr:
+            mode = "peer"
         self.hdl.barrier(channel=2 * channel)            # every rank's gradients are complete (stream ordered)
-        if self.mode == "multicast":
-            _lib.call("nrc_allreduce_mean_multicast", _lib.stream_ptr(), int(self.hdl.multicast_ptr), int(offset),
+        if mode == "multicast":
+            _lib.call("nrc_allreduce_mean_multicast", _lib.stream_ptr(), self.multicast_ptr, int(offset),
                       int(count), self.rank, self.world, int(num_ctas))
         else:
             _lib.call("nrc_allreduce_mean_peer", _lib.stream_ptr(), ctypes.cast(self._peers, ctypes.c_void_p), int(offset),

@@ -76,16 +76,19 @@ class FusedCacheStep:
             self._bg[key] = (sd, torch.ones((R, 1), device=dev, dtype=torch.float32))
         return self._bg[key]
 
-    def step(self, rays, u01, target_rgb, train_frac=1.0, extra=None, zero_grad=None, on_shader_grads=None):
+    def step(self, rays, u01, target_rgb, train_frac=1.0, extra=None, zero_grad=None, on_shader_grads=None,
+             on_proposal_grads=None):
         """One forward + loss + backward; gradients land in the registered sinks.  Returns the loss
         (device scalar) and leaves the per-level sampler state in self.last (for tests).
         `extra` = (rays, u01) of the backward-mask pass (train_utils.py:3348-3401) or None.
         `zero_grad` = callable that clears the gradient sinks (the 110 MB arena memset): issued here on a side
         stream beside the sampler's forward instead of in front of the step.
         `on_shader_grads` = callable invoked (in stream order on the main stream) as soon as every gradient of the
-        `Shader` parameters is final: a data-parallel harness forks that bucket's all-reduce there."""
+        `Shader` parameters is final: a data-parallel harness forks that bucket's all-reduce there.
+        `on_proposal_grads` = the same for the proposal levels' parameters (every sampler level but the last), invoked
+        on the proposal branch's side stream right after that branch's backward."""
         state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra, zero_grad=zero_grad,
-                                on_shader_grads=on_shader_grads)
+                                on_shader_grads=on_shader_grads, on_proposal_grads=on_proposal_grads)
         self.step_back(state)
         return state["loss"]
 
@@ -135,7 +138,7 @@ class FusedCacheStep:
         return _lib.ptr(self._bg[key])
 
     def step_front(self, rays, u01, target_rgb, train_frac=1.0, fork_proposals=False, extra=None, zero_grad=None,
-                   on_shader_grads=None):
+                   on_shader_grads=None, on_proposal_grads=None):
         """Forward, loss and the SHADER's backward: when this returns (in stream order) every gradient of the
         `Shader` parameters (appearance grid + all stacks) is final, so a data-parallel harness can start
         all-reducing that half of the gradient arena while step_back() produces the sampler's half."""
@@ -304,6 +307,8 @@ class FusedCacheStep:
                 if fork_proposals:
                     for i_level in range(nl - 2, -1, -1):
                         self._level_backward(levels[i_level], rays, g_w[i_level], None, None, R)
+                    if on_proposal_grads is not None:
+                        on_proposal_grads()
         else:
             interlevel()
         # ------------------------------------------------------------------ forward: shader + integrator + loss

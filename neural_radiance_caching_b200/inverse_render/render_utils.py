@@ -182,3 +182,38 @@ def microfacet_material(brdf_params, min_roughness=0.01, default_F_0=0.04):
     r = lambda t, *s: t.reshape(lead + s)
     return dict(albedo=r(albedo, 3), roughness=r(rough, 1), metalness=r(metal, 1), F_0=r(f0, 1),
                 specular_albedo=r(spec, 1))
+
+
+def transient_integrate_reflect_rays(material_type, use_brdf_correction, material, samples, use_diffuseness=False,
+                                     use_mirrorness=False, use_specular_albedo=False, direct=True, max_radiance=float("inf")):
+    """internal/inverse_render/render_utils.py:1195-1302.  direct=True is integrate_reflect_rays on [R,S,3] radiance;
+    direct=False takes a HISTOGRAM of incoming radiance per secondary ray, samples['radiance_in'] [R,S,n_bins,3], and returns
+    radiance_out / irradiance [R,n_bins,3] (nrc_ggx_integrate_transient_fwd).  Forward path."""
+    if direct:
+        return integrate_reflect_rays(material_type, use_brdf_correction, material, samples, use_diffuseness, use_mirrorness,
+                                      use_specular_albedo, max_radiance)
+    if use_brdf_correction or use_diffuseness or use_mirrorness or use_specular_albedo:
+        raise NotImplementedError("brdf correction / diffuseness / mirrorness / specular albedo are out of scope")
+    if material_type not in _LOBE_KINDS:
+        raise ValueError(f"unsupported material_type {material_type}")
+    wi = samples["local_lightdirs"].contiguous()
+    R, S = wi.shape[0], wi.shape[1]
+    wo = samples["local_viewdirs"].expand(R, S, 3).contiguous()
+    rad = samples["radiance_in"].contiguous()
+    B = rad.shape[2]
+    f = lambda k: samples[k].reshape(R, S).contiguous()
+    m = lambda k: material[k].reshape(R).contiguous() if k in material else None
+    occ = f("indirect_occ") if "indirect_occ" in samples else None
+    dev = wi.device
+    out = torch.empty((R, B, 3), device=dev, dtype=torch.float32)
+    irr = torch.empty((R, B, 3), device=dev, dtype=torch.float32)
+    occ_out = torch.empty((R,), device=dev, dtype=torch.float32) if occ is not None else None
+    _lib.call("nrc_ggx_integrate_transient_fwd", _lib.stream_ptr(), _lib.ptr(wi), _lib.ptr(wo), _lib.ptr(rad), _lib.ptr(f("weight")),
+              _lib.ptr(f("pdf")), _lib.ptr(occ), _lib.ptr(material["albedo"].reshape(R, 3).contiguous()), _lib.ptr(m("roughness")),
+              _lib.ptr(m("metalness")), _lib.ptr(m("F_0")), R, S, B, _LOBE_KINDS[material_type],
+              float(max_radiance if max_radiance != float("inf") else 3.4e38), _lib.ptr(out), _lib.ptr(irr), _lib.ptr(occ_out))
+    res = dict(radiance_out=out, irradiance=irr, indirect_occ=occ_out[:, None] if occ_out is not None else None)
+    if "brdf_correction" in samples:
+        res["integrated_multiplier"] = samples["brdf_correction"][:, 0]
+        res["integrated_multiplier_irradiance"] = samples["brdf_correction"][:, 0, :1]
+    return res

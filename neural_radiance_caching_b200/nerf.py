@@ -531,6 +531,17 @@ class TransientIndirectHead:
         return {"irradiance_layers_0": layer(self.in_dim, self.width), "irradiance_layers_1": layer(self.width, self.width),
                 "transient_indirect_layer": layer(self.width, self.n_bins * self.channels)}
 
+    def hidden(self, p, feature, lights):
+        """The irradiance stack up to its last ReLU (run_irradiance_network, internal/nerf.py:1757-1772): [P,64].  The
+        fused time-resolved kernel (render.volumetric_transient_rendering_fused) applies transient_indirect_layer itself."""
+        P = feature.shape[0]
+        l2 = lights.reshape(P, 3).contiguous()
+        enc = torch.empty((P, 3 + 6 * self.deg), device=feature.device, dtype=torch.float32)
+        _lib.call("nrc_pos_enc", _lib.stream_ptr(), _lib.ptr(l2), P, 3, 0, self.deg, 1, _lib.ptr(enc), enc.shape[1])
+        x = torch.cat([feature.reshape(P, -1), enc], dim=-1)
+        x = dense(p["irradiance_layers_0"], x, relu=True, bf16=self.bf16)
+        return dense(p["irradiance_layers_1"], x, relu=True, bf16=self.bf16)
+
     def __call__(self, p, feature, lights):
         """feature [P,96], lights [P,3] -> raw transient indirect [P, n_bins, C]."""
         P = feature.shape[0]

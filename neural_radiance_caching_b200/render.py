@@ -189,3 +189,64 @@ def volumetric_transient_rendering(direct_rgbs, diffuse_raw, specular, spec_scal
               int(bool(light_zero)), float(light_near), float(rgb_max), float(dark_level), _lib.ptr(t_direct),
               _lib.ptr(t_indirect), _lib.ptr(rgb))
     return dict(transient_direct=t_direct, transient_indirect=t_indirect, rgb=rgb, integrated_rgb=rgb.sum(-2))
+
+
+def gaussian_tfilter(tfilter_sigma, device):
+    """The temporal filter of volumetric_transient_rendering (internal/render.py:401-404): Gaussian over
+    round(-4 sigma) .. round(4 sigma) bins minus exp(-8), normalised; as a device tensor [taps]."""
+    import numpy as np
+    k = np.arange(round(-4 * tfilter_sigma), round(4 * tfilter_sigma) + 1).astype(np.float32)
+    f = np.exp(-(k ** 2) / np.float32(2 * tfilter_sigma ** 2)).astype(np.float32) - np.float32(np.exp(-8))
+    return torch.from_numpy((f / f.sum()).astype(np.float32)).to(device)
+
+
+def temporal_filter(x, filt):
+    """jax.scipy.signal.convolve(x, filt[None, :, None], mode='same') along the bin axis (internal/render.py:406-413):
+    x [R, n_bins, C], filt [taps] (impulse response or gaussian_tfilter)."""
+    x = _c(x)
+    R, B, Cc = x.shape
+    y = torch.empty_like(x)
+    _lib.call("nrc_transient_filter", _lib.stream_ptr(), _lib.ptr(x), _lib.ptr(_c(filt)), int(filt.shape[0]), R, B, Cc, _lib.ptr(y))
+    return y
+
+
+def volumetric_transient_rendering_fused(direct_rgbs, h_diffuse, diffuse_layer, h_specular, specular_layer, spec_scale, weights,
+                                         ray_dists, light_dists, cam_dists, n_bins=700, exposure_time=0.01, shift=0.0,
+                                         diffuse_bias=-2.0, spec_premult=1.0, spec_bias=-2.0, spec_max=float("inf"),
+                                         indirect_scale=1.0, bin_zero_threshold_light=0.0, light_zero=False, light_near=0.0,
+                                         rgb_max=10000.0, dark_level=0.0, impulse_response=None, tfilter_sigma=0.0,
+                                         filter_indirect=False):
+    """volumetric_transient_rendering (internal/render.py:250-449) with the LAST LAYER of the transient heads inside the
+    kernel (nrc_transient_head_render_fwd): h_diffuse [R,n,64] is the irradiance stack's last hidden activation and
+    diffuse_layer = {'kernel': [64, n_bins*C], 'bias'} its transient_indirect_layer (internal/nerf.py:1757-1777);
+    h_specular [R,n,128] / specular_layer the transient SurfaceLightField's last activation and output_rgba_layer
+    ([128, n_bins*C + 1]; the alpha column is not used); spec_scale [R,n,C] = tint * integrated BRDF.  The per-sample
+    histograms [R,n,n_bins,C] are never materialised.  Then the temporal filter (impulse_response / tfilter_sigma,
+    filter_indirect) as in the reference.  Forward path."""
+    R, n, Cc = direct_rgbs.shape
+    dev = direct_rgbs.device
+    new = lambda: torch.empty((R, n_bins, Cc), device=dev, dtype=torch.float32)
+    t_direct, t_indirect, rgb = new(), new(), new()
+    hd = _c(h_diffuse.reshape(R * n, -1)) if h_diffuse is not None else None
+    hs = _c(h_specular.reshape(R * n, -1)) if h_specular is not None else None
+    wd, bd = (diffuse_layer["kernel"], diffuse_layer["bias"]) if hd is not None else (None, None)
+    ws, bs = (specular_layer["kernel"], specular_layer["bias"]) if hs is not None else (None, None)
+    big = 3.0e38
+    _lib.call("nrc_transient_head_render_fwd", _lib.stream_ptr(), _lib.ptr(_c(direct_rgbs)),
+              _lib.ptr(hd), 64 if hd is not None else 0, _lib.ptr(wd), int(wd.shape[1]) if wd is not None else 0, _lib.ptr(bd),
+              _lib.ptr(hs), 128 if hs is not None else 0, _lib.ptr(ws), int(ws.shape[1]) if ws is not None else 0, _lib.ptr(bs),
+              _lib.ptr(_c(spec_scale)) if spec_scale is not None else None, _lib.ptr(_c(weights)), _lib.ptr(_c(ray_dists)),
+              _lib.ptr(_c(light_dists)), _lib.ptr(_c(cam_dists)), R, n, n_bins, Cc, float(exposure_time), float(shift),
+              float(diffuse_bias), float(spec_premult), float(spec_bias), float(min(spec_max, big)), float(indirect_scale),
+              float(bin_zero_threshold_light), int(bool(light_zero)), float(light_near), float(min(rgb_max, big)), float(dark_level),
+              _lib.ptr(t_direct), _lib.ptr(t_indirect), _lib.ptr(rgb))
+    out = dict(transient_direct_no_filter=t_direct, transient_indirect_no_filter=t_indirect)
+    if impulse_response is not None or tfilter_sigma != 0.0:
+        filt = impulse_response if impulse_response is not None else gaussian_tfilter(tfilter_sigma, dev)
+        t_direct = temporal_filter(t_direct, filt)
+        if filter_indirect:
+            t_indirect = temporal_filter(t_indirect, filt)
+        rgb = t_direct + t_indirect + dark_level
+    out.update(transient_direct=t_direct, transient_indirect=t_indirect, rgb=rgb, integrated_rgb=rgb.sum(-2),
+               direct_rgb=t_direct.sum(-2), indirect_rgb=t_indirect.sum(-2))
+    return out

@@ -252,7 +252,11 @@ class CacheTrainStep:
         off = 0
         ranges = {}
         self.shader_offset = 0
+        final_arena = sampler[f"MLP_{len(self.model.sampler.mlps) - 1}"]["density_grid"]["_arena"]
+        self.final_level_offset = 0
         for i, t in enumerate(self.leaves):
+            if t is final_arena:
+                self.final_level_offset = off  # flat_grad[:final_level_offset] = the proposal levels' MLPs and grids
             if i == self.num_sampler_leaves:
                 self.shader_offset = off       # flat_grad[:shader_offset] = sampler grads, [shader_offset:] = shader grads
             n = int(t.numel())
@@ -285,13 +289,13 @@ class CacheTrainStep:
         for lo, hi in self._zero_ranges:
             self.flat_grad[lo:hi].zero_()
 
-    def allreduce_grads(self, lo=0, hi=None, channel=0, num_ctas=0):
+    def allreduce_grads(self, lo=0, hi=None, channel=0, num_ctas=0, mode=None):
         """Mean over ranks of flat_grad[lo:hi] in place on the current stream (the reference's lax.pmean,
         internal/train_utils.py:3132-3136).  Concurrent buckets (different streams) need different channels."""
         from . import dist as _ndist
         hi = self.flat_grad.numel() if hi is None else hi
         if self.peer is not None:
-            self.peer.allreduce_mean_(lo, hi - lo, channel, num_ctas)
+            self.peer.allreduce_mean_(lo, hi - lo, channel, num_ctas, mode)
         else:
             _ndist.allreduce_mean_(self.flat_grad[lo:hi])
 
@@ -306,22 +310,37 @@ class CacheTrainStep:
         `extra` = (backward-mask rays, their u01): see backward_mask_rays_np."""
         if self.engine is not None:
             if fused_allreduce and self.peer is not None:
-                # Data parallel, all-reduce INSIDE the step (and inside its CUDA graph): the Shader bucket's peer-memory
-                # all-reduce is forked onto a communication stream the moment the shader's backward is done and runs
-                # beside the sampler's backward; the Sampler bucket follows at the end of the step.
+                # Data parallel, all-reduce INSIDE the step (and inside its CUDA graph), in three buckets that follow the
+                # order in which the backward pass finishes gradients:
+                #   proposal levels (MLP_0 / MLP_1 grids + MLPs, 17 MB): final as soon as the proposal branch's backward is
+                #     done - it runs beside the shader's forward - so this bucket hides behind the shader;
+                #   shader (appearance grid + stacks, 47 MB): forked the moment the shader's backward is done, beside the
+                #     final level's backward;
+                #   final level (MLP_2 grid + MLP, 47 MB): the only one left at the end of the step.
+                # The overlapped buckets run with few CTAs (they share the SMs with the backward kernels).
                 if self._comm is None:
-                    self._comm = torch.cuda.Stream()
-                comm, so = self._comm, self.shader_offset
+                    self._comm = (torch.cuda.Stream(), torch.cuda.Stream())
+                comm, comm_p = self._comm
+                so, fo = self.shader_offset, self.final_level_offset
+                n_overlap = int(os.environ.get("NRC_AR_CTAS_OVERLAP", "32" if self.peer.mode == "multicast" else "74"))
+                three = os.environ.get("NRC_AR_BUCKETS", "3") == "3" and fo > 0
 
                 def shader_bucket():
                     comm.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(comm):   # fewer CTAs: it shares the SMs with the sampler's backward
-                        self.allreduce_grads(so, None, channel=1, num_ctas=int(os.environ.get("NRC_AR_CTAS_OVERLAP", "74")))
+                        self.allreduce_grads(so, None, channel=1, num_ctas=n_overlap)
+
+                def proposal_bucket():              # called on the proposal branch's stream, after its backward
+                    comm_p.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(comm_p):
+                        self.allreduce_grads(0, fo, channel=2, num_ctas=n_overlap)
 
                 loss = self.engine.step(rays, u01, target_rgb, extra=extra, zero_grad=self.zero_grad,
-                                        on_shader_grads=shader_bucket)
-                self.allreduce_grads(0, so, channel=0)
+                                        on_shader_grads=shader_bucket, on_proposal_grads=proposal_bucket if three else None)
+                self.allreduce_grads(fo if three else 0, so, channel=0)
                 torch.cuda.current_stream().wait_stream(comm)
+                if three:
+                    torch.cuda.current_stream().wait_stream(comm_p)
                 return loss
             return self.engine.step(rays, u01, target_rgb, extra=extra, zero_grad=self.zero_grad)
         return self.step_autograd(rays, u01, target_rgb, extra)

@@ -87,3 +87,33 @@ def transient_render(direct_rgbs, diffuse_raw, specular, spec_scale, weights, ra
     indirect = diffuse + spec
     return volumetric_transient_rendering(direct_rgbs, indirect, weights, ray_dists, light_dists, n_bins, exposure_time, shift,
                                           dark_level)
+
+
+def gaussian_tfilter(tfilter_sigma):
+    """The temporal filter volumetric_transient_rendering builds from tfilter_sigma (render.py:401-404): a Gaussian over
+    round(-4 sigma) .. round(4 sigma) bins minus exp(-8), normalised."""
+    k = np.arange(round(-4 * tfilter_sigma), round(4 * tfilter_sigma) + 1).astype(np.float32)
+    f = np.exp(-(k ** 2) / np.float32(2 * tfilter_sigma ** 2)).astype(np.float32) - np.float32(np.exp(-8))
+    return torch.from_numpy((f / f.sum()).astype(np.float32))
+
+
+def temporal_filter(x, filt):
+    """jax.scipy.signal.convolve(x, filt[None, :, None], mode='same') (render.py:406-413): x [R, n_bins, C]."""
+    R, B, C = x.shape
+    taps = filt.shape[0]
+    xp = torch.nn.functional.pad(x.permute(0, 2, 1).reshape(R * C, 1, B), (taps - 1, taps - 1))
+    full = torch.nn.functional.conv1d(xp, filt.flip(0).reshape(1, 1, taps))[:, 0]          # full convolution, length B + taps - 1
+    lo = (taps - 1) // 2
+    return full[:, lo:lo + B].reshape(R, C, B).permute(0, 2, 1).contiguous()
+
+
+def transient_integrate_reflect_rays(lobe, weight, pdf, local_lightdirs, radiance_in, indirect_occ=None, max_radiance=float("inf")):
+    """transient_integrate_reflect_rays with direct=False (render_utils.py:1195-1302): lobe [R,S,3] (get_lobe),
+    weight / pdf [R,S,1], radiance_in [R,S,n_bins,3] -> radiance_out, irradiance [R,n_bins,3], indirect_occ [R,1]."""
+    den = torch.clamp(pdf, min=1e-5)
+    w = torch.clamp(weight, min=0.0)
+    w = torch.where(local_lightdirs[..., 2:] > 0.0, w, torch.zeros_like(w))
+    dl = torch.clamp(local_lightdirs[..., 2:], min=0.0) / np.pi
+    ro = (torch.clamp(radiance_in * lobe[..., None, :], 0.0, max_radiance) * w[..., None, :] / den[..., None, :]).mean(1)
+    ir = (torch.clamp(radiance_in * dl[..., None, :], 0.0, max_radiance) * w[..., None, :] / den[..., None, :]).mean(1)
+    return dict(radiance_out=ro, irradiance=ir, indirect_occ=indirect_occ.mean(1) if indirect_occ is not None else None)

@@ -627,6 +627,27 @@ def main():
     for k_name, v_ in zip(("origins", "directions", "viewdirs", "radii", "imageplane"), cres[:5]):
         out["cam_" + k_name] = np.asarray(v_)
 
+    # ---- the temporal filter of volumetric_transient_rendering (render.py:397-415): Gaussian of tfilter_sigma bins on the
+    #      direct histogram, and on the indirect one with filter_indirect; jax.scipy.signal.convolve(mode='same') ----------
+    import scipy.signal as _sps
+    shim.jscipy.signal = _types.SimpleNamespace(
+        convolve=lambda a_, b_, mode="full": _sps.convolve(np.asarray(a_, np.float32), np.asarray(b_, np.float32), mode=mode, method="direct").astype(np.float32))
+    for fi in (False, True):
+        res = rrender.volumetric_transient_rendering(
+            tdirect, tind, tw, tw, ttd, None, False, extras=dict(light_dists=tlight, ray_dists=tray, transient_indirect=None),
+            n_bins=Bt, shift=np.float32(0.0137), dark_level=np.float32(0.001), exposure_time=expo, config=cfg,
+            tfilter_sigma=np.float32(1.5), filter_indirect=fi)
+        for k_ in ("transient_direct", "transient_indirect", "rgb"):
+            out["tr_f%d_%s" % (int(fi), k_)] = res[k_]
+
+    # ---- transient_integrate_reflect_rays (render_utils.py:1195-1302), direct=False: time-resolved incoming radiance ----
+    trad = f(g.gamma(1.0, 1.0, size=(P_, S_, 24, 3)))
+    tsamples = dict(samples, radiance_in=trad)
+    out["ggxt_radiance_in"] = trad
+    tres = rru.transient_integrate_reflect_rays("microfacet", False, dict(material), tsamples, direct=False)
+    for k_ in ("radiance_out", "irradiance", "indirect_occ"):
+        out["ggxt_" + k_] = tres[k_]
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}   # see the shim's header
     path = os.path.join(HERE, "reference_np.npz")

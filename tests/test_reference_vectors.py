@@ -516,3 +516,31 @@ def test_pixels_to_rays():
     assert np.allclose(ocam.get_pixtocam(17.3, Wc, Hc).astype(np.float32), V["cam_pixtocam"], rtol=0, atol=0)
     for name, g_ in zip(("origins", "directions", "viewdirs", "radii", "imageplane"), got):
         close(torch.from_numpy(np.ascontiguousarray(g_)), "cam_" + name, 1e-6)
+
+
+def test_temporal_filter_and_transient_integration():
+    """The temporal filter of volumetric_transient_rendering (internal/render.py:397-415: Gaussian of tfilter_sigma bins,
+    jax.scipy.signal.convolve mode='same', on the direct histogram and - filter_indirect - on the indirect one) and
+    transient_integrate_reflect_rays with direct=False (internal/inverse_render/render_utils.py:1195-1302), both executed
+    from the reference."""
+    from oracle import render_utils as oru, transient as otr
+
+    w, direct, ind = T("tr_weights"), T("tr_direct"), T("tr_indirect")
+    ray, light = T("tr_ray_dists")[..., 0], T("tr_light_dists")[..., 0]
+    B = ind.shape[2]
+    base = otr.volumetric_transient_rendering(direct, ind, w, ray, light, B, exposure_time=0.01, shift=0.0137, dark_level=0.0)
+    filt = otr.gaussian_tfilter(1.5)
+    for fi in (0, 1):
+        td = otr.temporal_filter(base["transient_direct"], filt)
+        ti = otr.temporal_filter(base["transient_indirect"], filt) if fi else base["transient_indirect"]
+        close(td, f"tr_f{fi}_transient_direct", 2e-6)
+        close(ti, f"tr_f{fi}_transient_indirect", 2e-6)
+        close(td + ti + 0.001, f"tr_f{fi}_rgb", 2e-6)
+    material = {k: T("ggx_mat_" + k) for k in ("albedo", "roughness", "F_0", "metalness")}
+    ld = T("ggx_smp_local_lightdirs")
+    normal = torch.cat([torch.zeros_like(ld[..., :2]), torch.ones_like(ld[..., :1])], dim=-1)
+    lobe = oru.get_lobe(ld, T("ggx_smp_local_viewdirs"), normal, material, T("ggx_smp_brdf_correction"), "microfacet")
+    got = otr.transient_integrate_reflect_rays(lobe, T("ggx_smp_weight"), T("ggx_smp_pdf"), T("ggx_smp_local_lightdirs"),
+                                               T("ggxt_radiance_in"), T("ggx_smp_indirect_occ"))
+    for k in ("radiance_out", "irradiance", "indirect_occ"):
+        close(got[k], "ggxt_" + k, 1e-5)

@@ -82,3 +82,74 @@ def test_transient_indirect_head(cuda_device):
     got = head(p, feat.to(cuda_device), lights.to(cuda_device))
     assert got.shape == (P, B, 3)
     assert rel_err(got, want) <= 1e-5
+
+
+# ----------------------------------------------------------------------------- fused heads (config 4)
+V = np.load(__import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden",
+                                        "reference_np.npz"))
+
+
+@pytest.mark.parametrize("R,n,B", [(9, 8, 50), (5, 32, 700)])
+@pytest.mark.parametrize("heads", ["both", "diffuse", "specular"])
+def test_fused_heads_match_unfused(cuda_device, R, n, B, heads):
+    """nrc_transient_head_render_fwd (last layer of both transient heads on tensor cores + activation + masks + shift +
+    weighted reduction, per-sample histograms never written) against the unfused path that the other tests hold to the
+    oracle and to the reference's vectors: fp32 last layer -> [R,n,B,3] -> nrc_transient_render_fwd.  bf16 operands of
+    the fused GEMM: north-star tolerance of the bf16-MLP variant (2e-2), measured ~3e-3."""
+    dev = cuda_device
+    g = gen(700 + R + n)
+    x = {k: v.to(dev) for k, v in _inputs(g, R, n, B).items()}
+    hd = f32(np.maximum(g.normal(size=(R, n, 64)), 0.0)).to(dev)
+    hs = f32(np.maximum(g.normal(size=(R, n, 128)), 0.0)).to(dev)
+    ld = {"kernel": f32(g.normal(size=(64, B * 3)) * 0.2).to(dev), "bias": f32(g.normal(size=(B * 3,)) * 0.3).to(dev)}
+    ls = {"kernel": f32(g.normal(size=(128, B * 3 + 1)) * 0.15).to(dev), "bias": f32(g.normal(size=(B * 3 + 1,)) * 0.3).to(dev)}
+    kw = dict(exposure_time=0.01, shift=0.003, indirect_scale=0.7, bin_zero_threshold_light=1.5, light_zero=True,
+              light_near=0.08 * B * 0.01, rgb_max=2.0, dark_level=0.01)
+    use_d, use_s = heads in ("both", "diffuse"), heads in ("both", "specular")
+    # unfused reference path in fp32
+    raw_d = (hd.reshape(-1, 64) @ ld["kernel"] + ld["bias"]).reshape(R, n, B, 3) if use_d else None
+    ref = None
+    if use_s:
+        raw_s = (hs.reshape(-1, 128) @ ls["kernel"] + ls["bias"])[:, :B * 3].reshape(R, n, B, 3)
+        ref = torch.clamp(torch.nn.functional.softplus(raw_s - 2.0), 0.0, 5.0)        # SLF incoming_rgb: softplus(raw + rgb_bias), clip
+    want = nrender.volumetric_transient_rendering(x["direct"], raw_d, ref, x["spec_scale"] if use_s else None, x["weights"],
+                                                  x["ray_dists"], x["light_dists"], x["cam_dists"], n_bins=B, diffuse_bias=-2.0, **kw)
+    got = nrender.volumetric_transient_rendering_fused(
+        x["direct"], hd if use_d else None, ld if use_d else None, hs if use_s else None, ls if use_s else None,
+        x["spec_scale"] if use_s else None, x["weights"], x["ray_dists"], x["light_dists"], x["cam_dists"], n_bins=B,
+        diffuse_bias=-2.0, spec_bias=-2.0, spec_max=5.0, **kw)
+    assert torch.equal(got["transient_direct"], want["transient_direct"]) or rel_err(got["transient_direct"], want["transient_direct"]) <= 1e-6
+    for k in ("transient_indirect", "rgb"):
+        e = rel_err(got[k], want[k])
+        assert e <= 2e-2, (heads, k, e)
+
+
+def test_temporal_filter_and_transient_integration_against_reference(cuda_device):
+    """nrc_transient_filter against the temporal filter of the reference's volumetric_transient_rendering
+    (internal/render.py:397-415, Gaussian of 1.5 bins, direct only / direct + indirect), and
+    nrc_ggx_integrate_transient_fwd against transient_integrate_reflect_rays with direct=False
+    (internal/inverse_render/render_utils.py:1195-1302), both executed from the reference."""
+    from neural_radiance_caching_b200.inverse_render import render_utils as nru
+
+    dev = cuda_device
+    D = lambda k: torch.from_numpy(V[k]).to(dev).contiguous()
+    w, direct, ind = D("tr_weights"), D("tr_direct"), D("tr_indirect")
+    ray, light = D("tr_ray_dists")[..., 0].contiguous(), D("tr_light_dists")[..., 0].contiguous()
+    B = ind.shape[2]
+    base = nrender.volumetric_transient_rendering(direct, None, ind, torch.ones_like(direct), w, ray, light,
+                                                  torch.full_like(ray, -1e9), n_bins=B, exposure_time=0.01, shift=0.0137,
+                                                  indirect_scale=1.0, bin_zero_threshold_light=1e9, rgb_max=3e38)
+    filt = nrender.gaussian_tfilter(1.5, dev)
+    for fi in (0, 1):
+        td = nrender.temporal_filter(base["transient_direct"], filt)
+        ti = nrender.temporal_filter(base["transient_indirect"], filt) if fi else base["transient_indirect"]
+        assert rel_err(td, torch.from_numpy(V[f"tr_f{fi}_transient_direct"])) <= 2e-5
+        assert rel_err(ti, torch.from_numpy(V[f"tr_f{fi}_transient_indirect"])) <= 2e-5
+        assert rel_err(td + ti + 0.001, torch.from_numpy(V[f"tr_f{fi}_rgb"])) <= 2e-5
+    material = {k: D("ggx_mat_" + k) for k in ("albedo", "roughness", "F_0", "metalness")}
+    samples = {k: D("ggx_smp_" + k) for k in ("local_lightdirs", "local_viewdirs", "pdf", "weight", "indirect_occ")}
+    samples["radiance_in"] = D("ggxt_radiance_in")
+    res = nru.transient_integrate_reflect_rays("microfacet", False, material, samples, direct=False)
+    for k in ("radiance_out", "irradiance", "indirect_occ"):
+        e = rel_err(res[k], torch.from_numpy(V["ggxt_" + k]))
+        assert e <= 2e-5, (k, e)
