@@ -43,9 +43,10 @@ def parse():
     ap.add_argument("--no-others", action="store_true", help="skip the `others` table (configs 1, 3, 5, fp32, 16384 rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="print per-ABI-call device times")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config5"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
                     help="config2 (default, BASELINE metric): cache training step; config3: material-stage chunk "
-                         "(1024 points x 32 secondary rays); config5: full-view render in row bands")
+                         "(1024 points x 32 secondary rays); config4: time-resolved cache render chunk (700 bins); config5: "
+                         "full-view render in row bands")
     ap.add_argument("--image", type=int, default=800, help="config5: image side in pixels")
     ap.add_argument("--ncu-mode", action="store_true",
                     help="minimal run for an ncu launch list: 1 eager step, graph capture, 2 replays, no JSON")
@@ -493,8 +494,7 @@ def run_b200(args):
             guarded("config1_forward", lambda: measure_train_variant(dev, 1024, 1, 10, 3, pk, pk_kind, forward_only=True))
             guarded("config2_fp32", lambda: measure_train_variant(dev, 1024, 0, 10, 3, pk, pk_kind))
             guarded("config2_bf16_16384rays", lambda: measure_train_variant(dev, 16384, 1, 5, 3, pk, pk_kind))
-            others["config4"] = {"unmeasured": "time-resolved path: forward kernels only (nrc_transient_render_fwd + heads), "
-                                               "no end-to-end workload yet (DESIGN section 9)"}
+            guarded("config4_chunk", lambda: _slim(render_line(args, "config4", 1, 0, dev, 5, 3, rays=1024)))
     if rank == 0:
         line["others"] = others
         print(json.dumps(line))
@@ -786,6 +786,71 @@ def render_line(args, workload_name, world, rank, dev, steps, warmup, rays=None,
             roof["l2_gather"] = l2
             roof["l2_gather_frac"] = t_bound / (per_kernel[top] * 1e-3)
             roof["grows_s"] = rays * 8 * (64 * 13 + 32 * 8) / (per_kernel[top] * 1e-3) / 1e9
+        else:
+            roof.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], achieved=None, frac=None)
+    elif workload_name == "config4":
+        R = rays or args.rays
+        stage = workload.TransientRenderStep(dev, bf16=bool(args.bf16))
+        g = np.random.Generator(np.random.PCG64(workload.SEED + rank))
+        rn = stage.make_rays(g, R)
+        keys = sorted(rn.keys())
+        host = {k: torch.from_numpy(np.ascontiguousarray(rn[k], dtype=np.float32)).pin_memory() for k in keys}
+        drays = {k: v.to(dev) for k, v in host.items()}
+        u01 = [torch.rand((R, 1), device=dev) for _ in range(3)]
+        out_host = torch.zeros((R, stage.n_bins, 3), dtype=torch.float32).pin_memory()
+
+        def step():
+            return stage.render(drays, u01)["rgb"]
+
+        before = _lib.launch_count
+        step()
+        launches = _lib.launch_count - before
+        if args.ncu_mode:
+            step()
+            torch.cuda.synchronize()
+            print(json.dumps({"ncu_mode": True, "launches_per_step": launches}))
+            return None
+        per_kernel = profile_calls(step, _lib, iters=2)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_rgb = step()
+        use_graph = True
+
+        def gstep():
+            graph.replay()
+            return static_rgb
+
+        dev_ms = _timed(gstep, steps, warmup, flush, barrier)
+
+        def e2e_step():
+            for k in keys:
+                drays[k].copy_(host[k], non_blocking=True)
+            out_host.copy_(gstep(), non_blocking=True)
+
+        e2e_ms = _timed(e2e_step, steps, warmup, flush, barrier)
+        units = world * R * SAMPLES_PER_RAY
+        wl = ("config4 transient_simulation_ngp_yobo_cornell time-resolved cache, one chunk of %d primary rays: proposal sampler "
+              "(64,64,32), transient shader on the 32 final samples (appearance grid, bottleneck / roughness / tint / albedo / "
+              "integrated BRDF, irradiance stack 111->64->64 and transient SurfaceLightField 200->128x4), both transient heads' "
+              "last layers (64->2100, 128->2101) fused with activation, zero_invalid_bins, sub-bin shift and the weighted "
+              "reduction into [R,700,3] (the [R,32,700,3] histograms never reach HBM), direct splat, Gaussian temporal filter "
+              "(sigma 3 bins); direct term without shadow rays / light BRDF network; forward (render) path" % R)
+        h2d, d2h = int(sum(v.numel() for v in host.values()) * 4) * world, R * stage.n_bins * 3 * 4 * world
+        scaling = "weak"
+        top = max(per_kernel, key=per_kernel.get)
+        head_flops = 2.0 * R * 32 * (64 * stage.n_bins * 3 + 128 * (stage.n_bins * 3 + 1))
+        roof = {"kernel": top, "peak_source": pk_kind, "traffic": None}
+        if top == "nrc_transient_head_render_fwd":
+            ach = head_flops / (per_kernel[top] * 1e-3) / 1e12
+            roof.update(bound="tensor", unit="TFLOP/s", peak=pk["bf16_tflops"], achieved=ach, frac=ach / pk["bf16_tflops"],
+                        note="403 k MAC per shaded sample (SURVEY 8d) in the two head layers / per-launch device time; the "
+                             "kernel is mma.sync + shared-memory gather (the reduction over samples, not the GEMM, is its cost)")
         else:
             roof.update(bound="hbm", unit="GB/s", peak=pk["hbm_gbs"], achieved=None, frac=None)
     else:

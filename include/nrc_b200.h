@@ -605,7 +605,10 @@ int32_t nrc_geometry_losses(void* stream, const float* d_weights, const float* d
  *                specular = clip(spec_scale * clip(softplus(spec_premult * (h W + b) + spec_bias), 0, spec_max)
  *                                * indirect_scale, 0, rgb_max),   d_spec_scale [R,n,C] = tint * integrated BRDF
  *   either head may be NULL.  Validity masks, sub-bin shift, weighted reduction and outputs as nrc_transient_render_fwd.
- *   The head GEMMs run on the tensor cores with bf16 operands (north-star bf16-MLP variant). */
+ *   The head GEMMs run on the tensor cores with bf16 operands (north-star bf16-MLP variant); the activated values of a
+ *   ray's samples are staged in shared memory as bf16 before the reduction.
+ *   d_w_packed: caller-owned scratch of n_bins*C*192 bf16 holding both kernels in the kernel's operand order; written
+ *   when repack != 0 (first call / after a parameter update), reused otherwise. */
 int32_t nrc_transient_head_render_fwd(
     void* stream, const float* d_direct_rgbs, const float* d_h_diffuse, int32_t k_diffuse, const float* d_w_diffuse,
     int64_t ld_w_diffuse, const float* d_b_diffuse, const float* d_h_specular, int32_t k_specular, const float* d_w_specular,
@@ -613,7 +616,7 @@ int32_t nrc_transient_head_render_fwd(
     const float* d_light_dists, const float* d_cam_dists, int64_t num_rays, int32_t n, int32_t n_bins, int32_t channels,
     float exposure_time, float shift, float diffuse_bias, float spec_premult, float spec_bias, float spec_max,
     float indirect_scale, float bin_zero_threshold_light, int32_t light_zero, float light_near, float rgb_max, float dark_level,
-    float* d_transient_direct, float* d_transient_indirect, float* d_rgb);
+    void* d_w_packed, int32_t repack, float* d_transient_direct, float* d_transient_indirect, float* d_rgb);
 /* The temporal filter of volumetric_transient_rendering (internal/render.py:397-415): convolution along the bin axis with
  * the impulse response / normalised Gaussian d_filter [taps], mode 'same'.  d_x, d_y [R, n_bins, C] (not in place). */
 int32_t nrc_transient_filter(void* stream, const float* d_x, const float* d_filter, int32_t taps, int64_t num_rays,

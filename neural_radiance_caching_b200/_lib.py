@@ -121,7 +121,7 @@ PROTOTYPES = {
     "nrc_density_mlp_bwd_tangent": [_P, _P, _P, _P, _I64, _P, _P],
     "nrc_encode_tangent_bwd": [_P, _P, _P, _P, _P, _I64, _F],
     "nrc_transient_head_render_fwd": [_P, _P, _P, _I32, _P, _I64, _P, _P, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32,
-                                      _I32, _F, _F, _F, _F, _F, _F, _F, _F, _I32, _F, _F, _F, _P, _P, _P],
+                                      _I32, _F, _F, _F, _F, _F, _F, _F, _F, _I32, _F, _F, _F, _P, _I32, _P, _P, _P],
     "nrc_transient_filter": [_P, _P, _P, _I32, _I64, _I32, _I32, _P],
     "nrc_ggx_integrate_transient_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _P],
     "nrc_camera_rays": [_P, _P, _P, _I32, _I32, _I64, _P, _I64, _I64, _F, _F, _P, _P, _P, _P, _P, _P, _P],

@@ -114,12 +114,12 @@ __global__ void transient_indirect_kernel(const float* __restrict__ diffuse_raw,
 // at a time, the activated and masked values of those 16 samples are staged in shared memory in fp32 (134 KB), and the
 // sub-bin shift + weighted reduction over the samples reads them from there in the order of
 // transient_indirect_kernel (same taps, same summation order).  Only [R, n_bins, 3] leaves the SM.
-constexpr int kTrhThreads = 512;
-constexpr int kTrhRows = 16;          // samples per pass (one MMA row tile)
+constexpr int kTrhThreads = 256;
+constexpr int kTrhRows = 32;          // samples per pass (two MMA row tiles)
+constexpr int kTrhK = 64 + 128;       // packed K: diffuse hidden | specular hidden
 
 struct TrHeadParams {
-  int n, n_bins, C, Kd, Ks;
-  int64_t ld_wd, ld_ws;
+  int n, n_bins, C;
   float exposure_time, shift, diffuse_bias, spec_bias, spec_premult, spec_max, indirect_scale, bin_zero_threshold_light,
       light_near, rgb_max, dark_level;
   int light_zero;
@@ -130,120 +130,134 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
+
+// Both heads' last-layer kernels as ONE bf16 operand image [N][192]: row e = output column, K = [diffuse 64 | specular
+// 128]; inside every 16-wide K block the elements are stored in the order an mma.sync B fragment wants them
+// (thread t of a quad: k = 2t, 2t+1, 2t+8, 2t+9), so a fragment is one 8-byte load and a quad reads a whole 32-byte sector.
+// The fp32 kernels are read 0.8 M times per call otherwise (every CTA needs all of both layers): 3.3 GB of L2 traffic
+// at 1024 rays, which bound the first version of the fused kernel at 1.36 ms.
+__global__ void transient_pack_heads_kernel(const float* __restrict__ w_d, int64_t ld_d, const float* __restrict__ w_s, int64_t ld_s,
+                                            int N, __nv_bfloat16* __restrict__ packed) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(N) * kTrhK) return;
+  const int e = static_cast<int>(i % N);            // consecutive threads: consecutive columns (coalesced reads)
+  const int k = static_cast<int>(i / N);
+  float v = 0.f;
+  if (k < 64) { if (w_d) v = w_d[static_cast<int64_t>(k) * ld_d + e]; }
+  else if (w_s) v = w_s[static_cast<int64_t>(k - 64) * ld_s + e];
+  const int blk = k >> 4, r = k & 15;
+  const int t = (r & 7) >> 1, pos = 4 * t + (r & 1) + (r >= 8 ? 2 : 0);
+  packed[static_cast<int64_t>(e) * kTrhK + blk * 16 + pos] = __float2bfloat16_rn(v);
 }
 
-// One head's last layer for the 16 staged samples: stage[row][e] (+)= activate(h[row] . W[:, e] + b[e]).
-// h_s: [16][K + 8] bf16 in shared memory; W: Flax kernel [K][ld] fp32 in global memory (L2 resident: every CTA reads it).
-template <int K, bool SPECULAR>
-__device__ __forceinline__ void head_pass(const TrHeadParams& p, const __nv_bfloat16* __restrict__ h_s, const float* __restrict__ W,
-                                          int64_t ldw, const float* __restrict__ bias, int row0, const float* s_light,
-                                          const float* s_cam, const float* s_scale, float* __restrict__ stage, int N) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  constexpr int KS = K / 16, HS = K + 8;
-  uint32_t a[KS][4];
-#pragma unroll
-  for (int kk = 0; kk < KS; ++kk) {
-    const __nv_bfloat16* r0 = h_s + g * HS + kk * 16 + 2 * t;
-    const __nv_bfloat16* r1 = h_s + (g + 8) * HS + kk * 16 + 2 * t;
-    a[kk][0] = *reinterpret_cast<const uint32_t*>(r0);
-    a[kk][1] = *reinterpret_cast<const uint32_t*>(r1);
-    a[kk][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
-    a[kk][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
-  }
-  const float max_dists = static_cast<float>(p.n_bins - 1) * p.exposure_time;
-  const int n_tiles = (N + 7) >> 3;
-  for (int tile = warp; tile < n_tiles; tile += kTrhThreads / 32) {
-    const int nb = tile * 8 + g;                 // output column this thread's B fragment feeds
-    const bool nb_ok = nb < N;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int kk = 0; kk < KS; ++kk) {
-      const float* w = W + static_cast<int64_t>(kk * 16 + 2 * t) * ldw + nb;
-      float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-      if (nb_ok) { w0 = __ldg(w); w1 = __ldg(w + ldw); w2 = __ldg(w + 8 * ldw); w3 = __ldg(w + 9 * ldw); }
-      mma_bf16_16816(acc, a[kk], pack_bf16x2(w0, w1), pack_bf16x2(w2, w3));
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = g + (i >= 2 ? 8 : 0), e = tile * 8 + 2 * t + (i & 1);
-      if (e >= N) continue;
-      const int s = row0 + row;
-      float val = 0.f;
-      if (s < p.n) {
-        const int bin = e / p.C, c = e - bin * p.C;
-        // zero_invalid_bins (render_utils.py:1699-1767)
-        const float fb = static_cast<float>(bin);
-        bool ok = !((fb + p.bin_zero_threshold_light) * p.exposure_time < s_light[s]);
-        ok = ok && !((fb * p.exposure_time + s_cam[s]) > max_dists);
-        if (p.light_zero) ok = ok && !(s_light[s] < p.light_near);
-        if (ok) {
-          const float raw = acc[i] + __ldg(bias + e);
-          if (!SPECULAR) {
-            val = fminf(fmaxf(softplus_t(raw + p.diffuse_bias) * p.indirect_scale, 0.f), p.rgb_max);
-          } else {
-            const float ref = fminf(fmaxf(softplus_t(p.spec_premult * raw + p.spec_bias), 0.f), p.spec_max);
-            val = fminf(fmaxf(s_scale[s * p.C + c] * ref * p.indirect_scale, 0.f), p.rgb_max);
-          }
-        }
-      }
-      float* dst = stage + static_cast<size_t>(row) * N + e;
-      if (SPECULAR) *dst += val; else *dst = val;      // the same thread owns (row, e) in both heads
-    }
-  }
-}
+// softplus on the special-function units (the fused kernel evaluates it 134 k times per ray; its results are staged as
+// bf16): log(1 + e^x) with __expf / __logf, absolute error <= 1.2e-7 (the rounding of 1 + e^x) - below bf16 resolution
+// of every value that survives the weighted reduction.
+__device__ __forceinline__ float softplus_fast(float x) { return x > 15.f ? x : __logf(1.f + __expf(x)); }
 
-template <int KD, int KS_>
+template <int C_>
 __global__ void __launch_bounds__(kTrhThreads, 1)
-transient_head_render_kernel(const float* __restrict__ h_d, const float* __restrict__ w_d, const float* __restrict__ b_d,
-                             const float* __restrict__ h_s, const float* __restrict__ w_s, const float* __restrict__ b_s,
+transient_head_render_kernel(const float* __restrict__ h_d, const float* __restrict__ b_d, const float* __restrict__ h_s,
+                             const float* __restrict__ b_s, const __nv_bfloat16* __restrict__ w_packed,
                              const float* __restrict__ spec_scale, const float* __restrict__ weights,
                              const float* __restrict__ ray_dists, const float* __restrict__ light_dists,
                              const float* __restrict__ cam_dists, int64_t R, TrHeadParams p, const float* __restrict__ t_direct,
                              float* __restrict__ t_indirect, float* __restrict__ rgb) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int64_t ray = blockIdx.x;
-  const int N = p.n_bins * p.C;
-  float* stage = reinterpret_cast<float*>(smem);                               // [16][N]
-  float* s_w = stage + static_cast<size_t>(kTrhRows) * N;                      // per sample: weight, bins_move, light, cam
-  float* s_move = s_w + p.n;
+  constexpr int C = C_;
+  const int N = p.n_bins * C;
+  const int Ns = (N + 1) & ~1;
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(smem);                 // [32][Ns] activated, masked values
+  float* s_w = reinterpret_cast<float*>(stage + static_cast<size_t>(kTrhRows) * Ns);
+  float* s_move = s_w + p.n;                                                     // per sample: weight, bins_move, light, cam
   float* s_light = s_move + p.n;
   float* s_cam = s_light + p.n;
-  float* s_scale = s_cam + p.n;                                                // [n][C]
-  __nv_bfloat16* hd_s = reinterpret_cast<__nv_bfloat16*>(s_scale + p.n * p.C + ((p.n * p.C) & 1));
-  __nv_bfloat16* hs_s = hd_s + kTrhRows * (KD + 8);
+  float* s_scale = s_cam + p.n;                                                  // [n][C]
+  __nv_bfloat16* h_sm = reinterpret_cast<__nv_bfloat16*>(s_scale + p.n * C + ((p.n * C) & 1));   // [32][192 + 8]
+  constexpr int HS = kTrhK + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   for (int s = threadIdx.x; s < p.n; s += blockDim.x) {
     const int64_t i = ray * p.n + s;
     s_w[s] = weights[i];
     s_move[s] = (ray_dists[i] + p.shift) / p.exposure_time;
     s_light[s] = light_dists[i];
     s_cam[s] = cam_dists[i];
-    for (int c = 0; c < p.C; ++c) s_scale[s * p.C + c] = spec_scale ? spec_scale[i * p.C + c] : 0.f;
+    for (int c = 0; c < C; ++c) s_scale[s * C + c] = spec_scale ? spec_scale[i * C + c] : 0.f;
   }
-  constexpr int kMaxPer = 8;    // output elements per thread (N <= 8 * 512)
+  constexpr int kMaxPer = 16;    // output elements per thread (N <= 16 * 256)
   float out[kMaxPer];
 #pragma unroll
   for (int q = 0; q < kMaxPer; ++q) out[q] = 0.f;
+  const float max_dists = static_cast<float>(p.n_bins - 1) * p.exposure_time;
+  const int n_tiles = (N + 7) >> 3;
   for (int row0 = 0; row0 < p.n; row0 += kTrhRows) {
     __syncthreads();            // the previous pass's gather is done with `stage`; the per-sample arrays are written
-    for (int idx = threadIdx.x; idx < kTrhRows * KD; idx += blockDim.x) {
-      const int r = idx / KD, k = idx - r * KD, s = row0 + r;
-      hd_s[r * (KD + 8) + k] = __float2bfloat16_rn((h_d && s < p.n) ? h_d[(ray * p.n + s) * KD + k] : 0.f);
-    }
-    if (h_s)
-      for (int idx = threadIdx.x; idx < kTrhRows * KS_; idx += blockDim.x) {
-        const int r = idx / KS_, k = idx - r * KS_, s = row0 + r;
-        hs_s[r * (KS_ + 8) + k] = __float2bfloat16_rn(s < p.n ? h_s[(ray * p.n + s) * KS_ + k] : 0.f);
+    for (int idx = threadIdx.x; idx < kTrhRows * kTrhK; idx += blockDim.x) {
+      const int r = idx / kTrhK, k = idx - r * kTrhK, s = row0 + r;
+      float v = 0.f;
+      if (s < p.n) {
+        if (k < 64) { if (h_d) v = h_d[(ray * p.n + s) * 64 + k]; }
+        else if (h_s) v = h_s[(ray * p.n + s) * 128 + (k - 64)];
       }
+      h_sm[r * HS + k] = __float2bfloat16_rn(v);
+    }
     __syncthreads();
-    if (h_d) head_pass<KD, false>(p, hd_s, w_d, p.ld_wd, b_d, row0, s_light, s_cam, s_scale, stage, N);
-    else
-      for (int idx = threadIdx.x; idx < kTrhRows * N; idx += blockDim.x) stage[idx] = 0.f;
-    if (h_s) {
-      if (!h_d) __syncthreads();
-      head_pass<KS_, true>(p, hs_s, w_s, p.ld_ws, b_s, row0, s_light, s_cam, s_scale, stage, N);
+    // A fragments of the pass: 2 row tiles x 12 K blocks, kept in registers over all column tiles
+    uint32_t a[2][kTrhK / 16][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int kk = 0; kk < kTrhK / 16; ++kk) {
+        const __nv_bfloat16* r0 = h_sm + (mt * 16 + g) * HS + kk * 16 + 2 * t;
+        const __nv_bfloat16* r1 = r0 + 8 * HS;
+        a[mt][kk][0] = *reinterpret_cast<const uint32_t*>(r0);
+        a[mt][kk][1] = *reinterpret_cast<const uint32_t*>(r1);
+        a[mt][kk][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+        a[mt][kk][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+      }
+    for (int tile = warp; tile < n_tiles; tile += kTrhThreads / 32) {
+      const int nb = min(tile * 8 + g, N - 1);     // output column this thread's B fragments feed (clamped: unused beyond N)
+      const uint2* wrow = reinterpret_cast<const uint2*>(w_packed + static_cast<int64_t>(nb) * kTrhK) + t;
+      float accd[2][4], accs[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) accd[mt][i] = accs[mt][i] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < kTrhK / 16; ++kk) {
+        const uint2 bfrag = __ldg(wrow + kk * 4);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (kk < 4) mma_bf16_16816(accd[mt], a[mt][kk], bfrag.x, bfrag.y);
+          else mma_bf16_16816(accs[mt], a[mt][kk], bfrag.x, bfrag.y);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = mt * 16 + g + (i >= 2 ? 8 : 0), e = tile * 8 + 2 * t + (i & 1);
+          if (e >= N) continue;
+          const int s = row0 + row;
+          float val = 0.f;
+          if (s < p.n) {
+            const int bin = e / C, c = e - bin * C;
+            // zero_invalid_bins (render_utils.py:1699-1767)
+            const float fb = static_cast<float>(bin);
+            bool ok = !((fb + p.bin_zero_threshold_light) * p.exposure_time < s_light[s]);
+            ok = ok && !((fb * p.exposure_time + s_cam[s]) > max_dists);
+            if (p.light_zero) ok = ok && !(s_light[s] < p.light_near);
+            if (ok) {
+              if (h_d) val += fminf(fmaxf(softplus_fast(accd[mt][i] + __ldg(b_d + e) + p.diffuse_bias) * p.indirect_scale, 0.f), p.rgb_max);
+              if (h_s) {
+                const float ref = fminf(fmaxf(softplus_fast(p.spec_premult * (accs[mt][i] + __ldg(b_s + e)) + p.spec_bias), 0.f), p.spec_max);
+                val += fminf(fmaxf(s_scale[s * C + c] * ref * p.indirect_scale, 0.f), p.rgb_max);
+              }
+            }
+          }
+          stage[static_cast<size_t>(row) * Ns + e] = __float2bfloat16_rn(val);
+        }
     }
     __syncthreads();
     // shift_map_coordinates (order-1 map_coordinates along the bin axis, mode 'constant') + the weighted reduction,
@@ -252,7 +266,7 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
     for (int q = 0; q < kMaxPer; ++q) {
       const int e = threadIdx.x + q * kTrhThreads;
       if (e >= N) continue;
-      const int b = e / p.C, c = e - b * p.C;
+      const int b = e / C, c = e - b * C;
       float acc = out[q];
       const int s_end = min(kTrhRows, p.n - row0);
       for (int r = 0; r < s_end; ++r) {
@@ -267,7 +281,7 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
           const int bin = y0 + k;
           const float wk = k ? tt : 1.0f - tt;
           if (bin < 0 || bin >= p.n_bins || wk == 0.f) continue;
-          v += wk * stage[static_cast<size_t>(r) * N + bin * p.C + c];
+          v += wk * __bfloat162float(stage[static_cast<size_t>(r) * Ns + bin * C + c]);
         }
         acc += s_w[s] * v;
       }
@@ -345,17 +359,17 @@ extern "C" int32_t nrc_transient_head_render_fwd(
     const float* d_light_dists, const float* d_cam_dists, int64_t num_rays, int32_t n, int32_t n_bins, int32_t channels,
     float exposure_time, float shift, float diffuse_bias, float spec_premult, float spec_bias, float spec_max,
     float indirect_scale, float bin_zero_threshold_light, int32_t light_zero, float light_near, float rgb_max, float dark_level,
-    float* d_transient_direct, float* d_transient_indirect, float* d_rgb) {
+    void* d_w_packed, int32_t repack, float* d_transient_direct, float* d_transient_indirect, float* d_rgb) {
   if (num_rays < 0 || n < 1 || n > 1024 || n_bins < 1 || channels < 1 || channels > 4 || !(exposure_time > 0.f))
     return NRC_E_INVALID_ARG;
   const int64_t N = static_cast<int64_t>(n_bins) * channels;
-  if (N > 8 * kTrhThreads) return NRC_E_UNSUPPORTED;
+  if (N > 16 * kTrhThreads) return NRC_E_UNSUPPORTED;
   if ((d_h_diffuse && k_diffuse != 64) || (d_h_specular && k_specular != 128)) return NRC_E_UNSUPPORTED;
   if (num_rays == 0) return NRC_OK;
   if (!d_direct_rgbs || !d_weights || !d_ray_dists || !d_light_dists || !d_cam_dists || !d_transient_direct ||
-      !d_transient_indirect || !d_rgb || (!d_h_diffuse && !d_h_specular) || (d_h_diffuse && (!d_w_diffuse || !d_b_diffuse)) ||
-      (d_h_specular && (!d_w_specular || !d_b_specular || !d_spec_scale)) || ld_w_diffuse < (d_h_diffuse ? N : 0) ||
-      ld_w_specular < (d_h_specular ? N : 0))
+      !d_transient_indirect || !d_rgb || !d_w_packed || (!d_h_diffuse && !d_h_specular) ||
+      (d_h_diffuse && (!d_w_diffuse || !d_b_diffuse)) || (d_h_specular && (!d_w_specular || !d_b_specular || !d_spec_scale)) ||
+      ld_w_diffuse < (d_h_diffuse ? N : 0) || ld_w_specular < (d_h_specular ? N : 0))
     return NRC_E_INVALID_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   TransientParams dp{n, n_bins, channels, exposure_time, shift, diffuse_bias, indirect_scale, bin_zero_threshold_light,
@@ -366,20 +380,28 @@ extern "C" int32_t nrc_transient_head_render_fwd(
   transient_direct_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(d_direct_rgbs, d_weights, d_ray_dists,
                                                                                    d_light_dists, num_rays, dp,
                                                                                    d_transient_direct);
+  if (repack) {
+    const int64_t tw = N * kTrhK;
+    transient_pack_heads_kernel<<<static_cast<unsigned>((tw + 255) / 256), 256, 0, s>>>(
+        d_h_diffuse ? d_w_diffuse : nullptr, ld_w_diffuse, d_h_specular ? d_w_specular : nullptr, ld_w_specular,
+        static_cast<int>(N), static_cast<__nv_bfloat16*>(d_w_packed));
+  }
   TrHeadParams p{};
-  p.n = n; p.n_bins = n_bins; p.C = channels; p.Kd = 64; p.Ks = 128; p.ld_wd = ld_w_diffuse; p.ld_ws = ld_w_specular;
+  p.n = n; p.n_bins = n_bins; p.C = channels;
   p.exposure_time = exposure_time; p.shift = shift; p.diffuse_bias = diffuse_bias; p.spec_bias = spec_bias;
   p.spec_premult = spec_premult; p.spec_max = spec_max; p.indirect_scale = indirect_scale;
   p.bin_zero_threshold_light = bin_zero_threshold_light; p.light_near = light_near; p.rgb_max = rgb_max;
   p.dark_level = dark_level; p.light_zero = light_zero;
-  const size_t smem = static_cast<size_t>(kTrhRows) * N * sizeof(float) + static_cast<size_t>(n) * (4 + channels + 1) * sizeof(float) +
-                      static_cast<size_t>(kTrhRows) * (64 + 8 + 128 + 8) * 2 + 16;
+  const size_t Ns = static_cast<size_t>((N + 1) & ~1);
+  const size_t smem = static_cast<size_t>(kTrhRows) * Ns * 2 + static_cast<size_t>(n) * (4 + channels + 1) * sizeof(float) +
+                      static_cast<size_t>(kTrhRows) * (kTrhK + 8) * 2 + 16;
   if (smem > 227 * 1024) return NRC_E_UNSUPPORTED;
-  if (const int32_t st_attr = ensure_dynamic_smem<transient_head_render_kernel<64, 128>>(227 * 1024)   /* the size varies with n_bins: opt in to the maximum once */; st_attr != NRC_OK)
-    return st_attr;
-  transient_head_render_kernel<64, 128><<<static_cast<unsigned>(num_rays), kTrhThreads, smem, s>>>(
-      d_h_diffuse, d_w_diffuse, d_b_diffuse, d_h_specular, d_w_specular, d_b_specular, d_spec_scale, d_weights, d_ray_dists,
-      d_light_dists, d_cam_dists, num_rays, p, d_transient_direct, d_transient_indirect, d_rgb);
+  if (channels != 3) return NRC_E_UNSUPPORTED;   /* the fused kernel is compiled for RGB histograms */
+  if (const int32_t st_attr = ensure_dynamic_smem<transient_head_render_kernel<3>>(227 * 1024); st_attr != NRC_OK)
+    return st_attr;   /* the size varies with n_bins: opt in to the maximum once */
+  transient_head_render_kernel<3><<<static_cast<unsigned>(num_rays), kTrhThreads, smem, s>>>(
+      d_h_diffuse, d_b_diffuse, d_h_specular, d_b_specular, static_cast<const __nv_bfloat16*>(d_w_packed), d_spec_scale, d_weights,
+      d_ray_dists, d_light_dists, d_cam_dists, num_rays, p, d_transient_direct, d_transient_indirect, d_rgb);
   return check_launch();
 }
 

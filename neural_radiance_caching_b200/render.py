@@ -191,13 +191,21 @@ def volumetric_transient_rendering(direct_rgbs, diffuse_raw, specular, spec_scal
     return dict(transient_direct=t_direct, transient_indirect=t_indirect, rgb=rgb, integrated_rgb=rgb.sum(-2))
 
 
+_tfilter_cache = {}
+
+
 def gaussian_tfilter(tfilter_sigma, device):
     """The temporal filter of volumetric_transient_rendering (internal/render.py:401-404): Gaussian over
-    round(-4 sigma) .. round(4 sigma) bins minus exp(-8), normalised; as a device tensor [taps]."""
+    round(-4 sigma) .. round(4 sigma) bins minus exp(-8), normalised; as a device tensor [taps] (cached per sigma and
+    device: no host-to-device copy inside a captured CUDA graph)."""
     import numpy as np
+    key = (float(tfilter_sigma), str(device))
+    if key in _tfilter_cache:
+        return _tfilter_cache[key]
     k = np.arange(round(-4 * tfilter_sigma), round(4 * tfilter_sigma) + 1).astype(np.float32)
     f = np.exp(-(k ** 2) / np.float32(2 * tfilter_sigma ** 2)).astype(np.float32) - np.float32(np.exp(-8))
-    return torch.from_numpy((f / f.sum()).astype(np.float32)).to(device)
+    _tfilter_cache[key] = torch.from_numpy((f / f.sum()).astype(np.float32)).to(device)
+    return _tfilter_cache[key]
 
 
 def temporal_filter(x, filt):
@@ -215,7 +223,7 @@ def volumetric_transient_rendering_fused(direct_rgbs, h_diffuse, diffuse_layer, 
                                          diffuse_bias=-2.0, spec_premult=1.0, spec_bias=-2.0, spec_max=float("inf"),
                                          indirect_scale=1.0, bin_zero_threshold_light=0.0, light_zero=False, light_near=0.0,
                                          rgb_max=10000.0, dark_level=0.0, impulse_response=None, tfilter_sigma=0.0,
-                                         filter_indirect=False):
+                                         filter_indirect=False, pack_cache=None):
     """volumetric_transient_rendering (internal/render.py:250-449) with the LAST LAYER of the transient heads inside the
     kernel (nrc_transient_head_render_fwd): h_diffuse [R,n,64] is the irradiance stack's last hidden activation and
     diffuse_layer = {'kernel': [64, n_bins*C], 'bias'} its transient_indirect_layer (internal/nerf.py:1757-1777);
@@ -232,6 +240,14 @@ def volumetric_transient_rendering_fused(direct_rgbs, h_diffuse, diffuse_layer, 
     wd, bd = (diffuse_layer["kernel"], diffuse_layer["bias"]) if hd is not None else (None, None)
     ws, bs = (specular_layer["kernel"], specular_layer["bias"]) if hs is not None else (None, None)
     big = 3.0e38
+    # both kernels as one bf16 operand image, repacked when a kernel tensor changed (pack_cache: a dict the caller keeps)
+    key = tuple((id(t), t.data_ptr(), t._version) for t in (wd, ws) if t is not None)
+    cache = pack_cache if pack_cache is not None else {}
+    repack = cache.get("key") != key
+    if repack:
+        cache["key"], cache["keep"] = key, (wd, ws)
+        cache["buf"] = torch.empty((n_bins * Cc * 192,), device=dev, dtype=torch.bfloat16)
+    packed = cache["buf"]
     _lib.call("nrc_transient_head_render_fwd", _lib.stream_ptr(), _lib.ptr(_c(direct_rgbs)),
               _lib.ptr(hd), 64 if hd is not None else 0, _lib.ptr(wd), int(wd.shape[1]) if wd is not None else 0, _lib.ptr(bd),
               _lib.ptr(hs), 128 if hs is not None else 0, _lib.ptr(ws), int(ws.shape[1]) if ws is not None else 0, _lib.ptr(bs),
@@ -239,7 +255,7 @@ def volumetric_transient_rendering_fused(direct_rgbs, h_diffuse, diffuse_layer, 
               _lib.ptr(_c(light_dists)), _lib.ptr(_c(cam_dists)), R, n, n_bins, Cc, float(exposure_time), float(shift),
               float(diffuse_bias), float(spec_premult), float(spec_bias), float(min(spec_max, big)), float(indirect_scale),
               float(bin_zero_threshold_light), int(bool(light_zero)), float(light_near), float(min(rgb_max, big)), float(dark_level),
-              _lib.ptr(t_direct), _lib.ptr(t_indirect), _lib.ptr(rgb))
+              _lib.ptr(packed), int(repack), _lib.ptr(t_direct), _lib.ptr(t_indirect), _lib.ptr(rgb))
     out = dict(transient_direct_no_filter=t_direct, transient_indirect_no_filter=t_indirect)
     if impulse_response is not None or tfilter_sigma != 0.0:
         filt = impulse_response if impulse_response is not None else gaussian_tfilter(tfilter_sigma, dev)

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import torch
 
-from . import models
+from . import models, nerf
 
 SEED = 20200823  # the reference's Config.jax_rng_seed (internal/configs.py:180)
 SAMPLES_PER_RAY = (64, 64, 32)  # configs/nerf_ngp_yobo.gin:521-545
@@ -522,3 +522,97 @@ class FrameRenderer:
             out = st.render(means, rays["viewdirs"], normals, st.draws(R), st.light_lobes(R, means, normals))
             rgb = out["rgb"] * w + (1.0 - acc)
         return dict(rgb=rgb, cache_rgb=cache_rgb, acc=acc, albedo=out["material"]["albedo"])
+
+
+class TransientRenderStep:
+    """BASELINE config 4 (transient_simulation_ngp_yobo_cornell.gin, time-resolved cache): one chunk of primary rays through
+    the proposal sampler (64, 64, 32), the transient cache shader on the 32 final samples and the time-resolved integrator,
+    700 bins of 0.01 (Config.n_bins / exposure_time, gin:17-18), near 0.7 / far 4, light_near 0.7 with light_zero,
+    bin_zero_threshold_light 100, indirect_scale 0.05, rgb_max 100, tfilter_sigma 3 (internal/configs.py:710).
+
+    Per shaded sample: appearance feature (appearance grid) -> bottleneck, roughness, tint, albedo, integrated BRDF;
+    diffuse transient head = irradiance stack on [feature | pos_enc(light position)] (internal/nerf.py:1757-1777) and
+    specular transient head = transient SurfaceLightField on [bottleneck | IDE_5(reflection, roughness)]
+    (internal/surface_light_field.py:782-1069 with use_indirect: 128 -> 700*3 + 1); their LAST layers run inside the
+    time-resolved kernel (render.volumetric_transient_rendering_fused), so the [R, 32, 700, 3] histograms the reference
+    materialises three to four times never exist.  The direct term is the un-occluded diffuse response to the point light
+    (albedo n.l power / d^2 / pi, nerf.py:1141-1170,1474-1481); the shadow-ray visibility query and the light BRDF network
+    of the reference's active path are not part of this workload.  Forward (render) path."""
+
+    def __init__(self, device, n_bins=700, table_init_range=0.1, seed=SEED, bf16=True):
+        self.device, self.n_bins, self.bf16 = device, n_bins, bf16
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        self.cache = models.NeRFModel(bf16=bf16)
+        self.params = _cache_params(self.cache, device, gen, table_init_range)
+        self.head = nerf.TransientIndirectHead(n_bins=n_bins, bf16=bf16)
+
+        def layer(fi, fo):
+            return {"kernel": _he_uniform(gen, device, fi, fo), "bias": torch.zeros((fo,), device=device)}
+
+        t = self.head.init(device, gen)
+        t["albedo_layer"] = layer(96, 3)
+        slf, d = {}, 200
+        for j, name in enumerate(["layer_0", "layer_1", "layer_2", "layer_bottleneck"]):
+            slf[name] = layer(d, 128)
+            d = 128 + (200 if (j % 2 == 0 and j > 0) else 0)
+        slf["output_rgba_layer"] = layer(128, n_bins * 3 + 1)
+        t["TransientSurfaceLightField"] = slf
+        self.tparams = t
+        self.ide5 = nerf.generate_ide_fn(5)
+        self.cfg = dict(exposure_time=0.01, shift=0.0, diffuse_bias=-2.0, spec_bias=-2.0, indirect_scale=0.05,
+                        bin_zero_threshold_light=100.0, light_zero=True, light_near=0.7, rgb_max=100.0, dark_level=0.0,
+                        tfilter_sigma=3.0, filter_indirect=False)
+        self.light_power = float(np.exp(3.9))     # light_power_activation = safe_exp, light_power_bias = 3.9 (gin:111-114)
+        self._head_pack = {}                      # packed bf16 image of the two head layers (repacked when they change)
+
+    def make_rays(self, g, R):
+        """Synthetic rays of the Cornell-box scale: near 0.7 / far 4, a point light beside the camera."""
+        rn = make_rays_np(g, R, near=0.7, far=4.0, radius=2.0)
+        lights = (rn["origins"] + 0.05 * g.normal(size=(R, 3))).astype(np.float32)
+        return dict(rn, lights=lights, cam_origins=rn["origins"].copy())
+
+    def render(self, rays, u01):
+        from . import render as nrender
+        sp = torch.nn.functional.softplus
+        p, tp, b = self.params["Shader"], self.tparams, self.bf16
+        shader = self.cache.shader
+        with torch.no_grad():
+            last = self.cache.sampler(self.params["Sampler"], rays, u01, train=False)[-1]
+            means, feat, nrm, w = last["means"], last["feature"], last["normals_to_use"], last["weights"]
+            R, n = w.shape
+            P = R * n
+            feature = shader.predict_appearance_feature(p, feat, means).reshape(P, 96)
+            bott = nerf.dense(p["bottleneck_layer"], feature, bf16=b)
+            rough = sp(nerf.dense(p["roughness_layer"], feature, bf16=b) - 1.0)
+            tint = torch.sigmoid(nerf.dense(p["tint_layer"], feature, bf16=b))
+            albedo = torch.sigmoid(nerf.dense(tp["albedo_layer"], feature, bf16=b) - 1.0)
+            view = rays["viewdirs"][:, None, :].expand(R, n, 3).reshape(P, 3)
+            n2 = nrm.reshape(P, 3)
+            dot = torch.sum(n2 * (-view), dim=-1, keepdim=True)
+            x = nerf.dense(p["integrated_brdf_layers_0"], torch.cat([bott, dot], dim=-1), relu=True, bf16=b)
+            x = nerf.dense(p["integrated_brdf_layers_1"], x, relu=True, bf16=b)
+            F = torch.sigmoid(nerf.dense(p["output_integrated_brdf_layer"], x, bf16=b) + float(np.log(3.0)))
+            refdirs = nerf.reflect(-view, n2)
+            xin = torch.cat([bott, self.ide5(refdirs, rough)], dim=-1)
+            x = xin
+            for j, name in enumerate(["layer_0", "layer_1", "layer_2", "layer_bottleneck"]):
+                x = nerf.dense(tp["TransientSurfaceLightField"][name], x, relu=True, bf16=b)
+                if j % 2 == 0 and j > 0:
+                    x = torch.cat([x, xin], dim=-1)
+            h_s = x                                                                        # [P, 128]
+            m2 = means.reshape(P, 3)
+            lights = rays["lights"][:, None, :].expand(R, n, 3).reshape(P, 3)
+            h_d = self.head.hidden(tp, feature, lights)                                     # [P, 64]
+            off = lights - m2
+            light_d = torch.linalg.norm(off, dim=-1, keepdim=True)
+            n_dot_l = torch.clamp(torch.sum(n2 * (off / torch.clamp(light_d, min=1e-5)), dim=-1, keepdim=True), min=0.0)
+            radiance = self.light_power / torch.clamp(light_d ** 2, min=1e-5)
+            radiance = torch.where(light_d < self.cfg["light_near"], torch.zeros_like(radiance), radiance)
+            direct = torch.clamp(albedo * n_dot_l * radiance / np.pi, 0.0, self.cfg["rgb_max"]).reshape(R, n, 3)
+            ray_d = torch.linalg.norm(rays["origins"][:, None, :] - means, dim=-1)
+            cam_d = ray_d + torch.linalg.norm(rays["origins"] - rays["cam_origins"], dim=-1)[:, None]
+            return nrender.volumetric_transient_rendering_fused(
+                direct, h_d.reshape(R, n, 64), tp["transient_indirect_layer"], h_s.reshape(R, n, 128),
+                tp["TransientSurfaceLightField"]["output_rgba_layer"], (tint * F).reshape(R, n, 3), w, ray_d,
+                light_d.reshape(R, n), cam_d, n_bins=self.n_bins, pack_cache=self._head_pack, **self.cfg)
