@@ -53,17 +53,15 @@ def nvcc_path():
 
 
 def built_digest():
-    """Digest compiled into the existing library (nrc_build_digest), or None."""
+    """Digest compiled into the existing library (the string nrc_build_digest() returns), or None.  Read from the file's
+    bytes, not through dlopen: a library mapped here would stay mapped (same path) after a rebuild in this process,
+    and the loader in _lib.py would then see the stale image."""
     if not os.path.exists(LIB):
         return None
-    import ctypes
-    try:
-        lib = ctypes.CDLL(LIB)
-        fn = lib.nrc_build_digest
-    except (OSError, AttributeError):
-        return None
-    fn.restype = ctypes.c_char_p
-    return fn().decode()
+    import re
+    with open(LIB, "rb") as fh:
+        m = re.search(rb"nrc-build-digest:([0-9a-f]{64})", fh.read())
+    return m.group(1).decode() if m else None
 
 
 def build(force=False, verbose=False):
@@ -79,7 +77,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc_path(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", src, "-o", obj]
         if os.path.basename(src) == "encode.cu":   # exports nrc_build_digest()
-            cmd.insert(1, f'-DNRC_BUILD_DIGEST="{digest}"')
+            cmd.insert(1, f'-DNRC_BUILD_DIGEST="nrc-build-digest:{digest}"')
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -68,7 +68,9 @@ encode_bwd_kernel(const __grid_constant__ EncDev enc, const float* __restrict__ 
   const int l = blockIdx.y;
   const LevelDev& lv = enc.lv[l];
   if constexpr (kTableGrad && !kXGrad) {
-    if (aggregate && !lv.is_hash && lv.grad) {   // block-uniform: every lane stays for the shuffles
+    // aggregate: 1 = dense levels only, 2 = hash levels too (consecutive samples of a ray share fine cells wherever the
+    // sampler has concentrated them at a surface)
+    if (aggregate && lv.grad && (aggregate > 1 || !lv.is_hash)) {   // block-uniform: every lane stays for the shuffles
       const bool valid = p < P;
       const int64_t pc = valid ? p : P - 1;
       float xi[3] = {__ldg(x + 3 * pc), __ldg(x + 3 * pc + 1), __ldg(x + 3 * pc + 2)};
@@ -83,7 +85,7 @@ encode_bwd_kernel(const __grid_constant__ EncDev enc, const float* __restrict__ 
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         int bx, by, bz;
-        corner_bits(0, k, bx, by, bz);
+        corner_bits(lv.is_hash, k, bx, by, bz);
         const int32_t row = valid ? corner_row(lv, c, bx, by, bz) : -1;
         const float w = (bx ? c.cw[0] : c.fw[0]) * (by ? c.cw[1] : c.fw[1]) * (bz ? c.cw[2] : c.fw[2]);
         float gw[F];
@@ -226,7 +228,7 @@ template <int F>
 int32_t launch_bwd(cudaStream_t s, const EncDev& d, const float* x, const float* g, int64_t P,
                    float* g_x, bool table_grad) {
   dim3 grid(static_cast<unsigned>((P + kEncThreads - 1) / kEncThreads), d.L);
-  static const int agg = getenv("NRC_ENC_BWD_AGG") ? atoi(getenv("NRC_ENC_BWD_AGG")) : 1;
+  static const int agg = getenv("NRC_ENC_BWD_AGG") ? atoi(getenv("NRC_ENC_BWD_AGG")) : 2;
   if (table_grad && g_x) encode_bwd_kernel<F, true, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, 0);
   else if (table_grad) encode_bwd_kernel<F, true, false><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, agg);
   else if (g_x) encode_bwd_kernel<F, false, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, 0);
@@ -405,9 +407,10 @@ extern "C" int32_t nrc_encode_bwd(void* stream, const nrc_encoding_t* enc, const
 
 extern "C" int32_t nrc_abi_version(void) { return NRC_ABI_VERSION; }
 #ifndef NRC_BUILD_DIGEST
-#define NRC_BUILD_DIGEST "unknown"
+#define NRC_BUILD_DIGEST "nrc-build-digest:unknown"
 #endif
-extern "C" const char* nrc_build_digest(void) { return NRC_BUILD_DIGEST; }
+// the build stamps "nrc-build-digest:<sha256 of the sources>"; the prefix lets build.py find it in the file's bytes
+extern "C" const char* nrc_build_digest(void) { return NRC_BUILD_DIGEST + sizeof("nrc-build-digest:") - 1; }
 
 extern "C" const char* nrc_error_string(int32_t status) {
   switch (status) {

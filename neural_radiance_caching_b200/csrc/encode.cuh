@@ -402,8 +402,12 @@ __device__ __forceinline__ void warp_run_atomic_add(float* grad, int32_t row, fl
   const bool head = lane == 0 || rp != row;
   const uint32_t heads = __ballot_sync(0xffffffffu, head);
   const uint32_t after = lane == 31 ? 0xffffffffu : (heads >> (lane + 1));   // bit j: a run starts at lane+1+j
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
+  // longest run in the warp (warp-uniform, from the ballot): only ceil(log2(longest)) shuffle rounds are needed, and none
+  // when every lane heads its own run (the usual case on fine hash levels).  The fixed five rounds were 30 % of the
+  // F = 1 scatter's warp samples (profiles/r02i).
+  int longest = 1;
+  for (uint32_t t = ~heads; t; t &= t << 1) ++longest;
+  for (int d = 1; d < longest; d <<= 1) {
     float o[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) o[f] = __shfl_down_sync(0xffffffffu, gw[f], d);

@@ -103,7 +103,7 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmemBf16& s = *reinterpret_cast<FwdSmemBf16*>(smem_raw);
   const bool want_grad = kFused && out.raw_grad != nullptr;   // the launcher sizes the allocation accordingly
-  load_weights_bf16(s.w, want_grad ? &s.wg : nullptr, m);
+  load_weights_bf16<kBfThreads>(s.w, want_grad ? &s.wg : nullptr, m);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpScratch& ws = s.ws[warp];
@@ -359,16 +359,32 @@ mlp_bf16_fwd_kernel(const __grid_constant__ EncDev enc, const nrc_density_mlp_t 
 #pragma unroll
           for (int f = 0; f < F; ++f) g[f] = gs.g[lane][l * F + f] * enc.scale;
           float gl[3] = {0.f, 0.f, 0.f};
+          // all eight corner rows are requested before the first one is used (one exposed latency per level, not eight)
+          int32_t rows8[8];
+          FeatVec<F> v8[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             int bx, by, bz;
             corner_bits(lv.is_hash, k, bx, by, bz);
-            int32_t row = corner_row(lv, c, bx, by, bz);
-            if (row < 0) continue;
-            FeatVec<F> v = load_row<F>(lv.table, row);
+            rows8[k] = corner_row(lv, c, bx, by, bz);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (rows8[k] >= 0) {
+              v8[k] = load_row<F>(lv.table, rows8[k]);
+            } else {
+#pragma unroll
+              for (int f = 0; f < F; ++f) v8[k].v[f] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (rows8[k] < 0) continue;
+            int bx, by, bz;
+            corner_bits(lv.is_hash, k, bx, by, bz);
             float dot = 0.f;
 #pragma unroll
-            for (int f = 0; f < F; ++f) dot = fmaf(g[f], v.v[f], dot);
+            for (int f = 0; f < F; ++f) dot = fmaf(g[f], v8[k].v[f], dot);
             float wx = bx ? c.cw[0] : c.fw[0];
             float wy = by ? c.cw[1] : c.fw[1];
             float wz = bz ? c.cw[2] : c.fw[2];

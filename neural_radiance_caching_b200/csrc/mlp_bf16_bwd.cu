@@ -25,9 +25,6 @@ struct BwdSmemBf16 {
   __nv_bfloat16 g2[kBwTile][kWStride];
   __nv_bfloat16 g1[kBwTile][kWStride];
   __nv_bfloat16 go[kBwTile][8];
-  float db1[kHid];
-  float db0[kHid];
-  float dbo[4];
 };
 
 // Store an A-fragment image (16 rows x 64 cols, bf16) back to a row-major tile.
@@ -45,20 +42,40 @@ __device__ __forceinline__ void store_afrag(__nv_bfloat16* tile, int stride, int
   }
 }
 
-// Column sums of a 16 x 64 accumulator fragment, added into a shared fp32 vector.
-__device__ __forceinline__ void colsum_to_smem(const float (&acc)[8][4], float* dst, int lane) {
+// The warp's 32 feature rows are one contiguous block of 32 * in_dim floats: read it with 16-byte loads (all issued
+// before the first conversion) and scatter the bf16 values into the row-major tile.  Rows past `nvalid` are zeros.
+// The per-lane row-wise version (32 scalar loads of a 128-byte stride per lane) was 13 % of the kernel's warp
+// samples, stalled on the LSU queue (profiles/r02i).
+template <int KS0>
+__device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* tile, const float* __restrict__ src, int in_dim, int nvalid,
+                                               int lane) {
+  const int total = nvalid * in_dim, span = 32 * in_dim;
+  const bool vec = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  float4 v[4 * KS0];
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    float v0 = acc[nt][0] + acc[nt][2];
-    float v1 = acc[nt][1] + acc[nt][3];
-#pragma unroll
-    for (int o = 4; o < 32; o <<= 1) {
-      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+  for (int it = 0; it < 4 * KS0; ++it) {
+    const int e = 4 * (lane + 32 * it);
+    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e >= span) continue;
+    if (vec && e + 3 < total) {
+      v[it] = __ldg(reinterpret_cast<const float4*>(src + e));
+    } else {
+      if (e < total) v[it].x = __ldg(src + e);
+      if (e + 1 < total) v[it].y = __ldg(src + e + 1);
+      if (e + 2 < total) v[it].z = __ldg(src + e + 2);
+      if (e + 3 < total) v[it].w = __ldg(src + e + 3);
     }
-    if (lane < 4) {
-      atomicAdd(dst + nt * 8 + lane * 2, v0);
-      atomicAdd(dst + nt * 8 + lane * 2 + 1, v1);
+  }
+#pragma unroll
+  for (int it = 0; it < 4 * KS0; ++it) {
+    const int e = 4 * (lane + 32 * it);
+    if (e >= span) continue;
+    int row = e / in_dim, col = e - row * in_dim;
+    const float f[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (e + c < span) tile[row * kXStride + col] = __float2bfloat16(f[c]);
+      if (++col == in_dim) { col = 0; ++row; }
     }
   }
 }
@@ -77,15 +94,33 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
   const bool tangent = enc_dot != nullptr;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmemBf16& s = *reinterpret_cast<BwdSmemBf16*>(smem_raw);
-  load_weights_bf16(s.w, m);
-  for (int i = threadIdx.x; i < kHid; i += kBwThreads) { s.db1[i] = 0.f; s.db0[i] = 0.f; }
-  if (threadIdx.x < 4) s.dbo[threadIdx.x] = 0.f;
+  load_weights_bf16<kBwThreads>(s.w, m);
+  {
+    // the padding columns [in_dim, 16 KS0) of the feature tiles stay zero for the whole launch
+    uint32_t* z = reinterpret_cast<uint32_t*>(&s.x[0][0]);
+    for (int i = threadIdx.x; i < kBwTile * kXStride / 2; i += kBwThreads) z[i] = 0u;
+    if (tangent) {
+      z = reinterpret_cast<uint32_t*>(&s.xd[0][0]);
+      for (int i = threadIdx.x; i < kBwTile * kXStride / 2; i += kBwThreads) z[i] = 0u;
+    }
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int in_dim = m.in_dim;
   const int r = lane >> 2, cq = (lane & 3) * 2;
 
   float accW1[8][4], accW0[KS0][2][4], accWo[4];
+  // bias gradients = column sums of g2 / g1 / g_out over the points: the same tiles times an all-ones A operand in
+  // phase 2 (every row of the product is the column sum).  Replaces per-warp shuffle reductions + shared-memory
+  // atomics in phase 1 (ATOMS.CAST.SPIN loops, ~14 % of the warp samples in profiles/r02i).
+  float accB1[2][4], accB0[2][4], accBo[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { accB1[i][e] = 0.f; accB0[i][e] = 0.f; }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) accBo[e] = 0.f;
+  const uint32_t ones[4] = {0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u};
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -107,8 +142,13 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
       const int64_t p = base + lane;
       const bool valid = p < P;
       const int row = warp * 32 + lane;
-      for (int k = 0; k < KS0 * 16; ++k)
-        s.x[row][k] = __float2bfloat16((valid && k < in_dim) ? __ldg(enc + p * in_dim + k) : 0.f);
+      if (base < P) {
+        const int nvalid = static_cast<int>(P - base < 32 ? P - base : 32);
+        load_rows_bf16<KS0>(&s.x[warp * 32][0], enc + base * in_dim, in_dim, nvalid, lane);
+        if (tangent) load_rows_bf16<KS0>(&s.xd[warp * 32][0], enc_dot + base * in_dim, in_dim, nvalid, lane);
+      } else {
+        for (int k = 0; k < in_dim; ++k) { s.x[row][k] = __float2bfloat16(0.f); if (tangent) s.xd[row][k] = __float2bfloat16(0.f); }
+      }
       float go[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid && tangent) {
         go[0] = 1.0f;                                   // upstream of the tangent network: d rawdot = 1
@@ -118,20 +158,23 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
       }
       *reinterpret_cast<uint2*>(&s.go[row][0]) = make_uint2(pack_bf16(go[0], go[1]), pack_bf16(go[2], go[3]));
       *reinterpret_cast<uint2*>(&s.go[row][4]) = make_uint2(0u, 0u);
-      if (want_wgrad && !tangent) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float v = go[c];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) atomicAdd(&s.dbo[c], v);
-        }
-      }
     }
     __syncwarp();
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
       const int row0 = warp * 32 + mt * 16;
+      const int64_t pr[2] = {base + mt * 16 + r, base + mt * 16 + r + 8};
+      // upstream feature gradients of this 16-point tile: requested now, used after the recomputed forward
+      float2 gfr[8][2];
+      const bool has_gf = g_feat && !tangent;
+      if (has_gf) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            gfr[nt][h] = pr[h] < P ? __ldg(reinterpret_cast<const float2*>(g_feat + pr[h] * kHid + nt * 8 + cq))
+                                   : make_float2(0.f, 0.f);
+      }
       uint32_t a0[KS0][4];
 #pragma unroll
       for (int ks = 0; ks < KS0; ++ks) load_a_frag(a0[ks], &s.x[0][0], kXStride, row0, ks * 16, lane);
@@ -156,15 +199,7 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
           for (int e = 0; e < 4; ++e) m2 |= (acc[nt][e] > 0.f ? 1u : 0u) << (nt * 4 + e);
-        // tangent forward: the warp's rows of the x tile now take edot (they are private to the warp until phase 2)
-        __syncwarp();
-        if (mt == 0) {
-          const int64_t pl = base + lane;
-          const int rowl = warp * 32 + lane;
-          for (int k = 0; k < KS0 * 16; ++k)
-            s.xd[rowl][k] = __float2bfloat16((pl < P && k < in_dim) ? __ldg(enc_dot + pl * in_dim + k) : 0.f);
-        }
-        __syncwarp();
+        // tangent forward on edot (staged with the primal rows above)
 #pragma unroll
         for (int ks = 0; ks < KS0; ++ks) load_a_frag(a0[ks], &s.xd[0][0], kXStride, row0, ks * 16, lane);
         mma_layer64<KS0>(acc, a0, &s.w.w0t[0][0], kXStride, nullptr, lane);
@@ -183,7 +218,6 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
         store_afrag(&s.h2[0][0], kWStride, row0, f2, lane);                 // h2 tile <- h2dot
       }
       // g_h2 = (Wo go + g_feat) * [h2 > 0], in accumulator layout
-      const int64_t pr[2] = {base + mt * 16 + r, base + mt * 16 + r + 8};
       float gor[2][4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -201,17 +235,13 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
         for (int h = 0; h < 2; ++h) {
           float ga = gor[h][0] * w0.x + gor[h][1] * w0.y + gor[h][2] * w0.z + gor[h][3] * w0.w;
           float gb = gor[h][0] * w1.x + gor[h][1] * w1.y + gor[h][2] * w1.z + gor[h][3] * w1.w;
-          if (g_feat && !tangent && pr[h] < P) {
-            float2 gf = *reinterpret_cast<const float2*>(g_feat + pr[h] * kHid + col);
-            ga += gf.x; gb += gf.y;
-          }
+          if (has_gf) { ga += gfr[nt][h].x; gb += gfr[nt][h].y; }
           const bool on0 = tangent ? ((m2 >> (nt * 4 + 2 * h)) & 1u) : (acc[nt][2 * h] > 0.f);
           const bool on1 = tangent ? ((m2 >> (nt * 4 + 2 * h + 1)) & 1u) : (acc[nt][2 * h + 1] > 0.f);
           acc[nt][2 * h] = on0 ? ga : 0.f;
           acc[nt][2 * h + 1] = on1 ? gb : 0.f;
         }
       }
-      if (want_wgrad && !tangent) colsum_to_smem(acc, s.db1, lane);      // the tangent network has no biases
       acc_to_afrag<false>(acc, f2);
       store_afrag(&s.g2[0][0], kWStride, row0, f2, lane);
       // g_h1 = (g_h2 W1^T) * [h1 > 0]
@@ -226,7 +256,6 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
         acc[nt][2] = hi.x > 0.f ? acc[nt][2] : 0.f;
         acc[nt][3] = hi.y > 0.f ? acc[nt][3] : 0.f;
       }
-      if (want_wgrad && !tangent) colsum_to_smem(acc, s.db0, lane);
       acc_to_afrag<false>(acc, f2);
       store_afrag(&s.g1[0][0], kWStride, row0, f2, lane);
       if (g_enc) {
@@ -269,9 +298,12 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
         load_b_frag2_trans(b, &s.g2[0][0], kWStride, k0, np * 16, lane);
         mma_bf16(accW1[2 * np], a, b[0], b[1]);
         mma_bf16(accW1[2 * np + 1], a, b[2], b[3]);
+        if (np == warp) { mma_bf16(accB1[0], ones, b[0], b[1]); mma_bf16(accB1[1], ones, b[2], b[3]); }
       }
       // dW0[i][k]: all rows i, columns k = 16*warp..
       load_b_frag2_trans(b, &s.g1[0][0], kWStride, k0, warp * 16, lane);
+      mma_bf16(accB0[0], ones, b[0], b[1]);
+      mma_bf16(accB0[1], ones, b[2], b[3]);
 #pragma unroll
       for (int mi = 0; mi < KS0; ++mi) {
         load_a_frag_trans(a, tangent ? &s.xd[0][0] : &s.x[0][0], kXStride, k0, mi * 16, lane);
@@ -283,6 +315,7 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
       uint32_t bo[2];
       load_b_frag1_trans(bo, &s.go[0][0], 8, k0, 0, lane);
       mma_bf16(accWo, a, bo[0], bo[1]);
+      if (warp == 0) mma_bf16(accBo, ones, bo[0], bo[1]);
     }
     __syncthreads();
   }
@@ -328,13 +361,23 @@ mlp_bf16_bwd_kernel(const nrc_density_mlp_t m, const float* __restrict__ enc, co
     else if (c < 4 && grads.d_wn) atomicAdd(grads.d_wn + j * 3 + (c - 1), accWo[e]);
   }
   if (tangent) return;          // no bias terms in the tangent network (and the caller may not pass bias buffers)
-  __syncthreads();
-  for (int i = threadIdx.x; i < kHid; i += kBwThreads) {
-    atomicAdd(grads.d_b1 + i, s.db1[i]);
-    atomicAdd(grads.d_b0 + i, s.db0[i]);
+  if (lane < 4) {               // row 0 of the all-ones products: columns cq, cq + 1 of each 8-wide tile
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        atomicAdd(grads.d_b1 + warp * 16 + t * 8 + cq + e, accB1[t][e]);
+        atomicAdd(grads.d_b0 + warp * 16 + t * 8 + cq + e, accB0[t][e]);
+      }
+    if (warp == 0) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = cq + e;
+        if (c == 0) atomicAdd(grads.d_bd, accBo[e]);
+        else if (c < 4 && grads.d_bn) atomicAdd(grads.d_bn + (c - 1), accBo[e]);
+      }
+    }
   }
-  if (threadIdx.x == 0) atomicAdd(grads.d_bd, s.dbo[0]);
-  else if (threadIdx.x < 4 && grads.d_bn) atomicAdd(grads.d_bn + (threadIdx.x - 1), s.dbo[threadIdx.x]);
 }
 
 template <int KS0>

@@ -113,10 +113,12 @@ struct __align__(16) MlpWeightsGradBf16 {
 struct __align__(16) MlpWeightsBf16 : MlpWeightsFwdBf16, MlpWeightsGradBf16 {};
 
 // Global reads run in the parameters' own (Flax [in][out]) order, i.e. coalesced; the transposed copies are
-// scattered into shared memory instead (a strided global read costs one L1TEX wavefront per lane, and this
-// prologue runs once per CTA: with one tile per CTA at 1024 rays it was a visible share of the launch).
-__device__ __forceinline__ void load_weights_bf16(MlpWeightsFwdBf16& s, MlpWeightsGradBf16* g,
-                                                  const nrc_density_mlp_t& m) {
+// scattered into shared memory instead.  This prologue runs once per CTA, and at 1024 rays a CTA has ONE tile: the
+// scalar version below was 20-30 % of the density kernels' warp samples (profiles/r02i, long-scoreboard stalls on
+// 50 dependent 4-byte loads per thread).  The vector version issues every 16-byte load of a thread (two rows of the
+// matrix x four columns per item) before the first conversion, so the whole image costs about one L2 round trip.
+__device__ __forceinline__ void load_weights_bf16_scalar(MlpWeightsFwdBf16& s, MlpWeightsGradBf16* g,
+                                                         const nrc_density_mlp_t& m) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int in_dim = m.in_dim;
   for (int idx = tid; idx < kXStride * kHid; idx += nt) {          // idx = i * 64 + j
@@ -150,8 +152,76 @@ __device__ __forceinline__ void load_weights_bf16(MlpWeightsFwdBf16& s, MlpWeigh
   }
   if (tid < 4) s.bo[tid] = tid == 0 ? m.d_bd[0] : (m.d_bn ? m.d_bn[tid - 1] : 0.f);
 }
+
+// kThreads = blockDim.x (128 in every density kernel).
+template <int kThreads>
+__device__ __forceinline__ void load_weights_bf16(MlpWeightsFwdBf16& s, MlpWeightsGradBf16* g,
+                                                  const nrc_density_mlp_t& m) {
+  if (((reinterpret_cast<uintptr_t>(m.d_w0) | reinterpret_cast<uintptr_t>(m.d_w1)) & 15) != 0) {
+    load_weights_bf16_scalar(s, g, m);
+    return;
+  }
+  const int tid = threadIdx.x;
+  const int in_dim = m.in_dim;
+  constexpr int kQ = kHid / 4;                                   // column quads per matrix row
+  constexpr int kItems1 = (kHid / 2) * kQ / kThreads;            // (row pair, column quad) items of W1 per thread
+  constexpr int kItems0 = ((kXStride / 2) * kQ + kThreads - 1) / kThreads;
+  static_assert((kHid / 2) * kQ % kThreads == 0, "W1 items must divide evenly");
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 r1[kItems1][2], r0[kItems0][2];
+#pragma unroll
+  for (int n = 0; n < kItems1; ++n) {
+    const int it = tid + n * kThreads, kp = it / kQ, jq = it % kQ;
+    r1[n][0] = __ldg(reinterpret_cast<const float4*>(m.d_w1 + (2 * kp) * kHid) + jq);
+    r1[n][1] = __ldg(reinterpret_cast<const float4*>(m.d_w1 + (2 * kp + 1) * kHid) + jq);
+  }
+#pragma unroll
+  for (int n = 0; n < kItems0; ++n) {
+    const int it = tid + n * kThreads, ip = it / kQ, jq = it % kQ;
+    r0[n][0] = (2 * ip < in_dim) ? __ldg(reinterpret_cast<const float4*>(m.d_w0 + (2 * ip) * kHid) + jq) : zero4;
+    r0[n][1] = (2 * ip + 1 < in_dim) ? __ldg(reinterpret_cast<const float4*>(m.d_w0 + (2 * ip + 1) * kHid) + jq) : zero4;
+  }
+  float hd[4] = {0.f, 0.f, 0.f, 0.f}, bb0 = 0.f, bb1 = 0.f, bbo = 0.f;
+  if (tid < kHid) {
+    hd[0] = __ldg(m.d_wd + tid);
+    if (m.d_wn) { hd[1] = __ldg(m.d_wn + 3 * tid); hd[2] = __ldg(m.d_wn + 3 * tid + 1); hd[3] = __ldg(m.d_wn + 3 * tid + 2); }
+    bb0 = __ldg(m.d_b0 + tid);
+    bb1 = __ldg(m.d_b1 + tid);
+  }
+  if (tid < 4) bbo = tid == 0 ? __ldg(m.d_bd) : (m.d_bn ? __ldg(m.d_bn + tid - 1) : 0.f);
+#pragma unroll
+  for (int n = 0; n < kItems1; ++n) {
+    const int it = tid + n * kThreads, kp = it / kQ, jq = it % kQ;
+    const float a[4] = {r1[n][0].x, r1[n][0].y, r1[n][0].z, r1[n][0].w};
+    const float b[4] = {r1[n][1].x, r1[n][1].y, r1[n][1].z, r1[n][1].w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint32_t*>(&s.w1t[4 * jq + c][2 * kp]) = pack_bf16(a[c], b[c]);
+  }
+#pragma unroll
+  for (int n = 0; n < kItems0; ++n) {
+    const int it = tid + n * kThreads, ip = it / kQ, jq = it % kQ;
+    if (ip >= kXStride / 2) continue;
+    const float a[4] = {r0[n][0].x, r0[n][0].y, r0[n][0].z, r0[n][0].w};
+    const float b[4] = {r0[n][1].x, r0[n][1].y, r0[n][1].z, r0[n][1].w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint32_t*>(&s.w0t[4 * jq + c][2 * ip]) = pack_bf16(a[c], b[c]);
+  }
+  if (tid < kHid) {
+    *reinterpret_cast<uint4*>(&s.w1t[tid][kHid]) = make_uint4(0u, 0u, 0u, 0u);      // padding columns 64..71
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s.wot[c][tid] = __float2bfloat16(c < 4 ? hd[c] : 0.f);
+    s.b0[tid] = bb0;
+    s.b1[tid] = bb1;
+    if (g) *reinterpret_cast<float4*>(&g->wo[tid][0]) = make_float4(hd[0], hd[1], hd[2], hd[3]);
+  } else if (tid < kWStride) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s.wot[c][tid] = __float2bfloat16(0.f);
+  }
+  if (tid < 4) s.bo[tid] = bbo;
+}
+template <int kThreads>
 __device__ __forceinline__ void load_weights_bf16(MlpWeightsBf16& s, const nrc_density_mlp_t& m) {
-  load_weights_bf16(s, &s, m);
+  load_weights_bf16<kThreads>(s, &s, m);
 }
 
 // acc[nt][e] (16 rows x 64 cols, fp32) = bias + A(16 x 16*KS) * W^T, W^T stored [64][stride].
