@@ -114,6 +114,11 @@ int32_t nrc_encode_indices(void* stream, const nrc_encoding_t* enc, int32_t leve
  */
 int32_t nrc_encode_bwd(void* stream, const nrc_encoding_t* enc, const float* d_x,
                        const float* d_g_out, int64_t num_points, float* d_g_x);
+/* The table scatter of a fused point query's VJP (nrc_density_query_fwd saved d_enc_out, nrc_density_mlp_bwd produced
+ * d_g_out): x = contract(d_means / warp_c) is recomputed in the kernel (warp_c <= 0: identity), so no
+ * nrc_contract_fwd launch or [P,3] buffer sits in front of it.  levels[l].d_grad += scatter-add of g*w. */
+int32_t nrc_encode_bwd_warped(void* stream, const nrc_encoding_t* enc, const float* d_means, float warp_c,
+                              const float* d_g_out, int64_t num_points);
 
 /* -------------------------------------------------- contraction (row 7) ---- */
 /* coord.contract(x / c) (internal/coord.py:33-38,63-69); c <= 0 means identity. */

@@ -82,6 +82,7 @@ PROTOTYPES = {
     "nrc_encode_fwd": [_P, C.POINTER(nrc_encoding_t), _P, _I64, _P],
     "nrc_encode_indices": [_P, C.POINTER(nrc_encoding_t), _I32, _P, _I64, _P],
     "nrc_encode_bwd": [_P, C.POINTER(nrc_encoding_t), _P, _P, _I64, _P],
+    "nrc_encode_bwd_warped": [_P, C.POINTER(nrc_encoding_t), _P, _F, _P, _I64],
     "nrc_contract_fwd": [_P, _P, _I64, _F, _P],
     "nrc_contract_bwd": [_P, _P, _P, _I64, _F, _P],
     "nrc_density_mlp_fwd": [_P, C.POINTER(nrc_density_mlp_t), _P, _I64, _I32, _P, _P, _P],

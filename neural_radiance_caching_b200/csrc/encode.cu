@@ -63,7 +63,8 @@ encode_indices_kernel(const __grid_constant__ EncDev enc, int level, const float
 template <int F, bool kTableGrad, bool kXGrad>
 __global__ void __launch_bounds__(kEncThreads)
 encode_bwd_kernel(const __grid_constant__ EncDev enc, const float* __restrict__ x,
-                  const float* __restrict__ g_out, int64_t P, float* __restrict__ g_x, const int aggregate) {
+                  const float* __restrict__ g_out, int64_t P, float* __restrict__ g_x, const int aggregate,
+                  const float warp_c) {
   const int64_t p = static_cast<int64_t>(blockIdx.x) * kEncThreads + threadIdx.x;
   const int l = blockIdx.y;
   const LevelDev& lv = enc.lv[l];
@@ -74,6 +75,7 @@ encode_bwd_kernel(const __grid_constant__ EncDev enc, const float* __restrict__ 
       const bool valid = p < P;
       const int64_t pc = valid ? p : P - 1;
       float xi[3] = {__ldg(x + 3 * pc), __ldg(x + 3 * pc + 1), __ldg(x + 3 * pc + 2)};
+      contract_point(warp_c, xi[0], xi[1], xi[2], xi[0], xi[1], xi[2]);   // identity when warp_c <= 0
       float xn[3];
       normalise_point(enc, xi, xn);
       const Corners c = level_setup(lv, xn);
@@ -98,6 +100,7 @@ encode_bwd_kernel(const __grid_constant__ EncDev enc, const float* __restrict__ 
   }
   if (p >= P) return;
   float xi[3] = {__ldg(x + 3 * p), __ldg(x + 3 * p + 1), __ldg(x + 3 * p + 2)};
+  contract_point(warp_c, xi[0], xi[1], xi[2], xi[0], xi[1], xi[2]);
   float xn[3];
   normalise_point(enc, xi, xn);
   Corners c = level_setup(lv, xn);
@@ -226,12 +229,12 @@ int32_t launch_fwd(cudaStream_t s, const EncDev& d, const float* x, int64_t P, f
 
 template <int F>
 int32_t launch_bwd(cudaStream_t s, const EncDev& d, const float* x, const float* g, int64_t P,
-                   float* g_x, bool table_grad) {
+                   float* g_x, bool table_grad, float warp_c = 0.f) {
   dim3 grid(static_cast<unsigned>((P + kEncThreads - 1) / kEncThreads), d.L);
   static const int agg = getenv("NRC_ENC_BWD_AGG") ? atoi(getenv("NRC_ENC_BWD_AGG")) : 2;
-  if (table_grad && g_x) encode_bwd_kernel<F, true, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, 0);
-  else if (table_grad) encode_bwd_kernel<F, true, false><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, agg);
-  else if (g_x) encode_bwd_kernel<F, false, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, 0);
+  if (table_grad && g_x) encode_bwd_kernel<F, true, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, 0, warp_c);
+  else if (table_grad) encode_bwd_kernel<F, true, false><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, agg, warp_c);
+  else if (g_x) encode_bwd_kernel<F, false, true><<<grid, kEncThreads, 0, s>>>(d, x, g, P, g_x, 0, warp_c);
   return check_launch();
 }
 
@@ -401,6 +404,29 @@ extern "C" int32_t nrc_encode_bwd(void* stream, const nrc_encoding_t* enc, const
     case 2: return launch_bwd<2>(s, d, d_x, d_g_out, num_points, d_g_x, table_grad);
     case 4: return launch_bwd<4>(s, d, d_x, d_g_out, num_points, d_g_x, table_grad);
     case 8: return launch_bwd<8>(s, d, d_x, d_g_out, num_points, d_g_x, table_grad);
+  }
+  return NRC_E_UNSUPPORTED;
+}
+
+// Table scatter of a query's VJP straight from the sample means: the contraction is recomputed per thread (a dozen
+// flops) instead of a nrc_contract_fwd launch and a [P,3] round trip in front of every nrc_encode_bwd of the step.
+extern "C" int32_t nrc_encode_bwd_warped(void* stream, const nrc_encoding_t* enc, const float* d_means, float warp_c,
+                                         const float* d_g_out, int64_t num_points) {
+  EncDev d;
+  int32_t st = make_enc_dev(enc, d);
+  if (st != NRC_OK) return st;
+  if (num_points < 0) return NRC_E_INVALID_ARG;
+  if (num_points == 0) return NRC_OK;
+  if (!d_means || !d_g_out) return NRC_E_INVALID_ARG;
+  bool table_grad = false;
+  for (int l = 0; l < d.L; ++l) table_grad |= (d.lv[l].grad != nullptr);
+  if (!table_grad) return NRC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (d.F) {
+    case 1: return launch_bwd<1>(s, d, d_means, d_g_out, num_points, nullptr, true, warp_c);
+    case 2: return launch_bwd<2>(s, d, d_means, d_g_out, num_points, nullptr, true, warp_c);
+    case 4: return launch_bwd<4>(s, d, d_means, d_g_out, num_points, nullptr, true, warp_c);
+    case 8: return launch_bwd<8>(s, d, d_means, d_g_out, num_points, nullptr, true, warp_c);
   }
   return NRC_E_UNSUPPORTED;
 }

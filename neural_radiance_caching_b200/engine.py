@@ -17,7 +17,7 @@ Schedule (reference call sites in brackets):
   nrc_charb_srgb_loss, nrc_interlevel_loss x2     [loss + d loss / d rgb, d loss / d proposal weights;
                                                    image.py:192-200, loss_utils.py:74-108]
   nrc_ray_composite_bwd, shader_fused_backward, nrc_normals_bwd
-  per level l = 2,1,0   nrc_ray_alpha_weights_bwd, nrc_density_mlp_bwd, nrc_contract_fwd, nrc_encode_bwd
+  per level l = 2,1,0   nrc_ray_alpha_weights_bwd, nrc_density_mlp_bwd, nrc_encode_bwd_warped
 """
 import ctypes as C
 import os
@@ -77,7 +77,7 @@ class FusedCacheStep:
         return self._bg[key]
 
     def step(self, rays, u01, target_rgb, train_frac=1.0, extra=None, zero_grad=None, on_shader_grads=None,
-             on_proposal_grads=None):
+             on_proposal_grads=None, on_final_grads=None):
         """One forward + loss + backward; gradients land in the registered sinks.  Returns the loss
         (device scalar) and leaves the per-level sampler state in self.last (for tests).
         `extra` = (rays, u01) of the backward-mask pass (train_utils.py:3348-3401) or None.
@@ -87,10 +87,31 @@ class FusedCacheStep:
         `Shader` parameters is final: a data-parallel harness forks that bucket's all-reduce there.
         `on_proposal_grads` = the same for the proposal levels' parameters (every sampler level but the last), invoked
         on the proposal branch's side stream right after that branch's backward."""
-        state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra, zero_grad=zero_grad,
-                                on_shader_grads=on_shader_grads, on_proposal_grads=on_proposal_grads)
-        self.step_back(state)
+        hi = self._hi_stream()
+        if hi is None:
+            state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra, zero_grad=zero_grad,
+                                    on_shader_grads=on_shader_grads, on_proposal_grads=on_proposal_grads, on_final_grads=on_final_grads)
+            self.step_back(state)
+            return state["loss"]
+        # The step's main chain (sampler forward -> shader forward / backward -> final level's backward) is the critical
+        # path; the proposal supervision, the geometry losses and the backward-mask pass run beside it on the side
+        # streams.  The main chain is issued on a HIGH-priority stream (the priority is recorded in the captured kernel
+        # nodes), so that its CTAs - the chain kernel needs a whole SM each - are placed before the side branches'.
+        outer = torch.cuda.current_stream()
+        hi.wait_stream(outer)
+        with torch.cuda.stream(hi):
+            state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra, zero_grad=zero_grad,
+                                    on_shader_grads=on_shader_grads, on_proposal_grads=on_proposal_grads, on_final_grads=on_final_grads)
+            self.step_back(state)
+        outer.wait_stream(hi)
         return state["loss"]
+
+    def _hi_stream(self):
+        if not self.concurrent or os.environ.get("NRC_HI_PRIO", "1") != "1":
+            return None
+        if getattr(self, "_hi", None) is None:
+            self._hi = torch.cuda.Stream(priority=-1)
+        return self._hi
 
     def _weights_only_pass(self, rays, u01, train_frac, loss, grads_ready=None):
         """Backward-mask term: sampler-only forward on the extra rays (weights_only=True), mask loss against a zero
@@ -138,7 +159,7 @@ class FusedCacheStep:
         return _lib.ptr(self._bg[key])
 
     def step_front(self, rays, u01, target_rgb, train_frac=1.0, fork_proposals=False, extra=None, zero_grad=None,
-                   on_shader_grads=None, on_proposal_grads=None):
+                   on_shader_grads=None, on_proposal_grads=None, on_final_grads=None):
         """Forward, loss and the SHADER's backward: when this returns (in stream order) every gradient of the
         `Shader` parameters (appearance grid + all stacks) is final, so a data-parallel harness can start
         all-reducing that half of the gradient arena while step_back() produces the sampler's half."""
@@ -330,20 +351,41 @@ class FusedCacheStep:
                   R, k, float(self.charb_padding), 0 if mw is None else 1, 0.0 if mw is None else float(mw[0]),
                   0.0 if mw is None else float(mw[1]), _lib.ptr(loss), _lib.ptr(out_rgb), _lib.ptr(acc), _lib.ptr(gv),
                   _lib.ptr(g_w[-1]))
-        d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True)
+        # The final level's backward needs only the data gradients that leave the shader (d_feat, g_nrm): in the
+        # single-graph mode it forks off as soon as the trunk's data-gradient chain is done and runs beside the
+        # weight-gradient launch and the appearance-grid scatter instead of behind them (NRC_TAIL_FORK=0: old order).
+        tail = {}
+
+        def join_geometry(g_nrm):
+            if geo is not None:
+                if s_geo is not None:
+                    torch.cuda.current_stream().wait_stream(s_geo)
+                g_w[-1].add_(geo[0])
+                g_nrm.add_(geo[1].view_as(g_nrm))
+
+        def fork_tail(d_feat, g_nrm):
+            s_tail = self._streams(7)[6]
+            s_tail.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_tail):
+                join_geometry(g_nrm)
+                self._final_level_backward(L2, rays, g_w[-1], d_feat, g_nrm, R)
+                if on_final_grads is not None:
+                    on_final_grads()
+            tail["stream"] = s_tail
+
+        use_tail = fork_proposals and self.concurrent and os.environ.get("NRC_TAIL_FORK", "1") == "1"
+        d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True,
+                                                            on_data_grads=fork_tail if use_tail else None)
         if on_shader_grads is not None:
             on_shader_grads()
-        if geo is not None:
-            if s_geo is not None:
-                main.wait_stream(s_geo)
-            g_w[-1].add_(geo[0])
-            g_nrm.add_(geo[1].view_as(g_nrm))
+        if not use_tail:
+            join_geometry(g_nrm)
         if s_prop is not None and not fork_proposals:
             main.wait_stream(s_prop)     # split mode: the side stream only ran the interlevel losses
         self.last = dict(levels=levels, rgb=out_rgb, acc=acc, dist=dist, shader_rgb=rgb_s)
         return dict(loss=loss, levels=levels, rays=rays, g_w=g_w, d_feat=d_feat, g_nrm=g_nrm, R=R,
                     forked=s_prop if fork_proposals else None, keep=(saved, gv, g_rgb, g_acc, geo), extra=extra,
-                    extra_stream=s_x, train_frac=train_frac)
+                    extra_stream=s_x, train_frac=train_frac, tail_stream=tail.get("stream"))
 
     def step_back(self, state):
         """Backward of the proposal sampler (three levels) from the state of step_front()."""
@@ -372,9 +414,10 @@ class FusedCacheStep:
                 self._weights_only_pass(state["extra"][0], state["extra"][1], state["train_frac"], state["loss"])
         elif state.get("extra_stream") is not None:
             x_fork = state["extra_stream"]
-        g_gp = torch.empty((P2, 3), device=dev, dtype=torch.float32)
-        _lib.call("nrc_normals_bwd", _lib.stream_ptr(), _lib.ptr(L2["gp"]), _lib.ptr(state["g_nrm"]), P2, _lib.ptr(g_gp))
-        self._level_backward(L2, rays, g_w[nl - 1], state["d_feat"], g_gp if L2["gp"] is not None else None, R)
+        if state.get("tail_stream") is not None:    # already issued beside the shader's weight gradients (step_front)
+            main.wait_stream(state["tail_stream"])
+        else:
+            self._final_level_backward(L2, rays, g_w[nl - 1], state["d_feat"], state["g_nrm"], R)
         if x_fork is not None:
             main.wait_stream(x_fork)
         if s_prop is not None:
@@ -384,6 +427,13 @@ class FusedCacheStep:
         else:
             for i_level in range(nl - 2, -1, -1):
                 self._level_backward(levels[i_level], rays, g_w[i_level], None, None, R)
+
+    def _final_level_backward(self, L2, rays, g_weights, d_feat, g_nrm, R):
+        """Predicted-normal VJP + the final sampler level's backward (density features and normals from the shader)."""
+        P2 = R * L2["n"]
+        g_gp = torch.empty((P2, 3), device=L2["density"].device, dtype=torch.float32)
+        _lib.call("nrc_normals_bwd", _lib.stream_ptr(), _lib.ptr(L2["gp"]), _lib.ptr(g_nrm), P2, _lib.ptr(g_gp))
+        self._level_backward(L2, rays, g_weights, d_feat, g_gp if L2["gp"] is not None else None, R)
 
     def _level_backward(self, lv, rays, g_weights, g_feat, g_gp, R):
         """alpha-weights VJP -> fused density-MLP VJP -> hash-grid scatter of one sampler level."""
@@ -403,10 +453,9 @@ class FusedCacheStep:
         g_enc = new(P, mlp.in_dim)
         _lib.call("nrc_density_mlp_bwd", st(), C.byref(lv["desc"]), _lib.ptr(lv["enc_out"]), _lib.ptr(g_density),
                   _lib.ptr(lv["density"]), _lib.ptr(g_feat), _lib.ptr(g_gp), P, int(mlp.bf16), _lib.ptr(g_enc), C.byref(gd))
-        z = new(P, 3)
-        _lib.call("nrc_contract_fwd", st(), _lib.ptr(lv["means"].reshape(P, 3)), P, float(mlp.warp_c), _lib.ptr(z))
         enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(lv["arena"])), mlp.grid.tables(mlp.grid.views(t_sink)))
-        _lib.call("nrc_encode_bwd", st(), C.byref(enc), _lib.ptr(z), _lib.ptr(g_enc), P, None)
+        _lib.call("nrc_encode_bwd_warped", st(), C.byref(enc), _lib.ptr(lv["means"].reshape(P, 3)), float(mlp.warp_c),
+                  _lib.ptr(g_enc), P)
 
 
 class FusedCacheQuery:

@@ -165,13 +165,12 @@ class _DensityQueryFn(torch.autograd.Function):
                   C.byref(gd) if gd is not None else None)
         g_arena = None
         if want_t:
-            z = torch.empty_like(m2)
-            _lib.call("nrc_contract_fwd", _lib.stream_ptr(), _lib.ptr(m2), P, float(mlp.warp_c), _lib.ptr(z))
             t_sink = _lib.grad_sink(arena)
             g_arena = t_sink if t_sink is not None else torch.zeros_like(arena)
             enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)),
                                        mlp.grid.tables(mlp.grid.views(g_arena)))
-            _lib.call("nrc_encode_bwd", _lib.stream_ptr(), C.byref(enc), _lib.ptr(z), _lib.ptr(g_enc), P, None)
+            _lib.call("nrc_encode_bwd_warped", _lib.stream_ptr(), C.byref(enc), _lib.ptr(m2), float(mlp.warp_c),
+                      _lib.ptr(g_enc), P)
             if t_sink is not None:
                 g_arena = None
         if w_sunk:

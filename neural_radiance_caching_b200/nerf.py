@@ -293,11 +293,14 @@ def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, 
     return outs, saved, (lead, P, spr)
 
 
-def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_arena_grad=True):
+def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_arena_grad=True, on_data_grads=None):
     """Backward schedule: per-point `out` VJP, SurfaceLightField and integrated-BRDF data-gradient chains
     (the EnvMap's gradient is exactly zero: 1 - incoming_acc == 0), per-point `mid` VJP (IDE), trunk
     data-gradient chain, ONE weight-gradient launch for the three stacks, appearance-grid scatter.
-    Returns (d_density_feature [P,64], d_normals [P,3], g_arena | None, sinks, sunk)."""
+    Returns (d_density_feature [P,64], d_normals [P,3], g_arena | None, sinks, sunk).
+    `on_data_grads(d_feat, g_nrm)` is called (in stream order) as soon as the gradients that leave the shader towards
+    the density field are final, i.e. BEFORE the weight-gradient launch and the appearance-grid scatter: the caller
+    forks the final sampler level's backward there."""
     lead, P, spr = meta
     z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed = saved
     dev = z.device
@@ -332,6 +335,8 @@ def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_a
     d_feat, d_enc = new(P, 64), new(P, 32)
     dy_t = mlp_chain.run_backward_data(shader.trunk_chain, params[""], [[Img(img_db, 0, 2, 4), Img(img_db, 2, 2, 4)], g_heads],
                                        act_t, views[0], P, [(d_feat, False), (d_enc, False)])
+    if on_data_grads is not None:
+        on_data_grads(d_feat, g_nrm)
     named = {(scope, name): (flat[2 * i], flat[2 * i + 1]) for i, (scope, name) in enumerate(names)}
     sinks, sunk = mlp_chain.resolve_sinks({k: v for k, v in named.items() if k[0] != "EnvMap"})
     wptrs = mlp_chain._Ptrs()
