@@ -590,9 +590,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 // Fast epilogue of the common case - the accumulator becomes the next layer's bf16 operand and nothing else: TMEM ->
 // (+ staged bias) -> bf16 pairs -> ReLU / ReLU mask applied on the PACKED pairs (max(.,0) commutes with the rounding;
 // the mask is an AND) -> two 16-byte shared-memory stores per 16 columns.  ~45 instructions per chunk instead of ~80.
+// sig_bar != 0: the NEXT layer's UMMAs were split by K atom (chain2_build): every time this context has finished an
+// operand atom (64 columns, all 128 rows) it tells the issuer - proxy fence, the context's named barrier, one
+// arrival per CTA on the issuing CTA's operand barrier - so the k-steps that read atom 0 run while atom 1 is still
+// being drained from tensor memory.  (16 * part + k * 16 * nparts crosses a 64-column boundary at the same k for
+// every part: the barrier count is uniform over the context.)
 template <bool MASK>
 __device__ __forceinline__ void epi_slot_fast(uint32_t taddr, const float* bias_s, bool relu, uint32_t slot0_addr, int r, int npad,
-                                              int part, int nparts, const uint8_t* mask_tile, int mask_atom0) {
+                                              int part, int nparts, const uint8_t* mask_tile, int mask_atom0,
+                                              int sig_bar = 0, int sig_threads = 0, bool sig_t0 = false, uint32_t sig_remote = 0u) {
   // (two chunks per tensor-memory round trip were measured: the second 16-register buffer spills at the 96-register
   // cap of 18 warps and the SurfaceLightField forward went from 34.6 to 49 us)
   const bool has_bias = bias_s != nullptr;
@@ -635,6 +641,16 @@ __device__ __forceinline__ void epi_slot_fast(uint32_t taddr, const float* bias_
                  "r"(o[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + (((c8 + 1) ^ rx) << 4)), "r"(o[4]), "r"(o[5]),
                  "r"(o[6]), "r"(o[7]) : "memory");
+    if (sig_bar && (((j0 + 16 * nparts) ^ j0) >> 6)) {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_barrier_sync(sig_bar, sig_threads);
+      // one operand barrier per atom index: an arrival may only run ONE phase ahead of the issuer's wait (two
+      // completed phases look like none to a parity wait), and atom k+1 of this layer is announced before the issuer
+      // has necessarily consumed atom k
+      const uint32_t stage = static_cast<uint32_t>(j0 >> 6);
+      if (sig_t0) mbar_arrive_cluster(sig_remote + (stage ? 32u + 16u * stage : 0u));
+    }
   }
 }
 
@@ -724,6 +740,7 @@ __device__ __forceinline__ void epi_staged(uint32_t taddr, const float* bias_s, 
 //     weights (2-3 us) behind a cluster barrier.
 // Programs, weight images, tile images and the op semantics are those of the streaming kernel (a 256-row pair tile is
 // the two consecutive 128-row tiles 2t and 2t+1 of every tile image).
+constexpr uint8_t kFlagSplit = 0x80;   // DevOp.flags, set by chain2_build: EPI = announce every finished operand atom; GEMM = group announced that way
 constexpr int kTail2Bytes = 6144;   // shared-memory head: mbarriers (128 B), TMEM base (16 B), program, UMMA list, staged biases
 constexpr int kMaxMma = 96;     // UMMA instructions of one program (precomputed descriptor list in shared memory)
 constexpr int kMaxWcopy = 48;   // bulk copies that make a program's weights resident (one per K atom of every GEMM)
@@ -788,6 +805,8 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t w_ready = bar0;
   auto a_ready = [&](int c) { return bar0 + 8u * (2 + c); };
+  // operand atoms 1 and 2 of a split group (see chain2_build): barriers 8+c and 10+c, i.e. a_ready(c) + 48 / + 64
+  auto a_stage = [&](int c, uint32_t stage) { return bar0 + 8u * (2 + c) + (stage ? 32u + 16u * stage : 0u); };
   auto acc_ready = [&](int c) { return bar0 + 8u * (4 + c); };
   auto img_ready = [&](int c) { return bar0 + 8u * (6 + c); };
 
@@ -819,8 +838,13 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
     } else if (warp == 1) {
       if (lane == 0) {
         for (int c = 0; c < 2; ++c) {
-          if (!first) { mbar_inval(a_ready(c)); mbar_inval(acc_ready(c)); mbar_inval(img_ready(c)); }
+          if (!first) {
+            mbar_inval(a_ready(c)); mbar_inval(acc_ready(c)); mbar_inval(img_ready(c));
+            mbar_inval(a_stage(c, 1)); mbar_inval(a_stage(c, 2));
+          }
           mbar_init(a_ready(c), 2);
+          mbar_init(a_stage(c, 1), 2);
+          mbar_init(a_stage(c, 2), 2);
           mbar_init(acc_ready(c), 1);
           mbar_init(img_ready(c), 1);
         }
@@ -895,7 +919,7 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
     if (warp == 1) {
       // ===================================================================== UMMA issuer (even CTA of the pair)
       if (rank == 0 && lane == 0) {
-        uint32_t a_par[2] = {0u, 0u};
+        uint32_t a_par[2][3] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
         for (int q = q0; q < q0 + n_super; ++q) {
 #ifdef NRC_CHAIN_TRACE
           const int trace_it = q - q0;
@@ -907,23 +931,37 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
             while (j < nops && sops[j].kind == NRC_OP_GEMM) ++j;
             for (int c = 0; c < nctx; ++c) {
               if (nctx * q + c >= p.num_ptiles) continue;
-              mbar_wait_cluster(a_ready(c), a_par[c]);
-              a_par[c] ^= 1u;
-              tc_fence_after();
-#ifdef NRC_CHAIN_TRACE
-              if (blockIdx.x == 0 && first && c == 0 && trace_it < kTraceTiles && trace_g < 8) g_chain_mma[trace_it][trace_g][0] = clock64();
-#endif
               {
                 const int e0 = sops[i].ld, e1 = sops[j - 1].ld + sops[j - 1].col0;
                 const uint32_t d0 = tmem_base + static_cast<uint32_t>(c * kCtxTmemCols);
                 const uint32_t a_off = static_cast<uint32_t>(c * S) * (kAtomBytes >> 4) + (base >> 4);
                 const uint32_t b_off = base >> 4;
                 constexpr uint64_t kDescHi = static_cast<uint64_t>(64u | (1u << 14) | (2u << 29)) << 32;   // SBO 1024, v1, SW128
-                uint4 m = smma[e0];
-                for (int e = e0; e < e1; ++e) {
-                  const uint4 cur = m;
-                  if (e + 1 < e1) m = smma[e + 1];
-                  umma2_bf16(d0 + (cur.z & 0x7FFFFFFFu), kDescHi | (cur.x + a_off), kDescHi | (cur.y + b_off), cur.w, cur.z >> 31);
+                // The list is a sequence of SEGMENTS: the first instruction of a segment names the operand barrier to
+                // wait for (bits 29-30: atom index + 1) and the segment's length (bits 16-23); the instructions of a
+                // segment are issued by a tight loop with no barrier code in it (with the wait inside the loop the
+                // compiler stopped unrolling it and the issue rate dropped from ~120 to ~160 cycles per UMMA).
+                for (int e = e0; e < e1;) {
+                  uint4 m = smma[e];
+                  const uint32_t ws = (m.z >> 29) & 3u;
+                  const int seg_end = e + static_cast<int>((m.z >> 16) & 0xFFu);
+                  if (ws) {
+                    mbar_wait_cluster(a_stage(c, ws - 1u), a_par[c][ws - 1u]);
+                    a_par[c][ws - 1u] ^= 1u;
+                    tc_fence_after();
+                  }
+#ifdef NRC_CHAIN_TRACE
+                  if (e == e0 && blockIdx.x == 0 && first && c == 0 && trace_it < kTraceTiles && trace_g < 8) g_chain_mma[trace_it][trace_g][0] = clock64();
+#endif
+                  const uint4* seg = smma + e;
+                  const int n_seg = seg_end - e;
+#pragma unroll 4
+                  for (int t = 0; t < n_seg; ++t) {
+                    const uint4 cur = m;
+                    if (t + 1 < n_seg) m = seg[t + 1];
+                    umma2_bf16(d0 + (cur.z & 0x1FFu), kDescHi | (cur.x + a_off), kDescHi | (cur.y + b_off), cur.w, cur.z >> 31);
+                  }
+                  e = seg_end;
                 }
               }
               umma2_commit_mc(acc_ready(c), 3);
@@ -970,13 +1008,15 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
         for (int i = 0; i < nops;) {
           const DevOp& op = sops[i];
           if (op.kind == NRC_OP_GEMM) {
-            fence_proxy_async_smem();
-            tc_fence_before();
-            named_barrier_sync(1 + c, ctxT);
-            if (wg_tid == 0) {
-              if (!w_waited) { mbar_wait(w_ready, 0); w_waited = true; if (first) TRACE_MARK(11); }
-              if (img_pending) { mbar_arrive(img_ready(c)); mbar_wait(img_ready(c), img_par); img_par ^= 1u; img_pending = false; }
-              mbar_arrive_cluster(a_ready_remote);
+            if (!(op.flags & kFlagSplit)) {   // (a split group's operands were announced atom by atom by the epilogue before it)
+              fence_proxy_async_smem();
+              tc_fence_before();
+              named_barrier_sync(1 + c, ctxT);
+              if (wg_tid == 0) {
+                if (!w_waited) { mbar_wait(w_ready, 0); w_waited = true; if (first) TRACE_MARK(11); }
+                if (img_pending) { mbar_arrive(img_ready(c)); mbar_wait(img_ready(c), img_par); img_par ^= 1u; img_pending = false; }
+                mbar_arrive_cluster(a_ready_remote);
+              }
             }
             while (i < nops && sops[i].kind == NRC_OP_GEMM) ++i;
             mbar_wait(acc_ready(c), acc_par);
@@ -1056,6 +1096,7 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
             store_pending = true;
           } else {  // NRC_OP_EPI
             if (op.slot >= 0) guard_slots();
+            bool split_signalled = false;
             EpiArgs a;
             a.bias = static_cast<const float*>(op.ptr);
             a.bias_s = op.bias_off >= 0 ? sbias + op.bias_off : nullptr;
@@ -1082,8 +1123,12 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
                          a.accum, a.has_slot, a.slot0_addr, 1 + c, ctxT, wg_tid);
             } else if (a.has_slot && !out && op.ncols == op.npad && (!a.bias || a.bias_s) && (tile_ok || !op.mask)) {
               // the accumulator only becomes the next operand: tight path
-              if (a.mask_tile) epi_slot_fast<true>(a.taddr, nullptr, false, a.slot0_addr, r, op.npad, half, parts, a.mask_tile, a.mask_atom0);
-              else             epi_slot_fast<false>(a.taddr, a.bias ? a.bias_s : nullptr, relu, a.slot0_addr, r, op.npad, half, parts, nullptr, 0);
+              const int sb = (op.flags & kFlagSplit) ? 1 + c : 0;
+              if (a.mask_tile) epi_slot_fast<true>(a.taddr, nullptr, false, a.slot0_addr, r, op.npad, half, parts, a.mask_tile, a.mask_atom0,
+                                                   sb, ctxT, wg_tid == 0, a_ready_remote);
+              else             epi_slot_fast<false>(a.taddr, a.bias ? a.bias_s : nullptr, relu, a.slot0_addr, r, op.npad, half, parts, nullptr, 0,
+                                                    sb, ctxT, wg_tid == 0, a_ready_remote);
+              split_signalled = sb != 0;
             } else if (a.mask_tile) {
               if (full) epi_run<false, false, true, true>(a); else epi_run<false, false, true, false>(a);
             } else if (a.bias) {
@@ -1092,6 +1137,16 @@ chain2_kernel(const __grid_constant__ Chain2Params p) {
             } else {
               if (relu) { if (full) epi_run<false, true, false, true>(a); else epi_run<false, true, false, false>(a); }
               else      { if (full) epi_run<false, false, false, true>(a); else epi_run<false, false, false, false>(a); }
+            }
+            if ((op.flags & kFlagSplit) && !split_signalled) {
+              // a general-path epilogue in front of a split group (e.g. the rows past the end in the odd last tile):
+              // the issuer still expects one phase per operand atom
+              for (uint32_t k = 0; k < static_cast<uint32_t>(op.npad >> 6); ++k) {
+                fence_proxy_async_smem();
+                tc_fence_before();
+                named_barrier_sync(1 + c, ctxT);
+                if (wg_tid == 0) mbar_arrive_cluster(a_ready_remote + (k ? 32u + 16u * k : 0u));
+              }
             }
           }
 #ifdef NRC_CHAIN_TRACE
@@ -1435,27 +1490,122 @@ static int32_t chain2_build(const nrc_chain_program_t* prog, void* const* d_ptrs
       d.bias_off = static_cast<int16_t>(bias_cur);
       bias_cur += o.npad;
     }
-    if (o.kind == NRC_OP_GEMM) {
-      // this op's UMMA instructions as ready-made descriptor words (context 0, addresses relative to the CTA's dynamic
-      // shared memory; the issuer adds the base and the context's slot offset): the issuing thread spends a handful of
-      // instructions per UMMA instead of re-deriving everything from the program
-      if (i == 0 || prog->ops[i - 1].kind != NRC_OP_GEMM) ++n_groups;
-      const int first = pl.n_mma;
-      const uint32_t idesc = make_idesc(256, o.n, 0, 0);
-      const uint32_t half_bytes = static_cast<uint32_t>(o.n) * 64u;
-      for (int a = 0; a < o.n_atoms; ++a) {
-        const uint32_t a_addr = slot0 + static_cast<uint32_t>(o.a_slot[a]) * kAtomBytes;
-        const uint32_t b_addr = static_cast<uint32_t>(kTail2Bytes + w_off[i]) + static_cast<uint32_t>(a) * half_bytes;
-        for (int k = 0; k < (o.a_klen[a] >> 4); ++k) {
-          if (pl.n_mma >= kMaxMma) return NRC_E_UNSUPPORTED;
-          const uint32_t acc = ((o.flags & NRC_GEMM_ACCUMULATE) || a > 0 || k > 0) ? 0x80000000u : 0u;
-          pl.mma[pl.n_mma++] = make_uint4(((a_addr + 32u * k) >> 4) | (1u << 16), ((b_addr + 32u * k) >> 4) | (1u << 16),
-                                          static_cast<uint32_t>(o.tmem_col) | acc, idesc);
-        }
-      }
-      d.ld = first;
-      d.col0 = static_cast<int16_t>(pl.n_mma - first);
+  }
+  // UMMA instructions of every GEMM group as ready-made descriptor words (context 0, addresses relative to the CTA's
+  // dynamic shared memory; the issuer adds the base and the context's slot offset): the issuing thread spends a handful
+  // of instructions per UMMA instead of re-deriving everything from the program.
+  //
+  // SPLIT groups.  A hidden layer costs [epilogue of layer l: ~1.9 k cycles] -> barrier -> [UMMAs of layer l+1: ~1 k
+  // cycles of issue + completion latency] -> barrier -> ... strictly one after the other (trace build: the GEMM ops
+  // are 55 % of a SurfaceLightField tile and only a third of that is UMMA issue).  When the operand of a group is
+  // produced by the epilogue directly in front of it (only SAVEs in between), that epilogue announces every finished
+  // 64-column atom and the group's k-steps are ordered by the atom they read - operands that were resident before
+  // (skip connections) and atom 0 first - with a barrier wait where the next atom's k-steps begin.  The group
+  // accumulates in the OTHER 128-column half of the context's tensor memory, because the epilogue is still draining
+  // the previous accumulator.  Conditions: the working accumulators of the whole program live in columns [0, 128)
+  // (persistent input-gradient accumulators at >= 256 are left alone), 2-3 operand atoms, tight epilogue path.
+  static const bool split_on = !(getenv("NRC_CHAIN_SPLIT") && getenv("NRC_CHAIN_SPLIT")[0] == '0');
+  bool regions_free = true;     // nobody uses columns [128, 256)
+  for (int i = 0; i < nops; ++i) {
+    const nrc_chain_op_t& o = prog->ops[i];
+    const int w = o.kind == NRC_OP_GEMM ? o.n : (o.kind == NRC_OP_EPI ? o.npad : 0);
+    if (w > 0 && !(o.tmem_col + w <= 128 || o.tmem_col >= 256)) regions_free = false;
+  }
+  int region_prev = 0;
+  for (int i = 0; i < nops;) {
+    if (prog->ops[i].kind != NRC_OP_GEMM) { ++i; continue; }
+    int j = i;
+    while (j < nops && prog->ops[j].kind == NRC_OP_GEMM) ++j;
+    int jc = j;                                       // consumers: everything up to the next GEMM group
+    while (jc < nops && prog->ops[jc].kind != NRC_OP_GEMM) ++jc;
+    ++n_groups;
+    // the epilogue that produces this group's operand
+    int E = i - 1;
+    while (E >= 0 && prog->ops[E].kind == NRC_OP_SAVE) --E;
+    bool split = split_on && regions_free && E >= 0 && prog->ops[E].kind == NRC_OP_EPI;
+    int K = 0;
+    if (split) {
+      const nrc_chain_op_t& e = prog->ops[E];
+      K = e.npad >> 6;
+      split = e.slot >= 0 && e.out_ptr < 0 && e.ncols == e.npad && (e.npad & 63) == 0 && K >= 2 && K <= 3 && e.n == 0 &&
+              !(e.flags & NRC_EPI_DENSITY) && (e.ptr < 0 || pl.ops[E].bias_off >= 0);
     }
+    struct Ent { int op, a, k, stage; };
+    Ent ents[kMaxMma];
+    int ne = 0;
+    bool stage_seen[4] = {false, false, false, false};
+    for (int g = i; g < j; ++g) {
+      const nrc_chain_op_t& o = prog->ops[g];
+      for (int a = 0; a < o.n_atoms; ++a)
+        for (int k = 0; k < (o.a_klen[a] >> 4); ++k) {
+          if (ne >= kMaxMma) return NRC_E_UNSUPPORTED;
+          int stage = 0;
+          if (split) {
+            const int rel = o.a_slot[a] - prog->ops[E].slot;
+            stage = (rel >= 0 && rel < K) ? rel : 0;
+            stage_seen[stage] = true;
+          }
+          ents[ne++] = Ent{g, a, k, stage};
+        }
+    }
+    if (split)
+      for (int st = 0; st < K; ++st) split = split && stage_seen[st];
+    // accumulator targets of the group: equal or disjoint column ranges
+    for (int g = i; g < j && split; ++g)
+      for (int h = i; h < g; ++h) {
+        const nrc_chain_op_t &x = prog->ops[g], &y = prog->ops[h];
+        const bool same = x.tmem_col == y.tmem_col && x.n == y.n;
+        const bool disjoint = x.tmem_col + x.n <= y.tmem_col || y.tmem_col + y.n <= x.tmem_col;
+        if (!same && !disjoint) split = false;
+      }
+    const int region = split ? (region_prev ^ 1) : 0;
+    if (split) {
+      // stable order by stage
+      Ent sorted[kMaxMma];
+      int ns = 0;
+      for (int st = 0; st < K; ++st)
+        for (int e = 0; e < ne; ++e)
+          if (ents[e].stage == st) sorted[ns++] = ents[e];
+      for (int e = 0; e < ne; ++e) ents[e] = sorted[e];
+      pl.ops[E].flags |= kFlagSplit;
+      pl.ops[i].flags |= kFlagSplit;
+    }
+    if (pl.n_mma + ne > kMaxMma) return NRC_E_UNSUPPORTED;
+    const int first = pl.n_mma;
+    int stage_cur = -1;
+    for (int e = 0; e < ne; ++e) {
+      const nrc_chain_op_t& o = prog->ops[ents[e].op];
+      const int a = ents[e].a, k = ents[e].k;
+      const uint32_t half_bytes = static_cast<uint32_t>(o.n) * 64u;
+      const uint32_t a_addr = slot0 + static_cast<uint32_t>(o.a_slot[a]) * kAtomBytes;
+      const uint32_t b_addr = static_cast<uint32_t>(kTail2Bytes + w_off[ents[e].op]) + static_cast<uint32_t>(a) * half_bytes;
+      // accumulate unless this is the first instruction (in issue order) into a target that some op of the group resets
+      bool acc = true;
+      {
+        bool earlier = false, resets = false;
+        for (int f = 0; f < e; ++f) earlier = earlier || prog->ops[ents[f].op].tmem_col == o.tmem_col;
+        for (int g = i; g < j; ++g)
+          resets = resets || (prog->ops[g].tmem_col == o.tmem_col && !(prog->ops[g].flags & NRC_GEMM_ACCUMULATE));
+        if (!earlier && resets) acc = false;
+      }
+      uint32_t waits = 0;     // barrier of the atom index this stage waits for, + 1
+      if (ents[e].stage != stage_cur) { stage_cur = ents[e].stage; waits = static_cast<uint32_t>(stage_cur) + 1u; }
+      const uint32_t col = static_cast<uint32_t>(o.tmem_col + ((o.tmem_col < 128) ? region * 128 : 0));
+      pl.mma[pl.n_mma++] = make_uint4(((a_addr + 32u * k) >> 4) | (1u << 16), ((b_addr + 32u * k) >> 4) | (1u << 16),
+                                      col | (waits << 29) | (acc ? 0x80000000u : 0u), make_idesc(256, o.n, 0, 0));
+    }
+    for (int e = first; e < pl.n_mma;) {          // segment lengths into the segment heads (bits 16-23)
+      int e1 = e + 1;
+      while (e1 < pl.n_mma && ((pl.mma[e1].z >> 29) & 3u) == 0u) ++e1;
+      pl.mma[e].z |= static_cast<uint32_t>(e1 - e) << 16;
+      e = e1;
+    }
+    for (int g = i; g < j; ++g) { pl.ops[g].ld = first + (g == i ? 0 : ne); pl.ops[g].col0 = static_cast<int16_t>(g == i ? ne : 0); }
+    if (region)
+      for (int c = j; c < jc; ++c)
+        if (prog->ops[c].kind == NRC_OP_EPI && prog->ops[c].tmem_col < 128) pl.ops[c].tmem_col = static_cast<int16_t>(prog->ops[c].tmem_col + 128);
+    region_prev = region;
+    i = j;
   }
   out.weights = static_cast<const uint8_t*>(d_weights_packed);
   out.w_bytes = w_bytes;

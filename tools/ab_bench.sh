@@ -5,7 +5,7 @@ T=$1; shift; O=gpurun_out; mkdir -p $O
 i=0
 for v in "$@"; do
   i=$((i+1)); e="$v"; [ "$v" = "-" ] && e=""
-  env $e python bench.py --no-others --no-cpu-baseline > $O/${T}_v$i.json 2> $O/${T}_v$i.err; rc=$?
+  env $e timeout 240 python bench.py --no-others --no-cpu-baseline > $O/${T}_v$i.json 2> $O/${T}_v$i.err; rc=$?
   python - "$O/${T}_v$i.json" "$v" $rc <<'PY'
 import json, sys
 try:
