@@ -43,6 +43,7 @@ class FusedCacheStep:
         self.density_grid_regularizer = density_grid_regularizer   # Config.param_regularizers['density_grid']; None: off
         self._bg = {}
         self._side = None
+        self.final_grads_announced = False   # last step(): on_final_grads was invoked (the tail fork ran)
         self.concurrent = True   # independent branches of the schedule on side streams (fork/join events)
         if model.sampler.opaque_background:
             # nrc_ray_alpha_weights_bwd recomputes a finite density * delta for the last sample: with an opaque background
@@ -77,7 +78,7 @@ class FusedCacheStep:
         return self._bg[key]
 
     def step(self, rays, u01, target_rgb, train_frac=1.0, extra=None, zero_grad=None, on_shader_grads=None,
-             on_proposal_grads=None, on_final_grads=None):
+             on_proposal_grads=None, on_final_grads=None, on_grid_grads=None):
         """One forward + loss + backward; gradients land in the registered sinks.  Returns the loss
         (device scalar) and leaves the per-level sampler state in self.last (for tests).
         `extra` = (rays, u01) of the backward-mask pass (train_utils.py:3348-3401) or None.
@@ -86,12 +87,17 @@ class FusedCacheStep:
         `on_shader_grads` = callable invoked (in stream order on the main stream) as soon as every gradient of the
         `Shader` parameters is final: a data-parallel harness forks that bucket's all-reduce there.
         `on_proposal_grads` = the same for the proposal levels' parameters (every sampler level but the last), invoked
-        on the proposal branch's side stream right after that branch's backward."""
+        on the proposal branch's side stream right after that branch's backward.  `on_grid_grads` = the same for the
+        appearance grid alone (its scatter precedes the stacks' weight gradients), `on_final_grads` = for the final
+        sampler level's parameters, invoked on the stream that ran that level's backward (only when it was forked off
+        beside the shader's weight gradients: self.final_grads_announced tells)."""
         hi = self._hi_stream()
         if hi is None:
             state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra, zero_grad=zero_grad,
-                                    on_shader_grads=on_shader_grads, on_proposal_grads=on_proposal_grads, on_final_grads=on_final_grads)
+                                    on_shader_grads=on_shader_grads, on_proposal_grads=on_proposal_grads, on_final_grads=on_final_grads,
+                                    on_grid_grads=on_grid_grads)
             self.step_back(state)
+            self.final_grads_announced = state.get("final_grads_announced", False)
             return state["loss"]
         # The step's main chain (sampler forward -> shader forward / backward -> final level's backward) is the critical
         # path; the proposal supervision, the geometry losses and the backward-mask pass run beside it on the side
@@ -101,9 +107,11 @@ class FusedCacheStep:
         hi.wait_stream(outer)
         with torch.cuda.stream(hi):
             state = self.step_front(rays, u01, target_rgb, train_frac, fork_proposals=True, extra=extra, zero_grad=zero_grad,
-                                    on_shader_grads=on_shader_grads, on_proposal_grads=on_proposal_grads, on_final_grads=on_final_grads)
+                                    on_shader_grads=on_shader_grads, on_proposal_grads=on_proposal_grads, on_final_grads=on_final_grads,
+                                    on_grid_grads=on_grid_grads)
             self.step_back(state)
         outer.wait_stream(hi)
+        self.final_grads_announced = state.get("final_grads_announced", False)
         return state["loss"]
 
     def _hi_stream(self):
@@ -159,7 +167,7 @@ class FusedCacheStep:
         return _lib.ptr(self._bg[key])
 
     def step_front(self, rays, u01, target_rgb, train_frac=1.0, fork_proposals=False, extra=None, zero_grad=None,
-                   on_shader_grads=None, on_proposal_grads=None, on_final_grads=None):
+                   on_shader_grads=None, on_proposal_grads=None, on_final_grads=None, on_grid_grads=None):
         """Forward, loss and the SHADER's backward: when this returns (in stream order) every gradient of the
         `Shader` parameters (appearance grid + all stacks) is final, so a data-parallel harness can start
         all-reducing that half of the gradient arena while step_back() produces the sampler's half."""
@@ -371,11 +379,13 @@ class FusedCacheStep:
                 self._final_level_backward(L2, rays, g_w[-1], d_feat, g_nrm, R)
                 if on_final_grads is not None:
                     on_final_grads()
+                    tail["final_grads_announced"] = True
             tail["stream"] = s_tail
 
         use_tail = fork_proposals and self.concurrent and os.environ.get("NRC_TAIL_FORK", "1") == "1"
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True,
-                                                            on_data_grads=fork_tail if use_tail else None)
+                                                            on_data_grads=fork_tail if use_tail else None,
+                                                            on_grid_grads=on_grid_grads)
         if on_shader_grads is not None:
             on_shader_grads()
         if not use_tail:
@@ -385,7 +395,8 @@ class FusedCacheStep:
         self.last = dict(levels=levels, rgb=out_rgb, acc=acc, dist=dist, shader_rgb=rgb_s)
         return dict(loss=loss, levels=levels, rays=rays, g_w=g_w, d_feat=d_feat, g_nrm=g_nrm, R=R,
                     forked=s_prop if fork_proposals else None, keep=(saved, gv, g_rgb, g_acc, geo), extra=extra,
-                    extra_stream=s_x, train_frac=train_frac, tail_stream=tail.get("stream"))
+                    extra_stream=s_x, train_frac=train_frac, tail_stream=tail.get("stream"),
+                    final_grads_announced=tail.get("final_grads_announced", False))
 
     def step_back(self, state):
         """Backward of the proposal sampler (three levels) from the state of step_front()."""

@@ -293,10 +293,11 @@ def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, 
     return outs, saved, (lead, P, spr)
 
 
-def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_arena_grad=True, on_data_grads=None):
+def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_arena_grad=True, on_data_grads=None,
+                          on_grid_grads=None):
     """Backward schedule: per-point `out` VJP, SurfaceLightField and integrated-BRDF data-gradient chains
     (the EnvMap's gradient is exactly zero: 1 - incoming_acc == 0), per-point `mid` VJP (IDE), trunk
-    data-gradient chain, ONE weight-gradient launch for the three stacks, appearance-grid scatter.
+    data-gradient chain, appearance-grid scatter, ONE weight-gradient launch for the three stacks.
     Returns (d_density_feature [P,64], d_normals [P,3], g_arena | None, sinks, sunk).
     `on_data_grads(d_feat, g_nrm)` is called (in stream order) as soon as the gradients that leave the shader towards
     the density field are final, i.e. BEFORE the weight-gradient launch and the appearance-grid scatter: the caller
@@ -337,6 +338,19 @@ def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_a
                                        act_t, views[0], P, [(d_feat, False), (d_enc, False)])
     if on_data_grads is not None:
         on_data_grads(d_feat, g_nrm)
+    # appearance-grid scatter first: it is the large half of the shader's gradients (a data-parallel harness starts that
+    # bucket's all-reduce from `on_grid_grads`, beside the weight-gradient launch)
+    g_arena = None
+    if need_arena_grad:
+        sink = _lib.grad_sink(arena)
+        g_arena = sink if sink is not None else torch.zeros_like(arena)
+        desc = shader.grid._descriptor(shader.grid.tables(shader.grid.views(arena)),
+                                       shader.grid.tables(shader.grid.views(g_arena)))
+        _lib.call("nrc_encode_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(z), _lib.ptr(d_enc), P, None)
+        if sink is not None:
+            g_arena = None
+    if on_grid_grads is not None:
+        on_grid_grads()
     named = {(scope, name): (flat[2 * i], flat[2 * i + 1]) for i, (scope, name) in enumerate(names)}
     sinks, sunk = mlp_chain.resolve_sinks({k: v for k, v in named.items() if k[0] != "EnvMap"})
     wptrs = mlp_chain._Ptrs()
@@ -347,15 +361,6 @@ def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_a
         extra = {0: [mlp_chain.ImgRef(img_db, 2, 2, 4)]} if spec is shader.trunk_chain else None
         layers += mlp_chain.wgrad_layers(spec, act, dy, local, wptrs, extra_head_dy=extra)
     mlp_chain.wgrad_launch(layers, wptrs, P)
-    g_arena = None
-    if need_arena_grad:
-        sink = _lib.grad_sink(arena)
-        g_arena = sink if sink is not None else torch.zeros_like(arena)
-        desc = shader.grid._descriptor(shader.grid.tables(shader.grid.views(arena)),
-                                       shader.grid.tables(shader.grid.views(g_arena)))
-        _lib.call("nrc_encode_bwd", _lib.stream_ptr(), C.byref(desc), _lib.ptr(z), _lib.ptr(d_enc), P, None)
-        if sink is not None:
-            g_arena = None
     return d_feat, g_nrm, g_arena, sinks, sunk
 
 

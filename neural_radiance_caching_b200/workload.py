@@ -259,6 +259,9 @@ class CacheTrainStep:
                 self.final_level_offset = off  # flat_grad[:final_level_offset] = the proposal levels' MLPs and grids
             if i == self.num_sampler_leaves:
                 self.shader_offset = off       # flat_grad[:shader_offset] = sampler grads, [shader_offset:] = shader grads
+                if t is not shader["appearance_grid"]["_arena"]:
+                    raise RuntimeError("the appearance grid must be the shader's first leaf (gradient buckets)")
+                self.shader_grid_end = off + pad(int(t.numel()))
             n = int(t.numel())
             sink = self.flat_grad[off:off + n].view(t.shape)
             _lib.register_grad_sink(t, sink)
@@ -319,25 +322,43 @@ class CacheTrainStep:
                 #   final level (MLP_2 grid + MLP, 47 MB): the only one left at the end of the step.
                 # The overlapped buckets run with few CTAs (they share the SMs with the backward kernels).
                 if self._comm is None:
-                    self._comm = (torch.cuda.Stream(), torch.cuda.Stream())
-                comm, comm_p = self._comm
+                    self._comm = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
+                comm, comm_p, comm_f = self._comm
                 so, fo = self.shader_offset, self.final_level_offset
                 n_overlap = int(os.environ.get("NRC_AR_CTAS_OVERLAP", "32" if self.peer.mode == "multicast" else "74"))
                 three = os.environ.get("NRC_AR_BUCKETS", "3") == "3" and fo > 0
 
-                def shader_bucket():
+                go = self.shader_grid_end      # [so, go) = appearance grid, [go, end) = the stacks' weights
+
+                def grid_bucket():                  # the appearance grid's scatter is done (the stacks' wgrad follows)
                     comm.wait_stream(torch.cuda.current_stream())
-                    with torch.cuda.stream(comm):   # fewer CTAs: it shares the SMs with the sampler's backward
-                        self.allreduce_grads(so, None, channel=1, num_ctas=n_overlap)
+                    with torch.cuda.stream(comm):   # fewer CTAs: it shares the SMs with the backward kernels
+                        self.allreduce_grads(so, go, channel=1, num_ctas=n_overlap)
+
+                def shader_bucket():                # everything of the shader is final: the (small) rest, behind the grid
+                    comm.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(comm):
+                        self.allreduce_grads(go if split_shader else so, None, channel=1, num_ctas=n_overlap)
 
                 def proposal_bucket():              # called on the proposal branch's stream, after its backward
                     comm_p.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(comm_p):
                         self.allreduce_grads(0, fo, channel=2, num_ctas=n_overlap)
 
+                def final_bucket():                 # called on the stream of the final level's backward (engine tail fork)
+                    comm_f.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(comm_f):
+                        self.allreduce_grads(fo, so, channel=0)
+
+                split_shader = three and os.environ.get("NRC_AR_SPLIT_SHADER", "1") == "1"
                 loss = self.engine.step(rays, u01, target_rgb, extra=extra, zero_grad=self.zero_grad,
-                                        on_shader_grads=shader_bucket, on_proposal_grads=proposal_bucket if three else None)
-                self.allreduce_grads(fo if three else 0, so, channel=0)
+                                        on_shader_grads=shader_bucket, on_proposal_grads=proposal_bucket if three else None,
+                                        on_final_grads=final_bucket if three else None,
+                                        on_grid_grads=grid_bucket if split_shader else None)
+                if three and self.engine.final_grads_announced:
+                    torch.cuda.current_stream().wait_stream(comm_f)
+                else:
+                    self.allreduce_grads(fo if three else 0, so, channel=0)
                 torch.cuda.current_stream().wait_stream(comm)
                 if three:
                     torch.cuda.current_stream().wait_stream(comm_p)
