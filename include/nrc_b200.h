@@ -544,6 +544,20 @@ int32_t nrc_render_loss(void* stream, const float* d_values, const float* d_weig
                         const float* d_target, const float* d_mask, int64_t num_rays, int32_t n, float charb_padding,
                         int32_t use_mask, float opaque_weight, float empty_weight, float* d_loss, float* d_out_rgb,
                         float* d_acc, float* d_g_values, float* d_g_weights);
+/* The same tail with the cache shader's per-point `out` stage folded in on both sides (training path of the fused step):
+ * heads / f_raw / slf_raw / env_raw are the raw stack outputs nrc_shader_out_fwd takes (same column meaning and biases),
+ * d_weights [R,n] the final level's weights.  Per ray: out stage of its n samples -> rgb, acc -> data + mask terms ->
+ * VJP of the compositing (d_g_weights [R,n]) -> VJP of the out stage (d_g_heads [P,ldgh] columns 1-9, d_g_f_raw [P,ldgf]
+ * column 0, d_g_slf_raw [P,ldgs] columns 0-2; P = R*n).  d_rgb_samples [P,3] (may be NULL) receives the per-sample colours.
+ * Replaces nrc_shader_out_fwd + nrc_render_loss + nrc_shader_out_bwd (three dependent launches) with one; n <= 128. */
+int32_t nrc_shade_render_loss(void* stream, const float* d_heads, int64_t ldh, const float* d_f_raw, int64_t ldf,
+                              const float* d_slf_raw, int64_t lds, const float* d_env_raw, int64_t lde,
+                              float rgb_max, float diffuse_bias, float light_bias, float brdf_bias,
+                              const float* d_weights, const float* d_bg, const float* d_target, const float* d_mask,
+                              int64_t num_rays, int32_t n, float charb_padding, int32_t use_mask,
+                              float opaque_weight, float empty_weight, float* d_loss, float* d_rgb_samples,
+                              float* d_out_rgb, float* d_acc, float* d_g_weights, float* d_g_heads, int64_t ldgh,
+                              float* d_g_f_raw, int64_t ldgf, float* d_g_slf_raw, int64_t ldgs);
 /* Data term: loss += mean Charbonnier(linear_to_srgb(rgb) - target) (accumulated), d_g_rgb [R,3] written. */
 int32_t nrc_charb_srgb_loss(void* stream, const float* d_rgb, const float* d_target, int64_t num_rays,
                             float charb_padding, float* d_loss, float* d_g_rgb);

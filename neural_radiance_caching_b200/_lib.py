@@ -144,6 +144,8 @@ PROTOTYPES = {
     "nrc_interlevel_loss": [_P, _P, _P, _I32, _P, _P, _I32, _I64, _F, _F, _F, _P, _P, _P],
     "nrc_charb_srgb_loss": [_P, _P, _P, _I64, _F, _P, _P],
     "nrc_render_loss": [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _I32, _F, _F, _P, _P, _P, _P, _P],
+    "nrc_shade_render_loss": [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _F, _F, _F, _F, _P, _P, _P, _P, _I64, _I32, _F, _I32,
+                              _F, _F, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _I64],
     "nrc_cache_loss": [_P, _P, _P, _P, _I32, _P, _I32, _P, _I32, _I64, _F, _F, _P, _P, _P, _P],
     "nrc_pos_enc": [_P, _P, _I64, _I32, _I32, _I32, _I32, _P, _I64],
     "nrc_transient_render_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F, _F, _F, _F, _F, _I32, _F,

@@ -7,6 +7,7 @@
 // Reference: internal/render.py:106-247, internal/stepfun.py:125-250,306-314,
 // internal/math.py:295-341,412-457, internal/sampling.py:326-368,
 // internal/models.py:193-292.
+#include "loss_terms.cuh"
 #include "nrc_common.cuh"
 
 namespace nrc {
@@ -439,24 +440,9 @@ render_loss_kernel(const float* __restrict__ values, const float* __restrict__ w
     const float invR = 1.0f / static_cast<float>(R);
     if (lane < 3) {
       const float x = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
-      const float eps = f32_eps();
-      const float xc = fmaxf(x, eps);
-      const float p512 = powf(xc, 5.0f / 12.0f);
-      const bool lin = x <= 0.0031308f;
-      const float srgb = lin ? (323.0f / 25.0f) * x : (211.0f * p512 - 11.0f) / 200.0f;
-      const float dsrgb = lin ? (323.0f / 25.0f) : (x > eps ? (211.0f / 200.0f) * (5.0f / 12.0f) * p512 / xc : 0.f);
-      const float diff = srgb - target[3 * r + lane];
-      const float ch = sqrtf(diff * diff + charb_padding * charb_padding);
-      const float inv = 1.0f / (3.0f * static_cast<float>(R));
-      g = (diff / ch) * dsrgb * inv;
-      contrib = ch * inv;
+      contrib = charb_srgb_term(x, target[3 * r + lane], charb_padding, 1.0f / (3.0f * static_cast<float>(R)), g);
     } else if (lane == 3 && use_mask) {
-      const float mk = mask ? mask[r] : 1.0f;
-      const float wt = (mk > 0.5f ? opaque_w : empty_w) * invR;
-      const float diff = acc - mk;
-      const float ch = sqrtf(diff * diff + charb_padding * charb_padding);
-      g = wt * diff / ch;
-      contrib = wt * ch;
+      contrib = mask_term(acc, mask ? mask[r] : 1.0f, opaque_w, empty_w, invR, charb_padding, g);
     }
     const float go0 = __shfl_sync(0xffffffffu, g, 0), go1 = __shfl_sync(0xffffffffu, g, 1),
                 go2 = __shfl_sync(0xffffffffu, g, 2);

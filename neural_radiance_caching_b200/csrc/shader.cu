@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 
 #include "ide.cuh"
+#include "loss_terms.cuh"
 #include "tc05.cuh"
 
 namespace nrc {
@@ -230,28 +231,24 @@ shader_mid_bwd_kernel(const __grid_constant__ IdeTable tab, int n_sh_env, const 
 }
 
 // heads columns: 0 roughness, 1-3 ambient irradiance, 4-6 irradiance, 7-9 tint
-__global__ void shader_out_fwd_kernel(const float* __restrict__ heads, int64_t ldh, const float* __restrict__ f_raw,
-                                      int64_t ldf, const float* __restrict__ slf_raw, int64_t lds,
-                                      const float* __restrict__ env_raw, int64_t lde, int64_t P, float rgb_max,
-                                      float diffuse_bias, float light_bias, float brdf_bias, float* __restrict__ rgb,
-                                      float* __restrict__ extras) {
-  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const float* h = heads + p * ldh;
-  const float F = sigmoid_f(f_raw[p * ldf] + brdf_bias);
-  float* e = extras ? extras + p * 22 : nullptr;
+struct ShadeConsts { float rgb_max, diffuse_bias, light_bias, brdf_bias; };
+
+// `out` stage of one point: rgb (and the 22 diagnostic channels when e != nullptr).
+__device__ __forceinline__ void shade_point_fwd(const float* __restrict__ h, float f_raw, const float* __restrict__ slf,
+                                                const float* __restrict__ envr, const ShadeConsts k, float (&rgb)[3], float* e) {
+  const float F = sigmoid_f(f_raw + k.brdf_bias);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float amb_d = fminf(fmaxf(softplus_f(h[1 + c] + diffuse_bias), 0.f), rgb_max);
-    const float ind_d = fminf(fmaxf(softplus_f(h[4 + c] + diffuse_bias), 0.f), rgb_max);
+    const float amb_d = fminf(fmaxf(softplus_f(h[1 + c] + k.diffuse_bias), 0.f), k.rgb_max);
+    const float ind_d = fminf(fmaxf(softplus_f(h[4 + c] + k.diffuse_bias), 0.f), k.rgb_max);
     const float tint = sigmoid_f(h[7 + c]);
-    const float env = fmaxf(softplus_f(env_raw[p * lde + c] + light_bias), 0.f);
-    const float ref = fmaxf(softplus_f(slf_raw[p * lds + c] + light_bias), 0.f);
+    const float env = fmaxf(softplus_f(envr[c] + k.light_bias), 0.f);
+    const float ref = fmaxf(softplus_f(slf[c] + k.light_bias), 0.f);
     const float acc = 1.0f;   // incoming_acc of the IDE-form light field (surface_light_field.py:1046-1069)
-    const float amb_s = fminf(fmaxf(tint * F * (env * (1.0f - acc)), 0.f), rgb_max);
-    const float ind_s = fminf(fmaxf(tint * F * (ref * acc), 0.f), rgb_max);
+    const float amb_s = fminf(fmaxf(tint * F * (env * (1.0f - acc)), 0.f), k.rgb_max);
+    const float ind_s = fminf(fmaxf(tint * F * (ref * acc), 0.f), k.rgb_max);
     const float ambient = amb_d + amb_s, indirect = ind_d + ind_s;
-    rgb[3 * p + c] = ambient + indirect;
+    rgb[c] = ambient + indirect;
     if (e) {
       e[c] = amb_d + ind_d;       // diffuse_rgb
       e[3 + c] = amb_s + ind_s;   // specular_rgb
@@ -266,33 +263,143 @@ __global__ void shader_out_fwd_kernel(const float* __restrict__ heads, int64_t l
 }
 
 // VJP of rgb only (the extras are diagnostics; the cache loss reads rgb).
-__global__ void shader_out_bwd_kernel(const float* __restrict__ heads, int64_t ldh, const float* __restrict__ f_raw,
-                                      int64_t ldf, const float* __restrict__ slf_raw, int64_t lds, int64_t P,
-                                      float rgb_max, float diffuse_bias, float light_bias, float brdf_bias,
-                                      const float* __restrict__ g_rgb, float* __restrict__ g_heads, int64_t ldgh,
-                                      float* __restrict__ g_f, int64_t ldgf, float* __restrict__ g_slf, int64_t ldgs) {
-  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const float* h = heads + p * ldh;
-  const float F = sigmoid_f(f_raw[p * ldf] + brdf_bias);
+__device__ __forceinline__ void shade_point_bwd(const float* __restrict__ h, float f_raw, const float* __restrict__ slf,
+                                                const ShadeConsts k, const float (&g_rgb)[3], float* __restrict__ g_heads,
+                                                float* __restrict__ g_f, float* __restrict__ g_slf) {
+  const float F = sigmoid_f(f_raw + k.brdf_bias);
   float gF = 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float g = g_rgb[3 * p + c];
-    const float xa = h[1 + c] + diffuse_bias, xi = h[4 + c] + diffuse_bias;
+    const float g = g_rgb[c];
+    const float xa = h[1 + c] + k.diffuse_bias, xi = h[4 + c] + k.diffuse_bias;
     // clip passes the gradient on the closed interval [0, rgb_max] (jnp.clip / torch.clamp)
-    g_heads[p * ldgh + 1 + c] = softplus_f(xa) <= rgb_max ? g * sigmoid_f(xa) : 0.f;
-    g_heads[p * ldgh + 4 + c] = softplus_f(xi) <= rgb_max ? g * sigmoid_f(xi) : 0.f;
+    g_heads[1 + c] = softplus_f(xa) <= k.rgb_max ? g * sigmoid_f(xa) : 0.f;
+    g_heads[4 + c] = softplus_f(xi) <= k.rgb_max ? g * sigmoid_f(xi) : 0.f;
     const float tint = sigmoid_f(h[7 + c]);
-    const float xs = slf_raw[p * lds + c] + light_bias;
+    const float xs = slf[c] + k.light_bias;
     const float ref = fmaxf(softplus_f(xs), 0.f);
     const float spec = tint * F * ref;
-    const float gs = (spec >= 0.f && spec <= rgb_max) ? g : 0.f;
-    g_heads[p * ldgh + 7 + c] = gs * F * ref * tint * (1.f - tint);
+    const float gs = (spec >= 0.f && spec <= k.rgb_max) ? g : 0.f;
+    g_heads[7 + c] = gs * F * ref * tint * (1.f - tint);
     gF += gs * tint * ref;
-    g_slf[p * ldgs + c] = gs * tint * F * sigmoid_f(xs);
+    g_slf[c] = gs * tint * F * sigmoid_f(xs);
   }
-  g_f[p * ldgf] = gF * F * (1.f - F);
+  g_f[0] = gF * F * (1.f - F);
+}
+
+__global__ void shader_out_fwd_kernel(const float* __restrict__ heads, int64_t ldh, const float* __restrict__ f_raw,
+                                      int64_t ldf, const float* __restrict__ slf_raw, int64_t lds,
+                                      const float* __restrict__ env_raw, int64_t lde, int64_t P, const ShadeConsts k,
+                                      float* __restrict__ rgb, float* __restrict__ extras) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float v[3];
+  shade_point_fwd(heads + p * ldh, f_raw[p * ldf], slf_raw + p * lds, env_raw + p * lde, k, v, extras ? extras + p * 22 : nullptr);
+  rgb[3 * p] = v[0]; rgb[3 * p + 1] = v[1]; rgb[3 * p + 2] = v[2];
+}
+
+__global__ void shader_out_bwd_kernel(const float* __restrict__ heads, int64_t ldh, const float* __restrict__ f_raw,
+                                      int64_t ldf, const float* __restrict__ slf_raw, int64_t lds, int64_t P,
+                                      const ShadeConsts k, const float* __restrict__ g_rgb, float* __restrict__ g_heads,
+                                      int64_t ldgh, float* __restrict__ g_f, int64_t ldgf, float* __restrict__ g_slf,
+                                      int64_t ldgs) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float g[3] = {g_rgb[3 * p], g_rgb[3 * p + 1], g_rgb[3 * p + 2]};
+  shade_point_bwd(heads + p * ldh, f_raw[p * ldf], slf_raw + p * lds, k, g, g_heads + p * ldgh, g_f + p * ldgf, g_slf + p * ldgs);
+}
+
+// The tail of the cache training step's forward and the head of its backward in ONE launch, one warp per ray:
+// `out` stage of the ray's samples -> volumetric rendering (rgb, acc; internal/render.py:172-224) -> Charbonnier-sRGB data
+// term + mask loss -> VJP of the compositing -> VJP of the `out` stage.  Same expressions and summation order as
+// shader_out_fwd_kernel, render_loss_kernel (ray.cu) and shader_out_bwd_kernel, which it replaces on the training path
+// (three launches in a row on the step's critical path, each a fraction of a wave) and which remain the reference
+// points of the parity tests.  The per-sample colours stay in registers between the two halves (n <= 128).
+constexpr int kShadeLossWarps = 4;
+__global__ void __launch_bounds__(kShadeLossWarps * 32)
+shade_render_loss_kernel(const float* __restrict__ heads, int64_t ldh, const float* __restrict__ f_raw, int64_t ldf,
+                         const float* __restrict__ slf_raw, int64_t lds, const float* __restrict__ env_raw, int64_t lde,
+                         const ShadeConsts k, const float* __restrict__ weights, const float* __restrict__ bg,
+                         const float* __restrict__ target, const float* __restrict__ mask, int64_t R, int n,
+                         float charb_padding, int use_mask, float opaque_w, float empty_w, float* __restrict__ loss,
+                         float* __restrict__ rgb_s, float* __restrict__ out_rgb, float* __restrict__ acc_out,
+                         float* __restrict__ g_weights, float* __restrict__ g_heads, int64_t ldgh, float* __restrict__ g_f,
+                         int64_t ldgf, float* __restrict__ g_slf, int64_t ldgs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * kShadeLossWarps + warp;
+  float contrib = 0.f;
+  if (r < R) {
+    float col[4][3], w[4];
+    float a = 0.f, sc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = lane + 32 * q;
+      w[q] = 0.f;
+      col[q][0] = col[q][1] = col[q][2] = 0.f;
+      if (i < n) {
+        const int64_t p = r * n + i;
+        shade_point_fwd(heads + p * ldh, f_raw[p * ldf], slf_raw + p * lds, env_raw + p * lde, k, col[q], nullptr);
+        w[q] = weights[p];
+        if (rgb_s) { rgb_s[3 * p] = col[q][0]; rgb_s[3 * p + 1] = col[q][1]; rgb_s[3 * p + 2] = col[q][2]; }
+        a += w[q];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sc[c] += w[q] * col[q][c];
+      }
+    }
+    auto wsum = [](float v) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      return v;
+    };
+    const float acc = wsum(a);
+    const float bg_w = fmaxf(0.f, 1.0f - acc);
+    float out[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      out[c] = wsum(sc[c]);
+      if (bg) out[c] += bg_w * bg[3 * r + c];
+    }
+    if (lane < 3) out_rgb[3 * r + lane] = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
+    if (lane == 0 && acc_out) acc_out[r] = acc;
+    float g = 0.f;
+    const float invR = 1.0f / static_cast<float>(R);
+    if (lane < 3) {
+      const float x = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
+      contrib = charb_srgb_term(x, target[3 * r + lane], charb_padding, 1.0f / (3.0f * static_cast<float>(R)), g);
+    } else if (lane == 3 && use_mask) {
+      contrib = mask_term(acc, mask ? mask[r] : 1.0f, opaque_w, empty_w, invR, charb_padding, g);
+    }
+    const float go[3] = {__shfl_sync(0xffffffffu, g, 0), __shfl_sync(0xffffffffu, g, 1), __shfl_sync(0xffffffffu, g, 2)};
+    float gacc = __shfl_sync(0xffffffffu, g, 3);
+    if (bg && (1.0f - acc) > 0.f) {
+      gacc -= go[0] * bg[3 * r];
+      gacc -= go[1] * bg[3 * r + 1];
+      gacc -= go[2] * bg[3 * r + 2];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = lane + 32 * q;
+      if (i < n) {
+        const int64_t p = r * n + i;
+        float gw = gacc;
+        gw += go[0] * col[q][0]; gw += go[1] * col[q][1]; gw += go[2] * col[q][2];
+        g_weights[p] = gw;
+        const float gv[3] = {go[0] * w[q], go[1] * w[q], go[2] * w[q]};
+        shade_point_bwd(heads + p * ldh, f_raw[p * ldf], slf_raw + p * lds, k, gv, g_heads + p * ldgh, g_f + p * ldgf,
+                        g_slf + p * ldgs);
+      }
+    }
+    contrib = wsum(contrib);
+  }
+  __shared__ float part[kShadeLossWarps];
+  if (lane == 0) part[warp] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < kShadeLossWarps; ++q) sum += part[q];
+    atomicAdd(loss, sum);
+  }
 }
 
 // coord.pos_enc (internal/coord.py:298-312): [x, sin(2^j x), sin(2^j x + pi/2)], j = min_deg..max_deg-1
@@ -385,8 +492,8 @@ extern "C" int32_t nrc_shader_out_fwd(void* stream, const float* d_heads, int64_
   if (!d_heads || !d_f_raw || !d_slf_raw || !d_env_raw || !d_rgb) return NRC_E_INVALID_ARG;
   const unsigned grid = static_cast<unsigned>((num_points + 127) / 128);
   shader_out_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_heads, ldh, d_f_raw, ldf, d_slf_raw, lds, d_env_raw, lde, num_points, rgb_max, diffuse_bias, light_bias,
-      brdf_bias, d_rgb, d_extras);
+      d_heads, ldh, d_f_raw, ldf, d_slf_raw, lds, d_env_raw, lde, num_points,
+      nrc::ShadeConsts{rgb_max, diffuse_bias, light_bias, brdf_bias}, d_rgb, d_extras);
   return check_launch();
 }
 
@@ -401,7 +508,28 @@ extern "C" int32_t nrc_shader_out_bwd(void* stream, const float* d_heads, int64_
     return NRC_E_INVALID_ARG;
   const unsigned grid = static_cast<unsigned>((num_points + 127) / 128);
   shader_out_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_heads, ldh, d_f_raw, ldf, d_slf_raw, lds, num_points, rgb_max, diffuse_bias, light_bias, brdf_bias, d_g_rgb,
-      d_g_heads, ldgh, d_g_f_raw, ldgf, d_g_slf_raw, ldgs);
+      d_heads, ldh, d_f_raw, ldf, d_slf_raw, lds, num_points, nrc::ShadeConsts{rgb_max, diffuse_bias, light_bias, brdf_bias},
+      d_g_rgb, d_g_heads, ldgh, d_g_f_raw, ldgf, d_g_slf_raw, ldgs);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_shade_render_loss(void* stream, const float* d_heads, int64_t ldh, const float* d_f_raw, int64_t ldf,
+                                         const float* d_slf_raw, int64_t lds, const float* d_env_raw, int64_t lde,
+                                         float rgb_max, float diffuse_bias, float light_bias, float brdf_bias,
+                                         const float* d_weights, const float* d_bg, const float* d_target, const float* d_mask,
+                                         int64_t num_rays, int32_t n, float charb_padding, int32_t use_mask,
+                                         float opaque_weight, float empty_weight, float* d_loss, float* d_rgb_samples,
+                                         float* d_out_rgb, float* d_acc, float* d_g_weights, float* d_g_heads, int64_t ldgh,
+                                         float* d_g_f_raw, int64_t ldgf, float* d_g_slf_raw, int64_t ldgs) {
+  if (num_rays < 1 || n < 1 || n > 128 || ldh < 10 || ldf < 1 || lds < 3 || lde < 3 || ldgh < 10 || ldgf < 1 || ldgs < 3)
+    return NRC_E_INVALID_ARG;
+  if (!d_heads || !d_f_raw || !d_slf_raw || !d_env_raw || !d_weights || !d_target || !d_loss || !d_out_rgb || !d_g_weights ||
+      !d_g_heads || !d_g_f_raw || !d_g_slf_raw)
+    return NRC_E_INVALID_ARG;
+  const unsigned grid = static_cast<unsigned>((num_rays + nrc::kShadeLossWarps - 1) / nrc::kShadeLossWarps);
+  nrc::shade_render_loss_kernel<<<grid, nrc::kShadeLossWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_heads, ldh, d_f_raw, ldf, d_slf_raw, lds, d_env_raw, lde, nrc::ShadeConsts{rgb_max, diffuse_bias, light_bias, brdf_bias},
+      d_weights, d_bg, d_target, d_mask, num_rays, n, charb_padding, use_mask, opaque_weight, empty_weight, d_loss,
+      d_rgb_samples, d_out_rgb, d_acc, d_g_weights, d_g_heads, ldgh, d_g_f_raw, ldgf, d_g_slf_raw, ldgs);
   return check_launch();
 }

@@ -58,8 +58,10 @@ class FusedCacheStep:
         self._zero_mask(R, dev)
 
     def _streams(self, n):
-        if self._side is None or len(self._side) < n:
-            self._side = [torch.cuda.Stream() for _ in range(n)]
+        if self._side is None:
+            self._side = []
+        while len(self._side) < n:          # extend, never replace: streams handed out earlier stay valid
+            self._side.append(torch.cuda.Stream())
         return self._side
 
     def _bg_ones(self, R, dev):
@@ -344,21 +346,36 @@ class FusedCacheStep:
         if self.concurrent:
             main.wait_stream(s_pack)
             main.wait_stream(s_enc)
+        fuse_out = os.environ.get("NRC_FUSE_OUT", "1") == "1"
         outs, saved, meta = nerf.shader_fused_forward(
             shader, names, sflat, rays["viewdirs"], L2["means"], L2["feat"].reshape(R, L2["n"], 64),
             normals_pred.reshape(R, L2["n"], 3), app_arena, True, packed=packed, encoded=encoded, env_stream=s_env,
-            want_bottleneck=False)
-        rgb_s = outs[0].reshape(R, L2["n"], 3)
+            want_bottleneck=False, defer_out=fuse_out)
         bg = self._bg_ones(R, dev)
-        # volumetric rendering (rgb, acc), data term, mask loss and the compositing VJP: one launch
         out_rgb, acc, dist = new(R, 3), new(R), None
-        gv = new(R, k, 3)
-        g_rgb = g_acc = None
+        g_rgb = g_acc = gv = g_out = None
         mw = self.mask_weights
-        _lib.call("nrc_render_loss", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), _lib.ptr(bg), _lib.ptr(target_rgb), None,
-                  R, k, float(self.charb_padding), 0 if mw is None else 1, 0.0 if mw is None else float(mw[0]),
-                  0.0 if mw is None else float(mw[1]), _lib.ptr(loss), _lib.ptr(out_rgb), _lib.ptr(acc), _lib.ptr(gv),
-                  _lib.ptr(g_w[-1]))
+        if fuse_out:
+            # `out` stage, volumetric rendering (rgb, acc), data term, mask loss, the compositing VJP and the `out`
+            # stage's VJP: one launch, one warp per ray (nrc_shade_render_loss)
+            heads, fbuf, sbuf = saved[3], saved[4], saved[5]
+            ebuf, (rgb_max, d_bias, l_bias, b_bias) = saved[10]
+            rgb_s = new(R, k, 3)
+            g_out = (new(R * k, 16), new(R * k, 16), new(R * k, 16))
+            _lib.call("nrc_shade_render_loss", st(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
+                      _lib.ptr(sbuf), sbuf.shape[1], _lib.ptr(ebuf), ebuf.shape[1], rgb_max, d_bias, l_bias, b_bias,
+                      _lib.ptr(L2["weights"]), _lib.ptr(bg), _lib.ptr(target_rgb), None, R, k, float(self.charb_padding),
+                      0 if mw is None else 1, 0.0 if mw is None else float(mw[0]), 0.0 if mw is None else float(mw[1]),
+                      _lib.ptr(loss), _lib.ptr(rgb_s), _lib.ptr(out_rgb), _lib.ptr(acc), _lib.ptr(g_w[-1]),
+                      _lib.ptr(g_out[0]), 16, _lib.ptr(g_out[1]), 16, _lib.ptr(g_out[2]), 16)
+        else:
+            rgb_s = outs[0].reshape(R, L2["n"], 3)
+            # volumetric rendering (rgb, acc), data term, mask loss and the compositing VJP: one launch
+            gv = new(R, k, 3)
+            _lib.call("nrc_render_loss", st(), _lib.ptr(rgb_s), _lib.ptr(L2["weights"]), _lib.ptr(bg), _lib.ptr(target_rgb), None,
+                      R, k, float(self.charb_padding), 0 if mw is None else 1, 0.0 if mw is None else float(mw[0]),
+                      0.0 if mw is None else float(mw[1]), _lib.ptr(loss), _lib.ptr(out_rgb), _lib.ptr(acc), _lib.ptr(gv),
+                      _lib.ptr(g_w[-1]))
         # The final level's backward needs only the data gradients that leave the shader (d_feat, g_nrm): in the
         # single-graph mode it forks off as soon as the trunk's data-gradient chain is done and runs beside the
         # weight-gradient launch and the appearance-grid scatter instead of behind them (NRC_TAIL_FORK=0: old order).
@@ -385,7 +402,7 @@ class FusedCacheStep:
         use_tail = fork_proposals and self.concurrent and os.environ.get("NRC_TAIL_FORK", "1") == "1"
         d_feat, g_nrm, _, _, _ = nerf.shader_fused_backward(shader, names, sflat, saved, meta, app_arena, gv, True,
                                                             on_data_grads=fork_tail if use_tail else None,
-                                                            on_grid_grads=on_grid_grads)
+                                                            on_grid_grads=on_grid_grads, g_out=g_out)
         if on_shader_grads is not None:
             on_shader_grads()
         if not use_tail:

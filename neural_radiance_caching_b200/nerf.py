@@ -240,11 +240,13 @@ def shader_encode(shader, means, arena):
 
 
 def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, normals, arena, train, packed=None,
-                         encoded=None, env_stream=None, want_bottleneck=True):
+                         encoded=None, env_stream=None, want_bottleneck=True, defer_out=False):
     """Forward schedule of the bf16 cache shader (no autograd): 1 weight pack, contract + appearance-grid
     encode, trunk stack, per-point `mid` stage, integrated-BRDF / EnvMap / SurfaceLightField stacks,
     per-point `out` stage.  `packed` / `encoded` may be supplied by a caller that produced them earlier on
-    another stream; `env_stream` is accepted for compatibility (the EnvMap stack now shares one launch with the integrated-BRDF and SurfaceLightField stacks).  Returns (outputs,
+    another stream; defer_out=True leaves the per-point `out` stage to the caller (the training step folds it into
+    nrc_shade_render_loss: outputs[0:2] are None and saved carries the raw stack outputs + the stage's constants);
+    `env_stream` is accepted for compatibility (the EnvMap stack now shares one launch with the integrated-BRDF and SurfaceLightField stacks).  Returns (outputs,
     saved-for-backward, meta)."""
     lead = means.shape[:-1]
     P = means.numel() // 3
@@ -280,43 +282,52 @@ def shader_fused_forward(shader, names, flat, viewdirs, means, density_feature, 
     (sbuf,), _, act_s = mlp_chain.run_forward(shader.surface_lf.chain, params["SurfaceLightField"],
                                               [Img(img_in, 0, 2, 4), Img(img_in, 2, 2, 4)], views[2], save=train, P=P, batch=batch)
     batch.flush()
-    rgb = torch.empty((P, 3), device=dev, dtype=torch.float32)
-    extras = torch.empty((P, 22), device=dev, dtype=torch.float32)
     lb = float(shader.surface_lf.ambient_rgb_bias)
-    _lib.call("nrc_shader_out_fwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
-              _lib.ptr(sbuf), sbuf.shape[1], _lib.ptr(ebuf), ebuf.shape[1], P, float(shader.rgb_max), -2.0, lb,
-              float(np.log(3.0)), _lib.ptr(rgb), _lib.ptr(extras))
-    outs = (rgb.reshape(lead + (3,)), extras.reshape(lead + (22,)), rough.reshape(lead + (1,)),
+    rgb = extras = None
+    if not defer_out:
+        rgb = torch.empty((P, 3), device=dev, dtype=torch.float32)
+        extras = torch.empty((P, 22), device=dev, dtype=torch.float32)
+        _lib.call("nrc_shader_out_fwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
+                  _lib.ptr(sbuf), sbuf.shape[1], _lib.ptr(ebuf), ebuf.shape[1], P, float(shader.rgb_max), -2.0, lb,
+                  float(np.log(3.0)), _lib.ptr(rgb), _lib.ptr(extras))
+    outs = (rgb.reshape(lead + (3,)) if rgb is not None else None,
+            extras.reshape(lead + (22,)) if extras is not None else None, rough.reshape(lead + (1,)),
             bott.reshape(lead + (128,)) if bott is not None else None, refdirs.reshape(lead + (3,)),
             enc.reshape(lead + (-1,)))
     saved = (z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed)
+    if defer_out:
+        saved = saved + ((ebuf, (float(shader.rgb_max), -2.0, lb, float(np.log(3.0)))),)
     return outs, saved, (lead, P, spr)
 
 
 def shader_fused_backward(shader, names, flat, saved, meta, arena, g_rgb, need_arena_grad=True, on_data_grads=None,
-                          on_grid_grads=None):
+                          on_grid_grads=None, g_out=None):
     """Backward schedule: per-point `out` VJP, SurfaceLightField and integrated-BRDF data-gradient chains
     (the EnvMap's gradient is exactly zero: 1 - incoming_acc == 0), per-point `mid` VJP (IDE), trunk
     data-gradient chain, appearance-grid scatter, ONE weight-gradient launch for the three stacks.
     Returns (d_density_feature [P,64], d_normals [P,3], g_arena | None, sinks, sunk).
     `on_data_grads(d_feat, g_nrm)` is called (in stream order) as soon as the gradients that leave the shader towards
     the density field are final, i.e. BEFORE the weight-gradient launch and the appearance-grid scatter: the caller
-    forks the final sampler level's backward there."""
+    forks the final sampler level's backward there.  g_out = (g_heads, g_f, g_s) [P,16] each: the `out` stage's VJP was
+    already taken by the caller (nrc_shade_render_loss) and g_rgb is ignored."""
     lead, P, spr = meta
-    z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed = saved
+    z, nrm, vd, heads, fbuf, sbuf, act_t, act_b, act_s, packed = saved[:10]
     dev = z.device
     params = _unflatten_shader(names, flat)
     b0, views = 0, []
     for spec in (shader.trunk_chain, shader.brdf_chain, shader.surface_lf.chain, shader.env_map.chain):
         views.append(packed[b0 * (mlp_chain.ATOM_BYTES // 2):])
         b0 += mlp_chain._built(spec).num_chunks
-    g2 = g_rgb.reshape(P, 3).contiguous()
     new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
-    g_heads, g_f, g_s = new(P, 16), new(P, 16), new(P, 16)
     lb = float(shader.surface_lf.ambient_rgb_bias)
-    _lib.call("nrc_shader_out_bwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
-              _lib.ptr(sbuf), sbuf.shape[1], P, float(shader.rgb_max), -2.0, lb, float(np.log(3.0)), _lib.ptr(g2),
-              _lib.ptr(g_heads), 16, _lib.ptr(g_f), 16, _lib.ptr(g_s), 16)
+    if g_out is not None:
+        g_heads, g_f, g_s = g_out
+    else:
+        g2 = g_rgb.reshape(P, 3).contiguous()
+        g_heads, g_f, g_s = new(P, 16), new(P, 16), new(P, 16)
+        _lib.call("nrc_shader_out_bwd", _lib.stream_ptr(), _lib.ptr(heads), heads.shape[1], _lib.ptr(fbuf), fbuf.shape[1],
+                  _lib.ptr(sbuf), sbuf.shape[1], P, float(shader.rgb_max), -2.0, lb, float(np.log(3.0)), _lib.ptr(g2),
+                  _lib.ptr(g_heads), 16, _lib.ptr(g_f), 16, _lib.ptr(g_s), 16)
     # d(bottleneck) leaves the SurfaceLightField and integrated-BRDF gradient chains as bf16 atoms (two images; the
     # trunk's gradient chain takes their SUM as its upstream gradient: dX and dW are linear in dY)
     Img = mlp_chain.ImgRef

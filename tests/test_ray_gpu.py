@@ -229,3 +229,50 @@ def test_render_loss_fused(cuda_device, use_mask):
     assert rel_err(gw_f, gw_r) <= 1e-6
     lib = _lib.load()
     assert lib.nrc_render_loss(None, None, None, None, None, None, 4, 8, pad, 0, 0.0, 0.0, None, None, None, None, None) == -1
+
+
+@pytest.mark.parametrize("n,use_mask", [(32, True), (100, False)])
+def test_shade_render_loss_fused(cuda_device, n, use_mask):
+    """nrc_shade_render_loss (the shader's `out` stage + rendering + losses + both VJPs in one launch) against the three
+    launches it replaces in the training step (nrc_shader_out_fwd -> nrc_render_loss -> nrc_shader_out_bwd), which are
+    held to the oracle elsewhere: per-sample colours, rgb and acc bit-identical, loss and gradients to rounding."""
+    g = gen(334 + n)
+    R = 129
+    P = R * n
+    w = f32(g.dirichlet(np.ones(n) * 0.2, size=R) * g.uniform(0, 1.2, size=(R, 1)))
+    w[0] = 0.0
+    heads, fraw, slf, env = (f32(g.normal(size=(P, 16)) * 2.0) for _ in range(4))
+    heads[:n, 1:7] = 40.0                    # clipped diffuse branch (rgb_max)
+    bg, target = f32(g.uniform(size=(R, 3))), f32(g.uniform(size=(R, 3)))
+    d = lambda a: a.to(cuda_device).contiguous()
+    wd, hd, fd, sd, ed, bd, td = d(w), d(heads), d(fraw), d(slf), d(env), d(bg), d(target)
+    new = lambda *shape: torch.zeros(shape, device=cuda_device, dtype=torch.float32)
+    pad, ow, ew = 1e-3, 0.7, 0.3
+    consts = (8.0, -2.0, 0.3, float(np.log(3.0)))
+    st = _lib.stream_ptr
+    # reference sequence
+    rgb_r, loss_r = new(P, 3), new()
+    _lib.call("nrc_shader_out_fwd", st(), _lib.ptr(hd), 16, _lib.ptr(fd), 16, _lib.ptr(sd), 16, _lib.ptr(ed), 16, P, *consts,
+              _lib.ptr(rgb_r), None)
+    out_r, acc_r, gv_r, gw_r = new(R, 3), new(R), new(R, n, 3), new(R, n)
+    _lib.call("nrc_render_loss", st(), _lib.ptr(rgb_r), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(td), None, R, n, pad,
+              1 if use_mask else 0, ow, ew, _lib.ptr(loss_r), _lib.ptr(out_r), _lib.ptr(acc_r), _lib.ptr(gv_r), _lib.ptr(gw_r))
+    gh_r, gf_r, gs_r = new(P, 16), new(P, 16), new(P, 16)
+    _lib.call("nrc_shader_out_bwd", st(), _lib.ptr(hd), 16, _lib.ptr(fd), 16, _lib.ptr(sd), 16, P, *consts, _lib.ptr(gv_r),
+              _lib.ptr(gh_r), 16, _lib.ptr(gf_r), 16, _lib.ptr(gs_r), 16)
+    # fused
+    rgb_f, loss_f, out_f, acc_f, gw_f = new(P, 3), new(), new(R, 3), new(R), new(R, n)
+    gh_f, gf_f, gs_f = new(P, 16), new(P, 16), new(P, 16)
+    _lib.call("nrc_shade_render_loss", st(), _lib.ptr(hd), 16, _lib.ptr(fd), 16, _lib.ptr(sd), 16, _lib.ptr(ed), 16, *consts,
+              _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(td), None, R, n, pad, 1 if use_mask else 0, ow, ew, _lib.ptr(loss_f),
+              _lib.ptr(rgb_f), _lib.ptr(out_f), _lib.ptr(acc_f), _lib.ptr(gw_f), _lib.ptr(gh_f), 16, _lib.ptr(gf_f), 16,
+              _lib.ptr(gs_f), 16)
+    torch.cuda.synchronize()
+    assert torch.equal(rgb_f, rgb_r) and torch.equal(out_f, out_r) and torch.equal(acc_f, acc_r)
+    assert abs(float(loss_f) - float(loss_r)) <= 1e-6 * abs(float(loss_r))
+    assert rel_err(gw_f, gw_r) <= 1e-6
+    for a, b in ((gh_f, gh_r), (gf_f, gf_r), (gs_f, gs_r)):
+        assert rel_err(a, b) <= 1e-6
+    lib = _lib.load()
+    assert lib.nrc_shade_render_loss(None, None, 16, None, 16, None, 16, None, 16, *consts, None, None, None, None, 4, 8, pad, 0,
+                                     0.0, 0.0, None, None, None, None, None, None, 16, None, 16, None, 16) == -1
