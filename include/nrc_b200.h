@@ -230,6 +230,18 @@ int32_t nrc_ray_sample_cast(void* stream, const float* d_t, const float* d_w, co
                             float dom_lo, float dom_hi, const float* d_origins, const float* d_directions,
                             const float* d_near, const float* d_far, int32_t warp_kind, float p, float premult,
                             float* d_sdist_new, float* d_tdist, float* d_means);
+/* nrc_ray_sample_cast with compute_alpha_weights (internal/render.py:134-169) of the level being resampled folded into
+ * its head: the weights of the step function (d_t [R,m+1]) are computed from that level's densities d_density [R,m], its
+ * metric fenceposts d_tdist_prev [R,m+1] and the ray directions - bit-identical to nrc_ray_alpha_weights_fwd - used for
+ * the resampling and written to d_weights_out [R,m] (may be NULL).  Densities and weights make no HBM round trip between
+ * the density query and the resampling. */
+int32_t nrc_ray_weights_sample_cast(void* stream, const float* d_t, const float* d_density, const float* d_tdist_prev,
+                                    int32_t opaque_background, float* d_weights_out, const float* d_u01,
+                                    const float* d_u_base, int64_t num_rays, int32_t m, int32_t n, float anneal,
+                                    float padding, float max_jitter, float dom_lo, float dom_hi,
+                                    const float* d_origins, const float* d_directions, const float* d_near,
+                                    const float* d_far, int32_t warp_kind, float p, float premult,
+                                    float* d_sdist_new, float* d_tdist, float* d_means);
 
 /* render.volumetric_rendering (internal/render.py:172-247): acc, rgb (+bg), C channels
  * composited with `weights`, distance mean and percentiles (5,50,95) from

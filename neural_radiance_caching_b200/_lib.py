@@ -95,6 +95,8 @@ PROTOTYPES = {
     "nrc_ray_sample_intervals": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _F, _F, _P, _P],
     "nrc_ray_cast": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _P, _P],
     "nrc_ray_sample_cast": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _F, _F, _P, _P, _P, _P, _I32, _F, _F, _P, _P, _P],
+    "nrc_ray_weights_sample_cast": [_P, _P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _F, _F, _P, _P, _P, _P, _I32,
+                                    _F, _F, _P, _P, _P],
     "nrc_ray_composite_fwd": [_P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P],
     "nrc_ray_composite_bwd": [_P, _P, _P, _I32, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P],
     "nrc_ray_resample": [_P, _P, _P, _I64, _I32, _I32, _F, _F, _P, _P],

@@ -147,7 +147,11 @@ sample_intervals_kernel(const float* __restrict__ t_in, const float* __restrict_
                         // optional fused cast_rays (nrc_ray_sample_cast): tdist == nullptr -> sampling only
                         const float* __restrict__ origins, const float* __restrict__ directions,
                         const float* __restrict__ near, const float* __restrict__ far, int warp_kind, float p,
-                        float premult, float* __restrict__ tdist, float* __restrict__ means) {
+                        float premult, float* __restrict__ tdist, float* __restrict__ means,
+                        // optional fused compute_alpha_weights of the level being resampled (nrc_ray_weights_sample_cast):
+                        // w_in is ignored, the weights come from (density_prev, tdist_prev) and are written to weights_out
+                        const float* __restrict__ density_prev = nullptr, const float* __restrict__ tdist_prev = nullptr,
+                        int opaque = 0, float* __restrict__ weights_out = nullptr) {
   __shared__ float s_t[kRayWarps][kMaxN + 1];
   __shared__ float s_w[kRayWarps][kMaxN];       // softmax weights
   __shared__ float s_cw[kRayWarps][kMaxN + 1];  // integrated weights
@@ -157,10 +161,35 @@ sample_intervals_kernel(const float* __restrict__ t_in, const float* __restrict_
   const int64_t r = static_cast<int64_t>(blockIdx.x) * kRayWarps + warp;
   if (r >= R) return;
   for (int i = lane; i <= m; i += 32) s_t[warp][i] = t_in[r * (m + 1) + i];
+  if (density_prev) {
+    // same expressions as alpha_weights_fwd_kernel (render.compute_alpha_weights, internal/render.py:134-169); the
+    // weights never leave the SM between the density query and the resampling (they are also written out: the
+    // interlevel loss and the backward pass read them)
+    const float e0 = directions[3 * r], e1 = directions[3 * r + 1], e2 = directions[3 * r + 2];
+    const float dn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1)), __fmul_rn(e2, e2)));
+    const float* tp = tdist_prev + r * (m + 1);
+    for (int i = lane; i < m; i += 32) {
+      float delta = __fmul_rn(__fsub_rn(tp[i + 1], tp[i]), dn);
+      float dd = __fmul_rn(density_prev[r * m + i], fabsf(delta));
+      if (opaque && i == m - 1) dd = INFINITY;
+      s_c[warp][i] = dd;
+    }
+    __syncwarp();
+    window_cumsum(s_c[warp], s_s[warp], m - 1, lane);
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {
+      float a = __fsub_rn(1.0f, expf(-s_c[warp][i]));
+      float tr = expf(-(i == 0 ? 0.f : s_s[warp][i - 1]));
+      const float wgt = __fmul_rn(a, tr);
+      s_cw[warp][i] = wgt;
+      if (weights_out) weights_out[r * m + i] = wgt;
+    }
+    __syncwarp();
+  }
   // logits and softmax (jax.nn.softmax: exp(x - max) / sum)
   float lmax = -INFINITY;
   for (int i = lane; i < m; i += 32) {
-    float lg = __fmul_rn(anneal, safe_log(__fadd_rn(w_in[r * m + i], padding)));
+    float lg = __fmul_rn(anneal, safe_log(__fadd_rn(density_prev ? s_cw[warp][i] : w_in[r * m + i], padding)));
     s_w[warp][i] = lg;
     lmax = fmaxf(lmax, lg);
   }
@@ -588,6 +617,30 @@ extern "C" int32_t nrc_ray_sample_cast(void* stream, const float* d_t, const flo
   sample_intervals_kernel<<<ray_grid(num_rays), kRayThreads, 0, NRC_STREAM>>>(
       d_t, d_w, d_u01, d_u_base, num_rays, m, n, anneal, padding, max_jitter, dom_lo, dom_hi, d_sdist_new, nullptr,
       d_origins, d_directions, d_near, d_far, warp_kind, p, premult, d_tdist, d_means);
+  return check_launch();
+}
+
+// nrc_ray_sample_cast with compute_alpha_weights of the level being resampled folded into its head: the step function's
+// weights come from that level's densities (d_density [R,m], d_tdist_prev [R,m+1], ray directions) and are written to
+// d_weights_out [R,m] (may be NULL).  One launch instead of nrc_ray_alpha_weights_fwd + nrc_ray_sample_cast.
+extern "C" int32_t nrc_ray_weights_sample_cast(void* stream, const float* d_t, const float* d_density, const float* d_tdist_prev,
+                                               int32_t opaque_background, float* d_weights_out, const float* d_u01,
+                                               const float* d_u_base, int64_t num_rays, int32_t m, int32_t n, float anneal,
+                                               float padding, float max_jitter, float dom_lo, float dom_hi,
+                                               const float* d_origins, const float* d_directions, const float* d_near,
+                                               const float* d_far, int32_t warp_kind, float p, float premult,
+                                               float* d_sdist_new, float* d_tdist, float* d_means) {
+  if (num_rays < 0 || m < 1 || m > kMaxN || n <= 1 || n > kMaxN || (warp_kind != 0 && warp_kind != 1))
+    return NRC_E_INVALID_ARG;
+  if (warp_kind == 1 && (p == 1.0f || p == 0.0f || isinf(p))) return NRC_E_UNSUPPORTED;
+  if (num_rays == 0) return NRC_OK;
+  if (!d_t || !d_density || !d_tdist_prev || !d_u01 || !d_u_base || !d_sdist_new || !d_origins || !d_directions || !d_near ||
+      !d_far || !d_tdist)
+    return NRC_E_INVALID_ARG;
+  sample_intervals_kernel<<<ray_grid(num_rays), kRayThreads, 0, NRC_STREAM>>>(
+      d_t, nullptr, d_u01, d_u_base, num_rays, m, n, anneal, padding, max_jitter, dom_lo, dom_hi, d_sdist_new, nullptr,
+      d_origins, d_directions, d_near, d_far, warp_kind, p, premult, d_tdist, d_means, d_density, d_tdist_prev,
+      opaque_background, d_weights_out);
   return check_launch();
 }
 

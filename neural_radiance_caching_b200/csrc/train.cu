@@ -109,9 +109,10 @@ __global__ void cache_loss_kernel(const float* __restrict__ rgb, const float* __
 // stepfun.blur_and_resample_weights (internal/stepfun.py:463-483) over linspline.blur_stepfun /
 // compute_integral / interpolate_integral (internal/linspline.py:187-221, 95-109, 124-141), then the truncated
 // chi-squared loss max(0, w_blur - wp)^2 / (wp + eps).  w_blur is a stop_gradient in the reference, so the
-// only gradient is d loss / d wp, produced here together with the loss.  One warp per ray: lane 0 performs the
-// 2(m+1)-knot merge and the three running sums in the reference's left-to-right order (bitwise reproducible),
-// all lanes evaluate the piecewise quadratic at the proposal fenceposts.
+// only gradient is d loss / d wp, produced here together with the loss.  One warp per ray: the 2(m+1)-knot merge is a
+// rank computation, the three running sums are chunked warp scans carried in fp64 (rounded to fp32 per element: they
+// agree with a left-to-right fp64 sum except at rounding ties), all lanes evaluate the piecewise quadratic at the
+// proposal fenceposts.
 constexpr int kMaxKnots = 2 * (64 + 1);
 
 __device__ __forceinline__ float plus_eps_f(float x) {
@@ -155,31 +156,65 @@ __global__ void interlevel_loss_kernel(const float* __restrict__ t, const float*
     for (int i = lane; i <= m; i += 32)
       s.dy[i] = __fdiv_rn(__fsub_rn(s.pdf[i], i > 0 ? s.pdf[i - 1] : 0.f), __fsub_rn(s.hi[i], s.lo[i]));
     __syncwarp();
-    if (lane == 0) {
-      // merge of the (individually sorted) knots ts_lo, ts_hi; stable: on ties the ts_lo element (lower original
-      // index) comes first, like jnp.argsort.  Running sums in the reference's left-to-right order, every
-      // product / sum individually rounded (no FMA contraction) so they reproduce the fp32 oracle.
-      int il = 0, ih = 0;
-      for (int k = 0; k < K; ++k) {
-        const bool take_lo = il <= m && (ih > m || s.lo[il] <= s.hi[ih]);
-        if (take_lo) { s.tp[k] = s.lo[il]; s.dyp[k] = s.dy[il]; ++il; }
-        else         { s.tp[k] = s.hi[ih]; s.dyp[k] = -s.dy[ih]; ++ih; }
+    // Merge of the (individually sorted) knots ts_lo, ts_hi by rank: every knot's position is its own index plus the
+    // number of knots of the OTHER list in front of it (binary search); stable like jnp.argsort - on ties the ts_lo
+    // element (lower original index) comes first.  (A serial merge + three serial running sums on lane 0 were ~400
+    // dependent shared-memory iterations per ray: 25-70 us per launch on the proposal branch of the step.)
+    for (int i = lane; i <= m; i += 32) {
+      const float vl = s.lo[i], vh = s.hi[i];
+      int a0 = 0, a1 = m + 1;            // number of hi[j] <  lo[i]
+      while (a0 < a1) { const int mid = (a0 + a1) >> 1; if (s.hi[mid] < vl) a0 = mid + 1; else a1 = mid; }
+      int b0 = 0, b1 = m + 1;            // number of lo[j] <= hi[i]
+      while (b0 < b1) { const int mid = (b0 + b1) >> 1; if (s.lo[mid] <= vh) b0 = mid + 1; else b1 = mid; }
+      s.tp[i + a0] = vl; s.dyp[i + a0] = s.dy[i];
+      s.tp[i + b0] = vh; s.dyp[i + b0] = -s.dy[i];
+    }
+    __syncwarp();
+    // yp = [0, cumsum(diff(tp)[:-1] * cumsum(dyp[:K-2])), 0].  The double running sums are ill conditioned
+    // (O(p / halfwidth) terms that cancel back to zero at the last knot): they are carried in fp64 and rounded
+    // to fp32 per element -- what the oracle's torch.cumsum does on the host, and tighter than any fp32 order.
+    // Each lane owns a contiguous chunk; a warp scan of the chunk totals (fp64) gives its starting value.
+    auto excl_scan = [&](double v) {
+      double inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
       }
-      // yp = [0, cumsum(diff(tp)[:-1] * cumsum(dyp[:K-2])), 0].  The double running sums are ill conditioned
-      // (O(p / halfwidth) terms that cancel back to zero at the last knot): they are carried in fp64 and rounded
-      // to fp32 per element -- what the oracle's torch.cumsum does on the host, and tighter than any fp32 order.
-      double cs = 0.0, ys = 0.0;
-      s.yp[0] = 0.f;
-      for (int k = 0; k < K - 2; ++k) {
+      const double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+      return lane ? ex : 0.0;
+    };
+    {
+      const int n1 = K - 2, ch = (n1 + 31) / 32;
+      const int k0 = min(lane * ch, n1), k1 = min(k0 + ch, n1);
+      double tot = 0.0;
+      for (int k = k0; k < k1; ++k) tot += static_cast<double>(s.dyp[k]);
+      double cs = excl_scan(tot);
+      double tot2 = 0.0;
+      for (int k = k0; k < k1; ++k) {
         cs += static_cast<double>(s.dyp[k]);
-        ys += static_cast<double>(__fmul_rn(__fsub_rn(s.tp[k + 1], s.tp[k]), static_cast<float>(cs)));
+        const float term = __fmul_rn(__fsub_rn(s.tp[k + 1], s.tp[k]), static_cast<float>(cs));
+        s.c[k] = term;                       // scratch until the integral coefficients are written below
+        tot2 += static_cast<double>(term);
+      }
+      double ys = excl_scan(tot2);
+      for (int k = k0; k < k1; ++k) {
+        ys += static_cast<double>(s.c[k]);
         s.yp[k + 1] = static_cast<float>(ys);
       }
-      s.yp[K - 1] = 0.f;
+      if (lane == 0) { s.yp[0] = 0.f; s.yp[K - 1] = 0.f; }
+    }
+    __syncwarp();
+    {
       // compute_integral: a, b = yp[:-1], c
       const float e2 = f32_eps() * f32_eps();
-      double cc = 0.0;
-      for (int k = 0; k < K - 1; ++k) {
+      const int n2 = K - 1, ch = (n2 + 31) / 32;
+      const int k0 = min(lane * ch, n2), k1 = min(k0 + ch, n2);
+      double tot = 0.0;
+      for (int k = k0; k < k1; ++k)
+        if (k < K - 2) tot += static_cast<double>(__fmul_rn(__fsub_rn(s.tp[k + 1], s.tp[k]), __fadd_rn(s.yp[k], s.yp[k + 1])));
+      double cc = excl_scan(tot);
+      for (int k = k0; k < k1; ++k) {
         const float dt = __fsub_rn(s.tp[k + 1], s.tp[k]);
         s.a[k] = __fdiv_rn(__fsub_rn(s.yp[k + 1], s.yp[k]), fmaxf(e2, __fmul_rn(2.f, dt)));
         s.c[k] = __fmul_rn(0.5f, static_cast<float>(cc));

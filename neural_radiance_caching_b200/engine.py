@@ -134,12 +134,14 @@ class FusedCacheStep:
         new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
         anneal = sampler.anneal(train_frac)
         sdist, weights = self._initial_step_function(R, dev)
+        prev, fuse_w = None, os.environ.get("NRC_FUSE_WEIGHTS", "1") == "1"
         nl = len(sampler.sampling_strategy)
         lv = None
         for i_level, (i_mlp, _, n) in enumerate(sampler.sampling_strategy):
             mlp, p = sampler.mlps[i_mlp], sp[f"MLP_{i_mlp}"]
             last = i_level == nl - 1
-            sdist, tdist, means = sampler.sample_and_cast(u01[i_level], sdist, weights, n, anneal, rays, False)
+            sdist, tdist, means = sampler.sample_and_cast(u01[i_level], sdist, weights, n, anneal, rays, False, prev=prev)
+            prev = None
             P = R * n
             density = new(P)
             enc_out = new(P, mlp.in_dim) if last else None
@@ -149,8 +151,11 @@ class FusedCacheStep:
             _lib.call("nrc_density_query_fwd", st(), C.byref(enc), C.byref(desc), _lib.ptr(means), P, float(mlp.warp_c),
                       float(mlp.density_bias), int(mlp.bf16), _lib.ptr(density), None, None, None, None, _lib.ptr(enc_out))
             weights = new(R, n)
-            _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(density), _lib.ptr(tdist), _lib.ptr(rays["directions"]),
-                      R, n, int(sampler.opaque_background), _lib.ptr(weights), None, None)
+            if last or not fuse_w:
+                _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(density), _lib.ptr(tdist), _lib.ptr(rays["directions"]),
+                          R, n, int(sampler.opaque_background), _lib.ptr(weights), None, None)
+            else:
+                prev = (density, tdist)
             if last:
                 lv = dict(mlp=mlp, p=p, n=n, tdist=tdist, means=means, density=density, enc_out=enc_out, weights=weights,
                           arena=arena, flat=mlp._flatten(p), desc=geometry._mlp_desc(p, mlp.in_dim, mlp.enable_pred_normals))
@@ -242,11 +247,14 @@ class FusedCacheStep:
         # ------------------------------------------------------------------ forward: proposal sampler
         sdist, weights = self._initial_step_function(R, dev)
         levels = []
+        prev, fuse_w = None, os.environ.get("NRC_FUSE_WEIGHTS", "1") == "1"
         nl = len(sampler.sampling_strategy)
         for i_level, (i_mlp, _, n) in enumerate(sampler.sampling_strategy):
             mlp, p = sampler.mlps[i_mlp], sp[f"MLP_{i_mlp}"]
             last = i_level == nl - 1
-            sdist, tdist, means = sampler.sample_and_cast(u01[i_level], sdist, weights, n, anneal, rays, False)
+            # the previous level's alpha-compositing weights are computed in the head of this level's resampling launch
+            sdist, tdist, means = sampler.sample_and_cast(u01[i_level], sdist, weights, n, anneal, rays, False, prev=prev)
+            prev = None
             P = R * n
             if last:   # the appearance-grid gather only needs the final sample positions
                 if s_enc is not None:
@@ -268,8 +276,11 @@ class FusedCacheStep:
                       float(mlp.density_bias), int(mlp.bf16), _lib.ptr(density), None, _lib.ptr(feat), _lib.ptr(gp),
                       _lib.ptr(rg), _lib.ptr(enc_out))
             weights = new(R, n)
-            _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(density), _lib.ptr(tdist), _lib.ptr(rays["directions"]),
-                      R, n, int(sampler.opaque_background), _lib.ptr(weights), None, None)
+            if last or not fuse_w:
+                _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(density), _lib.ptr(tdist), _lib.ptr(rays["directions"]),
+                          R, n, int(sampler.opaque_background), _lib.ptr(weights), None, None)
+            else:
+                prev = (density, tdist)      # `weights` is filled by the next level's nrc_ray_weights_sample_cast
             levels.append(dict(mlp=mlp, p=p, n=n, sdist=sdist, tdist=tdist, means=means, density=density, enc_out=enc_out,
                                feat=feat, gp=gp, rg=rg, weights=weights, arena=arena, flat=flat, desc=desc))
         L2 = levels[-1]
@@ -526,11 +537,13 @@ class FusedCacheQuery:
         new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
         anneal = sampler.anneal(train_frac)
         sdist, weights, bg_one, bg_zero = self._initial(R, dev)
+        prev, fuse_w = None, os.environ.get("NRC_FUSE_WEIGHTS", "1") == "1"
         nl = len(sampler.sampling_strategy)
         for i_level, (i_mlp, _, n) in enumerate(sampler.sampling_strategy):
             mlp, p = sampler.mlps[i_mlp], sp[f"MLP_{i_mlp}"]
             last = i_level == nl - 1
-            sdist, tdist, means = sampler.sample_and_cast(u01[i_level], sdist, weights, n, anneal, rays, is_secondary)
+            sdist, tdist, means = sampler.sample_and_cast(u01[i_level], sdist, weights, n, anneal, rays, is_secondary, prev=prev)
+            prev = None
             P = R * n
             density = new(P)
             feat = new(P, 64) if last else None
@@ -544,8 +557,11 @@ class FusedCacheQuery:
                           float(mlp.warp_c), float(mlp.density_bias), int(mlp.bf16), _lib.ptr(density), None,
                           _lib.ptr(feat), _lib.ptr(gp), None, None)
             weights = new(R, n)
-            _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(density), _lib.ptr(tdist), _lib.ptr(rays["directions"]),
-                      R, n, int(sampler.opaque_background), _lib.ptr(weights), None, None)
+            if last or not fuse_w:
+                _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(density), _lib.ptr(tdist), _lib.ptr(rays["directions"]),
+                          R, n, int(sampler.opaque_background), _lib.ptr(weights), None, None)
+            else:
+                prev = (density, tdist)      # the next level's resampling launch computes (and stores) these weights
         n_last = n
         inds = None
         if resample:

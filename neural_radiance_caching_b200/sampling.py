@@ -101,10 +101,12 @@ class ProposalVolumeSampler:
                   1 if use_raydist_fn else 0, float(p), float(premult), _lib.ptr(tdist), _lib.ptr(means))
         return tdist, means
 
-    def sample_and_cast(self, u01, sdist, weights, num_samples, anneal, rays, use_raydist_fn):
+    def sample_and_cast(self, u01, sdist, weights, num_samples, anneal, rays, use_raydist_fn, prev=None):
         """One level of the sampler's resampling (sampling.py:340-349: annealed logits -> stepfun.sample_intervals)
         followed by render.cast_rays in ONE launch (nrc_ray_sample_cast): bit-identical to
-        stepfun.sample_intervals_from_weights(...) + self._cast(...).  Returns (sdist_new, tdist, means)."""
+        stepfun.sample_intervals_from_weights(...) + self._cast(...).  Returns (sdist_new, tdist, means).
+        prev = (density [R,m], tdist [R,m+1]) of the level being resampled: its alpha-compositing weights are computed
+        in the same launch (nrc_ray_weights_sample_cast) and written INTO `weights` (an output then)."""
         if num_samples <= 1:
             raise ValueError(f"num_samples must be > 1, is {num_samples}.")
         m = weights.shape[-1]
@@ -120,6 +122,16 @@ class ProposalVolumeSampler:
         tdist = torch.empty_like(sd)
         means = torch.empty((R, num_samples, 3), device=dev, dtype=torch.float32)
         p, premult = self.raydist
+        if prev is not None:
+            density, tdist_prev = prev
+            if not weights.is_contiguous():
+                raise ValueError("weights must be a contiguous output buffer")
+            _lib.call("nrc_ray_weights_sample_cast", _lib.stream_ptr(), _lib.ptr(sdist.contiguous()), _lib.ptr(density),
+                      _lib.ptr(tdist_prev), int(self.opaque_background), _lib.ptr(weights), _lib.ptr(u2.contiguous()),
+                      _lib.ptr(base), R, m, num_samples, float(anneal), float(self.resample_padding), max_jitter, 0.0, 1.0,
+                      _lib.ptr(rays["origins"]), _lib.ptr(rays["directions"]), _lib.ptr(rays["near"]), _lib.ptr(rays["far"]),
+                      1 if use_raydist_fn else 0, float(p), float(premult), _lib.ptr(sd), _lib.ptr(tdist), _lib.ptr(means))
+            return sd, tdist, means
         _lib.call("nrc_ray_sample_cast", _lib.stream_ptr(), _lib.ptr(sdist.contiguous()), _lib.ptr(weights.contiguous()),
                   _lib.ptr(u2.contiguous()), _lib.ptr(base), R, m, num_samples, float(anneal),
                   float(self.resample_padding), max_jitter, 0.0, 1.0, _lib.ptr(rays["origins"]), _lib.ptr(rays["directions"]),

@@ -276,3 +276,36 @@ def test_shade_render_loss_fused(cuda_device, n, use_mask):
     lib = _lib.load()
     assert lib.nrc_shade_render_loss(None, None, 16, None, 16, None, 16, None, 16, *consts, None, None, None, None, 4, 8, pad, 0,
                                      0.0, 0.0, None, None, None, None, None, None, 16, None, 16, None, 16) == -1
+
+
+@pytest.mark.parametrize("m,n,opaque", [(64, 64, 0), (64, 32, 0), (100, 128, 1)])
+def test_weights_sample_cast_fused(cuda_device, m, n, opaque):
+    """nrc_ray_weights_sample_cast == nrc_ray_alpha_weights_fwd followed by nrc_ray_sample_cast, bit for bit (weights,
+    resampled fenceposts, metric distances, means)."""
+    g = gen(900 + m + n)
+    R = 259
+    rays = to_dev(make_rays(g, R), cuda_device)
+    dens = f32(g.gamma(0.5, 4.0, size=(R, m)))
+    dens[0] = 0.0
+    dens[1] = 1e6
+    sd = f32(np.sort(g.uniform(size=(R, m + 1)), axis=-1))
+    sd[:, 0], sd[:, -1] = 0.0, 1.0
+    tprev = _tdist(g, R, m)
+    u = f32(g.uniform(size=(R,)))
+    d = lambda a: a.to(cuda_device).contiguous()
+    dd, sdd, tp, ud = d(dens), d(sd), d(tprev), d(u)
+    base, max_jitter = nstep.u_base(n, cuda_device)
+    new = lambda *shape: torch.empty(shape, device=cuda_device, dtype=torch.float32)
+    st = _lib.stream_ptr
+    common = (R, m, n, 0.7, 0.01, max_jitter, 0.0, 1.0, _lib.ptr(rays["origins"]), _lib.ptr(rays["directions"]),
+              _lib.ptr(rays["near"]), _lib.ptr(rays["far"]), 1, -1.5, 2.0)
+    w_r, s_r, t_r, m_r = new(R, m), new(R, n + 1), new(R, n + 1), new(R, n, 3)
+    _lib.call("nrc_ray_alpha_weights_fwd", st(), _lib.ptr(dd), _lib.ptr(tp), _lib.ptr(rays["directions"]), R, m, opaque,
+              _lib.ptr(w_r), None, None)
+    _lib.call("nrc_ray_sample_cast", st(), _lib.ptr(sdd), _lib.ptr(w_r), _lib.ptr(ud), _lib.ptr(base), *common,
+              _lib.ptr(s_r), _lib.ptr(t_r), _lib.ptr(m_r))
+    w_f, s_f, t_f, m_f = new(R, m), new(R, n + 1), new(R, n + 1), new(R, n, 3)
+    _lib.call("nrc_ray_weights_sample_cast", st(), _lib.ptr(sdd), _lib.ptr(dd), _lib.ptr(tp), opaque, _lib.ptr(w_f), _lib.ptr(ud),
+              _lib.ptr(base), *common, _lib.ptr(s_f), _lib.ptr(t_f), _lib.ptr(m_f))
+    torch.cuda.synchronize()
+    assert torch.equal(w_f, w_r) and torch.equal(s_f, s_r) and torch.equal(t_f, t_r) and torch.equal(m_f, m_r)
