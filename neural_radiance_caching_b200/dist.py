@@ -99,10 +99,14 @@ class PeerArena:
                       file=sys.stderr)
             return None
 
-    def allreduce_mean_(self, offset=0, count=None, channel=0, num_ctas=0, mode=None):
+    def allreduce_mean_(self, offset=0, count=None, channel=0, num_ctas=0, mode=None, leading_barrier=True,
+                        trailing_barrier=True):
         """Mean over ranks of buf[offset:offset+count] in place, on the current stream.  Concurrent calls (different
         streams) must use different `channel`s (each call uses barrier channels 2*channel and 2*channel+1).
-        `mode` overrides the arena's default kernel for this bucket ('peer' | 'multicast')."""
+        `mode` overrides the arena's default kernel for this bucket ('peer' | 'multicast').
+        leading_barrier=False: the caller has already passed a barrier that covers this range's producers (several
+        ranges behind one barrier); trailing_barrier=False: the caller issues ONE barrier() after all its buckets
+        instead of one per bucket (nothing may read the reduced range before that)."""
         from . import _lib
         count = self.buf.numel() - offset if count is None else count
         if offset % 4 or count % 4:
@@ -110,15 +114,21 @@ class PeerArena:
         mode = mode or self.mode
         if mode == "multicast" and not self.multicast_ptr:
             mode = "peer"
-        self.hdl.barrier(channel=2 * channel)            # every rank's gradients are complete (stream ordered)
+        if leading_barrier:
+            self.hdl.barrier(channel=2 * channel)        # every rank's gradients are complete (stream ordered)
         if mode == "multicast":
             _lib.call("nrc_allreduce_mean_multicast", _lib.stream_ptr(), self.multicast_ptr, int(offset),
                       int(count), self.rank, self.world, int(num_ctas))
         else:
             _lib.call("nrc_allreduce_mean_peer", _lib.stream_ptr(), ctypes.cast(self._peers, ctypes.c_void_p), int(offset),
                       int(count), self.rank, self.world, int(num_ctas))
-        self.hdl.barrier(channel=2 * channel + 1)        # every slice has been written everywhere
+        if trailing_barrier:
+            self.hdl.barrier(channel=2 * channel + 1)    # every slice has been written everywhere
         return self.buf
+
+    def barrier(self, channel=6):
+        """Stream-ordered cross-rank barrier (closes a group of allreduce_mean_(trailing_barrier=False) calls)."""
+        self.hdl.barrier(channel=channel)
 
 
 def gather_tiles(band, height):

@@ -267,7 +267,14 @@ class FusedCacheStep:
             feat = new(P, 64) if last else None
             gp = new(P, 3) if mlp.enable_pred_normals else None
             want_normals = (not mlp.normals_for_filter_only) and not mlp.disable_density_normals
-            rg = new(P, 3) if want_normals else None
+            # The analytic normals (d raw / d means: the query kernel's in-kernel back-propagation + corner re-gather,
+            # half of the final level's launch) are consumed by the geometry branch only: there the query is issued a
+            # second time for that output alone, beside the shader, and the launch on the critical path stays
+            # forward-only.  Measured (profiles/r02_ab_runs.txt): 0.692 vs 0.681 ms - the step is bound by total kernel work, the extra
+            # forward costs more than the shorter critical path gains - so it is OFF by default (NRC_SPLIT_NORMALS=1).
+            defer_rg = (want_normals and last and self.geometry_mults is not None and self.concurrent
+                        and os.environ.get("NRC_SPLIT_NORMALS", "0") == "1")
+            rg = new(P, 3) if (want_normals and not defer_rg) else None
             arena = p["density_grid"]["_arena"]
             enc = mlp.grid._descriptor(mlp.grid.tables(mlp.grid.views(arena)), None)
             flat = mlp._flatten(p)
@@ -282,7 +289,8 @@ class FusedCacheStep:
             else:
                 prev = (density, tdist)      # `weights` is filled by the next level's nrc_ray_weights_sample_cast
             levels.append(dict(mlp=mlp, p=p, n=n, sdist=sdist, tdist=tdist, means=means, density=density, enc_out=enc_out,
-                               feat=feat, gp=gp, rg=rg, weights=weights, arena=arena, flat=flat, desc=desc))
+                               feat=feat, gp=gp, rg=rg, weights=weights, arena=arena, flat=flat, desc=desc, enc=enc,
+                               defer_rg=defer_rg))
         L2 = levels[-1]
         P2 = R * L2["n"]
         normals_pred = new(P2, 3)
@@ -300,6 +308,14 @@ class FusedCacheStep:
         geo, s_geo = None, None
         if self.geometry_mults is not None:
             def geometry_branch():
+                if L2["defer_rg"]:
+                    mlp2 = L2["mlp"]
+                    L2["rg"] = new(P2, 3)
+                    _lib.call("nrc_density_query_fwd", _lib.stream_ptr(), C.byref(L2["enc"]), C.byref(L2["desc"]),
+                              _lib.ptr(L2["means"]), P2, float(mlp2.warp_c), float(mlp2.density_bias), int(mlp2.bf16),
+                              None, None, None, None, _lib.ptr(L2["rg"]), None)
+                    L2["normals"] = new(P2, 3)
+                    _lib.call("nrc_normals_fwd", _lib.stream_ptr(), _lib.ptr(L2["rg"]), P2, _lib.ptr(L2["normals"]))
                 gw_geo = torch.zeros((R, k), device=dev, dtype=torch.float32)
                 gnp_geo = torch.zeros((P2, 3), device=dev, dtype=torch.float32)
                 if self.distortion is not None:

@@ -292,13 +292,13 @@ class CacheTrainStep:
         for lo, hi in self._zero_ranges:
             self.flat_grad[lo:hi].zero_()
 
-    def allreduce_grads(self, lo=0, hi=None, channel=0, num_ctas=0, mode=None):
+    def allreduce_grads(self, lo=0, hi=None, channel=0, num_ctas=0, mode=None, leading_barrier=True, trailing_barrier=True):
         """Mean over ranks of flat_grad[lo:hi] in place on the current stream (the reference's lax.pmean,
         internal/train_utils.py:3132-3136).  Concurrent buckets (different streams) need different channels."""
         from . import dist as _ndist
         hi = self.flat_grad.numel() if hi is None else hi
         if self.peer is not None:
-            self.peer.allreduce_mean_(lo, hi - lo, channel, num_ctas, mode)
+            self.peer.allreduce_mean_(lo, hi - lo, channel, num_ctas, mode, leading_barrier, trailing_barrier)
         else:
             _ndist.allreduce_mean_(self.flat_grad[lo:hi])
 
@@ -330,38 +330,62 @@ class CacheTrainStep:
 
                 go = self.shader_grid_end      # [so, go) = appearance grid, [go, end) = the stacks' weights
 
+                # One trailing barrier for all buckets (nothing reads the reduced gradients before the end of the step)
+                # instead of one per bucket; the stacks' small range shares the final level's leading barrier.
+                lean = os.environ.get("NRC_AR_LEAN", "1") == "1"
+                tb = not lean
+                ev = {}
+
                 def grid_bucket():                  # the appearance grid's scatter is done (the stacks' wgrad follows)
                     comm.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(comm):   # fewer CTAs: it shares the SMs with the backward kernels
-                        self.allreduce_grads(so, go, channel=1, num_ctas=n_overlap)
+                        self.allreduce_grads(so, go, channel=1, num_ctas=n_overlap, trailing_barrier=tb)
 
-                def shader_bucket():                # everything of the shader is final: the (small) rest, behind the grid
+                def shader_bucket():                # everything of the shader is final
+                    if lean and split_shader and "final" in ev:
+                        # the stacks' weights (0.75 MB) ride behind the final level's barrier: both are complete now
+                        comm_f.wait_event(ev["final"])
+                        comm_f.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(comm_f):
+                            self.allreduce_grads(fo, so, channel=0, trailing_barrier=False)
+                            self.allreduce_grads(go, None, channel=0, leading_barrier=False, trailing_barrier=False)
+                        ev["final_done"] = True
+                        return
                     comm.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(comm):
-                        self.allreduce_grads(go if split_shader else so, None, channel=1, num_ctas=n_overlap)
+                        self.allreduce_grads(go if split_shader else so, None, channel=1, num_ctas=n_overlap, trailing_barrier=tb)
 
                 def proposal_bucket():              # called on the proposal branch's stream, after its backward
                     comm_p.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(comm_p):
-                        self.allreduce_grads(0, fo, channel=2, num_ctas=n_overlap)
+                        self.allreduce_grads(0, fo, channel=2, num_ctas=n_overlap, trailing_barrier=tb)
 
                 def final_bucket():                 # called on the stream of the final level's backward (engine tail fork)
+                    if lean and split_shader:       # reduced together with the stacks' range (shader_bucket)
+                        ev["final"] = torch.cuda.Event()
+                        ev["final"].record()
+                        return
                     comm_f.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(comm_f):
-                        self.allreduce_grads(fo, so, channel=0)
+                        self.allreduce_grads(fo, so, channel=0, trailing_barrier=tb)
 
                 split_shader = three and os.environ.get("NRC_AR_SPLIT_SHADER", "1") == "1"
                 loss = self.engine.step(rays, u01, target_rgb, extra=extra, zero_grad=self.zero_grad,
                                         on_shader_grads=shader_bucket, on_proposal_grads=proposal_bucket if three else None,
                                         on_final_grads=final_bucket if three else None,
                                         on_grid_grads=grid_bucket if split_shader else None)
+                cur = torch.cuda.current_stream()
                 if three and self.engine.final_grads_announced:
-                    torch.cuda.current_stream().wait_stream(comm_f)
+                    if lean and split_shader and not ev.get("final_done"):
+                        raise RuntimeError("final level's bucket was announced but not reduced")
+                    cur.wait_stream(comm_f)
                 else:
-                    self.allreduce_grads(fo if three else 0, so, channel=0)
-                torch.cuda.current_stream().wait_stream(comm)
+                    self.allreduce_grads(fo if three else 0, so, channel=0, trailing_barrier=tb)
+                cur.wait_stream(comm)
                 if three:
-                    torch.cuda.current_stream().wait_stream(comm_p)
+                    cur.wait_stream(comm_p)
+                if lean:
+                    self.peer.barrier()
                 return loss
             return self.engine.step(rays, u01, target_rgb, extra=extra, zero_grad=self.zero_grad)
         return self.step_autograd(rays, u01, target_rgb, extra)
