@@ -602,6 +602,8 @@ def roofline(per_kernel, R, pk, pk_kind, bf16, l2=None):
     per_kernel = dict(per_kernel)
     if "nrc_chain_run_multi" in per_kernel:   # the shader stacks run through both entry points: one roofline entry
         per_kernel["nrc_chain_run"] = per_kernel.get("nrc_chain_run", 0.0) + per_kernel.pop("nrc_chain_run_multi")
+    if "nrc_encode_bwd_warped" in per_kernel:  # the density grids' scatters (means in, contraction in the kernel) + the appearance grid's
+        per_kernel["nrc_encode_bwd"] = per_kernel.get("nrc_encode_bwd", 0.0) + per_kernel.pop("nrc_encode_bwd_warped")
     top = max(per_kernel, key=per_kernel.get)
     pts = {0: 64 * R, 1: 64 * R, 2: 32 * R}
     LF = {0: (6, 1), 1: (7, 1), 2: (8, 4)}

@@ -19,3 +19,4 @@ import launch_summary as L
 L.main('$O/${T}_ncu_launches_bf16_1024rays.csv', full=True)" > $O/${T}_launch_shares_bf16_1024rays.txt 2>&1
 python tools/traffic_from_csv.py $O/${T}_ncu_dram_bytes.csv $T > $O/${T}_traffic.log 2>&1
 head -c 400 $O/${T}_bench.json; echo; head -30 $O/${T}_launch_shares_bf16_1024rays.txt
+python tools/timeline.py > $O/${T}_timeline.txt 2>/dev/null; head -1 $O/${T}_timeline.txt
