@@ -544,3 +544,35 @@ def test_temporal_filter_and_transient_integration():
                                                T("ggxt_radiance_in"), T("ggx_smp_indirect_occ"))
     for k in ("radiance_out", "irradiance", "indirect_occ"):
         close(got[k], "ggxt_" + k, 1e-5)
+
+
+# ---- surface-light-field memory variant: oracle.surface_light_field against the reference's own class
+VS = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_slf.npz"))
+
+
+@pytest.mark.parametrize("tag,n,kw", [("slfm", 8, {}), ("slfm1", 1, dict(near=0.07, far=0.13))])
+def test_slf_memory(tag, n, kw):
+    from oracle import surface_light_field as oslf
+    from tests.util import SLF_GRID, slf_mem_params
+    net = oslf.SurfaceLightFieldMemMLP(num_distance_samples=n, grid=dict(SLF_GRID), reflectance_grid=dict(SLF_GRID, bbox_scaling=2.0))
+    assert net.grid.param_names() == list(VS[tag + "_grid_names"])
+    assert net.reflectance_grid.param_names() == list(VS[tag + "_ref_grid_names"])
+    p = slf_mem_params(net)
+    o, d = torch.from_numpy(VS[tag + "_origins"]), torch.from_numpy(VS[tag + "_viewdirs"])
+    res = net(p, o, d, **kw)
+    R = o.shape[0]
+    for k, tol in (("bottleneck", 2e-5), ("dist_net_outputs", 5e-5)):
+        ref = torch.from_numpy(VS[tag + "_" + k]).reshape(R, -1)
+        assert float((res[k] - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max())), k
+    # predict_points on the REFERENCE's own network outputs: a fold of s (floor parity) cannot flip on a 1e-5 input difference
+    raw = torch.from_numpy(VS[tag + "_dist_net_outputs"]).reshape(R, -1)
+    pp = oslf.predict_points(raw, o, d, n, net.distance_near, net.distance_far, kw.get("near", 0.0), kw.get("far", float("inf")))
+    for k, gk, tol in (("points_raw", "points", 2e-6), ("ref_weights", "incoming_weights", 2e-6), ("s_dist", "incoming_s_dist", 2e-6),
+                       ("distances", "incoming_dist", 2e-6), ("env_rgba", "incoming_env_rgba", 2e-6), ("ref_mask", "ref_mask", 0.0),
+                       ("s_distances", "s_distances", 2e-6), ("raw_weights", "raw_weights", 0.0)):
+        ref = torch.from_numpy(VS[tag + "_" + gk]).reshape(pp[k].shape)
+        assert float((pp[k] - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max())), k
+    for k, tol in (("incoming_rgb", 2e-5), ("incoming_ambient_rgb", 2e-5), ("incoming_alpha", 2e-5), ("incoming_weights", 2e-5),
+                   ("incoming_s_dist", 2e-5), ("incoming_dist", 2e-5), ("incoming_env_rgba", 2e-5), ("incoming_acc", 2e-5)):
+        ref = torch.from_numpy(VS[tag + "_" + k]).reshape(res[k].shape)
+        assert float((res[k] - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max())), k

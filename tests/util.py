@@ -84,3 +84,28 @@ def decode_image(img, img_atoms, atom0, ncols, P):
     byte = (tile * img_atoms + atom) * 16384 + (r // 8) * 1024 + (r % 8) * 128 + ((chunk ^ (r % 8)) << 4) + (c % 8) * 2
     vals = flat[(byte // 2).reshape(-1)].reshape(P, ncols)
     return vals.view(torch.bfloat16).to(torch.float32)
+
+
+# ---- surface-light-field memory variant: the closed-form parameters of tests/golden/make_reference_vectors_slf.py
+SLF_GRID = dict(hash_map_size=2 ** 14, max_grid_size=128, num_features=4)
+SLF_TABLE_GAIN = 40.0
+
+
+def slf_dense_params(n_in, n_out, salt, gain=100.0):
+    k = level_table((n_in, n_out), salt) * np.float32(gain * np.sqrt(6.0 / n_in))
+    return {"kernel": torch.from_numpy(k.astype(np.float32)),
+            "bias": torch.from_numpy((level_table((n_out,), salt + 50) * np.float32(10.0)).astype(np.float32))}
+
+
+def slf_mem_params(net):
+    """Parameters of an oracle SurfaceLightFieldMemMLP `net` as the generator assigned them to the reference's class."""
+    p = {}
+    for key, enc, salt0 in (("distance_grid", net.grid, 700), ("reflectance_grid", net.reflectance_grid, 720)):
+        p[key] = {name: torch.from_numpy(level_table(shape, salt0 + i + 1) * np.float32(SLF_TABLE_GAIN))
+                  for i, (name, (_, _, shape)) in enumerate(zip(enc.param_names(), enc.layout))}
+    salts = {"layers_0": 740, "layers_1": 741, "distance_layer_0": 750, "distance_layer_1": 751, "distance_layer_2": 752,
+             "distance_layer_3": 753, "distance_output_layer": 760, "layer_0": 770, "layer_bottleneck": 771,
+             "output_rgba_layer": 780, "output_ambient_rgb_layer": 781}
+    for name, fi, fo in net.layer_shapes():
+        p[name] = slf_dense_params(fi, fo, salts[name], gain=300.0 if name == "distance_output_layer" else 100.0)
+    return p
