@@ -726,6 +726,43 @@ int32_t nrc_ggx_integrate_bwd(void* stream, const float* d_wi, const float* d_wo
                               const float* d_g_irradiance, int64_t num_points, int32_t num_samples,
                               int32_t lobe_kind, float rgb_max, float* d_g_radiance);
 
+/* ------------------- surface-light-field memory variant (second half) ---- */
+/* Constants of BaseSurfaceLightFieldMLP.predict_points (internal/surface_light_field.py:594-780) as `surface_lf_mem` is
+ * configured (internal/models.py:813-833, configs/nerf_ngp_yobo.gin:97-165, ngp_yobo.gin:232-236). */
+typedef struct nrc_slf_points_t {
+  int32_t num_distance_samples; /* n: the distance network emits 8 n + 4 columns */
+  int32_t warp_kind;            /* raydist_fn: 0 identity, 1 math.power_ladder(p, premult) */
+  float distance_near, distance_far; /* the module's own range (ray warps, mask, clip) */
+  float near, far;              /* the call's `near` / `far` keyword arguments (mask only); 0 / +inf by default */
+  float distance_scale, distance_bias;
+  float rgb_premultiplier, rgb_bias, alpha_bias;
+  float warp_p, warp_premult;
+  float ref_warp_c;             /* ref_warp_fn = coord.contract_radius_c; <= 0: identity */
+} nrc_slf_points_t;
+
+/* predict_points for use_voxel_grid = use_sorted_distances = use_point_offsets = False, num_far_samples = 0,
+ * use_env_alpha = True, and the head of __call__ that follows it (:899-913): ref_warp_fn on the points, softmax of the raw
+ * weights, the weighted s-distance, weights * mask * env_alpha.
+ *   d_raw [P, 8n+4] (row stride ld_raw floats): per sample [offset, sigma, -, -, raw_weight, -, -, -], then env rgb (3) and
+ *   env alpha (1);  d_origins, d_refdirs [P,3]
+ *   -> d_points [P,n,3] (warped), d_weights [P,n], d_s_dist [P], d_distances [P,n] (clipped), d_env_rgba [P,4]. */
+int32_t nrc_slf_points_fwd(void* stream, const nrc_slf_points_t* cfg, const float* d_raw, int64_t ld_raw,
+                           const float* d_origins, const float* d_refdirs, int64_t num_points, float* d_points,
+                           float* d_weights, float* d_s_dist, float* d_distances, float* d_env_rgba);
+/* VJP of the above with respect to d_raw (origins and directions are stop-gradient inputs of the light field: models.py:854,
+ * utils.partial_stopgrad_rays).  Upstream gradients may be NULL (= zero).  d_g_raw [P, 8n+4] dense, every column written. */
+int32_t nrc_slf_points_bwd(void* stream, const nrc_slf_points_t* cfg, const float* d_raw, int64_t ld_raw,
+                           const float* d_origins, const float* d_refdirs, int64_t num_points, const float* d_g_points,
+                           const float* d_g_weights, const float* d_g_s_dist, const float* d_g_distances,
+                           const float* d_g_env_rgba, float* d_g_raw);
+/* Weighted feature sum over the predicted points (:981): d_feat [P,n,F], d_weights [P,n] -> d_out [P,F]. */
+int32_t nrc_slf_reduce_fwd(void* stream, const float* d_feat, const float* d_weights, int64_t num_points,
+                           int32_t num_samples, int32_t num_features, float* d_out);
+/* ... and its VJP: d_g_out [P,F] -> d_g_feat [P,n,F], d_g_weights [P,n]. */
+int32_t nrc_slf_reduce_bwd(void* stream, const float* d_feat, const float* d_weights, const float* d_g_out,
+                           int64_t num_points, int32_t num_samples, int32_t num_features, float* d_g_feat,
+                           float* d_g_weights);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,16 @@ class nrc_density_mlp_grad_t(C.Structure):
     ]
 
 
+class nrc_slf_points_t(C.Structure):
+    _fields_ = [
+        ("num_distance_samples", C.c_int32), ("warp_kind", C.c_int32),
+        ("distance_near", C.c_float), ("distance_far", C.c_float), ("near", C.c_float), ("far", C.c_float),
+        ("distance_scale", C.c_float), ("distance_bias", C.c_float),
+        ("rgb_premultiplier", C.c_float), ("rgb_bias", C.c_float), ("alpha_bias", C.c_float),
+        ("warp_p", C.c_float), ("warp_premult", C.c_float), ("ref_warp_c", C.c_float),
+    ]
+
+
 _P = C.c_void_p
 _I32 = C.c_int32
 _I64 = C.c_int64
@@ -157,6 +167,10 @@ PROTOTYPES = {
     "nrc_material_head": [_P, _P, _I64, _I64, _F, _F, _P, _P, _P, _P, _P],
     "nrc_ggx_integrate_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P],
     "nrc_ggx_integrate_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P],
+    "nrc_slf_points_fwd": [_P, C.POINTER(nrc_slf_points_t), _P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P],
+    "nrc_slf_points_bwd": [_P, C.POINTER(nrc_slf_points_t), _P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P],
+    "nrc_slf_reduce_fwd": [_P, _P, _P, _I64, _I32, _I32, _P],
+    "nrc_slf_reduce_bwd": [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P],
 }
 _RESTYPES = {"nrc_error_string": C.c_char_p, "nrc_build_digest": C.c_char_p}
 

@@ -101,6 +101,28 @@ __device__ __forceinline__ void contract_vjp(float c, float x0, float x1, float 
   o0 = a0 / c; o1 = a1 / c; o2 = a2 / c;
 }
 
+// power-ladder ray warp (ray.cu: cast and fused sample + cast; slf.cu: predicted distances)
+__device__ __forceinline__ float power_ladder_fwd(float x, float p, float premult) {
+  // math.power_ladder general branch (internal/math.py:295-316)
+  x = __fmul_rn(x, premult);
+  float xp = fabsf(x);
+  float xs = __fdiv_rn(xp, fmaxf(f32_tiny(), fabsf(p - 1.0f)));
+  float y = __fmul_rn(__fdiv_rn(fabsf(p - 1.0f), p), __fsub_rn(powf(__fadd_rn(xs, 1.0f), p), 1.0f));
+  return x < 0.f ? -y : y;
+}
+__device__ __forceinline__ float power_ladder_inv(float y, float p, float premult) {
+  // math.inv_power_ladder general branch (internal/math.py:319-341)
+  float yp = fabsf(y);
+  float ymax = nextafterf((p - 1.0f) / p, -INFINITY);  // minus_eps(power_ladder_max_output(p)), p < 0
+  if (p >= 0.f) ymax = f32_max();
+  yp = fminf(fmaxf(yp, -ymax), ymax);
+  float ratio = __fdiv_rn(p, fabsf(p - 1.0f));
+  float base = __fadd_rn(__fmul_rn(ratio, yp), 1.0f);
+  float x = __fmul_rn(fabsf(p - 1.0f), __fsub_rn(powf(base, __fdiv_rn(1.0f, p)), 1.0f));
+  x = y < 0.f ? -x : x;
+  return __fdiv_rn(x, premult);
+}
+
 // 16-byte vector reduction (sm_90+): one L2 atomic transaction for four adjacent floats.  The per-CTA weight-gradient
 // flushes put a few hundred CTAs' worth of partial sums onto the SAME few thousand addresses at the same moment, and the
 // L2 serialises same-address atomics: four floats per transaction is four times fewer of them.  addr must be 16-byte

@@ -112,27 +112,7 @@ alpha_weights_bwd_kernel(const float* __restrict__ density, const float* __restr
   }
 }
 
-// power-ladder ray warp (used by the cast below and by the fused sample + cast)
-__device__ __forceinline__ float power_ladder_fwd(float x, float p, float premult) {
-  // math.power_ladder general branch (internal/math.py:295-316)
-  x = __fmul_rn(x, premult);
-  float xp = fabsf(x);
-  float xs = __fdiv_rn(xp, fmaxf(f32_tiny(), fabsf(p - 1.0f)));
-  float y = __fmul_rn(__fdiv_rn(fabsf(p - 1.0f), p), __fsub_rn(powf(__fadd_rn(xs, 1.0f), p), 1.0f));
-  return x < 0.f ? -y : y;
-}
-__device__ __forceinline__ float power_ladder_inv(float y, float p, float premult) {
-  // math.inv_power_ladder general branch (internal/math.py:319-341)
-  float yp = fabsf(y);
-  float ymax = nextafterf((p - 1.0f) / p, -INFINITY);  // minus_eps(power_ladder_max_output(p)), p < 0
-  if (p >= 0.f) ymax = f32_max();
-  yp = fminf(fmaxf(yp, -ymax), ymax);
-  float ratio = __fdiv_rn(p, fabsf(p - 1.0f));
-  float base = __fadd_rn(__fmul_rn(ratio, yp), 1.0f);
-  float x = __fmul_rn(fabsf(p - 1.0f), __fsub_rn(powf(base, __fdiv_rn(1.0f, p)), 1.0f));
-  x = y < 0.f ? -x : x;
-  return __fdiv_rn(x, premult);
-}
+// power-ladder ray warp: power_ladder_fwd / power_ladder_inv live in nrc_common.cuh (shared with slf.cu)
 
 
 // --------------------------------------------------------- sample_intervals --

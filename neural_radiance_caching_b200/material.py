@@ -124,8 +124,16 @@ class MaterialModel:
     to one shaded sample) + environment map behind it -> GGX / Lambert Monte-Carlo integration."""
 
     def __init__(self, cache_model, bf16=True, n_specular=16, n_cosine=8, n_light=8, near_min=0.05, far=2.0,
-                 normal_eps=1e-2, rgb_max=10000.0):
+                 normal_eps=1e-2, rgb_max=10000.0, slf_variate=False, surface_lf_mem=None):
         self.cache = cache_model
+        # MaterialModel.slf_variate (nerf_ngp_yobo.gin:91) with NeRFModel.use_surface_light_field: the light field
+        # `surface_lf_mem` (models.py:813-833; distance_far = Config.env_map_distance) is queried on the SAME secondary rays
+        # and its integral subtracted (material._integrate_slf_variate, material.py:2433-2513)
+        self.slf_variate = slf_variate
+        self.surface_lf_mem = surface_lf_mem
+        if slf_variate and surface_lf_mem is None:
+            from . import surface_light_field
+            self.surface_lf_mem = surface_light_field.SurfaceLightFieldMemMLP(distance_far=far, bf16=bf16)
         # bf16 variant: the cache recursion runs as a hand-ordered launch schedule (engine.FusedCacheQuery)
         from . import engine
         self.fused_query = engine.FusedCacheQuery(cache_model) if bf16 else None
@@ -188,5 +196,26 @@ class MaterialModel:
             diff = render_utils.integrate_reflect_rays(
                 "microfacet_diffuse", False, material,
                 dict(smp_d, radiance_in=radiance_in[:, ns:].contiguous(), indirect_occ=occ[:, ns:]), max_radiance=self.rgb_max)
-        return dict(rgb=spec["radiance_out"] + diff["radiance_out"], specular=spec, diffuse=diff, material=material,
-                    radiance_in=radiance_in, acc=acc.reshape(R, S), rays=rays)
+            out = dict(rgb=spec["radiance_out"] + diff["radiance_out"], specular=spec, diffuse=diff, material=material,
+                       radiance_in=radiance_in, acc=acc.reshape(R, S), rays=rays)
+            if self.slf_variate:
+                # second get_outgoing_radiance call with radiance_cache_fn = surface_lf_fn on the rays and samples of the
+                # first (last_integrated_outputs, material.py:1378-1409): models.get_slf_results per ray, no environment
+                # composite (use_env_map=False, material.py:2246-2257), clamp at zero (:2273)
+                from . import surface_light_field
+                slf = self.surface_lf_mem.get_slf_results(params["SurfaceLightFieldMem"], rays["origins"], rays["viewdirs"])
+                rad_slf = slf["rgb"].reshape(R, S, 3)
+                occ_slf = slf["acc"].reshape(R, S, 1)
+                spec_l = render_utils.integrate_reflect_rays(
+                    "microfacet_specular", False, material,
+                    dict(smp_s, radiance_in=rad_slf[:, :ns].contiguous(), indirect_occ=occ_slf[:, :ns]), max_radiance=self.rgb_max)
+                diff_l = render_utils.integrate_reflect_rays(
+                    "microfacet_diffuse", False, material,
+                    dict(smp_d, radiance_in=rad_slf[:, ns:].contiguous(), indirect_occ=occ_slf[:, ns:]), max_radiance=self.rgb_max)
+                merged = surface_light_field.integrate_slf_variate(
+                    dict(radiance_out=out["rgb"], specular_radiance_out=spec["radiance_out"], diffuse_radiance_out=diff["radiance_out"]),
+                    dict(radiance_out=spec_l["radiance_out"] + diff_l["radiance_out"], specular_radiance_out=spec_l["radiance_out"],
+                         diffuse_radiance_out=diff_l["radiance_out"]))
+                out.update(merged, rgb=merged["radiance_out"], rgb_cache=merged["radiance_out_cache"],
+                           rgb_slf=merged["radiance_out_slf"], radiance_in_slf=rad_slf, acc_slf=occ_slf.reshape(R, S))
+        return out

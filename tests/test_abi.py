@@ -59,15 +59,17 @@ def test_struct_layouts_match_header(lib, tmp_path):
     src = tmp_path / "s.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "nrc_b200.h"\n'
-        "int main(void){ printf(\"%zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(nrc_level_t), sizeof(nrc_encoding_t),"
+        "int main(void){ printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(nrc_level_t), sizeof(nrc_encoding_t),"
         " offsetof(nrc_encoding_t, levels), offsetof(nrc_encoding_t, bbox_span), sizeof(nrc_density_mlp_t),"
-        " offsetof(nrc_density_mlp_t, in_dim), sizeof(nrc_density_mlp_grad_t)); return 0; }\n")
+        " offsetof(nrc_density_mlp_t, in_dim), sizeof(nrc_density_mlp_grad_t), sizeof(nrc_slf_points_t),"
+        " offsetof(nrc_slf_points_t, near), offsetof(nrc_slf_points_t, ref_warp_c)); return 0; }\n")
     exe = tmp_path / "s"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(_lib.nrc_level_t), ctypes.sizeof(_lib.nrc_encoding_t), _lib.nrc_encoding_t.levels.offset,
             _lib.nrc_encoding_t.bbox_span.offset, ctypes.sizeof(_lib.nrc_density_mlp_t),
-            _lib.nrc_density_mlp_t.in_dim.offset, ctypes.sizeof(_lib.nrc_density_mlp_grad_t)]
+            _lib.nrc_density_mlp_t.in_dim.offset, ctypes.sizeof(_lib.nrc_density_mlp_grad_t),
+            ctypes.sizeof(_lib.nrc_slf_points_t), _lib.nrc_slf_points_t.near.offset, _lib.nrc_slf_points_t.ref_warp_c.offset]
     assert got == want
 
 

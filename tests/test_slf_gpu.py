@@ -1,0 +1,253 @@
+"""Surface-light-field MEMORY variant (second half) on the GPU: nrc_slf_points_{fwd,bwd},
+nrc_slf_reduce_{fwd,bwd} and the SurfaceLightFieldMemMLP mirror against (1) the vectors the reference's own class
+produced (tests/golden/reference_slf.npz, internal/surface_light_field.py:594-1069 executed) and (2) the oracle's
+autograd for the gradients; the control-variate combination of material._integrate_slf_variate."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import coord as ocoord
+from oracle import surface_light_field as oslf
+from neural_radiance_caching_b200 import _lib
+from neural_radiance_caching_b200 import surface_light_field as nslf
+from tests.util import SLF_GRID, f32, gen, rel_err, rel_l2, slf_mem_params
+
+pytestmark = pytest.mark.gpu
+
+VS = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_slf.npz"))
+CASES = [("slfm", 8, {}), ("slfm1", 1, dict(near=0.07, far=0.13))]
+
+
+def _nets(n, bf16):
+    kw = dict(num_distance_samples=n, grid=dict(SLF_GRID), reflectance_grid=dict(SLF_GRID, bbox_scaling=2.0))
+    return oslf.SurfaceLightFieldMemMLP(**kw), nslf.SurfaceLightFieldMemMLP(bf16=bf16, **kw)
+
+
+def _close(got, want, tol, what):
+    want = torch.as_tensor(want).reshape(got.shape)
+    err = float((got.detach().cpu() - want).abs().max())
+    assert err <= tol * max(1.0, float(want.abs().max())), (what, err)
+
+
+@pytest.mark.parametrize("tag,n,kw", CASES)
+def test_slf_points_against_reference(cuda_device, tag, n, kw):
+    """The kernel through the C ABI on the REFERENCE's distance-network outputs: predict_points + weight head."""
+    _, net = _nets(n, False)
+    R = VS[tag + "_origins"].shape[0]
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    raw = d(VS[tag + "_dist_net_outputs"].reshape(R, -1))
+    o, v = d(VS[tag + "_origins"]), d(VS[tag + "_viewdirs"])
+    cfg = nslf._points_cfg(net, kw.get("near", 0.0), kw.get("far", float("inf")))
+    pts = torch.empty((R, n, 3), device=cuda_device); w = torch.empty((R, n), device=cuda_device)
+    sd = torch.empty((R, 1), device=cuda_device); dist = torch.empty((R, n), device=cuda_device)
+    env = torch.empty((R, 4), device=cuda_device)
+    _lib.call("nrc_slf_points_fwd", _lib.stream_ptr(), C.byref(cfg), _lib.ptr(raw), raw.shape[1], _lib.ptr(o), _lib.ptr(v), R,
+              _lib.ptr(pts), _lib.ptr(w), _lib.ptr(sd), _lib.ptr(dist), _lib.ptr(env))
+    torch.cuda.synchronize()
+    want_pts = ocoord.contract_radius(torch.from_numpy(VS[tag + "_points"]).reshape(R, n, 3), 2.0)   # ref_warp_fn (:905)
+    _close(pts, want_pts, 2e-6, "points")
+    _close(w, VS[tag + "_incoming_weights"], 2e-6, "weights")
+    _close(sd, VS[tag + "_incoming_s_dist"], 2e-6, "s_dist")
+    _close(dist, VS[tag + "_incoming_dist"], 2e-6, "distances")
+    _close(env, VS[tag + "_incoming_env_rgba"], 2e-6, "env_rgba")
+    assert bool(((w > 0).cpu() == torch.from_numpy(VS[tag + "_ref_mask"]).reshape(R, n).bool()).all())   # the mask, bit for bit
+
+
+@pytest.mark.parametrize("n,warp", [(8, (-1.5, 2.0)), (4, None), (1, (-1.5, 2.0))])
+def test_slf_points_backward(cuda_device, n, warp):
+    """VJP with respect to the network outputs against autograd through the oracle's predict_points (float64 inputs would
+    move the fold; the oracle runs in fp32 like the kernel, the comparison is on the L2 norm)."""
+    g = gen(5100 + n)
+    P, W = 333, 8 * n + 4
+    raw = f32(g.normal(size=(P, W)) * 1.5)
+    o = f32(g.normal(size=(P, 3)) * 1.2)
+    v = f32(g.normal(size=(P, 3))); v = v / v.norm(dim=-1, keepdim=True)
+    ups = [f32(g.normal(size=s)) for s in ((P, n, 3), (P, n), (P, 1), (P, n), (P, 4))]
+    near, far = 0.1, 1.7
+    rw = raw.clone().requires_grad_(True)
+    pp = oslf.predict_points(rw, o, v, n, 5e-2, 2.0, near, far, raydist=warp)
+    loss = sum((a * b).sum() for a, b in zip((pp["points"], pp["ref_weights"], pp["s_dist"], pp["distances"], pp["env_rgba"]), ups))
+    loss.backward()
+    _, net = _nets(n, False)
+    net.raydist = warp
+    cfg = nslf._points_cfg(net, near, far)
+    d = lambda t: t.to(cuda_device)
+    rg = d(raw).requires_grad_(True)
+    outs = nslf._SlfPointsFn.apply(rg, d(o), d(v), cfg)
+    for a, b, name in zip(outs, (pp["points"], pp["ref_weights"], pp["s_dist"], pp["distances"], pp["env_rgba"]),
+                          ("points", "weights", "s_dist", "distances", "env")):
+        assert rel_err(a, b) <= 1e-5, (name, rel_err(a, b))
+    sum((a * d(b)).sum() for a, b in zip(outs, ups)).backward()
+    assert rel_l2(rg.grad, rw.grad) <= 2e-5, rel_l2(rg.grad, rw.grad)
+    # columns the reference never reads get exactly zero
+    unused = [8 * i + c for i in range(n) for c in (2, 3, 5, 6, 7)]
+    assert float(rg.grad[:, unused].abs().max()) == 0.0
+    # NULL upstream gradients are zeros
+    g_raw = torch.full_like(rg, 7.0)
+    _lib.call("nrc_slf_points_bwd", _lib.stream_ptr(), C.byref(cfg), _lib.ptr(rg.detach()), W, _lib.ptr(d(o)), _lib.ptr(d(v)), P,
+              None, None, None, None, None, _lib.ptr(g_raw))
+    assert float(g_raw.abs().max()) == 0.0
+
+
+def test_slf_points_edge_cases(cuda_device):
+    _, net = _nets(8, False)
+    cfg = nslf._points_cfg(net, 0.0, float("inf"))
+    z = torch.zeros((1, 68), device=cuda_device)
+    lib = _lib.load()
+    sp = _lib.stream_ptr()
+    # empty batch: no launch, success
+    assert lib.nrc_slf_points_fwd(sp, C.byref(cfg), _lib.ptr(z), 68, _lib.ptr(z), _lib.ptr(z), 0, _lib.ptr(z), _lib.ptr(z),
+                                  _lib.ptr(z), _lib.ptr(z), _lib.ptr(z)) == 0
+    # row stride shorter than 8 n + 4, null output, too many samples
+    assert lib.nrc_slf_points_fwd(sp, C.byref(cfg), _lib.ptr(z), 67, _lib.ptr(z), _lib.ptr(z), 1, _lib.ptr(z), _lib.ptr(z),
+                                  _lib.ptr(z), _lib.ptr(z), _lib.ptr(z)) == -1
+    assert lib.nrc_slf_points_fwd(sp, C.byref(cfg), _lib.ptr(z), 68, _lib.ptr(z), _lib.ptr(z), 1, None, _lib.ptr(z),
+                                  _lib.ptr(z), _lib.ptr(z), _lib.ptr(z)) == -1
+    cfg.num_distance_samples = 33
+    assert lib.nrc_slf_points_fwd(sp, C.byref(cfg), _lib.ptr(z), 8 * 33 + 4, _lib.ptr(z), _lib.ptr(z), 1, _lib.ptr(z),
+                                  _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), _lib.ptr(z)) == -2
+    # a ragged last CTA and a padded row stride
+    cfg.num_distance_samples = 8
+    g = gen(5200)
+    P = 128 + 37
+    raw = f32(g.normal(size=(P, 72))).to(cuda_device)
+    o = f32(g.normal(size=(P, 3))).to(cuda_device)
+    v = torch.nn.functional.normalize(f32(g.normal(size=(P, 3))), dim=-1).to(cuda_device)
+    outs_a = nslf._SlfPointsFn.apply(raw[:, :68].contiguous(), o, v, cfg)
+    pts = torch.empty((P, 8, 3), device=cuda_device); w = torch.empty((P, 8), device=cuda_device)
+    sd = torch.empty((P, 1), device=cuda_device); dist = torch.empty((P, 8), device=cuda_device)
+    env = torch.empty((P, 4), device=cuda_device)
+    _lib.call("nrc_slf_points_fwd", sp, C.byref(cfg), _lib.ptr(raw), 72, _lib.ptr(o), _lib.ptr(v), P, _lib.ptr(pts), _lib.ptr(w),
+              _lib.ptr(sd), _lib.ptr(dist), _lib.ptr(env))
+    for a, b in zip(outs_a, (pts, w, sd, dist, env)):
+        assert torch.equal(a, b)
+
+
+def test_slf_reduce(cuda_device):
+    g = gen(5300)
+    for P, n, F in ((257, 8, 36), (5, 1, 28), (64, 3, 70)):
+        feat = f32(g.normal(size=(P, n, F))).to(cuda_device).requires_grad_(True)
+        w = f32(g.uniform(size=(P, n))).to(cuda_device).requires_grad_(True)
+        up = f32(g.normal(size=(P, F))).to(cuda_device)
+        out = nslf._SlfReduceFn.apply(feat, w)
+        (out * up).sum().backward()
+        f2, w2 = feat.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+        ref = (f2 * w2[..., None]).sum(dim=-2)
+        (ref * up).sum().backward()
+        assert rel_err(out, ref) <= 1e-6
+        assert rel_err(feat.grad, f2.grad) <= 1e-6 and rel_err(w.grad, w2.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("tag,n,kw", CASES)
+@pytest.mark.parametrize("bf16", [False, True])
+def test_slf_mem_against_reference(cuda_device, tag, n, kw, bf16):
+    """The whole light field (grids, three stacks, the point stage) against the reference's class: fp32 variant 2e-5 on the
+    smooth outputs, bf16 tensor-core variant 2e-2 (north_star's bf16-MLP tolerance)."""
+    onet, net = _nets(n, bf16)
+    p = net.from_oracle(slf_mem_params(onet), cuda_device)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    with torch.no_grad():
+        res = net(p, d(VS[tag + "_origins"]), d(VS[tag + "_viewdirs"]), **kw)
+    torch.cuda.synchronize()
+    # outputs downstream of the fold / the mask can jump when the network output moves: compare them where the mask agrees
+    mask_ref = torch.from_numpy(VS[tag + "_ref_mask"]).reshape(-1, n).bool()
+    same = ((res["incoming_weights"] > 0).cpu() == mask_ref).all(dim=-1)
+    assert float(same.float().mean()) >= (0.9 if bf16 else 1.0)
+    tol = 2e-2 if bf16 else 2e-5
+    for k in ("incoming_rgb", "incoming_ambient_rgb", "incoming_alpha", "incoming_env_rgba", "incoming_acc", "incoming_weights",
+              "incoming_s_dist", "incoming_dist"):
+        got = res[k].cpu()
+        want = torch.from_numpy(VS[tag + "_" + k]).reshape(got.shape)
+        err = float((got[same] - want[same]).abs().max()) / max(1.0, float(want.abs().max()))
+        assert err <= tol, (k, bf16, err)
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_slf_mem_gradients(cuda_device, bf16):
+    """Parameter gradients of the light field (tables of both grids, every Dense) against autograd through the oracle;
+    bf16: against the oracle with bf16-rounded operands (oracle.geometry.dense_bf16), L2 norm."""
+    from oracle import geometry as ogeo
+    g = gen(5400)
+    n, P = 8, 512
+    kw = dict(num_distance_samples=n, grid=dict(SLF_GRID), reflectance_grid=dict(SLF_GRID, bbox_scaling=2.0))
+    onet = oslf.SurfaceLightFieldMemMLP(dense=ogeo.dense_bf16 if bf16 else None, **kw)
+    net = nslf.SurfaceLightFieldMemMLP(bf16=bf16, **kw)
+    po = onet.init(g, table_init_range=0.3)
+    o = f32(g.normal(size=(P, 3)) * 1.0)
+    v = torch.nn.functional.normalize(f32(g.normal(size=(P, 3))), dim=-1)
+    ups = {k: f32(g.normal(size=s)) for k, s in (("incoming_rgb", (P, 3)), ("incoming_acc", (P,)), ("incoming_s_dist", (P, 1)),
+                                                   ("incoming_ambient_rgb", (P, 3)))}
+
+    def leaves(p):
+        out = []
+        for k in sorted(p):
+            for kk in sorted(p[k]):
+                if kk != "_arena":
+                    out.append((k + "/" + kk, p[k][kk]))
+        return out
+
+    for _, t in leaves(po):
+        t.requires_grad_(True)
+    res = onet(po, o, v)
+    sum((res[k] * u).sum() for k, u in ups.items()).backward()
+    pn = net.from_oracle(po, cuda_device)
+    arenas = {k: pn[k]["_arena"].requires_grad_(True) for k in ("distance_grid", "reflectance_grid")}
+    for k in arenas:
+        pn[k] = dict(net.grid.views(arenas[k]) if k == "distance_grid" else net.reflectance_grid.views(arenas[k]), _arena=arenas[k])
+    dense_leaves = [(k, t) for k, t in leaves(pn) if "grid" not in k]
+    for _, t in dense_leaves:
+        t.requires_grad_(True)
+    got = net(pn, o.to(cuda_device), v.to(cuda_device))
+    fwd_tol = 2e-2 if bf16 else 2e-5
+    for k in ups:
+        assert rel_err(got[k], res[k]) <= fwd_tol, (k, rel_err(got[k], res[k]))
+    sum((got[k] * u.to(cuda_device)).sum() for k, u in ups.items()).backward()
+    tol = 5e-2 if bf16 else 2e-4
+    want = dict(leaves(po))
+    for k, t in dense_leaves:
+        assert rel_l2(t.grad, want[k].grad) <= tol, (k, rel_l2(t.grad, want[k].grad))
+    for key, enc in (("distance_grid", onet.grid), ("reflectance_grid", onet.reflectance_grid)):
+        flat = torch.cat([po[key][name].grad.reshape(-1) for name in enc.param_names()])
+        assert rel_l2(arenas[key].grad, flat) <= tol, (key, rel_l2(arenas[key].grad, flat))
+
+
+def test_material_slf_variate(cuda_device):
+    """material._integrate_slf_variate (material.py:2433-2513): the light field is queried on the secondary rays of the cache
+    pass and its integral subtracted; the light-field radiance equals the oracle's on the same rays."""
+    from oracle import material as omat, models as omodels
+    from neural_radiance_caching_b200 import material as nmat, models as nmodels
+    from tests.test_material_gpu import _stage_inputs
+    g = gen(5500)
+    R, K = 16, 32
+    ocache = omodels.NeRFModel()
+    pc = ocache.init(g, table_init_range=0.1, bias_range=0.05)
+    omm = omat.MaterialModel(ocache)
+    po = {"Cache": pc, "Material": omm.material_mlp.init(g), "EnvMap": omm.env_map.init(g)}
+    oslf_net = oslf.SurfaceLightFieldMemMLP(grid=dict(SLF_GRID), reflectance_grid=dict(SLF_GRID, bbox_scaling=2.0))
+    pslf = oslf_net.init(g, table_init_range=0.3)
+    means, viewdirs, normals, draws, aux = _stage_inputs(g, R, K)
+    ncache = nmodels.NeRFModel(bf16=False)
+    slf_net = nslf.SurfaceLightFieldMemMLP(bf16=False, grid=dict(SLF_GRID), reflectance_grid=dict(SLF_GRID, bbox_scaling=2.0))
+    d = lambda t: t.to(cuda_device)
+    ddraws = dict(u=d(draws["u"]), latent=d(draws["latent"]), normal2=d(draws["normal2"]), u01=[d(t) for t in draws["u01"]],
+                  gumbel=d(draws["gumbel"]))
+    pn = {"Cache": ncache.from_oracle(pc, cuda_device), "SurfaceLightFieldMem": slf_net.from_oracle(pslf, cuda_device)}
+    plain = nmat.MaterialModel(ncache, bf16=False)
+    pn["Material"] = plain.material_mlp.from_oracle(po["Material"], cuda_device)
+    pn["EnvMap"] = plain.env_map.from_oracle(po["EnvMap"], cuda_device)
+    variate = nmat.MaterialModel(ncache, bf16=False, slf_variate=True, surface_lf_mem=slf_net)
+    lsr = {k: d(v) for k, v in aux.items()}
+    a = plain.render_chunk(pn, d(means), d(viewdirs), d(normals), ddraws, light_sampler_results=lsr)
+    b = variate.render_chunk(pn, d(means), d(viewdirs), d(normals), ddraws, light_sampler_results=lsr)
+    assert torch.equal(a["rgb"], b["rgb_cache"]) and torch.equal(a["rays"]["origins"], b["rays"]["origins"])
+    assert torch.equal(b["rgb"], b["rgb_cache"] - b["rgb_slf"])
+    assert torch.equal(b["specular_radiance_out"], b["specular_radiance_out_cache"] - b["specular_radiance_out_slf"])
+    want = oslf_net(pslf, b["rays"]["origins"].cpu(), b["rays"]["viewdirs"].cpu())
+    S = variate.num_secondary
+    assert rel_err(b["radiance_in_slf"].reshape(-1, 3), torch.clamp(want["incoming_rgb"], min=0.0)) <= 2e-5
+    assert rel_err(b["acc_slf"].reshape(-1), want["incoming_acc"]) <= 2e-5
+    assert b["rgb_slf"].shape == (R, 3) and bool((b["rgb_slf"] >= 0).all()) and float(b["rgb_slf"].abs().max()) > 0
+    assert b["radiance_in_slf"].shape == (R, S, 3)
