@@ -221,6 +221,15 @@ int32_t nrc_ray_cast(void* stream, const float* d_sdist, const float* d_origins,
                      const float* d_directions, const float* d_near, const float* d_far,
                      int64_t num_rays, int32_t n, int32_t warp_kind, float p, float premult,
                      float* d_tdist, float* d_means);
+/* The COVARIANCES of render.cast_rays (internal/render.py:26-131; `diag=False` at internal/sampling.py:361-368), on request:
+ * the BASELINE configs never read them ('mean' unscented basis), so the sampler's launches do not compute them.
+ *   ray_shape 0 'cone' (conical_frustum_to_gaussian :62-81), 1 'cylinder' (cylinder_to_gaussian :84-103);
+ *   d_tdist [R,n+1] metric fenceposts, d_directions [R,3], d_radii [R] (base radius at distance 1 / cylinder radius);
+ *   -> d_covs [R,n,3,3] (diag = 0) or [R,n,3] (diag = 1), may be NULL; d_means [R,n,3] (may be NULL; needs d_origins) -
+ *      the cone means equal nrc_ray_cast's, the cylinder means (t0+t1)/2 exist only here. */
+int32_t nrc_ray_cast_covs(void* stream, const float* d_tdist, const float* d_origins, const float* d_directions,
+                          const float* d_radii, int64_t num_rays, int32_t n, int32_t ray_shape, int32_t diag,
+                          float* d_covs, float* d_means);
 /* nrc_ray_sample_intervals followed by nrc_ray_cast in ONE launch (the sampler's per-level pair sampling.py:340-349 ->
  * render.cast_rays, internal/render.py:26-131): same arguments and bit-identical outputs; d_sdist_new [R,n+1] are the
  * resampled normalised fenceposts, d_tdist [R,n+1] their metric distances, d_means [R,n,3] (may be NULL) the

@@ -104,6 +104,7 @@ PROTOTYPES = {
     "nrc_ray_alpha_weights_bwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
     "nrc_ray_sample_intervals": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _F, _F, _P, _P],
     "nrc_ray_cast": [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _P, _P],
+    "nrc_ray_cast_covs": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P],
     "nrc_ray_sample_cast": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _F, _F, _P, _P, _P, _P, _I32, _F, _F, _P, _P, _P],
     "nrc_ray_weights_sample_cast": [_P, _P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _I32, _F, _F, _F, _F, _F, _P, _P, _P, _P, _I32,
                                     _F, _F, _P, _P, _P],

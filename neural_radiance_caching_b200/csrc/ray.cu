@@ -309,6 +309,63 @@ __global__ void ray_cast_kernel(const float* __restrict__ sdist, const float* __
   for (int a = 0; a < 3; ++a) mo[a] = __fadd_rn(__fmul_rn(directions[3 * r + a], t_mean), origins[3 * r + a]);
 }
 
+// ------------------------------------------------------------ ray cast: covs --
+// render.cast_rays covariances (internal/render.py:26-103): gaussianize_frustum (cone) or cylinder_to_gaussian, lifted by
+// lift_gaussian.  One thread per (ray, interval); diag: 3 floats, else the full symmetric 3 x 3 (9 floats).  Also the
+// cylinder MEAN (t0 + t1) / 2, which nrc_ray_cast (cone mean) does not produce.
+__global__ void ray_cast_covs_kernel(const float* __restrict__ tdist, const float* __restrict__ origins,
+                                     const float* __restrict__ directions, const float* __restrict__ radii, int64_t R, int n,
+                                     int cylinder, int diag, float* __restrict__ covs, float* __restrict__ means) {
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= R * n) return;
+  const int64_t r = gid / n;
+  const int i = static_cast<int>(gid - r * n);
+  const float t0 = tdist[r * (n + 1) + i], t1 = tdist[r * (n + 1) + i + 1];
+  const float rad = radii[r];
+  float t_mean, t_var, r_var;
+  if (cylinder) {
+    t_mean = (t0 + t1) / 2.0f;                                   // :100-103
+    r_var = rad * rad / 4.0f;
+    const float dd = t1 - t0;
+    t_var = dd * dd / 12.0f;
+  } else {
+    const float s = t0 + t1, d = t1 - t0;                        // :49-59
+    const float eps2 = f32_eps() * f32_eps();
+    const float d2 = d * d, s2 = s * s;
+    const float ratio = d2 / fmaxf(eps2, 3.0f * s2 + d2);
+    t_mean = s * (0.5f + ratio);
+    t_var = (1.0f / 12.0f) * d2 - (1.0f / 15.0f) * (ratio * ratio) * (12.0f * s2 - d2);
+    r_var = (1.0f / 16.0f) * s2 + d2 * (5.0f / 48.0f - (1.0f / 15.0f) * ratio);
+    r_var *= rad * rad;                                          // :79
+  }
+  const float d0 = directions[3 * r], d1 = directions[3 * r + 1], d2v = directions[3 * r + 2];
+  const float dv[3] = {d0, d1, d2v};
+  const float mag = fmaxf(1e-10f, d0 * d0 + d1 * d1 + d2v * d2v);   // :30
+  if (means != nullptr) {
+    float* mo = means + gid * 3;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) mo[a] = __fadd_rn(__fmul_rn(dv[a], t_mean), origins[3 * r + a]);
+  }
+  if (covs == nullptr) return;
+  if (diag) {
+    float* co = covs + gid * 3;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float outer = dv[a] * dv[a];
+      co[a] = t_var * outer + r_var * (1.0f - outer / mag);       // :33-38
+    }
+  } else {
+    float* co = covs + gid * 9;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const float null_outer = (a == b ? 1.0f : 0.0f) - dv[a] * (dv[b] / mag);   // :41-42
+        co[3 * a + b] = t_var * (dv[a] * dv[b]) + r_var * null_outer;              // :43-45
+      }
+  }
+}
+
 // ---------------------------------------------------------------- composite --
 __global__ void __launch_bounds__(kRayThreads)
 composite_fwd_kernel(const float* __restrict__ values, const float* __restrict__ weights, int k,
@@ -635,6 +692,20 @@ extern "C" int32_t nrc_ray_cast(void* stream, const float* d_sdist, const float*
   int64_t total = num_rays * (n + 1);
   ray_cast_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, NRC_STREAM>>>(
       d_sdist, d_origins, d_directions, d_near, d_far, num_rays, n, warp_kind, p, premult, d_tdist, d_means);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_ray_cast_covs(void* stream, const float* d_tdist, const float* d_origins, const float* d_directions,
+                                     const float* d_radii, int64_t num_rays, int32_t n, int32_t ray_shape, int32_t diag,
+                                     float* d_covs, float* d_means) {
+  using namespace nrc;
+  if (!d_tdist || !d_directions || !d_radii || num_rays < 0 || n < 1 || (ray_shape != 0 && ray_shape != 1)) return NRC_E_INVALID_ARG;
+  if (d_means && !d_origins) return NRC_E_INVALID_ARG;
+  if (!d_covs && !d_means) return NRC_E_INVALID_ARG;
+  if (num_rays == 0) return NRC_OK;
+  const int64_t total = num_rays * n;
+  ray_cast_covs_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, NRC_STREAM>>>(
+      d_tdist, d_origins, d_directions, d_radii, num_rays, n, ray_shape, diag != 0, d_covs, d_means);
   return check_launch();
 }
 

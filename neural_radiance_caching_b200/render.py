@@ -47,25 +47,37 @@ def compute_alpha_weights(density, tdist, dirs, opaque_background=False, delta=N
     return _AlphaWeightsFn.apply(density, tdist, dirs, bool(opaque_background))
 
 
-def cast_rays(tdist, origins, directions, radii, ray_shape, diag=True):
-    """Cast cone-shaped rays (internal/render.py:106-131): returns (means, covs).
+def cast_rays(tdist, origins, directions, radii, ray_shape, diag=True, want_covs=True):
+    """Cast cone- or cylinder-shaped rays (internal/render.py:106-131): returns (means, covs) like the reference.
 
-    Only the means feed the encoding under unscented basis 'mean' (SURVEY 8a row 13), so the
-    CUDA path returns covs=None; use ProposalVolumeSampler for the fused s->t + cast path.
-    """
-    if ray_shape != "cone":
-        raise ValueError("ray_shape must be 'cone' (cylinder rays are outside the hot path)")
+    Under unscented basis 'mean' only the means feed the encoding: the sampler's fused launches never
+    compute covariances, and `want_covs=False` skips them here too (covs=None).  With want_covs the covariances come from
+    nrc_ray_cast_covs: [...,n,3] (diag) or [...,n,3,3].  Forward only (the reference's callers on this path stop gradients
+    into the Gaussians' shapes)."""
+    if ray_shape not in ("cone", "cylinder"):
+        raise ValueError("ray_shape must be 'cone' or 'cylinder'")
     n = tdist.shape[-1] - 1
     t2 = _c(tdist.reshape(-1, n + 1))
     R = t2.shape[0]
     o2, d2 = _c(origins.reshape(-1, 3)), _c(directions.reshape(-1, 3))
-    zeros, ones = torch.zeros(R, device=t2.device), torch.ones(R, device=t2.device)
-    t_out = torch.empty_like(t2)
     means = torch.empty((R, n, 3), device=t2.device, dtype=torch.float32)
-    # identity warp: near=0, far=1 => t = s*1 + (1-s)*0
-    _lib.call("nrc_ray_cast", _lib.stream_ptr(), _lib.ptr(t2), _lib.ptr(o2), _lib.ptr(d2), _lib.ptr(zeros),
-              _lib.ptr(ones), R, n, 0, 0.0, 1.0, _lib.ptr(t_out), _lib.ptr(means))
-    return means.reshape(tdist.shape[:-1] + (n, 3)), None
+    cyl = ray_shape == "cylinder"
+    if not cyl:
+        zeros, ones = torch.zeros(R, device=t2.device), torch.ones(R, device=t2.device)
+        t_out = torch.empty_like(t2)
+        # identity warp: near=0, far=1 => t = s*1 + (1-s)*0
+        _lib.call("nrc_ray_cast", _lib.stream_ptr(), _lib.ptr(t2), _lib.ptr(o2), _lib.ptr(d2), _lib.ptr(zeros),
+                  _lib.ptr(ones), R, n, 0, 0.0, 1.0, _lib.ptr(t_out), _lib.ptr(means))
+    covs = None
+    if want_covs or cyl:
+        r2 = _c(radii.reshape(-1).expand(R) if radii.numel() == 1 else radii.reshape(R))
+        if want_covs:
+            covs = torch.empty((R, n, 3) if diag else (R, n, 3, 3), device=t2.device, dtype=torch.float32)
+        _lib.call("nrc_ray_cast_covs", _lib.stream_ptr(), _lib.ptr(t2), _lib.ptr(o2), _lib.ptr(d2), _lib.ptr(r2), R, n,
+                  int(cyl), int(bool(diag)), _lib.ptr(covs), _lib.ptr(means) if cyl else None)
+        if covs is not None:
+            covs = covs.reshape(tdist.shape[:-1] + covs.shape[1:])
+    return means.reshape(tdist.shape[:-1] + (n, 3)), covs
 
 
 class _CompositeFn(torch.autograd.Function):

@@ -140,13 +140,15 @@ class ProposalVolumeSampler:
         return sd, tdist, means
 
     def __call__(self, params, rays, u01_per_level, train_frac=1.0, train=False, use_raydist_fn=False,
-                 normals_all_levels=False, sdist_override=None, weights_only=False):
+                 normals_all_levels=False, sdist_override=None, weights_only=False, return_covs=False):
         """rays: dict of contiguous CUDA tensors origins/directions/viewdirs [R,3], near/far [R,1].
 
         `sdist_override` (list of per-level [R,n+1] tensors, test aid): use these fenceposts
         instead of the resampled ones, so that each level can be checked against the oracle on
         bit-identical sample positions; the resampled fenceposts are still computed and returned
-        as `sdist_sampled`."""
+        as `sdist_sampled`.  `return_covs`: also emit the reference's `covs` entry (render.cast_rays(..., diag=False),
+        sampling.py:361-368) per level from nrc_ray_cast_covs; off by default because no consumer on this path reads it
+        (unscented basis 'mean')."""
         near = rays["near"]
         R = near.shape[0]
         dev = near.device
@@ -200,5 +202,9 @@ class ProposalVolumeSampler:
                 density, tdist, rays["directions"], opaque_background=self.opaque_background)
             res.update(points=means, means=means, tdist=tdist, sdist=sdist, sdist_sampled=sdist_sampled,
                        weights=weights, alphas=alphas, trans=trans)
+            if return_covs:
+                with torch.no_grad():
+                    res["covs"] = render.cast_rays(tdist, rays["origins"], rays["directions"], rays["radii"], "cone",
+                                                   diag=False)[1]
             history.append(res)
         return history

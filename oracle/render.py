@@ -38,12 +38,17 @@ def lift_gaussian(d, t_mean, t_var, r_var, diag):
 
 
 def cast_rays(tdist, origins, directions, radii, ray_shape="cone", diag=True):
-    """internal/render.py:106-131 (cone: :62-81)."""
-    assert ray_shape == "cone"
+    """internal/render.py:106-131 (cone: :62-81, cylinder: :84-103)."""
+    assert ray_shape in ("cone", "cylinder")
     t0 = tdist[..., :-1]
     t1 = tdist[..., 1:]
-    t_mean, t_var, r_var = gaussianize_frustum(t0, t1)
-    r_var = r_var * radii**2
+    if ray_shape == "cone":
+        t_mean, t_var, r_var = gaussianize_frustum(t0, t1)
+        r_var = r_var * radii**2
+    else:
+        t_mean = (t0 + t1) / 2
+        r_var = radii**2 / 4 * torch.ones_like(t_mean)
+        t_var = (t1 - t0) ** 2 / 12
     means, covs = lift_gaussian(directions, t_mean, t_var, r_var, diag)
     means = means + origins[..., None, :]
     return means, covs

@@ -97,7 +97,14 @@ def main():
     origins = f(g.normal(size=(nr, 3)) * 4)
     radii = f(np.full((nr, 1), 5e-4))
     means, covs = rrender.cast_rays(tm, origins, dirs, radii, "cone", diag=False)
-    out.update(render_origins=origins, render_means=means)
+    out.update(render_origins=origins, render_means=means, render_radii=radii, render_covs=covs)
+    # covariances of the other three variants (diagonal; cylinder rays, render.py:84-103), with per-ray radii
+    radii_v = (radii * (1.0 + np.arange(nr, dtype=np.float32)[:, None] * np.float32(37.0))).astype(np.float32)
+    out["render_radii_v"] = radii_v
+    out["render_covs_diag"] = rrender.cast_rays(tm, origins, dirs, radii_v, "cone", diag=True)[1]
+    cyl_m, cyl_c = rrender.cast_rays(tm, origins, dirs, radii_v, "cylinder", diag=False)
+    out.update(render_cyl_means=cyl_m, render_cyl_covs=cyl_c,
+               render_cyl_covs_diag=rrender.cast_rays(tm, origins, dirs, radii_v, "cylinder", diag=True)[1])
     rgbs = f(g.uniform(size=(nr, n, 3)))
     bg = f(g.uniform(size=(nr, 3)))
     vr = rrender.volumetric_rendering(rgbs, wn, wn, tm, bg, True)

@@ -77,6 +77,15 @@ def test_render():
         close(tr, f"render_trans_{op}", 1e-6)
     means, _ = orender.cast_rays(tm, T("render_origins"), dirs, torch.full((64, 1), 5e-4), "cone", diag=False)
     exact(means, "render_means")                                                                     # :26-131
+    # covariances (full and diagonal; cone and cylinder rays with per-ray radii)
+    _, covs = orender.cast_rays(tm, T("render_origins"), dirs, T("render_radii"), "cone", diag=False)
+    close(covs, "render_covs", 1e-6)
+    rv = T("render_radii_v")
+    close(orender.cast_rays(tm, T("render_origins"), dirs, rv, "cone", diag=True)[1], "render_covs_diag", 1e-6)
+    cm, cc = orender.cast_rays(tm, T("render_origins"), dirs, rv, "cylinder", diag=False)
+    close(cm, "render_cyl_means", 1e-6)
+    close(cc, "render_cyl_covs", 1e-6)
+    close(orender.cast_rays(tm, T("render_origins"), dirs, rv, "cylinder", diag=True)[1], "render_cyl_covs_diag", 1e-6)
     vr = orender.volumetric_rendering(T("render_rgbs"), wn, wn, tm, T("render_bg"), True)            # :172-247
     for k in ("rgb", "acc", "distance_mean", "distance_median", "distance_percentile_5", "distance_percentile_95"):
         close(vr[k], "render_vr_" + k, 1e-6)

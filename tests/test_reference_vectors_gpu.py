@@ -74,6 +74,25 @@ def test_cast_rays_means(cuda_device):
     assert rel_err(means, torch.from_numpy(V["render_means"])) <= 1e-6
 
 
+def test_cast_rays_covs(cuda_device):
+    """nrc_ray_cast_covs against render.cast_rays of the reference (render.py:26-131): cone / cylinder, full / diagonal,
+    and the sampler's `covs` entry on request."""
+    from neural_radiance_caching_b200 import render as nrender
+    tm = D("dist_t", cuda_device)
+    o, dirs = D("render_origins", cuda_device), D("render_dirs", cuda_device)
+    m, c = nrender.cast_rays(tm, o, dirs, D("render_radii", cuda_device), "cone", diag=False)
+    assert rel_err(m, torch.from_numpy(V["render_means"])) <= 1e-6 and rel_err(c, torch.from_numpy(V["render_covs"])) <= 2e-6
+    assert torch.equal(c, c.transpose(-1, -2))
+    rv = D("render_radii_v", cuda_device)
+    assert rel_err(nrender.cast_rays(tm, o, dirs, rv, "cone", diag=True)[1], torch.from_numpy(V["render_covs_diag"])) <= 2e-6
+    cm, cc = nrender.cast_rays(tm, o, dirs, rv, "cylinder", diag=False)
+    assert rel_err(cm, torch.from_numpy(V["render_cyl_means"])) <= 1e-6 and rel_err(cc, torch.from_numpy(V["render_cyl_covs"])) <= 2e-6
+    assert rel_err(nrender.cast_rays(tm, o, dirs, rv, "cylinder", diag=True)[1], torch.from_numpy(V["render_cyl_covs_diag"])) <= 2e-6
+    assert nrender.cast_rays(tm, o, dirs, rv, "cone", want_covs=False)[1] is None
+    with pytest.raises(ValueError):
+        nrender.cast_rays(tm, o, dirs, rv, "sphere")
+
+
 def _history(dev):
     return [dict(sdist=D("step_t", dev), weights=D("loss_w0", dev)), dict(sdist=D("blur_tq", dev), weights=D("loss_w1", dev)),
             dict(sdist=D("blur_t", dev), weights=D("dist_w", dev), tdist=D("dist_t", dev))]

@@ -60,10 +60,13 @@ def test_sampler_end_to_end_forward(cuda_device):
     R = 256
     o, n, po, pn, rays, u = _setup(g, R, None, False, cuda_device)  # reference init: smooth field
     ho = o(po, rays, u)
-    hn = n(pn, to_dev(rays, cuda_device), to_dev(u, cuda_device))
+    hn = n(pn, to_dev(rays, cuda_device), to_dev(u, cuda_device), return_covs=True)
     for lvl, (a, b) in enumerate(zip(hn, ho)):
         for k in ("sdist", "tdist", "means", "density", "weights"):
             assert rel_err(a[k], b[k]) <= 1e-4, (lvl, k, rel_err(a[k], b[k]))
+        # the reference's `covs` entry (cast_rays diag=False, sampling.py:361-368), emitted on request
+        assert a["covs"].shape == b["covs"].shape and rel_err(a["covs"], b["covs"]) <= 1e-4, (lvl, rel_err(a["covs"], b["covs"]))
+    assert "covs" not in n(pn, to_dev(rays, cuda_device), to_dev(u, cuda_device))[0]
 
 
 def test_sampler_train_gradients(cuda_device):
