@@ -72,7 +72,9 @@ class EnvMapMLP:
     """Model-level environment map (models.py:801-812 with NeRFModel.env_map_params,
     configs/nerf_ngp_yobo.gin:253-297): pos_enc(viewdirs, 0..4) (27) -> 4 x Dense 256 + ReLU with the input
     re-concatenated after layer 2 -> output_rgba_layer (4) [+ output_ambient_rgb_layer (3)];
-    incoming_rgb = softplus(rgba[:3] + rgb_bias)."""
+    incoming_rgb = softplus(rgba[:3] + rgb_bias).  Under autograd (material-stage training) the parameter gradients come
+    from per-layer GEMMs; the view directions are not differentiated (secondary-ray directions enter the environment map
+    through utils.partial_stopgrad_rays, models.py:380)."""
 
     def __init__(self, deg_view=4, width=256, depth=4, skip=2, rgb_bias=-1.0, bf16=True):
         self.deg_view, self.width, self.depth, self.skip, self.rgb_bias = deg_view, width, depth, skip, rgb_bias
@@ -103,15 +105,20 @@ class EnvMapMLP:
         P = v2.shape[0]
         enc = torch.empty((P, self.in_dim), device=v2.device, dtype=torch.float32)
         _lib.call("nrc_pos_enc", _lib.stream_ptr(), _lib.ptr(v2), P, 3, 0, self.deg_view, 1, _lib.ptr(enc), self.in_dim)
-        if self.bf16:
+        if self.bf16 and not torch.is_grad_enabled():
+            # render path: the whole stack as one tcgen05 chain program
             rgba, amb = mlp_chain.forward_cached(self.chain, p, [enc], self._pack_cache)
         else:
+            # fp32 parity variant, and TRAINING of the bf16 variant: the chain kernel's data- / weight-gradient programs
+            # stop at 128-wide layers, so a 256-wide stack trains through per-layer GEMMs (nrc_dense_{fwd,bwd}: bf16
+            # mma.sync operands, fp32 accumulation) with the same rounding points as the chain program
             x = enc
             for i, n in enumerate(self.names):
-                x = nerf.dense(p[n], x, relu=True)
+                x = nerf.dense(p[n], x, relu=True, bf16=self.bf16)
                 if i % self.skip == 0 and i > 0:
                     x = torch.cat([x, enc], dim=-1)
-            rgba, amb = nerf.dense(p["output_rgba_layer"], x), nerf.dense(p["output_ambient_rgb_layer"], x)
+            rgba = nerf.dense(p["output_rgba_layer"], x, bf16=self.bf16)
+            amb = nerf.dense(p["output_ambient_rgb_layer"], x, bf16=self.bf16)
         rgb = torch.nn.functional.softplus(rgba[:, :3] + self.rgb_bias)
         return dict(incoming_rgb=rgb.reshape(lead + (3,)), incoming_alpha=rgba[:, 3:4].reshape(lead + (1,)),
                     incoming_ambient_raw=amb.reshape(lead + (3,)))

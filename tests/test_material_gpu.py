@@ -152,6 +152,46 @@ def test_material_mlp_and_env_map(cuda_device):
         assert rel_err(got_e, want_e) <= tol, (bf16, rel_err(got_e, want_e))
 
 
+@pytest.mark.parametrize("bf16", [False, True])
+def test_env_map_training_gradients(cuda_device, bf16):
+    """Row 20b training: parameter gradients of the 256-wide environment-map stack (models.py:801-812,
+    nerf_ngp_yobo.gin:253-297) against autograd through the oracle - fp32 1e-4; bf16 against the oracle with bf16-rounded
+    operands (L2 norm: a flipped ReLU mask moves single entries) - and the training forward equals the render-path chain."""
+    from oracle import geometry as ogeo
+    from neural_radiance_caching_b200 import material as nmat
+    from tests.util import rel_l2
+    g = gen(460)
+    oe = omat.EnvMapMLP()
+    pe = oe.init(g)
+    for k in pe:
+        pe[k]["bias"] = f32(g.normal(size=pe[k]["bias"].shape) * 0.1)
+    dirs = g.normal(size=(1111, 3))
+    dirs = f32(dirs / np.linalg.norm(dirs, axis=-1, keepdims=True))
+    up = f32(g.normal(size=(1111, 3)))
+    for k in pe:
+        for kk in pe[k]:
+            pe[k][kk].requires_grad_(True)
+    want = oe(pe, dirs, dense=ogeo.dense_bf16 if bf16 else None)["incoming_rgb"]
+    (want * up).sum().backward()
+    ne = nmat.EnvMapMLP(bf16=bf16)
+    pn = ne.from_oracle(pe, cuda_device)
+    for k in pn:
+        for kk in pn[k]:
+            pn[k][kk].requires_grad_(True)
+    got = ne(pn, dirs.to(cuda_device))["incoming_rgb"]
+    assert rel_err(got, want) <= (2e-2 if bf16 else 1e-5)
+    (got * up.to(cuda_device)).sum().backward()
+    for k in ("layer_0", "layer_1", "layer_2", "layer_bottleneck", "output_rgba_layer"):
+        for kk in ("kernel", "bias"):
+            err = rel_l2(pn[k][kk].grad, pe[k][kk].grad)
+            assert err <= (5e-2 if bf16 else 1e-4), (k, kk, err)
+    assert pn["output_ambient_rgb_layer"]["kernel"].grad is None or float(pn["output_ambient_rgb_layer"]["kernel"].grad.abs().max()) == 0.0
+    if bf16:
+        with torch.no_grad():
+            chain = ne({k: {kk: vv.detach() for kk, vv in v.items()} for k, v in pn.items()}, dirs.to(cuda_device))["incoming_rgb"]
+        assert rel_err(chain, got) <= 5e-3
+
+
 def test_material_stage_chunk(cuda_device):
     """BASELINE config 3 at a small size: 24 surface points x 32 secondary rays through sampler ->
     cache query (resampled) -> env map -> GGX/Lambert integration, fp32 variant vs the oracle."""

@@ -82,7 +82,7 @@ def test_cast_rays_covs(cuda_device):
     o, dirs = D("render_origins", cuda_device), D("render_dirs", cuda_device)
     m, c = nrender.cast_rays(tm, o, dirs, D("render_radii", cuda_device), "cone", diag=False)
     assert rel_err(m, torch.from_numpy(V["render_means"])) <= 1e-6 and rel_err(c, torch.from_numpy(V["render_covs"])) <= 2e-6
-    assert torch.equal(c, c.transpose(-1, -2))
+    assert rel_err(c, c.transpose(-1, -2)) <= 1e-6    # d (d / |d|^2)^T is symmetric up to rounding, in the reference as here
     rv = D("render_radii_v", cuda_device)
     assert rel_err(nrender.cast_rays(tm, o, dirs, rv, "cone", diag=True)[1], torch.from_numpy(V["render_covs_diag"])) <= 2e-6
     cm, cc = nrender.cast_rays(tm, o, dirs, rv, "cylinder", diag=False)
