@@ -633,6 +633,20 @@ int32_t nrc_geometry_losses(void* stream, const float* d_weights, const float* d
                             float predicted_normal_mult, float predicted_normal_reverse_mult, float stopgrad_weight,
                             float* d_loss, float* d_g_weights, float* d_g_normals_pred, float* d_g_normals);
 
+/* VJP of nrc_transient_render_fwd (training the time-resolved cache, config 4): d_g_transient_direct /
+ * d_g_transient_indirect [R,B,C] are the gradients of the two histograms (rgb = direct + indirect + dark_level: add rgb's
+ * gradient to both; either may be NULL = zero) -> d_g_direct_rgbs [R,n,C], d_g_diffuse_raw / d_g_specular [R,n,B,C] (NULL
+ * when that head is absent or its gradient is not wanted), d_g_spec_scale [R,n,C] (may be NULL), d_g_weights [R,n] - all
+ * WRITTEN.  The distances are stop-gradient inputs (internal/sampling.py:353-354).  Same constants as the forward. */
+int32_t nrc_transient_render_bwd(void* stream, const float* d_direct_rgbs, const float* d_diffuse_raw,
+                                 const float* d_specular, const float* d_spec_scale, const float* d_weights,
+                                 const float* d_ray_dists, const float* d_light_dists, const float* d_cam_dists,
+                                 int64_t num_rays, int32_t n, int32_t n_bins, int32_t channels, float exposure_time,
+                                 float shift, float diffuse_bias, float indirect_scale, float bin_zero_threshold_light,
+                                 int32_t light_zero, float light_near, float rgb_max, const float* d_g_transient_direct,
+                                 const float* d_g_transient_indirect, float* d_g_direct_rgbs, float* d_g_diffuse_raw,
+                                 float* d_g_specular, float* d_g_spec_scale, float* d_g_weights);
+
 /* ------------------------------------------- time-resolved path, fused (row 22, config 4) ---- */
 /* nrc_transient_render_fwd with the LAST LAYER of both transient heads inside: the per-sample histograms
  * [R, n, n_bins, C] the reference materialises (internal/nerf.py:1660-1777 get_indirect / transient SurfaceLightField

@@ -163,6 +163,8 @@ PROTOTYPES = {
     "nrc_pos_enc": [_P, _P, _I64, _I32, _I32, _I32, _I32, _P, _I64],
     "nrc_transient_render_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F, _F, _F, _F, _F, _I32, _F,
                                  _F, _F, _P, _P, _P],
+    "nrc_transient_render_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F, _F, _F, _F, _F, _I32, _F,
+                                 _F, _P, _P, _P, _P, _P, _P, _P],
     "nrc_secondary_sample": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _F, _P, _P, _P, _P,
                              _P, _P],
     "nrc_material_head": [_P, _P, _I64, _I64, _F, _F, _P, _P, _P, _P, _P],

@@ -298,6 +298,141 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// VJP of nrc_transient_render_fwd (training of the time-resolved cache): given the gradients of transient_direct and
+// transient_indirect [R, n_bins, C] (rgb = direct + indirect + dark_level: the caller adds rgb's gradient to both),
+//   direct splat   g_direct_rgbs[i] = w_i (w_lo G[i_lo] + w_hi G[i_hi]),  g_w_i += direct_i . (w_lo G[i_lo] + w_hi G[i_hi])
+//   indirect       out[b] = sum_s w_s ((1 - t_s) val_s[b - m_s] + t_s val_s[b - m_s + 1])   (order-1 shift, constant per sample)
+//                  => A_s[bin] = sum over the output bins b whose taps hit `bin` of tap weight x G[b]
+//                     g_val_s[bin] = w_s A_s[bin] [bin valid],   g_w_s += sum_bin,c val_s A_s
+//                  val = clip(softplus(raw + bias) scale, 0, max) + clip(spec_scale specular scale, 0, max)
+// The sample distances are stop-gradient inputs (the sampler detaches its fenceposts, internal/sampling.py:353-354).
+__global__ void transient_direct_bwd_kernel(const float* __restrict__ direct, const float* __restrict__ weights,
+                                            const float* __restrict__ ray_dists, const float* __restrict__ light_dists,
+                                            int64_t R, TransientParams p, const float* __restrict__ g_out,
+                                            float* __restrict__ g_direct, float* __restrict__ g_w) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= R * p.n) return;
+  const int64_t ray = i / p.n;
+  const float d = (light_dists[i] + ray_dists[i]) / p.exposure_time + p.shift / p.exposure_time;
+  const float lo = fmaxf(floorf(d), 0.f), hi = ceilf(d);
+  const float w_hi = d - lo, w_lo = 1.0f - w_hi;
+  const int64_t total = R * p.n_bins;
+  const int64_t i_lo = ray * p.n_bins + static_cast<int64_t>(static_cast<int32_t>(lo));
+  const int64_t i_hi = ray * p.n_bins + static_cast<int64_t>(static_cast<int32_t>(hi));
+  const float w = weights[i];
+  float gw = 0.f;
+  for (int c = 0; c < p.C; ++c) {
+    float a = 0.f;
+    if (g_out) {
+      if (i_lo >= 0 && i_lo < total) a += w_lo * g_out[i_lo * p.C + c];
+      if (i_hi >= 0 && i_hi < total) a += w_hi * g_out[i_hi * p.C + c];
+    }
+    g_direct[i * p.C + c] = w * a;
+    gw += direct[i * p.C + c] * a;
+  }
+  g_w[i] = gw;     // the indirect kernel (launched after this one) adds its part
+}
+
+__global__ void __launch_bounds__(256)
+transient_indirect_bwd_kernel(const float* __restrict__ diffuse_raw, const float* __restrict__ specular,
+                              const float* __restrict__ spec_scale, const float* __restrict__ weights,
+                              const float* __restrict__ ray_dists, const float* __restrict__ light_dists,
+                              const float* __restrict__ cam_dists, int64_t R, TransientParams p,
+                              const float* __restrict__ g_out, float* __restrict__ g_diffuse_raw,
+                              float* __restrict__ g_specular, float* __restrict__ g_spec_scale, float* __restrict__ g_w) {
+  const int64_t ray = blockIdx.x;
+  const int BC = p.n_bins * p.C;
+  const float max_dists = static_cast<float>(p.n_bins - 1) * p.exposure_time;
+  extern __shared__ float sm[];
+  float* s_g = sm;                       // [n_bins * C] upstream gradient of this ray
+  float* s_w = s_g + BC;
+  float* s_move = s_w + p.n;
+  float* s_light = s_move + p.n;
+  float* s_cam = s_light + p.n;
+  float* s_scale = s_cam + p.n;          // [n * C]
+  float* s_acc = s_scale + p.n * p.C;    // [n * (1 + C)]: g_w, g_spec_scale
+  for (int e = threadIdx.x; e < BC; e += blockDim.x) s_g[e] = g_out ? g_out[ray * BC + e] : 0.f;
+  for (int s = threadIdx.x; s < p.n; s += blockDim.x) {
+    const int64_t i = ray * p.n + s;
+    s_w[s] = weights[i];
+    s_move[s] = (ray_dists[i] + p.shift) / p.exposure_time;
+    s_light[s] = light_dists[i];
+    s_cam[s] = cam_dists[i];
+    for (int c = 0; c < p.C; ++c) s_scale[s * p.C + c] = spec_scale ? spec_scale[i * p.C + c] : 0.f;
+  }
+  for (int k = threadIdx.x; k < p.n * (1 + p.C); k += blockDim.x) s_acc[k] = 0.f;
+  __syncthreads();
+  for (int s = 0; s < p.n; ++s) {
+    const float move = s_move[s];
+    const int m0 = static_cast<int>(ceilf(move));
+    bool sample_ok = true;
+    if (p.light_zero) sample_ok = !(s_light[s] < p.light_near);
+    float part_w = 0.f, part_ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int e = threadIdx.x; e < BC; e += blockDim.x) {
+      const int bin = e / p.C, c = e - bin * p.C;
+      const int64_t idx = ((ray * p.n + s) * p.n_bins + bin) * p.C + c;
+      const float fb = static_cast<float>(bin);
+      bool ok = sample_ok && !((fb + p.bin_zero_threshold_light) * p.exposure_time < s_light[s]);
+      ok = ok && !((fb * p.exposure_time + s_cam[s]) > max_dists);
+      float gd = 0.f, gs = 0.f;
+      if (ok) {
+        // output bins whose two taps (y0, y0 + 1) of the forward pass land on `bin`
+        float A = 0.f;
+#pragma unroll
+        for (int j = -1; j <= 1; ++j) {
+          const int b = bin + m0 + j;
+          if (b < 0 || b >= p.n_bins) continue;
+          const float y = static_cast<float>(b) - move;
+          const float y0f = floorf(y);
+          const float t = y - y0f;
+          const int y0 = static_cast<int>(y0f);
+          if (y0 == bin) A += (1.0f - t) * s_g[b * p.C + c];
+          else if (y0 + 1 == bin) A += t * s_g[b * p.C + c];
+        }
+        float val = 0.f;
+        if (diffuse_raw) {
+          const float x = diffuse_raw[idx] + p.diffuse_bias;
+          const float v = softplus_t(x) * p.indirect_scale;
+          val += fminf(fmaxf(v, 0.f), p.rgb_max);
+          if (v >= 0.f && v <= p.rgb_max) gd = s_w[s] * A * p.indirect_scale / (1.0f + expf(-x));
+        }
+        if (specular) {
+          const float sc = s_scale[s * p.C + c], sp = specular[idx];
+          const float v = sc * sp * p.indirect_scale;
+          val += fminf(fmaxf(v, 0.f), p.rgb_max);
+          if (v >= 0.f && v <= p.rgb_max) {
+            gs = s_w[s] * A * sc * p.indirect_scale;
+            const float gsc = s_w[s] * A * sp * p.indirect_scale;
+            part_ss[0] += c == 0 ? gsc : 0.f; part_ss[1] += c == 1 ? gsc : 0.f;
+            part_ss[2] += c == 2 ? gsc : 0.f; part_ss[3] += c == 3 ? gsc : 0.f;
+          }
+        }
+        part_w += val * A;
+      }
+      if (g_diffuse_raw) g_diffuse_raw[idx] = gd;
+      if (g_specular) g_specular[idx] = gs;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      part_w += __shfl_xor_sync(0xffffffffu, part_w, o);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) part_ss[c] += __shfl_xor_sync(0xffffffffu, part_ss[c], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&s_acc[s * (1 + p.C)], part_w);
+      for (int c = 0; c < p.C; ++c) atomicAdd(&s_acc[s * (1 + p.C) + 1 + c], part_ss[c]);
+    }
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < p.n; s += blockDim.x) {
+    const int64_t i = ray * p.n + s;
+    g_w[i] += s_acc[s * (1 + p.C)];
+    if (g_spec_scale)
+      for (int c = 0; c < p.C; ++c) g_spec_scale[i * p.C + c] = s_acc[s * (1 + p.C) + 1 + c];
+  }
+}
+
 // Temporal filter of volumetric_transient_rendering (internal/render.py:397-415): jax.scipy.signal.convolve(x,
 // filter[None, :, None], mode='same') along the bin axis; `filt` is the impulse response or the normalised Gaussian the
 // reference builds from tfilter_sigma.  One thread per output element.
@@ -402,6 +537,40 @@ extern "C" int32_t nrc_transient_head_render_fwd(
   transient_head_render_kernel<3><<<static_cast<unsigned>(num_rays), kTrhThreads, smem, s>>>(
       d_h_diffuse, d_b_diffuse, d_h_specular, d_b_specular, static_cast<const __nv_bfloat16*>(d_w_packed), d_spec_scale, d_weights,
       d_ray_dists, d_light_dists, d_cam_dists, num_rays, p, d_transient_direct, d_transient_indirect, d_rgb);
+  return check_launch();
+}
+
+extern "C" int32_t nrc_transient_render_bwd(void* stream, const float* d_direct_rgbs, const float* d_diffuse_raw,
+                                            const float* d_specular, const float* d_spec_scale, const float* d_weights,
+                                            const float* d_ray_dists, const float* d_light_dists, const float* d_cam_dists,
+                                            int64_t num_rays, int32_t n, int32_t n_bins, int32_t channels,
+                                            float exposure_time, float shift, float diffuse_bias, float indirect_scale,
+                                            float bin_zero_threshold_light, int32_t light_zero, float light_near,
+                                            float rgb_max, const float* d_g_transient_direct,
+                                            const float* d_g_transient_indirect, float* d_g_direct_rgbs,
+                                            float* d_g_diffuse_raw, float* d_g_specular, float* d_g_spec_scale,
+                                            float* d_g_weights) {
+  if (num_rays < 0 || n < 1 || n > 1024 || n_bins < 1 || channels < 1 || channels > 4 || !(exposure_time > 0.f))
+    return NRC_E_INVALID_ARG;
+  if (num_rays == 0) return NRC_OK;
+  if (!d_direct_rgbs || !d_weights || !d_ray_dists || !d_light_dists || !d_cam_dists || !d_g_direct_rgbs || !d_g_weights ||
+      (d_specular && !d_spec_scale) || (d_g_diffuse_raw && !d_diffuse_raw) || (d_g_specular && !d_specular) ||
+      (d_g_spec_scale && !d_specular))
+    return NRC_E_INVALID_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  TransientParams p{n, n_bins, channels, exposure_time, shift, diffuse_bias, indirect_scale, bin_zero_threshold_light,
+                    light_near, rgb_max, 0.f, light_zero};
+  const int64_t tot = num_rays * n;
+  transient_direct_bwd_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(
+      d_direct_rgbs, d_weights, d_ray_dists, d_light_dists, num_rays, p, d_g_transient_direct, d_g_direct_rgbs, d_g_weights);
+  const size_t smem = (static_cast<size_t>(n_bins) * channels + static_cast<size_t>(n) * (5 + 2 * channels)) * sizeof(float);
+  if (smem > 48u * 1024u) {
+    int32_t st = ensure_dynamic_smem<transient_indirect_bwd_kernel>(static_cast<int>(smem));
+    if (st != NRC_OK) return st;
+  }
+  transient_indirect_bwd_kernel<<<static_cast<unsigned>(num_rays), 256, smem, s>>>(
+      d_diffuse_raw, d_specular, d_spec_scale, d_weights, d_ray_dists, d_light_dists, d_cam_dists, num_rays, p,
+      d_g_transient_indirect, d_g_diffuse_raw, d_g_specular, d_g_spec_scale, d_g_weights);
   return check_launch();
 }
 

@@ -181,6 +181,51 @@ def volumetric_rendering(
     return rendering
 
 
+class _TransientRenderFn(torch.autograd.Function):
+    """custom_vjp of the time-resolved rendering: nrc_transient_render_{fwd,bwd}.  Differentiable inputs: direct_rgbs,
+    diffuse_raw, specular, spec_scale, weights; the distances are stop-gradient inputs."""
+
+    @staticmethod
+    def forward(ctx, direct_rgbs, diffuse_raw, specular, spec_scale, weights, ray_dists, light_dists, cam_dists, consts):
+        R, n, C = direct_rgbs.shape
+        n_bins = consts[0]
+        dev = direct_rgbs.device
+        c = lambda t: t.contiguous() if t is not None else None
+        new = lambda: torch.empty((R, n_bins, C), device=dev, dtype=torch.float32)
+        t_direct, t_indirect, rgb = new(), new(), new()
+        args = [c(direct_rgbs), c(diffuse_raw), c(specular), c(spec_scale), c(weights), c(ray_dists), c(light_dists), c(cam_dists)]
+        _lib.call("nrc_transient_render_fwd", _lib.stream_ptr(), *[_lib.ptr(a) for a in args], R, n, n_bins, C, *consts[1:],
+                  _lib.ptr(t_direct), _lib.ptr(t_indirect), _lib.ptr(rgb))
+        ctx.save_for_backward(*[a if a is not None else torch.empty(0, device=dev) for a in args])
+        ctx.present = [a is not None for a in args]
+        ctx.consts = consts
+        return t_direct, t_indirect, rgb
+
+    @staticmethod
+    def backward(ctx, g_direct, g_indirect, g_rgb):
+        args = [a if ok else None for a, ok in zip(ctx.saved_tensors, ctx.present)]
+        direct_rgbs, diffuse_raw, specular, spec_scale = args[:4]
+        R, n, C = direct_rgbs.shape
+        consts = ctx.consts
+        n_bins = consts[0]
+        dev = direct_rgbs.device
+
+        def total(g):     # rgb = direct + indirect + dark_level
+            parts = [t for t in (g, g_rgb) if t is not None]
+            return None if not parts else (parts[0] if len(parts) == 1 else parts[0] + parts[1]).contiguous()
+
+        gd, gi = total(g_direct), total(g_indirect)
+        need = ctx.needs_input_grad
+        g_dir = torch.empty_like(direct_rgbs)
+        g_w = torch.empty((R, n), device=dev, dtype=torch.float32)
+        g_raw = torch.empty_like(diffuse_raw) if (diffuse_raw is not None and need[1]) else None
+        g_spec = torch.empty_like(specular) if (specular is not None and need[2]) else None
+        g_ss = torch.empty_like(spec_scale) if (specular is not None and need[3]) else None
+        _lib.call("nrc_transient_render_bwd", _lib.stream_ptr(), *[_lib.ptr(a) for a in args], R, n, n_bins, C, *consts[1:-1],
+                  _lib.ptr(gd), _lib.ptr(gi), _lib.ptr(g_dir), _lib.ptr(g_raw), _lib.ptr(g_spec), _lib.ptr(g_ss), _lib.ptr(g_w))
+        return g_dir, g_raw, g_spec, g_ss, g_w, None, None, None, None
+
+
 def volumetric_transient_rendering(direct_rgbs, diffuse_raw, specular, spec_scale, weights, ray_dists, light_dists,
                                    cam_dists, n_bins=700, exposure_time=0.01, shift=0.0, diffuse_bias=-1.0,
                                    indirect_scale=1.0, bin_zero_threshold_light=0.0, light_zero=False, light_near=0.0,
@@ -189,17 +234,13 @@ def volumetric_transient_rendering(direct_rgbs, diffuse_raw, specular, spec_scal
     (internal/nerf.py:1660-1777) and zero_invalid_bins (render_utils.py:1699-1767): see nrc_transient_render_fwd.
     direct_rgbs [R,n,C]; diffuse_raw / specular [R,n,B,C] (either may be None); spec_scale [R,n,C];
     weights / ray_dists / light_dists / cam_dists [R,n].  Returns dict(transient_direct, transient_indirect,
-    rgb [R,B,C], integrated_rgb [R,C]).  Forward path (the temporal filter convolution is not applied)."""
-    R, n, C = direct_rgbs.shape
-    dev = direct_rgbs.device
-    c = lambda t: t.contiguous() if t is not None else None
-    new = lambda: torch.empty((R, n_bins, C), device=dev, dtype=torch.float32)
-    t_direct, t_indirect, rgb = new(), new(), new()
-    args = [c(direct_rgbs), c(diffuse_raw), c(specular), c(spec_scale), c(weights), c(ray_dists), c(light_dists), c(cam_dists)]
-    _lib.call("nrc_transient_render_fwd", _lib.stream_ptr(), *[_lib.ptr(a) for a in args], R, n, n_bins, C,
-              float(exposure_time), float(shift), float(diffuse_bias), float(indirect_scale), float(bin_zero_threshold_light),
-              int(bool(light_zero)), float(light_near), float(rgb_max), float(dark_level), _lib.ptr(t_direct),
-              _lib.ptr(t_indirect), _lib.ptr(rgb))
+    rgb [R,B,C], integrated_rgb [R,C]).  Differentiable (nrc_transient_render_bwd) with respect to direct_rgbs, diffuse_raw,
+    specular, spec_scale and weights; the temporal filter is applied by temporal_filter (differentiable too)."""
+    consts = (int(n_bins), float(exposure_time), float(shift), float(diffuse_bias), float(indirect_scale),
+              float(bin_zero_threshold_light), int(bool(light_zero)), float(light_near), float(min(rgb_max, 3.0e38)),
+              float(dark_level))
+    t_direct, t_indirect, rgb = _TransientRenderFn.apply(direct_rgbs, diffuse_raw, specular, spec_scale, weights,
+                                                         ray_dists.detach(), light_dists.detach(), cam_dists.detach(), consts)
     return dict(transient_direct=t_direct, transient_indirect=t_indirect, rgb=rgb, integrated_rgb=rgb.sum(-2))
 
 
@@ -220,14 +261,35 @@ def gaussian_tfilter(tfilter_sigma, device):
     return _tfilter_cache[key]
 
 
+class _TemporalFilterFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, filt):
+        x = _c(x)
+        R, B, Cc = x.shape
+        y = torch.empty_like(x)
+        filt = _c(filt)
+        _lib.call("nrc_transient_filter", _lib.stream_ptr(), _lib.ptr(x), _lib.ptr(filt), int(filt.shape[0]), R, B, Cc, _lib.ptr(y))
+        ctx.save_for_backward(filt)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (filt,) = ctx.saved_tensors
+        taps = int(filt.shape[0])
+        if taps % 2 == 0:
+            raise NotImplementedError("the adjoint of a 'same' convolution with an even number of taps is not a 'same' convolution")
+        # adjoint of convolve(mode='same') with an odd filter = the same convolution with the filter reversed
+        g = _c(g)
+        R, B, Cc = g.shape
+        gx = torch.empty_like(g)
+        _lib.call("nrc_transient_filter", _lib.stream_ptr(), _lib.ptr(g), _lib.ptr(_c(filt.flip(0))), taps, R, B, Cc, _lib.ptr(gx))
+        return gx, None
+
+
 def temporal_filter(x, filt):
     """jax.scipy.signal.convolve(x, filt[None, :, None], mode='same') along the bin axis (internal/render.py:406-413):
-    x [R, n_bins, C], filt [taps] (impulse response or gaussian_tfilter)."""
-    x = _c(x)
-    R, B, Cc = x.shape
-    y = torch.empty_like(x)
-    _lib.call("nrc_transient_filter", _lib.stream_ptr(), _lib.ptr(x), _lib.ptr(_c(filt)), int(filt.shape[0]), R, B, Cc, _lib.ptr(y))
-    return y
+    x [R, n_bins, C], filt [taps] (impulse response or gaussian_tfilter); differentiable with respect to x."""
+    return _TemporalFilterFn.apply(x, filt)
 
 
 def volumetric_transient_rendering_fused(direct_rgbs, h_diffuse, diffuse_layer, h_specular, specular_layer, spec_scale, weights,

@@ -153,3 +153,51 @@ def test_temporal_filter_and_transient_integration_against_reference(cuda_device
     for k in ("radiance_out", "irradiance", "indirect_occ"):
         e = rel_err(res[k], torch.from_numpy(V["ggxt_" + k]))
         assert e <= 2e-5, (k, e)
+
+
+@pytest.mark.parametrize("R,n,B,heads", [(12, 8, 50, "both"), (5, 32, 700, "both"), (9, 16, 120, "diffuse"), (9, 16, 120, "specular")])
+@pytest.mark.parametrize("light_zero", [False, True])
+def test_transient_render_backward(cuda_device, R, n, B, heads, light_zero):
+    """nrc_transient_render_bwd (training the time-resolved cache): gradients of a random linear functional of the three
+    outputs, temporal filter included, with respect to direct_rgbs / diffuse_raw / specular / spec_scale / weights against
+    autograd through the oracle's restatement of volumetric_transient_rendering (render.py:250-449)."""
+    g = gen(700 + R + n)
+    x = _inputs(g, R, n, B)
+    if heads == "diffuse":
+        x["specular"] = None
+    if heads == "specular":
+        x["diffuse_raw"] = None
+    kw = dict(exposure_time=0.01, shift=0.003, diffuse_bias=-1.0, indirect_scale=0.7, bin_zero_threshold_light=1.5,
+              light_zero=light_zero, light_near=0.08 * B * 0.01, rgb_max=2.0, dark_level=0.01)
+    ups = {k: f32(g.normal(size=(R, B, 3))) for k in ("transient_direct", "transient_indirect", "rgb")}
+    filt = otr.gaussian_tfilter(1.5)
+    names = ("direct", "diffuse_raw", "specular", "spec_scale", "weights")
+
+    def run(lib, dev):
+        t = {k: (v.clone().to(dev).requires_grad_(True) if (v is not None and k in names) else (v.to(dev) if v is not None else None))
+             for k, v in x.items()}
+        zeros = torch.zeros((R, n, B, 3), device=dev)
+        if lib is otr:
+            res = otr.transient_render(t["direct"], t["diffuse_raw"] if t["diffuse_raw"] is not None else zeros - 1e4,
+                                       t["specular"] if t["specular"] is not None else zeros, t["spec_scale"], t["weights"],
+                                       t["ray_dists"], t["light_dists"], t["cam_dists"], B, **kw)
+            fd = otr.temporal_filter(res["transient_direct"], filt)
+        else:
+            res = nrender.volumetric_transient_rendering(t["direct"], t["diffuse_raw"], t["specular"], t["spec_scale"], t["weights"],
+                                                         t["ray_dists"], t["light_dists"], t["cam_dists"], n_bins=B, **kw)
+            fd = nrender.temporal_filter(res["transient_direct"], filt.to(dev))
+        loss = sum((res[k] * ups[k].to(dev)).sum() for k in ups) + (fd * ups["rgb"].to(dev)).sum() * 0.5
+        loss.backward()
+        return {k: t[k].grad for k in names if t[k] is not None}, res
+
+    want, _ = run(otr, "cpu")
+    got, res = run(nrender, cuda_device)
+    for k in want:
+        if k == "spec_scale" and x["specular"] is None:
+            assert got[k] is None or float(got[k].abs().max()) == 0.0
+            continue
+        assert got[k] is not None and got[k].shape == want[k].shape, k
+        assert rel_err(got[k], want[k]) <= 5e-5, (k, rel_err(got[k], want[k]))
+    # bins that zero_invalid_bins removed get exactly zero gradient
+    if x["diffuse_raw"] is not None:
+        assert bool((got["diffuse_raw"][want["diffuse_raw"].to(cuda_device) == 0] == 0).all()) or rel_err(got["diffuse_raw"], want["diffuse_raw"]) <= 5e-5
