@@ -582,7 +582,8 @@ class TransientRenderStep:
     time-resolved kernel (render.volumetric_transient_rendering_fused), so the [R, 32, 700, 3] histograms the reference
     materialises three to four times never exist.  The direct term is the un-occluded diffuse response to the point light
     (albedo n.l power / d^2 / pi, nerf.py:1141-1170,1474-1481); the shadow-ray visibility query and the light BRDF network
-    of the reference's active path are not part of this workload.  Forward (render) path."""
+    of the reference's active path are not part of this workload.  render() is the fused forward path; render_unfused() /
+    loss_and_grads() the differentiable one (training)."""
 
     def __init__(self, device, n_bins=700, table_init_range=0.1, seed=SEED, bf16=True):
         self.device, self.n_bins, self.bf16 = device, n_bins, bf16
@@ -617,13 +618,14 @@ class TransientRenderStep:
         lights = (rn["origins"] + 0.05 * g.normal(size=(R, 3))).astype(np.float32)
         return dict(rn, lights=lights, cam_origins=rn["origins"].copy())
 
-    def render(self, rays, u01):
-        from . import render as nrender
+    def _shade(self, rays, u01, train):
+        """Everything in front of the time-resolved integration: (direct, h_diffuse, h_specular, spec_scale, weights,
+        ray / light / camera distances).  Under autograd when `train`."""
         sp = torch.nn.functional.softplus
         p, tp, b = self.params["Shader"], self.tparams, self.bf16
         shader = self.cache.shader
-        with torch.no_grad():
-            last = self.cache.sampler(self.params["Sampler"], rays, u01, train=False)[-1]
+        with torch.enable_grad() if train else torch.no_grad():
+            last = self.cache.sampler(self.params["Sampler"], rays, u01, train=train)[-1]
             means, feat, nrm, w = last["means"], last["feature"], last["normals_to_use"], last["weights"]
             R, n = w.shape
             P = R * n
@@ -657,7 +659,79 @@ class TransientRenderStep:
             direct = torch.clamp(albedo * n_dot_l * radiance / np.pi, 0.0, self.cfg["rgb_max"]).reshape(R, n, 3)
             ray_d = torch.linalg.norm(rays["origins"][:, None, :] - means, dim=-1)
             cam_d = ray_d + torch.linalg.norm(rays["origins"] - rays["cam_origins"], dim=-1)[:, None]
+            return (direct, h_d.reshape(R, n, 64), h_s.reshape(R, n, 128), (tint * F).reshape(R, n, 3), w, ray_d.detach(),
+                    light_d.reshape(R, n).detach(), cam_d.detach())
+
+    def render(self, rays, u01):
+        from . import render as nrender
+        tp = self.tparams
+        direct, h_d, h_s, spec_scale, w, ray_d, light_d, cam_d = self._shade(rays, u01, train=False)
+        with torch.no_grad():
             return nrender.volumetric_transient_rendering_fused(
-                direct, h_d.reshape(R, n, 64), tp["transient_indirect_layer"], h_s.reshape(R, n, 128),
-                tp["TransientSurfaceLightField"]["output_rgba_layer"], (tint * F).reshape(R, n, 3), w, ray_d,
-                light_d.reshape(R, n), cam_d, n_bins=self.n_bins, pack_cache=self._head_pack, **self.cfg)
+                direct, h_d, tp["transient_indirect_layer"], h_s, tp["TransientSurfaceLightField"]["output_rgba_layer"],
+                spec_scale, w, ray_d, light_d, cam_d, n_bins=self.n_bins, pack_cache=self._head_pack, **self.cfg)
+
+    def render_unfused(self, rays, u01, train=False):
+        """The same frame through the UNFUSED kernels: both heads' last layers as GEMMs, their [R, n, n_bins, 3] histograms in
+        HBM (what the reference materialises), nrc_transient_render_fwd, temporal filter.  Differentiable when `train`
+        (nrc_transient_render_bwd + the Dense / encoding / sampler VJPs): the training path of config 4."""
+        from . import render as nrender
+        tp, c, b = self.tparams, self.cfg, self.bf16
+        direct, h_d, h_s, spec_scale, w, ray_d, light_d, cam_d = self._shade(rays, u01, train=train)
+        R, n = w.shape
+        B = self.n_bins
+        with torch.enable_grad() if train else torch.no_grad():
+            diffuse_raw = nerf.dense(tp["transient_indirect_layer"], h_d.reshape(R * n, 64), bf16=b).reshape(R, n, B, 3)
+            raw_s = nerf.dense(tp["TransientSurfaceLightField"]["output_rgba_layer"], h_s.reshape(R * n, 128), bf16=b)
+            # rgb_activation(rgb_premultiplier * raw + rgb_bias) of the transient light field (surface_light_field.py:1045-1047)
+            specular = torch.nn.functional.softplus(raw_s[:, :B * 3] + c["spec_bias"]).reshape(R, n, B, 3)
+            out = nrender.volumetric_transient_rendering(
+                direct, diffuse_raw, specular, spec_scale, w, ray_d, light_d, cam_d, n_bins=B, exposure_time=c["exposure_time"],
+                shift=c["shift"], diffuse_bias=c["diffuse_bias"], indirect_scale=c["indirect_scale"],
+                bin_zero_threshold_light=c["bin_zero_threshold_light"], light_zero=c["light_zero"], light_near=c["light_near"],
+                rgb_max=c["rgb_max"], dark_level=c["dark_level"])
+            t_direct, t_indirect = out["transient_direct"], out["transient_indirect"]
+            if c["tfilter_sigma"] != 0.0:
+                filt = nrender.gaussian_tfilter(c["tfilter_sigma"], t_direct.device)
+                t_direct = nrender.temporal_filter(t_direct, filt)
+                if c["filter_indirect"]:
+                    t_indirect = nrender.temporal_filter(t_indirect, filt)
+            rgb = t_direct + t_indirect + c["dark_level"]
+        return dict(transient_direct=t_direct, transient_indirect=t_indirect, rgb=rgb, integrated_rgb=rgb.sum(-2))
+
+    def trainable(self):
+        """name -> leaf tensor of every parameter the time-resolved objective reaches (grids as their flat arenas)."""
+        leaves = {}
+
+        def walk(prefix, node):
+            for k, v in node.items():
+                if isinstance(v, dict):
+                    if "_arena" in v:
+                        leaves[prefix + k] = v["_arena"]
+                    else:
+                        walk(prefix + k + "/", v)
+                elif isinstance(v, torch.Tensor) and v.is_floating_point():
+                    leaves[prefix + k] = v
+        walk("Transient/", self.tparams)
+        walk("Shader/", self.params["Shader"])
+        walk("Sampler/", self.params["Sampler"])
+        return leaves
+
+    def loss_and_grads(self, rays, u01, target):
+        """One training evaluation of config 4 on a synthetic target histogram [R, n_bins, 3]: mean squared error of the
+        time-resolved `rgb`, back-propagated through the integrator (nrc_transient_render_bwd), both heads, the shader and
+        the sampler's final level.  Returns (loss, {name: gradient}); parameters nothing reaches are absent."""
+        leaves = self.trainable()
+        for t in leaves.values():
+            t.requires_grad_(True)
+            t.grad = None
+        try:
+            out = self.render_unfused(rays, u01, train=True)
+            loss = torch.mean((out["rgb"] - target) ** 2)
+            loss.backward()
+            grads = {k: t.grad for k, t in leaves.items() if t.grad is not None}
+        finally:
+            for t in leaves.values():
+                t.requires_grad_(False)
+                t.grad = None
+        return loss.detach(), grads

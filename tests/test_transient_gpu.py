@@ -201,3 +201,47 @@ def test_transient_render_backward(cuda_device, R, n, B, heads, light_zero):
     # bins that zero_invalid_bins removed get exactly zero gradient
     if x["diffuse_raw"] is not None:
         assert bool((got["diffuse_raw"][want["diffuse_raw"].to(cuda_device) == 0] == 0).all()) or rel_err(got["diffuse_raw"], want["diffuse_raw"]) <= 5e-5
+
+
+def test_config4_training_path(cuda_device):
+    """workload.TransientRenderStep (BASELINE config 4): the differentiable unfused path equals the fused render path, and
+    loss_and_grads back-propagates through integrator, heads, shader and sampler - checked by central differences of the
+    objective along random directions of a few parameter tensors (fp32 variant)."""
+    from neural_radiance_caching_b200 import workload
+    R, B = 24, 60
+    stage = workload.TransientRenderStep(cuda_device, n_bins=B, bf16=False, table_init_range=0.05)
+    stage.cfg["exposure_time"] = 0.01 * 700 / B          # the same metric span on 60 bins
+    g = np.random.Generator(np.random.PCG64(8100))
+    rn = stage.make_rays(g, R)
+    rays = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(cuda_device) for k, v in rn.items()}
+    u01 = [f32(g.uniform(size=(R, 1))).to(cuda_device) for _ in range(3)]
+    fused = stage.render(rays, u01)
+    plain = stage.render_unfused(rays, u01)
+    for k in ("transient_direct", "transient_indirect", "rgb"):
+        assert float(fused[k].abs().max()) > 0
+        assert rel_err(plain[k], fused[k]) <= 2e-2, (k, rel_err(plain[k], fused[k]))     # the fused heads run on bf16 operands
+    target = (plain["rgb"] * 0.5 + 0.01 * f32(g.uniform(size=(R, B, 3))).to(cuda_device)).detach()
+    loss, grads = stage.loss_and_grads(rays, u01, target)
+    assert float(loss) > 0
+    leaves = stage.trainable()
+    picks = ["Transient/transient_indirect_layer/bias", "Transient/albedo_layer/kernel",
+             "Transient/TransientSurfaceLightField/layer_0/kernel", "Shader/bottleneck_layer/kernel", "Shader/appearance_grid",
+             "Sampler/MLP_2/output_density_layer/kernel"]
+    for name in picks:
+        assert name in grads and float(grads[name].abs().max()) > 0, name
+        t = leaves[name]
+        d = torch.from_numpy(g.normal(size=tuple(t.shape)).astype(np.float32)).to(cuda_device)
+        d = d / d.norm() * max(float(t.norm()), 1.0) * 0.02
+        want = float((grads[name].double() * d.double()).sum())
+
+        def at(sign):
+            with torch.no_grad():
+                t.add_(d, alpha=sign)
+            try:
+                return float(torch.mean((stage.render_unfused(rays, u01)["rgb"] - target).double() ** 2))
+            finally:
+                with torch.no_grad():
+                    t.sub_(d, alpha=sign)
+
+        fd = (at(1.0) - at(-1.0)) / 2.0
+        assert abs(fd - want) <= 5e-2 * abs(want) + 1e-9, (name, fd, want)
