@@ -508,6 +508,8 @@ def _slim(line, frame=False):
     out = {k: line[k] for k in ("metric", "value", "unit", "ms_per_step", "n_gpus", "steps", "dtype", "scaling",
                                 "gpu_launches_per_step", "roofline", "kernel_ms", "e2e")}
     out["workload"] = line["config"]["workload"]
+    if "train" in line:
+        out["train"] = line["train"]
     if frame:
         out["seconds_per_frame"] = line["ms_per_step"] * 1e-3
     return out
@@ -714,6 +716,7 @@ def render_line(args, workload_name, world, rank, dev, steps, warmup, rays=None,
     _lib.load()
     pk, pk_kind = peaks()
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+    extra = {}
 
     def barrier():
         if world > 1:
@@ -836,6 +839,13 @@ def render_line(args, workload_name, world, rank, dev, steps, warmup, rays=None,
             out_host.copy_(gstep(), non_blocking=True)
 
         e2e_ms = _timed(e2e_step, steps, warmup, flush, barrier)
+        # the training path of the same chunk: heads as GEMMs, [R,32,700,3] histograms in HBM, nrc_transient_render_{fwd,bwd},
+        # the Dense / encoding / sampler VJPs under autograd (eager launches, no graph); a synthetic target histogram
+        target = (gstep() * 0.5).clone()
+        train_ms = _timed(lambda: stage.loss_and_grads(drays, u01, target)[0], 3, 3, flush, barrier)
+        extra["train"] = {"ms_per_step": train_ms, "value": world * R * SAMPLES_PER_RAY / (train_ms * 1e-3), "unit": UNIT,
+                          "note": "forward + backward of one chunk through workload.TransientRenderStep.loss_and_grads (unfused, "
+                                  "eager); mean-squared-error objective on the time-resolved rgb"}
         units = world * R * SAMPLES_PER_RAY
         wl = ("config4 transient_simulation_ngp_yobo_cornell time-resolved cache, one chunk of %d primary rays: proposal sampler "
               "(64,64,32), transient shader on the 32 final samples (appearance grid, bottleneck / roughness / tint / albedo / "
@@ -913,7 +923,7 @@ def render_line(args, workload_name, world, rank, dev, steps, warmup, rays=None,
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "gpu_launches": launches * steps, "gpu_launches_per_step": launches, "roofline": roof,
-            "kernel_ms": {k: round(v, 5) for k, v in per_kernel.items()}}
+            "kernel_ms": {k: round(v, 5) for k, v in per_kernel.items()}, **extra}
 
 
 if __name__ == "__main__":
