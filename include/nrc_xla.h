@@ -119,6 +119,26 @@ void nrc_xla_ggx_integrate_fwd(void* stream, void** buffers, const char* opaque,
  *          -> g_radiance [R,S,3]                                                      (nrc_ggx_integrate_bwd) */
 void nrc_xla_ggx_integrate_bwd(void* stream, void** buffers, const char* opaque, size_t opaque_len);
 
+/* Surface-light-field memory variant (surface_lf_mem, internal/surface_light_field.py:594-780,899-913,981): the point stage
+ * between the distance network and the reflectance grid, and the weighted feature sum. */
+typedef struct {
+  int32_t version;
+  int32_t num_features;      /* reduce targets: F */
+  int64_t num_points;
+  int64_t ld_raw;            /* row stride of the distance-network output (>= 8 n + 4) */
+  nrc_slf_points_t cfg;
+} nrc_xla_slf_desc_t;
+/* buffers: raw [P, ld_raw], origins [P,3], refdirs [P,3]
+ *          -> points [P,n,3], weights [P,n], s_dist [P], distances [P,n], env_rgba [P,4]      (nrc_slf_points_fwd) */
+void nrc_xla_slf_points_fwd(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+/* buffers: raw, origins, refdirs, g_points, g_weights, g_s_dist, g_distances, g_env_rgba -> g_raw [P, 8n+4]
+ *                                                                                             (nrc_slf_points_bwd) */
+void nrc_xla_slf_points_bwd(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+/* buffers: feat [P,n,F], weights [P,n] -> out [P,F]                                            (nrc_slf_reduce_fwd) */
+void nrc_xla_slf_reduce_fwd(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+/* buffers: feat, weights, g_out [P,F] -> g_feat [P,n,F], g_weights [P,n]                       (nrc_slf_reduce_bwd) */
+void nrc_xla_slf_reduce_bwd(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
 /* Status of the last failing target on this thread (NRC_OK if none); reading clears it. */
 int32_t nrc_xla_last_status(void);
 /* NULL-terminated table of (name, function) pairs for registration loops. */

@@ -193,6 +193,35 @@ void nrc_xla_ggx_integrate_bwd(void* stream, void** b, const char* opaque, size_
                              F(b, 10), d.num_points, d.num_samples, d.lobe_kind, d.rgb_max, O(b, 11)));
 }
 
+void nrc_xla_slf_points_fwd(void* stream, void** b, const char* opaque, size_t len) {
+  nrc_xla_slf_desc_t d;
+  if (!unpack(opaque, len, d)) return;
+  if (d.version != NRC_XLA_DESC_VERSION) { g_xla_status = NRC_E_INVALID_ARG; return; }
+  done(nrc_slf_points_fwd(stream, &d.cfg, F(b, 0), d.ld_raw, F(b, 1), F(b, 2), d.num_points, O(b, 3), O(b, 4), O(b, 5), O(b, 6),
+                          O(b, 7)));
+}
+
+void nrc_xla_slf_points_bwd(void* stream, void** b, const char* opaque, size_t len) {
+  nrc_xla_slf_desc_t d;
+  if (!unpack(opaque, len, d)) return;
+  if (d.version != NRC_XLA_DESC_VERSION) { g_xla_status = NRC_E_INVALID_ARG; return; }
+  done(nrc_slf_points_bwd(stream, &d.cfg, F(b, 0), d.ld_raw, F(b, 1), F(b, 2), d.num_points, F(b, 3), F(b, 4), F(b, 5), F(b, 6),
+                          F(b, 7), O(b, 8)));
+}
+
+void nrc_xla_slf_reduce_fwd(void* stream, void** b, const char* opaque, size_t len) {
+  nrc_xla_slf_desc_t d;
+  if (!unpack(opaque, len, d)) return;
+  done(nrc_slf_reduce_fwd(stream, F(b, 0), F(b, 1), d.num_points, d.cfg.num_distance_samples, d.num_features, O(b, 2)));
+}
+
+void nrc_xla_slf_reduce_bwd(void* stream, void** b, const char* opaque, size_t len) {
+  nrc_xla_slf_desc_t d;
+  if (!unpack(opaque, len, d)) return;
+  done(nrc_slf_reduce_bwd(stream, F(b, 0), F(b, 1), F(b, 2), d.num_points, d.cfg.num_distance_samples, d.num_features, O(b, 3),
+                          O(b, 4)));
+}
+
 const nrc_xla_target_t* nrc_xla_targets(void) {
   static const nrc_xla_target_t table[] = {
       {"nrc_xla_encode_fwd", nrc_xla_encode_fwd},
@@ -210,6 +239,10 @@ const nrc_xla_target_t* nrc_xla_targets(void) {
       {"nrc_xla_ray_resample_gather", nrc_xla_ray_resample_gather},
       {"nrc_xla_ggx_integrate_fwd", nrc_xla_ggx_integrate_fwd},
       {"nrc_xla_ggx_integrate_bwd", nrc_xla_ggx_integrate_bwd},
+      {"nrc_xla_slf_points_fwd", nrc_xla_slf_points_fwd},
+      {"nrc_xla_slf_points_bwd", nrc_xla_slf_points_bwd},
+      {"nrc_xla_slf_reduce_fwd", nrc_xla_slf_reduce_fwd},
+      {"nrc_xla_slf_reduce_bwd", nrc_xla_slf_reduce_bwd},
       {nullptr, nullptr},
   };
   return table;

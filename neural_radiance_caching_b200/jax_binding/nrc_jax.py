@@ -54,10 +54,16 @@ class nrc_xla_ggx_desc_t(C.Structure):
                 ("has_occ", C.c_int32), ("rgb_max", C.c_float), ("pad", C.c_int32)]
 
 
+class nrc_xla_slf_desc_t(C.Structure):
+    _fields_ = [("version", C.c_int32), ("num_features", C.c_int32), ("num_points", C.c_int64), ("ld_raw", C.c_int64),
+                ("cfg", _lib.nrc_slf_points_t)]
+
+
 TARGETS = ("nrc_xla_encode_fwd", "nrc_xla_encode_bwd", "nrc_xla_contract_fwd", "nrc_xla_contract_bwd",
            "nrc_xla_density_query_fwd", "nrc_xla_ray_alpha_weights_fwd", "nrc_xla_ray_alpha_weights_bwd",
            "nrc_xla_ray_sample_intervals", "nrc_xla_ray_cast", "nrc_xla_ray_composite_fwd", "nrc_xla_ray_composite_bwd",
-           "nrc_xla_ray_resample", "nrc_xla_ray_resample_gather", "nrc_xla_ggx_integrate_fwd", "nrc_xla_ggx_integrate_bwd")
+           "nrc_xla_ray_resample", "nrc_xla_ray_resample_gather", "nrc_xla_ggx_integrate_fwd", "nrc_xla_ggx_integrate_bwd",
+           "nrc_xla_slf_points_fwd", "nrc_xla_slf_points_bwd", "nrc_xla_slf_reduce_fwd", "nrc_xla_slf_reduce_bwd")
 
 
 def _bytes(desc):
@@ -119,6 +125,15 @@ def pack_ggx(num_points, num_samples, lobe_kind=0, has_occ=False, rgb_max=3.4e38
     d = nrc_xla_ggx_desc_t()
     d.version, d.num_points, d.num_samples = DESC_VERSION, int(num_points), int(num_samples)
     d.lobe_kind, d.has_occ, d.rgb_max = int(lobe_kind), int(has_occ), float(rgb_max)
+    return d
+
+
+def pack_slf(num_points, cfg, ld_raw=None, num_features=0):
+    """cfg: a filled _lib.nrc_slf_points_t (module constants of the reference's surface_lf_mem)."""
+    d = nrc_xla_slf_desc_t()
+    d.version, d.num_points, d.num_features = DESC_VERSION, int(num_points), int(num_features)
+    d.ld_raw = int(ld_raw if ld_raw is not None else 8 * cfg.num_distance_samples + 4)
+    C.memmove(C.byref(d.cfg), C.byref(cfg), C.sizeof(_lib.nrc_slf_points_t))
     return d
 
 
@@ -355,6 +370,50 @@ def integrate_reflect_rays(lobe_kind, wi, wo, radiance, weight, pdf, albedo, rou
 
     f.defvjp(lambda rad: (f(rad), rad), bwd)
     return f(radiance)
+
+
+def slf_points(raw, origins, refdirs, cfg):
+    """BaseSurfaceLightFieldMLP.predict_points + ref_warp_fn + the weight head of __call__
+    (internal/surface_light_field.py:594-780,899-913) for the `surface_lf_mem` configuration, with its VJP w.r.t. the
+    distance-network outputs: -> (points [P,n,3], ref_weights [P,n], s_dist [P], distances [P,n], env_rgba [P,4])."""
+    jax, _, _, _, _ = _jax()
+    import jax.numpy as jnp
+    P, n = raw.shape[0], cfg.num_distance_samples
+    outs = [((P, n, 3), jnp.float32), ((P, n), jnp.float32), ((P,), jnp.float32), ((P, n), jnp.float32), ((P, 4), jnp.float32)]
+
+    @jax.custom_vjp
+    def f(r):
+        return tuple(_call("nrc_xla_slf_points_fwd", (r, origins, refdirs), pack_slf(P, cfg, r.shape[1]), outs))
+
+    def bwd(r, gs):
+        (g,) = _call("nrc_xla_slf_points_bwd", (r, origins, refdirs) + tuple(gs), pack_slf(P, cfg, r.shape[1]),
+                     [((P, 8 * n + 4), jnp.float32)])
+        return (g,)
+
+    f.defvjp(lambda r: (f(r), r), bwd)
+    return f(raw)
+
+
+def slf_reduce(feat, weights):
+    """(ref_grid_feat * ref_weights[..., None]).sum(axis=-2) (internal/surface_light_field.py:981) with its VJP."""
+    jax, _, _, _, _ = _jax()
+    import jax.numpy as jnp
+    P, n, F = feat.shape
+    cfg = _lib.nrc_slf_points_t()
+    cfg.num_distance_samples = n
+
+    @jax.custom_vjp
+    def f(x, w):
+        (out,) = _call("nrc_xla_slf_reduce_fwd", (x, w), pack_slf(P, cfg, num_features=F), [((P, F), jnp.float32)])
+        return out
+
+    def bwd(res, g):
+        x, w = res
+        return tuple(_call("nrc_xla_slf_reduce_bwd", (x, w, g), pack_slf(P, cfg, num_features=F),
+                           [((P, n, F), jnp.float32), ((P, n), jnp.float32)]))
+
+    f.defvjp(lambda x, w: (f(x, w), (x, w)), bwd)
+    return f(feat, weights)
 
 
 def install(grid_utils):

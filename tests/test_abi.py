@@ -117,7 +117,7 @@ def test_xla_custom_call_targets(lib, tmp_path):
     src = open(os.path.join(ROOT, "include", "nrc_xla.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     declared = sorted(set(re.findall(r"\bvoid\s+(nrc_xla_[a-z0-9_]+)\s*\(", src)))
-    assert declared == sorted(nrc_jax.TARGETS) and len(declared) == 15
+    assert declared == sorted(nrc_jax.TARGETS) and len(declared) == 19
     for name in declared:
         assert hasattr(lib, name), name
 
@@ -132,10 +132,11 @@ def test_xla_custom_call_targets(lib, tmp_path):
 
     c = tmp_path / "x.c"
     c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nrc_xla.h"\n'
-                 'int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(nrc_xla_encode_desc_t),'
+                 'int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(nrc_xla_encode_desc_t),'
                  ' offsetof(nrc_xla_encode_desc_t, enc), sizeof(nrc_xla_contract_desc_t), sizeof(nrc_xla_density_query_desc_t),'
                  ' offsetof(nrc_xla_density_query_desc_t, warp_c), sizeof(nrc_xla_ray_desc_t), offsetof(nrc_xla_ray_desc_t, bias),'
-                 ' sizeof(nrc_xla_ggx_desc_t), offsetof(nrc_xla_ggx_desc_t, rgb_max)); return 0; }\n')
+                 ' sizeof(nrc_xla_ggx_desc_t), offsetof(nrc_xla_ggx_desc_t, rgb_max), sizeof(nrc_xla_slf_desc_t),'
+                 ' offsetof(nrc_xla_slf_desc_t, cfg)); return 0; }\n')
     exe = tmp_path / "x"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
@@ -143,7 +144,7 @@ def test_xla_custom_call_targets(lib, tmp_path):
     want = [ctypes.sizeof(J.nrc_xla_encode_desc_t), J.nrc_xla_encode_desc_t.enc.offset, ctypes.sizeof(J.nrc_xla_contract_desc_t),
             ctypes.sizeof(J.nrc_xla_density_query_desc_t), J.nrc_xla_density_query_desc_t.warp_c.offset,
             ctypes.sizeof(J.nrc_xla_ray_desc_t), J.nrc_xla_ray_desc_t.bias.offset, ctypes.sizeof(J.nrc_xla_ggx_desc_t),
-            J.nrc_xla_ggx_desc_t.rgb_max.offset]
+            J.nrc_xla_ggx_desc_t.rgb_max.offset, ctypes.sizeof(J.nrc_xla_slf_desc_t), J.nrc_xla_slf_desc_t.cfg.offset]
     assert got == want
 
     lib.nrc_xla_last_status.restype = ctypes.c_int32

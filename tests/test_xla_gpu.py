@@ -18,7 +18,7 @@ from tests.util import ENC_CONFIGS, dense_params, f32, gen, level_table
 pytestmark = pytest.mark.gpu
 
 
-def xla_call(name, operands, results, desc):
+def xla_call(name, operands, results, desc, expect_status=0):
     """One custom call: buffers = operand pointers then result pointers; opaque = the packed descriptor."""
     lib = _lib.load()
     fn = getattr(lib, name)
@@ -27,7 +27,7 @@ def xla_call(name, operands, results, desc):
     opaque = bytes(memoryview(desc))
     fn(C.c_void_p(torch.cuda.current_stream().cuda_stream), bufs, opaque, len(opaque))
     lib.nrc_xla_last_status.restype = C.c_int32
-    assert lib.nrc_xla_last_status() == 0, name
+    assert lib.nrc_xla_last_status() == expect_status, name
     torch.cuda.synchronize()
 
 
@@ -180,3 +180,41 @@ def test_ggx_targets(cuda_device):
     ops = [wi, wo, rad, flat("weight"), flat("pdf"), material["albedo"], vec("roughness"), vec("metalness"), vec("F_0"), g_out, g_irr]
     xla_call("nrc_xla_ggx_integrate_bwd", ops, [g_rad], J.pack_ggx(R, S, 0, False))
     assert same(g_rad, samples["radiance_in"].grad)
+
+
+def test_slf_targets(cuda_device):
+    """The surface-light-field point stage and feature reduction through the XLA ABI == the C-ABI entry points."""
+    from neural_radiance_caching_b200 import surface_light_field as nslf
+    dev = cuda_device
+    g = gen(905)
+    P, n, Fq = 301, 8, 36
+    net = nslf.SurfaceLightFieldMemMLP(num_distance_samples=n, grid=dict(hash_map_size=2 ** 12, max_grid_size=64, num_features=4),
+                                       reflectance_grid=dict(hash_map_size=2 ** 12, max_grid_size=64, num_features=4))
+    cfg = nslf._points_cfg(net, 0.1, 1.7)
+    raw = f32(g.normal(size=(P, 8 * n + 4))).to(dev).requires_grad_(True)
+    o = f32(g.normal(size=(P, 3))).to(dev)
+    v = torch.nn.functional.normalize(f32(g.normal(size=(P, 3))), dim=-1).to(dev)
+    want = nslf._SlfPointsFn.apply(raw, o, v, cfg)
+    ups = [f32(g.normal(size=tuple(w.shape))).to(dev) for w in want]
+    sum((a * b).sum() for a, b in zip(want, ups)).backward()
+    new = lambda *s: torch.empty(s, device=dev)
+    outs = [new(P, n, 3), new(P, n), new(P), new(P, n), new(P, 4)]
+    xla_call("nrc_xla_slf_points_fwd", [raw.detach(), o, v], outs, J.pack_slf(P, cfg))
+    for a, b in zip(outs, want):
+        assert same(a.reshape(b.shape), b)
+    g_raw = new(P, 8 * n + 4)
+    xla_call("nrc_xla_slf_points_bwd", [raw.detach(), o, v, ups[0], ups[1], ups[2].reshape(P), ups[3], ups[4]], [g_raw], J.pack_slf(P, cfg))
+    assert same(g_raw, raw.grad)
+    feat = f32(g.normal(size=(P, n, Fq))).to(dev).requires_grad_(True)
+    w = f32(g.uniform(size=(P, n))).to(dev).requires_grad_(True)
+    red = nslf._SlfReduceFn.apply(feat, w)
+    up = f32(g.normal(size=(P, Fq))).to(dev)
+    (red * up).sum().backward()
+    out = new(P, Fq)
+    xla_call("nrc_xla_slf_reduce_fwd", [feat.detach(), w.detach()], [out], J.pack_slf(P, cfg, num_features=Fq))
+    assert same(out, red)
+    gf, gw = new(P, n, Fq), new(P, n)
+    xla_call("nrc_xla_slf_reduce_bwd", [feat.detach(), w.detach(), up], [gf, gw], J.pack_slf(P, cfg, num_features=Fq))
+    assert same(gf, feat.grad) and same(gw, w.grad)
+    # a descriptor of the wrong size is refused and reported
+    xla_call("nrc_xla_slf_points_fwd", [raw.detach(), o, v], outs, J.pack_ggx(1, 1), expect_status=-1)
