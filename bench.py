@@ -508,8 +508,9 @@ def _slim(line, frame=False):
     out = {k: line[k] for k in ("metric", "value", "unit", "ms_per_step", "n_gpus", "steps", "dtype", "scaling",
                                 "gpu_launches_per_step", "roofline", "kernel_ms", "e2e")}
     out["workload"] = line["config"]["workload"]
-    if "train" in line:
-        out["train"] = line["train"]
+    for k in ("train", "slf_variate"):
+        if k in line:
+            out[k] = line[k]
     if frame:
         out["seconds_per_frame"] = line["ms_per_step"] * 1e-3
     return out
@@ -771,6 +772,37 @@ def render_line(args, workload_name, world, rank, dev, steps, warmup, rays=None,
             out_host.copy_(gstep(), non_blocking=True)
 
         e2e_ms = _timed(e2e_step, steps, warmup, flush, barrier)
+        # the same chunk with the surface-light-field control variate (MaterialModel.slf_variate, nerf_ngp_yobo.gin:91):
+        # the light-field memory queried on the 32 768 secondary rays of the cache pass, its integral subtracted
+        try:
+            stage_v = workload.MaterialRenderStep(dev, bf16=bool(args.bf16), slf_variate=True)
+            draws_v = stage_v.draws(R)
+
+            def vstep():
+                m, v, n = (dbuf[i * R * 3:(i + 1) * R * 3].view(R, 3) for i in range(3))
+                return stage_v.render(m, v, n, draws_v, stage_v.light_lobes(R, m, n))["rgb"]
+
+            before_v = _lib.launch_count
+            vstep()
+            launches_v = _lib.launch_count - before_v
+            side_v = torch.cuda.Stream()
+            side_v.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side_v):
+                vstep()
+            torch.cuda.current_stream().wait_stream(side_v)
+            torch.cuda.synchronize()
+            graph_v = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_v):
+                static_v = vstep()
+            v_ms = _timed(lambda: graph_v.replay(), steps, warmup, flush, barrier)
+            extra["slf_variate"] = {"ms_per_step": v_ms, "gpu_launches_per_step": launches_v,
+                                    "note": "one CUDA graph like the plain chunk; adds distance grid + 3 stacks + "
+                                            "nrc_slf_points_fwd + reflectance grid at 8 points per ray + nrc_slf_reduce_fwd + 2 "
+                                            "GGX integrations on the same 32 768 secondary rays"}
+            del graph_v, static_v
+            del stage_v
+        except Exception as ex:      # a failing side measurement must not lose the line
+            extra["slf_variate"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
         units = world * R * S * SAMPLES_PER_RAY
         wl = ("config3 material_light_from_scratch_resample chunk: %d shaded points x 32 secondary rays (16 microfacet + 8 "
               "cosine + 8 vMF-mixture/128 lobes, MIS), cache query per ray (64,64,32, power-ladder warp, categorical "

@@ -468,20 +468,24 @@ class MaterialRenderStep:
 
     NUM_LOBES = 128
 
-    def __init__(self, device, table_init_range=0.1, seed=SEED, bf16=True):
+    def __init__(self, device, table_init_range=0.1, seed=SEED, bf16=True, slf_variate=False):
         from . import material
         self.device = device
         gen = torch.Generator(device=device)
         gen.manual_seed(seed)
         self.gen = gen
         self.cache = models.NeRFModel(bf16=bf16)
-        self.model = material.MaterialModel(self.cache, bf16=bf16)
+        # slf_variate: MaterialModel.slf_variate with NeRFModel.use_surface_light_field (nerf_ngp_yobo.gin:91): the
+        # surface-light-field memory is queried on the same secondary rays and its integral subtracted
+        self.model = material.MaterialModel(self.cache, bf16=bf16, slf_variate=slf_variate)
         from . import light_sampler
         self.light = light_sampler.LightMLP(bf16=bf16)      # the vMF lobes of the light sampler
         self.params = {"Cache": _cache_params(self.cache, device, gen, table_init_range),
                        "Material": self.model.material_mlp.init(device, gen, table_init_range),
                        "EnvMap": self.model.env_map.init(device, gen),
                        "Light": self.light.init(device, gen, table_init_range)}
+        if slf_variate:
+            self.params["SurfaceLightFieldMem"] = self.model.surface_lf_mem.init(device, gen, table_init_range)
         # LightMLP.get_vmfs adds a fixed-key normal draw * vmf_scale / 2 to the lobe means (light_sampler.py:141-143)
         self.means_random = torch.randn((self.NUM_LOBES, 3), device=device, generator=gen) * (self.light.vmf_scale / 2.0)
 
