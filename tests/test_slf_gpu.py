@@ -256,3 +256,32 @@ def test_material_slf_variate(cuda_device):
     assert rel_err(b["acc_slf"].reshape(-1), want["incoming_acc"]) <= 2e-5
     assert b["rgb_slf"].shape == (R, 3) and bool((b["rgb_slf"] >= 0).all()) and float(b["rgb_slf"].abs().max()) > 0
     assert b["radiance_in_slf"].shape == (R, S, 3)
+
+
+def test_new_entry_points_argument_checks(cuda_device):
+    """Error convention of the entry points added with the light field (status codes, no launch): empty batches succeed,
+    null / inconsistent arguments are NRC_E_INVALID_ARG."""
+    lib = _lib.load()
+    sp = _lib.stream_ptr()
+    z = torch.zeros(64, device=cuda_device)
+    P = _lib.ptr
+    # nrc_ray_cast_covs(stream, tdist, origins, directions, radii, R, n, ray_shape, diag, covs, means)
+    assert lib.nrc_ray_cast_covs(sp, P(z), P(z), P(z), P(z), 0, 4, 0, 0, P(z), None) == 0
+    assert lib.nrc_ray_cast_covs(sp, P(z), P(z), P(z), P(z), 1, 4, 2, 0, P(z), None) == -1          # unknown ray shape
+    assert lib.nrc_ray_cast_covs(sp, P(z), None, P(z), P(z), 1, 4, 0, 0, None, P(z)) == -1          # means without origins
+    assert lib.nrc_ray_cast_covs(sp, P(z), P(z), P(z), P(z), 1, 4, 0, 0, None, None) == -1          # nothing to write
+    # nrc_slf_reduce_{fwd,bwd}
+    assert lib.nrc_slf_reduce_fwd(sp, P(z), P(z), 0, 8, 4, P(z)) == 0
+    assert lib.nrc_slf_reduce_fwd(sp, P(z), P(z), 1, 0, 4, P(z)) == -1
+    assert lib.nrc_slf_reduce_bwd(sp, P(z), P(z), P(z), 1, 2, 4, None, P(z)) == -1
+    # nrc_transient_render_bwd: a head's gradient without the head, exposure_time <= 0
+    args = [P(z)] * 8
+    tail = lambda g_raw, g_spec: [P(z), P(z), P(z), g_raw, g_spec, None, P(z)]
+    call = lambda a, expo, t: lib.nrc_transient_render_bwd(sp, *a, 1, 2, 4, 3, expo, 0.0, -1.0, 1.0, 0.0, 0, 0.0, 10.0, *t)
+    assert call(args, 0.01, tail(None, None)) == 0
+    assert call(args, 0.0, tail(None, None)) == -1
+    no_diffuse = [P(z), None, P(z), P(z)] + [P(z)] * 4
+    assert call(no_diffuse, 0.01, tail(P(z), None)) == -1
+    no_scale = [P(z), P(z), P(z), None] + [P(z)] * 4
+    assert call(no_scale, 0.01, tail(None, None)) == -1
+    torch.cuda.synchronize()
