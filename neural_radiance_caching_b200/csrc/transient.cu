@@ -174,22 +174,47 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
   float* s_light = s_move + p.n;
   float* s_cam = s_light + p.n;
   float* s_scale = s_cam + p.n;                                                  // [n][C]
-  __nv_bfloat16* h_sm = reinterpret_cast<__nv_bfloat16*>(s_scale + p.n * C + ((p.n * C) & 1));   // [32][192 + 8]
+  float* s_wa = s_scale + p.n * C + ((p.n * C) & 1);                             // weight x (1 - t): tap at bin b + off
+  float* s_wb = s_wa + p.n;                                                      // weight x t:       tap at bin b + off + 1
+  int* s_off = reinterpret_cast<int*>(s_wb + p.n);
+  int* s_lo = s_off + p.n;                                                       // valid bins of zero_invalid_bins: [lo, hi]
+  int* s_hi = s_lo + p.n;
+  __nv_bfloat16* h_sm = reinterpret_cast<__nv_bfloat16*>(s_hi + p.n + (p.n & 1));   // [32][192 + 8]
   constexpr int HS = kTrhK + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float max_dists = static_cast<float>(p.n_bins - 1) * p.exposure_time;
   for (int s = threadIdx.x; s < p.n; s += blockDim.x) {
     const int64_t i = ray * p.n + s;
-    s_w[s] = weights[i];
-    s_move[s] = (ray_dists[i] + p.shift) / p.exposure_time;
-    s_light[s] = light_dists[i];
-    s_cam[s] = cam_dists[i];
+    const float w = weights[i], light = light_dists[i], cam = cam_dists[i];
+    const float move = (ray_dists[i] + p.shift) / p.exposure_time;
+    s_w[s] = w; s_move[s] = move; s_light[s] = light; s_cam[s] = cam;
     for (int c = 0; c < C; ++c) s_scale[s * C + c] = spec_scale ? spec_scale[i * C + c] : 0.f;
+    // order-1 shift: the value at y = b - move lies between bins b + off and b + off + 1 with the SAME fraction for every b
+    const float yf = floorf(-move);
+    const float tt = -move - yf;
+    s_off[s] = static_cast<int>(yf);
+    s_wa[s] = w * (1.0f - tt);
+    s_wb[s] = w * tt;
+    // zero_invalid_bins (render_utils.py:1699-1767): both predicates are monotone in the bin -> one valid range per sample,
+    // found with the exact float predicates of the unfused kernel
+    int lo = 0, hi = p.n_bins;
+    while (lo < hi) {                                       // first bin that is NOT too close to the light
+      const int mid = (lo + hi) >> 1;
+      if ((static_cast<float>(mid) + p.bin_zero_threshold_light) * p.exposure_time < light) lo = mid + 1; else hi = mid;
+    }
+    int flo = 0, fhi = p.n_bins;
+    while (flo < fhi) {                                     // first bin that is too far
+      const int mid = (flo + fhi) >> 1;
+      if ((static_cast<float>(mid) * p.exposure_time + cam) > max_dists) fhi = mid; else flo = mid + 1;
+    }
+    if (p.light_zero && light < p.light_near) lo = p.n_bins;
+    s_lo[s] = lo;
+    s_hi[s] = flo - 1;
   }
   constexpr int kMaxPer = 16;    // output elements per thread (N <= 16 * 256)
   float out[kMaxPer];
 #pragma unroll
   for (int q = 0; q < kMaxPer; ++q) out[q] = 0.f;
-  const float max_dists = static_cast<float>(p.n_bins - 1) * p.exposure_time;
   const int n_tiles = (N + 7) >> 3;
   for (int row0 = 0; row0 < p.n; row0 += kTrhRows) {
     __syncthreads();            // the previous pass's gather is done with `stage`; the per-sample arrays are written
@@ -216,9 +241,33 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
         a[mt][kk][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
         a[mt][kk][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
       }
-    for (int tile = warp; tile < n_tiles; tile += kTrhThreads / 32) {
+    // rows of this thread in the pass: valid-bin range (empty beyond the last sample) and the specular scale
+    int row_lo[4], row_hi[4];
+    float row_sc[4][C];
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+      const int sr = row0 + (ri >> 1) * 16 + g + 8 * (ri & 1);
+      const bool live = sr < p.n;
+      row_lo[ri] = live ? s_lo[sr] : 1;
+      row_hi[ri] = live ? s_hi[sr] : 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) row_sc[ri][c] = live ? s_scale[sr * C + c] : 0.f;
+    }
+    // B fragments of a column tile: 12 8-byte loads per thread (its output column nb, K blocks 0..11), software-pipelined -
+    // the next tile's loads are in flight (L2 latency) while this tile's MMAs and epilogue run
+    uint2 bnext[kTrhK / 16];
+    auto load_b = [&](int tile) {
       const int nb = min(tile * 8 + g, N - 1);     // output column this thread's B fragments feed (clamped: unused beyond N)
       const uint2* wrow = reinterpret_cast<const uint2*>(w_packed + static_cast<int64_t>(nb) * kTrhK) + t;
+#pragma unroll
+      for (int kk = 0; kk < kTrhK / 16; ++kk) bnext[kk] = __ldg(wrow + kk * 4);
+    };
+    if (warp < n_tiles) load_b(warp);
+    for (int tile = warp; tile < n_tiles; tile += kTrhThreads / 32) {
+      uint2 bcur[kTrhK / 16];
+#pragma unroll
+      for (int kk = 0; kk < kTrhK / 16; ++kk) bcur[kk] = bnext[kk];
+      if (tile + kTrhThreads / 32 < n_tiles) load_b(tile + kTrhThreads / 32);
       float accd[2][4], accs[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -226,38 +275,50 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
         for (int i = 0; i < 4; ++i) accd[mt][i] = accs[mt][i] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < kTrhK / 16; ++kk) {
-        const uint2 bfrag = __ldg(wrow + kk * 4);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          if (kk < 4) mma_bf16_16816(accd[mt], a[mt][kk], bfrag.x, bfrag.y);
-          else mma_bf16_16816(accs[mt], a[mt][kk], bfrag.x, bfrag.y);
+          if (kk < 4) mma_bf16_16816(accd[mt], a[mt][kk], bcur[kk].x, bcur[kk].y);
+          else mma_bf16_16816(accs[mt], a[mt][kk], bcur[kk].x, bcur[kk].y);
         }
       }
+      // epilogue: this thread owns columns e0, e0 + 1 of rows g, g + 8, 16 + g, 24 + g; the per-column and per-row terms are
+      // hoisted, the two bf16 values of a row leave as one 4-byte store
+      const int e0 = tile * 8 + 2 * t;
+      if (e0 < N) {
+        int binj[2], cj[2];
+        float bdj[2], bsj[2];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = mt * 16 + g + (i >= 2 ? 8 : 0), e = tile * 8 + 2 * t + (i & 1);
-          if (e >= N) continue;
-          const int s = row0 + row;
-          float val = 0.f;
-          if (s < p.n) {
-            const int bin = e / C, c = e - bin * C;
-            // zero_invalid_bins (render_utils.py:1699-1767)
-            const float fb = static_cast<float>(bin);
-            bool ok = !((fb + p.bin_zero_threshold_light) * p.exposure_time < s_light[s]);
-            ok = ok && !((fb * p.exposure_time + s_cam[s]) > max_dists);
-            if (p.light_zero) ok = ok && !(s_light[s] < p.light_near);
-            if (ok) {
-              if (h_d) val += fminf(fmaxf(softplus_fast(accd[mt][i] + __ldg(b_d + e) + p.diffuse_bias) * p.indirect_scale, 0.f), p.rgb_max);
-              if (h_s) {
-                const float ref = fminf(fmaxf(softplus_fast(p.spec_premult * (accs[mt][i] + __ldg(b_s + e)) + p.spec_bias), 0.f), p.spec_max);
-                val += fminf(fmaxf(s_scale[s * C + c] * ref * p.indirect_scale, 0.f), p.rgb_max);
-              }
-            }
-          }
-          stage[static_cast<size_t>(row) * Ns + e] = __float2bfloat16_rn(val);
+        for (int j = 0; j < 2; ++j) {
+          const int e = min(e0 + j, N - 1);
+          binj[j] = e / C;
+          cj[j] = e - binj[j] * C;
+          bdj[j] = h_d ? __ldg(b_d + e) + p.diffuse_bias : 0.f;
+          bsj[j] = h_s ? __ldg(b_s + e) : 0.f;
         }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int ri = mt * 2 + half, row = mt * 16 + g + 8 * half;
+            float val[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              float v = 0.f;
+              if (binj[j] >= row_lo[ri] && binj[j] <= row_hi[ri]) {
+                if (h_d) v += fminf(fmaxf(softplus_fast(accd[mt][half * 2 + j] + bdj[j]) * p.indirect_scale, 0.f), p.rgb_max);
+                if (h_s) {
+                  const float ref = fminf(fmaxf(softplus_fast(p.spec_premult * (accs[mt][half * 2 + j] + bsj[j]) + p.spec_bias), 0.f), p.spec_max);
+                  const float sc = cj[j] == 0 ? row_sc[ri][0] : (cj[j] == 1 ? row_sc[ri][1] : row_sc[ri][C - 1]);
+                  v += fminf(fmaxf(sc * ref * p.indirect_scale, 0.f), p.rgb_max);
+                }
+              }
+              val[j] = v;
+            }
+            __nv_bfloat16* dst = stage + static_cast<size_t>(row) * Ns + e0;
+            if (e0 + 1 < N) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(val[0], val[1]);
+            else *dst = __float2bfloat16_rn(val[0]);
+          }
+      }
     }
     __syncthreads();
     // shift_map_coordinates (order-1 map_coordinates along the bin axis, mode 'constant') + the weighted reduction,
@@ -266,24 +327,16 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
     for (int q = 0; q < kMaxPer; ++q) {
       const int e = threadIdx.x + q * kTrhThreads;
       if (e >= N) continue;
-      const int b = e / C, c = e - b * C;
+      const int b = e / C;
       float acc = out[q];
       const int s_end = min(kTrhRows, p.n - row0);
       for (int r = 0; r < s_end; ++r) {
-        const int s = row0 + r;
-        const float y = static_cast<float>(b) - s_move[s];
-        const float y0f = floorf(y);
-        const float tt = y - y0f;
-        const int y0 = static_cast<int>(y0f);
-        float v = 0.f;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int bin = y0 + k;
-          const float wk = k ? tt : 1.0f - tt;
-          if (bin < 0 || bin >= p.n_bins || wk == 0.f) continue;
-          v += wk * __bfloat162float(stage[static_cast<size_t>(r) * Ns + bin * C + c]);
-        }
-        acc += s_w[s] * v;
+        const int sidx = row0 + r;
+        const int bin0 = b + s_off[sidx];
+        const __nv_bfloat16* st = stage + static_cast<size_t>(r) * Ns + e + s_off[sidx] * C;
+        const float v0 = (bin0 >= 0 && bin0 < p.n_bins) ? __bfloat162float(st[0]) : 0.f;
+        const float v1 = (bin0 >= -1 && bin0 + 1 < p.n_bins) ? __bfloat162float(st[C]) : 0.f;
+        acc = fmaf(s_wa[sidx], v0, fmaf(s_wb[sidx], v1, acc));
       }
       out[q] = acc;
     }
@@ -528,7 +581,7 @@ extern "C" int32_t nrc_transient_head_render_fwd(
   p.bin_zero_threshold_light = bin_zero_threshold_light; p.light_near = light_near; p.rgb_max = rgb_max;
   p.dark_level = dark_level; p.light_zero = light_zero;
   const size_t Ns = static_cast<size_t>((N + 1) & ~1);
-  const size_t smem = static_cast<size_t>(kTrhRows) * Ns * 2 + static_cast<size_t>(n) * (4 + channels + 1) * sizeof(float) +
+  const size_t smem = static_cast<size_t>(kTrhRows) * Ns * 2 + static_cast<size_t>(n) * (4 + channels + 1 + 5 + 1) * sizeof(float) +
                       static_cast<size_t>(kTrhRows) * (kTrhK + 8) * 2 + 16;
   if (smem > 227 * 1024) return NRC_E_UNSUPPORTED;
   if (channels != 3) return NRC_E_UNSUPPORTED;   /* the fused kernel is compiled for RGB histograms */
