@@ -114,7 +114,8 @@ __global__ void transient_indirect_kernel(const float* __restrict__ diffuse_raw,
 // at a time, the activated and masked values of those 16 samples are staged in shared memory in fp32 (134 KB), and the
 // sub-bin shift + weighted reduction over the samples reads them from there in the order of
 // transient_indirect_kernel (same taps, same summation order).  Only [R, n_bins, 3] leaves the SM.
-constexpr int kTrhThreads = 256;
+constexpr int kTrhThreads = 512;     // 16 warps: 8 column-tile lanes x 2 row tiles (one 16-row MMA tile per warp)
+constexpr int kTrhColWarps = 8;
 constexpr int kTrhRows = 32;          // samples per pass (two MMA row tiles)
 constexpr int kTrhK = 64 + 128;       // packed K: diffuse hidden | specular hidden
 
@@ -211,7 +212,7 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
     s_lo[s] = lo;
     s_hi[s] = flo - 1;
   }
-  constexpr int kMaxPer = 16;    // output elements per thread (N <= 16 * 256)
+  constexpr int kMaxPer = 8;     // output elements per thread (N <= 8 * 512)
   float out[kMaxPer];
 #pragma unroll
   for (int q = 0; q < kMaxPer; ++q) out[q] = 0.f;
@@ -228,25 +229,24 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
       h_sm[r * HS + k] = __float2bfloat16_rn(v);
     }
     __syncthreads();
-    // A fragments of the pass: 2 row tiles x 12 K blocks, kept in registers over all column tiles
-    uint32_t a[2][kTrhK / 16][4];
+    // A fragments of the pass: this warp's row tile (16 samples) x 12 K blocks, kept in registers over all column tiles
+    const int mt = warp / kTrhColWarps, cw = warp % kTrhColWarps;
+    uint32_t a[kTrhK / 16][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int kk = 0; kk < kTrhK / 16; ++kk) {
-        const __nv_bfloat16* r0 = h_sm + (mt * 16 + g) * HS + kk * 16 + 2 * t;
-        const __nv_bfloat16* r1 = r0 + 8 * HS;
-        a[mt][kk][0] = *reinterpret_cast<const uint32_t*>(r0);
-        a[mt][kk][1] = *reinterpret_cast<const uint32_t*>(r1);
-        a[mt][kk][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
-        a[mt][kk][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
-      }
+    for (int kk = 0; kk < kTrhK / 16; ++kk) {
+      const __nv_bfloat16* r0 = h_sm + (mt * 16 + g) * HS + kk * 16 + 2 * t;
+      const __nv_bfloat16* r1 = r0 + 8 * HS;
+      a[kk][0] = *reinterpret_cast<const uint32_t*>(r0);
+      a[kk][1] = *reinterpret_cast<const uint32_t*>(r1);
+      a[kk][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+      a[kk][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+    }
     // rows of this thread in the pass: valid-bin range (empty beyond the last sample) and the specular scale
-    int row_lo[4], row_hi[4];
-    float row_sc[4][C];
+    int row_lo[2], row_hi[2];
+    float row_sc[2][C];
 #pragma unroll
-    for (int ri = 0; ri < 4; ++ri) {
-      const int sr = row0 + (ri >> 1) * 16 + g + 8 * (ri & 1);
+    for (int ri = 0; ri < 2; ++ri) {
+      const int sr = row0 + mt * 16 + g + 8 * ri;
       const bool live = sr < p.n;
       row_lo[ri] = live ? s_lo[sr] : 1;
       row_hi[ri] = live ? s_hi[sr] : 0;
@@ -262,24 +262,19 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
 #pragma unroll
       for (int kk = 0; kk < kTrhK / 16; ++kk) bnext[kk] = __ldg(wrow + kk * 4);
     };
-    if (warp < n_tiles) load_b(warp);
-    for (int tile = warp; tile < n_tiles; tile += kTrhThreads / 32) {
+    if (cw < n_tiles) load_b(cw);
+    for (int tile = cw; tile < n_tiles; tile += kTrhColWarps) {
       uint2 bcur[kTrhK / 16];
 #pragma unroll
       for (int kk = 0; kk < kTrhK / 16; ++kk) bcur[kk] = bnext[kk];
-      if (tile + kTrhThreads / 32 < n_tiles) load_b(tile + kTrhThreads / 32);
-      float accd[2][4], accs[2][4];
+      if (tile + kTrhColWarps < n_tiles) load_b(tile + kTrhColWarps);
+      float accd[4], accs[4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) accd[mt][i] = accs[mt][i] = 0.f;
+      for (int i = 0; i < 4; ++i) accd[i] = accs[i] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < kTrhK / 16; ++kk) {
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          if (kk < 4) mma_bf16_16816(accd[mt], a[mt][kk], bcur[kk].x, bcur[kk].y);
-          else mma_bf16_16816(accs[mt], a[mt][kk], bcur[kk].x, bcur[kk].y);
-        }
+        if (kk < 4) mma_bf16_16816(accd, a[kk], bcur[kk].x, bcur[kk].y);
+        else mma_bf16_16816(accs, a[kk], bcur[kk].x, bcur[kk].y);
       }
       // epilogue: this thread owns columns e0, e0 + 1 of rows g, g + 8, 16 + g, 24 + g; the per-column and per-row terms are
       // hoisted, the two bf16 values of a row leave as one 4-byte store
@@ -296,18 +291,16 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
           bsj[j] = h_s ? __ldg(b_s + e) : 0.f;
         }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int ri = mt * 2 + half, row = mt * 16 + g + 8 * half;
+        for (int half = 0; half < 2; ++half) {
+            const int ri = half, row = mt * 16 + g + 8 * half;
             float val[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               float v = 0.f;
               if (binj[j] >= row_lo[ri] && binj[j] <= row_hi[ri]) {
-                if (h_d) v += fminf(fmaxf(softplus_fast(accd[mt][half * 2 + j] + bdj[j]) * p.indirect_scale, 0.f), p.rgb_max);
+                if (h_d) v += fminf(fmaxf(softplus_fast(accd[half * 2 + j] + bdj[j]) * p.indirect_scale, 0.f), p.rgb_max);
                 if (h_s) {
-                  const float ref = fminf(fmaxf(softplus_fast(p.spec_premult * (accs[mt][half * 2 + j] + bsj[j]) + p.spec_bias), 0.f), p.spec_max);
+                  const float ref = fminf(fmaxf(softplus_fast(p.spec_premult * (accs[half * 2 + j] + bsj[j]) + p.spec_bias), 0.f), p.spec_max);
                   const float sc = cj[j] == 0 ? row_sc[ri][0] : (cj[j] == 1 ? row_sc[ri][1] : row_sc[ri][C - 1]);
                   v += fminf(fmaxf(sc * ref * p.indirect_scale, 0.f), p.rgb_max);
                 }
@@ -551,7 +544,7 @@ extern "C" int32_t nrc_transient_head_render_fwd(
   if (num_rays < 0 || n < 1 || n > 1024 || n_bins < 1 || channels < 1 || channels > 4 || !(exposure_time > 0.f))
     return NRC_E_INVALID_ARG;
   const int64_t N = static_cast<int64_t>(n_bins) * channels;
-  if (N > 16 * kTrhThreads) return NRC_E_UNSUPPORTED;
+  if (N > 8 * kTrhThreads) return NRC_E_UNSUPPORTED;
   if ((d_h_diffuse && k_diffuse != 64) || (d_h_specular && k_specular != 128)) return NRC_E_UNSUPPORTED;
   if (num_rays == 0) return NRC_OK;
   if (!d_direct_rgbs || !d_weights || !d_ray_dists || !d_light_dists || !d_cam_dists || !d_transient_direct ||
