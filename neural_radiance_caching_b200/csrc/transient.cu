@@ -180,10 +180,16 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
   int* s_off = reinterpret_cast<int*>(s_wb + p.n);
   int* s_lo = s_off + p.n;                                                       // valid bins of zero_invalid_bins: [lo, hi]
   int* s_hi = s_lo + p.n;
-  __nv_bfloat16* h_sm = reinterpret_cast<__nv_bfloat16*>(s_hi + p.n + (p.n & 1));   // [32][192 + 8]
+  float* s_bd = reinterpret_cast<float*>(s_hi + p.n + (p.n & 1));                // [N] diffuse bias + diffuse_bias
+  float* s_bs = s_bd + Ns;                                                       // [N] specular bias
+  __nv_bfloat16* h_sm = reinterpret_cast<__nv_bfloat16*>(s_bs + Ns);             // [32][192 + 8]
   constexpr int HS = kTrhK + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const float max_dists = static_cast<float>(p.n_bins - 1) * p.exposure_time;
+  for (int e = threadIdx.x; e < N; e += blockDim.x) {
+    s_bd[e] = h_d ? __ldg(b_d + e) + p.diffuse_bias : 0.f;
+    s_bs[e] = h_s ? __ldg(b_s + e) : 0.f;
+  }
   for (int s = threadIdx.x; s < p.n; s += blockDim.x) {
     const int64_t i = ray * p.n + s;
     const float w = weights[i], light = light_dists[i], cam = cam_dists[i];
@@ -219,14 +225,29 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
   const int n_tiles = (N + 7) >> 3;
   for (int row0 = 0; row0 < p.n; row0 += kTrhRows) {
     __syncthreads();            // the previous pass's gather is done with `stage`; the per-sample arrays are written
-    for (int idx = threadIdx.x; idx < kTrhRows * kTrhK; idx += blockDim.x) {
-      const int r = idx / kTrhK, k = idx - r * kTrhK, s = row0 + r;
-      float v = 0.f;
-      if (s < p.n) {
-        if (k < 64) { if (h_d) v = h_d[(ray * p.n + s) * 64 + k]; }
-        else if (h_s) v = h_s[(ray * p.n + s) * 128 + (k - 64)];
+    {
+      // hidden activations of the pass's 32 samples -> bf16 rows: every load issued before the first conversion (one L2
+      // round trip instead of one per element)
+      constexpr int kPer = kTrhRows * kTrhK / kTrhThreads;
+      static_assert(kTrhRows * kTrhK % kTrhThreads == 0, "staging loop is unrolled");
+      float hv[kPer];
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const int idx = threadIdx.x + q * kTrhThreads;
+        const int r = idx / kTrhK, k = idx - r * kTrhK, s = row0 + r;
+        float v = 0.f;
+        if (s < p.n) {
+          if (k < 64) { if (h_d) v = __ldg(h_d + (ray * p.n + s) * 64 + k); }
+          else if (h_s) v = __ldg(h_s + (ray * p.n + s) * 128 + (k - 64));
+        }
+        hv[q] = v;
       }
-      h_sm[r * HS + k] = __float2bfloat16_rn(v);
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const int idx = threadIdx.x + q * kTrhThreads;
+        const int r = idx / kTrhK, k = idx - r * kTrhK;
+        h_sm[r * HS + k] = __float2bfloat16_rn(hv[q]);
+      }
     }
     __syncthreads();
     // A fragments of the pass: this warp's row tile (16 samples) x 12 K blocks, kept in registers over all column tiles
@@ -287,8 +308,8 @@ transient_head_render_kernel(const float* __restrict__ h_d, const float* __restr
           const int e = min(e0 + j, N - 1);
           binj[j] = e / C;
           cj[j] = e - binj[j] * C;
-          bdj[j] = h_d ? __ldg(b_d + e) + p.diffuse_bias : 0.f;
-          bsj[j] = h_s ? __ldg(b_s + e) : 0.f;
+          bdj[j] = s_bd[e];
+          bsj[j] = s_bs[e];
         }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -575,7 +596,7 @@ extern "C" int32_t nrc_transient_head_render_fwd(
   p.dark_level = dark_level; p.light_zero = light_zero;
   const size_t Ns = static_cast<size_t>((N + 1) & ~1);
   const size_t smem = static_cast<size_t>(kTrhRows) * Ns * 2 + static_cast<size_t>(n) * (4 + channels + 1 + 5 + 1) * sizeof(float) +
-                      static_cast<size_t>(kTrhRows) * (kTrhK + 8) * 2 + 16;
+                      2 * Ns * sizeof(float) + static_cast<size_t>(kTrhRows) * (kTrhK + 8) * 2 + 16;
   if (smem > 227 * 1024) return NRC_E_UNSUPPORTED;
   if (channels != 3) return NRC_E_UNSUPPORTED;   /* the fused kernel is compiled for RGB histograms */
   if (const int32_t st_attr = ensure_dynamic_smem<transient_head_render_kernel<3>>(227 * 1024); st_attr != NRC_OK)
