@@ -37,6 +37,38 @@ __device__ __forceinline__ void window_cumsum(const float* src, float* dst, int 
   }
 }
 
+// Inclusive prefix sums / exclusive suffix sums of a shared-memory row by chunked warp scans (32 entries per pass): used
+// where the result feeds a gradient, not a fencepost (summation order differs from window_cumsum in the last bits).
+__device__ __forceinline__ void scan_prefix_inclusive(const float* src, float* dst, int n, int lane) {
+  float carry = 0.f;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int i = c0 + lane;
+    float x = i < n ? src[i] : 0.f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (i < n) dst[i] = carry + x;
+    carry += __shfl_sync(0xffffffffu, x, 31);
+  }
+}
+__device__ __forceinline__ void scan_suffix_exclusive(const float* src, float* dst, int n, int lane) {
+  float carry = 0.f;
+  for (int c0 = ((n - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
+    const int i = c0 + lane;
+    const float v = i < n ? src[i] : 0.f;
+    float x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float y = __shfl_down_sync(0xffffffffu, x, o);
+      if (lane + o < 32) x += y;
+    }
+    if (i < n) dst[i] = carry + (x - v);
+    carry += __shfl_sync(0xffffffffu, x, 0);
+  }
+}
+
 // ------------------------------------------------------------ alpha weights --
 __global__ void __launch_bounds__(kRayThreads)
 alpha_weights_fwd_kernel(const float* __restrict__ density, const float* __restrict__ tdist,
@@ -78,6 +110,7 @@ alpha_weights_bwd_kernel(const float* __restrict__ density, const float* __restr
   __shared__ float s_dd[kRayWarps][kMaxN];
   __shared__ float s_cs[kRayWarps][kMaxN];
   __shared__ float s_gt[kRayWarps][kMaxN];  // gT_k * T_k
+  __shared__ float s_tr[kRayWarps][kMaxN];  // T_k
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * kRayWarps + warp;
   if (r >= R) return;
@@ -89,7 +122,7 @@ alpha_weights_bwd_kernel(const float* __restrict__ density, const float* __restr
     s_dd[warp][i] = density[r * n + i] * fabsf(delta);
   }
   __syncwarp();
-  window_cumsum(s_dd[warp], s_cs[warp], n - 1, lane);
+  scan_prefix_inclusive(s_dd[warp], s_cs[warp], n - 1, lane);
   __syncwarp();
   for (int i = lane; i < n; i += 32) {
     float a = 1.0f - expf(-s_dd[warp][i]);
@@ -97,16 +130,16 @@ alpha_weights_bwd_kernel(const float* __restrict__ density, const float* __restr
     float gw = g_w ? g_w[r * n + i] : 0.f;
     float gT = (g_t ? g_t[r * n + i] : 0.f) + gw * a;
     s_gt[warp][i] = gT * tr;
+    s_tr[warp][i] = tr;
   }
+  __syncwarp();
+  scan_suffix_exclusive(s_gt[warp], s_cs[warp], n, lane);     // sum_{k > i} gT_k T_k (the transmittances are not needed any more)
   __syncwarp();
   for (int i = lane; i < n; i += 32) {
     float e = expf(-s_dd[warp][i]);
-    float tr = expf(-(i == 0 ? 0.f : s_cs[warp][i - 1]));
     float gw = g_w ? g_w[r * n + i] : 0.f;
-    float gA = (g_a ? g_a[r * n + i] : 0.f) + gw * tr;
-    float suffix = 0.f;
-    for (int k = n - 1; k > i; --k) suffix += s_gt[warp][k];
-    float g_dd = gA * e - suffix;
+    float gA = (g_a ? g_a[r * n + i] : 0.f) + gw * s_tr[warp][i];
+    float g_dd = gA * e - s_cs[warp][i];
     float delta = (t[i + 1] - t[i]) * dn;
     g_density[r * n + i] = g_dd * fabsf(delta);
   }
