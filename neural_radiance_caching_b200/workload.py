@@ -6,7 +6,7 @@ import os
 import numpy as np
 import torch
 
-from . import models, nerf
+from . import _lib, mlp_chain, models, nerf
 
 SEED = 20200823  # the reference's Config.jax_rng_seed (internal/configs.py:180)
 SAMPLES_PER_RAY = (64, 64, 32)  # configs/nerf_ngp_yobo.gin:521-545
@@ -615,6 +615,18 @@ class TransientRenderStep:
                         tfilter_sigma=3.0, filter_indirect=False)
         self.light_power = float(np.exp(3.9))     # light_power_activation = safe_exp, light_power_bias = 3.9 (gin:111-114)
         self._head_pack = {}                      # packed bf16 image of the two head layers (repacked when they change)
+        # render path of the bf16 variant: the shader-side Dense stacks as tcgen05 chain programs (spec, packed-weight cache);
+        # a stack whose LAST hidden activation is the product (h_diffuse, h_specular) ends in a linear head + ReLU
+        PC = mlp_chain.PackCache
+        self._chains = {
+            "trunk": (mlp_chain.ChainSpec(in_widths=[96], hidden=[], heads=[[("bottleneck_layer", 128)],
+                      [("roughness_layer", 1), ("tint_layer", 3), ("albedo_layer", 3)]]), PC()),
+            "brdf": (self.cache.shader.brdf_chain, PC()),
+            "slf": (mlp_chain.ChainSpec(in_widths=[128, 72], hidden=[("layer_0", 128, False), ("layer_1", 128, False),
+                    ("layer_2", 128, True)], heads=[[("layer_bottleneck", 128)]]), PC()),
+            "irr": (mlp_chain.ChainSpec(in_widths=[96, 15], hidden=[("irradiance_layers_0", 64, False)],
+                    heads=[[("irradiance_layers_1", 64)]]), PC()),
+        } if bf16 else None
 
     def make_rays(self, g, R):
         """Synthetic rays of the Cornell-box scale: near 0.7 / far 4, a point light beside the camera."""
@@ -634,27 +646,43 @@ class TransientRenderStep:
             R, n = w.shape
             P = R * n
             feature = shader.predict_appearance_feature(p, feat, means).reshape(P, 96)
-            bott = nerf.dense(p["bottleneck_layer"], feature, bf16=b)
-            rough = sp(nerf.dense(p["roughness_layer"], feature, bf16=b) - 1.0)
-            tint = torch.sigmoid(nerf.dense(p["tint_layer"], feature, bf16=b))
-            albedo = torch.sigmoid(nerf.dense(tp["albedo_layer"], feature, bf16=b) - 1.0)
             view = rays["viewdirs"][:, None, :].expand(R, n, 3).reshape(P, 3)
             n2 = nrm.reshape(P, 3)
             dot = torch.sum(n2 * (-view), dim=-1, keepdim=True)
-            x = nerf.dense(p["integrated_brdf_layers_0"], torch.cat([bott, dot], dim=-1), relu=True, bf16=b)
-            x = nerf.dense(p["integrated_brdf_layers_1"], x, relu=True, bf16=b)
-            F = torch.sigmoid(nerf.dense(p["output_integrated_brdf_layer"], x, bf16=b) + float(np.log(3.0)))
-            refdirs = nerf.reflect(-view, n2)
-            xin = torch.cat([bott, self.ide5(refdirs, rough)], dim=-1)
-            x = xin
-            for j, name in enumerate(["layer_0", "layer_1", "layer_2", "layer_bottleneck"]):
-                x = nerf.dense(tp["TransientSurfaceLightField"][name], x, relu=True, bf16=b)
-                if j % 2 == 0 and j > 0:
-                    x = torch.cat([x, xin], dim=-1)
-            h_s = x                                                                        # [P, 128]
             m2 = means.reshape(P, 3)
             lights = rays["lights"][:, None, :].expand(R, n, 3).reshape(P, 3)
-            h_d = self.head.hidden(tp, feature, lights)                                     # [P, 64]
+            chains = b and not train       # render path of the bf16 variant: the Dense stacks as tcgen05 chain programs
+            if chains:
+                ch, fc = self._chains, mlp_chain.forward_cached
+                slf = tp["TransientSurfaceLightField"]
+                bott, r_raw, t_raw, a_raw = fc(ch["trunk"][0], dict(p, albedo_layer=tp["albedo_layer"]), [feature], ch["trunk"][1])
+                rough, tint, albedo = sp(r_raw - 1.0), torch.sigmoid(t_raw), torch.sigmoid(a_raw - 1.0)
+                (f_raw,) = fc(ch["brdf"][0], p, [bott, dot], ch["brdf"][1])
+                F = torch.sigmoid(f_raw + float(np.log(3.0)))
+                refdirs = nerf.reflect(-view, n2)
+                (h_s,) = fc(ch["slf"][0], slf, [bott, self.ide5(refdirs, rough)], ch["slf"][1])
+                h_s = torch.relu(h_s)                                                      # [P, 128]
+                enc_l = torch.empty((P, 15), device=feature.device, dtype=torch.float32)
+                _lib.call("nrc_pos_enc", _lib.stream_ptr(), _lib.ptr(lights.contiguous()), P, 3, 0, 2, 1, _lib.ptr(enc_l), 15)
+                (h_d,) = fc(ch["irr"][0], tp, [feature, enc_l], ch["irr"][1])
+                h_d = torch.relu(h_d)                                                      # [P, 64]
+            else:
+                bott = nerf.dense(p["bottleneck_layer"], feature, bf16=b)
+                rough = sp(nerf.dense(p["roughness_layer"], feature, bf16=b) - 1.0)
+                tint = torch.sigmoid(nerf.dense(p["tint_layer"], feature, bf16=b))
+                albedo = torch.sigmoid(nerf.dense(tp["albedo_layer"], feature, bf16=b) - 1.0)
+                x = nerf.dense(p["integrated_brdf_layers_0"], torch.cat([bott, dot], dim=-1), relu=True, bf16=b)
+                x = nerf.dense(p["integrated_brdf_layers_1"], x, relu=True, bf16=b)
+                F = torch.sigmoid(nerf.dense(p["output_integrated_brdf_layer"], x, bf16=b) + float(np.log(3.0)))
+                refdirs = nerf.reflect(-view, n2)
+                xin = torch.cat([bott, self.ide5(refdirs, rough)], dim=-1)
+                x = xin
+                for j, name in enumerate(["layer_0", "layer_1", "layer_2", "layer_bottleneck"]):
+                    x = nerf.dense(tp["TransientSurfaceLightField"][name], x, relu=True, bf16=b)
+                    if j % 2 == 0 and j > 0:
+                        x = torch.cat([x, xin], dim=-1)
+                h_s = x                                                                    # [P, 128]
+                h_d = self.head.hidden(tp, feature, lights)                                 # [P, 64]
             off = lights - m2
             light_d = torch.linalg.norm(off, dim=-1, keepdim=True)
             n_dot_l = torch.clamp(torch.sum(n2 * (off / torch.clamp(light_d, min=1e-5)), dim=-1, keepdim=True), min=0.0)
