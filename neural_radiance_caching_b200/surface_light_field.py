@@ -123,7 +123,10 @@ class SurfaceLightFieldMemMLP:
         self.rgb_chain = mlp_chain.ChainSpec(
             in_widths=[self.nrf], hidden=[("layer_0", 64, False), ("layer_bottleneck", 128, False)],
             heads=[[("output_rgba_layer", 4), ("output_ambient_rgb_layer", 3)]])
-        self._pack_caches = (mlp_chain.PackCache(), mlp_chain.PackCache())
+        # render path: the bottleneck stack as one program too (its product is the last ACTIVATION: linear head + ReLU)
+        self.bottleneck_chain = mlp_chain.ChainSpec(in_widths=[self.nf], hidden=[("layers_0", 64, False)],
+                                                    heads=[[("layers_1", 64)]])
+        self._pack_caches = (mlp_chain.PackCache(), mlp_chain.PackCache(), mlp_chain.PackCache())
 
     def layer_shapes(self):
         s = [("layers_0", self.nf, 64), ("layers_1", 64, 64)]
@@ -177,6 +180,9 @@ class SurfaceLightFieldMemMLP:
         """predict_appearance_feature (shading.py:133-220) with one control point: grid features through run_network."""
         z = coord._ContractFn.apply(origins, self.warp_c)
         x = self.grid(p["distance_grid"], z).reshape(-1, self.nf)
+        if self.bf16 and not torch.is_grad_enabled():
+            (h,) = mlp_chain.forward_cached(self.bottleneck_chain, p, [x], self._pack_caches[2])
+            return torch.relu(h), z
         x = nerf.dense(p["layers_0"], x, relu=True, bf16=self.bf16)
         return nerf.dense(p["layers_1"], x, relu=True, bf16=self.bf16), z
 
