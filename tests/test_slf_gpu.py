@@ -285,3 +285,42 @@ def test_new_entry_points_argument_checks(cuda_device):
     no_scale = [P(z), P(z), P(z), None] + [P(z)] * 4
     assert call(no_scale, 0.01, tail(None, None)) == -1
     torch.cuda.synchronize()
+
+
+def test_slf_mem_full_size_properties(cuda_device):
+    """The light field at the material stage's full chunk size (32 768 secondary rays, bf16 render path, reference-sized
+    grids): size-independent properties of predict_points and of the outputs."""
+    g = gen(5600)
+    P = 32768
+    net = nslf.SurfaceLightFieldMemMLP(bf16=True)
+    gen_t = torch.Generator(device=cuda_device); gen_t.manual_seed(5600)
+    p = net.init(cuda_device, gen_t, table_init_range=0.3)
+    o = f32(g.normal(size=(P, 3)) * 1.5).to(cuda_device)
+    v = torch.nn.functional.normalize(f32(g.normal(size=(P, 3))), dim=-1).to(cuda_device)
+    with torch.no_grad():
+        res = net.get_slf_results(p, o, v)
+        bott, z = net.bottleneck(p, o)
+        raw = net.run_distances_network(p, bott, z, v)
+        pts, w, sd, dist, env = nslf._SlfPointsFn.apply(raw, o, v, nslf._points_cfg(net, 0.0, float("inf")))
+    torch.cuda.synchronize()
+    for k, t in res.items():
+        assert bool(torch.isfinite(t).all()), k
+    assert res["rgb"].shape == (P, 3) and res["acc"].shape == (P,)
+    assert float(res["rgb"].min()) >= 0.0
+    # weights = softmax x mask x sigmoid: non-negative, and their sum (acc) at most the environment alpha < 1
+    assert float(w.min()) >= 0.0 and float((w.sum(-1) - env[:, 3]).max()) <= 1e-5 and float(env[:, 3].max()) < 1.0
+    # distances are clipped to the module's range, the weighted s-distance is a convex combination of values in [0, 1]
+    assert float(dist.min()) >= net.distance_near - 1e-6 and float(dist.max()) <= net.distance_far + 1e-6
+    assert float(sd.min()) >= -1e-6 and float(sd.max()) <= 1.0 + 1e-6
+    # contracted points lie inside the ball of radius 2 (coord.contract)
+    assert float(pts.norm(dim=-1).max()) <= 2.0 + 1e-5
+    # the point stage is exactly reproducible and independent of the batch it runs in (ragged tail of the last CTA)
+    sub = slice(1000, 1000 + 333)
+    pts2, w2, sd2, dist2, env2 = nslf._SlfPointsFn.apply(raw[sub].contiguous(), o[sub].contiguous(), v[sub].contiguous(),
+                                                         nslf._points_cfg(net, 0.0, float("inf")))
+    assert torch.equal(pts2, pts[sub]) and torch.equal(w2, w[sub]) and torch.equal(sd2, sd[sub]) and torch.equal(env2, env[sub])
+    # the weighted feature sum is linear in the weights
+    feat = torch.rand((P, net.n, net.nrf), device=cuda_device)
+    a = nslf._SlfReduceFn.apply(feat, w)
+    b = nslf._SlfReduceFn.apply(feat, 2.0 * w)
+    assert rel_err(b, 2.0 * a) <= 1e-6
