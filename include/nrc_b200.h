@@ -597,6 +597,12 @@ int32_t nrc_grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult
 /* Same loss, but levels[l].d_grad is OVERWRITTEN with mult * T / numel(T) (plain stores): the launch doubles as the
  * per-step zero-fill of these gradient tables.  Must be ordered BEFORE every scatter into them. */
 int32_t nrc_grid_regularizer_init(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss);
+/* Zero-fill of up to 8 ranges [lo[k], hi[k]) (in floats, multiples of 4; d_base 16-byte aligned) of one buffer in ONE
+ * launch: the per-step clearing of the gradient arena minus the tables nrc_grid_regularizer_init overwrites.  lo / hi are
+ * HOST arrays (copied into the launch parameters).  streaming != 0: evict-first stores, so that the fill does not displace
+ * the level tables from L2 while the sampler's forward gathers them. */
+int32_t nrc_zero_ranges(void* stream, float* d_base, const int64_t* lo, const int64_t* hi, int32_t num_ranges,
+                        int32_t streaming);
 /* Gradient all-reduce (MEAN over ranks) of the flat gradient arena over NVLink / NVSwitch peer memory: the reference's
  * lax.pmean over the gradient pytree (internal/train_utils.py:3132-3136).  The arena is symmetric memory (same size on
  * every rank); rank r reduces the r-th slice of floats [offset, offset+count) and writes the mean into EVERY rank's copy.

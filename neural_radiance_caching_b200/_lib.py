@@ -125,6 +125,7 @@ PROTOTYPES = {
     "nrc_vmf_loss": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _I32, _P, _P, _P, _P],
     "nrc_grid_regularizer": [_P, _P, _F, _P],
     "nrc_grid_regularizer_init": [_P, _P, _F, _P],
+    "nrc_zero_ranges": [_P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _I32, _I32],
     "nrc_probe_gather": [_P, _P, _I64, _I32, _I64, _I32, _P],
     "nrc_allreduce_mean_multicast": [_P, _P, _I64, _I64, _I32, _I32, _I32],
     "nrc_allreduce_mean_peer": [_P, _P, _I64, _I64, _I32, _I32, _I32],

@@ -257,7 +257,11 @@ __global__ void __launch_bounds__(256) grid_regularizer_kernel(const __grid_cons
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(t) + i);
       const float k = mult * inv_n;
-      if (overwrite) {
+      if (overwrite == 2) {
+        // evict-first stores: the gradient tables are next touched by the backward scatters, the level TABLES are what the
+        // forward gathers (running beside this launch) want to keep in L2
+        __stcs(reinterpret_cast<float4*>(g + 4 * i), make_float4(k * v.x, k * v.y, k * v.z, k * v.w));
+      } else if (overwrite) {
         *reinterpret_cast<float4*>(g + 4 * i) = make_float4(k * v.x, k * v.y, k * v.z, k * v.w);
       } else {
         // 16-byte reduction: commutes with the scatter kernels' atomics on the same tables, so no stream ordering
@@ -284,6 +288,21 @@ __global__ void __launch_bounds__(256) grid_regularizer_kernel(const __grid_cons
     float sum = 0.f;
     for (int k = 0; k < 8; ++k) sum += part[k];
     atomicAdd(loss, 0.5f * mult * inv_n * sum);
+  }
+}
+
+// Zero-fill of up to 8 float ranges of one buffer in ONE launch (the gradient arena minus the tables the regularizer
+// initialises): 16-byte stores, optionally evict-first (streaming) so that the fill does not push the level tables out of L2
+// while the sampler's forward gathers them.
+struct ZeroRanges { int n; long long lo4[8], cnt4[8]; };
+__global__ void __launch_bounds__(256) zero_ranges_kernel(float* __restrict__ base, const ZeroRanges r, const int streaming) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < r.n; ++k) {
+    float4* p = reinterpret_cast<float4*>(base) + r.lo4[k];
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < r.cnt4[k];
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      if (streaming) __stcs(p + i, z); else p[i] = z;
+    }
   }
 }
 
@@ -338,7 +357,31 @@ extern "C" int32_t nrc_grid_regularizer(void* stream, const nrc_encoding_t* enc,
   return grid_regularizer(stream, enc, mult, d_loss, 0);
 }
 extern "C" int32_t nrc_grid_regularizer_init(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss) {
-  return grid_regularizer(stream, enc, mult, d_loss, 1);
+  // NRC_STREAM_FILLS=0: plain stores (the gradient lines then compete with the level tables for the L2 during the forward)
+  static const int mode = (getenv("NRC_STREAM_FILLS") && getenv("NRC_STREAM_FILLS")[0] == '0') ? 1 : 2;
+  return grid_regularizer(stream, enc, mult, d_loss, mode);
+}
+
+extern "C" int32_t nrc_zero_ranges(void* stream, float* d_base, const int64_t* lo, const int64_t* hi, int32_t num_ranges,
+                                   int32_t streaming) {
+  if (!d_base || num_ranges < 0 || num_ranges > 8 || (num_ranges > 0 && (!lo || !hi))) return NRC_E_INVALID_ARG;
+  nrc::ZeroRanges r;
+  r.n = 0;
+  long long most = 0;
+  for (int k = 0; k < num_ranges; ++k) {
+    if (lo[k] < 0 || hi[k] < lo[k] || (lo[k] & 3) || (hi[k] & 3)) return NRC_E_INVALID_ARG;
+    if (hi[k] == lo[k]) continue;
+    r.lo4[r.n] = lo[k] >> 2;
+    r.cnt4[r.n] = (hi[k] - lo[k]) >> 2;
+    most = r.cnt4[r.n] > most ? r.cnt4[r.n] : most;
+    ++r.n;
+  }
+  if ((reinterpret_cast<uintptr_t>(d_base) & 15) != 0) return NRC_E_INVALID_ARG;
+  if (r.n == 0) return NRC_OK;
+  const long long want = (most + 255) / 256;
+  const unsigned grid = static_cast<unsigned>(want < 4LL * nrc::num_sms() ? (want > 0 ? want : 1) : 4LL * nrc::num_sms());
+  nrc::zero_ranges_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_base, r, streaming);
+  return nrc::check_launch();
 }
 
 static int32_t grid_regularizer(void* stream, const nrc_encoding_t* enc, float mult, float* d_loss, int overwrite) {

@@ -289,8 +289,17 @@ class CacheTrainStep:
         if not skip_density_grids:
             self.flat_grad.zero_()
             return
-        for lo, hi in self._zero_ranges:
-            self.flat_grad[lo:hi].zero_()
+        mode = os.environ.get("NRC_STREAM_FILLS", "1")
+        rs = self._zero_ranges
+        if mode == "torch" or len(rs) > 8 or any((lo | hi) & 3 for lo, hi in rs):
+            for lo, hi in rs:
+                self.flat_grad[lo:hi].zero_()
+            return
+        # one launch for all ranges, evict-first stores (NRC_STREAM_FILLS=0: plain stores)
+        import ctypes as C
+        lo_a = (C.c_int64 * len(rs))(*[lo for lo, _ in rs])
+        hi_a = (C.c_int64 * len(rs))(*[hi for _, hi in rs])
+        _lib.call("nrc_zero_ranges", _lib.stream_ptr(), _lib.ptr(self.flat_grad), lo_a, hi_a, len(rs), int(mode != "0"))
 
     def allreduce_grads(self, lo=0, hi=None, channel=0, num_ctas=0, mode=None, leading_barrier=True, trailing_barrier=True):
         """Mean over ranks of flat_grad[lo:hi] in place on the current stream (the reference's lax.pmean,

@@ -131,3 +131,29 @@ def test_dense_level_matches_explicit_trilinear(cuda_device):
     centres = f32(np.stack(np.meshgrid(*[np.arange(N) + 0.5] * 3, indexing="ij"), -1).reshape(-1, 3))
     got_c = ng.trilerp(grid.to(cuda_device), centres.to(cuda_device), "grid").cpu()
     assert torch.equal(got_c, grid.reshape(-1, F))
+
+
+def test_zero_ranges(cuda_device):
+    """nrc_zero_ranges: several ranges of one buffer cleared in one launch, plain and evict-first stores; everything
+    outside the ranges untouched; argument checks."""
+    import ctypes as C
+    from neural_radiance_caching_b200 import _lib
+    lib = _lib.load()
+    n = 1 << 20
+    ranges = [(0, 4096), (8192, 8192), (100000, 700000), (n - 8, n)]
+    for streaming in (0, 1):
+        buf = torch.ones(n, device=cuda_device)
+        lo = (C.c_int64 * len(ranges))(*[a for a, _ in ranges])
+        hi = (C.c_int64 * len(ranges))(*[b for _, b in ranges])
+        _lib.call("nrc_zero_ranges", _lib.stream_ptr(), _lib.ptr(buf), lo, hi, len(ranges), streaming)
+        want = torch.ones(n)
+        for a, b in ranges:
+            want[a:b] = 0.0
+        assert torch.equal(buf.cpu(), want)
+    buf = torch.ones(64, device=cuda_device)
+    one = lambda a, b: ((C.c_int64 * 1)(a), (C.c_int64 * 1)(b))
+    assert lib.nrc_zero_ranges(_lib.stream_ptr(), _lib.ptr(buf), *one(2, 8), 1, 0) == -1      # not a multiple of 4 floats
+    assert lib.nrc_zero_ranges(_lib.stream_ptr(), _lib.ptr(buf), *one(8, 4), 1, 0) == -1      # hi < lo
+    assert lib.nrc_zero_ranges(_lib.stream_ptr(), _lib.ptr(buf), None, None, 0, 0) == 0
+    assert lib.nrc_zero_ranges(_lib.stream_ptr(), _lib.ptr(buf), *one(0, 4), 9, 0) == -1
+    assert float(buf.sum()) == 64.0
