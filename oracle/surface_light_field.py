@@ -12,7 +12,6 @@ import torch
 from . import coord as ocoord
 from . import geometry as ogeo
 from . import grid_utils as ogrid
-from . import ref_math
 
 DISTANCE_GRID = dict(hash_map_size=524288, max_grid_size=256, num_features=4)          # nerf_ngp_yobo.gin:156-161
 REFLECTANCE_GRID = dict(hash_map_size=524288, max_grid_size=256, num_features=4, bbox_scaling=2.0)   # :146-152

@@ -9,7 +9,6 @@ make_reference_vectors.py (same closed-form parameters); run from the repo root:
 
 The hash tables are scaled down (hash_map_size 2**14, max_grid_size 128) so that the tables need not be stored: they are
 the closed form `level_table` of the entry index, repeated in tests/util.py."""
-import functools
 import importlib
 import os
 import sys
