@@ -18,8 +18,6 @@
 
 namespace nrc {
 
-namespace {
-
 constexpr int kSlfMaxSamples = 32;
 
 struct SlfSample {
@@ -238,21 +236,19 @@ __global__ void slf_reduce_bwd_kernel(const float* __restrict__ feat, const floa
   if (lane == 0) g_w[row] = acc;
 }
 
-int slf_rows_per_cta(int n) {
+static int slf_rows_per_cta(int n) {
   const int W = 8 * n + 4;
   for (int rows = 128; rows >= 32; rows >>= 1)
     if (static_cast<size_t>(rows) * (W + 1) * sizeof(float) <= 48u * 1024u) return rows;
   return 0;
 }
 
-int32_t slf_check(const nrc_slf_points_t* cfg, const void* a, const void* b, const void* c2, int64_t ld, int64_t P) {
+static int32_t slf_check(const nrc_slf_points_t* cfg, const void* a, const void* b, const void* c2, int64_t ld, int64_t P) {
   if (!cfg || !a || !b || !c2 || P < 0) return NRC_E_INVALID_ARG;
   if (cfg->num_distance_samples < 1 || ld < 8 * static_cast<int64_t>(cfg->num_distance_samples) + 4) return NRC_E_INVALID_ARG;
   if (cfg->num_distance_samples > kSlfMaxSamples || (cfg->warp_kind != 0 && cfg->warp_kind != 1)) return NRC_E_UNSUPPORTED;
   return NRC_OK;
 }
-
-}  // namespace
 
 }  // namespace nrc
 
