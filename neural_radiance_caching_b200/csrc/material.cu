@@ -88,6 +88,23 @@ struct VmfMixture {
   }
 };
 
+// The same mixture with everything that does not depend on the query direction computed ONCE per shaded point and kept
+// in shared memory (the point's S sample threads evaluate it 1-2 times each over all K lobes): per lobe the normalised
+// mean, the exponent scale (kappa, or 0 for the uniform lobe) and coef = softmax(logits)_k kappa_k / (4 pi sinh kappa_k)
+// (1 / (4 pi) for the uniform lobe), so that pdf(x) = sum_k coef_k safe_exp(kappa_k <x, mean_k>).
+struct VmfTable {
+  const float* t;   // [K][5]: mean (3), exponent scale, coef
+  int K;
+  __device__ __forceinline__ float pdf(const float x[3]) const {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float* e = t + 5 * k;
+      acc += e[4] * safe_exp(e[3] * (x[0] * e[0] + x[1] * e[1] + x[2] * e[2]));
+    }
+    return fmaxf(acc, 0.f);
+  }
+};
+
 __device__ __forceinline__ void l2n3(float v[3]) {
   const float d = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
   const float inv = 1.0f / sqrtf(fmaxf(f32_tiny(), d));
@@ -96,6 +113,7 @@ __device__ __forceinline__ void l2n3(float v[3]) {
   for (int a = 0; a < 3; ++a) v[a] = zero ? 0.f : v[a] * inv;
 }
 
+template <bool kTable>
 __global__ void secondary_sample_kernel(const float* __restrict__ means, const float* __restrict__ viewdirs,
                                         const float* __restrict__ normals, const float* __restrict__ roughness,
                                         int64_t R, int n_micro, int n_cos, int n_light, const float* __restrict__ u,
@@ -107,9 +125,57 @@ __global__ void secondary_sample_kernel(const float* __restrict__ means, const f
                                         float* __restrict__ pdf_out, float* __restrict__ weight_out) {
   const int S = n_micro + n_cos + n_light;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  extern __shared__ float s_tab[];          // kTable: [points per CTA][K][5]
+  if constexpr (kTable) {
+    // blockDim.x is a multiple of S (the launcher checks): this CTA owns whole points p0 .. p0 + ppc - 1
+    const int ppc = blockDim.x / S;
+    const int64_t p0 = static_cast<int64_t>(blockIdx.x) * ppc;
+    // stage 1: per lobe - normalised mean, exponent scale, kappa / (4 pi sinh kappa); the logit waits in the coef slot
+    for (int j = threadIdx.x; j < ppc * K; j += blockDim.x) {
+      const int lp = j / K, k = j - lp * K;
+      const int64_t pp = p0 + lp;
+      float* e = s_tab + 5 * j;
+      if (pp >= R) { e[0] = e[1] = e[2] = e[3] = 0.f; e[4] = -INFINITY; continue; }
+      const float* mk = vmf_means + (pp * K + k) * 3;
+      const float a0 = mk[0], a1 = mk[1], a2 = mk[2];
+      const float d = a0 * a0 + a1 * a1 + a2 * a2;
+      const float inv = 1.0f / sqrtf(fmaxf(f32_tiny(), d));
+      const bool zero = d < f32_tiny();
+      e[0] = zero ? 0.f : a0 * inv; e[1] = zero ? 0.f : a1 * inv; e[2] = zero ? 0.f : a2 * inv;
+      const float kp = vmf_kappas[pp * K + k];
+      e[3] = kp <= f32_eps() ? 0.f : kp;
+      e[4] = vmf_logits[pp * K + k];
+    }
+    __syncthreads();
+    // stage 2: softmax over the point's K logits (the point's S threads share the lobes), folded into coef
+    {
+      const int lp = threadIdx.x / S, sl = threadIdx.x - lp * S;
+      float* tp = s_tab + 5 * lp * K;
+      float mx = -INFINITY, den = 0.f;
+      if (S == 32) {                         // one warp per point: lanes split the lobes, two shuffle reductions
+        for (int k = sl; k < K; k += 32) mx = fmaxf(mx, tp[5 * k + 4]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        for (int k = sl; k < K; k += 32) den += expf(tp[5 * k + 4] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+      } else {
+        for (int k = 0; k < K; ++k) mx = fmaxf(mx, tp[5 * k + 4]);
+        for (int k = 0; k < K; ++k) den += expf(tp[5 * k + 4] - mx);
+      }
+      __syncthreads();                       // every thread has read the logits before they are overwritten
+      for (int k = sl; k < K; k += S) {
+        const float kp = tp[5 * k + 3];
+        const float norm = kp == 0.f ? 1.0f / (4.0f * kPi) : kp / (4.0f * kPi * sinhf(kp));
+        tp[5 * k + 4] = expf(tp[5 * k + 4] - mx) / den * norm;
+      }
+      __syncthreads();
+    }
+  }
   if (idx >= R * S) return;
   const int64_t p = idx / S;
   const int s = static_cast<int>(idx - p * S);
+  const VmfTable tab{s_tab + 5 * (threadIdx.x / S) * K, K};
   Frame f;
   f.build(normals[3 * p], normals[3 * p + 1], normals[3 * p + 2]);
   const float gv[3] = {-viewdirs[3 * p], -viewdirs[3 * p + 1], -viewdirs[3 * p + 2]};   // global_viewdirs
@@ -168,7 +234,7 @@ __global__ void secondary_sample_kernel(const float* __restrict__ means, const f
     float g[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) g[c] = t[c] * (sq * v0) + b[c] * (sq * v1) + m[c] * w;
-    pdf = mix.pdf(g);
+    pdf = kTable ? tab.pdf(g) : mix.pdf(g);
     f.to_local(g, wi);    // global_dirs sampler: back to the local frame
   }
   // ---- MIS power heuristic over the samplers of the set (render_utils.py:817-853)
@@ -181,7 +247,7 @@ __global__ void secondary_sample_kernel(const float* __restrict__ means, const f
     if (n_light > 0) {
       float gl[3];
       f.to_global(wi, gl);
-      const float q = mix.pdf(gl) * n_light;
+      const float q = (kTable ? tab.pdf(gl) : mix.pdf(gl)) * n_light;
       den += q * q;
     }
     den = fmaxf(den, kDenEps);
@@ -240,10 +306,22 @@ extern "C" int32_t nrc_secondary_sample(void* stream, const float* d_means, cons
   if (n_light > 0 && (!d_vmf_means || !d_vmf_kappas || !d_vmf_logits || !d_latent || !d_normal2 || num_lobes < 1))
     return NRC_E_INVALID_ARG;
   const int64_t total = num_points * S;
-  secondary_sample_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_means, d_viewdirs, d_normals, d_roughness, num_points, n_microfacet, n_cosine, n_light, d_u, d_vmf_means,
-      d_vmf_kappas, d_vmf_logits, num_lobes, d_latent, d_normal2, normal_eps, d_origins, d_directions, d_local_lightdirs,
-      d_local_viewdirs, d_pdf, d_weight);
+  // whole points per CTA and a per-point lobe table in shared memory when the samples tile a 128-thread CTA (S = 32 in the
+  // configured material stage: 4 points, 10 KB at 128 lobes); otherwise every thread walks the raw lobes itself
+  const size_t tab_bytes = n_light > 0 ? static_cast<size_t>(128 / (S > 128 ? 128 : S)) * num_lobes * 5 * sizeof(float) : 0;
+  if (n_light > 0 && S <= 128 && 128 % S == 0 && tab_bytes <= 48u * 1024u) {
+    const int64_t ppc = 128 / S;
+    secondary_sample_kernel<true><<<static_cast<unsigned>((num_points + ppc - 1) / ppc), 128, tab_bytes,
+                                    static_cast<cudaStream_t>(stream)>>>(
+        d_means, d_viewdirs, d_normals, d_roughness, num_points, n_microfacet, n_cosine, n_light, d_u, d_vmf_means,
+        d_vmf_kappas, d_vmf_logits, num_lobes, d_latent, d_normal2, normal_eps, d_origins, d_directions, d_local_lightdirs,
+        d_local_viewdirs, d_pdf, d_weight);
+  } else {
+    secondary_sample_kernel<false><<<static_cast<unsigned>((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_means, d_viewdirs, d_normals, d_roughness, num_points, n_microfacet, n_cosine, n_light, d_u, d_vmf_means,
+        d_vmf_kappas, d_vmf_logits, num_lobes, d_latent, d_normal2, normal_eps, d_origins, d_directions, d_local_lightdirs,
+        d_local_viewdirs, d_pdf, d_weight);
+  }
   return check_launch();
 }
 
