@@ -122,6 +122,33 @@ def main():
         out.update({tag + "_bottleneck": bott, tag + "_dist_net_outputs": raw, tag + "_points": pts, tag + "_raw_weights": raw_w,
                     tag + "_ref_mask": mask, tag + "_s_distances": s_d, tag + "_distances": dist})
 
+    # ---- material._integrate_slf_variate (material.py:2433-2513): the reference's own method on a stand-in `self` whose
+    #      get_outgoing_radiance returns the cache integral on the first call and the light-field integral on the second
+    #      (it must be handed the first call's outputs as last_integrated_outputs: the SAME secondary rays) ----------------
+    keys = ("radiance_out", "diffuse_radiance_out", "specular_radiance_out", "irradiance", "indirect_occ")
+    cache_o = {k_: f(g.uniform(size=(12, 3))) for k_ in keys}
+    slf_o = {k_: f(g.uniform(size=(12, 3))) for k_ in keys if k_ != "indirect_occ"}
+    slf_o["only_slf"] = f(g.uniform(size=(12, 1)))
+    calls = []
+
+    def fake_get_outgoing_radiance(**kw):
+        calls.append(kw)
+        return dict(cache_o) if len(calls) == 1 else dict(slf_o)
+
+    me = types.SimpleNamespace(get_outgoing_radiance=fake_get_outgoing_radiance, get_num_secondary_samples_diff=lambda train: 4)
+    merged = R["material"].BaseMaterialMLP._integrate_slf_variate(
+        me, np.zeros(2, np.uint32), None, None, None, None, "cache_fn", "slf_fn", None, None, 1.0, False)
+    assert calls[0]["radiance_cache_fn"] == "cache_fn" and calls[1]["radiance_cache_fn"] == "slf_fn"
+    assert calls[1]["last_integrated_outputs"]["radiance_out"] is cache_o["radiance_out"]
+    for k_, v_ in cache_o.items():
+        out["variate_cache_" + k_] = v_
+    for k_, v_ in slf_o.items():
+        out["variate_slf_" + k_] = v_
+    out["variate_keys"] = np.array(sorted(merged.keys()))
+    for k_, v_ in merged.items():
+        if v_ is not None:
+            out["variate_out_" + k_] = np.asarray(v_)
+
     out = {k: np.asarray(v_) for k, v_ in out.items()}
     out = {k: (v_.astype(np.float32) if v_.dtype == np.float64 else v_) for k, v_ in out.items()}
     path = os.path.join(HERE, "reference_slf.npz")

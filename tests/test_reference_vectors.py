@@ -585,3 +585,20 @@ def test_slf_memory(tag, n, kw):
                    ("incoming_s_dist", 2e-5), ("incoming_dist", 2e-5), ("incoming_env_rgba", 2e-5), ("incoming_acc", 2e-5)):
         ref = torch.from_numpy(VS[tag + "_" + k]).reshape(res[k].shape)
         assert float((res[k] - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max())), k
+
+
+def test_slf_variate_merge():
+    """surface_light_field.integrate_slf_variate (host logic of the product; no kernel involved) against the reference's
+    own material._integrate_slf_variate executed on a stand-in `self` (material.py:2433-2513): same keys, differences for
+    the radiance keys, `_cache` / `_slf` copies (None where the light-field pass has no such entry)."""
+    from neural_radiance_caching_b200 import surface_light_field as nslf
+    cache = {k[len("variate_cache_"):]: torch.from_numpy(VS[k]) for k in VS.files if k.startswith("variate_cache_")}
+    slf = {k[len("variate_slf_"):]: torch.from_numpy(VS[k]) for k in VS.files if k.startswith("variate_slf_")}
+    got = nslf.integrate_slf_variate(cache, slf)
+    assert sorted(got.keys()) == list(VS["variate_keys"])
+    for k, v in got.items():
+        name = "variate_out_" + k
+        if v is None:
+            assert name not in VS.files, k
+        else:
+            assert np.array_equal(v.numpy(), VS[name]), k
